@@ -1,0 +1,152 @@
+"""ctypes binding of oracle/libha_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MZ = np.dtype([("x", "<u8"), ("info", "<u8")])
+HIT = np.dtype([("id_strand", "<u4"), ("offset", "<u4"), ("self_offset", "<u4"), ("cnt", "<u4")])
+MA = np.dtype([("qns", "<u8"), ("qe", "<u4"), ("tn", "<u4"), ("ts", "<u4"), ("te", "<u4"),
+               ("ml", "<u4"), ("rev", "<u4"), ("bl", "<u4"), ("del", "<u4"),
+               ("el", "u1"), ("no_l_indel", "u1"), ("pad", "u1", (6,))])
+OVLP = np.dtype([("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_id", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
+                 ("y_pos_strand", "<u4"), ("shared_seed", "<i4"), ("align_length", "<u4"),
+                 ("non_homopolymer_errors", "<u4"), ("overlapLen", "<u4"), ("is_match", "u1"),
+                 ("without_large_indel", "u1"), ("strong", "i1"), ("pad", "u1"), ("fc_off", "<u4"), ("fc_n", "<u4")])
+
+
+class Reads(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("len", C.c_void_p), ("off", C.c_void_p), ("packed", C.c_void_p),
+                ("n_off", C.c_void_p), ("n_pos", C.c_void_p)]
+
+
+class Opt(C.Structure):
+    _fields_ = [("k", C.c_int), ("w", C.c_int), ("is_hpc", C.c_int), ("mz_sample_dist", C.c_int),
+                ("mz_rewin", C.c_int), ("min_hist_kmer_cnt", C.c_int), ("high_factor", C.c_double),
+                ("max_kmer_cnt", C.c_int), ("max_n_chain", C.c_int), ("hom_cov", C.c_int), ("het_cov", C.c_int)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libha_oracle.so")
+        src = os.path.join(_HERE, "ha_oracle.c")
+        if (not os.path.exists(so)) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+            subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        L.hao_ft_gen.restype = C.c_void_p
+        L.hao_pt_gen.restype = C.c_void_p
+        L.hao_pt_get.restype = C.c_void_p
+        L.hao_ft_cnt.restype = C.c_int32
+        L.hao_ft_size.restype = C.c_uint64
+        L.hao_pt_tot_pos.restype = C.c_uint64
+        L.hao_pt_n_keys.restype = C.c_uint64
+        _LIB = L
+    return _LIB
+
+
+class Store:
+    """Keeps numpy arrays alive behind a hao_reads_t."""
+
+    def __init__(self, length, byte_off, packed, n_off=None, n_pos=None):
+        self.length = np.ascontiguousarray(length, dtype=np.uint64)
+        self.byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        self.packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        n = self.length.size
+        self.n_off = np.ascontiguousarray(n_off if n_off is not None else np.zeros(n + 1), dtype=np.uint64)
+        self.n_pos = np.ascontiguousarray(n_pos if n_pos is not None else np.zeros(1), dtype=np.uint64)
+        self.c = Reads(n, self.length.ctypes.data, self.byte_off.ctypes.data, self.packed.ctypes.data,
+                       self.n_off.ctypes.data, self.n_pos.ctypes.data)
+
+    @property
+    def n(self):
+        return int(self.length.size)
+
+    def decode(self, i) -> bytes:
+        buf = C.create_string_buffer(int(self.length[i]) + 1)
+        lib().hao_decode(C.byref(self.c), C.c_uint64(i), buf)
+        return buf.raw[:int(self.length[i])]
+
+    def decode_sub(self, i, start, ln, strand) -> bytes:
+        buf = C.create_string_buffer(int(ln) + 1)
+        lib().hao_decode_sub(C.byref(self.c), C.c_uint64(i), C.c_int64(start), C.c_int64(ln), C.c_int(strand), buf)
+        return buf.raw[:int(ln)]
+
+
+def default_opt() -> Opt:
+    o = Opt()
+    lib().hao_opt_default(C.byref(o))
+    return o
+
+
+def _take(ptr, n, dtype):
+    if n == 0:
+        if ptr.value:
+            lib().hao_free(ptr)
+        return np.zeros(0, dtype=dtype)
+    a = np.frombuffer((C.c_uint8 * (n * dtype.itemsize)).from_address(ptr.value), dtype=dtype).copy()
+    lib().hao_free(ptr)
+    return a
+
+
+def sketch(seq: bytes, w, k, rid, is_hpc, ft, sample_dist, rewin):
+    out = C.c_void_p(); n = C.c_uint32()
+    rc = lib().hao_sketch(seq, C.c_int(len(seq)), C.c_int(w), C.c_int(k), C.c_uint32(rid), C.c_int(is_hpc),
+                          C.c_void_p(ft), C.c_int(sample_dist), C.c_int(rewin), C.byref(out), C.byref(n))
+    assert rc == 0
+    return _take(out, n.value, MZ)
+
+
+def ft_gen(store: Store, opt: Opt):
+    hom = C.c_int()
+    ft = lib().hao_ft_gen(C.byref(store.c), C.byref(opt), C.byref(hom))
+    return ft, hom.value
+
+
+def pt_gen(store: Store, ft, opt: Opt):
+    hom = C.c_int(); het = C.c_int()
+    pt = lib().hao_pt_gen(C.byref(store.c), C.c_void_p(ft), C.byref(opt), C.byref(hom), C.byref(het))
+    return pt, hom.value, het.value
+
+
+def pt_get(pt, h):
+    n = C.c_int()
+    p = lib().hao_pt_get(C.c_void_p(pt), C.c_uint64(int(h)), C.byref(n))
+    if n.value == 0:
+        return np.zeros(0, dtype=np.uint64)
+    return np.frombuffer((C.c_uint8 * (n.value * 8)).from_address(p), dtype=np.uint64).copy()
+
+
+def anchors(store: Store, pt, mz: np.ndarray, high_occ, low_occ):
+    out = C.c_void_p(); n = C.c_uint64()
+    mz = np.ascontiguousarray(mz)
+    lib().hao_anchors(C.byref(store.c), C.c_void_p(pt), C.c_void_p(mz.ctypes.data), C.c_uint32(mz.size),
+                      C.c_uint32(high_occ), C.c_uint32(low_occ), C.byref(out), C.byref(n))
+    return _take(out, n.value, HIT)
+
+
+def lchain(store: Store, rid, hits: np.ndarray, bw, k, max_n_chain):
+    """-> (chains OVLP[], compacted hits HIT[], fake cigar pool u64[])"""
+    hits = np.ascontiguousarray(hits).copy()
+    nh = C.c_uint64(hits.size); out = C.c_void_p(); n = C.c_uint32(); fc = C.c_void_p(); nfc = C.c_uint64()
+    lib().hao_lchain(C.byref(store.c), C.c_uint32(rid), C.c_void_p(hits.ctypes.data), C.byref(nh), C.c_double(bw),
+                     C.c_int(k), C.c_int(max_n_chain), C.byref(out), C.byref(n), C.byref(fc), C.byref(nfc))
+    return _take(out, n.value, OVLP), hits[:nh.value], _take(fc, nfc.value, np.dtype("<u8"))
+
+
+def final_read(store: Store, pt, ft, opt: Opt, rid, in0: np.ndarray, in1: np.ndarray):
+    in0 = np.ascontiguousarray(in0).copy(); in1 = np.ascontiguousarray(in1)
+    o0 = C.c_void_p(); o1 = C.c_void_p(); m0 = C.c_uint32(); m1 = C.c_uint32()
+    lib().hao_final_read(C.byref(store.c), C.c_void_p(pt), C.c_void_p(ft), C.byref(opt), C.c_uint32(rid),
+                         C.c_void_p(in0.ctypes.data), C.c_uint32(in0.size), C.c_void_p(in1.ctypes.data), C.c_uint32(in1.size),
+                         C.byref(o0), C.byref(m0), C.byref(o1), C.byref(m1))
+    return _take(o0, m0.value, MA), _take(o1, m1.value, MA)

@@ -1,0 +1,173 @@
+// oracle/refdump.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Our own driver, linked against the UNMODIFIED reference objects
+// (oracle/_ref/libhifiasm_ref.so, built by oracle/Makefile from the sources
+// under /root/reference).  It replays the reference's overlap/EC stage the way
+// ha_assemble() does (Assembly.cpp:2055-2113) and dumps
+//   * per-read intermediate arrays of the hot path (sketch, index probe,
+//     anchors, chains) taken by calling the reference's own non-static
+//     functions (mz1_ha_sketch htab.h:121, ha_pt_get htab.h:85,
+//     minimizers_qgen0 anchor.cpp:987, h_ec_lchain anchor.cpp:2302), and
+//   * the read store and overlap lists before / after the final overlap pass
+//     (ha_ec_ff -> cal_ov_r, Assembly.cpp:1942 / ecovlp.cpp:6385) through the
+//     reference's own writers (write_All_reads Process_Read.cpp:69,
+//     write_ma_hit_ts Overlaps.cpp:23442).
+// The dumps are the golden vectors the oracle port and the CUDA path are pinned
+// against (tests/golden/, made by tests/golden/make_golden.py).
+//
+// usage: refdump <raw|final> <out_prefix> <hifiasm args...>
+//   raw   : filter table + round-0 index on the raw reads, stage dumps, exit
+//   final : 3 EC rounds, "<p>.pre.*" bins, final index, stage dumps,
+//           cal_ov_r, "<p>.fin.*" bins
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include "CommandLines.h"
+#include "Process_Read.h"
+#include "Overlaps.h"
+#include "Assembly.h"
+#include "htab.h"
+#include "Hash_Table.h"
+#include "ecovlp.h"
+
+// non-static reference functions that no header declares
+void ha_ec(int64_t round, int num_pround, int des_idx, uint64_t *tot_b, uint64_t *tot_e);
+void ha_opt_update_cov(hifiasm_opt_t *opt, int hom_cov);
+void ha_opt_reset_to_round(hifiasm_opt_t *asm_opt, int round);
+void write_ma_hit_ts(ma_hit_t_alloc *x, long long n_read, char *read_file_name);
+void minimizers_qgen0(ha_abuf_t *ab, char *rs, int64_t rl, uint64_t mz_w, uint64_t mz_k, Candidates_list *cl, kvec_t_u8_warp *k_flag,
+                      void *ha_flt_tab, ha_pt_t *ha_idx, All_reads *rdb, kvec_t_u64_warp *dbg_ct, st_mt_t *sp, uint32_t *high_occ, uint32_t *low_occ);
+void h_ec_lchain(ha_abuf_t *ab, uint32_t rid, char *rs, uint64_t rl, uint64_t mz_w, uint64_t mz_k, All_reads *rref, overlap_region_alloc *overlap_list, Candidates_list *cl, double bw_thres,
+                 int max_n_chain, int apend_be, kvec_t_u8_warp *k_flag, kvec_t_u64_warp *dbg_ct, st_mt_t *sp, uint32_t *high_occ, uint32_t *low_occ, uint32_t is_accurate, uint32_t gen_off, int64_t mcopy_num, double mcopy_rate, uint32_t chain_cutoff, uint32_t mcopy_khit_cut, uint64_t ocv_w);
+
+#define HA_KMER_GOOD_RATIO 0.333 /* ecovlp.cpp:9 */
+#define COV_W 3072               /* ecovlp.cpp:17 */
+
+static FILE *xopen(const char *pfx, const char *suf)
+{
+	char *fn = (char *)malloc(strlen(pfx) + strlen(suf) + 2);
+	sprintf(fn, "%s%s", pfx, suf);
+	FILE *fp = fopen(fn, "wb");
+	if (!fp) { fprintf(stderr, "refdump: cannot write %s\n", fn); exit(1); }
+	free(fn);
+	return fp;
+}
+
+// one record per chain: the overlap_region fields the hot path defines
+typedef struct {
+	uint32_t x_pos_s, x_pos_e, y_id, y_pos_s, y_pos_e, y_pos_strand;
+	int32_t shared_seed;
+	uint32_t first_hit; // overlap_region.non_homopolymer_errors (Hash_Table.cpp:2280)
+	uint32_t n_fc;      // f_cigar.length
+} chain_rec_t;
+
+static void dump_stages(const char *pfx, double bw_thres)
+{
+	uint64_t i, j, n_reads = R_INF.total_reads;
+	uint32_t high_occ = asm_opt.hom_cov * (2.0 - HA_KMER_GOOD_RATIO); // ecovlp.cpp:3952
+	uint32_t low_occ = asm_opt.hom_cov * HA_KMER_GOOD_RATIO;
+	FILE *fmz = xopen(pfx, ".mz.bin"), *fidx = xopen(pfx, ".idx.bin"), *fan = xopen(pfx, ".anchors.bin");
+	FILE *fch = xopen(pfx, ".chains.bin"), *fpa = xopen(pfx, ".params.txt");
+	UC_Read ur; init_UC_Read(&ur);
+	ha_abuf_t *ab = ha_abuf_init();
+	Candidates_list cl; init_Candidates_list(&cl);
+	overlap_region_alloc ol; init_overlap_region_alloc(&ol);
+	st_mt_t sp; memset(&sp, 0, sizeof(sp));
+	ha_mz1_v mz; memset(&mz, 0, sizeof(mz));
+
+	fprintf(fpa, "n_reads %lu\nk %d\nw %d\nhom_cov %d\nhet_cov %d\nmax_n_chain %d\nhigh_occ %u\nlow_occ %u\nbw_thres %.6f\nmz_sample_dist %d\nmz_rewin %d\nis_hpc %d\nhave_flt %d\n",
+	        (unsigned long)n_reads, asm_opt.k_mer_length, asm_opt.mz_win, asm_opt.hom_cov, asm_opt.het_cov, asm_opt.max_n_chain,
+	        high_occ, low_occ, bw_thres, asm_opt.mz_sample_dist, asm_opt.mz_rewin, !(asm_opt.flag & HA_F_NO_HPC), ha_flt_tab ? 1 : 0);
+	fclose(fpa);
+
+	for (i = 0; i < n_reads; i++) {
+		recover_UC_Read(&ur, &R_INF, i);
+		// (1) sketch, with the arguments minimizers_qgen0 passes (anchor.cpp:1003)
+		mz.n = 0;
+		mz1_ha_sketch(ur.seq, ur.length, asm_opt.mz_win, asm_opt.k_mer_length, 0, !(asm_opt.flag & HA_F_NO_HPC), &mz, ha_flt_tab,
+		              asm_opt.mz_sample_dist, NULL, NULL, NULL, -1, asm_opt.dp_min_len, -1, &sp, asm_opt.mz_rewin, 0, NULL);
+		uint32_t n = mz.n;
+		fwrite(&n, 4, 1, fmz);
+		fwrite(mz.a, sizeof(ha_mz1_t), n, fmz);
+		// (2) index probe of every query minimizer
+		for (j = 0; j < n; j++) {
+			int c; const ha_idxpos_t *p = ha_pt_get(ha_idx, mz.a[j].x, &c);
+			uint32_t cc = c;
+			fwrite(&mz.a[j].x, 8, 1, fidx); fwrite(&cc, 4, 1, fidx);
+			if (c) fwrite(p, sizeof(ha_idxpos_t), c, fidx);
+		}
+		// (3) anchors after sort + weighting (cl->list of minimizers_qgen0)
+		minimizers_qgen0(ab, ur.seq, ur.length, asm_opt.mz_win, asm_opt.k_mer_length, &cl, NULL, ha_flt_tab, ha_idx, &R_INF, NULL, &sp, &high_occ, &low_occ);
+		uint64_t na = cl.length;
+		fwrite(&na, 8, 1, fan);
+		fwrite(cl.list, sizeof(k_mer_hit), na, fan);
+		// (4) chains: the call worker_hap_dc_ec_gen_new_idx makes (ecovlp.cpp:3957) but with the mode's bw
+		h_ec_lchain(ab, i, ur.seq, ur.length, asm_opt.mz_win, asm_opt.k_mer_length, &R_INF, &ol, &cl, bw_thres, asm_opt.max_n_chain, 1, NULL, NULL, &sp, &high_occ, &low_occ, 1, 1, 3, 0.7, 2, 32, COV_W);
+		uint32_t nc = ol.length; uint64_t nh = cl.length;
+		fwrite(&nc, 4, 1, fch); fwrite(&nh, 8, 1, fch);
+		for (j = 0; j < nc; j++) {
+			overlap_region *o = &ol.list[j]; chain_rec_t r;
+			r.x_pos_s = o->x_pos_s; r.x_pos_e = o->x_pos_e; r.y_id = o->y_id; r.y_pos_s = o->y_pos_s; r.y_pos_e = o->y_pos_e;
+			r.y_pos_strand = o->y_pos_strand; r.shared_seed = o->shared_seed; r.first_hit = o->non_homopolymer_errors; r.n_fc = o->f_cigar.length;
+			fwrite(&r, sizeof(r), 1, fch);
+			fwrite(o->f_cigar.buffer, 8, o->f_cigar.length, fch);
+		}
+		fwrite(cl.list, sizeof(k_mer_hit), nh, fch); // compacted chain hits (des region)
+	}
+	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch);
+	destory_UC_Read(&ur);
+}
+
+static void write_bins(const char *pfx, const char *tag)
+{
+	char *fn = (char *)malloc(strlen(pfx) + strlen(tag) + 32);
+	sprintf(fn, "%s.%s.ec", pfx, tag); write_All_reads(&R_INF, fn);
+	sprintf(fn, "%s.%s.ovlp.source", pfx, tag); write_ma_hit_ts(R_INF.paf, R_INF.total_reads, fn);
+	sprintf(fn, "%s.%s.ovlp.reverse", pfx, tag); write_ma_hit_ts(R_INF.reverse_paf, R_INF.total_reads, fn);
+	free(fn);
+}
+
+int main(int argc, char *argv[])
+{
+	if (argc < 4) { fprintf(stderr, "usage: refdump <raw|final> <out_prefix> <hifiasm args...>\n"); return 1; }
+	const char *mode = argv[1], *pfx = argv[2];
+	int r, hom_cov = -1, het_cov = -1; uint64_t tot_b, tot_e;
+	yak_reset_realtime();
+	init_opt(&asm_opt);
+	argv[2] = argv[0];
+	if (!CommandLine_process(argc - 2, argv + 2, &asm_opt)) return 1;
+
+	ha_flt_tab = NULL; ha_idx = NULL;
+	if (!(asm_opt.flag & HA_F_NO_KMER_FLT)) { // Assembly.cpp:2081-2085
+		ha_flt_tab = ha_ft_gen(&asm_opt, &R_INF, &hom_cov, 0, 0);
+		ha_opt_update_cov(&asm_opt, hom_cov);
+	}
+	if (strcmp(mode, "raw") == 0) {
+		ha_idx = ha_pt_gen(&asm_opt, ha_flt_tab, 0, 0, &R_INF, &hom_cov, &het_cov); // Assembly.cpp:1007
+		asm_opt.hom_cov = hom_cov; asm_opt.het_cov = het_cov;
+		if (ha_flt_tab == 0) ha_opt_update_cov(&asm_opt, hom_cov);
+		write_bins(pfx, "raw");
+		dump_stages(pfx, asm_opt.is_ont ? 0.05 : 0.02); // bw of worker_hap_ec (ecovlp.cpp:3274)
+		return 0;
+	}
+	for (r = 0; r < asm_opt.number_of_round; ++r) { // Assembly.cpp:2088-2097
+		ha_opt_reset_to_round(&asm_opt, r);
+		tot_b = tot_e = 0;
+		ha_ec(r, asm_opt.number_of_pround, (r < asm_opt.number_of_round - 1) ? 1 : 0, &tot_b, &tot_e);
+		fprintf(stderr, "[refdump] round %d: bases %lu corrected %lu\n", r + 1, (unsigned long)tot_b, (unsigned long)tot_e);
+	}
+	ha_opt_reset_to_round(&asm_opt, asm_opt.number_of_round);
+	write_bins(pfx, "pre");
+	// ha_ec_ff(1), Assembly.cpp:1942-1959, opened up so the index can be probed
+	if (ha_idx) { ha_pt_destroy(ha_idx); ha_idx = NULL; }
+	ha_idx = ha_pt_gen(&asm_opt, ha_flt_tab, 1, 0, &R_INF, &hom_cov, &het_cov);
+	asm_opt.hom_cov = hom_cov; asm_opt.het_cov = het_cov;
+	dump_stages(pfx, 0.001); // bw of worker_hap_dc_ec_gen_new_idx (ecovlp.cpp:3957)
+	double t0 = yak_realtime();
+	cal_ov_r(asm_opt.thread_num, R_INF.total_reads, 1);
+	fprintf(stderr, "[refdump] cal_ov_r wall %.3f s\n", yak_realtime() - t0);
+	ha_pt_destroy(ha_idx); ha_idx = NULL;
+	write_bins(pfx, "fin");
+	return 0;
+}
