@@ -1130,3 +1130,169 @@ int hao_lchain(const hao_reads_t *r, uint32_t rid, hao_hit_t *hits, uint64_t *n_
 	if (fc) { *fc = ol.fc; *n_fc = ol.n_fc; } else free(ol.fc);
 	return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* final overlap pass for one read                                     */
+/* ------------------------------------------------------------------ */
+
+#define HA_KMER_GOOD_RATIO 0.333 /* ecovlp.cpp:9 */
+
+int hao_final_read(const hao_reads_t *r, const hao_pt_t *pt, const hao_ft_t *ft, const hao_opt_t *o, uint32_t rid,
+                   hao_ma_t *in0, uint32_t n0, const hao_ma_t *in1, uint32_t n1,
+                   hao_ma_t **out0, uint32_t *m0, hao_ma_t **out1, uint32_t *m1)
+{ /* worker_hap_dc_ec_gen_new_idx, ecovlp.cpp:3948-3992 */
+	uint32_t high_occ = (uint32_t)(o->hom_cov * (2.0 - HA_KMER_GOOD_RATIO)), low_occ = (uint32_t)(o->hom_cov * HA_KMER_GOOD_RATIO);
+	uint64_t rl = r->len[rid], n_hits, k, i, l, m, ns = 0, *srt; const double sh = 0.866666;
+	char *qs = MALLOC_N(char, rl + 1), *ts = 0; uint64_t ts_m = 0;
+	hao_mz_t *mz; uint32_t n_mz, n_ol, is_usrt = 0; hao_hit_t *hits; hao_ovlp_t *ol, t; int pass;
+
+	hao_decode(r, rid, qs);
+	hao_sketch(qs, (int)rl, o->w, o->k, 0, o->is_hpc, ft, o->mz_sample_dist, o->mz_rewin, &mz, &n_mz);
+	hao_anchors(r, pt, mz, n_mz, high_occ, low_occ, &hits, &n_hits);
+	hao_lchain(r, rid, hits, &n_hits, 0.001, o->k, o->max_n_chain, &ol, &n_ol, 0, 0);
+	free(mz); free(hits);
+	ol = (hao_ovlp_t *)realloc(ol, ((size_t)n_ol + n0 + 1) * sizeof(hao_ovlp_t));
+	ov_sort_y_id(ol, n_ol); /* ecovlp.cpp:3959 */
+
+	/* h_ec_lchain_fast_new, ecovlp.cpp:5047-5196 */
+	srt = MALLOC_N(uint64_t, (uint64_t)n0 + n1);
+	for (k = 0; k < n0; k++) srt[ns++] = ((uint64_t)in0[k].tn << 1 | (uint64_t)in0[k].rev) << 32 | (k << 1) | 0;
+	for (k = 0; k < n1; k++) srt[ns++] = ((uint64_t)in1[k].tn << 1 | (uint64_t)in1[k].rev) << 32 | (k << 1) | 1;
+	qsort(srt, ns, 8, u64_cmp); /* radix_sort_ec64: keys are distinct */
+	for (k = m = 0, i = 0; k < n_ol; k++) {
+		hao_ovlp_t *z = &ol[k]; uint64_t tid = z->y_id, trev = z->y_pos_strand, bq[2], bt[2]; int64_t om;
+		z->non_homopolymer_errors = 0;
+		bq[0] = z->x_pos_s; bq[1] = (uint64_t)z->x_pos_e + 1; bt[0] = z->y_pos_s; bt[1] = (uint64_t)z->y_pos_e + 1;
+		for (; i < ns && (srt[i] >> 32) < (tid << 1 | trev); i++) {}
+		if (i < ns && (srt[i] >> 32) == (tid << 1 | trev)) {
+			hao_ma_t *p; uint32_t is_match; uint64_t aq[2], at[2], os, oe, ovlp;
+			om = 1; z->shared_seed = 0; z->is_match = 0;
+			if (srt[i] & 1) { p = (hao_ma_t *)&in1[((uint32_t)srt[i]) >> 1]; is_match = 2; }
+			else { p = &in0[((uint32_t)srt[i]) >> 1]; is_match = 1; }
+			z->strong = (int8_t)p->ml; z->without_large_indel = p->no_l_indel;
+			aq[0] = (uint32_t)p->qns; aq[1] = p->qe; at[0] = p->ts; at[1] = p->te;
+			os = aq[0] > bq[0] ? aq[0] : bq[0]; oe = aq[1] < bq[1] ? aq[1] : bq[1];
+			ovlp = oe > os ? oe - os : 0;
+			if (!(ovlp && ovlp >= (aq[1] - aq[0]) * sh && ovlp >= (bq[1] - bq[0]) * sh)) om = 0;
+			z->non_homopolymer_errors += (uint32_t)((aq[1] - aq[0]) - ovlp);
+			os = at[0] > bt[0] ? at[0] : bt[0]; oe = at[1] < bt[1] ? at[1] : bt[1];
+			ovlp = oe > os ? oe - os : 0;
+			if (!(ovlp && ovlp >= (at[1] - at[0]) * sh && ovlp >= (bt[1] - bt[0]) * sh)) om = 0;
+			z->non_homopolymer_errors += (uint32_t)((at[1] - at[0]) - ovlp);
+			if (om) {
+				if (is_match == 1 && p->el == 1) p->el = 0;
+				if (bt[1] - bt[0] + 1 > ts_m) { ts_m = bt[1] - bt[0] + 1; ts = (char *)realloc(ts, ts_m); }
+				hao_decode_sub(r, tid, (int64_t)bt[0], (int64_t)(bt[1] - bt[0]), (int)trev, ts);
+				/* exact_ec_check, ecovlp.cpp:2803-2808 */
+				if (bq[1] - bq[0] == bt[1] - bt[0] && memcmp(qs + bq[0], ts, bq[1] - bq[0]) == 0) {
+					if (is_match == 2) { z->strong = 0; z->without_large_indel = 1; }
+					is_match = 1; z->shared_seed = 1;
+				}
+				z->is_match = (uint8_t)is_match;
+			}
+		} else {
+			om = 0;
+			if (bt[1] - bt[0] + 1 > ts_m) { ts_m = bt[1] - bt[0] + 1; ts = (char *)realloc(ts, ts_m); }
+			hao_decode_sub(r, tid, (int64_t)bt[0], (int64_t)(bt[1] - bt[0]), (int)trev, ts);
+			if (bq[1] - bq[0] == bt[1] - bt[0] && memcmp(qs + bq[0], ts, bq[1] - bq[0]) == 0) {
+				z->strong = 0; z->without_large_indel = 1; z->shared_seed = 1; z->is_match = 1; om = 1;
+			}
+		}
+		if (om) { if (m != k) { t = ol[m]; ol[m] = ol[k]; ol[k] = t; } m++; }
+	}
+	n_ol = (uint32_t)m;
+	for (k = 0; k < n0; k++) { /* 5138-5165: previous exact overlaps not found again */
+		if (in0[k].el) {
+			hao_ovlp_t *z = &ol[n_ol++];
+			memset(z, 0, sizeof(*z));
+			z->y_id = in0[k].tn; z->y_pos_strand = in0[k].rev;
+			z->x_pos_s = (uint32_t)in0[k].qns; z->x_pos_e = in0[k].qe - 1;
+			z->y_pos_s = in0[k].ts; z->y_pos_e = in0[k].te - 1;
+			z->align_length = z->overlapLen = z->x_pos_e + 1 - z->x_pos_s;
+			z->non_homopolymer_errors = 0; z->is_match = 1; z->shared_seed = 1;
+			z->strong = (int8_t)in0[k].ml; z->without_large_indel = in0[k].no_l_indel;
+			is_usrt = 1;
+		}
+	}
+	if (is_usrt) ov_sort_y_id(ol, n_ol);
+	if (n_ol > 1) { /* 5169-5195: best chain per target */
+		uint64_t mm_k, s; int64_t mm_sc, sc;
+		for (k = 1, l = m = 0; k <= n_ol; k++) {
+			if (k == n_ol || ol[k].y_id != ol[l].y_id) {
+				mm_k = l;
+				if (k - l > 1) {
+					for (s = l, mm_sc = INT32_MIN, mm_k = (uint64_t)-1; s < k; s++) {
+						hao_ovlp_t *z = &ol[s];
+						sc = z->non_homopolymer_errors; sc = -sc;
+						if (sc > mm_sc || (sc == mm_sc && (ol[mm_k].x_pos_e + 1 - ol[mm_k].x_pos_s) < (z->x_pos_e + 1 - z->x_pos_s))) { mm_sc = sc; mm_k = s; }
+					}
+				}
+				if (mm_k != (uint64_t)-1) {
+					if (mm_k != m) { t = ol[mm_k]; ol[mm_k] = ol[m]; ol[m] = t; }
+					m++;
+				}
+				l = k;
+			}
+		}
+		n_ol = (uint32_t)m;
+	}
+	/* push_ff_ovlp x2, ecovlp.cpp:2641-2694 */
+	*out0 = MALLOC_N(hao_ma_t, n_ol); *out1 = MALLOC_N(hao_ma_t, n_ol); *m0 = *m1 = 0;
+	for (pass = 1; pass <= 2; pass++) {
+		hao_ma_t *dst = pass == 1 ? *out0 : *out1; uint32_t *dn = pass == 1 ? m0 : m1;
+		for (k = 0; k < n_ol; k++) {
+			hao_ma_t *z;
+			if (ol[k].is_match != pass) continue;
+			z = &dst[(*dn)++]; memset(z, 0, sizeof(*z));
+			z->qns = (uint64_t)rid << 32 | ol[k].x_pos_s; z->tn = ol[k].y_id;
+			z->qe = ol[k].x_pos_e + 1; z->ts = ol[k].y_pos_s; z->te = ol[k].y_pos_e + 1;
+			z->rev = ol[k].y_pos_strand; z->bl = (uint32_t)r->len[ol[k].y_id] & 0x7fffffffu;
+			z->ml = ol[k].strong & 1; z->no_l_indel = ol[k].without_large_indel; z->el = (uint8_t)ol[k].shared_seed;
+			if (z->rev) { z->ts = z->bl - ol[k].y_pos_e - 1; z->te = z->bl - ol[k].y_pos_s; }
+			z->del = 0;
+		}
+	}
+	free(ol); free(srt); free(qs); free(ts);
+	return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* window alignment: banded semi-global Myers in one 64-bit word       */
+/* ------------------------------------------------------------------ */
+
+int hao_ed_semi_64_absent_diag(const char *pstr, int32_t pn, const char *tstr, int32_t tn, int32_t thre, int32_t abs_diag, int32_t *pe)
+{ /* ed_band_cal_semi_64_w_absent_diag, Levenshtein_distance.h:3727-3776 with
+     ed_core_64 (3116-3125).  Returns ez->err (INT32_MAX = not aligned), *pe = ez->pe */
+	uint64_t Peq[5] = { 0, 0, 0, 0, 0 }, VP = 0, VN, X, D0, HN, HP, mm;
+	int32_t bd, i, err = abs_diag, i_bd, tn0 = tn - 1, cut = thre + (thre << 1), best = INT32_MAX, site, ai, uge = INT32_MAX, c;
+	*pe = -1;
+	if (pn > tn + cut || tn > pn + cut) return best;
+	bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn;
+	for (i = 0, mm = 1ULL << abs_diag; i < bd; i++) { Peq[nt4(pstr[i])] |= mm; mm <<= 1; }
+	i_bd = (thre << 1) - abs_diag; VN = (1ULL << abs_diag) - 1;
+	Peq[4] = 0; mm = 1ULL << (thre << 1);
+	for (i = 0; i <= tn0; i++) {
+		X = Peq[nt4(tstr[i])] | VN;
+		D0 = ((VP + (X & VP)) ^ VP) | X;
+		HN = VP & D0; HP = VN | ~(VP | D0);
+		X = D0 >> 1;
+		VN = X & HP; VP = HN | ~(X | HP);
+		if (!(D0 & 1ULL)) { ++err; if (err > cut) return best; }
+		if (i == tn0) break;
+		Peq[0] >>= 1; Peq[1] >>= 1; Peq[2] >>= 1; Peq[3] >>= 1;
+		++i_bd; c = 4;
+		if (i_bd < pn) c = nt4(pstr[i_bd]);
+		if (c < 4) Peq[c] |= mm;
+	}
+	site = tn - 1 - abs_diag; ai = pn - tn + abs_diag;
+	for (i = 0; site < 0 && i < ai; i++, site++) { err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); }
+	if (err <= thre && err <= best) { best = err; *pe = site; }
+	site -= i;
+	while (i < ai) {
+		err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); ++i;
+		if (err <= thre && err <= best) { best = err; *pe = site + i; }
+		if (i == thre) uge = err;
+	}
+	if (uge <= thre && uge == best) *pe = site + thre;
+	return best;
+}

@@ -30,6 +30,7 @@
 #include "htab.h"
 #include "Hash_Table.h"
 #include "ecovlp.h"
+#include "Levenshtein_distance.h"
 
 // non-static reference functions that no header declares
 void ha_ec(int64_t round, int num_pround, int des_idx, uint64_t *tot_b, uint64_t *tot_e);
@@ -128,8 +129,31 @@ static void write_bins(const char *pfx, const char *tag)
 	free(fn);
 }
 
+// refdump edsemi <cases.bin> <out.bin>: runs the reference's window aligner
+// ed_band_cal_semi_64_w_absent_diag (Levenshtein_distance.h:3727) on a file of
+// cases {i32 pn, tn, thre, abs_diag; char p[pn], t[tn]} -> {i32 err, pe}
+static int run_edsemi(const char *in, const char *out)
+{
+	FILE *fi = fopen(in, "rb"), *fo = fopen(out, "wb"); int32_t n, k, h[4];
+	if (!fi || !fo) return 1;
+	bit_extz_t ez; init_bit_extz_t(&ez, 31);
+	if (fread(&n, 4, 1, fi) != 1) return 1;
+	for (k = 0; k < n; k++) {
+		if (fread(h, 4, 4, fi) != 4) return 1;
+		char *p = (char *)malloc(h[0] + 1), *t = (char *)malloc(h[1] + 1);
+		if (fread(p, 1, h[0], fi) != (size_t)h[0] || fread(t, 1, h[1], fi) != (size_t)h[1]) return 1;
+		ed_band_cal_semi_64_w_absent_diag(p, h[0], t, h[1], h[2], h[3], &ez);
+		int32_t r[2] = { ez.err, ez.pe };
+		fwrite(r, 4, 2, fo);
+		free(p); free(t);
+	}
+	fclose(fi); fclose(fo);
+	return 0;
+}
+
 int main(int argc, char *argv[])
 {
+	if (argc == 4 && strcmp(argv[1], "edsemi") == 0) return run_edsemi(argv[2], argv[3]);
 	if (argc < 4) { fprintf(stderr, "usage: refdump <raw|final> <out_prefix> <hifiasm args...>\n"); return 1; }
 	const char *mode = argv[1], *pfx = argv[2];
 	int r, hom_cov = -1, het_cov = -1; uint64_t tot_b, tot_e;

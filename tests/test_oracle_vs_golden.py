@@ -1,0 +1,90 @@
+"""Pins the CPU oracle (oracle/ha_oracle.c) to the reference: every stage of
+the hot path is compared with digests / dumps produced by the unmodified
+reference (tests/golden/*.npz <- oracle/_ref/refdump)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ha_oracle as ho
+from goldenlib import Golden, dg, chain_digest
+from hifiasm_b200 import binio
+
+
+def _store(rs):
+    return ho.Store(rs.length, rs.byte_off, rs.packed, rs.n_off, rs.n_pos)
+
+
+@pytest.fixture(scope="module", params=["g1", "g2"])
+def ctx(request):
+    g = Golden(request.param)
+    raw = _store(g.raw)
+    opt = ho.default_opt()
+    ft, hom = ho.ft_gen(raw, opt)
+    ho.lib().hao_opt_update_cov(C.byref(opt), hom)
+    return g, raw, opt, ft
+
+
+def _stages(g, mode, st, ft, opt, bw):
+    p = g.params(mode)
+    pt, hom, het = ho.pt_gen(st, ft, opt)
+    assert (hom, het) == (int(p["hom_cov"]), int(p["het_cov"]))
+    assert opt.max_n_chain == int(p["max_n_chain"])
+    for i in range(st.n):
+        mz = ho.sketch(st.decode(i), int(p["w"]), int(p["k"]), 0, 1, ft, int(p["mz_sample_dist"]), int(p["mz_rewin"]))
+        assert dg(mz.tobytes()) == int(g.digest(mode, "mz")[i]), "sketch read %d" % i
+        import hashlib
+        h = hashlib.blake2b(digest_size=8)
+        for x in mz["x"]:
+            pos = ho.pt_get(pt, x)
+            h.update(np.array([x], dtype="<u8").tobytes()); h.update(np.array([pos.size], dtype="<u4").tobytes()); h.update(pos.tobytes())
+        assert int.from_bytes(h.digest(), "little") == int(g.digest(mode, "idx")[i]), "index read %d" % i
+        an = ho.anchors(st, pt, mz, int(p["high_occ"]), int(p["low_occ"]))
+        assert dg(an.tobytes()) == int(g.digest(mode, "anchors")[i]), "anchors read %d" % i
+        ch, hits, fc = ho.lchain(st, i, an, bw, int(p["k"]), int(p["max_n_chain"]))
+        assert chain_digest(ch, fc) == int(g.digest(mode, "chains")[i]), "chains read %d" % i
+        assert dg(hits.tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain hits read %d" % i
+    return pt, hom, het
+
+
+def test_stages_raw(ctx):
+    g, raw, opt, ft = ctx
+    _stages(g, "raw", raw, ft, opt, 0.02)
+
+
+def test_stages_and_final_pass(ctx):
+    g, raw, opt, ft = ctx
+    st = _store(g.pre)
+    pt, hom, het = _stages(g, "final", st, ft, opt, 0.001)
+    opt.hom_cov, opt.het_cov = hom, het
+    p0, o0, _, _ = g.pre_src
+    p1, o1, _, _ = g.pre_rev
+    f0, fo0, _, _ = g.fin_src
+    f1, fo1, _, _ = g.fin_rev
+    m0, m1 = binio.disk_to_mem(p0), binio.disk_to_mem(p1)
+    for i in range(st.n):
+        a, b = ho.final_read(st, pt, ft, opt, i, m0[int(o0[i]):int(o0[i + 1])], m1[int(o1[i]):int(o1[i + 1])])
+        ra, rb = f0[int(fo0[i]):int(fo0[i + 1])], f1[int(fo1[i]):int(fo1[i + 1])]
+        assert a.size == ra.size and b.size == rb.size, "read %d" % i
+        for f in binio.MA_DISK.names:
+            assert (a[f] == ra[f]).all() and (b[f] == rb[f]).all(), "read %d field %s" % (i, f)
+
+
+def test_myers_window_vs_reference():
+    z = np.load(__import__("os").path.join(__import__("goldenlib").GOLDEN, "ed_semi.npz"))
+    hdr, pat, txt, res = z["hdr"], z["pat"], z["txt"], z["res"]
+    po = to = 0
+    L = ho.lib()
+    for i, (pn, tn, thre, ab) in enumerate(hdr):
+        p = pat[po:po + pn].tobytes(); t = txt[to:to + tn].tobytes(); po += pn; to += tn
+        pe = C.c_int32()
+        err = L.hao_ed_semi_64_absent_diag(p, int(pn), t, int(tn), int(thre), int(ab), C.byref(pe))
+        assert (err, pe.value) == (int(res[i, 0]), int(res[i, 1])), "case %d" % i
+
+
+def test_bin_roundtrip(tmp_path):
+    g = Golden("g1")
+    rec, off, fc, ab = g.fin_src
+    p = str(tmp_path / "x.bin")
+    binio.write_ovlp_bin(p, rec, off, fc, ab)
+    assert open(p, "rb").read() == g.z["fin_ovlp_source"].tobytes()
