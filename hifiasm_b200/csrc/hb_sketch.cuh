@@ -1,0 +1,228 @@
+// hb_sketch.cuh — minimizer sketch of one read.
+//
+// Behaviour of mz1_ha_sketch (sketch.cpp:454-579) + mz1_select_mz_h
+// (sketch.cpp:247-330) + mz1_hf_select (194-216), restructured for the GPU:
+// the read is streamed from its 2-bit packed form 32 bases per 64-bit load, the
+// (w)-slot candidate ring lives in shared memory (one column per thread), and
+// minimizers go straight to the read's slice of the batch output.
+#pragma once
+#include "hb_common.cuh"
+
+struct SketchPar { int32_t w, k, is_hpc, sample_dist, rewin; };
+
+// candidate = {x, meta}; meta = cnt:28 | pos:27 | rev:1 | span:8 (ha_mz1_t with
+// the filter-table count in .rid, sketch.cpp:516)
+#define SK_CNT(m) ((uint32_t)((m) & 0xfffffffULL))
+#define SK_DUMMY_META 0xfffffffULL
+HB_HD int sk_cmp(uint64_t ax, uint64_t am, uint64_t bx, uint64_t bm)
+{ // mz1_mzcmp, sketch.cpp:184
+	uint32_t ca = SK_CNT(am), cb = SK_CNT(bm);
+	if (ca != cb) return ca < cb ? -1 : 1;
+	return (ax > bx) - (ax < bx);
+}
+
+// Ring accessors: S = stride between consecutive slots of one thread's ring
+template <typename T> struct RingRef {
+	T *base; int stride;
+	HB_HD T &operator[](int j) const { return base[(size_t)j * stride]; }
+};
+
+struct SketchOut {
+	hb_mz_t *mz; uint32_t *l; uint32_t cap; uint32_t n; int ovf;
+	HB_HD void push(uint64_t x, uint64_t meta, uint32_t lv)
+	{
+		if (n < cap) { mz[n].x = x; mz[n].info = meta; l[n] = lv; }
+		else ovf = 1;
+		n++;
+	}
+};
+
+#define SK_MARK 0x80000000u
+#define SK_L(o, i) ((int64_t)((o).l[i] & 0x7fffffffu))
+#define SK_ACT(o, i) ((i) >= 0 && SK_CNT((o).mz[i].info) > 0)
+
+HB_HD int sk_cmp_l(const SketchOut &o, int32_t ai, int32_t bi)
+{ // mz1_mzcmp_l, sketch.cpp:217-225
+	if (ai >= 0 && bi >= 0) {
+		uint32_t ca = SK_CNT(o.mz[ai].info), cb = SK_CNT(o.mz[bi].info);
+		if (ca > 0 && cb > 0) return sk_cmp(o.mz[ai].x, o.mz[ai].info, o.mz[bi].x, o.mz[bi].info);
+		return (ca == 0) - (cb == 0);
+	}
+	return (ai < 0) - (bi < 0);
+}
+
+HB_HD void sk_rescan(SketchOut &o, int32_t si, int32_t i, int32_t *mi, int skip_inactive)
+{ // "new minimum of [si,i], then mark every equal" (sketch.cpp:232-241, 282-290, 297-305)
+	int32_t m;
+	for (m = si, *mi = -1; m <= i; m++) {
+		if (skip_inactive && !SK_ACT(o, m)) continue;
+		if (sk_cmp_l(o, *mi, m) >= 0) *mi = m;
+	}
+	if (SK_ACT(o, *mi))
+		for (m = si; m <= i; m++) {
+			if (!SK_ACT(o, m)) continue;
+			if (sk_cmp_l(o, *mi, m) == 0) o.l[m] |= SK_MARK;
+		}
+}
+
+HB_HD int sk_h_lt(const hb_mz_t &a, const hb_mz_t &b) { return sk_cmp(a.x, a.info, b.x, b.info) < 0; }
+HB_HD void sk_heapdown(int i, int n, hb_mz_t *l, int32_t *li)
+{ // ks_heapdown, ksort.h:43-53
+	int k = i; hb_mz_t tmp = l[i]; int32_t ti = li[i];
+	while ((k = (k << 1) + 1) < n) {
+		if (k != n - 1 && sk_h_lt(l[k], l[k + 1])) ++k;
+		if (sk_h_lt(l[k], tmp)) break;
+		l[i] = l[k]; li[i] = li[k]; i = k;
+	}
+	l[i] = tmp; li[i] = ti;
+}
+HB_HD void sk_hf_select(SketchOut &o, int32_t si, int32_t ei, int32_t n, int32_t len, int32_t sample_dist)
+{ // mz1_hf_select, sketch.cpp:194-216: keep the max_high_occ smallest of a streak
+	hb_mz_t b[16]; int32_t bi[16];
+	int32_t ps, pe, j, k, max_occ;
+	if (ei - si <= 1) return;
+	ps = si < 0 ? 0 : (int32_t)HB_MZ_POS(o.mz[si].info);
+	pe = ei == n ? len : (int32_t)HB_MZ_POS(o.mz[ei].info);
+	max_occ = (int32_t)((double)(pe - ps) / sample_dist + .499);
+	if (max_occ > 16) max_occ = 16;
+	for (j = si + 1, k = 0; j < ei && k < max_occ; ++j, ++k) { b[k] = o.mz[j]; bi[k] = j; }
+	for (int i = (k >> 1) - 1; i >= 0; --i) sk_heapdown(i, k, b, bi);
+	for (; j < ei; ++j)
+		if (sk_h_lt(o.mz[j], b[0])) { b[0] = o.mz[j]; bi[0] = j; sk_heapdown(0, k, b, bi); }
+	for (j = 0; j < k; ++j)
+		if ((int32_t)SK_CNT(b[j].info) < pe - ps) o.mz[bi[j]].info &= ~0xfffffffULL;
+}
+
+HB_HD void sk_select_mz_h(SketchOut &o, int32_t len, int32_t sample_dist, int32_t w, int32_t k, int32_t tot_l)
+{ // mz1_select_mz_h, sketch.cpp:247-330 (w = mz_rewin)
+	int32_t i, mi = -1, si, last0, n = (int32_t)o.n, m, ws = w + k - 1, any = 0;
+	if (n == 0) return;
+	for (i = 0, last0 = -1; i <= n; ++i) {
+		if (i == n || SK_CNT(o.mz[i].info) == 0) {
+			if (i - last0 > 1) {
+				int32_t ps = last0 < 0 ? 0 : (int32_t)HB_MZ_POS(o.mz[last0].info);
+				int32_t pe = i == n ? len : (int32_t)HB_MZ_POS(o.mz[i].info);
+				if (((int32_t)((double)(pe - ps) / sample_dist + .499)) > 0) { any = 1; break; }
+			}
+			last0 = i;
+		}
+	}
+	if (!any) return;
+	for (si = 0, i = 0, mi = -1; i < n; i++) {
+		if (SK_L(o, i) >= ws || (i + 1 < n && SK_L(o, i) < ws && SK_L(o, i + 1) > ws) || (i + 1 == n && tot_l >= ws && SK_L(o, i) < ws)) {
+			sk_rescan(o, si, i, &mi, 1);
+			break;
+		}
+	}
+	if (i < n) {
+		for (si = 0, i++; i < n; i++) {
+			for (; si < i; si++)
+				if (SK_L(o, si) + w > SK_L(o, i)) break;
+			if (sk_cmp_l(o, i, mi) <= 0) {
+				if (SK_ACT(o, mi)) o.l[mi] |= SK_MARK;
+				mi = i;
+			} else if (si > mi) {
+				if (SK_ACT(o, mi)) o.l[mi] |= SK_MARK;
+				sk_rescan(o, si, i, &mi, 0);
+			}
+		}
+		if (SK_ACT(o, mi)) o.l[mi] |= SK_MARK;
+		for (i = n - 1; si < n && SK_L(o, si) + w <= tot_l + 1; si++)
+			if (si > mi) {
+				if (SK_ACT(o, mi)) o.l[mi] |= SK_MARK;
+				sk_rescan(o, si, i, &mi, 0);
+			}
+		for (i = 0, last0 = -1; i <= n; ++i) {
+			if (i == n || SK_CNT(o.mz[i].info) == 0) {
+				if (i - last0 > 1) {
+					int32_t ps = last0 < 0 ? 0 : (int32_t)HB_MZ_POS(o.mz[last0].info);
+					int32_t pe = i == n ? len : (int32_t)HB_MZ_POS(o.mz[i].info);
+					if (((int32_t)((double)(pe - ps) / sample_dist + .499)) > 0) {
+						for (m = last0 + 1, mi = 0; m < i; ++m)
+							if (o.l[m] & SK_MARK) { o.mz[m].info &= ~0xfffffffULL; mi++; }
+						if (mi == 0) sk_hf_select(o, last0, i, n, len, sample_dist);
+					}
+				}
+				last0 = i;
+			}
+		}
+	}
+	for (i = n = 0; i < (int32_t)o.n; ++i)
+		if (SK_CNT(o.mz[i].info) == 0) { o.mz[n] = o.mz[i]; n++; }
+	o.n = (uint32_t)n;
+}
+
+// Sketch read `rid`; rx/rm/rl = this thread's candidate ring (w slots).
+// rid_out is written into ha_mz1_t.rid of the results (sketch.cpp:577).
+HB_HD void hb_sketch_read(const DevReads &R, const DevFt &ft, const SketchPar &P, uint64_t rid, uint32_t rid_out,
+                          RingRef<uint64_t> rx, RingRef<uint64_t> rm, RingRef<uint32_t> rl, SketchOut &o)
+{
+	const int32_t w = P.w, k = P.k, len = (int32_t)R.len[rid];
+	const uint64_t shift1 = k - 1, mask = (1ULL << k) - 1;
+	const uint8_t *seq = R.packed + R.off[rid];
+	const uint64_t *seq64 = (const uint64_t *)seq;
+	uint64_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, minx = ~0ULL, minm = SK_DUMMY_META, word = 0;
+	int32_t i, j, l = 0, tl = 0, bp = 0, min_bp = 0, span = 0, qf = 0, qc = 0;
+	uint32_t min_l = 0xffffffffu;
+	uint64_t ni = R.noff ? R.noff[rid] : 0, ne = R.noff ? R.noff[rid + 1] : 0;
+	int32_t next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX;
+	uint8_t q[64]; // run lengths of the last k HPC symbols (tiny_queue_t, htab.h:39-57); capped at 255: spans >= 256 are never candidates
+	o.n = 0; o.ovf = 0;
+	for (j = 0; j < w; j++) { rx[j] = ~0ULL; rm[j] = ~0ULL; rl[j] = 0; } // memset 0xff, sketch.cpp:470
+	int32_t wbase = -1; // index of the 64-bit word (32 bases) held in `word`
+#define SK_BASE(ii) ((int)(((((ii) >> 5) != wbase ? (wbase = (ii) >> 5, word = seq64[wbase]) : word) >> ((((ii) & 31) >> 2 << 3) + ((3 - ((ii) & 3)) << 1))) & 3))
+	for (i = 0; i < len; ++i) {
+		int c = SK_BASE(i);
+		uint64_t ix = ~0ULL, im = SK_DUMMY_META;
+		if (i == next_n) { c = 4; ++ni; next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX; }
+		if (c < 4) {
+			int z;
+			if (P.is_hpc) { // sketch.cpp:480-492
+				int32_t run = 1;
+				while (i + run < len && i + run != next_n && SK_BASE(i + run) == c) ++run;
+				i += run - 1;
+				q[(qc++ + qf) & 0x3f] = (uint8_t)(run > 255 ? 255 : run);
+				span += run > 255 ? 255 : run;
+				if (qc > k) { span -= q[qf++]; qf &= 0x3f; --qc; }
+			} else span = l + 1 < k ? l + 1 : k;
+			pl0 = (pl0 << 1 | (uint64_t)(c & 1)) & mask;
+			pl1 = (pl1 << 1 | (uint64_t)(c >> 1)) & mask;
+			pl2 = pl2 >> 1 | (uint64_t)(1 - (c & 1)) << shift1;
+			pl3 = pl3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift1;
+			if (pl1 == pl3) continue; // sketch.cpp:502
+			z = pl1 < pl3 ? 0 : 1;
+			++l; ++tl;
+			if (l >= k && span < 256) {
+				uint64_t y = z ? hb_hash64(pl2) + hb_hash64(pl3) : hb_hash64(pl0) + hb_hash64(pl1);
+				int32_t cnt = hb_ft_lookup(ft, y);
+				if (!(cnt >= 1 << 28)) { ix = y; im = (uint64_t)(uint32_t)cnt | (uint64_t)i << 28 | (uint64_t)z << 55 | (uint64_t)span << 56; }
+			}
+		} else { l = 0; qc = qf = 0; span = 0; }
+		rx[bp] = ix; rm[bp] = im; rl[bp] = (uint32_t)l;
+#define SK_POS(m) ((uint32_t)(((m) >> 28) & 0x7ffffffULL))
+		if (l == w + k - 1 && minx != ~0ULL) { // sketch.cpp:523-534
+			for (j = bp + 1; j < w; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(bm) != SK_POS(minm)) o.push(bx, bm, rl[j]); }
+			for (j = 0; j < bp; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(bm) != SK_POS(minm)) o.push(bx, bm, rl[j]); }
+		}
+		if (sk_cmp(minx, minm, ix, im) >= 0) { // sketch.cpp:543-547
+			if (l >= w + k && minx != ~0ULL) o.push(minx, minm, min_l);
+			minx = ix; minm = im; min_bp = bp; min_l = (uint32_t)l;
+		} else if (bp == min_bp) { // sketch.cpp:548-568
+			if (l >= w + k - 1 && minx != ~0ULL) o.push(minx, minm, min_l);
+			minx = ~0ULL; minm = SK_DUMMY_META;
+			for (j = bp + 1; j < w; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) >= 0) { minx = bx; minm = bm; min_bp = j; min_l = rl[j]; } }
+			for (j = 0; j <= bp; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) >= 0) { minx = bx; minm = bm; min_bp = j; min_l = rl[j]; } }
+			if (l >= w + k - 1 && minx != ~0ULL) {
+				for (j = bp + 1; j < w; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(minm) != SK_POS(bm)) o.push(bx, bm, rl[j]); }
+				for (j = 0; j <= bp; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(minm) != SK_POS(bm)) o.push(bx, bm, rl[j]); }
+			}
+		}
+		if (++bp == w) bp = 0;
+	}
+	if (minx != ~0ULL) o.push(minx, minm, min_l);
+	if (o.ovf) return;
+	if (P.sample_dist > w && ft.mask != 0) sk_select_mz_h(o, len, P.sample_dist, P.rewin, k, tl); // sketch.cpp:575 (a no-op without filter-table hits)
+	for (i = 0; i < (int32_t)o.n; ++i) o.mz[i].info = (o.mz[i].info & ~0xfffffffULL) | (rid_out & 0xfffffff);
+#undef SK_BASE
+#undef SK_POS
+}

@@ -1,0 +1,154 @@
+/* hifiasm_b200.h — C-ABI of the B200-native overlap engine.
+ *
+ * Drop-in boundary for hifiasm's overlap / error-correction stage (reference
+ * v0.25.0-r726).  hifiasm has no plugin API: the seam is a set of C++ free
+ * functions over process globals.  Every entry point below
+ * names the reference interface it replaces; INTEGRATION.md shows the shim a
+ * hifiasm maintainer links in place of ecovlp.o / htab.o for this path.
+ *
+ * Conventions: plain pointers and sizes only; all buffers are caller-owned
+ * host memory unless stated; every call returns 0 on success or a negative
+ * HB_E_* code (hb_last_error() gives the text).  There is NO CPU fallback:
+ * without a CUDA device hb_create() fails with HB_E_NO_DEVICE.
+ */
+#ifndef HIFIASM_B200_H
+#define HIFIASM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK            0
+#define HB_E_NO_DEVICE  (-1)
+#define HB_E_CUDA       (-2)
+#define HB_E_ARG        (-3)
+#define HB_E_STATE      (-4)
+#define HB_E_OVERFLOW   (-5)
+#define HB_E_NOMEM      (-6)
+
+typedef struct hb_ctx hb_ctx_t;
+
+/* The fields of hifiasm_opt_t (CommandLines.h:38-186) the path reads. */
+typedef struct {
+	int32_t k_mer_length;      /* -k, CommandLines.cpp:259 (51) */
+	int32_t mz_win;            /* -w, CommandLines.cpp:263 (51) */
+	int32_t is_hpc;            /* !(flag & HA_F_NO_HPC) */
+	int32_t mz_sample_dist;    /* CommandLines.cpp:268 (500) */
+	int32_t mz_rewin;          /* CommandLines.cpp:266 (1000) */
+	int32_t min_hist_kmer_cnt; /* CommandLines.cpp:277 (5) */
+	int32_t max_kmer_cnt;      /* CommandLines.cpp:270 (2000) */
+	int32_t max_n_chain;       /* -N, CommandLines.cpp:276 (100) */
+	double  high_factor;       /* -D, CommandLines.cpp:271 (5.0) */
+	int32_t hom_cov, het_cov;  /* asm_opt.hom_cov / het_cov */
+	int32_t is_ont;            /* --ont (not supported yet: must be 0) */
+} hb_opt_t;
+
+/* ha_mz1_t (htab.h:13-18): x = hash, info = rid:28 | pos:27 | rev:1 | span:8 */
+typedef struct { uint64_t x, info; } hb_mz_t;
+/* k_mer_hit (Hash_Table.h:116-120): id_strand = readID:31 | strand:1 */
+typedef struct { uint32_t id_strand, offset, self_offset, cnt; } hb_hit_t;
+/* ma_hit_t (Overlaps.h:116-124) with the bit-fields widened */
+typedef struct {
+	uint64_t qns; uint32_t qe, tn, ts, te;
+	uint32_t ml, rev, bl, del;
+	uint8_t el, no_l_indel, pad[6];
+} hb_ma_hit_t;
+/* the overlap_region fields the path defines (Hash_Table.h:78-106) */
+typedef struct {
+	uint32_t x_pos_s, x_pos_e, y_id, y_pos_s, y_pos_e, y_pos_strand;
+	int32_t shared_seed;
+	uint32_t first_hit;  /* overlap_region.non_homopolymer_errors after h_ec_lchain */
+	uint32_t n_hits;     /* number of anchors on the chain */
+	uint32_t fc_off, fc_n; /* Fake_Cigar entries (u64: x<<32 | |dd|<<1 | sign) in the per-read pool */
+	uint32_t pad;
+} hb_chain_t;
+
+void hb_opt_init(hb_opt_t *o);                       /* init_opt, CommandLines.cpp:243 */
+void hb_opt_update_cov(hb_opt_t *o, int hom_cov);    /* ha_opt_update_cov, CommandLines.cpp:411 */
+
+int hb_device_count(void);
+/* one context per GPU (one process per GPU in multi-GPU runs) */
+int hb_create(hb_ctx_t **ctx, int device, const hb_opt_t *opt);
+void hb_destroy(hb_ctx_t *ctx);
+const char *hb_last_error(const hb_ctx_t *ctx);
+int hb_set_opt(hb_ctx_t *ctx, const hb_opt_t *opt);
+int hb_get_opt(const hb_ctx_t *ctx, hb_opt_t *opt);
+
+/* ---- read store: All_reads R_INF (Process_Read.h:115-148) -------------------
+ * Mirrors read_length[], read_sperate[] (2-bit, ha_compress_base layout,
+ * Process_Read.cpp:792) and N_site[] into HBM.  packed = concatenated per-read
+ * byte arrays, byte_off[n+1]; n_pos/n_off = flattened N_site lists.          */
+int hb_reads_upload(hb_ctx_t *ctx, uint64_t n_reads, const uint64_t *read_length,
+                    const uint8_t *packed, const uint64_t *byte_off,
+                    const uint64_t *n_pos, const uint64_t *n_off);
+/* the same from the reference's own arrays of per-read pointers */
+int hb_reads_upload_ptrs(hb_ctx_t *ctx, uint64_t n_reads, const uint64_t *read_length,
+                         uint8_t *const *read_sperate, uint64_t *const *N_site);
+
+/* ---- index: ha_ft_gen / ha_pt_gen (htab.h:77,83; htab.cpp:1136,1232) -------
+ * hb_ft_gen counts all (HPC) k-mers of the resident reads exactly (-f0
+ * semantics) and keeps those occurring >= high_factor*peak_hom times.
+ * hb_pt_gen sketches every read, counts minimizers, derives hom/het peaks
+ * (ha_analyze_count, hist.cpp:74) and builds the position index in HBM.      */
+int hb_ft_gen(hb_ctx_t *ctx, int *hom_cov);
+int hb_ft_size(const hb_ctx_t *ctx, uint64_t *n);
+int hb_ft_cnt(hb_ctx_t *ctx, const uint64_t *hash, uint64_t n, int32_t *cnt); /* ha_ft_cnt, htab.cpp:1064 */
+void hb_ft_destroy(hb_ctx_t *ctx);                                           /* ha_ft_destroy */
+int hb_pt_gen(hb_ctx_t *ctx, int *hom_cov, int *het_cov);
+int hb_pt_stat(const hb_ctx_t *ctx, uint64_t *n_keys, uint64_t *n_pos);
+/* ha_pt_get (htab.cpp:518) batched: cnt[i] = occurrences of hash[i]; when pos
+ * != NULL it receives the concatenated ha_idxpos_t lists (pos_cap entries max) */
+int hb_pt_get(hb_ctx_t *ctx, const uint64_t *hash, uint64_t n, uint32_t *cnt, uint64_t *pos, uint64_t pos_cap);
+void hb_pt_destroy(hb_ctx_t *ctx);                                           /* ha_pt_destroy */
+
+/* ---- stages of h_ec_lchain (anchor.cpp:2302), for parity tests --------------
+ * Each works on the read-id range [r0, r1) of the resident store and returns
+ * flattened per-read arrays: off[r1-r0+1] + records.  Call with rec == NULL to
+ * get only off[] (sizes).                                                    */
+int hb_sketch(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *off, hb_mz_t *rec, uint64_t rec_cap);       /* mz1_ha_sketch, sketch.cpp:454 */
+int hb_anchors(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *off, hb_hit_t *rec, uint64_t rec_cap);     /* minimizers_qgen0, anchor.cpp:987 */
+/* chains after lchain_qgen_mcopy_fast (anchor.cpp:1920); hit_off/hits = the
+ * compacted chain anchors (cl->list[0..cl->length)); fc = fake-cigar pool     */
+int hb_chains(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres,
+              uint64_t *off, hb_chain_t *rec, uint64_t rec_cap,
+              uint64_t *hit_off, hb_hit_t *hits, uint64_t hit_cap,
+              uint64_t *fc_off, uint64_t *fc, uint64_t fc_cap);
+
+/* ---- final overlap pass: cal_ov_r(n_thre, n_a, new_idx=1) (ecovlp.h:15;
+ * ecovlp.cpp:6385 -> worker_hap_dc_ec_gen_new_idx 3948) -----------------------
+ * prev_* = R_INF.paf[] / R_INF.reverse_paf[] of the last EC round, flattened
+ * (off[n_reads+1]).  Results replace them: out_*_off[n_reads+1] and records
+ * (caps in entries).  stat[7] receives the counters ha_print_ovlp_stat_0
+ * prints (forward, reverse, strong, weak, exact, no_l_indel, inexact).
+ * Reads [r0,r1) only are processed (r0=0,r1=n_reads for the whole store);
+ * offsets are relative to r0.                                                */
+int hb_cal_ov_r(hb_ctx_t *ctx, uint64_t r0, uint64_t r1,
+                const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off,
+                const hb_ma_hit_t *prev_rev, const uint64_t *prev_rev_off,
+                hb_ma_hit_t *out_src, uint64_t *out_src_off, uint64_t out_src_cap,
+                hb_ma_hit_t *out_rev, uint64_t *out_rev_off, uint64_t out_rev_cap,
+                uint64_t *stat);
+/* device-resident variant used by bench.py: inputs staged once, result stays in
+ * HBM; returns totals only.  Timed region of `value` (no PCIe).               */
+int hb_cal_ov_r_resident(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *n_src, uint64_t *n_rev, uint64_t *stat);
+
+/* ---- window alignment: ed_band_cal_semi_64_w_absent_diag
+ * (Levenshtein_distance.h:3727) batched.  Case i: pattern = pat[pat_off[i]..
+ * pat_off[i+1]) (target slice, ASCII), text = txt[txt_off[i]..txt_off[i+1])
+ * (query window), thre[i], abs_diag[i]; err[i] = INT32_MAX when unaligned.   */
+int hb_ed_semi_64(hb_ctx_t *ctx, uint64_t n_cases, const char *pat, const uint64_t *pat_off,
+                  const char *txt, const uint64_t *txt_off, const int32_t *thre, const int32_t *abs_diag,
+                  int32_t *err, int32_t *pe);
+
+/* ---- instrumentation ---------------------------------------------------- */
+/* per-kernel launch counters and device time of the last hb_cal_ov_r* call:
+ * names[i] (static strings), launches[i], ms[i]; returns number of entries   */
+int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap);
+/* algorithmic byte counters of the last pass:
+ * c[0]=reads, c[1]=bases, c[2]=minimizers, c[3]=anchors, c[4]=groups, c[5]=chains */
+int hb_counters(const hb_ctx_t *ctx, uint64_t *c, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1296,3 +1296,15 @@ int hao_ed_semi_64_absent_diag(const char *pstr, int32_t pn, const char *tstr, i
 	if (uge <= thre && uge == best) *pe = site + thre;
 	return best;
 }
+
+/* table dumps for the host-emulation harness (tests/hostemu) */
+void hao_ft_dump(const hao_ft_t *ft, uint64_t *key, int32_t *val)
+{
+	uint64_t i;
+	for (i = 0; i < ft->n; i++) { key[i] = ft->key[i]; val[i] = ft->val[i] == INT16_MAX ? INT32_MAX : ft->val[i]; }
+}
+void hao_pt_dump(const hao_pt_t *pt, uint64_t *key, uint64_t *off, uint32_t *cnt, uint64_t *pos)
+{
+	memcpy(key, pt->key, pt->n_keys * 8); memcpy(off, pt->off, pt->n_keys * 8);
+	memcpy(cnt, pt->cnt, pt->n_keys * 4); memcpy(pos, pt->pos, pt->tot_pos * 8);
+}

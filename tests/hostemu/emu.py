@@ -1,0 +1,107 @@
+"""ctypes binding of tests/hostemu/libhostemu.so (TEST INFRASTRUCTURE ONLY):
+host-compiled bodies of the product's per-thread kernels."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import ha_oracle as ho
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = None
+MZ = ho.MZ
+HIT = ho.HIT
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libhostemu.so")
+        srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_ROOT, "hifiasm_b200", "csrc", f)
+                                                      for f in os.listdir(os.path.join(_ROOT, "hifiasm_b200", "csrc")) if f.endswith(".cuh")]
+        if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unused-function",
+                                   "-o", so, srcs[0]])
+        L = C.CDLL(so)
+        for f in ("emu_reads_create", "emu_ft_create", "emu_pt_create"):
+            getattr(L, f).restype = C.c_void_p
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Reads:
+    def __init__(self, rs):
+        self.keep = [np.ascontiguousarray(x) for x in (rs.length.astype(np.uint64), rs.packed, rs.byte_off.astype(np.uint64),
+                                                      rs.n_pos.astype(np.uint64) if rs.n_pos.size else np.zeros(1, np.uint64),
+                                                      rs.n_off.astype(np.uint64))]
+        ln, pk, bo, npos, noff = self.keep
+        self.n = ln.size
+        self.length = ln
+        self.h = C.c_void_p(lib().emu_reads_create(C.c_uint64(self.n), _p(ln), _p(pk), _p(bo), _p(npos), _p(noff)))
+
+
+def ft_from_oracle(ft):
+    n = int(ho.lib().hao_ft_size(C.c_void_p(ft)))
+    key = np.zeros(max(n, 1), np.uint64); val = np.zeros(max(n, 1), np.int32)
+    if n:
+        ho.lib().hao_ft_dump(C.c_void_p(ft), _p(key), _p(val))
+    return C.c_void_p(lib().emu_ft_create(C.c_uint64(n), _p(key), _p(val))), key[:n], val[:n]
+
+
+def pt_from_oracle(pt):
+    nk = int(ho.lib().hao_pt_n_keys(C.c_void_p(pt))); npos = int(ho.lib().hao_pt_tot_pos(C.c_void_p(pt)))
+    key = np.zeros(nk + 1, np.uint64); off = np.zeros(nk + 1, np.uint64); cnt = np.zeros(nk + 1, np.uint32); pos = np.zeros(npos + 1, np.uint64)
+    ho.lib().hao_pt_dump(C.c_void_p(pt), _p(key), _p(off), _p(cnt), _p(pos))
+    return C.c_void_p(lib().emu_pt_create(C.c_uint64(nk), _p(key), _p(off), _p(cnt), C.c_uint64(npos), _p(pos)))
+
+
+def sketch(reads, ft, p, rid, rid_out=0):
+    cap = int(reads.length[rid]) // 4 + 64
+    out = np.zeros(cap, MZ); n = C.c_uint32()
+    ovf = lib().emu_sketch(reads.h, ft, C.c_int(int(p["w"])), C.c_int(int(p["k"])), C.c_int(int(p["is_hpc"])),
+                           C.c_int(int(p["mz_sample_dist"])), C.c_int(int(p["mz_rewin"])), C.c_uint64(rid), C.c_uint32(rid_out),
+                           _p(out), C.c_uint32(cap), C.byref(n))
+    assert ovf == 0
+    return out[:n.value]
+
+
+CHAIN = np.dtype([("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_id", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
+                  ("y_pos_strand", "<u4"), ("shared_seed", "<i4"), ("first_hit", "<u4"), ("n_hits", "<u4"),
+                  ("fc_off", "<u4"), ("fc_n", "<u4"), ("pad", "<u4")])
+MA = ho.MA
+
+
+def anchors(reads, pt, mz, high_occ, low_occ):
+    L = lib(); L.emu_anchors.restype = C.c_uint64
+    mz = np.ascontiguousarray(mz)
+    na = L.emu_anchors(reads.h, pt, _p(mz), C.c_uint32(mz.size), C.c_uint32(high_occ), C.c_uint32(low_occ), C.c_void_p(0), C.c_uint64(0))
+    out = np.zeros(na + 1, HIT)
+    L.emu_anchors(reads.h, pt, _p(mz), C.c_uint32(mz.size), C.c_uint32(high_occ), C.c_uint32(low_occ), _p(out), C.c_uint64(na))
+    return out[:na]
+
+
+def chains(reads, rid, hits, bw, k, max_n_chain):
+    hits = np.ascontiguousarray(hits).copy()
+    n = hits.size
+    out = np.zeros(n + 4, CHAIN); no = C.c_uint32(); ch = np.zeros(n + 4, HIT); nch = C.c_uint64(); fc = np.zeros(3 * n + 16, np.uint64); nfc = C.c_uint64()
+    lib().emu_chains(reads.h, C.c_uint32(rid), _p(hits), C.c_uint64(n), C.c_double(bw), C.c_int(k), C.c_int(max_n_chain),
+                     _p(out), C.byref(no), _p(ch), C.byref(nch), _p(fc), C.byref(nfc))
+    return out[:no.value], ch[:nch.value], fc[:nfc.value], hits
+
+
+def final_read(reads, ft, pt, p, hom_cov, max_n_chain, rid, in0, in1):
+    in0 = np.ascontiguousarray(in0).copy(); in1 = np.ascontiguousarray(in1)
+    cap = 4096 + in0.size
+    o0 = np.zeros(cap, MA); o1 = np.zeros(cap, MA); m0 = C.c_uint32(); m1 = C.c_uint32()
+    rc = lib().emu_final_read(reads.h, ft, pt, C.c_int(int(p["w"])), C.c_int(int(p["k"])), C.c_int(int(p["is_hpc"])),
+                              C.c_int(int(p["mz_sample_dist"])), C.c_int(int(p["mz_rewin"])), C.c_int(hom_cov), C.c_int(max_n_chain),
+                              C.c_uint32(rid), _p(in0), C.c_uint32(in0.size), _p(in1), C.c_uint32(in1.size),
+                              _p(o0), C.byref(m0), _p(o1), C.byref(m1))
+    assert rc == 0
+    return o0[:m0.value], o1[:m1.value]

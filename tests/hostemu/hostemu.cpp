@@ -1,0 +1,211 @@
+// tests/hostemu/hostemu.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the bodies of the product's one-thread-per-unit kernels
+// (hifiasm_b200/csrc/*.cuh, the HB_HD functions) as plain host C++ so their
+// logic can be checked against the golden vectors in the GPU-less build
+// container.  Nothing here is part of, linked into, or called by the product:
+// libhifiasm_b200.so has no host path and fails loudly without a CUDA device.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <math.h>
+#include <map>
+#include <algorithm>
+#include "../../hifiasm_b200/csrc/hb_sketch.cuh"
+#include "../../hifiasm_b200/csrc/hb_final.cuh"
+
+struct EmuReads { DevReads d; std::vector<uint8_t> packed; std::vector<uint64_t> off, noff; std::vector<uint32_t> len, npos; };
+struct EmuFt { DevFt d; std::vector<uint64_t> key; std::vector<int32_t> val; };
+struct EmuPt { DevPt d; std::vector<ulonglong2> slot; std::vector<uint64_t> pos; };
+
+extern "C" {
+
+void *emu_reads_create(uint64_t n, const uint64_t *len, const uint8_t *packed, const uint64_t *byte_off, const uint64_t *n_pos, const uint64_t *n_off)
+{
+	EmuReads *r = new EmuReads();
+	r->off.resize(n + 1); r->len.resize(n); r->noff.resize(n + 1);
+	uint64_t o = 0;
+	for (uint64_t i = 0; i < n; i++) { r->off[i] = o; r->len[i] = (uint32_t)len[i]; o += ((len[i] / 4 + 1) + 7) & ~7ULL; }
+	r->off[n] = o; r->packed.assign(o + 8, 0);
+	for (uint64_t i = 0; i < n; i++) memcpy(&r->packed[r->off[i]], packed + byte_off[i], len[i] / 4 + 1);
+	for (uint64_t i = 0; i <= n; i++) r->noff[i] = n_off ? n_off[i] : 0;
+	r->npos.resize(r->noff[n] + 1);
+	for (uint64_t i = 0; i < r->noff[n]; i++) r->npos[i] = (uint32_t)n_pos[i];
+	r->d.n = n; r->d.packed = r->packed.data(); r->d.off = r->off.data(); r->d.len = r->len.data(); r->d.noff = r->noff.data(); r->d.npos = r->npos.data();
+	return r;
+}
+void emu_reads_destroy(void *p) { delete (EmuReads *)p; }
+
+void *emu_ft_create(uint64_t n, const uint64_t *key, const int32_t *val)
+{
+	EmuFt *f = new EmuFt();
+	if (n == 0) { f->d.mask = 0; f->d.key = 0; f->d.val = 0; return f; }
+	uint64_t cap = 16; while (cap < 2 * n) cap <<= 1;
+	f->key.assign(cap, 0); f->val.assign(cap, 0);
+	for (uint64_t i = 0; i < n; i++) {
+		uint64_t b = hb_bucket(key[i], cap - 1);
+		while (f->val[b] != 0) b = (b + 1) & (cap - 1);
+		f->key[b] = key[i]; f->val[b] = val[i];
+	}
+	f->d.mask = cap - 1; f->d.key = f->key.data(); f->d.val = f->val.data();
+	return f;
+}
+void emu_ft_destroy(void *p) { delete (EmuFt *)p; }
+
+void *emu_pt_create(uint64_t nk, const uint64_t *key, const uint64_t *off, const uint32_t *cnt, uint64_t npos, const uint64_t *pos)
+{
+	EmuPt *t = new EmuPt();
+	uint64_t cap = 16; while (cap < 2 * nk) cap <<= 1;
+	ulonglong2 z; z.x = 0; z.y = 0;
+	t->slot.assign(cap, z);
+	for (uint64_t i = 0; i < nk; i++) {
+		uint64_t b = hb_bucket(key[i], cap - 1);
+		while ((t->slot[b].y & 0xfff) != 0) b = (b + 1) & (cap - 1);
+		t->slot[b].x = key[i]; t->slot[b].y = off[i] << 12 | cnt[i];
+	}
+	t->pos.assign(pos, pos + npos);
+	t->d.mask = cap - 1; t->d.slot = t->slot.data(); t->d.pos = t->pos.data();
+	return t;
+}
+void emu_pt_destroy(void *p) { delete (EmuPt *)p; }
+
+int emu_sketch(void *reads, void *ft, int w, int k, int is_hpc, int sample_dist, int rewin, uint64_t rid, uint32_t rid_out,
+               hb_mz_t *out, uint32_t cap, uint32_t *n_out)
+{
+	EmuReads *r = (EmuReads *)reads; EmuFt *f = (EmuFt *)ft;
+	SketchPar P = { w, k, is_hpc, sample_dist, rewin };
+	std::vector<uint64_t> rx(256), rm(256); std::vector<uint32_t> rl(256), l(cap + 1);
+	SketchOut o; o.mz = out; o.l = l.data(); o.cap = cap; o.n = 0; o.ovf = 0;
+	RingRef<uint64_t> RX = { rx.data(), 1 }, RM = { rm.data(), 1 }; RingRef<uint32_t> RL = { rl.data(), 1 };
+	hb_sketch_read(r->d, f->d, P, rid, rid_out, RX, RM, RL, o);
+	*n_out = o.n;
+	return o.ovf;
+}
+
+
+// weight table of minimizers_qgen0 (anchor.cpp:1066-1075): w_tab[n_occ]
+static void weight_tab(uint32_t *w_tab, uint32_t high_occ, uint32_t low_occ)
+{
+	uint64_t max_cnt = high_occ < 2 ? 2 : high_occ, min_cnt = low_occ < 2 ? 2 : low_occ;
+	for (uint32_t n = 0; n < 4096; n++) {
+		uint32_t w;
+		if (n < max_cnt && n > min_cnt) w = 1;
+		else if (n <= min_cnt) w = 2;
+		else { w = (uint32_t)(1 + ((n + (max_cnt << 1) - 1) / (max_cnt << 1))); w = (uint32_t)pow((double)w, 1.1); }
+		w_tab[n] = w;
+	}
+}
+
+// sequential stand-in of the probe + group/scatter kernels (anchors.cu): same
+// output contract — anchors grouped by key = tid<<1|rev ascending, inside a
+// group in query-minimizer order then index-list order.
+uint64_t emu_anchors(void *reads, void *pt, const hb_mz_t *mz, uint32_t n_mz, uint32_t high_occ, uint32_t low_occ, hb_hit_t *out, uint64_t cap)
+{
+	EmuReads *r = (EmuReads *)reads; EmuPt *t = (EmuPt *)pt;
+	uint32_t w_tab[4096]; weight_tab(w_tab, high_occ, low_occ);
+	std::map<uint32_t, uint64_t> cnt;
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < n_mz; i++) {
+		uint64_t off; uint32_t n = hb_pt_lookup(t->d, mz[i].x, &off);
+		for (uint32_t j = 0; j < n; j++) { uint64_t y = t->d.pos[off + j]; uint32_t key = HB_MZ_RID(y) << 1 | (HB_MZ_REV(mz[i].info) ^ HB_MZ_REV(y)); cnt[key]++; tot++; }
+	}
+	if (tot > cap) return tot;
+	uint64_t base = 0;
+	for (auto &kv : cnt) { uint64_t c = kv.second; kv.second = base; base += c; }
+	for (uint32_t i = 0; i < n_mz; i++) {
+		uint64_t off; uint32_t n = hb_pt_lookup(t->d, mz[i].x, &off);
+		uint32_t zpos = HB_MZ_POS(mz[i].info), zspan = HB_MZ_SPAN(mz[i].info);
+		for (uint32_t j = 0; j < n; j++) {
+			uint64_t y = t->d.pos[off + j]; uint32_t tid = HB_MZ_RID(y), rev = HB_MZ_REV(mz[i].info) ^ HB_MZ_REV(y);
+			hb_hit_t &h = out[cnt[tid << 1 | rev]++];
+			uint32_t tl = r->d.len[tid];
+			h.id_strand = tid | rev << 31; h.self_offset = zpos;
+			h.offset = rev ? tl - 1 - (HB_MZ_POS(y) + 1 - HB_MZ_SPAN(y)) : HB_MZ_POS(y);
+			h.cnt = w_tab[n] << 8 | (zspan <= 255 ? zspan : 255);
+		}
+	}
+	return tot;
+}
+
+static ChainPar chain_par(double bw, int k, int max_n_chain)
+{
+	ChainPar P; double tmp = expf((float)(-0.01 * (double)k));
+	P.pen_gap = 0.5f; P.pen_skip = 0.0005f; P.pen_gap *= tmp; P.pen_skip *= tmp; P.bw_rate = bw;
+	P.max_skip = 25; P.max_iter = 5000; P.max_dis = 5000; P.mcopy_num = 3; P.mcopy_khit_cutoff = 32; P.mcopy_rate = 0.7;
+	P.max_n_chain = max_n_chain; P.chain_cutoff = 2; P.ocv_w = 3072;
+	return P;
+}
+
+struct EmuChains { std::vector<hb_chain_t> ch; std::vector<hb_hit_t> chits; std::vector<uint32_t> idx; uint32_t n_ol; std::vector<uint64_t> fc; };
+
+// the chain kernel (thread per group) + post kernel (thread per read), run
+// sequentially over one read's grouped anchors
+static void run_chains(EmuReads *r, uint32_t rid, hb_hit_t *hits, uint64_t n_hits, const ChainPar &P, EmuChains &E, bool want_fc)
+{
+	std::vector<GroupDir> dir; uint32_t slot = 0;
+	for (uint64_t l = 0, k = 1; k <= n_hits; k++)
+		if (k == n_hits || HB_HIT_ID(hits[k]) != HB_HIT_ID(hits[l])) {
+			GroupDir g; g.read = rid; g.start = (uint32_t)l; g.count = (uint32_t)(k - l); g.slot = slot;
+			if (HB_HIT_ID(hits[l]) != rid) { slot += g.count >= (uint32_t)P.mcopy_khit_cutoff ? P.mcopy_num : 1; dir.push_back(g); }
+			l = k;
+		}
+	E.ch.assign(slot + 1, hb_chain_t()); E.chits.assign(n_hits + 1, hb_hit_t()); E.idx.assign(slot + 1, 0);
+	E.fc.assign(want_fc ? n_hits + 2 * slot + 4 : 1, 0);
+	std::vector<int32_t> f(n_hits + 1), p(n_hits + 1), ii(n_hits + 1); std::vector<int64_t> t(n_hits + 1);
+	FcOut fc; fc.buf = want_fc ? E.fc.data() : 0; fc.n = 0; fc.cap = (uint32_t)E.fc.size(); fc.ovf = 0;
+	for (auto &g : dir) {
+		int32_t ns = g.count >= (uint32_t)P.mcopy_khit_cutoff ? P.mcopy_num : 1;
+		hb_chain_group(hits + g.start, (int32_t)g.count, E.chits.data() + g.start, g.start, f.data() + g.start, p.data() + g.start, t.data() + g.start, ii.data() + g.start,
+		               P, r->d.len[rid], r->d.len[HB_HIT_ID(hits[g.start])], E.ch.data() + g.slot, ns, fc);
+	}
+	E.fc.resize(fc.n);
+	std::vector<uint64_t> cc(r->d.len[rid] / P.ocv_w + 2);
+	E.n_ol = hb_chain_post(E.ch.data(), slot, E.chits.data(), E.idx.data(), cc.data(), r->d.len[rid], P);
+}
+
+// -> chains in final order (first_hit = compacted cl->list index), compacted chain anchors, fake cigars
+int emu_chains(void *reads, uint32_t rid, hb_hit_t *hits, uint64_t n_hits, double bw, int k, int max_n_chain,
+               hb_chain_t *out, uint32_t *n_out, hb_hit_t *chits_out, uint64_t *n_chits, uint64_t *fc_out, uint64_t *n_fc)
+{
+	EmuReads *r = (EmuReads *)reads; ChainPar P = chain_par(bw, k, max_n_chain); EmuChains E;
+	run_chains(r, rid, hits, n_hits, P, E, true);
+	uint64_t m = 0; uint32_t ord = 0;
+	for (size_t s = 0; s + 1 < E.ch.size(); s++) {
+		hb_chain_t &c = E.ch[s];
+		if (!c.n_hits) continue;
+		for (uint32_t h = 0; h < c.n_hits; h++) { chits_out[m] = E.chits[c.first_hit + h]; chits_out[m].id_strand = (chits_out[m].id_strand & 0x80000000u) | ord; m++; }
+		ord++;
+	}
+	*n_chits = m;
+	for (uint32_t i = 0; i < E.n_ol; i++) { out[i] = E.ch[E.idx[i]]; out[i].first_hit = out[i].pad; out[i].pad = 0; }
+	*n_out = E.n_ol;
+	memcpy(fc_out, E.fc.data(), E.fc.size() * 8); *n_fc = E.fc.size();
+	return 0;
+}
+
+// the whole final pass of one read through the product's device functions
+int emu_final_read(void *reads, void *ft, void *pt, int w, int k, int is_hpc, int sample_dist, int rewin, int hom_cov, int max_n_chain, uint32_t rid,
+                   hb_ma_hit_t *in0, uint32_t n0, const hb_ma_hit_t *in1, uint32_t n1, hb_ma_hit_t *out0, uint32_t *m0, hb_ma_hit_t *out1, uint32_t *m1)
+{
+	EmuReads *r = (EmuReads *)reads;
+	uint32_t high_occ = (uint32_t)(hom_cov * (2.0 - 0.333)), low_occ = (uint32_t)(hom_cov * 0.333); // ecovlp.cpp:3952-3953
+	uint32_t cap = r->d.len[rid] / 4 + 64, n_mz;
+	std::vector<hb_mz_t> mz(cap);
+	if (emu_sketch(reads, ft, w, k, is_hpc, sample_dist, rewin, rid, 0, mz.data(), cap, &n_mz)) return -1;
+	uint64_t na = emu_anchors(reads, pt, mz.data(), n_mz, high_occ, low_occ, 0, 0);
+	std::vector<hb_hit_t> hits(na + 1);
+	emu_anchors(reads, pt, mz.data(), n_mz, high_occ, low_occ, hits.data(), na);
+	ChainPar P = chain_par(0.001, k, max_n_chain); EmuChains E;
+	run_chains(r, rid, hits.data(), na, P, E, false);
+	std::vector<uint8_t> exact(E.ch.size() + 1, 0);
+	for (uint32_t i = 0; i < E.n_ol; i++) {
+		const hb_chain_t &c = E.ch[E.idx[i]];
+		exact[E.idx[i]] = (uint8_t)hb_exact_seq(r->d, rid, c.x_pos_s, (uint64_t)c.x_pos_e + 1, c.y_id, c.y_pos_s, (uint64_t)c.y_pos_e + 1, (int)c.y_pos_strand);
+	}
+	std::vector<FinOv> ov(E.n_ol + n0 + 1); std::vector<uint64_t> srt(n0 + n1 + 1);
+	unsigned long long stat[6];
+	hb_final_merge(r->d, rid, E.ch.data(), E.idx.data(), E.n_ol, exact.data(), in0, n0, in1, n1, ov.data(), srt.data(), out0, m0, out1, m1, stat);
+	return 0;
+}
+
+} // extern "C"

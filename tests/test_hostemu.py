@@ -1,0 +1,92 @@
+"""Host-compiled bodies of the product's per-thread kernels (tests/hostemu)
+against the golden vectors of the reference — the GPU-less half of the parity
+check of hifiasm_b200/csrc/*.cuh."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu"))
+import emu  # noqa: E402
+import ha_oracle as ho  # noqa: E402
+from goldenlib import Golden, dg  # noqa: E402
+
+
+@pytest.fixture(scope="module", params=["g1", "g2"])
+def ctx(request):
+    g = Golden(request.param)
+    raw = ho.Store(g.raw.length, g.raw.byte_off, g.raw.packed, g.raw.n_off, g.raw.n_pos)
+    opt = ho.default_opt()
+    ft, hom = ho.ft_gen(raw, opt)
+    ho.lib().hao_opt_update_cov(C.byref(opt), hom)
+    eft, _, _ = emu.ft_from_oracle(ft)
+    return g, opt, ft, eft
+
+
+@pytest.mark.parametrize("mode", ["raw", "final"])
+def test_sketch(ctx, mode):
+    g, opt, ft, eft = ctx
+    rs = g.raw if mode == "raw" else g.pre
+    er = emu.Reads(rs)
+    p = g.params(mode)
+    for i in range(er.n):
+        mz = emu.sketch(er, eft, p, i)
+        assert dg(mz.tobytes()) == int(g.digest(mode, "mz")[i]), "read %d" % i
+
+
+def _chain_digest(ch, fc):
+    import hashlib
+    from goldenlib import CH
+    h = hashlib.blake2b(digest_size=8)
+    for c in ch:
+        r = np.zeros(1, dtype=CH)
+        for f in ("x_pos_s", "x_pos_e", "y_id", "y_pos_s", "y_pos_e", "y_pos_strand", "shared_seed", "first_hit"):
+            r[f] = c[f]
+        r["n_fc"] = c["fc_n"]
+        h.update(r.tobytes())
+        h.update(np.ascontiguousarray(fc[int(c["fc_off"]):int(c["fc_off"]) + int(c["fc_n"])]).tobytes())
+    return int.from_bytes(h.digest(), "little")
+
+
+@pytest.mark.parametrize("mode", ["raw", "final"])
+def test_anchors_chains(ctx, mode):
+    g, opt, ft, eft = ctx
+    rs = g.raw if mode == "raw" else g.pre
+    st = ho.Store(rs.length, rs.byte_off, rs.packed, rs.n_off, rs.n_pos)
+    pt, hom, het = ho.pt_gen(st, ft, opt)
+    ept = emu.pt_from_oracle(pt)
+    er = emu.Reads(rs)
+    p = g.params(mode)
+    bw = float(p["bw_thres"])
+    for i in range(er.n):
+        mz = emu.sketch(er, eft, p, i)
+        an = emu.anchors(er, ept, mz, int(p["high_occ"]), int(p["low_occ"]))
+        ch, chits, fc, srt_hits = emu.chains(er, i, an, bw, int(p["k"]), int(p["max_n_chain"]))
+        # the chain kernel orders every group: the whole list is now minimizers_qgen0's cl->list
+        assert dg(srt_hits.tobytes()) == int(g.digest(mode, "anchors")[i]), "anchors read %d" % i
+        assert _chain_digest(ch, fc) == int(g.digest(mode, "chains")[i]), "chains read %d" % i
+        assert dg(chits.tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain hits read %d" % i
+
+
+def test_final_pass(ctx):
+    from hifiasm_b200 import binio
+    g, opt, ft, eft = ctx
+    rs = g.pre
+    st = ho.Store(rs.length, rs.byte_off, rs.packed, rs.n_off, rs.n_pos)
+    pt, hom, het = ho.pt_gen(st, ft, opt)
+    ept = emu.pt_from_oracle(pt)
+    er = emu.Reads(rs)
+    p = g.params("final")
+    p0, o0, _, _ = g.pre_src
+    p1, o1, _, _ = g.pre_rev
+    f0, fo0, _, _ = g.fin_src
+    f1, fo1, _, _ = g.fin_rev
+    m0, m1 = binio.disk_to_mem(p0), binio.disk_to_mem(p1)
+    for i in range(er.n):
+        a, b = emu.final_read(er, eft, ept, p, hom, int(p["max_n_chain"]), i, m0[int(o0[i]):int(o0[i + 1])], m1[int(o1[i]):int(o1[i + 1])])
+        ra, rb = f0[int(fo0[i]):int(fo0[i + 1])], f1[int(fo1[i]):int(fo1[i + 1])]
+        assert a.size == ra.size and b.size == rb.size, "read %d" % i
+        for f in binio.MA_DISK.names:
+            assert (a[f] == ra[f]).all() and (b[f] == rb[f]).all(), "read %d field %s" % (i, f)
