@@ -1,0 +1,701 @@
+// engine.cu — context, read store, and the host orchestration of the overlap
+// pass (C-ABI of include/hifiasm_b200.h).  Host code is plumbing only: buffer
+// management, launches, batch planning.  No compute runs on the host and there
+// is no CPU fallback.
+#include <stdarg.h>
+#include <math.h>
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include "hb_internal.h"
+#include "hb_kernels.cuh"
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+void hb_set_err(hb_ctx *ctx, int code, const char *fmt, ...)
+{
+	char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+	if (ctx) ctx->err = buf;
+	(void)code;
+}
+
+ProfScope::ProfScope(hb_ctx *c, const char *n) : ctx(c), name(n)
+{
+	cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream);
+}
+ProfScope::~ProfScope()
+{
+	float ms = 0; cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	for (auto &p : ctx->prof) if (p.name == name) { p.launches++; p.ms += ms; return; }
+	ProfEntry e = { name, 1, ms }; ctx->prof.push_back(e);
+}
+void hb_prof_reset(hb_ctx *ctx) { ctx->prof.clear(); memset(ctx->counters, 0, sizeof(ctx->counters)); }
+
+DevReads hb_dev_reads(const hb_ctx *ctx)
+{
+	DevReads R; R.n = ctx->n_reads; R.packed = ctx->d_packed; R.off = ctx->d_roff; R.len = ctx->d_rlen; R.noff = ctx->d_noff; R.npos = ctx->d_npos;
+	return R;
+}
+DevFt hb_dev_ft(const hb_ctx *ctx)
+{
+	DevFt f; f.mask = ctx->ft_n ? ctx->ft_cap - 1 : 0; f.key = ctx->d_ft_key; f.val = ctx->d_ft_val;
+	return f;
+}
+DevPt hb_dev_pt(const hb_ctx *ctx)
+{
+	DevPt p; p.mask = ctx->pt_cap - 1; p.slot = ctx->d_pt_slot; p.pos = ctx->d_pt_pos;
+	return p;
+}
+
+// stream-ordered allocations that free themselves (in stream order) on scope exit
+struct Arena {
+	hb_ctx *ctx; std::vector<void *> ptrs; bool failed;
+	Arena(hb_ctx *c) : ctx(c), failed(false) {}
+	template <typename T> T *get(uint64_t n)
+	{
+		void *p = 0;
+		if (cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ctx->stream) != cudaSuccess) { failed = true; cudaGetLastError(); return 0; }
+		ptrs.push_back(p);
+		return (T *)p;
+	}
+	template <typename T> T *zero(uint64_t n) { T *p = get<T>(n); if (p) cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream); return p; }
+	void release(void *p) { for (auto &q : ptrs) if (q == p) { cudaFreeAsync(q, ctx->stream); q = 0; } }
+	void *steal(void *p) { for (auto &q : ptrs) if (q == p) q = 0; return p; }
+	~Arena() { for (void *p : ptrs) if (p) cudaFreeAsync(p, ctx->stream); }
+};
+#define HB_ALLOC_CHECK(ar) do { if ((ar).failed) { hb_set_err(ctx, HB_E_NOMEM, "device allocation failed at %s:%d", __FILE__, __LINE__); return HB_E_NOMEM; } } while (0)
+
+static inline unsigned nblk(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return v; } };
+int hb_scan_u32_to_u64(hb_ctx *ctx, const uint32_t *d_in, uint64_t *d_out, uint64_t n)
+{ // exclusive sum over n+1 items (the last input is ignored by callers that pad with 0)
+	size_t tb = 0; Arena ar(ctx);
+	cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> in(d_in, U32ToU64());
+	HB_CUDA(cub::DeviceScan::ExclusiveSum(0, tb, in, d_out, n + 1, ctx->stream));
+	void *tmp = ar.get<uint8_t>(tb); HB_ALLOC_CHECK(ar);
+	HB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, in, d_out, n + 1, ctx->stream));
+	return HB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// options / context
+// ---------------------------------------------------------------------------
+extern "C" void hb_opt_init(hb_opt_t *o)
+{ // init_opt, CommandLines.cpp:243-380
+	memset(o, 0, sizeof(*o));
+	o->k_mer_length = 51; o->mz_win = 51; o->is_hpc = 1; o->mz_sample_dist = 500; o->mz_rewin = 1000;
+	o->min_hist_kmer_cnt = 5; o->max_kmer_cnt = 2000; o->max_n_chain = 100; o->high_factor = 5.0; o->hom_cov = 20; o->het_cov = -1024;
+}
+extern "C" void hb_opt_update_cov(hb_opt_t *o, int hom_cov)
+{ // ha_opt_update_cov, CommandLines.cpp:411-418
+	int m = (int)(hom_cov * o->high_factor + .499);
+	o->hom_cov = hom_cov;
+	if (o->max_n_chain < m) o->max_n_chain = m;
+}
+extern "C" int hb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+static int check_opt(hb_ctx *ctx, const hb_opt_t *o)
+{
+	if (o->k_mer_length < 2 || o->k_mer_length > 63 || o->mz_win < 1 || o->mz_win > 255) { hb_set_err(ctx, HB_E_ARG, "k must be in [2,63], w in [1,255]"); return HB_E_ARG; }
+	if (o->is_ont) { hb_set_err(ctx, HB_E_ARG, "--ont mode is not implemented on the GPU path yet"); return HB_E_ARG; }
+	return HB_OK;
+}
+
+extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
+{
+	int n = hb_device_count();
+	*out = 0;
+	if (n <= 0 || device < 0 || device >= n) return HB_E_NO_DEVICE; // no CUDA device: fail loudly, there is no CPU path
+	hb_ctx *ctx = new hb_ctx();
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return HB_E_CUDA; }
+	cudaDeviceProp pr; cudaGetDeviceProperties(&pr, device); ctx->sm_count = pr.multiProcessorCount;
+	cudaMemPool_t pool; cudaDeviceGetDefaultMemPool(&pool, device);
+	uint64_t thr = UINT64_MAX; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+	if (opt) ctx->opt = *opt; else hb_opt_init(&ctx->opt);
+	if (check_opt(ctx, &ctx->opt)) { cudaStreamDestroy(ctx->stream); delete ctx; return HB_E_ARG; }
+	ctx->n_reads = 0; ctx->d_packed = 0; ctx->d_roff = 0; ctx->d_rlen = 0; ctx->d_noff = 0; ctx->d_npos = 0;
+	ctx->ft_n = ctx->ft_cap = 0; ctx->d_ft_key = 0; ctx->d_ft_val = 0;
+	ctx->pt_keys = ctx->pt_npos = ctx->pt_cap = 0; ctx->d_pt_slot = 0; ctx->d_pt_pos = 0;
+	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
+	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
+	ctx->anchor_budget = 64ull << 20;
+	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
+	hb_prof_reset(ctx);
+	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
+	*out = ctx;
+	return HB_OK;
+}
+
+static void free_reads(hb_ctx *ctx)
+{
+	cudaFree(ctx->d_packed); cudaFree(ctx->d_roff); cudaFree(ctx->d_rlen); cudaFree(ctx->d_noff); cudaFree(ctx->d_npos);
+	ctx->d_packed = 0; ctx->d_roff = 0; ctx->d_rlen = 0; ctx->d_noff = 0; ctx->d_npos = 0; ctx->n_reads = 0;
+}
+static void free_prev(hb_ctx *ctx)
+{
+	cudaFree(ctx->d_prev0); cudaFree(ctx->d_prev1); cudaFree(ctx->d_prev0_off); cudaFree(ctx->d_prev1_off);
+	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0;
+}
+static void free_out(hb_ctx *ctx)
+{
+	cudaFree(ctx->d_out0); cudaFree(ctx->d_out1); cudaFree(ctx->d_out0_off); cudaFree(ctx->d_out1_off);
+	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
+}
+extern "C" void hb_destroy(hb_ctx_t *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+extern "C" const char *hb_last_error(const hb_ctx_t *ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+extern "C" int hb_set_opt(hb_ctx_t *ctx, const hb_opt_t *opt) { int rc = check_opt(ctx, opt); if (rc) return rc; ctx->opt = *opt; return HB_OK; }
+extern "C" int hb_get_opt(const hb_ctx_t *ctx, hb_opt_t *opt) { *opt = ctx->opt; return HB_OK; }
+
+// ---------------------------------------------------------------------------
+// read store
+// ---------------------------------------------------------------------------
+static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uint8_t *flat, const uint64_t *boff, uint8_t *const *ptrs,
+                         const uint64_t *n_pos, const uint64_t *n_off, uint64_t *const *N_site)
+{
+	cudaSetDevice(ctx->device);
+	free_reads(ctx);
+	if (n >= (1ull << 28)) { hb_set_err(ctx, HB_E_ARG, "no more than 2^28 reads (htab.cpp:765)"); return HB_E_ARG; }
+	std::vector<uint64_t> off(n + 1), noff(n + 1); std::vector<uint32_t> npos;
+	ctx->h_rlen.resize(n); ctx->total_bases = 0;
+	uint64_t o = 0;
+	for (uint64_t i = 0; i < n; i++) {
+		if (len[i] >= (1ull << 27)) { hb_set_err(ctx, HB_E_ARG, "read %llu longer than 2^27", (unsigned long long)i); return HB_E_ARG; }
+		off[i] = o; ctx->h_rlen[i] = (uint32_t)len[i]; ctx->total_bases += len[i];
+		o += ((len[i] / 4 + 1) + 7) & ~7ull; // 8-byte aligned reads
+	}
+	off[n] = o;
+	uint8_t *h_packed = 0;
+	if (cudaMallocHost((void **)&h_packed, o + 16) != cudaSuccess) { hb_set_err(ctx, HB_E_NOMEM, "pinned staging buffer"); return HB_E_NOMEM; }
+	memset(h_packed, 0, o + 16);
+	for (uint64_t i = 0; i < n; i++) {
+		const uint8_t *src = ptrs ? ptrs[i] : flat + boff[i];
+		uint64_t nb = len[i] / 4 + 1;
+		memcpy(h_packed + off[i], src, nb);
+		// mask the undefined pad bits so equal sequences have equal bytes
+		if (len[i] % 4 == 0) h_packed[off[i] + nb - 1] = 0;
+		else h_packed[off[i] + nb - 1] &= (uint8_t)(0xFF << (2 * (4 - len[i] % 4)));
+	}
+	noff[0] = 0;
+	for (uint64_t i = 0; i < n; i++) {
+		if (N_site) {
+			uint64_t c = N_site[i] ? N_site[i][0] : 0;
+			for (uint64_t j = 0; j < c; j++) npos.push_back((uint32_t)N_site[i][1 + j]);
+			noff[i + 1] = noff[i] + c;
+		} else if (n_off) {
+			for (uint64_t j = n_off[i]; j < n_off[i + 1]; j++) npos.push_back((uint32_t)n_pos[j]);
+			noff[i + 1] = n_off[i + 1];
+		} else noff[i + 1] = 0;
+	}
+	ctx->n_reads = n; ctx->packed_bytes = o; ctx->n_npos = npos.size();
+	int rc = HB_OK;
+	if (cudaMalloc((void **)&ctx->d_packed, o + 16) != cudaSuccess || cudaMalloc((void **)&ctx->d_roff, (n + 1) * 8) != cudaSuccess ||
+	    cudaMalloc((void **)&ctx->d_rlen, (n + 1) * 4) != cudaSuccess || cudaMalloc((void **)&ctx->d_noff, (n + 1) * 8) != cudaSuccess ||
+	    cudaMalloc((void **)&ctx->d_npos, (npos.size() + 1) * 4) != cudaSuccess) { hb_set_err(ctx, HB_E_NOMEM, "read store does not fit in HBM"); rc = HB_E_NOMEM; }
+	if (!rc) {
+		cudaMemcpyAsync(ctx->d_packed, h_packed, o + 16, cudaMemcpyHostToDevice, ctx->stream);
+		cudaMemcpyAsync(ctx->d_roff, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+		cudaMemcpyAsync(ctx->d_rlen, ctx->h_rlen.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream);
+		cudaMemcpyAsync(ctx->d_noff, noff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+		if (npos.size()) cudaMemcpyAsync(ctx->d_npos, npos.data(), npos.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+		if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { hb_set_err(ctx, HB_E_CUDA, "read upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = HB_E_CUDA; }
+	}
+	cudaFreeHost(h_packed);
+	if (rc) free_reads(ctx);
+	return rc;
+}
+extern "C" int hb_reads_upload(hb_ctx_t *ctx, uint64_t n, const uint64_t *len, const uint8_t *packed, const uint64_t *byte_off, const uint64_t *n_pos, const uint64_t *n_off)
+{ return upload_common(ctx, n, len, packed, byte_off, 0, n_pos, n_off, 0); }
+extern "C" int hb_reads_upload_ptrs(hb_ctx_t *ctx, uint64_t n, const uint64_t *len, uint8_t *const *read_sperate, uint64_t *const *N_site)
+{ return upload_common(ctx, n, len, 0, 0, read_sperate, 0, 0, N_site); }
+
+// ---------------------------------------------------------------------------
+// sketch of a read range -> dense minimizer arrays
+// ---------------------------------------------------------------------------
+int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch *out)
+{
+	(void)rid_mode;
+	uint64_t nR = r1 - r0; Arena ar(ctx);
+	SketchPar P = { ctx->opt.mz_win, ctx->opt.k_mer_length, ctx->opt.is_hpc, ctx->opt.mz_sample_dist, ctx->opt.mz_rewin };
+	out->mz = 0; out->off = 0; out->total = 0;
+	for (int attempt = 0, div = 12; attempt < 3; attempt++, div = div > 4 ? div / 3 : 1) {
+		std::vector<uint64_t> cap_off(nR + 1); uint64_t tot = 0;
+		for (uint64_t i = 0; i < nR; i++) { cap_off[i] = tot; tot += ctx->h_rlen[r0 + i] / div + 32; }
+		cap_off[nR] = tot;
+		uint64_t *d_cap = ar.get<uint64_t>(nR + 1); hb_mz_t *d_mz = ar.get<hb_mz_t>(tot); uint32_t *d_l = ar.get<uint32_t>(tot), *d_n = ar.zero<uint32_t>(nR + 1);
+		int *d_err = ar.zero<int>(1); uint64_t *d_off = ar.get<uint64_t>(nR + 2);
+		HB_ALLOC_CHECK(ar);
+		HB_CUDA(cudaMemcpyAsync(d_cap, cap_off.data(), (nR + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		{
+			ProfScope ps(ctx, "k_sketch");
+			if (P.w <= 160) {
+				size_t smem = (size_t)64 * P.w * 20;
+				cudaFuncSetAttribute(k_sketch<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				k_sketch<64><<<nblk(nR, 64), 64, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0, nR, d_cap, d_mz, d_l, d_n, d_err);
+			} else {
+				size_t smem = (size_t)32 * P.w * 20;
+				cudaFuncSetAttribute(k_sketch<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				k_sketch<32><<<nblk(nR, 32), 32, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0, nR, d_cap, d_mz, d_l, d_n, d_err);
+			}
+		}
+		HB_CUDA(cudaGetLastError());
+		int h_err = 0; HB_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (h_err) { ar.release(d_cap); ar.release(d_mz); ar.release(d_l); ar.release(d_n); ar.release(d_off); continue; } // a slice overflowed: retry with larger slices
+		int rc = hb_scan_u32_to_u64(ctx, d_n, d_off, nR); if (rc) return rc;
+		uint64_t total = 0; HB_CUDA(cudaMemcpyAsync(&total, d_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+		hb_mz_t *d_dense = ar.get<hb_mz_t>(total + 2); HB_ALLOC_CHECK(ar);
+		{
+			ProfScope ps(ctx, "k_compact_mz");
+			k_compact_mz<<<nblk(nR * 32, 256), 256, 0, ctx->stream>>>(nR, d_cap, d_off, d_mz, d_dense);
+		}
+		HB_CUDA(cudaGetLastError());
+		out->mz = (hb_mz_t *)ar.steal(d_dense); out->off = (uint64_t *)ar.steal(d_off); out->total = total;
+		return HB_OK;
+	}
+	hb_set_err(ctx, HB_E_OVERFLOW, "minimizer slices overflowed even at one slot per base");
+	return HB_E_OVERFLOW;
+}
+
+// ---------------------------------------------------------------------------
+// the overlap pass over reads [r0,r1)
+// ---------------------------------------------------------------------------
+struct PassOut { // what the stage APIs want back (device pointers, stolen from the pass arena)
+	int want_stage;            // 0 = final pass, 1 = sketch only, 2 = anchors, 3 = chains
+	// stage 2: grouped+ordered anchors for the whole range
+	hb_hit_t *hits; uint64_t *a_off; uint64_t n_hits;
+};
+
+static void weight_table(uint32_t *w_tab, uint32_t high_occ, uint32_t low_occ)
+{ // weight of an anchor from its minimizer's occurrence count (anchor.cpp:991-999,
+  // 1066-1075); tabulated once on the host (libm pow), 4096 entries (n <= 4094)
+	uint64_t max_cnt = high_occ < 2 ? 2 : high_occ, min_cnt = low_occ < 2 ? 2 : low_occ;
+	for (uint32_t n = 0; n < 4096; n++) {
+		uint32_t w;
+		if (n < max_cnt && n > min_cnt) w = 1;
+		else if (n <= min_cnt) w = 2;
+		else { w = (uint32_t)(1 + ((n + (max_cnt << 1) - 1) / (max_cnt << 1))); w = (uint32_t)pow((double)w, 1.1); }
+		if (w > 0xffffffu) w = 0xffffffu;
+		w_tab[n] = w;
+	}
+}
+
+static ChainPar chain_par(const hb_ctx *ctx, double bw)
+{ // set_lchain_dp_op(is_accurate=1), anchor.cpp:2272-2285; arguments of ecovlp.cpp:3957
+	ChainPar P; double tmp = expf((float)(-0.01 * (double)ctx->opt.k_mer_length));
+	P.pen_gap = 0.5f; P.pen_skip = 0.0005f; P.pen_gap *= tmp; P.pen_skip *= tmp; P.bw_rate = bw;
+	P.max_skip = 25; P.max_iter = 5000; P.max_dis = 5000; P.mcopy_num = 3; P.mcopy_khit_cutoff = 32; P.mcopy_rate = 0.7;
+	P.max_n_chain = ctx->opt.max_n_chain; P.chain_cutoff = 2; P.ocv_w = 3072;
+	return P;
+}
+
+__global__ void k_cap_per_read(uint64_t nR, const uint32_t *__restrict__ sc, const uint64_t *__restrict__ in0_off, uint32_t *__restrict__ cap)
+{ uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r < nR) cap[r] = sc[r] + (uint32_t)(in0_off[r + 1] - in0_off[r]); }
+__global__ void k_cc_per_read(uint64_t nR, uint64_t r0, const uint32_t *__restrict__ rlen, uint32_t ocv_w, uint32_t *__restrict__ cap)
+{ uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r < nR) cap[r] = rlen[r0 + r] / ocv_w + 2; }
+__global__ void k_rebase(uint64_t n, const uint64_t *__restrict__ in, uint64_t base, uint64_t *__restrict__ out)
+{ uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[i] - base; }
+__global__ void k_add_off(uint64_t n, uint64_t *__restrict__ a, uint64_t add)
+{ uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] += add; }
+// stage-3 output assembly: per read, chains in final order with compacted anchor index, chain anchors, fake cigars
+__global__ void k_stage3_counts(uint64_t nR, const uint64_t *__restrict__ c_off, const hb_chain_t *__restrict__ ch, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol,
+                                uint32_t *__restrict__ n_hit, uint32_t *__restrict__ n_fc)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	uint64_t cb = c_off[r]; uint32_t ns = (uint32_t)(c_off[r + 1] - cb), h = 0, f = 0;
+	for (uint32_t s = 0; s < ns; s++) h += ch[cb + s].n_hits;
+	for (uint32_t i = 0; i < n_ol[r]; i++) f += ch[cb + idx[cb + i]].fc_n;
+	n_hit[r] = h; n_fc[r] = f;
+}
+__global__ void k_stage3_fill(uint64_t nR, const uint64_t *__restrict__ c_off, const uint64_t *__restrict__ a_off, uint64_t a_base, const hb_chain_t *__restrict__ ch, const GroupDir *dirless,
+                              const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol, const hb_hit_t *__restrict__ chits, const uint64_t *__restrict__ fc,
+                              const uint64_t *__restrict__ o_ch, const uint64_t *__restrict__ o_hit, const uint64_t *__restrict__ o_fc,
+                              hb_chain_t *__restrict__ out_ch, hb_hit_t *__restrict__ out_hit, uint64_t *__restrict__ out_fc, const uint64_t *__restrict__ fc_grp_base)
+{
+	(void)dirless; (void)a_off; (void)a_base;
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	uint64_t cb = c_off[r]; uint32_t ns = (uint32_t)(c_off[r + 1] - cb), ord = 0; uint64_t m = o_hit[r], fo = o_fc[r];
+	for (uint32_t s = 0; s < ns; s++) { // compacted chain anchors, tagged with the chain ordinal (Hash_Table.cpp:2240,2279)
+		const hb_chain_t &c = ch[cb + s];
+		if (!c.n_hits) continue;
+		for (uint32_t h = 0; h < c.n_hits; h++) { hb_hit_t v = chits[c.first_hit + h]; v.id_strand = (v.id_strand & 0x80000000u) | ord; out_hit[m++] = v; }
+		ord++;
+	}
+	for (uint32_t i = 0; i < n_ol[r]; i++) {
+		hb_chain_t c = ch[cb + idx[cb + i]];
+		const uint64_t *src = fc + fc_grp_base[cb + idx[cb + i]] + c.fc_off;
+		for (uint32_t j = 0; j < c.fc_n; j++) out_fc[fo + j] = src[j];
+		c.fc_off = (uint32_t)(fo - o_fc[r]); fo += c.fc_n;
+		c.first_hit = c.pad; c.pad = 0;
+		out_ch[o_ch[r] + i] = c;
+	}
+}
+__global__ void k_fc_grp_base(const GroupDir *__restrict__ dir, const uint32_t *__restrict__ dir_n, const uint64_t *__restrict__ a_off, uint64_t a_base, const uint64_t *__restrict__ c_off,
+                              int32_t mcopy_num, int32_t cutoff, uint64_t *__restrict__ base)
+{
+	uint32_t n = *dir_n;
+	for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+		GroupDir d = dir[g]; if (d.slot == GRP_EMPTY) continue;
+		uint64_t ab = a_off[d.read] - a_base + d.start, cb = c_off[d.read] + d.slot; int32_t ns = d.count >= (uint32_t)cutoff ? mcopy_num : 1;
+		for (int32_t s = 0; s < ns; s++) base[cb + s] = ab + 2 * cb;
+	}
+}
+
+struct StageOut { // host destinations of the stage APIs (all optional)
+	uint64_t *off; void *rec; uint64_t rec_cap;      // stage 1: minimizers / stage 2: anchors / stage 3: chains
+	uint64_t *hit_off; hb_hit_t *hits; uint64_t hit_cap; uint64_t *fc_off; uint64_t *fc; uint64_t fc_cap;
+};
+
+// mode: 0 final pass (results kept in ctx->d_out*), 2 anchors, 3 chains
+static int run_pass(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, StageOut *so, uint64_t *stat_out)
+{
+	cudaSetDevice(ctx->device);
+	if (r1 > ctx->n_reads || r0 > r1) { hb_set_err(ctx, HB_E_ARG, "read range out of bounds"); return HB_E_ARG; }
+	if (!ctx->d_pt_slot) { hb_set_err(ctx, HB_E_STATE, "no position index: call hb_pt_gen first"); return HB_E_STATE; }
+	if (mode == 0 && !ctx->d_prev0_off) { hb_set_err(ctx, HB_E_STATE, "previous overlaps are not staged"); return HB_E_STATE; }
+	const uint64_t nR = r1 - r0; Arena ar(ctx); int rc;
+	DevReads R = hb_dev_reads(ctx); DevPt PT = hb_dev_pt(ctx);
+	const uint32_t high_occ = (uint32_t)(ctx->opt.hom_cov * (2.0 - 0.333)), low_occ = (uint32_t)(ctx->opt.hom_cov * 0.333); // ecovlp.cpp:3952-3953
+	uint32_t h_wtab[4096]; weight_table(h_wtab, high_occ, low_occ);
+	ChainPar CP = chain_par(ctx, bw);
+	hb_prof_reset(ctx);
+	if (nR == 0) { if (so && so->off) so->off[0] = 0; return HB_OK; }
+
+	// ---- sketch + probe for the whole range
+	DevSketch sk; rc = hb_run_sketch(ctx, r0, r1, 0, &sk); if (rc) return rc;
+	ar.ptrs.push_back(sk.mz); ar.ptrs.push_back(sk.off);
+	uint64_t *d_seeds = ar.get<uint64_t>(sk.total + 1); uint32_t *d_spre = ar.get<uint32_t>(sk.total + 1), *d_acnt = ar.zero<uint32_t>(nR + 1), *d_wtab = ar.get<uint32_t>(4096);
+	uint64_t *d_aoff = ar.get<uint64_t>(nR + 2);
+	HB_ALLOC_CHECK(ar);
+	HB_CUDA(cudaMemcpyAsync(d_wtab, h_wtab, sizeof(h_wtab), cudaMemcpyHostToDevice, ctx->stream));
+	{
+		ProfScope ps(ctx, "k_probe_count");
+		k_probe_count<<<nblk(nR * 32, 256), 256, 0, ctx->stream>>>(PT, nR, sk.off, sk.mz, d_seeds, d_spre, d_acnt);
+	}
+	HB_CUDA(cudaGetLastError());
+	rc = hb_scan_u32_to_u64(ctx, d_acnt, d_aoff, nR); if (rc) return rc;
+	std::vector<uint64_t> h_aoff(nR + 1), h_mzoff(nR + 1);
+	HB_CUDA(cudaMemcpyAsync(h_aoff.data(), d_aoff, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(h_mzoff.data(), sk.off, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->counters[0] = nR; ctx->counters[2] = sk.total; ctx->counters[3] = h_aoff[nR];
+	for (uint64_t i = r0; i < r1; i++) ctx->counters[1] += ctx->h_rlen[i];
+
+	// ---- whole-range outputs
+	hb_hit_t *d_all_hits = 0; // mode 2
+	if (mode == 2) { d_all_hits = ar.get<hb_hit_t>(h_aoff[nR] + 1); HB_ALLOC_CHECK(ar); }
+	std::vector<uint64_t> st3_off, st3_hit_off, st3_fc_off; // mode 3 host offsets (accumulated per batch)
+	uint64_t st3_n = 0, st3_nh = 0, st3_nf = 0;
+	if (mode == 3) { st3_off.assign(nR + 1, 0); st3_hit_off.assign(nR + 1, 0); st3_fc_off.assign(nR + 1, 0); }
+	unsigned long long *d_stat = ar.zero<unsigned long long>(8);
+	uint32_t *d_m0 = 0, *d_m1 = 0; // per-read result counts (final pass)
+	struct BatchRes { hb_ma_hit_t *o0, *o1; uint64_t *ooff; uint64_t b0, b1; };
+	std::vector<BatchRes> bres;
+	if (mode == 0) { d_m0 = ar.zero<uint32_t>(nR + 1); d_m1 = ar.zero<uint32_t>(nR + 1); }
+	HB_ALLOC_CHECK(ar);
+
+	// ---- batches bounded by the anchor budget
+	for (uint64_t b0 = 0; b0 < nR;) {
+		uint64_t b1 = b0 + 1;
+		while (b1 < nR && h_aoff[b1 + 1] - h_aoff[b0] <= ctx->anchor_budget) b1++;
+		const uint64_t nb = b1 - b0, B = h_aoff[b1] - h_aoff[b0], a_base = h_aoff[b0], mz_b = h_mzoff[b0], n_mz = h_mzoff[b1] - h_mzoff[b0];
+		if (B >= (1ull << 32)) { hb_set_err(ctx, HB_E_OVERFLOW, "a single read produces >= 2^32 anchors"); return HB_E_OVERFLOW; }
+		Arena ba(ctx);
+		hb_hit_t *d_raw = ba.get<hb_hit_t>(B + 1), *d_hits = mode == 2 ? d_all_hits + a_base : ba.get<hb_hit_t>(B + 1);
+		uint32_t *d_sc = ba.zero<uint32_t>(nb + 1), *d_dirn = ba.zero<uint32_t>(1); int *d_err = ba.zero<int>(1);
+		uint64_t *d_coff = ba.get<uint64_t>(nb + 2); unsigned long long *d_arena_used = ba.zero<unsigned long long>(1);
+		HB_ALLOC_CHECK(ba);
+		if (B) {
+			ProfScope ps(ctx, "k_expand");
+			unsigned grid = (unsigned)std::min<uint64_t>((n_mz * 16 + 255) / 256, (uint64_t)ctx->sm_count * 32);
+			k_expand<<<grid ? grid : 1, 256, 0, ctx->stream>>>(R, PT, r0, n_mz, sk.mz + mz_b, d_seeds + mz_b, d_spre + mz_b, d_aoff, a_base, d_wtab, d_raw);
+		}
+		HB_CUDA(cudaGetLastError());
+		// group: retried with a larger directory / arena when the first guess was too small
+		GroupDir *d_dir = 0; uint32_t h_dirn = 0; uint64_t dir_cap = B / 8 + 64 * nb + 1024, arena_words = 16ull << 20;
+		for (int attempt = 0;; attempt++) {
+			if (dir_cap > B + 1) dir_cap = B + 1;
+			d_dir = ba.get<GroupDir>(dir_cap); uint32_t *d_ar = ba.get<uint32_t>(arena_words);
+			HB_ALLOC_CHECK(ba);
+			HB_CUDA(cudaMemsetAsync(d_dirn, 0, 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_arena_used, 0, 8, ctx->stream));
+			GroupArgs G; G.nR = nb; G.r0 = r0 + b0; G.a_off = d_aoff + b0; G.a_base = a_base; G.raw = d_raw; G.hits = d_hits; G.dir = d_dir; G.dir_n = d_dirn; G.dir_cap = (uint32_t)dir_cap;
+			G.sc = d_sc; G.arena = d_ar; G.arena_used = d_arena_used; G.arena_words = arena_words; G.mcopy_num = CP.mcopy_num; G.mcopy_khit_cutoff = CP.mcopy_khit_cutoff; G.err = d_err;
+			{
+				ProfScope ps(ctx, "k_group");
+				k_group<<<nblk(nb, GRP_WARPS), GRP_WARPS * 32, GRP_SMEM_BYTES, ctx->stream>>>(G);
+			}
+			HB_CUDA(cudaGetLastError());
+			int h_err = 0;
+			HB_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_dirn, d_dirn, 4, cudaMemcpyDeviceToHost, ctx->stream));
+			HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (!h_err) { ba.release(d_ar); break; }
+			ba.release(d_dir); ba.release(d_ar);
+			if (attempt >= 4 || (h_err & 2)) { hb_set_err(ctx, HB_E_OVERFLOW, "anchor grouping overflow (flags %d)", h_err); return HB_E_OVERFLOW; }
+			if (h_err & 8) dir_cap = B + 1;
+			if (h_err & 4) arena_words *= 8;
+		}
+		ba.release(d_raw);
+		ctx->counters[4] += h_dirn;
+		rc = hb_scan_u32_to_u64(ctx, d_sc, d_coff, nb); if (rc) return rc;
+		uint64_t n_slots = 0; HB_CUDA(cudaMemcpyAsync(&n_slots, d_coff + nb, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+
+		// chain
+		hb_hit_t *d_chits = ba.get<hb_hit_t>(B + 1); int32_t *d_f = ba.get<int32_t>(B + 1), *d_p = ba.get<int32_t>(B + 1), *d_ii = ba.get<int32_t>(B + 1); int64_t *d_t = ba.get<int64_t>(B + 1);
+		hb_chain_t *d_ch = ba.zero<hb_chain_t>(n_slots + 1); uint32_t *d_slot_read = ba.get<uint32_t>(n_slots + 1);
+		uint64_t *d_fc = mode == 3 ? ba.get<uint64_t>(B + 2 * n_slots + 4) : 0;
+		HB_ALLOC_CHECK(ba);
+		{
+			ChainArgs C; C.R = R; C.r0 = r0 + b0; C.dir = d_dir; C.dir_n = d_dirn; C.a_off = d_aoff + b0; C.a_base = a_base; C.c_off = d_coff;
+			C.hits = d_hits; C.chits = d_chits; C.f = d_f; C.p = d_p; C.ii = d_ii; C.t = d_t; C.ch = d_ch; C.slot_read = d_slot_read; C.fc = d_fc; C.P = CP; C.err = d_err;
+			ProfScope ps(ctx, "k_chain");
+			k_chain<<<std::max(1u, std::min(nblk(h_dirn, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
+		}
+		HB_CUDA(cudaGetLastError());
+		if (mode == 2) { b0 = b1; continue; }
+		ba.release(d_f); ba.release(d_p); ba.release(d_ii); ba.release(d_t);
+
+		// post
+		uint32_t *d_idx = ba.get<uint32_t>(n_slots + 1), *d_nol = ba.zero<uint32_t>(nb + 1), *d_cccap = ba.get<uint32_t>(nb + 1); uint8_t *d_keep = ba.zero<uint8_t>(n_slots + 1), *d_exact = ba.zero<uint8_t>(n_slots + 1);
+		uint64_t *d_ccoff = ba.get<uint64_t>(nb + 2);
+		HB_ALLOC_CHECK(ba);
+		k_cc_per_read<<<nblk(nb, 256), 256, 0, ctx->stream>>>(nb, r0 + b0, ctx->d_rlen, CP.ocv_w, d_cccap);
+		rc = hb_scan_u32_to_u64(ctx, d_cccap, d_ccoff, nb - 0); if (rc) return rc;
+		uint64_t cc_tot = 0; for (uint64_t i = r0 + b0; i < r0 + b1; i++) cc_tot += ctx->h_rlen[i] / CP.ocv_w + 2;
+		uint64_t *d_cc = ba.get<uint64_t>(cc_tot + 1); HB_ALLOC_CHECK(ba);
+		{
+			PostArgs Pa; Pa.R = R; Pa.r0 = r0 + b0; Pa.nR = nb; Pa.c_off = d_coff; Pa.ch = d_ch; Pa.chits = d_chits; Pa.idx = d_idx; Pa.n_ol = d_nol; Pa.keep = d_keep; Pa.cc = d_cc; Pa.cc_off = d_ccoff; Pa.P = CP;
+			ProfScope ps(ctx, "k_post");
+			k_post<<<nblk(nb, 64), 64, 0, ctx->stream>>>(Pa);
+		}
+		HB_CUDA(cudaGetLastError());
+		ctx->counters[5] += n_slots;
+
+		if (mode == 3) { // assemble the stage-3 view of this batch and copy it out
+			uint32_t *d_nh = ba.get<uint32_t>(nb + 1), *d_nf = ba.get<uint32_t>(nb + 1); uint64_t *d_och = ba.get<uint64_t>(nb + 2), *d_oh = ba.get<uint64_t>(nb + 2), *d_of = ba.get<uint64_t>(nb + 2), *d_fcb = ba.get<uint64_t>(n_slots + 1);
+			HB_ALLOC_CHECK(ba);
+			k_stage3_counts<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, d_nh, d_nf);
+			k_fc_grp_base<<<std::max(1u, std::min(nblk(h_dirn, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(d_dir, d_dirn, d_aoff + b0, a_base, d_coff, CP.mcopy_num, CP.mcopy_khit_cutoff, d_fcb);
+			if ((rc = hb_scan_u32_to_u64(ctx, d_nol, d_och, nb)) || (rc = hb_scan_u32_to_u64(ctx, d_nh, d_oh, nb)) || (rc = hb_scan_u32_to_u64(ctx, d_nf, d_of, nb))) return rc;
+			std::vector<uint64_t> h_och(nb + 1), h_oh(nb + 1), h_of(nb + 1);
+			HB_CUDA(cudaMemcpyAsync(h_och.data(), d_och, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(h_oh.data(), d_oh, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			HB_CUDA(cudaMemcpyAsync(h_of.data(), d_of, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			hb_chain_t *d_o1 = ba.get<hb_chain_t>(h_och[nb] + 1); hb_hit_t *d_o2 = ba.get<hb_hit_t>(h_oh[nb] + 1); uint64_t *d_o3 = ba.get<uint64_t>(h_of[nb] + 1);
+			HB_ALLOC_CHECK(ba);
+			k_stage3_fill<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_aoff + b0, a_base, d_ch, 0, d_idx, d_nol, d_chits, d_fc, d_och, d_oh, d_of, d_o1, d_o2, d_o3, d_fcb);
+			HB_CUDA(cudaGetLastError());
+			if (so->rec && st3_n + h_och[nb] > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "chain output capacity"); return HB_E_OVERFLOW; }
+			if (so->hits && st3_nh + h_oh[nb] > so->hit_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "chain-anchor output capacity"); return HB_E_OVERFLOW; }
+			if (so->fc && st3_nf + h_of[nb] > so->fc_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "fake-cigar output capacity"); return HB_E_OVERFLOW; }
+			if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_chain_t *)so->rec + st3_n, d_o1, h_och[nb] * sizeof(hb_chain_t), cudaMemcpyDeviceToHost, ctx->stream));
+			if (so->hits) HB_CUDA(cudaMemcpyAsync(so->hits + st3_nh, d_o2, h_oh[nb] * sizeof(hb_hit_t), cudaMemcpyDeviceToHost, ctx->stream));
+			if (so->fc) HB_CUDA(cudaMemcpyAsync(so->fc + st3_nf, d_o3, h_of[nb] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			for (uint64_t i = 0; i <= nb; i++) { st3_off[b0 + i] = st3_n + h_och[i]; st3_hit_off[b0 + i] = st3_nh + h_oh[i]; st3_fc_off[b0 + i] = st3_nf + h_of[i]; }
+			st3_n += h_och[nb]; st3_nh += h_oh[nb]; st3_nf += h_of[nb];
+			b0 = b1; continue;
+		}
+
+		// exact + merge (final pass)
+		{
+			ExactArgs E; E.R = R; E.r0 = r0 + b0; E.n_slots = n_slots; E.ch = d_ch; E.slot_read = d_slot_read; E.keep = d_keep; E.exact = d_exact;
+			ProfScope ps(ctx, "k_exact");
+			if (n_slots) k_exact<<<nblk(n_slots * 32, 256), 256, 0, ctx->stream>>>(E);
+		}
+		HB_CUDA(cudaGetLastError());
+		const uint64_t g0 = r0 + b0, p0b = ctx->h_prev0_off[g0], p0e = ctx->h_prev0_off[g0 + nb], p1b = ctx->h_prev1_off[g0], p1e = ctx->h_prev1_off[g0 + nb];
+		hb_ma_hit_t *d_in0 = ba.get<hb_ma_hit_t>(p0e - p0b + 1); uint64_t *d_i0off = ba.get<uint64_t>(nb + 2), *d_i1off = ba.get<uint64_t>(nb + 2), *d_ooff = ba.get<uint64_t>(nb + 2);
+		uint32_t *d_cap = ba.get<uint32_t>(nb + 1);
+		HB_ALLOC_CHECK(ba);
+		HB_CUDA(cudaMemcpyAsync(d_in0, ctx->d_prev0 + p0b, (p0e - p0b) * sizeof(hb_ma_hit_t), cudaMemcpyDeviceToDevice, ctx->stream)); // in0 is consumed (el reset, ecovlp.cpp:5103)
+		k_rebase<<<nblk(nb + 1, 256), 256, 0, ctx->stream>>>(nb + 1, ctx->d_prev0_off + g0, p0b, d_i0off);
+		k_rebase<<<nblk(nb + 1, 256), 256, 0, ctx->stream>>>(nb + 1, ctx->d_prev1_off + g0, p1b, d_i1off);
+		k_cap_per_read<<<nblk(nb, 256), 256, 0, ctx->stream>>>(nb, d_sc, d_i0off, d_cap);
+		rc = hb_scan_u32_to_u64(ctx, d_cap, d_ooff, nb); if (rc) return rc;
+		const uint64_t o_tot = n_slots + (p0e - p0b);
+		FinOv *d_ov = ba.get<FinOv>(o_tot + 1); uint64_t *d_srt = ba.get<uint64_t>((p0e - p0b) + (p1e - p1b) + 1);
+		hb_ma_hit_t *d_o0 = ba.get<hb_ma_hit_t>(o_tot + 1), *d_o1 = ba.get<hb_ma_hit_t>(o_tot + 1);
+		HB_ALLOC_CHECK(ba);
+		{
+			MergeArgs M; M.R = R; M.r0 = g0; M.nR = nb; M.c_off = d_coff; M.ch = d_ch; M.idx = d_idx; M.n_ol = d_nol; M.exact = d_exact;
+			M.in0 = d_in0; M.in0_off = d_i0off; M.in1 = ctx->d_prev1 + p1b; M.in1_off = d_i1off; M.ov = d_ov; M.srt = d_srt; M.o_off = d_ooff;
+			M.out0 = d_o0; M.out1 = d_o1; M.m0 = d_m0 + b0; M.m1 = d_m1 + b0; M.stat = d_stat;
+			ProfScope ps(ctx, "k_merge");
+			k_merge<<<nblk(nb, 64), 64, 0, ctx->stream>>>(M);
+		}
+		HB_CUDA(cudaGetLastError());
+		BatchRes br; br.o0 = (hb_ma_hit_t *)ba.steal(d_o0); br.o1 = (hb_ma_hit_t *)ba.steal(d_o1); br.ooff = (uint64_t *)ba.steal(d_ooff); br.b0 = b0; br.b1 = b1;
+		bres.push_back(br);
+		b0 = b1;
+	}
+
+	if (mode == 2) {
+		if (so->off) for (uint64_t i = 0; i <= nR; i++) so->off[i] = h_aoff[i];
+		if (so->rec) {
+			if (h_aoff[nR] > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "anchor output capacity"); return HB_E_OVERFLOW; }
+			HB_CUDA(cudaMemcpyAsync(so->rec, d_all_hits, h_aoff[nR] * sizeof(hb_hit_t), cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		HB_CUDA(cudaStreamSynchronize(ctx->stream));
+		return HB_OK;
+	}
+	if (mode == 3) {
+		if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8);
+		if (so->hit_off) memcpy(so->hit_off, st3_hit_off.data(), (nR + 1) * 8);
+		if (so->fc_off) memcpy(so->fc_off, st3_fc_off.data(), (nR + 1) * 8);
+		return HB_OK;
+	}
+
+	// ---- final pass: dense result arrays, kept resident in the context
+	free_out(ctx);
+	HB_CUDA(cudaMalloc((void **)&ctx->d_out0_off, (nR + 2) * 8)); HB_CUDA(cudaMalloc((void **)&ctx->d_out1_off, (nR + 2) * 8));
+	if ((rc = hb_scan_u32_to_u64(ctx, d_m0, ctx->d_out0_off, nR)) || (rc = hb_scan_u32_to_u64(ctx, d_m1, ctx->d_out1_off, nR))) return rc;
+	HB_CUDA(cudaMemcpyAsync(&ctx->n_out0, ctx->d_out0_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(&ctx->n_out1, ctx->d_out1_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	HB_CUDA(cudaMalloc((void **)&ctx->d_out0, (ctx->n_out0 + 1) * sizeof(hb_ma_hit_t))); HB_CUDA(cudaMalloc((void **)&ctx->d_out1, (ctx->n_out1 + 1) * sizeof(hb_ma_hit_t)));
+	for (auto &br : bres) {
+		uint64_t nb = br.b1 - br.b0;
+		ProfScope ps(ctx, "k_gather_ma");
+		k_gather_ma<<<nblk(nb * 32, 256), 256, 0, ctx->stream>>>(nb, br.ooff, ctx->d_out0_off + br.b0, br.o0, ctx->d_out0);
+		k_gather_ma<<<nblk(nb * 32, 256), 256, 0, ctx->stream>>>(nb, br.ooff, ctx->d_out1_off + br.b0, br.o1, ctx->d_out1);
+		cudaFreeAsync(br.o0, ctx->stream); cudaFreeAsync(br.o1, ctx->stream); cudaFreeAsync(br.ooff, ctx->stream);
+	}
+	HB_CUDA(cudaGetLastError());
+	ctx->out_reads = nR;
+	unsigned long long h_stat[8] = { 0 };
+	HB_CUDA(cudaMemcpyAsync(h_stat, d_stat, 7 * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (h_stat[6]) { hb_set_err(ctx, HB_E_OVERFLOW, "a read has more overlaps than the in-kernel radix sort stack supports"); return HB_E_OVERFLOW; }
+	if (stat_out) { // forward, reverse, strong, weak, exact, no_l_indel, inexact (ecovlp.cpp:6173-6179)
+		for (int i = 0; i < 6; i++) stat_out[i] = h_stat[i];
+		stat_out[6] = h_stat[0] - h_stat[4];
+	}
+	return HB_OK;
+}
+
+// k_gather_ma reads d_off relative to the batch: d_off + b0 gives absolute dense offsets; fine since it subtracts nothing.
+
+// ---------------------------------------------------------------------------
+// public stage APIs
+// ---------------------------------------------------------------------------
+extern "C" int hb_sketch(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *off, hb_mz_t *rec, uint64_t rec_cap)
+{
+	cudaSetDevice(ctx->device);
+	if (r1 > ctx->n_reads || r0 > r1) { hb_set_err(ctx, HB_E_ARG, "read range out of bounds"); return HB_E_ARG; }
+	uint64_t nR = r1 - r0; DevSketch sk; Arena ar(ctx);
+	if (nR == 0) { off[0] = 0; return HB_OK; }
+	int rc = hb_run_sketch(ctx, r0, r1, 0, &sk); if (rc) return rc;
+	ar.ptrs.push_back(sk.mz); ar.ptrs.push_back(sk.off);
+	HB_CUDA(cudaMemcpyAsync(off, sk.off, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (rec) {
+		if (sk.total > rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "minimizer output capacity"); return HB_E_OVERFLOW; }
+		HB_CUDA(cudaMemcpyAsync(rec, sk.mz, sk.total * sizeof(hb_mz_t), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}
+extern "C" int hb_anchors(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *off, hb_hit_t *rec, uint64_t rec_cap)
+{
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap;
+	return run_pass(ctx, r0, r1, 2, 0.02, &so, 0);
+}
+extern "C" int hb_chains(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, uint64_t *off, hb_chain_t *rec, uint64_t rec_cap,
+                         uint64_t *hit_off, hb_hit_t *hits, uint64_t hit_cap, uint64_t *fc_off, uint64_t *fc, uint64_t fc_cap)
+{
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.hit_off = hit_off; so.hits = hits; so.hit_cap = hit_cap; so.fc_off = fc_off; so.fc = fc; so.fc_cap = fc_cap;
+	return run_pass(ctx, r0, r1, 3, bw_thres, &so, 0);
+}
+
+// ---------------------------------------------------------------------------
+// final pass
+// ---------------------------------------------------------------------------
+static int stage_prev(hb_ctx *ctx, const hb_ma_hit_t *p0, const uint64_t *o0, const hb_ma_hit_t *p1, const uint64_t *o1)
+{
+	uint64_t n = ctx->n_reads;
+	free_prev(ctx);
+	ctx->h_prev0_off.assign(o0, o0 + n + 1); ctx->h_prev1_off.assign(o1, o1 + n + 1);
+	ctx->n_prev0 = o0[n]; ctx->n_prev1 = o1[n];
+	HB_CUDA(cudaMalloc((void **)&ctx->d_prev0, (ctx->n_prev0 + 1) * sizeof(hb_ma_hit_t))); HB_CUDA(cudaMalloc((void **)&ctx->d_prev1, (ctx->n_prev1 + 1) * sizeof(hb_ma_hit_t)));
+	HB_CUDA(cudaMalloc((void **)&ctx->d_prev0_off, (n + 2) * 8)); HB_CUDA(cudaMalloc((void **)&ctx->d_prev1_off, (n + 2) * 8));
+	HB_CUDA(cudaMemcpyAsync(ctx->d_prev0, p0, ctx->n_prev0 * sizeof(hb_ma_hit_t), cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(ctx->d_prev1, p1, ctx->n_prev1 * sizeof(hb_ma_hit_t), cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(ctx->d_prev0_off, o0, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(ctx->d_prev1_off, o1, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}
+
+extern "C" int hb_cal_ov_r_resident(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *n_src, uint64_t *n_rev, uint64_t *stat)
+{
+	int rc = run_pass(ctx, r0, r1, 0, 0.001, 0, stat); // bw 0.001: ecovlp.cpp:3957
+	if (rc) return rc;
+	if (n_src) *n_src = ctx->n_out0;
+	if (n_rev) *n_rev = ctx->n_out1;
+	return HB_OK;
+}
+
+extern "C" int hb_cal_ov_r(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off, const hb_ma_hit_t *prev_rev, const uint64_t *prev_rev_off,
+                           hb_ma_hit_t *out_src, uint64_t *out_src_off, uint64_t out_src_cap, hb_ma_hit_t *out_rev, uint64_t *out_rev_off, uint64_t out_rev_cap, uint64_t *stat)
+{
+	cudaSetDevice(ctx->device);
+	if (prev_src_off) { int rc = stage_prev(ctx, prev_src, prev_src_off, prev_rev, prev_rev_off); if (rc) return rc; }
+	int rc = run_pass(ctx, r0, r1, 0, 0.001, 0, stat); if (rc) return rc;
+	uint64_t nR = r1 - r0;
+	if (ctx->n_out0 > out_src_cap || ctx->n_out1 > out_rev_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity: need %llu / %llu", (unsigned long long)ctx->n_out0, (unsigned long long)ctx->n_out1); return HB_E_OVERFLOW; }
+	if (nR == 0) { out_src_off[0] = out_rev_off[0] = 0; return HB_OK; }
+	HB_CUDA(cudaMemcpyAsync(out_src_off, ctx->d_out0_off, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(out_rev_off, ctx->d_out1_off, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(out_src, ctx->d_out0, ctx->n_out0 * sizeof(hb_ma_hit_t), cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(out_rev, ctx->d_out1, ctx->n_out1 * sizeof(hb_ma_hit_t), cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// window alignment
+// ---------------------------------------------------------------------------
+extern "C" int hb_ed_semi_64(hb_ctx_t *ctx, uint64_t n, const char *pat, const uint64_t *pat_off, const char *txt, const uint64_t *txt_off,
+                             const int32_t *thre, const int32_t *abs_diag, int32_t *err, int32_t *pe)
+{
+	cudaSetDevice(ctx->device);
+	Arena ar(ctx);
+	if (n == 0) return HB_OK;
+	for (uint64_t i = 0; i < n; i++) if (thre[i] < 0 || thre[i] > 31 || abs_diag[i] < 0 || abs_diag[i] > 2 * thre[i]) { hb_set_err(ctx, HB_E_ARG, "case %llu: thre must be in [0,31], abs_diag in [0,2*thre]", (unsigned long long)i); return HB_E_ARG; }
+	char *d_p = ar.get<char>(pat_off[n] + 1), *d_t = ar.get<char>(txt_off[n] + 1); uint64_t *d_po = ar.get<uint64_t>(n + 1), *d_to = ar.get<uint64_t>(n + 1);
+	int32_t *d_th = ar.get<int32_t>(n), *d_ab = ar.get<int32_t>(n), *d_e = ar.get<int32_t>(n), *d_pe = ar.get<int32_t>(n);
+	HB_ALLOC_CHECK(ar);
+	HB_CUDA(cudaMemcpyAsync(d_p, pat, pat_off[n], cudaMemcpyHostToDevice, ctx->stream)); HB_CUDA(cudaMemcpyAsync(d_t, txt, txt_off[n], cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(d_po, pat_off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)); HB_CUDA(cudaMemcpyAsync(d_to, txt_off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(d_th, thre, n * 4, cudaMemcpyHostToDevice, ctx->stream)); HB_CUDA(cudaMemcpyAsync(d_ab, abs_diag, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	{
+		ProfScope ps(ctx, "k_ed_semi64");
+		k_ed_semi64<<<nblk(n, 128), 128, 0, ctx->stream>>>(n, d_p, d_po, d_t, d_to, d_th, d_ab, d_e, d_pe);
+	}
+	HB_CUDA(cudaGetLastError());
+	HB_CUDA(cudaMemcpyAsync(err, d_e, n * 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(pe, d_pe, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// instrumentation
+// ---------------------------------------------------------------------------
+extern "C" int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap)
+{
+	int n = 0;
+	for (auto &p : ctx->prof) { if (n >= cap) break; names[n] = p.name; launches[n] = p.launches; ms[n] = p.ms; n++; }
+	return n;
+}
+extern "C" int hb_counters(const hb_ctx_t *ctx, uint64_t *c, int cap)
+{
+	int n = cap < 8 ? cap : 8;
+	for (int i = 0; i < n; i++) c[i] = ctx->counters[i];
+	return n;
+}

@@ -122,6 +122,22 @@ HB_HD void hb_heapsort_i64(int64_t *a, int64_t n)
 	}
 }
 
+// order a (nearly ordered) group: strand, then self_offset, then offset
+HB_HD void hb_order_group(hb_hit_t *a, int32_t a_n)
+{
+	for (int32_t i = 1; i < a_n; i++) {
+		hb_hit_t v = a[i]; int32_t j;
+		uint64_t kv = (uint64_t)(v.id_strand >> 31) << 63 | (uint64_t)v.self_offset << 32 | v.offset;
+		for (j = i; j > 0; --j) {
+			const hb_hit_t &u = a[j - 1];
+			uint64_t ku = (uint64_t)(u.id_strand >> 31) << 63 | (uint64_t)u.self_offset << 32 | u.offset;
+			if (ku <= kv) break;
+			a[j] = u;
+		}
+		if (j != i) a[j] = v;
+	}
+}
+
 // Chain one target group.  a[0..a_n): the group's anchors (same target id, both
 // strands), ordered here by (strand, self_offset, offset) — the order
 // minimizers_qgen0's sort produces (anchor.cpp:1046-1049).  des: a_n-sized
@@ -135,18 +151,7 @@ HB_HD int32_t hb_chain_group(hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t d
 	int32_t max, tmp, n_out = 0;
 	for (i = 0; i < n_slots; i++) out[i].n_hits = 0;
 	if (a_n <= 0) return 0;
-	// order the (nearly ordered) group: strand, then self_offset, then offset
-	for (i = 1; i < a_n; i++) {
-		hb_hit_t v = a[i];
-		uint64_t kv = (uint64_t)(v.id_strand >> 31) << 63 | (uint64_t)v.self_offset << 32 | v.offset;
-		for (j = i; j > 0; --j) {
-			const hb_hit_t &u = a[j - 1];
-			uint64_t ku = (uint64_t)(u.id_strand >> 31) << 63 | (uint64_t)u.self_offset << 32 | u.offset;
-			if (ku <= kv) break;
-			a[j] = u;
-		}
-		if (j != i) a[j] = v;
-	}
+	hb_order_group(a, a_n);
 	// quick_ck_lchain, Hash_Table.cpp:2007-2094
 	{
 		int64_t l, z, sorted = 1;
@@ -337,12 +342,13 @@ template <typename T, typename KEY> HB_HD void hb_rs_insertsort(T *beg, T *end, 
 			*j = tmp;
 		}
 }
-template <typename T, typename KEY> HB_HD void hb_rs_sort32(T *beg0, T *end0, KEY key)
-{
-	if (end0 - beg0 <= 64) { hb_rs_insertsort(beg0, end0, key); return; }
-	// explicit recursion stack: (range, shift); depth <= 4 levels, each level
-	// pushes at most 256 sub-ranges but they are processed depth-first
-	struct Fr { int32_t b, e, s; } st[4 * 256 + 4]; int sp = 0;
+#define HB_RS_STACK 320
+template <typename T, typename KEY> HB_HD int hb_rs_sort32(T *beg0, T *end0, KEY key)
+{ // returns 1 if the explicit stack overflowed (more than 65*HB_RS_STACK elements)
+	if (end0 - beg0 <= 64) { hb_rs_insertsort(beg0, end0, key); return 0; }
+	// explicit recursion stack of (range, shift): pending ranges are disjoint and
+	// each holds > 64 elements, so n <= 65*HB_RS_STACK never overflows it
+	struct Fr { int32_t b, e, s; } st[HB_RS_STACK]; int sp = 0;
 	st[sp].b = 0; st[sp].e = (int32_t)(end0 - beg0); st[sp].s = 24; sp++;
 	while (sp) {
 		Fr fr = st[--sp]; T *beg = beg0 + fr.b, *end = beg0 + fr.e; int s = fr.s;
@@ -366,11 +372,12 @@ template <typename T, typename KEY> HB_HD void hb_rs_sort32(T *beg0, T *end0, KE
 			// independent of the others, so the order of processing is free
 			for (k = 255; k >= 0; --k) {
 				int32_t lo = k ? be[k - 1] : 0, hi = be[k];
-				if (hi - lo > 64) { st[sp].b = fr.b + lo; st[sp].e = fr.b + hi; st[sp].s = ns; sp++; }
+				if (hi - lo > 64) { if (sp >= HB_RS_STACK) return 1; st[sp].b = fr.b + lo; st[sp].e = fr.b + hi; st[sp].s = ns; sp++; }
 				else if (hi - lo > 1) hb_rs_insertsort(beg + lo, beg + hi, key);
 			}
 		}
 	}
+	return 0;
 }
 
 HB_HD int hb_ov_type(const hb_chain_t &r, uint64_t len)

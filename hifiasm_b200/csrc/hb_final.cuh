@@ -58,7 +58,7 @@ HB_HD void hb_final_merge(const DevReads &R, uint32_t rid, const hb_chain_t *ch,
 		z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_id = c.y_id; z.y_pos_s = c.y_pos_s; z.y_pos_e = c.y_pos_e;
 		z.strand = (uint8_t)c.y_pos_strand; z.nhe = 0; z.slot = idx[k]; z.is_match = 0; z.el = 0; z.strong = 0; z.wli = 0;
 	}
-	hb_rs_sort32(ov, ov + n, key); // overlap_region_sort_y_id, ecovlp.cpp:3959
+	int rs_ovf = hb_rs_sort32(ov, ov + n, key); // overlap_region_sort_y_id, ecovlp.cpp:3959
 	for (k = 0; k < n0; k++) srt[ns++] = ((uint64_t)in0[k].tn << 1 | (uint64_t)in0[k].rev) << 32 | (k << 1) | 0; // ecovlp.cpp:5057-5070
 	for (k = 0; k < n1; k++) srt[ns++] = ((uint64_t)in1[k].tn << 1 | (uint64_t)in1[k].rev) << 32 | (k << 1) | 1;
 	for (i = 1; i < ns; i++) { uint64_t v = srt[i]; for (l = i; l > 0 && srt[l - 1] > v; --l) srt[l] = srt[l - 1]; srt[l] = v; } // keys distinct: any sort
@@ -108,7 +108,7 @@ HB_HD void hb_final_merge(const DevReads &R, uint32_t rid, const hb_chain_t *ch,
 			is_usrt = 1;
 		}
 	}
-	if (is_usrt) hb_rs_sort32(ov, ov + n, key);
+	if (is_usrt) rs_ovf |= hb_rs_sort32(ov, ov + n, key);
 	if (n > 1) { // ecovlp.cpp:5169-5195
 		uint64_t mm_k, s; int64_t mm_sc, sc;
 		for (k = 1, l = m = 0; k <= n; k++) {
@@ -130,7 +130,8 @@ HB_HD void hb_final_merge(const DevReads &R, uint32_t rid, const hb_chain_t *ch,
 		n = (uint32_t)m;
 	}
 	// push_ff_ovlp x2, ecovlp.cpp:2641-2694
-	uint32_t c0 = 0, c1 = 0; unsigned long long st[6] = { 0, 0, 0, 0, 0, 0 };
+	uint32_t c0 = 0, c1 = 0; unsigned long long st[7] = { 0, 0, 0, 0, 0, 0, 0 };
+	st[6] = (unsigned long long)rs_ovf; // sort stack overflow: the host fails the pass
 	for (k = 0; k < n; k++) {
 		const FinOv &o = ov[k]; hb_ma_hit_t *z;
 		if (o.is_match == 1) z = &out0[c0++]; else if (o.is_match == 2) z = &out1[c1++]; else continue;
@@ -145,5 +146,5 @@ HB_HD void hb_final_merge(const DevReads &R, uint32_t rid, const hb_chain_t *ch,
 	}
 	st[0] = c0; st[1] = c1;
 	*m0 = c0; *m1 = c1;
-	if (stat) for (int b = 0; b < 6; b++) stat[b] = st[b];
+	if (stat) for (int b = 0; b < 7; b++) stat[b] = st[b];
 }

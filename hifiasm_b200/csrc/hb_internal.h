@@ -1,0 +1,54 @@
+// hb_internal.h — context and host-side helpers shared by engine.cu / index.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "hb_common.cuh"
+
+#define HB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { hb_set_err(ctx, HB_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return HB_E_CUDA; } } while (0)
+
+struct ProfEntry { const char *name; uint64_t launches; double ms; };
+
+struct hb_ctx {
+	int device; cudaStream_t stream; hb_opt_t opt; std::string err;
+	int sm_count;
+	// read store
+	uint64_t n_reads, total_bases, packed_bytes, n_npos;
+	uint8_t *d_packed; uint64_t *d_roff; uint32_t *d_rlen; uint64_t *d_noff; uint32_t *d_npos;
+	std::vector<uint32_t> h_rlen;
+	// filter table
+	uint64_t ft_n, ft_cap; uint64_t *d_ft_key; int32_t *d_ft_val;
+	// position index
+	uint64_t pt_keys, pt_npos, pt_cap; ulonglong2 *d_pt_slot; uint64_t *d_pt_pos;
+	// staged previous overlaps for the resident final pass
+	hb_ma_hit_t *d_prev0, *d_prev1; uint64_t *d_prev0_off, *d_prev1_off; uint64_t n_prev0, n_prev1;
+	std::vector<uint64_t> h_prev0_off, h_prev1_off;
+	// results of the last final pass (device resident)
+	hb_ma_hit_t *d_out0, *d_out1; uint64_t *d_out0_off, *d_out1_off; uint64_t n_out0, n_out1, out_reads;
+	// instrumentation
+	std::vector<ProfEntry> prof; uint64_t counters[8];
+	uint64_t anchor_budget; // anchors per batch
+};
+
+void hb_set_err(hb_ctx *ctx, int code, const char *fmt, ...);
+DevReads hb_dev_reads(const hb_ctx *ctx);
+DevFt hb_dev_ft(const hb_ctx *ctx);
+DevPt hb_dev_pt(const hb_ctx *ctx);
+
+// profiling scope: cudaEvent pair on the context stream, accumulated by name
+struct ProfScope {
+	hb_ctx *ctx; const char *name; cudaEvent_t a, b;
+	ProfScope(hb_ctx *c, const char *n);
+	~ProfScope();
+};
+void hb_prof_reset(hb_ctx *ctx);
+
+// device exclusive scan helpers (CUB, stream-ordered); out has n+1 entries (out[n] = total)
+int hb_scan_u32_to_u64(hb_ctx *ctx, const uint32_t *d_in, uint64_t *d_out, uint64_t n);
+
+// batch sketch of reads [r0,r1): dense minimizer arrays + per-read offsets (device, cudaMallocAsync'd; caller frees)
+struct DevSketch { hb_mz_t *mz; uint64_t *off; uint64_t total; };
+int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch *out);

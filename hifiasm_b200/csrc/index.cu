@@ -1,0 +1,318 @@
+// index.cu — GPU construction of the high-count filter table (ha_ft_gen,
+// htab.cpp:1136) and of the minimizer position index (ha_pt_gen, htab.cpp:1232).
+//
+// The reference counts into 4096 khashl tables from a 3-stage CPU pipeline; here
+// counting is sort-based: hash every k-mer / sketch every read on the GPU, radix
+// sort the hashes (CUB; the sort is stable, which reproduces the index's
+// read-id / in-read position order, htab.cpp:646-672), run-length the sorted
+// keys, build the peak statistics from the count histogram (ha_analyze_count,
+// hist.cpp:74 — a 4096-bin histogram, evaluated on the host) and pour the kept
+// runs into one open-addressing table with 16-byte slots.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include "hb_internal.h"
+
+#define YAK_MAX_COUNT 4095 /* htab.cpp:13-15 */
+
+struct TmpBufs {
+	hb_ctx *ctx; std::vector<void *> p;
+	TmpBufs(hb_ctx *c) : ctx(c) {}
+	template <typename T> T *get(uint64_t n) { void *q = 0; if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return 0; } p.push_back(q); return (T *)q; }
+	void drop(void *q) { for (auto &x : p) if (x == q) { cudaFree(x); x = 0; } }
+	void *steal(void *q) { for (auto &x : p) if (x == q) x = 0; return q; }
+	~TmpBufs() { for (void *q : p) if (q) cudaFree(q); }
+};
+#define NEED(ptr) do { if (!(ptr)) { hb_set_err(ctx, HB_E_NOMEM, "device allocation failed at %s:%d", __FILE__, __LINE__); return HB_E_NOMEM; } } while (0)
+static inline unsigned nblk(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+// ---- ha_analyze_count (hist.cpp:74-157), host side on the 4096-bin histogram
+static int adj_peak_hom(int m_peak_hom, int max_i, int max2_i, int max3_i, int *peak_het)
+{ // adj_m_peak_hom, hist.cpp:46-72
+	int64_t mm[3], d, min_i = -1, min_d = -1, i;
+	mm[0] = max2_i; mm[1] = max_i; mm[2] = max3_i;
+	for (i = 0; i < 3; i++) {
+		if (mm[i] <= 0) continue;
+		d = mm[i] >= m_peak_hom ? mm[i] - m_peak_hom : m_peak_hom - mm[i];
+		if (min_d == -1 || min_d > d || (min_d == d && i == 1)) min_d = d, min_i = i;
+	}
+	if (min_i < 0) return m_peak_hom;
+	if (mm[min_i] < m_peak_hom) { d = m_peak_hom - mm[min_i]; if (d >= mm[min_i] * 0.51) { *peak_het = (int)mm[min_i]; return m_peak_hom; } }
+	for (i = min_i - 1; i >= 0; i--) { if (mm[i] <= 0) continue; *peak_het = (int)mm[i]; break; }
+	return (int)mm[min_i];
+}
+static int analyze_count(int n_cnt, int start_cnt, int m_peak_hom, const int64_t *cnt, int *peak_het)
+{
+	int i, start, low_i, max_i, max2_i, max3_i; int64_t max, max2, max3, min;
+	*peak_het = -1;
+	start = cnt[1] > 0 ? 1 : 2;
+	low_i = start > start_cnt ? start : start_cnt;
+	for (i = low_i + 1; i < n_cnt; ++i) if (cnt[i] > cnt[i - 1]) break;
+	low_i = i - 1;
+	if (low_i == n_cnt - 1) return -1;
+	max_i = low_i + 1, max = cnt[max_i];
+	for (i = low_i + 1; i < n_cnt; ++i) if (cnt[i] > max) max = cnt[i], max_i = i;
+	max2 = -1; max2_i = -1;
+	for (i = max_i - 1; i > low_i; --i) if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1]) if (cnt[i] > max2) max2 = cnt[i], max2_i = i;
+	if (max2_i > low_i && max2_i < max_i) {
+		for (i = max2_i + 1, min = max; i < max_i; ++i) if (cnt[i] < min) min = cnt[i];
+		if (max2 < max * 0.05 || min > max2 * 0.95) max2 = -1, max2_i = -1;
+	}
+	max3 = -1; max3_i = -1;
+	for (i = max_i + 1; i < n_cnt - 1; ++i) if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1]) if (cnt[i] > max3) max3 = cnt[i], max3_i = i;
+	if (max3_i > max_i) {
+		for (i = max_i + 1, min = max; i < max3_i; ++i) if (cnt[i] < min) min = cnt[i];
+		if (max3 < max * 0.05 || min > max3 * 0.95 || max3_i > max_i * 2.5) max3 = -1, max3_i = -1;
+	}
+	if (m_peak_hom > 0) return adj_peak_hom(m_peak_hom, max_i, max2_i, max3_i, peak_het);
+	if (max3_i > 0) { *peak_het = max_i; return max3_i; }
+	if (max2_i > 0) *peak_het = max2_i;
+	return max_i;
+}
+
+// ---- kernels ---------------------------------------------------------------
+// every (HPC) k-mer of a read, hashed like yak_hash_long (htab.h:162-167):
+// mz1_count_seq_buf_HPC / mz1_count_seq_buf (htab.cpp:608-645).  One thread per
+// read; slot i of the read's slice is written or left as the ~0 filler.
+__global__ void k_all_kmers(DevReads R, int k, int is_hpc, const uint64_t *__restrict__ koff, uint64_t *__restrict__ out, unsigned long long *__restrict__ n_real)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= R.n) return;
+	const uint8_t *seq = R.packed + R.off[r]; int32_t len = (int32_t)R.len[r], i, l = 0, last = -1;
+	uint64_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, mask = (1ULL << k) - 1, shift = k - 1, *dst = out + koff[r]; uint32_t w = 0;
+	uint64_t ni = R.noff[r], ne = R.noff[r + 1]; int32_t next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX;
+	for (i = 0; i < len; ++i) {
+		int c = hb_base(seq, (uint64_t)i);
+		if (i == next_n) { c = 4; ++ni; next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX; }
+		if (c < 4) {
+			if (!is_hpc || c != last) {
+				x0 = (x0 << 1 | (uint64_t)(c & 1)) & mask; x1 = (x1 << 1 | (uint64_t)(c >> 1)) & mask;
+				x2 = x2 >> 1 | (uint64_t)(1 - (c & 1)) << shift; x3 = x3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift;
+				if (++l >= k) dst[w++] = x1 < x3 ? hb_hash64(x0) + hb_hash64(x1) : hb_hash64(x2) + hb_hash64(x3);
+				last = c;
+			}
+		} else { l = 0; last = -1; x0 = x1 = x2 = x3 = 0; }
+	}
+	if (w) atomicAdd(n_real, (unsigned long long)w);
+}
+
+struct IsHead { const uint64_t *k; __host__ __device__ bool operator()(uint64_t i) const { return i == 0 || k[i] != k[i - 1]; } };
+
+// run lengths -> 4096-bin histogram of counts saturated at 4095 (ha_ct_hist, htab.cpp:240)
+__global__ void k_run_hist(uint64_t n_runs, const uint64_t *__restrict__ head, uint64_t n_real, unsigned long long *__restrict__ hist)
+{
+	__shared__ unsigned int sh[4096];
+	for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh[i] = 0;
+	__syncthreads();
+	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_runs; j += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t len = (j + 1 < n_runs ? head[j + 1] : n_real) - head[j];
+		atomicAdd(&sh[len > YAK_MAX_COUNT ? YAK_MAX_COUNT : (uint32_t)len], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 4096; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+// kept-run length (0 when dropped)
+__global__ void k_run_keep(uint64_t n_runs, const uint64_t *__restrict__ head, uint64_t n_real, uint32_t lo, uint32_t hi, uint32_t *__restrict__ keep_len)
+{
+	uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n_runs) return;
+	uint64_t len = (j + 1 < n_runs ? head[j + 1] : n_real) - head[j];
+	if (len > YAK_MAX_COUNT) len = YAK_MAX_COUNT;
+	keep_len[j] = (len >= lo && len <= hi) ? (uint32_t)len : 0;
+}
+// filter table insert: key -> count (INT32_MAX above max_cnt; gen_hh, htab.cpp:1038-1062)
+__global__ void k_ft_insert(uint64_t n_runs, const uint64_t *__restrict__ head, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ keep_len, uint32_t max_cnt,
+                            uint64_t mask, uint64_t *__restrict__ t_key, int32_t *__restrict__ t_val)
+{
+	uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n_runs || keep_len[j] == 0) return;
+	uint64_t key = keys[head[j]], b = hb_bucket(key, mask); int32_t v = keep_len[j] > max_cnt ? INT32_MAX : (int32_t)keep_len[j];
+	while (atomicCAS(&t_val[b], 0, v) != 0) b = (b + 1) & mask;
+	t_key[b] = key;
+}
+// position index: warp per kept run copies its ha_idxpos_t words and inserts the key
+__global__ void k_pt_fill(uint64_t n_runs, const uint64_t *__restrict__ head, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ infos, const uint32_t *__restrict__ keep_len,
+                          const uint64_t *__restrict__ pos_off, uint64_t mask, unsigned long long *t_slot /* ulonglong2 as 2 words */, uint64_t *__restrict__ pos)
+{
+	uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+	if (j >= n_runs) return;
+	uint32_t len = keep_len[j];
+	if (len == 0) return;
+	uint64_t h = head[j], o = pos_off[j];
+	for (uint32_t i = lane; i < len; i += 32) pos[o + i] = infos[h + i];
+	if (lane == 0) {
+		uint64_t key = keys[h], b = hb_bucket(key, mask), val = o << 12 | len;
+		while (atomicCAS(&t_slot[2 * b + 1], 0ull, (unsigned long long)val) != 0ull) b = (b + 1) & mask;
+		t_slot[2 * b] = key;
+	}
+}
+__global__ void k_ft_query(DevFt ft, uint64_t n, const uint64_t *__restrict__ h, int32_t *__restrict__ out)
+{ uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = hb_ft_lookup(ft, h[i]); }
+__global__ void k_pt_query(DevPt pt, uint64_t n, const uint64_t *__restrict__ h, uint32_t *__restrict__ cnt, uint64_t *__restrict__ off)
+{ uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) { uint64_t o; cnt[i] = hb_pt_lookup(pt, h[i], &o); off[i] = o; } }
+__global__ void k_pt_gather(DevPt pt, uint64_t n, const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, const uint64_t *__restrict__ dst_off, uint64_t *__restrict__ dst)
+{
+	uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+	if (j >= n) return;
+	for (uint32_t i = lane; i < cnt[j]; i += 32) dst[dst_off[j] + i] = pt.pos[off[j] + i];
+}
+
+// ---- sorted keys -> run heads + histogram ----------------------------------
+static int runs_of(hb_ctx *ctx, TmpBufs &tb, const uint64_t *d_keys, uint64_t n_real, uint64_t **d_head, uint64_t *n_runs, int64_t *h_hist)
+{
+	size_t tmpb = 0; uint64_t *d_nsel = tb.get<uint64_t>(1); NEED(d_nsel);
+	cub::CountingInputIterator<uint64_t> cnt_it(0); IsHead pred = { d_keys };
+	// pass 1 of DeviceSelect needs the output sized for the worst case; count heads first with a transform-reduce-free trick:
+	uint64_t *d_out = tb.get<uint64_t>(n_real + 1); NEED(d_out);
+	HB_CUDA(cub::DeviceSelect::If(0, tmpb, cnt_it, d_out, d_nsel, (int64_t)n_real, pred, ctx->stream));
+	void *tmp = tb.get<uint8_t>(tmpb); NEED(tmp);
+	HB_CUDA(cub::DeviceSelect::If(tmp, tmpb, cnt_it, d_out, d_nsel, (int64_t)n_real, pred, ctx->stream));
+	HB_CUDA(cudaMemcpyAsync(n_runs, d_nsel, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	tb.drop(tmp);
+	unsigned long long *d_hist = tb.get<unsigned long long>(4096); NEED(d_hist);
+	HB_CUDA(cudaMemsetAsync(d_hist, 0, 4096 * 8, ctx->stream));
+	if (*n_runs) k_run_hist<<<std::min<unsigned>(nblk(*n_runs, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(*n_runs, d_out, n_real, d_hist);
+	HB_CUDA(cudaGetLastError());
+	unsigned long long hh[4096];
+	HB_CUDA(cudaMemcpyAsync(hh, d_hist, sizeof(hh), cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < 4096; i++) h_hist[i] = (int64_t)hh[i];
+	*d_head = d_out;
+	return HB_OK;
+}
+
+// ---- ha_ft_gen ---------------------------------------------------------------
+extern "C" void hb_ft_destroy(hb_ctx_t *ctx)
+{
+	if (!ctx) return;
+	cudaFree(ctx->d_ft_key); cudaFree(ctx->d_ft_val); ctx->d_ft_key = 0; ctx->d_ft_val = 0; ctx->ft_n = ctx->ft_cap = 0;
+}
+extern "C" int hb_ft_size(const hb_ctx_t *ctx, uint64_t *n) { *n = ctx->ft_n; return HB_OK; }
+
+extern "C" int hb_ft_gen(hb_ctx_t *ctx, int *hom_cov)
+{
+	cudaSetDevice(ctx->device);
+	if (!ctx->n_reads) { hb_set_err(ctx, HB_E_STATE, "no reads resident"); return HB_E_STATE; }
+	hb_ft_destroy(ctx);
+	TmpBufs tb(ctx); const int k = ctx->opt.k_mer_length; const uint64_t n = ctx->n_reads;
+	std::vector<uint64_t> koff(n + 1); uint64_t tot = 0;
+	for (uint64_t i = 0; i < n; i++) { koff[i] = tot; tot += ctx->h_rlen[i] >= (uint32_t)k ? ctx->h_rlen[i] - k + 1 : 0; }
+	koff[n] = tot;
+	uint64_t *d_koff = tb.get<uint64_t>(n + 1), *d_a = tb.get<uint64_t>(tot + 1), *d_b = tb.get<uint64_t>(tot + 1); unsigned long long *d_nreal = tb.get<unsigned long long>(1);
+	NEED(d_koff); NEED(d_a); NEED(d_b); NEED(d_nreal);
+	HB_CUDA(cudaMemcpyAsync(d_koff, koff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	HB_CUDA(cudaMemsetAsync(d_a, 0xff, (tot + 1) * 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_nreal, 0, 8, ctx->stream));
+	{ ProfScope ps(ctx, "k_all_kmers"); k_all_kmers<<<nblk(n, 64), 64, 0, ctx->stream>>>(hb_dev_reads(ctx), k, ctx->opt.is_hpc, d_koff, d_a, d_nreal); }
+	HB_CUDA(cudaGetLastError());
+	unsigned long long n_real = 0; HB_CUDA(cudaMemcpyAsync(&n_real, d_nreal, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	size_t tmpb = 0; cub::DoubleBuffer<uint64_t> db(d_a, d_b);
+	HB_CUDA(cub::DeviceRadixSort::SortKeys(0, tmpb, db, (int64_t)tot, 0, 64, ctx->stream));
+	void *tmp = tb.get<uint8_t>(tmpb); NEED(tmp);
+	{ ProfScope ps(ctx, "sort_kmers"); HB_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmpb, db, (int64_t)tot, 0, 64, ctx->stream)); }
+	tb.drop(tmp); tb.drop(db.Alternate());
+	uint64_t *d_keys = db.Current(), *d_head = 0, n_runs = 0; int64_t hist[4096];
+	int rc = runs_of(ctx, tb, d_keys, n_real, &d_head, &n_runs, hist); if (rc) return rc; // the ~0 fillers sort last and are not counted
+	int peak_het, peak_hom = analyze_count(4096, ctx->opt.min_hist_kmer_cnt, -1, hist, &peak_het); // htab.cpp:1155-1161
+	if (hom_cov) *hom_cov = peak_hom;
+	int cutoff = (int)(peak_hom * ctx->opt.high_factor); if (cutoff > YAK_MAX_COUNT - 1) cutoff = YAK_MAX_COUNT - 1;
+	int max_cnt = ctx->opt.max_kmer_cnt; if (max_cnt > YAK_MAX_COUNT - 1) max_cnt = YAK_MAX_COUNT - 1;
+	uint64_t n_keep = 0; for (int i = cutoff < 0 ? 0 : cutoff; i <= YAK_MAX_COUNT; i++) n_keep += (uint64_t)hist[i]; // ha_ct_shrink(h, cutoff, YAK_MAX_COUNT)
+	ctx->ft_n = n_keep;
+	if (n_keep) {
+		uint64_t cap = 64; while (cap < 2 * n_keep) cap <<= 1;
+		uint32_t *d_keep = tb.get<uint32_t>(n_runs + 1); NEED(d_keep);
+		HB_CUDA(cudaMalloc((void **)&ctx->d_ft_key, cap * 8)); HB_CUDA(cudaMalloc((void **)&ctx->d_ft_val, cap * 4));
+		HB_CUDA(cudaMemsetAsync(ctx->d_ft_key, 0, cap * 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(ctx->d_ft_val, 0, cap * 4, ctx->stream));
+		k_run_keep<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, n_real, cutoff < 1 ? 1 : (uint32_t)cutoff, YAK_MAX_COUNT, d_keep);
+		k_ft_insert<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, d_keys, d_keep, (uint32_t)max_cnt, cap - 1, ctx->d_ft_key, ctx->d_ft_val);
+		HB_CUDA(cudaGetLastError());
+		ctx->ft_cap = cap;
+	}
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}
+
+extern "C" int hb_ft_cnt(hb_ctx_t *ctx, const uint64_t *hash, uint64_t n, int32_t *cnt)
+{
+	cudaSetDevice(ctx->device); TmpBufs tb(ctx);
+	if (n == 0) return HB_OK;
+	uint64_t *d_h = tb.get<uint64_t>(n); int32_t *d_c = tb.get<int32_t>(n); NEED(d_h); NEED(d_c);
+	HB_CUDA(cudaMemcpyAsync(d_h, hash, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	k_ft_query<<<nblk(n, 256), 256, 0, ctx->stream>>>(hb_dev_ft(ctx), n, d_h, d_c);
+	HB_CUDA(cudaMemcpyAsync(cnt, d_c, n * 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}
+
+// ---- ha_pt_gen ---------------------------------------------------------------
+extern "C" void hb_pt_destroy(hb_ctx_t *ctx)
+{
+	if (!ctx) return;
+	cudaFree(ctx->d_pt_slot); cudaFree(ctx->d_pt_pos); ctx->d_pt_slot = 0; ctx->d_pt_pos = 0; ctx->pt_keys = ctx->pt_npos = ctx->pt_cap = 0;
+}
+extern "C" int hb_pt_stat(const hb_ctx_t *ctx, uint64_t *n_keys, uint64_t *n_pos) { *n_keys = ctx->pt_keys; *n_pos = ctx->pt_npos; return HB_OK; }
+
+extern "C" int hb_pt_gen(hb_ctx_t *ctx, int *hom_cov, int *het_cov)
+{
+	cudaSetDevice(ctx->device);
+	if (!ctx->n_reads) { hb_set_err(ctx, HB_E_STATE, "no reads resident"); return HB_E_STATE; }
+	hb_pt_destroy(ctx);
+	TmpBufs tb(ctx); DevSketch sk; int rc = hb_run_sketch(ctx, 0, ctx->n_reads, 1, &sk); if (rc) return rc;
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	const uint64_t n = sk.total;
+	// split {x,info} into key / value arrays and sort by key (stable LSD radix)
+	uint64_t *d_k0 = tb.get<uint64_t>(n + 1), *d_k1 = tb.get<uint64_t>(n + 1), *d_v0 = tb.get<uint64_t>(n + 1), *d_v1 = tb.get<uint64_t>(n + 1);
+	NEED(d_k0); NEED(d_k1); NEED(d_v0); NEED(d_v1);
+	HB_CUDA(cudaMemcpy2DAsync(d_k0, 8, &sk.mz[0].x, 16, 8, n, cudaMemcpyDeviceToDevice, ctx->stream));
+	HB_CUDA(cudaMemcpy2DAsync(d_v0, 8, &sk.mz[0].info, 16, 8, n, cudaMemcpyDeviceToDevice, ctx->stream));
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	cudaFreeAsync(sk.mz, ctx->stream); cudaFreeAsync(sk.off, ctx->stream);
+	size_t tmpb = 0; cub::DoubleBuffer<uint64_t> dk(d_k0, d_k1), dv(d_v0, d_v1);
+	HB_CUDA(cub::DeviceRadixSort::SortPairs(0, tmpb, dk, dv, (int64_t)n, 0, 64, ctx->stream));
+	void *tmp = tb.get<uint8_t>(tmpb); NEED(tmp);
+	{ ProfScope ps(ctx, "sort_minimizers"); HB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpb, dk, dv, (int64_t)n, 0, 64, ctx->stream)); }
+	tb.drop(tmp); tb.drop(dk.Alternate()); tb.drop(dv.Alternate());
+	uint64_t *d_keys = dk.Current(), *d_infos = dv.Current(), *d_head = 0, n_runs = 0; int64_t hist[4096];
+	rc = runs_of(ctx, tb, d_keys, n, &d_head, &n_runs, hist); if (rc) return rc;
+	int peak_het, peak_hom = analyze_count(4096, ctx->opt.min_hist_kmer_cnt, -1, hist, &peak_het); // htab.cpp:1252-1257
+	if (hom_cov) *hom_cov = peak_hom;
+	if (het_cov) *het_cov = peak_het;
+	int lo = 2, hi = YAK_MAX_COUNT - 1; // htab.cpp:1259-1270
+	if (ctx->ft_n == 0 && ctx->d_ft_key == 0 && getenv("HB_NO_KMER_FLT")) { hi = (int)(peak_hom * ctx->opt.high_factor); if (hi > YAK_MAX_COUNT - 1) hi = YAK_MAX_COUNT - 1; }
+	uint64_t n_keys = 0, n_pos = 0;
+	for (int i = lo; i <= hi; i++) { n_keys += (uint64_t)hist[i]; n_pos += (uint64_t)hist[i] * i; }
+	uint64_t cap = 64; while (cap < 2 * n_keys) cap <<= 1;
+	uint32_t *d_keep = tb.get<uint32_t>(n_runs + 2); uint64_t *d_poff = tb.get<uint64_t>(n_runs + 2); NEED(d_keep); NEED(d_poff);
+	HB_CUDA(cudaMemsetAsync(d_keep, 0, (n_runs + 2) * 4, ctx->stream));
+	if (n_runs) k_run_keep<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, n, (uint32_t)lo, (uint32_t)hi, d_keep);
+	rc = hb_scan_u32_to_u64(ctx, d_keep, d_poff, n_runs); if (rc) return rc;
+	HB_CUDA(cudaMalloc((void **)&ctx->d_pt_slot, cap * 16)); HB_CUDA(cudaMalloc((void **)&ctx->d_pt_pos, (n_pos + 4) * 8));
+	HB_CUDA(cudaMemsetAsync(ctx->d_pt_slot, 0, cap * 16, ctx->stream)); HB_CUDA(cudaMemsetAsync(ctx->d_pt_pos, 0, (n_pos + 4) * 8, ctx->stream));
+	if (n_runs) { ProfScope ps(ctx, "k_pt_fill"); k_pt_fill<<<nblk(n_runs * 32, 256), 256, 0, ctx->stream>>>(n_runs, d_head, d_keys, d_infos, d_keep, d_poff, cap - 1, (unsigned long long *)ctx->d_pt_slot, ctx->d_pt_pos); }
+	HB_CUDA(cudaGetLastError());
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->pt_keys = n_keys; ctx->pt_npos = n_pos; ctx->pt_cap = cap;
+	return HB_OK;
+}
+
+extern "C" int hb_pt_get(hb_ctx_t *ctx, const uint64_t *hash, uint64_t n, uint32_t *cnt, uint64_t *pos, uint64_t pos_cap)
+{
+	cudaSetDevice(ctx->device); TmpBufs tb(ctx);
+	if (!ctx->d_pt_slot) { hb_set_err(ctx, HB_E_STATE, "no position index"); return HB_E_STATE; }
+	if (n == 0) return HB_OK;
+	uint64_t *d_h = tb.get<uint64_t>(n), *d_o = tb.get<uint64_t>(n), *d_do = tb.get<uint64_t>(n + 2); uint32_t *d_c = tb.get<uint32_t>(n + 1);
+	NEED(d_h); NEED(d_o); NEED(d_do); NEED(d_c);
+	HB_CUDA(cudaMemcpyAsync(d_h, hash, n * 8, cudaMemcpyHostToDevice, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_c, 0, (n + 1) * 4, ctx->stream));
+	k_pt_query<<<nblk(n, 256), 256, 0, ctx->stream>>>(hb_dev_pt(ctx), n, d_h, d_c, d_o);
+	HB_CUDA(cudaMemcpyAsync(cnt, d_c, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (pos) {
+		int rc = hb_scan_u32_to_u64(ctx, d_c, d_do, n); if (rc) return rc;
+		uint64_t tot = 0; HB_CUDA(cudaMemcpyAsync(&tot, d_do + n, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (tot > pos_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "position output capacity: need %llu", (unsigned long long)tot); return HB_E_OVERFLOW; }
+		uint64_t *d_p = tb.get<uint64_t>(tot + 1); NEED(d_p);
+		k_pt_gather<<<nblk(n * 32, 256), 256, 0, ctx->stream>>>(hb_dev_pt(ctx), n, d_c, d_o, d_do, d_p);
+		HB_CUDA(cudaMemcpyAsync(pos, d_p, tot * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}

@@ -1,0 +1,199 @@
+"""ctypes mirror of include/hifiasm_b200.h."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import binio
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MZ = np.dtype([("x", "<u8"), ("info", "<u8")])
+HIT = np.dtype([("id_strand", "<u4"), ("offset", "<u4"), ("self_offset", "<u4"), ("cnt", "<u4")])
+CHAIN = np.dtype([("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_id", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
+                  ("y_pos_strand", "<u4"), ("shared_seed", "<i4"), ("first_hit", "<u4"), ("n_hits", "<u4"),
+                  ("fc_off", "<u4"), ("fc_n", "<u4"), ("pad", "<u4")])
+MA = binio.MA_MEM
+
+
+class HBError(RuntimeError):
+    pass
+
+
+class Opt(C.Structure):
+    _fields_ = [("k_mer_length", C.c_int32), ("mz_win", C.c_int32), ("is_hpc", C.c_int32), ("mz_sample_dist", C.c_int32),
+                ("mz_rewin", C.c_int32), ("min_hist_kmer_cnt", C.c_int32), ("max_kmer_cnt", C.c_int32), ("max_n_chain", C.c_int32),
+                ("high_factor", C.c_double), ("hom_cov", C.c_int32), ("het_cov", C.c_int32), ("is_ont", C.c_int32)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libhifiasm_b200.so")
+
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise HBError("%s is missing: run __graft_entry__.build() (there is no CPU fallback)" % p)
+        L = C.CDLL(p)
+        L.hb_last_error.restype = C.c_char_p
+        L.hb_device_count.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One context per GPU (include/hifiasm_b200.h: hb_create)."""
+
+    def __init__(self, device: int = 0, **opt):
+        L = _lib()
+        self.opt = Opt()
+        L.hb_opt_init(C.byref(self.opt))
+        for k, v in opt.items():
+            setattr(self.opt, k, v)
+        self.h = C.c_void_p()
+        rc = L.hb_create(C.byref(self.h), C.c_int(device), C.byref(self.opt))
+        if rc != 0:
+            raise HBError("hb_create failed (%d): no CUDA device / bad options; this engine has no CPU path" % rc)
+        self.n_reads = 0
+
+    def close(self):
+        if self.h:
+            _lib().hb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HBError("hifiasm_b200 error %d: %s" % (rc, _lib().hb_last_error(self.h).decode()))
+
+    def set_opt(self, **kw):
+        for k, v in kw.items():
+            setattr(self.opt, k, v)
+        self._ck(_lib().hb_set_opt(self.h, C.byref(self.opt)))
+
+    def get_opt(self):
+        self._ck(_lib().hb_get_opt(self.h, C.byref(self.opt)))
+        return self.opt
+
+    def update_cov(self, hom):
+        _lib().hb_opt_update_cov(C.byref(self.opt), C.c_int(hom))
+        self._ck(_lib().hb_set_opt(self.h, C.byref(self.opt)))
+
+    # ---- read store
+    def upload_reads(self, length, packed, byte_off, n_pos=None, n_off=None):
+        length = np.ascontiguousarray(length, dtype=np.uint64); packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.uint64)
+        if n_off is None:
+            n_off = np.zeros(length.size + 1, np.uint64); n_pos = np.zeros(1, np.uint64)
+        n_pos = np.ascontiguousarray(n_pos if n_pos.size else np.zeros(1), dtype=np.uint64); n_off = np.ascontiguousarray(n_off, dtype=np.uint64)
+        self._ck(_lib().hb_reads_upload(self.h, C.c_uint64(length.size), _p(length), _p(packed), _p(byte_off), _p(n_pos), _p(n_off)))
+        self.n_reads = int(length.size)
+
+    def upload_store(self, rs: binio.ReadStore):
+        self.upload_reads(rs.length, rs.packed, rs.byte_off, rs.n_pos, rs.n_off)
+
+    # ---- index
+    def ft_gen(self) -> int:
+        hom = C.c_int()
+        self._ck(_lib().hb_ft_gen(self.h, C.byref(hom)))
+        return hom.value
+
+    def ft_size(self) -> int:
+        n = C.c_uint64(); _lib().hb_ft_size(self.h, C.byref(n)); return n.value
+
+    def ft_cnt(self, hashes):
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64); out = np.zeros(hashes.size, np.int32)
+        self._ck(_lib().hb_ft_cnt(self.h, _p(hashes), C.c_uint64(hashes.size), _p(out)))
+        return out
+
+    def pt_gen(self):
+        hom = C.c_int(); het = C.c_int()
+        self._ck(_lib().hb_pt_gen(self.h, C.byref(hom), C.byref(het)))
+        return hom.value, het.value
+
+    def pt_stat(self):
+        a = C.c_uint64(); b = C.c_uint64(); _lib().hb_pt_stat(self.h, C.byref(a), C.byref(b)); return a.value, b.value
+
+    def pt_get(self, hashes):
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64); cnt = np.zeros(hashes.size, np.uint32)
+        self._ck(_lib().hb_pt_get(self.h, _p(hashes), C.c_uint64(hashes.size), _p(cnt), C.c_void_p(0), C.c_uint64(0)))
+        tot = int(cnt.sum()); pos = np.zeros(tot + 1, np.uint64)
+        self._ck(_lib().hb_pt_get(self.h, _p(hashes), C.c_uint64(hashes.size), _p(cnt), _p(pos), C.c_uint64(tot)))
+        return cnt, pos[:tot]
+
+    # ---- stages
+    def sketch(self, r0, r1):
+        off = np.zeros(r1 - r0 + 1, np.uint64)
+        self._ck(_lib().hb_sketch(self.h, C.c_uint64(r0), C.c_uint64(r1), _p(off), C.c_void_p(0), C.c_uint64(0)))
+        rec = np.zeros(int(off[-1]) + 1, MZ)
+        self._ck(_lib().hb_sketch(self.h, C.c_uint64(r0), C.c_uint64(r1), _p(off), _p(rec), C.c_uint64(int(off[-1]))))
+        return off, rec[:int(off[-1])]
+
+    def anchors(self, r0, r1):
+        off = np.zeros(r1 - r0 + 1, np.uint64)
+        self._ck(_lib().hb_anchors(self.h, C.c_uint64(r0), C.c_uint64(r1), _p(off), C.c_void_p(0), C.c_uint64(0)))
+        rec = np.zeros(int(off[-1]) + 1, HIT)
+        self._ck(_lib().hb_anchors(self.h, C.c_uint64(r0), C.c_uint64(r1), _p(off), _p(rec), C.c_uint64(int(off[-1]))))
+        return off, rec[:int(off[-1])]
+
+    def chains(self, r0, r1, bw):
+        n = r1 - r0
+        off = np.zeros(n + 1, np.uint64); hoff = np.zeros(n + 1, np.uint64); foff = np.zeros(n + 1, np.uint64)
+        z = C.c_void_p(0)
+        self._ck(_lib().hb_chains(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), _p(off), z, C.c_uint64(0), _p(hoff), z, C.c_uint64(0), _p(foff), z, C.c_uint64(0)))
+        rec = np.zeros(int(off[-1]) + 1, CHAIN); hits = np.zeros(int(hoff[-1]) + 1, HIT); fc = np.zeros(int(foff[-1]) + 1, np.uint64)
+        self._ck(_lib().hb_chains(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), _p(off), _p(rec), C.c_uint64(rec.size),
+                                  _p(hoff), _p(hits), C.c_uint64(hits.size), _p(foff), _p(fc), C.c_uint64(fc.size)))
+        return off, rec[:int(off[-1])], hoff, hits[:int(hoff[-1])], foff, fc[:int(foff[-1])]
+
+    # ---- final pass
+    def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None):
+        r1 = self.n_reads if r1 is None else r1
+        prev_src = np.ascontiguousarray(prev_src, dtype=MA); prev_rev = np.ascontiguousarray(prev_rev, dtype=MA)
+        o0 = np.ascontiguousarray(prev_src_off, dtype=np.uint64); o1 = np.ascontiguousarray(prev_rev_off, dtype=np.uint64)
+        cap = cap or (4 * (prev_src.size + prev_rev.size) + 256 * (r1 - r0) + 1024)
+        out0 = np.zeros(cap, MA); out1 = np.zeros(cap, MA); oo0 = np.zeros(r1 - r0 + 1, np.uint64); oo1 = np.zeros(r1 - r0 + 1, np.uint64); stat = np.zeros(8, np.uint64)
+        self._ck(_lib().hb_cal_ov_r(self.h, C.c_uint64(r0), C.c_uint64(r1), _p(prev_src), _p(o0), _p(prev_rev), _p(o1),
+                                    _p(out0), _p(oo0), C.c_uint64(cap), _p(out1), _p(oo1), C.c_uint64(cap), _p(stat)))
+        return out0[:int(oo0[-1])], oo0, out1[:int(oo1[-1])], oo1, stat
+
+    def cal_ov_r_resident(self, r0=0, r1=None):
+        r1 = self.n_reads if r1 is None else r1
+        a = C.c_uint64(); b = C.c_uint64(); stat = np.zeros(8, np.uint64)
+        self._ck(_lib().hb_cal_ov_r_resident(self.h, C.c_uint64(r0), C.c_uint64(r1), C.byref(a), C.byref(b), _p(stat)))
+        return a.value, b.value, stat
+
+    # ---- window alignment
+    def ed_semi_64(self, pat, pat_off, txt, txt_off, thre, abs_diag):
+        n = len(thre)
+        pat = np.ascontiguousarray(pat, dtype=np.uint8); txt = np.ascontiguousarray(txt, dtype=np.uint8)
+        po = np.ascontiguousarray(pat_off, dtype=np.uint64); to = np.ascontiguousarray(txt_off, dtype=np.uint64)
+        th = np.ascontiguousarray(thre, dtype=np.int32); ab = np.ascontiguousarray(abs_diag, dtype=np.int32)
+        err = np.zeros(n, np.int32); pe = np.zeros(n, np.int32)
+        self._ck(_lib().hb_ed_semi_64(self.h, C.c_uint64(n), _p(pat), _p(po), _p(txt), _p(to), _p(th), _p(ab), _p(err), _p(pe)))
+        return err, pe
+
+    # ---- instrumentation
+    def profile(self):
+        names = (C.c_char_p * 64)(); launches = (C.c_uint64 * 64)(); ms = (C.c_double * 64)()
+        n = _lib().hb_profile(self.h, names, launches, ms, 64)
+        return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(n)}
+
+    def counters(self):
+        c = (C.c_uint64 * 8)(); _lib().hb_counters(self.h, c, 8)
+        return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots"), [int(x) for x in c[:6]]))

@@ -203,7 +203,7 @@ int emu_final_read(void *reads, void *ft, void *pt, int w, int k, int is_hpc, in
 		exact[E.idx[i]] = (uint8_t)hb_exact_seq(r->d, rid, c.x_pos_s, (uint64_t)c.x_pos_e + 1, c.y_id, c.y_pos_s, (uint64_t)c.y_pos_e + 1, (int)c.y_pos_strand);
 	}
 	std::vector<FinOv> ov(E.n_ol + n0 + 1); std::vector<uint64_t> srt(n0 + n1 + 1);
-	unsigned long long stat[6];
+	unsigned long long stat[8];
 	hb_final_merge(r->d, rid, E.ch.data(), E.idx.data(), E.n_ol, exact.data(), in0, n0, in1, n1, ov.data(), srt.data(), out0, m0, out1, m1, stat);
 	return 0;
 }

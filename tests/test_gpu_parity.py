@@ -1,0 +1,167 @@
+"""GPU parity suite: every stage of the CUDA path (through the C-ABI of
+include/hifiasm_b200.h) against the golden vectors of the unmodified reference
+and against the CPU oracle on the same inputs.  Bit-exact (integer/index work)."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import ha_oracle as ho  # noqa: E402
+from goldenlib import Golden, dg, CH, GOLDEN  # noqa: E402
+from hifiasm_b200 import binio  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hifiasm_b200
+    return hifiasm_b200
+
+
+@pytest.fixture(scope="module", params=["g1", "g2"])
+def ctx(request, hb):
+    g = Golden(request.param)
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    hom = eng.ft_gen()
+    eng.update_cov(hom)
+    return g, eng, hom
+
+
+def _chain_digest(ch, fc):
+    h = hashlib.blake2b(digest_size=8)
+    for c in ch:
+        r = np.zeros(1, dtype=CH)
+        for f in ("x_pos_s", "x_pos_e", "y_id", "y_pos_s", "y_pos_e", "y_pos_strand", "shared_seed", "first_hit"):
+            r[f] = c[f]
+        r["n_fc"] = c["fc_n"]
+        h.update(r.tobytes())
+        h.update(np.ascontiguousarray(fc[int(c["fc_off"]):int(c["fc_off"]) + int(c["fc_n"])]).tobytes())
+    return int.from_bytes(h.digest(), "little")
+
+
+def _check_stages(g, eng, mode, rs):
+    p = g.params(mode)
+    eng.upload_store(rs)
+    hom, het = eng.pt_gen()
+    assert (hom, het) == (int(p["hom_cov"]), int(p["het_cov"]))
+    assert eng.get_opt().max_n_chain == int(p["max_n_chain"])
+    eng.set_opt(hom_cov=hom, het_cov=het)
+    n = rs.n
+    off, mz = eng.sketch(0, n)
+    mzq = mz.copy(); mzq["info"] &= ~np.uint64(0xfffffff)  # the query path sketches with rid = 0 (anchor.cpp:1003)
+    for i in range(n):
+        assert dg(mzq[int(off[i]):int(off[i + 1])].tobytes()) == int(g.digest(mode, "mz")[i]), "sketch read %d" % i
+    # index: every query minimizer of every read, like refdump's .idx.bin
+    cnt, pos = eng.pt_get(mz["x"])
+    po = np.zeros(cnt.size + 1, np.uint64); np.cumsum(cnt, out=po[1:])
+    for i in range(n):
+        h = hashlib.blake2b(digest_size=8)
+        for j in range(int(off[i]), int(off[i + 1])):
+            h.update(np.array([mz["x"][j]], dtype="<u8").tobytes()); h.update(np.array([cnt[j]], dtype="<u4").tobytes())
+            h.update(pos[int(po[j]):int(po[j + 1])].tobytes())
+        assert int.from_bytes(h.digest(), "little") == int(g.digest(mode, "idx")[i]), "index read %d" % i
+    aoff, an = eng.anchors(0, n)
+    for i in range(n):
+        assert dg(an[int(aoff[i]):int(aoff[i + 1])].tobytes()) == int(g.digest(mode, "anchors")[i]), "anchors read %d" % i
+    coff, ch, hoff, hits, foff, fc = eng.chains(0, n, float(p["bw_thres"]))
+    for i in range(n):
+        assert _chain_digest(ch[int(coff[i]):int(coff[i + 1])], fc[int(foff[i]):int(foff[i + 1])]) == int(g.digest(mode, "chains")[i]), "chains read %d" % i
+        assert dg(hits[int(hoff[i]):int(hoff[i + 1])].tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain anchors read %d" % i
+    return hom, het
+
+
+def test_filter_table_vs_oracle(ctx):
+    g, eng, hom = ctx
+    raw = ho.Store(g.raw.length, g.raw.byte_off, g.raw.packed, g.raw.n_off, g.raw.n_pos)
+    opt = ho.default_opt()
+    ft, ohom = ho.ft_gen(raw, opt)
+    assert hom == ohom
+    n = int(ho.lib().hao_ft_size(C.c_void_p(ft)))
+    assert eng.ft_size() == n
+    key = np.zeros(max(n, 1), np.uint64); val = np.zeros(max(n, 1), np.int32)
+    if n:
+        ho.lib().hao_ft_dump(C.c_void_p(ft), C.c_void_p(key.ctypes.data), C.c_void_p(val.ctypes.data))
+        assert (eng.ft_cnt(key[:n]) == val[:n]).all()
+    rng = np.random.default_rng(1)
+    assert (eng.ft_cnt(rng.integers(0, 2**63, 1000, dtype=np.uint64)) == 0).all()
+
+
+def test_stages_raw(ctx):
+    g, eng, hom = ctx
+    _check_stages(g, eng, "raw", g.raw)
+
+
+def test_stages_final_and_cal_ov_r(ctx, tmp_path):
+    g, eng, hom = ctx
+    _check_stages(g, eng, "final", g.pre)
+    p0, o0, fc0, ab0 = g.pre_src
+    p1, o1, _, _ = g.pre_rev
+    out0, oo0, out1, oo1, stat = eng.cal_ov_r(binio.disk_to_mem(p0), o0, binio.disk_to_mem(p1), o1)
+    f0, fo0, ffc, fab = g.fin_src
+    f1, fo1, _, _ = g.fin_rev
+    assert (oo0 == fo0).all() and (oo1 == fo1).all()
+    for f in binio.MA_DISK.names:
+        assert (out0[f] == f0[f]).all(), "source field %s" % f
+        assert (out1[f] == f1[f]).all(), "reverse field %s" % f
+    # byte-identical .bin files through the reference's own format
+    a = str(tmp_path / "src.bin"); b = str(tmp_path / "rev.bin")
+    binio.write_ovlp_bin(a, out0, oo0, ffc, fab); binio.write_ovlp_bin(b, out1, oo1, g.fin_rev[2], g.fin_rev[3])
+    assert open(a, "rb").read() == g.z["fin_ovlp_source"].tobytes()
+    assert open(b, "rb").read() == g.z["fin_ovlp_reverse"].tobytes()
+    assert int(stat[0]) == f0.size and int(stat[1]) == f1.size
+    # a second run must give the same answer (the staged previous overlaps are not consumed)
+    n0, n1, stat2 = eng.cal_ov_r_resident()
+    assert (n0, n1) == (f0.size, f1.size) and (stat2 == stat).all()
+    prof = eng.profile()
+    for k in ("k_sketch", "k_probe_count", "k_expand", "k_group", "k_chain", "k_post", "k_exact", "k_merge"):
+        assert k in prof and prof[k][0] >= 1, k
+
+
+def test_small_batches_same_result(ctx, monkeypatch):
+    """anchor-budget batching must not change results"""
+    g, eng0, hom = ctx
+    import hifiasm_b200
+    monkeypatch.setenv("HB_ANCHOR_BUDGET", "200000")
+    eng = hifiasm_b200.Engine(0)
+    eng.upload_store(g.raw); eng.update_cov(eng.ft_gen())
+    eng.upload_store(g.pre)
+    hom, het = eng.pt_gen(); eng.set_opt(hom_cov=hom, het_cov=het)
+    p0, o0, _, _ = g.pre_src; p1, o1, _, _ = g.pre_rev
+    out0, oo0, out1, oo1, stat = eng.cal_ov_r(binio.disk_to_mem(p0), o0, binio.disk_to_mem(p1), o1)
+    f0, fo0, _, _ = g.fin_src; f1, fo1, _, _ = g.fin_rev
+    assert (oo0 == fo0).all() and (oo1 == fo1).all()
+    for f in binio.MA_DISK.names:
+        assert (out0[f] == f0[f]).all() and (out1[f] == f1[f]).all()
+    eng.close()
+
+
+def test_myers_window_vs_reference(hb):
+    z = np.load(os.path.join(GOLDEN, "ed_semi.npz"))
+    hdr, pat, txt, res = z["hdr"], z["pat"], z["txt"], z["res"]
+    po = np.zeros(hdr.shape[0] + 1, np.uint64); to = np.zeros(hdr.shape[0] + 1, np.uint64)
+    np.cumsum(hdr[:, 0], out=po[1:]); np.cumsum(hdr[:, 1], out=to[1:])
+    eng = hb.Engine(0)
+    err, pe = eng.ed_semi_64(pat, po, txt, to, hdr[:, 2], hdr[:, 3])
+    assert (err == res[:, 0]).all() and (pe == res[:, 1]).all()
+    eng.close()
+
+
+def test_empty_and_edge_inputs(hb):
+    eng = hb.Engine(0)
+    # a store of reads too short to carry any minimizer, plus one with only Ns
+    reads = [np.zeros(10, np.uint8), np.full(60, 4, np.uint8), np.arange(200, dtype=np.uint8) % 4]
+    from hifiasm_b200 import sim
+    flat, boff, ln, npos, noff = sim.pack_reads(reads)
+    eng.upload_reads(ln, flat, boff, npos, noff)
+    hom = eng.ft_gen()
+    hom2, het2 = eng.pt_gen()
+    off, mz = eng.sketch(0, 3)
+    assert off[1] == 0 and off[2] == 0  # no k-mer fits in the first two reads
+    e0 = np.zeros(0, binio.MA_MEM); z = np.zeros(4, np.uint64)
+    out0, oo0, out1, oo1, stat = eng.cal_ov_r(e0, z, e0, z)
+    assert out0.size == 0 and out1.size == 0
+    eng.close()
