@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — HiFi Gbp overlapped/sec on the north-star hot path.
+
+Workload (BASELINE.json configs[1], the single-GPU configuration): synthetic
+100 Mb diploid genome (0.1 % SNPs), 30x HiFi, 15 kb reads (sd 2 kb), k=51 w=51.
+A "step" = one final overlap pass (hifiasm's cal_ov_r: sketch -> probe of the
+GPU-resident ha_pt_t -> anchor grouping -> chaining -> exact-overlap test ->
+merge/emit ma_hit_t) over every read of this rank's shard, against the index of
+ALL reads.  The reads are the error-free ("corrected") reads the final pass sees
+in hifiasm; the previous-round overlap lists are empty (the EC rounds are not on
+the GPU yet — DESIGN.md §scope), so every chain is decided by the exact test.
+
+  value : bases processed by all ranks / device time (CUDA events on the engine's
+          own stream, max over ranks), reads + index + inputs resident in HBM.
+  e2e   : the same pass through the host-buffer C-ABI call (hb_reads_upload +
+          hb_cal_ov_r): H2D of the packed reads / previous overlaps and D2H of the
+          resulting ma_hit_t arrays inside the timed region.
+  --impl reference : the UNMODIFIED reference (oracle/_ref, built from
+          /root/reference) running its own cal_ov_r on the box's host cores on a
+          bounded sample of the same workload.
+
+Multi-GPU: one process per GPU (torchrun); index + reads replicated, query reads
+sharded contiguously, no data-path collective.  Weak scaling: the
+genome (and so the read set) grows with N so every rank always processes one
+configs[1]-sized shard (200k reads of a N x 100 Mb genome).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GENOME_MB = int(os.environ.get("HB_BENCH_GENOME_MB", "100"))
+COV = float(os.environ.get("HB_BENCH_COV", "30"))
+MEAN_LEN = 15000
+SD_LEN = 2000
+SNP = 0.001
+K, W = 51, 51
+
+
+# ----------------------------------------------------------------------------
+# synthetic reads, generated directly in hifiasm's 2-bit packing
+# ----------------------------------------------------------------------------
+def _pack(x):
+    x = x.reshape(-1, 4)
+    return ((x[:, 0] << 6) | (x[:, 1] << 4) | (x[:, 2] << 2) | x[:, 3]).astype(np.uint8)
+
+
+def make_dataset(genome_mb, cov, seed=20260922, fasta=None):
+    """Reads sampled from both haplotypes and strands; starts are multiples of 4
+    in the sampled strand so a read's packed form is a byte slice of the packed
+    strand (ha_compress_base layout)."""
+    rng = np.random.default_rng(seed)
+    G = genome_mb * 1000000
+    hap1 = rng.integers(0, 4, G, dtype=np.uint8)
+    hap2 = hap1.copy()
+    m = rng.random(G) < SNP
+    hap2[m] = (hap2[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+    srcs = [hap1, hap2, (3 - hap1[::-1]).astype(np.uint8), (3 - hap2[::-1]).astype(np.uint8)]
+    del hap1, hap2
+    packed_src = [np.concatenate([_pack(s), np.zeros(8, np.uint8)]) for s in srcs]
+    n = int(G * cov / MEAN_LEN)
+    lens = np.clip(rng.normal(MEAN_LEN, SD_LEN, n).astype(np.int64), 2000, G)
+    starts = ((rng.random(n) * (G - lens)).astype(np.int64) // 4) * 4
+    which = rng.integers(0, 4, n)
+    nbytes = lens // 4 + 1
+    boff = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(nbytes, out=boff[1:])
+    flat = np.empty(int(boff[-1]), dtype=np.uint8)
+    bo = boff.astype(np.int64)
+    for i in range(n):
+        a = starts[i] >> 2
+        flat[bo[i]:bo[i + 1]] = packed_src[which[i]][a:a + nbytes[i]]
+    if fasta:
+        tab = np.frombuffer(b"ACGT", dtype=np.uint8)
+        asc = [tab[s] for s in srcs]
+        with open(fasta, "wb") as f:
+            for i in range(n):
+                f.write(b">r%d\n" % i)
+                f.write(asc[which[i]][starts[i]:starts[i] + lens[i]].tobytes())
+                f.write(b"\n")
+    return flat, boff, lens.astype(np.uint64)
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.stop, self.t = dev, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
+
+    def __exit__(self, *a):
+        self.stop = True; self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[j] for r in self.rows for j in range(4) if len(r) > 2 + j and r[2 + j].lower().startswith("active")})
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ----------------------------------------------------------------------------
+def run_reference(flat_ds_args, warmup, steps, sample_reads=None):
+    """The unmodified reference's cal_ov_r on the host cores (oracle/_ref/refdump bench)."""
+    refdump = os.path.join(ROOT, "oracle", "_ref", "refdump")
+    if not os.path.exists(refdump):
+        return None, "oracle/_ref/refdump is missing (build it where /root/reference exists: make -C oracle ref)"
+    cores = os.cpu_count() or 1
+    genome_mb, cov = flat_ds_args
+    with tempfile.TemporaryDirectory() as td:
+        fa = os.path.join(td, "reads.fa")
+        flat, boff, lens = make_dataset(genome_mb, cov, fasta=fa)
+        n = lens.size
+        nq = min(n, sample_reads or max(2000, 400 * cores))
+        out = subprocess.run([refdump, "bench", str(nq), str(warmup), str(steps), "-o", os.path.join(td, "asm"), "-t%d" % cores, "-f0", fa],
+                             capture_output=True, text=True)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if out.returncode != 0 or not line:
+            return None, "refdump bench failed: %s" % out.stderr[-300:]
+        r = json.loads(line[-1])
+    r["cores"] = cores
+    r["gbp_per_s"] = r["query_bases"] / r["seconds"] / 1e9
+    r["sample"] = "cal_ov_r over the first %d of %d reads (%.3f Gbp) against the index of all reads, -t%d" % (r["query_reads"], r["total_reads"], r["query_bases"] / 1e9, cores)
+    return r, None
+
+
+# ----------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "final overlap pass (cal_ov_r) on synthetic %d Mb diploid x%d GPU(s), %gx HiFi, 15 kb reads, k=51 w=51, corrected reads, empty previous overlaps" % (GENOME_MB, world, COV)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r, why = run_reference((GENOME_MB, COV), args.warmup, args.steps)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": why})); return 0
+        v = r["gbp_per_s"]
+        print(json.dumps({"impl": "reference", "metric": "HiFi Gbp overlapped/sec", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64/f64 (integer + double chain scores)",
+                          "data": "synthetic", "config": {"workload": workload.replace("x%d GPU(s)" % world, "x1"), "sample": r["sample"]},
+                          "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+                          "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import hifiasm_b200
+    from hifiasm_b200 import binio
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    # ---- data: N x 100 Mb genome, every rank holds all reads + the full index, queries sharded
+    t0 = time.time()
+    flat, boff, lens = make_dataset(GENOME_MB * world, COV)
+    n = int(lens.size)
+    per = (n + world - 1) // world
+    r0, r1 = min(n, rank * per), min(n, (rank + 1) * per)
+    my_bases = int(lens[r0:r1].sum())
+    eng = hifiasm_b200.Engine(local)
+    eng.upload_reads(lens, flat, boff)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    hom_ft = None
+    if GENOME_MB * world * COV <= 3200:  # all-k-mer counting needs ~24 B per base of HBM: skip beyond ~3.2 Gbp (random genome: the table is empty anyway)
+        hom_ft = eng.ft_gen(); eng.update_cov(hom_ft)
+    hom, het = eng.pt_gen()
+    if hom_ft is None:
+        eng.update_cov(hom)
+    eng.set_opt(hom_cov=hom, het_cov=het)
+    t_idx = time.time() - t0
+    e0 = np.zeros(0, binio.MA_MEM); zoff = np.zeros(n + 1, np.uint64)
+    # stage the (empty) previous overlap lists once: the resident pass reuses them
+    out0, oo0, out1, oo1, stat = eng.cal_ov_r(e0, zoff, e0, zoff, r0, r1, cap=1 << 26)
+    n_src, n_rev = out0.size, out1.size
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.cal_ov_r_resident(r0, r1)
+    prof_acc = {}
+    barrier()
+    with ClockSampler(local) as cs:
+        dev_ms = 0.0
+        for _ in range(args.steps):
+            eng.cal_ov_r_resident(r0, r1)
+            dev_ms += eng.last_pass_ms()
+            for k, (l, ms) in eng.profile().items():
+                a = prof_acc.setdefault(k, [0, 0.0]); a[0] += l; a[1] += ms
+    barrier()
+    clocks = cs.summary()
+    counters = eng.counters()
+    t = torch.tensor([dev_ms, float(my_bases) * args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        dev_ms, tot_bases = float(tm[0]), float(ts[1])
+    else:
+        tot_bases = float(t[1])
+    value = tot_bases / (dev_ms / 1e3) / 1e9
+
+    # ---- e2e: host buffers through the C-ABI (H2D reads + prev lists, D2H results) every step
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        w0 = time.time()
+        for _ in range(args.steps):
+            eng.upload_reads(lens, flat, boff)
+            o0, q0, o1, q1, _ = eng.cal_ov_r(e0, zoff, e0, zoff, r0, r1, cap=max(1024, 2 * (n_src + n_rev)))
+        torch.cuda.synchronize()
+        wall = time.time() - w0
+        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        h2d = int(flat.nbytes + boff.nbytes + lens.size * 4 + 2 * zoff.nbytes)
+        d2h = int((o0.size + o1.size) * binio.MA_MEM.itemsize + 2 * (r1 - r0 + 1) * 8)
+        e2e = {"value": tot_bases / float(tw[0]) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the seed-hash probe (k_probe_count + k_expand), SURVEY.md §8(d):
+    # N_mz*(16 minimizer in + 16 bucket) + N_hit*(8 ha_idxpos_t in + 16 k_mer_hit out) per pass
+    peak, peak_src = measured_peak_gbs()
+    n_mz, n_hit = counters["minimizers"], counters["anchors"]
+    alg_bytes = n_mz * 32 + n_hit * 24
+    probe_ms = (prof_acc.get("k_probe_count", [0, 0])[1] + prof_acc.get("k_expand", [0, 0])[1]) / max(1, args.steps)
+    achieved = alg_bytes / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_probe_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_pass")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "k_probe_count+k_expand (seed-hash probe)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_ms_per_step": {k: v[1] / max(1, args.steps) for k, v in sorted(prof_acc.items())}}
+    cpu = None
+    if not args.no_cpu_baseline:
+        r, why = run_reference((GENOME_MB, COV), 0, 1)
+        cpu = ({"value": r["gbp_per_s"], "unit": "Gbp/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]} if r else {"value": None, "unit": "Gbp/s", "cores": os.cpu_count(), "kind": "reference", "sample": why})
+    out = {"metric": "HiFi Gbp overlapped/sec", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8/u64/f64 (integer + double chain scores)", "data": "synthetic",
+           "config": {"workload": workload, "reads_total": n, "reads_per_rank": r1 - r0, "bases_per_rank": my_bases, "parallelism": "query reads sharded x%d, index+reads replicated" % world,
+                      "l2": "inputs larger than L2 (packed reads %.2f GB + index)" % (flat.nbytes / 1e9), "hom_cov": hom, "overlaps_src": int(n_src), "overlaps_rev": int(n_rev),
+                      "setup_s": {"generate+upload": round(t_gen, 1), "index_build": round(t_idx, 2)}, "counters": counters},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in prof_acc.values())), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -122,7 +122,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->pt_keys = ctx->pt_npos = ctx->pt_cap = 0; ctx->d_pt_slot = 0; ctx->d_pt_pos = 0;
 	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
 	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
-	ctx->anchor_budget = 64ull << 20;
+	ctx->anchor_budget = 64ull << 20; ctx->last_pass_ms = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
@@ -356,7 +356,18 @@ struct StageOut { // host destinations of the stage APIs (all optional)
 };
 
 // mode: 0 final pass (results kept in ctx->d_out*), 2 anchors, 3 chains
+static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, StageOut *so, uint64_t *stat_out);
 static int run_pass(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, StageOut *so, uint64_t *stat_out)
+{ // brackets the pass with events on the context stream
+	cudaSetDevice(ctx->device);
+	cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream);
+	int rc = run_pass_impl(ctx, r0, r1, mode, bw, so, stat_out);
+	float ms = 0; cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	ctx->last_pass_ms = ms;
+	return rc;
+}
+static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, StageOut *so, uint64_t *stat_out)
 {
 	cudaSetDevice(ctx->device);
 	if (r1 > ctx->n_reads || r0 > r1) { hb_set_err(ctx, HB_E_ARG, "read range out of bounds"); return HB_E_ARG; }
@@ -693,6 +704,7 @@ extern "C" int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *lau
 	for (auto &p : ctx->prof) { if (n >= cap) break; names[n] = p.name; launches[n] = p.launches; ms[n] = p.ms; n++; }
 	return n;
 }
+extern "C" int hb_last_pass_ms(const hb_ctx_t *ctx, double *ms) { *ms = ctx->last_pass_ms; return HB_OK; }
 extern "C" int hb_counters(const hb_ctx_t *ctx, uint64_t *c, int cap)
 {
 	int n = cap < 8 ? cap : 8;

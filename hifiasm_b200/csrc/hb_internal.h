@@ -31,6 +31,7 @@ struct hb_ctx {
 	// instrumentation
 	std::vector<ProfEntry> prof; uint64_t counters[8];
 	uint64_t anchor_budget; // anchors per batch
+	double last_pass_ms;
 };
 
 void hb_set_err(hb_ctx *ctx, int code, const char *fmt, ...);

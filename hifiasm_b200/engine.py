@@ -194,6 +194,9 @@ class Engine:
         n = _lib().hb_profile(self.h, names, launches, ms, 64)
         return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(n)}
 
+    def last_pass_ms(self) -> float:
+        ms = C.c_double(); _lib().hb_last_pass_ms(self.h, C.byref(ms)); return ms.value
+
     def counters(self):
         c = (C.c_uint64 * 8)(); _lib().hb_counters(self.h, c, 8)
         return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots"), [int(x) for x in c[:6]]))

@@ -144,6 +144,9 @@ int hb_ed_semi_64(hb_ctx_t *ctx, uint64_t n_cases, const char *pat, const uint64
 /* per-kernel launch counters and device time of the last hb_cal_ov_r* call:
  * names[i] (static strings), launches[i], ms[i]; returns number of entries   */
 int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap);
+/* device time (ms) of the last pass, from CUDA events recorded on the context's
+ * own stream around the whole pass (first launch .. last result resident)     */
+int hb_last_pass_ms(const hb_ctx_t *ctx, double *ms);
 /* algorithmic byte counters of the last pass:
  * c[0]=reads, c[1]=bases, c[2]=minimizers, c[3]=anchors, c[4]=groups, c[5]=chains */
 int hb_counters(const hb_ctx_t *ctx, uint64_t *c, int cap);

@@ -151,9 +151,45 @@ static int run_edsemi(const char *in, const char *out)
 	return 0;
 }
 
+// refdump bench <n_query> <warmup> <steps> <hifiasm args...>: the reference's own final overlap
+// pass, timed.  Builds the filter table and the index like ha_assemble() does
+// (Assembly.cpp:2083, 1007), then runs cal_ov_r (ecovlp.cpp:6385) over the first
+// n_query reads (0 = all) with empty previous overlap lists and prints one JSON
+// line: seconds (wall of cal_ov_r alone), query bases, threads.
+static int run_bench(int argc, char *argv[])
+{
+	uint64_t nq = strtoull(argv[2], 0, 10), i, bases = 0; int hom_cov = -1, het_cov = -1, warm = atoi(argv[3]), steps = atoi(argv[4]), s;
+	yak_reset_realtime();
+	init_opt(&asm_opt);
+	argv[4] = argv[0];
+	if (!CommandLine_process(argc - 4, argv + 4, &asm_opt)) return 1;
+	ha_flt_tab = NULL; ha_idx = NULL;
+	double t0 = yak_realtime();
+	if (!(asm_opt.flag & HA_F_NO_KMER_FLT)) { ha_flt_tab = ha_ft_gen(&asm_opt, &R_INF, &hom_cov, 0, 0); ha_opt_update_cov(&asm_opt, hom_cov); }
+	ha_idx = ha_pt_gen(&asm_opt, ha_flt_tab, 0, 0, &R_INF, &hom_cov, &het_cov);
+	asm_opt.hom_cov = hom_cov; asm_opt.het_cov = het_cov;
+	if (ha_flt_tab == 0) ha_opt_update_cov(&asm_opt, hom_cov);
+	double t_idx = yak_realtime() - t0;
+	if (nq == 0 || nq > R_INF.total_reads) nq = R_INF.total_reads;
+	for (i = 0; i < nq; i++) bases += R_INF.read_length[i];
+	double dt = 0; uint64_t n_src = 0, n_rev = 0;
+	for (s = 0; s < warm + steps; s++) { // every step sees the same input: empty previous overlap lists
+		for (i = 0; i < R_INF.total_reads; i++) R_INF.paf[i].length = R_INF.reverse_paf[i].length = 0;
+		double t1 = yak_realtime();
+		cal_ov_r(asm_opt.thread_num, nq, 1);
+		if (s >= warm) dt += yak_realtime() - t1;
+	}
+	dt /= steps > 0 ? steps : 1;
+	for (i = 0; i < nq; i++) { n_src += R_INF.paf[i].length; n_rev += R_INF.reverse_paf[i].length; }
+	printf("{\"seconds\": %.6f, \"query_reads\": %lu, \"query_bases\": %lu, \"total_reads\": %lu, \"threads\": %d, \"index_seconds\": %.3f, \"n_src\": %lu, \"n_rev\": %lu, \"hom_cov\": %d}\n",
+	       dt, (unsigned long)nq, (unsigned long)bases, (unsigned long)R_INF.total_reads, asm_opt.thread_num, t_idx, (unsigned long)n_src, (unsigned long)n_rev, hom_cov);
+	return 0;
+}
+
 int main(int argc, char *argv[])
 {
 	if (argc == 4 && strcmp(argv[1], "edsemi") == 0) return run_edsemi(argv[2], argv[3]);
+	if (argc >= 6 && strcmp(argv[1], "bench") == 0) return run_bench(argc, argv);
 	if (argc < 4) { fprintf(stderr, "usage: refdump <raw|final> <out_prefix> <hifiasm args...>\n"); return 1; }
 	const char *mode = argv[1], *pfx = argv[2];
 	int r, hom_cov = -1, het_cov = -1; uint64_t tot_b, tot_e;
