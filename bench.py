@@ -270,21 +270,23 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the seed-hash probe (k_probe_count + k_expand), SURVEY.md §8(d):
-    # N_mz*(16 minimizer in + 16 bucket) + N_hit*(8 ha_idxpos_t in + 16 k_mer_hit out) per pass
+    # ---- roofline of the seed-hash probe kernel k_expand: per pass it reads
+    # N_mz*(16 minimizer + 8 seed + 4 prefix) + N_hit*8 (ha_idxpos_t) and writes N_hit*16 (k_mer_hit);
+    # achieved = algorithmic bytes of all its launches / their summed CUDA-event time (== bytes per launch / mean launch time)
     peak, peak_src = measured_peak_gbs()
     n_mz, n_hit = counters["minimizers"], counters["anchors"]
-    alg_bytes = n_mz * 32 + n_hit * 24
-    probe_ms = (prof_acc.get("k_probe_count", [0, 0])[1] + prof_acc.get("k_expand", [0, 0])[1]) / max(1, args.steps)
+    n_launch = max(1, prof_acc.get("k_expand", [0, 0])[0] // max(1, args.steps))
+    alg_bytes = (n_mz * 28 + n_hit * 24) / n_launch
+    probe_ms = prof_acc.get("k_expand", [0, 0])[1] / max(1, args.steps) / n_launch
     achieved = alg_bytes / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r1_probe_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_pass")
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": "k_probe_count+k_expand (seed-hash probe)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_expand (seed-hash probe)", "launches_per_step": n_launch, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_ms_per_step": {k: v[1] / max(1, args.steps) for k, v in sorted(prof_acc.items())}}
     cpu = None
