@@ -122,7 +122,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->pt_keys = ctx->pt_npos = ctx->pt_cap = 0; ctx->d_pt_slot = 0; ctx->d_pt_pos = 0;
 	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
 	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
-	ctx->anchor_budget = 64ull << 20; ctx->last_pass_ms = 0;
+	ctx->anchor_budget = 768ull << 20; ctx->last_pass_ms = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
@@ -407,7 +407,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	std::vector<uint64_t> st3_off, st3_hit_off, st3_fc_off; // mode 3 host offsets (accumulated per batch)
 	uint64_t st3_n = 0, st3_nh = 0, st3_nf = 0;
 	if (mode == 3) { st3_off.assign(nR + 1, 0); st3_hit_off.assign(nR + 1, 0); st3_fc_off.assign(nR + 1, 0); }
-	unsigned long long *d_stat = ar.zero<unsigned long long>(8);
+	unsigned long long *d_stat = ar.zero<unsigned long long>(16);
 	uint32_t *d_m0 = 0, *d_m1 = 0; // per-read result counts (final pass)
 	struct BatchRes { hb_ma_hit_t *o0, *o1; uint64_t *ooff; uint64_t b0, b1; };
 	std::vector<BatchRes> bres;
@@ -466,9 +466,10 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_ALLOC_CHECK(ba);
 		{
 			ChainArgs C; C.R = R; C.r0 = r0 + b0; C.dir = d_dir; C.dir_n = d_dirn; C.a_off = d_aoff + b0; C.a_base = a_base; C.c_off = d_coff;
-			C.hits = d_hits; C.chits = d_chits; C.f = d_f; C.p = d_p; C.ii = d_ii; C.t = d_t; C.ch = d_ch; C.slot_read = d_slot_read; C.fc = d_fc; C.P = CP; C.err = d_err;
+			C.hits = d_hits; C.chits = d_chits; C.f = d_f; C.p = d_p; C.ii = d_ii; C.t = d_t; C.ch = d_ch; C.slot_read = d_slot_read; C.fc = d_fc; C.P = CP; C.err = d_err; C.dbg = d_stat + 8;
 			ProfScope ps(ctx, "k_chain");
-			k_chain<<<std::max(1u, std::min(nblk(h_dirn, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
+			if (getenv("HB_CHAIN_THREAD")) k_chain<<<std::max(1u, std::min(nblk(h_dirn, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
+			else k_chain_warp<<<std::max(1u, std::min(nblk((uint64_t)h_dirn * 32, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
 		}
 		HB_CUDA(cudaGetLastError());
 		if (mode == 2) { b0 = b1; continue; }
@@ -581,8 +582,9 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	}
 	HB_CUDA(cudaGetLastError());
 	ctx->out_reads = nR;
-	unsigned long long h_stat[8] = { 0 };
-	HB_CUDA(cudaMemcpyAsync(h_stat, d_stat, 7 * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	unsigned long long h_stat[16] = { 0 };
+	HB_CUDA(cudaMemcpyAsync(h_stat, d_stat, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->counters[6] = h_stat[8]; ctx->counters[7] = h_stat[9];
 	if (h_stat[6]) { hb_set_err(ctx, HB_E_OVERFLOW, "a read has more overlaps than the in-kernel radix sort stack supports"); return HB_E_OVERFLOW; }
 	if (stat_out) { // forward, reverse, strong, weak, exact, no_l_indel, inexact (ecovlp.cpp:6173-6179)
 		for (int i = 0; i < 6; i++) stat_out[i] = h_stat[i];

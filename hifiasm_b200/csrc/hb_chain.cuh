@@ -138,21 +138,13 @@ HB_HD void hb_order_group(hb_hit_t *a, int32_t a_n)
 	}
 }
 
-// Chain one target group.  a[0..a_n): the group's anchors (same target id, both
-// strands), ordered here by (strand, self_offset, offset) — the order
-// minimizers_qgen0's sort produces (anchor.cpp:1046-1049).  des: a_n-sized
-// output slice for the chain anchors.  f,p,ii (int32) and t (int64): a_n-sized
-// scratch.  out: the group's chain slots (n_slots = a_n>=mcopy_khit_cutoff ? mcopy_num : 1).
-// Returns the number of chain anchors written to des.
-HB_HD int32_t hb_chain_group(hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t des_abs, int32_t *f, int32_t *p, int64_t *t, int32_t *ii,
-                             const ChainPar &P, int64_t xl, int64_t yl, hb_chain_t *out, int32_t n_slots, FcOut &fc)
+struct ChainState { int64_t plus, msc, msc_i, movl, si, ei; };
+
+// quick_ck_lchain, Hash_Table.cpp:2007-2094: strand blocks whose anchors are
+// already co-linear are resolved by a linear scan; [si,ei) is left for the DP
+HB_HD void hb_chain_quick(const hb_hit_t *a, int32_t a_n, int32_t *f, int32_t *p, int64_t *t, int32_t *ii, const ChainPar &P, int64_t xl, int64_t yl, ChainState &S)
 {
-	int64_t max_f, n_skip, st, max_j, end_j, sc, msc, msc_i, max_ii, ovl, movl, plus = 0, min_sc, ch_n, si, ei, i, k, j, cL = 0;
-	int32_t max, tmp, n_out = 0;
-	for (i = 0; i < n_slots; i++) out[i].n_hits = 0;
-	if (a_n <= 0) return 0;
-	hb_order_group(a, a_n);
-	// quick_ck_lchain, Hash_Table.cpp:2007-2094
+	int64_t k, sc, plus, msc, msc_i, movl, si, ei;
 	{
 		int64_t l, z, sorted = 1;
 		plus = 0; msc = msc_i = INT32_MIN; movl = INT32_MAX; si = 0; ei = a_n;
@@ -192,7 +184,15 @@ HB_HD int32_t hb_chain_group(hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t d
 			}
 		}
 	}
-	// DP, Hash_Table.cpp:2124-2176
+	S.plus = plus; S.msc = msc; S.msc_i = msc_i; S.movl = movl; S.si = si; S.ei = ei;
+}
+
+// the chaining DP over [si,ei), Hash_Table.cpp:2124-2176 (one thread)
+HB_HD void hb_chain_dp(const hb_hit_t *a, int32_t a_n, int32_t *f, int32_t *p, int64_t *t, int32_t *ii, const ChainPar &P, int64_t xl, int64_t yl, ChainState &S)
+{
+	int64_t max_f, n_skip, st, max_j, end_j, sc, msc = S.msc, msc_i = S.msc_i, max_ii, ovl, movl = S.movl, plus = S.plus, si = S.si, ei = S.ei, i, j;
+	int32_t max, tmp;
+	(void)a_n;
 	for (i = st = si, max_ii = -1; i < ei; ++i) {
 		max_f = a[i].cnt & 0xffu;
 		n_skip = 0; max_j = end_j = -1;
@@ -225,6 +225,16 @@ HB_HD int32_t hb_chain_group(hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t d
 		if (f[i] < plus) plus = f[i];
 		ii[i] = 0;
 	}
+	S.plus = plus; S.msc = msc; S.msc_i = msc_i; S.movl = movl;
+}
+
+// backtrack, secondary chains (mcopy), emission: Hash_Table.cpp:2178-2283
+HB_HD int32_t hb_chain_finish(const hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t des_abs, int32_t *f, int32_t *p, int64_t *t, int32_t *ii,
+                              const ChainPar &P, int64_t xl, int64_t yl, hb_chain_t *out, int32_t n_slots, FcOut &fc, const ChainState &S)
+{
+	int64_t sc, msc = S.msc, msc_i = S.msc_i, plus = S.plus, min_sc, ch_n, i, k, j, cL = 0;
+	int32_t n_out = 0;
+	(void)n_slots;
 	for (i = msc_i, cL = 0; i >= 0; i = p[i]) { ii[i] = 1; t[cL++] = i; } // Hash_Table.cpp:2178
 
 	if (P.mcopy_num > 1 && cL >= P.mcopy_khit_cutoff) { // Hash_Table.cpp:2180-2270
@@ -269,6 +279,25 @@ HB_HD int32_t hb_chain_group(hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t d
 		hb_gen_fcigar(fc, z, des, cL);
 	}
 	return (int32_t)cL;
+}
+
+// Chain one target group (one thread): order + quick check + DP + finish.
+// a[0..a_n): the group's anchors (same target id, both strands), ordered here by
+// (strand, self_offset, offset) — the order minimizers_qgen0's sort produces
+// (anchor.cpp:1046-1049).  des: a_n-sized output slice for the chain anchors.
+// f,p,ii (int32) and t (int64): a_n-sized scratch.  out: the group's chain slots
+// (n_slots = a_n>=mcopy_khit_cutoff ? mcopy_num : 1).  Returns the number of
+// chain anchors written to des.
+HB_HD int32_t hb_chain_group(hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t des_abs, int32_t *f, int32_t *p, int64_t *t, int32_t *ii,
+                             const ChainPar &P, int64_t xl, int64_t yl, hb_chain_t *out, int32_t n_slots, FcOut &fc)
+{
+	ChainState S;
+	for (int32_t i = 0; i < n_slots; i++) out[i].n_hits = 0;
+	if (a_n <= 0) return 0;
+	hb_order_group(a, a_n);
+	hb_chain_quick(a, a_n, f, p, t, ii, P, xl, yl, S);
+	hb_chain_dp(a, a_n, f, p, t, ii, P, xl, yl, S);
+	return hb_chain_finish(a, a_n, des, des_abs, f, p, t, ii, P, xl, yl, out, n_slots, fc, S);
 }
 
 // ---------------------------------------------------------------------------

@@ -120,8 +120,8 @@ __global__ void k_expand(DevReads R, DevPt pt, uint64_t r0, uint64_t n_mz, const
 // order, which only same-minimizer ties can violate).  Reads with more distinct
 // targets than the table holds fall back to tables in a global arena.
 // ----------------------------------------------------------------------------
-#define GRP_TS 2048
-#define GRP_MAXG 1024
+#define GRP_TS 1024
+#define GRP_MAXG 512
 #define GRP_EMPTY 0xffffffffu
 #define GRP_WARPS 4
 
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 // ----------------------------------------------------------------------------
 struct ChainArgs {
 	DevReads R; uint64_t r0; const GroupDir *dir; const uint32_t *dir_n; const uint64_t *a_off; uint64_t a_base; const uint64_t *c_off;
-	hb_hit_t *hits, *chits; int32_t *f, *p, *ii; int64_t *t; hb_chain_t *ch; uint32_t *slot_read; uint64_t *fc; ChainPar P; int *err;
+	hb_hit_t *hits, *chits; int32_t *f, *p, *ii; int64_t *t; hb_chain_t *ch; uint32_t *slot_read; uint64_t *fc; ChainPar P; int *err; unsigned long long *dbg;
 };
 __global__ void k_chain(ChainArgs A)
 {
@@ -270,6 +270,259 @@ __global__ void k_chain(ChainArgs A)
 		               (int64_t)A.R.len[A.r0 + d.read], (int64_t)A.R.len[tid], A.ch + cb, ns, fc);
 		for (int32_t s = 0; s < ns; s++) A.slot_read[cb + s] = d.read;
 		if (fc.ovf) atomicOr(A.err, 16);
+	}
+}
+
+// ----------------------------------------------------------------------------
+// chain, warp per group.  The common case — every strand block of the group is
+// already co-linear, which is what quick_ck_lchain (Hash_Table.cpp:2007-2094)
+// detects with a linear scan — is evaluated by the whole warp: 32 link scores
+// per step, chain scores by warp prefix sums, best end / minimum by warp
+// reductions, chain anchors copied with 128-bit loads.  Anything else (DP needed,
+// secondary chains possible, unordered group) is handed to lane 0, which runs the
+// sequential hb_chain_group on the same buffers: identical results by construction.
+// ----------------------------------------------------------------------------
+static __device__ __forceinline__ hb_hit_t hit_shfl_up1(const hb_hit_t &h)
+{
+	hb_hit_t r;
+	r.id_strand = __shfl_up_sync(HB_FULL, h.id_strand, 1); r.offset = __shfl_up_sync(HB_FULL, h.offset, 1);
+	r.self_offset = __shfl_up_sync(HB_FULL, h.self_offset, 1); r.cnt = __shfl_up_sync(HB_FULL, h.cnt, 1);
+	return r;
+}
+static __device__ __forceinline__ hb_hit_t hit_ld(const hb_hit_t *p) { uint4 v = *(const uint4 *)p; hb_hit_t h; h.id_strand = v.x; h.offset = v.y; h.self_offset = v.z; h.cnt = v.w; return h; }
+static __device__ __forceinline__ uint64_t hit_okey(const hb_hit_t &h) { return (uint64_t)(h.id_strand >> 31) << 63 | (uint64_t)h.self_offset << 32 | h.offset; }
+
+// is a[0..n) ordered by (strand, self_offset, offset)?  (warp-uniform result); *kb = first index of strand 1 (n if none)
+static __device__ bool warp_group_ordered(const hb_hit_t *a, int32_t n, int lane, int32_t *kb)
+{
+	bool bad = false; int32_t first1 = n;
+	for (int32_t base = 0; base < n; base += 32) {
+		int32_t z = base + lane; bool valid = z < n;
+		hb_hit_t h = hit_ld(a + (valid ? z : n - 1));
+		uint64_t kz = hit_okey(h), kp = __shfl_up_sync(HB_FULL, kz, 1);
+		if (lane == 0) kp = base ? hit_okey(hit_ld(a + base - 1)) : 0;
+		if (valid && z > 0 && kp > kz) bad = true;
+		unsigned m1 = __ballot_sync(HB_FULL, valid && (h.id_strand >> 31));
+		if (m1 && first1 == n) first1 = base + __ffs(m1) - 1;
+	}
+	*kb = first1;
+	return !__any_sync(HB_FULL, bad);
+}
+
+struct QBlock { bool resolved; int64_t msc0, msc_i0, plus0; };
+// quick_ck_lchain for one strand block [l,k) (Hash_Table.cpp:2023-2086), warp-parallel
+static __device__ QBlock warp_quick_block(const hb_hit_t *a, int32_t l, int32_t k, const ChainPar &P, int64_t xl, int64_t yl, int lane, int32_t *f = 0, int32_t *p = 0)
+{
+	QBlock q; q.resolved = false; q.msc0 = q.msc_i0 = q.plus0 = 0;
+	hb_hit_t first = hit_ld(a + l);
+	int64_t carry_f = first.cnt & 0xffu, msc0 = carry_f, msc_i0 = l, plus0 = 0, ddt = 0;
+	if (f && lane == 0) { f[l] = (int32_t)carry_f; p[l] = -1; }
+	for (int32_t base = l + 1; base < k; base += 32) {
+		int32_t z = base + lane; bool valid = z < k;
+		hb_hit_t h = hit_ld(a + (valid ? z : k - 1)), hp = hit_shfl_up1(h);
+		if (lane == 0) hp = hit_ld(a + base - 1);
+		int32_t dd = 0, s = HB_LINK_FAIL; bool viol = false;
+		if (valid) {
+			if (h.self_offset <= hp.self_offset || h.offset <= hp.offset) viol = true; // is_srt, Hash_Table.cpp:2090
+			else { s = hb_link_sc(h, hp, P, xl, yl, &dd); if (s == HB_LINK_FAIL) viol = true; }
+		}
+		int64_t inc = (valid && !viol) ? (int64_t)s : 0;
+		for (int d = 1; d < 32; d <<= 1) { int64_t v = __shfl_up_sync(HB_FULL, inc, d); if (lane >= d) inc += v; }
+		int64_t fz = carry_f + inc;
+		if (valid && !viol && fz < (int64_t)(h.cnt & 0xffu)) viol = true; // sc < csc, Hash_Table.cpp:2059
+		if (__any_sync(HB_FULL, viol)) return q; // the scan would stop before the block's end: not resolved
+		if (f && valid) { f[z] = (int32_t)fz; p[z] = z - 1; }
+		// running best end (>=: the later anchor wins ties), minimum, gap sum
+		int64_t bf = valid ? fz : INT64_MIN, bi = valid ? z : -1, mf = valid ? fz : INT64_MAX, sd = valid ? dd : 0;
+		for (int d = 16; d; d >>= 1) {
+			int64_t of = __shfl_xor_sync(HB_FULL, bf, d), oi = __shfl_xor_sync(HB_FULL, bi, d), om = __shfl_xor_sync(HB_FULL, mf, d), od = __shfl_xor_sync(HB_FULL, sd, d);
+			if (of > bf || (of == bf && oi > bi)) { bf = of; bi = oi; }
+			if (om < mf) mf = om;
+			sd += od;
+		}
+		if (bf >= msc0) { msc0 = bf; msc_i0 = bi; }
+		if (mf < plus0) plus0 = mf;
+		ddt += sd;
+		int last = (k - base < 32 ? k - base : 32) - 1;
+		carry_f = __shfl_sync(HB_FULL, fz, last);
+	}
+	if (msc_i0 != k - 1) return q;
+	if (k - l >= 2 && ddt > 16) { // Hash_Table.cpp:2071
+		hb_hit_t e = hit_ld(a + k - 1);
+		if (ddt > hb_link_bw(e, first, P.bw_rate, xl, yl)) return q;
+	}
+	q.resolved = true; q.msc0 = msc0; q.msc_i0 = msc_i0; q.plus0 = plus0;
+	return q;
+}
+
+// The chaining DP of lchain_qdp_mcopy_fast (Hash_Table.cpp:2124-2176) with the
+// predecessor scan spread over the warp: 32 predecessors per step, link scores in
+// parallel, the sequential semantics (running best, n_skip early stop, t[] marks)
+// resolved with a prefix max + ballots + a 32-step scalar walk.  Marks are written
+// optimistically by every lane of a step: a lane's own mark test can only be
+// affected by lanes that precede it in scan order (p[j'] < j'), and marks left
+// behind past a break carry the value i, which no later test looks for.
+static __device__ void warp_chain_dp(const hb_hit_t *a, int32_t kb, int32_t *f, int32_t *p, int64_t *t, int32_t *ii, const ChainPar &P, int64_t xl, int64_t yl, ChainState &S, int lane)
+{
+	int64_t msc = S.msc, msc_i = S.msc_i, movl = S.movl, plus = S.plus, st = S.si, max_ii = -1;
+	for (int64_t i = S.si; i < S.ei; ++i) {
+		const hb_hit_t ai = hit_ld(a + i); const uint32_t si_ = ai.id_strand >> 31;
+		int64_t max_f = ai.cnt & 0xffu, max_j = -1, end_j = -1; int32_t n_skip = 0; bool broke = false;
+		if (i - st > P.max_iter) st = i - P.max_iter;
+		if (si_ && st < kb) st = kb; // while (a[i].strand != a[st].strand) ++st;
+		for (int64_t jtop = i - 1; jtop >= st && !broke; jtop -= 32) {
+			const int64_t j = jtop - lane; const bool valid = j >= st;
+			int32_t s = HB_LINK_FAIL; int64_t cand = INT64_MIN; int32_t pj = -1;
+			if (valid) { hb_hit_t aj = hit_ld(a + j); s = hb_link_sc(ai, aj, P, xl, yl, 0); }
+			const bool proc = valid && s != HB_LINK_FAIL;
+			if (proc) { cand = (int64_t)s + f[j]; pj = p[j]; if (pj >= 0) t[pj] = i; }
+			__syncwarp();
+			const bool hit = proc && t[j] == (int64_t)(int32_t)i;
+			int64_t pm = cand;
+			for (int d = 1; d < 32; d <<= 1) { int64_t v = __shfl_up_sync(HB_FULL, pm, d); if (lane >= d && v > pm) pm = v; }
+			int64_t excl = __shfl_up_sync(HB_FULL, pm, 1); if (lane == 0) excl = INT64_MIN;
+			const int64_t run = excl > max_f ? excl : max_f;
+			const bool imp = proc && cand > run;
+			const unsigned impm = __ballot_sync(HB_FULL, imp), hitm = __ballot_sync(HB_FULL, hit && !imp), procm = __ballot_sync(HB_FULL, proc);
+			int brk = -1;
+			for (unsigned m = procm; m; m &= m - 1) {
+				int b = __ffs(m) - 1;
+				if (impm >> b & 1) { if (n_skip > 0) --n_skip; }
+				else if (hitm >> b & 1) { if (++n_skip > P.max_skip) { brk = b; break; } }
+			}
+			const int lim = brk < 0 ? 32 : brk;
+			int64_t bf = (imp && lane < lim) ? cand : INT64_MIN; int bl = lane;
+			for (int d = 16; d; d >>= 1) {
+				int64_t of = __shfl_xor_sync(HB_FULL, bf, d); int ol = __shfl_xor_sync(HB_FULL, bl, d);
+				if (of > bf || (of == bf && ol < bl)) { bf = of; bl = ol; }
+			}
+			if (bf > max_f) { max_f = bf; max_j = jtop - bl; }
+			if (brk >= 0) { broke = true; end_j = jtop - brk; }
+		}
+		if (!broke) end_j = st - 1;
+		bool redo = max_ii < 0;
+		hb_hit_t am; am.id_strand = am.offset = am.self_offset = am.cnt = 0;
+		if (!redo) { am = hit_ld(a + max_ii); redo = (int64_t)ai.self_offset > (int64_t)am.self_offset + P.max_dis || si_ != (am.id_strand >> 31); }
+		if (redo) { // Hash_Table.cpp:2145-2152
+			int64_t bf = INT64_MIN, bj = -1; bool stop = false;
+			for (int64_t jtop = i - 1; jtop >= st && !stop; jtop -= 32) {
+				const int64_t j = jtop - lane; bool ok = j >= st;
+				if (ok) { hb_hit_t aj = hit_ld(a + j); ok = (int64_t)ai.self_offset <= (int64_t)P.max_dis + (int64_t)aj.self_offset && si_ == (aj.id_strand >> 31); }
+				const unsigned okm = __ballot_sync(HB_FULL, ok);
+				// the scan stops at the first predecessor that fails the test: only the leading run of ok lanes counts
+				const unsigned lead = okm == HB_FULL ? HB_FULL : ((1u << (__ffs(~okm) - 1)) - 1);
+				if (lead != HB_FULL) stop = true;
+				int64_t cf = (lead >> lane & 1) ? (int64_t)f[j] : INT64_MIN, cj = j;
+				for (int d = 16; d; d >>= 1) {
+					int64_t of = __shfl_xor_sync(HB_FULL, cf, d), oj = __shfl_xor_sync(HB_FULL, cj, d);
+					if (of > cf || (of == cf && oj > cj)) { cf = of; cj = oj; }
+				}
+				if (cf > bf) { bf = cf; bj = cj; } // strict: an earlier (larger j) maximum is kept
+			}
+			max_ii = bf > (int64_t)INT32_MIN ? bj : -1;
+			if (max_ii >= 0) am = hit_ld(a + max_ii);
+		}
+		if (max_ii >= 0 && max_ii < end_j && si_ == (am.id_strand >> 31)) {
+			int32_t tmp = hb_link_sc(ai, am, P, xl, yl, 0);
+			if (tmp != HB_LINK_FAIL && max_f < (int64_t)tmp + f[max_ii]) { max_f = (int64_t)tmp + f[max_ii]; max_j = max_ii; }
+		}
+		if (lane == 0) { f[i] = (int32_t)max_f; p[i] = (int32_t)max_j; ii[i] = 0; }
+		__syncwarp();
+		if (max_ii < 0 || ((int64_t)ai.self_offset <= (int64_t)P.max_dis + (int64_t)am.self_offset && si_ == (am.id_strand >> 31) && (int64_t)f[max_ii] < max_f)) max_ii = i;
+		if (max_f >= msc) {
+			int64_t ovl = hb_chain_len(ai.self_offset, ai.self_offset, xl, ai.offset, ai.offset, yl);
+			if (max_f > msc || ovl < movl) { msc = max_f; msc_i = i; movl = ovl; }
+		}
+		if (max_f < plus) plus = max_f;
+	}
+	S.plus = plus; S.msc = msc; S.msc_i = msc_i; S.movl = movl;
+}
+
+__global__ void __launch_bounds__(128) k_chain_warp(ChainArgs A)
+{
+	const uint32_t n = *A.dir_n; const int lane = hb_lane();
+	const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t g = w0; g < n; g += nw) {
+		GroupDir d = A.dir[g];
+		const uint64_t ab = A.a_off[d.read] - A.a_base + d.start; hb_hit_t *a = A.hits + ab; const int32_t an = (int32_t)d.count;
+		int32_t kb;
+		bool ordered = warp_group_ordered(a, an, lane, &kb);
+		if (!ordered && lane == 0 && A.dbg) atomicAdd(&A.dbg[0], 1ull);
+		if (d.slot == GRP_EMPTY) { if (!ordered && lane == 0) hb_order_group(a, an); __syncwarp(); continue; }
+		const uint64_t cb = A.c_off[d.read] + d.slot;
+		const int32_t ns = d.count >= (uint32_t)A.P.mcopy_khit_cutoff ? A.P.mcopy_num : 1;
+		const int64_t xl = A.R.len[A.r0 + d.read], yl = A.R.len[HB_HIT_ID(hit_ld(a))];
+		bool simple = ordered; int64_t msc = INT32_MIN, msc_i = INT32_MIN, movl = INT32_MAX, plus = 0, other_max = INT64_MIN; int32_t lb = 0;
+		if (simple) { // quick_ck_lchain over the (at most two) strand blocks, Hash_Table.cpp:2015-2093
+			for (int b = 0; b < 2 && simple; b++) {
+				int32_t l = b ? kb : 0, k = b ? an : kb;
+				if (l >= k) continue;
+				QBlock q = warp_quick_block(a, l, k, A.P, xl, yl, lane);
+				if (!q.resolved) { simple = false; break; }
+				bool took = false;
+				if (q.msc0 >= msc) {
+					hb_hit_t e = hit_ld(a + q.msc_i0);
+					int64_t movl0 = hb_chain_len(e.self_offset, e.self_offset, xl, e.offset, e.offset, yl);
+					if (q.msc0 > msc || movl0 < movl) { if (msc_i != INT32_MIN) other_max = msc; msc = q.msc0; msc_i = q.msc_i0; movl = movl0; lb = l; took = true; }
+				}
+				if (!took) other_max = q.msc0;
+				if (q.plus0 < plus) plus = q.plus0;
+			}
+		}
+		if (simple) {
+			const int64_t cL = msc_i - lb + 1;
+			if (A.P.mcopy_num > 1 && cL >= A.P.mcopy_khit_cutoff && other_max != INT64_MIN) { // a secondary chain may qualify (Hash_Table.cpp:2184-2190)
+				int64_t min_sc = (int64_t)((double)(msc - plus) * A.P.mcopy_rate);
+				if (other_max - plus >= min_sc) simple = false;
+			}
+		}
+		if (simple) {
+			const int32_t cL = (int32_t)(msc_i - lb + 1);
+			hb_hit_t *des = A.chits + ab;
+			for (int32_t i = lane; i < cL; i += 32) *(uint4 *)(des + i) = *(const uint4 *)(a + lb + i);
+			__syncwarp();
+			if (lane == 0) {
+				hb_chain_t z; hb_hit_t hb = hit_ld(a + lb), he = hit_ld(a + msc_i);
+				hb_push_chain(z, xl, yl, msc, hb, he);
+				z.first_hit = (uint32_t)ab; z.n_hits = (uint32_t)cL;
+				if (A.fc) { FcOut fc; fc.n = 0; fc.ovf = 0; fc.buf = A.fc + ab + 2 * cb; fc.cap = d.count + 2 * ns; hb_gen_fcigar(fc, z, des, cL); if (fc.ovf) atomicOr(A.err, 16); }
+				A.ch[cb] = z;
+				for (int32_t s = 1; s < ns; s++) A.ch[cb + s].n_hits = 0;
+				for (int32_t s = 0; s < ns; s++) A.slot_read[cb + s] = d.read;
+			}
+		} else {
+			// the general case: quick check with f/p written out, warp-parallel DP over the
+			// unresolved range, then backtrack / secondary chains / emission on lane 0
+			int32_t *f = A.f + ab, *p = A.p + ab, *ii = A.ii + ab; int64_t *t = A.t + ab;
+			if (lane == 0 && A.dbg) atomicAdd(&A.dbg[1], 1ull);
+			if (!ordered) { if (lane == 0) hb_order_group(a, an); __syncwarp(); warp_group_ordered(a, an, lane, &kb); }
+			for (int32_t z = lane; z < an; z += 32) { t[z] = 0; ii[z] = 0; }
+			ChainState S; S.plus = 0; S.msc = S.msc_i = INT32_MIN; S.movl = INT32_MAX; S.si = 0; S.ei = an;
+			for (int b = 0; b < 2; b++) { // quick_ck_lchain, Hash_Table.cpp:2015-2093
+				int32_t l = b ? kb : 0, k = b ? an : kb;
+				if (l >= k) continue;
+				QBlock q = warp_quick_block(a, l, k, A.P, xl, yl, lane, f, p);
+				if (!q.resolved) continue;
+				if (q.msc0 >= S.msc) {
+					hb_hit_t e = hit_ld(a + q.msc_i0);
+					int64_t movl0 = hb_chain_len(e.self_offset, e.self_offset, xl, e.offset, e.offset, yl);
+					if (q.msc0 > S.msc || movl0 < S.movl) { S.msc = q.msc0; S.msc_i = q.msc_i0; S.movl = movl0; }
+				}
+				if (q.plus0 < S.plus) S.plus = q.plus0;
+				if (S.ei > k) S.si = k; else S.ei = l;
+			}
+			__syncwarp();
+			warp_chain_dp(a, kb, f, p, t, ii, A.P, xl, yl, S, lane);
+			__syncwarp();
+			if (lane == 0) {
+				FcOut fc; fc.n = 0; fc.ovf = 0; fc.buf = A.fc ? A.fc + ab + 2 * cb : 0; fc.cap = d.count + 2 * ns;
+				for (int32_t s = 0; s < ns; s++) A.ch[cb + s].n_hits = 0;
+				hb_chain_finish(a, an, A.chits + ab, ab, f, p, t, ii, A.P, xl, yl, A.ch + cb, ns, fc, S);
+				for (int32_t s = 0; s < ns; s++) A.slot_read[cb + s] = d.read;
+				if (fc.ovf) atomicOr(A.err, 16);
+			}
+		}
+		__syncwarp();
 	}
 }
 

@@ -199,4 +199,4 @@ class Engine:
 
     def counters(self):
         c = (C.c_uint64 * 8)(); _lib().hb_counters(self.h, c, 8)
-        return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots"), [int(x) for x in c[:6]]))
+        return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots", "groups_unordered", "groups_sequential"), [int(x) for x in c[:8]]))
