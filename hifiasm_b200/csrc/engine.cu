@@ -49,23 +49,49 @@ DevPt hb_dev_pt(const hb_ctx *ctx)
 	return p;
 }
 
-// stream-ordered allocations that free themselves (in stream order) on scope exit
+// ---------------------------------------------------------------------------
+// workspace: no allocator calls inside a pass
+// ---------------------------------------------------------------------------
+void hb_ws_reset(hb_ctx *ctx) { ctx->ws_lo = 0; ctx->ws_hi = ctx->ws_cap; }
+void *hb_ws_lo(hb_ctx *ctx, size_t bytes)
+{
+	bytes = (bytes + 255) & ~(size_t)255;
+	if (ctx->ws_lo + bytes > ctx->ws_hi) { size_t need = ctx->ws_lo + bytes + (ctx->ws_cap - ctx->ws_hi); if (need > ctx->ws_need) ctx->ws_need = need; return 0; }
+	void *p = ctx->ws + ctx->ws_lo; ctx->ws_lo += bytes; return p;
+}
+void *hb_ws_hi(hb_ctx *ctx, size_t bytes)
+{
+	bytes = (bytes + 255) & ~(size_t)255;
+	if (ctx->ws_lo + bytes > ctx->ws_hi) { size_t need = ctx->ws_lo + bytes + (ctx->ws_cap - ctx->ws_hi); if (need > ctx->ws_need) ctx->ws_need = need; return 0; }
+	ctx->ws_hi -= bytes; return ctx->ws + ctx->ws_hi;
+}
+int hb_ws_grow(hb_ctx *ctx)
+{ // called with the stack empty: replace the workspace by a larger one
+	size_t want = ctx->ws_cap ? ctx->ws_cap * 2 : ((size_t)256 << 20), fr = 0, tot = 0;
+	if (ctx->ws_need + (ctx->ws_need >> 2) > want) want = ctx->ws_need + (ctx->ws_need >> 2);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->ws) cudaFree(ctx->ws);
+	ctx->ws = 0; ctx->ws_cap = 0;
+	cudaMemGetInfo(&fr, &tot);
+	if (want > fr - (fr >> 4)) want = fr - (fr >> 4);
+	if (want < ctx->ws_need) { hb_set_err(ctx, HB_E_NOMEM, "workspace of %zu bytes does not fit in free HBM (%zu); lower HB_ANCHOR_BUDGET", ctx->ws_need, fr); return HB_E_NOMEM; }
+	if (cudaMalloc((void **)&ctx->ws, want) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "cudaMalloc(%zu) for the workspace failed", want); return HB_E_NOMEM; }
+	ctx->ws_cap = want; ctx->ws_need = 0; hb_ws_reset(ctx);
+	return HB_OK;
+}
+
+// scoped scratch from the low end of the workspace (rewound on scope exit); hi<T>() takes
+// from the high end and lives until the pass ends
 struct Arena {
-	hb_ctx *ctx; std::vector<void *> ptrs; bool failed;
-	Arena(hb_ctx *c) : ctx(c), failed(false) {}
-	template <typename T> T *get(uint64_t n)
-	{
-		void *p = 0;
-		if (cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ctx->stream) != cudaSuccess) { failed = true; cudaGetLastError(); return 0; }
-		ptrs.push_back(p);
-		return (T *)p;
-	}
+	hb_ctx *ctx; size_t mark; bool failed; std::vector<void *> ptrs; // ptrs: kept for source compatibility, unused
+	Arena(hb_ctx *c) : ctx(c), mark(c->ws_lo), failed(false) {}
+	template <typename T> T *get(uint64_t n) { void *p = hb_ws_lo(ctx, (n ? n : 1) * sizeof(T)); if (!p) failed = true; return (T *)p; }
 	template <typename T> T *zero(uint64_t n) { T *p = get<T>(n); if (p) cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream); return p; }
-	void release(void *p) { for (auto &q : ptrs) if (q == p) { cudaFreeAsync(q, ctx->stream); q = 0; } }
-	void *steal(void *p) { for (auto &q : ptrs) if (q == p) q = 0; return p; }
-	~Arena() { for (void *p : ptrs) if (p) cudaFreeAsync(p, ctx->stream); }
+	template <typename T> T *hi(uint64_t n) { void *p = hb_ws_hi(ctx, (n ? n : 1) * sizeof(T)); if (!p) failed = true; return (T *)p; }
+	void release(void *) {}
+	~Arena() { ctx->ws_lo = mark; }
 };
-#define HB_ALLOC_CHECK(ar) do { if ((ar).failed) { hb_set_err(ctx, HB_E_NOMEM, "device allocation failed at %s:%d", __FILE__, __LINE__); return HB_E_NOMEM; } } while (0)
+#define HB_ALLOC_CHECK(ar) do { if ((ar).failed) return HB_E_WS; } while (0)
 
 static inline unsigned nblk(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
@@ -123,6 +149,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
 	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
 	ctx->anchor_budget = 768ull << 20; ctx->last_pass_ms = 0;
+	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
@@ -143,13 +170,13 @@ static void free_prev(hb_ctx *ctx)
 static void free_out(hb_ctx *ctx)
 {
 	cudaFree(ctx->d_out0); cudaFree(ctx->d_out1); cudaFree(ctx->d_out0_off); cudaFree(ctx->d_out1_off);
-	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
+	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 }
 extern "C" void hb_destroy(hb_ctx_t *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
-	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx);
+	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->ws);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -253,17 +280,31 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 		if (h_err) { ar.release(d_cap); ar.release(d_mz); ar.release(d_l); ar.release(d_n); ar.release(d_off); continue; } // a slice overflowed: retry with larger slices
 		int rc = hb_scan_u32_to_u64(ctx, d_n, d_off, nR); if (rc) return rc;
 		uint64_t total = 0; HB_CUDA(cudaMemcpyAsync(&total, d_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-		hb_mz_t *d_dense = ar.get<hb_mz_t>(total + 2); HB_ALLOC_CHECK(ar);
+		hb_mz_t *d_dense = ar.hi<hb_mz_t>(total + 2); uint64_t *d_off_keep = ar.hi<uint64_t>(nR + 2); HB_ALLOC_CHECK(ar);
+		HB_CUDA(cudaMemcpyAsync(d_off_keep, d_off, (nR + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 		{
 			ProfScope ps(ctx, "k_compact_mz");
 			k_compact_mz<<<nblk(nR * 32, 256), 256, 0, ctx->stream>>>(nR, d_cap, d_off, d_mz, d_dense);
 		}
 		HB_CUDA(cudaGetLastError());
-		out->mz = (hb_mz_t *)ar.steal(d_dense); out->off = (uint64_t *)ar.steal(d_off); out->total = total;
+		out->mz = d_dense; out->off = d_off_keep; out->total = total;
 		return HB_OK;
 	}
 	hb_set_err(ctx, HB_E_OVERFLOW, "minimizer slices overflowed even at one slot per base");
 	return HB_E_OVERFLOW;
+}
+
+int hb_run_sketch_retry(hb_ctx *ctx, uint64_t r0, uint64_t r1, DevSketch *out)
+{ // for callers outside a pass: leaves the outputs on the hi side of a freshly reset workspace
+	int rc = HB_OK;
+	for (int attempt = 0; attempt < 12; attempt++) {
+		if (!ctx->ws && (rc = hb_ws_grow(ctx))) return rc;
+		hb_ws_reset(ctx);
+		rc = hb_run_sketch(ctx, r0, r1, 0, out);
+		if (rc != HB_E_WS) return rc;
+		if ((rc = hb_ws_grow(ctx))) return rc;
+	}
+	hb_set_err(ctx, HB_E_NOMEM, "workspace kept overflowing"); return HB_E_NOMEM;
 }
 
 // ---------------------------------------------------------------------------
@@ -361,14 +402,29 @@ static int run_pass(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, 
 { // brackets the pass with events on the context stream
 	cudaSetDevice(ctx->device);
 	cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream);
-	int rc = run_pass_impl(ctx, r0, r1, mode, bw, so, stat_out);
+	int rc = HB_OK;
+	for (int attempt = 0; attempt < 12; attempt++) { // a workspace that turns out too small is grown and the pass rerun (first pass only in steady state)
+		if (!ctx->ws && (rc = hb_ws_grow(ctx))) break;
+		hb_ws_reset(ctx);
+		rc = run_pass_impl(ctx, r0, r1, mode, bw, so, stat_out);
+		hb_ws_reset(ctx);
+		if (rc != HB_E_WS) break;
+		if ((rc = hb_ws_grow(ctx))) break;
+		cudaEventRecord(a, ctx->stream); // time the attempt that succeeds
+		rc = HB_E_WS;
+	}
+	if (rc == HB_E_WS) { hb_set_err(ctx, HB_E_NOMEM, "workspace kept overflowing"); rc = HB_E_NOMEM; }
 	float ms = 0; cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
 	cudaEventDestroy(a); cudaEventDestroy(b);
 	ctx->last_pass_ms = ms;
 	return rc;
 }
+#include <chrono>
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TRACE(label) do { if (trace) { cudaStreamSynchronize(ctx->stream); double t_ = now_ms(); fprintf(stderr, "[hb trace] %-18s +%8.2f ms (total %8.2f)\n", label, t_ - t_last, t_ - t_begin); t_last = now_ms(); } } while (0)
 static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, StageOut *so, uint64_t *stat_out)
 {
+	const bool trace = getenv("HB_TRACE") != 0; double t_begin = now_ms(), t_last = t_begin;
 	cudaSetDevice(ctx->device);
 	if (r1 > ctx->n_reads || r0 > r1) { hb_set_err(ctx, HB_E_ARG, "read range out of bounds"); return HB_E_ARG; }
 	if (!ctx->d_pt_slot) { hb_set_err(ctx, HB_E_STATE, "no position index: call hb_pt_gen first"); return HB_E_STATE; }
@@ -383,7 +439,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 
 	// ---- sketch + probe for the whole range
 	DevSketch sk; rc = hb_run_sketch(ctx, r0, r1, 0, &sk); if (rc) return rc;
-	ar.ptrs.push_back(sk.mz); ar.ptrs.push_back(sk.off);
+	TRACE("sketch");
 	uint64_t *d_seeds = ar.get<uint64_t>(sk.total + 1); uint32_t *d_spre = ar.get<uint32_t>(sk.total + 1), *d_acnt = ar.zero<uint32_t>(nR + 1), *d_wtab = ar.get<uint32_t>(4096);
 	uint64_t *d_aoff = ar.get<uint64_t>(nR + 2);
 	HB_ALLOC_CHECK(ar);
@@ -398,6 +454,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	HB_CUDA(cudaMemcpyAsync(h_aoff.data(), d_aoff, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	HB_CUDA(cudaMemcpyAsync(h_mzoff.data(), sk.off, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	TRACE("probe+scan");
 	ctx->counters[0] = nR; ctx->counters[2] = sk.total; ctx->counters[3] = h_aoff[nR];
 	for (uint64_t i = r0; i < r1; i++) ctx->counters[1] += ctx->h_rlen[i];
 
@@ -431,6 +488,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			k_expand<<<grid ? grid : 1, 256, 0, ctx->stream>>>(R, PT, r0, n_mz, sk.mz + mz_b, d_seeds + mz_b, d_spre + mz_b, d_aoff, a_base, d_wtab, d_raw);
 		}
 		HB_CUDA(cudaGetLastError());
+	TRACE("expand");
 		// group: retried with a larger directory / arena when the first guess was too small
 		GroupDir *d_dir = 0; uint32_t h_dirn = 0; uint64_t dir_cap = B / 8 + 64 * nb + 1024, arena_words = 16ull << 20;
 		for (int attempt = 0;; attempt++) {
@@ -454,6 +512,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			if (h_err & 8) dir_cap = B + 1;
 			if (h_err & 4) arena_words *= 8;
 		}
+	TRACE("group");
 		ba.release(d_raw);
 		ctx->counters[4] += h_dirn;
 		rc = hb_scan_u32_to_u64(ctx, d_sc, d_coff, nb); if (rc) return rc;
@@ -472,6 +531,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			else k_chain_warp<<<std::max(1u, std::min(nblk((uint64_t)h_dirn * 32, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
 		}
 		HB_CUDA(cudaGetLastError());
+	TRACE("chain");
 		if (mode == 2) { b0 = b1; continue; }
 		ba.release(d_f); ba.release(d_p); ba.release(d_ii); ba.release(d_t);
 
@@ -489,6 +549,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			k_post<<<nblk(nb, 64), 64, 0, ctx->stream>>>(Pa);
 		}
 		HB_CUDA(cudaGetLastError());
+	TRACE("post");
 		ctx->counters[5] += n_slots;
 
 		if (mode == 3) { // assemble the stage-3 view of this batch and copy it out
@@ -523,6 +584,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			if (n_slots) k_exact<<<nblk(n_slots * 32, 256), 256, 0, ctx->stream>>>(E);
 		}
 		HB_CUDA(cudaGetLastError());
+	TRACE("exact");
 		const uint64_t g0 = r0 + b0, p0b = ctx->h_prev0_off[g0], p0e = ctx->h_prev0_off[g0 + nb], p1b = ctx->h_prev1_off[g0], p1e = ctx->h_prev1_off[g0 + nb];
 		hb_ma_hit_t *d_in0 = ba.get<hb_ma_hit_t>(p0e - p0b + 1); uint64_t *d_i0off = ba.get<uint64_t>(nb + 2), *d_i1off = ba.get<uint64_t>(nb + 2), *d_ooff = ba.get<uint64_t>(nb + 2);
 		uint32_t *d_cap = ba.get<uint32_t>(nb + 1);
@@ -534,7 +596,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		rc = hb_scan_u32_to_u64(ctx, d_cap, d_ooff, nb); if (rc) return rc;
 		const uint64_t o_tot = n_slots + (p0e - p0b);
 		FinOv *d_ov = ba.get<FinOv>(o_tot + 1); uint64_t *d_srt = ba.get<uint64_t>((p0e - p0b) + (p1e - p1b) + 1);
-		hb_ma_hit_t *d_o0 = ba.get<hb_ma_hit_t>(o_tot + 1), *d_o1 = ba.get<hb_ma_hit_t>(o_tot + 1);
+		hb_ma_hit_t *d_o0 = ba.hi<hb_ma_hit_t>(o_tot + 1), *d_o1 = ba.hi<hb_ma_hit_t>(o_tot + 1); uint64_t *d_ooff_keep = ba.hi<uint64_t>(nb + 2);
 		HB_ALLOC_CHECK(ba);
 		{
 			MergeArgs M; M.R = R; M.r0 = g0; M.nR = nb; M.c_off = d_coff; M.ch = d_ch; M.idx = d_idx; M.n_ol = d_nol; M.exact = d_exact;
@@ -544,11 +606,14 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			k_merge<<<nblk(nb, 64), 64, 0, ctx->stream>>>(M);
 		}
 		HB_CUDA(cudaGetLastError());
-		BatchRes br; br.o0 = (hb_ma_hit_t *)ba.steal(d_o0); br.o1 = (hb_ma_hit_t *)ba.steal(d_o1); br.ooff = (uint64_t *)ba.steal(d_ooff); br.b0 = b0; br.b1 = b1;
+	TRACE("merge");
+		HB_CUDA(cudaMemcpyAsync(d_ooff_keep, d_ooff, (nb + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+		BatchRes br; br.o0 = d_o0; br.o1 = d_o1; br.ooff = d_ooff_keep; br.b0 = b0; br.b1 = b1;
 		bres.push_back(br);
 		b0 = b1;
 	}
 
+	TRACE("batches done");
 	if (mode == 2) {
 		if (so->off) for (uint64_t i = 0; i <= nR; i++) so->off[i] = h_aoff[i];
 		if (so->rec) {
@@ -566,21 +631,24 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	}
 
 	// ---- final pass: dense result arrays, kept resident in the context
-	free_out(ctx);
-	HB_CUDA(cudaMalloc((void **)&ctx->d_out0_off, (nR + 2) * 8)); HB_CUDA(cudaMalloc((void **)&ctx->d_out1_off, (nR + 2) * 8));
+	if (ctx->outoff_cap < nR + 2) {
+		cudaFree(ctx->d_out0_off); cudaFree(ctx->d_out1_off); ctx->d_out0_off = ctx->d_out1_off = 0; ctx->outoff_cap = 0;
+		HB_CUDA(cudaMalloc((void **)&ctx->d_out0_off, (nR + 2) * 8)); HB_CUDA(cudaMalloc((void **)&ctx->d_out1_off, (nR + 2) * 8)); ctx->outoff_cap = nR + 2;
+	}
 	if ((rc = hb_scan_u32_to_u64(ctx, d_m0, ctx->d_out0_off, nR)) || (rc = hb_scan_u32_to_u64(ctx, d_m1, ctx->d_out1_off, nR))) return rc;
 	HB_CUDA(cudaMemcpyAsync(&ctx->n_out0, ctx->d_out0_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	HB_CUDA(cudaMemcpyAsync(&ctx->n_out1, ctx->d_out1_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	HB_CUDA(cudaStreamSynchronize(ctx->stream));
-	HB_CUDA(cudaMalloc((void **)&ctx->d_out0, (ctx->n_out0 + 1) * sizeof(hb_ma_hit_t))); HB_CUDA(cudaMalloc((void **)&ctx->d_out1, (ctx->n_out1 + 1) * sizeof(hb_ma_hit_t)));
+	if (ctx->out0_cap < ctx->n_out0 + 1) { cudaFree(ctx->d_out0); ctx->d_out0 = 0; ctx->out0_cap = 0; HB_CUDA(cudaMalloc((void **)&ctx->d_out0, (ctx->n_out0 + 1 + (ctx->n_out0 >> 3)) * sizeof(hb_ma_hit_t))); ctx->out0_cap = ctx->n_out0 + 1 + (ctx->n_out0 >> 3); }
+	if (ctx->out1_cap < ctx->n_out1 + 1) { cudaFree(ctx->d_out1); ctx->d_out1 = 0; ctx->out1_cap = 0; HB_CUDA(cudaMalloc((void **)&ctx->d_out1, (ctx->n_out1 + 1 + (ctx->n_out1 >> 3)) * sizeof(hb_ma_hit_t))); ctx->out1_cap = ctx->n_out1 + 1 + (ctx->n_out1 >> 3); }
 	for (auto &br : bres) {
 		uint64_t nb = br.b1 - br.b0;
 		ProfScope ps(ctx, "k_gather_ma");
 		k_gather_ma<<<nblk(nb * 32, 256), 256, 0, ctx->stream>>>(nb, br.ooff, ctx->d_out0_off + br.b0, br.o0, ctx->d_out0);
 		k_gather_ma<<<nblk(nb * 32, 256), 256, 0, ctx->stream>>>(nb, br.ooff, ctx->d_out1_off + br.b0, br.o1, ctx->d_out1);
-		cudaFreeAsync(br.o0, ctx->stream); cudaFreeAsync(br.o1, ctx->stream); cudaFreeAsync(br.ooff, ctx->stream);
 	}
 	HB_CUDA(cudaGetLastError());
+	TRACE("gather");
 	ctx->out_reads = nR;
 	unsigned long long h_stat[16] = { 0 };
 	HB_CUDA(cudaMemcpyAsync(h_stat, d_stat, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -605,13 +673,13 @@ extern "C" int hb_sketch(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *off,
 	uint64_t nR = r1 - r0; DevSketch sk; Arena ar(ctx);
 	if (nR == 0) { off[0] = 0; return HB_OK; }
 	int rc = hb_run_sketch(ctx, r0, r1, 0, &sk); if (rc) return rc;
-	ar.ptrs.push_back(sk.mz); ar.ptrs.push_back(sk.off);
 	HB_CUDA(cudaMemcpyAsync(off, sk.off, (nR + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	if (rec) {
 		if (sk.total > rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "minimizer output capacity"); return HB_E_OVERFLOW; }
 		HB_CUDA(cudaMemcpyAsync(rec, sk.mz, sk.total * sizeof(hb_mz_t), cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	hb_ws_reset(ctx);
 	return HB_OK;
 }
 extern "C" int hb_anchors(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *off, hb_hit_t *rec, uint64_t rec_cap)
@@ -678,8 +746,11 @@ extern "C" int hb_ed_semi_64(hb_ctx_t *ctx, uint64_t n, const char *pat, const u
                              const int32_t *thre, const int32_t *abs_diag, int32_t *err, int32_t *pe)
 {
 	cudaSetDevice(ctx->device);
-	Arena ar(ctx);
 	if (n == 0) return HB_OK;
+	size_t need = pat_off[n] + txt_off[n] + n * 48 + (1 << 20);
+	if (ctx->ws_cap < need) { ctx->ws_need = need; int rc = hb_ws_grow(ctx); if (rc) return rc; }
+	hb_ws_reset(ctx);
+	Arena ar(ctx);
 	for (uint64_t i = 0; i < n; i++) if (thre[i] < 0 || thre[i] > 31 || abs_diag[i] < 0 || abs_diag[i] > 2 * thre[i]) { hb_set_err(ctx, HB_E_ARG, "case %llu: thre must be in [0,31], abs_diag in [0,2*thre]", (unsigned long long)i); return HB_E_ARG; }
 	char *d_p = ar.get<char>(pat_off[n] + 1), *d_t = ar.get<char>(txt_off[n] + 1); uint64_t *d_po = ar.get<uint64_t>(n + 1), *d_to = ar.get<uint64_t>(n + 1);
 	int32_t *d_th = ar.get<int32_t>(n), *d_ab = ar.get<int32_t>(n), *d_e = ar.get<int32_t>(n), *d_pe = ar.get<int32_t>(n);

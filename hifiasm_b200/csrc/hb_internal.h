@@ -32,7 +32,17 @@ struct hb_ctx {
 	std::vector<ProfEntry> prof; uint64_t counters[8];
 	uint64_t anchor_budget; // anchors per batch
 	double last_pass_ms;
+	// workspace: one device allocation used as a double-ended stack (lo: scoped scratch,
+	// hi: buffers that live until the end of the pass); grown between passes only
+	uint8_t *ws; size_t ws_cap, ws_lo, ws_hi, ws_need;
+	// capacity of the resident result arrays
+	uint64_t out0_cap, out1_cap, outoff_cap;
 };
+#define HB_E_WS (-100) /* internal: workspace too small, the caller grows it and reruns */
+int hb_ws_grow(hb_ctx *ctx);
+void hb_ws_reset(hb_ctx *ctx);
+void *hb_ws_lo(hb_ctx *ctx, size_t bytes);
+void *hb_ws_hi(hb_ctx *ctx, size_t bytes);
 
 void hb_set_err(hb_ctx *ctx, int code, const char *fmt, ...);
 DevReads hb_dev_reads(const hb_ctx *ctx);
@@ -53,3 +63,4 @@ int hb_scan_u32_to_u64(hb_ctx *ctx, const uint32_t *d_in, uint64_t *d_out, uint6
 // batch sketch of reads [r0,r1): dense minimizer arrays + per-read offsets (device, cudaMallocAsync'd; caller frees)
 struct DevSketch { hb_mz_t *mz; uint64_t *off; uint64_t total; };
 int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch *out);
+int hb_run_sketch_retry(hb_ctx *ctx, uint64_t r0, uint64_t r1, DevSketch *out); // outputs live on the workspace's hi side until hb_ws_reset

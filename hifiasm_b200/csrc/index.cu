@@ -257,7 +257,7 @@ extern "C" int hb_pt_gen(hb_ctx_t *ctx, int *hom_cov, int *het_cov)
 	cudaSetDevice(ctx->device);
 	if (!ctx->n_reads) { hb_set_err(ctx, HB_E_STATE, "no reads resident"); return HB_E_STATE; }
 	hb_pt_destroy(ctx);
-	TmpBufs tb(ctx); DevSketch sk; int rc = hb_run_sketch(ctx, 0, ctx->n_reads, 1, &sk); if (rc) return rc;
+	TmpBufs tb(ctx); DevSketch sk; int rc = hb_run_sketch_retry(ctx, 0, ctx->n_reads, &sk); if (rc) return rc;
 	HB_CUDA(cudaStreamSynchronize(ctx->stream));
 	const uint64_t n = sk.total;
 	// split {x,info} into key / value arrays and sort by key (stable LSD radix)
@@ -266,7 +266,7 @@ extern "C" int hb_pt_gen(hb_ctx_t *ctx, int *hom_cov, int *het_cov)
 	HB_CUDA(cudaMemcpy2DAsync(d_k0, 8, &sk.mz[0].x, 16, 8, n, cudaMemcpyDeviceToDevice, ctx->stream));
 	HB_CUDA(cudaMemcpy2DAsync(d_v0, 8, &sk.mz[0].info, 16, 8, n, cudaMemcpyDeviceToDevice, ctx->stream));
 	HB_CUDA(cudaStreamSynchronize(ctx->stream));
-	cudaFreeAsync(sk.mz, ctx->stream); cudaFreeAsync(sk.off, ctx->stream);
+	hb_ws_reset(ctx);
 	size_t tmpb = 0; cub::DoubleBuffer<uint64_t> dk(d_k0, d_k1), dv(d_v0, d_v1);
 	HB_CUDA(cub::DeviceRadixSort::SortPairs(0, tmpb, dk, dv, (int64_t)n, 0, 64, ctx->stream));
 	void *tmp = tb.get<uint8_t>(tmpb); NEED(tmp);
