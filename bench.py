@@ -192,7 +192,7 @@ def main():
     import torch
     import torch.distributed as dist
     import hifiasm_b200
-    from hifiasm_b200 import binio
+    from hifiasm_b200 import binio, dist as hdist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -201,8 +201,7 @@ def main():
     t0 = time.time()
     flat, boff, lens = make_dataset(GENOME_MB * world, COV)
     n = int(lens.size)
-    per = (n + world - 1) // world
-    r0, r1 = min(n, rank * per), min(n, (rank + 1) * per)
+    r0, r1 = hdist.shard_range(n, rank, world)
     my_bases = int(lens[r0:r1].sum())
     eng = hifiasm_b200.Engine(local)
     eng.upload_reads(lens, flat, boff)
@@ -240,12 +239,7 @@ def main():
     barrier()
     clocks = cs.summary()
     counters = eng.counters()
-    t = torch.tensor([dev_ms, float(my_bases) * args.steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX); ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        dev_ms, tot_bases = float(tm[0]), float(ts[1])
-    else:
-        tot_bases = float(t[1])
+    dev_ms, tot_bases = hdist.reduce_time_and_units(dev_ms, float(my_bases) * args.steps, device="cuda")
     value = tot_bases / (dev_ms / 1e3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI (H2D reads + prev lists, D2H results) every step
@@ -258,12 +252,10 @@ def main():
             o0, q0, o1, q1, _ = eng.cal_ov_r(e0, zoff, e0, zoff, r0, r1, cap=max(1024, 2 * (n_src + n_rev)))
         torch.cuda.synchronize()
         wall = time.time() - w0
-        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall, _ = hdist.reduce_time_and_units(wall, 0.0, device="cuda")
         h2d = int(flat.nbytes + boff.nbytes + lens.size * 4 + 2 * zoff.nbytes)
         d2h = int((o0.size + o1.size) * binio.MA_MEM.itemsize + 2 * (r1 - r0 + 1) * 8)
-        e2e = {"value": tot_bases / float(tw[0]) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        e2e = {"value": tot_bases / wall / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
     if rank != 0:
         if world > 1:

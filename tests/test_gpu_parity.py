@@ -139,6 +139,26 @@ def test_small_batches_same_result(ctx, monkeypatch):
     eng.close()
 
 
+def test_sharded_query_ranges_equal_full_pass(ctx):
+    """the multi-GPU decomposition: disjoint query ranges against the replicated
+    index give exactly the per-read results of the full pass"""
+    from hifiasm_b200 import dist as hdist
+    g, eng, hom = ctx
+    eng.upload_store(g.pre)
+    h, t = eng.pt_gen(); eng.set_opt(hom_cov=h, het_cov=t)
+    p0, o0, _, _ = g.pre_src; p1, o1, _, _ = g.pre_rev
+    m0, m1 = binio.disk_to_mem(p0), binio.disk_to_mem(p1)
+    full0, fo0, full1, fo1, _ = eng.cal_ov_r(m0, o0, m1, o1)
+    n = g.pre.n; parts0, parts1 = [], []
+    for rank in range(3):
+        a, b = hdist.shard_range(n, rank, 3)
+        x0, y0, x1, y1, _ = eng.cal_ov_r(m0, o0, m1, o1, a, b)
+        parts0.append((x0, y0)); parts1.append((x1, y1))
+    r0, q0 = hdist.merge_shards(parts0); r1, q1 = hdist.merge_shards(parts1)
+    assert (q0 == fo0).all() and (q1 == fo1).all()
+    assert r0.tobytes() == full0.tobytes() and r1.tobytes() == full1.tobytes()
+
+
 def test_myers_window_vs_reference(hb):
     z = np.load(os.path.join(GOLDEN, "ed_semi.npz"))
     hdr, pat, txt, res = z["hdr"], z["pat"], z["txt"], z["res"]
