@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <algorithm>
+#include <thread>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include "hb_internal.h"
@@ -149,7 +150,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
 	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
 	ctx->anchor_budget = 768ull << 20; ctx->last_pass_ms = 0;
-	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
+	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
@@ -160,7 +161,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 static void free_reads(hb_ctx *ctx)
 {
 	cudaFree(ctx->d_packed); cudaFree(ctx->d_roff); cudaFree(ctx->d_rlen); cudaFree(ctx->d_noff); cudaFree(ctx->d_npos);
-	ctx->d_packed = 0; ctx->d_roff = 0; ctx->d_rlen = 0; ctx->d_noff = 0; ctx->d_npos = 0; ctx->n_reads = 0;
+	ctx->d_packed = 0; ctx->d_roff = 0; ctx->d_rlen = 0; ctx->d_noff = 0; ctx->d_npos = 0; ctx->n_reads = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0;
 }
 static void free_prev(hb_ctx *ctx)
 {
@@ -176,7 +177,7 @@ extern "C" void hb_destroy(hb_ctx_t *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
-	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->ws);
+	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->ws); if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -187,11 +188,13 @@ extern "C" int hb_get_opt(const hb_ctx_t *ctx, hb_opt_t *opt) { *opt = ctx->opt;
 // ---------------------------------------------------------------------------
 // read store
 // ---------------------------------------------------------------------------
+// Mirrors the reads into HBM.  The host side only re-lays the packed bytes out on
+// 8-byte boundaries into a cached pinned staging buffer (several threads: this is a
+// memory copy, not compute) and issues one H2D copy per array.
 static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uint8_t *flat, const uint64_t *boff, uint8_t *const *ptrs,
                          const uint64_t *n_pos, const uint64_t *n_off, uint64_t *const *N_site)
 {
 	cudaSetDevice(ctx->device);
-	free_reads(ctx);
 	if (n >= (1ull << 28)) { hb_set_err(ctx, HB_E_ARG, "no more than 2^28 reads (htab.cpp:765)"); return HB_E_ARG; }
 	std::vector<uint64_t> off(n + 1), noff(n + 1); std::vector<uint32_t> npos;
 	ctx->h_rlen.resize(n); ctx->total_bases = 0;
@@ -202,16 +205,31 @@ static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uin
 		o += ((len[i] / 4 + 1) + 7) & ~7ull; // 8-byte aligned reads
 	}
 	off[n] = o;
-	uint8_t *h_packed = 0;
-	if (cudaMallocHost((void **)&h_packed, o + 16) != cudaSuccess) { hb_set_err(ctx, HB_E_NOMEM, "pinned staging buffer"); return HB_E_NOMEM; }
-	memset(h_packed, 0, o + 16);
-	for (uint64_t i = 0; i < n; i++) {
-		const uint8_t *src = ptrs ? ptrs[i] : flat + boff[i];
-		uint64_t nb = len[i] / 4 + 1;
-		memcpy(h_packed + off[i], src, nb);
-		// mask the undefined pad bits so equal sequences have equal bytes
-		if (len[i] % 4 == 0) h_packed[off[i] + nb - 1] = 0;
-		else h_packed[off[i] + nb - 1] &= (uint8_t)(0xFF << (2 * (4 - len[i] % 4)));
+	if (ctx->h_stage_cap < o + 16) {
+		if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+		ctx->h_stage = 0; ctx->h_stage_cap = 0;
+		if (cudaMallocHost((void **)&ctx->h_stage, o + 16 + (o >> 4)) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "pinned staging buffer"); return HB_E_NOMEM; }
+		ctx->h_stage_cap = o + 16 + (o >> 4);
+	}
+	uint8_t *h_packed = ctx->h_stage;
+	{
+		unsigned nt = std::thread::hardware_concurrency(); if (nt > 16) nt = 16; if (nt < 1) nt = 1; if (n < 4096) nt = 1;
+		auto work = [&](uint64_t a, uint64_t b) {
+			for (uint64_t i = a; i < b; i++) {
+				const uint8_t *src = ptrs ? ptrs[i] : flat + boff[i];
+				uint64_t nb = len[i] / 4 + 1, slot = off[i + 1] - off[i];
+				memcpy(h_packed + off[i], src, nb);
+				// mask the undefined pad bits so equal sequences have equal bytes
+				if (len[i] % 4 == 0) h_packed[off[i] + nb - 1] = 0;
+				else h_packed[off[i] + nb - 1] &= (uint8_t)(0xFF << (2 * (4 - len[i] % 4)));
+				memset(h_packed + off[i] + nb, 0, slot - nb);
+			}
+		};
+		std::vector<std::thread> th; uint64_t per = (n + nt - 1) / nt;
+		for (unsigned t = 1; t < nt; t++) th.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+		work(0, std::min(n, per));
+		for (auto &t : th) t.join();
+		memset(h_packed + o, 0, 16);
 	}
 	noff[0] = 0;
 	for (uint64_t i = 0; i < n; i++) {
@@ -224,20 +242,22 @@ static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uin
 			noff[i + 1] = n_off[i + 1];
 		} else noff[i + 1] = 0;
 	}
-	ctx->n_reads = n; ctx->packed_bytes = o; ctx->n_npos = npos.size();
 	int rc = HB_OK;
-	if (cudaMalloc((void **)&ctx->d_packed, o + 16) != cudaSuccess || cudaMalloc((void **)&ctx->d_roff, (n + 1) * 8) != cudaSuccess ||
-	    cudaMalloc((void **)&ctx->d_rlen, (n + 1) * 4) != cudaSuccess || cudaMalloc((void **)&ctx->d_noff, (n + 1) * 8) != cudaSuccess ||
-	    cudaMalloc((void **)&ctx->d_npos, (npos.size() + 1) * 4) != cudaSuccess) { hb_set_err(ctx, HB_E_NOMEM, "read store does not fit in HBM"); rc = HB_E_NOMEM; }
-	if (!rc) {
-		cudaMemcpyAsync(ctx->d_packed, h_packed, o + 16, cudaMemcpyHostToDevice, ctx->stream);
-		cudaMemcpyAsync(ctx->d_roff, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-		cudaMemcpyAsync(ctx->d_rlen, ctx->h_rlen.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream);
-		cudaMemcpyAsync(ctx->d_noff, noff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-		if (npos.size()) cudaMemcpyAsync(ctx->d_npos, npos.data(), npos.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-		if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { hb_set_err(ctx, HB_E_CUDA, "read upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = HB_E_CUDA; }
+	if (ctx->packed_cap < o + 16 || ctx->reads_cap < n + 1 || ctx->npos_cap < npos.size() + 1) {
+		free_reads(ctx);
+		uint64_t pc = o + 16 + (o >> 4), rc_ = n + 1 + (n >> 4), nc = npos.size() + 1 + (npos.size() >> 2);
+		if (cudaMalloc((void **)&ctx->d_packed, pc) != cudaSuccess || cudaMalloc((void **)&ctx->d_roff, (rc_ + 1) * 8) != cudaSuccess ||
+		    cudaMalloc((void **)&ctx->d_rlen, (rc_ + 1) * 4) != cudaSuccess || cudaMalloc((void **)&ctx->d_noff, (rc_ + 1) * 8) != cudaSuccess ||
+		    cudaMalloc((void **)&ctx->d_npos, nc * 4) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "read store does not fit in HBM"); free_reads(ctx); return HB_E_NOMEM; }
+		ctx->packed_cap = pc; ctx->reads_cap = rc_; ctx->npos_cap = nc;
 	}
-	cudaFreeHost(h_packed);
+	ctx->n_reads = n; ctx->packed_bytes = o; ctx->n_npos = npos.size();
+	cudaMemcpyAsync(ctx->d_packed, h_packed, o + 16, cudaMemcpyHostToDevice, ctx->stream);
+	cudaMemcpyAsync(ctx->d_roff, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+	cudaMemcpyAsync(ctx->d_rlen, ctx->h_rlen.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream);
+	cudaMemcpyAsync(ctx->d_noff, noff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+	if (npos.size()) cudaMemcpyAsync(ctx->d_npos, npos.data(), npos.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+	if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { hb_set_err(ctx, HB_E_CUDA, "read upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = HB_E_CUDA; }
 	if (rc) free_reads(ctx);
 	return rc;
 }
@@ -484,8 +504,18 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_ALLOC_CHECK(ba);
 		if (B) {
 			ProfScope ps(ctx, "k_expand");
-			unsigned grid = (unsigned)std::min<uint64_t>((n_mz * 16 + 255) / 256, (uint64_t)ctx->sm_count * 32);
-			k_expand<<<grid ? grid : 1, 256, 0, ctx->stream>>>(R, PT, r0, n_mz, sk.mz + mz_b, d_seeds + mz_b, d_spre + mz_b, d_aoff, a_base, d_wtab, d_raw);
+			static int var = getenv("HB_EXP_VAR") ? atoi(getenv("HB_EXP_VAR")) : 0;
+			const int U = var == 1 ? 8 : (var == 3 || var == 4) ? 4 : var == 6 ? 3 : 2;
+			unsigned grid = (unsigned)std::min<uint64_t>((n_mz * 16 / U + 255) / 256, (uint64_t)ctx->sm_count * 32);
+			if (!grid) grid = 1;
+#define EXP_ARGS R, PT, r0, n_mz, sk.mz + mz_b, d_seeds + mz_b, d_spre + mz_b, d_aoff, a_base, d_wtab, d_raw
+			if (var == 1) k_expand<8, 2><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
+			else if (var == 2) k_expand<2, 6><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
+			else if (var == 3) k_expand<4, 4><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
+			else if (var == 4) k_expand<4, 3><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
+			else if (var == 5) k_expand<2, 8><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
+			else if (var == 6) k_expand<3, 5><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
+			else k_expand<2, 6><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("expand");

@@ -37,6 +37,8 @@ struct hb_ctx {
 	uint8_t *ws; size_t ws_cap, ws_lo, ws_hi, ws_need;
 	// capacity of the resident result arrays
 	uint64_t out0_cap, out1_cap, outoff_cap;
+	// cached pinned staging buffer and capacities of the read-store arrays
+	uint8_t *h_stage; uint64_t h_stage_cap, packed_cap, reads_cap, npos_cap;
 };
 #define HB_E_WS (-100) /* internal: workspace too small, the caller grows it and reruns */
 int hb_ws_grow(hb_ctx *ctx);

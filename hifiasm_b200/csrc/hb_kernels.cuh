@@ -80,32 +80,65 @@ __global__ void k_probe_count(DevPt pt, uint64_t nR, const uint64_t *__restrict_
 // Algorithmic bytes: 16 (minimizer) + 8 (seed) + 4 (prefix) per minimizer,
 // 8 in + 16 out per hit.
 // ----------------------------------------------------------------------------
-__global__ void k_expand(DevReads R, DevPt pt, uint64_t r0, uint64_t n_mz, const hb_mz_t *__restrict__ mz, const uint64_t *__restrict__ seeds,
+template <int EXP_U, int MINB> // EXP_U query minimizers in flight per half-warp
+__global__ void __launch_bounds__(256, MINB) k_expand(DevReads R, DevPt pt, uint64_t r0, uint64_t n_mz, const hb_mz_t *__restrict__ mz, const uint64_t *__restrict__ seeds,
                          const uint32_t *__restrict__ spre, const uint64_t *__restrict__ a_off, uint64_t a_base, const uint32_t *__restrict__ w_tab, hb_hit_t *__restrict__ raw)
 { // mz/seeds/spre: the batch's minimizers; a_off: anchor offsets indexed by (read - r0); a_base = a_off of the batch's first read
-	uint64_t hw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, n_hw = ((uint64_t)gridDim.x * blockDim.x) >> 4;
-	int l16 = threadIdx.x & 15;
-	for (uint64_t s = hw; s < n_mz; s += n_hw) {
-		uint64_t sd = __ldg(&seeds[s]); uint32_t n = (uint32_t)(sd & 0xfff);
-		if (n == 0) continue;
-		uint64_t off = sd >> 12, zi = __ldg(&mz[s].info);
-		uint32_t zrev = HB_MZ_REV(zi), zpos = HB_MZ_POS(zi), zspan = HB_MZ_SPAN(zi), rid = HB_MZ_RID(zi);
-		uint32_t cnt = __ldg(&w_tab[n]) << 8 | (zspan <= 255 ? zspan : 255);
-		hb_hit_t *dst = raw + (a_off[rid - r0] - a_base) + spre[s];
-		uint64_t a0 = off & ~1ULL; uint32_t head = (uint32_t)(off - a0), span = head + n;
-		for (uint32_t e = 2 * l16; e < span; e += 32) {
-			ulonglong2 v = __ldg((const ulonglong2 *)(pt.pos + a0 + e));
+	const uint64_t hw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, n_hw = ((uint64_t)gridDim.x * blockDim.x) >> 4;
+	const int l16 = threadIdx.x & 15;
+	for (uint64_t s0 = hw * EXP_U; s0 < n_mz; s0 += n_hw * EXP_U) {
+		uint64_t sd[EXP_U], zi[EXP_U]; uint32_t sp[EXP_U];
+		// stage 1: all independent loads of EXP_U minimizers are issued before any is used
+#pragma unroll
+		for (int u = 0; u < EXP_U; u++) {
+			const uint64_t s = s0 + u; const bool in = s < n_mz;
+			sd[u] = in ? __ldg(&seeds[s]) : 0; zi[u] = in ? __ldg(&mz[s].info) : 0; sp[u] = in ? __ldg(&spre[s]) : 0;
+		}
+		uint64_t ao[EXP_U]; ulonglong2 v[EXP_U];
+#pragma unroll
+		for (int u = 0; u < EXP_U; u++) {
+			const uint32_t n = (uint32_t)(sd[u] & 0xfff); const uint64_t off = sd[u] >> 12, a0 = off & ~1ULL;
+			ao[u] = n ? __ldg(&a_off[HB_MZ_RID(zi[u]) - r0]) : 0;
+			v[u].x = v[u].y = 0;
+			if (n && (uint32_t)(2 * l16) < (uint32_t)(off - a0) + n) v[u] = __ldg((const ulonglong2 *)(pt.pos + a0 + 2 * l16));
+		}
+		// stage 2: first 32 list slots of each minimizer (covers the typical list), target-length gathers batched
+		uint32_t tl[EXP_U][2];
+#pragma unroll
+		for (int u = 0; u < EXP_U; u++) {
+			const uint32_t n = (uint32_t)(sd[u] & 0xfff), head = (uint32_t)((sd[u] >> 12) & 1);
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
-				int32_t j = (int32_t)(e + h) - (int32_t)head;
+				const int32_t j = (int32_t)(2 * l16 + h) - (int32_t)head;
+				tl[u][h] = (j >= 0 && j < (int32_t)n) ? __ldg(&R.len[HB_MZ_RID(h ? v[u].y : v[u].x)]) : 0;
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < EXP_U; u++) {
+			const uint32_t n = (uint32_t)(sd[u] & 0xfff);
+			if (n == 0) continue;
+			const uint64_t off = sd[u] >> 12, a0 = off & ~1ULL; const uint32_t head = (uint32_t)(off - a0), span = head + n;
+			const uint32_t zrev = HB_MZ_REV(zi[u]), zpos = HB_MZ_POS(zi[u]), zspan = HB_MZ_SPAN(zi[u]);
+			const uint32_t cnt = __ldg(&w_tab[n]) << 8 | (zspan <= 255 ? zspan : 255);
+			hb_hit_t *dst = raw + (ao[u] - a_base) + sp[u];
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const int32_t j = (int32_t)(2 * l16 + h) - (int32_t)head;
 				if (j < 0 || j >= (int32_t)n) continue;
-				uint64_t y = h ? v.y : v.x;
-				uint32_t tid = HB_MZ_RID(y), rev = zrev ^ HB_MZ_REV(y), tl = __ldg(&R.len[tid]);
-				uint4 o;
-				o.x = tid | rev << 31;
-				o.y = rev ? tl - 1 - (HB_MZ_POS(y) + 1 - HB_MZ_SPAN(y)) : HB_MZ_POS(y);
-				o.z = zpos; o.w = cnt;
+				const uint64_t y = h ? v[u].y : v[u].x; const uint32_t rev = zrev ^ HB_MZ_REV(y);
+				uint4 o; o.x = HB_MZ_RID(y) | rev << 31; o.y = rev ? tl[u][h] - 1 - (HB_MZ_POS(y) + 1 - HB_MZ_SPAN(y)) : HB_MZ_POS(y); o.z = zpos; o.w = cnt;
 				*(uint4 *)(dst + j) = o;
+			}
+			for (uint32_t e = 32 + 2 * l16; e < span; e += 32) { // long lists: the rest, 32 slots per step
+				const ulonglong2 w = __ldg((const ulonglong2 *)(pt.pos + a0 + e));
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					const int32_t j = (int32_t)(e + h) - (int32_t)head;
+					if (j >= (int32_t)n) continue;
+					const uint64_t y = h ? w.y : w.x; const uint32_t tid = HB_MZ_RID(y), rev = zrev ^ HB_MZ_REV(y), t2 = __ldg(&R.len[tid]);
+					uint4 o; o.x = tid | rev << 31; o.y = rev ? t2 - 1 - (HB_MZ_POS(y) + 1 - HB_MZ_SPAN(y)) : HB_MZ_POS(y); o.z = zpos; o.w = cnt;
+					*(uint4 *)(dst + j) = o;
+				}
 			}
 		}
 	}
