@@ -274,6 +274,8 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 	(void)rid_mode;
 	uint64_t nR = r1 - r0; Arena ar(ctx);
 	SketchPar P = { ctx->opt.mz_win, ctx->opt.k_mer_length, ctx->opt.is_hpc, ctx->opt.mz_sample_dist, ctx->opt.mz_rewin };
+	const bool legacy = getenv("HB_SKETCH_LEGACY") != 0; // the one-kernel formulation (ring in shared memory), kept for A/B checks
+	static const uint64_t chunk_bases = getenv("HB_SKETCH_CHUNK") ? strtoull(getenv("HB_SKETCH_CHUNK"), 0, 10) : 3300000000ull;
 	out->mz = 0; out->off = 0; out->total = 0;
 	for (int attempt = 0, div = 12; attempt < 3; attempt++, div = div > 4 ? div / 3 : 1) {
 		std::vector<uint64_t> cap_off(nR + 1); uint64_t tot = 0;
@@ -283,7 +285,7 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 		int *d_err = ar.zero<int>(1); uint64_t *d_off = ar.get<uint64_t>(nR + 2);
 		HB_ALLOC_CHECK(ar);
 		HB_CUDA(cudaMemcpyAsync(d_cap, cap_off.data(), (nR + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		{
+		if (legacy) {
 			ProfScope ps(ctx, "k_sketch");
 			if (P.w <= 160) {
 				size_t smem = (size_t)64 * P.w * 20;
@@ -294,10 +296,36 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 				cudaFuncSetAttribute(k_sketch<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				k_sketch<32><<<nblk(nR, 32), 32, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0, nR, d_cap, d_mz, d_l, d_n, d_err);
 			}
+		} else {
+			// chunks of reads whose event streams (20 B per base, worst case) fit the workspace comfortably
+			for (uint64_t c0 = 0; c0 < nR;) {
+				uint64_t c1 = c0, cb = 0;
+				while (c1 < nR && (c1 == c0 || cb + ctx->h_rlen[r0 + c1] + 1 <= chunk_bases)) { cb += ctx->h_rlen[r0 + c1] + 1; c1++; }
+				const uint64_t nc = c1 - c0; Arena ca(ctx);
+				std::vector<uint64_t> ev_off(nc + 1); uint64_t et = 0;
+				for (uint64_t i = 0; i < nc; i++) { ev_off[i] = et; et += ctx->h_rlen[r0 + c0 + i] + 1; }
+				ev_off[nc] = et;
+				uint64_t *d_evoff = ca.get<uint64_t>(nc + 1), *d_ex = ca.get<uint64_t>(et + 1), *d_em = ca.get<uint64_t>(et + 1); uint32_t *d_el = ca.get<uint32_t>(et + 1), *d_nev = ca.get<uint32_t>(nc + 1), *d_tl = ca.get<uint32_t>(nc + 1);
+				if (ca.failed) return HB_E_WS;
+				HB_CUDA(cudaMemcpyAsync(d_evoff, ev_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+				{
+					ProfScope ps(ctx, "k_sketch_events");
+					k_sketch_events<<<nblk(nc, 128), 128, 0, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_ex, d_em, d_el, d_nev, d_tl);
+				}
+				{
+					ProfScope ps(ctx, "k_sketch_select");
+					const int tile = (SK2_TS / P.w) * P.w; size_t smem = (size_t)(tile + P.w) * 40;
+					cudaFuncSetAttribute(k_sketch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+					k_sketch_select<<<(unsigned)nc, SK2_THREADS, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_ex, d_em, d_el, d_nev, d_tl, d_cap + c0, d_mz, d_l, d_n + c0, d_err);
+				}
+				HB_CUDA(cudaGetLastError());
+				HB_CUDA(cudaStreamSynchronize(ctx->stream)); // the host-side offset vector goes out of scope
+				c0 = c1;
+			}
 		}
 		HB_CUDA(cudaGetLastError());
 		int h_err = 0; HB_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-		if (h_err) { ar.release(d_cap); ar.release(d_mz); ar.release(d_l); ar.release(d_n); ar.release(d_off); continue; } // a slice overflowed: retry with larger slices
+		if (h_err) continue; // a slice overflowed: retry with larger slices
 		int rc = hb_scan_u32_to_u64(ctx, d_n, d_off, nR); if (rc) return rc;
 		uint64_t total = 0; HB_CUDA(cudaMemcpyAsync(&total, d_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 		hb_mz_t *d_dense = ar.hi<hb_mz_t>(total + 2); uint64_t *d_off_keep = ar.hi<uint64_t>(nR + 2); HB_ALLOC_CHECK(ar);

@@ -40,6 +40,126 @@ __global__ void __launch_bounds__(BLOCK) k_sketch(DevReads R, DevFt ft, SketchPa
 	if (o.ovf) atomicOr(err, 1);
 }
 
+// ----------------------------------------------------------------------------
+// two-stage sketch (production path; see hb_sketch.cuh)
+//   k_sketch_events : one thread per read, straight-line scan -> ring-event stream
+//   k_sketch_select : one block per read; tiles of events staged in shared memory,
+//                     blocked prefix/suffix minima (van Herk) give the window
+//                     minimum of every event, emissions are counted, scanned and
+//                     written in order
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sketch_events(DevReads R, DevFt ft, SketchPar P, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ ev_off,
+                                                        uint64_t *ex, uint64_t *em, uint32_t *el, uint32_t *n_ev, uint32_t *tl)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nR) return;
+	SkEv ev = { ex + ev_off[r], em + ev_off[r], el + ev_off[r] };
+	uint32_t n = 0, t = 0;
+	hb_sketch_events(R, ft, P, r0 + r, ev, &n, &t);
+	n_ev[r] = n; tl[r] = t;
+}
+
+#define SK2_TS 1024
+#define SK2_THREADS 128
+#define SK2_EMPTY 0x7fffffffu
+#define SK2_DUP 0x80000000u
+struct SmemView64 { const uint64_t *p; __device__ __forceinline__ uint64_t operator[](int32_t i) const { return p[i]; } };
+struct SmemView32 { const uint32_t *p; __device__ __forceinline__ uint32_t operator[](int32_t i) const { return p[i]; } };
+
+// right-most argmin of an older range `o` and the adjacent newer range `nw` (tile-relative
+// index | SK2_DUP when another entry of the range shares the minimum key; SK2_EMPTY = no entry)
+static __device__ __forceinline__ uint32_t sk2_comb(uint32_t o, uint32_t nw, const uint64_t *sx, const uint64_t *sm)
+{
+	if ((o & ~SK2_DUP) == SK2_EMPTY) return nw;
+	if ((nw & ~SK2_DUP) == SK2_EMPTY) return o;
+	const uint32_t io = o & ~SK2_DUP, in = nw & ~SK2_DUP;
+	const int c = sk_cmp(sx[in], sm[in], sx[io], sm[io]);
+	return c < 0 ? nw : c > 0 ? o : (in | SK2_DUP);
+}
+
+__global__ void __launch_bounds__(SK2_THREADS) k_sketch_select(DevReads R, DevFt ft, SketchPar P, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ ev_off,
+                                                                const uint64_t *__restrict__ ex, const uint64_t *__restrict__ em, const uint32_t *__restrict__ el,
+                                                                const uint32_t *__restrict__ n_ev, const uint32_t *__restrict__ tl_a,
+                                                                const uint64_t *__restrict__ cap_off, hb_mz_t *mz, uint32_t *mz_l, uint32_t *mz_n, int *err)
+{
+	extern __shared__ uint64_t sk2_smem[];
+	const int32_t w = P.w, k = P.k, tile = (SK2_TS / w) * w, capt = tile + w;
+	uint64_t *sx = sk2_smem, *sm = sx + capt; uint32_t *sl = (uint32_t *)(sm + capt), *bufA = sl + capt, *bufB = bufA + capt, *bufC = bufB + capt, *bufD = bufC + capt, *cnt = bufD + capt;
+	__shared__ uint32_t s_warp[SK2_THREADS / 32], s_on, s_ovf;
+	const uint64_t r = blockIdx.x;
+	if (r >= nR) return;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int32_t T = (int32_t)n_ev[r];
+	const uint64_t eb = ev_off[r];
+	hb_mz_t *out = mz + cap_off[r]; uint32_t *out_l = mz_l + cap_off[r]; const uint32_t cap = (uint32_t)(cap_off[r + 1] - cap_off[r]);
+	if (tid == 0) { s_on = 0; s_ovf = 0; }
+	__syncthreads();
+	SmemView64 X = { sx }, M = { sm }; SmemView32 L = { sl };
+	for (int32_t t0 = 0; t0 < T; t0 += tile) {
+		const int32_t lo = t0 >= w ? t0 - w : 0, hi = T < t0 + tile ? T : t0 + tile, n = hi - lo;
+		for (int32_t i = tid; i < n; i += SK2_THREADS) { sx[i] = ex[eb + lo + i]; sm[i] = em[eb + lo + i]; sl[i] = el[eb + lo + i]; bufA[i] = (uint32_t)i; bufC[i] = SK2_EMPTY; }
+		__syncthreads();
+		// window minima by doubling: level = argmin over the last 2^b events; acc picks the
+		// levels named by the bits of w so that acc ends as the argmin over the last w events
+		uint32_t *lev = bufA, *lev2 = bufB, *acc = bufC, *acc2 = bufD; int32_t acc_len = 0;
+		for (int b = 0; (1 << b) <= w; b++) {
+			const int32_t step = 1 << b; const bool take = (w >> b) & 1, grow = (2 << b) <= w;
+			for (int32_t i = tid; i < n; i += SK2_THREADS) {
+				if (take) acc2[i] = sk2_comb(i - acc_len >= 0 ? lev[i - acc_len] : SK2_EMPTY, acc[i], sx, sm);
+				if (grow) lev2[i] = sk2_comb(i - step >= 0 ? lev[i - step] : SK2_EMPTY, lev[i], sx, sm);
+			}
+			__syncthreads();
+			if (take) { uint32_t *q = acc; acc = acc2; acc2 = q; acc_len += step; }
+			if (grow) { uint32_t *q = lev; lev = lev2; lev2 = q; }
+		}
+		// acc[i] = right-most argmin (tile-relative) of events (t-w, t], t = lo + i
+		const int32_t per = (tile + SK2_THREADS - 1) / SK2_THREADS, a0 = t0 + tid * per, a1 = (a0 + per < hi) ? a0 + per : hi;
+		uint32_t mysum = 0;
+		for (int32_t t = a0; t < a1; t++) {
+			const uint32_t vp = t > 0 ? acc[t - 1 - lo] : SK2_EMPTY, vc = acc[t - lo];
+			const int32_t mp = t > 0 ? lo + (int32_t)(vp & ~SK2_DUP) : -1, mc = lo + (int32_t)(vc & ~SK2_DUP);
+			const uint32_t c = sk2_emit(X, M, L, lo, t, mp, mc, w, k, (hb_mz_t *)0, (uint32_t *)0, (vp & SK2_DUP) != 0, (vc & SK2_DUP) != 0);
+			cnt[t - t0] = c; mysum += c;
+		}
+		uint32_t inc = mysum;
+		for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(HB_FULL, inc, d); if (lane >= d) inc += v; }
+		if (lane == 31) s_warp[wid] = inc;
+		__syncthreads();
+		uint32_t wbase = 0, total = 0;
+		for (int i = 0; i < SK2_THREADS / 32; i++) { if (i < wid) wbase += s_warp[i]; total += s_warp[i]; }
+		uint32_t o = s_on + wbase + inc - mysum;
+		const bool last = hi == T;
+		const uint32_t vlast = last ? acc[T - 1 - lo] : SK2_EMPTY;
+		const bool flush = last && sx[vlast & ~SK2_DUP] != ~0ULL;
+		const bool fits = s_on + total + (flush ? 1u : 0u) <= cap;
+		if (fits) {
+			for (int32_t t = a0; t < a1; t++) {
+				const uint32_t c = cnt[t - t0];
+				if (c) {
+					const uint32_t vp = t > 0 ? acc[t - 1 - lo] : SK2_EMPTY, vc = acc[t - lo];
+					const int32_t mp = t > 0 ? lo + (int32_t)(vp & ~SK2_DUP) : -1, mc = lo + (int32_t)(vc & ~SK2_DUP);
+					sk2_emit(X, M, L, lo, t, mp, mc, w, k, out + o, out_l + o, (vp & SK2_DUP) != 0, (vc & SK2_DUP) != 0);
+					o += c;
+				}
+			}
+			if (flush && tid == 0) { const uint32_t m = vlast & ~SK2_DUP, at = s_on + total; out[at].x = sx[m]; out[at].info = sm[m]; out_l[at] = sl[m]; } // sketch.cpp:571-573
+		}
+		__syncthreads();
+		if (tid == 0) { if (fits) s_on += total + (flush ? 1u : 0u); else s_ovf = 1; }
+		__syncthreads();
+		if (s_ovf) break;
+	}
+	if (s_ovf) { if (tid == 0) { mz_n[r] = 0; atomicOr(err, 1); } return; }
+	if (tid == 0) {
+		SketchOut o; o.mz = out; o.l = out_l; o.cap = cap; o.n = s_on; o.ovf = 0;
+		if (P.sample_dist > w && ft.mask != 0) sk_select_mz_h(o, (int32_t)R.len[r0 + r], P.sample_dist, P.rewin, k, (int32_t)tl_a[r]); // sketch.cpp:575
+		s_on = o.n; mz_n[r] = o.n;
+	}
+	__syncthreads();
+	const uint32_t rid_out = (uint32_t)(r0 + r) & 0xfffffff;
+	for (uint32_t i = tid; i < s_on; i += SK2_THREADS) out[i].info = (out[i].info & ~0xfffffffULL) | rid_out; // sketch.cpp:577
+}
+
 // strided per-read slices -> dense array (warp per read)
 __global__ void k_compact_mz(uint64_t nR, const uint64_t *__restrict__ cap_off, const uint64_t *__restrict__ off, const hb_mz_t *__restrict__ in, hb_mz_t *__restrict__ out)
 {

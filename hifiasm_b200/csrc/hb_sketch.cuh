@@ -226,3 +226,124 @@ HB_HD void hb_sketch_read(const DevReads &R, const DevFt &ft, const SketchPar &P
 #undef SK_BASE
 #undef SK_POS
 }
+
+// ===========================================================================
+// Two-stage sketch (the production path): the sequential scan of a read only
+// produces its stream of ring events; window minima and emissions are then
+// decided independently per event.
+//
+// Why this is exact.  In mz1_ha_sketch (sketch.cpp:521-569) the ring advances
+// once per accepted HPC symbol (one whose k-mer is not strand-symmetric) and once
+// per N base; `min` is always the right-most minimal entry of the last w ring
+// entries (ties go to the newer entry: `>=` at 543 and 555-557; the initial 0xff
+// fill compares equal to a dummy).  So with E[t] the t-th ring event and
+// M(t) = right-most argmin of E(t-w, t], everything the loop emits at event t is a
+// function of M(t-1), M(t), E(t-w..t] and l(t):
+//   l == w+k-1 and M(t-1) real      -> entries of E[t-w+1, t-1] equal to M(t-1), other position   (523-534)
+//   E[t] <= M(t-1)                  -> M(t-1) if l >= w+k and real                                 (543-547)
+//   else if M(t-1) is E[t-w]        -> M(t-1) if l >= w+k-1 and real; then, if M(t) real, the
+//                                      entries of E[t-w+1, t] equal to M(t), other position       (548-568)
+// and the last M is flushed at the end (571-573).
+// ===========================================================================
+struct SkEv { uint64_t *x, *m; uint32_t *l; };
+
+// stage 1: one thread per read; writes the read's ring events (cap = read length + 1).
+// The k-symbol span queue of the reference (tiny_queue_t, htab.h:39-57) is replaced by a
+// second cursor into the packed read that trails k HPC symbols behind: the span of the
+// last k symbols is simply (current run end) - (trailing cursor) + 1, no per-thread array.
+HB_HD void hb_sketch_events(const DevReads &R, const DevFt &ft, const SketchPar &P, uint64_t rid, SkEv ev, uint32_t *n_ev, uint32_t *tl_out)
+{
+	const int32_t k = P.k, len = (int32_t)R.len[rid];
+	const uint64_t shift1 = k - 1, mask = (1ULL << k) - 1;
+	const uint64_t *seq64 = (const uint64_t *)(R.packed + R.off[rid]);
+	uint64_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, word = 0, tword = 0;
+	int32_t i, l = 0, tl = 0, span = 0, qc = 0, wbase = -1, tbase = -1, tail = 0; uint32_t t = 0;
+	uint64_t ni = R.noff[rid], ne = R.noff[rid + 1];
+	int32_t next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX;
+#define SK_BASE(ii) ((int)(((((ii) >> 5) != wbase ? (wbase = (ii) >> 5, word = seq64[wbase]) : word) >> ((((ii) & 31) >> 2 << 3) + ((3 - ((ii) & 3)) << 1))) & 3))
+#define SK_TBASE(ii) ((int)(((((ii) >> 5) != tbase ? (tbase = (ii) >> 5, tword = seq64[tbase]) : tword) >> ((((ii) & 31) >> 2 << 3) + ((3 - ((ii) & 3)) << 1))) & 3))
+	for (i = 0; i < len; ++i) {
+		int c = SK_BASE(i);
+		uint64_t ix = ~0ULL, im = SK_DUMMY_META;
+		if (i == next_n) { c = 4; ++ni; next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX; }
+		if (c < 4) {
+			int z;
+			if (P.is_hpc) { // sketch.cpp:480-492
+				const int32_t i0 = i;
+				while (i + 1 < len && i + 1 != next_n && SK_BASE(i + 1) == c) ++i;
+				if (qc == 0) tail = i0;
+				if (++qc > k) { // drop the oldest symbol: step the trailing cursor over its run
+					const int c0 = SK_TBASE(tail);
+					do ++tail; while (SK_TBASE(tail) == c0);
+					--qc;
+				}
+				span = i - tail + 1;
+			} else span = l + 1 < k ? l + 1 : k;
+			pl0 = (pl0 << 1 | (uint64_t)(c & 1)) & mask;
+			pl1 = (pl1 << 1 | (uint64_t)(c >> 1)) & mask;
+			pl2 = pl2 >> 1 | (uint64_t)(1 - (c & 1)) << shift1;
+			pl3 = pl3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift1;
+			if (pl1 == pl3) continue;
+			z = pl1 < pl3 ? 0 : 1;
+			++l; ++tl;
+			if (l >= k && span < 256) {
+				uint64_t y = z ? hb_hash64(pl2) + hb_hash64(pl3) : hb_hash64(pl0) + hb_hash64(pl1);
+				int32_t cnt = hb_ft_lookup(ft, y);
+				if (!(cnt >= 1 << 28)) { ix = y; im = (uint64_t)(uint32_t)cnt | (uint64_t)i << 28 | (uint64_t)z << 55 | (uint64_t)span << 56; }
+			}
+		} else { l = 0; qc = 0; span = 0; }
+		ev.x[t] = ix; ev.m[t] = im; ev.l[t] = (uint32_t)l; t++;
+	}
+#undef SK_BASE
+#undef SK_TBASE
+	*n_ev = t; *tl_out = (uint32_t)tl;
+}
+
+#define SK2_POS(m) ((uint32_t)(((m) >> 28) & 0x7ffffffULL))
+// right-most argmin of two candidates a (older range) and b (newer range); -1 = empty
+#define SK2_PICK(ax, am, ai, bx, bm, bi) (((bi) >= 0 && ((ai) < 0 || sk_cmp((bx), (bm), (ax), (am)) <= 0)) ? 1 : 0)
+
+// stage 2 helpers, written over a window view: X/Mt/L index events by t - base.
+// pre[t-base] / suf[t-base]: right-most argmin (absolute t) over [blockstart(t), t] / [t, blockend(t)], blocks of w aligned at 0.
+template <typename AX, typename AM>
+HB_HD int32_t sk2_window_min(const AX &X, const AM &Mt, const int32_t *pre, const int32_t *suf, int32_t base, int32_t t, int32_t w)
+{ // right-most argmin of E(t-w, t]; t < 0 -> -1 (dummy)
+	if (t < 0) return -1;
+	int32_t lo = t - w + 1;
+	if (lo <= 0 || lo % w == 0) return pre[t - base]; // window = one (possibly short) block prefix
+	int32_t a = suf[lo - base], b = pre[t - base];
+	return sk_cmp(X[b - base], Mt[b - base], X[a - base], Mt[a - base]) <= 0 ? b : a;
+}
+
+// emissions of event t; if out != 0 they are written to out[0..), returns their number
+template <typename AX, typename AM, typename AL>
+// dup_p / dup_c: "some other entry of that window has the same (count, hash) as its minimum"
+// (always safe to pass true; false skips the scans for identical minima)
+HB_HD uint32_t sk2_emit(const AX &X, const AM &Mt, const AL &L, int32_t base, int32_t t, int32_t mp /*M(t-1)*/, int32_t mc /*M(t)*/, int32_t w, int32_t k,
+                        hb_mz_t *out, uint32_t *out_l, bool dup_p = true, bool dup_c = true)
+{
+	const uint32_t l = L[t - base]; uint32_t n = 0;
+	const bool p_real = mp >= 0 && X[mp - base] != ~0ULL;
+	uint64_t px = p_real ? X[mp - base] : ~0ULL, pm = p_real ? Mt[mp - base] : SK_DUMMY_META;
+	if (mp >= 0 && !p_real) { px = X[mp - base]; pm = Mt[mp - base]; }
+	if ((int32_t)l == w + k - 1 && p_real && dup_p) { // sketch.cpp:523-534
+		for (int32_t u = t - w + 1 < 0 ? 0 : t - w + 1; u < t; u++)
+			if (sk_cmp(px, pm, X[u - base], Mt[u - base]) == 0 && SK2_POS(Mt[u - base]) != SK2_POS(pm)) {
+				if (out) { out[n].x = X[u - base]; out[n].info = Mt[u - base]; out_l[n] = L[u - base]; }
+				n++;
+			}
+	}
+	if (sk_cmp(px, pm, X[t - base], Mt[t - base]) >= 0) { // sketch.cpp:543-547
+		if ((int32_t)l >= w + k && p_real) { if (out) { out[n].x = px; out[n].info = pm; out_l[n] = L[mp - base]; } n++; }
+	} else if (mp == t - w) { // sketch.cpp:548-568
+		if ((int32_t)l >= w + k - 1 && p_real) { if (out) { out[n].x = px; out[n].info = pm; out_l[n] = L[mp - base]; } n++; }
+		const uint64_t cx = X[mc - base], cm = Mt[mc - base];
+		if ((int32_t)l >= w + k - 1 && cx != ~0ULL && dup_c)
+			for (int32_t u = t - w + 1 < 0 ? 0 : t - w + 1; u <= t; u++)
+				if (sk_cmp(cx, cm, X[u - base], Mt[u - base]) == 0 && SK2_POS(cm) != SK2_POS(Mt[u - base])) {
+					if (out) { out[n].x = X[u - base]; out[n].info = Mt[u - base]; out_l[n] = L[u - base]; }
+					n++;
+				}
+	}
+	return n;
+}

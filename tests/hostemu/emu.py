@@ -61,10 +61,11 @@ def pt_from_oracle(pt):
     return C.c_void_p(lib().emu_pt_create(C.c_uint64(nk), _p(key), _p(off), _p(cnt), C.c_uint64(npos), _p(pos)))
 
 
-def sketch(reads, ft, p, rid, rid_out=0):
+def sketch(reads, ft, p, rid, rid_out=0, two_stage=False):
     cap = int(reads.length[rid]) // 4 + 64
     out = np.zeros(cap, MZ); n = C.c_uint32()
-    ovf = lib().emu_sketch(reads.h, ft, C.c_int(int(p["w"])), C.c_int(int(p["k"])), C.c_int(int(p["is_hpc"])),
+    fn = lib().emu_sketch2 if two_stage else lib().emu_sketch
+    ovf = fn(reads.h, ft, C.c_int(int(p["w"])), C.c_int(int(p["k"])), C.c_int(int(p["is_hpc"])),
                            C.c_int(int(p["mz_sample_dist"])), C.c_int(int(p["mz_rewin"])), C.c_uint64(rid), C.c_uint32(rid_out),
                            _p(out), C.c_uint32(cap), C.byref(n))
     assert ovf == 0

@@ -83,6 +83,42 @@ int emu_sketch(void *reads, void *ft, int w, int k, int is_hpc, int sample_dist,
 }
 
 
+// two-stage sketch (event stream + per-event window minimum), driven sequentially
+int emu_sketch2(void *reads, void *ft, int w, int k, int is_hpc, int sample_dist, int rewin, uint64_t rid, uint32_t rid_out,
+                hb_mz_t *out, uint32_t cap, uint32_t *n_out)
+{
+	EmuReads *r = (EmuReads *)reads; EmuFt *f = (EmuFt *)ft;
+	SketchPar P = { w, k, is_hpc, sample_dist, rewin };
+	uint32_t len = r->d.len[rid], T = 0, tl = 0;
+	std::vector<uint64_t> ex(len + 1), em(len + 1); std::vector<uint32_t> el(len + 1), ol(cap + 1);
+	SkEv ev = { ex.data(), em.data(), el.data() };
+	hb_sketch_events(r->d, f->d, P, rid, ev, &T, &tl);
+	std::vector<int32_t> pre(T + 1), suf(T + 1);
+	for (uint32_t b = 0; b < T; b += w) {
+		uint32_t e = std::min<uint32_t>(T, b + w); int32_t cur = b;
+		for (uint32_t u = b; u < e; u++) { if (sk_cmp(ex[u], em[u], ex[cur], em[cur]) <= 0) cur = u; pre[u] = cur; }
+		cur = e - 1;
+		for (int32_t u = e - 1; u >= (int32_t)b; u--) { if (sk_cmp(ex[u], em[u], ex[cur], em[cur]) < 0) cur = u; suf[u] = cur; }
+	}
+	SketchOut o; o.mz = out; o.l = ol.data(); o.cap = cap; o.n = 0; o.ovf = 0;
+	const uint64_t *X = ex.data(), *M = em.data(); const uint32_t *L = el.data();
+	int32_t mp = -1;
+	for (int32_t t = 0; t < (int32_t)T; t++) {
+		int32_t mc = sk2_window_min(X, M, pre.data(), suf.data(), 0, t, w);
+		hb_mz_t tmp[600]; uint32_t tl_[600];
+		uint32_t n = sk2_emit(X, M, L, 0, t, mp, mc, w, k, tmp, tl_);
+		for (uint32_t i = 0; i < n; i++) o.push(tmp[i].x, tmp[i].info, tl_[i]);
+		mp = mc;
+	}
+	if (mp >= 0 && ex[mp] != ~0ULL) o.push(ex[mp], em[mp], el[mp]);
+	if (!o.ovf) {
+		if (sample_dist > w && f->d.mask != 0) sk_select_mz_h(o, (int32_t)len, sample_dist, rewin, k, (int32_t)tl);
+		for (uint32_t i = 0; i < o.n; i++) out[i].info = (out[i].info & ~0xfffffffULL) | (rid_out & 0xfffffff);
+	}
+	*n_out = o.n;
+	return o.ovf;
+}
+
 // weight table of minimizers_qgen0 (anchor.cpp:1066-1075): w_tab[n_occ]
 static void weight_tab(uint32_t *w_tab, uint32_t high_occ, uint32_t low_occ)
 {

@@ -34,6 +34,8 @@ def test_sketch(ctx, mode):
     for i in range(er.n):
         mz = emu.sketch(er, eft, p, i)
         assert dg(mz.tobytes()) == int(g.digest(mode, "mz")[i]), "read %d" % i
+        mz2 = emu.sketch(er, eft, p, i, two_stage=True)  # the production formulation: event stream + per-event window minimum
+        assert dg(mz2.tobytes()) == int(g.digest(mode, "mz")[i]), "two-stage sketch, read %d" % i
 
 
 def _chain_digest(ch, fc):
