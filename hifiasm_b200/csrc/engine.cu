@@ -154,6 +154,8 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
+	cudaFuncSetAttribute(k_post_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, POST_WARPS * POST_SMEM_PER_WARP);
+	cudaFuncSetAttribute(k_merge_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_WARPS * MERGE_SMEM_PER_WARP);
 	*out = ctx;
 	return HB_OK;
 }
@@ -202,14 +204,14 @@ static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uin
 	for (uint64_t i = 0; i < n; i++) {
 		if (len[i] >= (1ull << 27)) { hb_set_err(ctx, HB_E_ARG, "read %llu longer than 2^27", (unsigned long long)i); return HB_E_ARG; }
 		off[i] = o; ctx->h_rlen[i] = (uint32_t)len[i]; ctx->total_bases += len[i];
-		o += ((len[i] / 4 + 1) + 7) & ~7ull; // 8-byte aligned reads
+		o += ((len[i] / 4 + 1) + 31) & ~31ull; // 32-byte aligned reads: one sector = 128 bases
 	}
 	off[n] = o;
-	if (ctx->h_stage_cap < o + 16) {
+	if (ctx->h_stage_cap < o + 64) {
 		if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
 		ctx->h_stage = 0; ctx->h_stage_cap = 0;
-		if (cudaMallocHost((void **)&ctx->h_stage, o + 16 + (o >> 4)) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "pinned staging buffer"); return HB_E_NOMEM; }
-		ctx->h_stage_cap = o + 16 + (o >> 4);
+		if (cudaMallocHost((void **)&ctx->h_stage, o + 64 + (o >> 4)) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "pinned staging buffer"); return HB_E_NOMEM; }
+		ctx->h_stage_cap = o + 64 + (o >> 4);
 	}
 	uint8_t *h_packed = ctx->h_stage;
 	{
@@ -243,16 +245,16 @@ static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uin
 		} else noff[i + 1] = 0;
 	}
 	int rc = HB_OK;
-	if (ctx->packed_cap < o + 16 || ctx->reads_cap < n + 1 || ctx->npos_cap < npos.size() + 1) {
+	if (ctx->packed_cap < o + 64 || ctx->reads_cap < n + 1 || ctx->npos_cap < npos.size() + 1) {
 		free_reads(ctx);
-		uint64_t pc = o + 16 + (o >> 4), rc_ = n + 1 + (n >> 4), nc = npos.size() + 1 + (npos.size() >> 2);
+		uint64_t pc = o + 64 + (o >> 4), rc_ = n + 1 + (n >> 4), nc = npos.size() + 1 + (npos.size() >> 2);
 		if (cudaMalloc((void **)&ctx->d_packed, pc) != cudaSuccess || cudaMalloc((void **)&ctx->d_roff, (rc_ + 1) * 8) != cudaSuccess ||
 		    cudaMalloc((void **)&ctx->d_rlen, (rc_ + 1) * 4) != cudaSuccess || cudaMalloc((void **)&ctx->d_noff, (rc_ + 1) * 8) != cudaSuccess ||
 		    cudaMalloc((void **)&ctx->d_npos, nc * 4) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "read store does not fit in HBM"); free_reads(ctx); return HB_E_NOMEM; }
 		ctx->packed_cap = pc; ctx->reads_cap = rc_; ctx->npos_cap = nc;
 	}
 	ctx->n_reads = n; ctx->packed_bytes = o; ctx->n_npos = npos.size();
-	cudaMemcpyAsync(ctx->d_packed, h_packed, o + 16, cudaMemcpyHostToDevice, ctx->stream);
+	cudaMemcpyAsync(ctx->d_packed, h_packed, o + 16, cudaMemcpyHostToDevice, ctx->stream); // (+ the zeroed guard bytes)
 	cudaMemcpyAsync(ctx->d_roff, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
 	cudaMemcpyAsync(ctx->d_rlen, ctx->h_rlen.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream);
 	cudaMemcpyAsync(ctx->d_noff, noff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -305,18 +307,18 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 				std::vector<uint64_t> ev_off(nc + 1); uint64_t et = 0;
 				for (uint64_t i = 0; i < nc; i++) { ev_off[i] = et; et += ctx->h_rlen[r0 + c0 + i] + 1; }
 				ev_off[nc] = et;
-				uint64_t *d_evoff = ca.get<uint64_t>(nc + 1), *d_ex = ca.get<uint64_t>(et + 1), *d_em = ca.get<uint64_t>(et + 1); uint32_t *d_el = ca.get<uint32_t>(et + 1), *d_nev = ca.get<uint32_t>(nc + 1), *d_tl = ca.get<uint32_t>(nc + 1);
+				uint64_t *d_evoff = ca.get<uint64_t>(nc + 1); ulonglong2 *d_evs = ca.get<ulonglong2>(et + 1); uint32_t *d_nev = ca.get<uint32_t>(nc + 1), *d_tl = ca.get<uint32_t>(nc + 1);
 				if (ca.failed) return HB_E_WS;
 				HB_CUDA(cudaMemcpyAsync(d_evoff, ev_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 				{
 					ProfScope ps(ctx, "k_sketch_events");
-					k_sketch_events<<<nblk(nc, 128), 128, 0, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_ex, d_em, d_el, d_nev, d_tl);
+					k_sketch_events<<<nblk(nc, 128), 128, 0, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_evs, d_nev, d_tl);
 				}
 				{
 					ProfScope ps(ctx, "k_sketch_select");
 					const int tile = (SK2_TS / P.w) * P.w; size_t smem = (size_t)(tile + P.w) * 40;
 					cudaFuncSetAttribute(k_sketch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-					k_sketch_select<<<(unsigned)nc, SK2_THREADS, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_ex, d_em, d_el, d_nev, d_tl, d_cap + c0, d_mz, d_l, d_n + c0, d_err);
+					k_sketch_select<<<(unsigned)nc, SK2_THREADS, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_evs, d_nev, d_tl, d_cap + c0, d_mz, d_l, d_n + c0, d_err);
 				}
 				HB_CUDA(cudaGetLastError());
 				HB_CUDA(cudaStreamSynchronize(ctx->stream)); // the host-side offset vector goes out of scope
@@ -604,7 +606,8 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		{
 			PostArgs Pa; Pa.R = R; Pa.r0 = r0 + b0; Pa.nR = nb; Pa.c_off = d_coff; Pa.ch = d_ch; Pa.chits = d_chits; Pa.idx = d_idx; Pa.n_ol = d_nol; Pa.keep = d_keep; Pa.cc = d_cc; Pa.cc_off = d_ccoff; Pa.P = CP;
 			ProfScope ps(ctx, "k_post");
-			k_post<<<nblk(nb, 64), 64, 0, ctx->stream>>>(Pa);
+			if (getenv("HB_POST_THREAD")) k_post<<<nblk(nb, 64), 64, 0, ctx->stream>>>(Pa);
+			else k_post_warp<<<nblk(nb, POST_WARPS), POST_WARPS * 32, POST_WARPS * POST_SMEM_PER_WARP, ctx->stream>>>(Pa);
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("post");
@@ -661,7 +664,8 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			M.in0 = d_in0; M.in0_off = d_i0off; M.in1 = ctx->d_prev1 + p1b; M.in1_off = d_i1off; M.ov = d_ov; M.srt = d_srt; M.o_off = d_ooff;
 			M.out0 = d_o0; M.out1 = d_o1; M.m0 = d_m0 + b0; M.m1 = d_m1 + b0; M.stat = d_stat;
 			ProfScope ps(ctx, "k_merge");
-			k_merge<<<nblk(nb, 64), 64, 0, ctx->stream>>>(M);
+			if (getenv("HB_POST_THREAD")) k_merge<<<nblk(nb, 64), 64, 0, ctx->stream>>>(M);
+			else k_merge_warp<<<nblk(nb, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * MERGE_SMEM_PER_WARP, ctx->stream>>>(M);
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("merge");

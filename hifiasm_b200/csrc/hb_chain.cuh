@@ -372,16 +372,18 @@ template <typename T, typename KEY> HB_HD void hb_rs_insertsort(T *beg, T *end, 
 		}
 }
 #define HB_RS_STACK 320
-template <typename T, typename KEY> HB_HD int hb_rs_sort32(T *beg0, T *end0, KEY key)
+struct RsFrame { int32_t b, e, s; };
+struct RsScratch { int32_t *bb, *be; RsFrame *st; }; // 256 + 256 ints and HB_RS_STACK frames
+template <typename T, typename KEY> HB_HD int hb_rs_sort32(T *beg0, T *end0, KEY key, const RsScratch &W)
 { // returns 1 if the explicit stack overflowed (more than 65*HB_RS_STACK elements)
 	if (end0 - beg0 <= 64) { hb_rs_insertsort(beg0, end0, key); return 0; }
 	// explicit recursion stack of (range, shift): pending ranges are disjoint and
 	// each holds > 64 elements, so n <= 65*HB_RS_STACK never overflows it
-	struct Fr { int32_t b, e, s; } st[HB_RS_STACK]; int sp = 0;
+	RsFrame *st = W.st; int32_t *bb = W.bb, *be = W.be; int sp = 0;
 	st[sp].b = 0; st[sp].e = (int32_t)(end0 - beg0); st[sp].s = 24; sp++;
 	while (sp) {
-		Fr fr = st[--sp]; T *beg = beg0 + fr.b, *end = beg0 + fr.e; int s = fr.s;
-		int32_t bb[256], be[256]; int k;
+		RsFrame fr = st[--sp]; T *beg = beg0 + fr.b, *end = beg0 + fr.e; int s = fr.s;
+		int k;
 		for (k = 0; k < 256; ++k) bb[k] = be[k] = 0;
 		for (T *i = beg; i != end; ++i) ++be[key(*i) >> s & 255];
 		for (k = 1; k < 256; ++k) { be[k] += be[k - 1]; bb[k] = be[k - 1]; }
@@ -508,10 +510,19 @@ HB_HD uint32_t hb_chain_post(hb_chain_t *ch, uint32_t n_slots, const hb_hit_t *c
 					rs = zk.x_pos_s; re = (uint64_t)zk.x_pos_e + 1;
 					os = rs >= zs ? rs : zs; oe = re <= ze ? re : ze;
 					if (oe > os && oe - os >= ob) {
+						// count the chain's anchors lying inside [os,oe] (anchor.cpp:2077-2083).  The
+						// anchors are ordered by self_offset, so the count is taken over the slice
+						// [first anchor ending at or after os, last anchor ending at or before oe]
+						// instead of the whole chain: same count, a handful of loads.
 						mm = zk.first_hit; kn = 0;
-						for (hh = 0; hh < zk.n_hits && kn < ocn; hh++) {
-							me = chits[mm + hh].self_offset; ms = me - (chits[mm + hh].cnt & 0xffu);
-							if (ms >= os && me <= oe) kn++;
+						{
+							uint64_t lo_ = 0, hi_ = zk.n_hits;
+							while (lo_ < hi_) { uint64_t mid = (lo_ + hi_) >> 1; if (chits[mm + mid].self_offset < os) lo_ = mid + 1; else hi_ = mid; }
+							for (hh = lo_; hh < zk.n_hits && kn < ocn; hh++) {
+								me = chits[mm + hh].self_offset; if (me > oe) break;
+								ms = me - (chits[mm + hh].cnt & 0xffu);
+								if (ms >= os) kn++;
+							}
 						}
 						if (kn >= ocn) break;
 					}

@@ -20,8 +20,8 @@ struct ulonglong2 { unsigned long long x, y; };
 
 // ---- read store in HBM: All_reads (Process_Read.h:115-146), flattened ------
 // packed: 2-bit bases, byte = b0<<6|b1<<4|b2<<2|b3 (ha_compress_base,
-// Process_Read.cpp:792); every read starts on an 8-byte boundary so kernels
-// can stream 64-bit words (32 bases per load).
+// Process_Read.cpp:792); every read starts on a 32-byte boundary so kernels
+// can stream whole sectors (128 bases per load).
 struct DevReads {
 	uint64_t n;
 	const uint8_t *packed;

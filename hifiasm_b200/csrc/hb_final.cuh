@@ -49,7 +49,7 @@ HB_HD int hb_exact_seq(const DevReads &R, uint64_t qid, uint64_t qs, uint64_t qe
 // out0/out1 receive the new paf / reverse_paf (capacity n_ol + n0 each).
 HB_HD void hb_final_merge(const DevReads &R, uint32_t rid, const hb_chain_t *ch, const uint32_t *idx, uint32_t n_ol, const uint8_t *exact,
                           hb_ma_hit_t *in0, uint32_t n0, const hb_ma_hit_t *in1, uint32_t n1, FinOv *ov, uint64_t *srt,
-                          hb_ma_hit_t *out0, uint32_t *m0, hb_ma_hit_t *out1, uint32_t *m1, unsigned long long *stat)
+                          hb_ma_hit_t *out0, uint32_t *m0, hb_ma_hit_t *out1, uint32_t *m1, unsigned long long *stat, const RsScratch &W)
 {
 	const double sh = 0.866666; // ecovlp.cpp:3970
 	uint64_t k, i, l, m, ns = 0; uint32_t n = n_ol, is_usrt = 0; FinOv t; KeyYid key;
@@ -58,7 +58,7 @@ HB_HD void hb_final_merge(const DevReads &R, uint32_t rid, const hb_chain_t *ch,
 		z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_id = c.y_id; z.y_pos_s = c.y_pos_s; z.y_pos_e = c.y_pos_e;
 		z.strand = (uint8_t)c.y_pos_strand; z.nhe = 0; z.slot = idx[k]; z.is_match = 0; z.el = 0; z.strong = 0; z.wli = 0;
 	}
-	int rs_ovf = hb_rs_sort32(ov, ov + n, key); // overlap_region_sort_y_id, ecovlp.cpp:3959
+	int rs_ovf = hb_rs_sort32(ov, ov + n, key, W); // overlap_region_sort_y_id, ecovlp.cpp:3959
 	for (k = 0; k < n0; k++) srt[ns++] = ((uint64_t)in0[k].tn << 1 | (uint64_t)in0[k].rev) << 32 | (k << 1) | 0; // ecovlp.cpp:5057-5070
 	for (k = 0; k < n1; k++) srt[ns++] = ((uint64_t)in1[k].tn << 1 | (uint64_t)in1[k].rev) << 32 | (k << 1) | 1;
 	for (i = 1; i < ns; i++) { uint64_t v = srt[i]; for (l = i; l > 0 && srt[l - 1] > v; --l) srt[l] = srt[l - 1]; srt[l] = v; } // keys distinct: any sort
@@ -108,7 +108,7 @@ HB_HD void hb_final_merge(const DevReads &R, uint32_t rid, const hb_chain_t *ch,
 			is_usrt = 1;
 		}
 	}
-	if (is_usrt) rs_ovf |= hb_rs_sort32(ov, ov + n, key);
+	if (is_usrt) rs_ovf |= hb_rs_sort32(ov, ov + n, key, W);
 	if (n > 1) { // ecovlp.cpp:5169-5195
 		uint64_t mm_k, s; int64_t mm_sc, sc;
 		for (k = 1, l = m = 0; k <= n; k++) {

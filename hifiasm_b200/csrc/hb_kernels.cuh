@@ -49,11 +49,11 @@ __global__ void __launch_bounds__(BLOCK) k_sketch(DevReads R, DevFt ft, SketchPa
 //                     written in order
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_sketch_events(DevReads R, DevFt ft, SketchPar P, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ ev_off,
-                                                        uint64_t *ex, uint64_t *em, uint32_t *el, uint32_t *n_ev, uint32_t *tl)
+                                                        ulonglong2 *evs, uint32_t *n_ev, uint32_t *tl)
 {
 	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nR) return;
-	SkEv ev = { ex + ev_off[r], em + ev_off[r], el + ev_off[r] };
+	SkEv ev = { evs + ev_off[r] };
 	uint32_t n = 0, t = 0;
 	hb_sketch_events(R, ft, P, r0 + r, ev, &n, &t);
 	n_ev[r] = n; tl[r] = t;
@@ -78,26 +78,48 @@ static __device__ __forceinline__ uint32_t sk2_comb(uint32_t o, uint32_t nw, con
 }
 
 __global__ void __launch_bounds__(SK2_THREADS) k_sketch_select(DevReads R, DevFt ft, SketchPar P, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ ev_off,
-                                                                const uint64_t *__restrict__ ex, const uint64_t *__restrict__ em, const uint32_t *__restrict__ el,
+                                                                const ulonglong2 *__restrict__ evs,
                                                                 const uint32_t *__restrict__ n_ev, const uint32_t *__restrict__ tl_a,
                                                                 const uint64_t *__restrict__ cap_off, hb_mz_t *mz, uint32_t *mz_l, uint32_t *mz_n, int *err)
 {
 	extern __shared__ uint64_t sk2_smem[];
 	const int32_t w = P.w, k = P.k, tile = (SK2_TS / w) * w, capt = tile + w;
 	uint64_t *sx = sk2_smem, *sm = sx + capt; uint32_t *sl = (uint32_t *)(sm + capt), *bufA = sl + capt, *bufB = bufA + capt, *bufC = bufB + capt, *bufD = bufC + capt, *cnt = bufD + capt;
-	__shared__ uint32_t s_warp[SK2_THREADS / 32], s_on, s_ovf;
+	__shared__ uint32_t s_warp[SK2_THREADS / 32], s_on, s_ovf; __shared__ int32_t s_wmax[SK2_THREADS / 32], s_lastN;
 	const uint64_t r = blockIdx.x;
 	if (r >= nR) return;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int32_t T = (int32_t)n_ev[r];
 	const uint64_t eb = ev_off[r];
 	hb_mz_t *out = mz + cap_off[r]; uint32_t *out_l = mz_l + cap_off[r]; const uint32_t cap = (uint32_t)(cap_off[r + 1] - cap_off[r]);
-	if (tid == 0) { s_on = 0; s_ovf = 0; }
+	if (tid == 0) { s_on = 0; s_ovf = 0; s_lastN = -1; }
 	__syncthreads();
 	SmemView64 X = { sx }, M = { sm }; SmemView32 L = { sl };
 	for (int32_t t0 = 0; t0 < T; t0 += tile) {
 		const int32_t lo = t0 >= w ? t0 - w : 0, hi = T < t0 + tile ? T : t0 + tile, n = hi - lo;
-		for (int32_t i = tid; i < n; i += SK2_THREADS) { sx[i] = ex[eb + lo + i]; sm[i] = em[eb + lo + i]; sl[i] = el[eb + lo + i]; bufA[i] = (uint32_t)i; bufC[i] = SK2_EMPTY; }
+		for (int32_t i = tid; i < n; i += SK2_THREADS) { const ulonglong2 e = __ldg(&evs[eb + lo + i]); sx[i] = e.x; sm[i] = e.y; bufA[i] = (uint32_t)i; bufC[i] = SK2_EMPTY; }
+		__syncthreads();
+		{ // l(t) = events since the last N base (0 on an N): block-wide running max of the N indices
+			const int32_t pc = (n + SK2_THREADS - 1) / SK2_THREADS, c0 = tid * pc, c1 = c0 + pc < n ? c0 + pc : n;
+			int32_t mx = -1;
+			for (int32_t i = c0; i < c1; i++) if (sm[i] == SK_NMARK) mx = lo + i;
+			int32_t inc = mx;
+			for (int d = 1; d < 32; d <<= 1) { int32_t v = __shfl_up_sync(HB_FULL, inc, d); if (lane >= d && v > inc) inc = v; }
+			if (lane == 31) s_wmax[wid] = inc;
+			__syncthreads();
+			int32_t run = s_lastN;
+			for (int i = 0; i < wid; i++) if (s_wmax[i] > run) run = s_wmax[i];
+			int32_t ex_ = __shfl_up_sync(HB_FULL, inc, 1); if (lane == 0) ex_ = -1;
+			if (ex_ > run) run = ex_;
+			for (int32_t i = c0; i < c1; i++) {
+				if (sm[i] == SK_NMARK) { run = lo + i; sl[i] = 0; sm[i] = SK_DUMMY_META; }
+				else sl[i] = (uint32_t)(lo + i - run);
+			}
+			// carry for the next tile: the last N index below its first staged event (t0 + tile - w)
+			const int32_t nlo = t0 + tile - w - 1 - lo; // tile-relative index of the last event before the next tile's halo
+			__syncthreads();
+			if (nlo >= c0 && nlo < c1) s_lastN = (int32_t)(lo + nlo) - (int32_t)sl[nlo]; // an N event has l = 0, so this is its own index
+		}
 		__syncthreads();
 		// window minima by doubling: level = argmin over the last 2^b events; acc picks the
 		// levels named by the bits of w so that acc ends as the argmin over the last w events
@@ -696,6 +718,40 @@ __global__ void k_post(PostArgs A)
 	for (uint32_t i = 0; i < n; i++) A.keep[cb + A.idx[cb + i]] = 1;
 }
 
+// post, warp per read: the read's chain slots are staged in shared memory (48 B each,
+// 128-bit copies by the whole warp), lane 0 runs the sequential post-filter on the staged
+// copy (shared-memory latency instead of a dependent L2 access per comparison), the warp
+// writes the result back.  Reads with more slots than fit run on global memory as before.
+#define POST_WARPS 4
+#define POST_SMEM_PER_WARP 16384
+__global__ void __launch_bounds__(POST_WARPS * 32) k_post_warp(PostArgs A)
+{
+	extern __shared__ uint4 post_smem[];
+	const int wib = threadIdx.x >> 5, lane = hb_lane();
+	const uint64_t r = (uint64_t)blockIdx.x * POST_WARPS + wib;
+	if (r >= A.nR) return;
+	const uint64_t cb = A.c_off[r]; const uint32_t ns = (uint32_t)(A.c_off[r + 1] - cb);
+	uint4 *sw = post_smem + (size_t)wib * (POST_SMEM_PER_WARP / 16);
+	hb_chain_t *ch = A.ch + cb; uint32_t *idx = A.idx + cb; uint32_t n = 0;
+	if ((size_t)ns * (sizeof(hb_chain_t) + 4) + 16 <= POST_SMEM_PER_WARP) {
+		hb_chain_t *s_ch = (hb_chain_t *)sw; uint32_t *s_idx = (uint32_t *)(s_ch + ns);
+		const uint4 *src = (const uint4 *)ch;
+		for (uint32_t i = lane; i < ns * 3; i += 32) sw[i] = src[i];
+		__syncwarp();
+		if (lane == 0) n = hb_chain_post(s_ch, ns, A.chits, s_idx, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
+		n = __shfl_sync(HB_FULL, n, 0);
+		__syncwarp();
+		for (uint32_t i = lane; i < ns; i += 32) ch[i].pad = s_ch[i].pad;
+		for (uint32_t i = lane; i < n; i += 32) { const uint32_t s = s_idx[i]; idx[i] = s; A.keep[cb + s] = 1; }
+	} else {
+		if (lane == 0) n = hb_chain_post(ch, ns, A.chits, idx, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
+		n = __shfl_sync(HB_FULL, n, 0);
+		__syncwarp();
+		for (uint32_t i = lane; i < n; i += 32) A.keep[cb + idx[i]] = 1;
+	}
+	if (lane == 0) A.n_ol[r] = n;
+}
+
 // ----------------------------------------------------------------------------
 // exact: warp per chain slot.  exact_ec_check (ecovlp.cpp:2803) of the query
 // interval against the strand-oriented target interval, 16 bases (one 32-bit
@@ -760,8 +816,34 @@ __global__ void k_merge(MergeArgs A)
 	uint64_t cb = A.c_off[r], ob = A.o_off[r], i0 = A.in0_off[r], i1 = A.in1_off[r];
 	uint32_t n0 = (uint32_t)(A.in0_off[r + 1] - i0), n1 = (uint32_t)(A.in1_off[r + 1] - i1), m0, m1;
 	unsigned long long st[7];
+	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st };
 	hb_final_merge(A.R, (uint32_t)(A.r0 + r), A.ch + cb, A.idx + cb, A.n_ol[r], A.exact + cb, A.in0 + i0, n0, A.in1 + i1, n1,
-	               A.ov + ob, A.srt + i0 + i1, A.out0 + ob, &m0, A.out1 + ob, &m1, st);
+	               A.ov + ob, A.srt + i0 + i1, A.out0 + ob, &m0, A.out1 + ob, &m1, st, W);
+	A.m0[r] = m0; A.m1[r] = m1;
+	for (int b = 0; b < 7; b++) if (st[b]) atomicAdd(&A.stat[b], st[b]);
+}
+
+// merge, warp per read: the working list (FinOv) and the sort keys are staged in shared
+// memory; lane 0 runs the sequential merge there.
+#define MERGE_WARPS 4
+#define MERGE_SMEM_PER_WARP 14336
+#define MERGE_RS_BYTES (2 * 256 * 4 + HB_RS_STACK * 12) /* radix-sort scratch, first in the warp's slice */
+__global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_warp(MergeArgs A)
+{
+	extern __shared__ uint4 merge_smem[];
+	const int wib = threadIdx.x >> 5, lane = hb_lane();
+	const uint64_t r = (uint64_t)blockIdx.x * MERGE_WARPS + wib;
+	if (r >= A.nR) return;
+	if (lane != 0) return;
+	const uint64_t cb = A.c_off[r], ob = A.o_off[r], i0 = A.in0_off[r], i1 = A.in1_off[r];
+	const uint32_t n0 = (uint32_t)(A.in0_off[r + 1] - i0), n1 = (uint32_t)(A.in1_off[r + 1] - i1), n_ol = A.n_ol[r]; uint32_t m0, m1;
+	unsigned long long st[7];
+	uint8_t *sw = (uint8_t *)(merge_smem + (size_t)wib * (MERGE_SMEM_PER_WARP / 16));
+	RsScratch W = { (int32_t *)sw, (int32_t *)sw + 256, (RsFrame *)(sw + 2048) };
+	uint8_t *rest = sw + ((MERGE_RS_BYTES + 15) & ~15);
+	FinOv *ov = A.ov + ob; uint64_t *srt = A.srt + i0 + i1;
+	if ((size_t)(n_ol + n0) * sizeof(FinOv) + (size_t)(n0 + n1) * 8 + 16 + ((MERGE_RS_BYTES + 15) & ~15) <= MERGE_SMEM_PER_WARP) { srt = (uint64_t *)rest; ov = (FinOv *)(srt + n0 + n1); } // u64 keys first: FinOv is 36 bytes
+	hb_final_merge(A.R, (uint32_t)(A.r0 + r), A.ch + cb, A.idx + cb, n_ol, A.exact + cb, A.in0 + i0, n0, A.in1 + i1, n1, ov, srt, A.out0 + ob, &m0, A.out1 + ob, &m1, st, W);
 	A.m0[r] = m0; A.m1[r] = m1;
 	for (int b = 0; b < 7; b++) if (st[b]) atomicAdd(&A.stat[b], st[b]);
 }

@@ -245,36 +245,57 @@ HB_HD void hb_sketch_read(const DevReads &R, const DevFt &ft, const SketchPar &P
 //                                      entries of E[t-w+1, t] equal to M(t), other position       (548-568)
 // and the last M is flushed at the end (571-573).
 // ===========================================================================
-struct SkEv { uint64_t *x, *m; uint32_t *l; };
+// one ring event = 16 bytes {x, m}: m = ~0 marks an N base (l restarts), m = SK_DUMMY_META an
+// accepted symbol without a candidate k-mer; l is recomputed from the stream (l = events since the last N)
+struct SkEv { ulonglong2 *e; };
+#define SK_NMARK (~0ULL)
 
 // stage 1: one thread per read; writes the read's ring events (cap = read length + 1).
-// The k-symbol span queue of the reference (tiny_queue_t, htab.h:39-57) is replaced by a
-// second cursor into the packed read that trails k HPC symbols behind: the span of the
-// last k symbols is simply (current run end) - (trailing cursor) + 1, no per-thread array.
+// The read is streamed 128 bases (one 32-byte sector) per load.  The k-symbol span queue of
+// the reference (tiny_queue_t, htab.h:39-57) is replaced by a second cursor into the packed
+// read that trails k HPC symbols behind: span = (current run end) - (trailing cursor) + 1.
+struct SkChunk { uint64_t w0, w1, w2, w3; int32_t idx; };
+HB_HD void sk_chunk_load(SkChunk &c, const uint64_t *seq64, int32_t chunk)
+{
+#ifdef __CUDA_ARCH__
+	const ulonglong2 a = __ldg((const ulonglong2 *)(seq64 + 4 * (size_t)chunk)), b = __ldg((const ulonglong2 *)(seq64 + 4 * (size_t)chunk + 2));
+	c.w0 = a.x; c.w1 = a.y; c.w2 = b.x; c.w3 = b.y;
+#else
+	c.w0 = seq64[4 * (size_t)chunk]; c.w1 = seq64[4 * (size_t)chunk + 1]; c.w2 = seq64[4 * (size_t)chunk + 2]; c.w3 = seq64[4 * (size_t)chunk + 3];
+#endif
+	c.idx = chunk;
+}
+HB_HD int sk_chunk_base(SkChunk &c, const uint64_t *seq64, int32_t ii)
+{
+	if ((ii >> 7) != c.idx) sk_chunk_load(c, seq64, ii >> 7);
+	const int q = (ii >> 5) & 3;
+	const uint64_t w = q == 0 ? c.w0 : q == 1 ? c.w1 : q == 2 ? c.w2 : c.w3;
+	return (int)((w >> ((((ii) & 31) >> 2 << 3) + ((3 - ((ii) & 3)) << 1))) & 3);
+}
+
 HB_HD void hb_sketch_events(const DevReads &R, const DevFt &ft, const SketchPar &P, uint64_t rid, SkEv ev, uint32_t *n_ev, uint32_t *tl_out)
 {
 	const int32_t k = P.k, len = (int32_t)R.len[rid];
 	const uint64_t shift1 = k - 1, mask = (1ULL << k) - 1;
-	const uint64_t *seq64 = (const uint64_t *)(R.packed + R.off[rid]);
-	uint64_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, word = 0, tword = 0;
-	int32_t i, l = 0, tl = 0, span = 0, qc = 0, wbase = -1, tbase = -1, tail = 0; uint32_t t = 0;
+	const uint64_t *seq64 = (const uint64_t *)(R.packed + R.off[rid]); // 32-byte aligned
+	uint64_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0;
+	SkChunk cur, trail; cur.idx = trail.idx = -1; cur.w0 = cur.w1 = cur.w2 = cur.w3 = trail.w0 = trail.w1 = trail.w2 = trail.w3 = 0;
+	int32_t i, l = 0, tl = 0, span = 0, qc = 0, tail = 0; uint32_t t = 0;
 	uint64_t ni = R.noff[rid], ne = R.noff[rid + 1];
 	int32_t next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX;
-#define SK_BASE(ii) ((int)(((((ii) >> 5) != wbase ? (wbase = (ii) >> 5, word = seq64[wbase]) : word) >> ((((ii) & 31) >> 2 << 3) + ((3 - ((ii) & 3)) << 1))) & 3))
-#define SK_TBASE(ii) ((int)(((((ii) >> 5) != tbase ? (tbase = (ii) >> 5, tword = seq64[tbase]) : tword) >> ((((ii) & 31) >> 2 << 3) + ((3 - ((ii) & 3)) << 1))) & 3))
 	for (i = 0; i < len; ++i) {
-		int c = SK_BASE(i);
-		uint64_t ix = ~0ULL, im = SK_DUMMY_META;
+		int c = sk_chunk_base(cur, seq64, i);
+		ulonglong2 e; e.x = ~0ULL; e.y = SK_DUMMY_META;
 		if (i == next_n) { c = 4; ++ni; next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX; }
 		if (c < 4) {
 			int z;
 			if (P.is_hpc) { // sketch.cpp:480-492
 				const int32_t i0 = i;
-				while (i + 1 < len && i + 1 != next_n && SK_BASE(i + 1) == c) ++i;
+				while (i + 1 < len && i + 1 != next_n && sk_chunk_base(cur, seq64, i + 1) == c) ++i;
 				if (qc == 0) tail = i0;
 				if (++qc > k) { // drop the oldest symbol: step the trailing cursor over its run
-					const int c0 = SK_TBASE(tail);
-					do ++tail; while (SK_TBASE(tail) == c0);
+					const int c0 = sk_chunk_base(trail, seq64, tail);
+					do ++tail; while (sk_chunk_base(trail, seq64, tail) == c0);
 					--qc;
 				}
 				span = i - tail + 1;
@@ -289,13 +310,11 @@ HB_HD void hb_sketch_events(const DevReads &R, const DevFt &ft, const SketchPar 
 			if (l >= k && span < 256) {
 				uint64_t y = z ? hb_hash64(pl2) + hb_hash64(pl3) : hb_hash64(pl0) + hb_hash64(pl1);
 				int32_t cnt = hb_ft_lookup(ft, y);
-				if (!(cnt >= 1 << 28)) { ix = y; im = (uint64_t)(uint32_t)cnt | (uint64_t)i << 28 | (uint64_t)z << 55 | (uint64_t)span << 56; }
+				if (!(cnt >= 1 << 28)) { e.x = y; e.y = (uint64_t)(uint32_t)cnt | (uint64_t)i << 28 | (uint64_t)z << 55 | (uint64_t)span << 56; }
 			}
-		} else { l = 0; qc = 0; span = 0; }
-		ev.x[t] = ix; ev.m[t] = im; ev.l[t] = (uint32_t)l; t++;
+		} else { l = 0; qc = 0; span = 0; e.y = SK_NMARK; }
+		ev.e[t] = e; t++;
 	}
-#undef SK_BASE
-#undef SK_TBASE
 	*n_ev = t; *tl_out = (uint32_t)tl;
 }
 

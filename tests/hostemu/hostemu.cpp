@@ -25,8 +25,8 @@ void *emu_reads_create(uint64_t n, const uint64_t *len, const uint8_t *packed, c
 	EmuReads *r = new EmuReads();
 	r->off.resize(n + 1); r->len.resize(n); r->noff.resize(n + 1);
 	uint64_t o = 0;
-	for (uint64_t i = 0; i < n; i++) { r->off[i] = o; r->len[i] = (uint32_t)len[i]; o += ((len[i] / 4 + 1) + 7) & ~7ULL; }
-	r->off[n] = o; r->packed.assign(o + 8, 0);
+	for (uint64_t i = 0; i < n; i++) { r->off[i] = o; r->len[i] = (uint32_t)len[i]; o += ((len[i] / 4 + 1) + 31) & ~31ULL; }
+	r->off[n] = o; r->packed.assign(o + 64, 0);
 	for (uint64_t i = 0; i < n; i++) memcpy(&r->packed[r->off[i]], packed + byte_off[i], len[i] / 4 + 1);
 	for (uint64_t i = 0; i <= n; i++) r->noff[i] = n_off ? n_off[i] : 0;
 	r->npos.resize(r->noff[n] + 1);
@@ -90,9 +90,16 @@ int emu_sketch2(void *reads, void *ft, int w, int k, int is_hpc, int sample_dist
 	EmuReads *r = (EmuReads *)reads; EmuFt *f = (EmuFt *)ft;
 	SketchPar P = { w, k, is_hpc, sample_dist, rewin };
 	uint32_t len = r->d.len[rid], T = 0, tl = 0;
-	std::vector<uint64_t> ex(len + 1), em(len + 1); std::vector<uint32_t> el(len + 1), ol(cap + 1);
-	SkEv ev = { ex.data(), em.data(), el.data() };
+	std::vector<ulonglong2> evs(len + 2); std::vector<uint64_t> ex(len + 1), em(len + 1); std::vector<uint32_t> el(len + 1), ol(cap + 1);
+	SkEv ev = { evs.data() };
 	hb_sketch_events(r->d, f->d, P, rid, ev, &T, &tl);
+	{ // what k_sketch_select does when it stages a tile: split the records, l = events since the last N base
+		int64_t lastN = -1;
+		for (uint32_t t = 0; t < T; t++) {
+			ex[t] = evs[t].x; em[t] = evs[t].y;
+			if (em[t] == SK_NMARK) { lastN = t; el[t] = 0; em[t] = SK_DUMMY_META; } else el[t] = (uint32_t)(t - lastN);
+		}
+	}
 	std::vector<int32_t> pre(T + 1), suf(T + 1);
 	for (uint32_t b = 0; b < T; b += w) {
 		uint32_t e = std::min<uint32_t>(T, b + w); int32_t cur = b;
@@ -240,7 +247,8 @@ int emu_final_read(void *reads, void *ft, void *pt, int w, int k, int is_hpc, in
 	}
 	std::vector<FinOv> ov(E.n_ol + n0 + 1); std::vector<uint64_t> srt(n0 + n1 + 1);
 	unsigned long long stat[8];
-	hb_final_merge(r->d, rid, E.ch.data(), E.idx.data(), E.n_ol, exact.data(), in0, n0, in1, n1, ov.data(), srt.data(), out0, m0, out1, m1, stat);
+	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
+	hb_final_merge(r->d, rid, E.ch.data(), E.idx.data(), E.n_ol, exact.data(), in0, n0, in1, n1, ov.data(), srt.data(), out0, m0, out1, m1, stat, W);
 	return 0;
 }
 
