@@ -408,7 +408,7 @@ __global__ void k_stage3_counts(uint64_t nR, const uint64_t *__restrict__ c_off,
 	n_hit[r] = h; n_fc[r] = f;
 }
 __global__ void k_stage3_fill(uint64_t nR, const uint64_t *__restrict__ c_off, const uint64_t *__restrict__ a_off, uint64_t a_base, const hb_chain_t *__restrict__ ch, const GroupDir *dirless,
-                              const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol, const hb_hit_t *__restrict__ chits, const uint64_t *__restrict__ fc,
+                              const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol, const hb_hit_t *__restrict__ chits, const hb_hit_t *__restrict__ ghits, const uint64_t *__restrict__ fc,
                               const uint64_t *__restrict__ o_ch, const uint64_t *__restrict__ o_hit, const uint64_t *__restrict__ o_fc,
                               hb_chain_t *__restrict__ out_ch, hb_hit_t *__restrict__ out_hit, uint64_t *__restrict__ out_fc, const uint64_t *__restrict__ fc_grp_base)
 {
@@ -418,7 +418,8 @@ __global__ void k_stage3_fill(uint64_t nR, const uint64_t *__restrict__ c_off, c
 	for (uint32_t s = 0; s < ns; s++) { // compacted chain anchors, tagged with the chain ordinal (Hash_Table.cpp:2240,2279)
 		const hb_chain_t &c = ch[cb + s];
 		if (!c.n_hits) continue;
-		for (uint32_t h = 0; h < c.n_hits; h++) { hb_hit_t v = chits[c.first_hit + h]; v.id_strand = (v.id_strand & 0x80000000u) | ord; out_hit[m++] = v; }
+		const hb_hit_t *hb_ = (c.pad & HB_CHAIN_INPLACE) ? ghits : chits;
+		for (uint32_t h = 0; h < c.n_hits; h++) { hb_hit_t v = hb_[c.first_hit + h]; v.id_strand = (v.id_strand & 0x80000000u) | ord; out_hit[m++] = v; }
 		ord++;
 	}
 	for (uint32_t i = 0; i < n_ol[r]; i++) {
@@ -426,7 +427,7 @@ __global__ void k_stage3_fill(uint64_t nR, const uint64_t *__restrict__ c_off, c
 		const uint64_t *src = fc + fc_grp_base[cb + idx[cb + i]] + c.fc_off;
 		for (uint32_t j = 0; j < c.fc_n; j++) out_fc[fo + j] = src[j];
 		c.fc_off = (uint32_t)(fo - o_fc[r]); fo += c.fc_n;
-		c.first_hit = c.pad; c.pad = 0;
+		c.first_hit = c.pad & ~HB_CHAIN_INPLACE; c.pad = 0;
 		out_ch[o_ch[r] + i] = c;
 	}
 }
@@ -585,7 +586,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_ALLOC_CHECK(ba);
 		{
 			ChainArgs C; C.R = R; C.r0 = r0 + b0; C.dir = d_dir; C.dir_n = d_dirn; C.a_off = d_aoff + b0; C.a_base = a_base; C.c_off = d_coff;
-			C.hits = d_hits; C.chits = d_chits; C.f = d_f; C.p = d_p; C.ii = d_ii; C.t = d_t; C.ch = d_ch; C.slot_read = d_slot_read; C.fc = d_fc; C.P = CP; C.err = d_err; C.dbg = d_stat + 8;
+			C.hits = d_hits; C.chits = d_chits; C.f = d_f; C.p = d_p; C.ii = d_ii; C.t = d_t; C.ch = d_ch; C.slot_read = d_slot_read; C.fc = d_fc; C.P = CP; C.err = d_err; C.dbg = d_stat + 8; C.work = ba.zero<uint32_t>(1); HB_ALLOC_CHECK(ba);
 			ProfScope ps(ctx, "k_chain");
 			if (getenv("HB_CHAIN_THREAD")) k_chain<<<std::max(1u, std::min(nblk(h_dirn, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
 			else k_chain_warp<<<std::max(1u, std::min(nblk((uint64_t)h_dirn * 32, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
@@ -604,7 +605,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		uint64_t cc_tot = 0; for (uint64_t i = r0 + b0; i < r0 + b1; i++) cc_tot += ctx->h_rlen[i] / CP.ocv_w + 2;
 		uint64_t *d_cc = ba.get<uint64_t>(cc_tot + 1); HB_ALLOC_CHECK(ba);
 		{
-			PostArgs Pa; Pa.R = R; Pa.r0 = r0 + b0; Pa.nR = nb; Pa.c_off = d_coff; Pa.ch = d_ch; Pa.chits = d_chits; Pa.idx = d_idx; Pa.n_ol = d_nol; Pa.keep = d_keep; Pa.cc = d_cc; Pa.cc_off = d_ccoff; Pa.P = CP;
+			PostArgs Pa; Pa.R = R; Pa.r0 = r0 + b0; Pa.nR = nb; Pa.c_off = d_coff; Pa.ch = d_ch; Pa.chits = d_chits; Pa.ghits = d_hits; Pa.idx = d_idx; Pa.n_ol = d_nol; Pa.keep = d_keep; Pa.cc = d_cc; Pa.cc_off = d_ccoff; Pa.P = CP;
 			ProfScope ps(ctx, "k_post");
 			if (getenv("HB_POST_THREAD")) k_post<<<nblk(nb, 64), 64, 0, ctx->stream>>>(Pa);
 			else k_post_warp<<<nblk(nb, POST_WARPS), POST_WARPS * 32, POST_WARPS * POST_SMEM_PER_WARP, ctx->stream>>>(Pa);
@@ -624,7 +625,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			HB_CUDA(cudaMemcpyAsync(h_of.data(), d_of, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 			hb_chain_t *d_o1 = ba.get<hb_chain_t>(h_och[nb] + 1); hb_hit_t *d_o2 = ba.get<hb_hit_t>(h_oh[nb] + 1); uint64_t *d_o3 = ba.get<uint64_t>(h_of[nb] + 1);
 			HB_ALLOC_CHECK(ba);
-			k_stage3_fill<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_aoff + b0, a_base, d_ch, 0, d_idx, d_nol, d_chits, d_fc, d_och, d_oh, d_of, d_o1, d_o2, d_o3, d_fcb);
+			k_stage3_fill<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_aoff + b0, a_base, d_ch, 0, d_idx, d_nol, d_chits, d_hits, d_fc, d_och, d_oh, d_of, d_o1, d_o2, d_o3, d_fcb);
 			HB_CUDA(cudaGetLastError());
 			if (so->rec && st3_n + h_och[nb] > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "chain output capacity"); return HB_E_OVERFLOW; }
 			if (so->hits && st3_nh + h_oh[nb] > so->hit_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "chain-anchor output capacity"); return HB_E_OVERFLOW; }

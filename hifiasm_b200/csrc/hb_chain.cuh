@@ -19,6 +19,7 @@ struct ChainPar {
 };
 
 // group directory entry written by the probe/group kernel
+#define HB_CHAIN_INPLACE 0x80000000u // hb_chain_t.pad bit: the chain's anchors are a slice of the grouped anchor buffer, not of the chain-anchor buffer
 struct GroupDir { uint32_t read, start, count, slot; }; // start: rel. to the read's anchor base; slot: rel. to the read's chain-slot base
 
 #define HB_LINK_FAIL INT32_MIN
@@ -437,11 +438,11 @@ HB_HD void hb_cov_add(uint64_t *cc, uint64_t cwn, uint64_t ocv_w, uint64_t rl, c
 // first_hit); idx: n_slots scratch; cc: coverage-window scratch (rl/ocv_w+1).
 // Leaves the kept chains' slot numbers in idx[0..n), returns n; writes the
 // compacted anchor index (cl->list position, Hash_Table.cpp:2280) to .pad.
-HB_HD uint32_t hb_chain_post(hb_chain_t *ch, uint32_t n_slots, const hb_hit_t *chits, uint32_t *idx, uint64_t *cc, uint64_t rl, const ChainPar &P)
+HB_HD uint32_t hb_chain_post(hb_chain_t *ch, uint32_t n_slots, const hb_hit_t *chits_, const hb_hit_t *ghits, uint32_t *idx, uint64_t *cc, uint64_t rl, const ChainPar &P)
 {
 	uint64_t i, k, l, n = 0, lch = 0, cwn = 0, m = 0, max_n_chain = (uint64_t)P.max_n_chain; uint32_t t;
 	for (i = 0; i < n_slots; i++)
-		if (ch[i].n_hits) { idx[n++] = (uint32_t)i; ch[i].pad = (uint32_t)m; m += ch[i].n_hits; if (ch[i].n_hits < P.chain_cutoff) lch = 1; }
+		if (ch[i].n_hits) { idx[n++] = (uint32_t)i; ch[i].pad = (ch[i].pad & HB_CHAIN_INPLACE) | (uint32_t)m; m += ch[i].n_hits; if (ch[i].n_hits < P.chain_cutoff) lch = 1; }
 	if (P.chain_cutoff < 2) lch = 0;
 	k = n;
 	if (n > max_n_chain) { // anchor.cpp:1954-2058
@@ -516,6 +517,7 @@ HB_HD uint32_t hb_chain_post(hb_chain_t *ch, uint32_t n_slots, const hb_hit_t *c
 						// instead of the whole chain: same count, a handful of loads.
 						mm = zk.first_hit; kn = 0;
 						{
+							const hb_hit_t *chits = (zk.pad & HB_CHAIN_INPLACE) ? ghits : chits_;
 							uint64_t lo_ = 0, hi_ = zk.n_hits;
 							while (lo_ < hi_) { uint64_t mid = (lo_ + hi_) >> 1; if (chits[mm + mid].self_offset < os) lo_ = mid + 1; else hi_ = mid; }
 							for (hh = lo_; hh < zk.n_hits && kn < ocn; hh++) {

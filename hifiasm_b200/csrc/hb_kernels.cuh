@@ -348,11 +348,18 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 		if (lane == 0) s_nd[wib] = 0;
 		__syncwarp();
 		bool ovf = false;
-		for (uint32_t q = lane; q < n; q += 32) {
-			bool fresh; uint32_t s = grp_find_or_insert(keys, mask, grp_key(raw[q].id_strand), &fresh);
-			if (s == GRP_EMPTY) { ovf = true; continue; }
-			atomicAdd(&vals[s], 1u);
-			if (fresh && atomicAdd(&s_nd[wib], 1u) >= maxg) ovf = true;
+		for (uint32_t q0 = 0; q0 < n; q0 += 128) { // 4 x 32 anchors per step: the four key loads are in flight together
+			uint32_t kk[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) { const uint32_t q = q0 + 32 * u + lane; kk[u] = q < n ? grp_key(__ldg(&raw[q].id_strand)) : GRP_EMPTY; }
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (kk[u] == GRP_EMPTY) continue;
+				bool fresh; uint32_t s = grp_find_or_insert(keys, mask, kk[u], &fresh);
+				if (s == GRP_EMPTY) { ovf = true; continue; }
+				atomicAdd(&vals[s], 1u);
+				if (fresh && atomicAdd(&s_nd[wib], 1u) >= maxg) ovf = true;
+			}
 		}
 		__syncwarp();
 		if (!__any_sync(HB_FULL, ovf)) break;
@@ -412,14 +419,19 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 	if (lane == 0) A.sc[r] = run_s;
 	__syncwarp();
 	// phase C: ordered scatter (32 anchors at a time, in minimizer order)
-	for (uint32_t q0 = 0; q0 < n; q0 += 32) {
-		uint32_t q = q0 + lane;
-		if (q < n) {
-			uint4 h = *(const uint4 *)(raw + q);
-			uint32_t d = atomicAdd(&vals[grp_find(keys, mask, grp_key(h.x))], 1u);
-			*(uint4 *)(out + d) = h;
+	for (uint32_t q0 = 0; q0 < n; q0 += 128) { // 4 x 32 anchors loaded together, scattered 32 at a time in order
+		uint4 hh[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) { const uint32_t q = q0 + 32 * u + lane; if (q < n) hh[u] = __ldg((const uint4 *)(raw + q)); else hh[u].x = GRP_EMPTY; }
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const uint32_t q = q0 + 32 * u + lane;
+			if (q < n) {
+				uint32_t d = atomicAdd(&vals[grp_find(keys, mask, grp_key(hh[u].x))], 1u);
+				*(uint4 *)(out + d) = hh[u];
+			}
+			__syncwarp();
 		}
-		__syncwarp();
 	}
 }
 
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 // ----------------------------------------------------------------------------
 struct ChainArgs {
 	DevReads R; uint64_t r0; const GroupDir *dir; const uint32_t *dir_n; const uint64_t *a_off; uint64_t a_base; const uint64_t *c_off;
-	hb_hit_t *hits, *chits; int32_t *f, *p, *ii; int64_t *t; hb_chain_t *ch; uint32_t *slot_read; uint64_t *fc; ChainPar P; int *err; unsigned long long *dbg;
+	hb_hit_t *hits, *chits; int32_t *f, *p, *ii; int64_t *t; hb_chain_t *ch; uint32_t *slot_read; uint64_t *fc; ChainPar P; int *err; unsigned long long *dbg; uint32_t *work;
 };
 __global__ void k_chain(ChainArgs A)
 {
@@ -530,6 +542,89 @@ static __device__ QBlock warp_quick_block(const hb_hit_t *a, int32_t l, int32_t 
 	return q;
 }
 
+// One pass over an (expected ordered, expected co-linear) group: order check, strand-block
+// boundary, quick_ck_lchain for both strand blocks (segmented warp prefix sums), 32 anchors per
+// step with the next 32 already in flight.  ok = false sends the group to the general path.
+struct QFused { bool ok; int32_t kb; QBlock b[2]; };
+static __device__ QFused warp_quick_fused(const hb_hit_t *a, int32_t n, const ChainPar &P, int64_t xl, int64_t yl, int lane)
+{
+	QFused R; R.ok = false; R.kb = n; R.b[0].resolved = R.b[1].resolved = false; R.b[0].msc0 = R.b[0].msc_i0 = R.b[0].plus0 = R.b[1].msc0 = R.b[1].msc_i0 = R.b[1].plus0 = 0;
+	int64_t carry_f = 0, msc0[2] = { INT64_MIN, INT64_MIN }, msc_i0[2] = { -1, -1 }, plus0[2] = { 0, 0 }, ddt[2] = { 0, 0 };
+	hb_hit_t first[2], lasth, prev_last; first[0].id_strand = first[1].id_strand = 0; first[0].offset = first[0].self_offset = first[0].cnt = first[1].offset = first[1].self_offset = first[1].cnt = 0;
+	prev_last = first[0]; lasth = first[0];
+	int32_t cntb[2] = { 0, 0 };
+	hb_hit_t nxt = hit_ld(a + (lane < n ? lane : n - 1));
+	for (int32_t base = 0; base < n; base += 32) {
+		const int32_t z = base + lane; const bool valid = z < n;
+		const hb_hit_t h = nxt;
+		if (base + 32 < n) nxt = hit_ld(a + (z + 32 < n ? z + 32 : n - 1)); // prefetch
+		hb_hit_t hp = hit_shfl_up1(h); if (lane == 0) hp = prev_last;
+		const uint32_t sb = h.id_strand >> 31;
+		const bool start = valid && (z == 0 || sb != (hp.id_strand >> 31));
+		bool bad = false, viol = false; int32_t dd = 0, s = 0;
+		if (valid && z > 0 && hit_okey(hp) > hit_okey(h)) bad = true; // not in (strand, self_offset, offset) order
+		if (valid && !start) {
+			if (h.self_offset <= hp.self_offset || h.offset <= hp.offset) viol = true;
+			else { s = hb_link_sc(h, hp, P, xl, yl, &dd); if (s == HB_LINK_FAIL) viol = true; }
+		}
+		if (__any_sync(HB_FULL, bad || viol)) return R;
+		const int64_t v = !valid ? 0 : start ? (int64_t)(h.cnt & 0xffu) : (int64_t)s;
+		int64_t inc = v;
+		for (int d = 1; d < 32; d <<= 1) { int64_t u = __shfl_up_sync(HB_FULL, inc, d); if (lane >= d) inc += u; }
+		const unsigned sm = __ballot_sync(HB_FULL, start);
+		const unsigned below = sm & (lane == 31 ? 0xffffffffu : ((2u << lane) - 1));
+		const int sl = below ? 31 - __clz(below) : -1;
+		const int64_t excl_at_start = __shfl_sync(HB_FULL, inc - v, sl < 0 ? 0 : sl);
+		const int64_t fz = sl < 0 ? carry_f + inc : inc - excl_at_start;
+		if (__any_sync(HB_FULL, valid && !start && fz < (int64_t)(h.cnt & 0xffu))) return R; // sc < csc, Hash_Table.cpp:2059
+		if (sm) { // a block starts in this chunk
+			const int fl = __ffs(sm) - 1; // there is at most one start per strand; strand of the starting lane
+			for (unsigned m = sm; m; m &= m - 1) {
+				const int l0 = __ffs(m) - 1; const uint32_t bs = __shfl_sync(HB_FULL, sb, l0);
+				first[bs].id_strand = __shfl_sync(HB_FULL, h.id_strand, l0); first[bs].offset = __shfl_sync(HB_FULL, h.offset, l0);
+				first[bs].self_offset = __shfl_sync(HB_FULL, h.self_offset, l0); first[bs].cnt = __shfl_sync(HB_FULL, h.cnt, l0);
+				if (bs == 1) R.kb = base + l0;
+			}
+			(void)fl;
+		}
+		// per-block running best end (>=: later wins), minimum, gap sum, count
+		const unsigned vm = __ballot_sync(HB_FULL, valid), m1 = __ballot_sync(HB_FULL, valid && sb), m0 = vm & ~m1;
+		for (int bs = 0; bs < 2; bs++) {
+			const unsigned mm = bs ? m1 : m0;
+			if (!mm) continue;
+			const bool in = (mm >> lane) & 1;
+			int64_t bf = in ? fz : INT64_MIN, bi = in ? z : -1, mf = in ? fz : INT64_MAX, sd = (in && !start) ? dd : 0;
+			for (int d = 16; d; d >>= 1) {
+				int64_t of = __shfl_xor_sync(HB_FULL, bf, d), oi = __shfl_xor_sync(HB_FULL, bi, d), om = __shfl_xor_sync(HB_FULL, mf, d), od = __shfl_xor_sync(HB_FULL, sd, d);
+				if (of > bf || (of == bf && oi > bi)) { bf = of; bi = oi; }
+				if (om < mf) mf = om;
+				sd += od;
+			}
+			if (bf >= msc0[bs]) { msc0[bs] = bf; msc_i0[bs] = bi; }
+			if (mf < plus0[bs]) plus0[bs] = mf;
+			ddt[bs] += sd; cntb[bs] += __popc(mm);
+		}
+		const int lastl = (n - base < 32 ? n - base : 32) - 1;
+		carry_f = __shfl_sync(HB_FULL, fz, lastl);
+		prev_last.id_strand = __shfl_sync(HB_FULL, h.id_strand, lastl); prev_last.offset = __shfl_sync(HB_FULL, h.offset, lastl);
+		prev_last.self_offset = __shfl_sync(HB_FULL, h.self_offset, lastl); prev_last.cnt = __shfl_sync(HB_FULL, h.cnt, lastl);
+		if (m0) { const int l0 = 31 - __clz(m0); lasth.id_strand = __shfl_sync(HB_FULL, h.id_strand, l0); lasth.offset = __shfl_sync(HB_FULL, h.offset, l0); lasth.self_offset = __shfl_sync(HB_FULL, h.self_offset, l0); lasth.cnt = __shfl_sync(HB_FULL, h.cnt, l0); }
+	}
+	// lasth = last anchor of block 0 (if any); prev_last = last anchor of the group (= last of block 1 when it exists)
+	for (int bs = 0; bs < 2; bs++) {
+		if (!cntb[bs]) continue;
+		const int32_t l = bs ? R.kb : 0, kk = bs ? n : R.kb;
+		if (msc_i0[bs] != kk - 1) return R;
+		if (kk - l >= 2 && ddt[bs] > 16) { // Hash_Table.cpp:2071
+			const hb_hit_t e = (bs == 0 && cntb[1]) ? lasth : prev_last;
+			if (ddt[bs] > hb_link_bw(e, first[bs], P.bw_rate, xl, yl)) return R;
+		}
+		R.b[bs].resolved = true; R.b[bs].msc0 = msc0[bs]; R.b[bs].msc_i0 = msc_i0[bs]; R.b[bs].plus0 = plus0[bs];
+	}
+	R.ok = true;
+	return R;
+}
+
 // The chaining DP of lchain_qdp_mcopy_fast (Hash_Table.cpp:2124-2176) with the
 // predecessor scan spread over the warp: 32 predecessors per step, link scores in
 // parallel, the sequential semantics (running best, n_skip early stop, t[] marks)
@@ -616,29 +711,29 @@ static __device__ void warp_chain_dp(const hb_hit_t *a, int32_t kb, int32_t *f, 
 __global__ void __launch_bounds__(128) k_chain_warp(ChainArgs A)
 {
 	const uint32_t n = *A.dir_n; const int lane = hb_lane();
-	const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t g = w0; g < n; g += nw) {
+	for (;;) { // groups are handed out one at a time: a few of them (those needing the DP) cost 100x the rest
+		uint32_t g = 0;
+		if (lane == 0) g = atomicAdd(A.work, 1u);
+		g = __shfl_sync(HB_FULL, g, 0);
+		if (g >= n) break;
 		GroupDir d = A.dir[g];
 		const uint64_t ab = A.a_off[d.read] - A.a_base + d.start; hb_hit_t *a = A.hits + ab; const int32_t an = (int32_t)d.count;
-		int32_t kb;
-		bool ordered = warp_group_ordered(a, an, lane, &kb);
-		if (!ordered && lane == 0 && A.dbg) atomicAdd(&A.dbg[0], 1ull);
-		if (d.slot == GRP_EMPTY) { if (!ordered && lane == 0) hb_order_group(a, an); __syncwarp(); continue; }
+		int32_t kb = an; bool ordered = true;
+		if (d.slot == GRP_EMPTY) { ordered = warp_group_ordered(a, an, lane, &kb); if (!ordered && lane == 0) hb_order_group(a, an); __syncwarp(); continue; }
 		const uint64_t cb = A.c_off[d.read] + d.slot;
 		const int32_t ns = d.count >= (uint32_t)A.P.mcopy_khit_cutoff ? A.P.mcopy_num : 1;
 		const int64_t xl = A.R.len[A.r0 + d.read], yl = A.R.len[HB_HIT_ID(hit_ld(a))];
-		bool simple = ordered; int64_t msc = INT32_MIN, msc_i = INT32_MIN, movl = INT32_MAX, plus = 0, other_max = INT64_MIN; int32_t lb = 0;
-		if (simple) { // quick_ck_lchain over the (at most two) strand blocks, Hash_Table.cpp:2015-2093
-			for (int b = 0; b < 2 && simple; b++) {
-				int32_t l = b ? kb : 0, k = b ? an : kb;
-				if (l >= k) continue;
-				QBlock q = warp_quick_block(a, l, k, A.P, xl, yl, lane);
-				if (!q.resolved) { simple = false; break; }
-				bool took = false;
+		bool simple; int64_t msc = INT32_MIN, msc_i = INT32_MIN, movl = INT32_MAX, plus = 0, other_max = INT64_MIN; int32_t lb = 0;
+		{
+			const QFused Q = warp_quick_fused(a, an, A.P, xl, yl, lane);
+			simple = Q.ok; kb = Q.kb;
+			for (int b = 0; b < 2 && simple; b++) { // combine the strand blocks, Hash_Table.cpp:2072-2085
+				if (!Q.b[b].resolved) continue;
+				const QBlock &q = Q.b[b]; bool took = false;
 				if (q.msc0 >= msc) {
 					hb_hit_t e = hit_ld(a + q.msc_i0);
 					int64_t movl0 = hb_chain_len(e.self_offset, e.self_offset, xl, e.offset, e.offset, yl);
-					if (q.msc0 > msc || movl0 < movl) { if (msc_i != INT32_MIN) other_max = msc; msc = q.msc0; msc_i = q.msc_i0; movl = movl0; lb = l; took = true; }
+					if (q.msc0 > msc || movl0 < movl) { if (msc_i != INT32_MIN) other_max = msc; msc = q.msc0; msc_i = q.msc_i0; movl = movl0; lb = b ? kb : 0; took = true; }
 				}
 				if (!took) other_max = q.msc0;
 				if (q.plus0 < plus) plus = q.plus0;
@@ -651,16 +746,13 @@ __global__ void __launch_bounds__(128) k_chain_warp(ChainArgs A)
 				if (other_max - plus >= min_sc) simple = false;
 			}
 		}
-		if (simple) {
+		if (simple) { // the chain is the whole best block, already contiguous in the grouped buffer: no copy
 			const int32_t cL = (int32_t)(msc_i - lb + 1);
-			hb_hit_t *des = A.chits + ab;
-			for (int32_t i = lane; i < cL; i += 32) *(uint4 *)(des + i) = *(const uint4 *)(a + lb + i);
-			__syncwarp();
 			if (lane == 0) {
 				hb_chain_t z; hb_hit_t hb = hit_ld(a + lb), he = hit_ld(a + msc_i);
 				hb_push_chain(z, xl, yl, msc, hb, he);
-				z.first_hit = (uint32_t)ab; z.n_hits = (uint32_t)cL;
-				if (A.fc) { FcOut fc; fc.n = 0; fc.ovf = 0; fc.buf = A.fc + ab + 2 * cb; fc.cap = d.count + 2 * ns; hb_gen_fcigar(fc, z, des, cL); if (fc.ovf) atomicOr(A.err, 16); }
+				z.first_hit = (uint32_t)(ab + lb); z.n_hits = (uint32_t)cL; z.pad = HB_CHAIN_INPLACE;
+				if (A.fc) { FcOut fc; fc.n = 0; fc.ovf = 0; fc.buf = A.fc + ab + 2 * cb; fc.cap = d.count + 2 * ns; hb_gen_fcigar(fc, z, a + lb, cL); if (fc.ovf) atomicOr(A.err, 16); }
 				A.ch[cb] = z;
 				for (int32_t s = 1; s < ns; s++) A.ch[cb + s].n_hits = 0;
 				for (int32_t s = 0; s < ns; s++) A.slot_read[cb + s] = d.read;
@@ -670,7 +762,8 @@ __global__ void __launch_bounds__(128) k_chain_warp(ChainArgs A)
 			// unresolved range, then backtrack / secondary chains / emission on lane 0
 			int32_t *f = A.f + ab, *p = A.p + ab, *ii = A.ii + ab; int64_t *t = A.t + ab;
 			if (lane == 0 && A.dbg) atomicAdd(&A.dbg[1], 1ull);
-			if (!ordered) { if (lane == 0) hb_order_group(a, an); __syncwarp(); warp_group_ordered(a, an, lane, &kb); }
+			ordered = warp_group_ordered(a, an, lane, &kb);
+			if (!ordered) { if (lane == 0) { hb_order_group(a, an); if (A.dbg) atomicAdd(&A.dbg[0], 1ull); } __syncwarp(); warp_group_ordered(a, an, lane, &kb); }
 			for (int32_t z = lane; z < an; z += 32) { t[z] = 0; ii[z] = 0; }
 			ChainState S; S.plus = 0; S.msc = S.msc_i = INT32_MIN; S.movl = INT32_MAX; S.si = 0; S.ei = an;
 			for (int b = 0; b < 2; b++) { // quick_ck_lchain, Hash_Table.cpp:2015-2093
@@ -705,7 +798,7 @@ __global__ void __launch_bounds__(128) k_chain_warp(ChainArgs A)
 // post: one thread per read
 // ----------------------------------------------------------------------------
 struct PostArgs {
-	DevReads R; uint64_t r0, nR; const uint64_t *c_off; hb_chain_t *ch; const hb_hit_t *chits; uint32_t *idx; uint32_t *n_ol; uint8_t *keep;
+	DevReads R; uint64_t r0, nR; const uint64_t *c_off; hb_chain_t *ch; const hb_hit_t *chits, *ghits; uint32_t *idx; uint32_t *n_ol; uint8_t *keep;
 	uint64_t *cc; const uint64_t *cc_off; ChainPar P;
 };
 __global__ void k_post(PostArgs A)
@@ -713,7 +806,7 @@ __global__ void k_post(PostArgs A)
 	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= A.nR) return;
 	uint64_t cb = A.c_off[r]; uint32_t ns = (uint32_t)(A.c_off[r + 1] - cb);
-	uint32_t n = hb_chain_post(A.ch + cb, ns, A.chits, A.idx + cb, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
+	uint32_t n = hb_chain_post(A.ch + cb, ns, A.chits, A.ghits, A.idx + cb, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
 	A.n_ol[r] = n;
 	for (uint32_t i = 0; i < n; i++) A.keep[cb + A.idx[cb + i]] = 1;
 }
@@ -738,13 +831,13 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post_warp(PostArgs A)
 		const uint4 *src = (const uint4 *)ch;
 		for (uint32_t i = lane; i < ns * 3; i += 32) sw[i] = src[i];
 		__syncwarp();
-		if (lane == 0) n = hb_chain_post(s_ch, ns, A.chits, s_idx, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
+		if (lane == 0) n = hb_chain_post(s_ch, ns, A.chits, A.ghits, s_idx, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
 		n = __shfl_sync(HB_FULL, n, 0);
 		__syncwarp();
 		for (uint32_t i = lane; i < ns; i += 32) ch[i].pad = s_ch[i].pad;
 		for (uint32_t i = lane; i < n; i += 32) { const uint32_t s = s_idx[i]; idx[i] = s; A.keep[cb + s] = 1; }
 	} else {
-		if (lane == 0) n = hb_chain_post(ch, ns, A.chits, idx, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
+		if (lane == 0) n = hb_chain_post(ch, ns, A.chits, A.ghits, idx, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
 		n = __shfl_sync(HB_FULL, n, 0);
 		__syncwarp();
 		for (uint32_t i = lane; i < n; i += 32) A.keep[cb + idx[i]] = 1;

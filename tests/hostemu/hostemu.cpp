@@ -203,7 +203,7 @@ static void run_chains(EmuReads *r, uint32_t rid, hb_hit_t *hits, uint64_t n_hit
 	}
 	E.fc.resize(fc.n);
 	std::vector<uint64_t> cc(r->d.len[rid] / P.ocv_w + 2);
-	E.n_ol = hb_chain_post(E.ch.data(), slot, E.chits.data(), E.idx.data(), cc.data(), r->d.len[rid], P);
+	E.n_ol = hb_chain_post(E.ch.data(), slot, E.chits.data(), hits, E.idx.data(), cc.data(), r->d.len[rid], P);
 }
 
 // -> chains in final order (first_hit = compacted cl->list index), compacted chain anchors, fake cigars
