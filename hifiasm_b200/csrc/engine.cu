@@ -445,6 +445,7 @@ __global__ void k_fc_grp_base(const GroupDir *__restrict__ dir, const uint32_t *
 struct StageOut { // host destinations of the stage APIs (all optional)
 	uint64_t *off; void *rec; uint64_t rec_cap;      // stage 1: minimizers / stage 2: anchors / stage 3: chains
 	uint64_t *hit_off; hb_hit_t *hits; uint64_t hit_cap; uint64_t *fc_off; uint64_t *fc; uint64_t fc_cap;
+	double e_rate; int32_t w_l; // window pass
 };
 
 // mode: 0 final pass (results kept in ctx->d_out*), 2 anchors, 3 chains
@@ -514,7 +515,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	if (mode == 2) { d_all_hits = ar.get<hb_hit_t>(h_aoff[nR] + 1); HB_ALLOC_CHECK(ar); }
 	std::vector<uint64_t> st3_off, st3_hit_off, st3_fc_off; // mode 3 host offsets (accumulated per batch)
 	uint64_t st3_n = 0, st3_nh = 0, st3_nf = 0;
-	if (mode == 3) { st3_off.assign(nR + 1, 0); st3_hit_off.assign(nR + 1, 0); st3_fc_off.assign(nR + 1, 0); }
+	if (mode == 3 || mode == 4) { st3_off.assign(nR + 1, 0); st3_hit_off.assign(nR + 1, 0); st3_fc_off.assign(nR + 1, 0); }
 	unsigned long long *d_stat = ar.zero<unsigned long long>(16);
 	uint32_t *d_m0 = 0, *d_m1 = 0; // per-read result counts (final pass)
 	struct BatchRes { hb_ma_hit_t *o0, *o1; uint64_t *ooff; uint64_t b0, b1; };
@@ -582,7 +583,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		// chain
 		hb_hit_t *d_chits = ba.get<hb_hit_t>(B + 1); int32_t *d_f = ba.get<int32_t>(B + 1), *d_p = ba.get<int32_t>(B + 1), *d_ii = ba.get<int32_t>(B + 1); int64_t *d_t = ba.get<int64_t>(B + 1);
 		hb_chain_t *d_ch = ba.zero<hb_chain_t>(n_slots + 1); uint32_t *d_slot_read = ba.get<uint32_t>(n_slots + 1);
-		uint64_t *d_fc = mode == 3 ? ba.get<uint64_t>(B + 2 * n_slots + 4) : 0;
+		uint64_t *d_fc = (mode == 3 || mode == 4) ? ba.get<uint64_t>(B + 2 * n_slots + 4) : 0;
 		HB_ALLOC_CHECK(ba);
 		{
 			ChainArgs C; C.R = R; C.r0 = r0 + b0; C.dir = d_dir; C.dir_n = d_dirn; C.a_off = d_aoff + b0; C.a_base = a_base; C.c_off = d_coff;
@@ -614,6 +615,35 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	TRACE("post");
 		ctx->counters[5] += n_slots;
 
+		if (mode == 4) { // window pass of an EC round over the chains of this batch
+			uint32_t *d_wc = ba.zero<uint32_t>(nb + 1); uint64_t *d_woff = ba.get<uint64_t>(nb + 2), *d_fcb = ba.get<uint64_t>(n_slots + 1);
+			HB_ALLOC_CHECK(ba);
+			const int32_t w_l = so->w_l;
+			k_win_count<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, w_l, d_wc);
+			k_fc_grp_base<<<std::max(1u, std::min(nblk(h_dirn, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(d_dir, d_dirn, d_aoff + b0, a_base, d_coff, CP.mcopy_num, CP.mcopy_khit_cutoff, d_fcb);
+			if ((rc = hb_scan_u32_to_u64(ctx, d_wc, d_woff, nb))) return rc;
+			std::vector<uint64_t> h_woff(nb + 1);
+			HB_CUDA(cudaMemcpyAsync(h_woff.data(), d_woff, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			const uint64_t n_win = h_woff[nb];
+			WinDesc *d_desc = ba.get<WinDesc>(n_win + 1); hb_win_t *d_wout = ba.get<hb_win_t>(n_win + 1);
+			HB_ALLOC_CHECK(ba);
+			k_win_desc<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, w_l, d_woff, d_desc);
+			{
+				WinArgs W; W.R = R; W.r0 = r0 + b0; W.n_win = n_win; W.desc = d_desc; W.ch = d_ch; W.fc = d_fc; W.fc_grp_base = d_fcb; W.e_rate = so->e_rate; W.w_l = w_l; W.out = d_wout; W.err = d_err;
+				ProfScope ps(ctx, "k_windows");
+				if (n_win) k_windows<<<nblk(n_win, 128), 128, 0, ctx->stream>>>(W);
+			}
+			HB_CUDA(cudaGetLastError());
+			ctx->counters[8] += n_win;
+			int h_err2 = 0; HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "a window start fell outside its chain's fake cigar"); return HB_E_STATE; }
+			if (so->rec && st3_n + n_win > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "window output capacity"); return HB_E_OVERFLOW; }
+			if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_win_t *)so->rec + st3_n, d_wout, n_win * sizeof(hb_win_t), cudaMemcpyDeviceToHost, ctx->stream));
+			HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			for (uint64_t i = 0; i <= nb; i++) st3_off[b0 + i] = st3_n + h_woff[i];
+			st3_n += n_win;
+			b0 = b1; continue;
+		}
 		if (mode == 3) { // assemble the stage-3 view of this batch and copy it out
 			uint32_t *d_nh = ba.get<uint32_t>(nb + 1), *d_nf = ba.get<uint32_t>(nb + 1); uint64_t *d_och = ba.get<uint64_t>(nb + 2), *d_oh = ba.get<uint64_t>(nb + 2), *d_of = ba.get<uint64_t>(nb + 2), *d_fcb = ba.get<uint64_t>(n_slots + 1);
 			HB_ALLOC_CHECK(ba);
@@ -677,6 +707,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	}
 
 	TRACE("batches done");
+	{ unsigned long long h_dbg[2] = { 0, 0 }; HB_CUDA(cudaMemcpyAsync(h_dbg, d_stat + 8, 16, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream)); ctx->counters[6] = h_dbg[0]; ctx->counters[7] = h_dbg[1]; }
 	if (mode == 2) {
 		if (so->off) for (uint64_t i = 0; i <= nR; i++) so->off[i] = h_aoff[i];
 		if (so->rec) {
@@ -686,6 +717,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_CUDA(cudaStreamSynchronize(ctx->stream));
 		return HB_OK;
 	}
+	if (mode == 4) { if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8); return HB_OK; }
 	if (mode == 3) {
 		if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8);
 		if (so->hit_off) memcpy(so->hit_off, st3_hit_off.data(), (nR + 1) * 8);
@@ -755,6 +787,13 @@ extern "C" int hb_chains(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thre
 {
 	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.hit_off = hit_off; so.hits = hits; so.hit_cap = hit_cap; so.fc_off = fc_off; so.fc = fc; so.fc_cap = fc_cap;
 	return run_pass(ctx, r0, r1, 3, bw_thres, &so, 0);
+}
+
+extern "C" int hb_windows(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_win_t *rec, uint64_t rec_cap)
+{
+	if (w_l < 8 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be >= 8 and e_rate in [0,1]"); return HB_E_ARG; }
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l;
+	return run_pass(ctx, r0, r1, 4, bw_thres, &so, 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -843,7 +882,7 @@ extern "C" int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *lau
 extern "C" int hb_last_pass_ms(const hb_ctx_t *ctx, double *ms) { *ms = ctx->last_pass_ms; return HB_OK; }
 extern "C" int hb_counters(const hb_ctx_t *ctx, uint64_t *c, int cap)
 {
-	int n = cap < 8 ? cap : 8;
+	int n = cap < 12 ? cap : 12;
 	for (int i = 0; i < n; i++) c[i] = ctx->counters[i];
 	return n;
 }

@@ -29,7 +29,7 @@ struct hb_ctx {
 	// results of the last final pass (device resident)
 	hb_ma_hit_t *d_out0, *d_out1; uint64_t *d_out0_off, *d_out1_off; uint64_t n_out0, n_out1, out_reads;
 	// instrumentation
-	std::vector<ProfEntry> prof; uint64_t counters[8];
+	std::vector<ProfEntry> prof; uint64_t counters[12];
 	uint64_t anchor_budget; // anchors per batch
 	double last_pass_ms;
 	// workspace: one device allocation used as a double-ended stack (lo: scoped scratch,

@@ -952,6 +952,131 @@ __global__ void k_gather_ma(uint64_t nR, const uint64_t *__restrict__ o_off, con
 }
 
 // ----------------------------------------------------------------------------
+// window pass of an EC round: one thread per (chain, window).  The pattern (target
+// slice) and the text (query window) are read straight from the 2-bit packed reads;
+// the band (<= 63 bits) lives in one 64-bit register pair (row a8).
+// ----------------------------------------------------------------------------
+struct WinDesc { uint32_t read, slot, k, ord; }; // batch-local read, chain slot, window number, chain ordinal in the read's list
+struct WinArgs {
+	DevReads R; uint64_t r0, n_win; const WinDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
+	double e_rate; int32_t w_l; hb_win_t *out; int *err;
+};
+static __device__ __forceinline__ bool dev_is_n(const DevReads &R, uint64_t rid, uint32_t pos)
+{ // membership in the read's (ascending) N list
+	uint64_t lo = R.noff[rid], hi = R.noff[rid + 1];
+	while (lo < hi) { uint64_t mid = (lo + hi) >> 1; uint32_t v = R.npos[mid]; if (v < pos) lo = mid + 1; else hi = mid; }
+	return lo < R.noff[rid + 1] && R.npos[lo] == pos;
+}
+__global__ void __launch_bounds__(128) k_windows(WinArgs A)
+{
+	const uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (wi >= A.n_win) return;
+	const WinDesc d = A.desc[wi];
+	const hb_chain_t c = A.ch[d.slot];
+	const uint64_t qid = A.r0 + d.read, tid = c.y_id;
+	const uint64_t *fc = A.fc + A.fc_grp_base[d.slot] + c.fc_off;
+	const int64_t w_l = A.w_l, xs = c.x_pos_s, xe = c.x_pos_e, n_s = (xs / w_l) * w_l;
+	int64_t q_s = n_s + (int64_t)d.k * w_l, q_e = q_s + w_l - 1;
+	if (q_s < xs) q_s = xs;
+	if (q_e > xe) q_e = xe;
+	const int64_t q_l = 1 + q_e - q_s, t_tot_l = A.R.len[tid];
+	int64_t thre = (int64_t)((double)q_l * A.e_rate); // Correct.cpp:12962-12964
+	if (thre == 0 && q_l >= 4) thre = 1;
+	if (thre > 31) thre = 31;
+	int64_t t_s = (q_s - xs) + c.y_pos_s, sh = 0;
+	{ // y_start_offset, Hash_Table.h:165-189
+		const uint32_t n = c.fc_n; bool bad = false;
+		if (q_s == (int64_t)(fc[n - 1] >> 32)) sh = hb_fc_shift(fc[n - 1]);
+		else {
+			uint32_t i = 0;
+			for (; i < n; i++) if (q_s < (int64_t)(fc[i] >> 32)) break;
+			if (i == 0 || i == n) bad = true; else sh = hb_fc_shift(fc[i - 1]);
+		}
+		if (bad) atomicOr(A.err, 32);
+	}
+	t_s += sh;
+	hb_win_t rec; rec.chain = (int32_t)d.ord; rec.q_s = (int32_t)q_s; rec.q_e = (int32_t)q_e; rec.t_s = (int32_t)t_s; rec.t_pri_l = -1; rec.thre = (int32_t)thre;
+	rec.aux_beg = rec.aux_end = 0; rec.err = INT32_MAX; rec.pe = -1;
+	const int64_t aln_l = q_l + (thre << 1);
+	// init_waln, Correct.cpp:764-780
+	if (!(t_s < 0 || t_s >= t_tot_l || (t_tot_l - t_s + 2 * thre + 31) < aln_l)) {
+		int64_t aux_beg = 0, r_s = t_s - thre, r_l = t_tot_l - r_s; if (r_l > aln_l) r_l = aln_l;
+		const int64_t aux_end = aln_l - r_l;
+		if (r_s < 0) { aux_beg = -r_s; r_s = 0; r_l -= aux_beg; }
+		rec.t_s = (int32_t)r_s; rec.t_pri_l = (int32_t)r_l; rec.aux_beg = (int32_t)aux_beg; rec.aux_end = (int32_t)aux_end;
+		// ed_band_cal_semi_64_w_absent_diag(pattern = target[r_s, r_s+r_l) on the chain's strand, text = query[q_s, q_e])
+		const uint8_t *qp = A.R.packed + A.R.off[qid], *tp = A.R.packed + A.R.off[tid];
+		const bool q_has_n = A.R.noff[qid] != A.R.noff[qid + 1], t_has_n = A.R.noff[tid] != A.R.noff[tid + 1], rev = c.y_pos_strand != 0;
+		auto pat = [&](int32_t j) -> int { // pattern base j (4 = N)
+			const uint32_t fp = rev ? (uint32_t)(t_tot_l - 1 - (r_s + j)) : (uint32_t)(r_s + j);
+			if (t_has_n && dev_is_n(A.R, tid, fp)) return 4;
+			const int b = hb_base(tp, fp); return rev ? 3 - b : b;
+		};
+		auto txt = [&](int32_t i) -> int {
+			const uint32_t fp = (uint32_t)(q_s + i);
+			if (q_has_n && dev_is_n(A.R, qid, fp)) return 4;
+			return hb_base(qp, fp);
+		};
+		const int32_t pn = (int32_t)r_l, tn = (int32_t)q_l, th = (int32_t)thre, abs_diag = (int32_t)aux_beg;
+		uint64_t Peq[5] = { 0, 0, 0, 0, 0 }, VP = 0, VN, X, D0, HN, HP, mm;
+		int32_t bd, i, err = abs_diag, i_bd, tn0 = tn - 1, cut = th + (th << 1), best = INT32_MAX, pe = -1, site, ai, uge = INT32_MAX, chh;
+		bool dead = pn > tn + cut || tn > pn + cut;
+		if (!dead) {
+			bd = ((th << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn;
+			for (i = 0, mm = 1ULL << abs_diag; i < bd; i++) { Peq[pat(i)] |= mm; mm <<= 1; }
+			i_bd = (th << 1) - abs_diag; VN = (1ULL << abs_diag) - 1;
+			Peq[4] = 0; mm = 1ULL << (th << 1);
+			for (i = 0; i <= tn0; i++) {
+				X = Peq[txt(i)] | VN;
+				D0 = ((VP + (X & VP)) ^ VP) | X;
+				HN = VP & D0; HP = VN | ~(VP | D0);
+				X = D0 >> 1;
+				VN = X & HP; VP = HN | ~(X | HP);
+				if (!(D0 & 1ULL)) { ++err; if (err > cut) { dead = true; break; } }
+				if (i == tn0) break;
+				Peq[0] >>= 1; Peq[1] >>= 1; Peq[2] >>= 1; Peq[3] >>= 1;
+				++i_bd; chh = 4;
+				if (i_bd < pn) chh = pat(i_bd);
+				if (chh < 4) Peq[chh] |= mm;
+			}
+		}
+		if (!dead) {
+			site = tn - 1 - abs_diag; ai = pn - tn + abs_diag;
+			for (i = 0; site < 0 && i < ai; i++, site++) { err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); }
+			if (err <= th && err <= best) { best = err; pe = site; }
+			site -= i;
+			while (i < ai) {
+				err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); ++i;
+				if (err <= th && err <= best) { best = err; pe = site + i; }
+				if (i == th) uge = err;
+			}
+			if (uge <= th && uge == best) pe = site + th;
+		}
+		rec.err = best; rec.pe = pe;
+	}
+	A.out[wi] = rec;
+}
+
+// windows per read (thread per read) and their descriptors
+__global__ void k_win_count(uint64_t nR, const uint64_t *__restrict__ c_off, const hb_chain_t *__restrict__ ch, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol, int32_t w_l, uint32_t *__restrict__ wcnt)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	uint64_t cb = c_off[r]; uint32_t tot = 0;
+	for (uint32_t i = 0; i < n_ol[r]; i++) { const hb_chain_t &c = ch[cb + idx[cb + i]]; int64_t nl = ((int64_t)c.x_pos_e + 1) - ((int64_t)c.x_pos_s / w_l) * w_l; tot += (uint32_t)(nl / w_l + (nl % w_l > 0 ? 1 : 0)); } // get_num_wins, Correct.cpp:783
+	wcnt[r] = tot;
+}
+__global__ void k_win_desc(uint64_t nR, const uint64_t *__restrict__ c_off, const hb_chain_t *__restrict__ ch, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol, int32_t w_l, const uint64_t *__restrict__ w_off, WinDesc *__restrict__ desc)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	uint64_t cb = c_off[r], o = w_off[r];
+	for (uint32_t i = 0; i < n_ol[r]; i++) {
+		const uint32_t s = idx[cb + i]; const hb_chain_t &c = ch[cb + s];
+		int64_t nl = ((int64_t)c.x_pos_e + 1) - ((int64_t)c.x_pos_s / w_l) * w_l; uint32_t nw = (uint32_t)(nl / w_l + (nl % w_l > 0 ? 1 : 0));
+		for (uint32_t k = 0; k < nw; k++) { WinDesc d; d.read = (uint32_t)r; d.slot = (uint32_t)(cb + s); d.k = k; d.ord = i; desc[o++] = d; }
+	}
+}
+
+// ----------------------------------------------------------------------------
 // window alignment: ed_band_cal_semi_64_w_absent_diag
 // (Levenshtein_distance.h:3727-3776, ed_core_64 3116-3125), one thread per
 // window, the whole band (<= 63 bits) in one 64-bit register pair.

@@ -15,6 +15,7 @@ CHAIN = np.dtype([("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_id", "<u4"), ("y_p
                   ("y_pos_strand", "<u4"), ("shared_seed", "<i4"), ("first_hit", "<u4"), ("n_hits", "<u4"),
                   ("fc_off", "<u4"), ("fc_n", "<u4"), ("pad", "<u4")])
 MA = binio.MA_MEM
+WIN = np.dtype([(f, "<i4") for f in ("chain", "q_s", "q_e", "t_s", "t_pri_l", "thre", "aux_beg", "aux_end", "err", "pe")])
 
 
 class HBError(RuntimeError):
@@ -161,6 +162,15 @@ class Engine:
                                   _p(hoff), _p(hits), C.c_uint64(hits.size), _p(foff), _p(fc), C.c_uint64(fc.size)))
         return off, rec[:int(off[-1])], hoff, hits[:int(hoff[-1])], foff, fc[:int(foff[-1])]
 
+    def windows(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775):
+        """window pass of an EC round (row a8) -> (off, records WIN)"""
+        n = r1 - r0
+        off = np.zeros(n + 1, np.uint64)
+        self._ck(_lib().hb_windows(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), C.c_void_p(0), C.c_uint64(0)))
+        rec = np.zeros(int(off[-1]) + 1, WIN)
+        self._ck(_lib().hb_windows(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), _p(rec), C.c_uint64(rec.size)))
+        return off, rec[:int(off[-1])]
+
     # ---- final pass
     def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None):
         r1 = self.n_reads if r1 is None else r1
@@ -198,5 +208,5 @@ class Engine:
         ms = C.c_double(); _lib().hb_last_pass_ms(self.h, C.byref(ms)); return ms.value
 
     def counters(self):
-        c = (C.c_uint64 * 8)(); _lib().hb_counters(self.h, c, 8)
-        return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots", "groups_unordered", "groups_sequential"), [int(x) for x in c[:8]]))
+        c = (C.c_uint64 * 12)(); _lib().hb_counters(self.h, c, 12)
+        return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots", "groups_unordered", "groups_sequential", "windows"), [int(x) for x in c[:9]]))

@@ -114,6 +114,16 @@ int hb_chains(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres,
               uint64_t *hit_off, hb_hit_t *hits, uint64_t hit_cap,
               uint64_t *fc_off, uint64_t *fc, uint64_t fc_cap);
 
+/* ---- window pass of an EC round: for every chain h_ec_lchain returns for
+ * reads [r0,r1) and every WINDOW_HC-sized query window of it, the work align_hc_ed_post_extz does
+ * per window (Correct.cpp:12951-13011): threshold, target start from the fake cigar, init_waln
+ * clipping, ed_band_cal_semi_64_w_absent_diag (Levenshtein_distance.h:3727) on the packed reads.
+ * chain = index into the read's chain list (hb_chains order); err = INT32_MAX when the window does
+ * not align within thre, t_pri_l = -1 when init_waln rejects it.  off[r1-r0+1] + records.        */
+typedef struct { int32_t chain, q_s, q_e, t_s, t_pri_l, thre, aux_beg, aux_end, err, pe; } hb_win_t;
+int hb_windows(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
+               uint64_t *off, hb_win_t *rec, uint64_t rec_cap);
+
 /* ---- final overlap pass: cal_ov_r(n_thre, n_a, new_idx=1) (ecovlp.h:15;
  * ecovlp.cpp:6385 -> worker_hap_dc_ec_gen_new_idx 3948) -----------------------
  * prev_* = R_INF.paf[] / R_INF.reverse_paf[] of the last EC round, flattened

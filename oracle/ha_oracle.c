@@ -1308,3 +1308,71 @@ void hao_pt_dump(const hao_pt_t *pt, uint64_t *key, uint64_t *off, uint32_t *cnt
 	memcpy(key, pt->key, pt->n_keys * 8); memcpy(off, pt->off, pt->n_keys * 8);
 	memcpy(cnt, pt->cnt, pt->n_keys * 4); memcpy(pos, pt->pos, pt->tot_pos * 8);
 }
+
+/* ------------------------------------------------------------------ */
+/* window pass of the EC rounds (row a8)                               */
+/* ------------------------------------------------------------------ */
+
+static int64_t y_start_off(int64_t x_start, const uint64_t *fc, uint32_t n, int *bad)
+{ /* y_start_offset, Hash_Table.h:165-189 */
+	int64_t i;
+	if (x_start == (int64_t)(fc[n - 1] >> 32)) return fc_shift(fc[n - 1]);
+	for (i = 0; i < (int64_t)n; i++)
+		if (x_start < (int64_t)(fc[i] >> 32)) break;
+	if (i == 0 || i == (int64_t)n) { *bad = 1; return 0; }
+	return fc_shift(fc[i - 1]);
+}
+
+static int init_waln_(int64_t err, int64_t s, int64_t l, int64_t w_l, int64_t *aux_beg, int64_t *aux_end, int64_t *r_s, int64_t *r_l)
+{ /* init_waln, Correct.cpp:764-780 (THRESHOLD_MAX_SIZE = 31) */
+	*aux_beg = *aux_end = *r_s = *r_l = -1;
+	if (s < 0 || s >= l || (l - s + 2 * err + 31) < w_l) return 0;
+	*aux_beg = *aux_end = 0;
+	*r_s = s - err;
+	*r_l = l - *r_s; if (*r_l > w_l) *r_l = w_l;
+	*aux_end = w_l - *r_l;
+	if (*r_s < 0) { *aux_beg = -*r_s; *r_s = 0; *r_l -= *aux_beg; }
+	return 1;
+}
+
+typedef struct { int32_t chain, q_s, q_e, t_s, t_pri_l, thre, aux_beg, aux_end, err, pe; } hao_win_t;
+
+int hao_windows(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint32_t n_ch, const uint64_t *fc, double e_rate, int64_t w_l,
+                hao_win_t **out, uint32_t *n_out)
+{ /* the per-window work of align_hc_ed_post_extz (Correct.cpp:12951-13011) for every window of every chain,
+     without its early exit: window grid (get_num_wins 783, get_win_se_by_normalize_xs Correct.h:1328),
+     threshold (Adjust_Threshold Correct.h:46), target start from the fake cigar, init_waln, banded Myers */
+	uint64_t ql = r->len[rid], tm = 0; uint32_t j, n = 0, m = 0; hao_win_t *w = 0; int bad = 0;
+	char *qs = MALLOC_N(char, ql + 1), *ts = 0;
+	hao_decode(r, rid, qs);
+	for (j = 0; j < n_ch; j++) {
+		const hao_ovlp_t *z = &ch[j];
+		int64_t xs = z->x_pos_s, xe = z->x_pos_e, n_s = (xs / w_l) * w_l, nl = (xe + 1) - n_s, nw = nl / w_l + (nl % w_l > 0 ? 1 : 0), k;
+		int64_t q_s = n_s < xs ? xs : n_s, q_e = n_s + w_l - 1 > xe ? xe : n_s + w_l - 1;
+		for (k = 0; k < nw; k++) {
+			int64_t q_l = 1 + q_e - q_s, thre = (int64_t)(q_l * e_rate), t_s, aln_l, aux_beg, aux_end, t_pri_l, t_tot_l = (int64_t)r->len[z->y_id];
+			hao_win_t rec;
+			if (thre == 0 && q_l >= 4) thre = 1;
+			if (thre > 31) thre = 31;
+			t_s = (q_s - xs) + z->y_pos_s;
+			t_s += y_start_off(q_s, fc + z->fc_off, z->fc_n, &bad);
+			aln_l = q_l + (thre << 1);
+			rec.chain = (int32_t)j; rec.q_s = (int32_t)q_s; rec.q_e = (int32_t)q_e; rec.t_s = (int32_t)t_s; rec.t_pri_l = -1; rec.thre = (int32_t)thre;
+			rec.aux_beg = rec.aux_end = 0; rec.err = INT32_MAX; rec.pe = -1;
+			if (init_waln_(thre, t_s, t_tot_l, aln_l, &aux_beg, &aux_end, &t_s, &t_pri_l)) {
+				int32_t pe;
+				if ((uint64_t)t_pri_l + 1 > tm) { tm = t_pri_l + 64; ts = (char *)realloc(ts, tm); }
+				hao_decode_sub(r, z->y_id, t_s, t_pri_l, (int)z->y_pos_strand, ts);
+				rec.err = hao_ed_semi_64_absent_diag(ts, (int32_t)t_pri_l, qs + q_s, (int32_t)q_l, (int32_t)thre, (int32_t)aux_beg, &pe);
+				rec.pe = pe; rec.t_s = (int32_t)t_s; rec.t_pri_l = (int32_t)t_pri_l; rec.aux_beg = (int32_t)aux_beg; rec.aux_end = (int32_t)aux_end;
+			}
+			if (n == m) { m = m ? m << 1 : 256; w = (hao_win_t *)realloc(w, m * sizeof(hao_win_t)); }
+			w[n++] = rec;
+			q_s = q_e + 1; q_e = q_s + w_l - 1;
+			if (q_e >= xe) q_e = xe;
+		}
+	}
+	free(qs); free(ts);
+	*out = w; *n_out = n;
+	return bad ? -1 : 0;
+}

@@ -114,6 +114,9 @@ int hao_final_read(const hao_reads_t *r, const hao_pt_t *pt, const hao_ft_t *ft,
  * returns err (INT32_MAX if > thre semantics of the reference) and *pe */
 int hao_ed_semi_64_absent_diag(const char *pstr, int32_t pn, const char *tstr, int32_t tn, int32_t thre, int32_t abs_diag, int32_t *pe);
 
+/* per-window work of align_hc_ed_post_extz (Correct.cpp:12951-13011) for every window of every chain */
+typedef struct { int32_t chain, q_s, q_e, t_s, t_pri_l, thre, aux_beg, aux_end, err, pe; } hao_win_rec_t;
+
 void hao_free(void *p);
 #ifdef __cplusplus
 }

@@ -150,3 +150,15 @@ def final_read(store: Store, pt, ft, opt: Opt, rid, in0: np.ndarray, in1: np.nda
                          C.c_void_p(in0.ctypes.data), C.c_uint32(in0.size), C.c_void_p(in1.ctypes.data), C.c_uint32(in1.size),
                          C.byref(o0), C.byref(m0), C.byref(o1), C.byref(m1))
     return _take(o0, m0.value, MA), _take(o1, m1.value, MA)
+
+
+WIN = np.dtype([(f, "<i4") for f in ("chain", "q_s", "q_e", "t_s", "t_pri_l", "thre", "aux_beg", "aux_end", "err", "pe")])
+
+
+def windows(store: Store, rid, chains: np.ndarray, fc: np.ndarray, e_rate=0.04, w_l=775):
+    chains = np.ascontiguousarray(chains); fc = np.ascontiguousarray(fc if fc.size else np.zeros(1), dtype=np.uint64)
+    out = C.c_void_p(); n = C.c_uint32()
+    rc = lib().hao_windows(C.byref(store.c), C.c_uint32(rid), C.c_void_p(chains.ctypes.data), C.c_uint32(chains.size), C.c_void_p(fc.ctypes.data),
+                           C.c_double(e_rate), C.c_int64(w_l), C.byref(out), C.byref(n))
+    assert rc == 0
+    return _take(out, n.value, WIN)

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#include <vector>
 #include "CommandLines.h"
 #include "Process_Read.h"
 #include "Overlaps.h"
@@ -31,6 +32,7 @@
 #include "Hash_Table.h"
 #include "ecovlp.h"
 #include "Levenshtein_distance.h"
+#include "Correct.h"
 
 // non-static reference functions that no header declares
 void ha_ec(int64_t round, int num_pround, int des_idx, uint64_t *tot_b, uint64_t *tot_e);
@@ -41,6 +43,9 @@ void minimizers_qgen0(ha_abuf_t *ab, char *rs, int64_t rl, uint64_t mz_w, uint64
                       void *ha_flt_tab, ha_pt_t *ha_idx, All_reads *rdb, kvec_t_u64_warp *dbg_ct, st_mt_t *sp, uint32_t *high_occ, uint32_t *low_occ);
 void h_ec_lchain(ha_abuf_t *ab, uint32_t rid, char *rs, uint64_t rl, uint64_t mz_w, uint64_t mz_k, All_reads *rref, overlap_region_alloc *overlap_list, Candidates_list *cl, double bw_thres,
                  int max_n_chain, int apend_be, kvec_t_u8_warp *k_flag, kvec_t_u64_warp *dbg_ct, st_mt_t *sp, uint32_t *high_occ, uint32_t *low_occ, uint32_t is_accurate, uint32_t gen_off, int64_t mcopy_num, double mcopy_rate, uint32_t chain_cutoff, uint32_t mcopy_khit_cut, uint64_t ocv_w);
+
+int32_t init_waln(int64_t err, int64_t s, int64_t l, int64_t w_l, int64_t *aux_beg, int64_t *aux_end, int64_t *r_s, int64_t *r_l); // Correct.cpp:764
+int64_t get_num_wins(int64_t s, int64_t e, int64_t block_s); // Correct.cpp:783
 
 #define HA_KMER_GOOD_RATIO 0.333 /* ecovlp.cpp:9 */
 #define COV_W 3072               /* ecovlp.cpp:17 */
@@ -69,7 +74,9 @@ static void dump_stages(const char *pfx, double bw_thres)
 	uint32_t high_occ = asm_opt.hom_cov * (2.0 - HA_KMER_GOOD_RATIO); // ecovlp.cpp:3952
 	uint32_t low_occ = asm_opt.hom_cov * HA_KMER_GOOD_RATIO;
 	FILE *fmz = xopen(pfx, ".mz.bin"), *fidx = xopen(pfx, ".idx.bin"), *fan = xopen(pfx, ".anchors.bin");
-	FILE *fch = xopen(pfx, ".chains.bin"), *fpa = xopen(pfx, ".params.txt");
+	FILE *fch = xopen(pfx, ".chains.bin"), *fpa = xopen(pfx, ".params.txt"), *fwn = xopen(pfx, ".windows.bin");
+	UC_Read tr; init_UC_Read(&tr); bit_extz_t exz; init_bit_extz_t(&exz, 31);
+	const double e_rate = asm_opt.max_ov_diff_ec; const int64_t w_l = asm_opt.is_ont ? WINDOW_OHC : WINDOW_HC; // ecovlp.cpp:3288
 	UC_Read ur; init_UC_Read(&ur);
 	ha_abuf_t *ab = ha_abuf_init();
 	Candidates_list cl; init_Candidates_list(&cl);
@@ -115,8 +122,41 @@ static void dump_stages(const char *pfx, double bw_thres)
 			fwrite(o->f_cigar.buffer, 8, o->f_cigar.length, fch);
 		}
 		fwrite(cl.list, sizeof(k_mer_hit), nh, fch); // compacted chain hits (des region)
+		// (5) window pass: every 775-bp query window of every chain, exactly the per-window work of
+		// align_hc_ed_post_extz (Correct.cpp:12951-13011) without its early exit / gap filling:
+		// {chain, q_s, q_e, t_s, t_pri_l, thre, aux_beg, aux_end, err, pe}, err = INT32_MAX when unaligned,
+		// t_pri_l = -1 when init_waln rejects the window
+		{
+			std::vector<int32_t> wr;
+			for (j = 0; j < nc; j++) {
+				overlap_region *z = &ol.list[j];
+				int64_t q_s, q_e, nw, k, q_l, t_tot_l, aux_beg, aux_end, t_s, thre, aln_l, t_pri_l;
+				nw = get_num_wins(z->x_pos_s, z->x_pos_e + 1, w_l);
+				get_win_se_by_normalize_xs(z, (z->x_pos_s / w_l) * w_l, w_l, &q_s, &q_e);
+				for (k = 0; k < nw; k++) {
+					aux_beg = aux_end = 0; q_l = 1 + q_e - q_s;
+					thre = q_l * e_rate; thre = Adjust_Threshold(thre, q_l);
+					if (thre > THRESHOLD_MAX_SIZE) thre = THRESHOLD_MAX_SIZE;
+					t_s = (q_s - z->x_pos_s) + z->y_pos_s;
+					t_s += y_start_offset(q_s, &(z->f_cigar));
+					aln_l = q_l + (thre << 1); t_tot_l = Get_READ_LENGTH(R_INF, z->y_id);
+					int32_t rec[10] = { (int32_t)j, (int32_t)q_s, (int32_t)q_e, 0, -1, (int32_t)thre, 0, 0, INT32_MAX, -1 };
+					if (init_waln(thre, t_s, t_tot_l, aln_l, &aux_beg, &aux_end, &t_s, &t_pri_l)) {
+						resize_UC_Read(&tr, t_pri_l + 8);
+						recover_UC_Read_sub_region(tr.seq, t_s, t_pri_l, z->y_pos_strand, &R_INF, z->y_id);
+						ed_band_cal_semi_64_w_absent_diag(tr.seq, t_pri_l, ur.seq + q_s, q_l, thre, aux_beg, &exz);
+						rec[3] = (int32_t)t_s; rec[4] = (int32_t)t_pri_l; rec[6] = (int32_t)aux_beg; rec[7] = (int32_t)aux_end; rec[8] = exz.err; rec[9] = exz.pe;
+					} else { rec[3] = (int32_t)t_s; }
+					wr.insert(wr.end(), rec, rec + 10);
+					q_s = q_e + 1; q_e = q_s + w_l - 1;
+					if (q_e >= (int64_t)z->x_pos_e) q_e = z->x_pos_e;
+				}
+			}
+			uint32_t nwr = wr.size() / 10;
+			fwrite(&nwr, 4, 1, fwn); fwrite(wr.data(), 4, wr.size(), fwn);
+		}
 	}
-	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch);
+	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch); fclose(fwn);
 	destory_UC_Read(&ur);
 }
 

@@ -44,11 +44,11 @@ def dg(b: bytes) -> int:
 
 
 def read_stages(pfx, n_reads, keep=4):
-    out = {k: np.zeros(n_reads, dtype=np.uint64) for k in ("mz", "idx", "anchors", "chains", "chain_hits")}
-    cnt = {k: np.zeros(n_reads, dtype=np.uint64) for k in ("mz", "anchors", "chains", "chain_hits")}
+    out = {k: np.zeros(n_reads, dtype=np.uint64) for k in ("mz", "idx", "anchors", "chains", "chain_hits", "windows")}
+    cnt = {k: np.zeros(n_reads, dtype=np.uint64) for k in ("mz", "anchors", "chains", "chain_hits", "windows")}
     full = {}
     with open(pfx + ".mz.bin", "rb") as fm, open(pfx + ".idx.bin", "rb") as fi, \
-            open(pfx + ".anchors.bin", "rb") as fa, open(pfx + ".chains.bin", "rb") as fc:
+            open(pfx + ".anchors.bin", "rb") as fa, open(pfx + ".chains.bin", "rb") as fc, open(pfx + ".windows.bin", "rb") as fw:
         for i in range(n_reads):
             n = int(np.frombuffer(fm.read(4), dtype="<u4")[0])
             mz = fm.read(16 * n)
@@ -74,6 +74,9 @@ def read_stages(pfx, n_reads, keep=4):
             out["chains"][i] = int.from_bytes(h.digest(), "little"); cnt["chains"][i] = nc
             hb = fc.read(16 * nh)
             out["chain_hits"][i] = dg(hb); cnt["chain_hits"][i] = nh
+            nwin = int(np.frombuffer(fw.read(4), dtype="<u4")[0])
+            wb = fw.read(40 * nwin)  # {chain, q_s, q_e, t_s, t_pri_l, thre, aux_beg, aux_end, err, pe} per window
+            out["windows"][i] = dg(wb); cnt["windows"][i] = nwin
             if i < keep:
                 full["mz_%d" % i] = np.frombuffer(mz, dtype=np.uint8)
                 full["anchors_%d" % i] = np.frombuffer(an, dtype=np.uint8)

@@ -71,6 +71,11 @@ def _check_stages(g, eng, mode, rs):
     for i in range(n):
         assert _chain_digest(ch[int(coff[i]):int(coff[i + 1])], fc[int(foff[i]):int(foff[i + 1])]) == int(g.digest(mode, "chains")[i]), "chains read %d" % i
         assert dg(hits[int(hoff[i]):int(hoff[i + 1])].tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain anchors read %d" % i
+    # window pass of the EC rounds (row a8): every window of every chain
+    woff, win = eng.windows(0, n, float(p["bw_thres"]), 0.04, 775)
+    for i in range(n):
+        w = win[int(woff[i]):int(woff[i + 1])]
+        assert w.size == int(g.count(mode, "windows")[i]) and dg(w.tobytes()) == int(g.digest(mode, "windows")[i]), "window pass read %d" % i
     return hom, het
 
 
@@ -184,4 +189,60 @@ def test_empty_and_edge_inputs(hb):
     e0 = np.zeros(0, binio.MA_MEM); z = np.zeros(4, np.uint64)
     out0, oo0, out1, oo1, stat = eng.cal_ov_r(e0, z, e0, z)
     assert out0.size == 0 and out1.size == 0
+    eng.close()
+
+
+def test_gpu_vs_oracle_noisy_repeats(hb):
+    """seeded reads with errors, a repeat family and N bases (raw-read context: the
+    chaining DP, secondary chains, the per-type cap and the shadow filter are all
+    exercised); every read's anchors / chains / chain anchors / fake cigars equal the
+    CPU oracle's on the same inputs"""
+    from hifiasm_b200 import sim
+    h1, h2 = sim.sim_genome(500000, 21, snp_rate=0.003, repeat_frac=0.25, repeat_len=1800, repeat_div=0.01)
+    reads = sim.sim_reads(h1, h2, 24, 7000, 21, sd_len=2500, min_len=300, err=0.004, n_rate=1e-4)
+    flat, boff, ln, npos, noff = sim.pack_reads(reads)
+    n = len(reads)
+    eng = hb.Engine(0)
+    eng.upload_reads(ln, flat, boff, npos, noff)
+    hom = eng.ft_gen(); eng.update_cov(hom)
+    hom2, het2 = eng.pt_gen(); eng.set_opt(hom_cov=hom2, het_cov=het2)
+    st = ho.Store(ln, boff, flat, noff, npos)
+    opt = ho.default_opt()
+    ft, ohom = ho.ft_gen(st, opt)
+    ho.lib().hao_opt_update_cov(C.byref(opt), ohom)
+    pt, h3, t3 = ho.pt_gen(st, ft, opt)
+    assert (hom, hom2, het2) == (ohom, h3, t3)
+    assert eng.get_opt().max_n_chain == opt.max_n_chain
+    high, low = int(h3 * (2.0 - 0.333)), int(h3 * 0.333)
+    off, mz = eng.sketch(0, n)
+    aoff, an = eng.anchors(0, n)
+    coff, ch, hoff, hits, foff, fc = eng.chains(0, n, 0.02)
+    n_dp = 0
+    for i in range(n):
+        omz = ho.sketch(st.decode(i), 51, 51, i, 1, ft, 500, 1000)
+        assert mz[int(off[i]):int(off[i + 1])].tobytes() == omz.tobytes(), "sketch read %d" % i
+        oan = ho.anchors(st, pt, omz, high, low)
+        assert an[int(aoff[i]):int(aoff[i + 1])].tobytes() == oan.tobytes(), "anchors read %d" % i
+        och, ohits, ofc = ho.lchain(st, i, oan, 0.02, 51, opt.max_n_chain)
+        g = ch[int(coff[i]):int(coff[i + 1])]
+        assert g.size == och.size, "chain count read %d" % i
+        for f, of in (("x_pos_s", "x_pos_s"), ("x_pos_e", "x_pos_e"), ("y_id", "y_id"), ("y_pos_s", "y_pos_s"), ("y_pos_e", "y_pos_e"),
+                      ("y_pos_strand", "y_pos_strand"), ("shared_seed", "shared_seed"), ("first_hit", "non_homopolymer_errors"), ("fc_n", "fc_n")):
+            assert (g[f] == och[of]).all(), "read %d chain field %s" % (i, f)
+        assert hits[int(hoff[i]):int(hoff[i + 1])].tobytes() == ohits.tobytes(), "chain anchors read %d" % i
+        gfc = fc[int(foff[i]):int(foff[i + 1])]
+        ofc_cat = np.concatenate([ofc[int(c["fc_off"]):int(c["fc_off"]) + int(c["fc_n"])] for c in och]) if och.size else np.zeros(0, np.uint64)
+        gfc_cat = np.concatenate([gfc[int(c["fc_off"]):int(c["fc_off"]) + int(c["fc_n"])] for c in g]) if g.size else np.zeros(0, np.uint64)
+        assert gfc_cat.tobytes() == ofc_cat.tobytes(), "fake cigars read %d" % i
+    c = eng.counters()
+    assert c["groups_sequential"] > 0  # the general (DP) path really ran
+    woff, win = eng.windows(0, n, 0.02, 0.04, 775)
+    n_al = 0
+    for i in range(0, n, 7):
+        omz = ho.sketch(st.decode(i), 51, 51, i, 1, ft, 500, 1000)
+        och, ohits, ofc = ho.lchain(st, i, ho.anchors(st, pt, omz, high, low), 0.02, 51, opt.max_n_chain)
+        ow = ho.windows(st, i, och, ofc)
+        assert win[int(woff[i]):int(woff[i + 1])].tobytes() == ow.tobytes(), "window pass read %d" % i
+        n_al += int((ow["err"] != 2**31 - 1).sum())
+    assert n_al > 0
     eng.close()

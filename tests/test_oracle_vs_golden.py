@@ -44,6 +44,8 @@ def _stages(g, mode, st, ft, opt, bw):
         ch, hits, fc = ho.lchain(st, i, an, bw, int(p["k"]), int(p["max_n_chain"]))
         assert chain_digest(ch, fc) == int(g.digest(mode, "chains")[i]), "chains read %d" % i
         assert dg(hits.tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain hits read %d" % i
+        win = ho.windows(st, i, ch, fc)
+        assert win.size == int(g.count(mode, "windows")[i]) and dg(win.tobytes()) == int(g.digest(mode, "windows")[i]), "window pass read %d" % i
     return pt, hom, het
 
 
