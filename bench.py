@@ -164,6 +164,15 @@ def run_reference(flat_ds_args, warmup, steps, sample_reads=None):
 
 # ----------------------------------------------------------------------------
 def main():
+    try:
+        return _main()
+    except Exception:
+        import traceback
+        traceback.print_exc()
+        return 1
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -257,6 +266,17 @@ def main():
         d2h = int((o0.size + o1.size) * binio.MA_MEM.itemsize + 2 * (r1 - r0 + 1) * 8)
         e2e = {"value": tot_bases / wall / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
+    # ---- auxiliary: the window pass of an EC round (row a8) on a slice of this rank's reads
+    aux = None
+    if rank == 0 and not os.environ.get("HB_BENCH_NO_AUX"):
+        na = min(r1 - r0, 20000)
+        eng.windows(r0, r0 + na, 0.02, 0.04, 775)
+        woff, win = eng.windows(r0, r0 + na, 0.02, 0.04, 775)
+        kms = eng.profile().get("k_windows", (0, 0.0))[1]
+        cols = int((win["q_e"] - win["q_s"] + 1).sum())
+        aux = {"window_pass": {"reads": int(na), "windows": int(win.size), "aligned": int((win["err"] != 2**31 - 1).sum()), "k_windows_ms": kms,
+                               "gcups": (cols / (kms / 1e3) / 1e9) if kms > 0 else None, "note": "64-bit banded Myers column updates/s, one thread per 775-bp window"}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -291,7 +311,7 @@ def main():
            "config": {"workload": workload, "reads_total": n, "reads_per_rank": r1 - r0, "bases_per_rank": my_bases, "parallelism": "query reads sharded x%d, index+reads replicated" % world,
                       "l2": "inputs larger than L2 (packed reads %.2f GB + index)" % (flat.nbytes / 1e9), "hom_cov": hom, "overlaps_src": int(n_src), "overlaps_rev": int(n_rev),
                       "setup_s": {"generate+upload": round(t_gen, 1), "index_build": round(t_idx, 2)}, "counters": counters},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in prof_acc.values())), "roofline": roofline, "cpu_baseline": cpu}
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in prof_acc.values())), "roofline": roofline, "cpu_baseline": cpu, "aux": aux}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
