@@ -172,14 +172,19 @@ class Engine:
         return off, rec[:int(off[-1])]
 
     # ---- final pass
-    def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None):
+    def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None, out=None):
+        """out = (out0, out1) preallocated MA arrays to receive the records (reused across calls)"""
         r1 = self.n_reads if r1 is None else r1
         prev_src = np.ascontiguousarray(prev_src, dtype=MA); prev_rev = np.ascontiguousarray(prev_rev, dtype=MA)
         o0 = np.ascontiguousarray(prev_src_off, dtype=np.uint64); o1 = np.ascontiguousarray(prev_rev_off, dtype=np.uint64)
         cap = cap or (4 * (prev_src.size + prev_rev.size) + 256 * (r1 - r0) + 1024)
-        out0 = np.empty(cap, MA); out1 = np.empty(cap, MA); oo0 = np.zeros(r1 - r0 + 1, np.uint64); oo1 = np.zeros(r1 - r0 + 1, np.uint64); stat = np.zeros(8, np.uint64)
+        if out is not None:
+            out0, out1 = out
+        else:
+            out0 = np.empty(cap, MA); out1 = np.empty(cap, MA)
+        oo0 = np.zeros(r1 - r0 + 1, np.uint64); oo1 = np.zeros(r1 - r0 + 1, np.uint64); stat = np.zeros(8, np.uint64)
         self._ck(_lib().hb_cal_ov_r(self.h, C.c_uint64(r0), C.c_uint64(r1), _p(prev_src), _p(o0), _p(prev_rev), _p(o1),
-                                    _p(out0), _p(oo0), C.c_uint64(cap), _p(out1), _p(oo1), C.c_uint64(cap), _p(stat)))
+                                    _p(out0), _p(oo0), C.c_uint64(out0.size), _p(out1), _p(oo1), C.c_uint64(out1.size), _p(stat)))
         return out0[:int(oo0[-1])], oo0, out1[:int(oo1[-1])], oo1, stat
 
     def cal_ov_r_resident(self, r0=0, r1=None):
