@@ -283,8 +283,8 @@ def _main():
                                "gcups": (cols / (kms / 1e3) / 1e9) if kms > 0 else None, "note": "64-bit banded Myers column updates/s, one thread per 775-bp window"}}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        # stay alive until rank 0 has printed: a peer that leaves early can take rank 0's NCCL watchdog down with it
+        dist.barrier(); dist.destroy_process_group()
         return 0
 
     # ---- roofline of the seed-hash probe kernel k_expand: per pass it reads
@@ -317,9 +317,9 @@ def _main():
                       "l2": "inputs larger than L2 (packed reads %.2f GB + index)" % (flat.nbytes / 1e9), "hom_cov": hom, "overlaps_src": int(n_src), "overlaps_rev": int(n_rev),
                       "setup_s": {"generate+upload": round(t_gen, 1), "index_build": round(t_idx, 2)}, "counters": counters},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in prof_acc.values())), "roofline": roofline, "cpu_baseline": cpu, "aux": aux}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier(); dist.destroy_process_group()
     return 0
 
 
