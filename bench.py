@@ -203,6 +203,7 @@ def _main():
     import hifiasm_b200
     from hifiasm_b200 import binio, dist as hdist
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only (NCCL prints its version banner there otherwise)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
