@@ -163,7 +163,19 @@ def run_reference(flat_ds_args, warmup, steps, sample_reads=None):
 
 
 # ----------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n"); _JSON_OUT.flush()
+
+
 def main():
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner) go to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     try:
         return _main()
     except Exception:
@@ -189,9 +201,9 @@ def _main():
             return 0
         r, why = run_reference((GENOME_MB, COV), args.warmup, args.steps)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": why})); return 0
+            emit({"impl": "reference", "unavailable": why}); return 0
         v = r["gbp_per_s"]
-        print(json.dumps({"impl": "reference", "metric": "HiFi Gbp overlapped/sec", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        emit(({"impl": "reference", "metric": "HiFi Gbp overlapped/sec", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64/f64 (integer + double chain scores)",
                           "data": "synthetic", "config": {"workload": workload.replace("x%d GPU(s)" % world, "x1"), "sample": r["sample"]},
                           "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
@@ -203,7 +215,6 @@ def _main():
     import hifiasm_b200
     from hifiasm_b200 import binio, dist as hdist
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only (NCCL prints its version banner there otherwise)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
@@ -318,7 +329,7 @@ def _main():
                       "l2": "inputs larger than L2 (packed reads %.2f GB + index)" % (flat.nbytes / 1e9), "hom_cov": hom, "overlaps_src": int(n_src), "overlaps_rev": int(n_rev),
                       "setup_s": {"generate+upload": round(t_gen, 1), "index_build": round(t_idx, 2)}, "counters": counters},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in prof_acc.values())), "roofline": roofline, "cpu_baseline": cpu, "aux": aux}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     return 0

@@ -53,28 +53,42 @@ DevPt hb_dev_pt(const hb_ctx *ctx)
 // ---------------------------------------------------------------------------
 // workspace: no allocator calls inside a pass
 // ---------------------------------------------------------------------------
-void hb_ws_reset(hb_ctx *ctx) { ctx->ws_lo = 0; ctx->ws_hi = ctx->ws_cap; }
+void hb_ws_reset(hb_ctx *ctx) { ctx->ws_lo = 0; ctx->ws_hi = ctx->ws_cap; ctx->ws_virt = 0; }
+static void *ws_short(hb_ctx *ctx, size_t bytes)
+{ // a request that does not fit: keep counting what the caller goes on to ask for, so that ONE regrow is enough
+	ctx->ws_virt += bytes + 256;
+	size_t need = ctx->ws_lo + (ctx->ws_cap - ctx->ws_hi) + ctx->ws_virt; if (need > ctx->ws_need) ctx->ws_need = need;
+	return 0;
+}
 void *hb_ws_lo(hb_ctx *ctx, size_t bytes)
 {
 	bytes = (bytes + 255) & ~(size_t)255;
-	if (ctx->ws_lo + bytes > ctx->ws_hi) { size_t need = ctx->ws_lo + bytes + (ctx->ws_cap - ctx->ws_hi); if (need > ctx->ws_need) ctx->ws_need = need; return 0; }
+	if (ctx->ws_virt || ctx->ws_lo + bytes > ctx->ws_hi) return ws_short(ctx, bytes);
 	void *p = ctx->ws + ctx->ws_lo; ctx->ws_lo += bytes; return p;
 }
 void *hb_ws_hi(hb_ctx *ctx, size_t bytes)
 {
 	bytes = (bytes + 255) & ~(size_t)255;
-	if (ctx->ws_lo + bytes > ctx->ws_hi) { size_t need = ctx->ws_lo + bytes + (ctx->ws_cap - ctx->ws_hi); if (need > ctx->ws_need) ctx->ws_need = need; return 0; }
+	if (ctx->ws_virt || ctx->ws_lo + bytes + 256 > ctx->ws_hi) return ws_short(ctx, bytes);
+	ctx->ws_hi = (ctx->ws_hi - bytes) & ~(size_t)255; return ctx->ws + ctx->ws_hi;
+}
+void *hb_ws_hi_packed(hb_ctx *ctx, size_t bytes)
+{ // 16-byte granularity: consecutive calls return adjacent blocks (descending addresses)
+	bytes = (bytes + 15) & ~(size_t)15;
+	if (ctx->ws_virt || ctx->ws_lo + bytes > ctx->ws_hi) return ws_short(ctx, bytes);
 	ctx->ws_hi -= bytes; return ctx->ws + ctx->ws_hi;
 }
 int hb_ws_grow(hb_ctx *ctx)
 { // called with the stack empty: replace the workspace by a larger one
-	size_t want = ctx->ws_cap ? ctx->ws_cap * 2 : ((size_t)256 << 20), fr = 0, tot = 0;
-	if (ctx->ws_need + (ctx->ws_need >> 2) > want) want = ctx->ws_need + (ctx->ws_need >> 2);
+	size_t want = ctx->ws_cap ? ctx->ws_cap + (ctx->ws_cap >> 1) : ((size_t)256 << 20), fr = 0, tot = 0;
+	if (ctx->ws_need) want = ctx->ws_need + (ctx->ws_need >> 3);
+	if (want < ((size_t)256 << 20)) want = (size_t)256 << 20;
+	want = (want + 255) & ~(size_t)255;
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ws) cudaFree(ctx->ws);
 	ctx->ws = 0; ctx->ws_cap = 0;
 	cudaMemGetInfo(&fr, &tot);
-	if (want > fr - (fr >> 4)) want = fr - (fr >> 4);
+	if (want > fr - (fr >> 4)) want = (fr - (fr >> 4)) & ~(size_t)255;
 	if (want < ctx->ws_need) { hb_set_err(ctx, HB_E_NOMEM, "workspace of %zu bytes does not fit in free HBM (%zu); lower HB_ANCHOR_BUDGET", ctx->ws_need, fr); return HB_E_NOMEM; }
 	if (cudaMalloc((void **)&ctx->ws, want) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "cudaMalloc(%zu) for the workspace failed", want); return HB_E_NOMEM; }
 	ctx->ws_cap = want; ctx->ws_need = 0; hb_ws_reset(ctx);
@@ -150,7 +164,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
 	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
 	ctx->anchor_budget = 768ull << 20; ctx->last_pass_ms = 0;
-	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
+	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = ctx->ws_virt = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
@@ -271,14 +285,10 @@ extern "C" int hb_reads_upload_ptrs(hb_ctx_t *ctx, uint64_t n, const uint64_t *l
 // ---------------------------------------------------------------------------
 // sketch of a read range -> dense minimizer arrays
 // ---------------------------------------------------------------------------
-int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch *out)
-{
-	(void)rid_mode;
+static int hb_run_sketch_legacy(hb_ctx *ctx, uint64_t r0, uint64_t r1, DevSketch *out)
+{ // the one-kernel formulation (ring in shared memory), kept for A/B checks (HB_SKETCH_LEGACY)
 	uint64_t nR = r1 - r0; Arena ar(ctx);
 	SketchPar P = { ctx->opt.mz_win, ctx->opt.k_mer_length, ctx->opt.is_hpc, ctx->opt.mz_sample_dist, ctx->opt.mz_rewin };
-	const bool legacy = getenv("HB_SKETCH_LEGACY") != 0; // the one-kernel formulation (ring in shared memory), kept for A/B checks
-	static const uint64_t chunk_bases = getenv("HB_SKETCH_CHUNK") ? strtoull(getenv("HB_SKETCH_CHUNK"), 0, 10) : 3300000000ull;
-	out->mz = 0; out->off = 0; out->total = 0;
 	for (int attempt = 0, div = 12; attempt < 3; attempt++, div = div > 4 ? div / 3 : 1) {
 		std::vector<uint64_t> cap_off(nR + 1); uint64_t tot = 0;
 		for (uint64_t i = 0; i < nR; i++) { cap_off[i] = tot; tot += ctx->h_rlen[r0 + i] / div + 32; }
@@ -287,7 +297,7 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 		int *d_err = ar.zero<int>(1); uint64_t *d_off = ar.get<uint64_t>(nR + 2);
 		HB_ALLOC_CHECK(ar);
 		HB_CUDA(cudaMemcpyAsync(d_cap, cap_off.data(), (nR + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		if (legacy) {
+		{
 			ProfScope ps(ctx, "k_sketch");
 			if (P.w <= 160) {
 				size_t smem = (size_t)64 * P.w * 20;
@@ -297,32 +307,6 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 				size_t smem = (size_t)32 * P.w * 20;
 				cudaFuncSetAttribute(k_sketch<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				k_sketch<32><<<nblk(nR, 32), 32, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0, nR, d_cap, d_mz, d_l, d_n, d_err);
-			}
-		} else {
-			// chunks of reads whose event streams (20 B per base, worst case) fit the workspace comfortably
-			for (uint64_t c0 = 0; c0 < nR;) {
-				uint64_t c1 = c0, cb = 0;
-				while (c1 < nR && (c1 == c0 || cb + ctx->h_rlen[r0 + c1] + 1 <= chunk_bases)) { cb += ctx->h_rlen[r0 + c1] + 1; c1++; }
-				const uint64_t nc = c1 - c0; Arena ca(ctx);
-				std::vector<uint64_t> ev_off(nc + 1); uint64_t et = 0;
-				for (uint64_t i = 0; i < nc; i++) { ev_off[i] = et; et += ctx->h_rlen[r0 + c0 + i] + 1; }
-				ev_off[nc] = et;
-				uint64_t *d_evoff = ca.get<uint64_t>(nc + 1); ulonglong2 *d_evs = ca.get<ulonglong2>(et + 1); uint32_t *d_nev = ca.get<uint32_t>(nc + 1), *d_tl = ca.get<uint32_t>(nc + 1);
-				if (ca.failed) return HB_E_WS;
-				HB_CUDA(cudaMemcpyAsync(d_evoff, ev_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-				{
-					ProfScope ps(ctx, "k_sketch_events");
-					k_sketch_events<<<nblk(nc, 128), 128, 0, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_evs, d_nev, d_tl);
-				}
-				{
-					ProfScope ps(ctx, "k_sketch_select");
-					const int tile = (SK2_TS / P.w) * P.w; size_t smem = (size_t)(tile + P.w) * 40;
-					cudaFuncSetAttribute(k_sketch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-					k_sketch_select<<<(unsigned)nc, SK2_THREADS, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_evs, d_nev, d_tl, d_cap + c0, d_mz, d_l, d_n + c0, d_err);
-				}
-				HB_CUDA(cudaGetLastError());
-				HB_CUDA(cudaStreamSynchronize(ctx->stream)); // the host-side offset vector goes out of scope
-				c0 = c1;
 			}
 		}
 		HB_CUDA(cudaGetLastError());
@@ -337,6 +321,79 @@ int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch
 			k_compact_mz<<<nblk(nR * 32, 256), 256, 0, ctx->stream>>>(nR, d_cap, d_off, d_mz, d_dense);
 		}
 		HB_CUDA(cudaGetLastError());
+		out->mz = d_dense; out->off = d_off_keep; out->total = total;
+		return HB_OK;
+	}
+	hb_set_err(ctx, HB_E_OVERFLOW, "minimizer slices overflowed even at one slot per base");
+	return HB_E_OVERFLOW;
+}
+
+int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch *out)
+{ // two-stage sketch, one chunk of reads at a time so that the scratch (16 B event per base + per-read slices) stays
+  // bounded whatever the range.  Chunks run last to first and each one's dense minimizers are stacked downwards on the
+  // workspace's hi side, which leaves ONE contiguous array in read order when the first chunk is done.
+	(void)rid_mode;
+	out->mz = 0; out->off = 0; out->total = 0;
+	if (getenv("HB_SKETCH_LEGACY")) return hb_run_sketch_legacy(ctx, r0, r1, out);
+	const uint64_t nR = r1 - r0; Arena ar(ctx);
+	SketchPar P = { ctx->opt.mz_win, ctx->opt.k_mer_length, ctx->opt.is_hpc, ctx->opt.mz_sample_dist, ctx->opt.mz_rewin };
+	static const uint64_t chunk_bases = getenv("HB_SKETCH_CHUNK") ? strtoull(getenv("HB_SKETCH_CHUNK"), 0, 10) : 3300000000ull;
+	std::vector<uint64_t> cb(1, 0);
+	for (uint64_t c0 = 0; c0 < nR;) {
+		uint64_t c1 = c0, b = 0;
+		while (c1 < nR && (c1 == c0 || b + ctx->h_rlen[r0 + c1] + 1 <= chunk_bases)) { b += ctx->h_rlen[r0 + c1] + 1; c1++; }
+		cb.push_back(c1); c0 = c1;
+	}
+	uint32_t *d_n = ar.get<uint32_t>(nR + 1); int *d_err = ar.get<int>(1); uint64_t *d_off = ar.get<uint64_t>(nR + 2);
+	HB_ALLOC_CHECK(ar);
+	const size_t hi_mark = ctx->ws_hi & ~(size_t)255;
+	for (int attempt = 0, div = 12; attempt < 3; attempt++, div = div > 4 ? div / 3 : 1) {
+		ctx->ws_hi = hi_mark;
+		HB_CUDA(cudaMemsetAsync(d_n, 0, (nR + 1) * 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+		hb_mz_t *d_dense = (hb_mz_t *)hb_ws_hi_packed(ctx, 2 * sizeof(hb_mz_t)); // two mapped pad entries past the end
+		if (!d_dense) return HB_E_WS;
+		uint64_t total = 0; bool overflow = false;
+		for (size_t ci = cb.size() - 1; ci-- > 0 && !overflow;) {
+			const uint64_t c0 = cb[ci], nc = cb[ci + 1] - c0; Arena ca(ctx);
+			std::vector<uint64_t> cap_off(nc + 1), ev_off(nc + 1); uint64_t tot = 0, et = 0;
+			for (uint64_t i = 0; i < nc; i++) { const uint64_t l = ctx->h_rlen[r0 + c0 + i]; cap_off[i] = tot; tot += l / div + 32; ev_off[i] = et; et += l + 1; }
+			cap_off[nc] = tot; ev_off[nc] = et;
+			uint64_t *d_cap = ca.get<uint64_t>(nc + 1), *d_evoff = ca.get<uint64_t>(nc + 1), *d_loff = ca.get<uint64_t>(nc + 2);
+			hb_mz_t *d_mz = ca.get<hb_mz_t>(tot); uint32_t *d_l = ca.get<uint32_t>(tot);
+			ulonglong2 *d_evs = ca.get<ulonglong2>(et + 1); uint32_t *d_nev = ca.get<uint32_t>(nc + 1), *d_tl = ca.get<uint32_t>(nc + 1);
+			if (ca.failed) return HB_E_WS;
+			HB_CUDA(cudaMemcpyAsync(d_cap, cap_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+			HB_CUDA(cudaMemcpyAsync(d_evoff, ev_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+			{
+				ProfScope ps(ctx, "k_sketch_events");
+				k_sketch_events<<<nblk(nc, 128), 128, 0, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_evs, d_nev, d_tl);
+			}
+			{
+				ProfScope ps(ctx, "k_sketch_select");
+				const int tile = (SK2_TS / P.w) * P.w; size_t smem = (size_t)(tile + P.w) * 40;
+				cudaFuncSetAttribute(k_sketch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				k_sketch_select<<<(unsigned)nc, SK2_THREADS, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0 + c0, nc, d_evoff, d_evs, d_nev, d_tl, d_cap, d_mz, d_l, d_n + c0, d_err);
+			}
+			HB_CUDA(cudaGetLastError());
+			int rc = hb_scan_u32_to_u64(ctx, d_n + c0, d_loff, nc); if (rc) return rc;
+			struct { uint64_t tot; int err; } h = { 0, 0 };
+			HB_CUDA(cudaMemcpyAsync(&h.tot, d_loff + nc, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h.err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+			HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (h.err) { overflow = true; break; } // a slice overflowed: start over with larger slices
+			d_dense = (hb_mz_t *)hb_ws_hi_packed(ctx, h.tot * sizeof(hb_mz_t));
+			if (!d_dense) return HB_E_WS;
+			{
+				ProfScope ps(ctx, "k_compact_mz");
+				if (nc) k_compact_mz<<<nblk(nc * 32, 256), 256, 0, ctx->stream>>>(nc, d_cap, d_loff, d_mz, d_dense);
+			}
+			HB_CUDA(cudaGetLastError());
+			total += h.tot;
+			if (ci) HB_CUDA(cudaStreamSynchronize(ctx->stream)); // the chunk's scratch is reused by the next one
+		}
+		if (overflow) continue;
+		int rc = hb_scan_u32_to_u64(ctx, d_n, d_off, nR); if (rc) return rc;
+		uint64_t *d_off_keep = ar.hi<uint64_t>(nR + 2); HB_ALLOC_CHECK(ar);
+		HB_CUDA(cudaMemcpyAsync(d_off_keep, d_off, (nR + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 		out->mz = d_dense; out->off = d_off_keep; out->total = total;
 		return HB_OK;
 	}

@@ -34,7 +34,7 @@ struct hb_ctx {
 	double last_pass_ms;
 	// workspace: one device allocation used as a double-ended stack (lo: scoped scratch,
 	// hi: buffers that live until the end of the pass); grown between passes only
-	uint8_t *ws; size_t ws_cap, ws_lo, ws_hi, ws_need;
+	uint8_t *ws; size_t ws_cap, ws_lo, ws_hi, ws_need, ws_virt;
 	// capacity of the resident result arrays
 	uint64_t out0_cap, out1_cap, outoff_cap;
 	// cached pinned staging buffer and capacities of the read-store arrays
@@ -45,6 +45,7 @@ int hb_ws_grow(hb_ctx *ctx);
 void hb_ws_reset(hb_ctx *ctx);
 void *hb_ws_lo(hb_ctx *ctx, size_t bytes);
 void *hb_ws_hi(hb_ctx *ctx, size_t bytes);
+void *hb_ws_hi_packed(hb_ctx *ctx, size_t bytes);
 
 void hb_set_err(hb_ctx *ctx, int code, const char *fmt, ...);
 DevReads hb_dev_reads(const hb_ctx *ctx);
