@@ -503,6 +503,7 @@ struct StageOut { // host destinations of the stage APIs (all optional)
 	uint64_t *off; void *rec; uint64_t rec_cap;      // stage 1: minimizers / stage 2: anchors / stage 3: chains
 	uint64_t *hit_off; hb_hit_t *hits; uint64_t hit_cap; uint64_t *fc_off; uint64_t *fc; uint64_t fc_cap;
 	double e_rate; int32_t w_l; // window pass
+	hb_wl_t *wl; uint64_t wl_cap; uint16_t *cig; uint64_t cig_cap; uint64_t n_wl, n_cig; // step A of the EC alignment stage (mode 5)
 };
 
 // mode: 0 final pass (results kept in ctx->d_out*), 2 anchors, 3 chains
@@ -572,7 +573,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	if (mode == 2) { d_all_hits = ar.get<hb_hit_t>(h_aoff[nR] + 1); HB_ALLOC_CHECK(ar); }
 	std::vector<uint64_t> st3_off, st3_hit_off, st3_fc_off; // mode 3 host offsets (accumulated per batch)
 	uint64_t st3_n = 0, st3_nh = 0, st3_nf = 0;
-	if (mode == 3 || mode == 4) { st3_off.assign(nR + 1, 0); st3_hit_off.assign(nR + 1, 0); st3_fc_off.assign(nR + 1, 0); }
+	if (mode >= 3) { st3_off.assign(nR + 1, 0); st3_hit_off.assign(nR + 1, 0); st3_fc_off.assign(nR + 1, 0); }
 	unsigned long long *d_stat = ar.zero<unsigned long long>(16);
 	uint32_t *d_m0 = 0, *d_m1 = 0; // per-read result counts (final pass)
 	struct BatchRes { hb_ma_hit_t *o0, *o1; uint64_t *ooff; uint64_t b0, b1; };
@@ -640,7 +641,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		// chain
 		hb_hit_t *d_chits = ba.get<hb_hit_t>(B + 1); int32_t *d_f = ba.get<int32_t>(B + 1), *d_p = ba.get<int32_t>(B + 1), *d_ii = ba.get<int32_t>(B + 1); int64_t *d_t = ba.get<int64_t>(B + 1);
 		hb_chain_t *d_ch = ba.zero<hb_chain_t>(n_slots + 1); uint32_t *d_slot_read = ba.get<uint32_t>(n_slots + 1);
-		uint64_t *d_fc = (mode == 3 || mode == 4) ? ba.get<uint64_t>(B + 2 * n_slots + 4) : 0;
+		uint64_t *d_fc = mode >= 3 ? ba.get<uint64_t>(B + 2 * n_slots + 4) : 0;
 		HB_ALLOC_CHECK(ba);
 		{
 			ChainArgs C; C.R = R; C.r0 = r0 + b0; C.dir = d_dir; C.dir_n = d_dirn; C.a_off = d_aoff + b0; C.a_base = a_base; C.c_off = d_coff;
@@ -672,7 +673,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	TRACE("post");
 		ctx->counters[5] += n_slots;
 
-		if (mode == 4) { // window pass of an EC round over the chains of this batch
+		if (mode == 4 || mode == 5) { // window pass of an EC round over the chains of this batch
 			uint32_t *d_wc = ba.zero<uint32_t>(nb + 1); uint64_t *d_woff = ba.get<uint64_t>(nb + 2), *d_fcb = ba.get<uint64_t>(n_slots + 1);
 			HB_ALLOC_CHECK(ba);
 			const int32_t w_l = so->w_l;
@@ -694,6 +695,50 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			ctx->counters[8] += n_win;
 			int h_err2 = 0; HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 			if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "a window start fell outside its chain's fake cigar"); return HB_E_STATE; }
+			if (mode == 5) { // step A of the alignment stage: one thread per overlap consumes the window records
+				uint64_t *d_ooff = ba.get<uint64_t>(nb + 2); HB_ALLOC_CHECK(ba);
+				if ((rc = hb_scan_u32_to_u64(ctx, d_nol, d_ooff, nb))) return rc;
+				std::vector<uint64_t> h_ooff(nb + 1);
+				HB_CUDA(cudaMemcpyAsync(h_ooff.data(), d_ooff, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+				const uint64_t n_ov = h_ooff[nb];
+				const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 4)); const uint64_t nthr = (uint64_t)blocks * 64;
+				OvDesc *d_od = ba.get<OvDesc>(n_ov + 1); hb_aln_t *d_aln = ba.get<hb_aln_t>(n_ov + 1); hb_wl_t *d_wl = ba.zero<hb_wl_t>(n_win + 1);
+				uint64_t *d_path = ba.get<uint64_t>(nthr * (uint64_t)w_l * 5); uint16_t *d_ctmp = ba.get<uint16_t>(nthr * HB_EC_CIG_TMP);
+				unsigned long long *d_pused = ba.zero<unsigned long long>(1);
+				HB_ALLOC_CHECK(ba);
+				k_ov_desc<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, w_l, d_woff, d_ooff, d_od);
+				uint64_t pool_cap = n_win * 4 + 4096, pool_used = 0; uint16_t *d_pool = 0;
+				for (int attempt = 0;; attempt++) {
+					d_pool = ba.get<uint16_t>(pool_cap); HB_ALLOC_CHECK(ba);
+					HB_CUDA(cudaMemsetAsync(d_pused, 0, 8, ctx->stream));
+					EcAlnArgs E; E.R = R; E.r0 = r0 + b0; E.n_ov = n_ov; E.desc = d_od; E.ch = d_ch; E.fc = d_fc; E.fc_grp_base = d_fcb; E.win = d_wout; E.e_rate = so->e_rate; E.w_l = w_l;
+					E.wl = d_wl; E.out = d_aln; E.path = d_path; E.cig_tmp = d_ctmp; E.pool = d_pool; E.pool_used = d_pused; E.pool_cap = pool_cap; E.err = d_err;
+					{
+						ProfScope ps(ctx, "k_ec_overlap");
+						if (n_ov) k_ec_overlap<<<blocks, 64, 0, ctx->stream>>>(E);
+					}
+					HB_CUDA(cudaGetLastError());
+					HB_CUDA(cudaMemcpyAsync(&pool_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+					HB_CUDA(cudaStreamSynchronize(ctx->stream));
+					if (h_err2 & (32 | 64)) { hb_set_err(ctx, HB_E_STATE, "EC alignment: fake-cigar lookup or cigar scratch overflow (flags %d)", h_err2); return HB_E_STATE; }
+					if (pool_used <= pool_cap) break;
+					if (attempt >= 2) { hb_set_err(ctx, HB_E_OVERFLOW, "EC alignment: cigar pool"); return HB_E_OVERFLOW; }
+					ba.release(d_pool); pool_cap = pool_used + 4096; // the exact need is known now
+				}
+				ctx->counters[9] += n_ov;
+				if (so->rec && st3_n + n_ov > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
+				if (so->wl && so->n_wl + n_win > so->wl_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "window-list output capacity"); return HB_E_OVERFLOW; }
+				if (so->cig && so->n_cig + pool_used > so->cig_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "cigar output capacity"); return HB_E_OVERFLOW; }
+				if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_aln_t *)so->rec + st3_n, d_aln, n_ov * sizeof(hb_aln_t), cudaMemcpyDeviceToHost, ctx->stream));
+				if (so->wl) HB_CUDA(cudaMemcpyAsync(so->wl + so->n_wl, d_wl, n_win * sizeof(hb_wl_t), cudaMemcpyDeviceToHost, ctx->stream));
+				if (so->cig) HB_CUDA(cudaMemcpyAsync(so->cig + so->n_cig, d_pool, pool_used * 2, cudaMemcpyDeviceToHost, ctx->stream));
+				HB_CUDA(cudaStreamSynchronize(ctx->stream));
+				if (so->rec) for (uint64_t i = 0; i < n_ov; i++) ((hb_aln_t *)so->rec)[st3_n + i].w_off += so->n_wl; // batch-relative -> global
+				if (so->wl && so->n_cig) for (uint64_t i = 0; i < n_win; i++) if (so->wl[so->n_wl + i].clen) so->wl[so->n_wl + i].cidx += (uint32_t)so->n_cig;
+				for (uint64_t i = 0; i <= nb; i++) st3_off[b0 + i] = st3_n + h_ooff[i];
+				st3_n += n_ov; so->n_wl += n_win; so->n_cig += pool_used;
+				b0 = b1; continue;
+			}
 			if (so->rec && st3_n + n_win > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "window output capacity"); return HB_E_OVERFLOW; }
 			if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_win_t *)so->rec + st3_n, d_wout, n_win * sizeof(hb_win_t), cudaMemcpyDeviceToHost, ctx->stream));
 			HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -774,7 +819,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_CUDA(cudaStreamSynchronize(ctx->stream));
 		return HB_OK;
 	}
-	if (mode == 4) { if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8); return HB_OK; }
+	if (mode == 4 || mode == 5) { if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8); return HB_OK; }
 	if (mode == 3) {
 		if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8);
 		if (so->hit_off) memcpy(so->hit_off, st3_hit_off.data(), (nR + 1) * 8);
@@ -851,6 +896,19 @@ extern "C" int hb_windows(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thr
 	if (w_l < 8 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be >= 8 and e_rate in [0,1]"); return HB_E_ARG; }
 	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l;
 	return run_pass(ctx, r0, r1, 4, bw_thres, &so, 0);
+}
+
+extern "C" int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
+                           uint64_t *off, hb_aln_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
+                           uint64_t *n_wl, uint64_t *n_cig)
+{
+	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l;
+	so.wl = wl; so.wl_cap = wl_cap; so.cig = cig; so.cig_cap = cig_cap;
+	int rc = run_pass(ctx, r0, r1, 5, bw_thres, &so, 0);
+	if (n_wl) *n_wl = so.n_wl;
+	if (n_cig) *n_cig = so.n_cig;
+	return rc;
 }
 
 // ---------------------------------------------------------------------------

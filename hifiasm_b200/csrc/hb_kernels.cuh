@@ -18,6 +18,7 @@
 #pragma once
 #include "hb_sketch.cuh"
 #include "hb_final.cuh"
+#include "hb_ecaln.cuh"
 
 #define HB_FULL 0xffffffffu
 static __device__ __forceinline__ int hb_lane() { return threadIdx.x & 31; }
@@ -1053,7 +1054,7 @@ __global__ void __launch_bounds__(128) k_windows(WinArgs A)
 			if (uge <= th && uge == best) pe = site + th;
 		}
 		rec.err = best; rec.pe = pe;
-	}
+	} else rec.t_s = -1; // init_waln resets its r_s to -1 when it rejects the window (Correct.cpp:766)
 	A.out[wi] = rec;
 }
 
@@ -1073,6 +1074,41 @@ __global__ void k_win_desc(uint64_t nR, const uint64_t *__restrict__ c_off, cons
 		const uint32_t s = idx[cb + i]; const hb_chain_t &c = ch[cb + s];
 		int64_t nl = ((int64_t)c.x_pos_e + 1) - ((int64_t)c.x_pos_s / w_l) * w_l; uint32_t nw = (uint32_t)(nl / w_l + (nl % w_l > 0 ? 1 : 0));
 		for (uint32_t k = 0; k < nw; k++) { WinDesc d; d.read = (uint32_t)r; d.slot = (uint32_t)(cb + s); d.k = k; d.ord = i; desc[o++] = d; }
+	}
+}
+
+// ----------------------------------------------------------------------------
+// step A of the alignment stage of an EC round (rows a8 + a9): one thread per overlap consumes the window records
+// of k_windows (hb_ecaln.cuh).  Grid-stride over the overlaps so that the per-thread trace scratch (5 words per
+// column of one window) is bounded by the grid, not by the batch.
+// ----------------------------------------------------------------------------
+struct OvDesc { uint32_t read, slot, nw, pad; uint64_t w0; }; // batch-local read, chain slot, number of windows, first window
+__global__ void k_ov_desc(uint64_t nR, const uint64_t *__restrict__ c_off, const hb_chain_t *__restrict__ ch, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol, int32_t w_l,
+                          const uint64_t *__restrict__ w_off, const uint64_t *__restrict__ o_off, OvDesc *__restrict__ desc)
+{
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	uint64_t cb = c_off[r], w = w_off[r], o = o_off[r];
+	for (uint32_t i = 0; i < n_ol[r]; i++) {
+		const uint32_t s = idx[cb + i]; const hb_chain_t &c = ch[cb + s];
+		int64_t nl = ((int64_t)c.x_pos_e + 1) - ((int64_t)c.x_pos_s / w_l) * w_l; uint32_t nw = (uint32_t)(nl / w_l + (nl % w_l > 0 ? 1 : 0));
+		OvDesc d; d.read = (uint32_t)r; d.slot = (uint32_t)(cb + s); d.nw = nw; d.pad = 0; d.w0 = w; desc[o + i] = d; w += nw;
+	}
+}
+struct EcAlnArgs {
+	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base; const hb_win_t *win;
+	double e_rate; int32_t w_l; hb_wl_t *wl; hb_aln_t *out; uint64_t *path; uint16_t *cig_tmp; uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; int *err;
+};
+__global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
+{
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+	EcCtx C; C.R = A.R; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.err = A.err;
+	C.ez.path = A.path + tid * (uint64_t)A.w_l * 5; C.ez.cig = A.cig_tmp + tid * HB_EC_CIG_TMP; C.ez.cn = 0;
+	for (uint64_t o = tid; o < A.n_ov; o += nthr) {
+		const OvDesc d = A.desc[o]; const hb_chain_t c = A.ch[d.slot];
+		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand);
+		hb_aln_t res; res.w_off = d.w0; res.pad = 0;
+		hb_ec_overlap_A(C, c, A.fc + A.fc_grp_base[d.slot] + c.fc_off, A.win + d.w0, (int32_t)d.nw, A.wl + d.w0, &res);
+		A.out[o] = res;
 	}
 }
 

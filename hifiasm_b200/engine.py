@@ -18,6 +18,12 @@ MA = binio.MA_MEM
 WIN = np.dtype([(f, "<i4") for f in ("chain", "q_s", "q_e", "t_s", "t_pri_l", "thre", "aux_beg", "aux_end", "err", "pe")])
 
 
+WL = np.dtype([("x_start", "<i4"), ("x_end", "<i4"), ("y_start", "<i4"), ("y_end", "<i4"),
+               ("extra_begin", "<i2"), ("extra_end", "<i2"), ("error", "<i2"), ("error_threshold", "<i2"),
+               ("cidx", "<u4"), ("clen", "<u4")])  # window_list, Hash_Table.h:54-62
+ALN = np.dtype([("st", "<i4"), ("align_length", "<u4"), ("rr", "<f8"), ("re", "<i8"), ("w_off", "<u8"), ("w_n", "<u4"), ("pad", "<u4")])
+
+
 class HBError(RuntimeError):
     pass
 
@@ -170,6 +176,16 @@ class Engine:
         rec = np.zeros(int(off[-1]) + 1, WIN)
         self._ck(_lib().hb_windows(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), _p(rec), C.c_uint64(rec.size)))
         return off, rec[:int(off[-1])]
+
+    def ec_align(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775):
+        """step A of the alignment stage of an EC round (rows a8 + a9): -> (off, ALN records, WL window lists, cigar pool)"""
+        n = r1 - r0
+        off = np.zeros(n + 1, np.uint64); nw = C.c_uint64(); nc = C.c_uint64(); z = C.c_void_p(0)
+        a = (self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off))
+        self._ck(_lib().hb_ec_align(*a, z, C.c_uint64(0), z, C.c_uint64(0), z, C.c_uint64(0), C.byref(nw), C.byref(nc)))
+        rec = np.zeros(int(off[-1]) + 1, ALN); wl = np.zeros(nw.value + 1, WL); cig = np.zeros(2 * nc.value + 4096, np.uint16)
+        self._ck(_lib().hb_ec_align(*a, _p(rec), C.c_uint64(rec.size), _p(wl), C.c_uint64(wl.size), _p(cig), C.c_uint64(cig.size), C.byref(nw), C.byref(nc)))
+        return off, rec[:int(off[-1])], wl[:nw.value], cig[:nc.value]
 
     # ---- final pass
     def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None, out=None):

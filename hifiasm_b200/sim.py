@@ -60,9 +60,33 @@ def _mutate(seq: np.ndarray, rng, err: float) -> np.ndarray:
     return res
 
 
+def _damage(seq: np.ndarray, rng, burst_rate: float, sv_rate: float) -> np.ndarray:
+    """Local damage that makes alignment windows fail (exercises the gap-filling /
+    extension / re-chaining paths of the EC rounds): error bursts (60-300 bp at
+    8-25 % error) and block insertions / deletions of 20-400 bp."""
+    n = seq.size
+    nb = rng.poisson(burst_rate * n)
+    for _ in range(nb):
+        if seq.size < 400:
+            break
+        ln = int(rng.integers(60, 300)); s = int(rng.integers(0, seq.size - ln))
+        seq = np.concatenate([seq[:s], _mutate(seq[s:s + ln], rng, float(rng.uniform(0.08, 0.25))), seq[s + ln:]])
+    ns = rng.poisson(sv_rate * n)
+    for _ in range(ns):
+        if seq.size < 1000:
+            break
+        ln = int(rng.integers(20, 400)); s = int(rng.integers(0, seq.size - ln))
+        if rng.random() < 0.5:
+            seq = np.concatenate([seq[:s], rng.integers(0, 4, ln, dtype=np.uint8), seq[s:]])
+        else:
+            seq = np.concatenate([seq[:s], seq[s + ln:]])
+    return seq
+
+
 def sim_reads(hap1: np.ndarray, hap2: np.ndarray, cov: float, mean_len: int,
               seed: int, sd_len: int = 2000, min_len: int = 2000,
-              err: float = 0.002, n_rate: float = 0.0):
+              err: float = 0.002, n_rate: float = 0.0,
+              burst_rate: float = 0.0, sv_rate: float = 0.0):
     """Return list of uint8 code arrays (values 0..3, 4 = N)."""
     rng = np.random.default_rng(seed + 1000003)
     glen = hap1.size
@@ -79,6 +103,8 @@ def sim_reads(hap1: np.ndarray, hap2: np.ndarray, cov: float, mean_len: int,
             s = (3 - s[::-1]).astype(np.uint8)
         if err > 0:
             s = _mutate(s, rng, err)
+        if burst_rate > 0 or sv_rate > 0:
+            s = _damage(s, rng, burst_rate, sv_rate)
         if n_rate > 0:
             s = s.copy()
             s[rng.random(s.size) < n_rate] = 4

@@ -124,6 +124,20 @@ typedef struct { int32_t chain, q_s, q_e, t_s, t_pri_l, thre, aux_beg, aux_end, 
 int hb_windows(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
                uint64_t *off, hb_win_t *rec, uint64_t rec_cap);
 
+/* ---- alignment stage of an EC round, step A (SURVEY.md §8 rows a8 + a9): for every chain h_ec_lchain returns for
+ * reads [r0,r1), what gen_hc_r_alin (Correct.cpp:25617-25645) does before the base-level CIGAR:
+ * align_hc_ed_post_extz (12951: window pass, gap filling by push_hc_wlst_exz 12776, 0.9 aligned-fraction cut) and
+ * gen_extend_err_exz (13400: error estimate of the still unaligned windows by extension from their neighbours).
+ * hb_wl_t is window_list (Hash_Table.h:54-62); cidx indexes cig[] (uint16 = op<<14 | len, push_trace
+ * Levenshtein_distance.h:522).  st: 0 = rejected by the window pass, 1 = aligned but rr > e_rate, 2 = accepted with
+ * re = estimated number of errors.  off[r1-r0+1] counts overlaps per read (hb_chains order); rec[j].w_off/w_n
+ * locate the overlap's window list in wl[].  *n_wl / *n_cig receive the used sizes of wl[] / cig[].                */
+typedef struct { int32_t x_start, x_end, y_start, y_end; int16_t extra_begin, extra_end, error, error_threshold; uint32_t cidx, clen; } hb_wl_t;
+typedef struct { int32_t st; uint32_t align_length; double rr; int64_t re; uint64_t w_off; uint32_t w_n, pad; } hb_aln_t;
+int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
+                uint64_t *off, hb_aln_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
+                uint64_t *n_wl, uint64_t *n_cig);
+
 /* ---- final overlap pass: cal_ov_r(n_thre, n_a, new_idx=1) (ecovlp.h:15;
  * ecovlp.cpp:6385 -> worker_hap_dc_ec_gen_new_idx 3948) -----------------------
  * prev_* = R_INF.paf[] / R_INF.reverse_paf[] of the last EC round, flattened

@@ -1365,7 +1365,7 @@ int hao_windows(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint32
 				hao_decode_sub(r, z->y_id, t_s, t_pri_l, (int)z->y_pos_strand, ts);
 				rec.err = hao_ed_semi_64_absent_diag(ts, (int32_t)t_pri_l, qs + q_s, (int32_t)q_l, (int32_t)thre, (int32_t)aux_beg, &pe);
 				rec.pe = pe; rec.t_s = (int32_t)t_s; rec.t_pri_l = (int32_t)t_pri_l; rec.aux_beg = (int32_t)aux_beg; rec.aux_end = (int32_t)aux_end;
-			}
+			} else rec.t_s = -1; /* init_waln resets its r_s to -1 when it rejects the window (Correct.cpp:766) */
 			if (n == m) { m = m ? m << 1 : 256; w = (hao_win_t *)realloc(w, m * sizeof(hao_win_t)); }
 			w[n++] = rec;
 			q_s = q_e + 1; q_e = q_s + w_l - 1;
@@ -1376,3 +1376,6 @@ int hao_windows(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint32
 	*out = w; *n_out = n;
 	return bad ? -1 : 0;
 }
+
+/* the alignment stage of the EC rounds (rows a8-a11) lives in its own file but shares this translation unit's helpers */
+#include "ha_ec.c"

@@ -39,8 +39,8 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "libha_oracle.so")
-        src = os.path.join(_HERE, "ha_oracle.c")
-        if (not os.path.exists(so)) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+        srcs = [os.path.join(_HERE, f) for f in ("ha_oracle.c", "ha_ec.c")]
+        if (not os.path.exists(so)) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
             subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
         L = C.CDLL(so)
         L.hao_ft_gen.restype = C.c_void_p
@@ -162,3 +162,20 @@ def windows(store: Store, rid, chains: np.ndarray, fc: np.ndarray, e_rate=0.04, 
                            C.c_double(e_rate), C.c_int64(w_l), C.byref(out), C.byref(n))
     assert rc == 0
     return _take(out, n.value, WIN)
+
+
+WL = np.dtype([("x_start", "<i4"), ("x_end", "<i4"), ("y_start", "<i4"), ("y_end", "<i4"),
+               ("extra_begin", "<i2"), ("extra_end", "<i2"), ("error", "<i2"), ("error_threshold", "<i2"),
+               ("cidx", "<u4"), ("clen", "<u4")])
+ALN_A = np.dtype([("st", "<i4"), ("align_length", "<u4"), ("rr", "<f8"), ("re", "<i8"),
+                  ("w_off", "<u8"), ("w_n", "<u8"), ("c_off", "<u8"), ("c_n", "<u8")])
+
+
+def ec_align_A(store: Store, rid, chains: np.ndarray, fc: np.ndarray, e_rate=0.04, w_l=775):
+    """step A of gen_hc_r_alin for every chain of the read -> (ALN_A[n_ch], WL[], cigar u16[])"""
+    chains = np.ascontiguousarray(chains); fc = np.ascontiguousarray(fc if fc.size else np.zeros(1), dtype=np.uint64)
+    out = C.c_void_p(); wl = C.c_void_p(); cg = C.c_void_p(); nw = C.c_uint64(); nc = C.c_uint64()
+    rc = lib().hao_ec_align_A(C.byref(store.c), C.c_uint32(rid), C.c_void_p(chains.ctypes.data), C.c_uint32(chains.size), C.c_void_p(fc.ctypes.data),
+                              C.c_double(e_rate), C.c_int64(w_l), C.byref(out), C.byref(wl), C.byref(nw), C.byref(cg), C.byref(nc))
+    assert rc == 0
+    return _take(out, chains.size, ALN_A), _take(wl, nw.value, WL), _take(cg, nc.value, np.dtype("<u2"))

@@ -24,6 +24,7 @@
 #include <string.h>
 #include <stdint.h>
 #include <vector>
+#include <float.h>
 #include "CommandLines.h"
 #include "Process_Read.h"
 #include "Overlaps.h"
@@ -46,6 +47,11 @@ void h_ec_lchain(ha_abuf_t *ab, uint32_t rid, char *rs, uint64_t rl, uint64_t mz
 
 int32_t init_waln(int64_t err, int64_t s, int64_t l, int64_t w_l, int64_t *aux_beg, int64_t *aux_end, int64_t *r_s, int64_t *r_l); // Correct.cpp:764
 int64_t get_num_wins(int64_t s, int64_t e, int64_t block_s); // Correct.cpp:783
+uint32_t align_hc_ed_post_extz(overlap_region *z, All_reads *rref, char *qstr, char *tstr, bit_extz_t *exz, double e_rate, int64_t w_l, double ovlp_cut, int64_t force_aln, void *km); // Correct.cpp:12951
+double gen_extend_err_exz(overlap_region *z, const ul_idx_t *uref, hpc_t *hpc_g, All_reads *rref, char *qstr, char *tstr, bit_extz_t *exz, uint64_t *v_idx, int64_t block_s, double ovlp_cut, double e_rate, double e_max, int64_t max_err, int64_t sec_check, int64_t *r_e); // Correct.cpp:13400
+uint64_t gen_hc_fast_cigar(overlap_region *z, Candidates_list *cl, All_reads *rref, int64_t wl, char *qstr, UC_Read *tu, bit_extz_t *exz, overlap_region *aux_o, double e_rate, int64_t ql, int64_t rid, int64_t khit, int64_t *re); // Correct.cpp:25137
+void reassign_gaps(overlap_region *z, overlap_region *aux_o, char *qstr, int64_t ql, char *tstr, int64_t tl, All_reads *rref, UC_Read *tu, asg16_v *buf); // Correct.cpp:25409
+overlap_region *fetch_aux_ovlp(overlap_region_alloc *ol); // ecovlp.cpp:257
 
 #define HA_KMER_GOOD_RATIO 0.333 /* ecovlp.cpp:9 */
 #define COV_W 3072               /* ecovlp.cpp:17 */
@@ -68,6 +74,15 @@ typedef struct {
 	uint32_t n_fc;      // f_cigar.length
 } chain_rec_t;
 
+// one overlap's window list (Hash_Table.h:54-69): n, c.n, window_list[n] (32 B each), cigar pool u16[c.n]
+static void dump_wl(FILE *fp, const overlap_region *z)
+{
+	uint32_t h[2] = { (uint32_t)z->w_list.n, (uint32_t)z->w_list.c.n };
+	fwrite(h, 4, 2, fp);
+	fwrite(z->w_list.a, sizeof(window_list), z->w_list.n, fp);
+	fwrite(z->w_list.c.a, 2, z->w_list.c.n, fp);
+}
+
 static void dump_stages(const char *pfx, double bw_thres)
 {
 	uint64_t i, j, n_reads = R_INF.total_reads;
@@ -75,6 +90,7 @@ static void dump_stages(const char *pfx, double bw_thres)
 	uint32_t low_occ = asm_opt.hom_cov * HA_KMER_GOOD_RATIO;
 	FILE *fmz = xopen(pfx, ".mz.bin"), *fidx = xopen(pfx, ".idx.bin"), *fan = xopen(pfx, ".anchors.bin");
 	FILE *fch = xopen(pfx, ".chains.bin"), *fpa = xopen(pfx, ".params.txt"), *fwn = xopen(pfx, ".windows.bin");
+	FILE *fal = xopen(pfx, ".aln.bin"); asg16_v v16; memset(&v16, 0, sizeof(v16));
 	UC_Read tr; init_UC_Read(&tr); bit_extz_t exz; init_bit_extz_t(&exz, 31);
 	const double e_rate = asm_opt.max_ov_diff_ec; const int64_t w_l = asm_opt.is_ont ? WINDOW_OHC : WINDOW_HC; // ecovlp.cpp:3288
 	UC_Read ur; init_UC_Read(&ur);
@@ -155,8 +171,34 @@ static void dump_stages(const char *pfx, double bw_thres)
 			uint32_t nwr = wr.size() / 10;
 			fwrite(&nwr, 4, 1, fwn); fwrite(wr.data(), 4, wr.size(), fwn);
 		}
+		// (6) the alignment stage of an EC round, overlap by overlap, in the order and with the arguments of
+		// gen_hc_r_alin (Correct.cpp:25617-25675), the state dumped after each step:
+		//   A  align_hc_ed_post_extz (12951) + gen_extend_err_exz (13400): ok, align_length, rr, re, window list
+		//   B  gen_hc_fast_cigar (25137): re, window list (base-level cigars)
+		//   C  reassign_gaps (25409): window list
+		{
+			overlap_region *aux_o = fetch_aux_ovlp(&ol); // ecovlp.cpp:3279; may move ol.list
+			const double err = e_rate, e_max = err * 1.5; const int64_t ql = ur.length;
+			resize_UC_Read(&tr, ((w_l + (THRESHOLD_MAX_SIZE << 1) + 1) << 1) + 8);
+			fwrite(&nc, 4, 1, fal);
+			for (j = 0; j < nc; j++) {
+				overlap_region *z = &ol.list[j]; int64_t re = INT64_MAX; double rr = DBL_MAX;
+				z->shared_seed = z->non_homopolymer_errors;
+				int32_t ok = align_hc_ed_post_extz(z, &R_INF, ur.seq, tr.seq, &exz, err, w_l, OVERLAP_THRESHOLD_HIFI_FILTER, 0, NULL);
+				if (ok) rr = gen_extend_err_exz(z, NULL, NULL, &R_INF, ur.seq, tr.seq, &exz, NULL, w_l, -1, err, (e_max + 0.000001), THRESHOLD_MAX_SIZE, 0, &re);
+				int32_t st = !ok ? 0 : (rr > err ? 1 : 2); uint32_t al = z->align_length;
+				fwrite(&st, 4, 1, fal); fwrite(&al, 4, 1, fal); fwrite(&rr, 8, 1, fal); fwrite(&re, 8, 1, fal);
+				dump_wl(fal, z);
+				if (st != 2) continue;
+				z->is_match = 0; z->non_homopolymer_errors = re;
+				gen_hc_fast_cigar(z, &cl, &R_INF, w_l, ur.seq, &tr, &exz, aux_o, e_rate, ql, i, 31 /* E_KHIT, ecovlp.cpp */, &re);
+				fwrite(&re, 8, 1, fal); dump_wl(fal, z);
+				reassign_gaps(z, aux_o, ur.seq, ql, NULL, -1, &R_INF, &tr, &v16);
+				dump_wl(fal, z);
+			}
+		}
 	}
-	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch); fclose(fwn);
+	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch); fclose(fwn); fclose(fal);
 	destory_UC_Read(&ur);
 }
 

@@ -1,0 +1,68 @@
+"""Reader of refdump's alignment-stage dump (<pfx>.aln.bin, oracle/refdump.cpp step 6): per read and per
+overlap the state after each step of gen_hc_r_alin (Correct.cpp:25617): A = align_hc_ed_post_extz +
+gen_extend_err_exz, B = gen_hc_fast_cigar, C = reassign_gaps."""
+import struct
+
+import numpy as np
+
+WL = np.dtype([("x_start", "<i4"), ("x_end", "<i4"), ("y_start", "<i4"), ("y_end", "<i4"),
+               ("extra_begin", "<i2"), ("extra_end", "<i2"), ("error", "<i2"), ("error_threshold", "<i2"),
+               ("cidx", "<u4"), ("clen", "<u4")])  # window_list, Hash_Table.h:54-62
+
+
+def _wl(buf, o):
+    n, cn = struct.unpack_from("<II", buf, o); o += 8
+    w = np.frombuffer(buf, dtype=WL, count=n, offset=o); o += 32 * n
+    c = np.frombuffer(buf, dtype="<u2", count=cn, offset=o); o += 2 * cn
+    return (w, c), o
+
+
+def read_aln(path):
+    """-> list over reads of list over overlaps of dict(st, align_length, rr, re, A=(w,c)[, reB, B, C])"""
+    buf = open(path, "rb").read(); o = 0; out = []
+    while o < len(buf):
+        nc, = struct.unpack_from("<I", buf, o); o += 4
+        rl = []
+        for _ in range(nc):
+            st, al, rr, re = struct.unpack_from("<iIdq", buf, o); o += 24
+            d = dict(st=st, align_length=al, rr=rr, re=re)
+            d["A"], o = _wl(buf, o)
+            if st == 2:
+                d["reB"], = struct.unpack_from("<q", buf, o); o += 8
+                d["B"], o = _wl(buf, o)
+                d["C"], o = _wl(buf, o)
+            rl.append(d)
+        out.append(rl)
+    return out
+
+
+def wl_canon(w, c):
+    """window list with every cigar resolved (bytes): what must be identical, independent of pool order"""
+    parts = []
+    for r in w:
+        h = np.array([r["x_start"], r["x_end"], r["y_start"], r["y_end"], r["extra_begin"], r["extra_end"], r["error"],
+                      r["error_threshold"], r["clen"]], dtype="<i4")
+        parts.append(h.tobytes()); parts.append(np.ascontiguousarray(c[int(r["cidx"]):int(r["cidx"]) + int(r["clen"])]).tobytes())
+    return b"".join(parts)
+
+
+def _dg(parts):
+    import hashlib
+    h = hashlib.blake2b(digest_size=8)
+    for b in parts:
+        h.update(b)
+    return int.from_bytes(h.digest(), "little")
+
+
+def digest_A(ovl):
+    """per-read digest of step A: ovl = iterable of (st, align_length, rr, re, w, c)"""
+    return _dg(struct.pack("<iIdq", int(st), int(al), float(rr), int(re)) + wl_canon(w, c) for st, al, rr, re, w, c in ovl)
+
+
+def digest_B(ovl):
+    """per-read digest of step B (accepted overlaps only): ovl = iterable of (re, w, c)"""
+    return _dg(struct.pack("<q", int(re)) + wl_canon(w, c) for re, w, c in ovl)
+
+
+def digest_C(ovl):
+    return _dg(wl_canon(w, c) for w, c in ovl)

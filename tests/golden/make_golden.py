@@ -24,7 +24,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from hifiasm_b200 import sim  # noqa: E402
+import alnlib  # noqa: E402
 
 REFDUMP = os.path.join(ROOT, "oracle", "_ref", "refdump")
 CH = np.dtype([("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_id", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
@@ -36,6 +38,10 @@ DATASETS = {
            dict(cov=20, mean_len=6000, seed=5, sd_len=2000, min_len=400, n_rate=2e-4)),
     "g2": (dict(glen=150000, seed=9, snp_rate=0.001, repeat_frac=0.0),
            dict(cov=16, mean_len=9000, seed=9, sd_len=2500, min_len=1000)),
+    # damaged reads (error bursts, block indels, 0.4 % errors): windows fail, so the gap-filling / extension /
+    # re-chaining paths of the EC alignment stage run
+    "g3": (dict(glen=100000, seed=13, snp_rate=0.002, repeat_frac=0.1, repeat_len=1200, repeat_div=0.01),
+           dict(cov=18, mean_len=7000, seed=13, sd_len=2000, min_len=800, err=0.004, n_rate=1e-4, burst_rate=1.5e-4, sv_rate=6e-5)),
 }
 
 
@@ -82,6 +88,18 @@ def read_stages(pfx, n_reads, keep=4):
                 full["anchors_%d" % i] = np.frombuffer(an, dtype=np.uint8)
                 full["chains_%d" % i] = np.frombuffer(b"".join(chl), dtype=np.uint8)
                 full["chain_hits_%d" % i] = np.frombuffer(hb, dtype=np.uint8)
+    # alignment stage of an EC round (refdump step 6): per-read digests of the state after steps A, B, C
+    aln = alnlib.read_aln(pfx + ".aln.bin")
+    assert len(aln) == n_reads
+    for k in ("alnA", "alnB", "alnC"):
+        out[k] = np.zeros(n_reads, dtype=np.uint64)
+    cnt["aln_ok"] = np.zeros(n_reads, dtype=np.uint64)
+    for i, rl in enumerate(aln):
+        out["alnA"][i] = alnlib.digest_A((d["st"], d["align_length"], d["rr"], d["re"], d["A"][0], d["A"][1]) for d in rl)
+        acc = [d for d in rl if d["st"] == 2]
+        out["alnB"][i] = alnlib.digest_B((d["reB"], d["B"][0], d["B"][1]) for d in acc)
+        out["alnC"][i] = alnlib.digest_C(d["C"] for d in acc)
+        cnt["aln_ok"][i] = len(acc)
     return out, cnt, full
 
 

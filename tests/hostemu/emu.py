@@ -106,3 +106,26 @@ def final_read(reads, ft, pt, p, hom_cov, max_n_chain, rid, in0, in1):
                               _p(o0), C.byref(m0), _p(o1), C.byref(m1))
     assert rc == 0
     return o0[:m0.value], o1[:m1.value]
+
+
+ALN = np.dtype([("st", "<i4"), ("align_length", "<u4"), ("rr", "<f8"), ("re", "<i8"), ("w_off", "<u8"), ("w_n", "<u4"), ("pad", "<u4")])
+WL = ho.WL
+
+
+def to_chain(ovlp):
+    """oracle chain records (ho.OVLP) -> hb_chain_t"""
+    c = np.zeros(ovlp.size, CHAIN)
+    for f in ("x_pos_s", "x_pos_e", "y_id", "y_pos_s", "y_pos_e", "y_pos_strand", "shared_seed", "fc_off", "fc_n"):
+        c[f] = ovlp[f]
+    c["first_hit"] = ovlp["non_homopolymer_errors"]
+    return c
+
+
+def ec_align_A(reads, rid, ch, fc, win, e_rate=0.04, w_l=775):
+    """-> (ALN[n_ch], WL[n_win] (an overlap's list at w_off, w_n entries), cigar pool u16[])"""
+    ch = np.ascontiguousarray(ch); fc = np.ascontiguousarray(fc if fc.size else np.zeros(1, np.uint64)); win = np.ascontiguousarray(win)
+    out = np.zeros(ch.size + 1, ALN); wl = np.zeros(win.size + 1, WL); cap = 64 * win.size + 64; pool = np.zeros(cap, np.uint16); used = C.c_uint64()
+    rc = lib().emu_ec_align_A(reads.h, C.c_uint32(rid), _p(ch), C.c_uint32(ch.size), _p(fc), _p(win if win.size else np.zeros(1, ho.WIN)), C.c_uint32(win.size),
+                              C.c_double(e_rate), C.c_int32(w_l), _p(out), _p(wl), _p(pool), C.c_uint64(cap), C.byref(used))
+    assert rc == 0, rc
+    return out[:ch.size], wl[:win.size], pool[:used.value]

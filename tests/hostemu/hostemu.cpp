@@ -13,6 +13,7 @@
 #include <algorithm>
 #include "../../hifiasm_b200/csrc/hb_sketch.cuh"
 #include "../../hifiasm_b200/csrc/hb_final.cuh"
+#include "../../hifiasm_b200/csrc/hb_ecaln.cuh"
 
 struct EmuReads { DevReads d; std::vector<uint8_t> packed; std::vector<uint64_t> off, noff; std::vector<uint32_t> len, npos; };
 struct EmuFt { DevFt d; std::vector<uint64_t> key; std::vector<int32_t> val; };
@@ -250,6 +251,27 @@ int emu_final_read(void *reads, void *ft, void *pt, int w, int k, int is_hpc, in
 	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
 	hb_final_merge(r->d, rid, E.ch.data(), E.idx.data(), E.n_ol, exact.data(), in0, n0, in1, n1, ov.data(), srt.data(), out0, m0, out1, m1, stat, W);
 	return 0;
+}
+
+// step A of the EC alignment stage for every chain of one read (body of k_ec_overlap).  win[] = the window records of
+// the window pass (k_windows layout; rec.chain = chain ordinal, windows of a chain contiguous and in order).
+int emu_ec_align_A(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch, const uint64_t *fc, const hb_win_t *win, uint32_t n_win, double e_rate, int32_t w_l,
+                   hb_aln_t *out, hb_wl_t *wl, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used)
+{
+	EmuReads *r = (EmuReads *)reads; int err = 0; unsigned long long used = 0;
+	std::vector<uint64_t> path((size_t)w_l * 5); std::vector<uint16_t> ctmp(HB_EC_CIG_TMP);
+	EcCtx C; C.R = r->d; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap; C.err = &err;
+	C.ez.path = path.data(); C.ez.cig = ctmp.data(); C.ez.cn = 0;
+	uint32_t w0 = 0;
+	for (uint32_t j = 0; j < n_ch; j++) {
+		uint32_t w1 = w0; while (w1 < n_win && win[w1].chain == (int32_t)j) w1++;
+		C.q = hb_rd_view(r->d, rid, 0); C.t = hb_rd_view(r->d, ch[j].y_id, ch[j].y_pos_strand);
+		hb_aln_t res; res.w_off = w0; res.pad = 0;
+		hb_ec_overlap_A(C, ch[j], fc + ch[j].fc_off, win + w0, (int32_t)(w1 - w0), wl + w0, &res);
+		out[j] = res; w0 = w1;
+	}
+	*pool_used = used;
+	return err | (used > pool_cap ? 128 : 0);
 }
 
 } // extern "C"

@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 import ha_oracle as ho  # noqa: E402
 from goldenlib import Golden, dg, CH, GOLDEN  # noqa: E402
+import alnlib  # noqa: E402
 from hifiasm_b200 import binio  # noqa: E402
 
 
@@ -21,7 +22,7 @@ def hb():
     return hifiasm_b200
 
 
-@pytest.fixture(scope="module", params=["g1", "g2"])
+@pytest.fixture(scope="module", params=["g1", "g2", "g3"])
 def ctx(request, hb):
     g = Golden(request.param)
     eng = hb.Engine(0)
@@ -76,6 +77,14 @@ def _check_stages(g, eng, mode, rs):
     for i in range(n):
         w = win[int(woff[i]):int(woff[i + 1])]
         assert w.size == int(g.count(mode, "windows")[i]) and dg(w.tobytes()) == int(g.digest(mode, "windows")[i]), "window pass read %d" % i
+    # step A of the alignment stage (rows a8 + a9): k_windows + k_ec_overlap
+    ooff, A, W, Cg = eng.ec_align(0, n, float(p["bw_thres"]), 0.04, 775)
+    assert (ooff == coff).all()
+    for i in range(n):
+        a_i = A[int(ooff[i]):int(ooff[i + 1])]
+        da = alnlib.digest_A((a["st"], a["align_length"], a["rr"], a["re"], W[int(a["w_off"]):int(a["w_off"]) + int(a["w_n"])], Cg) for a in a_i)
+        assert da == int(g.digest(mode, "alnA")[i]), "EC alignment step A, read %d" % i
+        assert int((a_i["st"] == 2).sum()) == int(g.count(mode, "aln_ok")[i])
     return hom, het
 
 

@@ -14,7 +14,7 @@ import ha_oracle as ho  # noqa: E402
 from goldenlib import Golden, dg  # noqa: E402
 
 
-@pytest.fixture(scope="module", params=["g1", "g2"])
+@pytest.fixture(scope="module", params=["g1", "g2", "g3"])
 def ctx(request):
     g = Golden(request.param)
     raw = ho.Store(g.raw.length, g.raw.byte_off, g.raw.packed, g.raw.n_off, g.raw.n_pos)
@@ -70,6 +70,25 @@ def test_anchors_chains(ctx, mode):
         assert dg(srt_hits.tobytes()) == int(g.digest(mode, "anchors")[i]), "anchors read %d" % i
         assert _chain_digest(ch, fc) == int(g.digest(mode, "chains")[i]), "chains read %d" % i
         assert dg(chits.tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain hits read %d" % i
+
+
+def test_ec_align_step_A(ctx):
+    """body of k_ec_overlap (hb_ecaln.cuh) on the raw reads: gap filling, traced windows, extension estimate"""
+    import alnlib
+    g, opt, ft, eft = ctx
+    rs = g.raw
+    st = ho.Store(rs.length, rs.byte_off, rs.packed, rs.n_off, rs.n_pos)
+    pt, hom, het = ho.pt_gen(st, ft, opt)
+    er = emu.Reads(rs)
+    p = g.params("raw")
+    for i in range(er.n):
+        mz = ho.sketch(st.decode(i), int(p["w"]), int(p["k"]), 0, 1, ft, int(p["mz_sample_dist"]), int(p["mz_rewin"]))
+        an = ho.anchors(st, pt, mz, int(p["high_occ"]), int(p["low_occ"]))
+        ch, hits, fc = ho.lchain(st, i, an, float(p["bw_thres"]), int(p["k"]), int(p["max_n_chain"]))
+        win = ho.windows(st, i, ch, fc)
+        A, W, Cg = emu.ec_align_A(er, i, emu.to_chain(ch), fc, win)
+        da = alnlib.digest_A((a["st"], a["align_length"], a["rr"], a["re"], W[int(a["w_off"]):int(a["w_off"]) + int(a["w_n"])], Cg) for a in A)
+        assert da == int(g.digest("raw", "alnA")[i]), "read %d" % i
 
 
 def test_final_pass(ctx):

@@ -8,6 +8,7 @@ import pytest
 
 import ha_oracle as ho
 from goldenlib import Golden, dg, chain_digest
+import alnlib
 from hifiasm_b200 import binio
 
 
@@ -15,7 +16,7 @@ def _store(rs):
     return ho.Store(rs.length, rs.byte_off, rs.packed, rs.n_off, rs.n_pos)
 
 
-@pytest.fixture(scope="module", params=["g1", "g2"])
+@pytest.fixture(scope="module", params=["g1", "g2", "g3"])
 def ctx(request):
     g = Golden(request.param)
     raw = _store(g.raw)
@@ -46,6 +47,12 @@ def _stages(g, mode, st, ft, opt, bw):
         assert dg(hits.tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain hits read %d" % i
         win = ho.windows(st, i, ch, fc)
         assert win.size == int(g.count(mode, "windows")[i]) and dg(win.tobytes()) == int(g.digest(mode, "windows")[i]), "window pass read %d" % i
+        # step A of the alignment stage (rows a8 + a9): gap filling, traced windows, extension error estimate
+        A, W, Cg = ho.ec_align_A(st, i, ch, fc)
+        da = alnlib.digest_A((a["st"], a["align_length"], a["rr"], a["re"], W[int(a["w_off"]):int(a["w_off"] + a["w_n"])],
+                              Cg[int(a["c_off"]):int(a["c_off"] + a["c_n"])]) for a in A)
+        assert da == int(g.digest(mode, "alnA")[i]), "EC alignment step A, read %d" % i
+        assert int((A["st"] == 2).sum()) == int(g.count(mode, "aln_ok")[i])
     return pt, hom, het
 
 
