@@ -673,7 +673,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	TRACE("post");
 		ctx->counters[5] += n_slots;
 
-		if (mode == 4 || mode == 5) { // window pass of an EC round over the chains of this batch
+		if (mode >= 4) { // window pass of an EC round over the chains of this batch
 			uint32_t *d_wc = ba.zero<uint32_t>(nb + 1); uint64_t *d_woff = ba.get<uint64_t>(nb + 2), *d_fcb = ba.get<uint64_t>(n_slots + 1);
 			HB_ALLOC_CHECK(ba);
 			const int32_t w_l = so->w_l;
@@ -695,7 +695,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			ctx->counters[8] += n_win;
 			int h_err2 = 0; HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 			if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "a window start fell outside its chain's fake cigar"); return HB_E_STATE; }
-			if (mode == 5) { // step A of the alignment stage: one thread per overlap consumes the window records
+			if (mode >= 5) { // step A of the alignment stage: one thread per overlap consumes the window records
 				uint64_t *d_ooff = ba.get<uint64_t>(nb + 2); HB_ALLOC_CHECK(ba);
 				if ((rc = hb_scan_u32_to_u64(ctx, d_nol, d_ooff, nb))) return rc;
 				std::vector<uint64_t> h_ooff(nb + 1);
@@ -726,6 +726,71 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					ba.release(d_pool); pool_cap = pool_used + 4096; // the exact need is known now
 				}
 				ctx->counters[9] += n_ov;
+				if (mode == 6) { // step B: base-level CIGAR of the accepted overlaps (row a10)
+					uint32_t *d_cap = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_wboff = ba.get<uint64_t>(n_ov + 2); hb_alnb_t *d_alnb = ba.get<hb_alnb_t>(n_ov + 1), *d_alnb2 = ba.get<hb_alnb_t>(n_ov + 1);
+					unsigned int *d_ndef = (unsigned int *)ba.zero<uint32_t>(1);
+					int64_t *d_dpt = ba.get<int64_t>(2 * (B + 1)), *d_dpp = ba.get<int64_t>(2 * (B + 1)); int32_t *d_dpf = ba.get<int32_t>(2 * (B + 1));
+					HB_ALLOC_CHECK(ba);
+					k_ecb_cap<<<nblk(n_ov, 256), 256, 0, ctx->stream>>>(n_ov, d_od, d_ch, d_aln, d_cap);
+					if ((rc = hb_scan_u32_to_u64(ctx, d_cap, d_wboff, n_ov))) return rc;
+					uint64_t wb_tot = 0; HB_CUDA(cudaMemcpyAsync(&wb_tot, d_wboff + n_ov, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+					hb_wl_t *d_wlb = ba.zero<hb_wl_t>(wb_tot + 1); HB_ALLOC_CHECK(ba);
+					static const uint64_t path_words0 = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384;
+					uint64_t poolb_cap = (uint64_t)(h_aoff[b1] - h_aoff[b0]) / 8 + 16 * n_ov + 65536, poolb_used = 0; uint16_t *d_poolb = 0; unsigned int n_def = 0;
+					for (int attempt = 0;; attempt++) {
+						Arena pa(ctx); // scratch of this attempt
+						d_poolb = pa.get<uint16_t>(poolb_cap);
+						HB_CUDA(cudaMemsetAsync(d_pused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_ndef, 0, 4, ctx->stream));
+						for (int pass = 0; pass < 2; pass++) {
+							if (pass == 1 && !n_def) break;
+							const unsigned bl = pass == 0 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 2)) : 4u;
+							const uint64_t nt = (uint64_t)bl * 64, pw = pass == 0 ? path_words0 : (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5; const int32_t cw = pass == 0 ? 4096 : 65536;
+							Arena sa(ctx);
+							EcCigArgs G; G.R = R; G.r0 = r0 + b0; G.n_ov = n_ov; G.desc = d_od; G.ch = d_ch; G.fc = d_fc; G.fc_grp_base = d_fcb; G.aln = d_aln; G.wlA = d_wl;
+							G.chits = d_chits; G.ghits = d_hits; G.dp_half = B + 1; G.dp_t = d_dpt; G.dp_p = d_dpp; G.dp_f = d_dpf; G.e_rate = so->e_rate; G.w_l = w_l; G.pass = pass; G.refined = attempt > 0;
+							G.out = d_alnb; G.wl = d_wlb; G.wl_off = d_wboff; G.path = sa.get<uint64_t>(nt * pw); G.path_words = pw; G.vec = sa.get<uint64_t>(nt * 11 * HB_MW_MAXW);
+							G.cig_tmp = sa.get<uint16_t>(nt * 2 * (uint64_t)cw); G.cig_words = cw; G.pool = d_poolb; G.pool_used = d_pused; G.pool_cap = poolb_cap; G.n_deferred = d_ndef; G.err = d_err;
+							if (sa.failed || pa.failed) return HB_E_WS;
+							if (pass == 1) HB_CUDA(cudaMemsetAsync(d_ndef, 0, 4, ctx->stream));
+							{
+								ProfScope ps(ctx, pass == 0 ? "k_ec_cigar" : "k_ec_cigar_deferred");
+								if (n_ov) k_ec_cigar<<<bl, 64, 0, ctx->stream>>>(G);
+							}
+							HB_CUDA(cudaGetLastError());
+							HB_CUDA(cudaMemcpyAsync(&n_def, d_ndef, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							if (pass == 0) ctx->counters[10] += n_def;
+							if (pass == 1 && n_def) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: %u overlaps exceed the largest scratch", n_def); return HB_E_OVERFLOW; }
+						}
+						HB_CUDA(cudaMemcpyAsync(&poolb_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+						HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "EC base alignment: fake-cigar lookup failed"); return HB_E_STATE; }
+						if (poolb_used <= poolb_cap) {
+							// dense window lists for the host
+							uint32_t *d_wn = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_dense = ba.get<uint64_t>(n_ov + 2); HB_ALLOC_CHECK(ba);
+							k_ecb_wn<<<nblk(n_ov, 256), 256, 0, ctx->stream>>>(n_ov, d_alnb, d_wn);
+							if ((rc = hb_scan_u32_to_u64(ctx, d_wn, d_dense, n_ov))) return rc;
+							uint64_t nwd = 0; HB_CUDA(cudaMemcpyAsync(&nwd, d_dense + n_ov, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							hb_wl_t *d_wld = ba.get<hb_wl_t>(nwd + 1); HB_ALLOC_CHECK(ba);
+							k_gather_wl<<<nblk(n_ov, 256), 256, 0, ctx->stream>>>(n_ov, d_alnb, d_dense, d_wlb, d_alnb2, d_wld);
+							HB_CUDA(cudaGetLastError());
+							if (so->rec && st3_n + n_ov > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
+							if (so->wl && so->n_wl + nwd > so->wl_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "window-list output capacity"); return HB_E_OVERFLOW; }
+							if (so->cig && so->n_cig + poolb_used > so->cig_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "cigar output capacity"); return HB_E_OVERFLOW; }
+							if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_alnb_t *)so->rec + st3_n, d_alnb2, n_ov * sizeof(hb_alnb_t), cudaMemcpyDeviceToHost, ctx->stream));
+							if (so->wl) HB_CUDA(cudaMemcpyAsync(so->wl + so->n_wl, d_wld, nwd * sizeof(hb_wl_t), cudaMemcpyDeviceToHost, ctx->stream));
+							if (so->cig) HB_CUDA(cudaMemcpyAsync(so->cig + so->n_cig, d_poolb, poolb_used * 2, cudaMemcpyDeviceToHost, ctx->stream));
+							HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							if (so->rec) for (uint64_t i = 0; i < n_ov; i++) ((hb_alnb_t *)so->rec)[st3_n + i].w_off += so->n_wl;
+							if (so->wl && so->n_cig) for (uint64_t i = 0; i < nwd; i++) if (so->wl[so->n_wl + i].clen) so->wl[so->n_wl + i].cidx += (uint32_t)so->n_cig;
+							for (uint64_t i = 0; i <= nb; i++) st3_off[b0 + i] = st3_n + h_ooff[i];
+							st3_n += n_ov; so->n_wl += nwd; so->n_cig += poolb_used;
+							break;
+						}
+						if (attempt >= 2) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: cigar pool"); return HB_E_OVERFLOW; }
+						poolb_cap = poolb_used + 65536; n_def = 0; // the need is known now; the rerun takes the chains as already refined
+					}
+					b0 = b1; continue;
+				}
 				if (so->rec && st3_n + n_ov > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
 				if (so->wl && so->n_wl + n_win > so->wl_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "window-list output capacity"); return HB_E_OVERFLOW; }
 				if (so->cig && so->n_cig + pool_used > so->cig_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "cigar output capacity"); return HB_E_OVERFLOW; }
@@ -819,7 +884,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_CUDA(cudaStreamSynchronize(ctx->stream));
 		return HB_OK;
 	}
-	if (mode == 4 || mode == 5) { if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8); return HB_OK; }
+	if (mode >= 4) { if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8); return HB_OK; }
 	if (mode == 3) {
 		if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8);
 		if (so->hit_off) memcpy(so->hit_off, st3_hit_off.data(), (nR + 1) * 8);
@@ -906,6 +971,19 @@ extern "C" int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_th
 	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l;
 	so.wl = wl; so.wl_cap = wl_cap; so.cig = cig; so.cig_cap = cig_cap;
 	int rc = run_pass(ctx, r0, r1, 5, bw_thres, &so, 0);
+	if (n_wl) *n_wl = so.n_wl;
+	if (n_cig) *n_cig = so.n_cig;
+	return rc;
+}
+
+extern "C" int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
+                           uint64_t *off, hb_alnb_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
+                           uint64_t *n_wl, uint64_t *n_cig)
+{
+	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l;
+	so.wl = wl; so.wl_cap = wl_cap; so.cig = cig; so.cig_cap = cig_cap;
+	int rc = run_pass(ctx, r0, r1, 6, bw_thres, &so, 0);
 	if (n_wl) *n_wl = so.n_wl;
 	if (n_cig) *n_cig = so.n_cig;
 	return rc;

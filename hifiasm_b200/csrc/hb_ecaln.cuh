@@ -445,3 +445,479 @@ HB_HD void hb_ec_overlap_A(EcCtx &C, const hb_chain_t &c, const uint64_t *fc, co
 	if (bad) hb_flag(C.err, 32);
 	out->st = !ok ? 0 : (rr > C.e_rate ? 1 : 2); out->align_length = (uint32_t)z.align_length; out->rr = rr; out->re = re; out->w_n = (uint32_t)z.wn;
 }
+
+// =============================================================================================================
+// step B: base-level CIGAR of an accepted overlap — gen_hc_fast_cigar (Correct.cpp:25137 -> 17813, row a10):
+// return_t_chain (22997: lchain_refine of the chain's anchors), hc_ovlp_base_direct (17425: one alignment per
+// inter-anchor segment, exact shortcuts first, then hc_aln_exz_adv_hc 16178 with its threshold escalation
+// estimate -> len*e_rate -> x2 -> 0.51*len -> max), push_alnw (15988: consecutive aligned segments are fused into one
+// window whose cigar grows), update_overlap_region (17249).  Alignment = multi-word banded Myers with traceback
+// (ed_band_cal_{global,extension_0,extension_1,semi}_infi_w_trace, Levenshtein_distance.h:2516/2694/2823/3020).
+// One thread per overlap; scratch sizes are launch parameters, an overlap that does not fit is reported as deferred
+// (st = -1) and re-run by a second launch with few threads and large scratch.
+// =============================================================================================================
+#define HB_MAX_SIN_L 10000 // Levenshtein_distance.h:757
+#define HB_MAX_SIN_E 2047  // Levenshtein_distance.h:756
+#define HB_FORCE_SIN_L 512 // Levenshtein_distance.h:758
+#define HB_MW_MAXW 64      // words of a band of 2*2047+1 bits
+
+struct MwEz {
+	int32_t ps, pe, pl, ts, te, tl, thre, err, nword;
+	uint16_t *cig; int32_t cn, ccap;      // cigar of the last alignment
+	uint64_t *path; uint64_t pcap, pn;    // 5*nword words per column
+	uint64_t *vec;                        // 11 vectors of HB_MW_MAXW words: Peq[0..4], VP, VN, X, D0, HN, HP
+	int ovf;                              // scratch too small: the overlap is deferred
+};
+struct EcBCtx {
+	RdView q, t; int64_t ql, tl; double e_rate; int64_t w_l;
+	MwEz ez;
+	hb_wl_t *aw; int32_t awn, awcap;      // aux_o->w_list of the overlap
+	uint16_t *wc; int32_t wcn, wccap;     // cigar of the window under construction (aux_o->w_list.c tail), flushed to the pool when the window closes
+	int32_t open;                          // index of the window whose cigar is in wc (-1: none)
+	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap;
+	int bad;
+};
+
+HB_HD void hb_mez_push_trace(MwEz &ez, uint32_t c, uint32_t len)
+{
+	c <<= 14;
+	while (len >= 0x3fff) { if (ez.cn < ez.ccap) ez.cig[ez.cn] = (uint16_t)(c + 0x3fff); else ez.ovf = 1; ez.cn++; len -= 0x3fff; }
+	if (len) { if (ez.cn < ez.ccap) ez.cig[ez.cn] = (uint16_t)(c + len); else ez.ovf = 1; ez.cn++; }
+}
+HB_HD int hb_mw_bit(const uint64_t *x, int32_t b) { return (int)((x[b >> 6] >> (b & 63)) & 1ULL); }
+HB_HD void hb_mw_set_lsub(uint64_t *x, int32_t l, int32_t nw)
+{ // w_infi_set_bit_lsub, Levenshtein_distance.h:2136
+	for (int32_t k = 0; k < nw; k++) x[k] = k < (l >> 6) ? ~0ULL : 0ULL;
+	if (l & 63) x[l >> 6] = (1ULL << (l & 63)) - 1;
+}
+
+HB_HD void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
+{ // gen_trace, Levenshtein_distance.h:903-985
+	if (ez.err > ez.thre) return;
+	ez.cn = 0;
+	int32_t V, H, D, mn, cur = ez.err, tn = ez.te + 1 - ez.ts, pn = tn + (ez.thre << 1), bd = (ez.thre << 1) + 1;
+	const int32_t bs = (int32_t)(ez.pn / (uint64_t)tn), bbs = bs / 5;
+	int32_t poff = ez.pe, sft = bd - (pn - ez.pe - ptrim), i = tn, low = bd - 1, d = 0, pd = -1, pdn = 0;
+	while (i > 0 && cur > 0) {
+		const uint64_t *D0 = ez.path + (size_t)(i - 1) * bs, *VP = D0 + bbs, *VN = VP + bbs, *HP = VN + bbs, *HN = HP + bbs;
+		D = cur - (1 - hb_mw_bit(D0, sft)); d = 0; mn = D;
+		if (sft != low) { H = cur + hb_mw_bit(HN, sft) - hb_mw_bit(HP, sft); if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
+		if (sft != 0) { V = cur + hb_mw_bit(VN, sft - 1) - hb_mw_bit(VP, sft - 1); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
+		if (d == 0) { if (D != cur) d = 1; i--; poff--; }
+		else if (d == 2) { sft--; poff--; }
+		else { i--; sft++; }
+		if (d == pd) pdn++;
+		else { if (pdn > 0) hb_mez_push_trace(ez, (uint32_t)pd, (uint32_t)pdn); pd = d; pdn = 1; }
+		cur = mn;
+	}
+	if (i > 0) {
+		d = 0; poff -= i;
+		if (d == pd) pdn += i;
+		else { if (pdn > 0) hb_mez_push_trace(ez, (uint32_t)pd, (uint32_t)pdn); pd = d; pdn = i; }
+	}
+	poff++;
+	if (ez.ps < 0 || ez.ps >= ez.pl) ez.ps = poff;
+	else if (poff > ez.ps) {
+		d = 2; i = poff - ez.ps;
+		if (d == pd) pdn += i;
+		else { if (pdn > 0) hb_mez_push_trace(ez, (uint32_t)pd, (uint32_t)pdn); pd = d; pdn = i; }
+	}
+	if (pdn > 0) hb_mez_push_trace(ez, (uint32_t)pd, (uint32_t)pdn);
+	if (reverse && !ez.ovf) for (int32_t k = 0, h = ez.cn >> 1; k < h; k++) { const uint16_t t = ez.cig[k]; ez.cig[k] = ez.cig[ez.cn - k - 1]; ez.cig[ez.cn - k - 1] = t; }
+}
+
+// mode: 0 global, 1 forward extension, 2 backward extension, 3 semi-global with abs_diag absent leading diagonals.
+// pattern = target[ps0, ps0+pn) on the overlap's strand, text = query[qs0, qs0+tn).
+HB_HD void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, const RdView &Q, int64_t qs0, int32_t tn, int32_t thre, int32_t abs_diag, MwEz &ez)
+{
+	int32_t bd = (thre << 1) + 1; const int32_t nword = (bd >> 6) + ((bd & 63) ? 1 : 0), cut = thre + (thre << 1);
+	int32_t i, err, i_bd, c, pidx = 0, tidx = 0, tmp_e = INT32_MAX, k, poff;
+	ez.cn = 0; ez.thre = thre; ez.err = INT32_MAX; ez.pl = pn; ez.tl = tn;
+	if (mode == 0) { ez.ps = ez.ts = 0; if (pn > tn + thre || tn > pn + thre) return; }
+	else if (mode == 1) { ez.ps = ez.ts = 0; ez.pe = ez.te = -1; if (pn > tn + thre) pn = tn + thre; else if (tn > pn + thre) tn = pn + thre; }
+	else if (mode == 2) { ez.ps = ez.ts = INT32_MAX; ez.pe = pn - 1; ez.te = tn - 1; if (pn > tn + thre) pn = tn + thre; else if (tn > pn + thre) tn = pn + thre; pidx = ez.pe; tidx = ez.te; }
+	else { ez.ps = ez.pe = -1; ez.ts = 0; ez.te = tn - 1; if (pn > tn + cut || tn > pn + cut) return; }
+	const int32_t tn0 = tn - 1, pe = pn - 1;
+	ez.nword = nword;
+	if ((uint64_t)nword * (uint64_t)tn * 5 > ez.pcap) { ez.ovf = 1; return; }
+	uint64_t *Peq = ez.vec, *VP = ez.vec + 5 * HB_MW_MAXW, *VN = VP + HB_MW_MAXW, *X = VN + HB_MW_MAXW, *D0 = X + HB_MW_MAXW, *HN = D0 + HB_MW_MAXW, *HP = HN + HB_MW_MAXW;
+	for (k = 0; k < 5 * HB_MW_MAXW; k++) Peq[k] = 0;
+	auto pch = [&](int32_t j) -> int { return T.at(ps0 + (mode == 2 ? pidx - j : j)); };
+	auto tch = [&](int32_t j) -> int { return Q.at(qs0 + (mode == 2 ? tidx - j : j)); };
+	if (mode == 3) {
+		for (k = 0; k < nword; k++) VP[k] = 0;
+		hb_mw_set_lsub(VN, abs_diag, nword);
+		bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn; i_bd = abs_diag;
+		for (i = 0; i < bd; i++, i_bd++) { c = pch(i); Peq[c * HB_MW_MAXW + (i_bd >> 6)] |= 1ULL << (i_bd & 63); }
+		i_bd = (thre << 1) - abs_diag; err = abs_diag;
+	} else {
+		bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre;
+		for (i = 0; i < bd; i++, i_bd++) { c = pch(i); Peq[c * HB_MW_MAXW + (i_bd >> 6)] |= 1ULL << (i_bd & 63); }
+		i_bd = thre; err = thre;
+		hb_mw_set_lsub(VN, thre, nword); hb_mw_set_lsub(VP, (thre << 1) + 1, nword);
+		for (k = 0; k < nword; k++) VP[k] ^= VN[k];
+	}
+	for (k = 0; k < nword; k++) Peq[4 * HB_MW_MAXW + k] = 0;
+	ez.pn = 0;
+	const int32_t Peq_i = (thre << 1) >> 6; const uint64_t Peq_m = 1ULL << ((thre << 1) & 63);
+	for (i = 0; i <= tn0; i++) {
+		{ // ed_infi_core, Levenshtein_distance.h:2148-2174
+			const uint64_t *pq = Peq + tch(i) * HB_MW_MAXW; uint64_t ad = 0; int32_t w;
+			for (w = 0; w < nword; w++) {
+				const uint64_t x = pq[w] | VN[w], vp = VP[w]; uint64_t d0 = x & vp;
+				d0 += ad; ad = d0 < ad; d0 += vp; ad |= d0 < vp;
+				d0 ^= vp; d0 |= x;
+				X[w] = x; D0[w] = d0; HN[w] = vp & d0; HP[w] = ~(vp | d0) | VN[w];
+			}
+			for (w = nword - 1, ad = 0; w >= 0; w--) {
+				const uint64_t x = (D0[w] >> 1) | ad; ad = D0[w] << 63;
+				X[w] = x; VN[w] = x & HP[w]; VP[w] = ~(x | HP[w]) | HN[w];
+			}
+		}
+		if (!(D0[0] & 1ULL)) { ++err; if (err > cut) return; }
+		if (i < tn0) {
+			if (mode == 1 || mode == 2) { // running best end point of an extension (Levenshtein_distance.h:2758-2779 / 2889-2910)
+				poff = i - thre; k = i + thre - pe;
+				if (k >= 0) {
+					if (tmp_e == INT32_MAX) { tmp_e = err; for (k = 0; poff < pe; poff++, k++) { tmp_e += hb_mw_bit(VP, k); tmp_e -= hb_mw_bit(VN, k); } }
+					else { k = (thre << 1) - k; if (k >= 0) { tmp_e += hb_mw_bit(HP, k); tmp_e -= hb_mw_bit(HN, k); } }
+					if (tmp_e <= ez.thre && tmp_e < ez.err) { ez.err = tmp_e; if (mode == 1) { ez.pe = pe; ez.te = i; } else { ez.ps = pidx - pe; ez.ts = tidx - i; } }
+				}
+			}
+			for (k = 0; k < 4; k++) { // ed_infi_post_Peq
+				uint64_t *pk = Peq + k * HB_MW_MAXW;
+				for (int32_t w = 0; w + 1 < nword; w++) pk[w] = (pk[w] >> 1) | (pk[w + 1] << 63);
+				pk[nword - 1] >>= 1;
+			}
+			++i_bd; c = 4;
+			if (i_bd < pn) c = pch(i_bd);
+			if (c < 4) Peq[c * HB_MW_MAXW + Peq_i] |= Peq_m;
+		}
+		uint64_t *o = ez.path + ez.pn;
+		for (k = 0; k < nword; k++) { o[k] = D0[k]; o[nword + k] = VP[k]; o[2 * nword + k] = VN[k]; o[3 * nword + k] = HP[k]; o[4 * nword + k] = HN[k]; }
+		ez.pn += (uint64_t)nword * 5;
+	}
+	if (mode == 0) {
+		int32_t site = tn - 1 - thre; const int32_t ct = pn - 1;
+		for (i = 0; site < ct; site++, i++) { err += hb_mw_bit(VP, i); err -= hb_mw_bit(VN, i); }
+		if (site == ct && err <= thre) { ez.err = err; ez.pe = pn - 1; ez.te = tn - 1; }
+		hb_mw_gen_trace(ez, thre, 1);
+	} else if (mode == 1 || mode == 2) {
+		int32_t site = tn - 1 - thre; const int32_t ct = pn - 1;
+		for (i = 0; site < ct; i++) {
+			err += hb_mw_bit(VP, i); err -= hb_mw_bit(VN, i); site++;
+			if (err <= thre && err < ez.err) { ez.err = err; if (mode == 1) { ez.pe = site; ez.te = tn - 1; } else { ez.ps = pidx - site; ez.ts = tidx + 1 - tn; } }
+		}
+		if (err <= thre && err < ez.err) { ez.err = err; if (mode == 1) { ez.pe = site; ez.te = tn - 1; } else { ez.ps = pidx - site; ez.ts = tidx + 1 - tn; } }
+		if (ez.te - ez.ts + 1 != tn) { ez.pn /= (uint64_t)tn; ez.pn *= (uint64_t)(ez.te + 1 - ez.ts); }
+		if (mode == 1) hb_mw_gen_trace(ez, thre, 1);
+		else {
+			poff = ez.ps; ez.ps = pidx - ez.pe; ez.pe = pidx - poff;
+			hb_mw_gen_trace(ez, thre, 0);
+			poff = ez.ps; ez.ps = pidx - ez.pe; ez.pe = pidx - poff;
+		}
+	} else {
+		int32_t site = tn - 1 - abs_diag, uge = INT32_MAX; const int32_t ai = pn - tn + abs_diag;
+		for (i = 0; site < 0 && i < ai; i++, site++) { err += hb_mw_bit(VP, i); err -= hb_mw_bit(VN, i); }
+		if (err <= thre && err <= ez.err) { ez.err = err; ez.pe = site; }
+		site -= i;
+		while (i < ai) {
+			err += hb_mw_bit(VP, i); err -= hb_mw_bit(VN, i); ++i;
+			if (err <= thre && err <= ez.err) { ez.err = err; ez.pe = site + i; }
+			if (i == thre) uge = err;
+		}
+		if (uge <= thre && uge == ez.err) ez.pe = site + thre;
+		hb_mw_gen_trace(ez, abs_diag, 1);
+	}
+}
+
+// lchain_refine, Hash_Table.cpp:2457-2541 with des = a (in place); t / p / f = DP scratch of a_n entries
+HB_HD int64_t hb_lchain_refine(hb_hit_t *a, int64_t a_n, int64_t *t, int64_t *p, int32_t *f, int64_t max_skip, int64_t max_iter, int64_t max_dis, int64_t long_gap)
+{
+	if (a_n <= 0) return 0;
+	int64_t max_f, n_skip, st, max_j, sc, msc, msc_i, dq, dr, dd, i, j, cL = 0;
+	for (i = 1, f[0] = 0, p[0] = -1, msc_i = a_n - 1; i < a_n; i++) {
+		j = i - 1;
+		dq = (int64_t)a[i].self_offset - (int64_t)a[j].self_offset; dr = (int64_t)a[i].offset - (int64_t)a[j].offset;
+		dd = dr > dq ? dr - dq : dq - dr;
+		if (dd <= long_gap || dq > max_dis) { p[i] = i - 1; f[i] = (int32_t)i; }
+		else break;
+	}
+	if (i < a_n) {
+		for (j = 0; j < a_n; j++) t[j] = 0;
+		f[0] = 0; p[0] = -1;
+		for (i = 1, st = 0; i < a_n; ++i) {
+			max_f = INT32_MIN; n_skip = 0; max_j = -1;
+			if (i - st > max_iter) st = i - max_iter;
+			j = i - 1;
+			dq = (int64_t)a[i].self_offset - (int64_t)a[j].self_offset; dr = (int64_t)a[i].offset - (int64_t)a[j].offset;
+			dd = dr > dq ? dr - dq : dq - dr;
+			if (dd <= long_gap) dd = 0;
+			sc = f[j] - dd;
+			if (sc > max_f) { max_f = sc; max_j = j; }
+			if (p[j] >= 0) t[p[j]] = i;
+			for (--j; j >= st && (int64_t)a[i].self_offset <= max_dis + (int64_t)a[j].self_offset; --j) {
+				dq = (int64_t)a[i].self_offset - (int64_t)a[j].self_offset; dr = (int64_t)a[i].offset - (int64_t)a[j].offset;
+				dd = dr > dq ? dr - dq : dq - dr;
+				if (dd <= long_gap) dd = 0;
+				sc = f[j] - dd;
+				if (sc > max_f) { max_f = sc; max_j = j; if (n_skip > 0) --n_skip; }
+				else if (t[j] == (int32_t)i) { if (++n_skip > max_skip) break; }
+				if (p[j] >= 0) t[p[j]] = i;
+			}
+			f[i] = (int32_t)max_f; p[i] = max_j;
+		}
+		i = a_n - 1; msc = f[i]; msc_i = i;
+		for (j = i - 1; j >= 0 && (int64_t)a[i].self_offset <= max_dis + (int64_t)a[j].self_offset; --j)
+			if (msc < f[j] && p[j] >= 0) { msc = f[j]; msc_i = j; }
+	}
+	i = msc_i; cL = 0;
+	while (i >= 0) { t[cL++] = i; i = p[i]; }
+	for (i = 0, j = cL - 1; i < j; i++, j--) { const int64_t x = t[i]; t[i] = t[j]; t[j] = x; }
+	for (i = 0; i < cL; i++) a[i] = a[t[i]]; // t ascending and t[i] >= i: never reads an overwritten slot
+	return cL;
+}
+
+// ---- window list of the overlap under construction ------------------------------------------------------------
+HB_HD void hb_wc_push_trace(EcBCtx &C, uint32_t c, uint32_t len)
+{
+	c <<= 14;
+	while (len >= 0x3fff) { if (C.wcn < C.wccap) C.wc[C.wcn] = (uint16_t)(c + 0x3fff); else C.ez.ovf = 1; C.wcn++; len -= 0x3fff; }
+	if (len) { if (C.wcn < C.wccap) C.wc[C.wcn] = (uint16_t)(c + len); else C.ez.ovf = 1; C.wcn++; }
+}
+HB_HD void hb_b_flush(EcBCtx &C)
+{ // the open window's cigar leaves the per-thread buffer for the shared pool (one contiguous piece, like aux_o->w_list.c)
+	if (C.open < 0) return;
+	hb_wl_t *p = &C.aw[C.open]; const int32_t n = C.wcn;
+	if (!C.ez.ovf) {
+#ifdef __CUDA_ARCH__
+		const unsigned long long o = atomicAdd(C.pool_used, (unsigned long long)n);
+#else
+		const unsigned long long o = *C.pool_used; *C.pool_used += (unsigned long long)n;
+#endif
+		p->cidx = (uint32_t)o; p->clen = (uint32_t)n;
+		if (o + (unsigned long long)n <= C.pool_cap) for (int32_t k = 0; k < n; k++) C.pool[o + k] = C.wc[k];
+	}
+	C.open = -1; C.wcn = 0;
+}
+HB_HD void hb_push_alnw(EcBCtx &C)
+{ // push_alnw + append_wcigar, Correct.cpp:15988-16019, 15954-15986
+	const MwEz &ez = C.ez; hb_wl_t *p;
+	if (C.awn > 0 && C.open == C.awn - 1 && C.wcn > 0) {
+		p = &C.aw[C.awn - 1];
+		const int64_t t = (int64_t)p->error + (int64_t)ez.err;
+		if (p->x_end + 1 == ez.ts && p->y_end + 1 == ez.ps && t < INT16_MAX) {
+			p->x_end = ez.te; p->y_end = ez.pe; p->error = (int16_t)(p->error + ez.err);
+			if (ez.cn > 0 && !C.ez.ovf) {
+				const uint32_t c0 = C.wc[C.wcn - 1] >> 14, c = ez.cig[0] >> 14; uint32_t l0 = C.wc[C.wcn - 1] & 0x3fff, l = ez.cig[0] & 0x3fff; int32_t ci = 1;
+				for (; ci < ez.cn && (uint32_t)(ez.cig[ci] >> 14) == c; ci++) l += ez.cig[ci] & 0x3fff;
+				if (c0 == c) { l += l0; C.wcn--; }
+				hb_wc_push_trace(C, c, l);
+				for (int32_t k = ci; k < ez.cn; k++) { if (C.wcn < C.wccap) C.wc[C.wcn] = ez.cig[k]; else C.ez.ovf = 1; C.wcn++; }
+			}
+			return;
+		}
+	}
+	hb_b_flush(C);
+	if (C.awn >= C.awcap) { C.ez.ovf = 1; return; }
+	p = &C.aw[C.awn]; C.open = C.awn++;
+	p->x_start = ez.ts; p->x_end = ez.te; p->y_start = ez.ps; p->y_end = ez.pe; p->extra_begin = p->extra_end = 0;
+	p->error_threshold = 0; p->error = (int16_t)ez.err; p->cidx = 0; p->clen = (uint32_t)ez.cn;
+	for (int32_t k = 0; k < ez.cn; k++) { if (C.wcn < C.wccap) C.wc[C.wcn] = ez.cig[k]; else C.ez.ovf = 1; C.wcn++; }
+}
+HB_HD void hb_push_unmap_alnw(EcBCtx &C, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
+{ // push_unmap_alnw, Correct.cpp:16021-16030
+	hb_b_flush(C);
+	if (C.awn >= C.awcap) { C.ez.ovf = 1; return; }
+	hb_wl_t *p = &C.aw[C.awn++];
+	p->x_start = (int32_t)qs; p->x_end = (int32_t)qe; p->y_start = (int32_t)ts; p->y_end = (int32_t)te;
+	p->error_threshold = (int16_t)mode; p->error = INT16_MAX; p->extra_begin = p->extra_end = -1; p->cidx = p->clen = 0;
+}
+HB_HD void hb_set_exact(MwEz &ez, int64_t qs, int64_t qe, int64_t ts, int64_t te)
+{ // set_exact_exz, Correct.cpp:16167-16175
+	ez.thre = 0; ez.cn = 0; ez.err = 0; hb_mez_push_trace(ez, 0, (uint32_t)(qe - qs));
+	ez.pl = (int32_t)(te - ts); ez.ps = (int32_t)ts; ez.pe = (int32_t)(ts + ez.pl - 1);
+	ez.tl = (int32_t)(qe - qs); ez.ts = (int32_t)qs; ez.te = (int32_t)(qs + ez.tl - 1);
+}
+HB_HD int64_t hb_scale_ed_thre(uint32_t err, uint32_t max_err)
+{ // scale_ed_thre, Correct.cpp:14354-14360
+	uint64_t bd = ((uint64_t)err << 1) + 1, w = (bd >> 6) << 6; if (w < bd) w += 64;
+	err = (uint32_t)((w - 1) >> 1); if (err > max_err) err = max_err;
+	return err;
+}
+HB_HD void hb_adjust_ext_offset(int64_t *qs, int64_t *qe, int64_t *ts, int64_t *te, int64_t ql, int64_t tl, int64_t thre, int64_t mode)
+{ // adjust_ext_offset, Correct.cpp:14400-14422
+	int64_t qoff, toff;
+	if (mode == 1) { qoff = ql - *qs; toff = tl - *ts; if (qoff <= toff) { *qe = ql; *te = *ts + qoff + thre; } else { *te = tl; *qe = *qs + toff + thre; } }
+	else if (mode == 2) { qoff = *qe; toff = *te; if (qoff <= toff) { *qs = 0; *ts = *te - qoff - thre; } else { *ts = 0; *qs = *qe - toff - thre; } }
+	if (*qs < 0) *qs = 0;
+	if (*ts < 0) *ts = 0;
+	if (*qe > ql) *qe = ql;
+	if (*te > tl) *te = tl;
+}
+
+HB_HD int64_t hb_cal_estimate_err_hc(const EcZ &z, int64_t wl, int64_t qs, int64_t qe, int64_t ts, int64_t te, double e_rate, int64_t *exact)
+{ // cal_estimate_err_hc, Correct.cpp:15403-15455 (z.w / z.wn = step A's window list)
+	int64_t k, ws, we, wid, os, oe, ovlp, tot, cov_l, exa = 1, ots, ote, q0, t0; const int64_t est = (int64_t)((double)(qe - qs) * e_rate), wn = z.wn;
+	*exact = 0;
+	if (!wn) return est;
+	if (qs < z.x_pos_s) qs = z.x_pos_s;
+	if (qe > z.x_pos_e + 1) qe = z.x_pos_e + 1;
+	ws = qs / wl; ws *= wl; wid = (ws - (z.x_pos_s / wl) * wl) / wl;
+	if (wid >= wn) wid = wn - 1;
+	for (k = wid; k < wn && qs > z.w[k].x_end; k++);
+	if (k == wn) return est;
+	for (; k >= 0 && qs < z.w[k].x_start; k--);
+	if (k < 0) k = 0;
+	for (tot = cov_l = 0, ots = ote = -1; k < wn && z.w[k].x_start < qe; k++) {
+		if (z.w[k].y_end == -1) continue;
+		ws = z.w[k].x_start; we = (int64_t)z.w[k].x_end + 1;
+		os = qs > ws ? qs : ws; oe = qe < we ? qe : we;
+		ovlp = oe > os ? oe - os : 0;
+		if (!ovlp) continue;
+		cov_l += ovlp;
+		if (ovlp == we - ws) tot += z.w[k].error;
+		else tot = (int64_t)((double)tot + ((double)z.w[k].error) * ((double)ovlp) / ((double)(we - ws)));
+		if (z.w[k].error > 0) exa = 0;
+		if (exa) {
+			q0 = os - ws;
+			we = (int64_t)z.w[k].y_end + 1; ws = we - ((int64_t)z.w[k].x_end + 1 - z.w[k].x_start);
+			os = ts > ws ? ts : ws; oe = te < we ? te : we;
+			ovlp = oe > os ? oe - os : 0;
+			t0 = os - ws;
+			if (ovlp && q0 == t0) {
+				if (ote == -1) { ots = os; ote = oe; }
+				else if (ote == os) ote = oe;
+				else exa = 0;
+			} else exa = 0;
+		}
+	}
+	tot = (int64_t)((double)tot + (double)((qe - qs) - cov_l) * e_rate);
+	if (exa && (qe - qs) == cov_l) { if ((qe - qs) == (ote - ots) && ots == ts && ote == te) *exact = 1; }
+	return tot;
+}
+
+HB_HD int64_t hb_cal_exact(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
+{ // cal_exact_exz, Correct.cpp:15725-15762 (memcmp on decoded strings: an N only equals an N)
+	MwEz &ez = C.ez; int64_t ql = qe - qs, tl;
+	ez.err = INT32_MAX; ez.thre = 0; ez.cn = 0;
+	if (mode == 3) { ts = (qs - z.x_pos_s) + z.y_pos_s; ts += hb_y_start_offset(qs, z.fc, z.fc_n, &C.bad); te = ts + ql; }
+	else if (mode == 1) te = ts + ql;
+	else if (mode == 2) ts = te - ql;
+	if (ts < 0) ts = 0;
+	if (ts > C.tl) ts = C.tl;
+	if (te > C.tl) te = C.tl;
+	ql = qe - qs; tl = te - ts;
+	if (ql != tl) return 0;
+	for (int64_t k = 0; k < ql; k++) if (C.q.at(qs + k) != C.t.at(ts + k)) return 0;
+	ez.err = 0; hb_mez_push_trace(ez, 0, (uint32_t)ql);
+	ez.pl = (int32_t)tl; ez.ps = (int32_t)ts; ez.pe = (int32_t)(ts + tl - 1);
+	ez.tl = (int32_t)ql; ez.ts = (int32_t)qs; ez.te = (int32_t)(qs + ql - 1);
+	return 1;
+}
+
+HB_HD int64_t hb_cal_exz_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t thre, int64_t *pthre, int64_t mode)
+{ // cal_exz_infi_adv, Correct.cpp:15617-15666
+	MwEz &ez = C.ez; int64_t aux_beg = 0, ql = qe - qs, tl = te - ts, dd = ql > tl ? ql : tl;
+	ez.err = INT32_MAX;
+	if (mode == 3) { // update_semi_coord, Correct.cpp:14364-14381
+		const int64_t th = thre > dd ? dd : thre, aln_l = (qe - qs) + (th << 1); int64_t aux_end, l;
+		ts = (qs - z.x_pos_s) + z.y_pos_s; ts += hb_y_start_offset(qs, z.fc, z.fc_n, &C.bad);
+		if (!hb_init_waln(th, ts, C.tl, aln_l, &aux_beg, &aux_end, &ts, &l)) ts = te = aux_beg = -1;
+		else te = ts + l;
+	} else if (mode == 1 || mode == 2) hb_adjust_ext_offset(&qs, &qe, &ts, &te, C.ql, C.tl, thre > dd ? dd : thre, mode);
+	if (qe > qs && te > ts && ts != -1 && te != -1) {
+		ql = qe - qs; tl = te - ts; dd = ql > tl ? ql : tl;
+		if (thre > dd) thre = dd;
+		if (thre <= *pthre) return 0;
+		*pthre = thre;
+		hb_mw_align((int)mode, C.t, ts, (int32_t)tl, C.q, qs, (int32_t)ql, (int32_t)thre, (int32_t)aux_beg, ez);
+		if (ez.ovf) return 0;
+		if (ez.err <= ez.thre) { ez.ps += (int32_t)ts; ez.pe += (int32_t)ts; ez.ts += (int32_t)qs; ez.te += (int32_t)qs; return 1; }
+	}
+	return 0;
+}
+
+HB_HD int64_t hb_hc_aln_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
+{ // hc_aln_exz_adv_hc, Correct.cpp:16178-16260 (maxl = MAX_SIN_L, maxe = MAX_SIN_E, force_l = FORCE_SIN_L, estimate_err = -1)
+	MwEz &ez = C.ez; int64_t thre, thre0, pthre = -1, full = 0; const int64_t ql = qe - qs;
+	ez.err = INT32_MAX; ez.thre = 0;
+	if (ts == -1 && te == -1) mode = 3;
+	if (ql == 0 && te - ts == 0) return 1;
+	if (ql <= 0 || te - ts <= 0) return 0;
+	const int64_t est = hb_cal_estimate_err_hc(z, C.w_l, qs, qe, ts, te, C.e_rate, &full);
+	if (est == 0) {
+		if (full) { hb_set_exact(ez, qs, qe, ts, te); hb_push_alnw(C); return 1; }
+		else if (hb_cal_exact(C, z, qs, qe, ts, te, mode)) { hb_push_alnw(C); return 1; }
+	}
+	if (ql <= HB_MAX_SIN_L && (est >> 1) <= HB_MAX_SIN_E) {
+		thre = hb_scale_ed_thre((uint32_t)est, HB_MAX_SIN_E);
+		if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; }
+		if (ez.ovf) return 0;
+		thre0 = thre; thre = (int64_t)((double)ql * C.e_rate); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
+		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } if (ez.ovf) return 0; }
+		thre0 = thre; thre <<= 1; thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
+		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } if (ez.ovf) return 0; }
+		thre0 = thre; thre = (int64_t)((double)ql * 0.51); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
+		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } if (ez.ovf) return 0; }
+		if (ql <= HB_FORCE_SIN_L) { thre = HB_MAX_SIN_E; if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } }
+	}
+	return 0;
+}
+
+// One accepted overlap.  zA = the overlap with step A's window list; re_A = step A's error estimate; ch_a / ch_n = its chain
+// anchors (refined in place, dropped anchors get id 0x7fffffff like return_t_chain does).  Result: out->st = 2 done,
+// -1 deferred (scratch too small: nothing of this overlap is valid); out->need_rechain = 1 when an unaligned window of
+// >= FORCE_SIN_L remains, which the reference re-seeds (rechain_aln_hc, Correct.cpp:17669 — not built yet).
+HB_HD void hb_ec_overlap_B(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_hit_t *ch_a, int64_t scn, int refined, int64_t *dp_t, int64_t *dp_p, int32_t *dp_f, hb_alnb_t *out)
+{
+	C.awn = 0; C.wcn = 0; C.open = -1; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+	const int64_t ch_n = refined ? scn : hb_lchain_refine(ch_a, scn, dp_t, dp_p, dp_f, 50, 5000, 512, 16); // refined: a deferred overlap's second run
+	for (int64_t i = ch_n; i < scn; i++) ch_a[i].id_strand = (ch_a[i].id_strand & 0x80000000u) | 0x7fffffffu;
+	const int64_t ql = C.ql, tl = C.tl; int64_t q[2], t[2], mode, i, l; bool done = false;
+	out->need_rechain = 0; out->re = 0; out->w_n = 0;
+	if (ch_n <= 0) { out->st = 2; out->x_pos_s = (uint32_t)zA.x_pos_s; out->x_pos_e = (uint32_t)zA.x_pos_e; out->y_pos_s = (uint32_t)zA.y_pos_s; out->y_pos_e = 0; return; }
+	if (re_A == 0 && zA.wn) { // hc_ovlp_base_direct, Correct.cpp:17430-17459: every window exact and co-linear -> one exact window
+		const int32_t zn = zA.wn; int32_t k;
+		for (k = 1; k < zn; k++) {
+			if (zA.w[k].error == 0 && zA.w[k - 1].error == 0 && zA.w[k].x_start == zA.w[k - 1].x_end + 1 && zA.w[k].y_end == zA.w[k - 1].y_end + (zA.w[k].x_end - zA.w[k - 1].x_end)) continue;
+			break;
+		}
+		if (k >= zn) {
+			q[0] = zA.w[0].x_start; q[1] = zA.w[zn - 1].x_end; t[1] = zA.w[zn - 1].y_end; t[0] = (int64_t)zA.w[0].y_end - (zA.w[0].x_end - zA.w[0].x_start);
+			if (q[0] <= t[0]) { t[0] -= q[0]; q[0] = 0; } else { q[0] -= t[0]; t[0] = 0; }
+			const int64_t qr = ql - q[1] - 1, tr = tl - t[1] - 1;
+			if (qr <= tr) { q[1] = ql - 1; t[1] += qr; } else { t[1] = tl - 1; q[1] += tr; }
+			if (q[0] == zA.w[0].x_start && q[1] == zA.w[zn - 1].x_end) { hb_set_exact(C.ez, q[0], q[1] + 1, t[0], t[1] + 1); hb_push_alnw(C); done = true; }
+		}
+	}
+	for (l = -1, i = 0; !done && i <= ch_n && !C.ez.ovf; i++) { // Correct.cpp:17470-17507
+		q[0] = q[1] = t[0] = t[1] = mode = -1;
+		if (l >= 0) { q[0] = ch_a[l].self_offset; t[0] = ch_a[l].offset; } else q[0] = 0;
+		if (i < ch_n) { q[1] = ch_a[i].self_offset; t[1] = ch_a[i].offset; } else q[1] = ql;
+		if (t[0] != -1 && t[1] != -1) mode = 0;
+		else if (t[0] != -1 && t[1] == -1) mode = 1;
+		else if (t[0] == -1 && t[1] != -1) mode = 2;
+		else mode = 3;
+		if (mode == 1 || mode == 2) hb_adjust_ext_offset(&q[0], &q[1], &t[0], &t[1], ql, tl, 0, mode);
+		if (!hb_hc_aln_adv(C, zA, q[0], q[1], t[0], t[1], mode) && !C.ez.ovf) hb_push_unmap_alnw(C, q[0], q[1] - 1, t[0], t[1] - 1, mode);
+		l = i;
+	}
+	hb_b_flush(C);
+	if (C.ez.ovf) { out->st = -1; return; }
+	int64_t tot_e = 0, xs = zA.x_pos_s, xe = zA.x_pos_e, ys = zA.y_pos_s, ye = 0;
+	for (i = 0; i < C.awn; i++) { // rechain_aln_hc's entry test (Correct.cpp:17676) and the error total (17857-17866)
+		const hb_wl_t &u = C.aw[i];
+		if (u.error == INT16_MAX && u.clen == 0 && u.extra_end < 0) {
+			const int64_t xl = (int64_t)u.x_end + 1 - u.x_start, yl = (int64_t)u.y_end + 1 - u.y_start;
+			if (xl >= HB_FORCE_SIN_L && yl >= HB_FORCE_SIN_L) out->need_rechain = 1;
+			tot_e += xl >= yl ? xl : yl;
+		} else tot_e += u.error;
+	}
+	if (C.awn) { xs = C.aw[0].x_start; xe = C.aw[C.awn - 1].x_end; ys = C.aw[0].y_start; ye = C.aw[C.awn - 1].y_end; } // update_overlap_region, Correct.cpp:17249-17275
+	if (xs <= ys) { ys -= xs; xs = 0; } else { xs -= ys; ys = 0; }
+	{ const int64_t xr = ql - xe - 1, yr = tl - ye - 1; if (xr <= yr) { xe = ql - 1; ye += xr; } else { ye = tl - 1; xe += yr; } }
+	out->st = 2; out->re = tot_e; out->w_n = (uint32_t)C.awn;
+	out->x_pos_s = (uint32_t)xs; out->x_pos_e = (uint32_t)xe; out->y_pos_s = (uint32_t)ys; out->y_pos_e = (uint32_t)ye;
+	if (C.bad) out->st = -2;
+}

@@ -1113,6 +1113,62 @@ __global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
 }
 
 // ----------------------------------------------------------------------------
+// step B (row a10): base-level CIGAR of the accepted overlaps, one thread per overlap (hb_ecaln.cuh: hb_ec_overlap_B).
+// pass = 0: every overlap step A accepted; pass = 1: only the overlaps the first launch deferred for lack of scratch
+// (launched with few threads and scratch for the largest alignment the reference allows).
+// ----------------------------------------------------------------------------
+__global__ void k_ecb_cap(uint64_t n_ov, const OvDesc *__restrict__ desc, const hb_chain_t *__restrict__ ch, const hb_aln_t *__restrict__ aln, uint32_t *__restrict__ cap)
+{ // window capacity of an overlap = number of inter-anchor segments (+1 spare)
+	uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
+	cap[o] = aln[o].st == 2 ? ch[desc[o].slot].n_hits + 2 : 0;
+}
+struct EcCigArgs {
+	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
+	const hb_aln_t *aln; const hb_wl_t *wlA; hb_hit_t *chits, *ghits; uint64_t dp_half; int64_t *dp_t, *dp_p; int32_t *dp_f;
+	double e_rate; int32_t w_l; int pass, refined; // refined: the chains were refined by an earlier launch of this batch
+	hb_alnb_t *out; hb_wl_t *wl; const uint64_t *wl_off;
+	uint64_t *path; uint64_t path_words; uint64_t *vec; uint16_t *cig_tmp; int32_t cig_words;
+	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; unsigned int *n_deferred; int *err;
+};
+__global__ void __launch_bounds__(64) k_ec_cigar(EcCigArgs A)
+{
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap;
+	C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * (11 * HB_MW_MAXW);
+	C.ez.cig = A.cig_tmp + tid * 2 * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words; C.wc = C.ez.cig + A.cig_words; C.wccap = A.cig_words;
+	for (uint64_t o = tid; o < A.n_ov; o += nthr) {
+		const hb_aln_t a = A.aln[o];
+		if (A.pass == 0) { if (a.st != 2) { hb_alnb_t r; r.st = a.st; r.need_rechain = 0; r.re = 0; r.x_pos_s = r.x_pos_e = r.y_pos_s = r.y_pos_e = 0; r.w_off = A.wl_off[o]; r.w_n = 0; r.pad = 0; A.out[o] = r; continue; } }
+		else if (A.out[o].st != -1) continue;
+		const OvDesc d = A.desc[o]; const hb_chain_t c = A.ch[d.slot];
+		const bool inpl = (c.pad & HB_CHAIN_INPLACE) != 0;
+		hb_hit_t *ch_a = (inpl ? A.ghits : A.chits) + c.first_hit; const uint64_t dpo = (inpl ? A.dp_half : 0) + c.first_hit;
+		EcZ z; z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_pos_s = c.y_pos_s; z.y_id = c.y_id; z.rev = c.y_pos_strand;
+		z.fc = A.fc + A.fc_grp_base[d.slot] + c.fc_off; z.fc_n = c.fc_n; z.align_length = a.align_length; z.w = (hb_wl_t *)(A.wlA + a.w_off); z.wn = (int32_t)a.w_n;
+		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+		C.aw = A.wl + A.wl_off[o]; C.awcap = (int32_t)(A.wl_off[o + 1] - A.wl_off[o]);
+		hb_alnb_t r; r.w_off = A.wl_off[o]; r.pad = 0;
+		// the first launch refined the chain in place and tagged the dropped anchors: the second launch takes it as it is
+		int64_t scn = c.n_hits;
+		const int refined = A.pass == 1 || A.refined;
+		if (refined) { int64_t k = 0; while (k < scn && HB_HIT_ID(ch_a[k]) != 0x7fffffffu) k++; scn = k; }
+		hb_ec_overlap_B(C, z, a.re, ch_a, scn, refined, A.dp_t + dpo, A.dp_p + dpo, A.dp_f + dpo, &r);
+		if (r.st == -1) atomicAdd(A.n_deferred, 1u);
+		if (r.st == -2) atomicOr(A.err, 32);
+		A.out[o] = r;
+	}
+}
+__global__ void k_gather_wl(uint64_t n_ov, const hb_alnb_t *__restrict__ in, const uint64_t *__restrict__ dense_off, const hb_wl_t *__restrict__ wl, hb_alnb_t *__restrict__ out, hb_wl_t *__restrict__ dense)
+{ // capacity-strided window lists -> dense, one thread per overlap (lists are 1-2 entries long in the common case)
+	uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
+	hb_alnb_t r = in[o]; const uint64_t d = dense_off[o];
+	for (uint32_t k = 0; k < r.w_n; k++) dense[d + k] = wl[r.w_off + k];
+	r.w_off = d; out[o] = r;
+}
+__global__ void k_ecb_wn(uint64_t n_ov, const hb_alnb_t *__restrict__ in, uint32_t *__restrict__ wn)
+{ uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o < n_ov) wn[o] = in[o].w_n; }
+
+// ----------------------------------------------------------------------------
 // window alignment: ed_band_cal_semi_64_w_absent_diag
 // (Levenshtein_distance.h:3727-3776, ed_core_64 3116-3125), one thread per
 // window, the whole band (<= 63 bits) in one 64-bit register pair.

@@ -138,6 +138,18 @@ int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double
                 uint64_t *off, hb_aln_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
                 uint64_t *n_wl, uint64_t *n_cig);
 
+/* ---- alignment stage of an EC round, step B (row a10): base-level CIGAR of every overlap step A accepted —
+ * gen_hc_fast_cigar (Correct.cpp:25137 -> 17813): return_t_chain, hc_ovlp_base_direct, hc_aln_exz_adv_hc with its
+ * threshold escalation, multi-word banded Myers with traceback, push_alnw, update_overlap_region.
+ * rec[j] (hb_chains order): st = step A's status (2 = accepted and aligned here); re = error total (Correct.cpp:17857);
+ * x/y_pos_* = the overlap's coordinates after update_overlap_region; w_off/w_n locate its window list in wl[];
+ * need_rechain = 1 when a window of >= 512 bp stayed unaligned, which the reference re-seeds and re-chains
+ * (rechain_aln_hc, Correct.cpp:17669): that rescue is not built yet and such an overlap's result is not final.     */
+typedef struct { int32_t st, need_rechain; int64_t re; uint32_t x_pos_s, x_pos_e, y_pos_s, y_pos_e; uint64_t w_off; uint32_t w_n, pad; } hb_alnb_t;
+int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
+                uint64_t *off, hb_alnb_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
+                uint64_t *n_wl, uint64_t *n_cig);
+
 /* ---- final overlap pass: cal_ov_r(n_thre, n_a, new_idx=1) (ecovlp.h:15;
  * ecovlp.cpp:6385 -> worker_hap_dc_ec_gen_new_idx 3948) -----------------------
  * prev_* = R_INF.paf[] / R_INF.reverse_paf[] of the last EC round, flattened

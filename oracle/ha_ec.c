@@ -510,3 +510,549 @@ int hao_ec_align_A(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uin
 	*out = o; *wl = W; *n_wl = nw; *cig = C; *n_cig = nc;
 	return b.bad ? -1 : 0;
 }
+
+/* ================================================================================================== */
+/* step B: base-level CIGAR of an accepted overlap (gen_hc_fast_cigar, Correct.cpp:25137 -> 17813)     */
+/* ================================================================================================== */
+#define EC_MAX_SIN_L 10000 /* Levenshtein_distance.h:757 */
+#define EC_MAX_SIN_E 2047  /* Levenshtein_distance.h:756 */
+#define EC_FORCE_SIN_L 512 /* Levenshtein_distance.h:758 */
+
+static uint64_t lchain_refine_(const hao_hit_t *a, int64_t a_n, hao_hit_t *des, int64_t **t_io, int32_t **f_io, int64_t **p_io, int64_t *cap,
+                               int64_t max_skip, int64_t max_iter, int64_t max_dis, int64_t long_gap)
+{ /* lchain_refine, Hash_Table.cpp:2457-2541 */
+	if (a_n <= 0) return 0;
+	int64_t *p, *t, max_f, n_skip, st, max_j, sc, msc, msc_i, dq, dr, dd, i, j, cL = 0; int32_t *f;
+	if (a_n > *cap) { *cap = a_n * 2 + 64; *t_io = (int64_t *)realloc(*t_io, *cap * 8); *p_io = (int64_t *)realloc(*p_io, *cap * 8); *f_io = (int32_t *)realloc(*f_io, *cap * 4); }
+	t = *t_io; f = *f_io; p = *p_io; msc = msc_i = -1;
+	for (i = 1, f[0] = 0, p[0] = -1, msc_i = a_n - 1; i < a_n; i++) {
+		j = i - 1;
+		dq = (int64_t)a[i].self_offset - (int64_t)a[j].self_offset; dr = (int64_t)a[i].offset - (int64_t)a[j].offset;
+		dd = dr > dq ? dr - dq : dq - dr;
+		if (dd <= long_gap || dq > max_dis) { p[i] = i - 1; f[i] = (int32_t)i; }
+		else break;
+	}
+	if (i < a_n) {
+		memset(t, 0, (size_t)a_n * sizeof(*t));
+		f[0] = 0; p[0] = -1;
+		for (i = 1, st = 0; i < a_n; ++i) {
+			max_f = INT32_MIN; n_skip = 0; max_j = -1;
+			if (i - st > max_iter) st = i - max_iter;
+			j = i - 1;
+			dq = (int64_t)a[i].self_offset - (int64_t)a[j].self_offset; dr = (int64_t)a[i].offset - (int64_t)a[j].offset;
+			dd = dr > dq ? dr - dq : dq - dr;
+			if (dd <= long_gap) dd = 0;
+			sc = f[j] - dd;
+			if (sc > max_f) { max_f = sc; max_j = j; }
+			if (p[j] >= 0) t[p[j]] = i;
+			for (--j; j >= st && (int64_t)a[i].self_offset <= max_dis + (int64_t)a[j].self_offset; --j) {
+				dq = (int64_t)a[i].self_offset - (int64_t)a[j].self_offset; dr = (int64_t)a[i].offset - (int64_t)a[j].offset;
+				dd = dr > dq ? dr - dq : dq - dr;
+				if (dd <= long_gap) dd = 0;
+				sc = f[j] - dd;
+				if (sc > max_f) { max_f = sc; max_j = j; if (n_skip > 0) --n_skip; }
+				else if (t[j] == (int32_t)i) { if (++n_skip > max_skip) break; }
+				if (p[j] >= 0) t[p[j]] = i;
+			}
+			f[i] = (int32_t)max_f; p[i] = max_j;
+		}
+		i = a_n - 1; msc = f[i]; msc_i = i;
+		for (j = i - 1; j >= 0 && (int64_t)a[i].self_offset <= max_dis + (int64_t)a[j].self_offset; --j)
+			if (msc < f[j] && p[j] >= 0) { msc = f[j]; msc_i = j; }
+	}
+	i = msc_i; cL = 0;
+	while (i >= 0) { t[cL++] = i; i = p[i]; }
+	n_skip = cL >> 1;
+	for (i = 0; i < n_skip; i++) { msc_i = t[i]; t[i] = t[cL - i - 1]; t[cL - i - 1] = msc_i; }
+	if (des) { /* a may alias des: t[] is ascending, so des[i] = a[t[i]] with t[i] >= i never reads an overwritten slot */
+		for (i = 0; i < cL; i++) des[i] = a[t[i]];
+	}
+	return (uint64_t)cL;
+}
+
+/* ---- multi-word banded Myers with traceback: ed_band_cal_{global,extension_0,extension_1,semi..absent_diag}_infi_w_trace
+ * (Levenshtein_distance.h:2516, 2694, 2823, 3020; the _64 / _128 variants 1580-2133, 3370-3856 are the same algorithm for one
+ * and two words).  Band = 2*thre+1 bits in nword 64-bit words. */
+typedef struct { uint64_t *Peq[5], *VP, *VN, *X, *D0, *HN, *HP; int32_t nword, mword; } mwv_t;
+typedef struct {
+	int32_t ps, pe, pl, ts, te, tl, thre, err, nword;
+	uint16_t *cig; size_t cn, cm;
+	uint64_t *path; size_t pn, pm;
+	mwv_t v;
+} mez_t;
+
+static void mw_reserve(mez_t *ez, int32_t nword)
+{
+	int k;
+	if (nword > ez->v.mword) {
+		ez->v.mword = nword + 4;
+		for (k = 0; k < 5; k++) ez->v.Peq[k] = (uint64_t *)realloc(ez->v.Peq[k], (size_t)ez->v.mword * 8);
+		ez->v.VP = (uint64_t *)realloc(ez->v.VP, (size_t)ez->v.mword * 8); ez->v.VN = (uint64_t *)realloc(ez->v.VN, (size_t)ez->v.mword * 8);
+		ez->v.X = (uint64_t *)realloc(ez->v.X, (size_t)ez->v.mword * 8); ez->v.D0 = (uint64_t *)realloc(ez->v.D0, (size_t)ez->v.mword * 8);
+		ez->v.HN = (uint64_t *)realloc(ez->v.HN, (size_t)ez->v.mword * 8); ez->v.HP = (uint64_t *)realloc(ez->v.HP, (size_t)ez->v.mword * 8);
+	}
+	ez->v.nword = nword;
+}
+static inline void mw_set_lsub(uint64_t *x, int32_t l, int32_t nw)
+{ /* w_infi_set_bit_lsub, Levenshtein_distance.h:2136 */
+	memset(x, 0, (size_t)nw * 8);
+	if (l >> 6) memset(x, -1, (size_t)(l >> 6) * 8);
+	if (l & 63) x[l >> 6] = (1ULL << (l & 63)) - 1;
+}
+static inline int mw_bit(const uint64_t *x, int32_t b) { return (int)((x[b >> 6] >> (b & 63)) & 1ULL); }
+static inline void mw_core(mwv_t *v, int c)
+{ /* ed_infi_core, Levenshtein_distance.h:2148-2174 */
+	int32_t w, nw = v->nword; uint64_t ad = 0;
+	for (w = 0; w < nw; w++) {
+		v->X[w] = v->Peq[c][w] | v->VN[w];
+		v->D0[w] = v->X[w] & v->VP[w];
+		v->D0[w] += ad; ad = v->D0[w] < ad; v->D0[w] += v->VP[w]; ad |= v->D0[w] < v->VP[w];
+		v->D0[w] ^= v->VP[w];
+		v->D0[w] |= v->X[w];
+		v->HN[w] = v->VP[w] & v->D0[w];
+		v->HP[w] = ~(v->VP[w] | v->D0[w]);
+		v->HP[w] |= v->VN[w];
+	}
+	for (w = nw - 1, ad = 0; w >= 0; w--) {
+		v->X[w] = (v->D0[w] >> 1) | ad; ad = v->D0[w] << 63;
+		v->VN[w] = v->X[w] & v->HP[w];
+		v->VP[w] = ~(v->X[w] | v->HP[w]);
+		v->VP[w] |= v->HN[w];
+	}
+}
+static inline void mw_post_peq(mwv_t *v)
+{ /* ed_infi_post_Peq, Levenshtein_distance.h:2176-2189 */
+	int32_t w, nw = v->nword, k;
+	for (k = 0; k < 4; k++) {
+		for (w = 0; w + 1 < nw; w++) v->Peq[k][w] = (v->Peq[k][w] >> 1) | (v->Peq[k][w + 1] << 63);
+		v->Peq[k][nw - 1] >>= 1;
+	}
+}
+static inline void mw_path_push(mez_t *ez)
+{
+	size_t nw = (size_t)ez->v.nword;
+	memcpy(ez->path + ez->pn, ez->v.D0, nw * 8); ez->pn += nw; memcpy(ez->path + ez->pn, ez->v.VP, nw * 8); ez->pn += nw;
+	memcpy(ez->path + ez->pn, ez->v.VN, nw * 8); ez->pn += nw; memcpy(ez->path + ez->pn, ez->v.HP, nw * 8); ez->pn += nw;
+	memcpy(ez->path + ez->pn, ez->v.HN, nw * 8); ez->pn += nw;
+}
+static void mez_push_trace(mez_t *ez, uint16_t c, uint32_t len)
+{
+	c <<= 14;
+	while (len >= 0x3fff) { cig_push(&ez->cig, &ez->cn, &ez->cm, (uint16_t)(c + 0x3fff)); len -= 0x3fff; }
+	if (len) cig_push(&ez->cig, &ez->cn, &ez->cm, (uint16_t)(c + len));
+}
+
+static void mw_gen_trace(mez_t *ez, int32_t ptrim, int reverse)
+{ /* gen_trace, Levenshtein_distance.h:903-985 */
+	if (ez->err > ez->thre) return;
+	ez->cn = 0;
+	int32_t V, H, D, min, cur, tn = ez->te + 1 - ez->ts, pn = tn + (ez->thre << 1), bd = (ez->thre << 1) + 1;
+	int32_t bs = (int32_t)(ez->pn / (size_t)tn), bbs = bs / 5, poff = ez->pe, sft = bd - (pn - ez->pe - ptrim);
+	int32_t i = tn, low = bd - 1, d = 0, pd = -1, pdn = 0; cur = ez->err;
+	while (i > 0 && cur > 0) {
+		const uint64_t *D0 = ez->path + (size_t)(i - 1) * bs, *VP = D0 + bbs, *VN = VP + bbs, *HP = VN + bbs, *HN = HP + bbs;
+		D = cur - (1 - mw_bit(D0, sft)); d = 0; min = D;
+		H = V = INT32_MAX;
+		if (sft != low) { H = cur + mw_bit(HN, sft) - mw_bit(HP, sft); if (H + 1 == cur && H <= min) { min = H; d = 3; } }
+		if (sft != 0) { V = cur + mw_bit(VN, sft - 1) - mw_bit(VP, sft - 1); if (V + 1 == cur && V <= min) { min = V; d = 2; } }
+		if (d == 0) { if (D != cur) d = 1; i--; poff--; }
+		else if (d == 2) { sft--; poff--; }
+		else if (d == 3) { i--; sft++; }
+		if (d == pd) pdn++;
+		else { if (pdn > 0) mez_push_trace(ez, (uint16_t)pd, (uint32_t)pdn); pd = d; pdn = 1; }
+		cur = min;
+	}
+	if (i > 0) {
+		d = 0; poff -= i;
+		if (d == pd) pdn += i;
+		else { if (pdn > 0) mez_push_trace(ez, (uint16_t)pd, (uint32_t)pdn); pd = d; pdn = i; }
+	}
+	poff++;
+	if (ez->ps < 0 || ez->ps >= ez->pl) ez->ps = poff;
+	else if (poff > ez->ps) {
+		d = 2; i = poff - ez->ps;
+		if (d == pd) pdn += i;
+		else { if (pdn > 0) mez_push_trace(ez, (uint16_t)pd, (uint32_t)pdn); pd = d; pdn = i; }
+	}
+	if (pdn > 0) mez_push_trace(ez, (uint16_t)pd, (uint32_t)pdn);
+	if (reverse) { size_t k, h = ez->cn >> 1; for (k = 0; k < h; k++) { uint16_t t = ez->cig[k]; ez->cig[k] = ez->cig[ez->cn - k - 1]; ez->cig[ez->cn - k - 1] = t; } }
+}
+
+/* mode: 0 global, 1 forward extension, 2 backward extension, 3 semi-global (absent diagonals = aux_beg).  ez->err must be
+ * INT32_MAX on entry (cal_exz_infi_adv clears it, Correct.cpp:15621). */
+static void mw_align(int mode, const char *pstr, int32_t pn, const char *tstr, int32_t tn, int32_t thre, int32_t abs_diag, mez_t *ez)
+{
+	int32_t bd = (thre << 1) + 1, nword = (bd >> 6) + !!(bd & 63), i, err, tn0, cut = thre + (thre << 1), i_bd, c, Peq_i; uint64_t Peq_m;
+	int32_t pidx = 0, tidx = 0, pe, tmp_e = INT32_MAX, k, poff; mwv_t *v;
+	ez->cn = 0;
+	/* init_base_ed + per-mode start state */
+	ez->thre = thre; ez->err = INT32_MAX; ez->pl = pn; ez->tl = tn;
+	if (mode == 0) { ez->ps = ez->ts = 0; if (pn > tn + thre || tn > pn + thre) return; }
+	else if (mode == 1) { ez->ps = ez->ts = 0; ez->pe = ez->te = -1; if (pn > tn + thre) pn = tn + thre; else if (tn > pn + thre) tn = pn + thre; }
+	else if (mode == 2) { ez->ps = ez->ts = INT32_MAX; ez->pe = pn - 1; ez->te = tn - 1; if (pn > tn + thre) pn = tn + thre; else if (tn > pn + thre) tn = pn + thre; pidx = ez->pe; tidx = ez->te; }
+	else { ez->ps = ez->pe = -1; ez->ts = 0; ez->te = tn - 1; if (pn > tn + cut || tn > pn + cut) return; }
+	tn0 = tn - 1; pe = pn - 1;
+	ez->nword = nword; mw_reserve(ez, nword); v = &ez->v;
+	for (k = 0; k < 5; k++) memset(v->Peq[k], 0, (size_t)nword * 8);
+#define PCH(j) nt4(mode == 2 ? pstr[pidx - (j)] : pstr[(j)])
+#define TCH(j) nt4(mode == 2 ? tstr[tidx - (j)] : tstr[(j)])
+	if (mode == 3) {
+		memset(v->VP, 0, (size_t)nword * 8); mw_set_lsub(v->VN, abs_diag, nword);
+		bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn; i_bd = abs_diag;
+		for (i = 0; i < bd; i++, i_bd++) { c = PCH(i); v->Peq[c][i_bd >> 6] |= 1ULL << (i_bd & 63); }
+		i_bd = (thre << 1) - abs_diag; err = abs_diag;
+	} else {
+		bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre;
+		for (i = 0; i < bd; i++, i_bd++) { c = PCH(i); v->Peq[c][i_bd >> 6] |= 1ULL << (i_bd & 63); }
+		i_bd = thre; err = thre;
+		mw_set_lsub(v->VN, thre, nword); mw_set_lsub(v->VP, (thre << 1) + 1, nword);
+		for (k = 0; k < nword; k++) v->VP[k] ^= v->VN[k];
+	}
+	memset(v->Peq[4], 0, (size_t)nword * 8);
+	if ((size_t)nword * tn * 5 > ez->pm) { ez->pm = (size_t)nword * tn * 5 + 256; ez->path = (uint64_t *)realloc(ez->path, ez->pm * 8); }
+	ez->pn = 0;
+	Peq_i = (thre << 1) >> 6; Peq_m = 1ULL << ((thre << 1) & 63);
+	for (i = 0; i <= tn0; i++) {
+		mw_core(v, TCH(i));
+		if (!(v->D0[0] & 1ULL)) { ++err; if (err > cut) return; }
+		if (i < tn0) {
+			if (mode == 1 || mode == 2) { /* running best end point of an extension (2758-2779 / 2889-2910) */
+				poff = i - thre; k = i + thre - pe;
+				if (k >= 0) {
+					if (tmp_e == INT32_MAX) {
+						tmp_e = err;
+						for (k = 0; poff < pe; poff++, k++) { tmp_e += mw_bit(v->VP, k); tmp_e -= mw_bit(v->VN, k); }
+					} else {
+						k = (thre << 1) - k;
+						if (k >= 0) { tmp_e += mw_bit(v->HP, k); tmp_e -= mw_bit(v->HN, k); }
+					}
+					if (tmp_e <= ez->thre && tmp_e < ez->err) {
+						ez->err = tmp_e;
+						if (mode == 1) { ez->pe = pe; ez->te = i; } else { ez->ps = pidx - pe; ez->ts = tidx - i; }
+					}
+				}
+			}
+			mw_post_peq(v);
+			++i_bd; c = 4;
+			if (i_bd < pn) c = PCH(i_bd);
+			if (c < 4) v->Peq[c][Peq_i] |= Peq_m;
+		}
+		mw_path_push(ez);
+	}
+#undef PCH
+#undef TCH
+	if (mode == 0) {
+		int32_t site = tn - 1 - thre, ct = pn - 1;
+		for (i = 0; site < ct; site++, i++) { err += mw_bit(v->VP, i); err -= mw_bit(v->VN, i); }
+		if (site == ct && err <= thre) { ez->err = err; ez->pe = pn - 1; ez->te = tn - 1; }
+		mw_gen_trace(ez, thre, 1);
+	} else if (mode == 1 || mode == 2) {
+		int32_t site = tn - 1 - thre, ct = pn - 1;
+		for (i = 0; site < ct; i++) {
+			err += mw_bit(v->VP, i); err -= mw_bit(v->VN, i); site++;
+			if (err <= thre && err < ez->err) { ez->err = err; if (mode == 1) { ez->pe = site; ez->te = tn - 1; } else { ez->ps = pidx - site; ez->ts = tidx + 1 - tn; } }
+		}
+		if (err <= thre && err < ez->err) { ez->err = err; if (mode == 1) { ez->pe = site; ez->te = tn - 1; } else { ez->ps = pidx - site; ez->ts = tidx + 1 - tn; } }
+		if (ez->te - ez->ts + 1 != tn) { ez->pn /= (size_t)tn; ez->pn *= (size_t)(ez->te + 1 - ez->ts); }
+		if (mode == 1) mw_gen_trace(ez, thre, 1);
+		else {
+			poff = ez->ps; ez->ps = pidx - ez->pe; ez->pe = pidx - poff;
+			mw_gen_trace(ez, thre, 0);
+			poff = ez->ps; ez->ps = pidx - ez->pe; ez->pe = pidx - poff;
+		}
+	} else {
+		int32_t site = tn - 1 - abs_diag, ai = pn - tn + abs_diag, uge = INT32_MAX;
+		for (i = 0; site < 0 && i < ai; i++, site++) { err += mw_bit(v->VP, i); err -= mw_bit(v->VN, i); }
+		if (err <= thre && err <= ez->err) { ez->err = err; ez->pe = site; }
+		site -= i;
+		while (i < ai) {
+			err += mw_bit(v->VP, i); err -= mw_bit(v->VN, i); ++i;
+			if (err <= thre && err <= ez->err) { ez->err = err; ez->pe = site + i; }
+			if (i == thre) uge = err;
+		}
+		if (uge <= thre && uge == ez->err) ez->pe = site + thre;
+		mw_gen_trace(ez, abs_diag, 1);
+	}
+}
+
+/* ---- per-overlap driver of step B ------------------------------------------------------------------ */
+typedef struct { hao_wl_t *w; size_t wn, wm; uint16_t *c; size_t cn, cm; } wlv_t; /* window_list_alloc */
+typedef struct {
+	const hao_reads_t *r; const char *qstr; int64_t ql; char *tstr; size_t tm; mez_t ez; int bad;
+	int64_t *dp_t, *dp_p; int32_t *dp_f; int64_t dp_cap;
+} ecB_t;
+
+static hao_wl_t *wlv_pushp(wlv_t *v)
+{
+	if (v->wn == v->wm) { v->wm = v->wm ? v->wm << 1 : 16; v->w = (hao_wl_t *)realloc(v->w, v->wm * sizeof(hao_wl_t)); }
+	return &v->w[v->wn++];
+}
+static void wlv_push_trace(wlv_t *v, uint16_t c, uint32_t len)
+{
+	c <<= 14;
+	while (len >= 0x3fff) { cig_push(&v->c, &v->cn, &v->cm, (uint16_t)(c + 0x3fff)); len -= 0x3fff; }
+	if (len) cig_push(&v->c, &v->cn, &v->cm, (uint16_t)(c + len));
+}
+static void push_alnw_(wlv_t *aux, const mez_t *ez)
+{ /* push_alnw + append_wcigar, Correct.cpp:15988-16019, 15954-15986 */
+	hao_wl_t *p; size_t k;
+	if (aux->wn > 0) {
+		p = &aux->w[aux->wn - 1];
+		if (p->clen > 0) {
+			int64_t t = (int64_t)p->error + (int64_t)ez->err;
+			if (p->x_end + 1 == ez->ts && p->y_end + 1 == ez->ps && t < INT16_MAX) {
+				p->x_end = ez->te; p->y_end = ez->pe; p->error = (int16_t)(p->error + ez->err);
+				if (ez->cn > 0) { /* append_wcigar: merge the first run with the pool's last one when the op is the same */
+					uint16_t c0 = aux->c[aux->cn - 1] >> 14, c = ez->cig[0] >> 14; uint32_t l0 = aux->c[aux->cn - 1] & 0x3fff, l = ez->cig[0] & 0x3fff; size_t ci = 1;
+					for (; ci < ez->cn && (ez->cig[ci] >> 14) == c; ci++) l += ez->cig[ci] & 0x3fff; /* pop_trace */
+					if (c0 == c) { l += l0; aux->cn--; }
+					wlv_push_trace(aux, c, l);
+					for (k = ci; k < ez->cn; k++) cig_push(&aux->c, &aux->cn, &aux->cm, ez->cig[k]);
+					p->clen = (uint32_t)(aux->cn - p->cidx);
+				}
+				return;
+			}
+		}
+	}
+	p = wlv_pushp(aux);
+	p->x_start = ez->ts; p->x_end = ez->te; p->y_start = ez->ps; p->y_end = ez->pe;
+	p->extra_begin = p->extra_end = 0; /* not set by the reference (kv_pushp leaves the slot as it is); never read while clen > 0 */
+	p->error_threshold = 0; p->error = (int16_t)ez->err;
+	p->cidx = (uint32_t)aux->cn; p->clen = (uint32_t)ez->cn;
+	for (k = 0; k < ez->cn; k++) cig_push(&aux->c, &aux->cn, &aux->cm, ez->cig[k]);
+}
+static void push_unmap_alnw_(wlv_t *aux, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
+{ /* push_unmap_alnw, Correct.cpp:16021-16030 */
+	hao_wl_t *p = wlv_pushp(aux);
+	p->x_start = (int32_t)qs; p->x_end = (int32_t)qe; p->y_start = (int32_t)ts; p->y_end = (int32_t)te;
+	p->error_threshold = (int16_t)mode; p->error = INT16_MAX; p->extra_begin = p->extra_end = -1; p->cidx = p->clen = 0;
+}
+static void set_exact_(mez_t *ez, int64_t qs, int64_t qe, int64_t ts, int64_t te)
+{ /* set_exact_exz, Correct.cpp:16167-16175 */
+	ez->thre = 0; ez->cn = 0; ez->err = 0; mez_push_trace(ez, 0, (uint32_t)(qe - qs));
+	ez->pl = (int32_t)(te - ts); ez->ps = (int32_t)ts; ez->pe = (int32_t)(ts + ez->pl - 1);
+	ez->tl = (int32_t)(qe - qs); ez->ts = (int32_t)qs; ez->te = (int32_t)(qs + ez->tl - 1);
+}
+static inline int64_t scale_ed_thre_(uint32_t err, uint32_t max_err)
+{ /* scale_ed_thre, Correct.cpp:14354-14360 */
+	uint64_t bd = ((uint64_t)err << 1) + 1, w = (bd >> 6) << 6; if (w < bd) w += 64;
+	err = (uint32_t)((w - 1) >> 1); if (err > max_err) err = max_err;
+	return err;
+}
+static void adjust_ext_offset_(int64_t *qs, int64_t *qe, int64_t *ts, int64_t *te, int64_t ql, int64_t tl, int64_t thre, int64_t mode)
+{ /* adjust_ext_offset, Correct.cpp:14400-14422 */
+	int64_t qoff, toff;
+	if (mode == 1) { qoff = ql - *qs; toff = tl - *ts; if (qoff <= toff) { *qe = ql; *te = *ts + qoff + thre; } else { *te = tl; *qe = *qs + toff + thre; } }
+	else if (mode == 2) { qoff = *qe; toff = *te; if (qoff <= toff) { *qs = 0; *ts = *te - qoff - thre; } else { *ts = 0; *qs = *qe - toff - thre; } }
+	if (*qs < 0) *qs = 0;
+	if (*ts < 0) *ts = 0;
+	if (*qe > ql) *qe = ql;
+	if (*te > tl) *te = tl;
+}
+static void ecB_tbuf(ecB_t *b, int64_t n) { if ((size_t)n + 8 > b->tm) { b->tm = (size_t)n + 64; b->tstr = (char *)realloc(b->tstr, b->tm); } }
+
+static int64_t cal_estimate_err_hc_(const ecz_t *z, int64_t wl, int64_t qs, int64_t qe, int64_t ts, int64_t te, double e_rate, int64_t *exact)
+{ /* cal_estimate_err_hc, Correct.cpp:15403-15455 */
+	int64_t k, ws, we, wid, os, oe, ovlp, tot, cov_l, est = (int64_t)((qe - qs) * e_rate), wn = (int64_t)z->wn, exa = 1, ots, ote, q0, t0;
+	*exact = 0;
+	if (!wn) return est;
+	if (qs < z->x_pos_s) qs = z->x_pos_s;
+	if (qe > z->x_pos_e + 1) qe = z->x_pos_e + 1;
+	ws = qs / wl; ws *= wl; wid = win_by_s(z, ws, wl, NULL);
+	if (wid >= wn) wid = wn - 1;
+	for (k = wid; k < wn && qs > z->w[k].x_end; k++);
+	if (k == wn) return est;
+	for (; k >= 0 && qs < z->w[k].x_start; k--);
+	if (k < 0) k = 0;
+	for (tot = cov_l = 0, ots = ote = -1; k < wn && z->w[k].x_start < qe; k++) {
+		if (z->w[k].y_end == -1) continue;
+		ws = z->w[k].x_start; we = (int64_t)z->w[k].x_end + 1;
+		os = qs > ws ? qs : ws; oe = qe < we ? qe : we;
+		ovlp = oe > os ? oe - os : 0;
+		if (!ovlp) continue;
+		cov_l += ovlp;
+		if (ovlp == we - ws) tot += z->w[k].error;
+		else tot = (int64_t)((double)tot + ((double)z->w[k].error) * ((double)ovlp) / ((double)(we - ws)));
+		if (z->w[k].error > 0) exa = 0;
+		if (exa) {
+			q0 = os - ws;
+			we = (int64_t)z->w[k].y_end + 1; ws = we - ((int64_t)z->w[k].x_end + 1 - z->w[k].x_start);
+			os = ts > ws ? ts : ws; oe = te < we ? te : we;
+			ovlp = oe > os ? oe - os : 0;
+			t0 = os - ws;
+			if (ovlp && q0 == t0) {
+				if (ote == -1) { ots = os; ote = oe; }
+				else if (ote == os) ote = oe;
+				else exa = 0;
+			} else exa = 0;
+		}
+	}
+	tot = (int64_t)((double)tot + ((qe - qs) - cov_l) * e_rate);
+	if (exa && (qe - qs) == cov_l) { if ((qe - qs) == (ote - ots) && ots == ts && ote == te) *exact = 1; }
+	return tot;
+}
+
+static int64_t cal_exact_(ecB_t *b, const ecz_t *z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
+{ /* cal_exact_exz, Correct.cpp:15725-15762 */
+	mez_t *ez = &b->ez; int64_t ql = qe - qs, tl, t_tot_l = (int64_t)b->r->len[z->y_id];
+	ez->err = INT32_MAX; ez->thre = 0; ez->cn = 0;
+	if (mode == 3) { ts = (qs - z->x_pos_s) + z->y_pos_s; ts += y_start_off(qs, z->fc, z->fc_n, &b->bad); te = ts + ql; }
+	else if (mode == 1) te = ts + ql;
+	else if (mode == 2) ts = te - ql;
+	if (ts < 0) ts = 0;
+	if (ts > t_tot_l) ts = t_tot_l;
+	if (te > t_tot_l) te = t_tot_l;
+	ql = qe - qs; tl = te - ts;
+	if (ql != tl) return 0;
+	ecB_tbuf(b, tl); hao_decode_sub(b->r, z->y_id, ts, tl, (int)z->rev, b->tstr);
+	if (memcmp(b->qstr + qs, b->tstr, (size_t)ql)) return 0;
+	ez->err = 0; mez_push_trace(ez, 0, (uint32_t)ql);
+	ez->pl = (int32_t)tl; ez->ps = (int32_t)ts; ez->pe = (int32_t)(ts + tl - 1);
+	ez->tl = (int32_t)ql; ez->ts = (int32_t)qs; ez->te = (int32_t)(qs + ql - 1);
+	return 1;
+}
+
+static int64_t cal_exz_adv_(ecB_t *b, const ecz_t *z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t thre, int64_t *pthre, int64_t mode)
+{ /* cal_exz_infi_adv, Correct.cpp:15617-15666 */
+	mez_t *ez = &b->ez; int64_t aux_beg = 0, ql = qe - qs, tl = te - ts, t_tot_l = (int64_t)b->r->len[z->y_id], dd = ql > tl ? ql : tl;
+	ez->err = INT32_MAX;
+	if (mode == 3) { /* update_semi_coord, Correct.cpp:14364-14381 */
+		int64_t th = thre > dd ? dd : thre, aux_end, l, aln_l = (qe - qs) + (th << 1);
+		ts = (qs - z->x_pos_s) + z->y_pos_s; ts += y_start_off(qs, z->fc, z->fc_n, &b->bad);
+		if (!init_waln_(th, ts, t_tot_l, aln_l, &aux_beg, &aux_end, &ts, &l)) ts = te = aux_beg = -1;
+		else te = ts + l;
+	} else if (mode == 1 || mode == 2) adjust_ext_offset_(&qs, &qe, &ts, &te, b->ql, t_tot_l, thre > dd ? dd : thre, mode);
+	if (qe > qs && te > ts && ts != -1 && te != -1) {
+		ql = qe - qs; tl = te - ts; dd = ql > tl ? ql : tl;
+		if (thre > dd) thre = dd;
+		if (thre <= *pthre) return 0;
+		*pthre = thre;
+		ecB_tbuf(b, tl); hao_decode_sub(b->r, z->y_id, ts, tl, (int)z->rev, b->tstr);
+		mw_align((int)mode, b->tstr, (int32_t)tl, b->qstr + qs, (int32_t)ql, (int32_t)thre, (int32_t)aux_beg, ez);
+		if (ez->err <= ez->thre) { ez->ps += (int32_t)ts; ez->pe += (int32_t)ts; ez->ts += (int32_t)qs; ez->te += (int32_t)qs; return 1; }
+		return 0;
+	}
+	return 0;
+}
+
+static int64_t hc_aln_adv_(ecB_t *b, const ecz_t *z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode, int64_t wl, double e_rate, wlv_t *aux)
+{ /* hc_aln_exz_adv_hc, Correct.cpp:16178-16260 (maxl = MAX_SIN_L, maxe = MAX_SIN_E, force_l = FORCE_SIN_L, estimate_err = -1) */
+	mez_t *ez = &b->ez; int64_t thre, ql = qe - qs, thre0, pthre = -1, full = 0, est;
+	ez->err = INT32_MAX; ez->thre = 0;
+	if (ts == -1 && te == -1) mode = 3;
+	if (ql == 0 && te - ts == 0) return 1;
+	if (ql <= 0 || te - ts <= 0) return 0;
+	est = cal_estimate_err_hc_(z, wl, qs, qe, ts, te, e_rate, &full);
+	if (est == 0) {
+		if (full) { set_exact_(ez, qs, qe, ts, te); push_alnw_(aux, ez); return 1; }
+		else if (cal_exact_(b, z, qs, qe, ts, te, mode)) { push_alnw_(aux, ez); return 1; }
+	}
+	if (ql <= EC_MAX_SIN_L && (est >> 1) <= EC_MAX_SIN_E) {
+		thre = scale_ed_thre_((uint32_t)est, EC_MAX_SIN_E);
+		if (cal_exz_adv_(b, z, qs, qe, ts, te, thre, &pthre, mode)) { push_alnw_(aux, ez); return 1; }
+		thre0 = thre; thre = (int64_t)(ql * e_rate); thre = scale_ed_thre_((uint32_t)thre, EC_MAX_SIN_E);
+		if (thre > thre0) { if (cal_exz_adv_(b, z, qs, qe, ts, te, thre, &pthre, mode)) { push_alnw_(aux, ez); return 1; } }
+		thre0 = thre; thre <<= 1; thre = scale_ed_thre_((uint32_t)thre, EC_MAX_SIN_E);
+		if (thre > thre0) { if (cal_exz_adv_(b, z, qs, qe, ts, te, thre, &pthre, mode)) { push_alnw_(aux, ez); return 1; } }
+		thre0 = thre; thre = (int64_t)(ql * 0.51); thre = scale_ed_thre_((uint32_t)thre, EC_MAX_SIN_E);
+		if (thre > thre0) { if (cal_exz_adv_(b, z, qs, qe, ts, te, thre, &pthre, mode)) { push_alnw_(aux, ez); return 1; } }
+		if (ql <= EC_FORCE_SIN_L) { thre = EC_MAX_SIN_E; if (cal_exz_adv_(b, z, qs, qe, ts, te, thre, &pthre, mode)) { push_alnw_(aux, ez); return 1; } }
+	}
+	return 0;
+}
+
+static void hc_ovlp_base_direct_(ecB_t *b, const ecz_t *z, int64_t nh_err, const hao_hit_t *ch_a, int64_t ch_n, int64_t wl, double e_rate, int64_t tl, wlv_t *aux)
+{ /* hc_ovlp_base_direct, Correct.cpp:17425-17509 (pre_mode = -1) */
+	int64_t i, l, mode, q[2], t[2], qr, tr, zn, ql = b->ql;
+	if (nh_err == 0 && z->wn) {
+		zn = (int64_t)z->wn;
+		for (i = 1; i < zn; i++) {
+			if (z->w[i].error == 0 && z->w[i - 1].error == 0 && z->w[i].x_start == z->w[i - 1].x_end + 1 &&
+			    z->w[i].y_end == z->w[i - 1].y_end + (z->w[i].x_end - z->w[i - 1].x_end)) continue;
+			break;
+		}
+		if (i >= zn) {
+			q[0] = z->w[0].x_start; q[1] = z->w[zn - 1].x_end;
+			t[1] = z->w[zn - 1].y_end; t[0] = z->w[0].y_end - (z->w[0].x_end - z->w[0].x_start);
+			if (q[0] <= t[0]) { t[0] -= q[0]; q[0] = 0; } else { q[0] -= t[0]; t[0] = 0; }
+			qr = ql - q[1] - 1; tr = tl - t[1] - 1;
+			if (qr <= tr) { q[1] = ql - 1; t[1] += qr; } else { t[1] = tl - 1; q[1] += tr; }
+			if (q[0] == z->w[0].x_start && q[1] == z->w[zn - 1].x_end) { set_exact_(&b->ez, q[0], q[1] + 1, t[0], t[1] + 1); push_alnw_(aux, &b->ez); return; }
+		}
+	}
+	for (l = -1, i = 0; i <= ch_n; i++) {
+		q[0] = q[1] = t[0] = t[1] = mode = -1;
+		if (l >= 0) { q[0] = ch_a[l].self_offset; t[0] = ch_a[l].offset; } else q[0] = 0;
+		if (i < ch_n) { q[1] = ch_a[i].self_offset; t[1] = ch_a[i].offset; } else q[1] = ql;
+		if (t[0] != -1 && t[1] != -1) mode = 0;
+		else if (t[0] != -1 && t[1] == -1) mode = 1;
+		else if (t[0] == -1 && t[1] != -1) mode = 2;
+		else mode = 3;
+		if (mode == 1 || mode == 2) adjust_ext_offset_(&q[0], &q[1], &t[0], &t[1], ql, tl, 0, mode);
+		if (!hc_aln_adv_(b, z, q[0], q[1], t[0], t[1], mode, wl, e_rate, aux)) push_unmap_alnw_(aux, q[0], q[1] - 1, t[0], t[1] - 1, mode);
+		l = i;
+	}
+}
+
+typedef struct { int32_t st; int32_t need_rechain; int64_t re; uint32_t x_pos_s, x_pos_e, y_pos_s, y_pos_e; uint64_t w_off, w_n, c_off, c_n; } hao_alnB_t;
+
+/* step B for the accepted overlaps of read rid.  a[] / wlA / (cigars unused) = step A's output; hits = the compacted chain anchors
+ * (cl->list after h_ec_lchain; ch[j].non_homopolymer_errors = first anchor of chain j, modified in place by return_t_chain).
+ * need_rechain = 1 marks overlaps whose base alignment leaves a window >= FORCE_SIN_L unaligned: the reference re-seeds and
+ * re-chains those (rechain_aln_hc, Correct.cpp:17669) — not restated yet, their result is not comparable. */
+int hao_ec_align_B(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint32_t n_ch, const uint64_t *fc, hao_hit_t *hits, uint64_t n_hits,
+                   const hao_alnA_t *a, const hao_wl_t *wlA, double e_rate, int64_t w_l,
+                   hao_alnB_t **out, hao_wl_t **wl, uint64_t *n_wl, uint16_t **cig, uint64_t *n_cig)
+{
+	uint64_t ql = r->len[rid], nw = 0, mw = 0, nc = 0, mc = 0; uint32_t j; hao_wl_t *W = 0; uint16_t *C = 0;
+	char *qs = MALLOC_N(char, ql + 1); ecB_t b; ecz_t z; wlv_t aux; hao_alnB_t *o = CALLOC_N(hao_alnB_t, n_ch);
+	memset(&b, 0, sizeof(b)); memset(&z, 0, sizeof(z)); memset(&aux, 0, sizeof(aux));
+	hao_decode(r, rid, qs); b.r = r; b.qstr = qs; b.ql = (int64_t)ql;
+	for (j = 0; j < n_ch; j++) {
+		const hao_ovlp_t *c = &ch[j]; int64_t i, scn, cn, tl = (int64_t)r->len[c->y_id], tot_e = 0; hao_hit_t *ca; uint32_t pid;
+		o[j].st = a[j].st; o[j].w_off = nw; o[j].c_off = nc;
+		if (a[j].st != 2) continue;
+		z.x_pos_s = c->x_pos_s; z.x_pos_e = c->x_pos_e; z.y_pos_s = c->y_pos_s; z.y_pos_e = c->y_pos_e; z.y_id = c->y_id; z.rev = c->y_pos_strand;
+		z.fc = fc + c->fc_off; z.fc_n = c->fc_n; z.w = (hao_wl_t *)(wlA + a[j].w_off); z.wn = a[j].w_n;
+		/* return_t_chain, Correct.cpp:22997-23020 */
+		i = c->non_homopolymer_errors; pid = hits[i].id_strand & 0x7fffffffu;
+		for (; i < (int64_t)n_hits && (hits[i].id_strand & 0x7fffffffu) == pid && pid != 0x7fffffffu; i++);
+		scn = i - c->non_homopolymer_errors; ca = hits + c->non_homopolymer_errors;
+		cn = (int64_t)lchain_refine_(ca, scn, ca, &b.dp_t, &b.dp_f, &b.dp_p, &b.dp_cap, 50, 5000, 512, 16);
+		for (i = cn; i < scn; i++) ca[i].id_strand = (ca[i].id_strand & 0x80000000u) | 0x7fffffffu;
+		/* gen_hc_fast_cigar0, Correct.cpp:17813-17870 */
+		aux.wn = aux.cn = 0;
+		if (cn > 0) {
+			hc_ovlp_base_direct_(&b, &z, a[j].re, ca, cn, w_l, e_rate, tl, &aux);
+			for (i = 0; i < (int64_t)aux.wn; i++) {
+				const hao_wl_t *u = &aux.w[i];
+				if (!(u->error == INT16_MAX && u->clen == 0 && u->extra_end < 0)) continue;
+				if ((int64_t)u->x_end + 1 - u->x_start >= EC_FORCE_SIN_L && (int64_t)u->y_end + 1 - u->y_start >= EC_FORCE_SIN_L) o[j].need_rechain = 1;
+			}
+			/* update_overlap_region, Correct.cpp:17249-17275 */
+			if (aux.wn) { z.x_pos_s = aux.w[0].x_start; z.x_pos_e = aux.w[aux.wn - 1].x_end; z.y_pos_s = aux.w[0].y_start; z.y_pos_e = aux.w[aux.wn - 1].y_end; }
+			{
+				int64_t xr, yr;
+				if (z.x_pos_s <= z.y_pos_s) { z.y_pos_s -= z.x_pos_s; z.x_pos_s = 0; } else { z.x_pos_s -= z.y_pos_s; z.y_pos_s = 0; }
+				xr = (int64_t)ql - z.x_pos_e - 1; yr = tl - z.y_pos_e - 1;
+				if (xr <= yr) { z.x_pos_e = (int64_t)ql - 1; z.y_pos_e += xr; } else { z.y_pos_e = tl - 1; z.x_pos_e += yr; }
+			}
+			for (i = 0; i < (int64_t)aux.wn; i++) {
+				const hao_wl_t *u = &aux.w[i];
+				if (u->error == INT16_MAX && u->clen == 0 && u->extra_end < 0) { int64_t xe = (int64_t)u->x_end + 1 - u->x_start, ye = (int64_t)u->y_end + 1 - u->y_start; tot_e += xe >= ye ? xe : ye; }
+				else tot_e += u->error;
+			}
+		}
+		o[j].re = tot_e; o[j].x_pos_s = (uint32_t)z.x_pos_s; o[j].x_pos_e = (uint32_t)z.x_pos_e; o[j].y_pos_s = (uint32_t)z.y_pos_s; o[j].y_pos_e = (uint32_t)z.y_pos_e;
+		o[j].w_n = aux.wn; o[j].c_n = aux.cn;
+		if (nw + aux.wn > mw) { mw = (nw + aux.wn) * 2 + 64; W = (hao_wl_t *)realloc(W, mw * sizeof(hao_wl_t)); }
+		if (nc + aux.cn > mc) { mc = (nc + aux.cn) * 2 + 64; C = (uint16_t *)realloc(C, mc * 2); }
+		if (aux.wn) memcpy(W + nw, aux.w, aux.wn * sizeof(hao_wl_t));
+		if (aux.cn) memcpy(C + nc, aux.c, aux.cn * 2);
+		nw += aux.wn; nc += aux.cn;
+	}
+	{ int k; for (k = 0; k < 5; k++) free(b.ez.v.Peq[k]); free(b.ez.v.VP); free(b.ez.v.VN); free(b.ez.v.X); free(b.ez.v.D0); free(b.ez.v.HN); free(b.ez.v.HP); }
+	free(qs); free(b.tstr); free(b.ez.cig); free(b.ez.path); free(b.dp_t); free(b.dp_p); free(b.dp_f); free(aux.w); free(aux.c);
+	*out = o; *wl = W; *n_wl = nw; *cig = C; *n_cig = nc;
+	return b.bad ? -1 : 0;
+}

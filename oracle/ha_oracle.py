@@ -179,3 +179,19 @@ def ec_align_A(store: Store, rid, chains: np.ndarray, fc: np.ndarray, e_rate=0.0
                               C.c_double(e_rate), C.c_int64(w_l), C.byref(out), C.byref(wl), C.byref(nw), C.byref(cg), C.byref(nc))
     assert rc == 0
     return _take(out, chains.size, ALN_A), _take(wl, nw.value, WL), _take(cg, nc.value, np.dtype("<u2"))
+
+
+ALN_B = np.dtype([("st", "<i4"), ("need_rechain", "<i4"), ("re", "<i8"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
+                  ("w_off", "<u8"), ("w_n", "<u8"), ("c_off", "<u8"), ("c_n", "<u8")])
+
+
+def ec_align_B(store: Store, rid, chains, fc, hits, A, WA, e_rate=0.04, w_l=775):
+    """step B (base-level CIGAR) for the overlaps step A accepted -> (ALN_B[n_ch], WL[], cigar u16[])"""
+    chains = np.ascontiguousarray(chains); fc = np.ascontiguousarray(fc if fc.size else np.zeros(1), dtype=np.uint64)
+    hits = np.ascontiguousarray(hits).copy(); A = np.ascontiguousarray(A); WA = np.ascontiguousarray(WA if WA.size else np.zeros(1, WL))
+    out = C.c_void_p(); wl = C.c_void_p(); cg = C.c_void_p(); nw = C.c_uint64(); nc = C.c_uint64()
+    rc = lib().hao_ec_align_B(C.byref(store.c), C.c_uint32(rid), C.c_void_p(chains.ctypes.data), C.c_uint32(chains.size), C.c_void_p(fc.ctypes.data),
+                              C.c_void_p(hits.ctypes.data), C.c_uint64(hits.size), C.c_void_p(A.ctypes.data), C.c_void_p(WA.ctypes.data),
+                              C.c_double(e_rate), C.c_int64(w_l), C.byref(out), C.byref(wl), C.byref(nw), C.byref(cg), C.byref(nc))
+    assert rc == 0
+    return _take(out, chains.size, ALN_B), _take(wl, nw.value, WL), _take(cg, nc.value, np.dtype("<u2"))

@@ -36,11 +36,14 @@ def read_aln(path):
     return out
 
 
-def wl_canon(w, c):
-    """window list with every cigar resolved (bytes): what must be identical, independent of pool order"""
+def wl_canon(w, c, mask_extra=False):
+    """window list with every cigar resolved (bytes): what must be identical, independent of pool order.
+    mask_extra: push_alnw (Correct.cpp:15988) leaves extra_begin / extra_end of an aligned window undefined (stale heap
+    content in the reference), so steps B / C compare them only for windows without a cigar."""
     parts = []
     for r in w:
-        h = np.array([r["x_start"], r["x_end"], r["y_start"], r["y_end"], r["extra_begin"], r["extra_end"], r["error"],
+        eb, ee = (0, 0) if (mask_extra and r["clen"] > 0) else (r["extra_begin"], r["extra_end"])
+        h = np.array([r["x_start"], r["x_end"], r["y_start"], r["y_end"], eb, ee, r["error"],
                       r["error_threshold"], r["clen"]], dtype="<i4")
         parts.append(h.tobytes()); parts.append(np.ascontiguousarray(c[int(r["cidx"]):int(r["cidx"]) + int(r["clen"])]).tobytes())
     return b"".join(parts)
@@ -61,8 +64,8 @@ def digest_A(ovl):
 
 def digest_B(ovl):
     """per-read digest of step B (accepted overlaps only): ovl = iterable of (re, w, c)"""
-    return _dg(struct.pack("<q", int(re)) + wl_canon(w, c) for re, w, c in ovl)
+    return _dg(struct.pack("<q", int(re)) + wl_canon(w, c, True) for re, w, c in ovl)
 
 
 def digest_C(ovl):
-    return _dg(wl_canon(w, c) for w, c in ovl)
+    return _dg(wl_canon(w, c, True) for w, c in ovl)

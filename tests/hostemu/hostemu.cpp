@@ -274,4 +274,36 @@ int emu_ec_align_A(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 	return err | (used > pool_cap ? 128 : 0);
 }
 
+// step B (base-level CIGAR) for the overlaps step A accepted: body of k_ec_cigar.  hits = compacted chain anchors of the read
+// (modified in place like return_t_chain does), aln / wlA = step A's output.  path_words / cig_words = per-thread scratch sizes.
+int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch, const uint64_t *fc, hb_hit_t *hits, uint64_t n_hits,
+                   const hb_aln_t *aln, const hb_wl_t *wlA, double e_rate, int32_t w_l, uint64_t path_words, int32_t cig_words,
+                   hb_alnb_t *out, hb_wl_t *wl, uint64_t wl_cap, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used, uint64_t *n_wl)
+{
+	EmuReads *r = (EmuReads *)reads; unsigned long long used = 0; uint64_t nw = 0; int rc = 0;
+	std::vector<uint64_t> path(path_words), vec(11 * HB_MW_MAXW); std::vector<uint16_t> ecig(cig_words), wc(cig_words);
+	EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap;
+	C.ez.path = path.data(); C.ez.pcap = path_words; C.ez.vec = vec.data(); C.ez.cig = ecig.data(); C.ez.ccap = cig_words; C.wc = wc.data(); C.wccap = cig_words;
+	for (uint32_t j = 0; j < n_ch; j++) {
+		hb_alnb_t res; memset(&res, 0, sizeof(res)); res.st = aln[j].st; res.w_off = nw;
+		if (aln[j].st == 2) {
+			const hb_chain_t &c = ch[j];
+			uint64_t i = c.first_hit; const uint32_t pid = HB_HIT_ID(hits[i]);
+			for (; i < n_hits && HB_HIT_ID(hits[i]) == pid && pid != 0x7fffffffu; i++);
+			const int64_t scn = (int64_t)(i - c.first_hit);
+			std::vector<int64_t> t(scn + 1), p(scn + 1); std::vector<int32_t> f(scn + 1);
+			EcZ z; z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_pos_s = c.y_pos_s; z.y_id = c.y_id; z.rev = c.y_pos_strand; z.fc = fc + c.fc_off; z.fc_n = c.fc_n;
+			z.align_length = aln[j].align_length; z.w = (hb_wl_t *)(wlA + aln[j].w_off); z.wn = (int32_t)aln[j].w_n;
+			C.q = hb_rd_view(r->d, rid, 0); C.t = hb_rd_view(r->d, c.y_id, c.y_pos_strand); C.ql = r->d.len[rid]; C.tl = r->d.len[c.y_id];
+			C.aw = wl + nw; C.awcap = (int32_t)std::min<uint64_t>(wl_cap - nw, (uint64_t)scn + 2);
+			hb_ec_overlap_B(C, z, aln[j].re, hits + c.first_hit, scn, 0, t.data(), p.data(), f.data(), &res);
+			if (res.st < 0) rc |= res.st == -1 ? 1 : 2;
+			nw += res.w_n;
+		}
+		out[j] = res;
+	}
+	*pool_used = used; *n_wl = nw;
+	return rc | (used > pool_cap ? 128 : 0);
+}
+
 } // extern "C"

@@ -85,6 +85,15 @@ def _check_stages(g, eng, mode, rs):
         da = alnlib.digest_A((a["st"], a["align_length"], a["rr"], a["re"], W[int(a["w_off"]):int(a["w_off"]) + int(a["w_n"])], Cg) for a in a_i)
         assert da == int(g.digest(mode, "alnA")[i]), "EC alignment step A, read %d" % i
         assert int((a_i["st"] == 2).sum()) == int(g.count(mode, "aln_ok")[i])
+    # steps A + B (rows a8-a10): base-level CIGARs of the accepted overlaps, k_ec_cigar
+    boff, B, WB, CB = eng.ec_cigar(0, n, float(p["bw_thres"]), 0.04, 775)
+    assert (boff == coff).all() and (B["st"] == A["st"]).all()
+    for i in range(n):
+        acc = B[int(boff[i]):int(boff[i + 1])]; acc = acc[acc["st"] == 2]
+        if acc["need_rechain"].any():
+            continue
+        db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CB) for b in acc)
+        assert db == int(g.digest(mode, "alnB")[i]), "EC alignment step B, read %d" % i
     return hom, het
 
 
@@ -171,6 +180,36 @@ def test_sharded_query_ranges_equal_full_pass(ctx):
     r0, q0 = hdist.merge_shards(parts0); r1, q1 = hdist.merge_shards(parts1)
     assert (q0 == fo0).all() and (q1 == fo1).all()
     assert r0.tobytes() == full0.tobytes() and r1.tobytes() == full1.tobytes()
+
+
+def test_ec_cigar_small_scratch_defers_and_matches(ctx, monkeypatch):
+    """a trace scratch too small for some alignments: those overlaps go through the deferred second launch, same result"""
+    g, eng, hom = ctx
+    p = g.params("raw")
+    eng.upload_store(g.raw)
+    h, t = eng.pt_gen(); eng.set_opt(hom_cov=h, het_cov=t)
+    n = g.raw.n
+    ref = eng.ec_cigar(0, n, float(p["bw_thres"]), 0.04, 775)
+    import subprocess, sys, json
+    # HB_ECB_PATH_WORDS is read once per process: run the small-scratch pass in a child
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import hifiasm_b200; from goldenlib import Golden; import hashlib;"
+            "g = Golden(%r); e = hifiasm_b200.Engine(0); e.upload_store(g.raw); hom = e.ft_gen(); e.update_cov(hom); h, t = e.pt_gen(); e.set_opt(hom_cov=h, het_cov=t);"
+            "o, B, W, Cg = e.ec_cigar(0, g.raw.n, %f, 0.04, 775);"
+            "d = hashlib.blake2b(digest_size=8); [d.update(B[f].tobytes()) for f in ('st', 're', 'x_pos_s', 'x_pos_e', 'y_pos_s', 'y_pos_e', 'w_n')];"
+            "[d.update(np.ascontiguousarray(W[f]).tobytes()) for f in ('x_start', 'x_end', 'y_start', 'y_end', 'error', 'clen')];"
+            "print(json.dumps({'dg': d.hexdigest(), 'deferred': e.counters()['ec_deferred']}))") % (
+                os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), [k for k in ("g1", "g2", "g3") if Golden(k).raw.n == n][0], float(p["bw_thres"]))
+    env = dict(os.environ, HB_ECB_PATH_WORDS="4096")
+    res = json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1])
+    o, B, W, Cg = ref
+    d = hashlib.blake2b(digest_size=8)
+    for f in ("st", "re", "x_pos_s", "x_pos_e", "y_pos_s", "y_pos_e", "w_n"):
+        d.update(B[f].tobytes())
+    for f in ("x_start", "x_end", "y_start", "y_end", "error", "clen"):
+        d.update(np.ascontiguousarray(W[f]).tobytes())
+    assert res["dg"] == d.hexdigest()
+    if n == Golden("g3").raw.n:
+        assert res["deferred"] > 0  # the damaged set has alignments that need more than 4096 trace words
 
 
 def test_myers_window_vs_reference(hb):

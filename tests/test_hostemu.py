@@ -89,6 +89,18 @@ def test_ec_align_step_A(ctx):
         A, W, Cg = emu.ec_align_A(er, i, emu.to_chain(ch), fc, win)
         da = alnlib.digest_A((a["st"], a["align_length"], a["rr"], a["re"], W[int(a["w_off"]):int(a["w_off"]) + int(a["w_n"])], Cg) for a in A)
         assert da == int(g.digest("raw", "alnA")[i]), "read %d" % i
+        # step B: body of k_ec_cigar, with a small trace scratch every third read so that the deferral path runs too
+        small = (i % 3 == 0)
+        rc, B, WB, CB = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, path_words=(8192 if small else 1 << 22))
+        assert rc in ((0, 1) if small else (0,)), rc
+        if rc & 1:  # what the second launch does: the deferred overlaps again with the large scratch
+            rc, B, WB, CB = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W)
+            assert rc == 0
+        acc = B[B["st"] == 2]
+        assert acc.size == int(g.count("raw", "aln_ok")[i])
+        if not acc["need_rechain"].any():
+            db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CB) for b in acc)
+            assert db == int(g.digest("raw", "alnB")[i]), "step B, read %d" % i
 
 
 def test_final_pass(ctx):

@@ -26,6 +26,9 @@ def ctx(request):
     return g, raw, opt, ft
 
 
+n_rechain = [0]
+
+
 def _stages(g, mode, st, ft, opt, bw):
     p = g.params(mode)
     pt, hom, het = ho.pt_gen(st, ft, opt)
@@ -53,6 +56,14 @@ def _stages(g, mode, st, ft, opt, bw):
                               Cg[int(a["c_off"]):int(a["c_off"] + a["c_n"])]) for a in A)
         assert da == int(g.digest(mode, "alnA")[i]), "EC alignment step A, read %d" % i
         assert int((A["st"] == 2).sum()) == int(g.count(mode, "aln_ok")[i])
+        # step B (row a10): base-level CIGAR of the accepted overlaps
+        B, WB, CB = ho.ec_align_B(st, i, ch, fc, hits, A, W)
+        acc = B[B["st"] == 2]
+        if not acc["need_rechain"].any():  # an overlap that needs the re-chaining rescue (not restated yet) is not comparable
+            db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"] + b["w_n"])], CB[int(b["c_off"]):int(b["c_off"] + b["c_n"])]) for b in acc)
+            assert db == int(g.digest(mode, "alnB")[i]), "EC alignment step B, read %d" % i
+        else:
+            n_rechain[0] += 1
     return pt, hom, het
 
 
