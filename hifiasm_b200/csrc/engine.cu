@@ -502,7 +502,7 @@ __global__ void k_fc_grp_base(const GroupDir *__restrict__ dir, const uint32_t *
 struct StageOut { // host destinations of the stage APIs (all optional)
 	uint64_t *off; void *rec; uint64_t rec_cap;      // stage 1: minimizers / stage 2: anchors / stage 3: chains
 	uint64_t *hit_off; hb_hit_t *hits; uint64_t hit_cap; uint64_t *fc_off; uint64_t *fc; uint64_t fc_cap;
-	double e_rate; int32_t w_l; // window pass
+	double e_rate; int32_t w_l; int32_t gaps; // window pass; step C on/off
 	hb_wl_t *wl; uint64_t wl_cap; uint16_t *cig; uint64_t cig_cap; uint64_t n_wl, n_cig; // step A of the EC alignment stage (mode 5)
 };
 
@@ -747,7 +747,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							const uint64_t nt = (uint64_t)bl * 64, pw = pass == 0 ? path_words0 : (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5; const int32_t cw = pass == 0 ? 4096 : 65536;
 							Arena sa(ctx);
 							EcCigArgs G; G.R = R; G.r0 = r0 + b0; G.n_ov = n_ov; G.desc = d_od; G.ch = d_ch; G.fc = d_fc; G.fc_grp_base = d_fcb; G.aln = d_aln; G.wlA = d_wl;
-							G.chits = d_chits; G.ghits = d_hits; G.dp_half = B + 1; G.dp_t = d_dpt; G.dp_p = d_dpp; G.dp_f = d_dpf; G.e_rate = so->e_rate; G.w_l = w_l; G.pass = pass; G.refined = attempt > 0;
+							G.chits = d_chits; G.ghits = d_hits; G.dp_half = B + 1; G.dp_t = d_dpt; G.dp_p = d_dpp; G.dp_f = d_dpf; G.e_rate = so->e_rate; G.w_l = w_l; G.pass = pass; G.refined = attempt > 0; G.gaps = so->gaps;
 							G.out = d_alnb; G.wl = d_wlb; G.wl_off = d_wboff; G.path = sa.get<uint64_t>(nt * pw); G.path_words = pw; G.vec = sa.get<uint64_t>(nt * 11 * HB_MW_MAXW);
 							G.cig_tmp = sa.get<uint16_t>(nt * 2 * (uint64_t)cw); G.cig_words = cw; G.pool = d_poolb; G.pool_used = d_pused; G.pool_cap = poolb_cap; G.n_deferred = d_ndef; G.err = d_err;
 							if (sa.failed || pa.failed) return HB_E_WS;
@@ -976,13 +976,13 @@ extern "C" int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_th
 	return rc;
 }
 
-extern "C" int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
+extern "C" int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t gaps,
                            uint64_t *off, hb_alnb_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
                            uint64_t *n_wl, uint64_t *n_cig)
 {
 	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
 	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l;
-	so.wl = wl; so.wl_cap = wl_cap; so.cig = cig; so.cig_cap = cig_cap;
+	so.wl = wl; so.wl_cap = wl_cap; so.cig = cig; so.cig_cap = cig_cap; so.gaps = gaps;
 	int rc = run_pass(ctx, r0, r1, 6, bw_thres, &so, 0);
 	if (n_wl) *n_wl = so.n_wl;
 	if (n_cig) *n_cig = so.n_cig;

@@ -474,6 +474,7 @@ struct EcBCtx {
 	hb_wl_t *aw; int32_t awn, awcap;      // aux_o->w_list of the overlap
 	uint16_t *wc; int32_t wcn, wccap;     // cigar of the window under construction (aux_o->w_list.c tail), flushed to the pool when the window closes
 	int32_t open;                          // index of the window whose cigar is in wc (-1: none)
+	int32_t do_gaps; int64_t re_A, gap_re; // step C (reassign_gaps) applied when a window closes; errors removed by it
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap;
 	int bad;
 };
@@ -685,10 +686,94 @@ HB_HD void hb_wc_push_trace(EcBCtx &C, uint32_t c, uint32_t len)
 	while (len >= 0x3fff) { if (C.wcn < C.wccap) C.wc[C.wcn] = (uint16_t)(c + 0x3fff); else C.ez.ovf = 1; C.wcn++; len -= 0x3fff; }
 	if (len) { if (C.wcn < C.wccap) C.wc[C.wcn] = (uint16_t)(c + len); else C.ez.ovf = 1; C.wcn++; }
 }
+// ---- step C: reassign_gaps (Correct.cpp:25409-25430, row a11): move_wins (25274) left-normalises the indels of a window's
+// cigar (adjust_gap 25167 slides every gap base left through matching bases, turning mismatches that become matches into
+// matches) and turns leading / trailing mismatch runs into insertions (ajust_end_cigar 25252).  Runs on the finished
+// cigar of the window that is being closed: in = C.wc, out = C.ez.cig, scratch = C.ez.path (both free at that point).
+struct GapOut { uint16_t *c; int32_t n, cap; int ovf; };
+HB_HD void hb_go_append(GapOut &o, uint32_t op, uint32_t l)
+{ // append_cigar, Correct.cpp:25151-25165
+	if (l == 0) return;
+	if (o.n > 0 && (uint32_t)(o.c[o.n - 1] >> 14) == op) { l += o.c[o.n - 1] & 0x3fff; o.n--; }
+	const uint32_t c = op << 14;
+	while (l >= 0x3fff) { if (o.n < o.cap) o.c[o.n] = (uint16_t)(c + 0x3fff); else o.ovf = 1; o.n++; l -= 0x3fff; }
+	if (l) { if (o.n < o.cap) o.c[o.n] = (uint16_t)(c + l); else o.ovf = 1; o.n++; }
+}
+HB_HD int hb_adjust_gap(EcBCtx &C, GapOut &o, int64_t pi, int64_t ti, uint32_t op0, uint16_t *buf, int64_t bcap, int64_t *rd_err)
+{ // adjust_gap, Correct.cpp:25167-25250 (pstr = target on the overlap's strand, tstr = query)
+	*rd_err = 0;
+	if (o.n == 0) { hb_go_append(o, op0, 1); return 0; }
+	if (op0 != 2 && op0 != 3) return 0;
+	if (op0 == 2) ti--; else pi--;
+	int64_t ci = o.n, op, cl, k, l0 = 0, l1 = 0, bn = 0; int ff = 0;
+#define HB_BPUSH(v) do { if (bn < bcap) buf[bn] = (uint16_t)(v); else o.ovf = 1; bn++; } while (0)
+	for (ci--; ci >= 0; ci--) {
+		op = o.c[ci] >> 14; cl = o.c[ci] & 0x3fff;
+		if (op == 2 || op == 3) { HB_BPUSH((op0 << 14) + 1); l0 = cl; HB_BPUSH((op << 14) + l0); break; }
+		else if (op == 0) {
+			for (k = cl - 1; k >= 0; k--, pi--, ti--) if (C.t.at(pi) != C.q.at(ti)) break;
+			l1 = cl - k - 1; l0 = k + 1;
+			if (l1 > 0) { HB_BPUSH((op << 14) + l1); ff = 1; }
+			if (l0 > 0) { HB_BPUSH((op0 << 14) + 1); HB_BPUSH((op << 14) + l0); }
+		} else {
+			for (k = cl - 1, l0 = cl, l1 = 0; k >= 0; k--, pi--, ti--) {
+				if (C.t.at(pi) == C.q.at(ti)) {
+					l1 = l0 - k - 1; l0 = k;
+					if (l1 > 0) { HB_BPUSH((op << 14) + l1); ff = 1; }
+					HB_BPUSH(1); (*rd_err)++;
+				}
+			}
+			if (l0 > 0) HB_BPUSH((op << 14) + l0);
+			l0 = 0;
+		}
+		if (l0 > 0) break;
+	}
+#undef HB_BPUSH
+	if (o.ovf) return 0;
+	if (!ff) { hb_go_append(o, op0, 1); return 0; }
+	if (ci >= 0) o.n = (int32_t)ci;
+	else { o.n = 0; hb_go_append(o, op0, 1); }
+	for (k = bn - 1; k >= 0; k--) hb_go_append(o, buf[k] >> 14, buf[k] & 0x3fff);
+	return 1;
+}
+HB_HD int hb_adjust_end_cigar(hb_wl_t *p, uint16_t *ca, int32_t cn)
+{ // ajust_end_cigar, Correct.cpp:25252-25272
+	int rr = 0; int32_t ci;
+	for (ci = 0; ci < cn; ci++) { const uint32_t op = ca[ci] >> 14, cl = ca[ci] & 0x3fff; if (op != 1) break; ca[ci] = (uint16_t)((3u << 14) + cl); p->y_start += (int32_t)cl; rr = 1; }
+	for (ci = cn - 1; ci >= 0; ci--) { const uint32_t op = ca[ci] >> 14, cl = ca[ci] & 0x3fff; if (op != 1) break; ca[ci] = (uint16_t)((3u << 14) + cl); p->y_end -= (int32_t)cl; rr = 1; }
+	return rr;
+}
+// move_wins for the aligned window p whose cigar is C.wc[0..C.wcn): returns the cigar to flush (C.wc itself when unchanged in place)
+HB_HD const uint16_t *hb_move_wins(EcBCtx &C, hb_wl_t *p, int32_t *n_out)
+{
+	const uint16_t *cg = C.wc; const int32_t cn = C.wcn; int32_t ci; int mm;
+	*n_out = cn;
+	if (p->error == 0) return cg;
+	for (ci = 0, mm = 0; ci < cn; ci++) { const uint32_t op = cg[ci] >> 14; if (op < 2) mm = 1; else if (mm) break; }
+	if (ci >= cn) { hb_adjust_end_cigar(p, C.wc, cn); return cg; }
+	GapOut o; o.c = C.ez.cig; o.n = 0; o.cap = C.ez.ccap; o.ovf = 0;
+	uint16_t *buf = (uint16_t *)C.ez.path; const int64_t bcap = (int64_t)(C.ez.pcap * 4);
+	int64_t pi = p->y_start, ti = p->x_start, re;
+	for (ci = 0, mm = 0; ci < cn && !o.ovf; ci++) {
+		const uint32_t op = cg[ci] >> 14, cl = cg[ci] & 0x3fff;
+		if (op < 2) { hb_go_append(o, op, cl); pi += cl; ti += cl; mm = 1; }
+		else if (mm == 0) { hb_go_append(o, op, cl); if (op == 2) pi += cl; else ti += cl; }
+		else for (uint32_t k = 0; k < cl && !o.ovf; k++) {
+			if (hb_adjust_gap(C, o, pi, ti, op, buf, bcap, &re)) { p->error = (int16_t)(p->error - re); C.gap_re += re; }
+			if (op == 2) pi++; else ti++;
+		}
+	}
+	if (o.ovf) { C.ez.ovf = 1; return cg; }
+	hb_adjust_end_cigar(p, o.c, o.n);
+	*n_out = o.n;
+	return o.c;
+}
+
 HB_HD void hb_b_flush(EcBCtx &C)
 { // the open window's cigar leaves the per-thread buffer for the shared pool (one contiguous piece, like aux_o->w_list.c)
 	if (C.open < 0) return;
-	hb_wl_t *p = &C.aw[C.open]; const int32_t n = C.wcn;
+	hb_wl_t *p = &C.aw[C.open]; int32_t n = C.wcn; const uint16_t *src = C.wc;
+	if (C.do_gaps && C.re_A != 0 && !C.ez.ovf) src = hb_move_wins(C, p, &n);
 	if (!C.ez.ovf) {
 #ifdef __CUDA_ARCH__
 		const unsigned long long o = atomicAdd(C.pool_used, (unsigned long long)n);
@@ -696,7 +781,7 @@ HB_HD void hb_b_flush(EcBCtx &C)
 		const unsigned long long o = *C.pool_used; *C.pool_used += (unsigned long long)n;
 #endif
 		p->cidx = (uint32_t)o; p->clen = (uint32_t)n;
-		if (o + (unsigned long long)n <= C.pool_cap) for (int32_t k = 0; k < n; k++) C.pool[o + k] = C.wc[k];
+		if (o + (unsigned long long)n <= C.pool_cap) for (int32_t k = 0; k < n; k++) C.pool[o + k] = src[k];
 	}
 	C.open = -1; C.wcn = 0;
 }
@@ -871,11 +956,11 @@ HB_HD int64_t hb_hc_aln_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int
 // >= FORCE_SIN_L remains, which the reference re-seeds (rechain_aln_hc, Correct.cpp:17669 — not built yet).
 HB_HD void hb_ec_overlap_B(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_hit_t *ch_a, int64_t scn, int refined, int64_t *dp_t, int64_t *dp_p, int32_t *dp_f, hb_alnb_t *out)
 {
-	C.awn = 0; C.wcn = 0; C.open = -1; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+	C.awn = 0; C.wcn = 0; C.open = -1; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.re_A = re_A; C.gap_re = 0;
 	const int64_t ch_n = refined ? scn : hb_lchain_refine(ch_a, scn, dp_t, dp_p, dp_f, 50, 5000, 512, 16); // refined: a deferred overlap's second run
 	for (int64_t i = ch_n; i < scn; i++) ch_a[i].id_strand = (ch_a[i].id_strand & 0x80000000u) | 0x7fffffffu;
 	const int64_t ql = C.ql, tl = C.tl; int64_t q[2], t[2], mode, i, l; bool done = false;
-	out->need_rechain = 0; out->re = 0; out->w_n = 0;
+	out->need_rechain = 0; out->re = 0; out->w_n = 0; out->nh_err = re_A;
 	if (ch_n <= 0) { out->st = 2; out->x_pos_s = (uint32_t)zA.x_pos_s; out->x_pos_e = (uint32_t)zA.x_pos_e; out->y_pos_s = (uint32_t)zA.y_pos_s; out->y_pos_e = 0; return; }
 	if (re_A == 0 && zA.wn) { // hc_ovlp_base_direct, Correct.cpp:17430-17459: every window exact and co-linear -> one exact window
 		const int32_t zn = zA.wn; int32_t k;
@@ -917,7 +1002,7 @@ HB_HD void hb_ec_overlap_B(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_hit_t *ch_
 	if (C.awn) { xs = C.aw[0].x_start; xe = C.aw[C.awn - 1].x_end; ys = C.aw[0].y_start; ye = C.aw[C.awn - 1].y_end; } // update_overlap_region, Correct.cpp:17249-17275
 	if (xs <= ys) { ys -= xs; xs = 0; } else { xs -= ys; ys = 0; }
 	{ const int64_t xr = ql - xe - 1, yr = tl - ye - 1; if (xr <= yr) { xe = ql - 1; ye += xr; } else { ye = tl - 1; xe += yr; } }
-	out->st = 2; out->re = tot_e; out->w_n = (uint32_t)C.awn;
+	out->st = 2; out->re = tot_e + C.gap_re; out->w_n = (uint32_t)C.awn; out->nh_err = re_A - C.gap_re; // re = step B's total (before step C)
 	out->x_pos_s = (uint32_t)xs; out->x_pos_e = (uint32_t)xe; out->y_pos_s = (uint32_t)ys; out->y_pos_e = (uint32_t)ye;
 	if (C.bad) out->st = -2;
 }

@@ -1125,7 +1125,7 @@ __global__ void k_ecb_cap(uint64_t n_ov, const OvDesc *__restrict__ desc, const 
 struct EcCigArgs {
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
 	const hb_aln_t *aln; const hb_wl_t *wlA; hb_hit_t *chits, *ghits; uint64_t dp_half; int64_t *dp_t, *dp_p; int32_t *dp_f;
-	double e_rate; int32_t w_l; int pass, refined; // refined: the chains were refined by an earlier launch of this batch
+	double e_rate; int32_t w_l; int pass, refined, gaps; // refined: the chains were refined by an earlier launch of this batch
 	hb_alnb_t *out; hb_wl_t *wl; const uint64_t *wl_off;
 	uint64_t *path; uint64_t path_words; uint64_t *vec; uint16_t *cig_tmp; int32_t cig_words;
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; unsigned int *n_deferred; int *err;
@@ -1133,12 +1133,12 @@ struct EcCigArgs {
 __global__ void __launch_bounds__(64) k_ec_cigar(EcCigArgs A)
 {
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
-	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap;
+	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.do_gaps = A.gaps;
 	C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * (11 * HB_MW_MAXW);
 	C.ez.cig = A.cig_tmp + tid * 2 * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words; C.wc = C.ez.cig + A.cig_words; C.wccap = A.cig_words;
 	for (uint64_t o = tid; o < A.n_ov; o += nthr) {
 		const hb_aln_t a = A.aln[o];
-		if (A.pass == 0) { if (a.st != 2) { hb_alnb_t r; r.st = a.st; r.need_rechain = 0; r.re = 0; r.x_pos_s = r.x_pos_e = r.y_pos_s = r.y_pos_e = 0; r.w_off = A.wl_off[o]; r.w_n = 0; r.pad = 0; A.out[o] = r; continue; } }
+		if (A.pass == 0) { if (a.st != 2) { hb_alnb_t r; r.st = a.st; r.need_rechain = 0; r.re = 0; r.nh_err = 0; r.x_pos_s = r.x_pos_e = r.y_pos_s = r.y_pos_e = 0; r.w_off = A.wl_off[o]; r.w_n = 0; r.pad = 0; A.out[o] = r; continue; } }
 		else if (A.out[o].st != -1) continue;
 		const OvDesc d = A.desc[o]; const hb_chain_t c = A.ch[d.slot];
 		const bool inpl = (c.pad & HB_CHAIN_INPLACE) != 0;

@@ -24,7 +24,7 @@ WL = np.dtype([("x_start", "<i4"), ("x_end", "<i4"), ("y_start", "<i4"), ("y_end
 ALN = np.dtype([("st", "<i4"), ("align_length", "<u4"), ("rr", "<f8"), ("re", "<i8"), ("w_off", "<u8"), ("w_n", "<u4"), ("pad", "<u4")])
 
 
-ALNB = np.dtype([("st", "<i4"), ("need_rechain", "<i4"), ("re", "<i8"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
+ALNB = np.dtype([("st", "<i4"), ("need_rechain", "<i4"), ("re", "<i8"), ("nh_err", "<i8"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
                  ("w_off", "<u8"), ("w_n", "<u4"), ("pad", "<u4")])
 
 
@@ -191,12 +191,12 @@ class Engine:
         self._ck(_lib().hb_ec_align(*a, _p(rec), C.c_uint64(rec.size), _p(wl), C.c_uint64(wl.size), _p(cig), C.c_uint64(cig.size), C.byref(nw), C.byref(nc)))
         return off, rec[:int(off[-1])], wl[:nw.value], cig[:nc.value]
 
-    def ec_cigar(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775):
-        """steps A + B of the alignment stage of an EC round (rows a8-a10): base-level CIGARs of the accepted overlaps
+    def ec_cigar(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775, gaps=0):
+        """steps A + B (+ C when gaps) of the alignment stage of an EC round (rows a8-a11): base-level CIGARs of the accepted overlaps
         -> (off, ALNB records, WL window lists, cigar pool)"""
         n = r1 - r0
         off = np.zeros(n + 1, np.uint64); nw = C.c_uint64(); nc = C.c_uint64(); z = C.c_void_p(0)
-        a = (self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off))
+        a = (self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), C.c_int32(gaps), _p(off))
         self._ck(_lib().hb_ec_cigar(*a, z, C.c_uint64(0), z, C.c_uint64(0), z, C.c_uint64(0), C.byref(nw), C.byref(nc)))
         rec = np.zeros(int(off[-1]) + 1, ALNB); wl = np.zeros(nw.value + 1, WL); cig = np.zeros(2 * nc.value + 4096, np.uint16)
         self._ck(_lib().hb_ec_cigar(*a, _p(rec), C.c_uint64(rec.size), _p(wl), C.c_uint64(wl.size), _p(cig), C.c_uint64(cig.size), C.byref(nw), C.byref(nc)))

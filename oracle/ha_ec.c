@@ -1056,3 +1056,147 @@ int hao_ec_align_B(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uin
 	*out = o; *wl = W; *n_wl = nw; *cig = C; *n_cig = nc;
 	return b.bad ? -1 : 0;
 }
+
+/* ================================================================================================== */
+/* step C: reassign_gaps (Correct.cpp:25409-25430, row a11) — left-normalise the indels of every window  */
+/* ================================================================================================== */
+static void append_cigar_(hao_wl_t *idx, wlv_t *res, uint16_t c, uint32_t l)
+{ /* append_cigar, Correct.cpp:25151-25165 */
+	if (l <= 0) return;
+	uint16_t c0 = (uint16_t)-1; uint32_t l0 = 0;
+	if (idx->clen > 0) { c0 = res->c[res->cn - 1] >> 14; l0 = res->c[res->cn - 1] & 0x3fff; }
+	if (c0 == c) { l += l0; res->cn--; idx->clen--; }
+	wlv_push_trace(res, c, l);
+	idx->clen = (uint32_t)(res->cn - idx->cidx);
+}
+
+static uint16_t adjust_gap_(hao_wl_t *idx, wlv_t *res, const char *pstr, const char *tstr, int64_t pi, int64_t ti, uint16_t op0, uint16_t **buf, size_t *bm, int64_t *rd_err)
+{ /* adjust_gap, Correct.cpp:25167-25250 */
+	*rd_err = 0;
+	if (idx->clen == 0) { append_cigar_(idx, res, op0, 1); return 0; }
+	if (op0 != 2 && op0 != 3) return 0;
+	if (op0 == 2) ti--; else pi--;
+	uint16_t *ca = res->c + idx->cidx, p, ff; int64_t ci = idx->clen, op, cl, k, l[2]; size_t bn = 0;
+	for (ci--, ff = 0; ci >= 0; ci--) {
+		op = ca[ci] >> 14; cl = ca[ci] & 0x3fff;
+		if (op == 2 || op == 3) {
+			p = (uint16_t)((op0 << 14) + 1); cig_push(buf, &bn, bm, p);
+			l[0] = cl;
+			p = (uint16_t)((op << 14) + l[0]); cig_push(buf, &bn, bm, p);
+			break;
+		} else if (op == 0) {
+			for (k = cl - 1, l[0] = l[1] = 0; k >= 0; k--, pi--, ti--) if (pstr[pi] != tstr[ti]) break;
+			l[1] = cl - k - 1; l[0] = k + 1;
+			if (l[1] > 0) { p = (uint16_t)((op << 14) + l[1]); cig_push(buf, &bn, bm, p); ff = 1; }
+			if (l[0] > 0) { p = (uint16_t)((op0 << 14) + 1); cig_push(buf, &bn, bm, p); }
+			if (l[0] > 0) { p = (uint16_t)((op << 14) + l[0]); cig_push(buf, &bn, bm, p); }
+		} else {
+			for (k = cl - 1, l[0] = cl, l[1] = 0; k >= 0; k--, pi--, ti--) {
+				if (pstr[pi] == tstr[ti]) {
+					l[1] = l[0] - k - 1; l[0] = k;
+					if (l[1] > 0) { p = (uint16_t)((op << 14) + l[1]); cig_push(buf, &bn, bm, p); ff = 1; }
+					p = 1; cig_push(buf, &bn, bm, p); /* one match */
+					(*rd_err)++;
+				}
+			}
+			if (l[0] > 0) { p = (uint16_t)((op << 14) + l[0]); cig_push(buf, &bn, bm, p); }
+			l[0] = 0;
+		}
+		if (l[0] > 0) break;
+	}
+	if (!ff) { append_cigar_(idx, res, op0, 1); return 0; }
+	else if (ci >= 0) {
+		idx->clen = (uint32_t)ci; res->cn = idx->cidx + idx->clen;
+		for (k = (int64_t)bn - 1; k >= 0; k--) append_cigar_(idx, res, (*buf)[k] >> 14, (*buf)[k] & 0x3fff);
+	} else {
+		idx->clen = 0; res->cn = idx->cidx;
+		append_cigar_(idx, res, op0, 1);
+		for (k = (int64_t)bn - 1; k >= 0; k--) append_cigar_(idx, res, (*buf)[k] >> 14, (*buf)[k] & 0x3fff);
+	}
+	return 1;
+}
+
+static uint16_t ajust_end_cigar_(hao_wl_t *idx, wlv_t *res)
+{ /* ajust_end_cigar, Correct.cpp:25252-25272 */
+	uint16_t *ca = res->c + idx->cidx, rr = 0; int64_t ci, cn = idx->clen, op, cl;
+	if (cn <= 0) return rr;
+	for (ci = 0; ci < cn; ci++) { op = ca[ci] >> 14; cl = ca[ci] & 0x3fff; if (op != 1) break; ca[ci] = (uint16_t)((3 << 14) + cl); idx->y_start += (int32_t)cl; rr = 1; }
+	for (ci = cn - 1; ci >= 0; ci--) { op = ca[ci] >> 14; cl = ca[ci] & 0x3fff; if (op != 1) break; ca[ci] = (uint16_t)((3 << 14) + cl); idx->y_end -= (int32_t)cl; rr = 1; }
+	return rr;
+}
+
+static uint16_t move_wins_(const hao_wl_t *zw, const uint16_t *zc, wlv_t *aux, const char *tseq, const char *pseq, uint16_t **buf, size_t *bm, int64_t *tot_re)
+{ /* move_wins, Correct.cpp:25274-25365.  tseq = query, pseq = whole target read on the overlap's strand */
+	if (zw->error == INT16_MAX && zw->clen == 0 && zw->extra_end < 0) { *wlv_pushp(aux) = *zw; return 0; }
+	const uint16_t *cg = zc + zw->cidx; size_t cn = zw->clen, ci; hao_wl_t *p = wlv_pushp(aux); size_t pidx = aux->wn - 1, k2;
+	p->x_start = zw->x_start; p->x_end = zw->x_end; p->y_start = zw->y_start; p->y_end = zw->y_end; p->extra_begin = p->extra_end = 0;
+	p->error_threshold = 0; p->error = zw->error; p->cidx = (uint32_t)aux->cn; p->clen = 0;
+	int64_t pi = zw->y_start, ti = zw->x_start, cl, op, k, rr = 0, re; int mm;
+	if (zw->error == 0) { p->clen = (uint32_t)cn; for (k2 = 0; k2 < cn; k2++) cig_push(&aux->c, &aux->cn, &aux->cm, cg[k2]); return 0; }
+	for (ci = 0, mm = 0; ci < cn; ci++) { op = cg[ci] >> 14; if (op < 2) mm = 1; else if (mm) break; }
+	if (ci >= cn) {
+		p->clen = (uint32_t)cn; for (k2 = 0; k2 < cn; k2++) cig_push(&aux->c, &aux->cn, &aux->cm, cg[k2]);
+		p = &aux->w[pidx];
+		if (ajust_end_cigar_(p, aux)) rr = 1;
+		return (uint16_t)rr;
+	}
+	for (ci = 0, mm = 0; ci < cn; ci++) {
+		op = cg[ci] >> 14; cl = cg[ci] & 0x3fff; p = &aux->w[pidx];
+		if (op < 2) { append_cigar_(p, aux, (uint16_t)op, (uint32_t)cl); pi += cl; ti += cl; mm = 1; }
+		else if (mm == 0) { append_cigar_(p, aux, (uint16_t)op, (uint32_t)cl); if (op == 2) pi += cl; else ti += cl; }
+		else {
+			for (k = 0; k < cl; k++) {
+				if (adjust_gap_(p, aux, pseq, tseq, pi, ti, (uint16_t)op, buf, bm, &re)) { rr = 1; p->error = (int16_t)(p->error - re); *tot_re += re; }
+				if (op == 2) pi++; else ti++;
+			}
+		}
+	}
+	p = &aux->w[pidx];
+	if (ajust_end_cigar_(p, aux)) rr = 1;
+	return (uint16_t)rr;
+}
+
+typedef struct { int64_t nh_err; uint32_t x_pos_s, x_pos_e, y_pos_s, y_pos_e; uint64_t w_off, w_n, c_off, c_n; } hao_alnC_t;
+
+/* step C for the overlaps steps A + B accepted: a[] (re = the estimate reassign_gaps tests), bB / wlB / cigB = step B's output */
+int hao_ec_align_C(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint32_t n_ch, const hao_alnA_t *a, const hao_alnB_t *bB, const hao_wl_t *wlB, const uint16_t *cigB,
+                   hao_alnC_t **out, hao_wl_t **wl, uint64_t *n_wl, uint16_t **cig, uint64_t *n_cig)
+{
+	uint64_t ql = r->len[rid], nw = 0, mw = 0, nc = 0, mc = 0, tm = 0; uint32_t j; hao_wl_t *W = 0; uint16_t *C = 0, *buf = 0; size_t bm = 0;
+	char *qs = MALLOC_N(char, ql + 1), *ts = 0; wlv_t aux; hao_alnC_t *o = CALLOC_N(hao_alnC_t, n_ch);
+	memset(&aux, 0, sizeof(aux));
+	hao_decode(r, rid, qs);
+	for (j = 0; j < n_ch; j++) {
+		const hao_ovlp_t *c = &ch[j]; int64_t tl = (int64_t)r->len[c->y_id], k, rr = 0, re = 0; const hao_wl_t *zw = wlB + bB[j].w_off; const uint16_t *zc = cigB + bB[j].c_off;
+		const hao_wl_t *src_w = zw; const uint16_t *src_c = zc; uint64_t src_wn = bB[j].w_n, src_cn = bB[j].c_n;
+		o[j].w_off = nw; o[j].c_off = nc;
+		if (a[j].st != 2) continue;
+		o[j].nh_err = a[j].re; o[j].x_pos_s = bB[j].x_pos_s; o[j].x_pos_e = bB[j].x_pos_e; o[j].y_pos_s = bB[j].y_pos_s; o[j].y_pos_e = bB[j].y_pos_e;
+		if (a[j].re != 0) {
+			if ((uint64_t)tl + 1 > tm) { tm = (uint64_t)tl + 64; ts = (char *)realloc(ts, tm); }
+			hao_decode_sub(r, c->y_id, 0, tl, (int)c->y_pos_strand, ts); /* recover_UC_Read[_RC] */
+			aux.wn = aux.cn = 0;
+			for (k = 0; k < (int64_t)bB[j].w_n; k++) if (move_wins_(&zw[k], zc, &aux, qs, ts, &buf, &bm, &re)) rr = 1;
+			if (rr) { /* update_overlap_region */
+				int64_t xs, xe, ys, ye, xr, yr;
+				src_w = aux.w; src_c = aux.c; src_wn = aux.wn; src_cn = aux.cn;
+				xs = o[j].x_pos_s; xe = o[j].x_pos_e; ys = o[j].y_pos_s; ye = o[j].y_pos_e;
+				if (aux.wn) { xs = aux.w[0].x_start; xe = aux.w[aux.wn - 1].x_end; ys = aux.w[0].y_start; ye = aux.w[aux.wn - 1].y_end; }
+				if (xs <= ys) { ys -= xs; xs = 0; } else { xs -= ys; ys = 0; }
+				xr = (int64_t)ql - xe - 1; yr = tl - ye - 1;
+				if (xr <= yr) { xe = (int64_t)ql - 1; ye += xr; } else { ye = tl - 1; xe += yr; }
+				o[j].x_pos_s = (uint32_t)xs; o[j].x_pos_e = (uint32_t)xe; o[j].y_pos_s = (uint32_t)ys; o[j].y_pos_e = (uint32_t)ye;
+			}
+			o[j].nh_err = a[j].re - re;
+		}
+		o[j].w_n = src_wn; o[j].c_n = src_cn;
+		if (nw + src_wn > mw) { mw = (nw + src_wn) * 2 + 64; W = (hao_wl_t *)realloc(W, mw * sizeof(hao_wl_t)); }
+		if (nc + src_cn > mc) { mc = (nc + src_cn) * 2 + 64; C = (uint16_t *)realloc(C, mc * 2); }
+		if (src_wn) memcpy(W + nw, src_w, src_wn * sizeof(hao_wl_t));
+		if (src_cn) memcpy(C + nc, src_c, src_cn * 2);
+		nw += src_wn; nc += src_cn;
+	}
+	free(qs); free(ts); free(buf); free(aux.w); free(aux.c);
+	*out = o; *wl = W; *n_wl = nw; *cig = C; *n_cig = nc;
+	return 0;
+}

@@ -195,3 +195,18 @@ def ec_align_B(store: Store, rid, chains, fc, hits, A, WA, e_rate=0.04, w_l=775)
                               C.c_double(e_rate), C.c_int64(w_l), C.byref(out), C.byref(wl), C.byref(nw), C.byref(cg), C.byref(nc))
     assert rc == 0
     return _take(out, chains.size, ALN_B), _take(wl, nw.value, WL), _take(cg, nc.value, np.dtype("<u2"))
+
+
+ALN_C = np.dtype([("nh_err", "<i8"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
+                  ("w_off", "<u8"), ("w_n", "<u8"), ("c_off", "<u8"), ("c_n", "<u8")])
+
+
+def ec_align_C(store: Store, rid, chains, A, B, WB, CB):
+    """step C (reassign_gaps) -> (ALN_C[n_ch], WL[], cigar u16[]); cidx relative to the overlap's c_off"""
+    chains = np.ascontiguousarray(chains); A = np.ascontiguousarray(A); B = np.ascontiguousarray(B)
+    WB = np.ascontiguousarray(WB if WB.size else np.zeros(1, WL)); CB = np.ascontiguousarray(CB if CB.size else np.zeros(1, np.uint16))
+    out = C.c_void_p(); wl = C.c_void_p(); cg = C.c_void_p(); nw = C.c_uint64(); nc = C.c_uint64()
+    rc = lib().hao_ec_align_C(C.byref(store.c), C.c_uint32(rid), C.c_void_p(chains.ctypes.data), C.c_uint32(chains.size), C.c_void_p(A.ctypes.data), C.c_void_p(B.ctypes.data),
+                              C.c_void_p(WB.ctypes.data), C.c_void_p(CB.ctypes.data), C.byref(out), C.byref(wl), C.byref(nw), C.byref(cg), C.byref(nc))
+    assert rc == 0
+    return _take(out, chains.size, ALN_C), _take(wl, nw.value, WL), _take(cg, nc.value, np.dtype("<u2"))

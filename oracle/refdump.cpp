@@ -195,6 +195,7 @@ static void dump_stages(const char *pfx, double bw_thres)
 				fwrite(&re, 8, 1, fal); dump_wl(fal, z);
 				reassign_gaps(z, aux_o, ur.seq, ql, NULL, -1, &R_INF, &tr, &v16);
 				dump_wl(fal, z);
+				{ int64_t nhe = z->non_homopolymer_errors; uint32_t xy[4] = { z->x_pos_s, z->x_pos_e, z->y_pos_s, z->y_pos_e }; fwrite(&nhe, 8, 1, fal); fwrite(xy, 4, 4, fal); }
 			}
 		}
 	}

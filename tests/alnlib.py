@@ -31,6 +31,8 @@ def read_aln(path):
                 d["reB"], = struct.unpack_from("<q", buf, o); o += 8
                 d["B"], o = _wl(buf, o)
                 d["C"], o = _wl(buf, o)
+                d["nheC"], = struct.unpack_from("<q", buf, o); o += 8
+                d["xyC"] = struct.unpack_from("<4I", buf, o); o += 16
             rl.append(d)
         out.append(rl)
     return out
@@ -68,4 +70,5 @@ def digest_B(ovl):
 
 
 def digest_C(ovl):
-    return _dg(wl_canon(w, c, True) for w, c in ovl)
+    """per-read digest of step C: ovl = iterable of (non_homopolymer_errors, (x_pos_s, x_pos_e, y_pos_s, y_pos_e), w, c)"""
+    return _dg(struct.pack("<q4I", int(nhe), *[int(v) for v in xy]) + wl_canon(w, c, True) for nhe, xy, w, c in ovl)

@@ -98,7 +98,7 @@ def read_stages(pfx, n_reads, keep=4):
         out["alnA"][i] = alnlib.digest_A((d["st"], d["align_length"], d["rr"], d["re"], d["A"][0], d["A"][1]) for d in rl)
         acc = [d for d in rl if d["st"] == 2]
         out["alnB"][i] = alnlib.digest_B((d["reB"], d["B"][0], d["B"][1]) for d in acc)
-        out["alnC"][i] = alnlib.digest_C(d["C"] for d in acc)
+        out["alnC"][i] = alnlib.digest_C((d["nheC"], d["xyC"], d["C"][0], d["C"][1]) for d in acc)
         cnt["aln_ok"][i] = len(acc)
     return out, cnt, full
 

@@ -131,17 +131,17 @@ def ec_align_A(reads, rid, ch, fc, win, e_rate=0.04, w_l=775):
     return out[:ch.size], wl[:win.size], pool[:used.value]
 
 
-ALNB = np.dtype([("st", "<i4"), ("need_rechain", "<i4"), ("re", "<i8"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
+ALNB = np.dtype([("st", "<i4"), ("need_rechain", "<i4"), ("re", "<i8"), ("nh_err", "<i8"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
                  ("w_off", "<u8"), ("w_n", "<u4"), ("pad", "<u4")])
 
 
-def ec_align_B(reads, rid, ch, fc, hits, A, WA, e_rate=0.04, w_l=775, path_words=1 << 22, cig_words=1 << 15):
+def ec_align_B(reads, rid, ch, fc, hits, A, WA, e_rate=0.04, w_l=775, path_words=1 << 22, cig_words=1 << 15, gaps=0):
     """-> (rc, ALNB[n_ch], WL[], cigar pool); rc & 1 = some overlap deferred for lack of scratch"""
     ch = np.ascontiguousarray(ch); fc = np.ascontiguousarray(fc if fc.size else np.zeros(1, np.uint64)); hits = np.ascontiguousarray(hits).copy()
     A = np.ascontiguousarray(A); WA = np.ascontiguousarray(WA if WA.size else np.zeros(1, WL))
     out = np.zeros(ch.size + 1, ALNB); cap_w = hits.size + 2 * ch.size + 16; wl = np.zeros(cap_w, WL)
     cap = 1 << 22; pool = np.zeros(cap, np.uint16); used = C.c_uint64(); nw = C.c_uint64()
     rc = lib().emu_ec_align_B(reads.h, C.c_uint32(rid), _p(ch), C.c_uint32(ch.size), _p(fc), _p(hits), C.c_uint64(hits.size), _p(A), _p(WA),
-                              C.c_double(e_rate), C.c_int32(w_l), C.c_uint64(path_words), C.c_int32(cig_words),
+                              C.c_double(e_rate), C.c_int32(w_l), C.c_int32(gaps), C.c_uint64(path_words), C.c_int32(cig_words),
                               _p(out), _p(wl), C.c_uint64(cap_w), _p(pool), C.c_uint64(cap), C.byref(used), C.byref(nw))
     return rc, out[:ch.size], wl[:nw.value], pool[:used.value]

@@ -277,12 +277,12 @@ int emu_ec_align_A(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 // step B (base-level CIGAR) for the overlaps step A accepted: body of k_ec_cigar.  hits = compacted chain anchors of the read
 // (modified in place like return_t_chain does), aln / wlA = step A's output.  path_words / cig_words = per-thread scratch sizes.
 int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch, const uint64_t *fc, hb_hit_t *hits, uint64_t n_hits,
-                   const hb_aln_t *aln, const hb_wl_t *wlA, double e_rate, int32_t w_l, uint64_t path_words, int32_t cig_words,
+                   const hb_aln_t *aln, const hb_wl_t *wlA, double e_rate, int32_t w_l, int32_t gaps, uint64_t path_words, int32_t cig_words,
                    hb_alnb_t *out, hb_wl_t *wl, uint64_t wl_cap, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used, uint64_t *n_wl)
 {
 	EmuReads *r = (EmuReads *)reads; unsigned long long used = 0; uint64_t nw = 0; int rc = 0;
 	std::vector<uint64_t> path(path_words), vec(11 * HB_MW_MAXW); std::vector<uint16_t> ecig(cig_words), wc(cig_words);
-	EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap;
+	EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap; C.do_gaps = gaps;
 	C.ez.path = path.data(); C.ez.pcap = path_words; C.ez.vec = vec.data(); C.ez.cig = ecig.data(); C.ez.ccap = cig_words; C.wc = wc.data(); C.wccap = cig_words;
 	for (uint32_t j = 0; j < n_ch; j++) {
 		hb_alnb_t res; memset(&res, 0, sizeof(res)); res.st = aln[j].st; res.w_off = nw;

@@ -94,6 +94,15 @@ def _check_stages(g, eng, mode, rs):
             continue
         db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CB) for b in acc)
         assert db == int(g.digest(mode, "alnB")[i]), "EC alignment step B, read %d" % i
+    # + step C (row a11): reassign_gaps fused into the same kernel
+    goff, Gc, WG, CG = eng.ec_cigar(0, n, float(p["bw_thres"]), 0.04, 775, gaps=1)
+    assert (Gc["st"] == B["st"]).all() and (Gc["re"] == B["re"]).all()
+    for i in range(n):
+        acc = Gc[int(goff[i]):int(goff[i + 1])]; acc = acc[acc["st"] == 2]
+        if acc["need_rechain"].any():
+            continue
+        dc = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WG[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CG) for b in acc)
+        assert dc == int(g.digest(mode, "alnC")[i]), "EC alignment step C, read %d" % i
     return hom, het
 
 

@@ -101,6 +101,11 @@ def test_ec_align_step_A(ctx):
         if not acc["need_rechain"].any():
             db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CB) for b in acc)
             assert db == int(g.digest("raw", "alnB")[i]), "step B, read %d" % i
+            # steps B + C in one go (reassign_gaps applied as each window closes)
+            rc, Bc, WCc, CCc = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1)
+            assert rc == 0 and (Bc["re"] == B["re"]).all()
+            dc = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WCc[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CCc) for b in Bc[Bc["st"] == 2])
+            assert dc == int(g.digest("raw", "alnC")[i]), "step C, read %d" % i
 
 
 def test_final_pass(ctx):

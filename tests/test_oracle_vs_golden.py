@@ -62,6 +62,11 @@ def _stages(g, mode, st, ft, opt, bw):
         if not acc["need_rechain"].any():  # an overlap that needs the re-chaining rescue (not restated yet) is not comparable
             db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"] + b["w_n"])], CB[int(b["c_off"]):int(b["c_off"] + b["c_n"])]) for b in acc)
             assert db == int(g.digest(mode, "alnB")[i]), "EC alignment step B, read %d" % i
+            # step C (row a11): reassign_gaps
+            Cc, WC, CC = ho.ec_align_C(st, i, ch, A, B, WB, CB)
+            dc = alnlib.digest_C((c["nh_err"], (c["x_pos_s"], c["x_pos_e"], c["y_pos_s"], c["y_pos_e"]), WC[int(c["w_off"]):int(c["w_off"] + c["w_n"])],
+                                  CC[int(c["c_off"]):int(c["c_off"] + c["c_n"])]) for c, a in zip(Cc, A) if a["st"] == 2)
+            assert dc == int(g.digest(mode, "alnC")[i]), "EC alignment step C, read %d" % i
         else:
             n_rechain[0] += 1
     return pt, hom, het
