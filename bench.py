@@ -294,6 +294,37 @@ def _main():
         aux = {"window_pass": {"reads": int(na), "windows": int(win.size), "aligned": int((win["err"] != 2**31 - 1).sum()), "k_windows_ms": kms,
                                "gcups": (cols / (kms / 1e3) / 1e9) if kms > 0 else None, "note": "64-bit banded Myers column updates/s, one thread per 775-bp window"}}
 
+    # ---- auxiliary: the alignment stage of an EC round (rows a8-a11: window pass, gap filling + error estimate, base-level
+    # CIGAR, indel normalisation) on RAW reads (0.2 % errors) of a small separate genome — the final-pass workload above has
+    # error-free reads, on which this stage would only take its exact shortcuts
+    if rank == 0 and not os.environ.get("HB_BENCH_NO_AUX"):
+        try:
+            from hifiasm_b200 import sim
+            ta = time.time()
+            h1, h2 = sim.sim_genome(int(os.environ.get("HB_BENCH_EC_GENOME", "6000000")), 77, snp_rate=SNP)
+            rr = sim.sim_reads(h1, h2, COV, MEAN_LEN, 77, sd_len=SD_LEN, min_len=2000, err=0.002)
+            fl, bo, ln, npos, noff = sim.pack_reads(rr)
+            e2 = hifiasm_b200.Engine(local)
+            e2.upload_reads(ln, fl, bo, npos, noff)
+            hm = e2.ft_gen(); e2.update_cov(hm); hm2, ht2 = e2.pt_gen(); e2.set_opt(hom_cov=hm2, het_cov=ht2)
+            nq = len(rr)
+            e2.ec_cigar(0, nq, 0.02, 0.04, 775, gaps=1)
+            torch.cuda.synchronize(); tb = time.time()
+            goff, G, WG, CG = e2.ec_cigar(0, nq, 0.02, 0.04, 775, gaps=1)
+            torch.cuda.synchronize(); wall_ec = time.time() - tb
+            pr = e2.profile(); cn = e2.counters()
+            kms = {k: pr[k][1] for k in ("k_windows", "k_ec_overlap", "k_ec_cigar", "k_ec_cigar_deferred") if k in pr}
+            qb = int(ln.sum()); acc = G[G["st"] == 2]
+            aux = dict(aux or {})
+            aux["ec_alignment"] = {"reads": nq, "query_bases": qb, "overlaps": int(G.size), "accepted": int(acc.size), "need_rechain": int(acc["need_rechain"].sum()),
+                                   "deferred_to_large_scratch": cn.get("ec_deferred", 0), "windows": cn.get("windows", 0), "cigar_runs": int(CG.size),
+                                   "kernel_ms": kms, "stage_kernels_gbp_s": qb / (sum(kms.values()) / 1e3) / 1e9 if kms else None,
+                                   "pass_ms_with_seeding_and_host_copies": wall_ec * 1e3, "setup_s": round(tb - ta, 1),
+                                   "note": "steps A-C of gen_hc_r_alin on raw reads (0.2 % errors): one thread per window (k_windows), one thread per overlap (k_ec_overlap, k_ec_cigar)"}
+            e2.close()
+        except Exception as ex:  # the auxiliary measurement must never take the bench line down
+            sys.stderr.write("[bench] EC alignment aux failed: %r\n" % (ex,))
+
     if rank != 0:
         # stay alive until rank 0 has printed: a peer that leaves early can take rank 0's NCCL watchdog down with it
         dist.barrier(); dist.destroy_process_group()
