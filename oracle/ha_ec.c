@@ -1200,3 +1200,395 @@ int hao_ec_align_C(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uin
 	*out = o; *wl = W; *n_wl = nw; *cig = C; *n_cig = nc;
 	return 0;
 }
+
+/* ================================================================================================== */
+/* phasing: rphase_hc (Correct.cpp:20191-20320, row a13), HiFi path (bd = 0, occ_thres = 1, no HPC mask,   */
+/* no quality values, no large-indel phasing) + dedup_chains (ecovlp.cpp:2984-3030)                       */
+/* ================================================================================================== */
+#define EC_PH_WIN 428 /* WINDOW_MAX_SIZE = WINDOW (375) + (int)(1.0 / HA_MIN_OV_DIFF 0.02) + 3, Correct.h:27 */
+#define EC_RS_MIN 64  /* RS_MIN_SIZE, ksort.h */
+
+typedef struct { uint32_t site, overlapID, overlapSite; uint8_t type; uint32_t cov; char misBase; } hev_t; /* haplotype_evdience, Correct.h:130-143 */
+typedef struct { uint32_t id, overlap_num, occ_0, occ_1, occ_2; int score; uint32_t site; uint8_t is_homopolymer; } snp_t; /* SnpStats, Correct.h:152-167 */
+
+/* klib's in-place MSD radix sort (KRADIX_SORT_INIT, ksort.h:172-221) on elements of `es` bytes with a `kb`-byte key:
+ * unstable, restated move for move so that ties land where the reference puts them */
+typedef uint64_t (*rs_key_f)(const void *);
+static void grs_insertsort(char *beg, char *end, size_t es, rs_key_f key)
+{
+	char *i, *j, tmp[32];
+	for (i = beg + es; i < end; i += es)
+		if (key(i) < key(i - es)) {
+			memcpy(tmp, i, es);
+			for (j = i; j > beg && key(tmp) < key(j - es); j -= es) memcpy(j, j - es, es);
+			memcpy(j, tmp, es);
+		}
+}
+static void grs_sort(char *beg, char *end, size_t es, rs_key_f key, int n_bits, int s)
+{
+	int size = 1 << n_bits, m = size - 1, k; char *i; struct { char *b, *e; } b[256], *l;
+	for (k = 0; k < size; k++) b[k].b = b[k].e = beg;
+	for (i = beg; i != end; i += es) b[key(i) >> s & m].e += es;
+	for (k = 1; k < size; k++) { b[k].e += b[k - 1].e - beg; b[k].b = b[k - 1].e; }
+	for (k = 0; k < size;) {
+		if (b[k].b != b[k].e) {
+			if ((l = b + (key(b[k].b) >> s & m)) != b + k) {
+				char tmp[32], swap[32];
+				memcpy(tmp, b[k].b, es);
+				do { memcpy(swap, tmp, es); memcpy(tmp, l->b, es); memcpy(l->b, swap, es); l->b += es; l = b + (key(tmp) >> s & m); } while (l != b + k);
+				memcpy(b[k].b, tmp, es); b[k].b += es;
+			} else b[k].b += es;
+		} else ++k;
+	}
+	for (b[0].b = beg, k = 1; k < size; k++) b[k].b = b[k - 1].e;
+	if (s) {
+		s = s > n_bits ? s - n_bits : 0;
+		for (k = 0; k < size; k++) {
+			if ((b[k].e - b[k].b) / (ptrdiff_t)es > EC_RS_MIN) grs_sort(b[k].b, b[k].e, es, key, n_bits, s);
+			else if ((b[k].e - b[k].b) / (ptrdiff_t)es > 1) grs_insertsort(b[k].b, b[k].e, es, key);
+		}
+	}
+}
+static void grs_radix_sort(void *beg_, size_t n, size_t es, rs_key_f key, int key_bytes)
+{
+	char *beg = (char *)beg_, *end = beg + n * es;
+	if (n <= EC_RS_MIN) grs_insertsort(beg, end, es, key);
+	else grs_sort(beg, end, es, key, 8, key_bytes * 8 - 8);
+}
+static uint64_t key_u64(const void *p) { return *(const uint64_t *)p; }
+static uint64_t key_hev_site(const void *p) { return ((const hev_t *)p)->site; }
+static uint64_t key_hev_id(const void *p) { return ((const hev_t *)p)->overlapID; }
+
+typedef struct { hev_t *a; size_t n, m; } hevv_t;
+static void hev_push(hevv_t *v, const hev_t *e) { if (v->n == v->m) { v->m = v->m ? v->m << 1 : 256; v->a = (hev_t *)realloc(v->a, v->m * sizeof(hev_t)); } v->a[v->n++] = *e; }
+typedef struct { snp_t *a; size_t n, m; } snpv_t;
+static snp_t *snp_pushp(snpv_t *v) { if (v->n == v->m) { v->m = v->m ? v->m << 1 : 64; v->a = (snp_t *)realloc(v->a, v->m * sizeof(snp_t)); } return &v->a[v->n++]; }
+
+/* one accepted overlap as rphase_hc sees it */
+typedef struct { uint32_t y_id, rev, x_pos_s, x_pos_e, align_length; int64_t nh_err; const hao_wl_t *w; uint64_t wn; const uint16_t *c; uint8_t is_match; int8_t strong; } phov_t;
+
+/* extract_sub_cigar_hc (Correct.cpp:18541-18660) without its cursor bookkeeping: every query position of [s, e) the
+ * window's cigar covers with a match / mismatch column.  set_f: count mismatch columns into f[]; else emit evidence. */
+static void ph_walk(const hao_reads_t *r, const char *qstr, const phov_t *z, uint32_t ovid, const hao_wl_t *w, int64_t s, int64_t e, int set_f, uint8_t *f, hevv_t *hp)
+{
+	int64_t s0 = w->x_start, e0 = (int64_t)w->x_end + 1, xk = w->x_start, yk = w->y_start, ws, we, os, oe, t; uint32_t ci; int64_t s00 = s;
+	if (s < s0) s = s0;
+	if (e > e0) e = e0;
+	if (s >= e || !w->clen) return;
+	for (ci = 0; ci < w->clen && xk < e; ci++) {
+		uint32_t op = z->c[w->cidx + ci] >> 14, cl = z->c[w->cidx + ci] & 0x3fff;
+		ws = xk;
+		if (op != 2) xk += cl;
+		if (op != 3) yk += cl;
+		we = xk;
+		if (op != 0 && op != 1) continue;
+		os = s > ws ? s : ws; oe = e < we ? e : we;
+		if (oe <= os) continue;
+		for (t = os; t < oe; t++) {
+			uint8_t *ft = &f[t - s00];
+			if (set_f) { if (op == 1) *ft = (uint8_t)(*ft <= 126 ? *ft + 1 : 127); }
+			else if (*ft) {
+				hev_t ev; char yb;
+				ev.overlapID = ovid; ev.site = (uint32_t)t; ev.overlapSite = (uint32_t)(t - xk + yk); ev.cov = 1;
+				if (op == 0) { ev.misBase = qstr[t]; ev.type = 0; }
+				else { hao_decode_sub(r, z->y_id, t - xk + yk, 1, (int)z->rev, &yb); ev.misBase = yb; ev.type = 1; }
+				hev_push(hp, &ev);
+			}
+		}
+	}
+}
+
+static int nt6(char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; case 'N': case 'n': return 4; default: return 5; } } /* seq_nt6_table */
+
+static size_t ph_push_info(snpv_t *st, hev_t *a, size_t a_n, hev_t *u_a)
+{ /* push_info, Correct.cpp:10511-10600 (oa = NULL, v8 = NULL) */
+	uint64_t i, k, m, occ_0 = 0, occ_1[6] = { 0, 0, 0, 0, 0, 0 }, occ_2 = 0, diff = 0, rev_n; uint8_t ihpc = 0; snp_t *p;
+	grs_radix_sort(a, a_n, sizeof(hev_t), key_hev_id, 4);
+	for (k = 1, m = i = 0; k <= a_n; k++) {
+		if (k == a_n || a[k].overlapID != a[m].overlapID) {
+			a[i] = a[m];
+			if ((a[i].type & 1) == 0) { occ_0 += a[i].cov; if (!ihpc && ((a[i].type >> 1) & 1)) ihpc = 1; }
+			else { occ_1[nt6(a[i].misBase)] += a[i].cov; diff += a[i].cov; }
+			occ_2 += a[i].cov;
+			i++; m = k;
+		}
+	}
+	a_n = i;
+	if (occ_0 == 0 || diff <= 1) return 0;
+	rev_n = occ_2;
+	for (i = m = 0; i < 4; i++) {
+		if (occ_1[i] >= 2) {
+			p = snp_pushp(st);
+			p->id = (uint32_t)(st->n - 1); p->occ_0 = (uint32_t)(1 + occ_0); p->occ_1 = (uint32_t)occ_1[i]; p->occ_2 = (uint32_t)(occ_2 - p->occ_0 - p->occ_1);
+			p->site = a[0].site; p->score = -1; p->overlap_num = (uint32_t)rev_n; p->is_homopolymer = ihpc;
+			occ_1[i] = p->id; m++;
+		} else occ_1[i] = (uint64_t)-1;
+	}
+	occ_1[4] = occ_1[5] = (uint64_t)-1;
+	if (m == 0) return 0;
+	for (i = m = 0; i < a_n; i++) {
+		if ((a[i].type & 1) == 0) a[i].overlapSite = (uint32_t)(st->n - 1);
+		else if (occ_1[nt6(a[i].misBase)] != (uint64_t)-1) { a[i].cov = a[i].overlapSite; a[i].overlapSite = (uint32_t)occ_1[nt6(a[i].misBase)]; }
+		else continue;
+		u_a[m++] = a[i];
+	}
+	return m;
+}
+
+static void ph_naive_hifi(hevv_t *hap, snpv_t *st, phov_t *ol, double up, int s_hap_cov, int infor_cov)
+{ /* generate_haplotypes_naive_HiFi, Correct.cpp:8845-9110 (multi_check = 1, st_max = -1: is_st_bs is always false) */
+	if (hap->n == 0) return;
+	uint64_t k, l, i, o, *a, ii, m_snp = 0, m_list = 0, m_off, *srt = 0; size_t sn = 0, sm = 0; int64_t z; snp_t *s = 0, *t = 0;
+#define SRT_PUSH(x) do { if (sn == sm) { sm = sm ? sm << 1 : 64; srt = (uint64_t *)realloc(srt, sm * 8); } srt[sn++] = (x); } while (0)
+	for (k = 1, l = 0, i = 0; k <= st->n; ++k) { /* drop SNP sites adjacent to another SNP site */
+		if (k == st->n || st->a[k].site != st->a[l].site) {
+			if (l > 0 && st->a[l].site == st->a[l - 1].site + 1) { l = k; continue; }
+			if (k < st->n && st->a[l].site + 1 == st->a[k].site) { l = k; continue; }
+			for (; i < hap->n && hap->a[i].site != st->a[l].site; i++);
+			m_off = l - m_snp;
+			for (; i < hap->n && hap->a[i].site == st->a[l].site; i++) { hap->a[m_list] = hap->a[i]; hap->a[m_list++].overlapSite -= (uint32_t)m_off; }
+			for (; l < k; l++) st->a[m_snp++] = st->a[l];
+		}
+	}
+	st->n = m_snp; hap->n = m_list;
+	if (st->n == 0 || hap->n == 0) { free(srt); return; }
+	grs_radix_sort(hap->a, hap->n, sizeof(hev_t), key_hev_id, 4);
+#define REAL(s_) (!((s_)->occ_0 < 2 || (s_)->occ_1 < 2))
+	for (k = 1, l = 0; k <= hap->n; ++k) {
+		if (k == hap->n || hap->a[k].overlapID != hap->a[l].overlapID) {
+			for (i = l, o = 0; i < k; i++) {
+				if ((hap->a[i].type & 1) != 1) continue;
+				s = &st->a[hap->a[i].overlapSite];
+				if (!REAL(s)) continue;
+				if ((int)s->occ_0 >= s_hap_cov && (int)s->occ_1 >= infor_cov) o++;
+			}
+			if (o > 0) { o = ((uint32_t)-1) - o; o <<= 32; o += l; SRT_PUSH(o); }
+			l = k;
+		}
+	}
+	if (sn > 0) {
+		grs_radix_sort(srt, sn, 8, key_u64, 8);
+		for (k = 0; k < sn; k++) {
+			o = 0; l = (uint32_t)srt[k];
+			for (i = l; i < hap->n && hap->a[i].overlapID == hap->a[l].overlapID; i++) {
+				if ((hap->a[i].type & 1) != 1) continue;
+				s = &st->a[hap->a[i].overlapSite];
+				if (!REAL(s)) continue;
+				if ((int)s->occ_0 >= s_hap_cov && (int)s->occ_1 >= infor_cov) o++;
+			}
+			if (o == 0) continue;
+			ii = hap->a[l].overlapID;
+			if (ol[ii].is_match == 1) ol[ii].is_match = 2;
+			for (i = l; i < hap->n && hap->a[i].overlapID == hap->a[l].overlapID; i++) {
+				if ((hap->a[i].type & 1) == 1) { s = &st->a[hap->a[i].overlapSite]; s->score = 1; }
+				else {
+					s = &st->a[hap->a[i].overlapSite];
+					for (z = hap->a[i].overlapSite; z >= 0; z--) { t = &st->a[z]; if (s->site != t->site) break; t->occ_0 -= hap->a[i].cov; }
+				}
+			}
+		}
+		for (k = 0; k < sn; k++) {
+			o = 0; l = (uint32_t)srt[k];
+			for (i = l; i < hap->n && hap->a[i].overlapID == hap->a[l].overlapID; i++) {
+				if ((hap->a[i].type & 1) != 1) continue;
+				s = &st->a[hap->a[i].overlapSite];
+				if (!REAL(s)) continue;
+				if (s->score == 1) o++;
+			}
+			ii = hap->a[l].overlapID;
+			if (ol[ii].is_match == 1 && o > 0) ol[ii].is_match = 2;
+		}
+		for (k = 1, l = 0; k <= hap->n; ++k) {
+			if (k == hap->n || hap->a[k].overlapID != hap->a[l].overlapID) {
+				ii = hap->a[l].overlapID;
+				if (ol[ii].is_match == 1) for (i = l; i < k; i++) if ((hap->a[i].type & 1) == 1) st->a[hap->a[i].overlapSite].score = -1;
+				l = k;
+			}
+		}
+	}
+	/* multi_check */
+	sn = 0;
+	for (k = 1, l = 0; k <= hap->n; ++k) {
+		if (k == hap->n || hap->a[k].overlapID != hap->a[l].overlapID) {
+			if (ol[hap->a[l].overlapID].is_match == 2) { l = k; continue; }
+			for (i = l, o = 0; i < k; i++) {
+				if ((hap->a[i].type & 1) != 1) continue;
+				s = &st->a[hap->a[i].overlapSite];
+				if (!REAL(s)) continue;
+				if ((int)s->occ_0 >= s_hap_cov && (int)s->occ_1 >= infor_cov) continue;
+				if (s->score == 1) continue;
+				o++; SRT_PUSH(hap->a[i].overlapSite);
+			}
+			sn -= o;
+			if ((double)o >= (double)ol[hap->a[l].overlapID].align_length * up) {
+				grs_radix_sort(srt + sn, o, 8, key_u64, 8);
+				a = srt + sn;
+				for (i = z = 0; i < o; i++) { /* s / t keep their last values across overlaps, like the reference's locals */
+					if (i > 0) s = &st->a[a[i - 1]];
+					if (i + 1 < o) t = &st->a[a[i + 1]];
+					if (s && s->site + 32 > st->a[a[i]].site) continue;
+					if (t && st->a[a[i]].site + 32 > t->site) continue;
+					a[z] = a[i]; z++;
+				}
+				if (z >= 2) sn += (size_t)z;
+			}
+			l = k;
+		}
+	}
+	if (sn > 0) {
+		grs_radix_sort(srt, sn, 8, key_u64, 8);
+		for (k = 1, l = 0; k <= sn; ++k) {
+			if (k == sn || srt[k] != srt[l]) { if (k - l >= 2) st->a[srt[l]].score = 1; }
+			l = k;
+		}
+	}
+	for (k = 1, l = 0; k <= hap->n; ++k) {
+		if (k == hap->n || hap->a[k].overlapID != hap->a[l].overlapID) {
+			ii = hap->a[l].overlapID;
+			if (ol[ii].is_match == 2) ol[ii].strong = 1;
+			else if (ol[ii].is_match == 1) {
+				for (i = l; i < k; i++) {
+					s = &st->a[hap->a[i].overlapSite];
+					if (s->score == 1 && REAL(s)) { ol[ii].strong = 1; if ((hap->a[i].type & 1) == 1) { ol[ii].is_match = 2; break; } }
+				}
+			}
+			l = k;
+		}
+	}
+#undef REAL
+#undef SRT_PUSH
+	free(srt);
+}
+
+/* rphase_hc for one read.  ov[] = the accepted overlaps in list order (overlapID = index); on return is_match / strong are set. */
+static void ph_rphase(const hao_reads_t *r, uint32_t rid, phov_t *ov, uint32_t n_ov)
+{
+	int64_t ql = (int64_t)r->len[rid], s, e, k, i, t, srt_n, rr = 0, wl = EC_PH_WIN; uint32_t j, w; uint8_t flag[EC_PH_WIN];
+	char *qstr = MALLOC_N(char, ql + 1); hevv_t hp; snpv_t st; uint64_t *idx = 0, ni = 0, mi = 0, m, rm_n; uint32_t nn_snp = 0;
+	struct cw { uint32_t ov, w; } *cidx = 0; uint64_t nc = 0, mc = 0;
+	memset(&hp, 0, sizeof(hp)); memset(&st, 0, sizeof(st)); memset(flag, 0, sizeof(flag));
+	hao_decode(r, rid, qstr);
+#define IDX_PUSH(x) do { if (ni == mi) { mi = mi ? mi << 1 : 256; idx = (uint64_t *)realloc(idx, mi * 8); } idx[ni++] = (x); } while (0)
+	for (j = 0; j < n_ov; j++)
+		for (w = 0; w < ov[j].wn; w++) {
+			const hao_wl_t *u = &ov[j].w[w];
+			if (u->error == INT16_MAX && u->clen == 0 && u->extra_end < 0) continue;
+			if (u->x_end >= u->x_start) {
+				if (nc == mc) { mc = mc ? mc << 1 : 256; cidx = (struct cw *)realloc(cidx, mc * sizeof(*cidx)); }
+				IDX_PUSH(((uint64_t)u->x_start << 32) + nc);
+				cidx[nc].ov = j; cidx[nc].w = w; nc++;
+			}
+		}
+	srt_n = (int64_t)ni;
+	grs_radix_sort(idx, ni, 8, key_u64, 8);
+	for (k = 1, i = 0; k <= srt_n; k++) {
+		if (k == srt_n || (idx[k] >> 32) != (idx[i] >> 32)) {
+			if (k - i > 1) {
+				for (t = i; t < k; t++) { const struct cw *cp = &cidx[(uint32_t)idx[t]]; m = (uint64_t)(ov[cp->ov].w[cp->w].x_end + 1); m <<= 32; m += (uint32_t)idx[t]; idx[t] = m; }
+				grs_radix_sort(idx + i, (size_t)(k - i), 8, key_u64, 8);
+			}
+			i = k;
+		}
+	}
+	i = 0; s = 0; e = wl; e = e <= ql ? e : ql;
+	for (; s < ql;) {
+		size_t l0; int64_t wi, wl0; uint64_t si = (uint64_t)-1, ei = 0; int fi = 0;
+		if (rr) {
+			for (m = rm_n = (uint64_t)srt_n; m < ni; m++) {
+				const struct cw *cp = &cidx[idx[m]]; int64_t q0 = ov[cp->ov].w[cp->w].x_start, q1 = (int64_t)ov[cp->ov].w[cp->w].x_end + 1, os = q0 > s ? q0 : s, oe = q1 < e ? q1 : e;
+				if (oe > os) idx[rm_n++] = idx[m];
+			}
+			ni = rm_n;
+		}
+		for (; i < srt_n; ++i) {
+			const struct cw *cp = &cidx[(uint32_t)idx[i]]; int64_t q0 = ov[cp->ov].w[cp->w].x_start, q1 = (int64_t)ov[cp->ov].w[cp->w].x_end + 1, os, oe;
+			if (q0 >= e) break;
+			os = q0 > s ? q0 : s; oe = q1 < e ? q1 : e;
+			if (oe > os) IDX_PUSH((uint32_t)idx[i]);
+		}
+		l0 = hp.n; rr = 0;
+		for (m = (uint64_t)srt_n; m < ni; m++) { /* hc_phase_robust_rr(set_f = 1), Correct.cpp:19065-19079 */
+			const struct cw *cp = &cidx[idx[m]]; const hao_wl_t *u = &ov[cp->ov].w[cp->w];
+			if ((int64_t)u->x_end + 1 <= e) rr = 1;
+			ph_walk(r, qstr, &ov[cp->ov], cp->ov, u, s, e, 1, flag, &hp);
+		}
+		for (wi = 0, wl0 = e - s; wi < wl0; wi++) {
+			if (flag[wi] > 0) {
+				if (flag[wi] > 1) { fi = 1; nn_snp++; flag[wi] = 1; ei = (uint64_t)wi + 1; if (si == (uint64_t)-1) si = (uint64_t)wi; }
+				else flag[wi] = 0;
+			}
+		}
+		if (fi) {
+			rr = 0;
+			for (m = (uint64_t)srt_n; m < ni; m++) {
+				const struct cw *cp = &cidx[idx[m]]; const hao_wl_t *u = &ov[cp->ov].w[cp->w];
+				if ((int64_t)u->x_end + 1 <= e) rr = 1;
+				ph_walk(r, qstr, &ov[cp->ov], cp->ov, u, s, e, 0, flag, &hp);
+			}
+			if (hp.n > l0) grs_radix_sort(hp.a + l0, hp.n - l0, sizeof(hev_t), key_hev_site, 4);
+		}
+		if (ei > si) memset(flag + si, 0, (size_t)(ei - si));
+		s += wl; e += wl; e = e <= ql ? e : ql;
+	}
+	(void)nn_snp;
+	{
+		size_t n = hp.n, tt = 0, ii = 0, kk;
+		for (kk = 1; kk <= n; ++kk) if (kk == n || hp.a[kk].site != hp.a[ii].site) { tt += ph_push_info(&st, hp.a + ii, kk - ii, hp.a + tt); ii = kk; }
+		hp.n = tt;
+	}
+	ph_naive_hifi(&hp, &st, ov, 0.04, 3, 3); /* asm_opt.s_hap_cov = infor_cov = 3, CommandLines.cpp:333-334 */
+#undef IDX_PUSH
+	free(qstr); free(hp.a); free(st.a); free(idx); free(cidx);
+}
+
+typedef struct { uint32_t y_id, rev, x_pos_s, x_pos_e, y_pos_s, y_pos_e, nh_err, is_match; int32_t strong; } hao_phase_t;
+
+/* worker_hap_ec steps 5-6 (ecovlp.cpp:3299-3306) for one read: rphase_hc over the accepted overlaps (steps A-C output), then
+ * dedup_chains.  out = accepted overlaps after rphase_hc in list order; dd = the list dedup_chains leaves. */
+int hao_ec_phase(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint32_t n_ch, const hao_alnA_t *a, const hao_alnC_t *c, const hao_wl_t *wl, const uint16_t *cig,
+                 hao_phase_t **out, uint32_t *n_out, hao_phase_t **dd, uint32_t *n_dd)
+{
+	uint32_t j, n = 0, k, l, mm; phov_t *ov = MALLOC_N(phov_t, n_ch); hao_phase_t *o = MALLOC_N(hao_phase_t, n_ch), *d = MALLOC_N(hao_phase_t, n_ch);
+	for (j = 0; j < n_ch; j++) {
+		if (a[j].st != 2) continue;
+		ov[n].y_id = ch[j].y_id; ov[n].rev = ch[j].y_pos_strand; ov[n].x_pos_s = c[j].x_pos_s; ov[n].x_pos_e = c[j].x_pos_e; ov[n].align_length = a[j].align_length; ov[n].nh_err = c[j].nh_err;
+		ov[n].w = wl + c[j].w_off; ov[n].wn = c[j].w_n; ov[n].c = cig + c[j].c_off; ov[n].is_match = 1; ov[n].strong = 0;
+		o[n].y_id = ch[j].y_id; o[n].rev = ch[j].y_pos_strand; o[n].x_pos_s = c[j].x_pos_s; o[n].x_pos_e = c[j].x_pos_e; o[n].y_pos_s = c[j].y_pos_s; o[n].y_pos_e = c[j].y_pos_e; o[n].nh_err = (uint32_t)c[j].nh_err;
+		n++;
+	}
+	ph_rphase(r, rid, ov, n);
+	for (j = 0; j < n; j++) { o[j].is_match = ov[j].is_match; o[j].strong = ov[j].strong; d[j] = o[j]; }
+	*out = o; *n_out = n;
+	/* dedup_chains, ecovlp.cpp:2984-3030: sort by y_id (klib radix sort on the records), keep the best chain of every target */
+	mm = n;
+	if (n > 1) {
+		hao_ovlp_t *tmp = CALLOC_N(hao_ovlp_t, n); hao_phase_t *d2 = MALLOC_N(hao_phase_t, n);
+		for (j = 0; j < n; j++) { tmp[j].y_id = d[j].y_id; tmp[j].x_pos_s = j; } /* carry the index through the reference's unstable sort */
+		ov_sort_y_id(tmp, n);
+		for (j = 0; j < n; j++) d2[j] = d[tmp[j].x_pos_s];
+		memcpy(d, d2, n * sizeof(hao_phase_t)); free(tmp); free(d2);
+		for (k = 1, l = mm = 0; k <= n; k++) {
+			if (k == n || d[k].y_id != d[l].y_id) {
+				uint32_t mm_k = l, s, mm_m;
+				if (k - l > 1) {
+					int64_t mm_sc = INT32_MIN, sc;
+					for (s = l, mm_k = (uint32_t)-1, mm_m = 3; s < k; s++) {
+						int sf = 0;
+						sc = ((int64_t)d[s].x_pos_e + 1 - d[s].x_pos_s) - (int64_t)d[s].nh_err * 12;
+						if (d[s].is_match < mm_m) sf = 1;
+						else if (d[s].is_match == mm_m) {
+							if (sc > mm_sc) sf = 1;
+							else if (sc == mm_sc && (d[s].x_pos_e + 1 - d[s].x_pos_s) > (d[mm_k].x_pos_e + 1 - d[mm_k].x_pos_s)) sf = 1;
+						}
+						if (sf) { mm_sc = sc; mm_k = s; mm_m = d[s].is_match; }
+					}
+				}
+				if (mm_k != (uint32_t)-1) { if (mm_k != mm) { hao_phase_t t = d[mm_k]; d[mm_k] = d[mm]; d[mm] = t; } mm++; }
+				l = k;
+			}
+		}
+	}
+	*dd = d; *n_dd = mm;
+	free(ov);
+	return 0;
+}

@@ -210,3 +210,19 @@ def ec_align_C(store: Store, rid, chains, A, B, WB, CB):
                               C.c_void_p(WB.ctypes.data), C.c_void_p(CB.ctypes.data), C.byref(out), C.byref(wl), C.byref(nw), C.byref(cg), C.byref(nc))
     assert rc == 0
     return _take(out, chains.size, ALN_C), _take(wl, nw.value, WL), _take(cg, nc.value, np.dtype("<u2"))
+
+
+PHASE = np.dtype([("y_id", "<u4"), ("rev", "<u4"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"), ("nh_err", "<u4"),
+                  ("is_match", "<u4"), ("strong", "<i4")])
+
+
+def ec_phase(store: Store, rid, chains, A, Cc, WC, CC):
+    """rphase_hc + dedup_chains over the accepted overlaps -> (PHASE after phasing, PHASE after dedup)"""
+    chains = np.ascontiguousarray(chains); A = np.ascontiguousarray(A); Cc = np.ascontiguousarray(Cc)
+    WC = np.ascontiguousarray(WC if WC.size else np.zeros(1, WL)); CC = np.ascontiguousarray(CC if CC.size else np.zeros(1, np.uint16))
+    o = C.c_void_p(); d = C.c_void_p(); no = C.c_uint32(); nd = C.c_uint32()
+    rc = lib().hao_ec_phase(C.byref(store.c), C.c_uint32(rid), C.c_void_p(chains.ctypes.data), C.c_uint32(chains.size), C.c_void_p(A.ctypes.data), C.c_void_p(Cc.ctypes.data),
+                            C.c_void_p(WC.ctypes.data), C.c_void_p(CC.ctypes.data), C.byref(o), C.byref(no), C.byref(d), C.byref(nd))
+    assert rc == 0
+    a = _take(o, max(no.value, 1), PHASE)[:no.value]; b = _take(d, max(nd.value, 1), PHASE)[:nd.value]
+    return a, b

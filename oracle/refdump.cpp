@@ -52,6 +52,7 @@ double gen_extend_err_exz(overlap_region *z, const ul_idx_t *uref, hpc_t *hpc_g,
 uint64_t gen_hc_fast_cigar(overlap_region *z, Candidates_list *cl, All_reads *rref, int64_t wl, char *qstr, UC_Read *tu, bit_extz_t *exz, overlap_region *aux_o, double e_rate, int64_t ql, int64_t rid, int64_t khit, int64_t *re); // Correct.cpp:25137
 void reassign_gaps(overlap_region *z, overlap_region *aux_o, char *qstr, int64_t ql, char *tstr, int64_t tl, All_reads *rref, UC_Read *tu, asg16_v *buf); // Correct.cpp:25409
 overlap_region *fetch_aux_ovlp(overlap_region_alloc *ol); // ecovlp.cpp:257
+void dedup_chains(overlap_region_alloc *ol); // ecovlp.cpp:2984
 
 #define HA_KMER_GOOD_RATIO 0.333 /* ecovlp.cpp:9 */
 #define COV_W 3072               /* ecovlp.cpp:17 */
@@ -90,7 +91,8 @@ static void dump_stages(const char *pfx, double bw_thres)
 	uint32_t low_occ = asm_opt.hom_cov * HA_KMER_GOOD_RATIO;
 	FILE *fmz = xopen(pfx, ".mz.bin"), *fidx = xopen(pfx, ".idx.bin"), *fan = xopen(pfx, ".anchors.bin");
 	FILE *fch = xopen(pfx, ".chains.bin"), *fpa = xopen(pfx, ".params.txt"), *fwn = xopen(pfx, ".windows.bin");
-	FILE *fal = xopen(pfx, ".aln.bin"); asg16_v v16; memset(&v16, 0, sizeof(v16));
+	FILE *fal = xopen(pfx, ".aln.bin"), *fph = xopen(pfx, ".phase.bin"); asg16_v v16; memset(&v16, 0, sizeof(v16));
+	haplotype_evdience_alloc hap; InitHaplotypeEvdience(&hap); kv_ul_ov_t pidx; memset(&pidx, 0, sizeof(pidx)); asg64_v v64, buf0; memset(&v64, 0, sizeof(v64)); memset(&buf0, 0, sizeof(buf0));
 	UC_Read tr; init_UC_Read(&tr); bit_extz_t exz; init_bit_extz_t(&exz, 31);
 	const double e_rate = asm_opt.max_ov_diff_ec; const int64_t w_l = asm_opt.is_ont ? WINDOW_OHC : WINDOW_HC; // ecovlp.cpp:3288
 	UC_Read ur; init_UC_Read(&ur);
@@ -181,6 +183,7 @@ static void dump_stages(const char *pfx, double bw_thres)
 			const double err = e_rate, e_max = err * 1.5; const int64_t ql = ur.length;
 			resize_UC_Read(&tr, ((w_l + (THRESHOLD_MAX_SIZE << 1) + 1) << 1) + 8);
 			fwrite(&nc, 4, 1, fal);
+			uint64_t kacc = 0; // gen_hc_r_alin keeps the accepted overlaps at the front of the list, in order (Correct.cpp:25665-25671)
 			for (j = 0; j < nc; j++) {
 				overlap_region *z = &ol.list[j]; int64_t re = INT64_MAX; double rr = DBL_MAX;
 				z->shared_seed = z->non_homopolymer_errors;
@@ -189,17 +192,35 @@ static void dump_stages(const char *pfx, double bw_thres)
 				int32_t st = !ok ? 0 : (rr > err ? 1 : 2); uint32_t al = z->align_length;
 				fwrite(&st, 4, 1, fal); fwrite(&al, 4, 1, fal); fwrite(&rr, 8, 1, fal); fwrite(&re, 8, 1, fal);
 				dump_wl(fal, z);
+				z->is_match = 0;
 				if (st != 2) continue;
-				z->is_match = 0; z->non_homopolymer_errors = re;
+				z->non_homopolymer_errors = re;
 				gen_hc_fast_cigar(z, &cl, &R_INF, w_l, ur.seq, &tr, &exz, aux_o, e_rate, ql, i, 31 /* E_KHIT, ecovlp.cpp */, &re);
 				fwrite(&re, 8, 1, fal); dump_wl(fal, z);
 				reassign_gaps(z, aux_o, ur.seq, ql, NULL, -1, &R_INF, &tr, &v16);
 				dump_wl(fal, z);
 				{ int64_t nhe = z->non_homopolymer_errors; uint32_t xy[4] = { z->x_pos_s, z->x_pos_e, z->y_pos_s, z->y_pos_e }; fwrite(&nhe, 8, 1, fal); fwrite(xy, 4, 4, fal); }
+				if (kacc != j) { overlap_region t = ol.list[kacc]; ol.list[kacc] = ol.list[j]; ol.list[j] = t; }
+				z = &ol.list[kacc++]; z->is_match = 1; z->strong = z->without_large_indel = 0;
+			}
+			// (7) phasing and de-duplication of the accepted overlaps, as worker_hap_ec does next (ecovlp.cpp:3299-3306):
+			// rphase_hc (Correct.cpp:20191) marks overlaps that carry informative minor alleles is_match = 2; dedup_chains
+			// (ecovlp.cpp:2984) keeps the best chain per target.  Dumped per overlap, in list order:
+			// {y_id, strand, x_pos_s, x_pos_e, y_pos_s, y_pos_e, non_homopolymer_errors, is_match, strong}
+			ol.length = kacc; ol.mapped_overlaps_length = 0;
+			rphase_hc(&ol, &R_INF, &hap, &ur, &tr, &pidx, &v64, &buf0, 0, WINDOW_MAX_SIZE, ur.length, 1, i, 0, 0, NULL, NULL, NULL, 0);
+			for (int rep = 0; rep < 2; rep++) {
+				uint32_t n = ol.length; fwrite(&n, 4, 1, fph);
+				for (j = 0; j < ol.length; j++) {
+					overlap_region *z = &ol.list[j];
+					uint32_t r9[9] = { z->y_id, z->y_pos_strand, z->x_pos_s, z->x_pos_e, z->y_pos_s, z->y_pos_e, z->non_homopolymer_errors, z->is_match, (uint32_t)(int32_t)z->strong };
+					fwrite(r9, 4, 9, fph);
+				}
+				if (rep == 0) dedup_chains(&ol);
 			}
 		}
 	}
-	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch); fclose(fwn); fclose(fal);
+	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch); fclose(fwn); fclose(fal); fclose(fph);
 	destory_UC_Read(&ur);
 }
 

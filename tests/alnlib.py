@@ -72,3 +72,18 @@ def digest_B(ovl):
 def digest_C(ovl):
     """per-read digest of step C: ovl = iterable of (non_homopolymer_errors, (x_pos_s, x_pos_e, y_pos_s, y_pos_e), w, c)"""
     return _dg(struct.pack("<q4I", int(nhe), *[int(v) for v in xy]) + wl_canon(w, c, True) for nhe, xy, w, c in ovl)
+
+
+PH = np.dtype([(f, "<u4") for f in ("y_id", "rev", "x_pos_s", "x_pos_e", "y_pos_s", "y_pos_e", "nh_err", "is_match", "strong")])
+
+
+def read_phase(path):
+    """refdump's <pfx>.phase.bin: per read (accepted overlaps after rphase_hc, the list after dedup_chains)"""
+    buf = open(path, "rb").read(); o = 0; out = []
+    while o < len(buf):
+        pair = []
+        for _ in range(2):
+            n, = struct.unpack_from("<I", buf, o); o += 4
+            pair.append(np.frombuffer(buf, dtype=PH, count=n, offset=o)); o += 36 * n
+        out.append(tuple(pair))
+    return out

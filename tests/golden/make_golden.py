@@ -100,6 +100,14 @@ def read_stages(pfx, n_reads, keep=4):
         out["alnB"][i] = alnlib.digest_B((d["reB"], d["B"][0], d["B"][1]) for d in acc)
         out["alnC"][i] = alnlib.digest_C((d["nheC"], d["xyC"], d["C"][0], d["C"][1]) for d in acc)
         cnt["aln_ok"][i] = len(acc)
+    # phasing + de-duplication (refdump step 7): digest of the per-overlap records after rphase_hc and after dedup_chains
+    ph = alnlib.read_phase(pfx + ".phase.bin")
+    assert len(ph) == n_reads
+    out["phase"] = np.zeros(n_reads, dtype=np.uint64); out["dedup"] = np.zeros(n_reads, dtype=np.uint64)
+    cnt["phase_hap2"] = np.zeros(n_reads, dtype=np.uint64); cnt["dedup"] = np.zeros(n_reads, dtype=np.uint64)
+    for i, (a, b) in enumerate(ph):
+        out["phase"][i] = dg(np.ascontiguousarray(a).tobytes()); out["dedup"][i] = dg(np.ascontiguousarray(b).tobytes())
+        cnt["phase_hap2"][i] = int((a["is_match"] == 2).sum()); cnt["dedup"][i] = b.size
     return out, cnt, full
 
 

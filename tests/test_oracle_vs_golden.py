@@ -67,6 +67,13 @@ def _stages(g, mode, st, ft, opt, bw):
             dc = alnlib.digest_C((c["nh_err"], (c["x_pos_s"], c["x_pos_e"], c["y_pos_s"], c["y_pos_e"]), WC[int(c["w_off"]):int(c["w_off"] + c["w_n"])],
                                   CC[int(c["c_off"]):int(c["c_off"] + c["c_n"])]) for c, a in zip(Cc, A) if a["st"] == 2)
             assert dc == int(g.digest(mode, "alnC")[i]), "EC alignment step C, read %d" % i
+            # phasing (row a13) + dedup_chains: per-overlap is_match / strong, then the best chain per target
+            P, D = ho.ec_phase(st, i, ch, A, Cc, WC, CC)
+            pa = np.zeros(P.size, alnlib.PH); da = np.zeros(D.size, alnlib.PH)
+            for f in alnlib.PH.names:
+                pa[f] = P[f].astype(np.int64).astype(np.uint32); da[f] = D[f].astype(np.int64).astype(np.uint32)
+            assert dg(pa.tobytes()) == int(g.digest(mode, "phase")[i]), "rphase_hc, read %d" % i
+            assert dg(da.tobytes()) == int(g.digest(mode, "dedup")[i]), "dedup_chains, read %d" % i
         else:
             n_rechain[0] += 1
     return pt, hom, het
