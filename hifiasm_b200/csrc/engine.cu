@@ -735,30 +735,83 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					if ((rc = hb_scan_u32_to_u64(ctx, d_cap, d_wboff, n_ov))) return rc;
 					uint64_t wb_tot = 0; HB_CUDA(cudaMemcpyAsync(&wb_tot, d_wboff + n_ov, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 					hb_wl_t *d_wlb = ba.zero<hb_wl_t>(wb_tot + 1); HB_ALLOC_CHECK(ba);
-					static const uint64_t path_words0 = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384;
-					uint64_t poolb_cap = (uint64_t)(h_aoff[b1] - h_aoff[b0]) / 8 + 16 * n_ov + 65536, poolb_used = 0; uint16_t *d_poolb = 0; unsigned int n_def = 0;
+					static const uint64_t path_words1 = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384;
+					static const int32_t merge_cw0 = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
+					EcPrep *d_prep = ba.get<EcPrep>(n_ov + 1); uint32_t *d_nseg = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_segoff = ba.get<uint64_t>(n_ov + 2);
+					uint32_t *d_qn = ba.zero<uint32_t>(4); unsigned long long *d_spused = ba.zero<unsigned long long>(1);
+					HB_ALLOC_CHECK(ba);
+					EcCigArgs G; memset(&G, 0, sizeof(G));
+					G.R = R; G.r0 = r0 + b0; G.n_ov = n_ov; G.desc = d_od; G.ch = d_ch; G.fc = d_fc; G.fc_grp_base = d_fcb; G.aln = d_aln; G.wlA = d_wl;
+					G.chits = d_chits; G.ghits = d_hits; G.dp_half = B + 1; G.dp_t = d_dpt; G.dp_p = d_dpp; G.dp_f = d_dpf; G.e_rate = so->e_rate; G.w_l = w_l; G.gaps = so->gaps;
+					G.prep = d_prep; G.nseg = d_nseg; G.seg_off = d_segoff; G.out = d_alnb; G.wl = d_wlb; G.wl_off = d_wboff; G.n_deferred = d_ndef; G.err = d_err;
+					{
+						ProfScope ps(ctx, "k_ecb_prep");
+						if (n_ov) k_ecb_prep<<<nblk(n_ov, 128), 128, 0, ctx->stream>>>(G);
+					}
+					HB_CUDA(cudaGetLastError());
+					if ((rc = hb_scan_u32_to_u64(ctx, d_nseg, d_segoff, n_ov))) return rc;
+					uint64_t n_seg = 0; HB_CUDA(cudaMemcpyAsync(&n_seg, d_segoff + n_ov, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+					if (n_seg >= (1ull << 32)) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: >= 2^32 segments in one batch"); return HB_E_OVERFLOW; }
+					ctx->counters[11] += n_seg;
+					EcSeg *d_segs = ba.get<EcSeg>(n_seg + 1); uint32_t *d_q1 = ba.get<uint32_t>(n_seg + 1), *d_q2 = ba.get<uint32_t>(n_seg + 1);
+					HB_ALLOC_CHECK(ba);
+					G.n_seg = n_seg; G.segs = d_segs;
+					// ---- segments: tier 0 (private scratch) -> queue -> tier 1 (16 K trace words) -> queue -> tier 2 (the largest alignment the reference allows)
+					uint64_t spool_cap = n_seg / 2 + 65536, spool_used = 0; uint16_t *d_spool = 0; uint32_t h_q[4] = { 0, 0, 0, 0 };
 					for (int attempt = 0;; attempt++) {
-						Arena pa(ctx); // scratch of this attempt
+						d_spool = ba.get<uint16_t>(spool_cap); HB_ALLOC_CHECK(ba);
+						HB_CUDA(cudaMemsetAsync(d_spused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_qn, 0, 16, ctx->stream));
+						G.spool = d_spool; G.spool_used = d_spused; G.spool_cap = spool_cap;
+						G.q_in = 0; G.q_in_n = 0; G.q_out = d_q1; G.q_out_n = d_qn + 1;
+						{
+							ProfScope ps(ctx, "k_ecb_seg");
+							if (n_seg) k_ecb_seg<true><<<nblk(n_seg, 128), 128, 0, ctx->stream>>>(G);
+						}
+						HB_CUDA(cudaGetLastError());
+						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 16, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						for (int tier = 1; tier <= 2 && h_q[tier]; tier++) {
+							Arena sa(ctx);
+							const uint64_t pw = tier == 1 ? path_words1 : (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5; const int32_t cw = tier == 1 ? 4096 : 65535;
+							const unsigned bl = tier == 1 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)h_q[tier] + 127) / 128, (uint64_t)ctx->sm_count)) : 2u; const uint64_t nt = (uint64_t)bl * 128;
+							G.path = sa.get<uint64_t>(nt * pw); G.path_words = pw; G.vec = sa.get<uint64_t>(nt * 11 * HB_MW_MAXW); G.vstride = HB_MW_MAXW; G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)cw); G.cig_words = cw;
+							if (sa.failed) return HB_E_WS;
+							G.q_in = tier == 1 ? d_q1 : d_q2; G.q_in_n = d_qn + tier; G.q_out = tier == 1 ? d_q2 : 0; G.q_out_n = d_qn + tier + 1;
+							{
+								ProfScope ps(ctx, tier == 1 ? "k_ecb_seg_tier1" : "k_ecb_seg_tier2");
+								k_ecb_seg<false><<<bl, 128, 0, ctx->stream>>>(G);
+							}
+							HB_CUDA(cudaGetLastError());
+							HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 16, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						}
+						HB_CUDA(cudaMemcpyAsync(&spool_used, d_spused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+						HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "EC base alignment: fake-cigar lookup failed"); return HB_E_STATE; }
+						if (spool_used <= spool_cap && spool_used < (1ull << 32)) break;
+						if (attempt >= 2 || spool_used >= (1ull << 32)) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: segment cigar pool"); return HB_E_OVERFLOW; }
+						spool_cap = spool_used + 65536; // the need is known now; the segments are recomputed (the chains stay refined)
+					}
+					ctx->counters[10] += h_q[2]; // segments that needed the largest scratch tier
+					// ---- merge
+					uint64_t poolb_cap = n_seg / 4 + 16 * n_ov + 65536, poolb_used = 0; uint16_t *d_poolb = 0; unsigned int n_def = 0;
+					for (int attempt = 0;; attempt++) {
+						Arena pa(ctx);
 						d_poolb = pa.get<uint16_t>(poolb_cap);
 						HB_CUDA(cudaMemsetAsync(d_pused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_ndef, 0, 4, ctx->stream));
+						G.pool = d_poolb; G.pool_used = d_pused; G.pool_cap = poolb_cap;
 						for (int pass = 0; pass < 2; pass++) {
 							if (pass == 1 && !n_def) break;
-							const unsigned bl = pass == 0 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 2)) : 4u;
-							const uint64_t nt = (uint64_t)bl * 64, pw = pass == 0 ? path_words0 : (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5; const int32_t cw = pass == 0 ? 4096 : 65536;
+							const unsigned bl = pass == 0 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 8)) : 4u;
+							const uint64_t nt = (uint64_t)bl * 64; const int32_t cw = pass == 0 ? merge_cw0 : (1 << 20);
 							Arena sa(ctx);
-							EcCigArgs G; G.R = R; G.r0 = r0 + b0; G.n_ov = n_ov; G.desc = d_od; G.ch = d_ch; G.fc = d_fc; G.fc_grp_base = d_fcb; G.aln = d_aln; G.wlA = d_wl;
-							G.chits = d_chits; G.ghits = d_hits; G.dp_half = B + 1; G.dp_t = d_dpt; G.dp_p = d_dpp; G.dp_f = d_dpf; G.e_rate = so->e_rate; G.w_l = w_l; G.pass = pass; G.refined = attempt > 0; G.gaps = so->gaps;
-							G.out = d_alnb; G.wl = d_wlb; G.wl_off = d_wboff; G.path = sa.get<uint64_t>(nt * pw); G.path_words = pw; G.vec = sa.get<uint64_t>(nt * 11 * HB_MW_MAXW);
-							G.cig_tmp = sa.get<uint16_t>(nt * 2 * (uint64_t)cw); G.cig_words = cw; G.pool = d_poolb; G.pool_used = d_pused; G.pool_cap = poolb_cap; G.n_deferred = d_ndef; G.err = d_err;
+							G.cig_tmp = sa.get<uint16_t>(nt * 3 * (uint64_t)cw); G.cig_words = cw; G.pass = pass;
 							if (sa.failed || pa.failed) return HB_E_WS;
 							if (pass == 1) HB_CUDA(cudaMemsetAsync(d_ndef, 0, 4, ctx->stream));
 							{
-								ProfScope ps(ctx, pass == 0 ? "k_ec_cigar" : "k_ec_cigar_deferred");
-								if (n_ov) k_ec_cigar<<<bl, 64, 0, ctx->stream>>>(G);
+								ProfScope ps(ctx, pass == 0 ? "k_ecb_merge" : "k_ecb_merge_deferred");
+								if (n_ov) k_ecb_merge<<<bl, 64, 0, ctx->stream>>>(G);
 							}
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(&n_def, d_ndef, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-							if (pass == 0) ctx->counters[10] += n_def;
 							if (pass == 1 && n_def) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: %u overlaps exceed the largest scratch", n_def); return HB_E_OVERFLOW; }
 						}
 						HB_CUDA(cudaMemcpyAsync(&poolb_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -787,7 +840,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							break;
 						}
 						if (attempt >= 2) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: cigar pool"); return HB_E_OVERFLOW; }
-						poolb_cap = poolb_used + 65536; n_def = 0; // the need is known now; the rerun takes the chains as already refined
+						poolb_cap = poolb_used + 65536; n_def = 0; // the need is known now: only the merge is repeated
 					}
 					b0 = b1; continue;
 				}

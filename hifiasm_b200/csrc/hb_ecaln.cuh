@@ -455,6 +455,8 @@ HB_HD void hb_ec_overlap_A(EcCtx &C, const hb_chain_t &c, const uint64_t *fc, co
 // (ed_band_cal_{global,extension_0,extension_1,semi}_infi_w_trace, Levenshtein_distance.h:2516/2694/2823/3020).
 // One thread per overlap; scratch sizes are launch parameters, an overlap that does not fit is reported as deferred
 // (st = -1) and re-run by a second launch with few threads and large scratch.
+// On the GPU the three pieces of the step run as three kernels: prep (thread / overlap), segment (thread / inter-anchor segment — the
+// alignments are independent of each other), merge (thread / overlap).
 // =============================================================================================================
 #define HB_MAX_SIN_L 10000 // Levenshtein_distance.h:757
 #define HB_MAX_SIN_E 2047  // Levenshtein_distance.h:756
@@ -465,9 +467,11 @@ struct MwEz {
 	int32_t ps, pe, pl, ts, te, tl, thre, err, nword;
 	uint16_t *cig; int32_t cn, ccap;      // cigar of the last alignment
 	uint64_t *path; uint64_t pcap, pn;    // 5*nword words per column
-	uint64_t *vec;                        // 11 vectors of HB_MW_MAXW words: Peq[0..4], VP, VN, X, D0, HN, HP
-	int ovf;                              // scratch too small: the overlap is deferred
+	uint64_t *vec; int32_t vstride;       // 11 vectors of vstride words: Peq[0..4], VP, VN, X, D0, HN, HP
+	int ovf;                              // scratch too small: the unit is deferred to a launch with more scratch
 };
+// result of one segment's alignment as push_alnw consumes it
+struct AlnRes { int32_t ts, te, ps, pe, err, cn; const uint16_t *cig; };
 struct EcBCtx {
 	RdView q, t; int64_t ql, tl; double e_rate; int64_t w_l;
 	MwEz ez;
@@ -540,30 +544,31 @@ HB_HD void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, const
 	else { ez.ps = ez.pe = -1; ez.ts = 0; ez.te = tn - 1; if (pn > tn + cut || tn > pn + cut) return; }
 	const int32_t tn0 = tn - 1, pe = pn - 1;
 	ez.nword = nword;
-	if ((uint64_t)nword * (uint64_t)tn * 5 > ez.pcap) { ez.ovf = 1; return; }
-	uint64_t *Peq = ez.vec, *VP = ez.vec + 5 * HB_MW_MAXW, *VN = VP + HB_MW_MAXW, *X = VN + HB_MW_MAXW, *D0 = X + HB_MW_MAXW, *HN = D0 + HB_MW_MAXW, *HP = HN + HB_MW_MAXW;
-	for (k = 0; k < 5 * HB_MW_MAXW; k++) Peq[k] = 0;
+	if ((uint64_t)nword * (uint64_t)tn * 5 > ez.pcap || nword > ez.vstride) { ez.ovf = 1; return; }
+	const int32_t VS = ez.vstride;
+	uint64_t *Peq = ez.vec, *VP = ez.vec + 5 * VS, *VN = VP + VS, *X = VN + VS, *D0 = X + VS, *HN = D0 + VS, *HP = HN + VS;
+	for (k = 0; k < 5 * VS; k++) Peq[k] = 0;
 	auto pch = [&](int32_t j) -> int { return T.at(ps0 + (mode == 2 ? pidx - j : j)); };
 	auto tch = [&](int32_t j) -> int { return Q.at(qs0 + (mode == 2 ? tidx - j : j)); };
 	if (mode == 3) {
 		for (k = 0; k < nword; k++) VP[k] = 0;
 		hb_mw_set_lsub(VN, abs_diag, nword);
 		bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn; i_bd = abs_diag;
-		for (i = 0; i < bd; i++, i_bd++) { c = pch(i); Peq[c * HB_MW_MAXW + (i_bd >> 6)] |= 1ULL << (i_bd & 63); }
+		for (i = 0; i < bd; i++, i_bd++) { c = pch(i); Peq[c * VS + (i_bd >> 6)] |= 1ULL << (i_bd & 63); }
 		i_bd = (thre << 1) - abs_diag; err = abs_diag;
 	} else {
 		bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre;
-		for (i = 0; i < bd; i++, i_bd++) { c = pch(i); Peq[c * HB_MW_MAXW + (i_bd >> 6)] |= 1ULL << (i_bd & 63); }
+		for (i = 0; i < bd; i++, i_bd++) { c = pch(i); Peq[c * VS + (i_bd >> 6)] |= 1ULL << (i_bd & 63); }
 		i_bd = thre; err = thre;
 		hb_mw_set_lsub(VN, thre, nword); hb_mw_set_lsub(VP, (thre << 1) + 1, nword);
 		for (k = 0; k < nword; k++) VP[k] ^= VN[k];
 	}
-	for (k = 0; k < nword; k++) Peq[4 * HB_MW_MAXW + k] = 0;
+	for (k = 0; k < nword; k++) Peq[4 * VS + k] = 0;
 	ez.pn = 0;
 	const int32_t Peq_i = (thre << 1) >> 6; const uint64_t Peq_m = 1ULL << ((thre << 1) & 63);
 	for (i = 0; i <= tn0; i++) {
 		{ // ed_infi_core, Levenshtein_distance.h:2148-2174
-			const uint64_t *pq = Peq + tch(i) * HB_MW_MAXW; uint64_t ad = 0; int32_t w;
+			const uint64_t *pq = Peq + tch(i) * VS; uint64_t ad = 0; int32_t w;
 			for (w = 0; w < nword; w++) {
 				const uint64_t x = pq[w] | VN[w], vp = VP[w]; uint64_t d0 = x & vp;
 				d0 += ad; ad = d0 < ad; d0 += vp; ad |= d0 < vp;
@@ -586,13 +591,13 @@ HB_HD void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, const
 				}
 			}
 			for (k = 0; k < 4; k++) { // ed_infi_post_Peq
-				uint64_t *pk = Peq + k * HB_MW_MAXW;
+				uint64_t *pk = Peq + k * VS;
 				for (int32_t w = 0; w + 1 < nword; w++) pk[w] = (pk[w] >> 1) | (pk[w + 1] << 63);
 				pk[nword - 1] >>= 1;
 			}
 			++i_bd; c = 4;
 			if (i_bd < pn) c = pch(i_bd);
-			if (c < 4) Peq[c * HB_MW_MAXW + Peq_i] |= Peq_m;
+			if (c < 4) Peq[c * VS + Peq_i] |= Peq_m;
 		}
 		uint64_t *o = ez.path + ez.pn;
 		for (k = 0; k < nword; k++) { o[k] = D0[k]; o[nword + k] = VP[k]; o[2 * nword + k] = VN[k]; o[3 * nword + k] = HP[k]; o[4 * nword + k] = HN[k]; }
@@ -785,9 +790,9 @@ HB_HD void hb_b_flush(EcBCtx &C)
 	}
 	C.open = -1; C.wcn = 0;
 }
-HB_HD void hb_push_alnw(EcBCtx &C)
+HB_HD void hb_push_alnw(EcBCtx &C, const AlnRes &ez)
 { // push_alnw + append_wcigar, Correct.cpp:15988-16019, 15954-15986
-	const MwEz &ez = C.ez; hb_wl_t *p;
+	hb_wl_t *p;
 	if (C.awn > 0 && C.open == C.awn - 1 && C.wcn > 0) {
 		p = &C.aw[C.awn - 1];
 		const int64_t t = (int64_t)p->error + (int64_t)ez.err;
@@ -810,6 +815,7 @@ HB_HD void hb_push_alnw(EcBCtx &C)
 	p->error_threshold = 0; p->error = (int16_t)ez.err; p->cidx = 0; p->clen = (uint32_t)ez.cn;
 	for (int32_t k = 0; k < ez.cn; k++) { if (C.wcn < C.wccap) C.wc[C.wcn] = ez.cig[k]; else C.ez.ovf = 1; C.wcn++; }
 }
+HB_HD AlnRes hb_aln_of(const MwEz &ez) { AlnRes r; r.ts = ez.ts; r.te = ez.te; r.ps = ez.ps; r.pe = ez.pe; r.err = ez.err; r.cn = ez.cn; r.cig = ez.cig; return r; }
 HB_HD void hb_push_unmap_alnw(EcBCtx &C, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
 { // push_unmap_alnw, Correct.cpp:16021-16030
 	hb_b_flush(C);
@@ -923,47 +929,51 @@ HB_HD int64_t hb_cal_exz_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, in
 	return 0;
 }
 
-HB_HD int64_t hb_hc_aln_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
-{ // hc_aln_exz_adv_hc, Correct.cpp:16178-16260 (maxl = MAX_SIN_L, maxe = MAX_SIN_E, force_l = FORCE_SIN_L, estimate_err = -1)
+// hc_aln_exz_adv_hc, Correct.cpp:16178-16260 (maxl = MAX_SIN_L, maxe = MAX_SIN_E, force_l = FORCE_SIN_L, estimate_err = -1) without its
+// push_alnw: returns 1 = aligned (C.ez holds the result), 2 = empty segment (nothing to push), 0 = not aligned (or C.ez.ovf)
+HB_HD int hb_seg_align(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
+{
 	MwEz &ez = C.ez; int64_t thre, thre0, pthre = -1, full = 0; const int64_t ql = qe - qs;
 	ez.err = INT32_MAX; ez.thre = 0;
 	if (ts == -1 && te == -1) mode = 3;
-	if (ql == 0 && te - ts == 0) return 1;
+	if (ql == 0 && te - ts == 0) return 2;
 	if (ql <= 0 || te - ts <= 0) return 0;
 	const int64_t est = hb_cal_estimate_err_hc(z, C.w_l, qs, qe, ts, te, C.e_rate, &full);
 	if (est == 0) {
-		if (full) { hb_set_exact(ez, qs, qe, ts, te); hb_push_alnw(C); return 1; }
-		else if (hb_cal_exact(C, z, qs, qe, ts, te, mode)) { hb_push_alnw(C); return 1; }
+		if (full) { hb_set_exact(ez, qs, qe, ts, te); return 1; }
+		else if (hb_cal_exact(C, z, qs, qe, ts, te, mode)) return 1;
 	}
 	if (ql <= HB_MAX_SIN_L && (est >> 1) <= HB_MAX_SIN_E) {
 		thre = hb_scale_ed_thre((uint32_t)est, HB_MAX_SIN_E);
-		if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; }
+		if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1;
 		if (ez.ovf) return 0;
 		thre0 = thre; thre = (int64_t)((double)ql * C.e_rate); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
-		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } if (ez.ovf) return 0; }
+		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; if (ez.ovf) return 0; }
 		thre0 = thre; thre <<= 1; thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
-		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } if (ez.ovf) return 0; }
+		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; if (ez.ovf) return 0; }
 		thre0 = thre; thre = (int64_t)((double)ql * 0.51); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
-		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } if (ez.ovf) return 0; }
-		if (ql <= HB_FORCE_SIN_L) { thre = HB_MAX_SIN_E; if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { hb_push_alnw(C); return 1; } }
+		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; if (ez.ovf) return 0; }
+		if (ql <= HB_FORCE_SIN_L) { thre = HB_MAX_SIN_E; if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; }
 	}
 	return 0;
 }
 
-// One accepted overlap.  zA = the overlap with step A's window list; re_A = step A's error estimate; ch_a / ch_n = its chain
-// anchors (refined in place, dropped anchors get id 0x7fffffff like return_t_chain does).  Result: out->st = 2 done,
-// -1 deferred (scratch too small: nothing of this overlap is valid); out->need_rechain = 1 when an unaligned window of
-// >= FORCE_SIN_L remains, which the reference re-seeds (rechain_aln_hc, Correct.cpp:17669 — not built yet).
-HB_HD void hb_ec_overlap_B(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_hit_t *ch_a, int64_t scn, int refined, int64_t *dp_t, int64_t *dp_p, int32_t *dp_f, hb_alnb_t *out)
+// ---- the three pieces of step B ---------------------------------------------------------------------------------
+// prep   : return_t_chain (refine the chain in place) + hc_ovlp_base_direct's whole-overlap exact shortcut (Correct.cpp:17430-17459)
+// segment: one inter-anchor segment i of [0, ch_n]: coordinates (17470-17490) + hb_seg_align         -> EcSeg (independent of its neighbours)
+// merge  : push_alnw / push_unmap_alnw over the segments in order, reassign_gaps, totals, update_overlap_region
+struct EcPrep { int32_t ch_n, shortcut; int32_t q0, q1, t0, t1; }; // shortcut: one exact window [q0,q1) x [t0,t1)
+// status: 0 unmapped (ts,te,ps,pe = q0,q1-1,t0,t1-1), 1 aligned with its cigar at coff (cn runs) in the segment pool, 2 empty,
+//         3 aligned without error (cigar = one match run, not stored), 4 deferred (needs more scratch)
+struct EcSeg { int32_t ts, te, ps, pe, err; uint32_t coff; uint16_t cn; uint8_t status, mode; };
+
+HB_HD void hb_ecb_prep(const EcZ &zA, int64_t re_A, int64_t ql, int64_t tl, hb_hit_t *ch_a, int64_t scn, int64_t *dp_t, int64_t *dp_p, int32_t *dp_f, EcPrep *pr)
 {
-	C.awn = 0; C.wcn = 0; C.open = -1; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.re_A = re_A; C.gap_re = 0;
-	const int64_t ch_n = refined ? scn : hb_lchain_refine(ch_a, scn, dp_t, dp_p, dp_f, 50, 5000, 512, 16); // refined: a deferred overlap's second run
+	const int64_t ch_n = hb_lchain_refine(ch_a, scn, dp_t, dp_p, dp_f, 50, 5000, 512, 16);
 	for (int64_t i = ch_n; i < scn; i++) ch_a[i].id_strand = (ch_a[i].id_strand & 0x80000000u) | 0x7fffffffu;
-	const int64_t ql = C.ql, tl = C.tl; int64_t q[2], t[2], mode, i, l; bool done = false;
-	out->need_rechain = 0; out->re = 0; out->w_n = 0; out->nh_err = re_A;
-	if (ch_n <= 0) { out->st = 2; out->x_pos_s = (uint32_t)zA.x_pos_s; out->x_pos_e = (uint32_t)zA.x_pos_e; out->y_pos_s = (uint32_t)zA.y_pos_s; out->y_pos_e = 0; return; }
-	if (re_A == 0 && zA.wn) { // hc_ovlp_base_direct, Correct.cpp:17430-17459: every window exact and co-linear -> one exact window
-		const int32_t zn = zA.wn; int32_t k;
+	pr->ch_n = (int32_t)ch_n; pr->shortcut = 0; pr->q0 = pr->q1 = pr->t0 = pr->t1 = 0;
+	if (ch_n > 0 && re_A == 0 && zA.wn) {
+		const int32_t zn = zA.wn; int32_t k; int64_t q[2], t[2];
 		for (k = 1; k < zn; k++) {
 			if (zA.w[k].error == 0 && zA.w[k - 1].error == 0 && zA.w[k].x_start == zA.w[k - 1].x_end + 1 && zA.w[k].y_end == zA.w[k - 1].y_end + (zA.w[k].x_end - zA.w[k - 1].x_end)) continue;
 			break;
@@ -973,25 +983,40 @@ HB_HD void hb_ec_overlap_B(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_hit_t *ch_
 			if (q[0] <= t[0]) { t[0] -= q[0]; q[0] = 0; } else { q[0] -= t[0]; t[0] = 0; }
 			const int64_t qr = ql - q[1] - 1, tr = tl - t[1] - 1;
 			if (qr <= tr) { q[1] = ql - 1; t[1] += qr; } else { t[1] = tl - 1; q[1] += tr; }
-			if (q[0] == zA.w[0].x_start && q[1] == zA.w[zn - 1].x_end) { hb_set_exact(C.ez, q[0], q[1] + 1, t[0], t[1] + 1); hb_push_alnw(C); done = true; }
+			if (q[0] == zA.w[0].x_start && q[1] == zA.w[zn - 1].x_end) { pr->shortcut = 1; pr->q0 = (int32_t)q[0]; pr->q1 = (int32_t)(q[1] + 1); pr->t0 = (int32_t)t[0]; pr->t1 = (int32_t)(t[1] + 1); }
 		}
 	}
-	for (l = -1, i = 0; !done && i <= ch_n && !C.ez.ovf; i++) { // Correct.cpp:17470-17507
-		q[0] = q[1] = t[0] = t[1] = mode = -1;
-		if (l >= 0) { q[0] = ch_a[l].self_offset; t[0] = ch_a[l].offset; } else q[0] = 0;
-		if (i < ch_n) { q[1] = ch_a[i].self_offset; t[1] = ch_a[i].offset; } else q[1] = ql;
-		if (t[0] != -1 && t[1] != -1) mode = 0;
-		else if (t[0] != -1 && t[1] == -1) mode = 1;
-		else if (t[0] == -1 && t[1] != -1) mode = 2;
-		else mode = 3;
-		if (mode == 1 || mode == 2) hb_adjust_ext_offset(&q[0], &q[1], &t[0], &t[1], ql, tl, 0, mode);
-		if (!hb_hc_aln_adv(C, zA, q[0], q[1], t[0], t[1], mode) && !C.ez.ovf) hb_push_unmap_alnw(C, q[0], q[1] - 1, t[0], t[1] - 1, mode);
-		l = i;
-	}
+}
+// segment i of an overlap with refined chain ch_a[0..ch_n): returns hb_seg_align's status; unmapped coordinates in uq / ut
+HB_HD int hb_ecb_segment(EcBCtx &C, const EcZ &zA, const hb_hit_t *ch_a, int64_t ch_n, int64_t i, int64_t *uq, int64_t *ut, int64_t *umode)
+{
+	int64_t q[2], t[2], mode; const int64_t l = i - 1;
+	q[0] = q[1] = t[0] = t[1] = -1;
+	if (l >= 0) { q[0] = ch_a[l].self_offset; t[0] = ch_a[l].offset; } else q[0] = 0;
+	if (i < ch_n) { q[1] = ch_a[i].self_offset; t[1] = ch_a[i].offset; } else q[1] = C.ql;
+	if (t[0] != -1 && t[1] != -1) mode = 0;
+	else if (t[0] != -1 && t[1] == -1) mode = 1;
+	else if (t[0] == -1 && t[1] != -1) mode = 2;
+	else mode = 3;
+	if (mode == 1 || mode == 2) hb_adjust_ext_offset(&q[0], &q[1], &t[0], &t[1], C.ql, C.tl, 0, mode);
+	uq[0] = q[0]; uq[1] = q[1]; ut[0] = t[0]; ut[1] = t[1]; *umode = mode;
+	return hb_seg_align(C, zA, q[0], q[1], t[0], t[1], mode);
+}
+// what hc_ovlp_base_direct does with a segment's result
+HB_HD void hb_ecb_apply(EcBCtx &C, int status, const AlnRes &r, const int64_t *uq, const int64_t *ut, int64_t umode)
+{
+	if (status == 1) hb_push_alnw(C, r);
+	else if (status == 0) hb_push_unmap_alnw(C, uq[0], uq[1] - 1, ut[0], ut[1] - 1, umode);
+}
+// totals, rechain flag, update_overlap_region (Correct.cpp:17857-17866, 17676, 17249-17275) once every window is closed
+HB_HD void hb_ecb_finish(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_alnb_t *out)
+{
+	const int64_t ql = C.ql, tl = C.tl; int64_t i;
 	hb_b_flush(C);
+	out->need_rechain = 0; out->re = 0; out->w_n = 0; out->nh_err = re_A;
 	if (C.ez.ovf) { out->st = -1; return; }
 	int64_t tot_e = 0, xs = zA.x_pos_s, xe = zA.x_pos_e, ys = zA.y_pos_s, ye = 0;
-	for (i = 0; i < C.awn; i++) { // rechain_aln_hc's entry test (Correct.cpp:17676) and the error total (17857-17866)
+	for (i = 0; i < C.awn; i++) {
 		const hb_wl_t &u = C.aw[i];
 		if (u.error == INT16_MAX && u.clen == 0 && u.extra_end < 0) {
 			const int64_t xl = (int64_t)u.x_end + 1 - u.x_start, yl = (int64_t)u.y_end + 1 - u.y_start;
@@ -999,10 +1024,65 @@ HB_HD void hb_ec_overlap_B(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_hit_t *ch_
 			tot_e += xl >= yl ? xl : yl;
 		} else tot_e += u.error;
 	}
-	if (C.awn) { xs = C.aw[0].x_start; xe = C.aw[C.awn - 1].x_end; ys = C.aw[0].y_start; ye = C.aw[C.awn - 1].y_end; } // update_overlap_region, Correct.cpp:17249-17275
+	if (C.awn) { xs = C.aw[0].x_start; xe = C.aw[C.awn - 1].x_end; ys = C.aw[0].y_start; ye = C.aw[C.awn - 1].y_end; }
 	if (xs <= ys) { ys -= xs; xs = 0; } else { xs -= ys; ys = 0; }
 	{ const int64_t xr = ql - xe - 1, yr = tl - ye - 1; if (xr <= yr) { xe = ql - 1; ye += xr; } else { ye = tl - 1; xe += yr; } }
 	out->st = 2; out->re = tot_e + C.gap_re; out->w_n = (uint32_t)C.awn; out->nh_err = re_A - C.gap_re; // re = step B's total (before step C)
 	out->x_pos_s = (uint32_t)xs; out->x_pos_e = (uint32_t)xe; out->y_pos_s = (uint32_t)ys; out->y_pos_e = (uint32_t)ye;
 	if (C.bad) out->st = -2;
+}
+HB_HD void hb_ecb_begin(EcBCtx &C, int64_t re_A) { C.awn = 0; C.wcn = 0; C.open = -1; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.re_A = re_A; C.gap_re = 0; }
+
+// One accepted overlap.  zA = the overlap with step A's window list; re_A = step A's error estimate; ch_a / ch_n = its chain
+// anchors (refined in place, dropped anchors get id 0x7fffffff like return_t_chain does).  Result: out->st = 2 done,
+// -1 deferred (scratch too small: nothing of this overlap is valid); out->need_rechain = 1 when an unaligned window of
+// >= FORCE_SIN_L remains, which the reference re-seeds (rechain_aln_hc, Correct.cpp:17669 — not built yet).
+HB_HD void hb_ec_overlap_B(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_hit_t *ch_a, int64_t scn, int64_t *dp_t, int64_t *dp_p, int32_t *dp_f, hb_alnb_t *out)
+{ // the three pieces run back to back by one thread (host emulation and the reference for the parallel pipeline's results)
+	EcPrep pr; int64_t uq[2], ut[2], um;
+	hb_ecb_begin(C, re_A);
+	hb_ecb_prep(zA, re_A, C.ql, C.tl, ch_a, scn, dp_t, dp_p, dp_f, &pr);
+	if (pr.shortcut) { hb_set_exact(C.ez, pr.q0, pr.q1, pr.t0, pr.t1); hb_push_alnw(C, hb_aln_of(C.ez)); }
+	else for (int64_t i = 0; i <= pr.ch_n && pr.ch_n > 0 && !C.ez.ovf; i++) {
+		const int st = hb_ecb_segment(C, zA, ch_a, pr.ch_n, i, uq, ut, &um);
+		if (C.ez.ovf) break;
+		hb_ecb_apply(C, st, hb_aln_of(C.ez), uq, ut, um);
+	}
+	hb_ecb_finish(C, zA, re_A, out);
+}
+
+// ---- storing / loading a segment's result between the segment and the merge kernels -------------------------------
+HB_HD void hb_seg_store(EcBCtx &C, int st, const int64_t *uq, const int64_t *ut, int64_t um, EcSeg *sg, uint16_t *spool, unsigned long long *spool_used, uint64_t spool_cap)
+{
+	sg->mode = (uint8_t)um; sg->cn = 0; sg->coff = 0; sg->err = 0; sg->ts = sg->te = sg->ps = sg->pe = 0;
+	if (C.ez.ovf) { sg->status = 4; return; }
+	if (st == 0) { sg->status = 0; sg->ts = (int32_t)uq[0]; sg->te = (int32_t)(uq[1] - 1); sg->ps = (int32_t)ut[0]; sg->pe = (int32_t)(ut[1] - 1); return; }
+	if (st == 2) { sg->status = 2; return; }
+	const MwEz &ez = C.ez;
+	sg->ts = ez.ts; sg->te = ez.te; sg->ps = ez.ps; sg->pe = ez.pe; sg->err = ez.err; sg->cn = (uint16_t)ez.cn;
+	if (ez.cn == 1) { sg->status = 3; sg->coff = ez.cig[0]; return; } // a single run travels inside the record
+	if (ez.cn > 0xffff) { sg->status = 4; return; }
+#ifdef __CUDA_ARCH__
+	const unsigned long long o = atomicAdd(spool_used, (unsigned long long)ez.cn);
+#else
+	const unsigned long long o = *spool_used; *spool_used += (unsigned long long)ez.cn;
+#endif
+	sg->status = 1; sg->coff = (uint32_t)o;
+	if (o + (unsigned long long)ez.cn <= spool_cap && o + (unsigned long long)ez.cn < (1ull << 32)) for (int32_t k = 0; k < ez.cn; k++) spool[o + k] = ez.cig[k];
+}
+// merge: replay one overlap's stored segments (Correct.cpp:17470-17507 with the alignments already done)
+HB_HD void hb_ecb_merge(EcBCtx &C, const EcZ &zA, int64_t re_A, const EcPrep &pr, const EcSeg *segs, const uint16_t *spool, hb_alnb_t *out)
+{
+	hb_ecb_begin(C, re_A);
+	if (pr.shortcut) { hb_set_exact(C.ez, pr.q0, pr.q1, pr.t0, pr.t1); hb_push_alnw(C, hb_aln_of(C.ez)); }
+	else for (int32_t i = 0; i <= pr.ch_n && pr.ch_n > 0 && !C.ez.ovf; i++) {
+		const EcSeg sg = segs[i]; uint16_t one;
+		if (sg.status == 1 || sg.status == 3) {
+			AlnRes r; r.ts = sg.ts; r.te = sg.te; r.ps = sg.ps; r.pe = sg.pe; r.err = sg.err; r.cn = sg.cn;
+			if (sg.status == 3) { one = (uint16_t)sg.coff; r.cig = &one; } else r.cig = spool + sg.coff;
+			hb_push_alnw(C, r);
+		} else if (sg.status == 0) hb_push_unmap_alnw(C, sg.ts, sg.te, sg.ps, sg.pe, sg.mode);
+		else if (sg.status == 4) C.ez.ovf = 1; // a segment no tier could align: the overlap stays deferred (reported by the host)
+	}
+	hb_ecb_finish(C, zA, re_A, out);
 }

@@ -1113,9 +1113,10 @@ __global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
 }
 
 // ----------------------------------------------------------------------------
-// step B (row a10): base-level CIGAR of the accepted overlaps, one thread per overlap (hb_ecaln.cuh: hb_ec_overlap_B).
-// pass = 0: every overlap step A accepted; pass = 1: only the overlaps the first launch deferred for lack of scratch
-// (launched with few threads and scratch for the largest alignment the reference allows).
+// steps B + C (rows a10 + a11): base-level CIGAR of the accepted overlaps as three kernels (hb_ecaln.cuh):
+//   k_ecb_prep   thread / overlap : chain refinement, whole-overlap exact shortcut, segment count
+//   k_ecb_seg    thread / segment : the alignments (independent of each other); scratch tiers chained by queues
+//   k_ecb_merge  thread / overlap : window fusion over the stored results, indel normalisation, totals
 // ----------------------------------------------------------------------------
 __global__ void k_ecb_cap(uint64_t n_ov, const OvDesc *__restrict__ desc, const hb_chain_t *__restrict__ ch, const hb_aln_t *__restrict__ aln, uint32_t *__restrict__ cap)
 { // window capacity of an overlap = number of inter-anchor segments (+1 spare)
@@ -1125,34 +1126,86 @@ __global__ void k_ecb_cap(uint64_t n_ov, const OvDesc *__restrict__ desc, const 
 struct EcCigArgs {
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
 	const hb_aln_t *aln; const hb_wl_t *wlA; hb_hit_t *chits, *ghits; uint64_t dp_half; int64_t *dp_t, *dp_p; int32_t *dp_f;
-	double e_rate; int32_t w_l; int pass, refined, gaps; // refined: the chains were refined by an earlier launch of this batch
-	hb_alnb_t *out; hb_wl_t *wl; const uint64_t *wl_off;
-	uint64_t *path; uint64_t path_words; uint64_t *vec; uint16_t *cig_tmp; int32_t cig_words;
+	double e_rate; int32_t w_l; int gaps;
+	EcPrep *prep; uint32_t *nseg; const uint64_t *seg_off; uint64_t n_seg; EcSeg *segs; // segments of overlap o: segs[seg_off[o] .. seg_off[o+1])
+	uint16_t *spool; unsigned long long *spool_used; uint64_t spool_cap;                // cigars of the aligned segments
+	uint32_t *q_in; const uint32_t *q_in_n; uint32_t *q_out; uint32_t *q_out_n;         // deferred segments (ids) between scratch tiers
+	uint64_t *path; uint64_t path_words; uint64_t *vec; int32_t vstride; uint16_t *cig_tmp; int32_t cig_words; // per-thread scratch of the queue tiers / merge
+	int pass; hb_alnb_t *out; hb_wl_t *wl; const uint64_t *wl_off;
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; unsigned int *n_deferred; int *err;
 };
-__global__ void __launch_bounds__(64) k_ec_cigar(EcCigArgs A)
+static __device__ __forceinline__ void ecb_overlap_view(const EcCigArgs &A, uint64_t o, const hb_aln_t &a, OvDesc &d, hb_chain_t &c, EcZ &z, hb_hit_t *&ch_a, uint64_t &dpo)
+{
+	d = A.desc[o]; c = A.ch[d.slot];
+	const bool inpl = (c.pad & HB_CHAIN_INPLACE) != 0;
+	ch_a = (inpl ? A.ghits : A.chits) + c.first_hit; dpo = (inpl ? A.dp_half : 0) + c.first_hit;
+	z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_pos_s = c.y_pos_s; z.y_id = c.y_id; z.rev = c.y_pos_strand;
+	z.fc = A.fc + A.fc_grp_base[d.slot] + c.fc_off; z.fc_n = c.fc_n; z.align_length = a.align_length; z.w = (hb_wl_t *)(A.wlA + a.w_off); z.wn = (int32_t)a.w_n;
+}
+// prep: thread / overlap — refine the chain in place, whole-overlap exact shortcut, number of segments
+__global__ void __launch_bounds__(128) k_ecb_prep(EcCigArgs A)
+{
+	const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= A.n_ov) return;
+	const hb_aln_t a = A.aln[o]; EcPrep pr; pr.ch_n = 0; pr.shortcut = 0; pr.q0 = pr.q1 = pr.t0 = pr.t1 = 0; uint32_t ns = 0;
+	if (a.st == 2) {
+		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
+		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+		hb_ecb_prep(z, a.re, A.R.len[A.r0 + d.read], A.R.len[c.y_id], ch_a, c.n_hits, A.dp_t + dpo, A.dp_p + dpo, A.dp_f + dpo, &pr);
+		ns = (pr.shortcut || pr.ch_n <= 0) ? 0 : (uint32_t)pr.ch_n + 1;
+	}
+	A.prep[o] = pr; A.nseg[o] = ns;
+}
+// segment: thread / inter-anchor segment.  TIER0 = true: one thread per segment of the batch with a small private scratch (trace of
+// 640 words, 4-word band: enough for the ~35-bp segments between neighbouring minimizers); what does not fit goes to the queue.
+// TIER0 = false: grid-stride over a queue of deferred segments with launch-sized global scratch.
+#define ECB_T0_PATH 640
+#define ECB_T0_VS 4
+#define ECB_T0_CIG 72
+template <bool TIER0>
+__global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
+{
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t l_path[TIER0 ? ECB_T0_PATH : 1], l_vec[TIER0 ? 11 * ECB_T0_VS : 1]; uint16_t l_cig[TIER0 ? ECB_T0_CIG : 1];
+	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+	if (TIER0) { C.ez.path = l_path; C.ez.pcap = ECB_T0_PATH; C.ez.vec = l_vec; C.ez.vstride = ECB_T0_VS; C.ez.cig = l_cig; C.ez.ccap = ECB_T0_CIG; }
+	else { C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * 11 * (uint64_t)A.vstride; C.ez.vstride = A.vstride; C.ez.cig = A.cig_tmp + tid * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words; }
+	const uint64_t n_work = TIER0 ? A.n_seg : (uint64_t)*A.q_in_n;
+	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
+		const uint64_t sidx = TIER0 ? wk : A.q_in[wk];
+		uint64_t lo = 0, hi = A.n_ov; // overlap of the segment: last o with seg_off[o] <= sidx
+		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
+		const uint64_t o = lo; const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
+		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
+		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+		C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+		int64_t uq[2], ut[2], um;
+		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
+		if (C.bad) atomicOr(A.err, 32);
+		EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
+		if (sg.status == 4 && A.q_out) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; }
+		A.segs[sidx] = sg;
+	}
+}
+// merge: thread / overlap, grid-stride — push_alnw / push_unmap_alnw over the stored segments, reassign_gaps when a window closes,
+// totals and update_overlap_region.  pass = 1: only the overlaps the first launch deferred (cigar buffers too small).
+__global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
 {
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
 	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.do_gaps = A.gaps;
-	C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * (11 * HB_MW_MAXW);
-	C.ez.cig = A.cig_tmp + tid * 2 * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words; C.wc = C.ez.cig + A.cig_words; C.wccap = A.cig_words;
+	uint16_t *base = A.cig_tmp + tid * 3 * (uint64_t)A.cig_words; // wc | gap output | adjust_gap scratch
+	C.wc = base; C.wccap = A.cig_words; C.ez.cig = base + A.cig_words; C.ez.ccap = A.cig_words; C.ez.path = (uint64_t *)(base + 2 * (uint64_t)A.cig_words); C.ez.pcap = (uint64_t)A.cig_words / 4;
+	C.ez.vec = 0; C.ez.vstride = 0;
 	for (uint64_t o = tid; o < A.n_ov; o += nthr) {
 		const hb_aln_t a = A.aln[o];
 		if (A.pass == 0) { if (a.st != 2) { hb_alnb_t r; r.st = a.st; r.need_rechain = 0; r.re = 0; r.nh_err = 0; r.x_pos_s = r.x_pos_e = r.y_pos_s = r.y_pos_e = 0; r.w_off = A.wl_off[o]; r.w_n = 0; r.pad = 0; A.out[o] = r; continue; } }
 		else if (A.out[o].st != -1) continue;
-		const OvDesc d = A.desc[o]; const hb_chain_t c = A.ch[d.slot];
-		const bool inpl = (c.pad & HB_CHAIN_INPLACE) != 0;
-		hb_hit_t *ch_a = (inpl ? A.ghits : A.chits) + c.first_hit; const uint64_t dpo = (inpl ? A.dp_half : 0) + c.first_hit;
-		EcZ z; z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_pos_s = c.y_pos_s; z.y_id = c.y_id; z.rev = c.y_pos_strand;
-		z.fc = A.fc + A.fc_grp_base[d.slot] + c.fc_off; z.fc_n = c.fc_n; z.align_length = a.align_length; z.w = (hb_wl_t *)(A.wlA + a.w_off); z.wn = (int32_t)a.w_n;
+		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
+		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
 		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
 		C.aw = A.wl + A.wl_off[o]; C.awcap = (int32_t)(A.wl_off[o + 1] - A.wl_off[o]);
 		hb_alnb_t r; r.w_off = A.wl_off[o]; r.pad = 0;
-		// the first launch refined the chain in place and tagged the dropped anchors: the second launch takes it as it is
-		int64_t scn = c.n_hits;
-		const int refined = A.pass == 1 || A.refined;
-		if (refined) { int64_t k = 0; while (k < scn && HB_HIT_ID(ch_a[k]) != 0x7fffffffu) k++; scn = k; }
-		hb_ec_overlap_B(C, z, a.re, ch_a, scn, refined, A.dp_t + dpo, A.dp_p + dpo, A.dp_f + dpo, &r);
+		hb_ecb_merge(C, z, a.re, A.prep[o], A.segs + A.seg_off[o], A.spool, &r);
 		if (r.st == -1) atomicAdd(A.n_deferred, 1u);
 		if (r.st == -2) atomicOr(A.err, 32);
 		A.out[o] = r;

@@ -192,7 +192,7 @@ def test_sharded_query_ranges_equal_full_pass(ctx):
 
 
 def test_ec_cigar_small_scratch_defers_and_matches(ctx, monkeypatch):
-    """a trace scratch too small for some alignments: those overlaps go through the deferred second launch, same result"""
+    """scratch tiers too small for some segments / overlaps: they go through the next tier / the deferred merge, same result"""
     g, eng, hom = ctx
     p = g.params("raw")
     eng.upload_store(g.raw)
@@ -208,7 +208,7 @@ def test_ec_cigar_small_scratch_defers_and_matches(ctx, monkeypatch):
             "[d.update(np.ascontiguousarray(W[f]).tobytes()) for f in ('x_start', 'x_end', 'y_start', 'y_end', 'error', 'clen')];"
             "print(json.dumps({'dg': d.hexdigest(), 'deferred': e.counters()['ec_deferred']}))") % (
                 os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), [k for k in ("g1", "g2", "g3") if Golden(k).raw.n == n][0], float(p["bw_thres"]))
-    env = dict(os.environ, HB_ECB_PATH_WORDS="4096")
+    env = dict(os.environ, HB_ECB_PATH_WORDS="4096", HB_ECB_CIG_WORDS="64")
     res = json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1])
     o, B, W, Cg = ref
     d = hashlib.blake2b(digest_size=8)
@@ -218,7 +218,7 @@ def test_ec_cigar_small_scratch_defers_and_matches(ctx, monkeypatch):
         d.update(np.ascontiguousarray(W[f]).tobytes())
     assert res["dg"] == d.hexdigest()
     if n == Golden("g3").raw.n:
-        assert res["deferred"] > 0  # the damaged set has alignments that need more than 4096 trace words
+        assert res["deferred"] > 0  # the damaged set has segments that need more than 4096 trace words: they reach the last tier
 
 
 def test_myers_window_vs_reference(hb):

@@ -106,6 +106,16 @@ def test_ec_align_step_A(ctx):
             assert rc == 0 and (Bc["re"] == B["re"]).all()
             dc = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WCc[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CCc) for b in Bc[Bc["st"] == 2])
             assert dc == int(g.digest("raw", "alnC")[i]), "step C, read %d" % i
+            # the same through the pieces the GPU runs as three kernels (prep / independent segments with tiered scratch / merge);
+            # every other read with merge buffers too small for its longest cigars, so the deferral is reported
+            cw = 64 if i % 2 else 1 << 16
+            rc, Bp, WP, CP, tiers = emu.ec_align_B_par(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1, cig_words=cw)
+            if rc & 1:
+                assert cw == 64 and (Bp["st"] == -1).any()
+                rc, Bp, WP, CP, tiers = emu.ec_align_B_par(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1)
+            assert rc == 0 and (Bp["re"] == B["re"]).all()
+            dp = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WP[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CP) for b in Bp[Bp["st"] == 2])
+            assert dp == int(g.digest("raw", "alnC")[i]), "steps B + C, segment-parallel pipeline, read %d" % i
 
 
 def test_final_pass(ctx):
