@@ -245,5 +245,5 @@ class Engine:
 
     def counters(self):
         c = (C.c_uint64 * 12)(); _lib().hb_counters(self.h, c, 12)
-        return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots", "groups_unordered", "groups_sequential", "windows", "ec_overlaps", "ec_deferred"),
-                        [int(x) for x in c[:11]]))
+        return dict(zip(("reads", "bases", "minimizers", "anchors", "groups", "chain_slots", "groups_unordered", "groups_sequential", "windows", "ec_overlaps", "ec_deferred", "ec_segments"),
+                        [int(x) for x in c[:12]]))
