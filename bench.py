@@ -313,10 +313,11 @@ def _main():
             goff, G, WG, CG = e2.ec_cigar(0, nq, 0.02, 0.04, 775, gaps=1)
             torch.cuda.synchronize(); wall_ec = time.time() - tb
             pr = e2.profile(); cn = e2.counters()
-            kms = {k: pr[k][1] for k in ("k_windows", "k_ec_overlap", "k_ecb_prep", "k_ecb_seg", "k_ecb_seg_tier1", "k_ecb_seg_tier2", "k_ecb_merge", "k_ecb_merge_deferred") if k in pr}
+            poff, PH = e2.ec_phase(0, nq, 0.02, 0.04, 775); pr.update({k: v for k, v in e2.profile().items() if k.startswith("k_ph_")})
+            kms = {k: pr[k][1] for k in ("k_windows", "k_ec_overlap", "k_ecb_prep", "k_ecb_seg", "k_ecb_seg_tier1", "k_ecb_seg_tier2", "k_ecb_seg_tier3", "k_ecb_merge", "k_ecb_merge_deferred", "k_ph_count", "k_ph_decide") if k in pr}
             qb = int(ln.sum()); acc = G[G["st"] == 2]
             aux = dict(aux or {})
-            aux["ec_alignment"] = {"reads": nq, "query_bases": qb, "overlaps": int(G.size), "accepted": int(acc.size), "need_rechain": int(acc["need_rechain"].sum()),
+            aux["ec_alignment"] = {"reads": nq, "query_bases": qb, "overlaps": int(G.size), "accepted": int(acc.size), "other_haplotype": int((PH["is_match"] == 2).sum()), "need_rechain": int(acc["need_rechain"].sum()),
                                    "segments": cn.get("ec_segments", 0), "segments_in_largest_scratch_tier": cn.get("ec_deferred", 0), "windows": cn.get("windows", 0), "cigar_runs": int(CG.size),
                                    "kernel_ms": kms, "stage_kernels_gbp_s": qb / (sum(kms.values()) / 1e3) / 1e9 if kms else None,
                                    "pass_ms_with_seeding_and_host_copies": wall_ec * 1e3, "setup_s": round(tb - ta, 1),

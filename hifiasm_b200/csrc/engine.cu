@@ -726,7 +726,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					ba.release(d_pool); pool_cap = pool_used + 4096; // the exact need is known now
 				}
 				ctx->counters[9] += n_ov;
-				if (mode == 6) { // step B: base-level CIGAR of the accepted overlaps (row a10)
+				if (mode >= 6) { // step B: base-level CIGAR of the accepted overlaps (row a10)
 					uint32_t *d_cap = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_wboff = ba.get<uint64_t>(n_ov + 2); hb_alnb_t *d_alnb = ba.get<hb_alnb_t>(n_ov + 1), *d_alnb2 = ba.get<hb_alnb_t>(n_ov + 1);
 					unsigned int *d_ndef = (unsigned int *)ba.zero<uint32_t>(1);
 					int64_t *d_dpt = ba.get<int64_t>(2 * (B + 1)), *d_dpp = ba.get<int64_t>(2 * (B + 1)); int32_t *d_dpf = ba.get<int32_t>(2 * (B + 1));
@@ -735,7 +735,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					if ((rc = hb_scan_u32_to_u64(ctx, d_cap, d_wboff, n_ov))) return rc;
 					uint64_t wb_tot = 0; HB_CUDA(cudaMemcpyAsync(&wb_tot, d_wboff + n_ov, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 					hb_wl_t *d_wlb = ba.zero<hb_wl_t>(wb_tot + 1); HB_ALLOC_CHECK(ba);
-					static const uint64_t path_words1 = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384;
+					static const uint64_t path_words1 = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384; // half of tier 2's trace words
 					static const int32_t merge_cw0 = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
 					EcPrep *d_prep = ba.get<EcPrep>(n_ov + 1); uint32_t *d_nseg = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_segoff = ba.get<uint64_t>(n_ov + 2);
 					uint32_t *d_qn = ba.zero<uint32_t>(4); unsigned long long *d_spused = ba.zero<unsigned long long>(1);
@@ -769,15 +769,20 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						}
 						HB_CUDA(cudaGetLastError());
 						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 16, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-						for (int tier = 1; tier <= 2 && h_q[tier]; tier++) {
+						// scratch tiers 1..3: {trace words, band words, cigar runs, blocks of 128 threads}; a segment that overflows one tier queues for the next
+						const struct { uint64_t pw; int32_t vs, cw; unsigned bl; const char *name; } TIER[4] = {
+							{ 0, 0, 0, 0, "" }, { 4096, 8, 256, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier1" }, { path_words1 * 2, HB_MW_MAXW, 4096, (unsigned)ctx->sm_count, "k_ecb_seg_tier2" },
+							{ (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5, HB_MW_MAXW, 65535, 2u, "k_ecb_seg_tier3" } };
+						uint32_t *d_qs[5] = { 0, d_q1, d_q2, d_q1, 0 };
+						for (int tier = 1; tier <= 3 && h_q[tier]; tier++) {
 							Arena sa(ctx);
-							const uint64_t pw = tier == 1 ? path_words1 : (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5; const int32_t cw = tier == 1 ? 4096 : 65535;
-							const unsigned bl = tier == 1 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)h_q[tier] + 127) / 128, (uint64_t)ctx->sm_count)) : 2u; const uint64_t nt = (uint64_t)bl * 128;
-							G.path = sa.get<uint64_t>(nt * pw); G.path_words = pw; G.vec = sa.get<uint64_t>(nt * 11 * HB_MW_MAXW); G.vstride = HB_MW_MAXW; G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)cw); G.cig_words = cw;
+							const unsigned bl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)h_q[tier] + 127) / 128, (uint64_t)TIER[tier].bl)); const uint64_t nt = (uint64_t)bl * 128;
+							G.path = sa.get<uint64_t>(nt * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nt * 11 * (uint64_t)TIER[tier].vs); G.vstride = TIER[tier].vs;
+							G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw;
 							if (sa.failed) return HB_E_WS;
-							G.q_in = tier == 1 ? d_q1 : d_q2; G.q_in_n = d_qn + tier; G.q_out = tier == 1 ? d_q2 : 0; G.q_out_n = d_qn + tier + 1;
+							G.q_in = d_qs[tier]; G.q_in_n = d_qn + tier; G.q_out = tier < 3 ? d_qs[tier + 1] : 0; G.q_out_n = tier < 3 ? d_qn + tier + 1 : d_qn;
 							{
-								ProfScope ps(ctx, tier == 1 ? "k_ecb_seg_tier1" : "k_ecb_seg_tier2");
+								ProfScope ps(ctx, TIER[tier].name);
 								k_ecb_seg<false><<<bl, 128, 0, ctx->stream>>>(G);
 							}
 							HB_CUDA(cudaGetLastError());
@@ -790,7 +795,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						if (attempt >= 2 || spool_used >= (1ull << 32)) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: segment cigar pool"); return HB_E_OVERFLOW; }
 						spool_cap = spool_used + 65536; // the need is known now; the segments are recomputed (the chains stay refined)
 					}
-					ctx->counters[10] += h_q[2]; // segments that needed the largest scratch tier
+					ctx->counters[10] += h_q[3]; // segments that needed the largest scratch tier
 					// ---- merge
 					uint64_t poolb_cap = n_seg / 4 + 16 * n_ov + 65536, poolb_used = 0; uint16_t *d_poolb = 0; unsigned int n_def = 0;
 					for (int attempt = 0;; attempt++) {
@@ -817,6 +822,43 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						HB_CUDA(cudaMemcpyAsync(&poolb_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 						HB_CUDA(cudaStreamSynchronize(ctx->stream));
 						if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "EC base alignment: fake-cigar lookup failed"); return HB_E_STATE; }
+						if (poolb_used <= poolb_cap && mode == 7) { // phasing of the batch's reads over the step-C state that stays in HBM (row a13)
+							std::vector<uint64_t> h_boff(nb + 1, 0);
+							for (uint64_t i = 0; i < nb; i++) h_boff[i + 1] = h_boff[i] + ((ctx->h_rlen[r0 + b0 + i] + 8) & ~7ull);
+							uint64_t *d_boff = ba.get<uint64_t>(nb + 1); uint8_t *d_cnt = ba.zero<uint8_t>(h_boff[nb] + 8); PhOv *d_phov = ba.get<PhOv>(n_ov + 1);
+							uint32_t *d_nacc = ba.zero<uint32_t>(nb + 1), *d_nsite = ba.zero<uint32_t>(nb + 1), *d_nev = ba.zero<uint32_t>(nb + 1); uint64_t *d_soff = ba.get<uint64_t>(nb + 2), *d_eoff = ba.get<uint64_t>(nb + 2);
+							hb_phase_t *d_ph = ba.get<hb_phase_t>(n_ov + 1);
+							HB_ALLOC_CHECK(ba);
+							HB_CUDA(cudaMemcpyAsync(d_boff, h_boff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+							PhArgs P; memset(&P, 0, sizeof(P));
+							P.R = R; P.r0 = r0 + b0; P.nR = nb; P.o_off = d_ooff; P.desc = d_od; P.ch = d_ch; P.aln = d_aln; P.alnb = d_alnb; P.wl = d_wlb; P.pool = d_poolb;
+							P.ov = d_phov; P.n_acc = d_nacc; P.b_off = d_boff; P.cnt = d_cnt; P.n_site = d_nsite; P.n_ev = d_nev; P.out = d_ph; P.err = d_err;
+							{
+								ProfScope ps(ctx, "k_ph_count");
+								k_ph_count<<<nblk(nb, 128), 128, 0, ctx->stream>>>(P);
+							}
+							HB_CUDA(cudaGetLastError());
+							if ((rc = hb_scan_u32_to_u64(ctx, d_nsite, d_soff, nb)) || (rc = hb_scan_u32_to_u64(ctx, d_nev, d_eoff, nb))) return rc;
+							uint64_t tot_s = 0, tot_e = 0;
+							HB_CUDA(cudaMemcpyAsync(&tot_s, d_soff + nb, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&tot_e, d_eoff + nb, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							P.site_off = d_soff; P.ev_off = d_eoff;
+							P.site_pos = ba.get<uint32_t>(tot_s + 1); P.site_o = ba.get<uint32_t>(tot_s + nb + 2); P.ev = ba.get<PhEv>(tot_e + 2); P.ev2 = ba.get<PhEv>(tot_e + 2); P.snp = ba.get<PhSnp>(4 * tot_s + 1);
+							P.ord = ba.get<uint64_t>(n_ov + 1); P.ov_o = ba.get<uint32_t>(n_ov + nb + 2);
+							HB_ALLOC_CHECK(ba);
+							{
+								ProfScope ps(ctx, "k_ph_decide");
+								k_ph_decide<<<nblk(nb, 64), 64, 0, ctx->stream>>>(P);
+							}
+							HB_CUDA(cudaGetLastError());
+							HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "phasing: radix-sort stack"); return HB_E_OVERFLOW; }
+							if (so->rec && st3_n + n_ov > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
+							if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_phase_t *)so->rec + st3_n, d_ph, n_ov * sizeof(hb_phase_t), cudaMemcpyDeviceToHost, ctx->stream));
+							HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							for (uint64_t i = 0; i <= nb; i++) st3_off[b0 + i] = st3_n + h_ooff[i];
+							st3_n += n_ov;
+							break;
+						}
 						if (poolb_used <= poolb_cap) {
 							// dense window lists for the host
 							uint32_t *d_wn = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_dense = ba.get<uint64_t>(n_ov + 2); HB_ALLOC_CHECK(ba);
@@ -1040,6 +1082,13 @@ extern "C" int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_th
 	if (n_wl) *n_wl = so.n_wl;
 	if (n_cig) *n_cig = so.n_cig;
 	return rc;
+}
+
+extern "C" int hb_ec_phase(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_phase_t *rec, uint64_t rec_cap)
+{
+	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l; so.gaps = 1;
+	return run_pass(ctx, r0, r1, 7, bw_thres, &so, 0);
 }
 
 // ---------------------------------------------------------------------------

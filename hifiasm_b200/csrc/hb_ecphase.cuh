@@ -1,0 +1,211 @@
+// hb_ecphase.cuh — phasing of the accepted overlaps of one read: rphase_hc (Correct.cpp:20191-20320),
+// HiFi path (bd = 0, occ_thres = 1, no HPC mask, no base qualities, no large-indel phasing).
+//
+// The reference sweeps the query in 428-column windows with per-window cursors into every cigar; the quantities it derives are
+// position-local, so this version works on whole-read arrays instead:
+//   1. cnt[x]  = number of aligned windows whose cigar has a mismatch column at query position x (saturating at 127)   [extract_sub_cigar_hc, set_f]
+//   2. SNP candidate sites = positions with cnt > 1
+//   3. evidence = for every candidate site, every window that covers it with a match / mismatch column                   [extract_sub_cigar_hc, !set_f]
+//   4. per site: allele statistics (push_info, Correct.cpp:10511) -> per overlap: the greedy haplotype call
+//      (generate_haplotypes_naive_HiFi, Correct.cpp:8845) -> is_match 1 / 2 and `strong`
+// One thread per read: step 4 is a greedy sequential pass over the read's overlaps, and steps 1-3 only walk cigar RUNS
+// (a few thousand per read), so there is nothing to gain from splitting a read further.  Two launches: count (evidence
+// and site numbers per read), then fill + decide with exactly-sized scratch.
+#pragma once
+#include "hb_ecaln.cuh"
+#include "hb_chain.cuh"
+
+struct PhEv { uint32_t site, ov, osite; uint32_t cov; uint8_t type, base, pad[2]; };             // haplotype_evdience (Correct.h:130-143); base = 0..3, 4 = N
+struct PhSnp { uint32_t id, overlap_num, occ_0, occ_1, occ_2, site; int32_t score; uint32_t pad; }; // SnpStats (Correct.h:152-167)
+struct PhOv { const hb_wl_t *w; uint32_t wn; const uint16_t *pool; uint32_t y_id, rev, align_length; uint8_t is_match; int8_t strong; };
+
+HB_HD bool hb_ph_ualn(const hb_wl_t &u) { return u.error == INT16_MAX && u.clen == 0 && u.extra_end < 0; } // is_ualn_win, Correct.h:1362
+
+// pass 1 over a read: cnt[] (zeroed by the caller, ql bytes) -> number of candidate sites and of evidence records
+HB_HD void hb_ph_count(const PhOv *ov, uint32_t n_ov, uint8_t *cnt, int64_t ql, uint32_t *n_site, uint32_t *n_ev)
+{
+	for (uint32_t j = 0; j < n_ov; j++) for (uint32_t w = 0; w < ov[j].wn; w++) {
+		const hb_wl_t &u = ov[j].w[w];
+		if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
+		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1;
+		for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
+			const uint32_t op = ov[j].pool[u.cidx + ci] >> 14, cl = ov[j].pool[u.cidx + ci] & 0x3fff; const int64_t ws = xk;
+			if (op != 2) xk += cl;
+			if (op != 1) continue;
+			const int64_t oe = xk < e0 ? xk : e0;
+			for (int64_t t = ws; t < oe; t++) if (cnt[t] <= 126) cnt[t]++;
+		}
+	}
+	uint32_t ns = 0;
+	for (int64_t t = 0; t < ql; t++) { if (cnt[t] > 1) { cnt[t] = 1; ns++; } else cnt[t] = 0; } // flag: 1 = candidate site
+	uint32_t ne = 0;
+	for (uint32_t j = 0; j < n_ov; j++) for (uint32_t w = 0; w < ov[j].wn; w++) {
+		const hb_wl_t &u = ov[j].w[w];
+		if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
+		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1;
+		for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
+			const uint32_t op = ov[j].pool[u.cidx + ci] >> 14, cl = ov[j].pool[u.cidx + ci] & 0x3fff; const int64_t ws = xk;
+			if (op != 2) xk += cl;
+			if (op > 1) continue;
+			const int64_t oe = xk < e0 ? xk : e0;
+			for (int64_t t = ws; t < oe; t++) ne += cnt[t];
+		}
+	}
+	*n_site = ns; *n_ev = ne;
+}
+
+// pass 2: evidence in (site, overlap) order, allele statistics, haplotype call.
+// scratch: site_pos[n_site], site_off[n_site + 1], ev[n_ev], ev2[n_ev], snp[4 * n_site], ord[n_ov] (uint64)
+HB_HD void hb_ph_decide(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_ov, const uint8_t *flag, int64_t ql, uint32_t n_site, uint32_t n_ev,
+                        uint32_t *site_pos, uint32_t *site_off, PhEv *ev, PhEv *ev2, PhSnp *snp, uint64_t *ord, uint32_t *ov_off, const RsScratch &W, int s_hap_cov, int infor_cov, double up, int *ovf)
+{
+	if (!n_site || !n_ev) return;
+	const RdView Q = hb_rd_view(R, qid, 0);
+	uint32_t ns = 0;
+	for (int64_t t = 0; t < ql; t++) if (flag[t]) site_pos[ns++] = (uint32_t)t;
+	auto site_idx = [&](uint32_t t) -> uint32_t { uint32_t lo = 0, hi = ns; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (site_pos[mid] < t) lo = mid + 1; else hi = mid; } return lo; };
+	// counting sort by site: sizes, offsets, scatter (overlaps visited in ascending id => ascending id inside a site, which is also
+	// what push_info's sort by overlap id produces: the ids of a site are unique)
+	for (uint32_t k = 0; k <= ns; k++) site_off[k] = 0;
+	for (int pass = 0; pass < 2; pass++) {
+		for (uint32_t j = 0; j < n_ov; j++) {
+			const RdView T = hb_rd_view(R, ov[j].y_id, ov[j].rev);
+			for (uint32_t w = 0; w < ov[j].wn; w++) {
+				const hb_wl_t &u = ov[j].w[w];
+				if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
+				int64_t xk = u.x_start, yk = u.y_start; const int64_t e0 = (int64_t)u.x_end + 1;
+				for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
+					const uint32_t op = ov[j].pool[u.cidx + ci] >> 14, cl = ov[j].pool[u.cidx + ci] & 0x3fff; const int64_t ws = xk;
+					if (op != 2) xk += cl;
+					if (op != 3) yk += cl;
+					if (op > 1) continue;
+					const int64_t oe = xk < e0 ? xk : e0;
+					for (uint32_t si = site_idx((uint32_t)ws); si < ns && (int64_t)site_pos[si] < oe; si++) {
+						if (!pass) { site_off[si]++; continue; }
+						const int64_t t = site_pos[si]; PhEv e;
+						e.site = (uint32_t)t; e.ov = j; e.osite = (uint32_t)(t - xk + yk); e.cov = 1; e.type = (uint8_t)op; e.pad[0] = e.pad[1] = 0;
+						e.base = (uint8_t)(op == 0 ? Q.at(t) : T.at(t - xk + yk));
+						ev[site_off[si]++] = e;
+					}
+				}
+			}
+		}
+		if (!pass) { uint32_t acc = 0; for (uint32_t k = 0; k < ns; k++) { const uint32_t c = site_off[k]; site_off[k] = acc; acc += c; } } // start of every site; the scatter turns it into the end
+	}
+	// push_info per site (Correct.cpp:10511-10600, oa = NULL, v8 = NULL): allele statistics, evidence kept only for real alleles
+	uint32_t n_snp = 0, m_ev = 0, beg = 0;
+	for (uint32_t k = 0; k < ns; k++) {
+		const uint32_t end = site_off[k]; uint64_t occ_0 = 0, occ_1[5] = { 0, 0, 0, 0, 0 }, occ_2 = 0, diff = 0; int64_t sid[5] = { -1, -1, -1, -1, -1 };
+		for (uint32_t i = beg; i < end; i++) { if (ev[i].type == 0) occ_0++; else { occ_1[ev[i].base]++; diff++; } occ_2++; }
+		if (!(occ_0 == 0 || diff <= 1)) {
+			uint32_t m = 0;
+			for (int b = 0; b < 4; b++) if (occ_1[b] >= 2) {
+				PhSnp &p = snp[n_snp]; p.id = n_snp; p.occ_0 = (uint32_t)(1 + occ_0); p.occ_1 = (uint32_t)occ_1[b]; p.occ_2 = (uint32_t)(occ_2 - p.occ_0 - p.occ_1);
+				p.site = site_pos[k]; p.score = -1; p.overlap_num = (uint32_t)occ_2; p.pad = 0; sid[b] = n_snp++; m++;
+			}
+			if (m) for (uint32_t i = beg; i < end; i++) {
+				PhEv e = ev[i];
+				if (e.type == 0) e.osite = n_snp - 1;
+				else if (sid[e.base] >= 0) { e.cov = e.osite; e.osite = (uint32_t)sid[e.base]; }
+				else continue;
+				ev2[m_ev++] = e;
+			}
+		}
+		beg = end;
+	}
+	if (!m_ev) return;
+	// generate_haplotypes_naive_HiFi, Correct.cpp:8845-9110 (multi_check = 1, st_max = -1 => is_st_bs is never true)
+	// (a) drop the SNP sites that touch another SNP site; evidence follows its statistics
+	uint32_t m_snp = 0, m_list = 0;
+	{
+		uint32_t i = 0;
+		for (uint32_t k = 1, l = 0; k <= n_snp; ++k) {
+			if (k == n_snp || snp[k].site != snp[l].site) {
+				if (l > 0 && snp[l].site == snp[l - 1].site + 1) { l = k; continue; }
+				if (k < n_snp && snp[l].site + 1 == snp[k].site) { l = k; continue; }
+				for (; i < m_ev && ev2[i].site != snp[l].site; i++);
+				const uint32_t m_off = l - m_snp;
+				for (; i < m_ev && ev2[i].site == snp[l].site; i++) { ev2[m_list] = ev2[i]; ev2[m_list++].osite -= m_off; }
+				for (; l < k; l++) snp[m_snp++] = snp[l];
+			}
+		}
+	}
+	n_snp = m_snp; m_ev = m_list;
+	if (!n_snp || !m_ev) return;
+	// (b) evidence grouped by overlap with klib's unstable radix sort restated move for move (hb_rs_sort32): the order of an overlap's
+	//     sites decides which statistics the reference's stale `s` pointer refers to in the multi_check block below
+	{ auto key = [](const PhEv &e) -> uint32_t { return e.ov; }; if (hb_rs_sort32(ev2, ev2 + m_ev, key, W)) { *ovf = 1; return; } }
+	PhEv *L = ev2;
+	for (uint32_t j = 0; j <= n_ov; j++) ov_off[j] = 0;
+	for (uint32_t i = 0; i < m_ev; i++) ov_off[L[i].ov + 1]++;
+	for (uint32_t j = 0; j < n_ov; j++) ov_off[j + 1] += ov_off[j];
+#define PH_REAL(s_) (!((s_).occ_0 < 2 || (s_).occ_1 < 2))
+#define PH_ALLELE(s_) ((int)(s_).occ_0 >= s_hap_cov && (int)(s_).occ_1 >= infor_cov)
+	int64_t sp = -1, tp = -1; // the reference's function-level `SnpStats *s, *t` (indices; -1 = NULL): they are read stale further down
+	uint32_t n_ord = 0;
+	for (uint32_t j = 0; j < n_ov; j++) {
+		uint64_t o = 0;
+		for (uint32_t i = ov_off[j]; i < ov_off[j + 1]; i++) { if (L[i].type != 1) continue; sp = L[i].osite; const PhSnp &q = snp[sp]; if (PH_REAL(q) && PH_ALLELE(q)) o++; }
+		if (o > 0) ord[n_ord++] = ((uint64_t)(0xffffffffu - o) << 32) | ov_off[j]; // more alleles first, then list position
+	}
+	if (n_ord) {
+		for (uint32_t a = 1; a < n_ord; a++) { const uint64_t v = ord[a]; int32_t b = (int32_t)a - 1; while (b >= 0 && ord[b] > v) { ord[b + 1] = ord[b]; b--; } ord[b + 1] = v; } // keys are unique
+		for (uint32_t k = 0; k < n_ord; k++) {
+			const uint32_t l = (uint32_t)ord[k], j = L[l].ov; uint64_t o = 0;
+			for (uint32_t i = l; i < ov_off[j + 1]; i++) { if (L[i].type != 1) continue; sp = L[i].osite; const PhSnp &q = snp[sp]; if (PH_REAL(q) && PH_ALLELE(q)) o++; }
+			if (!o) continue;
+			if (ov[j].is_match == 1) ov[j].is_match = 2;
+			for (uint32_t i = l; i < ov_off[j + 1]; i++) {
+				sp = L[i].osite;
+				if (L[i].type == 1) snp[sp].score = 1;
+				else for (int64_t z = L[i].osite; z >= 0; z--) { tp = z; if (snp[sp].site != snp[z].site) break; snp[z].occ_0 -= L[i].cov; }
+			}
+		}
+		for (uint32_t k = 0; k < n_ord; k++) {
+			const uint32_t l = (uint32_t)ord[k], j = L[l].ov; uint64_t o = 0;
+			for (uint32_t i = l; i < ov_off[j + 1]; i++) { if (L[i].type != 1) continue; sp = L[i].osite; const PhSnp &q = snp[sp]; if (PH_REAL(q) && q.score == 1) o++; }
+			if (ov[j].is_match == 1 && o > 0) ov[j].is_match = 2;
+		}
+		for (uint32_t j = 0; j < n_ov; j++) if (ov[j].is_match == 1) for (uint32_t i = ov_off[j]; i < ov_off[j + 1]; i++) if (L[i].type == 1) snp[L[i].osite].score = -1;
+	}
+	// multi_check: isolated minor alleles shared by >= 2 same-haplotype overlaps (Correct.cpp:9036-9083); stat ids collected in `ev` (free now)
+	{
+		uint64_t *srt = (uint64_t *)ev; uint32_t sn = 0;
+		for (uint32_t j = 0; j < n_ov; j++) {
+			if (ov_off[j] == ov_off[j + 1] || ov[j].is_match == 2) continue;
+			uint32_t o = 0;
+			for (uint32_t i = ov_off[j]; i < ov_off[j + 1]; i++) {
+				if (L[i].type != 1) continue;
+				sp = L[i].osite; const PhSnp &q = snp[sp];
+				if (!PH_REAL(q) || PH_ALLELE(q) || q.score == 1) continue;
+				srt[sn + o++] = L[i].osite;
+			}
+			if ((double)o >= (double)ov[j].align_length * up) {
+				uint64_t *a = srt + sn; uint32_t z = 0;
+				for (uint32_t x = 1; x < o; x++) { const uint64_t v = a[x]; int32_t b = (int32_t)x - 1; while (b >= 0 && a[b] > v) { a[b + 1] = a[b]; b--; } a[b + 1] = v; }
+				for (uint32_t i = 0; i < o; i++) { // sp / tp are NOT reset here: for i = 0 and i = o-1 the reference reads what earlier code left in s / t
+					if (i > 0) sp = (int64_t)a[i - 1];
+					if (i + 1 < o) tp = (int64_t)a[i + 1];
+					if (sp >= 0 && snp[sp].site + 32 > snp[a[i]].site) continue;
+					if (tp >= 0 && snp[a[i]].site + 32 > snp[tp].site) continue;
+					a[z++] = a[i];
+				}
+				if (z >= 2) sn += z;
+			}
+		}
+		if (sn) {
+			for (uint32_t x = 1; x < sn; x++) { const uint64_t v = srt[x]; int32_t b = (int32_t)x - 1; while (b >= 0 && srt[b] > v) { srt[b + 1] = srt[b]; b--; } srt[b + 1] = v; }
+			for (uint32_t k = 1, l = 0; k <= sn; ++k) { if (k == sn || srt[k] != srt[l]) { if (k - l >= 2) snp[srt[l]].score = 1; } l = k; }
+		}
+	}
+	for (uint32_t j = 0; j < n_ov; j++) { // Correct.cpp:9085-9108
+		if (ov_off[j] == ov_off[j + 1]) continue;
+		if (ov[j].is_match == 2) ov[j].strong = 1;
+		else if (ov[j].is_match == 1) for (uint32_t i = ov_off[j]; i < ov_off[j + 1]; i++) {
+			const PhSnp &q = snp[L[i].osite];
+			if (q.score == 1 && PH_REAL(q)) { ov[j].strong = 1; if (L[i].type == 1) { ov[j].is_match = 2; break; } }
+		}
+	}
+#undef PH_REAL
+#undef PH_ALLELE
+}

@@ -19,6 +19,7 @@
 #include "hb_sketch.cuh"
 #include "hb_final.cuh"
 #include "hb_ecaln.cuh"
+#include "hb_ecphase.cuh"
 
 #define HB_FULL 0xffffffffu
 static __device__ __forceinline__ int hb_lane() { return threadIdx.x & 31; }
@@ -1156,9 +1157,9 @@ __global__ void __launch_bounds__(128) k_ecb_prep(EcCigArgs A)
 	A.prep[o] = pr; A.nseg[o] = ns;
 }
 // segment: thread / inter-anchor segment.  TIER0 = true: one thread per segment of the batch with a small private scratch (trace of
-// 640 words, 4-word band: enough for the ~35-bp segments between neighbouring minimizers); what does not fit goes to the queue.
+// 1024 words = 204 columns of a one-word band, 4-word band at most: the segments between neighbouring minimizers); what does not fit goes to the queue.
 // TIER0 = false: grid-stride over a queue of deferred segments with launch-sized global scratch.
-#define ECB_T0_PATH 640
+#define ECB_T0_PATH 1024
 #define ECB_T0_VS 4
 #define ECB_T0_CIG 72
 template <bool TIER0>
@@ -1220,6 +1221,48 @@ __global__ void k_gather_wl(uint64_t n_ov, const hb_alnb_t *__restrict__ in, con
 }
 __global__ void k_ecb_wn(uint64_t n_ov, const hb_alnb_t *__restrict__ in, uint32_t *__restrict__ wn)
 { uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o < n_ov) wn[o] = in[o].w_n; }
+
+// ----------------------------------------------------------------------------
+// phasing (row a13, hb_ecphase.cuh): thread / read.  k_ph_count gathers the read's accepted overlaps, counts mismatch columns
+// per query position and sizes the evidence; k_ph_decide collects the evidence, derives the allele statistics and makes the
+// greedy haplotype call (is_match 1 / 2, strong) with exactly-sized scratch.
+// ----------------------------------------------------------------------------
+struct PhArgs {
+	DevReads R; uint64_t r0, nR; const uint64_t *o_off; const OvDesc *desc; const hb_chain_t *ch; const hb_aln_t *aln; const hb_alnb_t *alnb; const hb_wl_t *wl; const uint16_t *pool;
+	PhOv *ov; uint32_t *n_acc; const uint64_t *b_off; uint8_t *cnt; uint32_t *n_site, *n_ev; const uint64_t *site_off, *ev_off;
+	uint32_t *site_pos, *site_o; PhEv *ev, *ev2; PhSnp *snp; uint64_t *ord; uint32_t *ov_o; hb_phase_t *out; int *err;
+};
+__global__ void __launch_bounds__(128) k_ph_count(PhArgs A)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= A.nR) return;
+	const uint64_t o0 = A.o_off[r], o1 = A.o_off[r + 1]; PhOv *ov = A.ov + o0; uint32_t n = 0;
+	for (uint64_t o = o0; o < o1; o++) {
+		const hb_alnb_t b = A.alnb[o]; if (b.st != 2) continue;
+		const hb_chain_t &c = A.ch[A.desc[o].slot];
+		PhOv v; v.w = A.wl + b.w_off; v.wn = b.w_n; v.pool = A.pool; v.y_id = c.y_id; v.rev = c.y_pos_strand; v.align_length = A.aln[o].align_length; v.is_match = 1; v.strong = 0;
+		ov[n++] = v;
+	}
+	uint32_t ns = 0, ne = 0;
+	if (n) hb_ph_count(ov, n, A.cnt + A.b_off[r], A.R.len[A.r0 + r], &ns, &ne);
+	A.n_acc[r] = n; A.n_site[r] = ns; A.n_ev[r] = ne;
+}
+__global__ void __launch_bounds__(64) k_ph_decide(PhArgs A)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= A.nR) return;
+	const uint64_t o0 = A.o_off[r], o1 = A.o_off[r + 1]; PhOv *ov = A.ov + o0; const uint32_t n = A.n_acc[r];
+	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st }; int ovf = 0;
+	if (n) hb_ph_decide(A.R, A.r0 + r, ov, n, A.cnt + A.b_off[r], A.R.len[A.r0 + r], A.n_site[r], A.n_ev[r], A.site_pos + A.site_off[r], A.site_o + A.site_off[r] + r,
+	                    A.ev + A.ev_off[r], A.ev2 + A.ev_off[r], A.snp + 4 * A.site_off[r], A.ord + o0, A.ov_o + o0 + r, W, 3, 3, 0.04, &ovf); // s_hap_cov = infor_cov = 3 (CommandLines.cpp:333-334), up = 0.04
+	if (ovf) atomicOr(A.err, 128);
+	uint32_t k = 0;
+	for (uint64_t o = o0; o < o1; o++) {
+		const hb_alnb_t b = A.alnb[o]; const hb_chain_t &c = A.ch[A.desc[o].slot]; hb_phase_t p;
+		p.st = b.st; p.y_id = c.y_id; p.rev = c.y_pos_strand; p.is_match = 0; p.strong = 0; p.need_rechain = 0;
+		if (b.st == 2) { p.x_pos_s = b.x_pos_s; p.x_pos_e = b.x_pos_e; p.y_pos_s = b.y_pos_s; p.y_pos_e = b.y_pos_e; p.nh_err = (uint32_t)b.nh_err; p.is_match = ov[k].is_match; p.strong = ov[k].strong; p.need_rechain = (uint32_t)b.need_rechain; k++; }
+		else { p.x_pos_s = c.x_pos_s; p.x_pos_e = c.x_pos_e; p.y_pos_s = c.y_pos_s; p.y_pos_e = c.y_pos_e; p.nh_err = 0; }
+		A.out[o] = p;
+	}
+}
 
 // ----------------------------------------------------------------------------
 // window alignment: ed_band_cal_semi_64_w_absent_diag

@@ -28,6 +28,10 @@ ALNB = np.dtype([("st", "<i4"), ("need_rechain", "<i4"), ("re", "<i8"), ("nh_err
                  ("w_off", "<u8"), ("w_n", "<u4"), ("pad", "<u4")])
 
 
+PHASE = np.dtype([("st", "<i4"), ("y_id", "<u4"), ("rev", "<u4"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"), ("nh_err", "<u4"),
+                  ("is_match", "<u4"), ("strong", "<i4"), ("need_rechain", "<u4"), ("pad", "<u4")])
+
+
 class HBError(RuntimeError):
     pass
 
@@ -201,6 +205,15 @@ class Engine:
         rec = np.zeros(int(off[-1]) + 1, ALNB); wl = np.zeros(nw.value + 1, WL); cig = np.zeros(2 * nc.value + 4096, np.uint16)
         self._ck(_lib().hb_ec_cigar(*a, _p(rec), C.c_uint64(rec.size), _p(wl), C.c_uint64(wl.size), _p(cig), C.c_uint64(cig.size), C.byref(nw), C.byref(nc)))
         return off, rec[:int(off[-1])], wl[:nw.value], cig[:nc.value]
+
+    def ec_phase(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775):
+        """alignment stage (rows a8-a11) + phasing (row a13) of an EC round -> (off, PHASE records, one per chain)"""
+        n = r1 - r0
+        off = np.zeros(n + 1, np.uint64)
+        self._ck(_lib().hb_ec_phase(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), C.c_void_p(0), C.c_uint64(0)))
+        rec = np.zeros(int(off[-1]) + 1, PHASE)
+        self._ck(_lib().hb_ec_phase(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), _p(rec), C.c_uint64(rec.size)))
+        return off, rec[:int(off[-1])]
 
     # ---- final pass
     def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None, out=None):

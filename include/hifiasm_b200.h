@@ -153,6 +153,13 @@ int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double
                 uint64_t *off, hb_alnb_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
                 uint64_t *n_wl, uint64_t *n_cig);
 
+/* ---- phasing of an EC round (row a13) on top of steps A-C: rphase_hc (Correct.cpp:20191, HiFi path) for every read of [r0,r1).
+ * rec[j] (hb_chains order): st = step A's status; for st == 2 the overlap's coordinates after step C, non_homopolymer_errors,
+ * is_match (1 = same haplotype, 2 = carries informative minor alleles: the other haplotype) and strong
+ * (overlap_region.is_match / strong, Hash_Table.h:78-106); is_match = 0 for overlaps the alignment stage rejected.          */
+typedef struct { int32_t st; uint32_t y_id, rev, x_pos_s, x_pos_e, y_pos_s, y_pos_e, nh_err, is_match; int32_t strong; uint32_t need_rechain, pad; } hb_phase_t;
+int hb_ec_phase(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_phase_t *rec, uint64_t rec_cap);
+
 /* ---- final overlap pass: cal_ov_r(n_thre, n_a, new_idx=1) (ecovlp.h:15;
  * ecovlp.cpp:6385 -> worker_hap_dc_ec_gen_new_idx 3948) -----------------------
  * prev_* = R_INF.paf[] / R_INF.reverse_paf[] of the last EC round, flattened

@@ -158,3 +158,13 @@ def ec_align_B_par(reads, rid, ch, fc, hits, A, WA, e_rate=0.04, w_l=775, gaps=0
                                   C.c_double(e_rate), C.c_int32(w_l), C.c_int32(gaps), C.c_int32(cig_words),
                                   _p(out), _p(wl), C.c_uint64(cap_w), _p(pool), C.c_uint64(cap), C.byref(used), C.byref(nw), nt)
     return rc, out[:ch.size], wl[:nw.value], pool[:used.value], (nt[0], nt[1])
+
+
+def ec_phase(reads, rid, ch, A, B, WB, CB):
+    """rphase_hc over the accepted overlaps (B = steps B + C output) -> (is_match u8[], strong i8[]) per accepted overlap"""
+    ch = np.ascontiguousarray(ch); A = np.ascontiguousarray(A); B = np.ascontiguousarray(B)
+    WB = np.ascontiguousarray(WB if WB.size else np.zeros(1, WL)); CB = np.ascontiguousarray(CB if CB.size else np.zeros(1, np.uint16))
+    im = np.zeros(ch.size + 1, np.uint8); st = np.zeros(ch.size + 1, np.int8); n = C.c_uint32()
+    rc = lib().emu_ec_phase(reads.h, C.c_uint32(rid), _p(ch), C.c_uint32(ch.size), _p(A), _p(B), _p(WB), _p(CB), _p(im), _p(st), C.byref(n))
+    assert rc == 0
+    return im[:n.value], st[:n.value]

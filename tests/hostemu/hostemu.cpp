@@ -14,6 +14,7 @@
 #include "../../hifiasm_b200/csrc/hb_sketch.cuh"
 #include "../../hifiasm_b200/csrc/hb_final.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecaln.cuh"
+#include "../../hifiasm_b200/csrc/hb_ecphase.cuh"
 
 struct EmuReads { DevReads d; std::vector<uint8_t> packed; std::vector<uint64_t> off, noff; std::vector<uint32_t> len, npos; };
 struct EmuFt { DevFt d; std::vector<uint64_t> key; std::vector<int32_t> val; };
@@ -356,6 +357,27 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 	}
 	*pool_used = used; *n_wl = nw;
 	return rc | (used > pool_cap ? 128 : 0);
+}
+
+// phasing (row a13) of the accepted overlaps of one read: bodies of k_ph_count / k_ph_decide.  alnb / wl / pool = output of steps B + C,
+// aln = step A (align_length).  is_match / strong are written per ACCEPTED overlap, in list order.
+int emu_ec_phase(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch, const hb_aln_t *aln, const hb_alnb_t *alnb, const hb_wl_t *wl, const uint16_t *pool,
+                 uint8_t *is_match, int8_t *strong, uint32_t *n_acc)
+{
+	EmuReads *r = (EmuReads *)reads; std::vector<PhOv> ov; int ovf = 0;
+	for (uint32_t j = 0; j < n_ch; j++) {
+		if (alnb[j].st != 2) continue;
+		PhOv o; o.w = wl + alnb[j].w_off; o.wn = alnb[j].w_n; o.pool = pool; o.y_id = ch[j].y_id; o.rev = ch[j].y_pos_strand; o.align_length = aln[j].align_length; o.is_match = 1; o.strong = 0;
+		ov.push_back(o);
+	}
+	const int64_t ql = r->d.len[rid]; std::vector<uint8_t> cnt(ql + 1, 0); uint32_t ns = 0, ne = 0;
+	hb_ph_count(ov.data(), (uint32_t)ov.size(), cnt.data(), ql, &ns, &ne);
+	std::vector<uint32_t> site_pos(ns + 1), site_off(ns + 2), ov_off(ov.size() + 2); std::vector<PhEv> ev(ne + 1), ev2(ne + 1); std::vector<PhSnp> snp(4 * (size_t)ns + 1); std::vector<uint64_t> ord(ov.size() + 1);
+	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
+	hb_ph_decide(r->d, rid, ov.data(), (uint32_t)ov.size(), cnt.data(), ql, ns, ne, site_pos.data(), site_off.data(), ev.data(), ev2.data(), snp.data(), ord.data(), ov_off.data(), W, 3, 3, 0.04, &ovf);
+	for (size_t k = 0; k < ov.size(); k++) { is_match[k] = ov[k].is_match; strong[k] = ov[k].strong; }
+	*n_acc = (uint32_t)ov.size();
+	return ovf;
 }
 
 } // extern "C"

@@ -103,6 +103,18 @@ def _check_stages(g, eng, mode, rs):
             continue
         dc = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WG[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CG) for b in acc)
         assert dc == int(g.digest(mode, "alnC")[i]), "EC alignment step C, read %d" % i
+    # phasing (row a13) on top of the step-C state: k_ph_count / k_ph_decide
+    poff, P = eng.ec_phase(0, n, float(p["bw_thres"]), 0.04, 775)
+    assert (poff == coff).all() and (P["st"] == B["st"]).all()
+    for i in range(n):
+        acc = P[int(poff[i]):int(poff[i + 1])]; acc = acc[acc["st"] == 2]
+        if acc["need_rechain"].any():
+            continue
+        pa = np.zeros(acc.size, alnlib.PH)
+        for f in alnlib.PH.names:
+            pa[f] = acc[f].astype(np.int64).astype(np.uint32)
+        assert dg(pa.tobytes()) == int(g.digest(mode, "phase")[i]), "rphase_hc, read %d" % i
+        assert int((acc["is_match"] == 2).sum()) == int(g.count(mode, "phase_hap2")[i])
     return hom, het
 
 

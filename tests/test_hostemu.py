@@ -116,6 +116,14 @@ def test_ec_align_step_A(ctx):
             assert rc == 0 and (Bp["re"] == B["re"]).all()
             dp = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WP[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CP) for b in Bp[Bp["st"] == 2])
             assert dp == int(g.digest("raw", "alnC")[i]), "steps B + C, segment-parallel pipeline, read %d" % i
+            # phasing (row a13): bodies of k_ph_count / k_ph_decide
+            im, sg = emu.ec_phase(er, i, emu.to_chain(ch), A, Bc, WCc, CCc)
+            acc_b = Bc[Bc["st"] == 2]; acc_c = ch[Bc["st"] == 2]
+            pa = np.zeros(acc_b.size, alnlib.PH)
+            pa["y_id"] = acc_c["y_id"]; pa["rev"] = acc_c["y_pos_strand"]; pa["nh_err"] = acc_b["nh_err"].astype(np.uint32); pa["is_match"] = im; pa["strong"] = sg.astype(np.int32).astype(np.uint32)
+            for f in ("x_pos_s", "x_pos_e", "y_pos_s", "y_pos_e"):
+                pa[f] = acc_b[f]
+            assert dg(pa.tobytes()) == int(g.digest("raw", "phase")[i]), "rphase_hc, read %d" % i
 
 
 def test_final_pass(ctx):
