@@ -545,6 +545,68 @@ HB_HD void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, const
 	const int32_t tn0 = tn - 1, pe = pn - 1;
 	ez.nword = nword;
 	if ((uint64_t)nword * (uint64_t)tn * 5 > ez.pcap || nword > ez.vstride) { ez.ovf = 1; return; }
+	if (nword == 1) { // the band fits one word (thre <= 31: the bulk of the segments): same algorithm with the vectors in registers
+		uint64_t P0 = 0, P1 = 0, P2 = 0, P3 = 0, VP, VN, X, D0 = 0, HN = 0, HP = 0;
+		auto pch1 = [&](int32_t j) -> int { return T.at(ps0 + (mode == 2 ? pidx - j : j)); };
+		auto tch1 = [&](int32_t j) -> int { return Q.at(qs0 + (mode == 2 ? tidx - j : j)); };
+		auto peq_or = [&](int cc, uint64_t m) { if (cc == 0) P0 |= m; else if (cc == 1) P1 |= m; else if (cc == 2) P2 |= m; else if (cc == 3) P3 |= m; };
+		if (mode == 3) { VP = 0; VN = (1ULL << abs_diag) - 1; bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn; i_bd = abs_diag; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = (thre << 1) - abs_diag; err = abs_diag; }
+		else { bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = thre; err = thre; VN = (1ULL << thre) - 1; VP = ((1ULL << ((thre << 1) + 1)) - 1) ^ VN; }
+		const uint64_t mm = 1ULL << (thre << 1);
+		ez.pn = 0;
+		for (i = 0; i <= tn0; i++) {
+			const int tc = tch1(i);
+			X = (tc == 0 ? P0 : tc == 1 ? P1 : tc == 2 ? P2 : tc == 3 ? P3 : 0ULL) | VN;
+			D0 = ((VP + (X & VP)) ^ VP) | X;
+			HN = VP & D0; HP = VN | ~(VP | D0);
+			X = D0 >> 1;
+			VN = X & HP; VP = HN | ~(X | HP);
+			if (!(D0 & 1ULL)) { ++err; if (err > cut) return; }
+			if (i < tn0) {
+				if (mode == 1 || mode == 2) {
+					poff = i - thre; k = i + thre - pe;
+					if (k >= 0) {
+						if (tmp_e == INT32_MAX) { tmp_e = err; for (k = 0; poff < pe; poff++, k++) { tmp_e += (int32_t)((VP >> k) & 1ULL); tmp_e -= (int32_t)((VN >> k) & 1ULL); } }
+						else { k = (thre << 1) - k; if (k >= 0) { tmp_e += (int32_t)((HP >> k) & 1ULL); tmp_e -= (int32_t)((HN >> k) & 1ULL); } }
+						if (tmp_e <= ez.thre && tmp_e < ez.err) { ez.err = tmp_e; if (mode == 1) { ez.pe = pe; ez.te = i; } else { ez.ps = pidx - pe; ez.ts = tidx - i; } }
+					}
+				}
+				P0 >>= 1; P1 >>= 1; P2 >>= 1; P3 >>= 1;
+				++i_bd;
+				if (i_bd < pn) peq_or(pch1(i_bd), mm);
+			}
+			uint64_t *o = ez.path + ez.pn; o[0] = D0; o[1] = VP; o[2] = VN; o[3] = HP; o[4] = HN; ez.pn += 5;
+		}
+		if (mode == 0) {
+			int32_t site = tn - 1 - thre; const int32_t ct = pn - 1;
+			for (i = 0; site < ct; site++, i++) { err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); }
+			if (site == ct && err <= thre) { ez.err = err; ez.pe = pn - 1; ez.te = tn - 1; }
+			hb_mw_gen_trace(ez, thre, 1);
+		} else if (mode == 1 || mode == 2) {
+			int32_t site = tn - 1 - thre; const int32_t ct = pn - 1;
+			for (i = 0; site < ct; i++) {
+				err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); site++;
+				if (err <= thre && err < ez.err) { ez.err = err; if (mode == 1) { ez.pe = site; ez.te = tn - 1; } else { ez.ps = pidx - site; ez.ts = tidx + 1 - tn; } }
+			}
+			if (err <= thre && err < ez.err) { ez.err = err; if (mode == 1) { ez.pe = site; ez.te = tn - 1; } else { ez.ps = pidx - site; ez.ts = tidx + 1 - tn; } }
+			if (ez.te - ez.ts + 1 != tn) { ez.pn /= (uint64_t)tn; ez.pn *= (uint64_t)(ez.te + 1 - ez.ts); }
+			if (mode == 1) hb_mw_gen_trace(ez, thre, 1);
+			else { poff = ez.ps; ez.ps = pidx - ez.pe; ez.pe = pidx - poff; hb_mw_gen_trace(ez, thre, 0); poff = ez.ps; ez.ps = pidx - ez.pe; ez.pe = pidx - poff; }
+		} else {
+			int32_t site = tn - 1 - abs_diag, uge = INT32_MAX; const int32_t ai = pn - tn + abs_diag;
+			for (i = 0; site < 0 && i < ai; i++, site++) { err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); }
+			if (err <= thre && err <= ez.err) { ez.err = err; ez.pe = site; }
+			site -= i;
+			while (i < ai) {
+				err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); ++i;
+				if (err <= thre && err <= ez.err) { ez.err = err; ez.pe = site + i; }
+				if (i == thre) uge = err;
+			}
+			if (uge <= thre && uge == ez.err) ez.pe = site + thre;
+			hb_mw_gen_trace(ez, abs_diag, 1);
+		}
+		return;
+	}
 	const int32_t VS = ez.vstride;
 	uint64_t *Peq = ez.vec, *VP = ez.vec + 5 * VS, *VN = VP + VS, *X = VN + VS, *D0 = X + VS, *HN = D0 + VS, *HP = HN + VS;
 	for (k = 0; k < 5 * VS; k++) Peq[k] = 0;

@@ -15,7 +15,7 @@
 #include "hb_ecaln.cuh"
 #include "hb_chain.cuh"
 
-struct PhEv { uint32_t site, ov, osite; uint32_t cov; uint8_t type, base, pad[2]; };             // haplotype_evdience (Correct.h:130-143); base = 0..3, 4 = N
+struct alignas(8) PhEv { uint32_t site, ov, osite, cov; uint8_t type, base, pad[6]; };           // haplotype_evdience (Correct.h:130-143); base = 0..3, 4 = N; 24 bytes: the array doubles as a u64 work list
 struct PhSnp { uint32_t id, overlap_num, occ_0, occ_1, occ_2, site; int32_t score; uint32_t pad; }; // SnpStats (Correct.h:152-167)
 struct PhOv { const hb_wl_t *w; uint32_t wn; const uint16_t *pool; uint32_t y_id, rev, align_length; uint8_t is_match; int8_t strong; };
 
@@ -83,7 +83,7 @@ HB_HD void hb_ph_decide(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_ov
 					for (uint32_t si = site_idx((uint32_t)ws); si < ns && (int64_t)site_pos[si] < oe; si++) {
 						if (!pass) { site_off[si]++; continue; }
 						const int64_t t = site_pos[si]; PhEv e;
-						e.site = (uint32_t)t; e.ov = j; e.osite = (uint32_t)(t - xk + yk); e.cov = 1; e.type = (uint8_t)op; e.pad[0] = e.pad[1] = 0;
+						e.site = (uint32_t)t; e.ov = j; e.osite = (uint32_t)(t - xk + yk); e.cov = 1; e.type = (uint8_t)op; for (int z = 0; z < 6; z++) e.pad[z] = 0;
 						e.base = (uint8_t)(op == 0 ? Q.at(t) : T.at(t - xk + yk));
 						ev[site_off[si]++] = e;
 					}
