@@ -502,7 +502,7 @@ __global__ void k_fc_grp_base(const GroupDir *__restrict__ dir, const uint32_t *
 struct StageOut { // host destinations of the stage APIs (all optional)
 	uint64_t *off; void *rec; uint64_t rec_cap;      // stage 1: minimizers / stage 2: anchors / stage 3: chains
 	uint64_t *hit_off; hb_hit_t *hits; uint64_t hit_cap; uint64_t *fc_off; uint64_t *fc; uint64_t fc_cap;
-	double e_rate; int32_t w_l; int32_t gaps; // window pass; step C on/off
+	double e_rate; int32_t w_l; int32_t gaps, use_prev; // window pass; step C on/off; row a12 (needs the previous round's overlaps staged)
 	hb_wl_t *wl; uint64_t wl_cap; uint16_t *cig; uint64_t cig_cap; uint64_t n_wl, n_cig; // step A of the EC alignment stage (mode 5)
 };
 
@@ -707,11 +707,18 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 				unsigned long long *d_pused = ba.zero<unsigned long long>(1);
 				HB_ALLOC_CHECK(ba);
 				k_ov_desc<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, w_l, d_woff, d_ooff, d_od);
+				uint8_t *d_ea = 0;
+				if (so->use_prev) { // row a12: the previous round's exact overlaps short-cut the alignment
+					if (!ctx->d_prev0_off) { hb_set_err(ctx, HB_E_STATE, "previous overlaps are not staged (hb_ec_stage_prev)"); return HB_E_STATE; }
+					d_ea = ba.zero<uint8_t>(n_ov + 1); HB_ALLOC_CHECK(ba);
+					ProfScope ps(ctx, "k_ec_ea");
+					if (n_ov) k_ec_ea<<<nblk(n_ov, 128), 128, 0, ctx->stream>>>(R, r0 + b0, n_ov, d_od, d_ch, ctx->d_prev0, ctx->d_prev0_off, d_ea);
+				}
 				uint64_t pool_cap = n_win * 4 + 4096, pool_used = 0; uint16_t *d_pool = 0;
 				for (int attempt = 0;; attempt++) {
 					d_pool = ba.get<uint16_t>(pool_cap); HB_ALLOC_CHECK(ba);
 					HB_CUDA(cudaMemsetAsync(d_pused, 0, 8, ctx->stream));
-					EcAlnArgs E; E.R = R; E.r0 = r0 + b0; E.n_ov = n_ov; E.desc = d_od; E.ch = d_ch; E.fc = d_fc; E.fc_grp_base = d_fcb; E.win = d_wout; E.e_rate = so->e_rate; E.w_l = w_l;
+					EcAlnArgs E; E.ea = d_ea; E.R = R; E.r0 = r0 + b0; E.n_ov = n_ov; E.desc = d_od; E.ch = d_ch; E.fc = d_fc; E.fc_grp_base = d_fcb; E.win = d_wout; E.e_rate = so->e_rate; E.w_l = w_l;
 					E.wl = d_wl; E.out = d_aln; E.path = d_path; E.cig_tmp = d_ctmp; E.pool = d_pool; E.pool_used = d_pused; E.pool_cap = pool_cap; E.err = d_err;
 					{
 						ProfScope ps(ctx, "k_ec_overlap");
@@ -738,7 +745,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					static const uint64_t path_words1 = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384; // half of tier 2's trace words
 					static const int32_t merge_cw0 = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
 					EcPrep *d_prep = ba.get<EcPrep>(n_ov + 1); uint32_t *d_nseg = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_segoff = ba.get<uint64_t>(n_ov + 2);
-					uint32_t *d_qn = ba.zero<uint32_t>(4); unsigned long long *d_spused = ba.zero<unsigned long long>(1);
+					uint32_t *d_qn = ba.zero<uint32_t>(8); unsigned long long *d_spused = ba.zero<unsigned long long>(1);
 					HB_ALLOC_CHECK(ba);
 					EcCigArgs G; memset(&G, 0, sizeof(G));
 					G.R = R; G.r0 = r0 + b0; G.n_ov = n_ov; G.desc = d_od; G.ch = d_ch; G.fc = d_fc; G.fc_grp_base = d_fcb; G.aln = d_aln; G.wlA = d_wl;
@@ -757,36 +764,40 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					HB_ALLOC_CHECK(ba);
 					G.n_seg = n_seg; G.segs = d_segs;
 					// ---- segments: tier 0 (private scratch) -> queue -> tier 1 (16 K trace words) -> queue -> tier 2 (the largest alignment the reference allows)
-					uint64_t spool_cap = n_seg / 2 + 65536, spool_used = 0; uint16_t *d_spool = 0; uint32_t h_q[4] = { 0, 0, 0, 0 };
+					uint64_t spool_cap = n_seg / 2 + 65536, spool_used = 0; uint16_t *d_spool = 0; uint32_t h_q[5] = { 0, 0, 0, 0, 0 };
 					for (int attempt = 0;; attempt++) {
 						d_spool = ba.get<uint16_t>(spool_cap); HB_ALLOC_CHECK(ba);
-						HB_CUDA(cudaMemsetAsync(d_spused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_qn, 0, 16, ctx->stream));
+						HB_CUDA(cudaMemsetAsync(d_spused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_qn, 0, 32, ctx->stream));
 						G.spool = d_spool; G.spool_used = d_spused; G.spool_cap = spool_cap;
-						G.q_in = 0; G.q_in_n = 0; G.q_out = d_q1; G.q_out_n = d_qn + 1;
+						// pre-pass: everything that needs no alignment; the rest goes to queue 0
+						G.q_in = 0; G.q_in_n = 0; G.q_out = d_q1; G.q_out_n = d_qn + 0;
 						{
-							ProfScope ps(ctx, "k_ecb_seg");
-							if (n_seg) k_ecb_seg<true><<<nblk(n_seg, 128), 128, 0, ctx->stream>>>(G);
+							ProfScope ps(ctx, "k_ecb_seg_fast");
+							if (n_seg) k_ecb_seg_fast<<<nblk(n_seg, 128), 128, 0, ctx->stream>>>(G);
 						}
 						HB_CUDA(cudaGetLastError());
-						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 16, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-						// scratch tiers 1..3: {trace words, band words, cigar runs, blocks of 128 threads}; a segment that overflows one tier queues for the next
+						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						// alignment tiers 0..3: {trace words, band words, cigar runs, blocks of 128 threads}; tier 0 keeps its scratch private (local memory);
+						// a segment that overflows one tier queues for the next (queues ping-pong between two arrays)
 						const struct { uint64_t pw; int32_t vs, cw; unsigned bl; const char *name; } TIER[4] = {
-							{ 0, 0, 0, 0, "" }, { 4096, 8, 256, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier1" }, { path_words1 * 2, HB_MW_MAXW, 4096, (unsigned)ctx->sm_count, "k_ecb_seg_tier2" },
+							{ 0, 0, 0, 0, "k_ecb_seg" }, { 4096, 8, 256, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier1" }, { path_words1 * 2, HB_MW_MAXW, 4096, (unsigned)ctx->sm_count, "k_ecb_seg_tier2" },
 							{ (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5, HB_MW_MAXW, 65535, 2u, "k_ecb_seg_tier3" } };
-						uint32_t *d_qs[5] = { 0, d_q1, d_q2, d_q1, 0 };
-						for (int tier = 1; tier <= 3 && h_q[tier]; tier++) {
+						for (int tier = 0; tier <= 3 && h_q[tier]; tier++) {
 							Arena sa(ctx);
-							const unsigned bl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)h_q[tier] + 127) / 128, (uint64_t)TIER[tier].bl)); const uint64_t nt = (uint64_t)bl * 128;
-							G.path = sa.get<uint64_t>(nt * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nt * 11 * (uint64_t)TIER[tier].vs); G.vstride = TIER[tier].vs;
-							G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw;
-							if (sa.failed) return HB_E_WS;
-							G.q_in = d_qs[tier]; G.q_in_n = d_qn + tier; G.q_out = tier < 3 ? d_qs[tier + 1] : 0; G.q_out_n = tier < 3 ? d_qn + tier + 1 : d_qn;
+							unsigned bl = (unsigned)(((uint64_t)h_q[tier] + 127) / 128);
+							if (tier > 0) {
+								bl = std::max(1u, std::min(bl, TIER[tier].bl)); const uint64_t nt = (uint64_t)bl * 128;
+								G.path = sa.get<uint64_t>(nt * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nt * 11 * (uint64_t)TIER[tier].vs); G.vstride = TIER[tier].vs;
+								G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw;
+								if (sa.failed) return HB_E_WS;
+							}
+							G.q_in = (tier & 1) ? d_q2 : d_q1; G.q_in_n = d_qn + tier; G.q_out = tier < 3 ? ((tier & 1) ? d_q1 : d_q2) : 0; G.q_out_n = d_qn + tier + 1;
 							{
 								ProfScope ps(ctx, TIER[tier].name);
-								k_ecb_seg<false><<<bl, 128, 0, ctx->stream>>>(G);
+								if (tier == 0) k_ecb_seg<true><<<bl, 128, 0, ctx->stream>>>(G); else k_ecb_seg<false><<<bl, 128, 0, ctx->stream>>>(G);
 							}
 							HB_CUDA(cudaGetLastError());
-							HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 16, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 						}
 						HB_CUDA(cudaMemcpyAsync(&spool_used, d_spused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 						HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1058,6 +1069,7 @@ extern "C" int hb_windows(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thr
 	return run_pass(ctx, r0, r1, 4, bw_thres, &so, 0);
 }
 
+static int stage_prev(hb_ctx *ctx, const hb_ma_hit_t *p0, const uint64_t *o0, const hb_ma_hit_t *p1, const uint64_t *o1);
 extern "C" int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l,
                            uint64_t *off, hb_aln_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,
                            uint64_t *n_wl, uint64_t *n_cig)
@@ -1077,13 +1089,18 @@ extern "C" int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_th
 {
 	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
 	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l;
-	so.wl = wl; so.wl_cap = wl_cap; so.cig = cig; so.cig_cap = cig_cap; so.gaps = gaps;
+	so.wl = wl; so.wl_cap = wl_cap; so.cig = cig; so.cig_cap = cig_cap; so.gaps = gaps & 1; so.use_prev = (gaps >> 1) & 1;
 	int rc = run_pass(ctx, r0, r1, 6, bw_thres, &so, 0);
 	if (n_wl) *n_wl = so.n_wl;
 	if (n_cig) *n_cig = so.n_cig;
 	return rc;
 }
 
+extern "C" int hb_ec_stage_prev(hb_ctx_t *ctx, const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off)
+{ // R_INF.paf[] of the previous EC round, flattened; only the source list matters to gen_hc_r_alin_ea
+	static const hb_ma_hit_t none = {}; std::vector<uint64_t> z(ctx->n_reads + 1, 0);
+	return stage_prev(ctx, prev_src, prev_src_off, &none, z.data());
+}
 extern "C" int hb_ec_phase(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_phase_t *rec, uint64_t rec_cap)
 {
 	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }

@@ -479,6 +479,7 @@ struct EcBCtx {
 	uint16_t *wc; int32_t wcn, wccap;     // cigar of the window under construction (aux_o->w_list.c tail), flushed to the pool when the window closes
 	int32_t open;                          // index of the window whose cigar is in wc (-1: none)
 	int32_t do_gaps; int64_t re_A, gap_re; // step C (reassign_gaps) applied when a window closes; errors removed by it
+	int32_t no_myers;                      // segment pre-pass: stop (status 5) where an alignment would start
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap;
 	int bad;
 };
@@ -950,6 +951,37 @@ HB_HD int64_t hb_cal_estimate_err_hc(const EcZ &z, int64_t wl, int64_t qs, int64
 	return tot;
 }
 
+HB_HD uint32_t hb_fwd16(const uint8_t *p, uint64_t pos)
+{ // 16 bases starting at `pos` as one word of 2-bit codes, first base in the top two bits (reads are padded: the 5-byte window never leaves the store)
+	const uint8_t *b = p + (pos >> 2); const uint32_t sh = (uint32_t)(pos & 3) << 1;
+	const uint64_t v = (uint64_t)b[0] << 32 | (uint64_t)b[1] << 24 | (uint64_t)b[2] << 16 | (uint64_t)b[3] << 8 | b[4];
+	return (uint32_t)(v >> (8 - sh));
+}
+HB_HD uint32_t hb_rc16(uint32_t w)
+{ // reverse the 16 2-bit groups and complement
+#ifdef __CUDA_ARCH__
+	w = __brev(w);
+#else
+	w = (w >> 16) | (w << 16); w = ((w & 0xff00ff00u) >> 8) | ((w & 0x00ff00ffu) << 8); w = ((w & 0xf0f0f0f0u) >> 4) | ((w & 0x0f0f0f0fu) << 4);
+	w = ((w & 0xccccccccu) >> 2) | ((w & 0x33333333u) << 2); w = ((w & 0xaaaaaaaau) >> 1) | ((w & 0x55555555u) << 1);
+#endif
+	w = ((w >> 1) & 0x55555555u) | ((w & 0x55555555u) << 1);
+	return ~w;
+}
+// query[qs, qs+n) == target-on-strand[ts, ts+n) ?  16 bases per step when neither read holds an N
+HB_HD bool hb_seq_equal(const RdView &Q, int64_t qs, const RdView &T, int64_t ts, int64_t n)
+{
+	int64_t k = 0;
+	if (!Q.nn && !T.nn) {
+		for (; k + 16 <= n; k += 16) {
+			const uint32_t a = hb_fwd16(Q.p, (uint64_t)(qs + k));
+			const uint32_t b = T.rev ? hb_rc16(hb_fwd16(T.p, (uint64_t)((int64_t)T.len - (ts + k) - 16))) : hb_fwd16(T.p, (uint64_t)(ts + k));
+			if (a != b) return false;
+		}
+	}
+	for (; k < n; k++) if (Q.at(qs + k) != T.at(ts + k)) return false;
+	return true;
+}
 HB_HD int64_t hb_cal_exact(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
 { // cal_exact_exz, Correct.cpp:15725-15762 (memcmp on decoded strings: an N only equals an N)
 	MwEz &ez = C.ez; int64_t ql = qe - qs, tl;
@@ -962,7 +994,7 @@ HB_HD int64_t hb_cal_exact(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int6
 	if (te > C.tl) te = C.tl;
 	ql = qe - qs; tl = te - ts;
 	if (ql != tl) return 0;
-	for (int64_t k = 0; k < ql; k++) if (C.q.at(qs + k) != C.t.at(ts + k)) return 0;
+	if (!hb_seq_equal(C.q, qs, C.t, ts, ql)) return 0;
 	ez.err = 0; hb_mez_push_trace(ez, 0, (uint32_t)ql);
 	ez.pl = (int32_t)tl; ez.ps = (int32_t)ts; ez.pe = (int32_t)(ts + tl - 1);
 	ez.tl = (int32_t)ql; ez.ts = (int32_t)qs; ez.te = (int32_t)(qs + ql - 1);
@@ -1006,6 +1038,7 @@ HB_HD int hb_seg_align(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t 
 		else if (hb_cal_exact(C, z, qs, qe, ts, te, mode)) return 1;
 	}
 	if (ql <= HB_MAX_SIN_L && (est >> 1) <= HB_MAX_SIN_E) {
+		if (C.no_myers) return 5;
 		thre = hb_scale_ed_thre((uint32_t)est, HB_MAX_SIN_E);
 		if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1;
 		if (ez.ovf) return 0;
@@ -1093,7 +1126,7 @@ HB_HD void hb_ecb_finish(EcBCtx &C, const EcZ &zA, int64_t re_A, hb_alnb_t *out)
 	out->x_pos_s = (uint32_t)xs; out->x_pos_e = (uint32_t)xe; out->y_pos_s = (uint32_t)ys; out->y_pos_e = (uint32_t)ye;
 	if (C.bad) out->st = -2;
 }
-HB_HD void hb_ecb_begin(EcBCtx &C, int64_t re_A) { C.awn = 0; C.wcn = 0; C.open = -1; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.re_A = re_A; C.gap_re = 0; }
+HB_HD void hb_ecb_begin(EcBCtx &C, int64_t re_A) { C.no_myers = 0; C.awn = 0; C.wcn = 0; C.open = -1; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.re_A = re_A; C.gap_re = 0; }
 
 // One accepted overlap.  zA = the overlap with step A's window list; re_A = step A's error estimate; ch_a / ch_n = its chain
 // anchors (refined in place, dropped anchors get id 0x7fffffff like return_t_chain does).  Result: out->st = 2 done,

@@ -1095,7 +1095,25 @@ __global__ void k_ov_desc(uint64_t nR, const uint64_t *__restrict__ c_off, const
 		OvDesc d; d.read = (uint32_t)r; d.slot = (uint32_t)(cb + s); d.nw = nw; d.pad = 0; d.w0 = w; desc[o + i] = d; w += nw;
 	}
 }
+// row a12 — gen_hc_r_alin_ea (ecovlp.cpp:2810-2866): a chain whose target / strand has an exact (el) record in the read's overlap list of
+// the previous round — the first such record in list order — with the same coordinates, and whose two substrings are still identical, is
+// accepted without alignment.  Thread per overlap; the lists are a few dozen records long.
+__global__ void k_ec_ea(DevReads R, uint64_t r0, uint64_t n_ov, const OvDesc *__restrict__ desc, const hb_chain_t *__restrict__ ch,
+                        const hb_ma_hit_t *__restrict__ prev, const uint64_t *__restrict__ prev_off, uint8_t *__restrict__ ea)
+{
+	const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
+	const OvDesc d = desc[o]; const hb_chain_t c = ch[d.slot]; const uint64_t g = r0 + d.read; uint8_t f = 0;
+	for (uint64_t k = prev_off[g]; k < prev_off[g + 1]; k++) {
+		const hb_ma_hit_t p = prev[k];
+		if (!p.el || p.tn != c.y_id || (p.rev & 1) != c.y_pos_strand) continue;
+		if (c.x_pos_s == (uint32_t)p.qns && c.x_pos_e + 1 == p.qe && c.y_pos_s == p.ts && c.y_pos_e + 1 == p.te)
+			f = (uint8_t)hb_exact_seq(R, g, (uint32_t)p.qns, p.qe, c.y_id, p.ts, p.te, (int)c.y_pos_strand);
+		break; // only the first exact record of the (target, strand) pair is looked at
+	}
+	ea[o] = f;
+}
 struct EcAlnArgs {
+	const uint8_t *ea; // row a12 flags (NULL: none)
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base; const hb_win_t *win;
 	double e_rate; int32_t w_l; hb_wl_t *wl; hb_aln_t *out; uint64_t *path; uint16_t *cig_tmp; uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; int *err;
 };
@@ -1108,7 +1126,8 @@ __global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
 		const OvDesc d = A.desc[o]; const hb_chain_t c = A.ch[d.slot];
 		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand);
 		hb_aln_t res; res.w_off = d.w0; res.pad = 0;
-		hb_ec_overlap_A(C, c, A.fc + A.fc_grp_base[d.slot] + c.fc_off, A.win + d.w0, (int32_t)d.nw, A.wl + d.w0, &res);
+		if (A.ea && A.ea[o]) { res.st = 3; res.align_length = 0; res.rr = 0; res.re = 0; res.w_n = 0; } // accepted by the previous round's exact record: no alignment
+		else hb_ec_overlap_A(C, c, A.fc + A.fc_grp_base[d.slot] + c.fc_off, A.win + d.w0, (int32_t)d.nw, A.wl + d.w0, &res);
 		A.out[o] = res;
 	}
 }
@@ -1122,7 +1141,7 @@ __global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
 __global__ void k_ecb_cap(uint64_t n_ov, const OvDesc *__restrict__ desc, const hb_chain_t *__restrict__ ch, const hb_aln_t *__restrict__ aln, uint32_t *__restrict__ cap)
 { // window capacity of an overlap = number of inter-anchor segments (+1 spare)
 	uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
-	cap[o] = aln[o].st == 2 ? ch[desc[o].slot].n_hits + 2 : 0;
+	cap[o] = aln[o].st == 2 ? ch[desc[o].slot].n_hits + 2 : (aln[o].st == 3 ? 2 : 0);
 }
 struct EcCigArgs {
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
@@ -1148,7 +1167,8 @@ __global__ void __launch_bounds__(128) k_ecb_prep(EcCigArgs A)
 {
 	const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= A.n_ov) return;
 	const hb_aln_t a = A.aln[o]; EcPrep pr; pr.ch_n = 0; pr.shortcut = 0; pr.q0 = pr.q1 = pr.t0 = pr.t1 = 0; uint32_t ns = 0;
-	if (a.st == 2) {
+	if (a.st == 3) { const hb_chain_t c = A.ch[A.desc[o].slot]; pr.shortcut = 1; pr.q0 = (int32_t)c.x_pos_s; pr.q1 = (int32_t)c.x_pos_e + 1; pr.t0 = (int32_t)c.y_pos_s; pr.t1 = (int32_t)c.y_pos_e + 1; }
+	else if (a.st == 2) {
 		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
 		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
 		hb_ecb_prep(z, a.re, A.R.len[A.r0 + d.read], A.R.len[c.y_id], ch_a, c.n_hits, A.dp_t + dpo, A.dp_p + dpo, A.dp_f + dpo, &pr);
@@ -1156,23 +1176,52 @@ __global__ void __launch_bounds__(128) k_ecb_prep(EcCigArgs A)
 	}
 	A.prep[o] = pr; A.nseg[o] = ns;
 }
-// segment: thread / inter-anchor segment.  TIER0 = true: one thread per segment of the batch with a small private scratch (trace of
-// 1024 words = 204 columns of a one-word band, 4-word band at most: the segments between neighbouring minimizers); what does not fit goes to the queue.
-// TIER0 = false: grid-stride over a queue of deferred segments with launch-sized global scratch.
+// segment pre-pass: thread / inter-anchor segment of the batch.  Everything that needs no alignment is decided here — empty segments,
+// segments inside exact windows, segments whose two substrings are identical (16 bases per compare) — and stored; the rest (an error
+// inside the segment: ~13 % at 0.2 % read error) is queued for the alignment kernel.  Light on registers, no private arrays.
+__global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
+{
+	const uint64_t sidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ uint64_t s_o;
+	if (threadIdx.x == 0) { // overlap of the block's first segment: last o with seg_off[o] <= sidx
+		const uint64_t s0 = (uint64_t)blockIdx.x * blockDim.x; uint64_t lo = 0, hi = A.n_ov;
+		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= s0) lo = mid; else hi = mid; }
+		s_o = lo;
+	}
+	__syncthreads();
+	if (sidx >= A.n_seg) return;
+	uint64_t o = s_o; while (A.seg_off[o + 1] <= sidx) o++;
+	const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
+	OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
+	ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+	uint16_t one[2];
+	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 1; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+	C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+	C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+	int64_t uq[2], ut[2], um;
+	const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
+	if (C.bad) atomicOr(A.err, 32);
+	if (st == 5 || C.ez.ovf) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; return; } // an alignment (or a > 32 k-base exact run) is needed
+	EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
+	A.segs[sidx] = sg;
+}
+// segment alignment: a queue of segment ids.  LOCAL = true: one thread per queued segment with a small private scratch (trace of 1024
+// words = 204 columns of a one-word band, 4-word band at most: the usual segment between neighbouring minimizers); LOCAL = false:
+// grid-stride with launch-sized global scratch.  A segment that overflows its scratch queues for the next tier.
 #define ECB_T0_PATH 1024
 #define ECB_T0_VS 4
 #define ECB_T0_CIG 72
-template <bool TIER0>
+template <bool LOCAL>
 __global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
 {
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
-	uint64_t l_path[TIER0 ? ECB_T0_PATH : 1], l_vec[TIER0 ? 11 * ECB_T0_VS : 1]; uint16_t l_cig[TIER0 ? ECB_T0_CIG : 1];
-	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
-	if (TIER0) { C.ez.path = l_path; C.ez.pcap = ECB_T0_PATH; C.ez.vec = l_vec; C.ez.vstride = ECB_T0_VS; C.ez.cig = l_cig; C.ez.ccap = ECB_T0_CIG; }
+	uint64_t l_path[LOCAL ? ECB_T0_PATH : 1], l_vec[LOCAL ? 11 * ECB_T0_VS : 1]; uint16_t l_cig[LOCAL ? ECB_T0_CIG : 1];
+	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+	if (LOCAL) { C.ez.path = l_path; C.ez.pcap = ECB_T0_PATH; C.ez.vec = l_vec; C.ez.vstride = ECB_T0_VS; C.ez.cig = l_cig; C.ez.ccap = ECB_T0_CIG; }
 	else { C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * 11 * (uint64_t)A.vstride; C.ez.vstride = A.vstride; C.ez.cig = A.cig_tmp + tid * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words; }
-	const uint64_t n_work = TIER0 ? A.n_seg : (uint64_t)*A.q_in_n;
+	const uint64_t n_work = (uint64_t)*A.q_in_n;
 	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
-		const uint64_t sidx = TIER0 ? wk : A.q_in[wk];
+		const uint64_t sidx = A.q_in[wk];
 		uint64_t lo = 0, hi = A.n_ov; // overlap of the segment: last o with seg_off[o] <= sidx
 		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
 		const uint64_t o = lo; const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
@@ -1199,7 +1248,7 @@ __global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
 	C.ez.vec = 0; C.ez.vstride = 0;
 	for (uint64_t o = tid; o < A.n_ov; o += nthr) {
 		const hb_aln_t a = A.aln[o];
-		if (A.pass == 0) { if (a.st != 2) { hb_alnb_t r; r.st = a.st; r.need_rechain = 0; r.re = 0; r.nh_err = 0; r.x_pos_s = r.x_pos_e = r.y_pos_s = r.y_pos_e = 0; r.w_off = A.wl_off[o]; r.w_n = 0; r.pad = 0; A.out[o] = r; continue; } }
+		if (A.pass == 0) { if (a.st != 2 && a.st != 3) { hb_alnb_t r; r.st = a.st; r.need_rechain = 0; r.re = 0; r.nh_err = 0; r.x_pos_s = r.x_pos_e = r.y_pos_s = r.y_pos_e = 0; r.w_off = A.wl_off[o]; r.w_n = 0; r.pad = 0; A.out[o] = r; continue; } }
 		else if (A.out[o].st != -1) continue;
 		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
 		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
@@ -1207,6 +1256,7 @@ __global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
 		C.aw = A.wl + A.wl_off[o]; C.awcap = (int32_t)(A.wl_off[o + 1] - A.wl_off[o]);
 		hb_alnb_t r; r.w_off = A.wl_off[o]; r.pad = 0;
 		hb_ecb_merge(C, z, a.re, A.prep[o], A.segs + A.seg_off[o], A.spool, &r);
+		if (a.st == 3 && r.st == 2) { r.x_pos_s = c.x_pos_s; r.x_pos_e = c.x_pos_e; r.y_pos_s = c.y_pos_s; r.y_pos_e = c.y_pos_e; r.pad = 1; } // no update_overlap_region on this path (ecovlp.cpp:2849-2852)
 		if (r.st == -1) atomicAdd(A.n_deferred, 1u);
 		if (r.st == -2) atomicOr(A.err, 32);
 		A.out[o] = r;

@@ -195,6 +195,11 @@ class Engine:
         self._ck(_lib().hb_ec_align(*a, _p(rec), C.c_uint64(rec.size), _p(wl), C.c_uint64(wl.size), _p(cig), C.c_uint64(cig.size), C.byref(nw), C.byref(nc)))
         return off, rec[:int(off[-1])], wl[:nw.value], cig[:nc.value]
 
+    def ec_stage_prev(self, prev_src, prev_src_off):
+        """stage R_INF.paf[] of the previous EC round (MA records + offsets) for the exact shortcut of row a12 (ec_cigar gaps & 2)"""
+        prev_src = np.ascontiguousarray(prev_src, dtype=MA); o = np.ascontiguousarray(prev_src_off, dtype=np.uint64)
+        self._ck(_lib().hb_ec_stage_prev(self.h, _p(prev_src if prev_src.size else np.zeros(1, MA)), _p(o)))
+
     def ec_cigar(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775, gaps=0):
         """steps A + B (+ C when gaps) of the alignment stage of an EC round (rows a8-a11): base-level CIGARs of the accepted overlaps
         -> (off, ALNB records, WL window lists, cigar pool)"""

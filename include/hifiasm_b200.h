@@ -147,7 +147,11 @@ int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double
  * (rechain_aln_hc, Correct.cpp:17669): that rescue is not built yet and such an overlap's result is not final.
  * gaps != 0 adds step C (row a11), reassign_gaps (Correct.cpp:25409): the indels of every window are left-normalised
  * (move_wins 25274, adjust_gap 25167, ajust_end_cigar 25252); nh_err = overlap_region.non_homopolymer_errors afterwards
- * (step A's estimate minus the mismatches the normalisation removed); re stays step B's total.                      */
+ * (step A's estimate minus the mismatches the normalisation removed); re stays step B's total.
+ * gaps & 2 adds row a12, the exact shortcut of gen_hc_r_alin_ea (ecovlp.cpp:2810): a chain that matches an exact (el) record of the read's
+ * overlap list of the previous round (staged with hb_ec_stage_prev = R_INF.paf[] flattened) in target, strand and coordinates, and whose
+ * substrings are still identical, is accepted without alignment: one exact window, nh_err = 0, pad = 1.                                  */
+int hb_ec_stage_prev(hb_ctx_t *ctx, const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off);
 typedef struct { int32_t st, need_rechain; int64_t re, nh_err; uint32_t x_pos_s, x_pos_e, y_pos_s, y_pos_e; uint64_t w_off; uint32_t w_n, pad; } hb_alnb_t;
 int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t gaps,
                 uint64_t *off, hb_alnb_t *rec, uint64_t rec_cap, hb_wl_t *wl, uint64_t wl_cap, uint16_t *cig, uint64_t cig_cap,

@@ -1592,3 +1592,35 @@ int hao_ec_phase(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint3
 	free(ov);
 	return 0;
 }
+
+/* ================================================================================================== */
+/* row a12: the exact shortcut of gen_hc_r_alin_ea (ecovlp.cpp:2810-2866)                               */
+/* ================================================================================================== */
+/* flag[j] = 1 when chain j is accepted without alignment: the read's overlap list of the previous round (in[], n_in) holds an
+ * exact (el) record for the same target and strand — the first such record in list order — with the same coordinates, and the
+ * two substrings are still identical. */
+int hao_ec_ea_flags(const hao_reads_t *r, uint32_t rid, const hao_ovlp_t *ch, uint32_t n_ch, const hao_ma_t *in, uint32_t n_in, uint8_t *flag)
+{
+	uint64_t *ei = MALLOC_N(uint64_t, n_in + 1), *oi = MALLOC_N(uint64_t, n_ch + 1), en = 0, k, i, ql = r->len[rid], tm = 0; char *qs = 0, *ts = 0;
+	memset(flag, 0, n_ch);
+	for (k = 0; k < n_in; k++) if (in[k].el) ei[en++] = ((((uint64_t)in[k].tn << 1) | (in[k].rev & 1)) << 32) | k;
+	if (!en) { free(ei); free(oi); return 0; }
+	for (k = 0; k < n_ch; k++) oi[k] = ((((uint64_t)ch[k].y_id << 1) | ch[k].y_pos_strand) << 32) | k;
+	qsort(ei, en, 8, u64_cmp); qsort(oi, n_ch, 8, u64_cmp); /* radix_sort_ec64 on unique keys */
+	qs = MALLOC_N(char, ql + 1); hao_decode(r, rid, qs);
+	for (k = i = 0; k < n_ch; k++) {
+		const hao_ovlp_t *z = &ch[(uint32_t)oi[k]]; uint64_t key = ((uint64_t)z->y_id << 1) | z->y_pos_strand;
+		for (; i < en && (ei[i] >> 32) < key; i++);
+		if (i < en && (ei[i] >> 32) == key) {
+			const hao_ma_t *p = &in[(uint32_t)ei[i]];
+			if (z->x_pos_s == (uint32_t)p->qns && z->x_pos_e + 1 == p->qe && z->y_pos_s == p->ts && z->y_pos_e + 1 == p->te) {
+				uint64_t tl = p->te - p->ts;
+				if (tl + 1 > tm) { tm = tl + 64; ts = (char *)realloc(ts, tm); }
+				hao_decode_sub(r, z->y_id, p->ts, (int64_t)tl, (int)z->y_pos_strand, ts);
+				if ((uint64_t)(p->qe - (uint32_t)p->qns) == tl && memcmp(qs + (uint32_t)p->qns, ts, tl) == 0) flag[(uint32_t)oi[k]] = 1; /* exact_ec_check, ecovlp.cpp:2803 */
+			}
+		}
+	}
+	free(ei); free(oi); free(qs); free(ts);
+	return 0;
+}

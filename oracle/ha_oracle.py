@@ -226,3 +226,13 @@ def ec_phase(store: Store, rid, chains, A, Cc, WC, CC):
     assert rc == 0
     a = _take(o, max(no.value, 1), PHASE)[:no.value]; b = _take(d, max(nd.value, 1), PHASE)[:nd.value]
     return a, b
+
+
+def ec_ea_flags(store: Store, rid, chains, prev: np.ndarray):
+    """row a12: which chains gen_hc_r_alin_ea accepts without alignment, given the read's overlap list of the previous round (MA records)"""
+    chains = np.ascontiguousarray(chains); prev = np.ascontiguousarray(prev, dtype=MA)
+    flag = np.zeros(max(chains.size, 1), np.uint8)
+    rc = lib().hao_ec_ea_flags(C.byref(store.c), C.c_uint32(rid), C.c_void_p(chains.ctypes.data), C.c_uint32(chains.size),
+                               C.c_void_p((prev if prev.size else np.zeros(1, MA)).ctypes.data), C.c_uint32(prev.size), C.c_void_p(flag.ctypes.data))
+    assert rc == 0
+    return flag[:chains.size]

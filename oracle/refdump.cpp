@@ -53,6 +53,8 @@ uint64_t gen_hc_fast_cigar(overlap_region *z, Candidates_list *cl, All_reads *rr
 void reassign_gaps(overlap_region *z, overlap_region *aux_o, char *qstr, int64_t ql, char *tstr, int64_t tl, All_reads *rref, UC_Read *tu, asg16_v *buf); // Correct.cpp:25409
 overlap_region *fetch_aux_ovlp(overlap_region_alloc *ol); // ecovlp.cpp:257
 void dedup_chains(overlap_region_alloc *ol); // ecovlp.cpp:2984
+void gen_hc_r_alin_ea(overlap_region_alloc *ol, Candidates_list *cl, All_reads *rref, UC_Read *qu, UC_Read *tu, bit_extz_t *exz, overlap_region *aux_o, double e_rate, int64_t wl, int64_t rid, int64_t khit, int64_t move_gap,
+                      asg16_v *buf, asg64_v *srt, ma_hit_t_alloc *in, uint8_t chem_drop, double align_gap_rate, int64_t align_gap_max); // ecovlp.cpp:2810
 
 #define HA_KMER_GOOD_RATIO 0.333 /* ecovlp.cpp:9 */
 #define COV_W 3072               /* ecovlp.cpp:17 */
@@ -91,7 +93,7 @@ static void dump_stages(const char *pfx, double bw_thres)
 	uint32_t low_occ = asm_opt.hom_cov * HA_KMER_GOOD_RATIO;
 	FILE *fmz = xopen(pfx, ".mz.bin"), *fidx = xopen(pfx, ".idx.bin"), *fan = xopen(pfx, ".anchors.bin");
 	FILE *fch = xopen(pfx, ".chains.bin"), *fpa = xopen(pfx, ".params.txt"), *fwn = xopen(pfx, ".windows.bin");
-	FILE *fal = xopen(pfx, ".aln.bin"), *fph = xopen(pfx, ".phase.bin"); asg16_v v16; memset(&v16, 0, sizeof(v16));
+	FILE *fal = xopen(pfx, ".aln.bin"), *fph = xopen(pfx, ".phase.bin"), *fea = xopen(pfx, ".ea.bin"); asg16_v v16; memset(&v16, 0, sizeof(v16));
 	haplotype_evdience_alloc hap; InitHaplotypeEvdience(&hap); kv_ul_ov_t pidx; memset(&pidx, 0, sizeof(pidx)); asg64_v v64, buf0; memset(&v64, 0, sizeof(v64)); memset(&buf0, 0, sizeof(buf0));
 	UC_Read tr; init_UC_Read(&tr); bit_extz_t exz; init_bit_extz_t(&exz, 31);
 	const double e_rate = asm_opt.max_ov_diff_ec; const int64_t w_l = asm_opt.is_ont ? WINDOW_OHC : WINDOW_HC; // ecovlp.cpp:3288
@@ -219,8 +221,23 @@ static void dump_stages(const char *pfx, double bw_thres)
 				if (rep == 0) dedup_chains(&ol);
 			}
 		}
+		// (8) the whole alignment stage as worker_hap_ec calls it (ecovlp.cpp:3288): gen_hc_r_alin_ea with the read's overlap list of the
+		// previous round — overlaps whose previous record was exact (el) and still is are accepted without alignment (row a12).
+		// Chains are rebuilt first (steps 6-7 consumed them).  Per accepted overlap, in list order:
+		// {y_id, strand, x_pos_s, x_pos_e, y_pos_s, y_pos_e, non_homopolymer_errors, is_match} + window list
+		{
+			h_ec_lchain(ab, i, ur.seq, ur.length, asm_opt.mz_win, asm_opt.k_mer_length, &R_INF, &ol, &cl, bw_thres, asm_opt.max_n_chain, 1, NULL, NULL, &sp, &high_occ, &low_occ, 1, 1, 3, 0.7, 2, 32, COV_W);
+			overlap_region *aux_o = fetch_aux_ovlp(&ol);
+			gen_hc_r_alin_ea(&ol, &cl, &R_INF, &ur, &tr, &exz, aux_o, e_rate, w_l, i, 31, 1, &v16, &v64, &(R_INF.paf[i]), 0, -1, -1);
+			uint32_t n = ol.length; fwrite(&n, 4, 1, fea);
+			for (j = 0; j < ol.length; j++) {
+				overlap_region *z = &ol.list[j];
+				uint32_t r8[8] = { z->y_id, z->y_pos_strand, z->x_pos_s, z->x_pos_e, z->y_pos_s, z->y_pos_e, z->non_homopolymer_errors, z->is_match };
+				fwrite(r8, 4, 8, fea); dump_wl(fea, z);
+			}
+		}
 	}
-	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch); fclose(fwn); fclose(fal); fclose(fph);
+	fclose(fmz); fclose(fidx); fclose(fan); fclose(fch); fclose(fwn); fclose(fal); fclose(fph); fclose(fea);
 	destory_UC_Read(&ur);
 }
 

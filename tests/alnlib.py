@@ -87,3 +87,22 @@ def read_phase(path):
             pair.append(np.frombuffer(buf, dtype=PH, count=n, offset=o)); o += 36 * n
         out.append(tuple(pair))
     return out
+
+
+def read_ea(path):
+    """refdump's <pfx>.ea.bin: per read the accepted overlaps after gen_hc_r_alin_ea: (record of 8 u32, (w, c))"""
+    buf = open(path, "rb").read(); o = 0; out = []
+    while o < len(buf):
+        n, = struct.unpack_from("<I", buf, o); o += 4
+        rl = []
+        for _ in range(n):
+            r8 = struct.unpack_from("<8I", buf, o); o += 32
+            wc, o = _wl(buf, o)
+            rl.append((r8, wc))
+        out.append(rl)
+    return out
+
+
+def digest_ea(ovl):
+    """ovl = iterable of ((y_id, rev, x_pos_s, x_pos_e, y_pos_s, y_pos_e, nh_err, is_match), w, c)"""
+    return _dg(struct.pack("<8I", *[int(v) & 0xffffffff for v in r8]) + wl_canon(w, c, True) for r8, w, c in ovl)

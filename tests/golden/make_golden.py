@@ -108,6 +108,12 @@ def read_stages(pfx, n_reads, keep=4):
     for i, (a, b) in enumerate(ph):
         out["phase"][i] = dg(np.ascontiguousarray(a).tobytes()); out["dedup"][i] = dg(np.ascontiguousarray(b).tobytes())
         cnt["phase_hap2"][i] = int((a["is_match"] == 2).sum()); cnt["dedup"][i] = b.size
+    # the whole alignment stage through gen_hc_r_alin_ea with the previous round's overlaps (refdump step 8, row a12)
+    ea = alnlib.read_ea(pfx + ".ea.bin")
+    assert len(ea) == n_reads
+    out["ea"] = np.zeros(n_reads, dtype=np.uint64); cnt["ea"] = np.zeros(n_reads, dtype=np.uint64)
+    for i, rl in enumerate(ea):
+        out["ea"][i] = alnlib.digest_ea((r8, w, c) for r8, (w, c) in rl); cnt["ea"][i] = len(rl)
     return out, cnt, full
 
 

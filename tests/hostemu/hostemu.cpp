@@ -283,7 +283,7 @@ int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 {
 	EmuReads *r = (EmuReads *)reads; unsigned long long used = 0; uint64_t nw = 0; int rc = 0;
 	std::vector<uint64_t> path(path_words), vec(11 * HB_MW_MAXW); std::vector<uint16_t> ecig(cig_words), wc(cig_words);
-	EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap; C.do_gaps = gaps;
+	EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap; C.do_gaps = gaps; C.no_myers = 0;
 	C.ez.path = path.data(); C.ez.pcap = path_words; C.ez.vec = vec.data(); C.ez.vstride = HB_MW_MAXW; C.ez.cig = ecig.data(); C.ez.ccap = cig_words; C.wc = wc.data(); C.wccap = cig_words;
 	for (uint32_t j = 0; j < n_ch; j++) {
 		hb_alnb_t res; memset(&res, 0, sizeof(res)); res.st = aln[j].st; res.w_off = nw;
@@ -327,13 +327,19 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 			std::vector<int64_t> t(scn + 1), p(scn + 1); std::vector<int32_t> f(scn + 1);
 			EcZ z; z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_pos_s = c.y_pos_s; z.y_id = c.y_id; z.rev = c.y_pos_strand; z.fc = fc + c.fc_off; z.fc_n = c.fc_n;
 			z.align_length = aln[j].align_length; z.w = (hb_wl_t *)(wlA + aln[j].w_off); z.wn = (int32_t)aln[j].w_n;
-			EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.do_gaps = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+			EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
 			C.q = hb_rd_view(r->d, rid, 0); C.t = hb_rd_view(r->d, c.y_id, c.y_pos_strand); C.ql = r->d.len[rid]; C.tl = r->d.len[c.y_id];
 			EcPrep pr; hb_ecb_prep(z, aln[j].re, C.ql, C.tl, hits + c.first_hit, scn, t.data(), p.data(), f.data(), &pr);
 			const int32_t ns = (pr.shortcut || pr.ch_n <= 0) ? 0 : pr.ch_n + 1;
 			std::vector<EcSeg> segs(ns + 1);
 			for (int32_t k = 0; k < ns; k++) {
 				int64_t uq[2], ut[2], um;
+				{ // the pre-pass: no scratch at all, stops where an alignment would start
+					uint16_t one[2]; C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.no_myers = 1;
+					const int st = hb_ecb_segment(C, z, hits + c.first_hit, pr.ch_n, k, uq, ut, &um);
+					C.no_myers = 0;
+					if (st != 5 && !C.ez.ovf) { hb_seg_store(C, st, uq, ut, um, &segs[k], spool.data(), &sused, spool.size()); n_tier[0]++; continue; }
+				}
 				for (int tier = 0; tier < 2; tier++) {
 					if (tier == 0) { C.ez.path = path0.data(); C.ez.pcap = 1024; C.ez.vec = vec0.data(); C.ez.vstride = 4; C.ez.cig = cig0.data(); C.ez.ccap = 72; }
 					else { C.ez.path = path1.data(); C.ez.pcap = path1.size(); C.ez.vec = vec1.data(); C.ez.vstride = HB_MW_MAXW; C.ez.cig = cig1.data(); C.ez.ccap = 65535; }
@@ -345,7 +351,7 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 				}
 				if (sused > spool.size()) return 256;
 			}
-			EcBCtx M; M.e_rate = e_rate; M.w_l = w_l; M.pool = pool; M.pool_used = &used; M.pool_cap = pool_cap; M.do_gaps = gaps;
+			EcBCtx M; M.no_myers = 0; M.e_rate = e_rate; M.w_l = w_l; M.pool = pool; M.pool_used = &used; M.pool_cap = pool_cap; M.do_gaps = gaps;
 			M.wc = mbuf.data(); M.wccap = cig_words; M.ez.cig = mbuf.data() + cig_words; M.ez.ccap = cig_words; M.ez.path = (uint64_t *)(mbuf.data() + 2 * (size_t)cig_words); M.ez.pcap = (uint64_t)cig_words / 4;
 			M.ez.vec = 0; M.ez.vstride = 0; M.q = C.q; M.t = C.t; M.ql = C.ql; M.tl = C.tl;
 			M.aw = wl + nw; M.awcap = (int32_t)std::min<uint64_t>(wl_cap - nw, (uint64_t)scn + 2);

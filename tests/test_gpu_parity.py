@@ -115,6 +115,22 @@ def _check_stages(g, eng, mode, rs):
             pa[f] = acc[f].astype(np.int64).astype(np.uint32)
         assert dg(pa.tobytes()) == int(g.digest(mode, "phase")[i]), "rphase_hc, read %d" % i
         assert int((acc["is_match"] == 2).sum()) == int(g.count(mode, "phase_hap2")[i])
+    # row a12: the whole alignment stage with the previous round's exact overlaps as a shortcut (gen_hc_r_alin_ea)
+    if mode == "final":
+        p0, o0, _, _ = g.pre_src
+        eng.ec_stage_prev(binio.disk_to_mem(p0), o0)
+    else:
+        eng.ec_stage_prev(np.zeros(0, binio.MA_MEM), np.zeros(n + 1, np.uint64))
+    eoff, E, WE, CE = eng.ec_cigar(0, n, float(p["bw_thres"]), 0.04, 775, gaps=3)
+    n_short = 0
+    for i in range(n):
+        acc = E[int(eoff[i]):int(eoff[i + 1])]; cc = ch[int(coff[i]):int(coff[i + 1])][acc["st"] == 2]; acc = acc[acc["st"] == 2]
+        if acc["need_rechain"].any():
+            continue
+        n_short += int(acc["pad"].sum())
+        de = alnlib.digest_ea(((c["y_id"], c["y_pos_strand"], b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"], b["nh_err"], 1), WE[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CE) for b, c in zip(acc, cc))
+        assert de == int(g.digest(mode, "ea")[i]), "gen_hc_r_alin_ea, read %d" % i
+    assert (n_short > 0) == (mode == "final")
     return hom, het
 
 

@@ -29,7 +29,28 @@ def ctx(request):
 n_rechain = [0]
 
 
-def _stages(g, mode, st, ft, opt, bw):
+def _ea_records(ch, fl, A, Cc, WC, CC):
+    """accepted overlaps after gen_hc_r_alin_ea: the exact shortcut's single window, or steps A-C's result"""
+    out = []
+    for j in range(ch.size):
+        c = ch[j]
+        if fl[j]:
+            L = int(c["x_pos_e"]) + 1 - int(c["x_pos_s"]); cg = []
+            while L >= 0x3fff:
+                cg.append(0x3fff); L -= 0x3fff
+            if L:
+                cg.append(L)
+            w = np.zeros(1, alnlib.WL)
+            w[0]["x_start"] = c["x_pos_s"]; w[0]["x_end"] = c["x_pos_e"]; w[0]["y_start"] = c["y_pos_s"]; w[0]["y_end"] = c["y_pos_e"]; w[0]["clen"] = len(cg)
+            out.append(((c["y_id"], c["y_pos_strand"], c["x_pos_s"], c["x_pos_e"], c["y_pos_s"], c["y_pos_e"], 0, 1), w, np.array(cg, np.uint16)))
+        elif A[j]["st"] == 2:
+            cc = Cc[j]
+            out.append(((c["y_id"], c["y_pos_strand"], cc["x_pos_s"], cc["x_pos_e"], cc["y_pos_s"], cc["y_pos_e"], cc["nh_err"], 1),
+                        WC[int(cc["w_off"]):int(cc["w_off"] + cc["w_n"])], CC[int(cc["c_off"]):int(cc["c_off"] + cc["c_n"])]))
+    return out
+
+
+def _stages(g, mode, st, ft, opt, bw, prev=None):
     p = g.params(mode)
     pt, hom, het = ho.pt_gen(st, ft, opt)
     assert (hom, het) == (int(p["hom_cov"]), int(p["het_cov"]))
@@ -74,6 +95,10 @@ def _stages(g, mode, st, ft, opt, bw):
                 pa[f] = P[f].astype(np.int64).astype(np.uint32); da[f] = D[f].astype(np.int64).astype(np.uint32)
             assert dg(pa.tobytes()) == int(g.digest(mode, "phase")[i]), "rphase_hc, read %d" % i
             assert dg(da.tobytes()) == int(g.digest(mode, "dedup")[i]), "dedup_chains, read %d" % i
+            # row a12: the exact shortcut from the previous round's overlap list (empty for the raw reads: round 0)
+            pm, po = prev if prev is not None else (np.zeros(0, ho.MA), np.zeros(st.n + 1, np.uint64))
+            fl = ho.ec_ea_flags(st, i, ch, pm[int(po[i]):int(po[i + 1])])
+            assert alnlib.digest_ea(_ea_records(ch, fl, A, Cc, WC, CC)) == int(g.digest(mode, "ea")[i]), "gen_hc_r_alin_ea, read %d" % i
         else:
             n_rechain[0] += 1
     return pt, hom, het
@@ -87,7 +112,8 @@ def test_stages_raw(ctx):
 def test_stages_and_final_pass(ctx):
     g, raw, opt, ft = ctx
     st = _store(g.pre)
-    pt, hom, het = _stages(g, "final", st, ft, opt, 0.001)
+    p0, o0, _, _ = g.pre_src
+    pt, hom, het = _stages(g, "final", st, ft, opt, 0.001, prev=(binio.disk_to_mem(p0), o0))
     opt.hom_cov, opt.het_cov = hom, het
     p0, o0, _, _ = g.pre_src
     p1, o1, _, _ = g.pre_rev
