@@ -314,7 +314,7 @@ def _main():
             torch.cuda.synchronize(); wall_ec = time.time() - tb
             pr = e2.profile(); cn = e2.counters()
             poff, PH = e2.ec_phase(0, nq, 0.02, 0.04, 775); pr.update({k: v for k, v in e2.profile().items() if k.startswith("k_ph_")})
-            kms = {k: pr[k][1] for k in ("k_windows", "k_ec_overlap", "k_ecb_prep", "k_ecb_seg", "k_ecb_seg_tier1", "k_ecb_seg_tier2", "k_ecb_seg_tier3", "k_ecb_merge", "k_ecb_merge_deferred", "k_ph_count", "k_ph_decide") if k in pr}
+            kms = {k: pr[k][1] for k in ("k_windows", "k_ec_overlap", "k_ec_ea", "k_ecb_prep", "k_ecb_seg_fast", "k_ecb_seg", "k_ecb_seg_tier1", "k_ecb_seg_tier2", "k_ecb_seg_tier3", "k_ecb_merge", "k_ecb_merge_deferred", "k_ph_count", "k_ph_decide") if k in pr}
             qb = int(ln.sum()); acc = G[G["st"] == 2]
             aux = dict(aux or {})
             aux["ec_alignment"] = {"reads": nq, "query_bases": qb, "overlaps": int(G.size), "accepted": int(acc.size), "other_haplotype": int((PH["is_match"] == 2).sum()), "need_rechain": int(acc["need_rechain"].sum()),

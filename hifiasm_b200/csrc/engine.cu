@@ -807,6 +807,8 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						spool_cap = spool_used + 65536; // the need is known now; the segments are recomputed (the chains stay refined)
 					}
 					ctx->counters[10] += h_q[3]; // segments that needed the largest scratch tier
+					if (getenv("HB_TRACE_EC")) fprintf(stderr, "[hb] EC base alignment: %llu overlaps, %llu segments; queued for alignment %u, past tier 0 %u, past tier 1 %u, past tier 2 %u; segment cigar pool %llu\n",
+					                                    (unsigned long long)n_ov, (unsigned long long)n_seg, h_q[0], h_q[1], h_q[2], h_q[3], (unsigned long long)spool_used);
 					// ---- merge
 					uint64_t poolb_cap = n_seg / 4 + 16 * n_ov + 65536, poolb_used = 0; uint16_t *d_poolb = 0; unsigned int n_def = 0;
 					for (int attempt = 0;; attempt++) {
@@ -833,7 +835,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						HB_CUDA(cudaMemcpyAsync(&poolb_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 						HB_CUDA(cudaStreamSynchronize(ctx->stream));
 						if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "EC base alignment: fake-cigar lookup failed"); return HB_E_STATE; }
-						if (poolb_used <= poolb_cap && mode == 7) { // phasing of the batch's reads over the step-C state that stays in HBM (row a13)
+						if (poolb_used <= poolb_cap && mode >= 7) { // phasing of the batch's reads over the step-C state that stays in HBM (row a13)
 							std::vector<uint64_t> h_boff(nb + 1, 0);
 							for (uint64_t i = 0; i < nb; i++) h_boff[i + 1] = h_boff[i] + ((ctx->h_rlen[r0 + b0 + i] + 8) & ~7ull);
 							uint64_t *d_boff = ba.get<uint64_t>(nb + 1); uint8_t *d_cnt = ba.zero<uint8_t>(h_boff[nb] + 8); PhOv *d_phov = ba.get<PhOv>(n_ov + 1);
@@ -863,6 +865,26 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 							if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "phasing: radix-sort stack"); return HB_E_OVERFLOW; }
+							if (mode == 8) { // the round's reverse_paf lists of the batch
+								hb_ma_hit_t *d_rp = ba.get<hb_ma_hit_t>(n_ov + 1); uint32_t *d_nrp = ba.zero<uint32_t>(nb + 1); HB_ALLOC_CHECK(ba);
+								{
+									ProfScope ps(ctx, "k_ec_rpaf");
+									k_ec_rpaf<<<nblk(nb, 64), 64, 0, ctx->stream>>>(R, r0 + b0, nb, d_ooff, d_ph, P.ord, d_rp, d_nrp, d_err);
+								}
+								HB_CUDA(cudaGetLastError());
+								std::vector<hb_ma_hit_t> h_rp(n_ov + 1); std::vector<uint32_t> h_nrp(nb + 1);
+								HB_CUDA(cudaMemcpyAsync(h_rp.data(), d_rp, n_ov * sizeof(hb_ma_hit_t), cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(h_nrp.data(), d_nrp, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+								HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+								if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "dedup_chains: radix-sort stack"); return HB_E_OVERFLOW; }
+								for (uint64_t i = 0; i < nb; i++) {
+									st3_off[b0 + i] = st3_n;
+									if (so->rec && st3_n + h_nrp[i] > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
+									if (so->rec) memcpy((hb_ma_hit_t *)so->rec + st3_n, h_rp.data() + h_ooff[i], h_nrp[i] * sizeof(hb_ma_hit_t));
+									st3_n += h_nrp[i];
+								}
+								st3_off[b0 + nb] = st3_n;
+								break;
+							}
 							if (so->rec && st3_n + n_ov > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
 							if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_phase_t *)so->rec + st3_n, d_ph, n_ov * sizeof(hb_phase_t), cudaMemcpyDeviceToHost, ctx->stream));
 							HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1096,6 +1118,12 @@ extern "C" int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_th
 	return rc;
 }
 
+extern "C" int hb_ec_reverse_paf(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_ma_hit_t *rec, uint64_t rec_cap)
+{
+	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l; so.gaps = 1;
+	return run_pass(ctx, r0, r1, 8, bw_thres, &so, 0);
+}
 extern "C" int hb_ec_stage_prev(hb_ctx_t *ctx, const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off)
 { // R_INF.paf[] of the previous EC round, flattened; only the source list matters to gen_hc_r_alin_ea
 	static const hb_ma_hit_t none = {}; std::vector<uint64_t> z(ctx->n_reads + 1, 0);

@@ -209,3 +209,47 @@ HB_HD void hb_ph_decide(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_ov
 #undef PH_REAL
 #undef PH_ALLELE
 }
+
+// ---- dedup_chains (ecovlp.cpp:2984-3030) + push_ne_ovlp(flag = 2, ec = NULL) (ecovlp.cpp:2585-2638): the round's reverse_paf[i] -------------
+// ph[0..n) = the read's overlaps after phasing (hb_phase_t, st == 2 = accepted, list order); ord = scratch of n u64 (y_id | index pairs for
+// overlap_region_sort_y_id, whose unstable radix sort is restated move for move); out = up to n records.  Returns the number of records.
+struct PhPair { uint32_t y_id, idx; };
+HB_HD uint32_t hb_ec_reverse_list(const DevReads &R, uint64_t qid, const hb_phase_t *ph, uint32_t n, PhPair *ord, const RsScratch &W, hb_ma_hit_t *out, int *ovf)
+{
+	uint32_t m = 0;
+	for (uint32_t j = 0; j < n; j++) if (ph[j].st == 2) { ord[m].y_id = ph[j].y_id; ord[m].idx = j; m++; }
+	uint32_t keep = m;
+	if (m > 1) {
+		auto key = [](const PhPair &p) -> uint32_t { return p.y_id; };
+		if (hb_rs_sort32(ord, ord + m, key, W)) { *ovf = 1; return 0; }
+		uint32_t k, l; keep = 0;
+		for (k = 1, l = 0; k <= m; k++) {
+			if (k == m || ord[k].y_id != ord[l].y_id) {
+				uint32_t mm_k = l;
+				if (k - l > 1) {
+					int64_t mm_sc = INT32_MIN; uint32_t mm_m = 3; mm_k = 0xffffffffu;
+					for (uint32_t s = l; s < k; s++) {
+						const hb_phase_t &z = ph[ord[s].idx]; const int64_t len = (int64_t)z.x_pos_e + 1 - z.x_pos_s, sc = len - (int64_t)z.nh_err * 12; bool sf = false;
+						if (z.is_match < mm_m) sf = true;
+						else if (z.is_match == mm_m) {
+							if (sc > mm_sc) sf = true;
+							else if (sc == mm_sc) { const hb_phase_t &b = ph[ord[mm_k].idx]; if (len > (int64_t)b.x_pos_e + 1 - b.x_pos_s) sf = true; }
+						}
+						if (sf) { mm_sc = sc; mm_k = s; mm_m = z.is_match; }
+					}
+				}
+				if (mm_k != 0xffffffffu) { if (mm_k != keep) { const PhPair t = ord[mm_k]; ord[mm_k] = ord[keep]; ord[keep] = t; } keep++; }
+				l = k;
+			}
+		}
+	}
+	uint32_t no = 0;
+	for (uint32_t k = 0; k < keep; k++) {
+		const hb_phase_t &z = ph[ord[k].idx];
+		if (z.is_match != 2) continue;
+		hb_ma_hit_t h; h.qns = (qid << 32) | z.x_pos_s; h.qe = z.x_pos_e + 1; h.tn = z.y_id; h.ts = z.y_pos_s; h.te = z.y_pos_e + 1; h.rev = z.rev;
+		h.bl = R.len[z.y_id]; h.ml = (uint32_t)z.strong; h.no_l_indel = 0; h.del = 0; h.el = 0; for (int b = 0; b < 6; b++) h.pad[b] = 0;
+		out[no++] = h;
+	}
+	return no;
+}

@@ -1314,6 +1314,16 @@ __global__ void __launch_bounds__(64) k_ph_decide(PhArgs A)
 	}
 }
 
+// the round's reverse_paf[i]: dedup_chains + push_ne_ovlp(flag 2) per read (hb_ecphase.cuh: hb_ec_reverse_list)
+__global__ void __launch_bounds__(64) k_ec_rpaf(DevReads R, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ o_off, const hb_phase_t *__restrict__ ph, uint64_t *ord, hb_ma_hit_t *out, uint32_t *n_out, int *err)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st }; int ovf = 0;
+	const uint64_t o0 = o_off[r];
+	n_out[r] = hb_ec_reverse_list(R, r0 + r, ph + o0, (uint32_t)(o_off[r + 1] - o0), (PhPair *)(ord + o0), W, out + o0, &ovf);
+	if (ovf) atomicOr(err, 128);
+}
+
 // ----------------------------------------------------------------------------
 // window alignment: ed_band_cal_semi_64_w_absent_diag
 // (Levenshtein_distance.h:3727-3776, ed_core_64 3116-3125), one thread per

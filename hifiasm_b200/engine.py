@@ -220,6 +220,15 @@ class Engine:
         self._ck(_lib().hb_ec_phase(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), _p(rec), C.c_uint64(rec.size)))
         return off, rec[:int(off[-1])]
 
+    def ec_reverse_paf(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775):
+        """R_INF.reverse_paf[i] of an EC round (other-haplotype overlaps after dedup_chains) -> (off, MA records)"""
+        n = r1 - r0
+        off = np.zeros(n + 1, np.uint64)
+        self._ck(_lib().hb_ec_reverse_paf(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), C.c_void_p(0), C.c_uint64(0)))
+        rec = np.zeros(int(off[-1]) + 1, MA)
+        self._ck(_lib().hb_ec_reverse_paf(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), _p(rec), C.c_uint64(rec.size)))
+        return off, rec[:int(off[-1])]
+
     # ---- final pass
     def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None, out=None):
         """out = (out0, out1) preallocated MA arrays to receive the records (reused across calls)"""

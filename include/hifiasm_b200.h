@@ -164,6 +164,11 @@ int hb_ec_cigar(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double
 typedef struct { int32_t st; uint32_t y_id, rev, x_pos_s, x_pos_e, y_pos_s, y_pos_e, nh_err, is_match; int32_t strong; uint32_t need_rechain, pad; } hb_phase_t;
 int hb_ec_phase(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_phase_t *rec, uint64_t rec_cap);
 
+/* ---- R_INF.reverse_paf[i] of an EC round (part of row a15): the overlaps phasing assigned to the other haplotype, after dedup_chains
+ * (ecovlp.cpp:2984: best chain per target), as push_ne_ovlp(flag = 2) emits them (ecovlp.cpp:2585; el / del are not defined on that
+ * path and come back 0).  off[r1-r0+1] + records.  The same-haplotype list (paf[i]) needs the consensus of row a14 and is not built yet. */
+int hb_ec_reverse_paf(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_ma_hit_t *rec, uint64_t rec_cap);
+
 /* ---- final overlap pass: cal_ov_r(n_thre, n_a, new_idx=1) (ecovlp.h:15;
  * ecovlp.cpp:6385 -> worker_hap_dc_ec_gen_new_idx 3948) -----------------------
  * prev_* = R_INF.paf[] / R_INF.reverse_paf[] of the last EC round, flattened

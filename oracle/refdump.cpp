@@ -53,6 +53,7 @@ uint64_t gen_hc_fast_cigar(overlap_region *z, Candidates_list *cl, All_reads *rr
 void reassign_gaps(overlap_region *z, overlap_region *aux_o, char *qstr, int64_t ql, char *tstr, int64_t tl, All_reads *rref, UC_Read *tu, asg16_v *buf); // Correct.cpp:25409
 overlap_region *fetch_aux_ovlp(overlap_region_alloc *ol); // ecovlp.cpp:257
 void dedup_chains(overlap_region_alloc *ol); // ecovlp.cpp:2984
+void push_ne_ovlp(ma_hit_t_alloc *paf, overlap_region_alloc *ov, uint32_t flag, All_reads *R_INF, asg16_v *ec); // ecovlp.cpp:2585
 void gen_hc_r_alin_ea(overlap_region_alloc *ol, Candidates_list *cl, All_reads *rref, UC_Read *qu, UC_Read *tu, bit_extz_t *exz, overlap_region *aux_o, double e_rate, int64_t wl, int64_t rid, int64_t khit, int64_t move_gap,
                       asg16_v *buf, asg64_v *srt, ma_hit_t_alloc *in, uint8_t chem_drop, double align_gap_rate, int64_t align_gap_max); // ecovlp.cpp:2810
 
@@ -219,6 +220,19 @@ static void dump_stages(const char *pfx, double bw_thres)
 					fwrite(r9, 4, 9, fph);
 				}
 				if (rep == 0) dedup_chains(&ol);
+			}
+			// the round's reverse_paf[i] as worker_hap_ec emits it (ecovlp.cpp:3321): push_ne_ovlp(flag = 2, ec = NULL) over the de-duplicated
+			// list; without_large_indel of these overlaps is 0 (wcns_gen only sets it for is_match == 1, ecovlp.cpp:2302-2303).
+			// Dumped fields: qns, qe, tn, ts, te, rev, bl, ml, no_l_indel (el / del are never written on this path)
+			{
+				static ma_hit_t_alloc tmp; uint32_t k;
+				for (j = 0; j < ol.length; j++) ol.list[j].without_large_indel = 0;
+				push_ne_ovlp(&tmp, &ol, 2, &R_INF, NULL);
+				uint32_t n = tmp.length; fwrite(&n, 4, 1, fph);
+				for (k = 0; k < n; k++) {
+					ma_hit_t *h = &tmp.buffer[k]; uint64_t q = h->qns; uint32_t r8[8] = { h->qe, h->tn, h->ts, h->te, (uint32_t)h->rev, h->bl, (uint32_t)h->ml, (uint32_t)h->no_l_indel };
+					fwrite(&q, 8, 1, fph); fwrite(r8, 4, 8, fph);
+				}
 			}
 		}
 		// (8) the whole alignment stage as worker_hap_ec calls it (ecovlp.cpp:3288): gen_hc_r_alin_ea with the read's overlap list of the

@@ -77,14 +77,19 @@ def digest_C(ovl):
 PH = np.dtype([(f, "<u4") for f in ("y_id", "rev", "x_pos_s", "x_pos_e", "y_pos_s", "y_pos_e", "nh_err", "is_match", "strong")])
 
 
+RPAF = np.dtype([("qns", "<u8"), ("qe", "<u4"), ("tn", "<u4"), ("ts", "<u4"), ("te", "<u4"), ("rev", "<u4"), ("bl", "<u4"), ("ml", "<u4"), ("no_l_indel", "<u4")])
+
+
 def read_phase(path):
-    """refdump's <pfx>.phase.bin: per read (accepted overlaps after rphase_hc, the list after dedup_chains)"""
+    """refdump's <pfx>.phase.bin: per read (accepted overlaps after rphase_hc, the list after dedup_chains, the round's reverse_paf records)"""
     buf = open(path, "rb").read(); o = 0; out = []
     while o < len(buf):
         pair = []
         for _ in range(2):
             n, = struct.unpack_from("<I", buf, o); o += 4
             pair.append(np.frombuffer(buf, dtype=PH, count=n, offset=o)); o += 36 * n
+        n, = struct.unpack_from("<I", buf, o); o += 4
+        pair.append(np.frombuffer(buf, dtype=RPAF, count=n, offset=o)); o += 40 * n
         out.append(tuple(pair))
     return out
 

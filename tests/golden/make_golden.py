@@ -105,7 +105,9 @@ def read_stages(pfx, n_reads, keep=4):
     assert len(ph) == n_reads
     out["phase"] = np.zeros(n_reads, dtype=np.uint64); out["dedup"] = np.zeros(n_reads, dtype=np.uint64)
     cnt["phase_hap2"] = np.zeros(n_reads, dtype=np.uint64); cnt["dedup"] = np.zeros(n_reads, dtype=np.uint64)
-    for i, (a, b) in enumerate(ph):
+    out["rpaf"] = np.zeros(n_reads, dtype=np.uint64); cnt["rpaf"] = np.zeros(n_reads, dtype=np.uint64)
+    for i, (a, b, rp) in enumerate(ph):
+        out["rpaf"][i] = dg(np.ascontiguousarray(rp).tobytes()); cnt["rpaf"][i] = rp.size
         out["phase"][i] = dg(np.ascontiguousarray(a).tobytes()); out["dedup"][i] = dg(np.ascontiguousarray(b).tobytes())
         cnt["phase_hap2"][i] = int((a["is_match"] == 2).sum()); cnt["dedup"][i] = b.size
     # the whole alignment stage through gen_hc_r_alin_ea with the previous round's overlaps (refdump step 8, row a12)

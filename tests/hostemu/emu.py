@@ -168,3 +168,15 @@ def ec_phase(reads, rid, ch, A, B, WB, CB):
     rc = lib().emu_ec_phase(reads.h, C.c_uint32(rid), _p(ch), C.c_uint32(ch.size), _p(A), _p(B), _p(WB), _p(CB), _p(im), _p(st), C.byref(n))
     assert rc == 0
     return im[:n.value], st[:n.value]
+
+
+PHASE = np.dtype([("st", "<i4"), ("y_id", "<u4"), ("rev", "<u4"), ("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"), ("nh_err", "<u4"),
+                  ("is_match", "<u4"), ("strong", "<i4"), ("need_rechain", "<u4"), ("pad", "<u4")])
+
+
+def ec_reverse(reads, rid, ph):
+    """dedup_chains + push_ne_ovlp(flag 2) over the phased overlaps (PHASE records) -> MA records"""
+    ph = np.ascontiguousarray(ph, dtype=PHASE); out = np.zeros(ph.size + 1, MA); n = C.c_uint32()
+    rc = lib().emu_ec_reverse(reads.h, C.c_uint32(rid), _p(ph if ph.size else np.zeros(1, PHASE)), C.c_uint32(ph.size), _p(out), C.byref(n))
+    assert rc == 0
+    return out[:n.value]

@@ -386,4 +386,13 @@ int emu_ec_phase(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch,
 	return ovf;
 }
 
+// the round's reverse_paf[i] from the phased overlaps (body of k_ec_rpaf)
+int emu_ec_reverse(void *reads, uint32_t rid, const hb_phase_t *ph, uint32_t n, hb_ma_hit_t *out, uint32_t *n_out)
+{
+	EmuReads *r = (EmuReads *)reads; int ovf = 0; std::vector<PhPair> ord(n + 1);
+	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
+	*n_out = hb_ec_reverse_list(r->d, rid, ph, n, ord.data(), W, out, &ovf);
+	return ovf;
+}
+
 } // extern "C"

@@ -115,6 +115,15 @@ def _check_stages(g, eng, mode, rs):
             pa[f] = acc[f].astype(np.int64).astype(np.uint32)
         assert dg(pa.tobytes()) == int(g.digest(mode, "phase")[i]), "rphase_hc, read %d" % i
         assert int((acc["is_match"] == 2).sum()) == int(g.count(mode, "phase_hap2")[i])
+    # the round's reverse_paf[i] (part of row a15): dedup_chains + push_ne_ovlp(flag 2)
+    roff, RP = eng.ec_reverse_paf(0, n, float(p["bw_thres"]), 0.04, 775)
+    for i in range(n):
+        if P[int(poff[i]):int(poff[i + 1])]["need_rechain"].any():
+            continue
+        rp = RP[int(roff[i]):int(roff[i + 1])]; ra = np.zeros(rp.size, alnlib.RPAF)
+        for f in alnlib.RPAF.names:
+            ra[f] = rp[f]
+        assert ra.size == int(g.count(mode, "rpaf")[i]) and dg(ra.tobytes()) == int(g.digest(mode, "rpaf")[i]), "reverse_paf of the round, read %d" % i
     # row a12: the whole alignment stage with the previous round's exact overlaps as a shortcut (gen_hc_r_alin_ea)
     if mode == "final":
         p0, o0, _, _ = g.pre_src

@@ -124,6 +124,14 @@ def test_ec_align_step_A(ctx):
             for f in ("x_pos_s", "x_pos_e", "y_pos_s", "y_pos_e"):
                 pa[f] = acc_b[f]
             assert dg(pa.tobytes()) == int(g.digest("raw", "phase")[i]), "rphase_hc, read %d" % i
+            # the round's reverse_paf[i]: dedup_chains + push_ne_ovlp(flag 2) (body of k_ec_rpaf)
+            ph = np.zeros(pa.size, emu.PHASE); ph["st"] = 2
+            for f in alnlib.PH.names:
+                ph[f] = pa[f].astype(np.int64).astype(ph[f].dtype)
+            rp = emu.ec_reverse(er, i, ph); ra = np.zeros(rp.size, alnlib.RPAF)
+            for f in alnlib.RPAF.names:
+                ra[f] = rp[f]
+            assert ra.size == int(g.count("raw", "rpaf")[i]) and dg(ra.tobytes()) == int(g.digest("raw", "rpaf")[i]), "reverse_paf, read %d" % i
 
 
 def test_final_pass(ctx):
