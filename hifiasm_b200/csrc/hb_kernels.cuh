@@ -1189,21 +1189,31 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		s_o = lo;
 	}
 	__syncthreads();
-	if (sidx >= A.n_seg) return;
-	uint64_t o = s_o; while (A.seg_off[o + 1] <= sidx) o++;
-	const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
-	OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
-	ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
-	uint16_t one[2];
-	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 1; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
-	C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
-	C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
-	int64_t uq[2], ut[2], um;
-	const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
-	if (C.bad) atomicOr(A.err, 32);
-	if (st == 5 || C.ez.ovf) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; return; } // an alignment (or a > 32 k-base exact run) is needed
-	EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
-	A.segs[sidx] = sg;
+	bool need = false;
+	if (sidx < A.n_seg) {
+		uint64_t o = s_o; while (A.seg_off[o + 1] <= sidx) o++;
+		const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
+		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
+		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+		uint16_t one[2];
+		EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 1; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+		C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+		int64_t uq[2], ut[2], um;
+		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
+		if (C.bad) atomicOr(A.err, 32);
+		need = st == 5 || C.ez.ovf; // an alignment (or a > 32 k-base exact run) is needed
+		if (!need) { EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap); A.segs[sidx] = sg; }
+	}
+	// one queue reservation per warp: the warp's segments stay together and in order, so the alignment kernel's warps mostly work
+	// on neighbouring segments of the same overlap (same two reads)
+	const unsigned m = __ballot_sync(0xffffffffu, need); const int lane = threadIdx.x & 31;
+	if (m) {
+		uint32_t base = 0;
+		if (lane == __ffs(m) - 1) base = atomicAdd(A.q_out_n, (uint32_t)__popc(m));
+		base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+		if (need) A.q_out[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)sidx;
+	}
 }
 // segment alignment: a queue of segment ids.  LOCAL = true: one thread per queued segment with a small private scratch (trace of 1024
 // words = 204 columns of a one-word band, 4-word band at most: the usual segment between neighbouring minimizers); LOCAL = false:
