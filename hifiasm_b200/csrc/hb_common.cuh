@@ -12,9 +12,11 @@
 #ifdef __CUDACC__
 #define HB_HD __host__ __device__ __forceinline__
 #define HB_D __device__ __forceinline__
+#define HB_HD_NI __host__ __device__ __noinline__ /* large bodies with several call sites: one copy per kernel keeps the code in the instruction cache */
 #else
 #define HB_HD inline
 #define HB_D inline
+#define HB_HD_NI inline
 struct ulonglong2 { unsigned long long x, y; };
 #endif
 

@@ -497,7 +497,7 @@ HB_HD void hb_mw_set_lsub(uint64_t *x, int32_t l, int32_t nw)
 	if (l & 63) x[l >> 6] = (1ULL << (l & 63)) - 1;
 }
 
-HB_HD void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
+HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 { // gen_trace, Levenshtein_distance.h:903-985
 	if (ez.err > ez.thre) return;
 	ez.cn = 0;
@@ -534,7 +534,7 @@ HB_HD void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 
 // mode: 0 global, 1 forward extension, 2 backward extension, 3 semi-global with abs_diag absent leading diagonals.
 // pattern = target[ps0, ps0+pn) on the overlap's strand, text = query[qs0, qs0+tn).
-HB_HD void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, const RdView &Q, int64_t qs0, int32_t tn, int32_t thre, int32_t abs_diag, MwEz &ez)
+HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, const RdView &Q, int64_t qs0, int32_t tn, int32_t thre, int32_t abs_diag, MwEz &ez)
 {
 	int32_t bd = (thre << 1) + 1; const int32_t nword = (bd >> 6) + ((bd & 63) ? 1 : 0), cut = thre + (thre << 1);
 	int32_t i, err, i_bd, c, pidx = 0, tidx = 0, tmp_e = INT32_MAX, k, poff;
@@ -1039,16 +1039,20 @@ HB_HD int hb_seg_align(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t 
 	}
 	if (ql <= HB_MAX_SIN_L && (est >> 1) <= HB_MAX_SIN_E) {
 		if (C.no_myers) return 5;
-		thre = hb_scale_ed_thre((uint32_t)est, HB_MAX_SIN_E);
-		if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1;
-		if (ez.ovf) return 0;
-		thre0 = thre; thre = (int64_t)((double)ql * C.e_rate); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
-		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; if (ez.ovf) return 0; }
-		thre0 = thre; thre <<= 1; thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
-		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; if (ez.ovf) return 0; }
-		thre0 = thre; thre = (int64_t)((double)ql * 0.51); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E);
-		if (thre > thre0) { if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; if (ez.ovf) return 0; }
-		if (ql <= HB_FORCE_SIN_L) { thre = HB_MAX_SIN_E; if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1; }
+		// thresholds in the reference's order: the estimate, len*e_rate, twice that, 0.51*len, and the maximum for short segments; each one
+		// (but the first and the last) only if it exceeds the one before — one call site, so the aligner exists once in the kernel
+		thre = 0; thre0 = -1;
+		for (int step = 0; step < 5; step++) {
+			bool go = true;
+			if (step == 0) thre = hb_scale_ed_thre((uint32_t)est, HB_MAX_SIN_E);
+			else if (step == 1) { thre0 = thre; thre = (int64_t)((double)ql * C.e_rate); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E); go = thre > thre0; }
+			else if (step == 2) { thre0 = thre; thre <<= 1; thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E); go = thre > thre0; }
+			else if (step == 3) { thre0 = thre; thre = (int64_t)((double)ql * 0.51); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E); go = thre > thre0; }
+			else { go = ql <= HB_FORCE_SIN_L; thre = HB_MAX_SIN_E; }
+			if (!go) continue;
+			if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1;
+			if (ez.ovf) return 0;
+		}
 	}
 	return 0;
 }
