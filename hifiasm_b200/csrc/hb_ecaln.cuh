@@ -506,9 +506,16 @@ HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 	int32_t poff = ez.pe, sft = bd - (pn - ez.pe - ptrim), i = tn, low = bd - 1, d = 0, pd = -1, pdn = 0;
 	while (i > 0 && cur > 0) {
 		const uint64_t *D0 = ez.path + (size_t)(i - 1) * bs, *VP = D0 + bbs, *VN = VP + bbs, *HP = VN + bbs, *HN = HP + bbs;
+		if (bbs == 1) { // one-word band: the five words of the column are one 40-byte row
+			const uint64_t d0 = D0[0], vp = D0[1], vn = D0[2], hp = D0[3], hn = D0[4];
+			D = cur - (1 - (int32_t)((d0 >> sft) & 1ULL)); d = 0; mn = D;
+			if (sft != low) { H = cur + (int32_t)((hn >> sft) & 1ULL) - (int32_t)((hp >> sft) & 1ULL); if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
+			if (sft != 0) { V = cur + (int32_t)((vn >> (sft - 1)) & 1ULL) - (int32_t)((vp >> (sft - 1)) & 1ULL); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
+		} else {
 		D = cur - (1 - hb_mw_bit(D0, sft)); d = 0; mn = D;
 		if (sft != low) { H = cur + hb_mw_bit(HN, sft) - hb_mw_bit(HP, sft); if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
 		if (sft != 0) { V = cur + hb_mw_bit(VN, sft - 1) - hb_mw_bit(VP, sft - 1); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
+		}
 		if (d == 0) { if (D != cur) d = 1; i--; poff--; }
 		else if (d == 2) { sft--; poff--; }
 		else { i--; sft++; }
