@@ -466,7 +466,8 @@ HB_HD void hb_ec_overlap_A(EcCtx &C, const hb_chain_t &c, const uint64_t *fc, co
 struct MwEz {
 	int32_t ps, pe, pl, ts, te, tl, thre, err, nword;
 	uint16_t *cig; int32_t cn, ccap;      // cigar of the last alignment
-	uint64_t *path; uint64_t pcap, pn;    // 5*nword words per column
+	uint64_t *path; uint64_t pcap, pn;    // 5*nword words per column; one-word bands (compact = 1): 2 header words (initial VP, VN) + 3 per column (D0, VP, VN)
+	int32_t compact;
 	uint64_t *vec; int32_t vstride;       // 11 vectors of vstride words: Peq[0..4], VP, VN, X, D0, HN, HP
 	int ovf;                              // scratch too small: the unit is deferred to a launch with more scratch
 };
@@ -502,12 +503,13 @@ HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 	if (ez.err > ez.thre) return;
 	ez.cn = 0;
 	int32_t V, H, D, mn, cur = ez.err, tn = ez.te + 1 - ez.ts, pn = tn + (ez.thre << 1), bd = (ez.thre << 1) + 1;
-	const int32_t bs = (int32_t)(ez.pn / (uint64_t)tn), bbs = bs / 5;
+	const int32_t bs = ez.compact ? 0 : (int32_t)(ez.pn / (uint64_t)tn), bbs = bs / 5;
 	int32_t poff = ez.pe, sft = bd - (pn - ez.pe - ptrim), i = tn, low = bd - 1, d = 0, pd = -1, pdn = 0;
 	while (i > 0 && cur > 0) {
 		const uint64_t *D0 = ez.path + (size_t)(i - 1) * bs, *VP = D0 + bbs, *VN = VP + bbs, *HP = VN + bbs, *HN = HP + bbs;
-		if (bbs == 1) { // one-word band: the five words of the column are one 40-byte row
-			const uint64_t d0 = D0[0], vp = D0[1], vn = D0[2], hp = D0[3], hn = D0[4];
+		if (ez.compact) { // one-word band: D0, VP, VN of the column; HN = VP' & D0, HP = VN' | ~(VP' | D0) with VP', VN' of the column before (header for column 0)
+			const uint64_t *row = ez.path + 2 + (size_t)(i - 1) * 3, *prv = i > 1 ? row - 3 + 1 : ez.path;
+			const uint64_t d0 = row[0], vp = row[1], vn = row[2], vpp = prv[0], vnp = prv[1], hn = vpp & d0, hp = vnp | ~(vpp | d0);
 			D = cur - (1 - (int32_t)((d0 >> sft) & 1ULL)); d = 0; mn = D;
 			if (sft != low) { H = cur + (int32_t)((hn >> sft) & 1ULL) - (int32_t)((hp >> sft) & 1ULL); if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
 			if (sft != 0) { V = cur + (int32_t)((vn >> (sft - 1)) & 1ULL) - (int32_t)((vp >> (sft - 1)) & 1ULL); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
@@ -552,7 +554,8 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 	else { ez.ps = ez.pe = -1; ez.ts = 0; ez.te = tn - 1; if (pn > tn + cut || tn > pn + cut) return; }
 	const int32_t tn0 = tn - 1, pe = pn - 1;
 	ez.nword = nword;
-	if ((uint64_t)nword * (uint64_t)tn * 5 > ez.pcap || nword > ez.vstride) { ez.ovf = 1; return; }
+	if ((nword == 1 ? 2 + 3 * (uint64_t)tn : (uint64_t)nword * (uint64_t)tn * 5) > ez.pcap || nword > ez.vstride) { ez.ovf = 1; return; }
+	ez.compact = nword == 1;
 	if (nword == 1) { // the band fits one word (thre <= 31: the bulk of the segments): same algorithm with the vectors in registers
 		uint64_t P0 = 0, P1 = 0, P2 = 0, P3 = 0, VP, VN, X, D0 = 0, HN = 0, HP = 0;
 		auto pch1 = [&](int32_t j) -> int { return T.at(ps0 + (mode == 2 ? pidx - j : j)); };
@@ -561,7 +564,7 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 		if (mode == 3) { VP = 0; VN = (1ULL << abs_diag) - 1; bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn; i_bd = abs_diag; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = (thre << 1) - abs_diag; err = abs_diag; }
 		else { bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = thre; err = thre; VN = (1ULL << thre) - 1; VP = ((1ULL << ((thre << 1) + 1)) - 1) ^ VN; }
 		const uint64_t mm = 1ULL << (thre << 1);
-		ez.pn = 0;
+		ez.path[0] = VP; ez.path[1] = VN; ez.pn = 2; // HP / HN of a column follow from its D0 and the column before: not stored
 		for (i = 0; i <= tn0; i++) {
 			const int tc = tch1(i);
 			X = (tc == 0 ? P0 : tc == 1 ? P1 : tc == 2 ? P2 : tc == 3 ? P3 : 0ULL) | VN;
@@ -583,7 +586,7 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 				++i_bd;
 				if (i_bd < pn) peq_or(pch1(i_bd), mm);
 			}
-			uint64_t *o = ez.path + ez.pn; o[0] = D0; o[1] = VP; o[2] = VN; o[3] = HP; o[4] = HN; ez.pn += 5;
+			uint64_t *o = ez.path + ez.pn; o[0] = D0; o[1] = VP; o[2] = VN; ez.pn += 3;
 		}
 		if (mode == 0) {
 			int32_t site = tn - 1 - thre; const int32_t ct = pn - 1;
@@ -597,7 +600,6 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 				if (err <= thre && err < ez.err) { ez.err = err; if (mode == 1) { ez.pe = site; ez.te = tn - 1; } else { ez.ps = pidx - site; ez.ts = tidx + 1 - tn; } }
 			}
 			if (err <= thre && err < ez.err) { ez.err = err; if (mode == 1) { ez.pe = site; ez.te = tn - 1; } else { ez.ps = pidx - site; ez.ts = tidx + 1 - tn; } }
-			if (ez.te - ez.ts + 1 != tn) { ez.pn /= (uint64_t)tn; ez.pn *= (uint64_t)(ez.te + 1 - ez.ts); }
 			if (mode == 1) hb_mw_gen_trace(ez, thre, 1);
 			else { poff = ez.ps; ez.ps = pidx - ez.pe; ez.pe = pidx - poff; hb_mw_gen_trace(ez, thre, 0); poff = ez.ps; ez.ps = pidx - ez.pe; ez.pe = pidx - poff; }
 		} else {

@@ -1215,10 +1215,10 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		if (need) A.q_out[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)sidx;
 	}
 }
-// segment alignment: a queue of segment ids.  LOCAL = true: one thread per queued segment with a small private scratch (trace of 1024
-// words = 204 columns of a one-word band, 4-word band at most: the usual segment between neighbouring minimizers); LOCAL = false:
+// segment alignment: a queue of segment ids.  LOCAL = true: one thread per queued segment with a small private scratch (trace of 640
+// words = 212 columns of a one-word band (3 words per column), 4-word band at most: the usual segment between neighbouring minimizers); LOCAL = false:
 // grid-stride with launch-sized global scratch.  A segment that overflows its scratch queues for the next tier.
-#define ECB_T0_PATH 1024
+#define ECB_T0_PATH 640
 #define ECB_T0_VS 4
 #define ECB_T0_CIG 72
 template <bool LOCAL>

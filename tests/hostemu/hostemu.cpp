@@ -307,14 +307,14 @@ int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 	return rc | (used > pool_cap ? 128 : 0);
 }
 
-// the same step as the GPU runs it: prep per overlap, every segment on its own with the tier-0 scratch (1024 trace words, 4-word band,
+// the same step as the GPU runs it: prep per overlap, every segment on its own with the tier-0 scratch (640 trace words, 4-word band,
 // 72 cigar runs) and, when that is too small, with the large one; then the merge over the stored results with cig_words-sized buffers.
 int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch, const uint64_t *fc, hb_hit_t *hits, uint64_t n_hits,
                        const hb_aln_t *aln, const hb_wl_t *wlA, double e_rate, int32_t w_l, int32_t gaps, int32_t cig_words,
                        hb_alnb_t *out, hb_wl_t *wl, uint64_t wl_cap, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used, uint64_t *n_wl, uint64_t *n_tier)
 {
 	EmuReads *r = (EmuReads *)reads; unsigned long long used = 0, sused = 0; uint64_t nw = 0; int rc = 0;
-	std::vector<uint64_t> path0(1024), vec0(11 * 4), path1((size_t)1 << 22), vec1(11 * HB_MW_MAXW); std::vector<uint16_t> cig0(72), cig1(65535), spool((size_t)1 << 22);
+	std::vector<uint64_t> path0(640), vec0(11 * 4), path1((size_t)1 << 22), vec1(11 * HB_MW_MAXW); std::vector<uint16_t> cig0(72), cig1(65535), spool((size_t)1 << 22);
 	std::vector<uint16_t> mbuf((size_t)3 * cig_words);
 	n_tier[0] = n_tier[1] = 0;
 	for (uint32_t j = 0; j < n_ch; j++) {
@@ -341,7 +341,7 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 					if (st != 5 && !C.ez.ovf) { hb_seg_store(C, st, uq, ut, um, &segs[k], spool.data(), &sused, spool.size()); n_tier[0]++; continue; }
 				}
 				for (int tier = 0; tier < 2; tier++) {
-					if (tier == 0) { C.ez.path = path0.data(); C.ez.pcap = 1024; C.ez.vec = vec0.data(); C.ez.vstride = 4; C.ez.cig = cig0.data(); C.ez.ccap = 72; }
+					if (tier == 0) { C.ez.path = path0.data(); C.ez.pcap = 640; C.ez.vec = vec0.data(); C.ez.vstride = 4; C.ez.cig = cig0.data(); C.ez.ccap = 72; }
 					else { C.ez.path = path1.data(); C.ez.pcap = path1.size(); C.ez.vec = vec1.data(); C.ez.vstride = HB_MW_MAXW; C.ez.cig = cig1.data(); C.ez.ccap = 65535; }
 					C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
 					const int st = hb_ecb_segment(C, z, hits + c.first_hit, pr.ch_n, k, uq, ut, &um);
