@@ -15,7 +15,8 @@
 // The dumps are the golden vectors the oracle port and the CUDA path are pinned
 // against (tests/golden/, made by tests/golden/make_golden.py).
 //
-// usage: refdump <raw|final> <out_prefix> <hifiasm args...>
+// usage: refdump <raw|final|roundK> <out_prefix> <hifiasm args...>
+//   roundK: EC rounds 0..K; of round K the states before / inside / after cal_ec_r (see the wrappers below)
 //   raw   : filter table + round-0 index on the raw reads, stage dumps, exit
 //   final : 3 EC rounds, "<p>.pre.*" bins, final index, stage dumps,
 //           cal_ov_r, "<p>.fin.*" bins
@@ -34,6 +35,7 @@
 #include "ecovlp.h"
 #include "Levenshtein_distance.h"
 #include "Correct.h"
+#include <dlfcn.h>
 
 // non-static reference functions that no header declares
 void ha_ec(int64_t round, int num_pround, int des_idx, uint64_t *tot_b, uint64_t *tot_e);
@@ -255,6 +257,61 @@ static void dump_stages(const char *pfx, double bw_thres)
 	destory_UC_Read(&ur);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// `round` mode: the states an error-correction round (cal_ec_r, ecovlp.cpp:6268) passes through, taken from the real run.
+// libhifiasm_ref.so is the unmodified reference compiled -fPIC, so its calls to its own global functions bind through the
+// PLT; defining sl_ec_r / cal_update_ec_multiple / cns_gen_full here (same signatures) puts this file between cal_ec_r and
+// them.  Each wrapper dumps R_INF with the reference's own writers and forwards to the reference's function (RTLD_NEXT).
+//   <p>.hap.*  after cal_ec_multiple = kt_for(worker_hap_ec) (ecovlp.cpp:6063): paf / reverse_paf as push_ne_ovlp left them
+//              (3320-3321), is_fully_corrected / is_abnormal (check_well_cal 2750), the edit scripts scc.a[i] (push_nec_re 2426)
+//   <p>.sl.ec  after sl_ec_r (6402, worker_sl_ec 5965): the corrected reads
+//   <p>.upd.*  after cal_update_ec_multiple (6095, worker_update_dc_ec 3808): paf with the exact intervals remapped
+//   <p>.post.* after cal_ec_r: reads reverse-complemented and lists flipped when the round does that (worker_hap_post_rev 3866)
+typedef struct { size_t n, m; asg16_v *a; uint8_t *f; } ref_cc_v; // layout of cc_v, ecovlp.cpp:100
+extern ref_cc_v scc;                                              // ecovlp.cpp:101
+struct ec_ovec_buf_t; struct cc_idx_t; struct cns_gfa;
+static const char *g_hook_pfx = NULL;
+static uint64_t g_full_calls = 0, g_full_bases = 0;
+static void write_tag(const char *tag, int reads, int lists)
+{
+	char *fn = (char *)malloc(strlen(g_hook_pfx) + strlen(tag) + 32);
+	if (reads) { sprintf(fn, "%s.%s.ec", g_hook_pfx, tag); write_All_reads(&R_INF, fn); }
+	if (lists) {
+		sprintf(fn, "%s.%s.ovlp.source", g_hook_pfx, tag); write_ma_hit_ts(R_INF.paf, R_INF.total_reads, fn);
+		sprintf(fn, "%s.%s.ovlp.reverse", g_hook_pfx, tag); write_ma_hit_ts(R_INF.reverse_paf, R_INF.total_reads, fn);
+	}
+	free(fn);
+}
+void sl_ec_r(uint64_t n_thre, uint64_t n_a)
+{
+	static void (*real)(uint64_t, uint64_t) = (void (*)(uint64_t, uint64_t))dlsym(RTLD_NEXT, "_Z7sl_ec_rmm");
+	if (g_hook_pfx) {
+		write_tag("hap", 0, 1);
+		FILE *fp = xopen(g_hook_pfx, ".hap.scc.bin"); uint64_t i;
+		for (i = 0; i < n_a; i++) { uint32_t n = scc.a[i].n; fwrite(&n, 4, 1, fp); fwrite(scc.a[i].a, 2, n, fp); }
+		fclose(fp);
+	}
+	real(n_thre, n_a);
+	if (g_hook_pfx) write_tag("sl", 1, 0);
+}
+void cal_update_ec_multiple(ec_ovec_buf_t *b, uint64_t n_thre, uint64_t n_a)
+{
+	static void (*real)(ec_ovec_buf_t *, uint64_t, uint64_t) = (void (*)(ec_ovec_buf_t *, uint64_t, uint64_t))dlsym(RTLD_NEXT, "_Z22cal_update_ec_multipleP13ec_ovec_buf_tmm");
+	real(b, n_thre, n_a);
+	if (g_hook_pfx) write_tag("upd", 0, 1);
+}
+// how often the graph consensus (cns_gen_full, ecovlp.cpp:1919) runs, and over how many query bases
+uint64_t cns_gen_full(overlap_region *ol, All_reads *rref, uint64_t s0, uint64_t e0, uint64_t wl, char *qstr, UC_Read *tu, bit_extz_t *exz, cc_idx_t *idx, uint64_t occ_tot, double occ_max,
+                      asg32_v *b32, cns_gfa *cns, uint64_t max_trace, window_list *ridx, window_list_alloc *res, uint32_t rid)
+{
+	typedef uint64_t (*fn_t)(overlap_region *, All_reads *, uint64_t, uint64_t, uint64_t, char *, UC_Read *, bit_extz_t *, cc_idx_t *, uint64_t, double, asg32_v *, cns_gfa *, uint64_t, window_list *, window_list_alloc *, uint32_t);
+	static fn_t real = (fn_t)dlsym(RTLD_NEXT, "_Z12cns_gen_fullP14overlap_regionP9All_readsmmmPcP7UC_ReadP10bit_extz_tP8cc_idx_tmdP7asg32_vP7cns_gfamP11window_listP17window_list_allocj");
+	__sync_fetch_and_add(&g_full_calls, 1); __sync_fetch_and_add(&g_full_bases, e0 - s0);
+	if (getenv("REFDUMP_FULL_TRACE")) fprintf(stderr, "[refdump] cns_gen_full rid %u [%lu, %lu)\n", rid, (unsigned long)s0, (unsigned long)e0);
+	return real(ol, rref, s0, e0, wl, qstr, tu, exz, idx, occ_tot, occ_max, b32, cns, max_trace, ridx, res, rid);
+}
+
 static void write_bins(const char *pfx, const char *tag)
 {
 	char *fn = (char *)malloc(strlen(pfx) + strlen(tag) + 32);
@@ -346,10 +403,21 @@ int main(int argc, char *argv[])
 		dump_stages(pfx, asm_opt.is_ont ? 0.05 : 0.02); // bw of worker_hap_ec (ecovlp.cpp:3274)
 		return 0;
 	}
+	int hook_round = -1;
+	if (strncmp(mode, "round", 5) == 0) hook_round = atoi(mode + 5); // round<K>: dump the states of EC round K, then stop
 	for (r = 0; r < asm_opt.number_of_round; ++r) { // Assembly.cpp:2088-2097
 		ha_opt_reset_to_round(&asm_opt, r);
 		tot_b = tot_e = 0;
+		if (r == hook_round) { g_hook_pfx = pfx; g_full_calls = g_full_bases = 0; if (r > 0) write_tag("pre", 1, 1); } // round 0 parses the input inside ha_pt_gen: its "pre" state is the raw read set, no overlaps
 		ha_ec(r, asm_opt.number_of_pround, (r < asm_opt.number_of_round - 1) ? 1 : 0, &tot_b, &tot_e);
+		if (r == hook_round) {
+			write_tag("post", 1, 1);
+			FILE *fpa = xopen(pfx, ".params.txt");
+			fprintf(fpa, "n_reads %lu\nround %d\nn_round %d\nhom_cov %d\nhet_cov %d\ntot_b %lu\ntot_e %lu\nfull_calls %lu\nfull_bases %lu\n", (unsigned long)R_INF.total_reads, r, asm_opt.number_of_round,
+			        asm_opt.hom_cov, asm_opt.het_cov, (unsigned long)tot_b, (unsigned long)tot_e, (unsigned long)g_full_calls, (unsigned long)g_full_bases);
+			fclose(fpa);
+			return 0;
+		}
 		fprintf(stderr, "[refdump] round %d: bases %lu corrected %lu\n", r + 1, (unsigned long)tot_b, (unsigned long)tot_e);
 	}
 	ha_opt_reset_to_round(&asm_opt, asm_opt.number_of_round);

@@ -180,3 +180,55 @@ def ec_reverse(reads, rid, ph):
     rc = lib().emu_ec_reverse(reads.h, C.c_uint32(rid), _p(ph if ph.size else np.zeros(1, PHASE)), C.c_uint32(ph.size), _p(out), C.byref(n))
     assert rc == 0
     return out[:n.value]
+
+
+# ---- closing steps of an EC round (hb_ecround.cuh: rows a15-a18) ----
+class DerivedReads:
+    """a read store made by emu_ec_apply / emu_ec_rc (owned by the library)"""
+    def __init__(self, h, n):
+        self.h = C.c_void_p(h); self.n = n
+        ln = np.zeros(n, np.uint64)
+        lib().emu_reads_export(self.h, _p(ln), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0))
+        self.length = ln
+
+    def export(self):
+        """-> binio.ReadStore in the All_reads layout"""
+        from hifiasm_b200 import binio
+        L = lib(); L.emu_reads_n_npos.restype = C.c_uint64
+        nb = self.length // 4 + 1
+        boff = np.zeros(self.n + 1, np.uint64); np.cumsum(nb, out=boff[1:])
+        packed = np.zeros(int(boff[-1]) + 1, np.uint8); noff = np.zeros(self.n + 1, np.uint64); npos = np.zeros(int(L.emu_reads_n_npos(self.h)) + 1, np.uint64)
+        L.emu_reads_export(self.h, C.c_void_p(0), _p(packed), _p(noff), _p(npos))
+        return binio.ReadStore(length=self.length.copy(), byte_off=boff, packed=packed[:int(boff[-1])], n_off=noff, n_pos=npos[:int(noff[-1])])
+
+
+def ec_apply(reads, scc, scc_off):
+    L = lib(); L.emu_ec_apply.restype = C.c_void_p
+    scc = np.ascontiguousarray(scc if scc.size else np.zeros(1, np.uint16)); scc_off = np.ascontiguousarray(scc_off, dtype=np.uint64)
+    return DerivedReads(L.emu_ec_apply(reads.h, _p(scc), _p(scc_off)), reads.n)
+
+
+def ec_rc(reads):
+    L = lib(); L.emu_ec_rc.restype = C.c_void_p
+    return DerivedReads(L.emu_ec_rc(reads.h), reads.n)
+
+
+def ec_update(reads, paf, off, scc, scc_off):
+    """worker_update_dc_ec over every list -> (updated MA records, number of exact records)"""
+    L = lib(); L.emu_ec_update.restype = C.c_uint64
+    paf = np.ascontiguousarray(paf, dtype=MA).copy(); off = np.ascontiguousarray(off, dtype=np.uint64)
+    scc = np.ascontiguousarray(scc if scc.size else np.zeros(1, np.uint16)); scc_off = np.ascontiguousarray(scc_off, dtype=np.uint64)
+    ne = L.emu_ec_update(reads.h, _p(paf if paf.size else np.zeros(1, MA)), _p(off), _p(scc), _p(scc_off))
+    return paf, int(ne)
+
+
+def ec_flip(reads, paf, off):
+    """flip_paf_rc over every list -> (records, off) compacted"""
+    paf = np.ascontiguousarray(paf, dtype=MA).copy(); off = np.ascontiguousarray(off, dtype=np.uint64)
+    n = off.size - 1; no = np.zeros(n + 1, np.uint32)
+    lib().emu_ec_flip(reads.h, _p(paf if paf.size else np.zeros(1, MA)), _p(off), _p(no))
+    keep = np.zeros(paf.size, bool); noff = np.zeros(n + 1, np.uint64)
+    for i in range(n):
+        keep[int(off[i]):int(off[i]) + int(no[i])] = True
+        noff[i + 1] = noff[i] + int(no[i])
+    return paf[keep], noff

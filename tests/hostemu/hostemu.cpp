@@ -15,6 +15,7 @@
 #include "../../hifiasm_b200/csrc/hb_final.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecaln.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecphase.cuh"
+#include "../../hifiasm_b200/csrc/hb_ecround.cuh"
 
 struct EmuReads { DevReads d; std::vector<uint8_t> packed; std::vector<uint64_t> off, noff; std::vector<uint32_t> len, npos; };
 struct EmuFt { DevFt d; std::vector<uint64_t> key; std::vector<int32_t> val; };
@@ -393,6 +394,67 @@ int emu_ec_reverse(void *reads, uint32_t rid, const hb_phase_t *ph, uint32_t n, 
 	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
 	*n_out = hb_ec_reverse_list(r->d, rid, ph, n, ord.data(), W, out, &ovf);
 	return ovf;
+}
+
+// ---- closing steps of an EC round (hb_ecround.cuh) ----
+// a16: a new read store = every read with its edit script applied (bodies of k_sl_len / k_sl_apply)
+void *emu_ec_apply(void *reads, const uint16_t *sc, const uint64_t *sc_off)
+{
+	EmuReads *r = (EmuReads *)reads, *o = new EmuReads(); const uint64_t n = r->d.n;
+	o->off.resize(n + 1); o->len.resize(n); o->noff.assign(n + 1, 0);
+	std::vector<uint32_t> changed(n);
+	uint64_t off = 0;
+	for (uint64_t i = 0; i < n; i++) {
+		hb_sl_len(sc + sc_off[i], (uint32_t)(sc_off[i + 1] - sc_off[i]), r->d.len[i], &o->len[i], &changed[i]);
+		o->off[i] = off; off += ((o->len[i] / 4 + 1) + 31) & ~31ULL;
+	}
+	o->off[n] = off; o->packed.assign(off + 64, 0);
+	std::vector<uint32_t> tmp(r->d.noff[n] + 1);
+	for (uint64_t i = 0; i < n; i++) {
+		uint32_t nn;
+		if (changed[i]) nn = hb_sl_apply(hb_rd_view(r->d, i, 0), sc + sc_off[i], (uint32_t)(sc_off[i + 1] - sc_off[i]), &o->packed[o->off[i]], tmp.data() + r->d.noff[i]);
+		else { memcpy(&o->packed[o->off[i]], r->d.packed + r->d.off[i], r->d.len[i] / 4 + 1); nn = (uint32_t)(r->d.noff[i + 1] - r->d.noff[i]); for (uint32_t k = 0; k < nn; k++) tmp[r->d.noff[i] + k] = r->d.npos[r->d.noff[i] + k]; }
+		o->noff[i + 1] = o->noff[i] + nn;
+	}
+	o->npos.resize(o->noff[n] + 1);
+	for (uint64_t i = 0; i < n; i++) for (uint64_t k = 0; k < o->noff[i + 1] - o->noff[i]; k++) o->npos[o->noff[i] + k] = tmp[r->d.noff[i] + k];
+	o->d.n = n; o->d.packed = o->packed.data(); o->d.off = o->off.data(); o->d.len = o->len.data(); o->d.noff = o->noff.data(); o->d.npos = o->npos.data();
+	return o;
+}
+// a18: reverse complement of every read (body of k_rc_reads)
+void *emu_ec_rc(void *reads)
+{
+	EmuReads *r = (EmuReads *)reads, *o = new EmuReads(); const uint64_t n = r->d.n;
+	o->off = r->off; o->len = r->len; o->noff = r->noff; o->npos.resize(r->npos.size()); o->packed.assign(r->packed.size(), 0);
+	for (uint64_t i = 0; i < n; i++) {
+		const RdView v = hb_rd_view(r->d, i, 0);
+		for (uint32_t j = 0; j < v.len / 4 + 1; j++) o->packed[o->off[i] + j] = hb_rc_byte(v, j);
+		for (uint32_t k = 0; k < v.nn; k++) o->npos[r->d.noff[i] + k] = v.len - 1 - v.npos[v.nn - 1 - k];
+	}
+	o->d.n = n; o->d.packed = o->packed.data(); o->d.off = o->off.data(); o->d.len = o->len.data(); o->d.noff = o->noff.data(); o->d.npos = o->npos.data();
+	return o;
+}
+// copy of a read store in the All_reads layout (len/4+1 bytes per read)
+void emu_reads_export(void *reads, uint64_t *len, uint8_t *packed, uint64_t *n_off, uint64_t *n_pos)
+{
+	EmuReads *r = (EmuReads *)reads; uint64_t o = 0;
+	for (uint64_t i = 0; i < r->d.n; i++) { if (len) len[i] = r->d.len[i]; if (packed) memcpy(packed + o, r->d.packed + r->d.off[i], r->d.len[i] / 4 + 1); o += r->d.len[i] / 4 + 1; }
+	if (n_off) for (uint64_t i = 0; i <= r->d.n; i++) n_off[i] = r->d.noff[i];
+	if (n_pos) for (uint64_t i = 0; i < r->d.noff[r->d.n]; i++) n_pos[i] = r->d.npos[i];
+}
+uint64_t emu_reads_n_npos(void *reads) { EmuReads *r = (EmuReads *)reads; return r->d.noff[r->d.n]; }
+// a17: every record of every paf[i] against the corrected read store (body of k_update_dc); returns the number of exact records
+uint64_t emu_ec_update(void *reads, hb_ma_hit_t *paf, const uint64_t *off, const uint16_t *sc, const uint64_t *sc_off)
+{
+	EmuReads *r = (EmuReads *)reads; uint64_t ne = 0;
+	for (uint64_t i = 0; i < r->d.n; i++) for (uint64_t k = off[i]; k < off[i + 1]; k++) ne += hb_update_dc(r->d, i, &paf[k], sc, sc_off);
+	return ne;
+}
+// a18: flip_paf_rc of one list; n_out[i] = new length of list i (records stay at off[i])
+void emu_ec_flip(void *reads, hb_ma_hit_t *paf, const uint64_t *off, uint32_t *n_out)
+{
+	EmuReads *r = (EmuReads *)reads;
+	for (uint64_t i = 0; i < r->d.n; i++) n_out[i] = hb_flip_paf(r->d.len, i, paf + off[i], (uint32_t)(off[i + 1] - off[i]));
 }
 
 } // extern "C"
