@@ -214,7 +214,8 @@ HB_HD void hb_ph_decide(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_ov
 // ph[0..n) = the read's overlaps after phasing (hb_phase_t, st == 2 = accepted, list order); ord = scratch of n u64 (y_id | index pairs for
 // overlap_region_sort_y_id, whose unstable radix sort is restated move for move); out = up to n records.  Returns the number of records.
 struct PhPair { uint32_t y_id, idx; };
-HB_HD uint32_t hb_ec_reverse_list(const DevReads &R, uint64_t qid, const hb_phase_t *ph, uint32_t n, PhPair *ord, const RsScratch &W, hb_ma_hit_t *out, int *ovf)
+// dedup_chains alone: ord[0..keep) = the surviving overlaps (indices into ph[]) in the order the reference leaves them
+HB_HD uint32_t hb_ec_dedup(const hb_phase_t *ph, uint32_t n, PhPair *ord, const RsScratch &W, int *ovf)
 {
 	uint32_t m = 0;
 	for (uint32_t j = 0; j < n; j++) if (ph[j].st == 2) { ord[m].y_id = ph[j].y_id; ord[m].idx = j; m++; }
@@ -243,6 +244,12 @@ HB_HD uint32_t hb_ec_reverse_list(const DevReads &R, uint64_t qid, const hb_phas
 			}
 		}
 	}
+	return keep;
+}
+HB_HD uint32_t hb_ec_reverse_list(const DevReads &R, uint64_t qid, const hb_phase_t *ph, uint32_t n, PhPair *ord, const RsScratch &W, hb_ma_hit_t *out, int *ovf)
+{
+	const uint32_t keep = hb_ec_dedup(ph, n, ord, W, ovf);
+	if (*ovf) return 0;
 	uint32_t no = 0;
 	for (uint32_t k = 0; k < keep; k++) {
 		const hb_phase_t &z = ph[ord[k].idx];

@@ -14,6 +14,7 @@
 #pragma once
 #include "hb_common.cuh"
 #include "hb_ecaln.cuh"
+#include "hb_ecphase.cuh"
 
 struct ScRun { uint32_t op, bq, bt, len; };
 HB_HD bool hb_ualn_w(const hb_wl_t &u) { return u.error == INT16_MAX && u.clen == 0 && u.extra_end < 0; } // is_ualn_win, Correct.h:1362
@@ -288,4 +289,25 @@ HB_HD void hb_check_well_cal(const uint16_t *sc, uint32_t scn, uint64_t *srt, co
 		if (old_dp == 0) { if (st > 0 && ed < len) *abnormal = 1; else if (*abnormal == 0) *abnormal = 2; }
 	}
 	if (*f_ec) { for (k = 0; k < scn && (sc[k] >> 14) == 0; k++) {} if (k < scn) *f_ec = 0; }
+}
+
+// the round's paf[i]: the same-haplotype overlaps (is_match == 1) of the de-duplicated list, in list order.  ph / alnb = the read's overlaps
+// (hb_chains order) after phasing / after step C; ord[0..keep) from hb_ec_dedup; wl / pool = window lists and cigars of step C; ec = the read's
+// edit script (ecn entries).  out = up to keep records.
+HB_HD uint32_t hb_ec_source_list(const DevReads &R, uint64_t qid, const hb_phase_t *ph, const hb_alnb_t *alnb, const PhPair *ord, uint32_t keep,
+                                 const hb_wl_t *wl, const uint16_t *pool, const uint16_t *ec, int64_t ecn, hb_ma_hit_t *out)
+{
+	uint32_t no = 0;
+	for (uint32_t k = 0; k < keep; k++) {
+		const hb_phase_t &z = ph[ord[k].idx]; const hb_alnb_t &b = alnb[ord[k].idx];
+		if (z.is_match != 1) continue;
+		const hb_wl_t *w = wl + b.w_off; uint32_t rxs, rxe, rys, rye;
+		hb_ma_hit_t h; h.qns = (qid << 32) | z.x_pos_s; h.qe = z.x_pos_e + 1; h.tn = z.y_id; h.ts = z.y_pos_s; h.te = z.y_pos_e + 1; h.rev = z.rev;
+		h.bl = R.len[z.y_id]; h.ml = (uint32_t)z.strong; h.no_l_indel = (uint8_t)hb_without_large_indel(w, b.w_n, pool, z.x_pos_s, z.x_pos_e); h.del = 0; h.el = 0;
+		for (int t = 0; t < 6; t++) h.pad[t] = 0;
+		hb_max_exact(w, b.w_n, pool, ec, ecn, &rxs, &rxe, &rys, &rye);
+		if (rxe > rxs) { h.qns = (qid << 32) | rxs; h.qe = rxe; h.ts = rys; h.te = rye; h.el = 1; }
+		out[no++] = h;
+	}
+	return no;
 }

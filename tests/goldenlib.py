@@ -30,6 +30,7 @@ def _load_bin(arr, loader):
 
 class Golden:
     def __init__(self, name):
+        self.name = name
         self.z = np.load(os.path.join(GOLDEN, name + ".npz"))
         self.raw = _load_bin(self.z["raw_ec"], binio.load_ec_bin)
         self.pre = _load_bin(self.z["pre_ec"], binio.load_ec_bin)

@@ -232,3 +232,14 @@ def ec_flip(reads, paf, off):
         keep[int(off[i]):int(off[i]) + int(no[i])] = True
         noff[i + 1] = noff[i] + int(no[i])
     return paf[keep], noff
+
+
+def ec_source(reads, rid, ph, alnb, wl, pool, ec):
+    """push_ne_ovlp(flag 1, ec) + check_well_cal -> (MA records, is_fully_corrected, is_abnormal); ph (PHASE) / alnb (ALNB) parallel, one per overlap"""
+    ph = np.ascontiguousarray(ph, dtype=PHASE); alnb = np.ascontiguousarray(alnb, dtype=ALNB); assert ph.size == alnb.size
+    wl = np.ascontiguousarray(wl if wl.size else np.zeros(1, WL)); pool = np.ascontiguousarray(pool if pool.size else np.zeros(1, np.uint16))
+    ec = np.ascontiguousarray(ec, dtype=np.uint16); out = np.zeros(ph.size + 1, MA); n = C.c_uint32(); fl = np.zeros(2, np.uint8)
+    rc = lib().emu_ec_source(reads.h, C.c_uint32(rid), _p(ph if ph.size else np.zeros(1, PHASE)), _p(alnb if alnb.size else np.zeros(1, ALNB)), C.c_uint32(ph.size), _p(wl), _p(pool),
+                             _p(ec if ec.size else np.zeros(1, np.uint16)), C.c_uint64(ec.size), _p(out), C.byref(n), _p(fl))
+    assert rc == 0
+    return out[:n.value], int(fl[0]), int(fl[1])

@@ -457,4 +457,19 @@ void emu_ec_flip(void *reads, hb_ma_hit_t *paf, const uint64_t *off, uint32_t *n
 	for (uint64_t i = 0; i < r->d.n; i++) n_out[i] = hb_flip_paf(r->d.len, i, paf + off[i], (uint32_t)(off[i + 1] - off[i]));
 }
 
+// a15: the round's paf[i] + is_fully_corrected / is_abnormal from the phased overlaps, the step-C window lists and the read's edit script
+// (bodies of k_ec_spaf).  ph / alnb: one entry per overlap of the read, parallel arrays.
+int emu_ec_source(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t *alnb, uint32_t n, const hb_wl_t *wl, const uint16_t *pool, const uint16_t *ec, uint64_t ecn,
+                  hb_ma_hit_t *out, uint32_t *n_out, uint8_t *flags)
+{
+	EmuReads *r = (EmuReads *)reads; int ovf = 0; std::vector<PhPair> ord(n + 1);
+	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
+	const uint32_t keep = hb_ec_dedup(ph, n, ord.data(), W, &ovf);
+	if (ovf) return ovf;
+	*n_out = hb_ec_source_list(r->d, rid, ph, alnb, ord.data(), keep, wl, pool, ec, (int64_t)ecn, out);
+	std::vector<uint64_t> srt(2 * (size_t)*n_out + 2);
+	hb_check_well_cal(ec, (uint32_t)ecn, srt.data(), out, *n_out, r->d.len[rid], 6 /* MIN_COVERAGE_THRESHOLD * 2, ecovlp.cpp:3324 */, &flags[0], &flags[1]);
+	return 0;
+}
+
 } // extern "C"

@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hos
 import emu  # noqa: E402
 import ha_oracle as ho  # noqa: E402
 from goldenlib import Golden, dg  # noqa: E402
+import roundlib  # noqa: E402
 
 
 @pytest.fixture(scope="module", params=["g1", "g2", "g3"])
@@ -81,6 +82,7 @@ def test_ec_align_step_A(ctx):
     pt, hom, het = ho.pt_gen(st, ft, opt)
     er = emu.Reads(rs)
     p = g.params("raw")
+    rd = roundlib.Rounds(g.name); rd_scc, rd_scc_off = rd.scc(0); h_src, h_soff, h_fc, h_ab = rd.hap(0, "src")
     for i in range(er.n):
         mz = ho.sketch(st.decode(i), int(p["w"]), int(p["k"]), 0, 1, ft, int(p["mz_sample_dist"]), int(p["mz_rewin"]))
         an = ho.anchors(st, pt, mz, int(p["high_occ"]), int(p["low_occ"]))
@@ -132,6 +134,14 @@ def test_ec_align_step_A(ctx):
             for f in alnlib.RPAF.names:
                 ra[f] = rp[f]
             assert ra.size == int(g.count("raw", "rpaf")[i]) and dg(ra.tobytes()) == int(g.digest("raw", "rpaf")[i]), "reverse_paf, read %d" % i
+            # the round's paf[i] (row a15): push_ne_ovlp(flag 1) with the longest exact interval mapped through the read's edit script (here the
+            # reference's own script of round 0), the large-indel flag and check_well_cal's two read flags — against the state after cal_ec_multiple
+            sc = rd_scc[int(rd_scc_off[i]):int(rd_scc_off[i + 1])]
+            sp, f_ec, f_ab = emu.ec_source(er, i, ph, acc_b, WCc, CCc, sc)
+            want = roundlib.canon_list(h_src[int(h_soff[i]):int(h_soff[i + 1])], 0)
+            assert sp.size == want.size, "paf, read %d" % i
+            assert roundlib.canon_list(sp, 0).tobytes() == want.tobytes(), "paf, read %d" % i
+            assert (f_ec, f_ab) == (int(h_fc[i]), int(h_ab[i])), "is_fully_corrected / is_abnormal, read %d" % i
 
 
 def test_final_pass(ctx):
