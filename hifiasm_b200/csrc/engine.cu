@@ -193,7 +193,7 @@ extern "C" void hb_destroy(hb_ctx_t *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
-	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->ws); if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->d_scc); cudaFree(ctx->d_scc_off); cudaFree(ctx->ws); if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -267,7 +267,7 @@ static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uin
 		    cudaMalloc((void **)&ctx->d_npos, nc * 4) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "read store does not fit in HBM"); free_reads(ctx); return HB_E_NOMEM; }
 		ctx->packed_cap = pc; ctx->reads_cap = rc_; ctx->npos_cap = nc;
 	}
-	ctx->n_reads = n; ctx->packed_bytes = o; ctx->n_npos = npos.size();
+	ctx->n_reads = n; ctx->packed_bytes = o; ctx->n_npos = npos.size(); ctx->scc_reads = 0; // staged edit scripts belong to the previous read set
 	cudaMemcpyAsync(ctx->d_packed, h_packed, o + 16, cudaMemcpyHostToDevice, ctx->stream); // (+ the zeroed guard bytes)
 	cudaMemcpyAsync(ctx->d_roff, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
 	cudaMemcpyAsync(ctx->d_rlen, ctx->h_rlen.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -504,6 +504,7 @@ struct StageOut { // host destinations of the stage APIs (all optional)
 	uint64_t *hit_off; hb_hit_t *hits; uint64_t hit_cap; uint64_t *fc_off; uint64_t *fc; uint64_t fc_cap;
 	double e_rate; int32_t w_l; int32_t gaps, use_prev; // window pass; step C on/off; row a12 (needs the previous round's overlaps staged)
 	hb_wl_t *wl; uint64_t wl_cap; uint16_t *cig; uint64_t cig_cap; uint64_t n_wl, n_cig; // step A of the EC alignment stage (mode 5)
+	hb_ma_hit_t *rec2; uint64_t rec2_cap; uint64_t *off2; uint8_t *flags; // mode 9: rec / off = the round's paf[], rec2 / off2 = reverse_paf[], flags = 2 bytes per read
 };
 
 // mode: 0 final pass (results kept in ctx->d_out*), 2 anchors, 3 chains
@@ -865,6 +866,34 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 							if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "phasing: radix-sort stack"); return HB_E_OVERFLOW; }
+							if (mode == 9) { // the round's paf[] / reverse_paf[] and the two read flags of the batch (rows a15, with the staged edit scripts)
+								hb_ma_hit_t *d_rp = ba.get<hb_ma_hit_t>(n_ov + 1), *d_sp = ba.get<hb_ma_hit_t>(n_ov + 1); uint32_t *d_nrp = ba.zero<uint32_t>(nb + 1), *d_nsp = ba.zero<uint32_t>(nb + 1);
+								uint64_t *d_srt = ba.get<uint64_t>(2 * n_ov + 2); uint8_t *d_fl = ba.zero<uint8_t>(2 * nb + 2); HB_ALLOC_CHECK(ba);
+								{
+									ProfScope ps(ctx, "k_ec_rpaf");
+									k_ec_rpaf<<<nblk(nb, 64), 64, 0, ctx->stream>>>(R, r0 + b0, nb, d_ooff, d_ph, P.ord, d_rp, d_nrp, d_err);
+								}
+								{
+									ProfScope ps(ctx, "k_ec_spaf");
+									k_ec_spaf<<<nblk(nb, 64), 64, 0, ctx->stream>>>(R, r0 + b0, nb, d_ooff, d_ph, d_alnb, d_wlb, d_poolb, ctx->d_scc, ctx->d_scc_off, P.ord, d_srt, d_sp, d_nsp, d_fl, d_err);
+								}
+								HB_CUDA(cudaGetLastError());
+								std::vector<hb_ma_hit_t> h_rp(n_ov + 1), h_sp(n_ov + 1); std::vector<uint32_t> h_nrp(nb + 1), h_nsp(nb + 1);
+								HB_CUDA(cudaMemcpyAsync(h_rp.data(), d_rp, n_ov * sizeof(hb_ma_hit_t), cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(h_nrp.data(), d_nrp, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+								HB_CUDA(cudaMemcpyAsync(h_sp.data(), d_sp, n_ov * sizeof(hb_ma_hit_t), cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(h_nsp.data(), d_nsp, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+								if (so->flags) HB_CUDA(cudaMemcpyAsync(so->flags + 2 * b0, d_fl, 2 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+								HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+								if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "dedup_chains: radix-sort stack"); return HB_E_OVERFLOW; }
+								for (uint64_t i = 0; i < nb; i++) {
+									st3_off[b0 + i] = st3_n; st3_hit_off[b0 + i] = st3_nh;
+									if ((so->rec && st3_n + h_nsp[i] > so->rec_cap) || (so->rec2 && st3_nh + h_nrp[i] > so->rec2_cap)) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
+									if (so->rec) memcpy((hb_ma_hit_t *)so->rec + st3_n, h_sp.data() + h_ooff[i], h_nsp[i] * sizeof(hb_ma_hit_t));
+									if (so->rec2) memcpy(so->rec2 + st3_nh, h_rp.data() + h_ooff[i], h_nrp[i] * sizeof(hb_ma_hit_t));
+									st3_n += h_nsp[i]; st3_nh += h_nrp[i];
+								}
+								st3_off[b0 + nb] = st3_n; st3_hit_off[b0 + nb] = st3_nh;
+								break;
+							}
 							if (mode == 8) { // the round's reverse_paf lists of the batch
 								hb_ma_hit_t *d_rp = ba.get<hb_ma_hit_t>(n_ov + 1); uint32_t *d_nrp = ba.zero<uint32_t>(nb + 1); HB_ALLOC_CHECK(ba);
 								{
@@ -1012,7 +1041,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_CUDA(cudaStreamSynchronize(ctx->stream));
 		return HB_OK;
 	}
-	if (mode >= 4) { if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8); return HB_OK; }
+	if (mode >= 4) { if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8); if (mode == 9 && so->off2) memcpy(so->off2, st3_hit_off.data(), (nR + 1) * 8); return HB_OK; }
 	if (mode == 3) {
 		if (so->off) memcpy(so->off, st3_off.data(), (nR + 1) * 8);
 		if (so->hit_off) memcpy(so->hit_off, st3_hit_off.data(), (nR + 1) * 8);
@@ -1123,6 +1152,15 @@ extern "C" int hb_ec_reverse_paf(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double
 	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
 	StageOut so; memset(&so, 0, sizeof(so)); so.off = off; so.rec = rec; so.rec_cap = rec_cap; so.e_rate = e_rate; so.w_l = w_l; so.gaps = 1;
 	return run_pass(ctx, r0, r1, 8, bw_thres, &so, 0);
+}
+extern "C" int hb_ec_round_lists(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t use_prev,
+                                 uint64_t *src_off, hb_ma_hit_t *src, uint64_t src_cap, uint64_t *rev_off, hb_ma_hit_t *rev, uint64_t rev_cap, uint8_t *flags)
+{
+	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
+	if (!ctx->n_reads || ctx->scc_reads != ctx->n_reads) { hb_set_err(ctx, HB_E_STATE, "edit scripts are not staged for the resident reads (hb_ec_stage_scc)"); return HB_E_STATE; }
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = src_off; so.rec = src; so.rec_cap = src_cap; so.off2 = rev_off; so.rec2 = rev; so.rec2_cap = rev_cap; so.flags = flags;
+	so.e_rate = e_rate; so.w_l = w_l; so.gaps = 1; so.use_prev = use_prev ? 1 : 0;
+	return run_pass(ctx, r0, r1, 9, bw_thres, &so, 0);
 }
 extern "C" int hb_ec_stage_prev(hb_ctx_t *ctx, const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off)
 { // R_INF.paf[] of the previous EC round, flattened; only the source list matters to gen_hc_r_alin_ea

@@ -12,7 +12,7 @@
 #ifdef __CUDACC__
 #define HB_HD __host__ __device__ __forceinline__
 #define HB_D __device__ __forceinline__
-#define HB_HD_NI __host__ __device__ __noinline__ /* large bodies with several call sites: one copy per kernel keeps the code in the instruction cache */
+#define HB_HD_NI static __host__ __device__ __noinline__ /* large bodies with several call sites: one copy per kernel keeps the code in the instruction cache */
 #else
 #define HB_HD inline
 #define HB_D inline

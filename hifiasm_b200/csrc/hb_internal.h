@@ -26,6 +26,8 @@ struct hb_ctx {
 	// staged previous overlaps for the resident final pass
 	hb_ma_hit_t *d_prev0, *d_prev1; uint64_t *d_prev0_off, *d_prev1_off; uint64_t n_prev0, n_prev1;
 	std::vector<uint64_t> h_prev0_off, h_prev1_off;
+	// edit scripts of the current EC round (scc.a[i], ecovlp.cpp:101), staged by hb_ec_stage_scc
+	uint16_t *d_scc; uint64_t *d_scc_off; uint64_t scc_reads, scc_total;
 	// results of the last final pass (device resident)
 	hb_ma_hit_t *d_out0, *d_out1; uint64_t *d_out0_off, *d_out1_off; uint64_t n_out0, n_out1, out_reads;
 	// instrumentation

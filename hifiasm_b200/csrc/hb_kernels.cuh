@@ -20,6 +20,7 @@
 #include "hb_final.cuh"
 #include "hb_ecaln.cuh"
 #include "hb_ecphase.cuh"
+#include "hb_ecround.cuh"
 
 #define HB_FULL 0xffffffffu
 static __device__ __forceinline__ int hb_lane() { return threadIdx.x & 31; }
@@ -1332,6 +1333,23 @@ __global__ void __launch_bounds__(64) k_ec_rpaf(DevReads R, uint64_t r0, uint64_
 	const uint64_t o0 = o_off[r];
 	n_out[r] = hb_ec_reverse_list(R, r0 + r, ph + o0, (uint32_t)(o_off[r + 1] - o0), (PhPair *)(ord + o0), W, out + o0, &ovf);
 	if (ovf) atomicOr(err, 128);
+}
+
+// the round's paf[i] (row a15): dedup_chains again on its own order array, push_ne_ovlp(flag 1, ec) with extract_max_exact through the read's
+// edit script, the large-indel flag, check_well_cal (hb_ecround.cuh).  srt = 2 words per overlap of scratch for the coverage sweep.
+__global__ void __launch_bounds__(64) k_ec_spaf(DevReads R, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ o_off, const hb_phase_t *__restrict__ ph, const hb_alnb_t *__restrict__ alnb,
+                                                const hb_wl_t *__restrict__ wl, const uint16_t *__restrict__ pool, const uint16_t *__restrict__ sc, const uint64_t *__restrict__ sc_off,
+                                                uint64_t *ord, uint64_t *srt, hb_ma_hit_t *out, uint32_t *n_out, uint8_t *flags, int *err)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st }; int ovf = 0;
+	const uint64_t o0 = o_off[r], rid = r0 + r; const uint32_t n = (uint32_t)(o_off[r + 1] - o0);
+	const uint16_t *ec = sc + sc_off[rid]; const uint32_t ecn = (uint32_t)(sc_off[rid + 1] - sc_off[rid]);
+	const uint32_t keep = hb_ec_dedup(ph + o0, n, (PhPair *)(ord + o0), W, &ovf);
+	if (ovf) { atomicOr(err, 128); n_out[r] = 0; flags[2 * r] = flags[2 * r + 1] = 0; return; }
+	const uint32_t no = hb_ec_source_list(R, rid, ph + o0, alnb + o0, (const PhPair *)(ord + o0), keep, wl, pool, ec, (int64_t)ecn, out + o0);
+	n_out[r] = no;
+	hb_check_well_cal(ec, ecn, srt + 2 * o0, out + o0, no, R.len[rid], 6 /* MIN_COVERAGE_THRESHOLD * 2, ecovlp.cpp:3324 */, &flags[2 * r], &flags[2 * r + 1]);
 }
 
 // ----------------------------------------------------------------------------

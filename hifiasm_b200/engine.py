@@ -229,6 +229,54 @@ class Engine:
         self._ck(_lib().hb_ec_reverse_paf(self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), _p(off), _p(rec), C.c_uint64(rec.size)))
         return off, rec[:int(off[-1])]
 
+    # ---- the rest of an EC round (rows a15-a18)
+    def ec_stage_scc(self, scc, scc_off):
+        """stage the round's edit scripts (scc.a[i]: uint16 runs, offsets n_reads + 1)"""
+        scc = np.ascontiguousarray(scc, dtype=np.uint16); o = np.ascontiguousarray(scc_off, dtype=np.uint64)
+        assert o.size == self.n_reads + 1
+        self._ck(_lib().hb_ec_stage_scc(self.h, _p(scc if scc.size else np.zeros(1, np.uint16)), _p(o)))
+
+    def ec_round_lists(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775, use_prev=0):
+        """what worker_hap_ec leaves in paf[i] / reverse_paf[i] -> (src_off, src MA, rev_off, rev MA, is_fully_corrected u8[], is_abnormal u8[])"""
+        n = r1 - r0
+        so = np.zeros(n + 1, np.uint64); ro = np.zeros(n + 1, np.uint64); fl = np.zeros(2 * n + 2, np.uint8); z = C.c_void_p(0)
+        a = (self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), C.c_int32(use_prev))
+        self._ck(_lib().hb_ec_round_lists(*a, _p(so), z, C.c_uint64(0), _p(ro), z, C.c_uint64(0), _p(fl)))
+        src = np.zeros(int(so[-1]) + 1, MA); rev = np.zeros(int(ro[-1]) + 1, MA)
+        self._ck(_lib().hb_ec_round_lists(*a, _p(so), _p(src), C.c_uint64(src.size), _p(ro), _p(rev), C.c_uint64(rev.size), _p(fl)))
+        return so, src[:int(so[-1])], ro, rev[:int(ro[-1])], fl[0:2 * n:2].copy(), fl[1:2 * n:2].copy()
+
+    def ec_apply(self):
+        """sl_ec_r: apply the staged edit scripts to the resident reads -> (reads changed, total bases)"""
+        a = C.c_uint64(); b = C.c_uint64()
+        self._ck(_lib().hb_ec_apply(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ec_update_paf(self, paf, off):
+        """cal_update_ec_multiple on the corrected store -> (updated MA records, exact, inexact)"""
+        paf = np.ascontiguousarray(paf, dtype=MA).copy(); off = np.ascontiguousarray(off, dtype=np.uint64)
+        a = C.c_uint64(); b = C.c_uint64()
+        self._ck(_lib().hb_ec_update_paf(self.h, _p(paf if paf.size else np.zeros(1, MA)), _p(off), C.byref(a), C.byref(b)))
+        return paf, a.value, b.value
+
+    def ec_post_rev(self, paf, off, rpaf, roff):
+        """worker_hap_post_rev: reverse-complement the resident reads, flip both lists -> (paf, off, rpaf, roff)"""
+        paf = np.ascontiguousarray(paf, dtype=MA).copy(); off = np.ascontiguousarray(off, dtype=np.uint64).copy()
+        rpaf = np.ascontiguousarray(rpaf, dtype=MA).copy(); roff = np.ascontiguousarray(roff, dtype=np.uint64).copy()
+        self._ck(_lib().hb_ec_post_rev(self.h, _p(paf if paf.size else np.zeros(1, MA)), _p(off), _p(rpaf if rpaf.size else np.zeros(1, MA)), _p(roff)))
+        return paf[:int(off[-1])], off, rpaf[:int(roff[-1])], roff
+
+    def download_reads(self):
+        """the resident read store -> binio.ReadStore (All_reads layout)"""
+        from . import binio
+        n = self.n_reads
+        ln = np.zeros(n, np.uint64); noff = np.zeros(n + 1, np.uint64); z = C.c_void_p(0)
+        self._ck(_lib().hb_reads_download(self.h, _p(ln), z, C.c_uint64(0), _p(noff), z, C.c_uint64(0)))
+        boff = np.zeros(n + 1, np.uint64); np.cumsum(ln // 4 + 1, out=boff[1:])
+        packed = np.zeros(int(boff[-1]) + 1, np.uint8); npos = np.zeros(int(noff[-1]) + 1, np.uint64)
+        self._ck(_lib().hb_reads_download(self.h, z, _p(packed), C.c_uint64(int(boff[-1])), z, _p(npos), C.c_uint64(int(noff[-1]))))
+        return binio.ReadStore(length=ln, byte_off=boff, packed=packed[:int(boff[-1])], n_off=noff, n_pos=npos[:int(noff[-1])])
+
     # ---- final pass
     def cal_ov_r(self, prev_src, prev_src_off, prev_rev, prev_rev_off, r0=0, r1=None, cap=None, out=None):
         """out = (out0, out1) preallocated MA arrays to receive the records (reused across calls)"""

@@ -166,8 +166,36 @@ int hb_ec_phase(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double
 
 /* ---- R_INF.reverse_paf[i] of an EC round (part of row a15): the overlaps phasing assigned to the other haplotype, after dedup_chains
  * (ecovlp.cpp:2984: best chain per target), as push_ne_ovlp(flag = 2) emits them (ecovlp.cpp:2585; el / del are not defined on that
- * path and come back 0).  off[r1-r0+1] + records.  The same-haplotype list (paf[i]) needs the consensus of row a14 and is not built yet. */
+ * path and come back 0).  off[r1-r0+1] + records.  hb_ec_round_lists below returns both lists of the round.                              */
 int hb_ec_reverse_paf(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, uint64_t *off, hb_ma_hit_t *rec, uint64_t rec_cap);
+
+/* ---- the rest of an EC round: cal_ec_r (ecovlp.h:13; ecovlp.cpp:6268) after the alignment and phasing of every read ------------------
+ * Edit scripts: scc.a[i] (ecovlp.cpp:101), one per read, the reference's own encoding (push_trace_bp_f, Levenshtein_distance.h:640):
+ * uint16 runs, op = w >> 14: 0 match (len 14 bits) / 1 mismatch (new base 2 bits, old base 2 bits, len 10 bits) / 2 insertion (base, len 12
+ * bits) / 3 deletion (base, len 12 bits).  The consensus that writes them (wcns_gen, row a14) is not on the device yet: hb_ec_stage_scc
+ * takes them from the caller (scc = concatenated scripts, scc_off[n_reads + 1]) and rows a15-a17 read them from HBM.                      */
+int hb_ec_stage_scc(hb_ctx_t *ctx, const uint16_t *scc, const uint64_t *scc_off);
+/* row a15 — what cal_ec_multiple / worker_hap_ec (ecovlp.cpp:6063, 3234) leaves in R_INF.paf[i] / R_INF.reverse_paf[i] for reads [r0,r1):
+ * alignment stage (use_prev != 0: with the exact shortcut of gen_hc_r_alin_ea against the lists staged by hb_ec_stage_prev), rphase_hc,
+ * dedup_chains, then push_ne_ovlp(flag 1, scc.a[i]) (2585: longest exact interval of each same-haplotype overlap mapped through the read's
+ * edit script by extract_max_exact 2520, no_l_indel from the large-indel test of wcns_gen 2299-2360), push_ne_ovlp(flag 2) and
+ * check_well_cal (2750): flags[2 i] = is_fully_corrected, flags[2 i + 1] = is_abnormal.  src_off / rev_off: r1 - r0 + 1 entries.          */
+int hb_ec_round_lists(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t use_prev,
+                      uint64_t *src_off, hb_ma_hit_t *src, uint64_t src_cap, uint64_t *rev_off, hb_ma_hit_t *rev, uint64_t rev_cap, uint8_t *flags);
+/* row a16 — sl_ec_r / worker_sl_ec (ecovlp.cpp:6402, 5965): every resident read with its staged edit script applied; the read store in
+ * HBM is replaced (new lengths, 2-bit bases, N lists).  The filter table and the position index still describe the old reads: rebuild
+ * them (hb_ft_gen / hb_pt_gen) before the next pass, as ha_ec does (Assembly.cpp:1007,1026).                                            */
+int hb_ec_apply(hb_ctx_t *ctx, uint64_t *n_changed, uint64_t *total_bases);
+/* row a17 — cal_update_ec_multiple / worker_update_dc_ec (ecovlp.cpp:6095, 3808) on the corrected store: every record of paf[] (flattened,
+ * paf_off[n_reads + 1], updated in place) whose el is set has its interval remapped through the TARGET's edit script
+ * (adjust_exact_match 3454), extended to the read ends and compared base by base (quick_exact_match 3521); el is rewritten.             */
+int hb_ec_update_paf(hb_ctx_t *ctx, hb_ma_hit_t *paf, const uint64_t *paf_off, uint64_t *n_exact, uint64_t *n_inexact);
+/* row a18 — worker_hap_post_rev (ecovlp.cpp:3866): resident reads reverse-complemented in HBM; both lists flipped by flip_paf_rc (3845),
+ * compacted in place (records and offsets are rewritten; lists only shrink).  Either list may be NULL.                                   */
+int hb_ec_post_rev(hb_ctx_t *ctx, hb_ma_hit_t *paf, uint64_t *paf_off, hb_ma_hit_t *rpaf, uint64_t *rpaf_off);
+/* the resident read store back in the All_reads layout (Process_Read.h:115-146): read_length[n], packed = len/4+1 bytes per read
+ * concatenated (pad bits zero), n_off[n + 1] / n_pos = the N_site lists.  Any output may be NULL.                                       */
+int hb_reads_download(hb_ctx_t *ctx, uint64_t *read_length, uint8_t *packed, uint64_t packed_cap, uint64_t *n_off, uint64_t *n_pos, uint64_t n_pos_cap);
 
 /* ---- final overlap pass: cal_ov_r(n_thre, n_a, new_idx=1) (ecovlp.h:15;
  * ecovlp.cpp:6385 -> worker_hap_dc_ec_gen_new_idx 3948) -----------------------

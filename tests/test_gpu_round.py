@@ -1,0 +1,101 @@
+"""GPU parity of the steps that close an error-correction round, through the C-ABI, against the states the
+unmodified reference passes through in its three rounds (tests/golden/g*_rounds.npz; see tests/golden/make_rounds.py).
+
+The rounds are chained on the device: the read store of round K + 1 is the one hb_ec_apply / hb_ec_post_rev leave in HBM in round K,
+the index is rebuilt on it (hb_pt_gen), and the previous round's lists feed the exact shortcut of the alignment stage.  The edit
+scripts are the reference's (the consensus, row a14, is not on the device yet)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from goldenlib import Golden  # noqa: E402
+import roundlib  # noqa: E402
+from hifiasm_b200 import binio  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hifiasm_b200
+    return hifiasm_b200
+
+
+@pytest.mark.parametrize("name", ["g1", "g2", "g3"])
+def test_round_closing_steps(hb, name):
+    """rows a16-a18 with the reference's lists as input: corrected reads, remapped exact intervals, reverse complement + flipped lists"""
+    g = Golden(name); rd = roundlib.Rounds(name)
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    for K in range(3):
+        scc, scc_off = rd.scc(K)
+        src, soff, fc, ab = rd.hap(K, "src"); rev, roff, _, _ = rd.hap(K, "rev")
+        eng.ec_stage_scc(scc, scc_off)
+        n_changed, tot = eng.ec_apply()
+        sl = eng.download_reads()
+        assert (roundlib.reads_digests(sl) == rd.digest(K, "sl_reads")).all(), "round %d: corrected reads" % K
+        assert tot == int(sl.length.sum()) and 0 <= n_changed <= sl.n
+        upd, n_exact, n_inexact = eng.ec_update_paf(binio.disk_to_mem(src), soff)
+        assert (roundlib.list_digests(upd, soff, 0) == rd.digest(K, "upd_src")).all(), "round %d: updated paf" % K
+        assert n_exact + n_inexact == src.size and n_exact == int((upd["el"] == 1).sum())
+        if K < 2:
+            psrc, psoff, prev, proff = eng.ec_post_rev(upd, soff, binio.disk_to_mem(rev), roff)
+        else:
+            psrc, psoff, prev, proff = upd, soff, binio.disk_to_mem(rev), roff
+        post = eng.download_reads()
+        assert (roundlib.reads_digests(post) == rd.digest(K, "post_reads")).all(), "round %d: reads after the round" % K
+        assert (roundlib.list_digests(psrc, psoff, 0) == rd.digest(K, "post_src")).all(), "round %d: paf after the round" % K
+        assert (roundlib.list_digests(prev, proff, 1) == rd.digest(K, "post_rev")).all(), "round %d: reverse_paf after the round" % K
+    assert (roundlib.reads_digests(eng.download_reads()) == roundlib.reads_digests(g.pre)).all()
+    eng.close()
+
+
+def _cmp_lists(tag, K, got, goff, want, woff, is_rev, skip):
+    bad = []
+    for i in range(goff.size - 1):
+        if skip[i]:
+            continue
+        a = roundlib.canon_list(got[int(goff[i]):int(goff[i + 1])], is_rev); b = roundlib.canon_list(want[int(woff[i]):int(woff[i + 1])], is_rev)
+        if a.tobytes() != b.tobytes():
+            bad.append(i)
+    assert not bad, "round %d %s: %d reads differ, first %s" % (K, tag, len(bad), bad[:5])
+
+
+@pytest.mark.parametrize("name", ["g1", "g2", "g3"])
+def test_round_lists_chained(hb, name):
+    """row a15 inside the whole device-side round: index -> alignment stage (with the previous round's exact shortcut) -> phasing -> dedup ->
+    paf[] / reverse_paf[] / is_fully_corrected / is_abnormal, then a16-a18 on the device's own lists; three rounds"""
+    g = Golden(name); rd = roundlib.Rounds(name)
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    hom = eng.ft_gen(); eng.update_cov(hom)   # the filter table of the raw reads serves all rounds (Assembly.cpp:2083)
+    n = g.raw.n
+    prev_src = np.zeros(0, binio.MA_MEM); prev_off = np.zeros(n + 1, np.uint64)
+    n_checked = 0
+    for K in range(3):
+        p = rd.params(K)
+        hom_k, het_k = eng.pt_gen()
+        assert (hom_k, het_k) == (int(p["hom_cov"]), int(p["het_cov"])), "round %d: coverage peaks" % K
+        eng.set_opt(hom_cov=hom_k, het_cov=het_k)
+        scc, scc_off = rd.scc(K)
+        eng.ec_stage_scc(scc, scc_off)
+        eng.ec_stage_prev(prev_src, prev_off)
+        poff, P = eng.ec_phase(0, n, 0.02, 0.04, 775)
+        skip = np.array([bool(P[int(poff[i]):int(poff[i + 1])]["need_rechain"].any()) for i in range(n)])  # rechain_aln_hc is not built: such reads are not final
+        so, S, ro, Rv, f_ec, f_ab = eng.ec_round_lists(0, n, 0.02, 0.04, 775, use_prev=1)
+        src, soff, fc, ab = rd.hap(K, "src"); rev, roff, _, _ = rd.hap(K, "rev")
+        _cmp_lists("paf", K, S, so, src, soff, 0, skip)
+        _cmp_lists("reverse_paf", K, Rv, ro, rev, roff, 1, skip)
+        keep = ~skip
+        assert (f_ec[keep] == fc[keep]).all() and (f_ab[keep] == ab[keep]).all(), "round %d: is_fully_corrected / is_abnormal" % K
+        n_checked += int(keep.sum())
+        # close the round on the device with the reference's lists where a read was skipped (so that the chain stays on the reference's path)
+        S2 = binio.disk_to_mem(src); R2 = binio.disk_to_mem(rev)
+        eng.ec_apply()
+        upd, _, _ = eng.ec_update_paf(S2, soff)
+        if K < 2:
+            prev_src, prev_off, _, _ = eng.ec_post_rev(upd, soff, R2, roff)
+        else:
+            prev_src, prev_off = upd, soff
+        assert (roundlib.reads_digests(eng.download_reads()) == rd.digest(K, "post_reads")).all(), "round %d: reads after the round" % K
+    assert n_checked > 2 * n
+    eng.close()
