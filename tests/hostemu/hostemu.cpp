@@ -16,6 +16,7 @@
 #include "../../hifiasm_b200/csrc/hb_ecaln.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecphase.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecround.cuh"
+#include "../../hifiasm_b200/csrc/hb_eccns.cuh"
 
 struct EmuReads { DevReads d; std::vector<uint8_t> packed; std::vector<uint64_t> off, noff; std::vector<uint32_t> len, npos; };
 struct EmuFt { DevFt d; std::vector<uint64_t> key; std::vector<int32_t> val; };
@@ -470,6 +471,28 @@ int emu_ec_source(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb
 	std::vector<uint64_t> srt(2 * (size_t)*n_out + 2);
 	hb_check_well_cal(ec, (uint32_t)ecn, srt.data(), out, *n_out, r->d.len[rid], 6 /* MIN_COVERAGE_THRESHOLD * 2, ecovlp.cpp:3324 */, &flags[0], &flags[1]);
 	return 0;
+}
+
+// a14: the read's edit script by window consensus (body of k_ec_cns) from the phased overlaps and the step-C window lists.
+// Returns 0 = script written, 1 = the read needs the graph consensus (not built), 2 = output capacity, < 0 = dedup overflow
+int emu_ec_cns(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t *alnb, uint32_t n, const hb_wl_t *wl, const uint16_t *pool, uint16_t *out, uint32_t out_cap, uint32_t *n_out, uint64_t *nec)
+{
+	EmuReads *r = (EmuReads *)reads; int ovf = 0; std::vector<PhPair> ord(n + 1);
+	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
+	const uint32_t keep = hb_ec_dedup(ph, n, ord.data(), W, &ovf);
+	if (ovf) return -1;
+	std::vector<CnsOv> ov; uint32_t n_ent = 0;
+	for (uint32_t k = 0; k < keep; k++) {
+		const hb_phase_t &z = ph[ord[k].idx]; const hb_alnb_t &b = alnb[ord[k].idx];
+		if (z.is_match != 1 || !b.w_n) continue;
+		CnsOv o; o.w = wl + b.w_off; o.wn = b.w_n; o.y_id = z.y_id; o.rev = z.rev; ov.push_back(o); n_ent += b.w_n;
+	}
+	std::vector<CnsEnt> ent(n_ent + 1); std::vector<uint32_t> srt(n_ent + 1), aa(n_ent + 1), ab(n_ent + 1), b32(n_ent + 1); std::vector<uint64_t> key(n_ent + 1), ct(2 * HB_CNS_WL);
+	CnsCtx C; C.R = r->d; C.q = hb_rd_view(r->d, rid, 0); C.ql = r->d.len[rid]; C.ov = ov.data(); C.pool = pool; C.ent = ent.data(); C.ct = ct.data(); C.b32 = b32.data();
+	C.out = out; C.out_cap = out_cap;
+	*nec = hb_cns_read(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
+	*n_out = C.out_n;
+	return C.need_full ? 1 : (C.ovf ? 2 : 0);
 }
 
 } // extern "C"

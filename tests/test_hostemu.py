@@ -83,6 +83,7 @@ def test_ec_align_step_A(ctx):
     er = emu.Reads(rs)
     p = g.params("raw")
     rd = roundlib.Rounds(g.name); rd_scc, rd_scc_off = rd.scc(0); h_src, h_soff, h_fc, h_ab = rd.hap(0, "src")
+    n_full = n_cns = tot_nec = 0
     for i in range(er.n):
         mz = ho.sketch(st.decode(i), int(p["w"]), int(p["k"]), 0, 1, ft, int(p["mz_sample_dist"]), int(p["mz_rewin"]))
         an = ho.anchors(st, pt, mz, int(p["high_occ"]), int(p["low_occ"]))
@@ -137,11 +138,20 @@ def test_ec_align_step_A(ctx):
             # the round's paf[i] (row a15): push_ne_ovlp(flag 1) with the longest exact interval mapped through the read's edit script (here the
             # reference's own script of round 0), the large-indel flag and check_well_cal's two read flags — against the state after cal_ec_multiple
             sc = rd_scc[int(rd_scc_off[i]):int(rd_scc_off[i + 1])]
+            # the read's edit script (row a14): window consensus, voted path; reads that need the graph consensus are reported, not corrected
+            st_c, my_sc, nec = emu.ec_cns(er, i, ph, acc_b, WCc, CCc)
+            n_full += st_c
+            if st_c == 0:
+                assert my_sc.tobytes() == sc.tobytes(), "edit script, read %d" % i
+                n_cns += 1; tot_nec += nec
             sp, f_ec, f_ab = emu.ec_source(er, i, ph, acc_b, WCc, CCc, sc)
             want = roundlib.canon_list(h_src[int(h_soff[i]):int(h_soff[i + 1])], 0)
             assert sp.size == want.size, "paf, read %d" % i
             assert roundlib.canon_list(sp, 0).tobytes() == want.tobytes(), "paf, read %d" % i
             assert (f_ec, f_ab) == (int(h_fc[i]), int(h_ab[i])), "is_fully_corrected / is_abnormal, read %d" % i
+    # almost every read is corrected by the voted path; the graph consensus ran cns_gen_full "full_calls" times in the reference's round 0
+    assert n_cns > 0 and n_full <= int(rd.params(0)["full_calls"]), (n_cns, n_full)
+    print("window consensus: %d reads by vote (%d corrected bases), %d need the graph consensus" % (n_cns, tot_nec, n_full))
 
 
 def test_final_pass(ctx):
