@@ -505,6 +505,7 @@ struct StageOut { // host destinations of the stage APIs (all optional)
 	double e_rate; int32_t w_l; int32_t gaps, use_prev; // window pass; step C on/off; row a12 (needs the previous round's overlaps staged)
 	hb_wl_t *wl; uint64_t wl_cap; uint16_t *cig; uint64_t cig_cap; uint64_t n_wl, n_cig; // step A of the EC alignment stage (mode 5)
 	hb_ma_hit_t *rec2; uint64_t rec2_cap; uint64_t *off2; uint8_t *flags; // mode 9: rec / off = the round's paf[], rec2 / off2 = reverse_paf[], flags = 2 bytes per read
+	int cns; std::vector<uint16_t> *h_scc; std::vector<uint64_t> *h_scc_off; uint8_t *status; uint64_t n_corrected; // mode 9 with the consensus on the device (row a14): scripts of the range, per-read status
 };
 
 // mode: 0 final pass (results kept in ctx->d_out*), 2 anchors, 3 chains
@@ -546,6 +547,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	uint32_t h_wtab[4096]; weight_table(h_wtab, high_occ, low_occ);
 	ChainPar CP = chain_par(ctx, bw);
 	hb_prof_reset(ctx);
+	if (mode == 9 && so->cns) { so->h_scc->clear(); so->h_scc_off->assign(nR + 1, 0); so->n_corrected = 0; } // (a rerun after a workspace growth starts over)
 	if (nR == 0) { if (so && so->off) so->off[0] = 0; return HB_OK; }
 
 	// ---- sketch + probe for the whole range
@@ -873,9 +875,57 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 									ProfScope ps(ctx, "k_ec_rpaf");
 									k_ec_rpaf<<<nblk(nb, 64), 64, 0, ctx->stream>>>(R, r0 + b0, nb, d_ooff, d_ph, P.ord, d_rp, d_nrp, d_err);
 								}
+								const uint16_t *d_sc_use = ctx->d_scc; const uint64_t *d_scoff_use = ctx->d_scc_off; uint64_t sc_rid0 = 0;
+								if (so->cns) { // row a14: the edit scripts of the batch's reads by window consensus, on the device
+									uint32_t *d_entcap = ba.zero<uint32_t>(nb + 1), *d_scn = ba.zero<uint32_t>(nb + 1); uint64_t *d_entoff = ba.get<uint64_t>(nb + 2), *d_slot = ba.get<uint64_t>(nb + 2), *d_scoff_b = ba.get<uint64_t>(nb + 2);
+									uint8_t *d_status = ba.zero<uint8_t>(nb + 8); unsigned long long *d_nec = ba.zero<unsigned long long>(1); CnsOv *d_cov = ba.get<CnsOv>(n_ov + 1);
+									HB_ALLOC_CHECK(ba);
+									k_cns_cap<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_ooff, d_alnb, d_entcap);
+									if ((rc = hb_scan_u32_to_u64(ctx, d_entcap, d_entoff, nb))) return rc;
+									uint64_t tot_ent = 0; HB_CUDA(cudaMemcpyAsync(&tot_ent, d_entoff + nb, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+									const unsigned cblocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nb + 63) / 64, (uint64_t)ctx->sm_count * 2)); const uint64_t cthr = (uint64_t)cblocks * 64;
+									CnsEnt *d_ent = ba.get<CnsEnt>(tot_ent + 1); uint32_t *d_csrt = ba.get<uint32_t>(tot_ent + 1), *d_acta = ba.get<uint32_t>(tot_ent + 1), *d_actb = ba.get<uint32_t>(tot_ent + 1), *d_b32 = ba.get<uint32_t>(tot_ent + 1);
+									uint64_t *d_key = ba.get<uint64_t>(tot_ent + 1), *d_ct = ba.get<uint64_t>(cthr * 2 * HB_CNS_WL);
+									HB_ALLOC_CHECK(ba);
+									std::vector<uint64_t> h_slot(nb + 1, 0); std::vector<uint32_t> h_scn(nb + 1); std::vector<uint64_t> h_scoff(nb + 1);
+									uint16_t *d_scslot = 0; uint64_t mult = 1;
+									for (int attempt = 0;; attempt++) {
+										for (uint64_t i = 0; i < nb; i++) h_slot[i + 1] = h_slot[i] + (128 + ctx->h_rlen[r0 + b0 + i] / 16) * mult;
+										d_scslot = ba.get<uint16_t>(h_slot[nb] + 1); HB_ALLOC_CHECK(ba);
+										HB_CUDA(cudaMemcpyAsync(d_slot, h_slot.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+										HB_CUDA(cudaMemsetAsync(d_nec, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+										CnsArgs CA; memset(&CA, 0, sizeof(CA));
+										CA.R = R; CA.r0 = r0 + b0; CA.nR = nb; CA.o_off = d_ooff; CA.ph = d_ph; CA.alnb = d_alnb; CA.wl = d_wlb; CA.pool = d_poolb; CA.ord = P.ord; CA.cov = d_cov; CA.ent_off = d_entoff; CA.ent = d_ent;
+										CA.srt = d_csrt; CA.act_a = d_acta; CA.act_b = d_actb; CA.b32 = d_b32; CA.key = d_key; CA.ct = d_ct; CA.out_off = d_slot; CA.out = d_scslot; CA.out_n = d_scn; CA.status = d_status; CA.nec = d_nec; CA.err = d_err;
+										{
+											ProfScope ps(ctx, "k_ec_cns");
+											k_ec_cns<<<cblocks, 64, 0, ctx->stream>>>(CA);
+										}
+										HB_CUDA(cudaGetLastError());
+										HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+										if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "dedup_chains: radix-sort stack"); return HB_E_OVERFLOW; }
+										if (!(h_err2 & 256)) break;
+										if (attempt >= 3) { hb_set_err(ctx, HB_E_OVERFLOW, "window consensus: edit-script buffer"); return HB_E_OVERFLOW; }
+										mult *= 8; // some script outgrew its slot: all reads of the batch again with larger slots
+									}
+									if ((rc = hb_scan_u32_to_u64(ctx, d_scn, d_scoff_b, nb))) return rc;
+									unsigned long long h_nec = 0;
+									HB_CUDA(cudaMemcpyAsync(h_scoff.data(), d_scoff_b, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_nec, d_nec, 8, cudaMemcpyDeviceToHost, ctx->stream));
+									if (so->status) HB_CUDA(cudaMemcpyAsync(so->status + b0, d_status, nb, cudaMemcpyDeviceToHost, ctx->stream));
+									HB_CUDA(cudaStreamSynchronize(ctx->stream));
+									uint16_t *d_scd = ba.get<uint16_t>(h_scoff[nb] + 1); HB_ALLOC_CHECK(ba);
+									k_sc_compact<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_slot, d_scoff_b, d_scslot, d_scd);
+									HB_CUDA(cudaGetLastError());
+									const size_t base = so->h_scc->size(); so->h_scc->resize(base + h_scoff[nb]);
+									if (h_scoff[nb]) HB_CUDA(cudaMemcpyAsync(so->h_scc->data() + base, d_scd, h_scoff[nb] * 2, cudaMemcpyDeviceToHost, ctx->stream));
+									HB_CUDA(cudaStreamSynchronize(ctx->stream));
+									for (uint64_t i = 0; i <= nb; i++) (*so->h_scc_off)[b0 + i] = base + h_scoff[i];
+									so->n_corrected += h_nec;
+									d_sc_use = d_scd; d_scoff_use = d_scoff_b; sc_rid0 = r0 + b0;
+								}
 								{
 									ProfScope ps(ctx, "k_ec_spaf");
-									k_ec_spaf<<<nblk(nb, 64), 64, 0, ctx->stream>>>(R, r0 + b0, nb, d_ooff, d_ph, d_alnb, d_wlb, d_poolb, ctx->d_scc, ctx->d_scc_off, P.ord, d_srt, d_sp, d_nsp, d_fl, d_err);
+									k_ec_spaf<<<nblk(nb, 64), 64, 0, ctx->stream>>>(R, r0 + b0, nb, d_ooff, d_ph, d_alnb, d_wlb, d_poolb, d_sc_use, d_scoff_use, sc_rid0, P.ord, d_srt, d_sp, d_nsp, d_fl, d_err);
 								}
 								HB_CUDA(cudaGetLastError());
 								std::vector<hb_ma_hit_t> h_rp(n_ov + 1), h_sp(n_ov + 1); std::vector<uint32_t> h_nrp(nb + 1), h_nsp(nb + 1);
@@ -1161,6 +1211,27 @@ extern "C" int hb_ec_round_lists(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double
 	StageOut so; memset(&so, 0, sizeof(so)); so.off = src_off; so.rec = src; so.rec_cap = src_cap; so.off2 = rev_off; so.rec2 = rev; so.rec2_cap = rev_cap; so.flags = flags;
 	so.e_rate = e_rate; so.w_l = w_l; so.gaps = 1; so.use_prev = use_prev ? 1 : 0;
 	return run_pass(ctx, r0, r1, 9, bw_thres, &so, 0);
+}
+extern "C" int hb_ec_stage_scc(hb_ctx_t *ctx, const uint16_t *scc, const uint64_t *scc_off);
+extern "C" int hb_ec_round(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t use_prev,
+                           uint64_t *src_off, hb_ma_hit_t *src, uint64_t src_cap, uint64_t *rev_off, hb_ma_hit_t *rev, uint64_t rev_cap, uint8_t *flags,
+                           uint64_t *scc_off, uint16_t *scc, uint64_t scc_cap, uint8_t *status, uint64_t *n_corrected)
+{
+	if (w_l < 8 || w_l > 4096 || e_rate < 0 || e_rate > 1) { hb_set_err(ctx, HB_E_ARG, "window length must be in [8,4096] and e_rate in [0,1]"); return HB_E_ARG; }
+	std::vector<uint16_t> h_scc; std::vector<uint64_t> h_off;
+	StageOut so; memset(&so, 0, sizeof(so)); so.off = src_off; so.rec = src; so.rec_cap = src_cap; so.off2 = rev_off; so.rec2 = rev; so.rec2_cap = rev_cap; so.flags = flags;
+	so.e_rate = e_rate; so.w_l = w_l; so.gaps = 1; so.use_prev = use_prev ? 1 : 0; so.cns = 1; so.h_scc = &h_scc; so.h_scc_off = &h_off; so.status = status;
+	int rc = run_pass(ctx, r0, r1, 9, bw_thres, &so, 0); if (rc) return rc;
+	const uint64_t nR = r1 - r0;
+	if (h_off.size() != nR + 1) h_off.assign(nR + 1, 0);
+	if (scc_off) memcpy(scc_off, h_off.data(), (nR + 1) * 8);
+	if (scc) {
+		if (h_scc.size() > scc_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "edit-script output capacity: need %llu", (unsigned long long)h_scc.size()); return HB_E_OVERFLOW; }
+		if (h_scc.size()) memcpy(scc, h_scc.data(), h_scc.size() * 2);
+	}
+	if (n_corrected) *n_corrected = so.n_corrected;
+	if (r0 == 0 && r1 == ctx->n_reads && nR) return hb_ec_stage_scc(ctx, h_scc.data(), h_off.data()); // the whole store: the scripts stay in HBM for hb_ec_apply / hb_ec_update_paf
+	return HB_OK;
 }
 extern "C" int hb_ec_stage_prev(hb_ctx_t *ctx, const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off)
 { // R_INF.paf[] of the previous EC round, flattened; only the source list matters to gen_hc_r_alin_ea

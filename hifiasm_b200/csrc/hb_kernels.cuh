@@ -21,6 +21,7 @@
 #include "hb_ecaln.cuh"
 #include "hb_ecphase.cuh"
 #include "hb_ecround.cuh"
+#include "hb_eccns.cuh"
 
 #define HB_FULL 0xffffffffu
 static __device__ __forceinline__ int hb_lane() { return threadIdx.x & 31; }
@@ -1338,18 +1339,64 @@ __global__ void __launch_bounds__(64) k_ec_rpaf(DevReads R, uint64_t r0, uint64_
 // the round's paf[i] (row a15): dedup_chains again on its own order array, push_ne_ovlp(flag 1, ec) with extract_max_exact through the read's
 // edit script, the large-indel flag, check_well_cal (hb_ecround.cuh).  srt = 2 words per overlap of scratch for the coverage sweep.
 __global__ void __launch_bounds__(64) k_ec_spaf(DevReads R, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ o_off, const hb_phase_t *__restrict__ ph, const hb_alnb_t *__restrict__ alnb,
-                                                const hb_wl_t *__restrict__ wl, const uint16_t *__restrict__ pool, const uint16_t *__restrict__ sc, const uint64_t *__restrict__ sc_off,
+                                                const hb_wl_t *__restrict__ wl, const uint16_t *__restrict__ pool, const uint16_t *__restrict__ sc, const uint64_t *__restrict__ sc_off, uint64_t sc_rid0,
                                                 uint64_t *ord, uint64_t *srt, hb_ma_hit_t *out, uint32_t *n_out, uint8_t *flags, int *err)
 {
 	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
 	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st }; int ovf = 0;
 	const uint64_t o0 = o_off[r], rid = r0 + r; const uint32_t n = (uint32_t)(o_off[r + 1] - o0);
-	const uint16_t *ec = sc + sc_off[rid]; const uint32_t ecn = (uint32_t)(sc_off[rid + 1] - sc_off[rid]);
+	const uint16_t *ec = sc + sc_off[rid - sc_rid0]; const uint32_t ecn = (uint32_t)(sc_off[rid - sc_rid0 + 1] - sc_off[rid - sc_rid0]); // sc_off[0] belongs to read sc_rid0
 	const uint32_t keep = hb_ec_dedup(ph + o0, n, (PhPair *)(ord + o0), W, &ovf);
 	if (ovf) { atomicOr(err, 128); n_out[r] = 0; flags[2 * r] = flags[2 * r + 1] = 0; return; }
 	const uint32_t no = hb_ec_source_list(R, rid, ph + o0, alnb + o0, (const PhPair *)(ord + o0), keep, wl, pool, ec, (int64_t)ecn, out + o0);
 	n_out[r] = no;
 	hb_check_well_cal(ec, ecn, srt + 2 * o0, out + o0, no, R.len[rid], 6 /* MIN_COVERAGE_THRESHOLD * 2, ecovlp.cpp:3324 */, &flags[2 * r], &flags[2 * r + 1]);
+}
+
+// window consensus of a batch of reads (row a14, hb_eccns.cuh): one thread per read, grid-stride (the per-thread vote array, 2 * HB_CNS_WL words, is
+// bounded by the grid).  ent_cap[r] = windows of the read's accepted overlaps (upper bound of its entries); scripts go to fixed per-read slots.
+__global__ void k_cns_cap(uint64_t nR, const uint64_t *__restrict__ o_off, const hb_alnb_t *__restrict__ alnb, uint32_t *__restrict__ ent_cap)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	uint32_t c = 0;
+	for (uint64_t j = o_off[r]; j < o_off[r + 1]; j++) if (alnb[j].st == 2) c += alnb[j].w_n;
+	ent_cap[r] = c;
+}
+struct CnsArgs {
+	DevReads R; uint64_t r0, nR; const uint64_t *o_off; const hb_phase_t *ph; const hb_alnb_t *alnb; const hb_wl_t *wl; const uint16_t *pool;
+	uint64_t *ord; CnsOv *cov; const uint64_t *ent_off; CnsEnt *ent; uint32_t *srt, *act_a, *act_b, *b32; uint64_t *key; uint64_t *ct;
+	const uint64_t *out_off; uint16_t *out; uint32_t *out_n; uint8_t *status; unsigned long long *nec; int *err;
+};
+__global__ void __launch_bounds__(64) k_ec_cns(CnsArgs A)
+{
+	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st };
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t r = tid; r < A.nR; r += nthr) {
+		const uint64_t o0 = A.o_off[r], rid = A.r0 + r, e0 = A.ent_off[r]; const uint32_t n = (uint32_t)(A.o_off[r + 1] - o0); int ovf = 0;
+		PhPair *ord = (PhPair *)(A.ord + o0); uint8_t st = 0;
+		for (uint32_t j = 0; j < n; j++) if (A.ph[o0 + j].st == 2 && A.ph[o0 + j].need_rechain) st |= 4; // an overlap of this read wanted rechain_aln_hc (not built): its lists are not final either
+		const uint32_t keep = hb_ec_dedup(A.ph + o0, n, ord, W, &ovf);
+		if (ovf) { atomicOr(A.err, 128); A.out_n[r] = 0; A.status[r] = st | 2; continue; }
+		CnsOv *ov = A.cov + o0; uint32_t n_ov = 0;
+		for (uint32_t k = 0; k < keep; k++) {
+			const hb_phase_t &z = A.ph[o0 + ord[k].idx]; const hb_alnb_t &b = A.alnb[o0 + ord[k].idx];
+			if (z.is_match != 1 || !b.w_n) continue;
+			CnsOv o; o.w = A.wl + b.w_off; o.wn = b.w_n; o.y_id = z.y_id; o.rev = z.rev; ov[n_ov++] = o;
+		}
+		CnsCtx C; C.R = A.R; C.q = hb_rd_view(A.R, rid, 0); C.ql = A.R.len[rid]; C.ov = ov; C.pool = A.pool; C.ent = A.ent + e0; C.ct = A.ct + tid * (2 * HB_CNS_WL); C.b32 = A.b32 + e0;
+		C.out = A.out + A.out_off[r]; C.out_cap = (uint32_t)(A.out_off[r + 1] - A.out_off[r]);
+		const uint64_t nec = hb_cns_read(C, n_ov, A.srt + e0, A.act_a + e0, A.act_b + e0, A.key + e0);
+		if (C.need_full) { A.out_n[r] = 0; A.status[r] = st | 1; continue; }   // the graph consensus (cns_gen_full) is not built: no script for this read
+		if (C.ovf) { A.out_n[r] = 0; A.status[r] = st | 2; atomicOr(A.err, 256); continue; }
+		A.out_n[r] = C.out_n; A.status[r] = st;
+		atomicAdd(A.nec, (unsigned long long)nec);
+	}
+}
+__global__ void k_sc_compact(uint64_t nR, const uint64_t *__restrict__ slot_off, const uint64_t *__restrict__ dense_off, const uint16_t *__restrict__ in, uint16_t *__restrict__ out)
+{
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
+	const uint64_t a = slot_off[r], b = dense_off[r], c = dense_off[r + 1] - b;
+	for (uint64_t k = 0; k < c; k++) out[b + k] = in[a + k];
 }
 
 // ----------------------------------------------------------------------------

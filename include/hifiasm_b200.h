@@ -172,8 +172,8 @@ int hb_ec_reverse_paf(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, 
 /* ---- the rest of an EC round: cal_ec_r (ecovlp.h:13; ecovlp.cpp:6268) after the alignment and phasing of every read ------------------
  * Edit scripts: scc.a[i] (ecovlp.cpp:101), one per read, the reference's own encoding (push_trace_bp_f, Levenshtein_distance.h:640):
  * uint16 runs, op = w >> 14: 0 match (len 14 bits) / 1 mismatch (new base 2 bits, old base 2 bits, len 10 bits) / 2 insertion (base, len 12
- * bits) / 3 deletion (base, len 12 bits).  The consensus that writes them (wcns_gen, row a14) is not on the device yet: hb_ec_stage_scc
- * takes them from the caller (scc = concatenated scripts, scc_off[n_reads + 1]) and rows a15-a17 read them from HBM.                      */
+ * bits) / 3 deletion (base, len 12 bits).  hb_ec_round writes them on the device (row a14); hb_ec_stage_scc takes them from the caller instead
+ * (scc = concatenated scripts, scc_off[n_reads + 1]: scripts gathered from other GPUs' shards, or the reference's own).  Rows a15-a17 read them from HBM. */
 int hb_ec_stage_scc(hb_ctx_t *ctx, const uint16_t *scc, const uint64_t *scc_off);
 /* row a15 — what cal_ec_multiple / worker_hap_ec (ecovlp.cpp:6063, 3234) leaves in R_INF.paf[i] / R_INF.reverse_paf[i] for reads [r0,r1):
  * alignment stage (use_prev != 0: with the exact shortcut of gen_hc_r_alin_ea against the lists staged by hb_ec_stage_prev), rphase_hc,
@@ -182,6 +182,15 @@ int hb_ec_stage_scc(hb_ctx_t *ctx, const uint16_t *scc, const uint64_t *scc_off)
  * check_well_cal (2750): flags[2 i] = is_fully_corrected, flags[2 i + 1] = is_abnormal.  src_off / rev_off: r1 - r0 + 1 entries.          */
 int hb_ec_round_lists(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t use_prev,
                       uint64_t *src_off, hb_ma_hit_t *src, uint64_t src_cap, uint64_t *rev_off, hb_ma_hit_t *rev, uint64_t rev_cap, uint8_t *flags);
+/* rows a14 + a15 — the same with the consensus on the device: wcns_gen (ecovlp.cpp:2293) writes each read's edit script (wcns_vote 2185 per 512
+ * columns, anchors by push_cns_anchor 2109, stretches between anchors voted by cns_gen0 1159), which then feeds push_ne_ovlp / check_well_cal as above.
+ * scc_off[r1 - r0 + 1] + scc = the scripts of the range (scc may be NULL: sizes only); *n_corrected = corrected bases (cal_ec_multiple's second counter).
+ * status[i]: 0 = done; bit 0 = the read needs the graph consensus (cns_gen_full, ecovlp.cpp:1919), which is NOT built yet — it gets an empty script and
+ * its lists carry no exact intervals; bit 2 = an overlap of the read wanted the re-chaining rescue (rechain_aln_hc), also not built.  When the range is
+ * the whole store the scripts stay staged in HBM (as by hb_ec_stage_scc) for hb_ec_apply / hb_ec_update_paf.                                       */
+int hb_ec_round(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t use_prev,
+                uint64_t *src_off, hb_ma_hit_t *src, uint64_t src_cap, uint64_t *rev_off, hb_ma_hit_t *rev, uint64_t rev_cap, uint8_t *flags,
+                uint64_t *scc_off, uint16_t *scc, uint64_t scc_cap, uint8_t *status, uint64_t *n_corrected);
 /* row a16 — sl_ec_r / worker_sl_ec (ecovlp.cpp:6402, 5965): every resident read with its staged edit script applied; the read store in
  * HBM is replaced (new lengths, 2-bit bases, N lists).  The filter table and the position index still describe the old reads: rebuild
  * them (hb_ft_gen / hb_pt_gen) before the next pass, as ha_ec does (Assembly.cpp:1007,1026).                                            */

@@ -60,10 +60,12 @@ def _cmp_lists(tag, K, got, goff, want, woff, is_rev, skip):
     assert not bad, "round %d %s: %d reads differ, first %s" % (K, tag, len(bad), bad[:5])
 
 
-@pytest.mark.parametrize("name", ["g1", "g2", "g3"])
-def test_round_lists_chained(hb, name):
-    """row a15 inside the whole device-side round: index -> alignment stage (with the previous round's exact shortcut) -> phasing -> dedup ->
-    paf[] / reverse_paf[] / is_fully_corrected / is_abnormal, then a16-a18 on the device's own lists; three rounds"""
+@pytest.mark.parametrize("name", ["g1", "g3"])
+def test_round_chained_on_device(hb, name):
+    """a whole round on the device, three rounds chained: index -> alignment stage (with the previous round's exact shortcut) -> phasing -> dedup ->
+    window consensus (row a14: edit scripts) -> paf[] / reverse_paf[] / is_fully_corrected / is_abnormal (row a15) -> rows a16-a18.
+    Reads whose consensus needs the graph path (status bit 0) or whose alignment wanted rechain_aln_hc (bit 2) are reported by the engine and
+    compared nowhere; after the comparison the chain continues with the reference's scripts and lists so that every round starts from the reference's state."""
     g = Golden(name); rd = roundlib.Rounds(name)
     eng = hb.Engine(0)
     eng.upload_store(g.raw)
@@ -76,26 +78,51 @@ def test_round_lists_chained(hb, name):
         hom_k, het_k = eng.pt_gen()
         assert (hom_k, het_k) == (int(p["hom_cov"]), int(p["het_cov"])), "round %d: coverage peaks" % K
         eng.set_opt(hom_cov=hom_k, het_cov=het_k)
-        scc, scc_off = rd.scc(K)
-        eng.ec_stage_scc(scc, scc_off)
         eng.ec_stage_prev(prev_src, prev_off)
-        poff, P = eng.ec_phase(0, n, 0.02, 0.04, 775)
-        skip = np.array([bool(P[int(poff[i]):int(poff[i + 1])]["need_rechain"].any()) for i in range(n)])  # rechain_aln_hc is not built: such reads are not final
-        so, S, ro, Rv, f_ec, f_ab = eng.ec_round_lists(0, n, 0.02, 0.04, 775, use_prev=1)
+        r = eng.ec_round(0, n, 0.02, 0.04, 775, use_prev=1)
+        scc, scc_off = rd.scc(K)
         src, soff, fc, ab = rd.hap(K, "src"); rev, roff, _, _ = rd.hap(K, "rev")
-        _cmp_lists("paf", K, S, so, src, soff, 0, skip)
-        _cmp_lists("reverse_paf", K, Rv, ro, rev, roff, 1, skip)
-        keep = ~skip
-        assert (f_ec[keep] == fc[keep]).all() and (f_ab[keep] == ab[keep]).all(), "round %d: is_fully_corrected / is_abnormal" % K
-        n_checked += int(keep.sum())
-        # close the round on the device with the reference's lists where a read was skipped (so that the chain stays on the reference's path)
-        S2 = binio.disk_to_mem(src); R2 = binio.disk_to_mem(rev)
+        ok = r["status"] == 0
+        assert int((r["status"] & 1).sum()) <= int(p["full_calls"]), "round %d: more reads sent to the graph consensus than the reference has calls of it" % K
+        bad = [i for i in range(n) if ok[i] and r["scc"][int(r["scc_off"][i]):int(r["scc_off"][i + 1])].tobytes() != scc[int(scc_off[i]):int(scc_off[i + 1])].tobytes()]
+        assert not bad, "round %d edit scripts: %d reads differ, first %s" % (K, len(bad), bad[:5])
+        _cmp_lists("paf", K, r["src"], r["src_off"], src, soff, 0, ~ok)
+        _cmp_lists("reverse_paf", K, r["rev"], r["rev_off"], rev, roff, 1, (r["status"] & 4) != 0)   # the reverse list does not depend on the script
+        assert (r["is_fully_corrected"][ok] == fc[ok]).all() and (r["is_abnormal"][ok] == ab[ok]).all(), "round %d: is_fully_corrected / is_abnormal" % K
+        if ok.all():
+            assert r["n_corrected"] == int(p["tot_e"])
+        n_checked += int(ok.sum())
+        # close the round on the device from the reference's scripts and lists
+        eng.ec_stage_scc(scc, scc_off)
         eng.ec_apply()
-        upd, _, _ = eng.ec_update_paf(S2, soff)
+        upd, _, _ = eng.ec_update_paf(binio.disk_to_mem(src), soff)
         if K < 2:
-            prev_src, prev_off, _, _ = eng.ec_post_rev(upd, soff, R2, roff)
+            prev_src, prev_off, _, _ = eng.ec_post_rev(upd, soff, binio.disk_to_mem(rev), roff)
         else:
             prev_src, prev_off = upd, soff
         assert (roundlib.reads_digests(eng.download_reads()) == rd.digest(K, "post_reads")).all(), "round %d: reads after the round" % K
     assert n_checked > 2 * n
+    eng.close()
+
+
+def test_round_lists_from_staged_scripts(hb):
+    """row a15 alone: the round's lists from edit scripts the caller stages (here the reference's of round 0), as a shard of a multi-GPU run does
+    with the scripts gathered from the other ranks"""
+    g = Golden("g2"); rd = roundlib.Rounds("g2")
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    hom = eng.ft_gen(); eng.update_cov(hom)
+    hom_k, het_k = eng.pt_gen(); eng.set_opt(hom_cov=hom_k, het_cov=het_k)
+    n = g.raw.n
+    scc, scc_off = rd.scc(0)
+    eng.ec_stage_scc(scc, scc_off)
+    eng.ec_stage_prev(np.zeros(0, binio.MA_MEM), np.zeros(n + 1, np.uint64))
+    poff, P = eng.ec_phase(0, n, 0.02, 0.04, 775)
+    skip = np.array([bool(P[int(poff[i]):int(poff[i + 1])]["need_rechain"].any()) for i in range(n)])
+    so, S, ro, Rv, f_ec, f_ab = eng.ec_round_lists(0, n, 0.02, 0.04, 775, use_prev=1)
+    src, soff, fc, ab = rd.hap(0, "src"); rev, roff, _, _ = rd.hap(0, "rev")
+    _cmp_lists("paf", 0, S, so, src, soff, 0, skip)
+    _cmp_lists("reverse_paf", 0, Rv, ro, rev, roff, 1, skip)
+    keep = ~skip
+    assert keep.sum() > n // 2 and (f_ec[keep] == fc[keep]).all() and (f_ab[keep] == ab[keep]).all()
     eng.close()
