@@ -893,7 +893,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 										for (uint64_t i = 0; i < nb; i++) h_slot[i + 1] = h_slot[i] + (128 + ctx->h_rlen[r0 + b0 + i] / 16) * mult;
 										d_scslot = ba.get<uint16_t>(h_slot[nb] + 1); HB_ALLOC_CHECK(ba);
 										HB_CUDA(cudaMemcpyAsync(d_slot, h_slot.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-										HB_CUDA(cudaMemsetAsync(d_nec, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+										HB_CUDA(cudaMemsetAsync(d_nec, 0, 8, ctx->stream)); if (attempt) HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream)); // (bit 256 of the attempt before; no other bit was set)
 										CnsArgs CA; memset(&CA, 0, sizeof(CA));
 										CA.R = R; CA.r0 = r0 + b0; CA.nR = nb; CA.o_off = d_ooff; CA.ph = d_ph; CA.alnb = d_alnb; CA.wl = d_wlb; CA.pool = d_poolb; CA.ord = P.ord; CA.cov = d_cov; CA.ent_off = d_entoff; CA.ent = d_ent;
 										CA.srt = d_csrt; CA.act_a = d_acta; CA.act_b = d_actb; CA.b32 = d_b32; CA.key = d_key; CA.ct = d_ct; CA.out_off = d_slot; CA.out = d_scslot; CA.out_n = d_scn; CA.status = d_status; CA.nec = d_nec; CA.err = d_err;
