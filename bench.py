@@ -322,6 +322,26 @@ def _main():
                                    "kernel_ms": kms, "stage_kernels_gbp_s": qb / (sum(kms.values()) / 1e3) / 1e9 if kms else None,
                                    "pass_ms_with_seeding_and_host_copies": wall_ec * 1e3, "setup_s": round(tb - ta, 1),
                                    "note": "steps A-C of gen_hc_r_alin on raw reads (0.2 % errors): thread per window (k_windows), per overlap (k_ec_overlap, k_ecb_prep, k_ecb_merge), per inter-anchor segment (k_ecb_seg)"}
+            # ---- the whole round on the device (rows a8-a18): alignment, phasing, window consensus, lists, then apply / update / reverse
+            try:
+                caps = (int(G.size) + 16, int(G.size) + 16, 256 * nq + qb // 8)
+                e2.ec_stage_prev(np.zeros(0, hifiasm_b200.binio.MA_MEM), np.zeros(nq + 1, np.uint64))
+                torch.cuda.synchronize(); tr = time.time()
+                rr_ = e2.ec_round(0, nq, 0.02, 0.04, 775, use_prev=1, caps=caps)
+                torch.cuda.synchronize(); wall_round = time.time() - tr
+                prr = dict(e2.profile())
+                tc = time.time(); n_chg, tot_b = e2.ec_apply(); prr.update(e2.profile())
+                upd, n_ex, n_inex = e2.ec_update_paf(rr_["src"], rr_["src_off"]); prr.update(e2.profile())
+                e2.ec_post_rev(upd, rr_["src_off"], rr_["rev"], rr_["rev_off"]); prr.update(e2.profile())
+                torch.cuda.synchronize(); wall_close = time.time() - tc
+                names = ("k_ec_rpaf", "k_ec_cns", "k_ec_spaf", "k_sl_len", "k_sl_apply", "k_update_dc", "k_flip_paf", "k_rc_reads")
+                aux["ec_round"] = {"reads": nq, "query_bases": qb, "round_pass_ms": wall_round * 1e3, "round_pass_gbp_s": qb / wall_round / 1e9,
+                                   "closing_steps_ms_with_host_copies": wall_close * 1e3, "kernel_ms": {k: prr[k][1] for k in names if k in prr},
+                                   "corrected_bases": rr_["n_corrected"], "reads_changed": int(n_chg), "reads_needing_graph_consensus": int((rr_["status"] & 1).sum()),
+                                   "paf_records": int(rr_["src"].size), "reverse_paf_records": int(rr_["rev"].size), "exact_after_update": int(n_ex),
+                                   "note": "hb_ec_round (index resident): seeding + alignment stage + rphase_hc + wcns_gen (voted path) + push_ne_ovlp / check_well_cal, lists and scripts to the host; then hb_ec_apply / hb_ec_update_paf / hb_ec_post_rev"}
+            except Exception as ex:
+                sys.stderr.write("[bench] EC round aux failed: %r\n" % (ex,))
             e2.close()
         except Exception as ex:  # the auxiliary measurement must never take the bench line down
             sys.stderr.write("[bench] EC alignment aux failed: %r\n" % (ex,))

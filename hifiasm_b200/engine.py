@@ -246,14 +246,16 @@ class Engine:
         self._ck(_lib().hb_ec_round_lists(*a, _p(so), _p(src), C.c_uint64(src.size), _p(ro), _p(rev), C.c_uint64(rev.size), _p(fl)))
         return so, src[:int(so[-1])], ro, rev[:int(ro[-1])], fl[0:2 * n:2].copy(), fl[1:2 * n:2].copy()
 
-    def ec_round(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775, use_prev=0):
-        """rows a14 + a15: consensus on the device -> dict(src_off, src, rev_off, rev, is_fully_corrected, is_abnormal, scc_off, scc, status, n_corrected)"""
+    def ec_round(self, r0, r1, bw=0.02, e_rate=0.04, w_l=775, use_prev=0, caps=None):
+        """rows a14 + a15: consensus on the device -> dict(src_off, src, rev_off, rev, is_fully_corrected, is_abnormal, scc_off, scc, status, n_corrected).
+        caps = (paf records, reverse_paf records, edit-script words): one pass with these capacities; None: a sizing pass first"""
         n = r1 - r0
         so = np.zeros(n + 1, np.uint64); ro = np.zeros(n + 1, np.uint64); co = np.zeros(n + 1, np.uint64); fl = np.zeros(2 * n + 2, np.uint8); st = np.zeros(n + 1, np.uint8); z = C.c_void_p(0); nc = C.c_uint64()
         a = (self.h, C.c_uint64(r0), C.c_uint64(r1), C.c_double(bw), C.c_double(e_rate), C.c_int32(w_l), C.c_int32(use_prev))
-        # sizes first (one extra pass: fine for tests; a caller that knows its capacities passes them once)
-        self._ck(_lib().hb_ec_round(*a, _p(so), z, C.c_uint64(0), _p(ro), z, C.c_uint64(0), _p(fl), _p(co), z, C.c_uint64(0), _p(st), C.byref(nc)))
-        src = np.zeros(int(so[-1]) + 1, MA); rev = np.zeros(int(ro[-1]) + 1, MA); scc = np.zeros(int(co[-1]) + 1, np.uint16)
+        if caps is None:
+            self._ck(_lib().hb_ec_round(*a, _p(so), z, C.c_uint64(0), _p(ro), z, C.c_uint64(0), _p(fl), _p(co), z, C.c_uint64(0), _p(st), C.byref(nc)))
+            caps = (int(so[-1]), int(ro[-1]), int(co[-1]))
+        src = np.zeros(caps[0] + 1, MA); rev = np.zeros(caps[1] + 1, MA); scc = np.zeros(caps[2] + 1, np.uint16)
         self._ck(_lib().hb_ec_round(*a, _p(so), _p(src), C.c_uint64(src.size), _p(ro), _p(rev), C.c_uint64(rev.size), _p(fl), _p(co), _p(scc), C.c_uint64(scc.size), _p(st), C.byref(nc)))
         return dict(src_off=so, src=src[:int(so[-1])], rev_off=ro, rev=rev[:int(ro[-1])], is_fully_corrected=fl[0:2 * n:2].copy(), is_abnormal=fl[1:2 * n:2].copy(),
                     scc_off=co, scc=scc[:int(co[-1])], status=st[:n].copy(), n_corrected=int(nc.value))
