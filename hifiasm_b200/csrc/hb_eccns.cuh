@@ -22,8 +22,9 @@
 struct CnsEnt { uint32_t ov, wid, xoff, yoff; int32_t coff; };  // ul_ov_t as wcns_gen uses it (ovlp_id, cur_wid, cur_xoff, cur_yoff, cur_coff; bd = 0, ylen = 0)
 struct CnsOv { const hb_wl_t *w; uint32_t wn, y_id, rev; };    // a same-haplotype overlap: its step-C window list (cigars in the shared pool)
 struct CnsIt { const uint32_t *srt; uint32_t *act; int64_t i, srt_n, act_n, rr, ru; uint64_t mms, mme; }; // cc_idx_t (274-279): act = idx->a + srt_n
+struct CnsG;
 struct CnsCtx {
-	DevReads R; RdView q; int64_t ql;
+	DevReads R; RdView q; int64_t ql; CnsG *g;   // g: arena of the graph consensus (hb_eccns_full.cuh); NULL = voted path only
 	const CnsOv *ov; const uint16_t *pool; CnsEnt *ent;
 	CnsIt A, B; uint64_t *ct; uint32_t *b32; uint32_t b32_n;
 	uint16_t *out; uint32_t out_n, out_cap; int32_t ax_start, ax_end; int has_win;   // aux_o's single window: the script under construction
@@ -223,6 +224,7 @@ HB_HD uint64_t hb_cns_push0(CnsCtx &C, uint32_t len0, uint32_t rc, int64_t qoff)
 	return nec;
 }
 
+HB_HD uint64_t hb_cns_full_(CnsCtx &C, int64_t s0, int64_t e0); // cns_gen_full (hb_eccns_full.cuh); sets C.need_full = 2 when the arena is too small
 // push_cns_anchor, ecovlp.cpp:2109-2163
 HB_HD uint64_t hb_cns_anchor(CnsCtx &C, uint64_t s, uint64_t e, int is_tail)
 {
@@ -235,7 +237,11 @@ HB_HD uint64_t hb_cns_anchor(CnsCtx &C, uint64_t s, uint64_t e, int is_tail)
 		if (hb_cns_gen0(C, (int64_t)e0, (int64_t)s, &rc)) {
 			if (C.ax_start == -1 || C.ax_end == -1) { C.ax_start = (int32_t)e0; C.ax_end = (int32_t)s - 1; }
 			nec += hb_cns_push0(C, 0xffffffffu, rc, (int64_t)e0);
-		} else { C.need_full = 1; return nec; } // cns_gen_full (ecovlp.cpp:1919): graph consensus, not built yet
+		} else {
+			if (!C.g) { C.need_full = 1; return nec; } // no graph arena in this launch: the read is redone by the launch that has one
+			nec += hb_cns_full_(C, (int64_t)e0, (int64_t)s);
+			if (C.need_full) return nec;
+		}
 		C.ax_end = (int32_t)s - 1;
 	}
 	if (C.ax_start == -1 || C.ax_end == -1) { C.ax_start = (int32_t)s; C.ax_end = (int32_t)e - 1; }

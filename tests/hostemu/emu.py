@@ -245,12 +245,13 @@ def ec_source(reads, rid, ph, alnb, wl, pool, ec):
     return out[:n.value], int(fl[0]), int(fl[1])
 
 
-def ec_cns(reads, rid, ph, alnb, wl, pool, cap=1 << 16):
-    """wcns_gen -> (status, edit script u16[], corrected bases); status 0 = done, 1 = the read needs the graph consensus (not built yet)"""
+def ec_cns(reads, rid, ph, alnb, wl, pool, cap=1 << 16, g_nodes=0, g_arcs=0):
+    """wcns_gen -> (status, edit script u16[], corrected bases); status 0 = done, 1 = the read needs the graph consensus and no arena was given
+    (g_nodes = 0: the first launch of the GPU path), 3 = the arena (g_nodes nodes, g_arcs arcs) was too small"""
     ph = np.ascontiguousarray(ph, dtype=PHASE); alnb = np.ascontiguousarray(alnb, dtype=ALNB); assert ph.size == alnb.size
     wl = np.ascontiguousarray(wl if wl.size else np.zeros(1, WL)); pool = np.ascontiguousarray(pool if pool.size else np.zeros(1, np.uint16))
     out = np.zeros(cap, np.uint16); n = C.c_uint32(); nec = C.c_uint64()
     rc = lib().emu_ec_cns(reads.h, C.c_uint32(rid), _p(ph if ph.size else np.zeros(1, PHASE)), _p(alnb if alnb.size else np.zeros(1, ALNB)), C.c_uint32(ph.size), _p(wl), _p(pool),
-                          _p(out), C.c_uint32(cap), C.byref(n), C.byref(nec))
-    assert rc in (0, 1), rc
+                          _p(out), C.c_uint32(cap), C.byref(n), C.byref(nec), C.c_uint32(g_nodes), C.c_uint32(g_arcs))
+    assert rc in (0, 1, 3), rc
     return rc, out[:n.value], int(nec.value)

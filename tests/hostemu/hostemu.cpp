@@ -17,6 +17,7 @@
 #include "../../hifiasm_b200/csrc/hb_ecphase.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecround.cuh"
 #include "../../hifiasm_b200/csrc/hb_eccns.cuh"
+#include "../../hifiasm_b200/csrc/hb_eccns_full.cuh"
 
 struct EmuReads { DevReads d; std::vector<uint8_t> packed; std::vector<uint64_t> off, noff; std::vector<uint32_t> len, npos; };
 struct EmuFt { DevFt d; std::vector<uint64_t> key; std::vector<int32_t> val; };
@@ -474,8 +475,9 @@ int emu_ec_source(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb
 }
 
 // a14: the read's edit script by window consensus (body of k_ec_cns) from the phased overlaps and the step-C window lists.
-// Returns 0 = script written, 1 = the read needs the graph consensus (not built), 2 = output capacity, < 0 = dedup overflow
-int emu_ec_cns(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t *alnb, uint32_t n, const hb_wl_t *wl, const uint16_t *pool, uint16_t *out, uint32_t out_cap, uint32_t *n_out, uint64_t *nec)
+// Returns 0 = script written, 1 = the read needs the graph consensus and no arena was given (g_nodes == 0), 2 = output capacity, 3 = graph arena too small, < 0 = dedup overflow
+int emu_ec_cns(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t *alnb, uint32_t n, const hb_wl_t *wl, const uint16_t *pool, uint16_t *out, uint32_t out_cap, uint32_t *n_out, uint64_t *nec,
+               uint32_t g_nodes, uint32_t g_arcs)
 {
 	EmuReads *r = (EmuReads *)reads; int ovf = 0; std::vector<PhPair> ord(n + 1);
 	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
@@ -489,10 +491,19 @@ int emu_ec_cns(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t 
 	}
 	std::vector<CnsEnt> ent(n_ent + 1); std::vector<uint32_t> srt(n_ent + 1), aa(n_ent + 1), ab(n_ent + 1), b32(n_ent + 1); std::vector<uint64_t> key(n_ent + 1), ct(2 * HB_CNS_WL);
 	CnsCtx C; C.R = r->d; C.q = hb_rd_view(r->d, rid, 0); C.ql = r->d.len[rid]; C.ov = ov.data(); C.pool = pool; C.ent = ent.data(); C.ct = ct.data(); C.b32 = b32.data();
-	C.out = out; C.out_cap = out_cap;
+	C.out = out; C.out_cap = out_cap; C.g = 0;
+	// with_graph: the arena of the graph consensus (what the second launch of the GPU path owns per thread); sizes are parameters so that the overflow report can be tested
+	std::vector<CnsNode> nd(g_nodes + 1); std::vector<CnsArc> arcs(g_arcs + 1); std::vector<uint32_t> gq(g_nodes + 1), gb32(g_arcs + 1), gnp(4100); std::vector<uint8_t> gns(4100);
+	std::vector<uint64_t> path(32768), vec(11 * 2 + 4); std::vector<uint16_t> gcig(4096);
+	CnsG G; memset(&G, 0, sizeof(G));
+	if (g_nodes) {
+		G.nd = nd.data(); G.ncap = g_nodes; G.arc = arcs.data(); G.arc_cap = g_arcs; G.q = gq.data(); G.q_cap = g_nodes; G.b32 = gb32.data(); G.b32_cap = g_arcs;
+		G.nseq = gns.data(); G.nseq_np = gnp.data(); G.nseq_cap = 4096; G.ez.path = path.data(); G.ez.pcap = path.size(); G.ez.vec = vec.data(); G.ez.vstride = 2; G.ez.cig = gcig.data(); G.ez.ccap = (int32_t)gcig.size();
+		C.g = &G;
+	}
 	*nec = hb_cns_read(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
 	*n_out = C.out_n;
-	return C.need_full ? 1 : (C.ovf ? 2 : 0);
+	return C.need_full ? (C.need_full == 2 ? 3 : 1) : (C.ovf ? 2 : 0);
 }
 
 } // extern "C"
