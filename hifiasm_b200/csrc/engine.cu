@@ -899,11 +899,32 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 										CA.srt = d_csrt; CA.act_a = d_acta; CA.act_b = d_actb; CA.b32 = d_b32; CA.key = d_key; CA.ct = d_ct; CA.out_off = d_slot; CA.out = d_scslot; CA.out_n = d_scn; CA.status = d_status; CA.nec = d_nec; CA.err = d_err;
 										{
 											ProfScope ps(ctx, "k_ec_cns");
-											k_ec_cns<<<cblocks, 64, 0, ctx->stream>>>(CA);
+											k_ec_cns<false><<<cblocks, 64, 0, ctx->stream>>>(CA);
 										}
 										HB_CUDA(cudaGetLastError());
-										HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+										std::vector<uint8_t> h_st(nb + 1);
+										HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(h_st.data(), d_status, nb, cudaMemcpyDeviceToHost, ctx->stream));
+										HB_CUDA(cudaStreamSynchronize(ctx->stream));
 										if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "dedup_chains: radix-sort stack"); return HB_E_OVERFLOW; }
+										std::vector<uint32_t> h_queue; for (uint64_t i = 0; i < nb; i++) if (h_st[i] & 1) h_queue.push_back((uint32_t)i);
+										if (!h_queue.empty()) { // second launch: the reads whose stretches need the graph consensus (cns_gen_full), each thread with a graph arena
+											Arena sa(ctx);
+											const unsigned gblocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((h_queue.size() + 31) / 32, (uint64_t)ctx->sm_count * 4)); const uint64_t gthr = (uint64_t)gblocks * 32;
+											static const uint32_t G_NODES = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096, G_ARCS = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
+											CnsArgs CB = CA; CB.n_queue = (uint32_t)h_queue.size(); CB.g_nodes = G_NODES; CB.g_arcs = G_ARCS; CB.g_nseq = 2048; CB.g_pcap = 8192; CB.g_ccap = 2048;
+											uint32_t *d_queue = sa.get<uint32_t>(h_queue.size()); CB.queue = d_queue;
+											CB.g_nd = sa.get<CnsNode>(gthr * CB.g_nodes); CB.g_arc = sa.get<CnsArc>(gthr * CB.g_arcs); CB.g_q = sa.get<uint32_t>(gthr * CB.g_nodes); CB.g_b32 = sa.get<uint32_t>(gthr * CB.g_arcs);
+											CB.g_np = sa.get<uint32_t>(gthr * CB.g_nseq); CB.g_ns = sa.get<uint8_t>(gthr * CB.g_nseq); CB.g_path = sa.get<uint64_t>(gthr * CB.g_pcap); CB.g_vec = sa.get<uint64_t>(gthr * 32); CB.g_cig = sa.get<uint16_t>(gthr * CB.g_ccap);
+											CB.ct = sa.get<uint64_t>(gthr * 2 * HB_CNS_WL);
+											if (sa.failed) return HB_E_WS;
+											HB_CUDA(cudaMemcpyAsync(d_queue, h_queue.data(), h_queue.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+											{
+												ProfScope ps(ctx, "k_ec_cns_graph");
+												k_ec_cns<true><<<gblocks, 32, 0, ctx->stream>>>(CB);
+											}
+											HB_CUDA(cudaGetLastError());
+											HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+										}
 										if (!(h_err2 & 256)) break;
 										if (attempt >= 3) { hb_set_err(ctx, HB_E_OVERFLOW, "window consensus: edit-script buffer"); return HB_E_OVERFLOW; }
 										mult *= 8; // some script outgrew its slot: all reads of the batch again with larger slots

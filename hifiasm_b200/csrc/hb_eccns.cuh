@@ -226,7 +226,7 @@ HB_HD uint64_t hb_cns_push0(CnsCtx &C, uint32_t len0, uint32_t rc, int64_t qoff)
 
 HB_HD uint64_t hb_cns_full_(CnsCtx &C, int64_t s0, int64_t e0); // cns_gen_full (hb_eccns_full.cuh); sets C.need_full = 2 when the arena is too small
 // push_cns_anchor, ecovlp.cpp:2109-2163
-HB_HD uint64_t hb_cns_anchor(CnsCtx &C, uint64_t s, uint64_t e, int is_tail)
+template <bool GRAPH> HB_HD uint64_t hb_cns_anchor(CnsCtx &C, uint64_t s, uint64_t e, int is_tail)
 {
 	if (!is_tail && s >= e) return 0;
 	uint64_t e0 = 0, nec = 0; uint32_t rc;
@@ -238,7 +238,7 @@ HB_HD uint64_t hb_cns_anchor(CnsCtx &C, uint64_t s, uint64_t e, int is_tail)
 			if (C.ax_start == -1 || C.ax_end == -1) { C.ax_start = (int32_t)e0; C.ax_end = (int32_t)s - 1; }
 			nec += hb_cns_push0(C, 0xffffffffu, rc, (int64_t)e0);
 		} else {
-			if (!C.g) { C.need_full = 1; return nec; } // no graph arena in this launch: the read is redone by the launch that has one
+			if (!GRAPH || !C.g) { C.need_full = 1; return nec; } // no graph arena in this launch (GRAPH = false compiles the graph code out): the read is redone by the launch that has one
 			nec += hb_cns_full_(C, (int64_t)e0, (int64_t)s);
 			if (C.need_full) return nec;
 		}
@@ -251,7 +251,7 @@ HB_HD uint64_t hb_cns_anchor(CnsCtx &C, uint64_t s, uint64_t e, int is_tail)
 }
 
 // wcns_vote, ecovlp.cpp:2185-2272: one block [s, e) of the sweep; id_a = the entries covering it (iterator A), the stretches are voted through iterator B
-HB_HD int64_t hb_cns_vote(CnsCtx &C, uint32_t id_n, uint64_t s, uint64_t e, uint64_t *nec)
+template <bool GRAPH> HB_HD int64_t hb_cns_vote(CnsCtx &C, uint32_t id_n, uint64_t s, uint64_t e, uint64_t *nec)
 {
 	uint64_t k, rr = 0, os, oe, wl, oc0, oc1, fI; CnsIt &occ = C.B;
 	for (k = 0; k < id_n; k++) {
@@ -269,16 +269,16 @@ HB_HD int64_t hb_cns_vote(CnsCtx &C, uint32_t id_n, uint64_t s, uint64_t e, uint
 			oc0 = (C.ct[(k << 1) + 1] >> 32) + 1; oc1 = (uint32_t)C.ct[(k << 1) + 1] + 1;
 			if (hb_cns_pass(oc0, oc1, 3, 0.500001) || oc1 < 3) fI = 0;
 			if (fI) {
-				if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor(C, os, oe, 0); if (C.need_full) return 0; }
+				if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor<GRAPH>(C, os, oe, 0); if (C.need_full) return 0; }
 				os = oe = (uint64_t)-1;
 			}
 			if (s + k == oe) oe++;
 			else {
-				if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor(C, os, oe, 0); if (C.need_full) return 0; }
+				if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor<GRAPH>(C, os, oe, 0); if (C.need_full) return 0; }
 				os = s + k; oe = s + k + 1;
 			}
 		} else {
-			if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor(C, os, oe, 0); if (C.need_full) return 0; }
+			if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor<GRAPH>(C, os, oe, 0); if (C.need_full) return 0; }
 			os = oe = (uint64_t)-1;
 		}
 		C.ct[k << 1] = C.ct[(k << 1) + 1] = 0;
@@ -291,7 +291,7 @@ HB_HD int64_t hb_cns_vote(CnsCtx &C, uint32_t id_n, uint64_t s, uint64_t e, uint
 // wcns_gen, ecovlp.cpp:2293-2424.  ov[0..n_ov) = the read's same-haplotype overlaps in the order of the de-duplicated list; ent / srt / act_a / act_b:
 // room for one entry per aligned window of those overlaps (b32 too); key: one word per entry; ct: 2 * HB_CNS_WL words (zeroed here).
 // Returns the number of corrected bases; C.out / C.out_n = the edit script; C.need_full / C.ovf tell when there is none.
-HB_HD uint64_t hb_cns_read(CnsCtx &C, uint32_t n_ov, uint32_t *srt, uint32_t *act_a, uint32_t *act_b, uint64_t *key)
+template <bool GRAPH> HB_HD uint64_t hb_cns_read(CnsCtx &C, uint32_t n_ov, uint32_t *srt, uint32_t *act_a, uint32_t *act_b, uint64_t *key)
 {
 	uint32_t n_ent = 0; uint64_t nec = 0;
 	for (uint32_t k = 0; k < n_ov; k++) {
@@ -326,11 +326,11 @@ HB_HD uint64_t hb_cns_read(CnsCtx &C, uint32_t n_ov, uint32_t *srt, uint32_t *ac
 	int64_t s = 0, e = HB_CNS_WL, rr = 0; if (e > C.ql) e = C.ql;
 	for (; s < C.ql;) {
 		const uint32_t rn = hb_cns_iter(C, C.A, s, e, rr, 0);
-		rr = hb_cns_vote(C, rn, (uint64_t)s, (uint64_t)e, &nec);
+		rr = hb_cns_vote<GRAPH>(C, rn, (uint64_t)s, (uint64_t)e, &nec);
 		if (C.need_full) return nec;
 		s += HB_CNS_WL; e += HB_CNS_WL; if (e > C.ql) e = C.ql;
 	}
-	if (C.B.mme > C.B.mms && C.B.mms != (uint64_t)-1) { nec += hb_cns_anchor(C, C.B.mms, C.B.mme, 0); if (C.need_full) return nec; }
-	nec += hb_cns_anchor(C, (uint64_t)C.ql, (uint64_t)C.ql, 1);
+	if (C.B.mme > C.B.mms && C.B.mms != (uint64_t)-1) { nec += hb_cns_anchor<GRAPH>(C, C.B.mms, C.B.mme, 0); if (C.need_full) return nec; }
+	nec += hb_cns_anchor<GRAPH>(C, (uint64_t)C.ql, (uint64_t)C.ql, 1);
 	return nec;
 }

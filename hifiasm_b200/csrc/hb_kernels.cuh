@@ -22,6 +22,7 @@
 #include "hb_ecphase.cuh"
 #include "hb_ecround.cuh"
 #include "hb_eccns.cuh"
+#include "hb_eccns_full.cuh"
 
 #define HB_FULL 0xffffffffu
 static __device__ __forceinline__ int hb_lane() { return threadIdx.x & 31; }
@@ -1366,12 +1367,23 @@ struct CnsArgs {
 	DevReads R; uint64_t r0, nR; const uint64_t *o_off; const hb_phase_t *ph; const hb_alnb_t *alnb; const hb_wl_t *wl; const uint16_t *pool;
 	uint64_t *ord; CnsOv *cov; const uint64_t *ent_off; CnsEnt *ent; uint32_t *srt, *act_a, *act_b, *b32; uint64_t *key; uint64_t *ct;
 	const uint64_t *out_off; uint16_t *out; uint32_t *out_n; uint8_t *status; unsigned long long *nec; int *err;
+	// second launch: the reads the first one reported (queue), each thread with the arena of the graph consensus
+	const uint32_t *queue; uint32_t n_queue, g_nodes, g_arcs, g_nseq, g_pcap, g_ccap;
+	CnsNode *g_nd; CnsArc *g_arc; uint32_t *g_q, *g_b32, *g_np; uint8_t *g_ns; uint64_t *g_path, *g_vec; uint16_t *g_cig;
 };
-__global__ void __launch_bounds__(64) k_ec_cns(CnsArgs A)
+template <bool GRAPH> __global__ void __launch_bounds__(64) k_ec_cns(CnsArgs A)
 {
 	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st };
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t r = tid; r < A.nR; r += nthr) {
+	const uint64_t n_units = GRAPH ? A.n_queue : A.nR;
+	CnsG G; memset(&G, 0, sizeof(G));
+	if (GRAPH) {
+		G.nd = A.g_nd + tid * A.g_nodes; G.ncap = A.g_nodes; G.arc = A.g_arc + tid * A.g_arcs; G.arc_cap = A.g_arcs; G.q = A.g_q + tid * A.g_nodes; G.q_cap = A.g_nodes;
+		G.b32 = A.g_b32 + tid * A.g_arcs; G.b32_cap = A.g_arcs; G.nseq = A.g_ns + tid * A.g_nseq; G.nseq_np = A.g_np + tid * A.g_nseq; G.nseq_cap = A.g_nseq;
+		G.ez.path = A.g_path + tid * A.g_pcap; G.ez.pcap = A.g_pcap; G.ez.vec = A.g_vec + tid * 32; G.ez.vstride = 2; G.ez.cig = A.g_cig + tid * A.g_ccap; G.ez.ccap = (int32_t)A.g_ccap;
+	}
+	for (uint64_t u = tid; u < n_units; u += nthr) {
+		const uint64_t r = GRAPH ? A.queue[u] : u;
 		const uint64_t o0 = A.o_off[r], rid = A.r0 + r, e0 = A.ent_off[r]; const uint32_t n = (uint32_t)(A.o_off[r + 1] - o0); int ovf = 0;
 		PhPair *ord = (PhPair *)(A.ord + o0); uint8_t st = 0;
 		for (uint32_t j = 0; j < n; j++) if (A.ph[o0 + j].st == 2 && A.ph[o0 + j].need_rechain) st |= 4; // an overlap of this read wanted rechain_aln_hc (not built): its lists are not final either
@@ -1384,9 +1396,9 @@ __global__ void __launch_bounds__(64) k_ec_cns(CnsArgs A)
 			CnsOv o; o.w = A.wl + b.w_off; o.wn = b.w_n; o.y_id = z.y_id; o.rev = z.rev; ov[n_ov++] = o;
 		}
 		CnsCtx C; C.R = A.R; C.q = hb_rd_view(A.R, rid, 0); C.ql = A.R.len[rid]; C.ov = ov; C.pool = A.pool; C.ent = A.ent + e0; C.ct = A.ct + tid * (2 * HB_CNS_WL); C.b32 = A.b32 + e0;
-		C.out = A.out + A.out_off[r]; C.out_cap = (uint32_t)(A.out_off[r + 1] - A.out_off[r]);
-		const uint64_t nec = hb_cns_read(C, n_ov, A.srt + e0, A.act_a + e0, A.act_b + e0, A.key + e0);
-		if (C.need_full) { A.out_n[r] = 0; A.status[r] = st | 1; continue; }   // the graph consensus (cns_gen_full) is not built: no script for this read
+		C.out = A.out + A.out_off[r]; C.out_cap = (uint32_t)(A.out_off[r + 1] - A.out_off[r]); C.g = GRAPH ? &G : (CnsG *)0;
+		const uint64_t nec = hb_cns_read<GRAPH>(C, n_ov, A.srt + e0, A.act_a + e0, A.act_b + e0, A.key + e0);
+		if (C.need_full) { A.out_n[r] = 0; A.status[r] = st | 1 | (C.need_full == 2 ? 8 : 0); continue; } // first launch: queued for the second; second launch: the arena was too small (bit 3)
 		if (C.ovf) { A.out_n[r] = 0; A.status[r] = st | 2; atomicOr(A.err, 256); continue; }
 		A.out_n[r] = C.out_n; A.status[r] = st;
 		atomicAdd(A.nec, (unsigned long long)nec);

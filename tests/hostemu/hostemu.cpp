@@ -501,7 +501,7 @@ int emu_ec_cns(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t 
 		G.nseq = gns.data(); G.nseq_np = gnp.data(); G.nseq_cap = 4096; G.ez.path = path.data(); G.ez.pcap = path.size(); G.ez.vec = vec.data(); G.ez.vstride = 2; G.ez.cig = gcig.data(); G.ez.ccap = (int32_t)gcig.size();
 		C.g = &G;
 	}
-	*nec = hb_cns_read(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
+	*nec = g_nodes ? hb_cns_read<true>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data()) : hb_cns_read<false>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
 	*n_out = C.out_n;
 	return C.need_full ? (C.need_full == 2 ? 3 : 1) : (C.ovf ? 2 : 0);
 }
