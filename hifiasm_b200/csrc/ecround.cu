@@ -236,3 +236,30 @@ extern "C" int hb_ec_post_rev(hb_ctx_t *ctx, hb_ma_hit_t *paf, uint64_t *paf_off
 	ctx->d_packed = (uint8_t *)n_packed.take(); ctx->d_npos = (uint32_t *)n_npos.take();
 	return HB_OK;
 }
+
+// ---- cal_ec_r (ecovlp.h:13; ecovlp.cpp:6268-6309) as one call on the resident store: cal_ec_multiple -> sl_ec_r -> cal_update_ec_multiple ->
+// worker_hap_post_rev, in that order, every step on the device.  Host code only passes buffers along.
+extern "C" int hb_ec_stage_prev(hb_ctx_t *ctx, const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off);
+extern "C" int hb_ec_round(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t use_prev,
+                           uint64_t *src_off, hb_ma_hit_t *src, uint64_t src_cap, uint64_t *rev_off, hb_ma_hit_t *rev, uint64_t rev_cap, uint8_t *flags,
+                           uint64_t *scc_off, uint16_t *scc, uint64_t scc_cap, uint8_t *status, uint64_t *n_corrected);
+extern "C" int hb_cal_ec_r(hb_ctx_t *ctx, uint64_t round, uint64_t n_round, uint64_t is_sv, double e_rate, int32_t w_l,
+                           const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off,
+                           hb_ma_hit_t *out_src, uint64_t *out_src_off, uint64_t out_src_cap, hb_ma_hit_t *out_rev, uint64_t *out_rev_off, uint64_t out_rev_cap,
+                           uint8_t *flags, uint8_t *status, uint64_t *tot_b, uint64_t *tot_e, uint64_t *n_exact, uint64_t *n_inexact)
+{
+	cudaSetDevice(ctx->device);
+	const uint64_t n = ctx->n_reads; int rc;
+	if (!n) { hb_set_err(ctx, HB_E_STATE, "no reads resident"); return HB_E_STATE; }
+	if (n_round) { hb_set_err(ctx, HB_E_ARG, "cal_sec_ec_multiple (number_of_pround > 0, CommandLines.cpp:281) is not supported"); return HB_E_ARG; }
+	if (!out_src || !out_src_off || !out_rev || !out_rev_off) { hb_set_err(ctx, HB_E_ARG, "output buffers are required"); return HB_E_ARG; }
+	if ((rc = hb_ec_stage_prev(ctx, prev_src, prev_src_off))) return rc;                                   // gen_hc_r_alin_ea reads the previous paf[i] (ecovlp.cpp:3288)
+	if (tot_b) *tot_b = ctx->total_bases;                                                                  // cnt[0]: bases of the reads as they enter the round (3276)
+	uint64_t nec = 0;
+	if ((rc = hb_ec_round(ctx, 0, n, ctx->opt.is_ont ? 0.05 : 0.02, e_rate, w_l, 1, out_src_off, out_src, out_src_cap, out_rev_off, out_rev, out_rev_cap, flags, 0, 0, 0, status, &nec))) return rc;
+	if (tot_e) *tot_e = nec;
+	if ((rc = hb_ec_apply(ctx, 0, 0))) return rc;                                                          // sl_ec_r
+	if ((rc = hb_ec_update_paf(ctx, out_src, out_src_off, n_exact, n_inexact))) return rc;                // cal_update_ec_multiple
+	if (!is_sv || (round & 1)) if ((rc = hb_ec_post_rev(ctx, out_src, out_src_off, out_rev, out_rev_off))) return rc; // ecovlp.cpp:6293-6295
+	return HB_OK;
+}

@@ -260,6 +260,18 @@ class Engine:
         return dict(src_off=so, src=src[:int(so[-1])], rev_off=ro, rev=rev[:int(ro[-1])], is_fully_corrected=fl[0:2 * n:2].copy(), is_abnormal=fl[1:2 * n:2].copy(),
                     scc_off=co, scc=scc[:int(co[-1])], status=st[:n].copy(), n_corrected=int(nc.value))
 
+    def cal_ec_r(self, round_, is_sv, prev_src, prev_src_off, e_rate=0.04, w_l=775, cap=None):
+        """cal_ec_r as one call -> dict(src, src_off, rev, rev_off, is_fully_corrected, is_abnormal, status, tot_b, tot_e, n_exact, n_inexact)"""
+        n = self.n_reads
+        prev_src = np.ascontiguousarray(prev_src, dtype=MA); po = np.ascontiguousarray(prev_src_off, dtype=np.uint64)
+        cap = cap or (2 * prev_src.size + 256 * n + 1024)
+        src = np.zeros(cap, MA); rev = np.zeros(cap, MA); so = np.zeros(n + 1, np.uint64); ro = np.zeros(n + 1, np.uint64); fl = np.zeros(2 * n + 2, np.uint8); st = np.zeros(n + 1, np.uint8)
+        tb = C.c_uint64(); te = C.c_uint64(); ne = C.c_uint64(); ni = C.c_uint64()
+        self._ck(_lib().hb_cal_ec_r(self.h, C.c_uint64(round_), C.c_uint64(0), C.c_uint64(is_sv), C.c_double(e_rate), C.c_int32(w_l), _p(prev_src if prev_src.size else np.zeros(1, MA)), _p(po),
+                                    _p(src), _p(so), C.c_uint64(cap), _p(rev), _p(ro), C.c_uint64(cap), _p(fl), _p(st), C.byref(tb), C.byref(te), C.byref(ne), C.byref(ni)))
+        return dict(src=src[:int(so[-1])], src_off=so, rev=rev[:int(ro[-1])], rev_off=ro, is_fully_corrected=fl[0:2 * n:2].copy(), is_abnormal=fl[1:2 * n:2].copy(), status=st[:n].copy(),
+                    tot_b=int(tb.value), tot_e=int(te.value), n_exact=int(ne.value), n_inexact=int(ni.value))
+
     def ec_apply(self):
         """sl_ec_r: apply the staged edit scripts to the resident reads -> (reads changed, total bases)"""
         a = C.c_uint64(); b = C.c_uint64()

@@ -202,6 +202,16 @@ int hb_ec_update_paf(hb_ctx_t *ctx, hb_ma_hit_t *paf, const uint64_t *paf_off, u
 /* row a18 — worker_hap_post_rev (ecovlp.cpp:3866): resident reads reverse-complemented in HBM; both lists flipped by flip_paf_rc (3845),
  * compacted in place (records and offsets are rewritten; lists only shrink).  Either list may be NULL.                                   */
 int hb_ec_post_rev(hb_ctx_t *ctx, hb_ma_hit_t *paf, uint64_t *paf_off, hb_ma_hit_t *rpaf, uint64_t *rpaf_off);
+/* cal_ec_r(n_thre, round, n_round, n_a, is_sv, &tot_b, &tot_e) (ecovlp.h:13; ecovlp.cpp:6268) as one call on the resident store and index: the five
+ * steps above in the reference's order.  prev_src = R_INF.paf[] of the previous round (empty offsets in round 0); out_* = this round's paf[] /
+ * reverse_paf[] as the round leaves them (updated, flipped when the round reverses: !is_sv || (round & 1)); flags / status as hb_ec_round; tot_b /
+ * tot_e = the two counters of the "[M::pec] # bases / # corrected bases" line, n_exact / n_inexact those of "# exact o / # non-exact o".
+ * e_rate = asm_opt.max_ov_diff_ec (0.04), w_l = WINDOW_HC (775).  n_round (asm_opt.number_of_pround) must be 0.  The corrected reads stay in HBM
+ * (hb_reads_download copies them back); the index describes the old reads and must be rebuilt before the next pass.                           */
+int hb_cal_ec_r(hb_ctx_t *ctx, uint64_t round, uint64_t n_round, uint64_t is_sv, double e_rate, int32_t w_l,
+                const hb_ma_hit_t *prev_src, const uint64_t *prev_src_off,
+                hb_ma_hit_t *out_src, uint64_t *out_src_off, uint64_t out_src_cap, hb_ma_hit_t *out_rev, uint64_t *out_rev_off, uint64_t out_rev_cap,
+                uint8_t *flags, uint8_t *status, uint64_t *tot_b, uint64_t *tot_e, uint64_t *n_exact, uint64_t *n_inexact);
 /* the resident read store back in the All_reads layout (Process_Read.h:115-146): read_length[n], packed = len/4+1 bytes per read
  * concatenated (pad bits zero), n_off[n + 1] / n_pos = the N_site lists.  Any output may be NULL.                                       */
 int hb_reads_download(hb_ctx_t *ctx, uint64_t *read_length, uint8_t *packed, uint64_t packed_cap, uint64_t *n_off, uint64_t *n_pos, uint64_t n_pos_cap);

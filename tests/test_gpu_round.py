@@ -127,3 +127,38 @@ def test_round_lists_from_staged_scripts(hb):
     keep = ~skip
     assert keep.sum() > n // 2 and (f_ec[keep] == fc[keep]).all() and (f_ab[keep] == ab[keep]).all()
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["g1", "g2", "g3"])
+def test_whole_stage_from_raw_reads(hb, name, tmp_path):
+    """the north-star property on the golden sets: raw reads in, the whole overlap / error-correction stage on the device with NO reference state
+    fed back — filter table, then three EC rounds (index, alignment, phasing, consensus, lists, apply, update, reverse), then the final index and
+    cal_ov_r — and out come the reference's corrected reads and byte-identical ovlp.source.bin / ovlp.reverse.bin"""
+    g = Golden(name); rd = roundlib.Rounds(name)
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    hom = eng.ft_gen(); eng.update_cov(hom)
+    n = g.raw.n
+    src = np.zeros(0, binio.MA_MEM); soff = np.zeros(n + 1, np.uint64); rev = src.copy(); roff = soff.copy()
+    for K in range(3):
+        hom_k, het_k = eng.pt_gen(); eng.set_opt(hom_cov=hom_k, het_cov=het_k)      # ha_ec: index of the round on the current reads (Assembly.cpp:1007)
+        r = eng.cal_ec_r(K, 1 if K == 2 else 0, src, soff)                           # is_sv only in the last round (Assembly.cpp:1021)
+        assert not r["status"].any(), "round %d: reads the engine could not finish: %s" % (K, np.nonzero(r["status"])[0][:8])
+        p = rd.params(K)
+        assert (r["tot_b"], r["tot_e"]) == (int(p["tot_b"]), int(p["tot_e"])), "round %d: the [M::pec] counters" % K
+        src, soff, rev, roff = r["src"], r["src_off"], r["rev"], r["rev_off"]
+        assert (roundlib.list_digests(src, soff, 0) == rd.digest(K, "post_src")).all(), "round %d: paf" % K
+        assert (roundlib.list_digests(rev, roff, 1) == rd.digest(K, "post_rev")).all(), "round %d: reverse_paf" % K
+        h_src, _, fc, ab = rd.hap(K, "src")
+        assert (r["is_fully_corrected"] == fc).all() and (r["is_abnormal"] == ab).all(), "round %d: read flags" % K
+        assert r["n_exact"] + r["n_inexact"] == h_src.size
+    reads = eng.download_reads()
+    assert (roundlib.reads_digests(reads) == roundlib.reads_digests(g.pre)).all(), "corrected reads (ec.bin after canonicalisation)"
+    hom_f, het_f = eng.pt_gen(); eng.set_opt(hom_cov=hom_f, het_cov=het_f)
+    out0, oo0, out1, oo1, stat = eng.cal_ov_r(src, soff, rev, roff)
+    p0, p1 = str(tmp_path / "src.bin"), str(tmp_path / "rev.bin")
+    f0, fo0, fc0, ab0 = g.fin_src; f1, fo1, fc1, ab1 = g.fin_rev
+    binio.write_ovlp_bin(p0, out0, oo0, fc0, ab0); binio.write_ovlp_bin(p1, out1, oo1, fc1, ab1)   # the two read flags are those of round 3 (checked in test_round_chained_on_device)
+    assert open(p0, "rb").read() == g.z["fin_ovlp_source"].tobytes(), "ovlp.source.bin"
+    assert open(p1, "rb").read() == g.z["fin_ovlp_reverse"].tobytes(), "ovlp.reverse.bin"
+    eng.close()
