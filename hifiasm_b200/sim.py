@@ -60,10 +60,12 @@ def _mutate(seq: np.ndarray, rng, err: float) -> np.ndarray:
     return res
 
 
-def _damage(seq: np.ndarray, rng, burst_rate: float, sv_rate: float) -> np.ndarray:
+def _damage(seq: np.ndarray, rng, burst_rate: float, sv_rate: float, block_rate: float = 0.0) -> np.ndarray:
     """Local damage that makes alignment windows fail (exercises the gap-filling /
     extension / re-chaining paths of the EC rounds): error bursts (60-300 bp at
-    8-25 % error) and block insertions / deletions of 20-400 bp."""
+    8-25 % error), block insertions / deletions of 20-400 bp, and (block_rate)
+    replacements of 560-1000 bp by a short tandem repeat of about the same length — the
+    unaligned stretches >= 512 bp on both reads that rechain_aln_hc re-seeds."""
     n = seq.size
     nb = rng.poisson(burst_rate * n)
     for _ in range(nb):
@@ -80,13 +82,20 @@ def _damage(seq: np.ndarray, rng, burst_rate: float, sv_rate: float) -> np.ndarr
             seq = np.concatenate([seq[:s], rng.integers(0, 4, ln, dtype=np.uint8), seq[s:]])
         else:
             seq = np.concatenate([seq[:s], seq[s + ln:]])
+    if block_rate > 0:
+        for _ in range(rng.poisson(block_rate * n)):
+            if seq.size < 6000:
+                break
+            ln = int(rng.integers(560, 1000)); ln2 = ln + int(rng.integers(-20, 21)); s = int(rng.integers(1000, seq.size - ln - 1000))
+            unit = rng.integers(0, 4, int(rng.integers(2, 7)), dtype=np.uint8)
+            seq = np.concatenate([seq[:s], np.resize(unit, ln2), seq[s + ln:]])
     return seq
 
 
 def sim_reads(hap1: np.ndarray, hap2: np.ndarray, cov: float, mean_len: int,
               seed: int, sd_len: int = 2000, min_len: int = 2000,
               err: float = 0.002, n_rate: float = 0.0,
-              burst_rate: float = 0.0, sv_rate: float = 0.0):
+              burst_rate: float = 0.0, sv_rate: float = 0.0, block_rate: float = 0.0):
     """Return list of uint8 code arrays (values 0..3, 4 = N)."""
     rng = np.random.default_rng(seed + 1000003)
     glen = hap1.size
@@ -103,8 +112,8 @@ def sim_reads(hap1: np.ndarray, hap2: np.ndarray, cov: float, mean_len: int,
             s = (3 - s[::-1]).astype(np.uint8)
         if err > 0:
             s = _mutate(s, rng, err)
-        if burst_rate > 0 or sv_rate > 0:
-            s = _damage(s, rng, burst_rate, sv_rate)
+        if burst_rate > 0 or sv_rate > 0 or block_rate > 0:
+            s = _damage(s, rng, burst_rate, sv_rate, block_rate)
         if n_rate > 0:
             s = s.copy()
             s[rng.random(s.size) < n_rate] = 4
