@@ -482,6 +482,7 @@ struct EcBCtx {
 	int32_t do_gaps; int64_t re_A, gap_re; // step C (reassign_gaps) applied when a window closes; errors removed by it
 	int32_t no_myers;                      // segment pre-pass: stop (status 5) where an alignment would start
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap;
+	uint16_t *gout; int32_t gcap;          // output of reassign_gaps at a flush; 0: ez.cig (only where no alignment result is pending in it when a window closes)
 	int bad;
 };
 
@@ -828,7 +829,7 @@ HB_HD const uint16_t *hb_move_wins(EcBCtx &C, hb_wl_t *p, int32_t *n_out)
 	if (p->error == 0) return cg;
 	for (ci = 0, mm = 0; ci < cn; ci++) { const uint32_t op = cg[ci] >> 14; if (op < 2) mm = 1; else if (mm) break; }
 	if (ci >= cn) { hb_adjust_end_cigar(p, C.wc, cn); return cg; }
-	GapOut o; o.c = C.ez.cig; o.n = 0; o.cap = C.ez.ccap; o.ovf = 0;
+	GapOut o; o.c = C.gout ? C.gout : C.ez.cig; o.n = 0; o.cap = C.gout ? C.gcap : C.ez.ccap; o.ovf = 0;
 	uint16_t *buf = (uint16_t *)C.ez.path; const int64_t bcap = (int64_t)(C.ez.pcap * 4);
 	int64_t pi = p->y_start, ti = p->x_start, re;
 	for (ci = 0, mm = 0; ci < cn && !o.ovf; ci++) {

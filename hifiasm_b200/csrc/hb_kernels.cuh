@@ -1199,7 +1199,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
 		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
 		uint16_t one[2];
-		EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 1; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+		EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 1; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
 		C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
 		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
 		int64_t uq[2], ut[2], um;
@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
 {
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
 	uint64_t l_path[LOCAL ? ECB_T0_PATH : 1], l_vec[LOCAL ? 11 * ECB_T0_VS : 1]; uint16_t l_cig[LOCAL ? ECB_T0_CIG : 1];
-	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
 	if (LOCAL) { C.ez.path = l_path; C.ez.pcap = ECB_T0_PATH; C.ez.vec = l_vec; C.ez.vstride = ECB_T0_VS; C.ez.cig = l_cig; C.ez.ccap = ECB_T0_CIG; }
 	else { C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * 11 * (uint64_t)A.vstride; C.ez.vstride = A.vstride; C.ez.cig = A.cig_tmp + tid * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words; }
 	const uint64_t n_work = (uint64_t)*A.q_in_n;
@@ -1255,7 +1255,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
 __global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
 {
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
-	EcBCtx C; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.do_gaps = A.gaps;
+	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.do_gaps = A.gaps;
 	uint16_t *base = A.cig_tmp + tid * 3 * (uint64_t)A.cig_words; // wc | gap output | adjust_gap scratch
 	C.wc = base; C.wccap = A.cig_words; C.ez.cig = base + A.cig_words; C.ez.ccap = A.cig_words; C.ez.path = (uint64_t *)(base + 2 * (uint64_t)A.cig_words); C.ez.pcap = (uint64_t)A.cig_words / 4;
 	C.ez.vec = 0; C.ez.vstride = 0;

@@ -64,7 +64,8 @@ def _damage(seq: np.ndarray, rng, burst_rate: float, sv_rate: float, block_rate:
     """Local damage that makes alignment windows fail (exercises the gap-filling /
     extension / re-chaining paths of the EC rounds): error bursts (60-300 bp at
     8-25 % error), block insertions / deletions of 20-400 bp, and (block_rate)
-    replacements of 560-1000 bp by a short tandem repeat of about the same length — the
+    replacements of 540-900 bp by a short tandem repeat of about the same length, often with a noisy
+    stretch (6-15 % errors) next to it — the
     unaligned stretches >= 512 bp on both reads that rechain_aln_hc re-seeds."""
     n = seq.size
     nb = rng.poisson(burst_rate * n)
@@ -86,9 +87,15 @@ def _damage(seq: np.ndarray, rng, burst_rate: float, sv_rate: float, block_rate:
         for _ in range(rng.poisson(block_rate * n)):
             if seq.size < 6000:
                 break
-            ln = int(rng.integers(560, 1000)); ln2 = ln + int(rng.integers(-20, 21)); s = int(rng.integers(1000, seq.size - ln - 1000))
+            ln = int(rng.integers(540, 900)); ln2 = ln + int(rng.integers(-20, 21)); s = int(rng.integers(50, seq.size - ln - 50))
             unit = rng.integers(0, 4, int(rng.integers(2, 7)), dtype=np.uint8)
-            seq = np.concatenate([seq[:s], np.resize(unit, ln2), seq[s + ln:]])
+            nz = int(rng.integers(0, int(0.4 * ln))) if rng.random() < 0.5 else 0   # a noisy stretch next to it: too many errors for 51-mers, exact runs of >= 10 bases remain
+            e = min(seq.size, s + ln + nz)
+            noisy = _mutate(seq[s + ln:e], rng, float(rng.uniform(0.06, 0.15))) if nz else seq[s + ln:e]
+            parts = [seq[:s], np.resize(unit, ln2), noisy, seq[e:]]
+            if rng.random() < 0.5:
+                parts = [seq[:s], noisy, np.resize(unit, ln2), seq[e:]]
+            seq = np.concatenate(parts)
     return seq
 
 

@@ -42,6 +42,11 @@ DATASETS = {
     # re-chaining paths of the EC alignment stage run
     "g3": (dict(glen=100000, seed=13, snp_rate=0.002, repeat_frac=0.1, repeat_len=1200, repeat_div=0.01),
            dict(cov=18, mean_len=7000, seed=13, sd_len=2000, min_len=800, err=0.004, n_rate=1e-4, burst_rate=1.5e-4, sv_rate=6e-5)),
+    # long reads with tandem-repeat blocks of 540-900 bp (plus noisy stretches): accepted overlaps keep unaligned windows of >= 512 bp on
+    # both reads, which the reference re-seeds (rechain_aln_hc, Correct.cpp:17669) — all three window modes, the replaced-window case, the
+    # quick check, the fixed-end DP in both directions and the end-point re-chaining (lchain_simple) occur
+    "g4": (dict(glen=300000, seed=53, snp_rate=0.002, repeat_frac=0.0),
+           dict(cov=16, mean_len=40000, seed=53, sd_len=6000, min_len=25000, err=0.003, n_rate=1e-4, burst_rate=5e-5, sv_rate=3e-5, block_rate=3e-5)),
 }
 
 
@@ -185,10 +190,14 @@ def make_ed_golden():
 def main():
     if not os.path.exists(REFDUMP):
         sys.exit("build oracle/_ref first: make -C oracle ref")
-    make_ed_golden()
+    only = [a for a in sys.argv[1:] if a in DATASETS]   # `make_golden.py g4` regenerates only that set
+    if not only:
+        make_ed_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "ed":
         return
     for name, (gk, rk) in DATASETS.items():
+        if only and name not in only:
+            continue
         h1, h2 = sim.sim_genome(**gk)
         reads = sim.sim_reads(h1, h2, **rk)
         with tempfile.TemporaryDirectory() as td:

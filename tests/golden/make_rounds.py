@@ -32,7 +32,10 @@ import roundlib  # noqa: E402
 def main():
     if not os.path.exists(mg.REFDUMP):
         sys.exit("build oracle/_ref first: make -C oracle ref")
+    only = [a for a in sys.argv[1:] if a in mg.DATASETS]
     for name, (gk, rk) in mg.DATASETS.items():
+        if only and name not in only:
+            continue
         h1, h2 = sim.sim_genome(**gk)
         reads = sim.sim_reads(h1, h2, **rk)
         arrs = {}

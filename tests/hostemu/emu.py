@@ -135,28 +135,30 @@ ALNB = np.dtype([("st", "<i4"), ("need_rechain", "<i4"), ("re", "<i8"), ("nh_err
                  ("w_off", "<u8"), ("w_n", "<u4"), ("pad", "<u4")])
 
 
-def ec_align_B(reads, rid, ch, fc, hits, A, WA, e_rate=0.04, w_l=775, path_words=1 << 22, cig_words=1 << 15, gaps=0):
+def ec_align_B(reads, rid, ch, fc, hits, A, WA, e_rate=0.04, w_l=775, path_words=1 << 22, cig_words=1 << 15, gaps=0, poolA=None, rechain=0):
     """-> (rc, ALNB[n_ch], WL[], cigar pool); rc & 1 = some overlap deferred for lack of scratch"""
     ch = np.ascontiguousarray(ch); fc = np.ascontiguousarray(fc if fc.size else np.zeros(1, np.uint64)); hits = np.ascontiguousarray(hits).copy()
     A = np.ascontiguousarray(A); WA = np.ascontiguousarray(WA if WA.size else np.zeros(1, WL))
-    out = np.zeros(ch.size + 1, ALNB); cap_w = hits.size + 2 * ch.size + 16; wl = np.zeros(cap_w, WL)
+    out = np.zeros(ch.size + 1, ALNB); cap_w = hits.size + (2 + 8) * ch.size + 16; wl = np.zeros(cap_w, WL)
     cap = 1 << 22; pool = np.zeros(cap, np.uint16); used = C.c_uint64(); nw = C.c_uint64()
     rc = lib().emu_ec_align_B(reads.h, C.c_uint32(rid), _p(ch), C.c_uint32(ch.size), _p(fc), _p(hits), C.c_uint64(hits.size), _p(A), _p(WA),
                               C.c_double(e_rate), C.c_int32(w_l), C.c_int32(gaps), C.c_uint64(path_words), C.c_int32(cig_words),
-                              _p(out), _p(wl), C.c_uint64(cap_w), _p(pool), C.c_uint64(cap), C.byref(used), C.byref(nw))
+                              _p(out), _p(wl), C.c_uint64(cap_w), _p(pool), C.c_uint64(cap), C.byref(used), C.byref(nw),
+                              _p(np.ascontiguousarray(poolA if poolA is not None and poolA.size else np.zeros(1, np.uint16))), C.c_int32(rechain))
     return rc, out[:ch.size], wl[:nw.value], pool[:used.value]
 
 
-def ec_align_B_par(reads, rid, ch, fc, hits, A, WA, e_rate=0.04, w_l=775, gaps=0, cig_words=1 << 16):
+def ec_align_B_par(reads, rid, ch, fc, hits, A, WA, e_rate=0.04, w_l=775, gaps=0, cig_words=1 << 16, poolA=None, rechain=0):
     """step B (+C) the way the GPU pipeline runs it: prep, independent segments with tiered scratch, merge.
     -> (rc, ALNB[n_ch], WL[], cigar pool, (segments computed in tier 0, recomputed in the large tier))"""
     ch = np.ascontiguousarray(ch); fc = np.ascontiguousarray(fc if fc.size else np.zeros(1, np.uint64)); hits = np.ascontiguousarray(hits).copy()
     A = np.ascontiguousarray(A); WA = np.ascontiguousarray(WA if WA.size else np.zeros(1, WL))
-    out = np.zeros(ch.size + 1, ALNB); cap_w = hits.size + 2 * ch.size + 16; wl = np.zeros(cap_w, WL)
+    out = np.zeros(ch.size + 1, ALNB); cap_w = hits.size + (2 + 8) * ch.size + 16; wl = np.zeros(cap_w, WL)
     cap = 1 << 22; pool = np.zeros(cap, np.uint16); used = C.c_uint64(); nw = C.c_uint64(); nt = (C.c_uint64 * 2)()
     rc = lib().emu_ec_align_B_par(reads.h, C.c_uint32(rid), _p(ch), C.c_uint32(ch.size), _p(fc), _p(hits), C.c_uint64(hits.size), _p(A), _p(WA),
                                   C.c_double(e_rate), C.c_int32(w_l), C.c_int32(gaps), C.c_int32(cig_words),
-                                  _p(out), _p(wl), C.c_uint64(cap_w), _p(pool), C.c_uint64(cap), C.byref(used), C.byref(nw), nt)
+                                  _p(out), _p(wl), C.c_uint64(cap_w), _p(pool), C.c_uint64(cap), C.byref(used), C.byref(nw), nt,
+                                  _p(np.ascontiguousarray(poolA if poolA is not None and poolA.size else np.zeros(1, np.uint16))), C.c_int32(rechain))
     return rc, out[:ch.size], wl[:nw.value], pool[:used.value], (nt[0], nt[1])
 
 

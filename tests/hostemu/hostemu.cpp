@@ -14,6 +14,7 @@
 #include "../../hifiasm_b200/csrc/hb_sketch.cuh"
 #include "../../hifiasm_b200/csrc/hb_final.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecaln.cuh"
+#include "../../hifiasm_b200/csrc/hb_ecrechain.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecphase.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecround.cuh"
 #include "../../hifiasm_b200/csrc/hb_eccns.cuh"
@@ -195,6 +196,7 @@ static void run_chains(EmuReads *r, uint32_t rid, hb_hit_t *hits, uint64_t n_hit
 		if (k == n_hits || HB_HIT_ID(hits[k]) != HB_HIT_ID(hits[l])) {
 			GroupDir g; g.read = rid; g.start = (uint32_t)l; g.count = (uint32_t)(k - l); g.slot = slot;
 			if (HB_HIT_ID(hits[l]) != rid) { slot += g.count >= (uint32_t)P.mcopy_khit_cutoff ? P.mcopy_num : 1; dir.push_back(g); }
+			else hb_order_group(hits + l, (int32_t)(k - l)); // self hits get no chain slot but are ordered like every group (k_chain_warp, slot == GRP_EMPTY)
 			l = k;
 		}
 	E.ch.assign(slot + 1, hb_chain_t()); E.chits.assign(n_hits + 1, hb_hit_t()); E.idx.assign(slot + 1, 0);
@@ -278,15 +280,32 @@ int emu_ec_align_A(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 	return err | (used > pool_cap ? 128 : 0);
 }
 
+// scratch of the re-seeding rescue (hb_ecrechain.cuh), what k_ecb_rechain gives each of its threads
+struct RcScratch {
+	std::vector<hb_wl_t> zw; std::vector<uint16_t> zc, cig1; std::vector<uint64_t> path1; std::vector<hb_hit_t> rh; std::vector<int64_t> rt, rp; std::vector<int32_t> rf, bb, be; std::vector<RsFrame> fr;
+	unsigned long long zc_used; int rc_err; EcRc S;
+	RcScratch(const DevReads &R, const uint16_t *poolA, int32_t w_l, int32_t hcap) : zw(1024), zc((size_t)1 << 16), cig1(HB_EC_CIG_TMP), path1((size_t)w_l * 5), rh(hcap), rt(hcap), rp(hcap), rf(hcap), bb(256), be(256), fr(HB_RS_STACK), zc_used(0), rc_err(0)
+	{
+		S.R = R; S.zw = zw.data(); S.zcap = (int32_t)zw.size(); S.poolA = poolA; S.zc = zc.data(); S.zc_used = &zc_used; S.zc_cap = zc.size(); S.path1 = path1.data(); S.cig1 = cig1.data();
+		S.h = rh.data(); S.hcap = hcap; S.hn = 0; S.t = rt.data(); S.p = rp.data(); S.f = rf.data(); S.rs.bb = bb.data(); S.rs.be = be.data(); S.rs.st = fr.data(); S.err = &rc_err; S.ovf = 0;
+		const double tmp = expf((float)(-0.01 * (double)HB_E_KHIT)); S.pen_gap = 0.5f; S.pen_skip = 0.0005f; S.pen_gap *= tmp; S.pen_skip *= tmp; S.h_khit = HB_E_KHIT; // set_lchain_dp_op, anchor.cpp:2272
+	}
+};
+
 // step B (base-level CIGAR) for the overlaps step A accepted: body of k_ec_cigar.  hits = compacted chain anchors of the read
 // (modified in place like return_t_chain does), aln / wlA = step A's output.  path_words / cig_words = per-thread scratch sizes.
+// rechain != 0: the re-seeding rescue (hb_ecb_rechain, body of k_ecb_rechain) runs on the overlaps that ask for it; poolA = step A's cigar pool;
+// rechain = (hit capacity << 8) | 1 (0 in the upper bits: 8192 hits)
 int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch, const uint64_t *fc, hb_hit_t *hits, uint64_t n_hits,
                    const hb_aln_t *aln, const hb_wl_t *wlA, double e_rate, int32_t w_l, int32_t gaps, uint64_t path_words, int32_t cig_words,
-                   hb_alnb_t *out, hb_wl_t *wl, uint64_t wl_cap, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used, uint64_t *n_wl)
+                   hb_alnb_t *out, hb_wl_t *wl, uint64_t wl_cap, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used, uint64_t *n_wl,
+                   const uint16_t *poolA, int32_t rechain)
 {
 	EmuReads *r = (EmuReads *)reads; unsigned long long used = 0; uint64_t nw = 0; int rc = 0;
+	RcScratch RS(r->d, poolA, w_l, (rechain >> 8) ? (rechain >> 8) : 8192); EcRc &S = RS.S; int &rc_err = RS.rc_err;
 	std::vector<uint64_t> path(path_words), vec(11 * HB_MW_MAXW); std::vector<uint16_t> ecig(cig_words), wc(cig_words);
-	EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap; C.do_gaps = gaps; C.no_myers = 0;
+	std::vector<uint16_t> gout(cig_words);
+	EcBCtx C; C.gout = gout.data(); C.gcap = cig_words; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap; C.do_gaps = gaps; C.no_myers = 0;
 	C.ez.path = path.data(); C.ez.pcap = path_words; C.ez.vec = vec.data(); C.ez.vstride = HB_MW_MAXW; C.ez.cig = ecig.data(); C.ez.ccap = cig_words; C.wc = wc.data(); C.wccap = cig_words;
 	for (uint32_t j = 0; j < n_ch; j++) {
 		hb_alnb_t res; memset(&res, 0, sizeof(res)); res.st = aln[j].st; res.w_off = nw;
@@ -301,6 +320,11 @@ int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 			C.q = hb_rd_view(r->d, rid, 0); C.t = hb_rd_view(r->d, c.y_id, c.y_pos_strand); C.ql = r->d.len[rid]; C.tl = r->d.len[c.y_id];
 			C.aw = wl + nw; C.awcap = (int32_t)std::min<uint64_t>(wl_cap - nw, (uint64_t)scn + 2);
 			hb_ec_overlap_B(C, z, aln[j].re, hits + c.first_hit, scn, t.data(), p.data(), f.data(), &res);
+			if ((rechain & 1) && res.st == 2 && res.need_rechain) {
+				C.awcap = (int32_t)std::min<uint64_t>(wl_cap - nw, (uint64_t)scn + 2 + HB_RC_SPARE_WIN);
+				hb_ecb_rechain(C, z, aln[j].re, S, &res);
+				if (rc_err) rc |= 2;
+			}
 			if (res.st < 0) rc |= res.st == -1 ? 1 : 2;
 			nw += res.w_n;
 		}
@@ -314,9 +338,11 @@ int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 // 72 cigar runs) and, when that is too small, with the large one; then the merge over the stored results with cig_words-sized buffers.
 int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch, const uint64_t *fc, hb_hit_t *hits, uint64_t n_hits,
                        const hb_aln_t *aln, const hb_wl_t *wlA, double e_rate, int32_t w_l, int32_t gaps, int32_t cig_words,
-                       hb_alnb_t *out, hb_wl_t *wl, uint64_t wl_cap, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used, uint64_t *n_wl, uint64_t *n_tier)
+                       hb_alnb_t *out, hb_wl_t *wl, uint64_t wl_cap, uint16_t *pool, uint64_t pool_cap, uint64_t *pool_used, uint64_t *n_wl, uint64_t *n_tier,
+                       const uint16_t *poolA, int32_t rechain)
 {
 	EmuReads *r = (EmuReads *)reads; unsigned long long used = 0, sused = 0; uint64_t nw = 0; int rc = 0;
+	RcScratch RS(r->d, poolA, w_l, 8192); std::vector<uint16_t> rbuf((size_t)3 * 65535);
 	std::vector<uint64_t> path0(640), vec0(11 * 4), path1((size_t)1 << 22), vec1(11 * HB_MW_MAXW); std::vector<uint16_t> cig0(72), cig1(65535), spool((size_t)1 << 22);
 	std::vector<uint16_t> mbuf((size_t)3 * cig_words);
 	n_tier[0] = n_tier[1] = 0;
@@ -330,7 +356,7 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 			std::vector<int64_t> t(scn + 1), p(scn + 1); std::vector<int32_t> f(scn + 1);
 			EcZ z; z.x_pos_s = c.x_pos_s; z.x_pos_e = c.x_pos_e; z.y_pos_s = c.y_pos_s; z.y_id = c.y_id; z.rev = c.y_pos_strand; z.fc = fc + c.fc_off; z.fc_n = c.fc_n;
 			z.align_length = aln[j].align_length; z.w = (hb_wl_t *)(wlA + aln[j].w_off); z.wn = (int32_t)aln[j].w_n;
-			EcBCtx C; C.e_rate = e_rate; C.w_l = w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+			EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = e_rate; C.w_l = w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
 			C.q = hb_rd_view(r->d, rid, 0); C.t = hb_rd_view(r->d, c.y_id, c.y_pos_strand); C.ql = r->d.len[rid]; C.tl = r->d.len[c.y_id];
 			EcPrep pr; hb_ecb_prep(z, aln[j].re, C.ql, C.tl, hits + c.first_hit, scn, t.data(), p.data(), f.data(), &pr);
 			const int32_t ns = (pr.shortcut || pr.ch_n <= 0) ? 0 : pr.ch_n + 1;
@@ -354,11 +380,19 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 				}
 				if (sused > spool.size()) return 256;
 			}
-			EcBCtx M; M.no_myers = 0; M.e_rate = e_rate; M.w_l = w_l; M.pool = pool; M.pool_used = &used; M.pool_cap = pool_cap; M.do_gaps = gaps;
+			EcBCtx M; M.gout = 0; M.gcap = 0; M.no_myers = 0; M.e_rate = e_rate; M.w_l = w_l; M.pool = pool; M.pool_used = &used; M.pool_cap = pool_cap; M.do_gaps = gaps;
 			M.wc = mbuf.data(); M.wccap = cig_words; M.ez.cig = mbuf.data() + cig_words; M.ez.ccap = cig_words; M.ez.path = (uint64_t *)(mbuf.data() + 2 * (size_t)cig_words); M.ez.pcap = (uint64_t)cig_words / 4;
 			M.ez.vec = 0; M.ez.vstride = 0; M.q = C.q; M.t = C.t; M.ql = C.ql; M.tl = C.tl;
-			M.aw = wl + nw; M.awcap = (int32_t)std::min<uint64_t>(wl_cap - nw, (uint64_t)scn + 2);
+			M.aw = wl + nw; M.awcap = (int32_t)std::min<uint64_t>(wl_cap - nw, (uint64_t)scn + 2 + HB_RC_SPARE_WIN);
 			hb_ecb_merge(M, z, aln[j].re, pr, segs.data(), spool.data(), &res);
+			if (rechain && res.st == 2 && res.need_rechain) { // what k_ecb_rechain does: a fresh context with the large aligner scratch over the merged list
+				EcBCtx Rc; Rc.gout = rbuf.data() + 2 * 65535; Rc.gcap = 65535; Rc.e_rate = e_rate; Rc.w_l = w_l; Rc.pool = pool; Rc.pool_used = &used; Rc.pool_cap = pool_cap; Rc.do_gaps = gaps; Rc.no_myers = 0;
+				Rc.q = C.q; Rc.t = C.t; Rc.ql = C.ql; Rc.tl = C.tl; Rc.aw = M.aw; Rc.awcap = M.awcap;
+				Rc.ez.path = path1.data(); Rc.ez.pcap = path1.size(); Rc.ez.vec = vec1.data(); Rc.ez.vstride = HB_MW_MAXW; Rc.ez.cig = rbuf.data(); Rc.ez.ccap = 65535;
+				Rc.wc = rbuf.data() + 65535; Rc.wccap = 65535;
+				hb_ecb_rechain(Rc, z, aln[j].re, RS.S, &res);
+				if (RS.rc_err) rc |= 2;
+			}
 			if (res.st < 0) rc |= res.st == -1 ? 1 : 2;
 			nw += res.w_n;
 		}

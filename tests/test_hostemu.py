@@ -15,7 +15,7 @@ from goldenlib import Golden, dg  # noqa: E402
 import roundlib  # noqa: E402
 
 
-@pytest.fixture(scope="module", params=["g1", "g2", "g3"])
+@pytest.fixture(scope="module", params=["g1", "g2", "g3", "g4"])
 def ctx(request):
     g = Golden(request.param)
     raw = ho.Store(g.raw.length, g.raw.byte_off, g.raw.packed, g.raw.n_off, g.raw.n_pos)
@@ -83,7 +83,7 @@ def test_ec_align_step_A(ctx):
     er = emu.Reads(rs)
     p = g.params("raw")
     rd = roundlib.Rounds(g.name); rd_scc, rd_scc_off = rd.scc(0); h_src, h_soff, h_fc, h_ab = rd.hap(0, "src")
-    n_full = n_cns = tot_nec = 0
+    n_full = n_cns = tot_nec = n_rechain = n_reported = 0
     for i in range(er.n):
         mz = ho.sketch(st.decode(i), int(p["w"]), int(p["k"]), 0, 1, ft, int(p["mz_sample_dist"]), int(p["mz_rewin"]))
         an = ho.anchors(st, pt, mz, int(p["high_occ"]), int(p["low_occ"]))
@@ -94,28 +94,36 @@ def test_ec_align_step_A(ctx):
         assert da == int(g.digest("raw", "alnA")[i]), "read %d" % i
         # step B: body of k_ec_cigar, with a small trace scratch every third read so that the deferral path runs too
         small = (i % 3 == 0)
-        rc, B, WB, CB = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, path_words=(8192 if small else 1 << 22))
+        # rechain = 1: overlaps that keep an unaligned window of >= 512 bp on both reads go through the re-seeding rescue (body of k_ecb_rechain)
+        rc, B, WB, CB = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, path_words=(8192 if small else 1 << 22), poolA=Cg, rechain=1)
         assert rc in ((0, 1) if small else (0,)), rc
         if rc & 1:  # what the second launch does: the deferred overlaps again with the large scratch
-            rc, B, WB, CB = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W)
+            rc, B, WB, CB = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, poolA=Cg, rechain=1)
             assert rc == 0
         acc = B[B["st"] == 2]
         assert acc.size == int(g.count("raw", "aln_ok")[i])
-        if not acc["need_rechain"].any():
+        if g.name == "g4":  # how many overlaps asked for the rescue; with a hit buffer that is too small the overlap is reported, never silently wrong
+            _, B0, _, _ = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W)
+            n_rechain += int(B0[B0["st"] == 2]["need_rechain"].sum())
+            if B0[B0["st"] == 2]["need_rechain"].any():
+                _, B1, _, _ = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, poolA=Cg, rechain=(1 << 8) | 1)
+                n_reported += int(B1[B1["st"] == 2]["need_rechain"].sum())
+        assert not acc["need_rechain"].any()
+        if True:
             db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CB) for b in acc)
             assert db == int(g.digest("raw", "alnB")[i]), "step B, read %d" % i
             # steps B + C in one go (reassign_gaps applied as each window closes)
-            rc, Bc, WCc, CCc = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1)
+            rc, Bc, WCc, CCc = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1, poolA=Cg, rechain=1)
             assert rc == 0 and (Bc["re"] == B["re"]).all()
             dc = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WCc[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CCc) for b in Bc[Bc["st"] == 2])
             assert dc == int(g.digest("raw", "alnC")[i]), "step C, read %d" % i
             # the same through the pieces the GPU runs as three kernels (prep / independent segments with tiered scratch / merge);
             # every other read with merge buffers too small for its longest cigars, so the deferral is reported
             cw = 64 if i % 2 else 1 << 16
-            rc, Bp, WP, CP, tiers = emu.ec_align_B_par(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1, cig_words=cw)
+            rc, Bp, WP, CP, tiers = emu.ec_align_B_par(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1, cig_words=cw, poolA=Cg, rechain=1)
             if rc & 1:
                 assert cw == 64 and (Bp["st"] == -1).any()
-                rc, Bp, WP, CP, tiers = emu.ec_align_B_par(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1)
+                rc, Bp, WP, CP, tiers = emu.ec_align_B_par(er, i, emu.to_chain(ch), fc, hits, A, W, gaps=1, poolA=Cg, rechain=1)
             assert rc == 0 and (Bp["re"] == B["re"]).all()
             dp = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WP[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CP) for b in Bp[Bp["st"] == 2])
             assert dp == int(g.digest("raw", "alnC")[i]), "steps B + C, segment-parallel pipeline, read %d" % i
@@ -156,6 +164,9 @@ def test_ec_align_step_A(ctx):
             assert (f_ec, f_ab) == (int(h_fc[i]), int(h_ab[i])), "is_fully_corrected / is_abnormal, read %d" % i
     # almost every read is corrected by the voted path; the graph consensus ran cns_gen_full "full_calls" times in the reference's round 0
     assert n_cns > 0 and 0 < n_full <= int(rd.params(0)["full_calls"]), (n_cns, n_full)
+    if g.name == "g4":
+        assert n_rechain >= 20 and 0 < n_reported <= n_rechain, (n_rechain, n_reported)
+        print("re-seeding rescue (rechain_aln_hc): %d overlaps; %d of them reported when the hit buffer holds one hit" % (n_rechain, n_reported))
     print("window consensus: %d reads (%d corrected bases), %d of them through the graph consensus" % (n_cns, tot_nec, n_full))
 
 

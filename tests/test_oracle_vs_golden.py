@@ -16,7 +16,7 @@ def _store(rs):
     return ho.Store(rs.length, rs.byte_off, rs.packed, rs.n_off, rs.n_pos)
 
 
-@pytest.fixture(scope="module", params=["g1", "g2", "g3"])
+@pytest.fixture(scope="module", params=["g1", "g2", "g3", "g4"])
 def ctx(request):
     g = Golden(request.param)
     raw = _store(g.raw)
