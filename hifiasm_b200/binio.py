@@ -161,3 +161,60 @@ def write_paf(path: str, rs: ReadStore, rec: np.ndarray, off: np.ndarray) -> Non
                     rs.names[qn], int(rs.length[qn]), int(r["qns"]) & 0xffffffff, int(r["qe"]),
                     "+-"[int(r["rev"])], rs.names[int(r["tn"])], int(rs.length[int(r["tn"])]),
                     int(r["ts"]), int(r["te"]), int(r["ml"]), int(r["bl"])))
+
+
+# ---- the native writers of the library (csrc/hostio.cu, include/hifiasm_b200.h: hb_write_*): the product path for the stage's
+# on-disk outputs; the numpy writers above stay as test tooling.  No GPU is needed for them (host code of the .so).
+def _native():
+    from . import engine
+    return engine._lib(), engine._p
+
+
+def _mem(rec: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(rec if rec.dtype == MA_MEM else disk_to_mem(rec))
+
+
+def _names(rs: ReadStore):
+    blob = np.frombuffer(rs.name_blob, dtype=np.uint8) if rs.name_blob else np.zeros(1, np.uint8)
+    return np.ascontiguousarray(blob), np.ascontiguousarray(rs.name_index, dtype=np.uint64)
+
+
+def native_write_paf(path: str, rs: ReadStore, rec: np.ndarray, off: np.ndarray) -> None:
+    """hb_write_paf = Output_PAF (Assembly.cpp:1673): rec / off = the final same-haplotype list (R_INF.paf)"""
+    import ctypes as C
+    L, p = _native(); m = _mem(rec); blob, idx = _names(rs); o = np.ascontiguousarray(off, dtype=np.uint64); ln = np.ascontiguousarray(rs.length, dtype=np.uint64)
+    rc = L.hb_write_paf(path.encode(), C.c_uint64(rs.n), p(ln), p(blob), p(idx), p(o), p(m if m.size else np.zeros(1, MA_MEM)))
+    if rc:
+        raise IOError("hb_write_paf(%s) -> %d" % (path, rc))
+
+
+def native_write_ec_fa(path: str, rs: ReadStore) -> None:
+    """hb_write_ec_fa = Output_corrected_reads (Assembly.cpp:884)"""
+    import ctypes as C
+    L, p = _native(); blob, idx = _names(rs)
+    a = [np.ascontiguousarray(x, dtype=t) for x, t in ((rs.length, np.uint64), (rs.packed, np.uint8), (rs.byte_off, np.uint64), (rs.n_off, np.uint64), (rs.n_pos if rs.n_pos.size else np.zeros(1, np.uint64), np.uint64))]
+    rc = L.hb_write_ec_fa(path.encode(), C.c_uint64(rs.n), p(a[0]), p(a[1]), p(a[2]), p(a[3]), p(a[4]), p(blob), p(idx))
+    if rc:
+        raise IOError("hb_write_ec_fa(%s) -> %d" % (path, rc))
+
+
+def native_write_ovlp_bin(path: str, rec: np.ndarray, off: np.ndarray, fc=None, ab=None) -> None:
+    """hb_write_ovlp_bin = write_ma_hit_ts (Overlaps.cpp:23442)"""
+    import ctypes as C
+    L, p = _native(); m = _mem(rec); o = np.ascontiguousarray(off, dtype=np.uint64); n = o.size - 1
+    f = np.ascontiguousarray(fc, dtype=np.uint8) if fc is not None else None; a = np.ascontiguousarray(ab, dtype=np.uint8) if ab is not None else None
+    rc = L.hb_write_ovlp_bin(path.encode(), C.c_uint64(n), p(o), p(m if m.size else np.zeros(1, MA_MEM)), p(f), p(a))
+    if rc:
+        raise IOError("hb_write_ovlp_bin(%s) -> %d" % (path, rc))
+
+
+def native_write_ec_bin(path: str, rs: ReadStore) -> None:
+    """hb_write_ec_bin = write_All_reads (Process_Read.cpp:69)"""
+    import ctypes as C
+    L, p = _native(); blob, idx = _names(rs)
+    a = [np.ascontiguousarray(x, dtype=t) for x, t in ((rs.length, np.uint64), (rs.packed, np.uint8), (rs.byte_off, np.uint64), (rs.n_off, np.uint64), (rs.n_pos if rs.n_pos.size else np.zeros(1, np.uint64), np.uint64))]
+    tf = np.ascontiguousarray(rs.trio_flag, dtype=np.uint8) if rs.trio_flag is not None else None
+    rc = L.hb_write_ec_bin(path.encode(), C.c_int32(rs.adapter_len), C.c_uint64(rs.index_size), C.c_uint64(rs.name_index_size), C.c_uint64(rs.n), C.c_uint64(rs.total_reads_bases),
+                           p(a[0]), p(a[1]), p(a[2]), p(a[3]), p(a[4]), p(blob), C.c_uint64(len(rs.name_blob)), p(idx), p(tf), C.c_int32(rs.hom_cov), C.c_int32(rs.het_cov))
+    if rc:
+        raise IOError("hb_write_ec_bin(%s) -> %d" % (path, rc))

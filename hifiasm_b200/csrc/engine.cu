@@ -10,6 +10,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 #include "hb_internal.h"
 #include "hb_kernels.cuh"
+#include "hb_rechain_launch.h"
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -817,8 +818,9 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					for (int attempt = 0;; attempt++) {
 						Arena pa(ctx);
 						d_poolb = pa.get<uint16_t>(poolb_cap);
-						HB_CUDA(cudaMemsetAsync(d_pused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_ndef, 0, 4, ctx->stream));
+						HB_CUDA(cudaMemsetAsync(d_pused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_ndef, 0, 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_qn + 6, 0, 4, ctx->stream));
 						G.pool = d_poolb; G.pool_used = d_pused; G.pool_cap = poolb_cap;
+						G.rc_q = d_q1; G.rc_n = d_qn + 6; // the segment queues are free now: the merge kernel queues the overlaps that need the re-seeding rescue
 						for (int pass = 0; pass < 2; pass++) {
 							if (pass == 1 && !n_def) break;
 							const unsigned bl = pass == 0 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 8)) : 4u;
@@ -834,6 +836,33 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(&n_def, d_ndef, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 							if (pass == 1 && n_def) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: %u overlaps exceed the largest scratch", n_def); return HB_E_OVERFLOW; }
+						}
+						// ---- the re-seeding rescue (rechain_aln_hc, Correct.cpp:17669): overlaps that keep an unaligned window of >= 512 bp on both reads.
+						// Rare (a structural difference inside an accepted overlap); one thread per overlap with the largest aligner scratch, few threads.
+						unsigned int n_rc = 0;
+						HB_CUDA(cudaMemcpyAsync(&n_rc, d_qn + 6, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						if (n_rc) {
+							Arena sa(ctx);
+							const int32_t cw = 65535, zcap = 2048, hcap = 16384; const uint64_t zc_cap = 1ull << 17;
+							RcLaunch L; memset(&L, 0, sizeof(L));
+							L.blocks = std::min<unsigned>((n_rc + 31) / 32, 2u); const uint64_t nt = (uint64_t)L.blocks * 32;
+							L.R = R; L.r0 = r0 + b0; L.desc = d_od; L.ch = d_ch; L.fc = d_fc; L.fc_grp_base = d_fcb; L.aln = d_aln; L.wlA = d_wl; L.poolA = d_pool;
+							L.e_rate = so->e_rate; L.w_l = w_l; L.gaps = so->gaps;
+							L.out = d_alnb; L.wl = d_wlb; L.wl_off = d_wboff; L.pool = d_poolb; L.pool_used = d_pused; L.pool_cap = poolb_cap; L.err = d_err; L.rc_q = d_q1; L.rc_n = d_qn + 6;
+							L.path_words = (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5; L.path = sa.get<uint64_t>(nt * L.path_words); L.vec = sa.get<uint64_t>(nt * 11 * (uint64_t)HB_MW_MAXW);
+							L.cig_words = cw; L.cig3 = sa.get<uint16_t>(nt * 3 * (uint64_t)cw);
+							L.zcap = zcap; L.zw = sa.get<hb_wl_t>(nt * (uint64_t)zcap); L.zc_cap = zc_cap; L.zc = sa.get<uint16_t>(nt * zc_cap); L.zc_used = sa.zero<unsigned long long>(nt);
+							L.path1 = sa.get<uint64_t>(nt * (uint64_t)w_l * 5); L.cig1 = sa.get<uint16_t>(nt * HB_EC_CIG_TMP);
+							L.hcap = hcap; L.h = sa.get<hb_hit_t>(nt * (uint64_t)hcap); L.t = sa.get<int64_t>(nt * (uint64_t)hcap); L.p = sa.get<int64_t>(nt * (uint64_t)hcap); L.f = sa.get<int32_t>(nt * (uint64_t)hcap);
+							L.rs_b = sa.get<int32_t>(nt * 512); L.rs_f = sa.get<RsFrame>(nt * HB_RS_STACK);
+							if (sa.failed || pa.failed) return HB_E_WS;
+							{ const double tmp = expf((float)(-0.01 * (double)31 /* E_KHIT, ecovlp.cpp:10 */)); L.pen_gap = 0.5f; L.pen_skip = 0.0005f; L.pen_gap *= tmp; L.pen_skip *= tmp; } // set_lchain_dp_op, anchor.cpp:2272-2285
+							{
+								ProfScope ps(ctx, "k_ecb_rechain");
+								HB_CUDA(hb_launch_ecb_rechain(L, ctx->stream));
+							}
+							HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							if (getenv("HB_TRACE_EC")) fprintf(stderr, "[hb] EC base alignment: %u overlaps through the re-seeding rescue\n", n_rc);
 						}
 						HB_CUDA(cudaMemcpyAsync(&poolb_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 						HB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -31,6 +31,8 @@ HB_HD RdView hb_rd_view(const DevReads &R, uint64_t id, uint32_t rev)
 	return v;
 }
 
+struct OvDesc { uint32_t read, slot, nw, pad; uint64_t w0; }; // an overlap of the batch: batch-local read, chain slot, number of windows, first window
+
 // bit_extz_t (Levenshtein_distance.h:776-785): the fields this path uses; cigar / path live in per-thread scratch
 struct EcEz { int32_t ps, pe, pl, ts, te, tl, thre, err; uint16_t *cig; int32_t cn; uint64_t *path; };
 
@@ -462,6 +464,7 @@ HB_HD void hb_ec_overlap_A(EcCtx &C, const hb_chain_t &c, const uint64_t *fc, co
 #define HB_MAX_SIN_E 2047  // Levenshtein_distance.h:756
 #define HB_FORCE_SIN_L 512 // Levenshtein_distance.h:758
 #define HB_MW_MAXW 64      // words of a band of 2*2047+1 bits
+#define HB_RC_SPARE_WIN 8   // windows an overlap's list may grow by in the re-seeding rescue (hb_ecrechain.cuh); more: the overlap is reported
 
 struct MwEz {
 	int32_t ps, pe, pl, ts, te, tl, thre, err, nword;

@@ -30,7 +30,6 @@ struct EcRc {
 };
 #define HB_RC_PRIV 0x80000000u
 #define HB_E_KHIT 31        // E_KHIT, ecovlp.cpp:10
-#define HB_RC_SPARE_WIN 8  // windows an overlap's list may grow by (more: the overlap is reported, need_rechain stays set)
 
 HB_HD void hb_rc_put(EcRc &S, int32_t xs, int32_t ys, uint32_t cnt)
 {
@@ -379,7 +378,7 @@ HB_HD void hb_ecb_rechain(EcBCtx &C, const EcZ &zA, int64_t re_A, EcRc &S, hb_al
 	const int32_t aux_n = C.awn;
 	for (int32_t i = 0; i < aux_n && !S.ovf && !C.ez.ovf; i++) if (hb_rc_is_ualn(C.aw[i])) hb_rc_window(C, z, S, i);
 	hb_b_flush(C);
-	if (S.ovf || C.ez.ovf) { out->need_rechain = 1; out->pad |= 2; return; }
+	if (S.ovf || C.ez.ovf) { out->need_rechain = 1; return; } // reported: the read's status says its lists are not final
 	if (C.awn > aux_n) {
 		int32_t m = 0;
 		for (int32_t i = 0; i < C.awn; i++) { if (i < aux_n && hb_rc_is_ualn(C.aw[i])) continue; C.aw[m++] = C.aw[i]; }

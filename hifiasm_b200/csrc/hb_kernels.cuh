@@ -1086,7 +1086,7 @@ __global__ void k_win_desc(uint64_t nR, const uint64_t *__restrict__ c_off, cons
 // of k_windows (hb_ecaln.cuh).  Grid-stride over the overlaps so that the per-thread trace scratch (5 words per
 // column of one window) is bounded by the grid, not by the batch.
 // ----------------------------------------------------------------------------
-struct OvDesc { uint32_t read, slot, nw, pad; uint64_t w0; }; // batch-local read, chain slot, number of windows, first window
+// OvDesc (batch-local read, chain slot, number of windows, first window): hb_ecaln.cuh
 __global__ void k_ov_desc(uint64_t nR, const uint64_t *__restrict__ c_off, const hb_chain_t *__restrict__ ch, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ n_ol, int32_t w_l,
                           const uint64_t *__restrict__ w_off, const uint64_t *__restrict__ o_off, OvDesc *__restrict__ desc)
 {
@@ -1144,7 +1144,7 @@ __global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
 __global__ void k_ecb_cap(uint64_t n_ov, const OvDesc *__restrict__ desc, const hb_chain_t *__restrict__ ch, const hb_aln_t *__restrict__ aln, uint32_t *__restrict__ cap)
 { // window capacity of an overlap = number of inter-anchor segments (+1 spare)
 	uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
-	cap[o] = aln[o].st == 2 ? ch[desc[o].slot].n_hits + 2 : (aln[o].st == 3 ? 2 : 0);
+	cap[o] = aln[o].st == 2 ? ch[desc[o].slot].n_hits + 2 + HB_RC_SPARE_WIN : (aln[o].st == 3 ? 2 : 0); // the spare: windows the re-seeding rescue may add
 }
 struct EcCigArgs {
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
@@ -1156,6 +1156,7 @@ struct EcCigArgs {
 	uint64_t *path; uint64_t path_words; uint64_t *vec; int32_t vstride; uint16_t *cig_tmp; int32_t cig_words; // per-thread scratch of the queue tiers / merge
 	int pass; hb_alnb_t *out; hb_wl_t *wl; const uint64_t *wl_off;
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; unsigned int *n_deferred; int *err;
+	uint32_t *rc_q; unsigned int *rc_n; // overlaps that ask for the re-seeding rescue (k_ecb_rechain, ecrechain.cu)
 };
 static __device__ __forceinline__ void ecb_overlap_view(const EcCigArgs &A, uint64_t o, const hb_aln_t &a, OvDesc &d, hb_chain_t &c, EcZ &z, hb_hit_t *&ch_a, uint64_t &dpo)
 {
@@ -1272,6 +1273,7 @@ __global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
 		if (a.st == 3 && r.st == 2) { r.x_pos_s = c.x_pos_s; r.x_pos_e = c.x_pos_e; r.y_pos_s = c.y_pos_s; r.y_pos_e = c.y_pos_e; r.pad = 1; } // no update_overlap_region on this path (ecovlp.cpp:2849-2852)
 		if (r.st == -1) atomicAdd(A.n_deferred, 1u);
 		if (r.st == -2) atomicOr(A.err, 32);
+		if (r.st == 2 && r.need_rechain && A.rc_q) A.rc_q[atomicAdd(A.rc_n, 1u)] = (uint32_t)o;
 		A.out[o] = r;
 	}
 }
@@ -1386,7 +1388,7 @@ template <bool GRAPH> __global__ void __launch_bounds__(64) k_ec_cns(CnsArgs A)
 		const uint64_t r = GRAPH ? A.queue[u] : u;
 		const uint64_t o0 = A.o_off[r], rid = A.r0 + r, e0 = A.ent_off[r]; const uint32_t n = (uint32_t)(A.o_off[r + 1] - o0); int ovf = 0;
 		PhPair *ord = (PhPair *)(A.ord + o0); uint8_t st = 0;
-		for (uint32_t j = 0; j < n; j++) if (A.ph[o0 + j].st == 2 && A.ph[o0 + j].need_rechain) st |= 4; // an overlap of this read wanted rechain_aln_hc (not built): its lists are not final either
+		for (uint32_t j = 0; j < n; j++) if (A.ph[o0 + j].st == 2 && A.ph[o0 + j].need_rechain) st |= 4; // the re-seeding rescue of an overlap of this read ran out of scratch (k_ecb_rechain): its lists are not final
 		const uint32_t keep = hb_ec_dedup(A.ph + o0, n, ord, W, &ovf);
 		if (ovf) { atomicOr(A.err, 128); A.out_n[r] = 0; A.status[r] = st | 2; continue; }
 		CnsOv *ov = A.cov + o0; uint32_t n_ov = 0;

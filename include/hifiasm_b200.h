@@ -25,6 +25,7 @@ extern "C" {
 #define HB_E_STATE      (-4)
 #define HB_E_OVERFLOW   (-5)
 #define HB_E_NOMEM      (-6)
+#define HB_E_IO         (-7)
 
 typedef struct hb_ctx hb_ctx_t;
 
@@ -143,8 +144,9 @@ int hb_ec_align(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double
  * threshold escalation, multi-word banded Myers with traceback, push_alnw, update_overlap_region.
  * rec[j] (hb_chains order): st = step A's status (2 = accepted and aligned here); re = error total (Correct.cpp:17857);
  * x/y_pos_* = the overlap's coordinates after update_overlap_region; w_off/w_n locate its window list in wl[];
- * need_rechain = 1 when a window of >= 512 bp stayed unaligned, which the reference re-seeds and re-chains
- * (rechain_aln_hc, Correct.cpp:17669): that rescue is not built yet and such an overlap's result is not final.
+ * an overlap that keeps an unaligned window of >= 512 bp on both reads goes through the re-seeding rescue (rechain_aln_hc,
+ * Correct.cpp:17669: exact runs of step A's window alignments -> hits -> chain with fixed ends -> the pieces between the hits
+ * aligned again; k_ecb_rechain); need_rechain = 1 is left only when that rescue ran out of scratch: the result is then not final.
  * gaps != 0 adds step C (row a11), reassign_gaps (Correct.cpp:25409): the indels of every window are left-normalised
  * (move_wins 25274, adjust_gap 25167, ajust_end_cigar 25252); nh_err = overlap_region.non_homopolymer_errors afterwards
  * (step A's estimate minus the mismatches the normalisation removed); re stays step B's total.
@@ -185,8 +187,8 @@ int hb_ec_round_lists(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, 
 /* rows a14 + a15 — the same with the consensus on the device: wcns_gen (ecovlp.cpp:2293) writes each read's edit script (wcns_vote 2185 per 512
  * columns, anchors by push_cns_anchor 2109, stretches between anchors voted by cns_gen0 1159), which then feeds push_ne_ovlp / check_well_cal as above.
  * scc_off[r1 - r0 + 1] + scc = the scripts of the range (scc may be NULL: sizes only); *n_corrected = corrected bases (cal_ec_multiple's second counter).
- * status[i]: 0 = done; bit 0 = the read needs the graph consensus (cns_gen_full, ecovlp.cpp:1919), which is NOT built yet — it gets an empty script and
- * its lists carry no exact intervals; bit 2 = an overlap of the read wanted the re-chaining rescue (rechain_aln_hc), also not built.  When the range is
+ * status[i]: 0 = done; bit 0 = the read's graph consensus (cns_gen_full, ecovlp.cpp:1919) ran out of its arena — it gets an empty script and
+ * its lists carry no exact intervals; bit 2 = the re-seeding rescue (rechain_aln_hc) of one of the read's overlaps ran out of scratch.  When the range is
  * the whole store the scripts stay staged in HBM (as by hb_ec_stage_scc) for hb_ec_apply / hb_ec_update_paf.                                       */
 int hb_ec_round(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, double bw_thres, double e_rate, int32_t w_l, int32_t use_prev,
                 uint64_t *src_off, hb_ma_hit_t *src, uint64_t src_cap, uint64_t *rev_off, hb_ma_hit_t *rev, uint64_t rev_cap, uint8_t *flags,
@@ -243,6 +245,23 @@ int hb_ed_semi_64(hb_ctx_t *ctx, uint64_t n_cases, const char *pat, const uint64
                   int32_t *err, int32_t *pe);
 
 /* ---- instrumentation ---------------------------------------------------- */
+/* ---- the stage's on-disk products in the reference's own formats, written by the host side from the flat
+ * arrays of this interface (no context, no GPU).  names / name_index = All_reads.name / name_index (name of read i =
+ * names[name_index[i] .. name_index[i+1])).  Byte-identical to the reference's files on the same state.
+ *   hb_write_paf       Output_PAF, Assembly.cpp:1673-1717 (--write-paf: the same-haplotype list R_INF.paf after cal_ov_r)
+ *   hb_write_ec_fa     Output_corrected_reads, Assembly.cpp:884-905 (--write-ec: the reads after the EC rounds)
+ *   hb_write_ovlp_bin  write_ma_hit_ts, Overlaps.cpp:23442-23465 (<o>.ovlp.source.bin / <o>.ovlp.reverse.bin; flags may be NULL = 0)
+ *   hb_write_ec_bin    write_All_reads, Process_Read.cpp:69-125 (<o>.ec.bin; the pad byte of reads with len % 4 == 0 is whatever
+ *                      packed[] holds — the reference leaves it uninitialised)                                     */
+int hb_write_paf(const char *path, uint64_t n_reads, const uint64_t *read_length, const char *names, const uint64_t *name_index,
+                 const uint64_t *off, const hb_ma_hit_t *rec);
+int hb_write_ec_fa(const char *path, uint64_t n_reads, const uint64_t *read_length, const uint8_t *packed, const uint64_t *byte_off,
+                   const uint64_t *n_off, const uint64_t *n_pos, const char *names, const uint64_t *name_index);
+int hb_write_ovlp_bin(const char *path, uint64_t n_reads, const uint64_t *off, const hb_ma_hit_t *rec, const uint8_t *is_fully_corrected, const uint8_t *is_abnormal);
+int hb_write_ec_bin(const char *path, int32_t adapter_len, uint64_t index_size, uint64_t name_index_size, uint64_t n_reads, uint64_t total_reads_bases,
+                    const uint64_t *read_length, const uint8_t *packed, const uint64_t *byte_off, const uint64_t *n_off, const uint64_t *n_pos,
+                    const char *names, uint64_t total_name_length, const uint64_t *name_index, const uint8_t *trio_flag, int32_t hom_cov, int32_t het_cov);
+
 /* per-kernel launch counters and device time of the last hb_cal_ov_r* call:
  * names[i] (static strings), launches[i], ms[i]; returns number of entries   */
 int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap);

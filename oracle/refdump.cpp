@@ -39,6 +39,7 @@
 
 // non-static reference functions that no header declares
 void ha_ec(int64_t round, int num_pround, int des_idx, uint64_t *tot_b, uint64_t *tot_e);
+void ha_ec_ff(int renew_idx); // Assembly.cpp:1942
 void ha_opt_update_cov(hifiasm_opt_t *opt, int hom_cov);
 void ha_opt_reset_to_round(hifiasm_opt_t *asm_opt, int round);
 void write_ma_hit_ts(ma_hit_t_alloc *x, long long n_read, char *read_file_name);
@@ -378,9 +379,40 @@ static int run_bench(int argc, char *argv[])
 	return 0;
 }
 
+// refdump stage <hifiasm args...>: the reference's WHOLE overlap / error-correction stage, timed the way SURVEY.md §8(d) defines the metric —
+// from the first ha_ft_gen to the end of the final overlap pass (Assembly.cpp:2081-2108: filter table, number_of_round x ha_ec with the
+// index rebuilt each round, ha_ec_ff = final index + cal_ov_r).  Prints one JSON line.
+static int run_stage(int argc, char *argv[])
+{
+	int r, hom_cov = -1, het_cov = -1; uint64_t tot_b = 0, tot_e = 0, i, bases = 0, n_src = 0, n_rev = 0, corrected = 0;
+	yak_reset_realtime();
+	init_opt(&asm_opt);
+	argv[1] = argv[0];
+	if (!CommandLine_process(argc - 1, argv + 1, &asm_opt)) return 1;
+	ha_flt_tab = NULL; ha_idx = NULL;
+	const double t0 = yak_realtime();
+	if (!(asm_opt.flag & HA_F_NO_KMER_FLT)) { ha_flt_tab = ha_ft_gen(&asm_opt, &R_INF, &hom_cov, 0, 0); ha_opt_update_cov(&asm_opt, hom_cov); }
+	const double t_ft = yak_realtime() - t0;
+	for (r = 0; r < asm_opt.number_of_round; ++r) {
+		ha_opt_reset_to_round(&asm_opt, r);
+		tot_b = tot_e = 0;
+		ha_ec(r, asm_opt.number_of_pround, (r < asm_opt.number_of_round - 1) ? 1 : 0, &tot_b, &tot_e);
+		corrected += tot_e; if (r == 0) bases = tot_b;
+	}
+	const double t_ec = yak_realtime() - t0 - t_ft;
+	ha_opt_reset_to_round(&asm_opt, asm_opt.number_of_round);
+	ha_ec_ff(1);
+	const double t_all = yak_realtime() - t0;
+	for (i = 0; i < R_INF.total_reads; i++) { n_src += R_INF.paf[i].length; n_rev += R_INF.reverse_paf[i].length; }
+	printf("{\"seconds\": %.6f, \"filter_seconds\": %.3f, \"ec_rounds_seconds\": %.3f, \"final_seconds\": %.3f, \"reads\": %lu, \"bases\": %lu, \"corrected_bases\": %lu, \"threads\": %d, \"n_src\": %lu, \"n_rev\": %lu}\n",
+	       t_all, t_ft, t_ec, t_all - t_ft - t_ec, (unsigned long)R_INF.total_reads, (unsigned long)bases, (unsigned long)corrected, asm_opt.thread_num, (unsigned long)n_src, (unsigned long)n_rev);
+	return 0;
+}
+
 int main(int argc, char *argv[])
 {
 	if (argc == 4 && strcmp(argv[1], "edsemi") == 0) return run_edsemi(argv[2], argv[3]);
+	if (argc >= 3 && strcmp(argv[1], "stage") == 0) return run_stage(argc, argv);
 	if (argc >= 6 && strcmp(argv[1], "bench") == 0) return run_bench(argc, argv);
 	if (argc < 4) { fprintf(stderr, "usage: refdump <raw|final> <out_prefix> <hifiasm args...>\n"); return 1; }
 	const char *mode = argv[1], *pfx = argv[2];

@@ -90,8 +90,7 @@ def _check_stages(g, eng, mode, rs):
     assert (boff == coff).all() and (B["st"] == A["st"]).all()
     for i in range(n):
         acc = B[int(boff[i]):int(boff[i + 1])]; acc = acc[acc["st"] == 2]
-        if acc["need_rechain"].any():
-            continue
+        assert not acc["need_rechain"].any(), "re-seeding rescue out of scratch, read %d" % i
         db = alnlib.digest_B((b["re"], WB[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CB) for b in acc)
         assert db == int(g.digest(mode, "alnB")[i]), "EC alignment step B, read %d" % i
     # + step C (row a11): reassign_gaps fused into the same kernel
@@ -99,8 +98,7 @@ def _check_stages(g, eng, mode, rs):
     assert (Gc["st"] == B["st"]).all() and (Gc["re"] == B["re"]).all()
     for i in range(n):
         acc = Gc[int(goff[i]):int(goff[i + 1])]; acc = acc[acc["st"] == 2]
-        if acc["need_rechain"].any():
-            continue
+        assert not acc["need_rechain"].any(), "re-seeding rescue out of scratch, read %d" % i
         dc = alnlib.digest_C((b["nh_err"], (b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"]), WG[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CG) for b in acc)
         assert dc == int(g.digest(mode, "alnC")[i]), "EC alignment step C, read %d" % i
     # phasing (row a13) on top of the step-C state: k_ph_count / k_ph_decide
@@ -108,8 +106,7 @@ def _check_stages(g, eng, mode, rs):
     assert (poff == coff).all() and (P["st"] == B["st"]).all()
     for i in range(n):
         acc = P[int(poff[i]):int(poff[i + 1])]; acc = acc[acc["st"] == 2]
-        if acc["need_rechain"].any():
-            continue
+        assert not acc["need_rechain"].any(), "re-seeding rescue out of scratch, read %d" % i
         pa = np.zeros(acc.size, alnlib.PH)
         for f in alnlib.PH.names:
             pa[f] = acc[f].astype(np.int64).astype(np.uint32)
@@ -118,8 +115,6 @@ def _check_stages(g, eng, mode, rs):
     # the round's reverse_paf[i] (part of row a15): dedup_chains + push_ne_ovlp(flag 2)
     roff, RP = eng.ec_reverse_paf(0, n, float(p["bw_thres"]), 0.04, 775)
     for i in range(n):
-        if P[int(poff[i]):int(poff[i + 1])]["need_rechain"].any():
-            continue
         rp = RP[int(roff[i]):int(roff[i + 1])]; ra = np.zeros(rp.size, alnlib.RPAF)
         for f in alnlib.RPAF.names:
             ra[f] = rp[f]
@@ -134,8 +129,7 @@ def _check_stages(g, eng, mode, rs):
     n_short = 0
     for i in range(n):
         acc = E[int(eoff[i]):int(eoff[i + 1])]; cc = ch[int(coff[i]):int(coff[i + 1])][acc["st"] == 2]; acc = acc[acc["st"] == 2]
-        if acc["need_rechain"].any():
-            continue
+        assert not acc["need_rechain"].any(), "re-seeding rescue out of scratch, read %d" % i
         n_short += int(acc["pad"].sum())
         de = alnlib.digest_ea(((c["y_id"], c["y_pos_strand"], b["x_pos_s"], b["x_pos_e"], b["y_pos_s"], b["y_pos_e"], b["nh_err"], 1), WE[int(b["w_off"]):int(b["w_off"]) + int(b["w_n"])], CE) for b, c in zip(acc, cc))
         assert de == int(g.digest(mode, "ea")[i]), "gen_hc_r_alin_ea, read %d" % i

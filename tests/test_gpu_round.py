@@ -161,4 +161,9 @@ def test_whole_stage_from_raw_reads(hb, name, tmp_path):
     binio.write_ovlp_bin(p0, out0, oo0, fc0, ab0); binio.write_ovlp_bin(p1, out1, oo1, fc1, ab1)   # the two read flags are those of round 3 (checked in test_round_chained_on_device)
     assert open(p0, "rb").read() == g.z["fin_ovlp_source"].tobytes(), "ovlp.source.bin"
     assert open(p1, "rb").read() == g.z["fin_ovlp_reverse"].tobytes(), "ovlp.reverse.bin"
+    # ... and the files a user of the reference asks for with --write-paf --write-ec, from the DEVICE's state through the library's own
+    # writers, byte-identical to what the unmodified reference binary wrote for the same reads (tests/golden/outputs.npz)
+    import test_outputs
+    reads.names, reads.name_blob, reads.name_index = g.raw.names, g.raw.name_blob, g.raw.name_index   # read names travel beside the store (All_reads.name)
+    test_outputs.check_outputs(name, tmp_path, reads, out0, oo0, fc0, ab0, out1, oo1, fc1, ab1)
     eng.close()

@@ -1,0 +1,54 @@
+"""GPU parity on golden set g4: 40 kb reads with tandem-repeat blocks, where accepted overlaps keep unaligned windows of
+>= 512 bp on both reads and the reference re-seeds them (rechain_aln_hc, Correct.cpp:17669; here hb_ecrechain.cuh /
+k_ecb_rechain).  The device BODY of the rescue is pinned bit-for-bit in host emulation (tests/test_hostemu.py, g4: steps B / C,
+phasing, consensus, lists of all 120 reads identical to the reference); the kernel launch around it was written after the
+round's GPU budget was spent and has not run on a B200 yet, hence the non-strict xfail marks: a pass shows up as XPASS, a
+failure does not hide the rest of the suite.  The file sorts last so that every other GPU test runs before it."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from goldenlib import Golden  # noqa: E402
+
+pytestmark = [pytest.mark.gpu]
+NOT_RUN_YET = pytest.mark.xfail(reason="k_ecb_rechain's launch path has not run on a B200 yet (round-1 GPU budget spent); its device body is pinned in host emulation", strict=False)
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hifiasm_b200
+    return hifiasm_b200
+
+
+@NOT_RUN_YET
+def test_stages_raw_g4(hb):
+    """every stage of an EC round on the raw reads of g4 through the C-ABI, incl. the rescue (no overlap may keep need_rechain)"""
+    import test_gpu_parity as tp
+    g = Golden("g4")
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    hom = eng.ft_gen(); eng.update_cov(hom)
+    tp._check_stages(g, eng, "raw", g.raw)
+    assert eng.profile().get("k_ecb_rechain", (0, 0.0))[0] >= 1, "the rescue kernel did not launch"
+    eng.close()
+
+
+@NOT_RUN_YET
+def test_stages_final_g4(hb):
+    """the same on the corrected reads with the previous round's lists (exact shortcut + rescue)"""
+    import test_gpu_parity as tp
+    g = Golden("g4")
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    hom = eng.ft_gen(); eng.update_cov(hom)
+    tp._check_stages(g, eng, "final", g.pre)
+    eng.close()
+
+
+@NOT_RUN_YET
+def test_whole_stage_from_raw_reads_g4(hb, tmp_path):
+    """raw reads -> three EC rounds -> final pass on the device, byte-identical ovlp.*.bin, with the rescue on the path"""
+    import test_gpu_round as tr
+    tr.test_whole_stage_from_raw_reads(hb, "g4", tmp_path)
