@@ -460,10 +460,30 @@ static void count_hpc_kmers(u64v_t *v, int k, int len, const char *seq, int is_h
 	}
 }
 
-hao_ft_t *hao_ft_gen(const hao_reads_t *r, const hao_opt_t *o, int *hom_cov)
-{ /* ha_ft_gen, htab.cpp:1136-1169, exact counting (bf_shift = 0) */
+/* yak_bf_insert, htab.cpp:98-115: blocked Bloom filter, one 512-bit block per k-mer, n_hashes bits; returns how many of them were set */
+static int bf_insert(uint8_t *b, int n_shift, int n_hashes, uint64_t hash)
+{
+	int x = n_shift - 9, i, z, cnt = 0;
+	uint64_t y = hash & ((1ULL << x) - 1);
+	int h1 = (int)(hash >> x & 511), h2 = (int)(hash >> n_shift & 511);
+	uint8_t *p = &b[y << 6];
+	if ((h2 & 31) == 0) h2 = (h2 + 1) & 511;
+	for (i = 0, z = h1; i < n_hashes; z = (z + h2) & 511) {
+		uint8_t *q = &p[z >> 3], u = (uint8_t)(1 << (z & 7));
+		cnt += !!(*q & u); *q |= u; ++i;
+	}
+	return cnt;
+}
+
+hao_ft_t *hao_ft_gen_bf(const hao_reads_t *r, const hao_opt_t *o, int bf_shift, int *hom_cov)
+{ /* ha_ft_gen, htab.cpp:1136-1169.  bf_shift = asm_opt.bf_shift (-f): with bf_shift - 12 >= 9 every one of the 4096 sub-tables has a blocked
+     Bloom filter of 2^(bf_shift-12) bits (ha_ct_init 140-158, yak_bf_init 78-91) and ha_ct_insert_list (181-214) only counts an occurrence
+     whose 4 bits were all set before — the first occurrence of a k-mer is lost unless it is a false positive — and a k-mer enters the
+     table with count 1 + 1.  The k-mers go through it in read order, position order (the pipeline fills the 4096 buffers sequentially,
+     826-833, and each buffer is inserted by one thread, 690-698), so the counts are a function of the input alone. */
 	u64v_t v = { 0, 0, 0 }; uint64_t i, j, maxl = 0, *tmp; char *buf;
 	int64_t cnt[4096]; int peak_hom, peak_het, cutoff, max_cnt;
+	const int bf_local = bf_shift - 12, use_bf = bf_shift > 12 && bf_local >= 9 && bf_local + 9 <= 64;
 	hao_ft_t *ft = CALLOC_N(hao_ft_t, 1);
 	for (i = 0; i < r->n; i++) if (r->len[i] > maxl) maxl = r->len[i];
 	buf = MALLOC_N(char, maxl + 1);
@@ -472,13 +492,21 @@ hao_ft_t *hao_ft_gen(const hao_reads_t *r, const hao_opt_t *o, int *hom_cov)
 		count_hpc_kmers(&v, o->k, (int)r->len[i], buf, o->is_hpc);
 	}
 	free(buf);
+	if (use_bf) { /* keep the occurrences the filter lets through; one extra copy of each k-mer that got in stands for the initial count of 1 */
+		const uint64_t sub_bytes = 1ULL << (bf_local - 3); uint64_t m = 0;
+		uint8_t *bf = (uint8_t *)calloc(4096, sub_bytes);
+		for (i = 0; i < v.n; i++)
+			if (bf_insert(bf + (v.a[i] & 0xfff) * sub_bytes, bf_local, 4, v.a[i] >> 12) == 4) v.a[m++] = v.a[i];
+		free(bf);
+		v.n = m;
+	}
 	tmp = MALLOC_N(uint64_t, v.n);
 	radix_sort_u64(v.a, tmp, v.n);
 	free(tmp);
 	memset(cnt, 0, sizeof(cnt));
 	for (i = 0; i < v.n; i = j) { /* ha_ct_hist, htab.cpp:240; counts saturate at 4095 (181-214) */
 		for (j = i + 1; j < v.n && v.a[j] == v.a[i]; j++) {}
-		cnt[j - i > 4095 ? 4095 : j - i]++;
+		cnt[j - i + use_bf > 4095 ? 4095 : j - i + use_bf]++;
 	}
 	peak_hom = hao_analyze_count(4096, o->min_hist_kmer_cnt, -1, cnt, &peak_het);
 	if (hom_cov) *hom_cov = peak_hom;
@@ -490,7 +518,7 @@ hao_ft_t *hao_ft_gen(const hao_reads_t *r, const hao_opt_t *o, int *hom_cov)
 	for (i = 0; i < v.n; i = j) {
 		int c;
 		for (j = i + 1; j < v.n && v.a[j] == v.a[i]; j++) {}
-		c = j - i > 4095 ? 4095 : (int)(j - i);
+		c = j - i + use_bf > 4095 ? 4095 : (int)(j - i + use_bf);
 		if (c >= cutoff && c <= 4095) { /* ha_ct_shrink(h, cutoff, YAK_MAX_COUNT) */
 			ft->key[ft->n] = v.a[i];
 			ft->val[ft->n] = c > max_cnt ? INT16_MAX : (int16_t)c;
@@ -499,6 +527,21 @@ hao_ft_t *hao_ft_gen(const hao_reads_t *r, const hao_opt_t *o, int *hom_cov)
 	}
 	free(v.a);
 	return ft;
+}
+hao_ft_t *hao_ft_gen(const hao_reads_t *r, const hao_opt_t *o, int *hom_cov) { return hao_ft_gen_bf(r, o, 0, hom_cov); } /* exact counting (-f0) */
+
+/* every HPC k-mer hash of the store in read / position order (test tooling: the probes of the filter-table parity tests) */
+uint64_t hao_all_kmers(const hao_reads_t *r, const hao_opt_t *o, uint64_t *out, uint64_t cap)
+{
+	u64v_t v = { 0, 0, 0 }; uint64_t i, maxl = 0, n; char *buf;
+	for (i = 0; i < r->n; i++) if (r->len[i] > maxl) maxl = r->len[i];
+	buf = MALLOC_N(char, maxl + 1);
+	for (i = 0; i < r->n; i++) { hao_decode(r, i, buf); count_hpc_kmers(&v, o->k, (int)r->len[i], buf, o->is_hpc); }
+	free(buf);
+	n = v.n;
+	if (out) memcpy(out, v.a, (n < cap ? n : cap) * 8);
+	free(v.a);
+	return n;
 }
 
 /* ------------------------------------------------------------------ */

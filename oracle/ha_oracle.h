@@ -80,6 +80,8 @@ int hao_sketch(const char *s, int len, int w, int k, uint32_t rid, int is_hpc, c
 
 /* ha_ft_gen (htab.cpp:1136) with exact counting (-f0) */
 hao_ft_t *hao_ft_gen(const hao_reads_t *r, const hao_opt_t *o, int *hom_cov);
+hao_ft_t *hao_ft_gen_bf(const hao_reads_t *r, const hao_opt_t *o, int bf_shift, int *hom_cov); /* -f bf_shift: the Bloom-filtered counting of ha_ft_gen */
+uint64_t hao_all_kmers(const hao_reads_t *r, const hao_opt_t *o, uint64_t *out, uint64_t cap);
 int32_t hao_ft_cnt(const hao_ft_t *ft, uint64_t y); /* ha_ft_cnt htab.cpp:1064 */
 uint64_t hao_ft_size(const hao_ft_t *ft);
 void hao_ft_destroy(hao_ft_t *ft);

@@ -44,6 +44,7 @@ def lib():
             subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
         L = C.CDLL(so)
         L.hao_ft_gen.restype = C.c_void_p
+        L.hao_ft_gen_bf.restype = C.c_void_p
         L.hao_pt_gen.restype = C.c_void_p
         L.hao_pt_get.restype = C.c_void_p
         L.hao_ft_cnt.restype = C.c_int32
@@ -106,10 +107,20 @@ def sketch(seq: bytes, w, k, rid, is_hpc, ft, sample_dist, rewin):
     return _take(out, n.value, MZ)
 
 
-def ft_gen(store: Store, opt: Opt):
+def ft_gen(store: Store, opt: Opt, bf_shift: int = 0):
+    """bf_shift = hifiasm's -f: 0 = exact counting, >= 21 = through the blocked Bloom filter (37 is hifiasm's default)"""
     hom = C.c_int()
-    ft = lib().hao_ft_gen(C.byref(store.c), C.byref(opt), C.byref(hom))
+    ft = lib().hao_ft_gen_bf(C.byref(store.c), C.byref(opt), C.c_int(bf_shift), C.byref(hom))
     return ft, hom.value
+
+
+def all_kmers(store: Store, opt: Opt):
+    """every HPC k-mer hash of the store, in read / position order"""
+    L = lib(); L.hao_all_kmers.restype = C.c_uint64
+    n = L.hao_all_kmers(C.byref(store.c), C.byref(opt), C.c_void_p(0), C.c_uint64(0))
+    out = np.zeros(max(int(n), 1), np.uint64)
+    L.hao_all_kmers(C.byref(store.c), C.byref(opt), C.c_void_p(out.ctypes.data), C.c_uint64(int(n)))
+    return out[:int(n)]
 
 
 def pt_gen(store: Store, ft, opt: Opt):

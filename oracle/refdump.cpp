@@ -409,9 +409,27 @@ static int run_stage(int argc, char *argv[])
 	return 0;
 }
 
+// refdump ftq <hashes.bin> <counts.bin> <hifiasm args...>: the reference's filter table (ha_ft_gen with the given -f, i.e. with its Bloom
+// filter when -f >= 21) probed with ha_ft_cnt (htab.cpp:1064) for every 64-bit hash of hashes.bin -> int32 counts; prints hom_cov.
+static int run_ftq(int argc, char *argv[])
+{
+	int hom_cov = -1; const char *fin = argv[2], *fout = argv[3];
+	yak_reset_realtime();
+	init_opt(&asm_opt);
+	argv[3] = argv[0];
+	if (!CommandLine_process(argc - 3, argv + 3, &asm_opt)) return 1;
+	ha_flt_tab = ha_ft_gen(&asm_opt, &R_INF, &hom_cov, 0, 0);
+	FILE *fi = fopen(fin, "rb"), *fo = fopen(fout, "wb"); if (!fi || !fo) return 1;
+	uint64_t h; while (fread(&h, 8, 1, fi) == 1) { int32_t c = ha_ft_cnt(ha_flt_tab, h); fwrite(&c, 4, 1, fo); }
+	fclose(fi); fclose(fo);
+	printf("{\"hom_cov\": %d, \"bf_shift\": %d}\n", hom_cov, asm_opt.bf_shift);
+	return 0;
+}
+
 int main(int argc, char *argv[])
 {
 	if (argc == 4 && strcmp(argv[1], "edsemi") == 0) return run_edsemi(argv[2], argv[3]);
+	if (argc >= 5 && strcmp(argv[1], "ftq") == 0) return run_ftq(argc, argv);
 	if (argc >= 3 && strcmp(argv[1], "stage") == 0) return run_stage(argc, argv);
 	if (argc >= 6 && strcmp(argv[1], "bench") == 0) return run_bench(argc, argv);
 	if (argc < 4) { fprintf(stderr, "usage: refdump <raw|final> <out_prefix> <hifiasm args...>\n"); return 1; }
