@@ -14,6 +14,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include "hb_internal.h"
+#include "hb_bloom.cuh"
 
 #define YAK_MAX_COUNT 4095 /* htab.cpp:13-15 */
 
@@ -98,27 +99,33 @@ __global__ void k_all_kmers(DevReads R, int k, int is_hpc, const uint64_t *__res
 	if (w) atomicAdd(n_real, (unsigned long long)w);
 }
 
+__global__ void k_iota(uint64_t n, uint64_t *__restrict__ out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = i; }
+
 struct IsHead { const uint64_t *k; __host__ __device__ bool operator()(uint64_t i) const { return i == 0 || k[i] != k[i - 1]; } };
 
 // run lengths -> 4096-bin histogram of counts saturated at 4095 (ha_ct_hist, htab.cpp:240)
-__global__ void k_run_hist(uint64_t n_runs, const uint64_t *__restrict__ head, uint64_t n_real, unsigned long long *__restrict__ hist)
+// fp != NULL: counting behind the Bloom filter (hb_bloom.cuh): fp[j] = the k-mer's first occurrence was a false positive; a k-mer whose
+// only counted occurrences are none never entered the table and is not in the histogram
+__global__ void k_run_hist(uint64_t n_runs, const uint64_t *__restrict__ head, uint64_t n_real, const uint8_t *__restrict__ fp, unsigned long long *__restrict__ hist)
 {
 	__shared__ unsigned int sh[4096];
 	for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh[i] = 0;
 	__syncthreads();
 	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_runs; j += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t len = (j + 1 < n_runs ? head[j + 1] : n_real) - head[j];
+		if (fp) { len = hb_bf_count(len, fp[j]); if (!len) continue; }
 		atomicAdd(&sh[len > YAK_MAX_COUNT ? YAK_MAX_COUNT : (uint32_t)len], 1u);
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < 4096; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
 // kept-run length (0 when dropped)
-__global__ void k_run_keep(uint64_t n_runs, const uint64_t *__restrict__ head, uint64_t n_real, uint32_t lo, uint32_t hi, uint32_t *__restrict__ keep_len)
+__global__ void k_run_keep(uint64_t n_runs, const uint64_t *__restrict__ head, uint64_t n_real, uint32_t lo, uint32_t hi, const uint8_t *__restrict__ fp, uint32_t *__restrict__ keep_len)
 {
 	uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n_runs) return;
 	uint64_t len = (j + 1 < n_runs ? head[j + 1] : n_real) - head[j];
+	if (fp) len = hb_bf_count(len, fp[j]);
 	if (len > YAK_MAX_COUNT) len = YAK_MAX_COUNT;
 	keep_len[j] = (len >= lo && len <= hi) ? (uint32_t)len : 0;
 }
@@ -159,7 +166,42 @@ __global__ void k_pt_gather(DevPt pt, uint64_t n, const uint32_t *__restrict__ c
 	for (uint32_t i = lane; i < cnt[j]; i += 32) dst[dst_off[j] + i] = pt.pos[off[j] + i];
 }
 
+// ---- the Bloom filter of ha_ft_gen (hb_bloom.cuh) --------------------------------------------------------------------------
+// key of a distinct k-mer (run j of the sorted hashes): its filter block, then the ordinal of its first occurrence (the pair sort is
+// stable, so the first value of a run is the smallest ordinal)
+__global__ void k_bf_key(uint64_t n_runs, const uint64_t *__restrict__ head, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ ord, int bf_local, int tbits,
+                         uint64_t *__restrict__ skey, uint64_t *__restrict__ ridx)
+{
+	uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n_runs) return;
+	skey[j] = hb_bf_block(keys[head[j]], bf_local) << tbits | ord[head[j]]; ridx[j] = j;
+}
+// one thread walks a block's k-mers in first-occurrence order through the block's 512 bits (8 registers): fp = all 4 bits set before
+__global__ void k_bf_walk(uint64_t n_runs, const uint64_t *__restrict__ skey, const uint64_t *__restrict__ ridx, int tbits, const uint64_t *__restrict__ head,
+                          const uint64_t *__restrict__ keys, int bf_local, uint8_t *__restrict__ fp)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_runs) return;
+	const uint64_t b = skey[i] >> tbits;
+	if (i && (skey[i - 1] >> tbits) == b) return; // not the first k-mer of its block
+	uint64_t st[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	for (uint64_t j = i; j < n_runs && (skey[j] >> tbits) == b; j++) { const uint64_t r = ridx[j]; fp[r] = hb_bf_insert(st, keys[head[r]], bf_local) == 4; }
+}
+
 // ---- sorted keys -> run heads + histogram ----------------------------------
+static int hist_of(hb_ctx *ctx, TmpBufs &tb, const uint64_t *d_head, uint64_t n_runs, uint64_t n_real, const uint8_t *d_fp, int64_t *h_hist)
+{
+	unsigned long long *d_hist = tb.get<unsigned long long>(4096); NEED(d_hist);
+	HB_CUDA(cudaMemsetAsync(d_hist, 0, 4096 * 8, ctx->stream));
+	if (n_runs) k_run_hist<<<std::min<unsigned>(nblk(n_runs, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(n_runs, d_head, n_real, d_fp, d_hist);
+	HB_CUDA(cudaGetLastError());
+	unsigned long long hh[4096];
+	HB_CUDA(cudaMemcpyAsync(hh, d_hist, sizeof(hh), cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < 4096; i++) h_hist[i] = (int64_t)hh[i];
+	tb.drop(d_hist);
+	return HB_OK;
+}
+// h_hist == NULL: run heads only
 static int runs_of(hb_ctx *ctx, TmpBufs &tb, const uint64_t *d_keys, uint64_t n_real, uint64_t **d_head, uint64_t *n_runs, int64_t *h_hist)
 {
 	size_t tmpb = 0; uint64_t *d_nsel = tb.get<uint64_t>(1); NEED(d_nsel);
@@ -171,15 +213,8 @@ static int runs_of(hb_ctx *ctx, TmpBufs &tb, const uint64_t *d_keys, uint64_t n_
 	HB_CUDA(cub::DeviceSelect::If(tmp, tmpb, cnt_it, d_out, d_nsel, (int64_t)n_real, pred, ctx->stream));
 	HB_CUDA(cudaMemcpyAsync(n_runs, d_nsel, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 	tb.drop(tmp);
-	unsigned long long *d_hist = tb.get<unsigned long long>(4096); NEED(d_hist);
-	HB_CUDA(cudaMemsetAsync(d_hist, 0, 4096 * 8, ctx->stream));
-	if (*n_runs) k_run_hist<<<std::min<unsigned>(nblk(*n_runs, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(*n_runs, d_out, n_real, d_hist);
-	HB_CUDA(cudaGetLastError());
-	unsigned long long hh[4096];
-	HB_CUDA(cudaMemcpyAsync(hh, d_hist, sizeof(hh), cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-	for (int i = 0; i < 4096; i++) h_hist[i] = (int64_t)hh[i];
 	*d_head = d_out;
-	return HB_OK;
+	return h_hist ? hist_of(ctx, tb, d_out, *n_runs, n_real, 0, h_hist) : HB_OK;
 }
 
 // ---- ha_ft_gen ---------------------------------------------------------------
@@ -207,12 +242,44 @@ extern "C" int hb_ft_gen(hb_ctx_t *ctx, int *hom_cov)
 	HB_CUDA(cudaGetLastError());
 	unsigned long long n_real = 0; HB_CUDA(cudaMemcpyAsync(&n_real, d_nreal, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 	size_t tmpb = 0; cub::DoubleBuffer<uint64_t> db(d_a, d_b);
-	HB_CUDA(cub::DeviceRadixSort::SortKeys(0, tmpb, db, (int64_t)tot, 0, 64, ctx->stream));
-	void *tmp = tb.get<uint8_t>(tmpb); NEED(tmp);
-	{ ProfScope ps(ctx, "sort_kmers"); HB_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmpb, db, (int64_t)tot, 0, 64, ctx->stream)); }
-	tb.drop(tmp); tb.drop(db.Alternate());
-	uint64_t *d_keys = db.Current(), *d_head = 0, n_runs = 0; int64_t hist[4096];
-	int rc = runs_of(ctx, tb, d_keys, n_real, &d_head, &n_runs, hist); if (rc) return rc; // the ~0 fillers sort last and are not counted
+	const int bf_shift = ctx->opt.bf_shift, bf_local = bf_shift - 12; const bool use_bf = hb_bf_active(bf_shift);
+	uint64_t *d_keys = 0, *d_head = 0, n_runs = 0; int64_t hist[4096]; uint8_t *d_fp = 0; int rc;
+	if (!use_bf) {
+		HB_CUDA(cub::DeviceRadixSort::SortKeys(0, tmpb, db, (int64_t)tot, 0, 64, ctx->stream));
+		void *tmp = tb.get<uint8_t>(tmpb); NEED(tmp);
+		{ ProfScope ps(ctx, "sort_kmers"); HB_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmpb, db, (int64_t)tot, 0, 64, ctx->stream)); }
+		tb.drop(tmp); tb.drop(db.Alternate());
+		d_keys = db.Current();
+		rc = runs_of(ctx, tb, d_keys, n_real, &d_head, &n_runs, hist); if (rc) return rc; // the ~0 fillers sort last and are not counted
+	} else {
+		// the reference's Bloom filter (hb_bloom.cuh): the counts depend on WHEN a k-mer first occurs, so the hashes travel with their ordinal
+		// (slot in the (read, position)-ordered array) through a stable pair sort
+		int tbits = 1; while (tbits < 64 && (tot >> tbits)) tbits++;
+		if (12 + (bf_local - 9) + tbits > 64) { hb_set_err(ctx, HB_E_ARG, "Bloom-filtered counting (-f %d) of %llu k-mers does not fit one pass (chunked counting is not built)", bf_shift, (unsigned long long)tot); return HB_E_ARG; }
+		uint64_t *d_va = tb.get<uint64_t>(tot + 1), *d_vb = tb.get<uint64_t>(tot + 1); NEED(d_va); NEED(d_vb);
+		k_iota<<<nblk(tot, 256), 256, 0, ctx->stream>>>(tot, d_va);
+		cub::DoubleBuffer<uint64_t> dv(d_va, d_vb);
+		HB_CUDA(cub::DeviceRadixSort::SortPairs(0, tmpb, db, dv, (int64_t)tot, 0, 64, ctx->stream));
+		void *tmp = tb.get<uint8_t>(tmpb); NEED(tmp);
+		{ ProfScope ps(ctx, "sort_kmers"); HB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpb, db, dv, (int64_t)tot, 0, 64, ctx->stream)); }
+		tb.drop(tmp); tb.drop(db.Alternate()); tb.drop(dv.Alternate());
+		d_keys = db.Current(); const uint64_t *d_ord = dv.Current();
+		rc = runs_of(ctx, tb, d_keys, n_real, &d_head, &n_runs, 0); if (rc) return rc;
+		uint64_t *d_sk = tb.get<uint64_t>(n_runs + 1), *d_sk2 = tb.get<uint64_t>(n_runs + 1), *d_ri = tb.get<uint64_t>(n_runs + 1), *d_ri2 = tb.get<uint64_t>(n_runs + 1);
+		d_fp = tb.get<uint8_t>(n_runs + 1); NEED(d_sk); NEED(d_sk2); NEED(d_ri); NEED(d_ri2); NEED(d_fp);
+		if (n_runs) {
+			k_bf_key<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, d_keys, d_ord, bf_local, tbits, d_sk, d_ri);
+			cub::DoubleBuffer<uint64_t> bk(d_sk, d_sk2), bv(d_ri, d_ri2); size_t tb2 = 0;
+			HB_CUDA(cub::DeviceRadixSort::SortPairs(0, tb2, bk, bv, (int64_t)n_runs, 0, 64, ctx->stream));
+			void *tmp2 = tb.get<uint8_t>(tb2); NEED(tmp2);
+			HB_CUDA(cub::DeviceRadixSort::SortPairs(tmp2, tb2, bk, bv, (int64_t)n_runs, 0, 64, ctx->stream));
+			{ ProfScope ps(ctx, "k_bf_walk"); k_bf_walk<<<nblk(n_runs, 128), 128, 0, ctx->stream>>>(n_runs, bk.Current(), bv.Current(), tbits, d_head, d_keys, bf_local, d_fp); }
+			HB_CUDA(cudaGetLastError()); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			tb.drop(tmp2);
+		}
+		tb.drop(d_sk); tb.drop(d_sk2); tb.drop(d_ri); tb.drop(d_ri2); tb.drop((void *)d_ord);
+		rc = hist_of(ctx, tb, d_head, n_runs, n_real, d_fp, hist); if (rc) return rc;
+	}
 	int peak_het, peak_hom = analyze_count(4096, ctx->opt.min_hist_kmer_cnt, -1, hist, &peak_het); // htab.cpp:1155-1161
 	if (hom_cov) *hom_cov = peak_hom;
 	int cutoff = (int)(peak_hom * ctx->opt.high_factor); if (cutoff > YAK_MAX_COUNT - 1) cutoff = YAK_MAX_COUNT - 1;
@@ -224,7 +291,7 @@ extern "C" int hb_ft_gen(hb_ctx_t *ctx, int *hom_cov)
 		uint32_t *d_keep = tb.get<uint32_t>(n_runs + 1); NEED(d_keep);
 		HB_CUDA(cudaMalloc((void **)&ctx->d_ft_key, cap * 8)); HB_CUDA(cudaMalloc((void **)&ctx->d_ft_val, cap * 4));
 		HB_CUDA(cudaMemsetAsync(ctx->d_ft_key, 0, cap * 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(ctx->d_ft_val, 0, cap * 4, ctx->stream));
-		k_run_keep<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, n_real, cutoff < 1 ? 1 : (uint32_t)cutoff, YAK_MAX_COUNT, d_keep);
+		k_run_keep<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, n_real, cutoff < 1 ? 1 : (uint32_t)cutoff, YAK_MAX_COUNT, d_fp, d_keep);
 		k_ft_insert<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, d_keys, d_keep, (uint32_t)max_cnt, cap - 1, ctx->d_ft_key, ctx->d_ft_val);
 		HB_CUDA(cudaGetLastError());
 		ctx->ft_cap = cap;
@@ -284,7 +351,7 @@ extern "C" int hb_pt_gen(hb_ctx_t *ctx, int *hom_cov, int *het_cov)
 	uint64_t cap = 64; while (cap < 2 * n_keys) cap <<= 1;
 	uint32_t *d_keep = tb.get<uint32_t>(n_runs + 2); uint64_t *d_poff = tb.get<uint64_t>(n_runs + 2); NEED(d_keep); NEED(d_poff);
 	HB_CUDA(cudaMemsetAsync(d_keep, 0, (n_runs + 2) * 4, ctx->stream));
-	if (n_runs) k_run_keep<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, n, (uint32_t)lo, (uint32_t)hi, d_keep);
+	if (n_runs) k_run_keep<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, n, (uint32_t)lo, (uint32_t)hi, 0, d_keep);
 	rc = hb_scan_u32_to_u64(ctx, d_keep, d_poff, n_runs); if (rc) return rc;
 	HB_CUDA(cudaMalloc((void **)&ctx->d_pt_slot, cap * 16)); HB_CUDA(cudaMalloc((void **)&ctx->d_pt_pos, (n_pos + 4) * 8));
 	HB_CUDA(cudaMemsetAsync(ctx->d_pt_slot, 0, cap * 16, ctx->stream)); HB_CUDA(cudaMemsetAsync(ctx->d_pt_pos, 0, (n_pos + 4) * 8, ctx->stream));

@@ -39,7 +39,7 @@ class HBError(RuntimeError):
 class Opt(C.Structure):
     _fields_ = [("k_mer_length", C.c_int32), ("mz_win", C.c_int32), ("is_hpc", C.c_int32), ("mz_sample_dist", C.c_int32),
                 ("mz_rewin", C.c_int32), ("min_hist_kmer_cnt", C.c_int32), ("max_kmer_cnt", C.c_int32), ("max_n_chain", C.c_int32),
-                ("high_factor", C.c_double), ("hom_cov", C.c_int32), ("het_cov", C.c_int32), ("is_ont", C.c_int32)]
+                ("high_factor", C.c_double), ("hom_cov", C.c_int32), ("het_cov", C.c_int32), ("is_ont", C.c_int32), ("bf_shift", C.c_int32)]
 
 
 def lib_path() -> str:

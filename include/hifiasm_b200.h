@@ -42,6 +42,8 @@ typedef struct {
 	double  high_factor;       /* -D, CommandLines.cpp:271 (5.0) */
 	int32_t hom_cov, het_cov;  /* asm_opt.hom_cov / het_cov */
 	int32_t is_ont;            /* --ont (not supported yet: must be 0) */
+	int32_t bf_shift;          /* -f, CommandLines.cpp:269: bits of the Bloom filter in front of ha_ft_gen's counting; 0 (hb_opt_init) = exact
+	                              counting = hifiasm -f0; hifiasm's own default is 37.  Active from 21 (htab.cpp:140-158, 78-91) */
 } hb_opt_t;
 
 /* ha_mz1_t (htab.h:13-18): x = hash, info = rid:28 | pos:27 | rev:1 | span:8 */

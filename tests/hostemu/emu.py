@@ -257,3 +257,11 @@ def ec_cns(reads, rid, ph, alnb, wl, pool, cap=1 << 16, g_nodes=0, g_arcs=0):
                           _p(out), C.c_uint32(cap), C.byref(n), C.byref(nec), C.c_uint32(g_nodes), C.c_uint32(g_arcs))
     assert rc in (0, 1, 3), rc
     return rc, out[:n.value], int(nec.value)
+
+
+def bf_counts(hashes, bf_shift):
+    """counting behind the reference's Bloom filter as index.cu evaluates it -> (keys, counts) of the k-mers in the table, by key"""
+    h = np.ascontiguousarray(hashes, dtype=np.uint64); L = lib(); L.emu_bf_counts.restype = C.c_uint64
+    key = np.zeros(h.size + 1, np.uint64); cnt = np.zeros(h.size + 1, np.uint32)
+    m = L.emu_bf_counts(_p(h), C.c_uint64(h.size), C.c_int(bf_shift), _p(key), _p(cnt), C.c_uint64(h.size))
+    return key[:m], cnt[:m]

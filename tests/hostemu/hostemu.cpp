@@ -15,6 +15,7 @@
 #include "../../hifiasm_b200/csrc/hb_final.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecaln.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecrechain.cuh"
+#include "../../hifiasm_b200/csrc/hb_bloom.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecphase.cuh"
 #include "../../hifiasm_b200/csrc/hb_ecround.cuh"
 #include "../../hifiasm_b200/csrc/hb_eccns.cuh"
@@ -538,6 +539,37 @@ int emu_ec_cns(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t 
 	*nec = g_nodes ? hb_cns_read<true>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data()) : hb_cns_read<false>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
 	*n_out = C.out_n;
 	return C.need_full ? (C.need_full == 2 ? 3 : 1) : (C.ovf ? 2 : 0);
+}
+
+// counting behind the reference's Bloom filter the way index.cu evaluates it (hb_bloom.cuh): distinct k-mers with the ordinal of their first
+// occurrence, grouped by filter block, walked in first-occurrence order.  hashes = every k-mer of the store in (read, position) order.
+// -> (key, count) of the k-mers that entered the table, by key.
+uint64_t emu_bf_counts(const uint64_t *hashes, uint64_t n, int bf_shift, uint64_t *out_key, uint32_t *out_cnt, uint64_t cap)
+{
+	const int bf_local = bf_shift - 12; const bool use_bf = hb_bf_active(bf_shift);
+	std::vector<std::pair<uint64_t, uint64_t>> a(n); // (hash, ordinal): the stable pair sort
+	for (uint64_t i = 0; i < n; i++) a[i] = std::make_pair(hashes[i], i);
+	std::sort(a.begin(), a.end());
+	struct Run { uint64_t key, first, len; uint8_t fp; };
+	std::vector<Run> runs;
+	for (uint64_t i = 0, j; i < n; i = j) { for (j = i + 1; j < n && a[j].first == a[i].first; j++) {} Run r = { a[i].first, a[i].second, j - i, 0 }; runs.push_back(r); }
+	if (use_bf) {
+		std::vector<std::pair<std::pair<uint64_t, uint64_t>, uint64_t>> o(runs.size()); // ((block, first ordinal), run)
+		for (uint64_t j = 0; j < runs.size(); j++) o[j] = std::make_pair(std::make_pair(hb_bf_block(runs[j].key, bf_local), runs[j].first), j);
+		std::sort(o.begin(), o.end());
+		for (uint64_t i = 0, j; i < o.size(); i = j) {
+			uint64_t st[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			for (j = i; j < o.size() && o[j].first.first == o[i].first.first; j++) runs[o[j].second].fp = hb_bf_insert(st, runs[o[j].second].key, bf_local) == 4;
+		}
+	}
+	uint64_t m = 0;
+	for (auto &r : runs) {
+		const uint32_t c = use_bf ? hb_bf_count(r.len, r.fp) : (uint32_t)(r.len > 4095 ? 4095 : r.len);
+		if (!c) continue;
+		if (m < cap) { out_key[m] = r.key; out_cnt[m] = c; }
+		m++;
+	}
+	return m;
 }
 
 } // extern "C"

@@ -1,7 +1,7 @@
 """The filter table with the reference's Bloom filter (hifiasm -f 21 / 22 / 24; -f 37 is its default): tests/golden/bloom.npz holds what the
 UNMODIFIED reference's ha_ft_gen + ha_ft_cnt answer for every distinct k-mer of a read set on which the filter changes the table
 (tests/golden/make_bloom.py).  CPU: the oracle restatement (hao_ft_gen_bf) and the device function of the filter (hb_bf_insert, host
-emulation).  GPU (test_gpu_bloom): hb_ft_gen with opt.bf_shift through the C-ABI."""
+emulation).  GPU: tests/test_zz_gpu_rechain.py::test_gpu_bloom, hb_ft_gen with opt.bf_shift through the C-ABI."""
 import ctypes as C
 import os
 import sys
@@ -40,19 +40,18 @@ def test_oracle_bloom_counting_vs_reference(data, shift):
         assert key.size > z["f0_key"].size
 
 
-@pytest.mark.gpu
-@pytest.mark.xfail(reason="hb_ft_gen's Bloom path (opt.bf_shift > 0) was written after the round's GPU budget was spent: not yet run on a B200", strict=False)
 @pytest.mark.parametrize("shift", make_bloom.SHIFTS)
-def test_gpu_bloom(data, shift):
-    import hifiasm_b200
+def test_device_formulation_vs_reference(data, shift):
+    """hb_bloom.cuh + the way index.cu evaluates the filter (distinct k-mers grouped by filter block, walked in first-occurrence order)
+    instead of streaming every occurrence through 4096 filters: same table as the reference"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu"))
+    import emu
     z, (ln, flat, boff, npos, noff) = data
-    eng = hifiasm_b200.Engine(0)
-    eng.set_opt(bf_shift=shift)
-    eng.upload_reads(ln, flat, boff, npos, noff)
-    hom = eng.ft_gen()
-    key, cnt = z["f%d_key" % shift], z["f%d_cnt" % shift]
-    assert hom == int(z["f%d_hom" % shift][0]) and eng.ft_size() == key.size
-    assert (eng.ft_cnt(key) == cnt).all()
-    rng = np.random.default_rng(1)
-    assert (eng.ft_cnt(rng.integers(0, 2**63, 1000, dtype=np.uint64)) == 0).all()
-    eng.close()
+    st = ho.Store(ln, boff, flat, noff, npos)
+    key, cnt = emu.bf_counts(ho.all_kmers(st, ho.default_opt()), shift)
+    hom = int(z["f%d_hom" % shift][0]); cutoff = int(hom * 5.0)   # ha_ft_gen: cutoff = peak_hom * high_factor, table = counts in [cutoff, 4095]
+    rk, rc = z["f%d_key" % shift], z["f%d_cnt" % shift]
+    keep = cnt >= cutoff
+    assert int(keep.sum()) == rk.size and (key[keep] == rk).all()
+    c = cnt[keep].astype(np.int64); c[c > 2000] = 2**31 - 1   # gen_hh: counts above max_kmer_cnt read as INT32_MAX (htab.cpp:1038-1070)
+    assert (c == rc.astype(np.int64)).all()

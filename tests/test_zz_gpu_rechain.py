@@ -52,3 +52,28 @@ def test_whole_stage_from_raw_reads_g4(hb, tmp_path):
     """raw reads -> three EC rounds -> final pass on the device, byte-identical ovlp.*.bin, with the rescue on the path"""
     import test_gpu_round as tr
     tr.test_whole_stage_from_raw_reads(hb, "g4", tmp_path)
+
+
+# ---- the filter table behind the reference's Bloom filter (opt.bf_shift = hifiasm -f): CPU side in tests/test_bloom.py
+import numpy as np  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+
+@pytest.mark.xfail(reason="hb_ft_gen's Bloom path (opt.bf_shift > 0) was written after the round's GPU budget was spent: not yet run on a B200; its formulation is pinned in host emulation (tests/test_bloom.py)", strict=False)
+@pytest.mark.parametrize("shift", [0, 21, 22, 24])
+def test_gpu_bloom(hb, shift):
+    import make_bloom
+    from goldenlib import GOLDEN
+    from hifiasm_b200 import sim
+    z = np.load(os.path.join(GOLDEN, "bloom.npz"))
+    flat, boff, ln, npos, noff = sim.pack_reads(make_bloom.reads())
+    eng = hb.Engine(0)
+    eng.set_opt(bf_shift=shift)
+    eng.upload_reads(ln, flat, boff, npos, noff)
+    hom = eng.ft_gen()
+    key, cnt = z["f%d_key" % shift], z["f%d_cnt" % shift]
+    assert hom == int(z["f%d_hom" % shift][0]) and eng.ft_size() == key.size
+    assert (eng.ft_cnt(key) == cnt).all()
+    rng = np.random.default_rng(1)
+    assert (eng.ft_cnt(rng.integers(0, 2**63, 1000, dtype=np.uint64)) == 0).all()
+    eng.close()
