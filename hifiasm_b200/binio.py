@@ -218,3 +218,30 @@ def native_write_ec_bin(path: str, rs: ReadStore) -> None:
                            p(a[0]), p(a[1]), p(a[2]), p(a[3]), p(a[4]), p(blob), C.c_uint64(len(rs.name_blob)), p(idx), p(tf), C.c_int32(rs.hom_cov), C.c_int32(rs.het_cov))
     if rc:
         raise IOError("hb_write_ec_bin(%s) -> %d" % (path, rc))
+
+
+def native_load_reads(paths, adapter_len: int = 0) -> ReadStore:
+    """hb_readset_load: FASTA / FASTQ (plain or gzip) -> ReadStore, the reference's ingest (htab.cpp:761-813, ha_compress_base Process_Read.cpp:792)"""
+    import ctypes as C
+    L, p = _native()
+
+    class RS(C.Structure):
+        _fields_ = [(k, C.c_uint64) for k in ("n_reads", "total_bases", "total_name_length", "index_size", "name_index_size")] + \
+                   [(k, C.c_void_p) for k in ("read_length", "byte_off", "packed", "n_off", "n_pos", "names", "name_index")]
+    if isinstance(paths, str):
+        paths = [paths]
+    arr = (C.c_char_p * len(paths))(*[q.encode() for q in paths]); rs = RS()
+    rc = L.hb_readset_load(arr, C.c_int(len(paths)), C.c_int32(adapter_len), C.byref(rs))
+    if rc:
+        raise IOError("hb_readset_load(%s) -> %d" % (paths, rc))
+
+    def take(ptr, n, dt):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(int(n) * np.dtype(dt).itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
+    n = int(rs.n_reads)
+    boff = take(rs.byte_off, n + 1, np.uint64); noff = take(rs.n_off, n + 1, np.uint64)
+    out = ReadStore(length=take(rs.read_length, n, np.uint64), byte_off=boff, packed=take(rs.packed, int(boff[-1]), np.uint8), n_off=noff, n_pos=take(rs.n_pos, int(noff[-1]), np.uint64),
+                    trio_flag=np.zeros(n, np.uint8), adapter_len=adapter_len, index_size=int(rs.index_size), name_index_size=int(rs.name_index_size), total_reads_bases=int(rs.total_bases),
+                    name_blob=take(rs.names, int(rs.total_name_length), np.uint8).tobytes(), name_index=take(rs.name_index, int(rs.name_index_size), np.uint64))
+    out.names = [out.name_blob[int(out.name_index[i]):int(out.name_index[i + 1])].decode() for i in range(n)]
+    L.hb_readset_free(C.byref(rs))
+    return out

@@ -255,6 +255,16 @@ int hb_ed_semi_64(hb_ctx_t *ctx, uint64_t n_cases, const char *pat, const uint64
  *   hb_write_ovlp_bin  write_ma_hit_ts, Overlaps.cpp:23442-23465 (<o>.ovlp.source.bin / <o>.ovlp.reverse.bin; flags may be NULL = 0)
  *   hb_write_ec_bin    write_All_reads, Process_Read.cpp:69-125 (<o>.ec.bin; the pad byte of reads with len % 4 == 0 is whatever
  *                      packed[] holds — the reference leaves it uninitialised)                                     */
+/* ingest (htab.cpp:761-813 step 0 + ha_insert_read_len Process_Read.cpp:414 + ha_compress_base 792): FASTA / FASTQ files, plain or gzip, ->
+ * the flat All_reads arrays hb_reads_upload takes (read i: packed[byte_off[i] .. +len/4+1), N sites n_pos[n_off[i] .. n_off[i+1]), name
+ * names[name_index[i] .. name_index[i+1])).  adapter_len = -z (bases trimmed from both ends; reads that become empty are skipped).
+ * All arrays are malloc-owned: hb_readset_free releases them.                                                                        */
+typedef struct {
+	uint64_t n_reads, total_bases, total_name_length, index_size, name_index_size; /* the All_reads header fields write_All_reads stores */
+	uint64_t *read_length, *byte_off; uint8_t *packed; uint64_t *n_off, *n_pos; char *names; uint64_t *name_index;
+} hb_readset_t;
+int hb_readset_load(const char *const *paths, int n_paths, int32_t adapter_len, hb_readset_t *out);
+void hb_readset_free(hb_readset_t *rs);
 int hb_write_paf(const char *path, uint64_t n_reads, const uint64_t *read_length, const char *names, const uint64_t *name_index,
                  const uint64_t *off, const hb_ma_hit_t *rec);
 int hb_write_ec_fa(const char *path, uint64_t n_reads, const uint64_t *read_length, const uint8_t *packed, const uint64_t *byte_off,

@@ -59,3 +59,37 @@ def test_writers_report_io_errors(tmp_path):
     bad = binio.disk_to_mem(f0[:1].copy()); bad["tn"] = g.pre.n + 5
     with pytest.raises(IOError):
         binio.native_write_paf(str(tmp_path / "x.paf"), g.pre, bad, np.array([0, 1] + [1] * (g.pre.n - 1), np.uint64))
+
+
+@pytest.mark.parametrize("name", ["g1", "g3"])
+def test_native_ingest_matches_the_reference(name, tmp_path):
+    """hb_readset_load (FASTA / gzip FASTA / FASTQ -> the All_reads layout) against the reference's own R_INF right after it parsed the same
+    file (the golden raw ec.bin): lengths, 2-bit reads, N sites, names, and the header fields write_All_reads stores"""
+    import gzip
+    import sys
+    sys.path.insert(0, os.path.join(GOLDEN))
+    import make_golden as mg
+    from hifiasm_b200 import sim
+    g = Golden(name); gk, rk = mg.DATASETS[name]
+    h1, h2 = sim.sim_genome(**gk); reads = sim.sim_reads(h1, h2, **rk)
+    fa = str(tmp_path / "reads.fa"); sim.write_fasta(fa, reads)
+    gz = str(tmp_path / "reads.fa.gz"); open(gz, "wb").write(gzip.compress(open(fa, "rb").read()))
+    fq = str(tmp_path / "reads.fq")   # FASTQ with wrapped lines and a description after the name
+    with open(fq, "w") as f:
+        for nm, r in zip(g.raw.names, reads):
+            s = np.frombuffer(b"ACGTN", np.uint8)[r].tobytes().decode()
+            f.write("@%s some description\n%s\n%s\n+\n%s\n" % (nm, s[:70], s[70:], "I" * len(s)))
+    for path in (fa, gz, fq):
+        rs = binio.native_load_reads(path)
+        assert rs.n == g.raw.n and (rs.length == g.raw.length).all() and rs.names == g.raw.names
+        assert (rs.n_off == g.raw.n_off).all() and (rs.n_pos == g.raw.n_pos).all()
+        assert (binio.canonical_packed(rs) == binio.canonical_packed(g.raw)).all()
+        assert (rs.index_size, rs.name_index_size, rs.total_reads_bases, rs.name_blob) == (g.raw.index_size, g.raw.name_index_size, g.raw.total_reads_bases, g.raw.name_blob)
+        assert (rs.name_index[:rs.n + 1] == g.raw.name_index[:rs.n + 1]).all()
+    # two files = one read set in file order; adapter trimming drops what becomes empty
+    two = binio.native_load_reads([fa, gz])
+    assert two.n == 2 * g.raw.n and (two.length[g.raw.n:] == g.raw.length).all()
+    cut = binio.native_load_reads(fa, adapter_len=int(g.raw.length.min()) // 2 + 1)
+    assert cut.n < g.raw.n and (cut.length > 0).all()
+    with pytest.raises(IOError):
+        binio.native_load_reads(str(tmp_path / "missing.fa"))

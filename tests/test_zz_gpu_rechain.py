@@ -77,3 +77,25 @@ def test_gpu_bloom(hb, shift):
     rng = np.random.default_rng(1)
     assert (eng.ft_cnt(rng.integers(0, 2**63, 1000, dtype=np.uint64)) == 0).all()
     eng.close()
+
+
+# ---- FASTA in, the reference's files out: hifiasm_b200.stage.run_stage (every step a C-ABI call that is GPU-checked on its own; this glue is new)
+@pytest.mark.xfail(reason="stage.run_stage (glue over GPU-checked C-ABI calls) was written after the round's GPU budget was spent: not yet run on a B200", strict=False)
+@pytest.mark.parametrize("name", ["g1", "g3"])
+def test_run_stage_fasta_to_files(hb, name, tmp_path):
+    import hashlib
+    import make_golden as mg
+    from goldenlib import GOLDEN
+    from hifiasm_b200 import sim, binio, stage
+    gk, rk = mg.DATASETS[name]
+    h1, h2 = sim.sim_genome(**gk)
+    fa = str(tmp_path / "reads.fa"); sim.write_fasta(fa, sim.sim_reads(h1, h2, **rk))
+    pfx = str(tmp_path / "asm")
+    info = stage.run_stage(fa, pfx)
+    z = np.load(os.path.join(GOLDEN, "outputs.npz"))
+    for suf, key in (("ovlp.paf", "paf"), ("ec.fa", "ecfa"), ("ovlp.source.bin", "src"), ("ovlp.reverse.bin", "rev")):
+        b = open("%s.%s" % (pfx, suf), "rb").read()
+        assert len(b) == int(z["%s_%s_size" % (name, key)][0]) and (np.frombuffer(hashlib.blake2b(b, digest_size=16).digest(), np.uint8) == z["%s_%s_dg" % (name, key)]).all(), suf
+    g = Golden(name); mine = binio.load_ec_bin(pfx + ".ec.bin")
+    assert (mine.length == g.pre.length).all() and (binio.canonical_packed(mine) == binio.canonical_packed(g.pre)).all() and mine.name_blob == g.pre.name_blob
+    assert mine.total_reads_bases == g.pre.total_reads_bases and info["reads"] == g.pre.n and os.path.getsize(pfx + ".ec.bin") == int(z["%s_ecbin_size" % name][0])
