@@ -292,6 +292,13 @@ class Engine:
         self._ck(_lib().hb_ec_post_rev(self.h, _p(paf if paf.size else np.zeros(1, MA)), _p(off), _p(rpaf if rpaf.size else np.zeros(1, MA)), _p(roff)))
         return paf[:int(off[-1])], off, rpaf[:int(roff[-1])], roff
 
+    def read_lengths(self):
+        """lengths of the resident reads (u64[n])"""
+        n = self.n_reads
+        ln = np.zeros(n, np.uint64); noff = np.zeros(n + 1, np.uint64); z = C.c_void_p(0)
+        self._ck(_lib().hb_reads_download(self.h, _p(ln), z, C.c_uint64(0), _p(noff), z, C.c_uint64(0)))
+        return ln
+
     def download_reads(self):
         """the resident read store -> binio.ReadStore (All_reads layout)"""
         from . import binio

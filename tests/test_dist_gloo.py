@@ -55,3 +55,52 @@ def test_shard_range_edges():
     assert hdist.shard_range(2, 3, 4) == (2, 2)  # empty shard
     tot = sum(b - a for a, b in (hdist.shard_range(12345, r, 8) for r in range(8)))
     assert tot == 12345
+
+
+# ---- the exchange step that ends an EC round on N GPUs (hifiasm_b200.dist.all_gather_ragged / cal_ec_r_sharded) ----
+def _worker_ragged(rank, world, port, n_reads, q):
+    from hifiasm_b200 import binio
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r0, r1 = hdist.shard_range(n_reads, rank, world)
+    # overlap records (48-byte ma_hit_t mirror) and edit scripts (uint16 runs) of the shard: read i has i % 4 records and (7 * i) % 5 runs
+    cnt = np.array([i % 4 for i in range(r0, r1)], dtype=np.uint64); off = np.zeros(r1 - r0 + 1, np.uint64); np.cumsum(cnt, out=off[1:])
+    rec = np.zeros(int(off[-1]), binio.MA_MEM); rec["qns"] = np.repeat(np.arange(r0, r1, dtype=np.uint64), cnt.astype(np.int64)) << np.uint64(32); rec["tn"] = np.arange(rec.size) + 1000 * rank
+    c2 = np.array([(7 * i) % 5 for i in range(r0, r1)], dtype=np.uint64); o2 = np.zeros(r1 - r0 + 1, np.uint64); np.cumsum(c2, out=o2[1:])
+    sc = (np.repeat(np.arange(r0, r1, dtype=np.uint64), c2.astype(np.int64)) & np.uint64(0xffff)).astype(np.uint16)
+    big = np.zeros(int(off[-1]) + 7, binio.MA_MEM); big[:rec.size] = rec   # buffers may be larger than what the offsets cover
+    a_rec, a_off = hdist.all_gather_ragged(big, off)
+    s_rec, s_off = hdist.all_gather_ragged(sc, o2)
+    flags = np.concatenate(hdist.all_gather_bytes(np.full((r1 - r0, 3), rank, np.uint8))).reshape(-1, 3)
+    q.put((rank, a_rec.tobytes(), a_off, s_rec.tobytes(), s_off, flags))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_ragged_world2():
+    from hifiasm_b200 import binio
+    world, n_reads = 2, 203
+    ctx = mp.get_context("spawn"); q = ctx.Queue(); port = _free_port()
+    ps = [ctx.Process(target=_worker_ragged, args=(r, world, port, n_reads, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda x: x[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # every rank ends with the same global arrays, in read-id order
+    assert res[0][1] == res[1][1] and (res[0][2] == res[1][2]).all() and res[0][3] == res[1][3] and (res[0][4] == res[1][4]).all() and (res[0][5] == res[1][5]).all()
+    rec = np.frombuffer(res[0][1], binio.MA_MEM); off = res[0][2]; sc = np.frombuffer(res[0][3], np.uint16); so = res[0][4]
+    assert off.size == n_reads + 1 and int(off[-1]) == rec.size and so.size == n_reads + 1 and int(so[-1]) == sc.size
+    for i in (0, 1, 50, 101, 102, 150, 202):
+        assert int(off[i + 1] - off[i]) == i % 4 and ((rec["qns"][int(off[i]):int(off[i + 1])] >> np.uint64(32)) == i).all()
+        assert int(so[i + 1] - so[i]) == (7 * i) % 5 and (sc[int(so[i]):int(so[i + 1])] == i).all()
+    r0, r1 = hdist.shard_range(n_reads, 1, world)
+    assert (res[0][5][:r0] == 0).all() and (res[0][5][r0:] == 1).all()
+
+
+def test_single_process_is_the_identity():
+    from hifiasm_b200 import binio
+    rec = np.zeros(5, binio.MA_MEM); rec["tn"] = np.arange(5); off = np.array([0, 2, 2, 5], np.uint64)
+    a, o = hdist.all_gather_ragged(rec, off)
+    assert a.tobytes() == rec.tobytes() and (o == off).all()

@@ -99,3 +99,27 @@ def test_run_stage_fasta_to_files(hb, name, tmp_path):
     g = Golden(name); mine = binio.load_ec_bin(pfx + ".ec.bin")
     assert (mine.length == g.pre.length).all() and (binio.canonical_packed(mine) == binio.canonical_packed(g.pre)).all() and mine.name_blob == g.pre.name_blob
     assert mine.total_reads_bases == g.pre.total_reads_bases and info["reads"] == g.pre.n and os.path.getsize(pfx + ".ec.bin") == int(z["%s_ecbin_size" % name][0])
+
+
+# ---- the EC rounds sharded over ranks (hifiasm_b200.dist.cal_ec_r_sharded): with one process it must equal hb_cal_ec_r; N > 1 runs under
+# torchrun with tools/ec_sharded_check.py (the exchange helpers are covered by tests/test_dist_gloo.py on the CPU)
+@pytest.mark.xfail(reason="dist.cal_ec_r_sharded (granular C-ABI calls + all-gather) was written after the round's GPU budget was spent: not yet run on a B200", strict=False)
+def test_sharded_round_single_rank_equals_cal_ec_r(hb):
+    import roundlib
+    from hifiasm_b200 import binio, dist as hdist
+    g = Golden("g1"); rd = roundlib.Rounds("g1")
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw)
+    hom = eng.ft_gen(); eng.update_cov(hom)
+    n = g.raw.n
+    src = np.zeros(0, binio.MA_MEM); soff = np.zeros(n + 1, np.uint64)
+    for K in range(3):
+        hom_k, het_k = eng.pt_gen(); eng.set_opt(hom_cov=hom_k, het_cov=het_k)
+        r = hdist.cal_ec_r_sharded(eng, K, 1 if K == 2 else 0, src, soff)
+        assert not r["status"].any()
+        p = rd.params(K)
+        assert (r["tot_b"], r["tot_e"]) == (int(p["tot_b"]), int(p["tot_e"]))
+        src, soff, rev, roff = r["src"], r["src_off"], r["rev"], r["rev_off"]
+        assert (roundlib.list_digests(src, soff, 0) == rd.digest(K, "post_src")).all() and (roundlib.list_digests(rev, roff, 1) == rd.digest(K, "post_rev")).all()
+    assert (roundlib.reads_digests(eng.download_reads()) == roundlib.reads_digests(g.pre)).all()
+    eng.close()
