@@ -5,9 +5,10 @@
 #   2. the whole GPU suite
 #   3. one default bench run (JSON line -> gpurun_out/bench_n1.json, stderr -> gpurun_out/bench_n1.err)
 # Usage: /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
+# then, on 2 GPUs:  /usr/local/graft/bin/gpurun --gpus 2 --timeout 600 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ec_sharded_check.py g1'
 mkdir -p gpurun_out
 export HB_TRACE_EC=1
-for t in test_whole_stage_from_raw_reads_g4 test_stages_raw_g4 test_stages_final_g4 test_gpu_bloom test_run_stage_fasta_to_files; do
+for t in test_whole_stage_from_raw_reads_g4 test_stages_raw_g4 test_stages_final_g4 test_gpu_bloom test_run_stage_fasta_to_files test_sharded_round_single_rank_equals_cal_ec_r; do
 	timeout 300 python -m pytest tests/test_zz_gpu_rechain.py -m gpu -q -x --runxfail -k "$t" > gpurun_out/zz_$t.log 2>&1
 	echo "== $t: $(tail -1 gpurun_out/zz_$t.log)"
 done
