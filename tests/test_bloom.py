@@ -1,7 +1,7 @@
 """The filter table with the reference's Bloom filter (hifiasm -f 21 / 22 / 24; -f 37 is its default): tests/golden/bloom.npz holds what the
 UNMODIFIED reference's ha_ft_gen + ha_ft_cnt answer for every distinct k-mer of a read set on which the filter changes the table
 (tests/golden/make_bloom.py).  CPU: the oracle restatement (hao_ft_gen_bf) and the device function of the filter (hb_bf_insert, host
-emulation).  GPU: tests/test_zz_gpu_rechain.py::test_gpu_bloom, hb_ft_gen with opt.bf_shift through the C-ABI."""
+emulation).  GPU: tests/test_zz_gpu_not_yet_run.py::test_gpu_bloom, hb_ft_gen with opt.bf_shift through the C-ABI."""
 import ctypes as C
 import os
 import sys

@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of a round (run under gpurun from the repo root):
-#   1. the device paths written after round 1's GPU budget was spent (tests/test_zz_gpu_rechain.py), each in its own process with --runxfail,
+#   1. the device paths written after round 1's GPU budget was spent (tests/test_zz_gpu_not_yet_run.py), each in its own process with --runxfail,
 #      so a failure shows its traceback and a crash cannot poison the next one
 #   2. the whole GPU suite
 #   3. one default bench run (JSON line -> gpurun_out/bench_n1.json, stderr -> gpurun_out/bench_n1.err)
@@ -9,7 +9,7 @@
 mkdir -p gpurun_out
 export HB_TRACE_EC=1
 for t in test_whole_stage_from_raw_reads_g4 test_stages_raw_g4 test_stages_final_g4 test_gpu_bloom test_run_stage_fasta_to_files test_sharded_round_single_rank_equals_cal_ec_r; do
-	timeout 300 python -m pytest tests/test_zz_gpu_rechain.py -m gpu -q -x --runxfail -k "$t" > gpurun_out/zz_$t.log 2>&1
+	timeout 300 python -m pytest tests/test_zz_gpu_not_yet_run.py -m gpu -q -x --runxfail -k "$t" > gpurun_out/zz_$t.log 2>&1
 	echo "== $t: $(tail -1 gpurun_out/zz_$t.log)"
 done
 unset HB_TRACE_EC
