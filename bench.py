@@ -184,6 +184,64 @@ def main():
         return 1
 
 
+def whole_stage_aux(local):
+    """child process of the bench (--aux-whole-stage): the whole stage on the small raw read set of the EC aux, one JSON line on stdout"""
+    import torch
+    import hifiasm_b200
+    from hifiasm_b200 import sim
+    torch.cuda.set_device(local)
+    h1, h2 = sim.sim_genome(int(os.environ.get("HB_BENCH_EC_GENOME", "6000000")), 77, snp_rate=SNP)
+    rr = sim.sim_reads(h1, h2, COV, MEAN_LEN, 77, sd_len=SD_LEN, min_len=2000, err=0.002)
+    fl, bo, ln, npos, noff = sim.pack_reads(rr)
+    nq = len(rr); qb = int(ln.sum()); aux = {}
+    # ---- the WHOLE stage the way SURVEY.md §8(d) defines the metric (first ha_ft_gen -> end of the final overlap pass), on the same small raw
+    # read set: filter table, 3 x (index build + hb_cal_ec_r), final index, hb_cal_ov_r — host buffers in and out of every C-ABI call — next to
+    # the unmodified reference doing the same on the host cores (oracle/_ref/refdump stage).  Not the headline yet (DESIGN.md §8).
+    try:
+        e3 = hifiasm_b200.Engine(local)
+        torch.cuda.synchronize(); tw = time.time()
+        e3.upload_reads(ln, fl, bo, npos, noff)
+        hm3 = e3.ft_gen(); e3.update_cov(hm3)
+        MA = hifiasm_b200.binio.MA_MEM
+        src = np.zeros(0, MA); soff = np.zeros(nq + 1, np.uint64); rev = src.copy(); roff = soff.copy(); t_round = []; unfinished = 0; tot_e = 0; kms_ws = {}
+        for K in range(3):
+            tk = time.time()
+            a3, b3 = e3.pt_gen(); e3.set_opt(hom_cov=a3, het_cov=b3)
+            rr3 = e3.cal_ec_r(K, 1 if K == 2 else 0, src, soff)
+            src, soff, rev, roff = rr3["src"], rr3["src_off"], rr3["rev"], rr3["rev_off"]
+            unfinished += int((rr3["status"] != 0).sum()); tot_e += rr3["tot_e"]
+            torch.cuda.synchronize(); t_round.append(round((time.time() - tk) * 1e3, 1))
+            for k, v in e3.profile().items():
+                kms_ws[k] = kms_ws.get(k, 0.0) + v[1]
+        tk = time.time()
+        a3, b3 = e3.pt_gen(); e3.set_opt(hom_cov=a3, het_cov=b3)
+        o0, q0, o1, q1, _ = e3.cal_ov_r(src, soff, rev, roff)
+        torch.cuda.synchronize(); t_final = time.time() - tk; wall_ws = time.time() - tw
+        top = sorted(kms_ws.items(), key=lambda kv: -kv[1])[:8]
+        aux["whole_stage"] = {"reads": nq, "bases": qb, "seconds": wall_ws, "gbp_s": qb / wall_ws / 1e9, "round_ms": t_round, "final_ms": round(t_final * 1e3, 1),
+                              "corrected_bases": int(tot_e), "reads_not_finished": unfinished, "overlaps_src": int(o0.size), "overlaps_rev": int(o1.size),
+                              "top_kernels_ms_in_ec_rounds": {k: round(v, 2) for k, v in top},
+                              "note": "raw reads in host memory -> ft_gen, 3 x (pt_gen + hb_cal_ec_r), pt_gen, hb_cal_ov_r -> final ma_hit_t lists in host memory; one GPU"}
+        e3.close()
+        refdump = os.path.join(ROOT, "oracle", "_ref", "refdump")
+        if os.path.exists(refdump) and not os.environ.get("HB_BENCH_NO_REF_STAGE"):
+            with tempfile.TemporaryDirectory() as td:
+                fa = os.path.join(td, "reads.fa"); sim.write_fasta(fa, rr)
+                cores = os.cpu_count() or 1
+                out = subprocess.run([refdump, "stage", "-o", os.path.join(td, "asm"), "-t%d" % cores, "-f0", fa], capture_output=True, text=True, timeout=600)
+                line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+                if out.returncode == 0 and line:
+                    rs = json.loads(line[-1])
+                    aux["whole_stage"]["cpu_reference"] = {"seconds": rs["seconds"], "gbp_s": rs["bases"] / rs["seconds"] / 1e9, "cores": cores, "ec_rounds_seconds": rs["ec_rounds_seconds"], "final_seconds": rs["final_seconds"],
+                                                           "corrected_bases": rs["corrected_bases"], "overlaps_src": rs["n_src"], "overlaps_rev": rs["n_rev"],
+                                                           "note": "unmodified reference, same reads from a FASTA file (parsing included), -t%d -f0" % cores}
+    except Exception as ex:
+        sys.stderr.write("[bench] whole-stage aux failed: %r\n" % (ex,))
+        return 1
+    emit(aux["whole_stage"])   # the real stdout (fd 1 itself is redirected to stderr in main())
+    return 0
+
+
 def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,7 +250,11 @@ def _main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--aux-whole-stage", action="store_true")
+    ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args()
+    if args.aux_whole_stage:
+        return whole_stage_aux(args.device)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = "final overlap pass (cal_ov_r) on synthetic %d Mb diploid x%d GPU(s), %gx HiFi, 15 kb reads, k=51 w=51, corrected reads, empty previous overlaps" % (GENOME_MB, world, COV)
 
@@ -344,46 +406,15 @@ def _main():
                 sys.stderr.write("[bench] EC round aux failed: %r\n" % (ex,))
             e2.close()
             # ---- the WHOLE stage the way SURVEY.md §8(d) defines the metric (first ha_ft_gen -> end of the final overlap pass), on the same small raw
-            # read set: filter table, 3 x (index build + hb_cal_ec_r), final index, hb_cal_ov_r — host buffers in and out of every C-ABI call — next to
-            # the unmodified reference doing the same on the host cores (oracle/_ref/refdump stage).  Not the headline yet.
+            # read set, next to the unmodified reference doing the same on the host cores.  Runs in a child process (`bench.py --aux-whole-stage`):
+            # a new call sequence must not be able to take the bench line down with it.  Not the headline yet.
             try:
-                e3 = hifiasm_b200.Engine(local)
-                torch.cuda.synchronize(); tw = time.time()
-                e3.upload_reads(ln, fl, bo, npos, noff)
-                hm3 = e3.ft_gen(); e3.update_cov(hm3)
-                MA = hifiasm_b200.binio.MA_MEM
-                src = np.zeros(0, MA); soff = np.zeros(nq + 1, np.uint64); rev = src.copy(); roff = soff.copy(); t_round = []; unfinished = 0; tot_e = 0; kms_ws = {}
-                for K in range(3):
-                    tk = time.time()
-                    a3, b3 = e3.pt_gen(); e3.set_opt(hom_cov=a3, het_cov=b3)
-                    rr3 = e3.cal_ec_r(K, 1 if K == 2 else 0, src, soff)
-                    src, soff, rev, roff = rr3["src"], rr3["src_off"], rr3["rev"], rr3["rev_off"]
-                    unfinished += int((rr3["status"] != 0).sum()); tot_e += rr3["tot_e"]
-                    torch.cuda.synchronize(); t_round.append(round((time.time() - tk) * 1e3, 1))
-                    for k, v in e3.profile().items():
-                        kms_ws[k] = kms_ws.get(k, 0.0) + v[1]
-                tk = time.time()
-                a3, b3 = e3.pt_gen(); e3.set_opt(hom_cov=a3, het_cov=b3)
-                o0, q0, o1, q1, _ = e3.cal_ov_r(src, soff, rev, roff)
-                torch.cuda.synchronize(); t_final = time.time() - tk; wall_ws = time.time() - tw
-                top = sorted(kms_ws.items(), key=lambda kv: -kv[1])[:8]
-                aux["whole_stage"] = {"reads": nq, "bases": qb, "seconds": wall_ws, "gbp_s": qb / wall_ws / 1e9, "round_ms": t_round, "final_ms": round(t_final * 1e3, 1),
-                                      "corrected_bases": int(tot_e), "reads_not_finished": unfinished, "overlaps_src": int(o0.size), "overlaps_rev": int(o1.size),
-                                      "top_kernels_ms_in_ec_rounds": {k: round(v, 2) for k, v in top},
-                                      "note": "raw reads in host memory -> ft_gen, 3 x (pt_gen + hb_cal_ec_r), pt_gen, hb_cal_ov_r -> final ma_hit_t lists in host memory; one GPU"}
-                e3.close()
-                refdump = os.path.join(ROOT, "oracle", "_ref", "refdump")
-                if os.path.exists(refdump) and not os.environ.get("HB_BENCH_NO_REF_STAGE"):
-                    with tempfile.TemporaryDirectory() as td:
-                        fa = os.path.join(td, "reads.fa"); sim.write_fasta(fa, rr)
-                        cores = os.cpu_count() or 1
-                        out = subprocess.run([refdump, "stage", "-o", os.path.join(td, "asm"), "-t%d" % cores, "-f0", fa], capture_output=True, text=True, timeout=600)
-                        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
-                        if out.returncode == 0 and line:
-                            rs = json.loads(line[-1])
-                            aux["whole_stage"]["cpu_reference"] = {"seconds": rs["seconds"], "gbp_s": rs["bases"] / rs["seconds"] / 1e9, "cores": cores, "ec_rounds_seconds": rs["ec_rounds_seconds"], "final_seconds": rs["final_seconds"],
-                                                                   "corrected_bases": rs["corrected_bases"], "overlaps_src": rs["n_src"], "overlaps_rev": rs["n_rev"],
-                                                                   "note": "unmodified reference, same reads from a FASTA file (parsing included), -t%d -f0" % cores}
+                ch = subprocess.run([sys.executable, os.path.abspath(__file__), "--aux-whole-stage", "--device", str(local)], capture_output=True, text=True, timeout=900)
+                line = [l for l in ch.stdout.splitlines() if l.startswith("{")]
+                if ch.returncode == 0 and line:
+                    aux["whole_stage"] = json.loads(line[-1])
+                else:
+                    sys.stderr.write("[bench] whole-stage aux: child exited %d: %s\n" % (ch.returncode, ch.stderr[-400:]))
             except Exception as ex:
                 sys.stderr.write("[bench] whole-stage aux failed: %r\n" % (ex,))
         except Exception as ex:  # the auxiliary measurement must never take the bench line down
