@@ -50,6 +50,13 @@ DATASETS = {
 }
 
 
+# fuzzing against the reference (tools/fuzz_vs_reference.py): extra data sets and another output directory through the environment
+OUT_DIR = os.environ.get("HB_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden"))
+if os.environ.get("HB_GOLDEN_EXTRA"):
+    import json
+    DATASETS.update({k: (v[0], v[1]) for k, v in json.loads(os.environ["HB_GOLDEN_EXTRA"]).items()})
+
+
 def dg(b: bytes) -> int:
     return int.from_bytes(hashlib.blake2b(b, digest_size=8).digest(), "little")
 
@@ -226,7 +233,7 @@ def main():
                         if tag == "fin" and suf == "ec":
                             continue
                         arrs["%s_%s" % (tag, suf.replace(".", "_"))] = np.fromfile("%s.%s.%s.bin" % (pfx, tag, suf), dtype=np.uint8)
-            out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+            out = os.path.join(OUT_DIR, name + ".npz")
             np.savez_compressed(out, **arrs)
             print(name, len(reads), "reads", sum(r.size for r in reads), "bases ->", out, os.path.getsize(out), "bytes")
 

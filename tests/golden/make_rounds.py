@@ -66,7 +66,7 @@ def main():
                     arrs["r%d_dg_%s_%s" % (K, tag, "rev" if is_rev else "src")] = roundlib.list_digests(rec, o, is_rev)
                 arrs["r%d_params" % K] = np.array(["%s=%s" % kv for kv in sorted(p.items())])
                 print(name, "round", K, {k: p[k] for k in ("tot_b", "tot_e", "full_calls", "full_bases")})
-        out = os.path.join(ROOT, "tests", "golden", name + "_rounds.npz")
+        out = os.path.join(mg.OUT_DIR, name + "_rounds.npz")
         np.savez_compressed(out, **arrs)
         print(name, "->", out, os.path.getsize(out), "bytes")
 

@@ -9,7 +9,7 @@ import numpy as np
 
 from hifiasm_b200 import binio
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = os.environ.get("HB_GOLDEN_DIR", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))  # the override: tools/fuzz_vs_reference.py
 CH = np.dtype([("x_pos_s", "<u4"), ("x_pos_e", "<u4"), ("y_id", "<u4"), ("y_pos_s", "<u4"), ("y_pos_e", "<u4"),
                ("y_pos_strand", "<u4"), ("shared_seed", "<i4"), ("first_hit", "<u4"), ("n_fc", "<u4")])
 

@@ -15,7 +15,10 @@ from goldenlib import Golden, dg  # noqa: E402
 import roundlib  # noqa: E402
 
 
-@pytest.fixture(scope="module", params=["g1", "g2", "g3", "g4"])
+SETS = os.environ["HB_GOLDEN_NAMES"].split(",") if os.environ.get("HB_GOLDEN_NAMES") else ["g1", "g2", "g3", "g4"]   # the override: tools/fuzz_vs_reference.py
+
+
+@pytest.fixture(scope="module", params=SETS)
 def ctx(request):
     g = Golden(request.param)
     raw = ho.Store(g.raw.length, g.raw.byte_off, g.raw.packed, g.raw.n_off, g.raw.n_pos)
@@ -102,7 +105,7 @@ def test_ec_align_step_A(ctx):
             assert rc == 0
         acc = B[B["st"] == 2]
         assert acc.size == int(g.count("raw", "aln_ok")[i])
-        if g.name == "g4":  # how many overlaps asked for the rescue; with a hit buffer that is too small the overlap is reported, never silently wrong
+        if g.name == "g4" or g.name.startswith("fz"):  # how many overlaps asked for the rescue; with a hit buffer that is too small the overlap is reported, never silently wrong
             _, B0, _, _ = emu.ec_align_B(er, i, emu.to_chain(ch), fc, hits, A, W)
             n_rechain += int(B0[B0["st"] == 2]["need_rechain"].sum())
             if B0[B0["st"] == 2]["need_rechain"].any():
@@ -163,7 +166,7 @@ def test_ec_align_step_A(ctx):
             assert roundlib.canon_list(sp, 0).tobytes() == want.tobytes(), "paf, read %d" % i
             assert (f_ec, f_ab) == (int(h_fc[i]), int(h_ab[i])), "is_fully_corrected / is_abnormal, read %d" % i
     # almost every read is corrected by the voted path; the graph consensus ran cns_gen_full "full_calls" times in the reference's round 0
-    assert n_cns > 0 and 0 < n_full <= int(rd.params(0)["full_calls"]), (n_cns, n_full)
+    assert n_cns > 0 and (0 < n_full or g.name.startswith("fz")) and n_full <= int(rd.params(0)["full_calls"]), (n_cns, n_full)
     if g.name == "g4":
         assert n_rechain >= 20 and 0 < n_reported <= n_rechain, (n_rechain, n_reported)
         print("re-seeding rescue (rechain_aln_hc): %d overlaps; %d of them reported when the hit buffer holds one hit" % (n_rechain, n_reported))

@@ -18,7 +18,7 @@ import roundlib  # noqa: E402
 import emu  # noqa: E402
 
 
-@pytest.mark.parametrize("name", ["g1", "g2", "g3", "g4"])
+@pytest.mark.parametrize("name", os.environ["HB_GOLDEN_NAMES"].split(",") if os.environ.get("HB_GOLDEN_NAMES") else ["g1", "g2", "g3", "g4"])
 def test_round_closing_steps(name):
     """rounds 0, 1, 2 chained: the read store of round K+1 is the one these steps produce in round K"""
     g = goldenlib.Golden(name); rd = roundlib.Rounds(name)
