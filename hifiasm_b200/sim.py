@@ -102,7 +102,7 @@ def _damage(seq: np.ndarray, rng, burst_rate: float, sv_rate: float, block_rate:
 def sim_reads(hap1: np.ndarray, hap2: np.ndarray, cov: float, mean_len: int,
               seed: int, sd_len: int = 2000, min_len: int = 2000,
               err: float = 0.002, n_rate: float = 0.0,
-              burst_rate: float = 0.0, sv_rate: float = 0.0, block_rate: float = 0.0):
+              burst_rate: float = 0.0, sv_rate: float = 0.0, block_rate: float = 0.0, dup_rate: float = 0.0):
     """Return list of uint8 code arrays (values 0..3, 4 = N)."""
     rng = np.random.default_rng(seed + 1000003)
     glen = hap1.size
@@ -125,6 +125,8 @@ def sim_reads(hap1: np.ndarray, hap2: np.ndarray, cov: float, mean_len: int,
             s = s.copy()
             s[rng.random(s.size) < n_rate] = 4
         reads.append(np.ascontiguousarray(s))
+        if dup_rate > 0 and rng.random() < dup_rate:   # an exact duplicate of the read (PCR-like): identical overlaps, ties everywhere
+            reads.append(reads[-1].copy())
     return reads
 
 
