@@ -520,6 +520,9 @@ HB_HD uint32_t hb_chain_post(hb_chain_t *ch, uint32_t n_slots, const hb_hit_t *c
 							const hb_hit_t *chits = (zk.pad & HB_CHAIN_INPLACE) ? ghits : chits_;
 							uint64_t lo_ = 0, hi_ = zk.n_hits;
 							while (lo_ < hi_) { uint64_t mid = (lo_ + hi_) >> 1; if (chits[mm + mid].self_offset < os) lo_ = mid + 1; else hi_ = mid; }
+							// ... plus the chain's first anchors when they start at the read's first bases: the reference's `ms = me - span` is unsigned
+							// and wraps below zero there (self_offset + 1 == span gives ms = 2^64 - 1), so such an anchor passes `ms >= os` whatever os is
+							for (hh = 0; hh < lo_ && kn < ocn; hh++) { me = chits[mm + hh].self_offset; if (me >= 256) break; if (me < (chits[mm + hh].cnt & 0xffu)) kn++; }
 							for (hh = lo_; hh < zk.n_hits && kn < ocn; hh++) {
 								me = chits[mm + hh].self_offset; if (me > oe) break;
 								ms = me - (chits[mm + hh].cnt & 0xffu);

@@ -2,6 +2,7 @@
 the hot path is compared with digests / dumps produced by the unmodified
 reference (tests/golden/*.npz <- oracle/_ref/refdump)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -16,7 +17,7 @@ def _store(rs):
     return ho.Store(rs.length, rs.byte_off, rs.packed, rs.n_off, rs.n_pos)
 
 
-@pytest.fixture(scope="module", params=["g1", "g2", "g3", "g4"])
+@pytest.fixture(scope="module", params=os.environ["HB_GOLDEN_NAMES"].split(",") if os.environ.get("HB_GOLDEN_NAMES") else ["g1", "g2", "g3", "g4"])
 def ctx(request):
     g = Golden(request.param)
     raw = _store(g.raw)
