@@ -13,7 +13,7 @@ for t in test_whole_stage_from_raw_reads_g4 test_stages_raw_g4 test_stages_final
 	timeout 300 python -m pytest tests/test_zz_gpu_not_yet_run.py -m gpu -q -x --runxfail -k "$t" > gpurun_out/zz_$t.log 2>&1
 	echo "== $t: $(tail -1 gpurun_out/zz_$t.log)"
 done
-timeout 900 python tools/fuzz_gpu_stage.py 5000 9 > gpurun_out/fuzz_gpu_stage.log 2>&1; tail -4 gpurun_out/fuzz_gpu_stage.log
+timeout 900 python tools/fuzz_gpu_stage.py 5000 11 > gpurun_out/fuzz_gpu_stage.log 2>&1; tail -4 gpurun_out/fuzz_gpu_stage.log
 unset HB_TRACE_EC
 timeout 600 python -m pytest tests -m gpu -q -rxX > gpurun_out/gpu_all.log 2>&1; tail -3 gpurun_out/gpu_all.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.json

@@ -15,7 +15,7 @@ import fuzz_vs_reference as fz  # noqa: E402
 
 
 def main():
-    seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 5000; n = int(sys.argv[2]) if len(sys.argv) > 2 else 9
+    seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 5000; n = int(sys.argv[2]) if len(sys.argv) > 2 else 11
     ref = os.path.join(ROOT, "oracle", "_ref", "hifiasm"); bad = []
     if not os.path.exists(ref):
         sys.exit("oracle/_ref/hifiasm is missing (built where /root/reference exists: make -C oracle ref)")
@@ -38,7 +38,7 @@ def main():
                 x, y = binio.load_ec_bin(os.path.join(td, "ref.ec.bin")), binio.load_ec_bin(os.path.join(td, "gpu.ec.bin"))
                 if not ((x.length == y.length).all() and (binio.canonical_packed(x) == binio.canonical_packed(y)).all() and x.name_blob == y.name_blob and (x.hom_cov, x.het_cov) == (y.hom_cov, y.het_cov)):
                     diff.append("ec.bin")
-            print("config %d (seed %d, kind %d): %d reads, %s" % (i, seed0 + i, i % 9, len(reads), "identical" if not diff else "DIFFERENT: " + "; ".join(diff)), flush=True)
+            print("config %d (seed %d, kind %d): %d reads, %s" % (i, seed0 + i, i % 11, len(reads), "identical" if not diff else "DIFFERENT: " + "; ".join(diff)), flush=True)
             if diff:
                 bad.append(seed0 + i)
     print("different:", bad)
