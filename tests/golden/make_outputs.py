@@ -29,14 +29,17 @@ def main():
     if not os.path.exists(HIFIASM):
         sys.exit("build oracle/_ref first: make -C oracle ref")
     arrs = {}
+    only = [a for a in sys.argv[1:] if a in mg.DATASETS]   # `make_outputs.py fz3` (tools/fuzz_vs_reference.py): only that set, into mg.OUT_DIR
     for name, (gk, rk) in mg.DATASETS.items():
+        if only and name not in only:
+            continue
         h1, h2 = sim.sim_genome(**gk)
         reads = sim.sim_reads(h1, h2, **rk)
         with tempfile.TemporaryDirectory() as td:
             fa = os.path.join(td, "reads.fa"); sim.write_fasta(fa, reads)
             pfx = os.path.join(td, "asm")
             subprocess.run([HIFIASM, "-o", pfx, "-t4", "-f0", "--write-paf", "--write-ec", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False)  # the graph stages after the overlap stage may find nothing to assemble on toy data: only the stage's files matter
-            z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+            z = np.load(os.path.join(mg.OUT_DIR, name + ".npz"))
             for suf, key in (("ovlp.paf", "paf"), ("ec.fa", "ecfa"), ("ovlp.source.bin", "src"), ("ovlp.reverse.bin", "rev"), ("ec.bin", "ecbin")):
                 b = open("%s.%s" % (pfx, suf), "rb").read()
                 arrs["%s_%s_size" % (name, key)] = np.array([len(b)], np.uint64); arrs["%s_%s_dg" % (name, key)] = dg16(b)
@@ -49,7 +52,7 @@ def main():
                 tf.write(z["pre_ec"].tobytes()); tf.flush(); b = binio.load_ec_bin(tf.name)
             assert (a.length == b.length).all() and (binio.canonical_packed(a) == binio.canonical_packed(b)).all() and a.name_blob == b.name_blob, name  # ec.bin: identical after masking the pad bytes the reference leaves uninitialised
             print(name, {k: int(arrs["%s_%s_size" % (name, k)][0]) for k in ("paf", "ecfa", "src", "rev", "ecbin")})
-    out = os.path.join(ROOT, "tests", "golden", "outputs.npz")
+    out = os.path.join(mg.OUT_DIR, "outputs.npz")
     np.savez_compressed(out, **arrs)
     print("->", out, os.path.getsize(out), "bytes")
 

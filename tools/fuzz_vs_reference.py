@@ -48,9 +48,9 @@ def main():
         name = "fz%d" % i; g, r = config(i, seed0 + i)
         with tempfile.TemporaryDirectory() as td:
             env = dict(os.environ, HB_GOLDEN_DIR=td, HB_GOLDEN_EXTRA=json.dumps({name: [g, r]}), HB_GOLDEN_NAMES=name)
-            for script in ("make_golden.py", "make_rounds.py"):
+            for script in ("make_golden.py", "make_rounds.py", "make_outputs.py"):
                 subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "golden", script), name], env=env, stdout=subprocess.DEVNULL)
-            rc = subprocess.call([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_hostemu.py"), os.path.join(ROOT, "tests", "test_hostemu_round.py"), "-x", "-q", "-s"], env=env, cwd=ROOT)
+            rc = subprocess.call([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_hostemu.py"), os.path.join(ROOT, "tests", "test_hostemu_round.py"), os.path.join(ROOT, "tests", "test_outputs.py"), "-k", "not ingest and not io_errors", "-x", "-q", "-s"], env=env, cwd=ROOT)
             print("== config %d (seed %d, kind %d): %s" % (i, seed0 + i, i % 11, "ok" if rc == 0 else "MISMATCH"), flush=True)
             if rc:
                 bad.append((i, seed0 + i))
