@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(32) k_ecb_rechain(RcLaunch L)
 	const uint64_t n = *L.rc_n; if (tid >= n) return;
 	const uint64_t cw = (uint64_t)L.cig_words;
 	EcBCtx C; C.e_rate = L.e_rate; C.w_l = L.w_l; C.pool = L.pool; C.pool_used = L.pool_used; C.pool_cap = L.pool_cap; C.do_gaps = L.gaps; C.no_myers = 0;
-	C.ez.path = L.path + tid * L.path_words; C.ez.pcap = L.path_words; C.ez.vec = L.vec + tid * 11 * (uint64_t)HB_MW_MAXW; C.ez.vstride = HB_MW_MAXW;
+	C.ez.path = L.path + tid * L.path_words; C.ez.pcap = L.path_words; C.ez.vec = L.vec + tid * 11 * (uint64_t)HB_MW_MAXW; C.ez.vstride = HB_MW_MAXW; C.ez.warp = 0;
 	C.ez.cig = L.cig3 + tid * 3 * cw; C.ez.ccap = L.cig_words; C.wc = C.ez.cig + cw; C.wccap = L.cig_words; C.gout = C.ez.cig + 2 * cw; C.gcap = L.cig_words;
 	EcRc S; S.R = L.R; S.zw = L.zw + tid * (uint64_t)L.zcap; S.zcap = L.zcap; S.poolA = L.poolA; S.zc = L.zc + tid * L.zc_cap; S.zc_used = L.zc_used + tid; S.zc_cap = L.zc_cap;
 	S.path1 = L.path1 + tid * (uint64_t)L.w_l * 5; S.cig1 = L.cig1 + tid * HB_EC_CIG_TMP;

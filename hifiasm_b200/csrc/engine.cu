@@ -61,15 +61,18 @@ static void *ws_short(hb_ctx *ctx, size_t bytes)
 	size_t need = ctx->ws_lo + (ctx->ws_cap - ctx->ws_hi) + ctx->ws_virt; if (need > ctx->ws_need) ctx->ws_need = need;
 	return 0;
 }
+static const bool g_trace_ws = getenv("HB_TRACE_WS") != 0;
 void *hb_ws_lo(hb_ctx *ctx, size_t bytes)
 {
 	bytes = (bytes + 255) & ~(size_t)255;
+	if (g_trace_ws && bytes >= ((size_t)256 << 20)) fprintf(stderr, "[hb ws] lo %.2f GB at %.2f GB (cap %.2f)\n", bytes / 1e9, ctx->ws_lo / 1e9, ctx->ws_cap / 1e9);
 	if (ctx->ws_virt || ctx->ws_lo + bytes > ctx->ws_hi) return ws_short(ctx, bytes);
 	void *p = ctx->ws + ctx->ws_lo; ctx->ws_lo += bytes; return p;
 }
 void *hb_ws_hi(hb_ctx *ctx, size_t bytes)
 {
 	bytes = (bytes + 255) & ~(size_t)255;
+	if (g_trace_ws && bytes >= ((size_t)256 << 20)) fprintf(stderr, "[hb ws] hi %.2f GB (hi at %.2f of %.2f GB)\n", bytes / 1e9, ctx->ws_hi / 1e9, ctx->ws_cap / 1e9);
 	if (ctx->ws_virt || ctx->ws_lo + bytes + 256 > ctx->ws_hi) return ws_short(ctx, bytes);
 	ctx->ws_hi = (ctx->ws_hi - bytes) & ~(size_t)255; return ctx->ws + ctx->ws_hi;
 }
@@ -164,9 +167,10 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->pt_keys = ctx->pt_npos = ctx->pt_cap = 0; ctx->d_pt_slot = 0; ctx->d_pt_pos = 0;
 	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
 	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
-	ctx->anchor_budget = 768ull << 20; ctx->last_pass_ms = 0;
+	ctx->anchor_budget = 96ull << 20; ctx->last_pass_ms = 0;
 	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = ctx->ws_virt = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
+	ctx->cns_g_nodes = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096; ctx->cns_g_arcs = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
 	cudaFuncSetAttribute(k_post_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, POST_WARPS * POST_SMEM_PER_WARP);
@@ -783,22 +787,24 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 						// alignment tiers 0..3: {trace words, band words, cigar runs, blocks of 128 threads}; tier 0 keeps its scratch private (local memory);
 						// a segment that overflows one tier queues for the next (queues ping-pong between two arrays)
-						const struct { uint64_t pw; int32_t vs, cw; unsigned bl; const char *name; } TIER[4] = {
-							{ 0, 0, 0, 0, "k_ecb_seg" }, { 4096, 8, 256, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier1" }, { path_words1 * 2, HB_MW_MAXW, 4096, (unsigned)ctx->sm_count, "k_ecb_seg_tier2" },
-							{ (uint64_t)HB_MW_MAXW * HB_MAX_SIN_L * 5, HB_MW_MAXW, 65535, 2u, "k_ecb_seg_tier3" } };
+						// tiers 1..3 give a WARP to a segment (k_ecb_seg_w): {trace words per warp, cigar runs, warps}; the largest holds the longest alignment the reference
+						// attempts (HB_MAX_SIN_L columns x 64 band words x 3 trace words)
+						const struct { uint64_t pw; int32_t cw; unsigned warps; const char *name; } TIER[4] = {
+							{ 0, 0, 0, "k_ecb_seg" }, { 16384, 1024, (unsigned)ctx->sm_count * 16, "k_ecb_seg_tier1" }, { 262144, 8192, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier2" },
+							{ (uint64_t)HB_MW_MAXW * (2 + 3 * (uint64_t)HB_MAX_SIN_L), 65535, (unsigned)ctx->sm_count * 2, "k_ecb_seg_tier3" } };
 						for (int tier = 0; tier <= 3 && h_q[tier]; tier++) {
 							Arena sa(ctx);
 							unsigned bl = (unsigned)(((uint64_t)h_q[tier] + 127) / 128);
 							if (tier > 0) {
-								bl = std::max(1u, std::min(bl, TIER[tier].bl)); const uint64_t nt = (uint64_t)bl * 128;
-								G.path = sa.get<uint64_t>(nt * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nt * 11 * (uint64_t)TIER[tier].vs); G.vstride = TIER[tier].vs;
-								G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw;
+								const uint64_t nw = std::max<uint64_t>(4, std::min<uint64_t>(((uint64_t)h_q[tier] + 3) & ~3ull, TIER[tier].warps)); bl = (unsigned)(nw / 4);
+								G.path = sa.get<uint64_t>(nw * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nw * 2 * (uint64_t)HB_MW_MAXW); G.vstride = HB_MW_MAXW;
+								G.cig_tmp = sa.get<uint16_t>(nw * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw; G.work = sa.zero<uint32_t>(1);
 								if (sa.failed) return HB_E_WS;
 							}
 							G.q_in = (tier & 1) ? d_q2 : d_q1; G.q_in_n = d_qn + tier; G.q_out = tier < 3 ? ((tier & 1) ? d_q1 : d_q2) : 0; G.q_out_n = d_qn + tier + 1;
 							{
 								ProfScope ps(ctx, TIER[tier].name);
-								if (tier == 0) k_ecb_seg<true><<<bl, 128, 0, ctx->stream>>>(G); else k_ecb_seg<false><<<bl, 128, 0, ctx->stream>>>(G);
+								if (tier == 0) k_ecb_seg<<<bl, 128, 0, ctx->stream>>>(G); else k_ecb_seg_w<<<bl, 128, 0, ctx->stream>>>(G);
 							}
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -912,9 +918,10 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 									k_cns_cap<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_ooff, d_alnb, d_entcap);
 									if ((rc = hb_scan_u32_to_u64(ctx, d_entcap, d_entoff, nb))) return rc;
 									uint64_t tot_ent = 0; HB_CUDA(cudaMemcpyAsync(&tot_ent, d_entoff + nb, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-									const unsigned cblocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nb + 63) / 64, (uint64_t)ctx->sm_count * 2)); const uint64_t cthr = (uint64_t)cblocks * 64;
+									const unsigned cblocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nb + CNS_WARPS - 1) / CNS_WARPS, (uint64_t)ctx->sm_count * 3)); const uint64_t cwarps = (uint64_t)cblocks * CNS_WARPS;
+									const size_t cns_smem = (size_t)CNS_WARPS * HB_CNS_SMEM_WORDS * 8;
 									CnsEnt *d_ent = ba.get<CnsEnt>(tot_ent + 1); uint32_t *d_csrt = ba.get<uint32_t>(tot_ent + 1), *d_acta = ba.get<uint32_t>(tot_ent + 1), *d_actb = ba.get<uint32_t>(tot_ent + 1), *d_b32 = ba.get<uint32_t>(tot_ent + 1);
-									uint64_t *d_key = ba.get<uint64_t>(tot_ent + 1), *d_ct = ba.get<uint64_t>(cthr * 2 * HB_CNS_WL);
+									uint64_t *d_key = ba.get<uint64_t>(tot_ent + 1); int32_t *d_rs = ba.get<int32_t>(cwarps * HB_CNS_RS_WORDS); uint32_t *d_cwork = ba.zero<uint32_t>(2);
 									HB_ALLOC_CHECK(ba);
 									std::vector<uint64_t> h_slot(nb + 1, 0); std::vector<uint32_t> h_scn(nb + 1); std::vector<uint64_t> h_scoff(nb + 1);
 									uint16_t *d_scslot = 0; uint64_t mult = 1;
@@ -922,13 +929,14 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 										for (uint64_t i = 0; i < nb; i++) h_slot[i + 1] = h_slot[i] + (128 + ctx->h_rlen[r0 + b0 + i] / 16) * mult;
 										d_scslot = ba.get<uint16_t>(h_slot[nb] + 1); HB_ALLOC_CHECK(ba);
 										HB_CUDA(cudaMemcpyAsync(d_slot, h_slot.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-										HB_CUDA(cudaMemsetAsync(d_nec, 0, 8, ctx->stream)); if (attempt) HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream)); // (bit 256 of the attempt before; no other bit was set)
+										HB_CUDA(cudaMemsetAsync(d_nec, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_cwork, 0, 8, ctx->stream)); if (attempt) HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream)); // (bit 256 of the attempt before; no other bit was set)
 										CnsArgs CA; memset(&CA, 0, sizeof(CA));
 										CA.R = R; CA.r0 = r0 + b0; CA.nR = nb; CA.o_off = d_ooff; CA.ph = d_ph; CA.alnb = d_alnb; CA.wl = d_wlb; CA.pool = d_poolb; CA.ord = P.ord; CA.cov = d_cov; CA.ent_off = d_entoff; CA.ent = d_ent;
-										CA.srt = d_csrt; CA.act_a = d_acta; CA.act_b = d_actb; CA.b32 = d_b32; CA.key = d_key; CA.ct = d_ct; CA.out_off = d_slot; CA.out = d_scslot; CA.out_n = d_scn; CA.status = d_status; CA.nec = d_nec; CA.err = d_err;
+										CA.srt = d_csrt; CA.act_a = d_acta; CA.act_b = d_actb; CA.b32 = d_b32; CA.key = d_key; CA.rs = d_rs; CA.work = d_cwork; CA.out_off = d_slot; CA.out = d_scslot; CA.out_n = d_scn; CA.status = d_status; CA.nec = d_nec; CA.err = d_err;
 										{
 											ProfScope ps(ctx, "k_ec_cns");
-											k_ec_cns<false><<<cblocks, 64, 0, ctx->stream>>>(CA);
+											HB_CUDA(cudaFuncSetAttribute(k_ec_cns_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cns_smem));
+											k_ec_cns_w<false><<<cblocks, CNS_WARPS * 32, cns_smem, ctx->stream>>>(CA);
 										}
 										HB_CUDA(cudaGetLastError());
 										std::vector<uint8_t> h_st(nb + 1);
@@ -936,20 +944,20 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 										HB_CUDA(cudaStreamSynchronize(ctx->stream));
 										if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "dedup_chains: radix-sort stack"); return HB_E_OVERFLOW; }
 										std::vector<uint32_t> h_queue; for (uint64_t i = 0; i < nb; i++) if (h_st[i] & 1) h_queue.push_back((uint32_t)i);
-										if (!h_queue.empty()) { // second launch: the reads whose stretches need the graph consensus (cns_gen_full), each thread with a graph arena
+										if (!h_queue.empty()) { // second launch: the reads whose stretches need the graph consensus (cns_gen_full), each warp with a graph arena
 											Arena sa(ctx);
-											const unsigned gblocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((h_queue.size() + 31) / 32, (uint64_t)ctx->sm_count * 4)); const uint64_t gthr = (uint64_t)gblocks * 32;
-											static const uint32_t G_NODES = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096, G_ARCS = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
-											CnsArgs CB = CA; CB.n_queue = (uint32_t)h_queue.size(); CB.g_nodes = G_NODES; CB.g_arcs = G_ARCS; CB.g_nseq = 2048; CB.g_pcap = 8192; CB.g_ccap = 2048;
-											uint32_t *d_queue = sa.get<uint32_t>(h_queue.size()); CB.queue = d_queue;
+											const unsigned gblocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((h_queue.size() + CNS_WARPS - 1) / CNS_WARPS, (uint64_t)ctx->sm_count * 2)); const uint64_t gthr = (uint64_t)gblocks * CNS_WARPS;
+											CnsArgs CB = CA; CB.n_queue = (uint32_t)h_queue.size(); CB.g_nodes = ctx->cns_g_nodes; CB.g_arcs = ctx->cns_g_arcs; CB.g_nseq = 2048; CB.g_pcap = 8192; CB.g_ccap = 2048;
+											uint32_t *d_queue = sa.get<uint32_t>(h_queue.size()); CB.queue = d_queue; CB.work = d_cwork + 1;
 											CB.g_nd = sa.get<CnsNode>(gthr * CB.g_nodes); CB.g_arc = sa.get<CnsArc>(gthr * CB.g_arcs); CB.g_q = sa.get<uint32_t>(gthr * CB.g_nodes); CB.g_b32 = sa.get<uint32_t>(gthr * CB.g_arcs);
 											CB.g_np = sa.get<uint32_t>(gthr * CB.g_nseq); CB.g_ns = sa.get<uint8_t>(gthr * CB.g_nseq); CB.g_path = sa.get<uint64_t>(gthr * CB.g_pcap); CB.g_vec = sa.get<uint64_t>(gthr * 32); CB.g_cig = sa.get<uint16_t>(gthr * CB.g_ccap);
-											CB.ct = sa.get<uint64_t>(gthr * 2 * HB_CNS_WL);
+											CB.rs = sa.get<int32_t>(gthr * HB_CNS_RS_WORDS);
 											if (sa.failed) return HB_E_WS;
 											HB_CUDA(cudaMemcpyAsync(d_queue, h_queue.data(), h_queue.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 											{
 												ProfScope ps(ctx, "k_ec_cns_graph");
-												k_ec_cns<true><<<gblocks, 32, 0, ctx->stream>>>(CB);
+												HB_CUDA(cudaFuncSetAttribute(k_ec_cns_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cns_smem));
+												k_ec_cns_w<true><<<gblocks, CNS_WARPS * 32, cns_smem, ctx->stream>>>(CB);
 											}
 											HB_CUDA(cudaGetLastError());
 											HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1378,6 +1386,7 @@ extern "C" int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *lau
 	for (auto &p : ctx->prof) { if (n >= cap) break; names[n] = p.name; launches[n] = p.launches; ms[n] = p.ms; n++; }
 	return n;
 }
+extern "C" void hb_profile_reset(hb_ctx_t *ctx) { ctx->prof.clear(); }
 extern "C" int hb_last_pass_ms(const hb_ctx_t *ctx, double *ms) { *ms = ctx->last_pass_ms; return HB_OK; }
 extern "C" int hb_counters(const hb_ctx_t *ctx, uint64_t *c, int cap)
 {

@@ -470,7 +470,8 @@ struct MwEz {
 	int32_t ps, pe, pl, ts, te, tl, thre, err, nword;
 	uint16_t *cig; int32_t cn, ccap;      // cigar of the last alignment
 	uint64_t *path; uint64_t pcap, pn;    // 5*nword words per column; one-word bands (compact = 1): 2 header words (initial VP, VN) + 3 per column (D0, VP, VN)
-	int32_t compact;
+	int32_t compact;                      // trace layout: 0 = 5 words per band word and column, 1 = one-word band (3 per column), 2 = hb_mw_align_w's (3 per band word and column)
+	int32_t warp;                         // != 0: the calling WARP runs the aligner together (hb_mwalign_w.cuh); every lane holds the same MwEz
 	uint64_t *vec; int32_t vstride;       // 11 vectors of vstride words: Peq[0..4], VP, VN, X, D0, HN, HP
 	int ovf;                              // scratch too small: the unit is deferred to a launch with more scratch
 };
@@ -511,7 +512,13 @@ HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 	int32_t poff = ez.pe, sft = bd - (pn - ez.pe - ptrim), i = tn, low = bd - 1, d = 0, pd = -1, pdn = 0;
 	while (i > 0 && cur > 0) {
 		const uint64_t *D0 = ez.path + (size_t)(i - 1) * bs, *VP = D0 + bbs, *VN = VP + bbs, *HP = VN + bbs, *HN = HP + bbs;
-		if (ez.compact) { // one-word band: D0, VP, VN of the column; HN = VP' & D0, HP = VN' | ~(VP' | D0) with VP', VN' of the column before (header for column 0)
+		if (ez.compact == 2) { // rows of 3 * nword words (D0 | VP | VN) behind a header of the initial VP | VN: HN / HP from the row before, bit by bit
+			const int32_t nw = ez.nword; const uint64_t *row = ez.path + 2 * (size_t)nw + (size_t)(i - 1) * 3 * nw, *pvp = i > 1 ? row - 2 * nw : ez.path, *pvn = pvp + nw;
+			const int d0b = hb_mw_bit(row, sft);
+			D = cur - (1 - d0b); d = 0; mn = D;
+			if (sft != low) { const int vppb = hb_mw_bit(pvp, sft), hn = vppb & d0b, hp = hb_mw_bit(pvn, sft) | (1 - (vppb | d0b)); H = cur + hn - hp; if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
+			if (sft != 0) { V = cur + hb_mw_bit(row + 2 * nw, sft - 1) - hb_mw_bit(row + nw, sft - 1); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
+		} else if (ez.compact) { // one-word band: D0, VP, VN of the column; HN = VP' & D0, HP = VN' | ~(VP' | D0) with VP', VN' of the column before (header for column 0)
 			const uint64_t *row = ez.path + 2 + (size_t)(i - 1) * 3, *prv = i > 1 ? row - 3 + 1 : ez.path;
 			const uint64_t d0 = row[0], vp = row[1], vn = row[2], vpp = prv[0], vnp = prv[1], hn = vpp & d0, hp = vnp | ~(vpp | d0);
 			D = cur - (1 - (int32_t)((d0 >> sft) & 1ULL)); d = 0; mn = D;
@@ -712,6 +719,8 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 		hb_mw_gen_trace(ez, abs_diag, 1);
 	}
 }
+
+template <int WPL> HB_HD_NI void hb_mw_align_w(int mode, const RdView &T, int64_t ps0, int32_t pn, const RdView &Q, int64_t qs0, int32_t tn, int32_t thre, int32_t abs_diag, MwEz &ez); // hb_mwalign_w.cuh
 
 // lchain_refine, Hash_Table.cpp:2457-2541 with des = a (in place); t / p / f = DP scratch of a_n entries
 HB_HD int64_t hb_lchain_refine(hb_hit_t *a, int64_t a_n, int64_t *t, int64_t *p, int32_t *f, int64_t max_skip, int64_t max_iter, int64_t max_dis, int64_t long_gap)
@@ -1029,7 +1038,10 @@ HB_HD int64_t hb_cal_exz_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, in
 		if (thre > dd) thre = dd;
 		if (thre <= *pthre) return 0;
 		*pthre = thre;
-		hb_mw_align((int)mode, C.t, ts, (int32_t)tl, C.q, qs, (int32_t)ql, (int32_t)thre, (int32_t)aux_beg, ez);
+		if (ez.warp) { // the band over the lanes: one word per lane up to 32 words, two beyond
+			if ((((int32_t)thre << 1) + 1 + 63) >> 6 <= 32) hb_mw_align_w<1>((int)mode, C.t, ts, (int32_t)tl, C.q, qs, (int32_t)ql, (int32_t)thre, (int32_t)aux_beg, ez);
+			else hb_mw_align_w<2>((int)mode, C.t, ts, (int32_t)tl, C.q, qs, (int32_t)ql, (int32_t)thre, (int32_t)aux_beg, ez);
+		} else hb_mw_align((int)mode, C.t, ts, (int32_t)tl, C.q, qs, (int32_t)ql, (int32_t)thre, (int32_t)aux_beg, ez);
 		if (ez.ovf) return 0;
 		if (ez.err <= ez.thre) { ez.ps += (int32_t)ts; ez.pe += (int32_t)ts; ez.ts += (int32_t)qs; ez.te += (int32_t)qs; return 1; }
 	}
@@ -1198,3 +1210,4 @@ HB_HD void hb_ecb_merge(EcBCtx &C, const EcZ &zA, int64_t re_A, const EcPrep &pr
 	}
 	hb_ecb_finish(C, zA, re_A, out);
 }
+#include "hb_mwalign_w.cuh"

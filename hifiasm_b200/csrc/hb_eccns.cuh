@@ -334,3 +334,175 @@ template <bool GRAPH> HB_HD uint64_t hb_cns_read(CnsCtx &C, uint32_t n_ov, uint3
 	nec += hb_cns_anchor<GRAPH>(C, (uint64_t)C.ql, (uint64_t)C.ql, 1);
 	return nec;
 }
+
+// =====================================================================================================================================
+// The same consensus with one WARP per read (hb_warp.cuh).  What changes is the shape of the work, not its result:
+//   * the pile-up of a 512-column block — wcns_vote's first loop, which in the reference (and in hb_cns_vote above) touches two counters per
+//     column per covering alignment — becomes RANGE UPDATES on a difference array in shared memory: a lane owns a covering alignment, walks its
+//     cigar RUNS and adds +v / -v at the two ends of the word range a run votes on (the reference's misplaced count-array offset, os - s WORDS,
+//     only shifts where the range lands: a range of words base + 2 (t - s) + c is contiguous inside its parity class, so there is one
+//     difference array per parity); one warp scan turns the differences into the per-column (match << 32 | voters) words;
+//   * the per-column majority tests run one column per lane and leave two 512-bit masks (column kept / an insertion in front of it);
+//   * lane 0 walks the masks run by run (count-trailing-zeros over 64-bit words), so the sequential part of a block is proportional to the
+//     number of anchors, not of columns, and only there calls the reference's stretch vote (hb_cns_gen0) and script writer.
+// =====================================================================================================================================
+#include "hb_warp.cuh"
+#define HB_CNS_DW 560                       // words of one parity class: 513 used, stored with one pad word per 16 (shared-memory banks)
+#define HB_CNS_SMEM_WORDS (2 * HB_CNS_DW + 16) // per warp: two difference arrays + the two masks
+HB_HD uint32_t hb_cns_dix(int64_t k) { return (uint32_t)(k + (k >> 4)); }
+
+// extract_sub_cigar_mm (ecovlp.cpp:283-360) as range updates.  base = the word offset the reference adds to the count array (os - s of the block)
+HB_HD void hb_cns_sub_mm_d(CnsCtx &C, CnsEnt &p, int64_t s, int64_t e, int64_t base, uint64_t *D)
+{
+	const hb_wl_t &w = C.ov[p.ov].w[p.wid];
+	int64_t xk = p.xoff, yk = p.yoff, ck = p.coff, os, oe;
+	const int64_t s0 = w.x_start, e0 = (int64_t)w.x_end + 1;
+	if (s < s0) s = s0; if (e > e0) e = e0;
+	if (s >= e) return;
+	const uint16_t *cg = C.pool + w.cidx; const int64_t cn = w.clen;
+	if (!cn) return;
+	int64_t op, ws, we, ovlp;
+	auto radd = [&](int64_t c, int64_t a, int64_t b, uint64_t v) { // words base + 2 (t - s) + c, t in [a, b)
+		const int64_t w0 = base + c, h = w0 >> 1; uint64_t *d = D + (w0 & 1) * HB_CNS_DW;
+		hb_atom_add64(d + hb_cns_dix(h + (a - s)), v); hb_atom_add64(d + hb_cns_dix(h + (b - s)), 0 - v);
+	};
+	if (ck < 0 || ck > cn) { ck = 0; xk = w.x_start; yk = w.y_start; }
+	while (ck > 0 && xk >= s) { --ck; op = cg[ck] >> 14; if (op != 2) xk -= cg[ck] & 0x3fff; if (op != 3) yk -= cg[ck] & 0x3fff; }
+	while (ck < cn && xk < e) {
+		ws = xk; op = cg[ck] >> 14;
+		if (op != 2) xk += cg[ck] & 0x3fff; if (op != 3) yk += cg[ck] & 0x3fff;
+		ck++; we = xk;
+		os = s > ws ? s : ws; oe = e < we ? e : we; ovlp = oe > os ? oe - os : 0;
+		if (op != 2) { if (!ovlp) continue; } else { if (ws < s || ws >= e) continue; }
+		if (op != 2) {
+			const uint64_t v = op == 0 ? 0x100000001ULL : 1ULL;
+			radd(0, os, oe, v);
+			const int64_t a = os > ws ? os : os + 1; // the gap in front of the run's first column belongs to the previous run
+			if (a < oe) radd(1, a, oe, v);
+		} else radd(1, ws, ws + 1, 1);
+	}
+	p.xoff = (uint32_t)xk; p.yoff = (uint32_t)yk; p.coff = (int32_t)ck;
+}
+
+// number of consecutive bits equal to `want` from bit k on (bits >= n do not count)
+HB_HD uint32_t hb_bits_run(const uint64_t *m, uint32_t k, uint32_t n, int want)
+{
+	const uint32_t k0 = k;
+	while (k < n) {
+		uint64_t v = m[k >> 6]; if (want) v = ~v; // bits that differ from `want`
+		v >>= (k & 63);                           // (the zeros shifted in at the top read as "equal": a set bit is always inside the word)
+		if (v) { k += (uint32_t)hb_ctz64(v); break; }
+		k += 64 - (k & 63);
+	}
+	if (k > n) k = n;
+	return k - k0;
+}
+
+// wcns_vote for a warp.  S = the warp's shared-memory words (HB_CNS_SMEM_WORDS).  Lane 0 owns the sequential state in C; every lane returns rr / sees need_full.
+template <bool GRAPH> HB_HD int64_t hb_cns_vote_w(CnsCtx &C, uint64_t *S, uint32_t id_n, uint64_t s, uint64_t e, uint64_t *nec, int *need_full)
+{
+	const int lane = hb_lane(); uint64_t *D = S, *mP = S + 2 * HB_CNS_DW, *mI = mP + 8; const uint64_t wl = e - s;
+	for (uint32_t k = lane; k < HB_CNS_SMEM_WORDS; k += HB_WS) S[k] = 0;
+	hb_wsync();
+	bool rrl = false;
+	for (uint32_t k = lane; k < id_n; k += HB_WS) {
+		CnsEnt &p = C.ent[C.A.act[k]]; const hb_wl_t &w = C.ov[p.ov].w[p.wid];
+		const uint64_t q0 = (uint64_t)(int64_t)w.x_start, q1 = (uint64_t)((int64_t)w.x_end + 1);
+		if (q1 <= e) rrl = true;
+		const uint64_t os = q0 > s ? q0 : s, oe = q1 < e ? q1 : e;
+		if (oe > os) hb_cns_sub_mm_d(C, p, (int64_t)os, (int64_t)oe, (int64_t)(os - s), D);
+	}
+	const int64_t rr = hb_any(rrl) ? 1 : 0;
+	hb_wsync();
+	{ // differences -> counts -> the two masks
+		const uint32_t per = HB_CNS_WL / HB_WS, k0 = (uint32_t)lane * per; uint64_t a0 = 0, a1 = 0, t0, t1;
+		for (uint32_t j = 0; j < per; j++) { a0 += D[hb_cns_dix(k0 + j)]; a1 += D[HB_CNS_DW + hb_cns_dix(k0 + j)]; }
+		uint64_t c0 = hb_wscan64(a0, &t0), c1 = hb_wscan64(a1, &t1), accP = 0, accI = 0; int cw = -1;
+		for (uint32_t j = 0; j < per; j++) {
+			const uint32_t k = k0 + j; c0 += D[hb_cns_dix(k)]; c1 += D[HB_CNS_DW + hb_cns_dix(k)];
+			if (k >= wl) break;
+			if ((int)(k >> 6) != cw) { if (cw >= 0) { if (accP) hb_atom_or64(mP + cw, accP); if (accI) hb_atom_or64(mI + cw, accI); } cw = (int)(k >> 6); accP = accI = 0; }
+			uint64_t oc0 = (c0 >> 32) + 1, oc1 = (uint32_t)c0 + 1;
+			if (hb_cns_pass(oc0, oc1, 3, 0.500001) || oc1 < 3) {
+				accP |= 1ULL << (k & 63);
+				oc0 = (c1 >> 32) + 1; oc1 = (uint32_t)c1 + 1;
+				if (!(hb_cns_pass(oc0, oc1, 3, 0.500001) || oc1 < 3)) accI |= 1ULL << (k & 63);
+			}
+		}
+		if (cw >= 0) { if (accP) hb_atom_or64(mP + cw, accP); if (accI) hb_atom_or64(mI + cw, accI); }
+	}
+	hb_wsync();
+	int nf = 0;
+	if (lane == 0) {
+		CnsIt &occ = C.B; uint64_t os = occ.mms, oe = occ.mme; uint32_t k = 0; uint64_t mC[8];
+		for (int i = 0; i < 8; i++) mC[i] = mP[i] & ~mI[i];
+#define HB_CNS_FLUSH() do { if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor<GRAPH>(C, os, oe, 0); if (C.need_full) { nf = 1; } } } while (0)
+		while (k < wl && !nf) {
+			if ((mP[k >> 6] >> (k & 63)) & 1) {
+				if ((mI[k >> 6] >> (k & 63)) & 1) { HB_CNS_FLUSH(); if (nf) break; os = oe = (uint64_t)-1; }
+				if (s + k == oe) { const uint32_t r = hb_bits_run(mC, k, (uint32_t)wl, 1); oe += r; k += r; } // columns kept with nothing inserted in front of them extend the anchor
+				else { HB_CNS_FLUSH(); if (nf) break; os = s + k; oe = s + k + 1; k++; }
+			} else {
+				HB_CNS_FLUSH(); if (nf) break; os = oe = (uint64_t)-1;
+				k += hb_bits_run(mP, k, (uint32_t)wl, 0);
+			}
+		}
+#undef HB_CNS_FLUSH
+		if (!nf) { occ.mms = occ.mme = (uint64_t)-1; if (oe > os && os != (uint64_t)-1) { occ.mms = os; occ.mme = oe; } }
+	}
+	*need_full = (int)hb_bcast((uint32_t)nf, 0);
+	return rr;
+}
+
+// wcns_gen for a warp: same arguments as hb_cns_read, called by every lane; S = the warp's shared-memory words.  The edit script, nec, C.need_full, C.ovf are lane 0's.
+template <bool GRAPH> HB_HD uint64_t hb_cns_read_w(CnsCtx &C, uint64_t *S, uint32_t n_ov, uint32_t *srt, uint32_t *act_a, uint32_t *act_b, uint64_t *key)
+{
+	const int lane = hb_lane(); uint32_t n_ent = 0; uint64_t nec = 0;
+	if (lane == 0) {
+		for (uint32_t k = 0; k < n_ov; k++) {
+			const CnsOv &z = C.ov[k];
+			for (uint32_t i = 0; i < z.wn; i++) {
+				if (hb_ualn_w(z.w[i])) continue;
+				if (z.w[i].x_end >= z.w[i].x_start) {
+					key[n_ent] = ((uint64_t)(uint32_t)z.w[i].x_start << 32) + n_ent;
+					CnsEnt &p = C.ent[n_ent]; p.ov = k; p.wid = i; p.xoff = (uint32_t)z.w[i].x_start; p.yoff = (uint32_t)z.w[i].y_start; p.coff = 0;
+					n_ent++;
+				}
+			}
+		}
+		hb_heapsort64(key, n_ent);
+		int64_t k, i, t;
+		for (k = 1, i = 0; k < (int64_t)n_ent; k++) {
+			if ((key[k] >> 32) != (key[i] >> 32)) {
+				if (k - i > 1) {
+					for (t = i; t < k; t++) { const CnsEnt &cp = C.ent[(uint32_t)key[t]]; uint64_t m = (uint64_t)((int64_t)C.ov[cp.ov].w[cp.wid].x_end + 1); m <<= 32; m += (uint32_t)key[t]; key[t] = m; }
+					hb_heapsort64(key + i, (uint32_t)(k - i));
+				}
+				i = k;
+			}
+		}
+		for (uint32_t t2 = 0; t2 < n_ent; t2++) srt[t2] = (uint32_t)key[t2];
+	}
+	n_ent = hb_bcast(n_ent, 0);
+	C.A.srt = srt; C.A.act = act_a; C.A.i = 0; C.A.srt_n = n_ent; C.A.act_n = 0; C.A.rr = C.A.ru = 0; C.A.mms = C.A.mme = (uint64_t)-1;
+	C.B.srt = srt; C.B.act = act_b; C.B.i = 0; C.B.srt_n = n_ent; C.B.act_n = 0; C.B.rr = C.B.ru = 0; C.B.mms = C.B.mme = (uint64_t)-1;
+	C.out_n = 0; C.has_win = 0; C.ax_start = C.ax_end = -1; C.ovf = 0; C.need_full = 0; C.b32_n = 0;
+	hb_wsync();
+	int64_t s = 0, e = HB_CNS_WL, rr = 0; if (e > C.ql) e = C.ql;
+	for (; s < C.ql;) {
+		uint32_t rn = 0;
+		if (lane == 0) rn = hb_cns_iter(C, C.A, s, e, rr, 0);
+		rn = hb_bcast(rn, 0);
+		hb_wsync();
+		int nf = 0;
+		rr = hb_cns_vote_w<GRAPH>(C, S, rn, (uint64_t)s, (uint64_t)e, &nec, &nf);
+		if (nf) { C.need_full = C.need_full ? C.need_full : 1; return nec; }
+		s += HB_CNS_WL; e += HB_CNS_WL; if (e > C.ql) e = C.ql;
+	}
+	if (lane == 0) {
+		if (C.B.mme > C.B.mms && C.B.mms != (uint64_t)-1) nec += hb_cns_anchor<GRAPH>(C, C.B.mms, C.B.mme, 0);
+		if (!C.need_full) nec += hb_cns_anchor<GRAPH>(C, (uint64_t)C.ql, (uint64_t)C.ql, 1);
+	}
+	C.need_full = (int)hb_bcast((uint32_t)C.need_full, 0);
+	return nec;
+}

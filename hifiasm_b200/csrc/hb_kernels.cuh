@@ -25,7 +25,7 @@
 #include "hb_eccns_full.cuh"
 
 #define HB_FULL 0xffffffffu
-static __device__ __forceinline__ int hb_lane() { return threadIdx.x & 31; }
+#include "hb_warp.cuh"
 
 // ----------------------------------------------------------------------------
 // sketch
@@ -1152,7 +1152,7 @@ struct EcCigArgs {
 	double e_rate; int32_t w_l; int gaps;
 	EcPrep *prep; uint32_t *nseg; const uint64_t *seg_off; uint64_t n_seg; EcSeg *segs; // segments of overlap o: segs[seg_off[o] .. seg_off[o+1])
 	uint16_t *spool; unsigned long long *spool_used; uint64_t spool_cap;                // cigars of the aligned segments
-	uint32_t *q_in; const uint32_t *q_in_n; uint32_t *q_out; uint32_t *q_out_n;         // deferred segments (ids) between scratch tiers
+	uint32_t *q_in; const uint32_t *q_in_n; uint32_t *q_out; uint32_t *q_out_n; uint32_t *work; // deferred segments (ids) between scratch tiers; work: the warp tiers' dynamic counter
 	uint64_t *path; uint64_t path_words; uint64_t *vec; int32_t vstride; uint16_t *cig_tmp; int32_t cig_words; // per-thread scratch of the queue tiers / merge
 	int pass; hb_alnb_t *out; hb_wl_t *wl; const uint64_t *wl_off;
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; unsigned int *n_deferred; int *err;
@@ -1201,7 +1201,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
 		uint16_t one[2];
 		EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 1; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
-		C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+		C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.warp = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
 		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
 		int64_t uq[2], ut[2], um;
 		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
@@ -1219,20 +1219,17 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		if (need) A.q_out[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)sidx;
 	}
 }
-// segment alignment: a queue of segment ids.  LOCAL = true: one thread per queued segment with a small private scratch (trace of 640
-// words = 212 columns of a one-word band (3 words per column), 4-word band at most: the usual segment between neighbouring minimizers); LOCAL = false:
-// grid-stride with launch-sized global scratch.  A segment that overflows its scratch queues for the next tier.
+// segment alignment, tier 0: one thread per queued segment with a small private scratch (trace of 640 words = 212 columns of a one-word band
+// (3 words per column), 4-word band at most: the usual segment between neighbouring minimizers).  A segment that overflows it queues for the warp tiers.
 #define ECB_T0_PATH 640
 #define ECB_T0_VS 4
 #define ECB_T0_CIG 72
-template <bool LOCAL>
 __global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
 {
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
-	uint64_t l_path[LOCAL ? ECB_T0_PATH : 1], l_vec[LOCAL ? 11 * ECB_T0_VS : 1]; uint16_t l_cig[LOCAL ? ECB_T0_CIG : 1];
+	uint64_t l_path[ECB_T0_PATH], l_vec[11 * ECB_T0_VS]; uint16_t l_cig[ECB_T0_CIG];
 	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
-	if (LOCAL) { C.ez.path = l_path; C.ez.pcap = ECB_T0_PATH; C.ez.vec = l_vec; C.ez.vstride = ECB_T0_VS; C.ez.cig = l_cig; C.ez.ccap = ECB_T0_CIG; }
-	else { C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * 11 * (uint64_t)A.vstride; C.ez.vstride = A.vstride; C.ez.cig = A.cig_tmp + tid * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words; }
+	C.ez.path = l_path; C.ez.pcap = ECB_T0_PATH; C.ez.vec = l_vec; C.ez.vstride = ECB_T0_VS; C.ez.warp = 0; C.ez.cig = l_cig; C.ez.ccap = ECB_T0_CIG;
 	const uint64_t n_work = (uint64_t)*A.q_in_n;
 	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
 		const uint64_t sidx = A.q_in[wk];
@@ -1251,6 +1248,39 @@ __global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
 		A.segs[sidx] = sg;
 	}
 }
+// segment alignment, warp tiers: one WARP per queued segment, handed out dynamically (A.work).  Every lane runs the reference's scalar logic of the
+// segment (coordinates, error estimate, threshold escalation) identically; inside the aligner the band's words are spread over the lanes
+// (hb_mwalign_w.cuh) and the trace goes to the warp's slice of a launch-sized scratch.  A segment that overflows the slice queues for the next tier.
+__global__ void __launch_bounds__(128) k_ecb_seg_w(EcCigArgs A)
+{
+	const uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+	C.ez.path = A.path + wid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + wid * 2 * (uint64_t)A.vstride; C.ez.vstride = A.vstride; C.ez.warp = 1; C.ez.cig = A.cig_tmp + wid * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words;
+	const uint32_t n_work = *A.q_in_n;
+	for (;;) {
+		uint32_t wk = 0; if (lane == 0) wk = atomicAdd(A.work, 1u);
+		wk = __shfl_sync(0xffffffffu, wk, 0);
+		if (wk >= n_work) break;
+		const uint64_t sidx = A.q_in[wk];
+		uint64_t lo = 0, hi = A.n_ov;
+		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
+		const uint64_t o = lo; const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
+		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
+		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+		C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+		int64_t uq[2], ut[2], um;
+		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
+		__syncwarp();
+		if (lane == 0) {
+			if (C.bad) atomicOr(A.err, 32);
+			EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
+			if (sg.status == 4 && A.q_out) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; }
+			A.segs[sidx] = sg;
+		}
+		__syncwarp(); // the cigar scratch is read by lane 0 above and rewritten by the next segment
+	}
+}
 // merge: thread / overlap, grid-stride — push_alnw / push_unmap_alnw over the stored segments, reassign_gaps when a window closes,
 // totals and update_overlap_region.  pass = 1: only the overlaps the first launch deferred (cigar buffers too small).
 __global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
@@ -1259,7 +1289,7 @@ __global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
 	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.do_gaps = A.gaps;
 	uint16_t *base = A.cig_tmp + tid * 3 * (uint64_t)A.cig_words; // wc | gap output | adjust_gap scratch
 	C.wc = base; C.wccap = A.cig_words; C.ez.cig = base + A.cig_words; C.ez.ccap = A.cig_words; C.ez.path = (uint64_t *)(base + 2 * (uint64_t)A.cig_words); C.ez.pcap = (uint64_t)A.cig_words / 4;
-	C.ez.vec = 0; C.ez.vstride = 0;
+	C.ez.vec = 0; C.ez.vstride = 0; C.ez.warp = 0;
 	for (uint64_t o = tid; o < A.n_ov; o += nthr) {
 		const hb_aln_t a = A.aln[o];
 		if (A.pass == 0) { if (a.st != 2 && a.st != 3) { hb_alnb_t r; r.st = a.st; r.need_rechain = 0; r.re = 0; r.nh_err = 0; r.x_pos_s = r.x_pos_e = r.y_pos_s = r.y_pos_e = 0; r.w_off = A.wl_off[o]; r.w_n = 0; r.pad = 0; A.out[o] = r; continue; } }
@@ -1365,45 +1395,62 @@ __global__ void k_cns_cap(uint64_t nR, const uint64_t *__restrict__ o_off, const
 	for (uint64_t j = o_off[r]; j < o_off[r + 1]; j++) if (alnb[j].st == 2) c += alnb[j].w_n;
 	ent_cap[r] = c;
 }
+#define HB_CNS_RS_WORDS (512 + 3 * HB_RS_STACK)
 struct CnsArgs {
 	DevReads R; uint64_t r0, nR; const uint64_t *o_off; const hb_phase_t *ph; const hb_alnb_t *alnb; const hb_wl_t *wl; const uint16_t *pool;
-	uint64_t *ord; CnsOv *cov; const uint64_t *ent_off; CnsEnt *ent; uint32_t *srt, *act_a, *act_b, *b32; uint64_t *key; uint64_t *ct;
+	uint64_t *ord; CnsOv *cov; const uint64_t *ent_off; CnsEnt *ent; uint32_t *srt, *act_a, *act_b, *b32; uint64_t *key; int32_t *rs; uint32_t *work; // rs: HB_CNS_RS_WORDS per warp (dedup_chains' sort scratch)
 	const uint64_t *out_off; uint16_t *out; uint32_t *out_n; uint8_t *status; unsigned long long *nec; int *err;
 	// second launch: the reads the first one reported (queue), each thread with the arena of the graph consensus
 	const uint32_t *queue; uint32_t n_queue, g_nodes, g_arcs, g_nseq, g_pcap, g_ccap;
 	CnsNode *g_nd; CnsArc *g_arc; uint32_t *g_q, *g_b32, *g_np; uint8_t *g_ns; uint64_t *g_path, *g_vec; uint16_t *g_cig;
 };
-template <bool GRAPH> __global__ void __launch_bounds__(64) k_ec_cns(CnsArgs A)
+// One WARP per read (hb_cns_read_w): the 512-column pile-up as range updates on a difference array in the warp's shared memory, the majority tests one
+// column per lane, lane 0 for the sequential tail (stretch votes between anchors, script).  Reads are handed out dynamically (A.work); the first launch
+// (GRAPH = false) is compiled without the graph consensus and queues the reads that need it for the second, whose warps own a graph arena each.
+#define CNS_WARPS 8
+template <bool GRAPH> __global__ void __launch_bounds__(CNS_WARPS * 32) k_ec_cns_w(CnsArgs A)
 {
-	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st };
-	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+	extern __shared__ uint64_t cns_smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; uint64_t *S = cns_smem + (size_t)warp * HB_CNS_SMEM_WORDS;
+	const uint64_t wid = (uint64_t)blockIdx.x * CNS_WARPS + warp;
+	RsScratch W; { int32_t *b = A.rs + wid * HB_CNS_RS_WORDS; W.bb = b; W.be = b + 256; W.st = (RsFrame *)(b + 512); }
 	const uint64_t n_units = GRAPH ? A.n_queue : A.nR;
 	CnsG G; memset(&G, 0, sizeof(G));
 	if (GRAPH) {
-		G.nd = A.g_nd + tid * A.g_nodes; G.ncap = A.g_nodes; G.arc = A.g_arc + tid * A.g_arcs; G.arc_cap = A.g_arcs; G.q = A.g_q + tid * A.g_nodes; G.q_cap = A.g_nodes;
-		G.b32 = A.g_b32 + tid * A.g_arcs; G.b32_cap = A.g_arcs; G.nseq = A.g_ns + tid * A.g_nseq; G.nseq_np = A.g_np + tid * A.g_nseq; G.nseq_cap = A.g_nseq;
-		G.ez.path = A.g_path + tid * A.g_pcap; G.ez.pcap = A.g_pcap; G.ez.vec = A.g_vec + tid * 32; G.ez.vstride = 2; G.ez.cig = A.g_cig + tid * A.g_ccap; G.ez.ccap = (int32_t)A.g_ccap;
+		G.nd = A.g_nd + wid * A.g_nodes; G.ncap = A.g_nodes; G.arc = A.g_arc + wid * A.g_arcs; G.arc_cap = A.g_arcs; G.q = A.g_q + wid * A.g_nodes; G.q_cap = A.g_nodes;
+		G.b32 = A.g_b32 + wid * A.g_arcs; G.b32_cap = A.g_arcs; G.nseq = A.g_ns + wid * A.g_nseq; G.nseq_np = A.g_np + wid * A.g_nseq; G.nseq_cap = A.g_nseq;
+		G.ez.path = A.g_path + wid * A.g_pcap; G.ez.pcap = A.g_pcap; G.ez.vec = A.g_vec + wid * 32; G.ez.vstride = 2; G.ez.warp = 0; G.ez.cig = A.g_cig + wid * A.g_ccap; G.ez.ccap = (int32_t)A.g_ccap;
 	}
-	for (uint64_t u = tid; u < n_units; u += nthr) {
+	for (;;) {
+		uint32_t u = 0; if (lane == 0) u = atomicAdd(A.work, 1u);
+		u = __shfl_sync(0xffffffffu, u, 0);
+		if (u >= n_units) break;
 		const uint64_t r = GRAPH ? A.queue[u] : u;
-		const uint64_t o0 = A.o_off[r], rid = A.r0 + r, e0 = A.ent_off[r]; const uint32_t n = (uint32_t)(A.o_off[r + 1] - o0); int ovf = 0;
-		PhPair *ord = (PhPair *)(A.ord + o0); uint8_t st = 0;
-		for (uint32_t j = 0; j < n; j++) if (A.ph[o0 + j].st == 2 && A.ph[o0 + j].need_rechain) st |= 4; // the re-seeding rescue of an overlap of this read ran out of scratch (k_ecb_rechain): its lists are not final
-		const uint32_t keep = hb_ec_dedup(A.ph + o0, n, ord, W, &ovf);
-		if (ovf) { atomicOr(A.err, 128); A.out_n[r] = 0; A.status[r] = st | 2; continue; }
-		CnsOv *ov = A.cov + o0; uint32_t n_ov = 0;
-		for (uint32_t k = 0; k < keep; k++) {
-			const hb_phase_t &z = A.ph[o0 + ord[k].idx]; const hb_alnb_t &b = A.alnb[o0 + ord[k].idx];
-			if (z.is_match != 1 || !b.w_n) continue;
-			CnsOv o; o.w = A.wl + b.w_off; o.wn = b.w_n; o.y_id = z.y_id; o.rev = z.rev; ov[n_ov++] = o;
+		const uint64_t o0 = A.o_off[r], rid = A.r0 + r, e0 = A.ent_off[r]; const uint32_t n = (uint32_t)(A.o_off[r + 1] - o0);
+		PhPair *ord = (PhPair *)(A.ord + o0); CnsOv *ov = A.cov + o0; uint32_t n_ov = 0, hdr = 0; // hdr: bit 0-3 status bits, bit 8 = dedup overflow
+		if (lane == 0) {
+			int ovf = 0; uint8_t st = 0;
+			for (uint32_t j = 0; j < n; j++) if (A.ph[o0 + j].st == 2 && A.ph[o0 + j].need_rechain) st |= 4; // the re-seeding rescue of an overlap of this read ran out of scratch: its lists are not final
+			const uint32_t keep = hb_ec_dedup(A.ph + o0, n, ord, W, &ovf);
+			if (!ovf) for (uint32_t k = 0; k < keep; k++) {
+				const hb_phase_t &z = A.ph[o0 + ord[k].idx]; const hb_alnb_t &b = A.alnb[o0 + ord[k].idx];
+				if (z.is_match != 1 || !b.w_n) continue;
+				CnsOv o; o.w = A.wl + b.w_off; o.wn = b.w_n; o.y_id = z.y_id; o.rev = z.rev; ov[n_ov++] = o;
+			}
+			hdr = st | (ovf ? 256u : 0u);
 		}
-		CnsCtx C; C.R = A.R; C.q = hb_rd_view(A.R, rid, 0); C.ql = A.R.len[rid]; C.ov = ov; C.pool = A.pool; C.ent = A.ent + e0; C.ct = A.ct + tid * (2 * HB_CNS_WL); C.b32 = A.b32 + e0;
+		n_ov = __shfl_sync(0xffffffffu, n_ov, 0); hdr = __shfl_sync(0xffffffffu, hdr, 0); __syncwarp();
+		const uint8_t st = (uint8_t)(hdr & 0xff);
+		if (hdr & 256) { if (lane == 0) { atomicOr(A.err, 128); A.out_n[r] = 0; A.status[r] = st | 2; } continue; }
+		CnsCtx C; C.R = A.R; C.q = hb_rd_view(A.R, rid, 0); C.ql = A.R.len[rid]; C.ov = ov; C.pool = A.pool; C.ent = A.ent + e0; C.ct = 0; C.b32 = A.b32 + e0;
 		C.out = A.out + A.out_off[r]; C.out_cap = (uint32_t)(A.out_off[r + 1] - A.out_off[r]); C.g = GRAPH ? &G : (CnsG *)0;
-		const uint64_t nec = hb_cns_read<GRAPH>(C, n_ov, A.srt + e0, A.act_a + e0, A.act_b + e0, A.key + e0);
-		if (C.need_full) { A.out_n[r] = 0; A.status[r] = st | 1 | (C.need_full == 2 ? 8 : 0); continue; } // first launch: queued for the second; second launch: the arena was too small (bit 3)
-		if (C.ovf) { A.out_n[r] = 0; A.status[r] = st | 2; atomicOr(A.err, 256); continue; }
-		A.out_n[r] = C.out_n; A.status[r] = st;
-		atomicAdd(A.nec, (unsigned long long)nec);
+		const uint64_t nec = hb_cns_read_w<GRAPH>(C, S, n_ov, A.srt + e0, A.act_a + e0, A.act_b + e0, A.key + e0);
+		if (lane == 0) {
+			if (C.need_full) { A.out_n[r] = 0; A.status[r] = st | 1 | (C.need_full == 2 ? 8 : 0); } // first launch: queued for the second; second launch: the arena was too small (bit 3)
+			else if (C.ovf) { A.out_n[r] = 0; A.status[r] = st | 2; atomicOr(A.err, 256); }
+			else { A.out_n[r] = C.out_n; A.status[r] = st; atomicAdd(A.nec, (unsigned long long)nec); }
+		}
+		__syncwarp();
 	}
 }
 __global__ void k_sc_compact(uint64_t nR, const uint64_t *__restrict__ slot_off, const uint64_t *__restrict__ dense_off, const uint16_t *__restrict__ in, uint16_t *__restrict__ out)

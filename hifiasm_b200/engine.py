@@ -348,6 +348,9 @@ class Engine:
         n = _lib().hb_profile(self.h, names, launches, ms, 64)
         return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(n)}
 
+    def profile_reset(self):
+        _lib().hb_profile_reset(self.h)
+
     def last_pass_ms(self) -> float:
         ms = C.c_double(); _lib().hb_last_pass_ms(self.h, C.byref(ms)); return ms.value
 

@@ -277,6 +277,7 @@ int hb_write_ec_bin(const char *path, int32_t adapter_len, uint64_t index_size, 
 /* per-kernel launch counters and device time of the last hb_cal_ov_r* call:
  * names[i] (static strings), launches[i], ms[i]; returns number of entries   */
 int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap);
+void hb_profile_reset(hb_ctx_t *ctx); /* the counters also restart at the beginning of every pass */
 /* device time (ms) of the last pass, from CUDA events recorded on the context's
  * own stream around the whole pass (first launch .. last result resident)     */
 int hb_last_pass_ms(const hb_ctx_t *ctx, double *ms);

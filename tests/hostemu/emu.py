@@ -265,3 +265,11 @@ def bf_counts(hashes, bf_shift):
     key = np.zeros(h.size + 1, np.uint64); cnt = np.zeros(h.size + 1, np.uint32)
     m = L.emu_bf_counts(_p(h), C.c_uint64(h.size), C.c_int(bf_shift), _p(key), _p(cnt), C.c_uint64(h.size))
     return key[:m], cnt[:m]
+
+
+def mw_align(reads, qid, tid, rev, mode, ps0, pn, qs0, tn, thre, abs_diag, which):
+    """one call of the step-B aligner (which = 0: hb_mw_align, 1: hb_mw_align_w over virtual lanes) -> (ovf, (err, ps, pe, ts, te), cigar u16[])"""
+    res = np.zeros(6, np.int32); cig = np.zeros(1 << 16, np.uint16)
+    ovf = lib().emu_mw_align(reads.h, C.c_uint32(qid), C.c_uint32(tid), C.c_uint32(rev), C.c_int(mode), C.c_int64(ps0), C.c_int32(pn), C.c_int64(qs0), C.c_int32(tn),
+                             C.c_int32(thre), C.c_int32(abs_diag), C.c_int(which), _p(res), _p(cig), C.c_int32(cig.size))
+    return ovf, tuple(int(x) for x in res[:5]), cig[:int(res[5])].copy()

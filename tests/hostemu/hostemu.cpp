@@ -307,7 +307,7 @@ int emu_ec_align_B(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_c
 	std::vector<uint64_t> path(path_words), vec(11 * HB_MW_MAXW); std::vector<uint16_t> ecig(cig_words), wc(cig_words);
 	std::vector<uint16_t> gout(cig_words);
 	EcBCtx C; C.gout = gout.data(); C.gcap = cig_words; C.e_rate = e_rate; C.w_l = w_l; C.pool = pool; C.pool_used = &used; C.pool_cap = pool_cap; C.do_gaps = gaps; C.no_myers = 0;
-	C.ez.path = path.data(); C.ez.pcap = path_words; C.ez.vec = vec.data(); C.ez.vstride = HB_MW_MAXW; C.ez.cig = ecig.data(); C.ez.ccap = cig_words; C.wc = wc.data(); C.wccap = cig_words;
+	C.ez.path = path.data(); C.ez.pcap = path_words; C.ez.vec = vec.data(); C.ez.vstride = HB_MW_MAXW; C.ez.warp = 0; C.ez.cig = ecig.data(); C.ez.ccap = cig_words; C.wc = wc.data(); C.wccap = cig_words;
 	for (uint32_t j = 0; j < n_ch; j++) {
 		hb_alnb_t res; memset(&res, 0, sizeof(res)); res.st = aln[j].st; res.w_off = nw;
 		if (aln[j].st == 2) {
@@ -365,14 +365,14 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 			for (int32_t k = 0; k < ns; k++) {
 				int64_t uq[2], ut[2], um;
 				{ // the pre-pass: no scratch at all, stops where an alignment would start
-					uint16_t one[2]; C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.no_myers = 1;
+					uint16_t one[2]; C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.warp = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0; C.no_myers = 1;
 					const int st = hb_ecb_segment(C, z, hits + c.first_hit, pr.ch_n, k, uq, ut, &um);
 					C.no_myers = 0;
 					if (st != 5 && !C.ez.ovf) { hb_seg_store(C, st, uq, ut, um, &segs[k], spool.data(), &sused, spool.size()); n_tier[0]++; continue; }
 				}
-				for (int tier = 0; tier < 2; tier++) {
-					if (tier == 0) { C.ez.path = path0.data(); C.ez.pcap = 640; C.ez.vec = vec0.data(); C.ez.vstride = 4; C.ez.cig = cig0.data(); C.ez.ccap = 72; }
-					else { C.ez.path = path1.data(); C.ez.pcap = path1.size(); C.ez.vec = vec1.data(); C.ez.vstride = HB_MW_MAXW; C.ez.cig = cig1.data(); C.ez.ccap = 65535; }
+				for (int tier = getenv("HB_EMU_ALN_ALLWARP") ? 1 : 0; tier < 2; tier++) {
+					if (tier == 0) { C.ez.path = path0.data(); C.ez.pcap = 640; C.ez.vec = vec0.data(); C.ez.vstride = 4; C.ez.warp = 0; C.ez.cig = cig0.data(); C.ez.ccap = 72; }
+					else { C.ez.path = path1.data(); C.ez.pcap = path1.size(); C.ez.vec = vec1.data(); C.ez.vstride = HB_MW_MAXW; C.ez.warp = getenv("HB_EMU_ALN_THREAD") ? 0 : 1; /* the queue tiers run hb_mw_align_w (virtual lanes) */ C.ez.cig = cig1.data(); C.ez.ccap = 65535; }
 					C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
 					const int st = hb_ecb_segment(C, z, hits + c.first_hit, pr.ch_n, k, uq, ut, &um);
 					hb_seg_store(C, st, uq, ut, um, &segs[k], spool.data(), &sused, spool.size());
@@ -383,13 +383,13 @@ int emu_ec_align_B_par(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t
 			}
 			EcBCtx M; M.gout = 0; M.gcap = 0; M.no_myers = 0; M.e_rate = e_rate; M.w_l = w_l; M.pool = pool; M.pool_used = &used; M.pool_cap = pool_cap; M.do_gaps = gaps;
 			M.wc = mbuf.data(); M.wccap = cig_words; M.ez.cig = mbuf.data() + cig_words; M.ez.ccap = cig_words; M.ez.path = (uint64_t *)(mbuf.data() + 2 * (size_t)cig_words); M.ez.pcap = (uint64_t)cig_words / 4;
-			M.ez.vec = 0; M.ez.vstride = 0; M.q = C.q; M.t = C.t; M.ql = C.ql; M.tl = C.tl;
+			M.ez.vec = 0; M.ez.vstride = 0; M.ez.warp = 0; M.q = C.q; M.t = C.t; M.ql = C.ql; M.tl = C.tl;
 			M.aw = wl + nw; M.awcap = (int32_t)std::min<uint64_t>(wl_cap - nw, (uint64_t)scn + 2 + HB_RC_SPARE_WIN);
 			hb_ecb_merge(M, z, aln[j].re, pr, segs.data(), spool.data(), &res);
 			if (rechain && res.st == 2 && res.need_rechain) { // what k_ecb_rechain does: a fresh context with the large aligner scratch over the merged list
 				EcBCtx Rc; Rc.gout = rbuf.data() + 2 * 65535; Rc.gcap = 65535; Rc.e_rate = e_rate; Rc.w_l = w_l; Rc.pool = pool; Rc.pool_used = &used; Rc.pool_cap = pool_cap; Rc.do_gaps = gaps; Rc.no_myers = 0;
 				Rc.q = C.q; Rc.t = C.t; Rc.ql = C.ql; Rc.tl = C.tl; Rc.aw = M.aw; Rc.awcap = M.awcap;
-				Rc.ez.path = path1.data(); Rc.ez.pcap = path1.size(); Rc.ez.vec = vec1.data(); Rc.ez.vstride = HB_MW_MAXW; Rc.ez.cig = rbuf.data(); Rc.ez.ccap = 65535;
+				Rc.ez.path = path1.data(); Rc.ez.pcap = path1.size(); Rc.ez.vec = vec1.data(); Rc.ez.vstride = HB_MW_MAXW; Rc.ez.warp = 0; Rc.ez.cig = rbuf.data(); Rc.ez.ccap = 65535;
 				Rc.wc = rbuf.data() + 65535; Rc.wccap = 65535;
 				hb_ecb_rechain(Rc, z, aln[j].re, RS.S, &res);
 				if (RS.rc_err) rc |= 2;
@@ -533,12 +533,31 @@ int emu_ec_cns(void *reads, uint32_t rid, const hb_phase_t *ph, const hb_alnb_t 
 	CnsG G; memset(&G, 0, sizeof(G));
 	if (g_nodes) {
 		G.nd = nd.data(); G.ncap = g_nodes; G.arc = arcs.data(); G.arc_cap = g_arcs; G.q = gq.data(); G.q_cap = g_nodes; G.b32 = gb32.data(); G.b32_cap = g_arcs;
-		G.nseq = gns.data(); G.nseq_np = gnp.data(); G.nseq_cap = 4096; G.ez.path = path.data(); G.ez.pcap = path.size(); G.ez.vec = vec.data(); G.ez.vstride = 2; G.ez.cig = gcig.data(); G.ez.ccap = (int32_t)gcig.size();
+		G.nseq = gns.data(); G.nseq_np = gnp.data(); G.nseq_cap = 4096; G.ez.path = path.data(); G.ez.pcap = path.size(); G.ez.vec = vec.data(); G.ez.vstride = 2; G.ez.warp = 0; G.ez.cig = gcig.data(); G.ez.ccap = (int32_t)gcig.size();
 		C.g = &G;
 	}
-	*nec = g_nodes ? hb_cns_read<true>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data()) : hb_cns_read<false>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
+	std::vector<uint64_t> S(HB_CNS_SMEM_WORDS); // the warp's shared-memory words (a warp of one lane here)
+	if (getenv("HB_EMU_CNS_THREAD")) *nec = g_nodes ? hb_cns_read<true>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data()) : hb_cns_read<false>(C, (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
+	else *nec = g_nodes ? hb_cns_read_w<true>(C, S.data(), (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data()) : hb_cns_read_w<false>(C, S.data(), (uint32_t)ov.size(), srt.data(), aa.data(), ab.data(), key.data());
 	*n_out = C.out_n;
 	return C.need_full ? (C.need_full == 2 ? 3 : 1) : (C.ovf ? 2 : 0);
+}
+
+
+// one call of the step-B aligner on two reads of the store: which = 0 hb_mw_align (thread), 1 hb_mw_align_w (band over virtual lanes).
+// pattern = target[ps0, ps0 + pn) on strand rev, text = query[qs0, qs0 + tn).  -> res[6] = err, ps, pe, ts, te, cn; returns ez.ovf
+int emu_mw_align(void *reads, uint32_t qid, uint32_t tid, uint32_t rev, int mode, int64_t ps0, int32_t pn, int64_t qs0, int32_t tn, int32_t thre, int32_t abs_diag, int which,
+                 int32_t *res, uint16_t *cig, int32_t ccap)
+{
+	EmuReads *r = (EmuReads *)reads;
+	const RdView Q = hb_rd_view(r->d, qid, 0), T = hb_rd_view(r->d, tid, rev);
+	std::vector<uint64_t> path((size_t)HB_MW_MAXW * 5 * (tn + 2) + 256), vec(11 * HB_MW_MAXW);
+	MwEz ez; memset(&ez, 0, sizeof(ez)); ez.path = path.data(); ez.pcap = path.size(); ez.vec = vec.data(); ez.vstride = HB_MW_MAXW; ez.cig = cig; ez.ccap = ccap; ez.warp = which;
+	if (which == 0) hb_mw_align(mode, T, ps0, pn, Q, qs0, tn, thre, abs_diag, ez);
+	else if ((((thre << 1) + 1 + 63) >> 6) <= 32) hb_mw_align_w<1>(mode, T, ps0, pn, Q, qs0, tn, thre, abs_diag, ez);
+	else hb_mw_align_w<2>(mode, T, ps0, pn, Q, qs0, tn, thre, abs_diag, ez);
+	res[0] = ez.err; res[1] = ez.ps; res[2] = ez.pe; res[3] = ez.ts; res[4] = ez.te; res[5] = ez.err <= ez.thre ? ez.cn : 0;
+	return ez.ovf;
 }
 
 // counting behind the reference's Bloom filter the way index.cu evaluates it (hb_bloom.cuh): distinct k-mers with the ordinal of their first
