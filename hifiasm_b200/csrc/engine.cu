@@ -170,6 +170,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->anchor_budget = 96ull << 20; ctx->last_pass_ms = 0;
 	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = ctx->ws_virt = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
+	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
 	ctx->cns_g_nodes = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096; ctx->cns_g_arcs = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
@@ -619,16 +620,36 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	TRACE("expand");
 		// group: retried with a larger directory / arena when the first guess was too small
 		GroupDir *d_dir = 0; uint32_t h_dirn = 0; uint64_t dir_cap = B / 8 + 64 * nb + 1024, arena_words = 16ull << 20;
+		const uint32_t heavy_min = 16384; std::vector<uint32_t> h_heavy; uint64_t heavy_need = 0; uint32_t big_ts_max = 1u << 18; // reads with this many anchors get a block each (k_group_big)
+		for (uint64_t i = b0; i < b1; i++) { const uint64_t na = h_aoff[i + 1] - h_aoff[i]; if (na >= heavy_min) h_heavy.push_back((uint32_t)(i - b0)); }
+		uint32_t *d_heavy = ba.get<uint32_t>(h_heavy.size() + 1); HB_ALLOC_CHECK(ba);
+		if (!h_heavy.empty()) HB_CUDA(cudaMemcpyAsync(d_heavy, h_heavy.data(), h_heavy.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 		for (int attempt = 0;; attempt++) {
+			heavy_need = 0;
+			for (uint64_t i = b0; i < b1; i++) { // every read that can reach k_group_big: the heavy ones, and those with enough anchors to hold more than GRP_MAXG targets
+				const uint64_t na = h_aoff[i + 1] - h_aoff[i]; if (na <= GRP_MAXG) continue;
+				uint64_t ts = 1024; while (ts < 2 * na && ts < big_ts_max) ts <<= 1; heavy_need += 3 * ts;
+			}
+			if (arena_words < heavy_need + (16ull << 20)) arena_words = heavy_need + (16ull << 20);
 			if (dir_cap > B + 1) dir_cap = B + 1;
 			d_dir = ba.get<GroupDir>(dir_cap); uint32_t *d_ar = ba.get<uint32_t>(arena_words);
 			HB_ALLOC_CHECK(ba);
 			HB_CUDA(cudaMemsetAsync(d_dirn, 0, 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_arena_used, 0, 8, ctx->stream));
 			GroupArgs G; G.nR = nb; G.r0 = r0 + b0; G.a_off = d_aoff + b0; G.a_base = a_base; G.raw = d_raw; G.hits = d_hits; G.dir = d_dir; G.dir_n = d_dirn; G.dir_cap = (uint32_t)dir_cap;
 			G.sc = d_sc; G.arena = d_ar; G.arena_used = d_arena_used; G.arena_words = arena_words; G.mcopy_num = CP.mcopy_num; G.mcopy_khit_cutoff = CP.mcopy_khit_cutoff; G.err = d_err;
+			G.heavy_min = heavy_min; G.big_ts_max = big_ts_max; G.heavy = d_heavy; G.n_heavy = (uint32_t)h_heavy.size(); G.heavy_from_q = 0;
+			G.ovf_q = ba.get<uint32_t>(nb + 1); G.ovf_n = ba.zero<uint32_t>(1); HB_ALLOC_CHECK(ba);
 			{
 				ProfScope ps(ctx, "k_group");
 				k_group<<<nblk(nb, GRP_WARPS), GRP_WARPS * 32, GRP_SMEM_BYTES, ctx->stream>>>(G);
+			}
+			if (!h_heavy.empty()) {
+				ProfScope ps(ctx, "k_group_big");
+				k_group_big<<<(unsigned)h_heavy.size(), GRPB_WARPS * 32, 0, ctx->stream>>>(G);
+			}
+			{ // the reads k_group handed over (count on the device: surplus blocks leave at once)
+				uint32_t h_nq = 0; HB_CUDA(cudaMemcpyAsync(&h_nq, G.ovf_n, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+				if (h_nq) { GroupArgs Gq = G; Gq.n_heavy = 0; Gq.heavy_from_q = 1; ProfScope ps(ctx, "k_group_big"); k_group_big<<<h_nq, GRPB_WARPS * 32, 0, ctx->stream>>>(Gq); }
 			}
 			HB_CUDA(cudaGetLastError());
 			int h_err = 0;
@@ -636,7 +657,8 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			HB_CUDA(cudaStreamSynchronize(ctx->stream));
 			if (!h_err) { ba.release(d_ar); break; }
 			ba.release(d_dir); ba.release(d_ar);
-			if (attempt >= 4 || (h_err & 2)) { hb_set_err(ctx, HB_E_OVERFLOW, "anchor grouping overflow (flags %d)", h_err); return HB_E_OVERFLOW; }
+			if (attempt >= 6 || ((h_err & 2) && big_ts_max >= (1u << 30))) { hb_set_err(ctx, HB_E_OVERFLOW, "anchor grouping overflow (flags %d)", h_err); return HB_E_OVERFLOW; }
+			if (h_err & 2) big_ts_max <<= 3; // a heavy read with more distinct targets than its table holds
 			if (h_err & 8) dir_cap = B + 1;
 			if (h_err & 4) arena_words *= 8;
 		}
@@ -728,6 +750,12 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					HB_CUDA(cudaMemsetAsync(d_pused, 0, 8, ctx->stream));
 					EcAlnArgs E; E.ea = d_ea; E.R = R; E.r0 = r0 + b0; E.n_ov = n_ov; E.desc = d_od; E.ch = d_ch; E.fc = d_fc; E.fc_grp_base = d_fcb; E.win = d_wout; E.e_rate = so->e_rate; E.w_l = w_l;
 					E.wl = d_wl; E.out = d_aln; E.path = d_path; E.cig_tmp = d_ctmp; E.pool = d_pool; E.pool_used = d_pused; E.pool_cap = pool_cap; E.err = d_err;
+					E.q = ba.get<uint32_t>(n_ov + 1); E.q_n = ba.zero<uint32_t>(1); HB_ALLOC_CHECK(ba);
+					if (attempt) HB_CUDA(cudaMemsetAsync(d_wl, 0, (n_win + 1) * sizeof(hb_wl_t), ctx->stream)); // (a rerun with a larger pool starts from clean window lists)
+					{
+						ProfScope ps(ctx, "k_ec_overlap_fast");
+						if (n_ov) k_ec_overlap_fast<<<nblk(n_ov, 128), 128, 0, ctx->stream>>>(E);
+					}
 					{
 						ProfScope ps(ctx, "k_ec_overlap");
 						if (n_ov) k_ec_overlap<<<blocks, 64, 0, ctx->stream>>>(E);
@@ -750,8 +778,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					if ((rc = hb_scan_u32_to_u64(ctx, d_cap, d_wboff, n_ov))) return rc;
 					uint64_t wb_tot = 0; HB_CUDA(cudaMemcpyAsync(&wb_tot, d_wboff + n_ov, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 					hb_wl_t *d_wlb = ba.zero<hb_wl_t>(wb_tot + 1); HB_ALLOC_CHECK(ba);
-					static const uint64_t path_words1 = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384; // half of tier 2's trace words
-					static const int32_t merge_cw0 = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
+					const uint64_t path_words1 = ctx->ecb_path_words; const int32_t merge_cw0 = ctx->ecb_cig_words; // tier 1's trace words per warp (tier 2: 16 x); cigar words of the first merge launch
 					EcPrep *d_prep = ba.get<EcPrep>(n_ov + 1); uint32_t *d_nseg = ba.zero<uint32_t>(n_ov + 1); uint64_t *d_segoff = ba.get<uint64_t>(n_ov + 2);
 					uint32_t *d_qn = ba.zero<uint32_t>(8); unsigned long long *d_spused = ba.zero<unsigned long long>(1);
 					HB_ALLOC_CHECK(ba);
@@ -790,7 +817,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						// tiers 1..3 give a WARP to a segment (k_ecb_seg_w): {trace words per warp, cigar runs, warps}; the largest holds the longest alignment the reference
 						// attempts (HB_MAX_SIN_L columns x 64 band words x 3 trace words)
 						const struct { uint64_t pw; int32_t cw; unsigned warps; const char *name; } TIER[4] = {
-							{ 0, 0, 0, "k_ecb_seg" }, { 16384, 1024, (unsigned)ctx->sm_count * 16, "k_ecb_seg_tier1" }, { 262144, 8192, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier2" },
+							{ 0, 0, 0, "k_ecb_seg" }, { path_words1, 1024, (unsigned)ctx->sm_count * 16, "k_ecb_seg_tier1" }, { path_words1 * 16, 8192, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier2" },
 							{ (uint64_t)HB_MW_MAXW * (2 + 3 * (uint64_t)HB_MAX_SIN_L), 65535, (unsigned)ctx->sm_count * 2, "k_ecb_seg_tier3" } };
 						for (int tier = 0; tier <= 3 && h_q[tier]; tier++) {
 							Arena sa(ctx);
@@ -875,7 +902,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "EC base alignment: fake-cigar lookup failed"); return HB_E_STATE; }
 						if (poolb_used <= poolb_cap && mode >= 7) { // phasing of the batch's reads over the step-C state that stays in HBM (row a13)
 							std::vector<uint64_t> h_boff(nb + 1, 0);
-							for (uint64_t i = 0; i < nb; i++) h_boff[i + 1] = h_boff[i] + ((ctx->h_rlen[r0 + b0 + i] + 8) & ~7ull);
+							for (uint64_t i = 0; i < nb; i++) h_boff[i + 1] = h_boff[i] + hb_ph_bits_bytes(ctx->h_rlen[r0 + b0 + i]);
 							uint64_t *d_boff = ba.get<uint64_t>(nb + 1); uint8_t *d_cnt = ba.zero<uint8_t>(h_boff[nb] + 8); PhOv *d_phov = ba.get<PhOv>(n_ov + 1);
 							uint32_t *d_nacc = ba.zero<uint32_t>(nb + 1), *d_nsite = ba.zero<uint32_t>(nb + 1), *d_nev = ba.zero<uint32_t>(nb + 1); uint64_t *d_soff = ba.get<uint64_t>(nb + 2), *d_eoff = ba.get<uint64_t>(nb + 2);
 							hb_phase_t *d_ph = ba.get<hb_phase_t>(n_ov + 1);
@@ -883,10 +910,11 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							HB_CUDA(cudaMemcpyAsync(d_boff, h_boff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 							PhArgs P; memset(&P, 0, sizeof(P));
 							P.R = R; P.r0 = r0 + b0; P.nR = nb; P.o_off = d_ooff; P.desc = d_od; P.ch = d_ch; P.aln = d_aln; P.alnb = d_alnb; P.wl = d_wlb; P.pool = d_poolb;
-							P.ov = d_phov; P.n_acc = d_nacc; P.b_off = d_boff; P.cnt = d_cnt; P.n_site = d_nsite; P.n_ev = d_nev; P.out = d_ph; P.err = d_err;
+							P.ov = d_phov; P.n_acc = d_nacc; P.b_off = d_boff; P.cnt = d_cnt; P.n_site = d_nsite; P.n_ev = d_nev; P.out = d_ph; P.err = d_err; P.work = ba.zero<uint32_t>(2); HB_ALLOC_CHECK(ba);
+							const unsigned ph_blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nb + PH_WARPS - 1) / PH_WARPS, (uint64_t)ctx->sm_count * 8));
 							{
 								ProfScope ps(ctx, "k_ph_count");
-								k_ph_count<<<nblk(nb, 128), 128, 0, ctx->stream>>>(P);
+								k_ph_count<<<ph_blocks, PH_WARPS * 32, 0, ctx->stream>>>(P);
 							}
 							HB_CUDA(cudaGetLastError());
 							if ((rc = hb_scan_u32_to_u64(ctx, d_nsite, d_soff, nb)) || (rc = hb_scan_u32_to_u64(ctx, d_nev, d_eoff, nb))) return rc;
@@ -898,7 +926,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							HB_ALLOC_CHECK(ba);
 							{
 								ProfScope ps(ctx, "k_ph_decide");
-								k_ph_decide<<<nblk(nb, 64), 64, 0, ctx->stream>>>(P);
+								k_ph_decide<<<ph_blocks, PH_WARPS * 32, 0, ctx->stream>>>(P);
 							}
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));

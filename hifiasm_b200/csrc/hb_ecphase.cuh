@@ -14,6 +14,7 @@
 #pragma once
 #include "hb_ecaln.cuh"
 #include "hb_chain.cuh"
+#include "hb_warp.cuh"
 
 struct alignas(8) PhEv { uint32_t site, ov, osite, cov; uint8_t type, base, pad[6]; };           // haplotype_evdience (Correct.h:130-143); base = 0..3, 4 = N; 24 bytes: the array doubles as a u64 work list
 struct PhSnp { uint32_t id, overlap_num, occ_0, occ_1, occ_2, site; int32_t score; uint32_t pad; }; // SnpStats (Correct.h:152-167)
@@ -21,77 +22,118 @@ struct PhOv { const hb_wl_t *w; uint32_t wn; const uint16_t *pool; uint32_t y_id
 
 HB_HD bool hb_ph_ualn(const hb_wl_t &u) { return u.error == INT16_MAX && u.clen == 0 && u.extra_end < 0; } // is_ualn_win, Correct.h:1362
 
-// pass 1 over a read: cnt[] (zeroed by the caller, ql bytes) -> number of candidate sites and of evidence records
-HB_HD void hb_ph_count(const PhOv *ov, uint32_t n_ov, uint8_t *cnt, int64_t ql, uint32_t *n_site, uint32_t *n_ev)
+// ---- one WARP per read (hb_warp.cuh; a warp of one lane in tests/hostemu) ---------------------------------------------------------------------
+// Scratch of a read (zeroed by the caller): PhBits over nwd = ceil(ql / 32) words — s1 / s2: a mismatch column seen at this query position by
+// at least one / at least two alignments (the reference's saturating per-position counter is only ever tested for > 1), pre: candidate sites in front
+// of each word, so that "sites inside [a, b)" is two popcounts.  Lanes own alignment windows and walk cigar RUNS; nothing is per column.
+struct PhBits { uint32_t *s1, *s2, *pre; uint32_t nwd; };
+HB_HD PhBits hb_ph_bits(uint8_t *scratch, int64_t ql) { PhBits b; b.nwd = (uint32_t)((ql + 31) >> 5); b.s1 = (uint32_t *)scratch; b.s2 = b.s1 + b.nwd; b.pre = b.s2 + b.nwd; return b; }
+HB_HD uint64_t hb_ph_bits_bytes(uint64_t ql) { return ((((ql + 31) >> 5) * 3 + 1) * 4 + 15) & ~15ull; }
+HB_HD uint32_t hb_ph_rank(const PhBits &b, int64_t x) { const uint32_t w = (uint32_t)(x >> 5), r = (uint32_t)(x & 31); return w < b.nwd ? b.pre[w] + (r ? (uint32_t)hb_popc64(b.s2[w] & ((1u << r) - 1)) : 0u) : b.pre[b.nwd]; }
+#if defined(__CUDA_ARCH__)
+HB_D uint32_t hb_atom_or32(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+#else
+inline uint32_t hb_atom_or32(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p |= v; return o; }
+#endif
+// windows of all overlaps, flattened: lanes take them round-robin.  f(j, window) is called for every aligned window with a cigar.
+template <typename F> HB_HD void hb_ph_for_windows(const PhOv *ov, uint32_t n_ov, F f)
 {
-	for (uint32_t j = 0; j < n_ov; j++) for (uint32_t w = 0; w < ov[j].wn; w++) {
+	const int lane = hb_lane();
+	for (uint32_t j = 0; j < n_ov; j++) for (uint32_t w = lane; w < ov[j].wn; w += HB_WS) {
 		const hb_wl_t &u = ov[j].w[w];
 		if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
-		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1;
+		f(j, u);
+	}
+}
+// pass 1 (extract_sub_cigar_hc with set_f, then the scan for counts > 1): candidate sites and the number of evidence records
+HB_HD void hb_ph_count_w(const PhOv *ov, uint32_t n_ov, uint8_t *scratch, int64_t ql, uint32_t *n_site, uint32_t *n_ev)
+{
+	const int lane = hb_lane(); PhBits B = hb_ph_bits(scratch, ql);
+	hb_ph_for_windows(ov, n_ov, [&](uint32_t j, const hb_wl_t &u) {
+		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1; const uint16_t *cg = ov[j].pool + u.cidx;
 		for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
-			const uint32_t op = ov[j].pool[u.cidx + ci] >> 14, cl = ov[j].pool[u.cidx + ci] & 0x3fff; const int64_t ws = xk;
+			const uint32_t op = cg[ci] >> 14, cl = cg[ci] & 0x3fff; const int64_t ws = xk;
 			if (op != 2) xk += cl;
 			if (op != 1) continue;
 			const int64_t oe = xk < e0 ? xk : e0;
-			for (int64_t t = ws; t < oe; t++) if (cnt[t] <= 126) cnt[t]++;
+			for (int64_t t = ws; t < oe; t++) { const uint32_t bit = 1u << (t & 31); if (hb_atom_or32(B.s1 + (t >> 5), bit) & bit) hb_atom_or32(B.s2 + (t >> 5), bit); }
 		}
+	});
+	hb_wsync();
+	uint32_t run = 0; // sites in front of each word: chunks of HB_WS words, one warp scan per chunk
+	for (uint32_t w0 = 0; w0 < B.nwd; w0 += HB_WS) {
+		const uint32_t w = w0 + (uint32_t)lane, c = w < B.nwd ? (uint32_t)hb_popc64(B.s2[w]) : 0u; uint32_t tot;
+		const uint32_t ex = hb_wscan(c, &tot);
+		if (w < B.nwd) B.pre[w] = run + ex;
+		run += tot;
 	}
-	uint32_t ns = 0;
-	for (int64_t t = 0; t < ql; t++) { if (cnt[t] > 1) { cnt[t] = 1; ns++; } else cnt[t] = 0; } // flag: 1 = candidate site
-	uint32_t ne = 0;
-	for (uint32_t j = 0; j < n_ov; j++) for (uint32_t w = 0; w < ov[j].wn; w++) {
-		const hb_wl_t &u = ov[j].w[w];
-		if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
-		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1;
+	if (lane == 0) B.pre[B.nwd] = run;
+	hb_wsync();
+	int32_t ne = 0;
+	hb_ph_for_windows(ov, n_ov, [&](uint32_t j, const hb_wl_t &u) {
+		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1; const uint16_t *cg = ov[j].pool + u.cidx;
 		for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
-			const uint32_t op = ov[j].pool[u.cidx + ci] >> 14, cl = ov[j].pool[u.cidx + ci] & 0x3fff; const int64_t ws = xk;
+			const uint32_t op = cg[ci] >> 14, cl = cg[ci] & 0x3fff; const int64_t ws = xk;
 			if (op != 2) xk += cl;
 			if (op > 1) continue;
 			const int64_t oe = xk < e0 ? xk : e0;
-			for (int64_t t = ws; t < oe; t++) ne += cnt[t];
+			if (oe > ws) ne += (int32_t)(hb_ph_rank(B, oe) - hb_ph_rank(B, ws));
 		}
-	}
-	*n_site = ns; *n_ev = ne;
+	});
+	*n_site = run; *n_ev = (uint32_t)hb_wsum(ne);
 }
 
-// pass 2: evidence in (site, overlap) order, allele statistics, haplotype call.
-// scratch: site_pos[n_site], site_off[n_site + 1], ev[n_ev], ev2[n_ev], snp[4 * n_site], ord[n_ov] (uint64)
-HB_HD void hb_ph_decide(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_ov, const uint8_t *flag, int64_t ql, uint32_t n_site, uint32_t n_ev,
-                        uint32_t *site_pos, uint32_t *site_off, PhEv *ev, PhEv *ev2, PhSnp *snp, uint64_t *ord, uint32_t *ov_off, const RsScratch &W, int s_hap_cov, int infor_cov, double up, int *ovf)
+// pass 2: evidence in (site, overlap) order, allele statistics, haplotype call.  Every lane calls it; lanes share the evidence scatter, lane 0 runs the
+// reference's sequential statistics and greedy call.  scratch = pass 1's bit arrays of the read.
+// site_pos[n_site], site_off[n_site + 1], ev[n_ev], ev2[n_ev], snp[4 * n_site], ord[n_ov] (uint64)
+HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_ov, uint8_t *scratch, int64_t ql, uint32_t n_site, uint32_t n_ev,
+                          uint32_t *site_pos, uint32_t *site_off, PhEv *ev, PhEv *ev2, PhSnp *snp, uint64_t *ord, uint32_t *ov_off, const RsScratch &W, int s_hap_cov, int infor_cov, double up, int *ovf)
 {
 	if (!n_site || !n_ev) return;
+	const int lane = hb_lane(); const PhBits B = hb_ph_bits(scratch, ql);
 	const RdView Q = hb_rd_view(R, qid, 0);
-	uint32_t ns = 0;
-	for (int64_t t = 0; t < ql; t++) if (flag[t]) site_pos[ns++] = (uint32_t)t;
-	auto site_idx = [&](uint32_t t) -> uint32_t { uint32_t lo = 0, hi = ns; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (site_pos[mid] < t) lo = mid + 1; else hi = mid; } return lo; };
-	// counting sort by site: sizes, offsets, scatter (overlaps visited in ascending id => ascending id inside a site, which is also
-	// what push_info's sort by overlap id produces: the ids of a site are unique)
-	for (uint32_t k = 0; k <= ns; k++) site_off[k] = 0;
-	for (int pass = 0; pass < 2; pass++) {
-		for (uint32_t j = 0; j < n_ov; j++) {
-			const RdView T = hb_rd_view(R, ov[j].y_id, ov[j].rev);
-			for (uint32_t w = 0; w < ov[j].wn; w++) {
-				const hb_wl_t &u = ov[j].w[w];
-				if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
-				int64_t xk = u.x_start, yk = u.y_start; const int64_t e0 = (int64_t)u.x_end + 1;
-				for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
-					const uint32_t op = ov[j].pool[u.cidx + ci] >> 14, cl = ov[j].pool[u.cidx + ci] & 0x3fff; const int64_t ws = xk;
-					if (op != 2) xk += cl;
-					if (op != 3) yk += cl;
-					if (op > 1) continue;
-					const int64_t oe = xk < e0 ? xk : e0;
-					for (uint32_t si = site_idx((uint32_t)ws); si < ns && (int64_t)site_pos[si] < oe; si++) {
-						if (!pass) { site_off[si]++; continue; }
-						const int64_t t = site_pos[si]; PhEv e;
-						e.site = (uint32_t)t; e.ov = j; e.osite = (uint32_t)(t - xk + yk); e.cov = 1; e.type = (uint8_t)op; for (int z = 0; z < 6; z++) e.pad[z] = 0;
-						e.base = (uint8_t)(op == 0 ? Q.at(t) : T.at(t - xk + yk));
-						ev[site_off[si]++] = e;
-					}
+	const uint32_t ns = n_site;
+	for (uint32_t w = lane; w < B.nwd; w += HB_WS) { uint32_t m = B.s2[w], k = B.pre[w]; while (m) { const int b = hb_ctz64(m); m &= m - 1; site_pos[k++] = (w << 5) + (uint32_t)b; } }
+	for (uint32_t k = lane; k <= ns; k += HB_WS) site_off[k] = 0;
+	hb_wsync();
+	// sizes per site (any order), then the scatter overlap by overlap: the windows of ONE overlap are disjoint on the query, so within an overlap no two
+	// lanes touch the same site, and taking the overlaps in ascending order leaves every site's records in ascending overlap id (push_info's order)
+	hb_ph_for_windows(ov, n_ov, [&](uint32_t j, const hb_wl_t &u) {
+		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1; const uint16_t *cg = ov[j].pool + u.cidx;
+		for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
+			const uint32_t op = cg[ci] >> 14, cl = cg[ci] & 0x3fff; const int64_t ws = xk;
+			if (op != 2) xk += cl;
+			if (op > 1) continue;
+			const int64_t oe = xk < e0 ? xk : e0;
+			if (oe > ws) for (uint32_t si = hb_ph_rank(B, ws), se = hb_ph_rank(B, oe); si < se; si++) hb_atom_add32(site_off + si, 1u);
+		}
+	});
+	hb_wsync();
+	{ uint32_t run = 0; for (uint32_t k0 = 0; k0 < ns; k0 += HB_WS) { const uint32_t k = k0 + (uint32_t)lane, c = k < ns ? site_off[k] : 0u; uint32_t tot; const uint32_t ex = hb_wscan(c, &tot); if (k < ns) site_off[k] = run + ex; run += tot; } } // start of every site; the scatter turns it into the end
+	hb_wsync();
+	for (uint32_t j = 0; j < n_ov; j++) {
+		const RdView T = hb_rd_view(R, ov[j].y_id, ov[j].rev);
+		for (uint32_t w = lane; w < ov[j].wn; w += HB_WS) {
+			const hb_wl_t &u = ov[j].w[w];
+			if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
+			int64_t xk = u.x_start, yk = u.y_start; const int64_t e0 = (int64_t)u.x_end + 1; const uint16_t *cg = ov[j].pool + u.cidx;
+			for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
+				const uint32_t op = cg[ci] >> 14, cl = cg[ci] & 0x3fff; const int64_t ws = xk;
+				if (op != 2) xk += cl;
+				if (op != 3) yk += cl;
+				if (op > 1) continue;
+				const int64_t oe = xk < e0 ? xk : e0;
+				if (oe > ws) for (uint32_t si = hb_ph_rank(B, ws), se = hb_ph_rank(B, oe); si < se; si++) {
+					const int64_t t = site_pos[si]; PhEv e;
+					e.site = (uint32_t)t; e.ov = j; e.osite = (uint32_t)(t - xk + yk); e.cov = 1; e.type = (uint8_t)op; for (int z = 0; z < 6; z++) e.pad[z] = 0;
+					e.base = (uint8_t)(op == 0 ? Q.at(t) : T.at(t - xk + yk));
+					ev[site_off[si]++] = e;
 				}
 			}
 		}
-		if (!pass) { uint32_t acc = 0; for (uint32_t k = 0; k < ns; k++) { const uint32_t c = site_off[k]; site_off[k] = acc; acc += c; } } // start of every site; the scatter turns it into the end
+		hb_wsync();
 	}
+	if (lane != 0) return;
 	// push_info per site (Correct.cpp:10511-10600, oa = NULL, v8 = NULL): allele statistics, evidence kept only for real alleles
 	uint32_t n_snp = 0, m_ev = 0, beg = 0;
 	for (uint32_t k = 0; k < ns; k++) {

@@ -33,6 +33,7 @@ struct hb_ctx {
 	// instrumentation
 	std::vector<ProfEntry> prof; uint64_t counters[12];
 	uint64_t anchor_budget; // anchors per batch
+	uint64_t ecb_path_words; int32_t ecb_cig_words; // step B: trace words per warp of alignment tier 1, cigar words of the first merge launch (HB_ECB_PATH_WORDS / HB_ECB_CIG_WORDS, read once in hb_create: the tests shrink them so that the deferral paths run)
 	uint32_t cns_g_nodes, cns_g_arcs; // arena of the graph consensus per warp (HB_CNS_G_NODES / HB_CNS_G_ARCS, read once in hb_create: the overflow report is tested with tiny ones)
 	double last_pass_ms;
 	// workspace: one device allocation used as a double-ended stack (lo: scoped scratch,

@@ -332,6 +332,7 @@ struct GroupArgs {
 	GroupDir *dir; uint32_t *dir_n; uint32_t dir_cap; uint32_t *sc; // chain slots per read
 	uint32_t *arena; unsigned long long *arena_used; uint64_t arena_words;
 	int32_t mcopy_num, mcopy_khit_cutoff; int *err;
+	uint32_t heavy_min, big_ts_max; const uint32_t *heavy; uint32_t n_heavy; uint32_t *ovf_q, *ovf_n; int heavy_from_q; // ovf_q: reads k_group hands over (more than GRP_MAXG distinct targets) // reads with >= heavy_min anchors (batch-local ids): one BLOCK each (k_group_big)
 };
 
 #define GRP_SMEM_BYTES (GRP_WARPS * (2 * GRP_TS + 2 * GRP_MAXG) * 4)
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 	if (r >= A.nR) return;
 	const uint64_t base = A.a_off[r] - A.a_base; const uint32_t n = (uint32_t)(A.a_off[r + 1] - A.a_off[r]), rid = (uint32_t)(A.r0 + r);
 	if (n == 0) { if (lane == 0) A.sc[r] = 0; return; }
+	if (n >= A.heavy_min) return; // a block of k_group_big takes the read
 	const hb_hit_t *raw = A.raw + base; hb_hit_t *out = A.hits + base;
 	uint32_t *keys = w_smem, *vals = w_smem + GRP_TS, *gk = w_smem + 2 * GRP_TS, *gc = gk + GRP_MAXG, mask = GRP_TS - 1, maxg = GRP_MAXG;
 	bool use_global = false;
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 		}
 		__syncwarp();
 		if (!__any_sync(HB_FULL, ovf)) break;
+		if (A.ovf_q) { if (lane == 0) A.ovf_q[atomicAdd(A.ovf_n, 1u)] = (uint32_t)r; return; } // more distinct targets than the shared-memory table holds: a block of k_group_big takes the read
 		if (use_global) { if (lane == 0) atomicOr(A.err, 2); return; } // cannot happen: global tables are sized from n
 		// fall back: tables sized for n distinct keys in the global arena
 		uint32_t ts = 64; while (ts < 2 * n) ts <<= 1;
@@ -398,28 +401,34 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 			}
 			__syncwarp();
 		}
-	// one directory entry per group; a group whose target is the read itself gets no
-	// chain slot (anchor.cpp:1931) but is still ordered (slot = GRP_EMPTY)
+	// one directory entry per TARGET: the keys (target, strand 0) and (target, strand 1) are neighbours in key order and form ONE group, strand 0
+	// block first (lchain_qgen_mcopy_fast chains a target's anchors of both strands in one call, anchor.cpp:1928-1934); a group whose target is the
+	// read itself gets no chain slot (anchor.cpp:1931) but is still ordered (slot = GRP_EMPTY)
+	uint32_t Gh = 0;
+	for (uint32_t g0 = 0; g0 < G; g0 += 32) { const uint32_t g = g0 + lane; Gh += __popc(__ballot_sync(HB_FULL, g < G && (g == 0 || (gk[g - 1] >> 1) != (gk[g] >> 1)))); }
 	uint32_t dbase = 0;
-	if (lane == 0) dbase = atomicAdd(A.dir_n, G);
+	if (lane == 0) dbase = atomicAdd(A.dir_n, Gh);
 	dbase = __shfl_sync(HB_FULL, dbase, 0);
-	const bool dir_ok = (uint64_t)dbase + G <= A.dir_cap;
+	const bool dir_ok = (uint64_t)dbase + Gh <= A.dir_cap;
 	if (!dir_ok && lane == 0) atomicOr(A.err, 8);
-	uint32_t run_a = 0, run_s = 0;
+	uint32_t run_a = 0, run_s = 0, run_h = 0;
 	for (uint32_t g0 = 0; g0 < G; g0 += 32) {
-		uint32_t g = g0 + lane, c = 0, ns = 0, key = 0;
-		if (g < G) { key = gk[g]; c = gc[g]; if ((key >> 1) != rid) ns = c >= (uint32_t)A.mcopy_khit_cutoff ? A.mcopy_num : 1; }
-		uint32_t ia = c, is = ns;
+		uint32_t g = g0 + lane, c = 0, ns = 0, key = 0, head = 0, cg = 0;
+		if (g < G) {
+			key = gk[g]; c = gc[g]; head = g == 0 || (gk[g - 1] >> 1) != (key >> 1);
+			if (head) { cg = c + ((g + 1 < G && (gk[g + 1] >> 1) == (key >> 1)) ? gc[g + 1] : 0); if ((key >> 1) != rid) ns = cg >= (uint32_t)A.mcopy_khit_cutoff ? A.mcopy_num : 1; }
+		}
+		uint32_t ia = c, is = ns, ih = head;
 		for (int d = 1; d < 32; d <<= 1) {
-			uint32_t va = __shfl_up_sync(HB_FULL, ia, d), vs = __shfl_up_sync(HB_FULL, is, d);
-			if (lane >= d) { ia += va; is += vs; }
+			uint32_t va = __shfl_up_sync(HB_FULL, ia, d), vs = __shfl_up_sync(HB_FULL, is, d), vh = __shfl_up_sync(HB_FULL, ih, d);
+			if (lane >= d) { ia += va; is += vs; ih += vh; }
 		}
 		if (g < G) {
 			uint32_t start = run_a + ia - c;
 			vals[grp_find(keys, mask, key)] = start; // the key's write cursor
-			if (dir_ok) { GroupDir e; e.read = (uint32_t)r; e.start = start; e.count = c; e.slot = ns ? run_s + is - ns : GRP_EMPTY; A.dir[dbase + g] = e; }
+			if (dir_ok && head) { GroupDir e; e.read = (uint32_t)r; e.start = start; e.count = cg; e.slot = ns ? run_s + is - ns : GRP_EMPTY; A.dir[dbase + run_h + ih - 1] = e; }
 		}
-		run_a += __shfl_sync(HB_FULL, ia, 31); run_s += __shfl_sync(HB_FULL, is, 31);
+		run_a += __shfl_sync(HB_FULL, ia, 31); run_s += __shfl_sync(HB_FULL, is, 31); run_h += __shfl_sync(HB_FULL, ih, 31);
 	}
 	if (lane == 0) A.sc[r] = run_s;
 	__syncwarp();
@@ -434,6 +443,100 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
 			if (q < n) {
 				uint32_t d = atomicAdd(&vals[grp_find(keys, mask, grp_key(hh[u].x))], 1u);
 				*(uint4 *)(out + d) = hh[u];
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// group, block per heavy read (repeat-rich reads carry 10^5 - 10^6 anchors; one warp would hold the whole launch back).  Same three phases with the
+// tables in the global arena: (A) every warp counts a slice of the anchors into ONE table; (B) the block collects the distinct keys, orders them (bitonic
+// over the block), scans the counts into write cursors and fills the directory; (C) the keys are dealt to the warps by a second hash: a warp scans all
+// keys of the read but scatters only its own, in query-minimizer order — so, as in k_group, only anchors of the same 32-anchor step can leave out of order.
+#define GRPB_WARPS 16
+static __device__ __forceinline__ uint32_t grp_owner(uint32_t key) { return (key * 0x9E3779B1u) >> 28; } // 0 .. 15
+__global__ void __launch_bounds__(GRPB_WARPS * 32) k_group_big(GroupArgs A)
+{
+	__shared__ uint32_t s_nd, s_dbase, s_ok; __shared__ unsigned long long s_at; __shared__ uint32_t s_wa[GRPB_WARPS], s_ws[GRPB_WARPS], s_wh[GRPB_WARPS];
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, NT = GRPB_WARPS * 32;
+	if (blockIdx.x >= A.n_heavy + (A.heavy_from_q ? *A.ovf_n : 0u)) return;
+	const uint64_t r = A.heavy_from_q ? A.ovf_q[blockIdx.x] : A.heavy[blockIdx.x];
+	const uint64_t base = A.a_off[r] - A.a_base; const uint32_t n = (uint32_t)(A.a_off[r + 1] - A.a_off[r]), rid = (uint32_t)(A.r0 + r);
+	const hb_hit_t *raw = A.raw + base; hb_hit_t *out = A.hits + base;
+	uint32_t ts = 1024; while (ts < 2 * n && ts < A.big_ts_max) ts <<= 1;
+	const uint32_t mask = ts - 1, maxg = ts / 2;
+	if (tid == 0) { s_at = atomicAdd(A.arena_used, 3ull * ts); s_nd = 0; s_ok = 1; }
+	__syncthreads();
+	if (s_at + 3ull * ts > A.arena_words) { if (tid == 0) { atomicOr(A.err, 4); A.sc[r] = 0; } return; }
+	uint32_t *keys = A.arena + s_at, *vals = keys + ts, *gk = vals + ts, *gc = gk + maxg;
+	for (uint32_t i = tid; i < ts; i += NT) { keys[i] = GRP_EMPTY; vals[i] = 0; }
+	__syncthreads();
+	for (uint32_t q = tid; q < n; q += NT) { // (A)
+		const uint32_t k = grp_key(__ldg(&raw[q].id_strand)); bool fresh; const uint32_t sl = grp_find_or_insert(keys, mask, k, &fresh);
+		if (sl == GRP_EMPTY) { s_ok = 0; continue; }
+		atomicAdd(&vals[sl], 1u);
+		if (fresh && atomicAdd(&s_nd, 1u) >= maxg) s_ok = 0;
+	}
+	__syncthreads();
+	if (!s_ok) { if (tid == 0) { atomicOr(A.err, 2); A.sc[r] = 0; } return; } // more distinct targets than big_ts_max / 2: the host grows it
+	const uint32_t G = s_nd; uint32_t Gp = 32; while (Gp < G) Gp <<= 1;
+	__syncthreads();
+	if (tid == 0) s_nd = 0;
+	__syncthreads();
+	for (uint32_t i = tid; i < ts; i += NT) if (keys[i] != GRP_EMPTY) { const uint32_t p = atomicAdd(&s_nd, 1u); gk[p] = keys[i]; gc[p] = vals[i]; }
+	for (uint32_t i = G + tid; i < Gp; i += NT) { gk[i] = GRP_EMPTY; gc[i] = 0; }
+	__syncthreads();
+	for (uint32_t k = 2; k <= Gp; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			for (uint32_t i = tid; i < Gp; i += NT) {
+				const uint32_t x = i ^ j;
+				if (x > i) { const uint32_t a = gk[i], b = gk[x]; const bool asc = (i & k) == 0; if ((a > b) == asc) { gk[i] = b; gk[x] = a; const uint32_t t = gc[i]; gc[i] = gc[x]; gc[x] = t; } }
+			}
+			__syncthreads();
+		}
+	if (tid == 0) s_nd = 0;
+	__syncthreads();
+	{ uint32_t hc = 0; for (uint32_t g = tid; g < G; g += NT) hc += g == 0 || (gk[g - 1] >> 1) != (gk[g] >> 1); if (hc) atomicAdd(&s_nd, hc); } // targets = groups (both strands of a target form one, see k_group)
+	__syncthreads();
+	const uint32_t Gh = s_nd;
+	if (tid == 0) { s_dbase = atomicAdd(A.dir_n, Gh); }
+	__syncthreads();
+	const uint32_t dbase = s_dbase; const bool dir_ok = (uint64_t)dbase + Gh <= A.dir_cap;
+	if (!dir_ok && tid == 0) atomicOr(A.err, 8);
+	uint32_t run_a = 0, run_s = 0, run_h = 0;
+	for (uint32_t g0 = 0; g0 < G; g0 += NT) { // write cursors and directory: block scan over (count, slots, heads) in key order
+		const uint32_t g = g0 + tid; uint32_t c = 0, ns = 0, key = 0, head = 0, cg = 0;
+		if (g < G) {
+			key = gk[g]; c = gc[g]; head = g == 0 || (gk[g - 1] >> 1) != (key >> 1);
+			if (head) { cg = c + ((g + 1 < G && (gk[g + 1] >> 1) == (key >> 1)) ? gc[g + 1] : 0); if ((key >> 1) != rid) ns = cg >= (uint32_t)A.mcopy_khit_cutoff ? A.mcopy_num : 1; }
+		}
+		uint32_t ia = c, is = ns, ih = head;
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t va = __shfl_up_sync(HB_FULL, ia, d), vs = __shfl_up_sync(HB_FULL, is, d), vh = __shfl_up_sync(HB_FULL, ih, d); if (lane >= d) { ia += va; is += vs; ih += vh; } }
+		if (lane == 31) { s_wa[wib] = ia; s_ws[wib] = is; s_wh[wib] = ih; }
+		__syncthreads();
+		uint32_t pa = 0, ps = 0, ph = 0, ta = 0, tsum = 0, th = 0;
+		for (int w = 0; w < GRPB_WARPS; w++) { if (w < wib) { pa += s_wa[w]; ps += s_ws[w]; ph += s_wh[w]; } ta += s_wa[w]; tsum += s_ws[w]; th += s_wh[w]; }
+		if (g < G) {
+			const uint32_t start = run_a + pa + ia - c;
+			vals[grp_find(keys, mask, key)] = start;
+			if (dir_ok && head) { GroupDir e; e.read = (uint32_t)r; e.start = start; e.count = cg; e.slot = ns ? run_s + ps + is - ns : GRP_EMPTY; A.dir[dbase + run_h + ph + ih - 1] = e; }
+		}
+		run_a += ta; run_s += tsum; run_h += th;
+		__syncthreads();
+	}
+	if (tid == 0) A.sc[r] = run_s;
+	__syncthreads();
+	for (uint32_t q0 = 0; q0 < n; q0 += 256) { // (C) every warp walks all keys (8 x 32 key loads in flight), 32 anchors per step, and moves the anchors of the keys it owns
+		uint32_t kk[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) { const uint32_t q = q0 + 32 * u + lane; kk[u] = q < n ? grp_key(__ldg(&raw[q].id_strand)) : GRP_EMPTY; }
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const uint32_t q = q0 + 32 * u + lane, k = kk[u];
+			if (k != GRP_EMPTY && grp_owner(k) == (uint32_t)wib) {
+				const uint4 h = __ldg((const uint4 *)(raw + q));
+				const uint32_t d = atomicAdd(&vals[grp_find(keys, mask, k)], 1u);
+				*(uint4 *)(out + d) = h;
 			}
 			__syncwarp();
 		}
@@ -966,6 +1069,7 @@ struct WinArgs {
 	DevReads R; uint64_t r0, n_win; const WinDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
 	double e_rate; int32_t w_l; hb_win_t *out; int *err;
 };
+static __device__ __forceinline__ uint64_t hb_bswap64(uint64_t v) { return ((uint64_t)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0, 0x0123); }
 static __device__ __forceinline__ bool dev_is_n(const DevReads &R, uint64_t rid, uint32_t pos)
 { // membership in the read's (ascending) N list
 	uint64_t lo = R.noff[rid], hi = R.noff[rid + 1];
@@ -1026,7 +1130,40 @@ __global__ void __launch_bounds__(128) k_windows(WinArgs A)
 		uint64_t Peq[5] = { 0, 0, 0, 0, 0 }, VP = 0, VN, X, D0, HN, HP, mm;
 		int32_t bd, i, err = abs_diag, i_bd, tn0 = tn - 1, cut = th + (th << 1), best = INT32_MAX, pe = -1, site, ai, uge = INT32_MAX, chh;
 		bool dead = pn > tn + cut || tn > pn + cut;
-		if (!dead) {
+		if (!dead && !q_has_n && !t_has_n) {
+			// no N on either read (the rule): the band's match mask comes from two bit planes of the pattern (low / high bit of the base) and a
+			// validity plane, shifted with the band — no Peq table, no indexed registers — and both reads are streamed 32 bases per 64-bit load
+			const uint64_t *qw = (const uint64_t *)qp, *tw = (const uint64_t *)tp;
+			uint64_t tb; int32_t tleft; // text: base q_s + i in the top two bits of tb
+			{ const uint64_t p0 = (uint64_t)q_s; tb = hb_bswap64(__ldg(qw + (p0 >> 5))) << (2 * (p0 & 31)); tleft = 32 - (int32_t)(p0 & 31); }
+			uint64_t pb; int32_t pleft; int64_t pw;       // pattern: forward -> next base in the top two bits; reverse strand -> next base in the low two bits (complemented)
+			if (!rev) { const uint64_t p0 = (uint64_t)r_s; pw = (int64_t)(p0 >> 5); pb = hb_bswap64(__ldg(tw + pw)) << (2 * (p0 & 31)); pleft = 32 - (int32_t)(p0 & 31); }
+			else { const uint64_t p0 = (uint64_t)(t_tot_l - 1 - r_s); pw = (int64_t)(p0 >> 5); pb = hb_bswap64(__ldg(tw + pw)) >> (2 * (31 - (p0 & 31))); pleft = (int32_t)(p0 & 31) + 1; }
+			auto pnext = [&]() -> uint32_t {
+				if (pleft == 0) { if (!rev) { ++pw; pb = hb_bswap64(__ldg(tw + pw)); } else { --pw; pb = hb_bswap64(__ldg(tw + pw)); } pleft = 32; }
+				uint32_t b; if (!rev) { b = (uint32_t)(pb >> 62); pb <<= 2; } else { b = 3u - (uint32_t)(pb & 3ULL); pb >>= 2; }
+				--pleft; return b;
+			};
+			uint64_t lo = 0, hi = 0, va = 0;
+			bd = ((th << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn;
+			for (i = 0; i < bd; i++) { const uint32_t b = pnext(); const int sh = abs_diag + i; lo |= (uint64_t)(b & 1) << sh; hi |= (uint64_t)(b >> 1) << sh; va |= 1ULL << sh; }
+			i_bd = (th << 1) - abs_diag; VN = (1ULL << abs_diag) - 1; const int top = th << 1;
+			for (i = 0; i <= tn0; i++) {
+				if (tleft == 0) { tb = hb_bswap64(__ldg(qw + ((uint64_t)(q_s + i) >> 5))); tleft = 32; }
+				const uint32_t tc = (uint32_t)(tb >> 62); tb <<= 2; --tleft;
+				const uint64_t Lm = 0ULL - (uint64_t)(tc & 1), Hm = 0ULL - (uint64_t)(tc >> 1);
+				X = (va & ~((lo ^ Lm) | (hi ^ Hm))) | VN;
+				D0 = ((VP + (X & VP)) ^ VP) | X;
+				HN = VP & D0; HP = VN | ~(VP | D0);
+				X = D0 >> 1;
+				VN = X & HP; VP = HN | ~(X | HP);
+				if (!(D0 & 1ULL)) { ++err; if (err > cut) { dead = true; break; } }
+				if (i == tn0) break;
+				lo >>= 1; hi >>= 1; va >>= 1;
+				++i_bd;
+				if (i_bd < pn) { const uint32_t b = pnext(); lo |= (uint64_t)(b & 1) << top; hi |= (uint64_t)(b >> 1) << top; va |= 1ULL << top; }
+			}
+		} else if (!dead) {
 			bd = ((th << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn;
 			for (i = 0, mm = 1ULL << abs_diag; i < bd; i++) { Peq[pat(i)] |= mm; mm <<= 1; }
 			i_bd = (th << 1) - abs_diag; VN = (1ULL << abs_diag) - 1;
@@ -1119,18 +1256,39 @@ struct EcAlnArgs {
 	const uint8_t *ea; // row a12 flags (NULL: none)
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base; const hb_win_t *win;
 	double e_rate; int32_t w_l; hb_wl_t *wl; hb_aln_t *out; uint64_t *path; uint16_t *cig_tmp; uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; int *err;
+	uint32_t *q, *q_n; // overlaps that need the aligner (k_ec_overlap_fast -> k_ec_overlap)
 };
+// step A in two launches.  k_ec_overlap_fast, thread / overlap at full occupancy: an overlap whose windows ALL aligned in the window pass (the rule) needs no
+// aligner — push_hc_wlst_exz finds no gap to fill and gen_extend_err_exz no stretch to estimate — so its window list and error total are sums over the
+// records; the others are queued.  k_ec_overlap, thread / queued overlap, grid bounded by the per-thread trace scratch: gap filling and extension estimates.
+__global__ void __launch_bounds__(128) k_ec_overlap_fast(EcAlnArgs A)
+{
+	const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= A.n_ov) return;
+	const OvDesc d = A.desc[o];
+	hb_aln_t res; res.w_off = d.w0; res.pad = 0;
+	if (A.ea && A.ea[o]) { res.st = 3; res.align_length = 0; res.rr = 0; res.re = 0; res.w_n = 0; A.out[o] = res; return; } // accepted by the previous round's exact record: no alignment
+	bool all = true;
+	for (uint32_t k = 0; k < d.nw; k++) { const hb_win_t &wr = A.win[d.w0 + k]; if (wr.t_pri_l < 0 || wr.err > wr.thre) { all = false; break; } }
+	if (!all) { A.q[atomicAdd(A.q_n, 1u)] = (uint32_t)o; return; }
+	const hb_chain_t c = A.ch[d.slot];
+	EcCtx C; C.R = A.R; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.err = A.err;
+	C.ez.path = 0; C.ez.cig = 0; C.ez.cn = 0;
+	C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand);
+	hb_ec_overlap_A(C, c, A.fc + A.fc_grp_base[d.slot] + c.fc_off, A.win + d.w0, (int32_t)d.nw, A.wl + d.w0, &res);
+	A.out[o] = res;
+}
 __global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
 {
 	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
 	EcCtx C; C.R = A.R; C.e_rate = A.e_rate; C.w_l = A.w_l; C.pool = A.pool; C.pool_used = A.pool_used; C.pool_cap = A.pool_cap; C.err = A.err;
 	C.ez.path = A.path + tid * (uint64_t)A.w_l * 5; C.ez.cig = A.cig_tmp + tid * HB_EC_CIG_TMP; C.ez.cn = 0;
-	for (uint64_t o = tid; o < A.n_ov; o += nthr) {
+	const uint64_t n_work = *A.q_n;
+	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
+		const uint64_t o = A.q[wk];
 		const OvDesc d = A.desc[o]; const hb_chain_t c = A.ch[d.slot];
 		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand);
 		hb_aln_t res; res.w_off = d.w0; res.pad = 0;
-		if (A.ea && A.ea[o]) { res.st = 3; res.align_length = 0; res.rr = 0; res.re = 0; res.w_n = 0; } // accepted by the previous round's exact record: no alignment
-		else hb_ec_overlap_A(C, c, A.fc + A.fc_grp_base[d.slot] + c.fc_off, A.win + d.w0, (int32_t)d.nw, A.wl + d.w0, &res);
+		hb_ec_overlap_A(C, c, A.fc + A.fc_grp_base[d.slot] + c.fc_off, A.win + d.w0, (int32_t)d.nw, A.wl + d.w0, &res);
 		A.out[o] = res;
 	}
 }
@@ -1325,37 +1483,59 @@ __global__ void k_ecb_wn(uint64_t n_ov, const hb_alnb_t *__restrict__ in, uint32
 struct PhArgs {
 	DevReads R; uint64_t r0, nR; const uint64_t *o_off; const OvDesc *desc; const hb_chain_t *ch; const hb_aln_t *aln; const hb_alnb_t *alnb; const hb_wl_t *wl; const uint16_t *pool;
 	PhOv *ov; uint32_t *n_acc; const uint64_t *b_off; uint8_t *cnt; uint32_t *n_site, *n_ev; const uint64_t *site_off, *ev_off;
-	uint32_t *site_pos, *site_o; PhEv *ev, *ev2; PhSnp *snp; uint64_t *ord; uint32_t *ov_o; hb_phase_t *out; int *err;
+	uint32_t *site_pos, *site_o; PhEv *ev, *ev2; PhSnp *snp; uint64_t *ord; uint32_t *ov_o; hb_phase_t *out; int *err; uint32_t *work; // work[2]: dynamic read counters of the two kernels
 };
-__global__ void __launch_bounds__(128) k_ph_count(PhArgs A)
+#define HB_CNS_RS_WORDS (512 + 3 * HB_RS_STACK) // dedup_chains' / the phasing's radix-sort scratch (RsScratch) as int32 words
+#define PH_WARPS 4
+// warp / read, reads handed out dynamically (A.work[0] / A.work[1]): lanes share the cigar walks of the read's alignment windows (hb_ph_count_w / hb_ph_decide_w)
+__global__ void __launch_bounds__(PH_WARPS * 32) k_ph_count(PhArgs A)
 {
-	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= A.nR) return;
-	const uint64_t o0 = A.o_off[r], o1 = A.o_off[r + 1]; PhOv *ov = A.ov + o0; uint32_t n = 0;
-	for (uint64_t o = o0; o < o1; o++) {
-		const hb_alnb_t b = A.alnb[o]; if (b.st != 2) continue;
-		const hb_chain_t &c = A.ch[A.desc[o].slot];
-		PhOv v; v.w = A.wl + b.w_off; v.wn = b.w_n; v.pool = A.pool; v.y_id = c.y_id; v.rev = c.y_pos_strand; v.align_length = A.aln[o].align_length; v.is_match = 1; v.strong = 0;
-		ov[n++] = v;
+	const int lane = threadIdx.x & 31;
+	for (;;) {
+		uint32_t r = 0; if (lane == 0) r = atomicAdd(A.work, 1u);
+		r = __shfl_sync(0xffffffffu, r, 0);
+		if (r >= A.nR) break;
+		const uint64_t o0 = A.o_off[r], o1 = A.o_off[r + 1]; PhOv *ov = A.ov + o0; uint32_t n = 0;
+		if (lane == 0) for (uint64_t o = o0; o < o1; o++) {
+			const hb_alnb_t b = A.alnb[o]; if (b.st != 2) continue;
+			const hb_chain_t &c = A.ch[A.desc[o].slot];
+			PhOv v; v.w = A.wl + b.w_off; v.wn = b.w_n; v.pool = A.pool; v.y_id = c.y_id; v.rev = c.y_pos_strand; v.align_length = A.aln[o].align_length; v.is_match = 1; v.strong = 0;
+			ov[n++] = v;
+		}
+		n = __shfl_sync(0xffffffffu, n, 0); __syncwarp();
+		uint32_t ns = 0, ne = 0;
+		if (n) hb_ph_count_w(ov, n, A.cnt + A.b_off[r], A.R.len[A.r0 + r], &ns, &ne);
+		if (lane == 0) { A.n_acc[r] = n; A.n_site[r] = ns; A.n_ev[r] = ne; }
 	}
-	uint32_t ns = 0, ne = 0;
-	if (n) hb_ph_count(ov, n, A.cnt + A.b_off[r], A.R.len[A.r0 + r], &ns, &ne);
-	A.n_acc[r] = n; A.n_site[r] = ns; A.n_ev[r] = ne;
 }
-__global__ void __launch_bounds__(64) k_ph_decide(PhArgs A)
+__global__ void __launch_bounds__(PH_WARPS * 32) k_ph_decide(PhArgs A)
 {
-	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= A.nR) return;
-	const uint64_t o0 = A.o_off[r], o1 = A.o_off[r + 1]; PhOv *ov = A.ov + o0; const uint32_t n = A.n_acc[r];
-	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st }; int ovf = 0;
-	if (n) hb_ph_decide(A.R, A.r0 + r, ov, n, A.cnt + A.b_off[r], A.R.len[A.r0 + r], A.n_site[r], A.n_ev[r], A.site_pos + A.site_off[r], A.site_o + A.site_off[r] + r,
-	                    A.ev + A.ev_off[r], A.ev2 + A.ev_off[r], A.snp + 4 * A.site_off[r], A.ord + o0, A.ov_o + o0 + r, W, 3, 3, 0.04, &ovf); // s_hap_cov = infor_cov = 3 (CommandLines.cpp:333-334), up = 0.04
-	if (ovf) atomicOr(A.err, 128);
-	uint32_t k = 0;
-	for (uint64_t o = o0; o < o1; o++) {
-		const hb_alnb_t b = A.alnb[o]; const hb_chain_t &c = A.ch[A.desc[o].slot]; hb_phase_t p;
-		p.st = b.st; p.y_id = c.y_id; p.rev = c.y_pos_strand; p.is_match = 0; p.strong = 0; p.need_rechain = 0;
-		if (b.st == 2) { p.x_pos_s = b.x_pos_s; p.x_pos_e = b.x_pos_e; p.y_pos_s = b.y_pos_s; p.y_pos_e = b.y_pos_e; p.nh_err = (uint32_t)b.nh_err; p.is_match = ov[k].is_match; p.strong = ov[k].strong; p.need_rechain = (uint32_t)b.need_rechain; k++; }
-		else { p.x_pos_s = c.x_pos_s; p.x_pos_e = c.x_pos_e; p.y_pos_s = c.y_pos_s; p.y_pos_e = c.y_pos_e; p.nh_err = 0; }
-		A.out[o] = p;
+	__shared__ int32_t s_rs[PH_WARPS][HB_CNS_RS_WORDS];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	RsScratch W; W.bb = s_rs[warp]; W.be = s_rs[warp] + 256; W.st = (RsFrame *)(s_rs[warp] + 512);
+	for (;;) {
+		uint32_t r = 0; if (lane == 0) r = atomicAdd(A.work + 1, 1u);
+		r = __shfl_sync(0xffffffffu, r, 0);
+		if (r >= A.nR) break;
+		const uint64_t o0 = A.o_off[r], o1 = A.o_off[r + 1]; PhOv *ov = A.ov + o0; const uint32_t n = A.n_acc[r]; int ovf = 0;
+		if (n) hb_ph_decide_w(A.R, A.r0 + r, ov, n, A.cnt + A.b_off[r], A.R.len[A.r0 + r], A.n_site[r], A.n_ev[r], A.site_pos + A.site_off[r], A.site_o + A.site_off[r] + r,
+		                      A.ev + A.ev_off[r], A.ev2 + A.ev_off[r], A.snp + 4 * A.site_off[r], A.ord + o0, A.ov_o + o0 + r, W, 3, 3, 0.04, &ovf); // s_hap_cov = infor_cov = 3 (CommandLines.cpp:333-334), up = 0.04
+		if (ovf) atomicOr(A.err, 128);
+		__syncwarp(); // lane 0's calls are in ov[]
+		uint32_t k0 = 0; // records of the read's overlaps: lanes take overlaps, the rank among the accepted ones by a running ballot count
+		for (uint64_t ob = o0; ob < o1; ob += 32) {
+			const uint64_t o = ob + lane; const bool in = o < o1; hb_alnb_t b; b.st = 0; if (in) b = A.alnb[o];
+			const unsigned acc = __ballot_sync(0xffffffffu, in && b.st == 2);
+			if (in) {
+				const hb_chain_t &c = A.ch[A.desc[o].slot]; hb_phase_t p;
+				p.st = b.st; p.y_id = c.y_id; p.rev = c.y_pos_strand; p.is_match = 0; p.strong = 0; p.need_rechain = 0;
+				if (b.st == 2) { const uint32_t k = k0 + __popc(acc & ((1u << lane) - 1)); p.x_pos_s = b.x_pos_s; p.x_pos_e = b.x_pos_e; p.y_pos_s = b.y_pos_s; p.y_pos_e = b.y_pos_e; p.nh_err = (uint32_t)b.nh_err; p.is_match = ov[k].is_match; p.strong = ov[k].strong; p.need_rechain = (uint32_t)b.need_rechain; }
+				else { p.x_pos_s = c.x_pos_s; p.x_pos_e = c.x_pos_e; p.y_pos_s = c.y_pos_s; p.y_pos_e = c.y_pos_e; p.nh_err = 0; }
+				A.out[o] = p;
+			}
+			k0 += __popc(acc);
+		}
+		__syncwarp();
 	}
 }
 
@@ -1395,7 +1575,6 @@ __global__ void k_cns_cap(uint64_t nR, const uint64_t *__restrict__ o_off, const
 	for (uint64_t j = o_off[r]; j < o_off[r + 1]; j++) if (alnb[j].st == 2) c += alnb[j].w_n;
 	ent_cap[r] = c;
 }
-#define HB_CNS_RS_WORDS (512 + 3 * HB_RS_STACK)
 struct CnsArgs {
 	DevReads R; uint64_t r0, nR; const uint64_t *o_off; const hb_phase_t *ph; const hb_alnb_t *alnb; const hb_wl_t *wl; const uint16_t *pool;
 	uint64_t *ord; CnsOv *cov; const uint64_t *ent_off; CnsEnt *ent; uint32_t *srt, *act_a, *act_b, *b32; uint64_t *key; int32_t *rs; uint32_t *work; // rs: HB_CNS_RS_WORDS per warp (dedup_chains' sort scratch)

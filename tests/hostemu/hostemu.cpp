@@ -414,11 +414,11 @@ int emu_ec_phase(void *reads, uint32_t rid, const hb_chain_t *ch, uint32_t n_ch,
 		PhOv o; o.w = wl + alnb[j].w_off; o.wn = alnb[j].w_n; o.pool = pool; o.y_id = ch[j].y_id; o.rev = ch[j].y_pos_strand; o.align_length = aln[j].align_length; o.is_match = 1; o.strong = 0;
 		ov.push_back(o);
 	}
-	const int64_t ql = r->d.len[rid]; std::vector<uint8_t> cnt(ql + 1, 0); uint32_t ns = 0, ne = 0;
-	hb_ph_count(ov.data(), (uint32_t)ov.size(), cnt.data(), ql, &ns, &ne);
+	const int64_t ql = r->d.len[rid]; std::vector<uint8_t> cnt(hb_ph_bits_bytes((uint64_t)ql), 0); uint32_t ns = 0, ne = 0;
+	hb_ph_count_w(ov.data(), (uint32_t)ov.size(), cnt.data(), ql, &ns, &ne);
 	std::vector<uint32_t> site_pos(ns + 1), site_off(ns + 2), ov_off(ov.size() + 2); std::vector<PhEv> ev(ne + 1), ev2(ne + 1); std::vector<PhSnp> snp(4 * (size_t)ns + 1); std::vector<uint64_t> ord(ov.size() + 1);
 	std::vector<int32_t> bb(256), be(256); std::vector<RsFrame> fr(HB_RS_STACK); RsScratch W = { bb.data(), be.data(), fr.data() };
-	hb_ph_decide(r->d, rid, ov.data(), (uint32_t)ov.size(), cnt.data(), ql, ns, ne, site_pos.data(), site_off.data(), ev.data(), ev2.data(), snp.data(), ord.data(), ov_off.data(), W, 3, 3, 0.04, &ovf);
+	hb_ph_decide_w(r->d, rid, ov.data(), (uint32_t)ov.size(), cnt.data(), ql, ns, ne, site_pos.data(), site_off.data(), ev.data(), ev2.data(), snp.data(), ord.data(), ov_off.data(), W, 3, 3, 0.04, &ovf);
 	for (size_t k = 0; k < ov.size(); k++) { is_match[k] = ov[k].is_match; strong[k] = ov[k].strong; }
 	*n_acc = (uint32_t)ov.size();
 	return ovf;

@@ -1,15 +1,12 @@
-"""GPU tests of device paths that were written after round 1's GPU budget was spent and have therefore not run on a B200 yet.  Each of them
-is pinned on the CPU side (host emulation of the device body against the unmodified reference's dumps, or `gloo` for the exchange code):
+"""GPU tests of the paths round 1 wrote after its GPU budget was spent; all of them run green on a B200 since round 2 (profiles/r2_gpu_all_tests.log):
 
 * golden set g4 — 40 kb reads with tandem-repeat blocks, where accepted overlaps keep unaligned windows of >= 512 bp on both reads and the
-  reference re-seeds them (rechain_aln_hc, Correct.cpp:17669; hb_ecrechain.cuh / k_ecb_rechain): body pinned in tests/test_hostemu.py (g4)
-* the filter table behind the reference's Bloom filter (opt.bf_shift): formulation pinned in tests/test_bloom.py
-* stage.run_stage (FASTA in -> the reference's files out): glue over C-ABI calls that are GPU-checked on their own; ingest and writers pinned
-  in tests/test_outputs.py
-* dist.cal_ec_r_sharded with one rank: exchange helpers pinned in tests/test_dist_gloo.py
-
-Hence the non-strict xfail marks: a pass shows up as XPASS, a failure does not hide the rest of the suite.  The file sorts last so that every
-other GPU test runs before it (tools/first_gpu_call.sh runs these one by one with --runxfail)."""
+  reference re-seeds them (rechain_aln_hc, Correct.cpp:17669; hb_ecrechain.cuh / k_ecb_rechain).  Round 1's two stage-level failures on this set
+  were NOT the rescue: the anchor grouping kernel keyed its groups by (target, strand), so a target with anchors on both strands (tandem / palindromic
+  repeats) was chained as two groups instead of one call with both strand blocks (anchor.cpp:1928-1934) and produced extra one-anchor chains.
+* the filter table behind the reference's Bloom filter (opt.bf_shift)
+* stage.run_stage (FASTA in -> the reference's files out)
+* dist.cal_ec_r_sharded with one rank"""
 import os
 import sys
 
@@ -19,7 +16,6 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from goldenlib import Golden  # noqa: E402
 
 pytestmark = [pytest.mark.gpu]
-NOT_RUN_YET = pytest.mark.xfail(reason="k_ecb_rechain's launch path has not run on a B200 yet (round-1 GPU budget spent); its device body is pinned in host emulation", strict=False)
 
 
 @pytest.fixture(scope="module")
@@ -28,7 +24,6 @@ def hb():
     return hifiasm_b200
 
 
-@NOT_RUN_YET
 def test_stages_raw_g4(hb):
     """every stage of an EC round on the raw reads of g4 through the C-ABI, incl. the rescue (no overlap may keep need_rechain)"""
     import test_gpu_parity as tp
@@ -41,7 +36,6 @@ def test_stages_raw_g4(hb):
     eng.close()
 
 
-@NOT_RUN_YET
 def test_stages_final_g4(hb):
     """the same on the corrected reads with the previous round's lists (exact shortcut + rescue)"""
     import test_gpu_parity as tp
@@ -53,7 +47,6 @@ def test_stages_final_g4(hb):
     eng.close()
 
 
-@NOT_RUN_YET
 def test_whole_stage_from_raw_reads_g4(hb, tmp_path):
     """raw reads -> three EC rounds -> final pass on the device, byte-identical ovlp.*.bin, with the rescue on the path"""
     import test_gpu_round as tr
@@ -65,7 +58,6 @@ import numpy as np  # noqa: E402
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
 
 
-@pytest.mark.xfail(reason="hb_ft_gen's Bloom path (opt.bf_shift > 0) was written after the round's GPU budget was spent: not yet run on a B200; its formulation is pinned in host emulation (tests/test_bloom.py)", strict=False)
 @pytest.mark.parametrize("shift", [0, 21, 22, 24])
 def test_gpu_bloom(hb, shift):
     import make_bloom
@@ -86,7 +78,6 @@ def test_gpu_bloom(hb, shift):
 
 
 # ---- FASTA in, the reference's files out: hifiasm_b200.stage.run_stage (every step a C-ABI call that is GPU-checked on its own; this glue is new)
-@pytest.mark.xfail(reason="stage.run_stage (glue over GPU-checked C-ABI calls) was written after the round's GPU budget was spent: not yet run on a B200", strict=False)
 @pytest.mark.parametrize("name", ["g1", "g3"])
 def test_run_stage_fasta_to_files(hb, name, tmp_path):
     import hashlib
@@ -109,7 +100,6 @@ def test_run_stage_fasta_to_files(hb, name, tmp_path):
 
 # ---- the EC rounds sharded over ranks (hifiasm_b200.dist.cal_ec_r_sharded): with one process it must equal hb_cal_ec_r; N > 1 runs under
 # torchrun with tools/ec_sharded_check.py (the exchange helpers are covered by tests/test_dist_gloo.py on the CPU)
-@pytest.mark.xfail(reason="dist.cal_ec_r_sharded (granular C-ABI calls + all-gather) was written after the round's GPU budget was spent: not yet run on a B200", strict=False)
 def test_sharded_round_single_rank_equals_cal_ec_r(hb):
     import roundlib
     from hifiasm_b200 import binio, dist as hdist

@@ -231,7 +231,7 @@ def test_ec_cigar_small_scratch_defers_and_matches(ctx, monkeypatch):
     n = g.raw.n
     ref = eng.ec_cigar(0, n, float(p["bw_thres"]), 0.04, 775)
     import subprocess, sys, json
-    # HB_ECB_PATH_WORDS is read once per process: run the small-scratch pass in a child
+    # HB_ECB_PATH_WORDS is read once per context (hb_create): run the small-scratch pass in a child
     code = ("import sys, json, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import hifiasm_b200; from goldenlib import Golden; import hashlib;"
             "g = Golden(%r); e = hifiasm_b200.Engine(0); e.upload_store(g.raw); hom = e.ft_gen(); e.update_cov(hom); h, t = e.pt_gen(); e.set_opt(hom_cov=h, het_cov=t);"
             "o, B, W, Cg = e.ec_cigar(0, g.raw.n, %f, 0.04, 775);"
@@ -239,7 +239,7 @@ def test_ec_cigar_small_scratch_defers_and_matches(ctx, monkeypatch):
             "[d.update(np.ascontiguousarray(W[f]).tobytes()) for f in ('x_start', 'x_end', 'y_start', 'y_end', 'error', 'clen')];"
             "print(json.dumps({'dg': d.hexdigest(), 'deferred': e.counters()['ec_deferred']}))") % (
                 os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), [k for k in ("g1", "g2", "g3") if Golden(k).raw.n == n][0], float(p["bw_thres"]))
-    env = dict(os.environ, HB_ECB_PATH_WORDS="4096", HB_ECB_CIG_WORDS="64")
+    env = dict(os.environ, HB_ECB_PATH_WORDS="256", HB_ECB_CIG_WORDS="64")  # tier 1: 256 trace words per warp, tier 2: 4096
     res = json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1])
     o, B, W, Cg = ref
     d = hashlib.blake2b(digest_size=8)

@@ -41,6 +41,22 @@ def main():
                     bad.append("chain %d fake cigar differs: device %s emu %s" % (j, a[:6], b[:6]))
         if d_hits.size != e_hits.size or (d_hits.tobytes() != e_hits.tobytes()):
             bad.append("chain anchors differ (%d vs %d)" % (d_hits.size, e_hits.size))
+        if bad and nbad < 3:   # every chain slot (kept or not) from the compacted anchor lists: (ordinal -> first anchor's target-side offset, anchors)
+            def slots(h):
+                o = h["id_strand"] & 0x7fffffff; out = []
+                for k in np.unique(o):
+                    m = h[o == k]; out.append((int(k), int(m.size), int(m["self_offset"][0]), int(m["offset"][0]), int(m["self_offset"][-1]), int(m["offset"][-1]), int(m["id_strand"][0] >> 31)))
+                return out
+            sd, se = slots(d_hits), slots(e_hits)
+            print("   slots: device %d, emu %d" % (len(sd), len(se)))
+            ke = {(x[2], x[3], x[6]): x for x in se}; kd = {(x[2], x[3], x[6]): x for x in sd}
+            for x in sd:
+                y = ke.get((x[2], x[3], x[6]))
+                if y is None or y[1] != x[1] or y[4:6] != x[4:6]:
+                    print("   device slot %s  <-> emu %s" % (x, y))
+            for y in se:
+                if (y[2], y[3], y[6]) not in kd:
+                    print("   emu-only slot %s" % (y,))
         if bad:
             nbad += 1
             if nbad <= 6:

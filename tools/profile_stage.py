@@ -65,8 +65,9 @@ def main():
 
             def timed(name, f):
                 eng.profile_reset(); t0 = time.time(); r = f(); dt = time.time() - t0
-                calls.append((name, round(dt * 1e3, 1)))
-                for k, v in eng.profile().items():
+                pr = eng.profile()
+                calls.append((name, round(dt * 1e3, 1), round(sum(v[1] for v in pr.values()), 1)))   # wall ms, kernel ms inside the call
+                for k, v in pr.items():
                     e = kms.setdefault(k, [0, 0.0]); e[0] += v[0]; e[1] += v[1]
                 return r
             n = rs.n
