@@ -1,32 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — HiFi Gbp overlapped/sec on the north-star hot path.
+"""bench.py — HiFi Gbp overlapped/sec of the WHOLE overlap + error-correction stage (BASELINE.json metric).
 
-Workload (BASELINE.json configs[1], the single-GPU configuration): synthetic
-100 Mb diploid genome (0.1 % SNPs), 30x HiFi, 15 kb reads (sd 2 kb), k=51 w=51.
-A "step" = one final overlap pass (hifiasm's cal_ov_r: sketch -> probe of the
-GPU-resident ha_pt_t -> anchor grouping -> chaining -> exact-overlap test ->
-merge/emit ma_hit_t) over every read of this rank's shard, against the index of
-ALL reads.  The reads are the error-free ("corrected") reads the final pass sees
-in hifiasm; the previous-round overlap lists are empty (the EC rounds are not on
-the GPU yet — DESIGN.md §scope), so every chain is decided by the exact test.
+Workload (BASELINE.json configs[1]): synthetic 100 Mb diploid genome (0.1 % SNPs, 5 % of it in 50-copy 5 kb repeat families), 30x HiFi reads of
+15 kb (sd 2 kb) with 0.2 % errors (sub / ins / del 35 / 30 / 35 %), k = 51, w = 51: 200 k reads, 3.0 Gbp (tools/simgen.c, seeded).
 
-  value : bases processed by all ranks / device time (CUDA events on the engine's
-          own stream, max over ranks), reads + index + inputs resident in HBM.
-  e2e   : the same pass through the host-buffer C-ABI call (hb_reads_upload +
-          hb_cal_ov_r): H2D of the packed reads / previous overlaps and D2H of the
-          resulting ma_hit_t arrays inside the timed region.
-  --impl reference : the UNMODIFIED reference (oracle/_ref, built from
-          /root/reference) running its own cal_ov_r on the box's host cores on a
-          bounded sample of the same workload.
-
-Multi-GPU: one process per GPU (torchrun); index + reads replicated, query reads
-sharded contiguously, no data-path collective.  Weak scaling: the
-genome (and so the read set) grows with N so every rank always processes one
-configs[1]-sized shard (200k reads of a N x 100 Mb genome).
+A step = the stage hifiasm runs between reading the reads and building the string graph (Assembly.cpp:2076-2108), as ONE C-ABI call on the raw reads:
+hb_stage_run = ha_ft_gen, 3 x (ha_pt_gen + cal_ec_r), ha_pt_gen + cal_ov_r -> the final R_INF.paf[] / reverse_paf[] of every read in host memory and the
+corrected reads in HBM.  Every step starts from the RAW reads (the EC rounds rewrite the store), so each step uploads them again:
+  value : bases / device time of hb_stage_run (CUDA events on the engine's stream, max over ranks), raw reads resident in HBM when the region starts;
+  e2e   : bases / wall time of {hb_reads_upload from pinned host buffers + hb_stage_run + the lists read on the host}, max over ranks.
+Multi-GPU (torchrun, one process per GPU): STRONG scaling — the same 100 Mb read set at every N; reads + index replicated, the query reads of every pass
+sharded over the ranks, one NCCL all-gather of edit scripts + overlap lists per EC round (and of the final lists).
+--impl reference: the UNMODIFIED hifiasm binary (oracle/_ref/hifiasm, built from /root/reference) running the same stage on the host cores, timed by its own
+stage stamp ("found overlaps for the final round"), on a bounded sample of the workload (same generator, smaller genome).
 """
 import argparse
+import hashlib
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -37,63 +29,20 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-GENOME_MB = int(os.environ.get("HB_BENCH_GENOME_MB", "100"))
+GENOME_MB = float(os.environ.get("HB_BENCH_GENOME_MB", "100"))
+REF_SAMPLE_MB = float(os.environ.get("HB_BENCH_REF_MB", "4"))
 COV = float(os.environ.get("HB_BENCH_COV", "30"))
-MEAN_LEN = 15000
-SD_LEN = 2000
-SNP = 0.001
-K, W = 51, 51
+SEED = 20260923
+METRIC = "HiFi Gbp overlapped/sec"
 
 
-# ----------------------------------------------------------------------------
-# synthetic reads, generated directly in hifiasm's 2-bit packing
-# ----------------------------------------------------------------------------
-def _pack(x):
-    x = x.reshape(-1, 4)
-    return ((x[:, 0] << 6) | (x[:, 1] << 4) | (x[:, 2] << 2) | x[:, 3]).astype(np.uint8)
+def workload_name(mb):
+    return ("whole overlap + EC stage (ha_ft_gen, 3 x (ha_pt_gen + cal_ec_r), ha_pt_gen + cal_ov_r) on synthetic %g Mb diploid, %gx HiFi, 15 kb reads, 0.2 %% errors, "
+            "5 %% of the genome in 50-copy 5 kb repeats, k=51 w=51") % (mb, COV)
 
 
-def make_dataset(genome_mb, cov, seed=20260922, fasta=None):
-    """Reads sampled from both haplotypes and strands; starts are multiples of 4
-    in the sampled strand so a read's packed form is a byte slice of the packed
-    strand (ha_compress_base layout)."""
-    rng = np.random.default_rng(seed)
-    G = genome_mb * 1000000
-    hap1 = rng.integers(0, 4, G, dtype=np.uint8)
-    hap2 = hap1.copy()
-    m = rng.random(G) < SNP
-    hap2[m] = (hap2[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
-    srcs = [hap1, hap2, (3 - hap1[::-1]).astype(np.uint8), (3 - hap2[::-1]).astype(np.uint8)]
-    del hap1, hap2
-    packed_src = [np.concatenate([_pack(s), np.zeros(8, np.uint8)]) for s in srcs]
-    n = int(G * cov / MEAN_LEN)
-    lens = np.clip(rng.normal(MEAN_LEN, SD_LEN, n).astype(np.int64), 2000, G)
-    starts = ((rng.random(n) * (G - lens)).astype(np.int64) // 4) * 4
-    which = rng.integers(0, 4, n)
-    nbytes = lens // 4 + 1
-    boff = np.zeros(n + 1, dtype=np.uint64)
-    np.cumsum(nbytes, out=boff[1:])
-    flat = np.empty(int(boff[-1]), dtype=np.uint8)
-    bo = boff.astype(np.int64)
-    for i in range(n):
-        a = starts[i] >> 2
-        flat[bo[i]:bo[i + 1]] = packed_src[which[i]][a:a + nbytes[i]]
-    if fasta:
-        tab = np.frombuffer(b"ACGT", dtype=np.uint8)
-        asc = [tab[s] for s in srcs]
-        with open(fasta, "wb") as f:
-            for i in range(n):
-                f.write(b">r%d\n" % i)
-                f.write(asc[which[i]][starts[i]:starts[i] + lens[i]].tobytes())
-                f.write(b"\n")
-    return flat, boff, lens.astype(np.uint64)
-
-
-# ----------------------------------------------------------------------------
-# clocks
-# ----------------------------------------------------------------------------
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -103,13 +52,12 @@ class ClockSampler:
     def _run(self):
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
                 if o:
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
@@ -118,8 +66,7 @@ class ClockSampler:
         self.stop = True; self.t.join(timeout=6)
 
     def summary(self):
-        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]; mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[j] for r in self.rows for j in range(4) if len(r) > 2 + j and r[2 + j].lower().startswith("active")})
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
@@ -135,34 +82,60 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ----------------------------------------------------------------------------
-# reference arm / cpu baseline
-# ----------------------------------------------------------------------------
-def run_reference(flat_ds_args, warmup, steps, sample_reads=None):
-    """The unmodified reference's cal_ov_r on the host cores (oracle/_ref/refdump bench)."""
-    refdump = os.path.join(ROOT, "oracle", "_ref", "refdump")
-    if not os.path.exists(refdump):
-        return None, "oracle/_ref/refdump is missing (build it where /root/reference exists: make -C oracle ref)"
-    cores = os.cpu_count() or 1
-    genome_mb, cov = flat_ds_args
+# ---- the reference on the host cores ----------------------------------------------------------------------------------------------------------
+def run_reference_stage(genome_mb, threads, reps=1):
+    """-> list of dicts (one per repetition): stage seconds from the binary's own stamp, bases"""
+    import simgen
+    ref = os.path.join(ROOT, "oracle", "_ref", "hifiasm")
+    if not os.path.exists(ref):
+        return None, "oracle/_ref/hifiasm is missing (it is built where /root/reference exists: make -C oracle ref)"
+    out = []
     with tempfile.TemporaryDirectory() as td:
         fa = os.path.join(td, "reads.fa")
-        flat, boff, lens = make_dataset(genome_mb, cov, fasta=fa)
-        n = lens.size
-        nq = min(n, sample_reads or max(2000, 400 * cores))
-        out = subprocess.run([refdump, "bench", str(nq), str(warmup), str(steps), "-o", os.path.join(td, "asm"), "-t%d" % cores, "-f0", fa],
-                             capture_output=True, text=True)
-        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
-        if out.returncode != 0 or not line:
-            return None, "refdump bench failed: %s" % out.stderr[-300:]
-        r = json.loads(line[-1])
-    r["cores"] = cores
-    r["gbp_per_s"] = r["query_bases"] / r["seconds"] / 1e9
-    r["sample"] = "cal_ov_r over the first %d of %d reads (%.3f Gbp) against the index of all reads, -t%d" % (r["query_reads"], r["total_reads"], r["query_bases"] / 1e9, cores)
-    return r, None
+        rs = simgen.make(genome_mb, COV, seed=SEED, fasta=fa)
+        for _ in range(reps):
+            t = time.time()
+            p = subprocess.run([ref, "-o", os.path.join(td, "ref"), "-t%d" % threads, "-f0", "--bin-only", fa], capture_output=True, text=True)
+            wall = time.time() - t
+            m = re.search(r"\[M::ha_assemble::([0-9.]+)\*[0-9.]+@[0-9.]+GB\] ==> found overlaps for the final round", p.stderr)
+            if p.returncode != 0 or not m:
+                return None, "the reference binary failed: %s" % p.stderr[-300:]
+            out.append({"stage_s": float(m.group(1)), "wall_s": wall, "bases": rs.bases, "reads": rs.n,
+                        "pec_s": [float(x) for x in re.findall(r"\[M::pec::([0-9.]+)\]", p.stderr)]})
+    return out, None
 
 
-# ----------------------------------------------------------------------------
+def reference_sample_text(r, threads):
+    return ("unmodified hifiasm binary, same generator and seed at %g Mb (%d reads, %.3f Gbp), whole stage from FASTA (parsing runs inside its first counting pass), -t%d -f0; "
+            "time = its own stamp at 'found overlaps for the final round'") % (REF_SAMPLE_MB, r["reads"], r["bases"] / 1e9, threads)
+
+
+# ---- algorithmic bytes of the kernels that can top the stage (DESIGN.md §4; SURVEY.md §8d) -----------------------------------------------------
+def algorithmic_bytes(kernel, c, bases):
+    """bytes the kernel has to move for the whole stage, from the stage's counters (sums over its 4 passes)"""
+    mz, an, win, ov, seg = c["minimizers"], c["anchors"], c["windows"], c["ec_overlaps"], c["ec_segments"]
+    f = {
+        "k_expand": mz * 28 + an * 24,
+        "k_group": an * 16 * 2 + an * 4,                       # anchors in (keys once more) and out
+        "k_group_big": an * 16 * 2 + an * 4,
+        "k_chain": an * 16 + c["chain_slots"] * 48,
+        "k_windows": win * ((775 + 837) // 4 + 40),            # the two packed substrings + the record
+        "k_sketch_events": bases * 8 // 4 // 4 + bases * 16 * 8,   # 8 sketch passes (4 index + 4 query): packed reads in, 16-byte events out
+        "k_sketch_select": bases * 16 * 8 + mz * 16 * 2,
+        "k_ec_overlap": win * 40 + ov * 32,
+        "k_ec_overlap_fast": win * 40 + ov * 32,
+        "k_ecb_seg_fast": seg * 32 + bases * 60 // 4,         # one record per segment + both substrings (about 2 x coverage x bases / 4 per pass)
+        "k_ecb_seg": seg * 0.15 * (2 * 100 // 4 + 32 + 100 * 24),  # queued segments (~15 %): substrings, record, 24-byte trace rows
+        "k_ecb_seg_tier1": seg * 0.01 * (2 * 400 // 4 + 32 + 400 * 24),
+        "k_ph_decide": ov * 48 + win * 32,
+        "k_ph_count": win * 32 + ov * 48,
+        "k_ec_cns": win * 32 + bases // 4,
+        "k_post": c["chain_slots"] * 48 * 2,
+        "k_ecb_merge": seg * 32 + win * 32,
+    }
+    return float(f.get(kernel, 0))
+
+
 _JSON_OUT = None
 
 
@@ -184,277 +157,136 @@ def main():
         return 1
 
 
-def whole_stage_aux(local):
-    """child process of the bench (--aux-whole-stage): the whole stage on the small raw read set of the EC aux, one JSON line on stdout"""
-    import torch
-    import hifiasm_b200
-    from hifiasm_b200 import sim
-    torch.cuda.set_device(local)
-    h1, h2 = sim.sim_genome(int(os.environ.get("HB_BENCH_EC_GENOME", "6000000")), 77, snp_rate=SNP)
-    rr = sim.sim_reads(h1, h2, COV, MEAN_LEN, 77, sd_len=SD_LEN, min_len=2000, err=0.002)
-    fl, bo, ln, npos, noff = sim.pack_reads(rr)
-    nq = len(rr); qb = int(ln.sum()); aux = {}
-    # ---- the WHOLE stage the way SURVEY.md §8(d) defines the metric (first ha_ft_gen -> end of the final overlap pass), on the same small raw
-    # read set: filter table, 3 x (index build + hb_cal_ec_r), final index, hb_cal_ov_r — host buffers in and out of every C-ABI call — next to
-    # the unmodified reference doing the same on the host cores (oracle/_ref/refdump stage).  Not the headline yet (DESIGN.md §8).
-    try:
-        e3 = hifiasm_b200.Engine(local)
-        torch.cuda.synchronize(); tw = time.time()
-        e3.upload_reads(ln, fl, bo, npos, noff)
-        hm3 = e3.ft_gen(); e3.update_cov(hm3)
-        MA = hifiasm_b200.binio.MA_MEM
-        src = np.zeros(0, MA); soff = np.zeros(nq + 1, np.uint64); rev = src.copy(); roff = soff.copy(); t_round = []; unfinished = 0; tot_e = 0; kms_ws = {}
-        for K in range(3):
-            tk = time.time()
-            a3, b3 = e3.pt_gen(); e3.set_opt(hom_cov=a3, het_cov=b3)
-            rr3 = e3.cal_ec_r(K, 1 if K == 2 else 0, src, soff)
-            src, soff, rev, roff = rr3["src"], rr3["src_off"], rr3["rev"], rr3["rev_off"]
-            unfinished += int((rr3["status"] != 0).sum()); tot_e += rr3["tot_e"]
-            torch.cuda.synchronize(); t_round.append(round((time.time() - tk) * 1e3, 1))
-            for k, v in e3.profile().items():
-                kms_ws[k] = kms_ws.get(k, 0.0) + v[1]
-        tk = time.time()
-        a3, b3 = e3.pt_gen(); e3.set_opt(hom_cov=a3, het_cov=b3)
-        o0, q0, o1, q1, _ = e3.cal_ov_r(src, soff, rev, roff)
-        torch.cuda.synchronize(); t_final = time.time() - tk; wall_ws = time.time() - tw
-        top = sorted(kms_ws.items(), key=lambda kv: -kv[1])[:8]
-        aux["whole_stage"] = {"reads": nq, "bases": qb, "seconds": wall_ws, "gbp_s": qb / wall_ws / 1e9, "round_ms": t_round, "final_ms": round(t_final * 1e3, 1),
-                              "corrected_bases": int(tot_e), "reads_not_finished": unfinished, "overlaps_src": int(o0.size), "overlaps_rev": int(o1.size),
-                              "top_kernels_ms_in_ec_rounds": {k: round(v, 2) for k, v in top},
-                              "note": "raw reads in host memory -> ft_gen, 3 x (pt_gen + hb_cal_ec_r), pt_gen, hb_cal_ov_r -> final ma_hit_t lists in host memory; one GPU"}
-        e3.close()
-        refdump = os.path.join(ROOT, "oracle", "_ref", "refdump")
-        if os.path.exists(refdump) and not os.environ.get("HB_BENCH_NO_REF_STAGE"):
-            with tempfile.TemporaryDirectory() as td:
-                fa = os.path.join(td, "reads.fa"); sim.write_fasta(fa, rr)
-                cores = os.cpu_count() or 1
-                out = subprocess.run([refdump, "stage", "-o", os.path.join(td, "asm"), "-t%d" % cores, "-f0", fa], capture_output=True, text=True, timeout=600)
-                line = [l for l in out.stdout.splitlines() if l.startswith("{")]
-                if out.returncode == 0 and line:
-                    rs = json.loads(line[-1])
-                    aux["whole_stage"]["cpu_reference"] = {"seconds": rs["seconds"], "gbp_s": rs["bases"] / rs["seconds"] / 1e9, "cores": cores, "ec_rounds_seconds": rs["ec_rounds_seconds"], "final_seconds": rs["final_seconds"],
-                                                           "corrected_bases": rs["corrected_bases"], "overlaps_src": rs["n_src"], "overlaps_rev": rs["n_rev"],
-                                                           "note": "unmodified reference, same reads from a FASTA file (parsing included), -t%d -f0" % cores}
-    except Exception as ex:
-        sys.stderr.write("[bench] whole-stage aux failed: %r\n" % (ex,))
-        return 1
-    emit(aux["whole_stage"])   # the real stdout (fd 1 itself is redirected to stderr in main())
-    return 0
-
-
 def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--aux-whole-stage", action="store_true")
-    ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args()
-    if args.aux_whole_stage:
-        return whole_stage_aux(args.device)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "final overlap pass (cal_ov_r) on synthetic %d Mb diploid x%d GPU(s), %gx HiFi, 15 kb reads, k=51 w=51, corrected reads, empty previous overlaps" % (GENOME_MB, world, COV)
+    threads = len(os.sched_getaffinity(0))
+    dtype = "u8/u64/f64 (2-bit bases, 64-bit bit-vectors, double chain scores)"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r, why = run_reference((GENOME_MB, COV), args.warmup, args.steps)
-        if r is None:
+        runs, why = run_reference_stage(REF_SAMPLE_MB, threads, reps=max(1, min(args.warmup, 1)) + args.steps)  # one untimed run (page cache, CPU clocks), then the timed steps
+        if runs is None:
             emit({"impl": "reference", "unavailable": why}); return 0
-        v = r["gbp_per_s"]
-        emit(({"impl": "reference", "metric": "HiFi Gbp overlapped/sec", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64/f64 (integer + double chain scores)",
-                          "data": "synthetic", "config": {"workload": workload.replace("x%d GPU(s)" % world, "x1"), "sample": r["sample"]},
-                          "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
-                          "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        timed = runs[-args.steps:]
+        secs = sum(r["stage_s"] for r in timed); v = sum(r["bases"] for r in timed) / secs / 1e9
+        sample = reference_sample_text(timed[0], threads)
+        emit({"impl": "reference", "metric": METRIC, "value": v, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+              "config": {"workload": workload_name(GENOME_MB), "sample": sample, "stage_s_per_step": [r["stage_s"] for r in timed], "ec_round_s": timed[0]["pec_s"]},
+              "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": threads, "kind": "reference", "sample": sample},
+              "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
 
     import torch
     import torch.distributed as dist
     import hifiasm_b200
-    from hifiasm_b200 import binio, dist as hdist
+    from hifiasm_b200 import dist as hdist
+    from hifiasm_b200.engine import torch_allgather
+    import simgen
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    tdev = torch.device("cuda", local)
 
-    # ---- data: N x 100 Mb genome, every rank holds all reads + the full index, queries sharded
     t0 = time.time()
-    flat, boff, lens = make_dataset(GENOME_MB * world, COV)
-    n = int(lens.size)
-    r0, r1 = hdist.shard_range(n, rank, world)
-    my_bases = int(lens[r0:r1].sum())
-    eng = hifiasm_b200.Engine(local)
-    eng.upload_reads(lens, flat, boff)
+    rs = simgen.make(GENOME_MB, COV, seed=SEED)
+    # pinned host copies: the e2e region uploads from these
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in (("len", rs.length), ("flat", rs.flat), ("boff", rs.byte_off))}
+    h_len, h_flat, h_boff = pin["len"].numpy(), pin["flat"].numpy(), pin["boff"].numpy()
     t_gen = time.time() - t0
-    t0 = time.time()
-    hom_ft = None
-    if GENOME_MB * world * COV <= 3200:  # all-k-mer counting needs ~24 B per base of HBM: skip beyond ~3.2 Gbp (random genome: the table is empty anyway)
-        hom_ft = eng.ft_gen(); eng.update_cov(hom_ft)
-    hom, het = eng.pt_gen()
-    if hom_ft is None:
-        eng.update_cov(hom)
-    eng.set_opt(hom_cov=hom, het_cov=het)
-    t_idx = time.time() - t0
-    e0 = np.zeros(0, binio.MA_MEM); zoff = np.zeros(n + 1, np.uint64)
-    # stage the (empty) previous overlap lists once: the resident pass reuses them
-    out0, oo0, out1, oo1, stat = eng.cal_ov_r(e0, zoff, e0, zoff, r0, r1, cap=1 << 26)
-    n_src, n_rev = out0.size, out1.size
+    n = rs.n; bases = rs.bases
+    eng = hifiasm_b200.Engine(local)
+    cb = torch_allgather(tdev) if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        eng.cal_ov_r_resident(r0, r1)
-    prof_acc = {}
+    def step():
+        torch.cuda.synchronize(); ta = time.time()
+        eng.upload_reads(h_len, h_flat, h_boff)
+        torch.cuda.synchronize(); tb = time.time()
+        r = eng.stage_run(3, rank, world, cb, copy=False)
+        n_src, n_rev = int(r["src"].shape[0]), int(r["rev"].shape[0])
+        # the result is read on the host: totals of the two lists' records (touches every record)
+        chk = int(r["src"]["qe"].astype(np.uint64).sum() + r["rev"]["qe"].astype(np.uint64).sum())
+        tc = time.time()
+        return r, (tb - ta), (tc - tb), (tc - ta), n_src, n_rev, chk
+
+    digest = None
+    for w in range(args.warmup):
+        r, t_up, t_st, t_all, n_src, n_rev, chk = step()
+        if w == 0:
+            if r["n_unfinished"]:
+                raise RuntimeError("%d reads could not be finished on the device" % r["n_unfinished"])
+            h = hashlib.blake2b(digest_size=8)
+            for f in ("qns", "qe", "tn", "ts", "te", "el", "no_l_indel", "ml", "rev", "bl"):
+                h.update(np.ascontiguousarray(r["src"][f]).tobytes()); h.update(np.ascontiguousarray(r["rev"][f]).tobytes())
+            h.update(r["src_off"].tobytes()); h.update(r["rev_off"].tobytes())
+            digest = h.hexdigest(); corrected = r["corrected_bases"]; hom = r["hom_cov"]
+        sys.stderr.write("[bench] rank %d warm-up %d: upload %.3f s, stage %.3f s (device %.3f s; exchange %.3f s)\n" % (rank, w, t_up, t_st, r["device_ms"] / 1e3, r["ms"]["exchange"] / 1e3))
     barrier()
+    dev_ms = 0.0; e2e_s = 0.0; up_s = 0.0; ex_ms = 0.0; kms = {}; counters = None; step_ms = []
     with ClockSampler(local) as cs:
-        dev_ms = 0.0
         for _ in range(args.steps):
-            eng.cal_ov_r_resident(r0, r1)
-            dev_ms += eng.last_pass_ms()
-            for k, (l, ms) in eng.profile().items():
-                a = prof_acc.setdefault(k, [0, 0.0]); a[0] += l; a[1] += ms
+            r, t_up, t_st, t_all, n_src, n_rev, chk = step()
+            dev_ms += r["device_ms"]; e2e_s += t_all; up_s += t_up; ex_ms += r["ms"]["exchange"]; step_ms.append(round(r["device_ms"], 1))
+            pk, counters = eng.stage_profile()
+            for k, v in pk.items():
+                a = kms.setdefault(k, [0, 0.0]); a[0] += v[0]; a[1] += v[1]
+            last_ms = r["ms"]
     barrier()
     clocks = cs.summary()
-    counters = eng.counters()
-    dev_ms, tot_bases = hdist.reduce_time_and_units(dev_ms, float(my_bases) * args.steps, device="cuda")
-    value = tot_bases / (dev_ms / 1e3) / 1e9
-
-    # ---- e2e: host buffers through the C-ABI (H2D reads + prev lists, D2H results) every step
-    e2e = None
-    if not args.no_e2e:
-        obuf = (np.zeros(max(1024, n_src + n_src // 4), binio.MA_MEM), np.zeros(max(1024, n_rev + n_rev // 4), binio.MA_MEM))  # host result buffers, reused
-        eng.upload_reads(lens, flat, boff); eng.cal_ov_r(e0, zoff, e0, zoff, r0, r1, out=obuf)  # one untimed warm-up of the host path
-        barrier()
-        w0 = time.time(); t_up = 0.0
-        for _ in range(args.steps):
-            tu = time.time()
-            eng.upload_reads(lens, flat, boff)
-            t_up += time.time() - tu
-            o0, q0, o1, q1, _ = eng.cal_ov_r(e0, zoff, e0, zoff, r0, r1, out=obuf)
-        torch.cuda.synchronize()
-        wall = time.time() - w0
-        sys.stderr.write("[bench] e2e: %.3f s/step, of which read upload %.3f s\n" % (wall / args.steps, t_up / args.steps))
-        wall, _ = hdist.reduce_time_and_units(wall, 0.0, device="cuda")
-        h2d = int(flat.nbytes + boff.nbytes + lens.size * 4 + 2 * zoff.nbytes)
-        d2h = int((o0.size + o1.size) * binio.MA_MEM.itemsize + 2 * (r1 - r0 + 1) * 8)
-        e2e = {"value": tot_bases / wall / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
-
-    # ---- auxiliary: the window pass of an EC round (row a8) on a slice of this rank's reads
-    aux = None
-    if rank == 0 and not os.environ.get("HB_BENCH_NO_AUX"):
-        na = min(r1 - r0, 20000)
-        eng.windows(r0, r0 + na, 0.02, 0.04, 775)
-        woff, win = eng.windows(r0, r0 + na, 0.02, 0.04, 775)
-        kms = eng.profile().get("k_windows", (0, 0.0))[1]
-        cols = int((win["q_e"] - win["q_s"] + 1).sum())
-        aux = {"window_pass": {"reads": int(na), "windows": int(win.size), "aligned": int((win["err"] != 2**31 - 1).sum()), "k_windows_ms": kms,
-                               "gcups": (cols / (kms / 1e3) / 1e9) if kms > 0 else None, "note": "64-bit banded Myers column updates/s, one thread per 775-bp window"}}
-
-    # ---- auxiliary: the alignment stage of an EC round (rows a8-a11: window pass, gap filling + error estimate, base-level
-    # CIGAR, indel normalisation) on RAW reads (0.2 % errors) of a small separate genome — the final-pass workload above has
-    # error-free reads, on which this stage would only take its exact shortcuts
-    if rank == 0 and not os.environ.get("HB_BENCH_NO_AUX"):
-        try:
-            from hifiasm_b200 import sim
-            ta = time.time()
-            h1, h2 = sim.sim_genome(int(os.environ.get("HB_BENCH_EC_GENOME", "6000000")), 77, snp_rate=SNP)
-            rr = sim.sim_reads(h1, h2, COV, MEAN_LEN, 77, sd_len=SD_LEN, min_len=2000, err=0.002)
-            fl, bo, ln, npos, noff = sim.pack_reads(rr)
-            e2 = hifiasm_b200.Engine(local)
-            e2.upload_reads(ln, fl, bo, npos, noff)
-            hm = e2.ft_gen(); e2.update_cov(hm); hm2, ht2 = e2.pt_gen(); e2.set_opt(hom_cov=hm2, het_cov=ht2)
-            nq = len(rr)
-            e2.ec_cigar(0, nq, 0.02, 0.04, 775, gaps=1)
-            torch.cuda.synchronize(); tb = time.time()
-            goff, G, WG, CG = e2.ec_cigar(0, nq, 0.02, 0.04, 775, gaps=1)
-            torch.cuda.synchronize(); wall_ec = time.time() - tb
-            pr = e2.profile(); cn = e2.counters()
-            poff, PH = e2.ec_phase(0, nq, 0.02, 0.04, 775); pr.update({k: v for k, v in e2.profile().items() if k.startswith("k_ph_")})
-            kms = {k: pr[k][1] for k in ("k_windows", "k_ec_overlap", "k_ec_ea", "k_ecb_prep", "k_ecb_seg_fast", "k_ecb_seg", "k_ecb_seg_tier1", "k_ecb_seg_tier2", "k_ecb_seg_tier3", "k_ecb_merge", "k_ecb_merge_deferred", "k_ph_count", "k_ph_decide") if k in pr}
-            qb = int(ln.sum()); acc = G[G["st"] == 2]
-            aux = dict(aux or {})
-            aux["ec_alignment"] = {"reads": nq, "query_bases": qb, "overlaps": int(G.size), "accepted": int(acc.size), "other_haplotype": int((PH["is_match"] == 2).sum()), "need_rechain": int(acc["need_rechain"].sum()),
-                                   "segments": cn.get("ec_segments", 0), "segments_in_largest_scratch_tier": cn.get("ec_deferred", 0), "windows": cn.get("windows", 0), "cigar_runs": int(CG.size),
-                                   "kernel_ms": kms, "stage_kernels_gbp_s": qb / (sum(kms.values()) / 1e3) / 1e9 if kms else None,
-                                   "pass_ms_with_seeding_and_host_copies": wall_ec * 1e3, "setup_s": round(tb - ta, 1),
-                                   "note": "steps A-C of gen_hc_r_alin on raw reads (0.2 % errors): thread per window (k_windows), per overlap (k_ec_overlap, k_ecb_prep, k_ecb_merge), per inter-anchor segment (k_ecb_seg)"}
-            # ---- the whole round on the device (rows a8-a18): alignment, phasing, window consensus, lists, then apply / update / reverse
-            try:
-                caps = (int(G.size) + 16, int(G.size) + 16, 256 * nq + qb // 8)
-                e2.ec_stage_prev(np.zeros(0, hifiasm_b200.binio.MA_MEM), np.zeros(nq + 1, np.uint64))
-                torch.cuda.synchronize(); tr = time.time()
-                rr_ = e2.ec_round(0, nq, 0.02, 0.04, 775, use_prev=1, caps=caps)
-                torch.cuda.synchronize(); wall_round = time.time() - tr
-                prr = dict(e2.profile())
-                tc = time.time(); n_chg, tot_b = e2.ec_apply(); prr.update(e2.profile())
-                upd, n_ex, n_inex = e2.ec_update_paf(rr_["src"], rr_["src_off"]); prr.update(e2.profile())
-                e2.ec_post_rev(upd, rr_["src_off"], rr_["rev"], rr_["rev_off"]); prr.update(e2.profile())
-                torch.cuda.synchronize(); wall_close = time.time() - tc
-                names = ("k_ec_rpaf", "k_ec_cns", "k_ec_spaf", "k_sl_len", "k_sl_apply", "k_update_dc", "k_flip_paf", "k_rc_reads")
-                aux["ec_round"] = {"reads": nq, "query_bases": qb, "round_pass_ms": wall_round * 1e3, "round_pass_gbp_s": qb / wall_round / 1e9,
-                                   "closing_steps_ms_with_host_copies": wall_close * 1e3, "kernel_ms": {k: prr[k][1] for k in names if k in prr},
-                                   "corrected_bases": rr_["n_corrected"], "reads_changed": int(n_chg), "reads_needing_graph_consensus": int((rr_["status"] & 1).sum()),
-                                   "paf_records": int(rr_["src"].size), "reverse_paf_records": int(rr_["rev"].size), "exact_after_update": int(n_ex),
-                                   "note": "hb_ec_round (index resident): seeding + alignment stage + rphase_hc + wcns_gen (voted path, then graph consensus) + push_ne_ovlp / check_well_cal, lists and scripts to the host; then hb_ec_apply / hb_ec_update_paf / hb_ec_post_rev"}
-            except Exception as ex:
-                sys.stderr.write("[bench] EC round aux failed: %r\n" % (ex,))
-            e2.close()
-            # ---- the WHOLE stage the way SURVEY.md §8(d) defines the metric (first ha_ft_gen -> end of the final overlap pass), on the same small raw
-            # read set, next to the unmodified reference doing the same on the host cores.  Runs in a child process (`bench.py --aux-whole-stage`):
-            # a new call sequence must not be able to take the bench line down with it.  Not the headline yet (DESIGN.md §8).
-            try:
-                ch = subprocess.run([sys.executable, os.path.abspath(__file__), "--aux-whole-stage", "--device", str(local)], capture_output=True, text=True, timeout=900)
-                line = [l for l in ch.stdout.splitlines() if l.startswith("{")]
-                if ch.returncode == 0 and line:
-                    aux["whole_stage"] = json.loads(line[-1])
-                else:
-                    sys.stderr.write("[bench] whole-stage aux: child exited %d: %s\n" % (ch.returncode, ch.stderr[-400:]))
-            except Exception as ex:
-                sys.stderr.write("[bench] whole-stage aux failed: %r\n" % (ex,))
-        except Exception as ex:  # the auxiliary measurement must never take the bench line down
-            sys.stderr.write("[bench] EC alignment aux failed: %r\n" % (ex,))
+    dev_ms_max, _ = hdist.reduce_time_and_units(dev_ms, 0.0, device="cuda")
+    e2e_max, _ = hdist.reduce_time_and_units(e2e_s, 0.0, device="cuda")
+    tot_bases = float(bases) * args.steps
+    value = tot_bases / (dev_ms_max / 1e3) / 1e9
+    h2d = int(h_flat.nbytes + h_boff.nbytes + h_len.size * 4)
+    d2h = int((n_src + n_rev) * 48 + 2 * (n + 1) * 8)
+    e2e = {"value": tot_bases / e2e_max / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "note": "hb_reads_upload from pinned host buffers + hb_stage_run + the final lists read on the host; the EC rounds move their lists through host memory inside the call (the reference's structures are host arrays)"}
 
     if rank != 0:
-        # stay alive until rank 0 has printed: a peer that leaves early can take rank 0's NCCL watchdog down with it
-        dist.barrier(); dist.destroy_process_group()
+        dist.barrier(); dist.destroy_process_group()   # stay alive until rank 0 has printed
         return 0
 
-    # ---- roofline of the seed-hash probe kernel k_expand (DESIGN.md §4, SURVEY.md §8d): per pass it reads
-    # N_mz*(16 minimizer + 8 seed + 4 prefix) + N_hit*8 (ha_idxpos_t) and writes N_hit*16 (k_mer_hit);
-    # achieved = algorithmic bytes of all its launches / their summed CUDA-event time (== bytes per launch / mean launch time)
+    # ---- roofline of the kernel with the largest share of the step
     peak, peak_src = measured_peak_gbs()
-    n_mz, n_hit = counters["minimizers"], counters["anchors"]
-    n_launch = max(1, prof_acc.get("k_expand", [0, 0])[0] // max(1, args.steps))
-    alg_bytes = (n_mz * 28 + n_hit * 24) / n_launch
-    probe_ms = prof_acc.get("k_expand", [0, 0])[1] / max(1, args.steps) / n_launch
-    achieved = alg_bytes / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_probe_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-    roofline = {"bound": "hbm", "kernel": "k_expand (seed-hash probe)", "launches_per_step": n_launch, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "kernel_ms_per_step": {k: v[1] / max(1, args.steps) for k, v in sorted(prof_acc.items())}}
+    per_step = {k: v[1] / args.steps for k, v in kms.items()}
+    top = max(per_step.items(), key=lambda kv: kv[1]) if per_step else (None, 0.0)
+    launches = kms[top[0]][0] // args.steps if top[0] else 0
+    alg = algorithmic_bytes(top[0], counters, bases) if top[0] else 0.0
+    achieved = (alg / (top[1] / 1e3) / 1e9) if top[1] > 0 and alg > 0 else None
+    roofline = {"bound": "hbm", "kernel": top[0], "kernel_ms_per_step": round(top[1], 2), "share_of_step": round(top[1] / (dev_ms / args.steps), 3) if dev_ms else None,
+                "launches_per_step": launches, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": (alg / launches) if launches else None, "peak_source": peak_src,
+                "note": "achieved = algorithmic bytes of all its launches in a step (DESIGN.md §4) / their summed CUDA-event time; the kernel is latency / integer-issue bound, not byte bound (SURVEY.md §8d)",
+                "kernels_ms_per_step": {k: round(v, 2) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
     cpu = None
-    if not args.no_cpu_baseline:
-        r, why = run_reference((GENOME_MB, COV), 0, 1)
-        cpu = ({"value": r["gbp_per_s"], "unit": "Gbp/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]} if r else {"value": None, "unit": "Gbp/s", "cores": os.cpu_count(), "kind": "reference", "sample": why})
-    out = {"metric": "HiFi Gbp overlapped/sec", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "u8/u64/f64 (integer + double chain scores)", "data": "synthetic",
-           "config": {"workload": workload, "reads_total": n, "reads_per_rank": r1 - r0, "bases_per_rank": my_bases, "parallelism": "query reads sharded x%d, index+reads replicated" % world,
-                      "l2": "inputs larger than L2 (packed reads %.2f GB + index)" % (flat.nbytes / 1e9), "hom_cov": hom, "overlaps_src": int(n_src), "overlaps_rev": int(n_rev),
-                      "setup_s": {"generate+upload": round(t_gen, 1), "index_build": round(t_idx, 2)}, "counters": counters},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in prof_acc.values())), "roofline": roofline, "cpu_baseline": cpu, "aux": aux}
+    if not args.no_cpu_baseline and world == 1:
+        runs, why = run_reference_stage(REF_SAMPLE_MB, threads, reps=1)
+        if runs:
+            v = runs[0]["bases"] / runs[0]["stage_s"] / 1e9
+            cpu = {"value": v, "unit": "Gbp/s", "cores": threads, "kind": "reference", "sample": reference_sample_text(runs[0], threads), "stage_s": runs[0]["stage_s"], "ec_round_s": runs[0]["pec_s"]}
+        else:
+            cpu = {"value": None, "unit": "Gbp/s", "cores": threads, "kind": "reference", "sample": why}
+    out = {"metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+           "config": {"workload": workload_name(GENOME_MB), "reads": n, "bases": bases, "parallelism": "query reads of every pass sharded x%d; reads + index replicated; one all-gather of edit scripts + lists per EC round" % world,
+                      "l2": "inputs larger than L2 (packed reads %.2f GB + index + %.0f M anchors per pass)" % (h_flat.nbytes / 1e9, counters["anchors"] / 4e6),
+                      "hom_cov": hom, "corrected_bases_per_round": corrected, "overlaps_src": n_src, "overlaps_rev": n_rev, "result_digest": digest,
+                      "step_device_ms": step_ms, "last_step_host_ms": {k: (round(v, 1) if not isinstance(v, list) else [round(x, 1) for x in v]) for k, v in last_ms.items()},
+                      "upload_s_per_step": round(up_s / args.steps, 3), "exchange_ms_per_step": round(ex_ms / args.steps, 1), "setup_s": {"generate": round(t_gen, 1)}, "counters": counters},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in kms.values())), "roofline": roofline, "cpu_baseline": cpu}
     emit(out)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

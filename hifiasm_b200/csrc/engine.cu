@@ -30,10 +30,17 @@ ProfScope::~ProfScope()
 {
 	float ms = 0; cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
 	cudaEventDestroy(a); cudaEventDestroy(b);
+	if (ctx->in_stage) { bool f = false; for (auto &p : ctx->prof_stage) if (p.name == name) { p.launches++; p.ms += ms; f = true; break; } if (!f) { ProfEntry e = { name, 1, ms }; ctx->prof_stage.push_back(e); } }
 	for (auto &p : ctx->prof) if (p.name == name) { p.launches++; p.ms += ms; return; }
 	ProfEntry e = { name, 1, ms }; ctx->prof.push_back(e);
 }
-void hb_prof_reset(hb_ctx *ctx) { ctx->prof.clear(); memset(ctx->counters, 0, sizeof(ctx->counters)); }
+void hb_prof_reset(hb_ctx *ctx)
+{ // start of a pass: the per-pass table and counters restart; inside hb_stage_run the finished pass's counters are added to the stage's
+	if (ctx->in_stage) for (int i = 0; i < 12; i++) ctx->stage_counters[i] += ctx->counters[i];
+	ctx->prof.clear(); memset(ctx->counters, 0, sizeof(ctx->counters));
+}
+void hb_stage_prof_begin(hb_ctx *ctx) { ctx->prof_stage.clear(); memset(ctx->stage_counters, 0, sizeof(ctx->stage_counters)); memset(ctx->counters, 0, sizeof(ctx->counters)); ctx->in_stage = 1; }
+void hb_stage_prof_end(hb_ctx *ctx) { for (int i = 0; i < 12; i++) ctx->stage_counters[i] += ctx->counters[i]; ctx->in_stage = 0; }
 
 DevReads hb_dev_reads(const hb_ctx *ctx)
 {
@@ -167,7 +174,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->pt_keys = ctx->pt_npos = ctx->pt_cap = 0; ctx->d_pt_slot = 0; ctx->d_pt_pos = 0;
 	ctx->d_prev0 = ctx->d_prev1 = 0; ctx->d_prev0_off = ctx->d_prev1_off = 0; ctx->n_prev0 = ctx->n_prev1 = 0;
 	ctx->d_out0 = ctx->d_out1 = 0; ctx->d_out0_off = ctx->d_out1_off = 0; ctx->n_out0 = ctx->n_out1 = ctx->out_reads = 0;
-	ctx->anchor_budget = 96ull << 20; ctx->last_pass_ms = 0;
+	ctx->anchor_budget = 96ull << 20; ctx->last_pass_ms = 0; ctx->stage_buf = 0; ctx->in_stage = 0; memset(ctx->stage_counters, 0, sizeof(ctx->stage_counters));
 	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = ctx->ws_virt = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
@@ -200,6 +207,7 @@ extern "C" void hb_destroy(hb_ctx_t *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
 	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->d_scc); cudaFree(ctx->d_scc_off); cudaFree(ctx->ws); if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+	hb_stage_buf_free(ctx);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -1416,6 +1424,13 @@ extern "C" int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *lau
 }
 extern "C" void hb_profile_reset(hb_ctx_t *ctx) { ctx->prof.clear(); }
 extern "C" int hb_last_pass_ms(const hb_ctx_t *ctx, double *ms) { *ms = ctx->last_pass_ms; return HB_OK; }
+extern "C" int hb_stage_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap, uint64_t *counters, int ccap)
+{ // per-kernel launch counts / device time and the counters summed over every pass of the last hb_stage_run
+	int n = 0;
+	for (auto &p : ctx->prof_stage) { if (n >= cap) break; names[n] = p.name; launches[n] = p.launches; ms[n] = p.ms; n++; }
+	for (int i = 0; i < ccap && i < 12; i++) counters[i] = ctx->stage_counters[i];
+	return n;
+}
 extern "C" int hb_counters(const hb_ctx_t *ctx, uint64_t *c, int cap)
 {
 	int n = cap < 12 ? cap : 12;

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include "hb_common.cuh"
 
 #define HB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { hb_set_err(ctx, HB_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return HB_E_CUDA; } } while (0)
@@ -31,7 +32,7 @@ struct hb_ctx {
 	// results of the last final pass (device resident)
 	hb_ma_hit_t *d_out0, *d_out1; uint64_t *d_out0_off, *d_out1_off; uint64_t n_out0, n_out1, out_reads;
 	// instrumentation
-	std::vector<ProfEntry> prof; uint64_t counters[12];
+	std::vector<ProfEntry> prof, prof_stage; uint64_t counters[12], stage_counters[12]; int in_stage; // prof_stage / stage_counters: sums over all passes of the running hb_stage_run
 	uint64_t anchor_budget; // anchors per batch
 	uint64_t ecb_path_words; int32_t ecb_cig_words; // step B: trace words per warp of alignment tier 1, cigar words of the first merge launch (HB_ECB_PATH_WORDS / HB_ECB_CIG_WORDS, read once in hb_create: the tests shrink them so that the deferral paths run)
 	uint32_t cns_g_nodes, cns_g_arcs; // arena of the graph consensus per warp (HB_CNS_G_NODES / HB_CNS_G_ARCS, read once in hb_create: the overflow report is tested with tiny ones)
@@ -43,7 +44,9 @@ struct hb_ctx {
 	uint64_t out0_cap, out1_cap, outoff_cap;
 	// cached pinned staging buffer and capacities of the read-store arrays
 	uint8_t *h_stage; uint64_t h_stage_cap, packed_cap, reads_cap, npos_cap;
+	void *stage_buf; // hb_stage_run's host-side lists (stage.cu)
 };
+void hb_stage_buf_free(hb_ctx *ctx);
 #define HB_E_WS (-100) /* internal: workspace too small, the caller grows it and reruns */
 int hb_ws_grow(hb_ctx *ctx);
 void hb_ws_reset(hb_ctx *ctx);
@@ -63,6 +66,8 @@ struct ProfScope {
 	~ProfScope();
 };
 void hb_prof_reset(hb_ctx *ctx);
+void hb_stage_prof_begin(hb_ctx *ctx);
+void hb_stage_prof_end(hb_ctx *ctx);
 
 // device exclusive scan helpers (CUB, stream-ordered); out has n+1 entries (out[n] = total)
 int hb_scan_u32_to_u64(hb_ctx *ctx, const uint32_t *d_in, uint64_t *d_out, uint64_t n);

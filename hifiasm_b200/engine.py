@@ -32,6 +32,37 @@ PHASE = np.dtype([("st", "<i4"), ("y_id", "<u4"), ("rev", "<u4"), ("x_pos_s", "<
                   ("is_match", "<u4"), ("strong", "<i4"), ("need_rechain", "<u4"), ("pad", "<u4")])
 
 
+
+class StageResult(C.Structure):
+    """hb_stage_result_t"""
+    _fields_ = [("n_reads", C.c_uint64), ("n_src", C.c_uint64), ("n_rev", C.c_uint64), ("src", C.c_void_p), ("rev", C.c_void_p), ("src_off", C.c_void_p), ("rev_off", C.c_void_p),
+                ("is_fully_corrected", C.c_void_p), ("is_abnormal", C.c_void_p), ("hom_cov", C.c_int32), ("het_cov", C.c_int32), ("corrected_bases", C.c_uint64 * 8), ("n_unfinished", C.c_uint64),
+                ("ms_ft", C.c_double), ("ms_pt", C.c_double * 9), ("ms_ec", C.c_double * 8), ("ms_final", C.c_double), ("ms_exchange", C.c_double), ("ms_total", C.c_double), ("device_ms", C.c_double)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+def torch_allgather(device):
+    """hb_allgather_fn over torch.distributed (NCCL when `device` is a CUDA device, gloo on the CPU): fixed-size byte strings in host memory"""
+    import torch
+    import torch.distributed as dist
+
+    def cb(user, send, recv, nbytes):
+        try:
+            world = dist.get_world_size()
+            a = torch.frombuffer((C.c_uint8 * nbytes).from_address(send), dtype=torch.uint8)
+            out = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(out, a.to(device)) if device is not None and str(device) != "cpu" else dist.all_gather(list(out.view(world, nbytes).unbind(0)), a.clone())
+            torch.frombuffer((C.c_uint8 * (world * nbytes)).from_address(recv), dtype=torch.uint8).copy_(out.cpu() if out.is_cuda else out)
+            return 0
+        except Exception as ex:  # the C side turns a non-zero return into an error of the call
+            import sys
+            sys.stderr.write("[hifiasm_b200] all-gather callback failed: %r\n" % (ex,))
+            return 1
+    return ALLGATHER_FN(cb)
+
+
 class HBError(RuntimeError):
     pass
 
@@ -332,6 +363,21 @@ class Engine:
         self._ck(_lib().hb_cal_ov_r_resident(self.h, C.c_uint64(r0), C.c_uint64(r1), C.byref(a), C.byref(b), _p(stat)))
         return a.value, b.value, stat
 
+
+    # ---- the whole stage as one call
+    def stage_run(self, n_round=3, rank=0, world=1, allgather=None, copy=True):
+        """hb_stage_run -> dict(src, src_off, rev, rev_off, is_fully_corrected, is_abnormal, hom_cov, het_cov, corrected_bases, n_unfinished, ms = per-step host wall clock, device_ms)"""
+        res = StageResult(); n = self.n_reads
+        cb = allgather if allgather is not None else C.cast(None, ALLGATHER_FN)
+        self._ck(_lib().hb_stage_run(self.h, C.c_int(n_round), C.c_int(rank), C.c_int(world), cb, C.c_void_p(0), C.byref(res)))
+        def arr(ptr, cnt, dt):
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(1, cnt) * np.dtype(dt).itemsize,)).view(dt)[:cnt]
+            return a.copy() if copy else a
+        return dict(src=arr(res.src, res.n_src, MA), src_off=arr(res.src_off, n + 1, np.uint64), rev=arr(res.rev, res.n_rev, MA), rev_off=arr(res.rev_off, n + 1, np.uint64),
+                    is_fully_corrected=arr(res.is_fully_corrected, n, np.uint8), is_abnormal=arr(res.is_abnormal, n, np.uint8), hom_cov=res.hom_cov, het_cov=res.het_cov,
+                    corrected_bases=[int(x) for x in res.corrected_bases[:n_round]], n_unfinished=int(res.n_unfinished), device_ms=res.device_ms,
+                    ms=dict(ft=res.ms_ft, pt=list(res.ms_pt[:n_round + 1]), ec=list(res.ms_ec[:n_round]), final=res.ms_final, exchange=res.ms_exchange, total=res.ms_total))
+
     # ---- window alignment
     def ed_semi_64(self, pat, pat_off, txt, txt_off, thre, abs_diag):
         n = len(thre)
@@ -347,6 +393,13 @@ class Engine:
         names = (C.c_char_p * 64)(); launches = (C.c_uint64 * 64)(); ms = (C.c_double * 64)()
         n = _lib().hb_profile(self.h, names, launches, ms, 64)
         return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(n)}
+
+    def stage_profile(self):
+        """(kernels {name: (launches, ms)}, counters) summed over every pass of the last stage_run"""
+        names = (C.c_char_p * 96)(); launches = (C.c_uint64 * 96)(); ms = (C.c_double * 96)(); c = (C.c_uint64 * 12)()
+        n = _lib().hb_stage_profile(self.h, names, launches, ms, 96, c, 12)
+        keys = ("reads", "bases", "minimizers", "anchors", "groups", "chain_slots", "groups_unordered", "groups_sequential", "windows", "ec_overlaps", "ec_deferred", "ec_segments")
+        return {names[i].decode(): (int(launches[i]), float(ms[i])) for i in range(n)}, dict(zip(keys, [int(x) for x in c]))
 
     def profile_reset(self):
         _lib().hb_profile_reset(self.h)

@@ -31,32 +31,22 @@ def run_stage(paths, out_prefix: str, device: int = 0, n_round: int = 3, write_p
     try:
         eng.set_opt(bf_shift=bf_shift)
         eng.upload_store(rs)
-        hom = eng.ft_gen(); eng.update_cov(hom)                                     # Assembly.cpp:2081-2085
-        src = np.zeros(0, binio.MA_MEM); soff = np.zeros(n + 1, np.uint64); rev = src.copy(); roff = soff.copy()
-        fc = np.zeros(n, np.uint8); ab = np.zeros(n, np.uint8); corrected = []
-        hom_k = het_k = 0
-        for k in range(n_round):                                                      # ha_ec, Assembly.cpp:996-1030
-            hom_k, het_k = eng.pt_gen(); eng.set_opt(hom_cov=hom_k, het_cov=het_k)
-            r = eng.cal_ec_r(k, 1 if k == n_round - 1 else 0, src, soff) if world == 1 else hdist.cal_ec_r_sharded(eng, k, 1 if k == n_round - 1 else 0, src, soff, device=tdev)
-            if r["status"].any():
-                raise RuntimeError("round %d: %d reads could not be finished on the device (status bits %s)" % (k, int((r["status"] != 0).sum()), sorted(set(int(x) for x in r["status"][r["status"] != 0]))))
-            src, soff, rev, roff, fc, ab = r["src"], r["src_off"], r["rev"], r["rev_off"], r["is_fully_corrected"], r["is_abnormal"]
-            corrected.append(r["tot_e"])
-        reads = eng.download_reads()
+        # the stage itself is ONE C-ABI call (hb_stage_run, csrc/stage.cu): filter table, n_round x (index + cal_ec_r), index + cal_ov_r; with more than one
+        # rank it shards every pass and exchanges edit scripts + lists through the all-gather callback (NCCL via torch.distributed)
+        from .engine import torch_allgather
+        r = eng.stage_run(n_round, rank, world, torch_allgather(tdev) if world > 1 else None)
+        if r["n_unfinished"]:
+            raise RuntimeError("%d reads could not be finished on the device (consensus arena / rescue scratch)" % r["n_unfinished"])
+        out0, oo0, out1, oo1, fc, ab, corrected = r["src"], r["src_off"], r["rev"], r["rev_off"], r["is_fully_corrected"], r["is_abnormal"], r["corrected_bases"]
+        hom_f, het_f = r["hom_cov"], r["het_cov"]
+        reads = eng.download_reads()                                                  # the corrected reads (the final pass does not change them)
         reads.names, reads.name_blob, reads.name_index = rs.names, rs.name_blob, rs.name_index
         reads.index_size, reads.name_index_size, reads.total_reads_bases, reads.adapter_len = rs.index_size, rs.name_index_size, rs.total_reads_bases, rs.adapter_len   # total_reads_bases keeps the pre-correction total (Process_Read.cpp:79)
         reads.trio_flag = np.zeros(n, np.uint8)                                       # AMBIGU after cal_ec_r (ecovlp.cpp:6301)
         if write_ec and rank == 0:
             binio.native_write_ec_fa(out_prefix + ".ec.fa", reads)                   # Assembly.cpp:2097-2100
-        hom_f, het_f = eng.pt_gen(); eng.set_opt(hom_cov=hom_f, het_cov=het_f)       # ha_ec_ff(1), Assembly.cpp:1942-1959
-        if world == 1:
-            out0, oo0, out1, oo1, stat = eng.cal_ov_r(src, soff, rev, roff)
-        else:
-            r0, r1 = hdist.shard_range(n, rank, world)
-            p0, q0, p1, q1, stat = eng.cal_ov_r(src, soff, rev, roff, r0, r1)
-            out0, oo0 = hdist.all_gather_ragged(p0, q0, tdev); out1, oo1 = hdist.all_gather_ragged(p1, q1, tdev)
         reads.hom_cov, reads.het_cov = hom_f, het_f
-        info = dict(reads=n, bases=int(rs.length.sum()), corrected_bases=corrected, overlaps_src=int(out0.size), overlaps_rev=int(out1.size), hom_cov=hom_f, het_cov=het_f)
+        info = dict(reads=n, bases=int(rs.length.sum()), corrected_bases=corrected, overlaps_src=int(out0.size), overlaps_rev=int(out1.size), hom_cov=hom_f, het_cov=het_f, ms=r["ms"], device_ms=r["device_ms"])
         if rank != 0:
             return info
         if write_paf:

@@ -238,6 +238,26 @@ int hb_cal_ov_r(hb_ctx_t *ctx, uint64_t r0, uint64_t r1,
  * HBM; returns totals only.  Timed region of `value` (no PCIe).               */
 int hb_cal_ov_r_resident(hb_ctx_t *ctx, uint64_t r0, uint64_t r1, uint64_t *n_src, uint64_t *n_rev, uint64_t *stat);
 
+
+/* ---- the whole stage as one call: what ha_assemble() runs between reading the reads and building the string graph (Assembly.cpp:2076-2108) on the
+ * resident store — ha_ft_gen, n_round x ha_ec (ha_pt_gen + cal_ec_r, Assembly.cpp:996-1030), ha_ec_ff (ha_pt_gen + cal_ov_r, 1942-1959).  The
+ * corrected reads stay in HBM (hb_reads_download); the final R_INF.paf[] / R_INF.reverse_paf[] come back flattened in host memory owned by the
+ * context (valid until the next hb_stage_run / hb_destroy), with the last EC round's is_fully_corrected / is_abnormal flags.
+ * world > 1 (one process per GPU, every rank holds all reads): the query reads of every pass are sharded contiguously over the ranks, and each EC
+ * round ends with one all-gather of the shard's edit scripts + lists through the caller's transport: allgather(user, send, recv, bytes) must deliver
+ * `bytes` bytes from every rank into recv[rank * bytes ..] (host memory) on all ranks, and return 0.  Every rank leaves with the same lists.        */
+typedef int (*hb_allgather_fn)(void *user, const void *send, void *recv, uint64_t bytes_per_rank);
+typedef struct {
+	uint64_t n_reads, n_src, n_rev;
+	const hb_ma_hit_t *src, *rev; const uint64_t *src_off, *rev_off; /* n_reads + 1 offsets each */
+	const uint8_t *is_fully_corrected, *is_abnormal;
+	int32_t hom_cov, het_cov;                                        /* of the final index (written to <o>.ec.bin) */
+	uint64_t corrected_bases[8], n_unfinished;                       /* per round: the second counter of "[M::pec] # corrected bases"; reads a round reported (status != 0) */
+	double ms_ft, ms_pt[9], ms_ec[8], ms_final, ms_exchange, ms_total; /* host wall clock per step */
+	double device_ms;                                                /* CUDA events on the context's stream around the whole call */
+} hb_stage_result_t;
+int hb_stage_run(hb_ctx_t *ctx, int n_round, int rank, int world, hb_allgather_fn allgather, void *user, hb_stage_result_t *res);
+
 /* ---- window alignment: ed_band_cal_semi_64_w_absent_diag
  * (Levenshtein_distance.h:3727) batched.  Case i: pattern = pat[pat_off[i]..
  * pat_off[i+1]) (target slice, ASCII), text = txt[txt_off[i]..txt_off[i+1])
@@ -277,7 +297,9 @@ int hb_write_ec_bin(const char *path, int32_t adapter_len, uint64_t index_size, 
 /* per-kernel launch counters and device time of the last hb_cal_ov_r* call:
  * names[i] (static strings), launches[i], ms[i]; returns number of entries   */
 int hb_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap);
-void hb_profile_reset(hb_ctx_t *ctx); /* the counters also restart at the beginning of every pass */
+void hb_profile_reset(hb_ctx_t *ctx);
+/* the same summed over every pass of the last hb_stage_run, with the counters of hb_counters summed likewise */
+int hb_stage_profile(const hb_ctx_t *ctx, const char **names, uint64_t *launches, double *ms, int cap, uint64_t *counters, int ccap); /* the counters also restart at the beginning of every pass */
 /* device time (ms) of the last pass, from CUDA events recorded on the context's
  * own stream around the whole pass (first launch .. last result resident)     */
 int hb_last_pass_ms(const hb_ctx_t *ctx, double *ms);
