@@ -9,6 +9,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include "hb_internal.h"
+#define HB_KERNELS_MAIN
 #include "hb_kernels.cuh"
 #include "hb_rechain_launch.h"
 
@@ -68,7 +69,7 @@ static void *ws_short(hb_ctx *ctx, size_t bytes)
 	size_t need = ctx->ws_lo + (ctx->ws_cap - ctx->ws_hi) + ctx->ws_virt; if (need > ctx->ws_need) ctx->ws_need = need;
 	return 0;
 }
-static const bool g_trace_ws = getenv("HB_TRACE_WS") != 0;
+static const bool g_trace_ws = getenv("HB_TRACE_WS") != 0; // (diagnostics: one process-wide read)
 void *hb_ws_lo(hb_ctx *ctx, size_t bytes)
 {
 	bytes = (bytes + 255) & ~(size_t)255;
@@ -177,10 +178,10 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->anchor_budget = 96ull << 20; ctx->last_pass_ms = 0; ctx->stage_buf = 0; ctx->in_stage = 0; memset(ctx->stage_counters, 0, sizeof(ctx->stage_counters));
 	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = ctx->ws_virt = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
-	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 16384; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
+	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 4096; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
+	ctx->trace = getenv("HB_TRACE") != 0; ctx->trace_ec = getenv("HB_TRACE_EC") != 0;
 	ctx->cns_g_nodes = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096; ctx->cns_g_arcs = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
 	hb_prof_reset(ctx);
-	cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES);
 	cudaFuncSetAttribute(k_post_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, POST_WARPS * POST_SMEM_PER_WARP);
 	cudaFuncSetAttribute(k_merge_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_WARPS * MERGE_SMEM_PER_WARP);
 	*out = ctx;
@@ -299,59 +300,15 @@ extern "C" int hb_reads_upload_ptrs(hb_ctx_t *ctx, uint64_t n, const uint64_t *l
 // ---------------------------------------------------------------------------
 // sketch of a read range -> dense minimizer arrays
 // ---------------------------------------------------------------------------
-static int hb_run_sketch_legacy(hb_ctx *ctx, uint64_t r0, uint64_t r1, DevSketch *out)
-{ // the one-kernel formulation (ring in shared memory), kept for A/B checks (HB_SKETCH_LEGACY)
-	uint64_t nR = r1 - r0; Arena ar(ctx);
-	SketchPar P = { ctx->opt.mz_win, ctx->opt.k_mer_length, ctx->opt.is_hpc, ctx->opt.mz_sample_dist, ctx->opt.mz_rewin };
-	for (int attempt = 0, div = 12; attempt < 3; attempt++, div = div > 4 ? div / 3 : 1) {
-		std::vector<uint64_t> cap_off(nR + 1); uint64_t tot = 0;
-		for (uint64_t i = 0; i < nR; i++) { cap_off[i] = tot; tot += ctx->h_rlen[r0 + i] / div + 32; }
-		cap_off[nR] = tot;
-		uint64_t *d_cap = ar.get<uint64_t>(nR + 1); hb_mz_t *d_mz = ar.get<hb_mz_t>(tot); uint32_t *d_l = ar.get<uint32_t>(tot), *d_n = ar.zero<uint32_t>(nR + 1);
-		int *d_err = ar.zero<int>(1); uint64_t *d_off = ar.get<uint64_t>(nR + 2);
-		HB_ALLOC_CHECK(ar);
-		HB_CUDA(cudaMemcpyAsync(d_cap, cap_off.data(), (nR + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		{
-			ProfScope ps(ctx, "k_sketch");
-			if (P.w <= 160) {
-				size_t smem = (size_t)64 * P.w * 20;
-				cudaFuncSetAttribute(k_sketch<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				k_sketch<64><<<nblk(nR, 64), 64, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0, nR, d_cap, d_mz, d_l, d_n, d_err);
-			} else {
-				size_t smem = (size_t)32 * P.w * 20;
-				cudaFuncSetAttribute(k_sketch<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				k_sketch<32><<<nblk(nR, 32), 32, smem, ctx->stream>>>(hb_dev_reads(ctx), hb_dev_ft(ctx), P, r0, nR, d_cap, d_mz, d_l, d_n, d_err);
-			}
-		}
-		HB_CUDA(cudaGetLastError());
-		int h_err = 0; HB_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-		if (h_err) continue; // a slice overflowed: retry with larger slices
-		int rc = hb_scan_u32_to_u64(ctx, d_n, d_off, nR); if (rc) return rc;
-		uint64_t total = 0; HB_CUDA(cudaMemcpyAsync(&total, d_off + nR, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-		hb_mz_t *d_dense = ar.hi<hb_mz_t>(total + 2); uint64_t *d_off_keep = ar.hi<uint64_t>(nR + 2); HB_ALLOC_CHECK(ar);
-		HB_CUDA(cudaMemcpyAsync(d_off_keep, d_off, (nR + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-		{
-			ProfScope ps(ctx, "k_compact_mz");
-			k_compact_mz<<<nblk(nR * 32, 256), 256, 0, ctx->stream>>>(nR, d_cap, d_off, d_mz, d_dense);
-		}
-		HB_CUDA(cudaGetLastError());
-		out->mz = d_dense; out->off = d_off_keep; out->total = total;
-		return HB_OK;
-	}
-	hb_set_err(ctx, HB_E_OVERFLOW, "minimizer slices overflowed even at one slot per base");
-	return HB_E_OVERFLOW;
-}
-
 int hb_run_sketch(hb_ctx *ctx, uint64_t r0, uint64_t r1, int rid_mode, DevSketch *out)
 { // two-stage sketch, one chunk of reads at a time so that the scratch (16 B event per base + per-read slices) stays
   // bounded whatever the range.  Chunks run last to first and each one's dense minimizers are stacked downwards on the
   // workspace's hi side, which leaves ONE contiguous array in read order when the first chunk is done.
 	(void)rid_mode;
 	out->mz = 0; out->off = 0; out->total = 0;
-	if (getenv("HB_SKETCH_LEGACY")) return hb_run_sketch_legacy(ctx, r0, r1, out);
 	const uint64_t nR = r1 - r0; Arena ar(ctx);
 	SketchPar P = { ctx->opt.mz_win, ctx->opt.k_mer_length, ctx->opt.is_hpc, ctx->opt.mz_sample_dist, ctx->opt.mz_rewin };
-	static const uint64_t chunk_bases = getenv("HB_SKETCH_CHUNK") ? strtoull(getenv("HB_SKETCH_CHUNK"), 0, 10) : 3300000000ull;
+	const uint64_t chunk_bases = 1600000000ull; // reads per chunk: 16 bytes of event scratch per base (26 GB at most)
 	std::vector<uint64_t> cb(1, 0);
 	for (uint64_t c0 = 0; c0 < nR;) {
 		uint64_t c1 = c0, b = 0;
@@ -550,7 +507,7 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 #define TRACE(label) do { if (trace) { cudaStreamSynchronize(ctx->stream); double t_ = now_ms(); fprintf(stderr, "[hb trace] %-18s +%8.2f ms (total %8.2f)\n", label, t_ - t_last, t_ - t_begin); t_last = now_ms(); } } while (0)
 static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, StageOut *so, uint64_t *stat_out)
 {
-	const bool trace = getenv("HB_TRACE") != 0; double t_begin = now_ms(), t_last = t_begin;
+	const bool trace = ctx->trace != 0; double t_begin = now_ms(), t_last = t_begin;
 	cudaSetDevice(ctx->device);
 	if (r1 > ctx->n_reads || r0 > r1) { hb_set_err(ctx, HB_E_ARG, "read range out of bounds"); return HB_E_ARG; }
 	if (!ctx->d_pt_slot) { hb_set_err(ctx, HB_E_STATE, "no position index: call hb_pt_gen first"); return HB_E_STATE; }
@@ -611,65 +568,16 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		HB_ALLOC_CHECK(ba);
 		if (B) {
 			ProfScope ps(ctx, "k_expand");
-			static int var = getenv("HB_EXP_VAR") ? atoi(getenv("HB_EXP_VAR")) : 0;
-			const int U = var == 1 ? 8 : (var == 3 || var == 4) ? 4 : var == 6 ? 3 : 2;
+			const int U = 2; // query minimizers in flight per half-warp: full occupancy at 40 registers (0.62 of the measured HBM peak; 1 / 4 / 8 in flight were slower)
 			unsigned grid = (unsigned)std::min<uint64_t>((n_mz * 16 / U + 255) / 256, (uint64_t)ctx->sm_count * 32);
 			if (!grid) grid = 1;
-#define EXP_ARGS R, PT, r0, n_mz, sk.mz + mz_b, d_seeds + mz_b, d_spre + mz_b, d_aoff, a_base, d_wtab, d_raw
-			if (var == 1) k_expand<8, 2><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
-			else if (var == 2) k_expand<2, 6><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
-			else if (var == 3) k_expand<4, 4><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
-			else if (var == 4) k_expand<4, 3><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
-			else if (var == 5) k_expand<2, 8><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
-			else if (var == 6) k_expand<3, 5><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
-			else k_expand<2, 6><<<grid, 256, 0, ctx->stream>>>(EXP_ARGS);
+			k_expand<2, 6><<<grid, 256, 0, ctx->stream>>>(R, PT, r0, n_mz, sk.mz + mz_b, d_seeds + mz_b, d_spre + mz_b, d_aoff, a_base, d_wtab, d_raw);
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("expand");
-		// group: retried with a larger directory / arena when the first guess was too small
-		GroupDir *d_dir = 0; uint32_t h_dirn = 0; uint64_t dir_cap = B / 8 + 64 * nb + 1024, arena_words = 16ull << 20;
-		const uint32_t heavy_min = 16384; std::vector<uint32_t> h_heavy; uint64_t heavy_need = 0; uint32_t big_ts_max = 1u << 18; // reads with this many anchors get a block each (k_group_big)
-		for (uint64_t i = b0; i < b1; i++) { const uint64_t na = h_aoff[i + 1] - h_aoff[i]; if (na >= heavy_min) h_heavy.push_back((uint32_t)(i - b0)); }
-		uint32_t *d_heavy = ba.get<uint32_t>(h_heavy.size() + 1); HB_ALLOC_CHECK(ba);
-		if (!h_heavy.empty()) HB_CUDA(cudaMemcpyAsync(d_heavy, h_heavy.data(), h_heavy.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-		for (int attempt = 0;; attempt++) {
-			heavy_need = 0;
-			for (uint64_t i = b0; i < b1; i++) { // every read that can reach k_group_big: the heavy ones, and those with enough anchors to hold more than GRP_MAXG targets
-				const uint64_t na = h_aoff[i + 1] - h_aoff[i]; if (na <= GRP_MAXG) continue;
-				uint64_t ts = 1024; while (ts < 2 * na && ts < big_ts_max) ts <<= 1; heavy_need += 3 * ts;
-			}
-			if (arena_words < heavy_need + (16ull << 20)) arena_words = heavy_need + (16ull << 20);
-			if (dir_cap > B + 1) dir_cap = B + 1;
-			d_dir = ba.get<GroupDir>(dir_cap); uint32_t *d_ar = ba.get<uint32_t>(arena_words);
-			HB_ALLOC_CHECK(ba);
-			HB_CUDA(cudaMemsetAsync(d_dirn, 0, 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_err, 0, 4, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_arena_used, 0, 8, ctx->stream));
-			GroupArgs G; G.nR = nb; G.r0 = r0 + b0; G.a_off = d_aoff + b0; G.a_base = a_base; G.raw = d_raw; G.hits = d_hits; G.dir = d_dir; G.dir_n = d_dirn; G.dir_cap = (uint32_t)dir_cap;
-			G.sc = d_sc; G.arena = d_ar; G.arena_used = d_arena_used; G.arena_words = arena_words; G.mcopy_num = CP.mcopy_num; G.mcopy_khit_cutoff = CP.mcopy_khit_cutoff; G.err = d_err;
-			G.heavy_min = heavy_min; G.big_ts_max = big_ts_max; G.heavy = d_heavy; G.n_heavy = (uint32_t)h_heavy.size(); G.heavy_from_q = 0;
-			G.ovf_q = ba.get<uint32_t>(nb + 1); G.ovf_n = ba.zero<uint32_t>(1); HB_ALLOC_CHECK(ba);
-			{
-				ProfScope ps(ctx, "k_group");
-				k_group<<<nblk(nb, GRP_WARPS), GRP_WARPS * 32, GRP_SMEM_BYTES, ctx->stream>>>(G);
-			}
-			if (!h_heavy.empty()) {
-				ProfScope ps(ctx, "k_group_big");
-				k_group_big<<<(unsigned)h_heavy.size(), GRPB_WARPS * 32, 0, ctx->stream>>>(G);
-			}
-			{ // the reads k_group handed over (count on the device: surplus blocks leave at once)
-				uint32_t h_nq = 0; HB_CUDA(cudaMemcpyAsync(&h_nq, G.ovf_n, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-				if (h_nq) { GroupArgs Gq = G; Gq.n_heavy = 0; Gq.heavy_from_q = 1; ProfScope ps(ctx, "k_group_big"); k_group_big<<<h_nq, GRPB_WARPS * 32, 0, ctx->stream>>>(Gq); }
-			}
-			HB_CUDA(cudaGetLastError());
-			int h_err = 0;
-			HB_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_dirn, d_dirn, 4, cudaMemcpyDeviceToHost, ctx->stream));
-			HB_CUDA(cudaStreamSynchronize(ctx->stream));
-			if (!h_err) { ba.release(d_ar); break; }
-			ba.release(d_dir); ba.release(d_ar);
-			if (attempt >= 6 || ((h_err & 2) && big_ts_max >= (1u << 30))) { hb_set_err(ctx, HB_E_OVERFLOW, "anchor grouping overflow (flags %d)", h_err); return HB_E_OVERFLOW; }
-			if (h_err & 2) big_ts_max <<= 3; // a heavy read with more distinct targets than its table holds
-			if (h_err & 8) dir_cap = B + 1;
-			if (h_err & 4) arena_words *= 8;
-		}
+		// group: one stable device-wide sort of the batch's anchors on (read, target, strand) + run-length encoding (group.cu)
+		GroupDir *d_dir = 0; uint32_t h_dirn = 0;
+		if ((rc = hb_group_sort(ctx, nb, r0 + b0, d_aoff + b0, a_base, B, d_raw, d_hits, &d_dir, d_dirn, &h_dirn, d_sc, CP.mcopy_num, CP.mcopy_khit_cutoff))) return rc;
 	TRACE("group");
 		ba.release(d_raw);
 		ctx->counters[4] += h_dirn;
@@ -685,8 +593,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			ChainArgs C; C.R = R; C.r0 = r0 + b0; C.dir = d_dir; C.dir_n = d_dirn; C.a_off = d_aoff + b0; C.a_base = a_base; C.c_off = d_coff;
 			C.hits = d_hits; C.chits = d_chits; C.f = d_f; C.p = d_p; C.ii = d_ii; C.t = d_t; C.ch = d_ch; C.slot_read = d_slot_read; C.fc = d_fc; C.P = CP; C.err = d_err; C.dbg = d_stat + 8; C.work = ba.zero<uint32_t>(1); HB_ALLOC_CHECK(ba);
 			ProfScope ps(ctx, "k_chain");
-			if (getenv("HB_CHAIN_THREAD")) k_chain<<<std::max(1u, std::min(nblk(h_dirn, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
-			else k_chain_warp<<<std::max(1u, std::min(nblk((uint64_t)h_dirn * 32, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
+			k_chain_warp<<<std::max(1u, std::min(nblk((uint64_t)h_dirn * 32, 128), (unsigned)ctx->sm_count * 16)), 128, 0, ctx->stream>>>(C);
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("chain");
@@ -704,8 +611,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		{
 			PostArgs Pa; Pa.R = R; Pa.r0 = r0 + b0; Pa.nR = nb; Pa.c_off = d_coff; Pa.ch = d_ch; Pa.chits = d_chits; Pa.ghits = d_hits; Pa.idx = d_idx; Pa.n_ol = d_nol; Pa.keep = d_keep; Pa.cc = d_cc; Pa.cc_off = d_ccoff; Pa.P = CP;
 			ProfScope ps(ctx, "k_post");
-			if (getenv("HB_POST_THREAD")) k_post<<<nblk(nb, 64), 64, 0, ctx->stream>>>(Pa);
-			else k_post_warp<<<nblk(nb, POST_WARPS), POST_WARPS * 32, POST_WARPS * POST_SMEM_PER_WARP, ctx->stream>>>(Pa);
+			k_post_warp<<<nblk(nb, POST_WARPS), POST_WARPS * 32, POST_WARPS * POST_SMEM_PER_WARP, ctx->stream>>>(Pa);
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("post");
@@ -762,11 +668,11 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					if (attempt) HB_CUDA(cudaMemsetAsync(d_wl, 0, (n_win + 1) * sizeof(hb_wl_t), ctx->stream)); // (a rerun with a larger pool starts from clean window lists)
 					{
 						ProfScope ps(ctx, "k_ec_overlap_fast");
-						if (n_ov) k_ec_overlap_fast<<<nblk(n_ov, 128), 128, 0, ctx->stream>>>(E);
+						if (n_ov) hb_k_ecaln(0, nblk(n_ov, 128), ctx->stream, E);
 					}
 					{
 						ProfScope ps(ctx, "k_ec_overlap");
-						if (n_ov) k_ec_overlap<<<blocks, 64, 0, ctx->stream>>>(E);
+						if (n_ov) hb_k_ecaln(1, blocks, ctx->stream, E);
 					}
 					HB_CUDA(cudaGetLastError());
 					HB_CUDA(cudaMemcpyAsync(&pool_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -796,14 +702,14 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					G.prep = d_prep; G.nseg = d_nseg; G.seg_off = d_segoff; G.out = d_alnb; G.wl = d_wlb; G.wl_off = d_wboff; G.n_deferred = d_ndef; G.err = d_err;
 					{
 						ProfScope ps(ctx, "k_ecb_prep");
-						if (n_ov) k_ecb_prep<<<nblk(n_ov, 128), 128, 0, ctx->stream>>>(G);
+						if (n_ov) hb_k_ecb(HB_K_ECB_PREP, nblk(n_ov, 128), 128, ctx->stream, G);
 					}
 					HB_CUDA(cudaGetLastError());
 					if ((rc = hb_scan_u32_to_u64(ctx, d_nseg, d_segoff, n_ov))) return rc;
 					uint64_t n_seg = 0; HB_CUDA(cudaMemcpyAsync(&n_seg, d_segoff + n_ov, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 					if (n_seg >= (1ull << 32)) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: >= 2^32 segments in one batch"); return HB_E_OVERFLOW; }
 					ctx->counters[11] += n_seg;
-					EcSeg *d_segs = ba.get<EcSeg>(n_seg + 1); uint32_t *d_q1 = ba.get<uint32_t>(n_seg + 1), *d_q2 = ba.get<uint32_t>(n_seg + 1);
+					EcSeg *d_segs = ba.get<EcSeg>(n_seg + 1); uint32_t *d_q1 = ba.get<uint32_t>(n_seg + 1), *d_q2 = ba.get<uint32_t>(n_seg + 1), *d_qkey = ba.get<uint32_t>(n_seg + 1);
 					HB_ALLOC_CHECK(ba);
 					G.n_seg = n_seg; G.segs = d_segs;
 					// ---- segments: tier 0 (private scratch) -> queue -> tier 1 (16 K trace words) -> queue -> tier 2 (the largest alignment the reference allows)
@@ -813,25 +719,35 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						HB_CUDA(cudaMemsetAsync(d_spused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_qn, 0, 32, ctx->stream));
 						G.spool = d_spool; G.spool_used = d_spused; G.spool_cap = spool_cap;
 						// pre-pass: everything that needs no alignment; the rest goes to queue 0
-						G.q_in = 0; G.q_in_n = 0; G.q_out = d_q1; G.q_out_n = d_qn + 0;
+						G.q_in = 0; G.q_in_n = 0; G.q_out = d_q2; G.q_out_n = d_qn + 0; G.q_key = d_qkey;
 						{
 							ProfScope ps(ctx, "k_ecb_seg_fast");
-							if (n_seg) k_ecb_seg_fast<<<nblk(n_seg, 128), 128, 0, ctx->stream>>>(G);
+							if (n_seg) hb_k_ecb(HB_K_ECB_SEG_FAST, nblk(n_seg, 128), 128, ctx->stream, G);
 						}
 						HB_CUDA(cudaGetLastError());
 						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						G.q_key = 0;
+						if (h_q[0]) { // the queue ordered by segment length (12-bit key): the 32 segments of a warp of tier 0 need about the same number of columns
+							Arena sa(ctx);
+							if ((rc = hb_sort_pairs_u32(ctx, d_qkey, d_q2, d_q1, h_q[0], 12))) return rc;
+						}
 						// alignment tiers 0..3: {trace words, band words, cigar runs, blocks of 128 threads}; tier 0 keeps its scratch private (local memory);
 						// a segment that overflows one tier queues for the next (queues ping-pong between two arrays)
-						// tiers 1..3 give a WARP to a segment (k_ecb_seg_w): {trace words per warp, cigar runs, warps}; the largest holds the longest alignment the reference
-						// attempts (HB_MAX_SIN_L columns x 64 band words x 3 trace words)
-						const struct { uint64_t pw; int32_t cw; unsigned warps; const char *name; } TIER[4] = {
-							{ 0, 0, 0, "k_ecb_seg" }, { path_words1, 1024, (unsigned)ctx->sm_count * 16, "k_ecb_seg_tier1" }, { path_words1 * 16, 8192, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier2" },
+						// tier 1: thread / segment with global scratch (trace words per thread, 8-word band); tiers 2..3 give a WARP to a segment (k_ecb_seg_w): {trace words per
+						// unit, cigar runs, units}; the largest holds the longest alignment the reference attempts (HB_MAX_SIN_L columns x 64 band words x 3 trace words)
+						const struct { uint64_t pw; int32_t cw; unsigned units; const char *name; } TIER[4] = {
+							{ 0, 0, 0, "k_ecb_seg" }, { path_words1, 256, (unsigned)ctx->sm_count * 8 * 128, "k_ecb_seg_tier1" }, { path_words1 * 64, 8192, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier2" },
 							{ (uint64_t)HB_MW_MAXW * (2 + 3 * (uint64_t)HB_MAX_SIN_L), 65535, (unsigned)ctx->sm_count * 2, "k_ecb_seg_tier3" } };
 						for (int tier = 0; tier <= 3 && h_q[tier]; tier++) {
 							Arena sa(ctx);
 							unsigned bl = (unsigned)(((uint64_t)h_q[tier] + 127) / 128);
-							if (tier > 0) {
-								const uint64_t nw = std::max<uint64_t>(4, std::min<uint64_t>(((uint64_t)h_q[tier] + 3) & ~3ull, TIER[tier].warps)); bl = (unsigned)(nw / 4);
+							if (tier == 1) {
+								bl = std::max(1u, std::min(bl, TIER[1].units / 128)); const uint64_t nt = (uint64_t)bl * 128;
+								G.path = sa.get<uint64_t>(nt * TIER[1].pw); G.path_words = TIER[1].pw; G.vec = sa.get<uint64_t>(nt * 11 * 8); G.vstride = 8;
+								G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)TIER[1].cw); G.cig_words = TIER[1].cw;
+								if (sa.failed) return HB_E_WS;
+							} else if (tier > 1) {
+								const uint64_t nw = std::max<uint64_t>(4, std::min<uint64_t>(((uint64_t)h_q[tier] + 3) & ~3ull, TIER[tier].units)); bl = (unsigned)(nw / 4);
 								G.path = sa.get<uint64_t>(nw * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nw * 2 * (uint64_t)HB_MW_MAXW); G.vstride = HB_MW_MAXW;
 								G.cig_tmp = sa.get<uint16_t>(nw * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw; G.work = sa.zero<uint32_t>(1);
 								if (sa.failed) return HB_E_WS;
@@ -839,7 +755,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							G.q_in = (tier & 1) ? d_q2 : d_q1; G.q_in_n = d_qn + tier; G.q_out = tier < 3 ? ((tier & 1) ? d_q1 : d_q2) : 0; G.q_out_n = d_qn + tier + 1;
 							{
 								ProfScope ps(ctx, TIER[tier].name);
-								if (tier == 0) k_ecb_seg<<<bl, 128, 0, ctx->stream>>>(G); else k_ecb_seg_w<<<bl, 128, 0, ctx->stream>>>(G);
+								hb_k_ecb(tier == 0 ? HB_K_ECB_SEG : tier == 1 ? HB_K_ECB_SEG_G : HB_K_ECB_SEG_W, bl, 128, ctx->stream, G);
 							}
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -852,7 +768,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						spool_cap = spool_used + 65536; // the need is known now; the segments are recomputed (the chains stay refined)
 					}
 					ctx->counters[10] += h_q[3]; // segments that needed the largest scratch tier
-					if (getenv("HB_TRACE_EC")) fprintf(stderr, "[hb] EC base alignment: %llu overlaps, %llu segments; queued for alignment %u, past tier 0 %u, past tier 1 %u, past tier 2 %u; segment cigar pool %llu\n",
+					if (ctx->trace_ec) fprintf(stderr, "[hb] EC base alignment: %llu overlaps, %llu segments; queued for alignment %u, past tier 0 %u, past tier 1 %u, past tier 2 %u; segment cigar pool %llu\n",
 					                                    (unsigned long long)n_ov, (unsigned long long)n_seg, h_q[0], h_q[1], h_q[2], h_q[3], (unsigned long long)spool_used);
 					// ---- merge
 					uint64_t poolb_cap = n_seg / 4 + 16 * n_ov + 65536, poolb_used = 0; uint16_t *d_poolb = 0; unsigned int n_def = 0;
@@ -872,7 +788,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							if (pass == 1) HB_CUDA(cudaMemsetAsync(d_ndef, 0, 4, ctx->stream));
 							{
 								ProfScope ps(ctx, pass == 0 ? "k_ecb_merge" : "k_ecb_merge_deferred");
-								if (n_ov) k_ecb_merge<<<bl, 64, 0, ctx->stream>>>(G);
+								if (n_ov) hb_k_ecb(HB_K_ECB_MERGE, bl, 64, ctx->stream, G);
 							}
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(&n_def, d_ndef, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -903,7 +819,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 								HB_CUDA(hb_launch_ecb_rechain(L, ctx->stream));
 							}
 							HB_CUDA(cudaStreamSynchronize(ctx->stream));
-							if (getenv("HB_TRACE_EC")) fprintf(stderr, "[hb] EC base alignment: %u overlaps through the re-seeding rescue\n", n_rc);
+							if (ctx->trace_ec) fprintf(stderr, "[hb] EC base alignment: %u overlaps through the re-seeding rescue\n", n_rc);
 						}
 						HB_CUDA(cudaMemcpyAsync(&poolb_used, d_pused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 						HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -922,7 +838,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							const unsigned ph_blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nb + PH_WARPS - 1) / PH_WARPS, (uint64_t)ctx->sm_count * 8));
 							{
 								ProfScope ps(ctx, "k_ph_count");
-								k_ph_count<<<ph_blocks, PH_WARPS * 32, 0, ctx->stream>>>(P);
+								hb_k_ph(0, ph_blocks, ctx->stream, P);
 							}
 							HB_CUDA(cudaGetLastError());
 							if ((rc = hb_scan_u32_to_u64(ctx, d_nsite, d_soff, nb)) || (rc = hb_scan_u32_to_u64(ctx, d_nev, d_eoff, nb))) return rc;
@@ -934,7 +850,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							HB_ALLOC_CHECK(ba);
 							{
 								ProfScope ps(ctx, "k_ph_decide");
-								k_ph_decide<<<ph_blocks, PH_WARPS * 32, 0, ctx->stream>>>(P);
+								hb_k_ph(1, ph_blocks, ctx->stream, P);
 							}
 							HB_CUDA(cudaGetLastError());
 							HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -955,7 +871,6 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 									if ((rc = hb_scan_u32_to_u64(ctx, d_entcap, d_entoff, nb))) return rc;
 									uint64_t tot_ent = 0; HB_CUDA(cudaMemcpyAsync(&tot_ent, d_entoff + nb, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 									const unsigned cblocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nb + CNS_WARPS - 1) / CNS_WARPS, (uint64_t)ctx->sm_count * 3)); const uint64_t cwarps = (uint64_t)cblocks * CNS_WARPS;
-									const size_t cns_smem = (size_t)CNS_WARPS * HB_CNS_SMEM_WORDS * 8;
 									CnsEnt *d_ent = ba.get<CnsEnt>(tot_ent + 1); uint32_t *d_csrt = ba.get<uint32_t>(tot_ent + 1), *d_acta = ba.get<uint32_t>(tot_ent + 1), *d_actb = ba.get<uint32_t>(tot_ent + 1), *d_b32 = ba.get<uint32_t>(tot_ent + 1);
 									uint64_t *d_key = ba.get<uint64_t>(tot_ent + 1); int32_t *d_rs = ba.get<int32_t>(cwarps * HB_CNS_RS_WORDS); uint32_t *d_cwork = ba.zero<uint32_t>(2);
 									HB_ALLOC_CHECK(ba);
@@ -971,8 +886,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 										CA.srt = d_csrt; CA.act_a = d_acta; CA.act_b = d_actb; CA.b32 = d_b32; CA.key = d_key; CA.rs = d_rs; CA.work = d_cwork; CA.out_off = d_slot; CA.out = d_scslot; CA.out_n = d_scn; CA.status = d_status; CA.nec = d_nec; CA.err = d_err;
 										{
 											ProfScope ps(ctx, "k_ec_cns");
-											HB_CUDA(cudaFuncSetAttribute(k_ec_cns_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cns_smem));
-											k_ec_cns_w<false><<<cblocks, CNS_WARPS * 32, cns_smem, ctx->stream>>>(CA);
+											if (hb_k_cns(0, cblocks, ctx->stream, CA)) { hb_set_err(ctx, HB_E_CUDA, "window consensus: shared-memory attribute"); return HB_E_CUDA; }
 										}
 										HB_CUDA(cudaGetLastError());
 										std::vector<uint8_t> h_st(nb + 1);
@@ -992,8 +906,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 											HB_CUDA(cudaMemcpyAsync(d_queue, h_queue.data(), h_queue.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 											{
 												ProfScope ps(ctx, "k_ec_cns_graph");
-												HB_CUDA(cudaFuncSetAttribute(k_ec_cns_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cns_smem));
-												k_ec_cns_w<true><<<gblocks, CNS_WARPS * 32, cns_smem, ctx->stream>>>(CB);
+												if (hb_k_cns(1, gblocks, ctx->stream, CB)) { hb_set_err(ctx, HB_E_CUDA, "window consensus: shared-memory attribute"); return HB_E_CUDA; }
 											}
 											HB_CUDA(cudaGetLastError());
 											HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1163,8 +1076,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			M.in0 = d_in0; M.in0_off = d_i0off; M.in1 = ctx->d_prev1 + p1b; M.in1_off = d_i1off; M.ov = d_ov; M.srt = d_srt; M.o_off = d_ooff;
 			M.out0 = d_o0; M.out1 = d_o1; M.m0 = d_m0 + b0; M.m1 = d_m1 + b0; M.stat = d_stat;
 			ProfScope ps(ctx, "k_merge");
-			if (getenv("HB_POST_THREAD")) k_merge<<<nblk(nb, 64), 64, 0, ctx->stream>>>(M);
-			else k_merge_warp<<<nblk(nb, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * MERGE_SMEM_PER_WARP, ctx->stream>>>(M);
+			k_merge_warp<<<nblk(nb, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * MERGE_SMEM_PER_WARP, ctx->stream>>>(M);
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("merge");

@@ -35,6 +35,7 @@ struct hb_ctx {
 	std::vector<ProfEntry> prof, prof_stage; uint64_t counters[12], stage_counters[12]; int in_stage; // prof_stage / stage_counters: sums over all passes of the running hb_stage_run
 	uint64_t anchor_budget; // anchors per batch
 	uint64_t ecb_path_words; int32_t ecb_cig_words; // step B: trace words per warp of alignment tier 1, cigar words of the first merge launch (HB_ECB_PATH_WORDS / HB_ECB_CIG_WORDS, read once in hb_create: the tests shrink them so that the deferral paths run)
+	int trace, trace_ec; // HB_TRACE / HB_TRACE_EC (diagnostics), read once in hb_create
 	uint32_t cns_g_nodes, cns_g_arcs; // arena of the graph consensus per warp (HB_CNS_G_NODES / HB_CNS_G_ARCS, read once in hb_create: the overflow report is tested with tiny ones)
 	double last_pass_ms;
 	// workspace: one device allocation used as a double-ended stack (lo: scoped scratch,
@@ -47,6 +48,10 @@ struct hb_ctx {
 	void *stage_buf; // hb_stage_run's host-side lists (stage.cu)
 };
 void hb_stage_buf_free(hb_ctx *ctx);
+struct GroupDir;
+int hb_group_sort(hb_ctx *ctx, uint64_t nb, uint64_t r0_batch, const uint64_t *d_aoff, uint64_t a_base, uint64_t B, const hb_hit_t *d_raw, hb_hit_t *d_hits,
+                  GroupDir **dir_out, uint32_t *d_dirn, uint32_t *h_dirn, uint32_t *d_sc, int mcopy_num, int cutoff); // group.cu
+int hb_sort_pairs_u32(hb_ctx *ctx, const uint32_t *d_keys, const uint32_t *d_vals_in, uint32_t *d_vals_out, uint64_t n, int bits); // group.cu
 #define HB_E_WS (-100) /* internal: workspace too small, the caller grows it and reruns */
 int hb_ws_grow(hb_ctx *ctx);
 void hb_ws_reset(hb_ctx *ctx);

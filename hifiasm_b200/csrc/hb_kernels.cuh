@@ -1,20 +1,12 @@
-// hb_kernels.cuh — the sm_100a kernels of the overlap hot path.
+// hb_kernels.cuh — the sm_100a kernels of the overlap / error-correction hot path (no tensor-core work exists on it: integer / byte streams; what
+// matters is coalesced 128-bit access, shared-memory staging, warp collectives and grids sized from the SM count).
 //
-//   k_sketch        one thread per read, candidate ring in shared memory      (a2)
-//   k_probe_count   warp per read: 128-bit bucket loads of the GPU ha_pt_t    (a4)
-//   k_expand        half-warp per minimizer: 128-bit loads of the packed
-//                   position lists -> k_mer_hit records (THE probe kernel)     (a4/a5)
-//   k_group         warp per read: shared-memory hash grouping by (target,
-//                   strand) + ordered scatter — replaces the anchor radix sort (a5)
-//   k_chain         thread per (query,target) group: quick check + DP          (a6)
-//   k_post          thread per read: chain capping / sorting / shadow filter   (a7)
-//   k_exact         warp per chain: 2-bit packed exact-overlap test            (a19)
-//   k_merge         thread per read: merge with previous overlaps, emit        (a19)
-//   k_ed_semi64     thread per window: banded Myers in one 64-bit register     (a8)
-//
-// No tensor-core work exists on this path (integer / byte streams); the design
-// rules that matter are coalesced 128-bit access, shared-memory staging and
-// grids sized from the SM count.
+// The kernels are compiled in three translation units so that the build parallelises (HB_KERNELS_* selects the bodies; the argument structs and
+// launch constants are visible everywhere):
+//   HB_KERNELS_MAIN (engine.cu)   sketch, probe, expand, chain, chain post-filter, exact test, final merge, window pass, list emission, small helpers
+//   HB_KERNELS_ECB  (kern_ecb.cu) step A (k_ec_overlap_fast / k_ec_overlap) and step B (k_ecb_prep, k_ecb_seg_fast, k_ecb_seg, k_ecb_seg_g, k_ecb_seg_w, k_ecb_merge)
+//   HB_KERNELS_ECP  (kern_ecp.cu) phasing (k_ph_count, k_ph_decide) and window consensus (k_ec_cns_w)
+// engine.cu launches the kernels of the other two units through the hb_k_* functions declared at the end of this file.
 #pragma once
 #include "hb_sketch.cuh"
 #include "hb_final.cuh"
@@ -27,23 +19,11 @@
 #define HB_FULL 0xffffffffu
 #include "hb_warp.cuh"
 
+#ifdef HB_KERNELS_MAIN
+
 // ----------------------------------------------------------------------------
 // sketch
 // ----------------------------------------------------------------------------
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_sketch(DevReads R, DevFt ft, SketchPar P, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ cap_off,
-                                                   hb_mz_t *mz, uint32_t *mz_l, uint32_t *mz_n, int *err)
-{
-	extern __shared__ uint64_t sk_smem[];
-	uint64_t r = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
-	if (r >= nR) return;
-	RingRef<uint64_t> rx = { sk_smem + threadIdx.x, BLOCK }, rm = { sk_smem + (size_t)P.w * BLOCK + threadIdx.x, BLOCK };
-	RingRef<uint32_t> rl = { (uint32_t *)(sk_smem + (size_t)2 * P.w * BLOCK) + threadIdx.x, BLOCK };
-	SketchOut o; o.mz = mz + cap_off[r]; o.l = mz_l + cap_off[r]; o.cap = (uint32_t)(cap_off[r + 1] - cap_off[r]); o.n = 0; o.ovf = 0;
-	hb_sketch_read(R, ft, P, r0 + r, (uint32_t)(r0 + r), rx, rm, rl, o);
-	mz_n[r] = o.ovf ? 0 : o.n;
-	if (o.ovf) atomicOr(err, 1);
-}
 
 // ----------------------------------------------------------------------------
 // two-stage sketch (production path; see hb_sketch.cuh)
@@ -291,257 +271,7 @@ __global__ void __launch_bounds__(256, MINB) k_expand(DevReads R, DevPt pt, uint
 	}
 }
 
-// ----------------------------------------------------------------------------
-// group: warp per read.  Groups the read's anchors by key = target<<1|strand
-// with a hash table in shared memory (count -> order keys -> ordered scatter),
-// which is what radix_sort_ha_an1 + per-run radix_sort_ha_an3 (anchor.cpp:
-// 1046-1049) achieve on the CPU: anchors leave in key order and, inside a key,
-// in query-minimizer order (the chain kernel finishes the (self_offset,offset)
-// order, which only same-minimizer ties can violate).  Reads with more distinct
-// targets than the table holds fall back to tables in a global arena.
-// ----------------------------------------------------------------------------
-#define GRP_TS 1024
-#define GRP_MAXG 512
-#define GRP_EMPTY 0xffffffffu
-#define GRP_WARPS 4
-
-static __device__ __forceinline__ uint32_t grp_key(uint32_t id_strand) { return id_strand << 1 | id_strand >> 31; }
-static __device__ __forceinline__ uint32_t grp_hash(uint32_t key, uint32_t mask) { return (key * 2654435761u >> 7) & mask; }
-
-// returns slot, or GRP_EMPTY when the table is full
-static __device__ __forceinline__ uint32_t grp_find_or_insert(uint32_t *keys, uint32_t mask, uint32_t key, bool *fresh)
-{
-	uint32_t h = grp_hash(key, mask);
-	for (uint32_t p = 0; p <= mask; p++) {
-		uint32_t old = atomicCAS(&keys[h], GRP_EMPTY, key);
-		if (old == GRP_EMPTY) { *fresh = true; return h; }
-		if (old == key) { *fresh = false; return h; }
-		h = (h + 1) & mask;
-	}
-	return GRP_EMPTY;
-}
-static __device__ __forceinline__ uint32_t grp_find(const uint32_t *keys, uint32_t mask, uint32_t key)
-{
-	uint32_t h = grp_hash(key, mask);
-	while (keys[h] != key) h = (h + 1) & mask;
-	return h;
-}
-
-struct GroupArgs {
-	uint64_t nR, r0; const uint64_t *a_off; uint64_t a_base; const hb_hit_t *raw; hb_hit_t *hits; // r0: id of the batch's first read; a_off indexed by batch-local read
-	GroupDir *dir; uint32_t *dir_n; uint32_t dir_cap; uint32_t *sc; // chain slots per read
-	uint32_t *arena; unsigned long long *arena_used; uint64_t arena_words;
-	int32_t mcopy_num, mcopy_khit_cutoff; int *err;
-	uint32_t heavy_min, big_ts_max; const uint32_t *heavy; uint32_t n_heavy; uint32_t *ovf_q, *ovf_n; int heavy_from_q; // ovf_q: reads k_group hands over (more than GRP_MAXG distinct targets) // reads with >= heavy_min anchors (batch-local ids): one BLOCK each (k_group_big)
-};
-
-#define GRP_SMEM_BYTES (GRP_WARPS * (2 * GRP_TS + 2 * GRP_MAXG) * 4)
-__global__ void __launch_bounds__(GRP_WARPS * 32) k_group(GroupArgs A)
-{
-	extern __shared__ uint32_t grp_smem[];
-	__shared__ uint32_t s_nd[GRP_WARPS];
-	const int wib = threadIdx.x >> 5, lane = hb_lane();
-	uint32_t *const w_smem = grp_smem + (size_t)wib * (2 * GRP_TS + 2 * GRP_MAXG);
-	uint64_t r = (uint64_t)blockIdx.x * GRP_WARPS + wib;
-	if (r >= A.nR) return;
-	const uint64_t base = A.a_off[r] - A.a_base; const uint32_t n = (uint32_t)(A.a_off[r + 1] - A.a_off[r]), rid = (uint32_t)(A.r0 + r);
-	if (n == 0) { if (lane == 0) A.sc[r] = 0; return; }
-	if (n >= A.heavy_min) return; // a block of k_group_big takes the read
-	const hb_hit_t *raw = A.raw + base; hb_hit_t *out = A.hits + base;
-	uint32_t *keys = w_smem, *vals = w_smem + GRP_TS, *gk = w_smem + 2 * GRP_TS, *gc = gk + GRP_MAXG, mask = GRP_TS - 1, maxg = GRP_MAXG;
-	bool use_global = false;
-	for (;;) { // phase A: count anchors per key
-		for (uint32_t i = lane; i <= mask; i += 32) { keys[i] = GRP_EMPTY; vals[i] = 0; }
-		if (lane == 0) s_nd[wib] = 0;
-		__syncwarp();
-		bool ovf = false;
-		for (uint32_t q0 = 0; q0 < n; q0 += 128) { // 4 x 32 anchors per step: the four key loads are in flight together
-			uint32_t kk[4];
-#pragma unroll
-			for (int u = 0; u < 4; u++) { const uint32_t q = q0 + 32 * u + lane; kk[u] = q < n ? grp_key(__ldg(&raw[q].id_strand)) : GRP_EMPTY; }
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				if (kk[u] == GRP_EMPTY) continue;
-				bool fresh; uint32_t s = grp_find_or_insert(keys, mask, kk[u], &fresh);
-				if (s == GRP_EMPTY) { ovf = true; continue; }
-				atomicAdd(&vals[s], 1u);
-				if (fresh && atomicAdd(&s_nd[wib], 1u) >= maxg) ovf = true;
-			}
-		}
-		__syncwarp();
-		if (!__any_sync(HB_FULL, ovf)) break;
-		if (A.ovf_q) { if (lane == 0) A.ovf_q[atomicAdd(A.ovf_n, 1u)] = (uint32_t)r; return; } // more distinct targets than the shared-memory table holds: a block of k_group_big takes the read
-		if (use_global) { if (lane == 0) atomicOr(A.err, 2); return; } // cannot happen: global tables are sized from n
-		// fall back: tables sized for n distinct keys in the global arena
-		uint32_t ts = 64; while (ts < 2 * n) ts <<= 1;
-		unsigned long long need = 3ull * ts, at = 0;
-		if (lane == 0) at = atomicAdd(A.arena_used, need);
-		at = __shfl_sync(HB_FULL, at, 0);
-		if (at + need > A.arena_words) { if (lane == 0) { atomicOr(A.err, 4); A.sc[r] = 0; } return; }
-		keys = A.arena + at; vals = keys + ts; gk = vals + ts; gc = gk + ts / 2; mask = ts - 1; maxg = ts / 2; use_global = true;
-	}
-	const uint32_t G = s_nd[wib];
-	uint32_t Gp = 32; while (Gp < G) Gp <<= 1;
-	__syncwarp();
-	// phase B: collect the distinct keys, order them (bitonic, padded with +inf)
-	if (lane == 0) s_nd[wib] = 0;
-	__syncwarp();
-	for (uint32_t i = lane; i <= mask; i += 32)
-		if (keys[i] != GRP_EMPTY) { uint32_t p = atomicAdd(&s_nd[wib], 1u); gk[p] = keys[i]; gc[p] = vals[i]; }
-	for (uint32_t i = G + lane; i < Gp; i += 32) { gk[i] = GRP_EMPTY; gc[i] = 0; }
-	__syncwarp();
-	for (uint32_t k = 2; k <= Gp; k <<= 1)
-		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t i = lane; i < Gp; i += 32) {
-				uint32_t x = i ^ j;
-				if (x > i) {
-					uint32_t a = gk[i], b = gk[x]; bool asc = (i & k) == 0;
-					if ((a > b) == asc) { gk[i] = b; gk[x] = a; uint32_t t = gc[i]; gc[i] = gc[x]; gc[x] = t; }
-				}
-			}
-			__syncwarp();
-		}
-	// one directory entry per TARGET: the keys (target, strand 0) and (target, strand 1) are neighbours in key order and form ONE group, strand 0
-	// block first (lchain_qgen_mcopy_fast chains a target's anchors of both strands in one call, anchor.cpp:1928-1934); a group whose target is the
-	// read itself gets no chain slot (anchor.cpp:1931) but is still ordered (slot = GRP_EMPTY)
-	uint32_t Gh = 0;
-	for (uint32_t g0 = 0; g0 < G; g0 += 32) { const uint32_t g = g0 + lane; Gh += __popc(__ballot_sync(HB_FULL, g < G && (g == 0 || (gk[g - 1] >> 1) != (gk[g] >> 1)))); }
-	uint32_t dbase = 0;
-	if (lane == 0) dbase = atomicAdd(A.dir_n, Gh);
-	dbase = __shfl_sync(HB_FULL, dbase, 0);
-	const bool dir_ok = (uint64_t)dbase + Gh <= A.dir_cap;
-	if (!dir_ok && lane == 0) atomicOr(A.err, 8);
-	uint32_t run_a = 0, run_s = 0, run_h = 0;
-	for (uint32_t g0 = 0; g0 < G; g0 += 32) {
-		uint32_t g = g0 + lane, c = 0, ns = 0, key = 0, head = 0, cg = 0;
-		if (g < G) {
-			key = gk[g]; c = gc[g]; head = g == 0 || (gk[g - 1] >> 1) != (key >> 1);
-			if (head) { cg = c + ((g + 1 < G && (gk[g + 1] >> 1) == (key >> 1)) ? gc[g + 1] : 0); if ((key >> 1) != rid) ns = cg >= (uint32_t)A.mcopy_khit_cutoff ? A.mcopy_num : 1; }
-		}
-		uint32_t ia = c, is = ns, ih = head;
-		for (int d = 1; d < 32; d <<= 1) {
-			uint32_t va = __shfl_up_sync(HB_FULL, ia, d), vs = __shfl_up_sync(HB_FULL, is, d), vh = __shfl_up_sync(HB_FULL, ih, d);
-			if (lane >= d) { ia += va; is += vs; ih += vh; }
-		}
-		if (g < G) {
-			uint32_t start = run_a + ia - c;
-			vals[grp_find(keys, mask, key)] = start; // the key's write cursor
-			if (dir_ok && head) { GroupDir e; e.read = (uint32_t)r; e.start = start; e.count = cg; e.slot = ns ? run_s + is - ns : GRP_EMPTY; A.dir[dbase + run_h + ih - 1] = e; }
-		}
-		run_a += __shfl_sync(HB_FULL, ia, 31); run_s += __shfl_sync(HB_FULL, is, 31); run_h += __shfl_sync(HB_FULL, ih, 31);
-	}
-	if (lane == 0) A.sc[r] = run_s;
-	__syncwarp();
-	// phase C: ordered scatter (32 anchors at a time, in minimizer order)
-	for (uint32_t q0 = 0; q0 < n; q0 += 128) { // 4 x 32 anchors loaded together, scattered 32 at a time in order
-		uint4 hh[4];
-#pragma unroll
-		for (int u = 0; u < 4; u++) { const uint32_t q = q0 + 32 * u + lane; if (q < n) hh[u] = __ldg((const uint4 *)(raw + q)); else hh[u].x = GRP_EMPTY; }
-#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			const uint32_t q = q0 + 32 * u + lane;
-			if (q < n) {
-				uint32_t d = atomicAdd(&vals[grp_find(keys, mask, grp_key(hh[u].x))], 1u);
-				*(uint4 *)(out + d) = hh[u];
-			}
-			__syncwarp();
-		}
-	}
-}
-
-// group, block per heavy read (repeat-rich reads carry 10^5 - 10^6 anchors; one warp would hold the whole launch back).  Same three phases with the
-// tables in the global arena: (A) every warp counts a slice of the anchors into ONE table; (B) the block collects the distinct keys, orders them (bitonic
-// over the block), scans the counts into write cursors and fills the directory; (C) the keys are dealt to the warps by a second hash: a warp scans all
-// keys of the read but scatters only its own, in query-minimizer order — so, as in k_group, only anchors of the same 32-anchor step can leave out of order.
-#define GRPB_WARPS 16
-static __device__ __forceinline__ uint32_t grp_owner(uint32_t key) { return (key * 0x9E3779B1u) >> 28; } // 0 .. 15
-__global__ void __launch_bounds__(GRPB_WARPS * 32) k_group_big(GroupArgs A)
-{
-	__shared__ uint32_t s_nd, s_dbase, s_ok; __shared__ unsigned long long s_at; __shared__ uint32_t s_wa[GRPB_WARPS], s_ws[GRPB_WARPS], s_wh[GRPB_WARPS];
-	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, NT = GRPB_WARPS * 32;
-	if (blockIdx.x >= A.n_heavy + (A.heavy_from_q ? *A.ovf_n : 0u)) return;
-	const uint64_t r = A.heavy_from_q ? A.ovf_q[blockIdx.x] : A.heavy[blockIdx.x];
-	const uint64_t base = A.a_off[r] - A.a_base; const uint32_t n = (uint32_t)(A.a_off[r + 1] - A.a_off[r]), rid = (uint32_t)(A.r0 + r);
-	const hb_hit_t *raw = A.raw + base; hb_hit_t *out = A.hits + base;
-	uint32_t ts = 1024; while (ts < 2 * n && ts < A.big_ts_max) ts <<= 1;
-	const uint32_t mask = ts - 1, maxg = ts / 2;
-	if (tid == 0) { s_at = atomicAdd(A.arena_used, 3ull * ts); s_nd = 0; s_ok = 1; }
-	__syncthreads();
-	if (s_at + 3ull * ts > A.arena_words) { if (tid == 0) { atomicOr(A.err, 4); A.sc[r] = 0; } return; }
-	uint32_t *keys = A.arena + s_at, *vals = keys + ts, *gk = vals + ts, *gc = gk + maxg;
-	for (uint32_t i = tid; i < ts; i += NT) { keys[i] = GRP_EMPTY; vals[i] = 0; }
-	__syncthreads();
-	for (uint32_t q = tid; q < n; q += NT) { // (A)
-		const uint32_t k = grp_key(__ldg(&raw[q].id_strand)); bool fresh; const uint32_t sl = grp_find_or_insert(keys, mask, k, &fresh);
-		if (sl == GRP_EMPTY) { s_ok = 0; continue; }
-		atomicAdd(&vals[sl], 1u);
-		if (fresh && atomicAdd(&s_nd, 1u) >= maxg) s_ok = 0;
-	}
-	__syncthreads();
-	if (!s_ok) { if (tid == 0) { atomicOr(A.err, 2); A.sc[r] = 0; } return; } // more distinct targets than big_ts_max / 2: the host grows it
-	const uint32_t G = s_nd; uint32_t Gp = 32; while (Gp < G) Gp <<= 1;
-	__syncthreads();
-	if (tid == 0) s_nd = 0;
-	__syncthreads();
-	for (uint32_t i = tid; i < ts; i += NT) if (keys[i] != GRP_EMPTY) { const uint32_t p = atomicAdd(&s_nd, 1u); gk[p] = keys[i]; gc[p] = vals[i]; }
-	for (uint32_t i = G + tid; i < Gp; i += NT) { gk[i] = GRP_EMPTY; gc[i] = 0; }
-	__syncthreads();
-	for (uint32_t k = 2; k <= Gp; k <<= 1)
-		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t i = tid; i < Gp; i += NT) {
-				const uint32_t x = i ^ j;
-				if (x > i) { const uint32_t a = gk[i], b = gk[x]; const bool asc = (i & k) == 0; if ((a > b) == asc) { gk[i] = b; gk[x] = a; const uint32_t t = gc[i]; gc[i] = gc[x]; gc[x] = t; } }
-			}
-			__syncthreads();
-		}
-	if (tid == 0) s_nd = 0;
-	__syncthreads();
-	{ uint32_t hc = 0; for (uint32_t g = tid; g < G; g += NT) hc += g == 0 || (gk[g - 1] >> 1) != (gk[g] >> 1); if (hc) atomicAdd(&s_nd, hc); } // targets = groups (both strands of a target form one, see k_group)
-	__syncthreads();
-	const uint32_t Gh = s_nd;
-	if (tid == 0) { s_dbase = atomicAdd(A.dir_n, Gh); }
-	__syncthreads();
-	const uint32_t dbase = s_dbase; const bool dir_ok = (uint64_t)dbase + Gh <= A.dir_cap;
-	if (!dir_ok && tid == 0) atomicOr(A.err, 8);
-	uint32_t run_a = 0, run_s = 0, run_h = 0;
-	for (uint32_t g0 = 0; g0 < G; g0 += NT) { // write cursors and directory: block scan over (count, slots, heads) in key order
-		const uint32_t g = g0 + tid; uint32_t c = 0, ns = 0, key = 0, head = 0, cg = 0;
-		if (g < G) {
-			key = gk[g]; c = gc[g]; head = g == 0 || (gk[g - 1] >> 1) != (key >> 1);
-			if (head) { cg = c + ((g + 1 < G && (gk[g + 1] >> 1) == (key >> 1)) ? gc[g + 1] : 0); if ((key >> 1) != rid) ns = cg >= (uint32_t)A.mcopy_khit_cutoff ? A.mcopy_num : 1; }
-		}
-		uint32_t ia = c, is = ns, ih = head;
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t va = __shfl_up_sync(HB_FULL, ia, d), vs = __shfl_up_sync(HB_FULL, is, d), vh = __shfl_up_sync(HB_FULL, ih, d); if (lane >= d) { ia += va; is += vs; ih += vh; } }
-		if (lane == 31) { s_wa[wib] = ia; s_ws[wib] = is; s_wh[wib] = ih; }
-		__syncthreads();
-		uint32_t pa = 0, ps = 0, ph = 0, ta = 0, tsum = 0, th = 0;
-		for (int w = 0; w < GRPB_WARPS; w++) { if (w < wib) { pa += s_wa[w]; ps += s_ws[w]; ph += s_wh[w]; } ta += s_wa[w]; tsum += s_ws[w]; th += s_wh[w]; }
-		if (g < G) {
-			const uint32_t start = run_a + pa + ia - c;
-			vals[grp_find(keys, mask, key)] = start;
-			if (dir_ok && head) { GroupDir e; e.read = (uint32_t)r; e.start = start; e.count = cg; e.slot = ns ? run_s + ps + is - ns : GRP_EMPTY; A.dir[dbase + run_h + ph + ih - 1] = e; }
-		}
-		run_a += ta; run_s += tsum; run_h += th;
-		__syncthreads();
-	}
-	if (tid == 0) A.sc[r] = run_s;
-	__syncthreads();
-	for (uint32_t q0 = 0; q0 < n; q0 += 256) { // (C) every warp walks all keys (8 x 32 key loads in flight), 32 anchors per step, and moves the anchors of the keys it owns
-		uint32_t kk[8];
-#pragma unroll
-		for (int u = 0; u < 8; u++) { const uint32_t q = q0 + 32 * u + lane; kk[u] = q < n ? grp_key(__ldg(&raw[q].id_strand)) : GRP_EMPTY; }
-#pragma unroll
-		for (int u = 0; u < 8; u++) {
-			const uint32_t q = q0 + 32 * u + lane, k = kk[u];
-			if (k != GRP_EMPTY && grp_owner(k) == (uint32_t)wib) {
-				const uint4 h = __ldg((const uint4 *)(raw + q));
-				const uint32_t d = atomicAdd(&vals[grp_find(keys, mask, k)], 1u);
-				*(uint4 *)(out + d) = h;
-			}
-			__syncwarp();
-		}
-	}
-}
+#define GRP_EMPTY 0xffffffffu // GroupDir.slot of a group that is not chained (the read's hits on itself); groups are built in group.cu
 
 // ----------------------------------------------------------------------------
 // chain: one thread per (query, target) group
@@ -550,23 +280,6 @@ struct ChainArgs {
 	DevReads R; uint64_t r0; const GroupDir *dir; const uint32_t *dir_n; const uint64_t *a_off; uint64_t a_base; const uint64_t *c_off;
 	hb_hit_t *hits, *chits; int32_t *f, *p, *ii; int64_t *t; hb_chain_t *ch; uint32_t *slot_read; uint64_t *fc; ChainPar P; int *err; unsigned long long *dbg; uint32_t *work;
 };
-__global__ void k_chain(ChainArgs A)
-{
-	const uint32_t n = *A.dir_n;
-	for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
-		GroupDir d = A.dir[g];
-		uint64_t ab = A.a_off[d.read] - A.a_base + d.start;
-		if (d.slot == GRP_EMPTY) { hb_order_group(A.hits + ab, (int32_t)d.count); continue; }
-		uint64_t cb = A.c_off[d.read] + d.slot;
-		int32_t ns = d.count >= (uint32_t)A.P.mcopy_khit_cutoff ? A.P.mcopy_num : 1;
-		uint32_t tid = HB_HIT_ID(A.hits[ab]);
-		FcOut fc; fc.n = 0; fc.ovf = 0; fc.buf = A.fc ? A.fc + ab + 2 * cb : 0; fc.cap = d.count + 2 * ns;
-		hb_chain_group(A.hits + ab, (int32_t)d.count, A.chits + ab, ab, A.f + ab, A.p + ab, A.t + ab, A.ii + ab, A.P,
-		               (int64_t)A.R.len[A.r0 + d.read], (int64_t)A.R.len[tid], A.ch + cb, ns, fc);
-		for (int32_t s = 0; s < ns; s++) A.slot_read[cb + s] = d.read;
-		if (fc.ovf) atomicOr(A.err, 16);
-	}
-}
 
 // ----------------------------------------------------------------------------
 // chain, warp per group.  The common case — every strand block of the group is
@@ -909,15 +622,6 @@ struct PostArgs {
 	DevReads R; uint64_t r0, nR; const uint64_t *c_off; hb_chain_t *ch; const hb_hit_t *chits, *ghits; uint32_t *idx; uint32_t *n_ol; uint8_t *keep;
 	uint64_t *cc; const uint64_t *cc_off; ChainPar P;
 };
-__global__ void k_post(PostArgs A)
-{
-	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= A.nR) return;
-	uint64_t cb = A.c_off[r]; uint32_t ns = (uint32_t)(A.c_off[r + 1] - cb);
-	uint32_t n = hb_chain_post(A.ch + cb, ns, A.chits, A.ghits, A.idx + cb, A.cc + A.cc_off[r], A.R.len[A.r0 + r], A.P);
-	A.n_ol[r] = n;
-	for (uint32_t i = 0; i < n; i++) A.keep[cb + A.idx[cb + i]] = 1;
-}
 
 // post, warp per read: the read's chain slots are staged in shared memory (48 B each,
 // 128-bit copies by the whole warp), lane 0 runs the sequential post-filter on the staged
@@ -1010,19 +714,6 @@ struct MergeArgs {
 	FinOv *ov; uint64_t *srt; const uint64_t *o_off; // o_off[r] = sum(slots + n0) before r
 	hb_ma_hit_t *out0, *out1; uint32_t *m0, *m1; unsigned long long *stat;
 };
-__global__ void k_merge(MergeArgs A)
-{
-	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= A.nR) return;
-	uint64_t cb = A.c_off[r], ob = A.o_off[r], i0 = A.in0_off[r], i1 = A.in1_off[r];
-	uint32_t n0 = (uint32_t)(A.in0_off[r + 1] - i0), n1 = (uint32_t)(A.in1_off[r + 1] - i1), m0, m1;
-	unsigned long long st[7];
-	int32_t l_bb[256], l_be[256]; RsFrame l_st[HB_RS_STACK]; RsScratch W = { l_bb, l_be, l_st };
-	hb_final_merge(A.R, (uint32_t)(A.r0 + r), A.ch + cb, A.idx + cb, A.n_ol[r], A.exact + cb, A.in0 + i0, n0, A.in1 + i1, n1,
-	               A.ov + ob, A.srt + i0 + i1, A.out0 + ob, &m0, A.out1 + ob, &m1, st, W);
-	A.m0[r] = m0; A.m1[r] = m1;
-	for (int b = 0; b < 7; b++) if (st[b]) atomicAdd(&A.stat[b], st[b]);
-}
 
 // merge, warp per read: the working list (FinOv) and the sort keys are staged in shared
 // memory; lane 0 runs the sequential merge there.
@@ -1252,12 +943,14 @@ __global__ void k_ec_ea(DevReads R, uint64_t r0, uint64_t n_ov, const OvDesc *__
 	}
 	ea[o] = f;
 }
+#endif // HB_KERNELS_MAIN
 struct EcAlnArgs {
 	const uint8_t *ea; // row a12 flags (NULL: none)
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base; const hb_win_t *win;
 	double e_rate; int32_t w_l; hb_wl_t *wl; hb_aln_t *out; uint64_t *path; uint16_t *cig_tmp; uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; int *err;
 	uint32_t *q, *q_n; // overlaps that need the aligner (k_ec_overlap_fast -> k_ec_overlap)
 };
+#ifdef HB_KERNELS_ECB
 // step A in two launches.  k_ec_overlap_fast, thread / overlap at full occupancy: an overlap whose windows ALL aligned in the window pass (the rule) needs no
 // aligner — push_hc_wlst_exz finds no gap to fill and gen_extend_err_exz no stretch to estimate — so its window list and error total are sums over the
 // records; the others are queued.  k_ec_overlap, thread / queued overlap, grid bounded by the per-thread trace scratch: gap filling and extension estimates.
@@ -1293,29 +986,33 @@ __global__ void __launch_bounds__(64) k_ec_overlap(EcAlnArgs A)
 	}
 }
 
+#endif // HB_KERNELS_ECB
 // ----------------------------------------------------------------------------
 // steps B + C (rows a10 + a11): base-level CIGAR of the accepted overlaps as three kernels (hb_ecaln.cuh):
 //   k_ecb_prep   thread / overlap : chain refinement, whole-overlap exact shortcut, segment count
 //   k_ecb_seg    thread / segment : the alignments (independent of each other); scratch tiers chained by queues
 //   k_ecb_merge  thread / overlap : window fusion over the stored results, indel normalisation, totals
 // ----------------------------------------------------------------------------
+#ifdef HB_KERNELS_MAIN
 __global__ void k_ecb_cap(uint64_t n_ov, const OvDesc *__restrict__ desc, const hb_chain_t *__restrict__ ch, const hb_aln_t *__restrict__ aln, uint32_t *__restrict__ cap)
 { // window capacity of an overlap = number of inter-anchor segments (+1 spare)
 	uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
 	cap[o] = aln[o].st == 2 ? ch[desc[o].slot].n_hits + 2 + HB_RC_SPARE_WIN : (aln[o].st == 3 ? 2 : 0); // the spare: windows the re-seeding rescue may add
 }
+#endif // HB_KERNELS_MAIN
 struct EcCigArgs {
 	DevReads R; uint64_t r0, n_ov; const OvDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
 	const hb_aln_t *aln; const hb_wl_t *wlA; hb_hit_t *chits, *ghits; uint64_t dp_half; int64_t *dp_t, *dp_p; int32_t *dp_f;
 	double e_rate; int32_t w_l; int gaps;
 	EcPrep *prep; uint32_t *nseg; const uint64_t *seg_off; uint64_t n_seg; EcSeg *segs; // segments of overlap o: segs[seg_off[o] .. seg_off[o+1])
 	uint16_t *spool; unsigned long long *spool_used; uint64_t spool_cap;                // cigars of the aligned segments
-	uint32_t *q_in; const uint32_t *q_in_n; uint32_t *q_out; uint32_t *q_out_n; uint32_t *work; // deferred segments (ids) between scratch tiers; work: the warp tiers' dynamic counter
+	uint32_t *q_in; const uint32_t *q_in_n; uint32_t *q_out; uint32_t *q_out_n; uint32_t *work, *q_key; // deferred segments (ids) between scratch tiers; work: the warp tiers' dynamic counter
 	uint64_t *path; uint64_t path_words; uint64_t *vec; int32_t vstride; uint16_t *cig_tmp; int32_t cig_words; // per-thread scratch of the queue tiers / merge
 	int pass; hb_alnb_t *out; hb_wl_t *wl; const uint64_t *wl_off;
 	uint16_t *pool; unsigned long long *pool_used; uint64_t pool_cap; unsigned int *n_deferred; int *err;
 	uint32_t *rc_q; unsigned int *rc_n; // overlaps that ask for the re-seeding rescue (k_ecb_rechain, ecrechain.cu)
 };
+#ifdef HB_KERNELS_ECB
 static __device__ __forceinline__ void ecb_overlap_view(const EcCigArgs &A, uint64_t o, const hb_aln_t &a, OvDesc &d, hb_chain_t &c, EcZ &z, hb_hit_t *&ch_a, uint64_t &dpo)
 {
 	d = A.desc[o]; c = A.ch[d.slot];
@@ -1351,7 +1048,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		s_o = lo;
 	}
 	__syncthreads();
-	bool need = false;
+	bool need = false; uint32_t qlen = 0;
 	if (sidx < A.n_seg) {
 		uint64_t o = s_o; while (A.seg_off[o + 1] <= sidx) o++;
 		const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
@@ -1365,6 +1062,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
 		if (C.bad) atomicOr(A.err, 32);
 		need = st == 5 || C.ez.ovf; // an alignment (or a > 32 k-base exact run) is needed
+		{ const int64_t l = uq[1] - uq[0]; qlen = (uint32_t)(l < 0 ? 0 : l > 4095 ? 4095 : l); } // sort key of the queue: lanes of a warp of the alignment kernel then step about the same number of columns
 		if (!need) { EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap); A.segs[sidx] = sg; }
 	}
 	// one queue reservation per warp: the warp's segments stay together and in order, so the alignment kernel's warps mostly work
@@ -1374,7 +1072,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		uint32_t base = 0;
 		if (lane == __ffs(m) - 1) base = atomicAdd(A.q_out_n, (uint32_t)__popc(m));
 		base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-		if (need) A.q_out[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)sidx;
+		if (need) { const uint32_t qi = base + __popc(m & ((1u << lane) - 1)); A.q_out[qi] = (uint32_t)sidx; if (A.q_key) A.q_key[qi] = qlen; }
 	}
 }
 // segment alignment, tier 0: one thread per queued segment with a small private scratch (trace of 640 words = 212 columns of a one-word band
@@ -1392,6 +1090,31 @@ __global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
 	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
 		const uint64_t sidx = A.q_in[wk];
 		uint64_t lo = 0, hi = A.n_ov; // overlap of the segment: last o with seg_off[o] <= sidx
+		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
+		const uint64_t o = lo; const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
+		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
+		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+		C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
+		int64_t uq[2], ut[2], um;
+		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
+		if (C.bad) atomicOr(A.err, 32);
+		EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
+		if (sg.status == 4 && A.q_out) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; }
+		A.segs[sidx] = sg;
+	}
+}
+// segment alignment, tier 1: one thread per queued segment, grid-stride, with a launch-sized slice of global scratch (4096 trace words, 8-word band): the
+// one- and few-word bands that only outgrew tier 0's private trace (long error-free stretches between distant anchors) — a warp per segment would idle 31 lanes on them
+__global__ void __launch_bounds__(128) k_ecb_seg_g(EcCigArgs A)
+{
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
+	C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * 11 * (uint64_t)A.vstride; C.ez.vstride = A.vstride; C.ez.warp = 0; C.ez.cig = A.cig_tmp + tid * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words;
+	const uint64_t n_work = (uint64_t)*A.q_in_n;
+	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
+		const uint64_t sidx = A.q_in[wk];
+		uint64_t lo = 0, hi = A.n_ov;
 		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
 		const uint64_t o = lo; const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
 		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
@@ -1465,6 +1188,8 @@ __global__ void __launch_bounds__(64) k_ecb_merge(EcCigArgs A)
 		A.out[o] = r;
 	}
 }
+#endif // HB_KERNELS_ECB
+#ifdef HB_KERNELS_MAIN
 __global__ void k_gather_wl(uint64_t n_ov, const hb_alnb_t *__restrict__ in, const uint64_t *__restrict__ dense_off, const hb_wl_t *__restrict__ wl, hb_alnb_t *__restrict__ out, hb_wl_t *__restrict__ dense)
 { // capacity-strided window lists -> dense, one thread per overlap (lists are 1-2 entries long in the common case)
 	uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
@@ -1475,6 +1200,7 @@ __global__ void k_gather_wl(uint64_t n_ov, const hb_alnb_t *__restrict__ in, con
 __global__ void k_ecb_wn(uint64_t n_ov, const hb_alnb_t *__restrict__ in, uint32_t *__restrict__ wn)
 { uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o < n_ov) wn[o] = in[o].w_n; }
 
+#endif // HB_KERNELS_MAIN
 // ----------------------------------------------------------------------------
 // phasing (row a13, hb_ecphase.cuh): thread / read.  k_ph_count gathers the read's accepted overlaps, counts mismatch columns
 // per query position and sizes the evidence; k_ph_decide collects the evidence, derives the allele statistics and makes the
@@ -1487,6 +1213,7 @@ struct PhArgs {
 };
 #define HB_CNS_RS_WORDS (512 + 3 * HB_RS_STACK) // dedup_chains' / the phasing's radix-sort scratch (RsScratch) as int32 words
 #define PH_WARPS 4
+#ifdef HB_KERNELS_ECP
 // warp / read, reads handed out dynamically (A.work[0] / A.work[1]): lanes share the cigar walks of the read's alignment windows (hb_ph_count_w / hb_ph_decide_w)
 __global__ void __launch_bounds__(PH_WARPS * 32) k_ph_count(PhArgs A)
 {
@@ -1539,6 +1266,8 @@ __global__ void __launch_bounds__(PH_WARPS * 32) k_ph_decide(PhArgs A)
 	}
 }
 
+#endif // HB_KERNELS_ECP
+#ifdef HB_KERNELS_MAIN
 // the round's reverse_paf[i]: dedup_chains + push_ne_ovlp(flag 2) per read (hb_ecphase.cuh: hb_ec_reverse_list)
 __global__ void __launch_bounds__(64) k_ec_rpaf(DevReads R, uint64_t r0, uint64_t nR, const uint64_t *__restrict__ o_off, const hb_phase_t *__restrict__ ph, uint64_t *ord, hb_ma_hit_t *out, uint32_t *n_out, int *err)
 {
@@ -1575,6 +1304,7 @@ __global__ void k_cns_cap(uint64_t nR, const uint64_t *__restrict__ o_off, const
 	for (uint64_t j = o_off[r]; j < o_off[r + 1]; j++) if (alnb[j].st == 2) c += alnb[j].w_n;
 	ent_cap[r] = c;
 }
+#endif // HB_KERNELS_MAIN
 struct CnsArgs {
 	DevReads R; uint64_t r0, nR; const uint64_t *o_off; const hb_phase_t *ph; const hb_alnb_t *alnb; const hb_wl_t *wl; const uint16_t *pool;
 	uint64_t *ord; CnsOv *cov; const uint64_t *ent_off; CnsEnt *ent; uint32_t *srt, *act_a, *act_b, *b32; uint64_t *key; int32_t *rs; uint32_t *work; // rs: HB_CNS_RS_WORDS per warp (dedup_chains' sort scratch)
@@ -1583,10 +1313,11 @@ struct CnsArgs {
 	const uint32_t *queue; uint32_t n_queue, g_nodes, g_arcs, g_nseq, g_pcap, g_ccap;
 	CnsNode *g_nd; CnsArc *g_arc; uint32_t *g_q, *g_b32, *g_np; uint8_t *g_ns; uint64_t *g_path, *g_vec; uint16_t *g_cig;
 };
+#define CNS_WARPS 8
+#ifdef HB_KERNELS_ECP
 // One WARP per read (hb_cns_read_w): the 512-column pile-up as range updates on a difference array in the warp's shared memory, the majority tests one
 // column per lane, lane 0 for the sequential tail (stretch votes between anchors, script).  Reads are handed out dynamically (A.work); the first launch
 // (GRAPH = false) is compiled without the graph consensus and queues the reads that need it for the second, whose warps own a graph arena each.
-#define CNS_WARPS 8
 template <bool GRAPH> __global__ void __launch_bounds__(CNS_WARPS * 32) k_ec_cns_w(CnsArgs A)
 {
 	extern __shared__ uint64_t cns_smem[];
@@ -1632,6 +1363,8 @@ template <bool GRAPH> __global__ void __launch_bounds__(CNS_WARPS * 32) k_ec_cns
 		__syncwarp();
 	}
 }
+#endif // HB_KERNELS_ECP
+#ifdef HB_KERNELS_MAIN
 __global__ void k_sc_compact(uint64_t nR, const uint64_t *__restrict__ slot_off, const uint64_t *__restrict__ dense_off, const uint16_t *__restrict__ in, uint16_t *__restrict__ out)
 {
 	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (r >= nR) return;
@@ -1691,3 +1424,11 @@ __global__ void k_ed_semi64(uint64_t n_cases, const char *__restrict__ pat, cons
 	}
 	err_o[c] = best; pe_o[c] = pe;
 }
+#endif // HB_KERNELS_MAIN
+
+// ---- launchers of the kernels compiled in kern_ecb.cu / kern_ecp.cu ----
+enum { HB_K_ECB_PREP, HB_K_ECB_SEG_FAST, HB_K_ECB_SEG, HB_K_ECB_SEG_G, HB_K_ECB_SEG_W, HB_K_ECB_MERGE };
+void hb_k_ecaln(int slow, unsigned grid, cudaStream_t st, const EcAlnArgs &A);                 // k_ec_overlap_fast (128 threads) / k_ec_overlap (64)
+void hb_k_ecb(int which, unsigned grid, unsigned block, cudaStream_t st, const EcCigArgs &A);
+void hb_k_ph(int decide, unsigned grid, cudaStream_t st, const PhArgs &A);                     // PH_WARPS * 32 threads
+int hb_k_cns(int graph, unsigned grid, cudaStream_t st, const CnsArgs &A);                     // CNS_WARPS * 32 threads, CNS_WARPS * HB_CNS_SMEM_WORDS * 8 bytes of shared memory

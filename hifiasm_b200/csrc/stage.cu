@@ -13,6 +13,8 @@ static double wall_ms() { return std::chrono::duration<double, std::milli>(std::
 
 struct StageBuf { // the stage's host-side state between calls: lists of all reads, grown on demand
 	std::vector<hb_ma_hit_t> src, rev, t_src, t_rev; std::vector<uint64_t> src_off, rev_off, t_so, t_ro, scc_off; std::vector<uint16_t> scc; std::vector<uint8_t> flags, status, fc, ab, blob, all;
+	uint8_t *xbuf = 0; uint64_t xcap = 0; // page-locked exchange buffer (send | recv)
+	~StageBuf() { if (xbuf) cudaFreeHost(xbuf); }
 };
 static StageBuf *stage_buf(hb_ctx *ctx) { if (!ctx->stage_buf) ctx->stage_buf = new StageBuf(); return (StageBuf *)ctx->stage_buf; }
 void hb_stage_buf_free(hb_ctx *ctx) { delete (StageBuf *)ctx->stage_buf; ctx->stage_buf = 0; }
@@ -27,11 +29,14 @@ static int gather_blobs(hb_ctx *ctx, int world, hb_allgather_fn ag, void *user, 
 	if (ag(user, &sz, sizes.data(), 8)) { hb_set_err(ctx, HB_E_STATE, "the all-gather callback failed (sizes)"); return HB_E_STATE; }
 	uint64_t mx = 8; for (int r = 0; r < world; r++) mx = std::max(mx, sizes[r]);
 	mx = (mx + 15) & ~15ull;
-	std::vector<uint8_t> send(mx, 0), recv(mx * world); if (sz) memcpy(send.data(), mine.data(), sz);
-	if (ag(user, send.data(), recv.data(), mx)) { hb_set_err(ctx, HB_E_STATE, "the all-gather callback failed (payload)"); return HB_E_STATE; }
+	// the exchange buffers are page-locked (and kept): the transport copies them to and from the device
+	StageBuf &B = *stage_buf(ctx); const uint64_t need = mx * (uint64_t)(world + 1);
+	if (B.xcap < need) { if (B.xbuf) cudaFreeHost(B.xbuf); B.xbuf = 0; B.xcap = 0; if (cudaHostAlloc((void **)&B.xbuf, need + need / 4, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hb_set_err(ctx, HB_E_NOMEM, "page-locked exchange buffer"); return HB_E_NOMEM; } B.xcap = need + need / 4; }
+	uint8_t *send = B.xbuf, *recv = B.xbuf + mx; if (sz) memcpy(send, mine.data(), sz);
+	if (ag(user, send, recv, mx)) { hb_set_err(ctx, HB_E_STATE, "the all-gather callback failed (payload)"); return HB_E_STATE; }
 	uint64_t tot = 0; for (int r = 0; r < world; r++) tot += sizes[r];
 	all.resize(tot); uint64_t o = 0;
-	for (int r = 0; r < world; r++) { if (sizes[r]) memcpy(all.data() + o, recv.data() + (uint64_t)r * mx, sizes[r]); o += sizes[r]; }
+	for (int r = 0; r < world; r++) { if (sizes[r]) memcpy(all.data() + o, recv + (uint64_t)r * mx, sizes[r]); o += sizes[r]; }
 	return HB_OK;
 }
 template <typename T> static void put(std::vector<uint8_t> &b, const T *p, uint64_t n) { const size_t o = b.size(); b.resize(o + n * sizeof(T)); if (n) memcpy(b.data() + o, p, n * sizeof(T)); }

@@ -52,9 +52,15 @@ def torch_allgather(device):
         try:
             world = dist.get_world_size()
             a = torch.frombuffer((C.c_uint8 * nbytes).from_address(send), dtype=torch.uint8)
-            out = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
-            dist.all_gather_into_tensor(out, a.to(device)) if device is not None and str(device) != "cpu" else dist.all_gather(list(out.view(world, nbytes).unbind(0)), a.clone())
-            torch.frombuffer((C.c_uint8 * (world * nbytes)).from_address(recv), dtype=torch.uint8).copy_(out.cpu() if out.is_cuda else out)
+            r = torch.frombuffer((C.c_uint8 * (world * nbytes)).from_address(recv), dtype=torch.uint8)
+            if device is not None and str(device) != "cpu":   # NCCL: the library's buffers are page-locked, so both copies are plain DMA
+                out = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
+                dist.all_gather_into_tensor(out, a.to(device, non_blocking=True))
+                r.copy_(out)
+            else:
+                parts = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+                dist.all_gather(parts, a.clone())
+                r.copy_(torch.cat(parts))
             return 0
         except Exception as ex:  # the C side turns a non-zero return into an error of the call
             import sys

@@ -80,6 +80,7 @@ static void unflatten(const std::vector<hb_ma_hit_t> &rec, const std::vector<uin
 void cal_ov_r(uint64_t n_thre, uint64_t n_a, uint64_t new_idx)
 {
 	(void)n_thre; (void)new_idx;
+	const double tt0 = yak_realtime_0();
 	hb_load_and_index();
 	std::vector<hb_ma_hit_t> p0, p1, o0, o1; std::vector<uint64_t> f0, f1, g0(n_a + 1), g1(n_a + 1); uint64_t st[8];
 	flatten(R_INF.paf, R_INF.total_reads, p0, f0); flatten(R_INF.reverse_paf, R_INF.total_reads, p1, f1);
@@ -96,12 +97,14 @@ void cal_ov_r(uint64_t n_thre, uint64_t n_a, uint64_t new_idx)
 	fprintf(stderr, "[M::ha_print_ovlp_stat_0] # weak overlaps: %lu\n", (unsigned long)st[3]);     fprintf(stderr, "[M::ha_print_ovlp_stat_0] # exact overlaps: %lu\n", (unsigned long)st[4]);
 	fprintf(stderr, "[M::ha_print_ovlp_stat_0] # inexact overlaps: %lu\n", (unsigned long)st[6]);  fprintf(stderr, "[M::ha_print_ovlp_stat_0] # overlaps without large indels: %lu\n", (unsigned long)st[5]);
 	fprintf(stderr, "[M::ha_print_ovlp_stat_0] # reverse overlaps: %lu\n", (unsigned long)st[1]);
+	fprintf(stderr, "[M::ha_print_ovlp_stat_0] # running time: %.3f\n", yak_realtime_0() - tt0);
 }
 
 // cal_ec_r, ecovlp.cpp:6268: reads, both lists and the two read flags in R_INF, *tot_b / *tot_e, the [M::pec] lines (ecovlp.cpp:6089, 6180)
 void cal_ec_r(uint64_t n_thre, uint64_t round, uint64_t n_round, uint64_t n_a, uint64_t is_sv, uint64_t *tot_b, uint64_t *tot_e)
 {
 	(void)n_thre;
+	const double tt0 = yak_realtime_0();
 	hb_load_and_index();
 	std::vector<hb_ma_hit_t> p0, o0, o1; std::vector<uint64_t> f0, g0(n_a + 1), g1(n_a + 1); std::vector<uint8_t> fl(2 * n_a + 2), st(n_a + 1);
 	flatten(R_INF.paf, n_a, p0, f0);                                             // gen_hc_r_alin_ea reads the previous round's paf[i] (ecovlp.cpp:3288)
@@ -114,8 +117,8 @@ void cal_ec_r(uint64_t n_thre, uint64_t round, uint64_t n_round, uint64_t n_a, u
 	}
 	if (rc) hb_die("hb_cal_ec_r");
 	for (uint64_t i = 0; i < n_a; i++) if (st[i]) { fprintf(stderr, "[hifiasm_b200] read %lu could not be finished on the device (status %d)\n", (unsigned long)i, (int)st[i]); exit(1); }
-	fprintf(stderr, "[M::pec] # bases: %lu; # corrected bases: %lu\n", (unsigned long)*tot_b, (unsigned long)*tot_e);
-	fprintf(stderr, "[M::pec] # exact o: %lu; # non-exact o: %lu\n", (unsigned long)n_ex, (unsigned long)n_inex);
+	fprintf(stderr, "[M::pec::%.3f] # bases: %lu; # corrected bases: %lu\n", yak_realtime_0() - tt0, (unsigned long)*tot_b, (unsigned long)*tot_e);   // ecovlp.cpp:6089
+	fprintf(stderr, "[M::pec::%.3f] # exact o: %lu; # non-exact o: %lu\n", yak_realtime_0() - tt0, (unsigned long)n_ex, (unsigned long)n_inex);       // ecovlp.cpp:6108
 	unflatten(o0, g0, R_INF.paf, n_a); unflatten(o1, g1, R_INF.reverse_paf, n_a);
 	for (uint64_t i = 0; i < n_a; i++) { R_INF.paf[i].is_fully_corrected = fl[2 * i]; R_INF.paf[i].is_abnormal = fl[2 * i + 1]; R_INF.trio_flag[i] = AMBIGU; }
 	// corrected reads back into R_INF (malloc-owned, read_size >= length: worker_sl_ec's realloc rule, ecovlp.cpp:6017)

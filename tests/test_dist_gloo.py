@@ -104,3 +104,31 @@ def test_single_process_is_the_identity():
     rec = np.zeros(5, binio.MA_MEM); rec["tn"] = np.arange(5); off = np.array([0, 2, 2, 5], np.uint64)
     a, o = hdist.all_gather_ragged(rec, off)
     assert a.tobytes() == rec.tobytes() and (o == off).all()
+
+
+# ---- the transport hb_stage_run calls for its exchange (hifiasm_b200.engine.torch_allgather: an hb_allgather_fn over torch.distributed) ----
+def _cb_worker(rank, world, port, q):
+    import ctypes as C
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hifiasm_b200.engine import torch_allgather
+    cb = torch_allgather(None)
+    nbytes = 4096 + 16
+    send = (C.c_uint8 * nbytes)(*([(rank * 37 + i) & 0xff for i in range(nbytes)])); recv = (C.c_uint8 * (nbytes * world))()
+    rc = cb(None, C.addressof(send), C.addressof(recv), nbytes)
+    q.put((rank, rc, bytes(recv)))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_allgather_callback_world2():
+    world = 2; ctx = mp.get_context("spawn"); q = ctx.Queue(); port = _free_port()
+    ps = [ctx.Process(target=_cb_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps])
+    for p in ps:
+        p.join(timeout=60); assert p.exitcode == 0
+    nbytes = 4096 + 16
+    want = b"".join(bytes([(r * 37 + i) & 0xff for i in range(nbytes)]) for r in range(world))
+    for rank, rc, got in res:
+        assert rc == 0 and got == want   # every rank holds every rank's bytes, in rank order

@@ -180,7 +180,7 @@ def test_stages_final_and_cal_ov_r(ctx, tmp_path):
     n0, n1, stat2 = eng.cal_ov_r_resident()
     assert (n0, n1) == (f0.size, f1.size) and (stat2 == stat).all()
     prof = eng.profile()
-    for k in ("k_sketch_events", "k_sketch_select", "k_probe_count", "k_expand", "k_group", "k_chain", "k_post", "k_exact", "k_merge"):
+    for k in ("k_sketch_events", "k_sketch_select", "k_probe_count", "k_expand", "sort_anchors", "k_chain", "k_post", "k_exact", "k_merge"):
         assert k in prof and prof[k][0] >= 1, k
 
 
@@ -239,7 +239,7 @@ def test_ec_cigar_small_scratch_defers_and_matches(ctx, monkeypatch):
             "[d.update(np.ascontiguousarray(W[f]).tobytes()) for f in ('x_start', 'x_end', 'y_start', 'y_end', 'error', 'clen')];"
             "print(json.dumps({'dg': d.hexdigest(), 'deferred': e.counters()['ec_deferred']}))") % (
                 os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), [k for k in ("g1", "g2", "g3") if Golden(k).raw.n == n][0], float(p["bw_thres"]))
-    env = dict(os.environ, HB_ECB_PATH_WORDS="256", HB_ECB_CIG_WORDS="64")  # tier 1: 256 trace words per warp, tier 2: 4096
+    env = dict(os.environ, HB_ECB_PATH_WORDS="64", HB_ECB_CIG_WORDS="64")  # tier 1: 64 trace words per thread, tier 2: 4096 per warp
     res = json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1])
     o, B, W, Cg = ref
     d = hashlib.blake2b(digest_size=8)
