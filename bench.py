@@ -222,17 +222,20 @@ def _main():
         tc = time.time()
         return r, (tb - ta), (tc - tb), (tc - ta), n_src, n_rev, chk
 
+    def summarize(r):
+        if r["n_unfinished"]:
+            raise RuntimeError("%d reads could not be finished on the device" % r["n_unfinished"])
+        h = hashlib.blake2b(digest_size=8)
+        for f in ("qns", "qe", "tn", "ts", "te", "el", "no_l_indel", "ml", "rev", "bl"):
+            h.update(np.ascontiguousarray(r["src"][f]).tobytes()); h.update(np.ascontiguousarray(r["rev"][f]).tobytes())
+        h.update(r["src_off"].tobytes()); h.update(r["rev_off"].tobytes())
+        return h.hexdigest(), r["corrected_bases"], r["hom_cov"]
+
     digest = None
     for w in range(args.warmup):
         r, t_up, t_st, t_all, n_src, n_rev, chk = step()
         if w == 0:
-            if r["n_unfinished"]:
-                raise RuntimeError("%d reads could not be finished on the device" % r["n_unfinished"])
-            h = hashlib.blake2b(digest_size=8)
-            for f in ("qns", "qe", "tn", "ts", "te", "el", "no_l_indel", "ml", "rev", "bl"):
-                h.update(np.ascontiguousarray(r["src"][f]).tobytes()); h.update(np.ascontiguousarray(r["rev"][f]).tobytes())
-            h.update(r["src_off"].tobytes()); h.update(r["rev_off"].tobytes())
-            digest = h.hexdigest(); corrected = r["corrected_bases"]; hom = r["hom_cov"]
+            digest, corrected, hom = summarize(r)
         sys.stderr.write("[bench] rank %d warm-up %d: upload %.3f s, stage %.3f s (device %.3f s; exchange %.3f s)\n" % (rank, w, t_up, t_st, r["device_ms"] / 1e3, r["ms"]["exchange"] / 1e3))
     barrier()
     dev_ms = 0.0; e2e_s = 0.0; up_s = 0.0; ex_ms = 0.0; kms = {}; counters = None; step_ms = []
@@ -240,6 +243,8 @@ def _main():
         for _ in range(args.steps):
             r, t_up, t_st, t_all, n_src, n_rev, chk = step()
             dev_ms += r["device_ms"]; e2e_s += t_all; up_s += t_up; ex_ms += r["ms"]["exchange"]; step_ms.append(round(r["device_ms"], 1))
+            if digest is None:
+                digest, corrected, hom = summarize(r)
             pk, counters = eng.stage_profile()
             for k, v in pk.items():
                 a = kms.setdefault(k, [0, 0.0]); a[0] += v[0]; a[1] += v[1]

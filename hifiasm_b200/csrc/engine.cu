@@ -645,7 +645,8 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 				std::vector<uint64_t> h_ooff(nb + 1);
 				HB_CUDA(cudaMemcpyAsync(h_ooff.data(), d_ooff, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 				const uint64_t n_ov = h_ooff[nb];
-				const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 4)); const uint64_t nthr = (uint64_t)blocks * 64;
+				// the queued (aligner) pass of step A: its grid is bounded by the per-thread trace scratch (31 KB); up to 8 GB of it, so that in the usual case every queued overlap has a thread
+				const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, std::max<uint64_t>((uint64_t)ctx->sm_count * 4, (8ull << 30) / ((uint64_t)w_l * 40 + 2 * HB_EC_CIG_TMP) / 64))); const uint64_t nthr = (uint64_t)blocks * 64;
 				OvDesc *d_od = ba.get<OvDesc>(n_ov + 1); hb_aln_t *d_aln = ba.get<hb_aln_t>(n_ov + 1); hb_wl_t *d_wl = ba.zero<hb_wl_t>(n_win + 1);
 				uint64_t *d_path = ba.get<uint64_t>(nthr * (uint64_t)w_l * 5); uint16_t *d_ctmp = ba.get<uint16_t>(nthr * HB_EC_CIG_TMP);
 				unsigned long long *d_pused = ba.zero<unsigned long long>(1);
@@ -780,7 +781,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						G.rc_q = d_q1; G.rc_n = d_qn + 6; // the segment queues are free now: the merge kernel queues the overlaps that need the re-seeding rescue
 						for (int pass = 0; pass < 2; pass++) {
 							if (pass == 1 && !n_def) break;
-							const unsigned bl = pass == 0 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 8)) : 4u;
+							const unsigned bl = pass == 0 ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, (uint64_t)ctx->sm_count * 32)) : 4u; // 24 KB of cigar scratch per thread: 7 GB at most
 							const uint64_t nt = (uint64_t)bl * 64; const int32_t cw = pass == 0 ? merge_cw0 : (1 << 20);
 							Arena sa(ctx);
 							G.cig_tmp = sa.get<uint16_t>(nt * 3 * (uint64_t)cw); G.cig_words = cw; G.pass = pass;

@@ -112,3 +112,11 @@ HB_HD int64_t hb_chain_len(int64_t xb, int64_t xe, int64_t xl, int64_t yb, int64
 	if (xr <= yr) xe = xl - 1; else xe += yr;
 	return xe - xb + 1;
 }
+
+// in-place heapsort of bare 64-bit keys (where the reference radix-sorts key arrays without payload, any sort gives the same array)
+HB_HD void hb_heapsort64(uint64_t *a, uint32_t n)
+{
+	if (n < 2) return;
+	for (uint32_t s = n / 2; s-- > 0;) { uint32_t i = s; const uint64_t v = a[i]; for (;;) { uint32_t c = 2 * i + 1; if (c >= n) break; if (c + 1 < n && a[c + 1] > a[c]) c++; if (a[c] <= v) break; a[i] = a[c]; i = c; } a[i] = v; }
+	for (uint32_t e = n - 1; e > 0; e--) { const uint64_t v = a[e]; a[e] = a[0]; uint32_t i = 0; for (;;) { uint32_t c = 2 * i + 1; if (c >= e) break; if (c + 1 < e && a[c + 1] > a[c]) c++; if (a[c] <= v) break; a[i] = a[c]; i = c; } a[i] = v; }
+}

@@ -470,7 +470,7 @@ struct MwEz {
 	int32_t ps, pe, pl, ts, te, tl, thre, err, nword;
 	uint16_t *cig; int32_t cn, ccap;      // cigar of the last alignment
 	uint64_t *path; uint64_t pcap, pn;    // 5*nword words per column; one-word bands (compact = 1): 2 header words (initial VP, VN) + 3 per column (D0, VP, VN)
-	int32_t compact;                      // trace layout: 0 = 5 words per band word and column, 1 = one-word band (3 per column), 2 = hb_mw_align_w's (3 per band word and column)
+	int32_t compact;                      // trace layout: 0 = 5 words per band word and column, 1 = one-word band (3 per column), 2 = hb_mw_align_w's (3 per band word and column), 3 = one-word band of <= 21 bits (1 per column)
 	int32_t warp;                         // != 0: the calling WARP runs the aligner together (hb_mwalign_w.cuh); every lane holds the same MwEz
 	uint64_t *vec; int32_t vstride;       // 11 vectors of vstride words: Peq[0..4], VP, VN, X, D0, HN, HP
 	int ovf;                              // scratch too small: the unit is deferred to a launch with more scratch
@@ -518,6 +518,13 @@ HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 			D = cur - (1 - d0b); d = 0; mn = D;
 			if (sft != low) { const int vppb = hb_mw_bit(pvp, sft), hn = vppb & d0b, hp = hb_mw_bit(pvn, sft) | (1 - (vppb | d0b)); H = cur + hn - hp; if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
 			if (sft != 0) { V = cur + hb_mw_bit(row + 2 * nw, sft - 1) - hb_mw_bit(row + nw, sft - 1); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
+		} else if (ez.compact == 3) { // one-word band of <= 21 bits: one trace word per column (D0 | VP << 21 | VN << 42), header = initial VP | VN << 21
+			const uint64_t w = ez.path[i], pw = ez.path[i - 1]; // column i-1 sits at path[1 + (i-1)]
+			const uint64_t d0 = w & 0x1fffffULL, vp = (w >> 21) & 0x1fffffULL, vn = (w >> 42) & 0x1fffffULL;
+			const uint64_t vpp = i > 1 ? (pw >> 21) & 0x1fffffULL : pw & 0x1fffffULL, vnp = i > 1 ? (pw >> 42) & 0x1fffffULL : (pw >> 21) & 0x1fffffULL, hn = vpp & d0, hp = vnp | ~(vpp | d0);
+			D = cur - (1 - (int32_t)((d0 >> sft) & 1ULL)); d = 0; mn = D;
+			if (sft != low) { H = cur + (int32_t)((hn >> sft) & 1ULL) - (int32_t)((hp >> sft) & 1ULL); if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
+			if (sft != 0) { V = cur + (int32_t)((vn >> (sft - 1)) & 1ULL) - (int32_t)((vp >> (sft - 1)) & 1ULL); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
 		} else if (ez.compact) { // one-word band: D0, VP, VN of the column; HN = VP' & D0, HP = VN' | ~(VP' | D0) with VP', VN' of the column before (header for column 0)
 			const uint64_t *row = ez.path + 2 + (size_t)(i - 1) * 3, *prv = i > 1 ? row - 3 + 1 : ez.path;
 			const uint64_t d0 = row[0], vp = row[1], vn = row[2], vpp = prv[0], vnp = prv[1], hn = vpp & d0, hp = vnp | ~(vpp | d0);
@@ -565,8 +572,9 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 	else { ez.ps = ez.pe = -1; ez.ts = 0; ez.te = tn - 1; if (pn > tn + cut || tn > pn + cut) return; }
 	const int32_t tn0 = tn - 1, pe = pn - 1;
 	ez.nword = nword;
-	if ((nword == 1 ? 2 + 3 * (uint64_t)tn : (uint64_t)nword * (uint64_t)tn * 5) > ez.pcap || nword > ez.vstride) { ez.ovf = 1; return; }
-	ez.compact = nword == 1;
+	const bool pk21 = bd <= 21; // the whole band in 21 bits (thre <= 10: the usual segment): D0 | VP | VN of a column share ONE trace word
+	if ((nword == 1 ? (pk21 ? 1 + (uint64_t)tn : 2 + 3 * (uint64_t)tn) : (uint64_t)nword * (uint64_t)tn * 5) > ez.pcap || nword > ez.vstride) { ez.ovf = 1; return; }
+	ez.compact = nword == 1 ? (pk21 ? 3 : 1) : 0;
 	if (nword == 1) { // the band fits one word (thre <= 31: the bulk of the segments): same algorithm with the vectors in registers
 		uint64_t P0 = 0, P1 = 0, P2 = 0, P3 = 0, VP, VN, X, D0 = 0, HN = 0, HP = 0;
 		auto pch1 = [&](int32_t j) -> int { return T.at(ps0 + (mode == 2 ? pidx - j : j)); };
@@ -575,7 +583,9 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 		if (mode == 3) { VP = 0; VN = (1ULL << abs_diag) - 1; bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn; i_bd = abs_diag; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = (thre << 1) - abs_diag; err = abs_diag; }
 		else { bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = thre; err = thre; VN = (1ULL << thre) - 1; VP = ((1ULL << ((thre << 1) + 1)) - 1) ^ VN; }
 		const uint64_t mm = 1ULL << (thre << 1);
-		ez.path[0] = VP; ez.path[1] = VN; ez.pn = 2; // HP / HN of a column follow from its D0 and the column before: not stored
+		const uint64_t M21 = (1ULL << 21) - 1;
+		if (pk21) { ez.path[0] = (VP & M21) | (VN & M21) << 21; ez.pn = 1; }
+		else { ez.path[0] = VP; ez.path[1] = VN; ez.pn = 2; } // HP / HN of a column follow from its D0 and the column before: not stored
 		for (i = 0; i <= tn0; i++) {
 			const int tc = tch1(i);
 			X = (tc == 0 ? P0 : tc == 1 ? P1 : tc == 2 ? P2 : tc == 3 ? P3 : 0ULL) | VN;
@@ -597,7 +607,8 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 				++i_bd;
 				if (i_bd < pn) peq_or(pch1(i_bd), mm);
 			}
-			uint64_t *o = ez.path + ez.pn; o[0] = D0; o[1] = VP; o[2] = VN; ez.pn += 3;
+			if (pk21) { ez.path[ez.pn++] = (D0 & M21) | (VP & M21) << 21 | (VN & M21) << 42; }
+			else { uint64_t *o = ez.path + ez.pn; o[0] = D0; o[1] = VP; o[2] = VN; ez.pn += 3; }
 		}
 		if (mode == 0) {
 			int32_t site = tn - 1 - thre; const int32_t ct = pn - 1;

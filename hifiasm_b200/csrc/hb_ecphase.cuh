@@ -224,7 +224,7 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 			}
 			if ((double)o >= (double)ov[j].align_length * up) {
 				uint64_t *a = srt + sn; uint32_t z = 0;
-				for (uint32_t x = 1; x < o; x++) { const uint64_t v = a[x]; int32_t b = (int32_t)x - 1; while (b >= 0 && a[b] > v) { a[b + 1] = a[b]; b--; } a[b + 1] = v; }
+				hb_heapsort64(a, o); // (bare keys: any sort gives the reference's array; an insertion sort is quadratic on repeat-rich reads)
 				for (uint32_t i = 0; i < o; i++) { // sp / tp are NOT reset here: for i = 0 and i = o-1 the reference reads what earlier code left in s / t
 					if (i > 0) sp = (int64_t)a[i - 1];
 					if (i + 1 < o) tp = (int64_t)a[i + 1];
@@ -236,7 +236,7 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 			}
 		}
 		if (sn) {
-			for (uint32_t x = 1; x < sn; x++) { const uint64_t v = srt[x]; int32_t b = (int32_t)x - 1; while (b >= 0 && srt[b] > v) { srt[b + 1] = srt[b]; b--; } srt[b + 1] = v; }
+			hb_heapsort64(srt, sn);
 			for (uint32_t k = 1, l = 0; k <= sn; ++k) { if (k == sn || srt[k] != srt[l]) { if (k - l >= 2) snp[srt[l]].score = 1; } l = k; }
 		}
 	}

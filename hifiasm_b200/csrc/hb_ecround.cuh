@@ -261,12 +261,6 @@ HB_HD uint32_t hb_without_large_indel(const hb_wl_t *w, uint32_t wn, const uint1
 	return l_nid ? 0 : 1;
 }
 // check_well_cal (ecovlp.cpp:2750-2801): coverage sweep over the emitted records' query intervals; srt = scratch of 2 n words
-HB_HD void hb_heapsort64(uint64_t *a, uint32_t n)
-{
-	if (n < 2) return;
-	for (uint32_t s = n / 2; s-- > 0;) { uint32_t i = s; const uint64_t v = a[i]; for (;;) { uint32_t c = 2 * i + 1; if (c >= n) break; if (c + 1 < n && a[c + 1] > a[c]) c++; if (a[c] <= v) break; a[i] = a[c]; i = c; } a[i] = v; }
-	for (uint32_t e = n - 1; e > 0; e--) { const uint64_t v = a[e]; a[e] = a[0]; uint32_t i = 0; for (;;) { uint32_t c = 2 * i + 1; if (c >= e) break; if (c + 1 < e && a[c + 1] > a[c]) c++; if (a[c] <= v) break; a[i] = a[c]; i = c; } a[i] = v; }
-}
 HB_HD void hb_check_well_cal(const uint16_t *sc, uint32_t scn, uint64_t *srt, const hb_ma_hit_t *a, uint32_t n, int64_t len, int64_t min_dp, uint8_t *f_ec, uint8_t *abnormal)
 {
 	uint32_t k, m = 0; int64_t dp = 0, old_dp, st = 0, ed = 0;
