@@ -35,11 +35,12 @@ HB_D uint32_t hb_atom_or32(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 #else
 inline uint32_t hb_atom_or32(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p |= v; return o; }
 #endif
-// windows of all overlaps, flattened: lanes take them round-robin.  f(j, window) is called for every aligned window with a cigar.
+// f(j, window) for every aligned window with a cigar of every overlap.
 template <typename F> HB_HD void hb_ph_for_windows(const PhOv *ov, uint32_t n_ov, F f)
 {
+	// lanes take OVERLAPS (after step B an overlap's aligned stretch is mostly ONE fused window with a long cigar: windows give no parallelism)
 	const int lane = hb_lane();
-	for (uint32_t j = 0; j < n_ov; j++) for (uint32_t w = lane; w < ov[j].wn; w += HB_WS) {
+	for (uint32_t j = lane; j < n_ov; j += HB_WS) for (uint32_t w = 0; w < ov[j].wn; w++) {
 		const hb_wl_t &u = ov[j].w[w];
 		if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
 		f(j, u);
@@ -94,10 +95,13 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 	const RdView Q = hb_rd_view(R, qid, 0);
 	const uint32_t ns = n_site;
 	for (uint32_t w = lane; w < B.nwd; w += HB_WS) { uint32_t m = B.s2[w], k = B.pre[w]; while (m) { const int b = hb_ctz64(m); m &= m - 1; site_pos[k++] = (w << 5) + (uint32_t)b; } }
-	for (uint32_t k = lane; k <= ns; k += HB_WS) site_off[k] = 0;
+	// evidence in (site, overlap) order without an ordered pass: a bit mask per site over the overlaps that cover it with a match / mismatch column
+	// (pass A, lanes over overlaps, atomicOr) gives every record its place — start of the site + number of covering overlaps below it (popcounts) —
+	// and pass B writes it there.  The masks borrow ev2 (unused until the statistics): ns * MW words, MW = ceil(n_ov / 32).
+	const uint32_t MW = (n_ov + 31) >> 5; uint32_t *mask = (uint32_t *)ev2;
+	if ((uint64_t)ns * MW * 4 > (uint64_t)n_ev * sizeof(PhEv)) { *ovf = 1; return; } // cannot happen while every site has >= 2 records and n_ov <= 384
+	for (uint64_t k = lane; k < (uint64_t)ns * MW; k += HB_WS) mask[k] = 0;
 	hb_wsync();
-	// sizes per site (any order), then the scatter overlap by overlap: the windows of ONE overlap are disjoint on the query, so within an overlap no two
-	// lanes touch the same site, and taking the overlaps in ascending order leaves every site's records in ascending overlap id (push_info's order)
 	hb_ph_for_windows(ov, n_ov, [&](uint32_t j, const hb_wl_t &u) {
 		int64_t xk = u.x_start; const int64_t e0 = (int64_t)u.x_end + 1; const uint16_t *cg = ov[j].pool + u.cidx;
 		for (uint32_t ci = 0; ci < u.clen && xk < e0; ci++) {
@@ -105,15 +109,24 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 			if (op != 2) xk += cl;
 			if (op > 1) continue;
 			const int64_t oe = xk < e0 ? xk : e0;
-			if (oe > ws) for (uint32_t si = hb_ph_rank(B, ws), se = hb_ph_rank(B, oe); si < se; si++) hb_atom_add32(site_off + si, 1u);
+			if (oe > ws) for (uint32_t si = hb_ph_rank(B, ws), se = hb_ph_rank(B, oe); si < se; si++) hb_atom_or32(mask + (uint64_t)si * MW + (j >> 5), 1u << (j & 31));
 		}
 	});
 	hb_wsync();
-	{ uint32_t run = 0; for (uint32_t k0 = 0; k0 < ns; k0 += HB_WS) { const uint32_t k = k0 + (uint32_t)lane, c = k < ns ? site_off[k] : 0u; uint32_t tot; const uint32_t ex = hb_wscan(c, &tot); if (k < ns) site_off[k] = run + ex; run += tot; } } // start of every site; the scatter turns it into the end
+	{ uint32_t run = 0; // site_off[k] = start of site k
+		for (uint32_t k0 = 0; k0 < ns; k0 += HB_WS) {
+			const uint32_t k = k0 + (uint32_t)lane; uint32_t c = 0, tot;
+			if (k < ns) for (uint32_t q = 0; q < MW; q++) c += (uint32_t)hb_popc64(mask[(uint64_t)k * MW + q]);
+			const uint32_t ex = hb_wscan(c, &tot);
+			if (k < ns) site_off[k] = run + ex;
+			run += tot;
+		}
+		if (lane == 0) site_off[ns] = run;
+	}
 	hb_wsync();
-	for (uint32_t j = 0; j < n_ov; j++) {
+	for (uint32_t j = lane; j < n_ov; j += HB_WS) {
 		const RdView T = hb_rd_view(R, ov[j].y_id, ov[j].rev);
-		for (uint32_t w = lane; w < ov[j].wn; w += HB_WS) {
+		for (uint32_t w = 0; w < ov[j].wn; w++) {
 			const hb_wl_t &u = ov[j].w[w];
 			if (hb_ph_ualn(u) || u.x_end < u.x_start || !u.clen) continue;
 			int64_t xk = u.x_start, yk = u.y_start; const int64_t e0 = (int64_t)u.x_end + 1; const uint16_t *cg = ov[j].pool + u.cidx;
@@ -124,13 +137,21 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 				if (op > 1) continue;
 				const int64_t oe = xk < e0 ? xk : e0;
 				if (oe > ws) for (uint32_t si = hb_ph_rank(B, ws), se = hb_ph_rank(B, oe); si < se; si++) {
+					const uint32_t *m = mask + (uint64_t)si * MW; uint32_t rk = (uint32_t)hb_popc64(m[j >> 5] & ((1u << (j & 31)) - 1));
+					for (uint32_t q = 0; q < (j >> 5); q++) rk += (uint32_t)hb_popc64(m[q]);
 					const int64_t t = site_pos[si]; PhEv e;
 					e.site = (uint32_t)t; e.ov = j; e.osite = (uint32_t)(t - xk + yk); e.cov = 1; e.type = (uint8_t)op; for (int z = 0; z < 6; z++) e.pad[z] = 0;
 					e.base = (uint8_t)(op == 0 ? Q.at(t) : T.at(t - xk + yk));
-					ev[site_off[si]++] = e;
+					ev[site_off[si] + rk] = e;
 				}
 			}
 		}
+	}
+	hb_wsync();
+	for (uint32_t k0 = 0; k0 < ns; k0 += HB_WS) { // the statistics below read site_off[k] as the END of site k: shift by one, chunk by chunk in ascending order
+		const uint32_t k = k0 + (uint32_t)lane, v = k < ns ? site_off[k + 1] : 0u;
+		hb_wsync();
+		if (k < ns) site_off[k] = v;
 		hb_wsync();
 	}
 	if (lane != 0) return;
