@@ -11,6 +11,7 @@
 #include "hb_internal.h"
 #define HB_KERNELS_MAIN
 #include "hb_kernels.cuh"
+#include "hb_kernels_ea.cuh"
 #include "hb_rechain_launch.h"
 
 // ---------------------------------------------------------------------------
@@ -657,7 +658,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					if (!ctx->d_prev0_off) { hb_set_err(ctx, HB_E_STATE, "previous overlaps are not staged (hb_ec_stage_prev)"); return HB_E_STATE; }
 					d_ea = ba.zero<uint8_t>(n_ov + 1); HB_ALLOC_CHECK(ba);
 					ProfScope ps(ctx, "k_ec_ea");
-					if (n_ov) k_ec_ea<<<nblk(n_ov, 128), 128, 0, ctx->stream>>>(R, r0 + b0, n_ov, d_od, d_ch, ctx->d_prev0, ctx->d_prev0_off, d_ea);
+					if (n_ov) k_ec_ea_w<<<nblk(n_ov * 32, 128), 128, 0, ctx->stream>>>(R, r0 + b0, n_ov, d_od, d_ch, ctx->d_prev0, ctx->d_prev0_off, d_ea);
 				}
 				uint64_t pool_cap = n_win * 4 + 4096, pool_used = 0; uint16_t *d_pool = 0;
 				for (int attempt = 0;; attempt++) {
