@@ -127,6 +127,7 @@ extern "C" int hb_ec_apply(hb_ctx_t *ctx, uint64_t *n_changed, uint64_t *total_b
 	// swap the new store in
 	cudaFree(ctx->d_packed); cudaFree(ctx->d_roff); cudaFree(ctx->d_noff); cudaFree(ctx->d_npos);
 	ctx->d_packed = (uint8_t *)n_packed.take(); ctx->d_roff = (uint64_t *)n_roff.take(); ctx->d_noff = (uint64_t *)n_noff.take(); ctx->d_npos = (uint32_t *)n_npos.take();
+	hb_pt_destroy(ctx); // the position index describes the reads as they were: a pass without a fresh hb_pt_gen now fails loudly ("no position index") instead of chaining stale positions
 	ctx->packed_cap = pc; ctx->reads_cap = std::min<uint64_t>(ctx->reads_cap, rcap); ctx->npos_cap = npc;
 	ctx->packed_bytes = o; ctx->n_npos = noff[n]; ctx->total_bases = tb;
 	for (uint64_t i = 0; i < n; i++) ctx->h_rlen[i] = h_len[i];
@@ -221,10 +222,10 @@ extern "C" int hb_ec_post_rev(hb_ctx_t *ctx, hb_ma_hit_t *paf, uint64_t *paf_off
 	cudaSetDevice(ctx->device);
 	const uint64_t n = ctx->n_reads; int rc;
 	if (!n) { hb_set_err(ctx, HB_E_STATE, "no reads resident"); return HB_E_STATE; }
+	DevBuf n_packed, n_npos;
+	HB_DEVALLOC(n_packed, ctx->packed_cap); HB_DEVALLOC(n_npos, ctx->npos_cap * 4); // (allocations first: a failure must not leave the lists flipped and the reads not)
 	if (paf_off && (rc = flip_list(ctx, paf, paf_off))) return rc;   // flip_paf_rc only needs the read lengths, which the reverse complement keeps
 	if (rpaf_off && (rc = flip_list(ctx, rpaf, rpaf_off))) return rc;
-	DevBuf n_packed, n_npos;
-	HB_DEVALLOC(n_packed, ctx->packed_cap); HB_DEVALLOC(n_npos, ctx->npos_cap * 4);
 	HB_CUDA(cudaMemsetAsync(n_packed.p, 0, ctx->packed_cap, ctx->stream));
 	{
 		ProfScope ps(ctx, "k_rc_reads");
@@ -234,6 +235,7 @@ extern "C" int hb_ec_post_rev(hb_ctx_t *ctx, hb_ma_hit_t *paf, uint64_t *paf_off
 	HB_CUDA(cudaStreamSynchronize(ctx->stream));
 	cudaFree(ctx->d_packed); cudaFree(ctx->d_npos);
 	ctx->d_packed = (uint8_t *)n_packed.take(); ctx->d_npos = (uint32_t *)n_npos.take();
+	hb_pt_destroy(ctx); // target positions and strands changed: the index must be rebuilt before the next pass
 	return HB_OK;
 }
 

@@ -227,6 +227,7 @@ static int upload_common(hb_ctx *ctx, uint64_t n, const uint64_t *len, const uin
                          const uint64_t *n_pos, const uint64_t *n_off, uint64_t *const *N_site)
 {
 	cudaSetDevice(ctx->device);
+	hb_pt_destroy(ctx); // a new read store: the resident index (if any) describes the old one
 	if (n >= (1ull << 28)) { hb_set_err(ctx, HB_E_ARG, "no more than 2^28 reads (htab.cpp:765)"); return HB_E_ARG; }
 	std::vector<uint64_t> off(n + 1), noff(n + 1); std::vector<uint32_t> npos;
 	ctx->h_rlen.resize(n); ctx->total_bases = 0;
@@ -631,8 +632,26 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			WinDesc *d_desc = ba.get<WinDesc>(n_win + 1); hb_win_t *d_wout = ba.get<hb_win_t>(n_win + 1);
 			HB_ALLOC_CHECK(ba);
 			k_win_desc<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, w_l, d_woff, d_desc);
+			// row a12 first (as gen_hc_r_alin_ea does, ecovlp.cpp:2810): an overlap the previous round's exact record still covers needs no window alignment at all —
+			// in rounds 2 and 3 that is most of them — so the window pass skips its windows
+			uint64_t *d_ooff = 0; OvDesc *d_od = 0; uint8_t *d_ea = 0; uint64_t n_ov = 0; std::vector<uint64_t> h_ooff;
+			if (mode >= 5) {
+				d_ooff = ba.get<uint64_t>(nb + 2); HB_ALLOC_CHECK(ba);
+				if ((rc = hb_scan_u32_to_u64(ctx, d_nol, d_ooff, nb))) return rc;
+				h_ooff.resize(nb + 1);
+				HB_CUDA(cudaMemcpyAsync(h_ooff.data(), d_ooff, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+				n_ov = h_ooff[nb];
+				d_od = ba.get<OvDesc>(n_ov + 1); HB_ALLOC_CHECK(ba);
+				k_ov_desc<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, w_l, d_woff, d_ooff, d_od);
+				if (so->use_prev) {
+					if (!ctx->d_prev0_off) { hb_set_err(ctx, HB_E_STATE, "previous overlaps are not staged (hb_ec_stage_prev)"); return HB_E_STATE; }
+					d_ea = ba.zero<uint8_t>(n_ov + 1); HB_ALLOC_CHECK(ba);
+					ProfScope ps(ctx, "k_ec_ea");
+					if (n_ov) k_ec_ea_w<<<nblk(n_ov * 32, 128), 128, 0, ctx->stream>>>(R, r0 + b0, n_ov, d_od, d_ch, ctx->d_prev0, ctx->d_prev0_off, d_ea);
+				}
+			}
 			{
-				WinArgs W; W.R = R; W.r0 = r0 + b0; W.n_win = n_win; W.desc = d_desc; W.ch = d_ch; W.fc = d_fc; W.fc_grp_base = d_fcb; W.e_rate = so->e_rate; W.w_l = w_l; W.out = d_wout; W.err = d_err;
+				WinArgs W; W.R = R; W.r0 = r0 + b0; W.n_win = n_win; W.desc = d_desc; W.ch = d_ch; W.fc = d_fc; W.fc_grp_base = d_fcb; W.e_rate = so->e_rate; W.w_l = w_l; W.out = d_wout; W.err = d_err; W.ea = d_ea; W.o_off = d_ooff;
 				ProfScope ps(ctx, "k_windows");
 				if (n_win) k_windows<<<nblk(n_win, 128), 128, 0, ctx->stream>>>(W);
 			}
@@ -641,25 +660,12 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			int h_err2 = 0; HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 			if (h_err2 & 32) { hb_set_err(ctx, HB_E_STATE, "a window start fell outside its chain's fake cigar"); return HB_E_STATE; }
 			if (mode >= 5) { // step A of the alignment stage: one thread per overlap consumes the window records
-				uint64_t *d_ooff = ba.get<uint64_t>(nb + 2); HB_ALLOC_CHECK(ba);
-				if ((rc = hb_scan_u32_to_u64(ctx, d_nol, d_ooff, nb))) return rc;
-				std::vector<uint64_t> h_ooff(nb + 1);
-				HB_CUDA(cudaMemcpyAsync(h_ooff.data(), d_ooff, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
-				const uint64_t n_ov = h_ooff[nb];
 				// the queued (aligner) pass of step A: its grid is bounded by the per-thread trace scratch (31 KB); up to 8 GB of it, so that in the usual case every queued overlap has a thread
 				const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_ov + 63) / 64, std::max<uint64_t>((uint64_t)ctx->sm_count * 4, (8ull << 30) / ((uint64_t)w_l * 40 + 2 * HB_EC_CIG_TMP) / 64))); const uint64_t nthr = (uint64_t)blocks * 64;
-				OvDesc *d_od = ba.get<OvDesc>(n_ov + 1); hb_aln_t *d_aln = ba.get<hb_aln_t>(n_ov + 1); hb_wl_t *d_wl = ba.zero<hb_wl_t>(n_win + 1);
+				hb_aln_t *d_aln = ba.get<hb_aln_t>(n_ov + 1); hb_wl_t *d_wl = ba.zero<hb_wl_t>(n_win + 1);
 				uint64_t *d_path = ba.get<uint64_t>(nthr * (uint64_t)w_l * 5); uint16_t *d_ctmp = ba.get<uint16_t>(nthr * HB_EC_CIG_TMP);
 				unsigned long long *d_pused = ba.zero<unsigned long long>(1);
 				HB_ALLOC_CHECK(ba);
-				k_ov_desc<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_coff, d_ch, d_idx, d_nol, w_l, d_woff, d_ooff, d_od);
-				uint8_t *d_ea = 0;
-				if (so->use_prev) { // row a12: the previous round's exact overlaps short-cut the alignment
-					if (!ctx->d_prev0_off) { hb_set_err(ctx, HB_E_STATE, "previous overlaps are not staged (hb_ec_stage_prev)"); return HB_E_STATE; }
-					d_ea = ba.zero<uint8_t>(n_ov + 1); HB_ALLOC_CHECK(ba);
-					ProfScope ps(ctx, "k_ec_ea");
-					if (n_ov) k_ec_ea_w<<<nblk(n_ov * 32, 128), 128, 0, ctx->stream>>>(R, r0 + b0, n_ov, d_od, d_ch, ctx->d_prev0, ctx->d_prev0_off, d_ea);
-				}
 				uint64_t pool_cap = n_win * 4 + 4096, pool_used = 0; uint16_t *d_pool = 0;
 				for (int attempt = 0;; attempt++) {
 					d_pool = ba.get<uint16_t>(pool_cap); HB_ALLOC_CHECK(ba);

@@ -375,13 +375,15 @@ template <typename T, typename KEY> HB_HD void hb_rs_insertsort(T *beg, T *end, 
 #define HB_RS_STACK 320
 struct RsFrame { int32_t b, e, s; };
 struct RsScratch { int32_t *bb, *be; RsFrame *st; }; // 256 + 256 ints and HB_RS_STACK frames
-template <typename T, typename KEY> HB_HD int hb_rs_sort32(T *beg0, T *end0, KEY key, const RsScratch &W)
+// top_shift: the highest digit level at which the keys can differ (24 = all of them).  A level whose digit is the same for every key leaves one bucket,
+// moves nothing and recurses into the whole range one level down, so starting below it is the same sequence of moves.
+template <typename T, typename KEY> HB_HD int hb_rs_sort32(T *beg0, T *end0, KEY key, const RsScratch &W, int top_shift = 24)
 { // returns 1 if the explicit stack overflowed (more than 65*HB_RS_STACK elements)
 	if (end0 - beg0 <= 64) { hb_rs_insertsort(beg0, end0, key); return 0; }
 	// explicit recursion stack of (range, shift): pending ranges are disjoint and
 	// each holds > 64 elements, so n <= 65*HB_RS_STACK never overflows it
 	RsFrame *st = W.st; int32_t *bb = W.bb, *be = W.be; int sp = 0;
-	st[sp].b = 0; st[sp].e = (int32_t)(end0 - beg0); st[sp].s = 24; sp++;
+	st[sp].b = 0; st[sp].e = (int32_t)(end0 - beg0); st[sp].s = top_shift; sp++;
 	while (sp) {
 		RsFrame fr = st[--sp]; T *beg = beg0 + fr.b, *end = beg0 + fr.e; int s = fr.s;
 		int k;

@@ -154,28 +154,40 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 		if (k < ns) site_off[k] = v;
 		hb_wsync();
 	}
-	if (lane != 0) return;
-	// push_info per site (Correct.cpp:10511-10600, oa = NULL, v8 = NULL): allele statistics, evidence kept only for real alleles
-	uint32_t n_snp = 0, m_ev = 0, beg = 0;
-	for (uint32_t k = 0; k < ns; k++) {
-		const uint32_t end = site_off[k]; uint64_t occ_0 = 0, occ_1[5] = { 0, 0, 0, 0, 0 }, occ_2 = 0, diff = 0; int64_t sid[5] = { -1, -1, -1, -1, -1 };
-		for (uint32_t i = beg; i < end; i++) { if (ev[i].type == 0) occ_0++; else { occ_1[ev[i].base]++; diff++; } occ_2++; }
-		if (!(occ_0 == 0 || diff <= 1)) {
-			uint32_t m = 0;
-			for (int b = 0; b < 4; b++) if (occ_1[b] >= 2) {
-				PhSnp &p = snp[n_snp]; p.id = n_snp; p.occ_0 = (uint32_t)(1 + occ_0); p.occ_1 = (uint32_t)occ_1[b]; p.occ_2 = (uint32_t)(occ_2 - p.occ_0 - p.occ_1);
-				p.site = site_pos[k]; p.score = -1; p.overlap_num = (uint32_t)occ_2; p.pad = 0; sid[b] = n_snp++; m++;
-			}
-			if (m) for (uint32_t i = beg; i < end; i++) {
-				PhEv e = ev[i];
-				if (e.type == 0) e.osite = n_snp - 1;
-				else if (sid[e.base] >= 0) { e.cov = e.osite; e.osite = (uint32_t)sid[e.base]; }
-				else continue;
-				ev2[m_ev++] = e;
+	// push_info per site (Correct.cpp:10511-10600, oa = NULL, v8 = NULL): allele statistics, evidence kept only for real alleles.  A lane takes a site
+	// (its records are contiguous); the places of its statistics and kept records come from two warp scans over the chunk of 32 sites.
+	uint32_t n_snp = 0, m_ev = 0;
+	for (uint32_t k0 = 0; k0 < ns; k0 += HB_WS) {
+		const uint32_t k = k0 + (uint32_t)lane; uint32_t beg = 0, end = 0, m = 0, nrec = 0;
+		uint64_t occ_0 = 0, occ_1[5] = { 0, 0, 0, 0, 0 }, occ_2 = 0, diff = 0;
+		if (k < ns) {
+			beg = k ? site_off[k - 1] : 0; end = site_off[k];
+			for (uint32_t i = beg; i < end; i++) { if (ev[i].type == 0) occ_0++; else { occ_1[ev[i].base]++; diff++; } occ_2++; }
+			if (!(occ_0 == 0 || diff <= 1)) {
+				for (int b = 0; b < 4; b++) if (occ_1[b] >= 2) m++;
+				if (m) for (uint32_t i = beg; i < end; i++) { const PhEv &e = ev[i]; if (e.type == 0 || occ_1[e.base < 4 ? e.base : 4] >= 2 && e.base < 4) nrec++; }
 			}
 		}
-		beg = end;
+		uint32_t tm, tr; const uint32_t em = hb_wscan(m, &tm), er = hb_wscan(nrec, &tr);
+		if (m) {
+			int64_t sid[5] = { -1, -1, -1, -1, -1 }; uint32_t q = n_snp + em;
+			for (int b = 0; b < 4; b++) if (occ_1[b] >= 2) {
+				PhSnp &p = snp[q]; p.id = q; p.occ_0 = (uint32_t)(1 + occ_0); p.occ_1 = (uint32_t)occ_1[b]; p.occ_2 = (uint32_t)(occ_2 - p.occ_0 - p.occ_1);
+				p.site = site_pos[k]; p.score = -1; p.overlap_num = (uint32_t)occ_2; p.pad = 0; sid[b] = q++;
+			}
+			uint32_t w = m_ev + er;
+			for (uint32_t i = beg; i < end; i++) {
+				PhEv e = ev[i];
+				if (e.type == 0) e.osite = q - 1;
+				else if (e.base < 4 && sid[e.base] >= 0) { e.cov = e.osite; e.osite = (uint32_t)sid[e.base]; }
+				else continue;
+				ev2[w++] = e;
+			}
+		}
+		n_snp += tm; m_ev += tr;
 	}
+	hb_wsync();
+	if (lane != 0) return;
 	if (!m_ev) return;
 	// generate_haplotypes_naive_HiFi, Correct.cpp:8845-9110 (multi_check = 1, st_max = -1 => is_st_bs is never true)
 	// (a) drop the SNP sites that touch another SNP site; evidence follows its statistics
@@ -197,7 +209,7 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 	if (!n_snp || !m_ev) return;
 	// (b) evidence grouped by overlap with klib's unstable radix sort restated move for move (hb_rs_sort32): the order of an overlap's
 	//     sites decides which statistics the reference's stale `s` pointer refers to in the multi_check block below
-	{ auto key = [](const PhEv &e) -> uint32_t { return e.ov; }; if (hb_rs_sort32(ev2, ev2 + m_ev, key, W)) { *ovf = 1; return; } }
+	{ auto key = [](const PhEv &e) -> uint32_t { return e.ov; }; if (hb_rs_sort32(ev2, ev2 + m_ev, key, W, n_ov <= 256 ? 0 : n_ov <= 65536 ? 8 : 24)) { *ovf = 1; return; } } // (keys < n_ov: the upper digit levels would find one bucket each and move nothing)
 	PhEv *L = ev2;
 	for (uint32_t j = 0; j <= n_ov; j++) ov_off[j] = 0;
 	for (uint32_t i = 0; i < m_ev; i++) ov_off[L[i].ov + 1]++;

@@ -759,6 +759,7 @@ struct WinDesc { uint32_t read, slot, k, ord; }; // batch-local read, chain slot
 struct WinArgs {
 	DevReads R; uint64_t r0, n_win; const WinDesc *desc; const hb_chain_t *ch; const uint64_t *fc; const uint64_t *fc_grp_base;
 	double e_rate; int32_t w_l; hb_win_t *out; int *err;
+	const uint8_t *ea; const uint64_t *o_off; // row a12 flags per overlap (NULL: none) and the overlap offset of every read: windows of overlaps accepted by the exact shortcut are not aligned
 };
 static __device__ __forceinline__ uint64_t hb_bswap64(uint64_t v) { return ((uint64_t)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0, 0x0123); }
 static __device__ __forceinline__ bool dev_is_n(const DevReads &R, uint64_t rid, uint32_t pos)
@@ -772,6 +773,7 @@ __global__ void __launch_bounds__(128) k_windows(WinArgs A)
 	const uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (wi >= A.n_win) return;
 	const WinDesc d = A.desc[wi];
+	if (A.ea && A.ea[A.o_off[d.read] + d.ord]) return; // step A never reads the windows of an overlap the exact shortcut accepted
 	const hb_chain_t c = A.ch[d.slot];
 	const uint64_t qid = A.r0 + d.read, tid = c.y_id;
 	const uint64_t *fc = A.fc + A.fc_grp_base[d.slot] + c.fc_off;
@@ -925,23 +927,6 @@ __global__ void k_ov_desc(uint64_t nR, const uint64_t *__restrict__ c_off, const
 		int64_t nl = ((int64_t)c.x_pos_e + 1) - ((int64_t)c.x_pos_s / w_l) * w_l; uint32_t nw = (uint32_t)(nl / w_l + (nl % w_l > 0 ? 1 : 0));
 		OvDesc d; d.read = (uint32_t)r; d.slot = (uint32_t)(cb + s); d.nw = nw; d.pad = 0; d.w0 = w; desc[o + i] = d; w += nw;
 	}
-}
-// row a12 — gen_hc_r_alin_ea (ecovlp.cpp:2810-2866): a chain whose target / strand has an exact (el) record in the read's overlap list of
-// the previous round — the first such record in list order — with the same coordinates, and whose two substrings are still identical, is
-// accepted without alignment.  Thread per overlap; the lists are a few dozen records long.
-__global__ void k_ec_ea(DevReads R, uint64_t r0, uint64_t n_ov, const OvDesc *__restrict__ desc, const hb_chain_t *__restrict__ ch,
-                        const hb_ma_hit_t *__restrict__ prev, const uint64_t *__restrict__ prev_off, uint8_t *__restrict__ ea)
-{
-	const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (o >= n_ov) return;
-	const OvDesc d = desc[o]; const hb_chain_t c = ch[d.slot]; const uint64_t g = r0 + d.read; uint8_t f = 0;
-	for (uint64_t k = prev_off[g]; k < prev_off[g + 1]; k++) {
-		const hb_ma_hit_t p = prev[k];
-		if (!p.el || p.tn != c.y_id || (p.rev & 1) != c.y_pos_strand) continue;
-		if (c.x_pos_s == (uint32_t)p.qns && c.x_pos_e + 1 == p.qe && c.y_pos_s == p.ts && c.y_pos_e + 1 == p.te)
-			f = (uint8_t)hb_exact_seq(R, g, (uint32_t)p.qns, p.qe, c.y_id, p.ts, p.te, (int)c.y_pos_strand);
-		break; // only the first exact record of the (target, strand) pair is looked at
-	}
-	ea[o] = f;
 }
 #endif // HB_KERNELS_MAIN
 struct EcAlnArgs {

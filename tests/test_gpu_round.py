@@ -167,3 +167,20 @@ def test_whole_stage_from_raw_reads(hb, name, tmp_path):
     reads.names, reads.name_blob, reads.name_index = g.raw.names, g.raw.name_blob, g.raw.name_index   # read names travel beside the store (All_reads.name)
     test_outputs.check_outputs(name, tmp_path, reads, out0, oo0, fc0, ab0, out1, oo1, fc1, ab1)
     eng.close()
+
+
+def test_stale_index_is_refused(hb):
+    """a pass after the read store changed (hb_ec_apply / hb_ec_post_rev / a new upload) without a fresh hb_pt_gen must fail loudly, not chain stale positions"""
+    from hifiasm_b200.engine import HBError
+    g = Golden("g1"); rd = roundlib.Rounds("g1")
+    eng = hb.Engine(0)
+    eng.upload_store(g.raw); eng.update_cov(eng.ft_gen()); h, t = eng.pt_gen(); eng.set_opt(hom_cov=h, het_cov=t)
+    eng.chains(0, 8, 0.02)                       # fine: the index describes the store
+    scc, scc_off = rd.scc(0); eng.ec_stage_scc(scc, scc_off); eng.ec_apply()
+    with pytest.raises(HBError):
+        eng.chains(0, 8, 0.02)
+    eng.pt_gen(); eng.chains(0, 8, 0.02)         # rebuilt: fine again
+    eng.upload_store(g.raw)
+    with pytest.raises(HBError):
+        eng.chains(0, 8, 0.02)
+    eng.close()
