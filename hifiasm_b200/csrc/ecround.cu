@@ -7,6 +7,7 @@
 // Host code is plumbing (allocation, copies, launches); the per-read / per-record work is in hb_ecround.cuh.
 #include <algorithm>
 #include "hb_internal.h"
+#include <chrono>
 #include "hb_ecround.cuh"
 
 static inline unsigned nblk(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
@@ -255,13 +256,21 @@ extern "C" int hb_cal_ec_r(hb_ctx_t *ctx, uint64_t round, uint64_t n_round, uint
 	if (!n) { hb_set_err(ctx, HB_E_STATE, "no reads resident"); return HB_E_STATE; }
 	if (n_round) { hb_set_err(ctx, HB_E_ARG, "cal_sec_ec_multiple (number_of_pround > 0, CommandLines.cpp:281) is not supported"); return HB_E_ARG; }
 	if (!out_src || !out_src_off || !out_rev || !out_rev_off) { hb_set_err(ctx, HB_E_ARG, "output buffers are required"); return HB_E_ARG; }
+	// HB_TRACE: the host clock around the five steps of the round (stderr; the device is drained at each stamp)
+	auto stamp = [&](const char *what) { static thread_local double t_prev = 0; if (!ctx->trace) return; cudaStreamSynchronize(ctx->stream); const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); if (what) fprintf(stderr, "[hb trace] cal_ec_r %-12s %9.2f ms\n", what, t - t_prev); t_prev = t; };
+	stamp(0);
 	if ((rc = hb_ec_stage_prev(ctx, prev_src, prev_src_off))) return rc;                                   // gen_hc_r_alin_ea reads the previous paf[i] (ecovlp.cpp:3288)
+	stamp("stage_prev");
 	if (tot_b) *tot_b = ctx->total_bases;                                                                  // cnt[0]: bases of the reads as they enter the round (3276)
 	uint64_t nec = 0;
 	if ((rc = hb_ec_round(ctx, 0, n, ctx->opt.is_ont ? 0.05 : 0.02, e_rate, w_l, 1, out_src_off, out_src, out_src_cap, out_rev_off, out_rev, out_rev_cap, flags, 0, 0, 0, status, &nec))) return rc;
 	if (tot_e) *tot_e = nec;
+	stamp("ec_round");
 	if ((rc = hb_ec_apply(ctx, 0, 0))) return rc;                                                          // sl_ec_r
+	stamp("apply");
 	if ((rc = hb_ec_update_paf(ctx, out_src, out_src_off, n_exact, n_inexact))) return rc;                // cal_update_ec_multiple
+	stamp("update_paf");
 	if (!is_sv || (round & 1)) if ((rc = hb_ec_post_rev(ctx, out_src, out_src_off, out_rev, out_rev_off))) return rc; // ecovlp.cpp:6293-6295
+	stamp("post_rev");
 	return HB_OK;
 }

@@ -509,7 +509,7 @@ HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 	ez.cn = 0;
 	int32_t V, H, D, mn, cur = ez.err, tn = ez.te + 1 - ez.ts, pn = tn + (ez.thre << 1), bd = (ez.thre << 1) + 1;
 	const int32_t bs = ez.compact ? 0 : (int32_t)(ez.pn / (uint64_t)tn), bbs = bs / 5;
-	int32_t poff = ez.pe, sft = bd - (pn - ez.pe - ptrim), i = tn, low = bd - 1, d = 0, pd = -1, pdn = 0;
+	int32_t poff = ez.pe, sft = bd - (pn - ez.pe - ptrim), i = tn, low = bd - 1, d = 0, pd = -1, pdn = 0, c3_i = -1; uint64_t c3_w = 0, c3_pw = 0, c3_nx = 0;
 	while (i > 0 && cur > 0) {
 		const uint64_t *D0 = ez.path + (size_t)(i - 1) * bs, *VP = D0 + bbs, *VN = VP + bbs, *HP = VN + bbs, *HN = HP + bbs;
 		if (ez.compact == 2) { // rows of 3 * nword words (D0 | VP | VN) behind a header of the initial VP | VN: HN / HP from the row before, bit by bit
@@ -519,7 +519,8 @@ HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 			if (sft != low) { const int vppb = hb_mw_bit(pvp, sft), hn = vppb & d0b, hp = hb_mw_bit(pvn, sft) | (1 - (vppb | d0b)); H = cur + hn - hp; if (H + 1 == cur && H <= mn) { mn = H; d = 3; } }
 			if (sft != 0) { V = cur + hb_mw_bit(row + 2 * nw, sft - 1) - hb_mw_bit(row + nw, sft - 1); if (V + 1 == cur && V <= mn) { mn = V; d = 2; } }
 		} else if (ez.compact == 3) { // one-word band of <= 21 bits: one trace word per column (D0 | VP << 21 | VN << 42), header = initial VP | VN << 21
-			const uint64_t w = ez.path[i], pw = ez.path[i - 1]; // column i-1 sits at path[1 + (i-1)]
+			if (c3_i != i) { c3_w = ez.path[i]; c3_pw = ez.path[i - 1]; c3_nx = i > 1 ? ez.path[i - 2] : 0; c3_i = i; } // rows i, i-1 in registers, row i-2 already on its way
+			const uint64_t w = c3_w, pw = c3_pw; // column i-1 sits at path[1 + (i-1)]
 			const uint64_t d0 = w & 0x1fffffULL, vp = (w >> 21) & 0x1fffffULL, vn = (w >> 42) & 0x1fffffULL;
 			const uint64_t vpp = i > 1 ? (pw >> 21) & 0x1fffffULL : pw & 0x1fffffULL, vnp = i > 1 ? (pw >> 42) & 0x1fffffULL : (pw >> 21) & 0x1fffffULL, hn = vpp & d0, hp = vnp | ~(vpp | d0);
 			D = cur - (1 - (int32_t)((d0 >> sft) & 1ULL)); d = 0; mn = D;
@@ -539,6 +540,7 @@ HB_HD_NI void hb_mw_gen_trace(MwEz &ez, int32_t ptrim, int reverse)
 		if (d == 0) { if (D != cur) d = 1; i--; poff--; }
 		else if (d == 2) { sft--; poff--; }
 		else { i--; sft++; }
+		if (ez.compact == 3 && c3_i == i + 1 && i > 0) { c3_w = c3_pw; c3_pw = c3_nx; c3_i = i; c3_nx = i > 1 ? ez.path[i - 2] : 0; } // the column moved back by one: shift the rows, fetch the next one early
 		if (d == pd) pdn++;
 		else { if (pdn > 0) hb_mez_push_trace(ez, (uint32_t)pd, (uint32_t)pdn); pd = d; pdn = 1; }
 		cur = mn;
@@ -584,8 +586,10 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 		else { bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = thre; err = thre; VN = (1ULL << thre) - 1; VP = ((1ULL << ((thre << 1) + 1)) - 1) ^ VN; }
 		const uint64_t mm = 1ULL << (thre << 1);
 		const uint64_t M21 = (1ULL << 21) - 1;
-		if (pk21) { ez.path[0] = (VP & M21) | (VN & M21) << 21; ez.pn = 1; }
-		else { ez.path[0] = VP; ez.path[1] = VN; ez.pn = 2; } // HP / HN of a column follow from its D0 and the column before: not stored
+		uint64_t *pp = ez.path; // the trace cursor lives in a register for the loop (ez is a struct in memory: its fields would be reloaded every column)
+		if (pk21) { *pp++ = (VP & M21) | (VN & M21) << 21; }
+		else { pp[0] = VP; pp[1] = VN; pp += 2; } // HP / HN of a column follow from its D0 and the column before: not stored
+		const int32_t ethre = ez.thre;
 		for (i = 0; i <= tn0; i++) {
 			const int tc = tch1(i);
 			X = (tc == 0 ? P0 : tc == 1 ? P1 : tc == 2 ? P2 : tc == 3 ? P3 : 0ULL) | VN;
@@ -600,16 +604,17 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 					if (k >= 0) {
 						if (tmp_e == INT32_MAX) { tmp_e = err; for (k = 0; poff < pe; poff++, k++) { tmp_e += (int32_t)((VP >> k) & 1ULL); tmp_e -= (int32_t)((VN >> k) & 1ULL); } }
 						else { k = (thre << 1) - k; if (k >= 0) { tmp_e += (int32_t)((HP >> k) & 1ULL); tmp_e -= (int32_t)((HN >> k) & 1ULL); } }
-						if (tmp_e <= ez.thre && tmp_e < ez.err) { ez.err = tmp_e; if (mode == 1) { ez.pe = pe; ez.te = i; } else { ez.ps = pidx - pe; ez.ts = tidx - i; } }
+						if (tmp_e <= ethre && tmp_e < ez.err) { ez.err = tmp_e; if (mode == 1) { ez.pe = pe; ez.te = i; } else { ez.ps = pidx - pe; ez.ts = tidx - i; } }
 					}
 				}
 				P0 >>= 1; P1 >>= 1; P2 >>= 1; P3 >>= 1;
 				++i_bd;
 				if (i_bd < pn) peq_or(pch1(i_bd), mm);
 			}
-			if (pk21) { ez.path[ez.pn++] = (D0 & M21) | (VP & M21) << 21 | (VN & M21) << 42; }
-			else { uint64_t *o = ez.path + ez.pn; o[0] = D0; o[1] = VP; o[2] = VN; ez.pn += 3; }
+			if (pk21) { *pp++ = (D0 & M21) | (VP & M21) << 21 | (VN & M21) << 42; }
+			else { pp[0] = D0; pp[1] = VP; pp[2] = VN; pp += 3; }
 		}
+		ez.pn = (uint64_t)(pp - ez.path);
 		if (mode == 0) {
 			int32_t site = tn - 1 - thre; const int32_t ct = pn - 1;
 			for (i = 0; site < ct; site++, i++) { err += (int32_t)((VP >> i) & 1ULL); err -= (int32_t)((VN >> i) & 1ULL); }

@@ -1,6 +1,7 @@
-"""Multi-GPU plumbing: query reads shard across ranks, index + reads replicated,
-no data-path collective.  torch.distributed is used only to
-agree on the timing (max over ranks) and the totals."""
+"""Multi-GPU plumbing on the Python side: query reads shard across ranks, index + reads replicated.
+The stage's own exchange (one all-gather per EC round + one of the final lists) lives in csrc/stage.cu behind the hb_allgather_fn callback
+(engine.torch_allgather = NCCL); what is here: the shard arithmetic, timing / totals agreement, and cal_ec_r_sharded — the same round
+composed from the step calls of the C-ABI, kept as the step-level check of the exchange (tests, tools/ec_sharded_check.py)."""
 from __future__ import annotations
 
 
@@ -21,6 +22,17 @@ def reduce_time_and_units(dev_ms: float, units: float, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t[0]), float(u[0])
+
+
+def agree_max(v: int, device=None) -> int:
+    """MAX of one small integer over the ranks (v itself without a process group): how the ranks agree on an error before a collective."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return int(v)
+    t = torch.tensor([int(v)], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
 
 
 def merge_shards(parts):
@@ -92,8 +104,24 @@ def cal_ec_r_sharded(eng, round_, is_sv, prev_src, prev_src_off, e_rate=0.04, w_
     eng.ec_stage_prev(prev_src, prev_src_off)
     ln = eng.read_lengths()
     tot_b = int(ln.sum())                                                            # cnt[0]: bases of the reads as they enter the round (ecovlp.cpp:3276)
-    cap = 2 * int(np.asarray(prev_src).size) + 256 * (r1 - r0) + 1024                # one pass with these capacities (no sizing pass), like Engine.cal_ec_r
-    r = eng.ec_round(r0, r1, 0.02, e_rate, w_l, use_prev=1, caps=(cap, cap, 256 * (r1 - r0) + int(ln[r0:r1].sum()) // 8 + 1024))
+    # one pass with these capacities (no sizing pass).  A rank whose shard overflows them must not leave the others waiting in the all-gather: every rank
+    # reports its status, the worst one is agreed on (MAX of -code), and either all ranks repeat the round with four times the room or all raise together.
+    from .engine import HBError
+    cap = 2 * int(np.asarray(prev_src).size) + 256 * (r1 - r0) + 1024
+    scc_cap = 256 * (r1 - r0) + int(ln[r0:r1].sum()) // 8 + 1024
+    for attempt in range(4):
+        r, err = None, None
+        try:
+            r = eng.ec_round(r0, r1, 0.02, e_rate, w_l, use_prev=1, caps=(cap, cap, scc_cap))
+        except HBError as e:
+            err = e
+        worst = agree_max(-(err.code or -1) if err is not None else 0, device)
+        if worst == 0:
+            break
+        if worst == 5 and attempt < 3:                                                # HB_E_OVERFLOW on some rank: all ranks retry with more room
+            cap, scc_cap = cap * 4, scc_cap * 4
+            continue
+        raise err if err is not None else HBError("another rank failed the EC round (code %d)" % -worst)
     src, soff = all_gather_ragged(r["src"], r["src_off"], device)
     rev, roff = all_gather_ragged(r["rev"], r["rev_off"], device)
     scc, scc_off = all_gather_ragged(r["scc"], r["scc_off"], device)

@@ -70,7 +70,7 @@ def torch_allgather(device):
 
 
 class HBError(RuntimeError):
-    pass
+    code = 0                                                                          # the HB_E_* code of include/hifiasm_b200.h, when the error came from the library
 
 
 class Opt(C.Structure):
@@ -131,7 +131,9 @@ class Engine:
 
     def _ck(self, rc):
         if rc != 0:
-            raise HBError("hifiasm_b200 error %d: %s" % (rc, _lib().hb_last_error(self.h).decode()))
+            e = HBError("hifiasm_b200 error %d: %s" % (rc, _lib().hb_last_error(self.h).decode()))
+            e.code = rc
+            raise e
 
     def set_opt(self, **kw):
         for k, v in kw.items():

@@ -2,8 +2,8 @@
 
 Host-side mirror of the stage part of ha_assemble() (Assembly.cpp:2076-2108): filter table, number_of_round x ha_ec (index of the
 round + cal_ec_r), --write-ec, ha_ec_ff (final index + cal_ov_r), --write-paf, and the three .bin dumps a later hifiasm run reloads
-instead of recomputing the stage.  Every step is a C-ABI call of include/hifiasm_b200.h (hb_readset_load, hb_reads_upload, hb_ft_gen,
-hb_pt_gen, hb_cal_ec_r, hb_reads_download, hb_cal_ov_r, hb_write_*); nothing is computed here.
+instead of recomputing the stage.  Every step is a C-ABI call of include/hifiasm_b200.h (hb_readset_load, hb_reads_upload, hb_stage_run =
+hb_ft_gen + n x (hb_pt_gen + hb_cal_ec_r) + hb_pt_gen + hb_cal_ov_r, hb_reads_download, hb_write_*); nothing is computed here.
 """
 from __future__ import annotations
 
@@ -16,9 +16,10 @@ from .engine import Engine
 def run_stage(paths, out_prefix: str, device: int = 0, n_round: int = 3, write_paf: bool = True, write_ec: bool = True, bf_shift: int = 0, adapter_len: int = 0):
     """-> dict(reads, bases, corrected_bases per round, overlaps).  Files: <out>.ec.bin, <out>.ovlp.source.bin, <out>.ovlp.reverse.bin and,
     on request, <out>.ec.fa (hifiasm --write-ec) and <out>.ovlp.paf (--write-paf).  bf_shift = hifiasm's -f (0 = exact counting).
-    Under torchrun (torch.distributed initialised, one process per GPU) every pass is sharded over the ranks: reads + index replicated, the
-    EC rounds through dist.cal_ec_r_sharded (all-gather of edit scripts and lists), the final pass on the rank's shard with the lists
-    all-gathered; rank 0 writes the files."""
+    bf_shift defaults to 0, NOT to hifiasm's own default of 37: the files equal those of `hifiasm -f0`; pass bf_shift=37 for the files of a default run.
+    Under torchrun (torch.distributed initialised, one process per GPU) hb_stage_run shards every pass over the ranks: reads + index replicated, one
+    all-gather of edit scripts + lists + flags per EC round and one of the final lists (csrc/stage.cu; a rank that fails says so in its blob, so the
+    others raise instead of waiting); rank 0 writes the files."""
     from . import dist as hdist
     rank, world = hdist._world()
     tdev = None
