@@ -181,6 +181,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 4096; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
 	ctx->trace = getenv("HB_TRACE") != 0; ctx->trace_ec = getenv("HB_TRACE_EC") != 0;
+	ctx->n_lanes = getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 2; if (ctx->n_lanes < 1 || ctx->n_lanes > 2) ctx->n_lanes = 2; ctx->lane2 = 0;
 	ctx->cns_g_nodes = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096; ctx->cns_g_arcs = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_post_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, POST_WARPS * POST_SMEM_PER_WARP);
@@ -209,7 +210,7 @@ extern "C" void hb_destroy(hb_ctx_t *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
 	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->d_scc); cudaFree(ctx->d_scc_off); cudaFree(ctx->ws); if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-	hb_stage_buf_free(ctx);
+	hb_stage_buf_free(ctx); hb_lane_free(ctx);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -494,6 +495,7 @@ static int run_pass(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, 
 		rc = run_pass_impl(ctx, r0, r1, mode, bw, so, stat_out);
 		hb_ws_reset(ctx);
 		if (rc != HB_E_WS) break;
+		if (ctx->lane2 && ctx->lane2->ws_need) { hb_ws_reset(ctx->lane2); if ((rc = hb_ws_grow(ctx->lane2))) { hb_set_err(ctx, rc, "%s", ctx->lane2->err.c_str()); break; } if (!ctx->ws_need) { rc = HB_E_WS; continue; } } // (only the second lane ran short)
 		if ((rc = hb_ws_grow(ctx))) break;
 		cudaEventRecord(a, ctx->stream); // time the attempt that succeeds
 		rc = HB_E_WS;
@@ -505,6 +507,90 @@ static int run_pass(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, 
 	return rc;
 }
 #include <chrono>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
+#include <functional>
+
+// ---- lanes: the batches of a pass on two streams (see run_pass_impl) ----
+// What a batch adds to the host-side results of the pass is added in batch order: commit(k, fn) runs fn when the batches before k have committed.
+#define HB_E_ABORTED (-101) /* internal: the batch gave up because another one failed */
+struct PassOrder {
+	std::mutex mu; std::condition_variable cv; size_t next; bool aborted; std::vector<char> done;
+	explicit PassOrder(size_t n) : next(0), aborted(false), done(n, 0) {}
+	template <typename F> int commit(size_t k, F fn)
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		cv.wait(lk, [&]() { return next == k || aborted; });
+		if (aborted) return HB_E_ABORTED; // (another batch failed: its error is the one reported)
+		const int rc = fn();
+		if (rc) aborted = true; else { done[k] = 1; next = k + 1; }
+		lk.unlock(); cv.notify_all();
+		return rc;
+	}
+	void abort() { { std::lock_guard<std::mutex> lk(mu); aborted = true; } cv.notify_all(); }
+};
+// the second lane's context: a copy of the pass's context (read store, index, staged lists, options: shared, read-only inside a pass) with a stream, workspace,
+// profile and counters of its own.  Owns only its stream and workspace (hb_lane_free).
+static int lane_refresh(hb_ctx *ctx)
+{
+	hb_ctx *L = ctx->lane2; cudaStream_t st = 0; uint8_t *ws = 0; size_t ws_cap = 0, ws_need = 0;
+	if (L) { st = L->stream; ws = L->ws; ws_cap = L->ws_cap; ws_need = L->ws_need; }
+	else { L = new hb_ctx(); if (cudaStreamCreate(&st) != cudaSuccess) { delete L; hb_set_err(ctx, HB_E_CUDA, "second stream"); return HB_E_CUDA; } }
+	*L = *ctx;
+	L->stream = st; L->ws = ws; L->ws_cap = ws_cap; L->ws_need = ws_need; L->lane2 = 0; L->n_lanes = 1; L->stage_buf = 0; L->h_stage = 0; L->h_stage_cap = 0;
+	L->prof.clear(); L->prof_stage.clear(); L->in_stage = 0; memset(L->counters, 0, sizeof(L->counters)); memset(L->stage_counters, 0, sizeof(L->stage_counters)); L->err.clear();
+	ctx->lane2 = L;
+	if (!L->ws) { L->ws_need = std::max<size_t>(L->ws_need, std::max<size_t>(ctx->ws_cap / 2, (size_t)256 << 20)); /* a first guess: half of what the pass's own lane has grown to */ int rc = hb_ws_grow(L); if (rc) { hb_set_err(ctx, rc, "%s", L->err.c_str()); return rc; } }
+	hb_ws_reset(L);
+	return HB_OK;
+}
+void hb_lane_free(hb_ctx *ctx)
+{
+	hb_ctx *L = ctx->lane2; if (!L) return;
+	cudaStreamSynchronize(L->stream); cudaFree(L->ws); cudaStreamDestroy(L->stream);
+	delete L; ctx->lane2 = 0;
+}
+static void lane_merge(hb_ctx *ctx, hb_ctx *L)
+{ // the lane's kernel times and counters into the pass's
+	for (auto &q : L->prof) {
+		bool f = false; for (auto &p : ctx->prof) if (p.name == q.name) { p.launches += q.launches; p.ms += q.ms; f = true; break; } if (!f) ctx->prof.push_back(q);
+		if (ctx->in_stage) { f = false; for (auto &p : ctx->prof_stage) if (p.name == q.name) { p.launches += q.launches; p.ms += q.ms; f = true; break; } if (!f) ctx->prof_stage.push_back(q); }
+	}
+	for (int i = 0; i < 12; i++) ctx->counters[i] += L->counters[i];
+}
+typedef std::function<int(hb_ctx *, size_t)> BatchFn;
+static int run_batches(hb_ctx *ctx, int mode, size_t n, PassOrder &order, const BatchFn &body)
+{
+	// the stage views (modes 2..8) place their output at running offsets all through the batch: one lane
+	const int lanes = (mode == 0 || mode == 9) && !ctx->trace && n > 1 ? ctx->n_lanes : 1;
+	auto one = [&](hb_ctx *c, size_t k) -> int {
+		int rc = body(c, k);
+		if (!rc) { bool d; { std::lock_guard<std::mutex> lk(order.mu); d = order.done[k] != 0; } if (!d) rc = order.commit(k, []() { return HB_OK; }); }
+		if (rc) order.abort();
+		return rc;
+	};
+	if (lanes < 2) { for (size_t k = 0; k < n; k++) { const int rc = one(ctx, k); if (rc) return rc; } return HB_OK; }
+	int rc = lane_refresh(ctx); if (rc) return rc;
+	hb_ctx *L = ctx->lane2; std::atomic<size_t> nextk(0); int rcs[2] = { HB_OK, HB_OK };
+	auto worker = [&](hb_ctx *c, int *out) {
+		cudaSetDevice(c->device);
+		for (;;) { const size_t k = nextk.fetch_add(1); if (k >= n) break; { std::lock_guard<std::mutex> lk(order.mu); if (order.aborted) break; } const int r = one(c, k); if (r) { *out = r; break; } }
+		cudaStreamSynchronize(c->stream);
+	};
+	std::thread t2(worker, L, &rcs[1]);
+	worker(ctx, &rcs[0]);
+	t2.join();
+	lane_merge(ctx, L);
+	// which error to report: a workspace that was too small on either lane first (the pass is rerun after growing it), then the lane that failed by itself
+	if (rcs[0] == HB_E_WS || rcs[1] == HB_E_WS) return HB_E_WS;
+	if (rcs[0] && rcs[0] != HB_E_ABORTED) return rcs[0];
+	if (rcs[1] && rcs[1] != HB_E_ABORTED) { hb_set_err(ctx, rcs[1], "%s", L->err.c_str()); return rcs[1]; }
+	if (rcs[0] || rcs[1]) { hb_set_err(ctx, HB_E_STATE, "a batch was abandoned without an error"); return HB_E_STATE; }
+	return HB_OK;
+}
+
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define TRACE(label) do { if (trace) { cudaStreamSynchronize(ctx->stream); double t_ = now_ms(); fprintf(stderr, "[hb trace] %-18s +%8.2f ms (total %8.2f)\n", label, t_ - t_last, t_ - t_begin); t_last = now_ms(); } } while (0)
 static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, StageOut *so, uint64_t *stat_out)
@@ -557,10 +643,20 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	if (mode == 0) { d_m0 = ar.zero<uint32_t>(nR + 1); d_m1 = ar.zero<uint32_t>(nR + 1); }
 	HB_ALLOC_CHECK(ar);
 
-	// ---- batches bounded by the anchor budget
+	// ---- batches bounded by the anchor budget.  The batches are independent: with two lanes (HB_LANES, default 2) two host threads take them in turn, each with
+	// its own stream and workspace (a clone of the context, lane_refresh), so that the launches of one batch whose time is set by their heaviest read (phasing, chain
+	// post-processing, the merge of step B: one wave of warps, most SMs idle behind the last one) share the device with the throughput-bound launches of the other.
+	// What a batch adds to the pass's host-side results is added in batch order (PassOrder), so the results do not depend on which lane ran what.
+	std::vector<std::pair<uint64_t, uint64_t>> batches;
 	for (uint64_t b0 = 0; b0 < nR;) {
 		uint64_t b1 = b0 + 1;
 		while (b1 < nR && h_aoff[b1 + 1] - h_aoff[b0] <= ctx->anchor_budget) b1++;
+		batches.push_back(std::make_pair(b0, b1)); b0 = b1;
+	}
+	PassOrder order(batches.size());
+	hb_ctx *const pass_ctx = ctx;
+	auto batch_body = [&](hb_ctx *ctx, const size_t bk) -> int { // `ctx` = the lane's context: stream, workspace, profile and counters of its own; everything else is shared and read-only
+		const uint64_t b0 = batches[bk].first, b1 = batches[bk].second; int rc;
 		const uint64_t nb = b1 - b0, B = h_aoff[b1] - h_aoff[b0], a_base = h_aoff[b0], mz_b = h_mzoff[b0], n_mz = h_mzoff[b1] - h_mzoff[b0];
 		if (B >= (1ull << 32)) { hb_set_err(ctx, HB_E_OVERFLOW, "a single read produces >= 2^32 anchors"); return HB_E_OVERFLOW; }
 		Arena ba(ctx);
@@ -599,7 +695,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 		}
 		HB_CUDA(cudaGetLastError());
 	TRACE("chain");
-		if (mode == 2) { b0 = b1; continue; }
+		if (mode == 2) return HB_OK;
 		ba.release(d_f); ba.release(d_p); ba.release(d_ii); ba.release(d_t);
 
 		// post
@@ -871,6 +967,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 									k_ec_rpaf<<<nblk(nb, 64), 64, 0, ctx->stream>>>(R, r0 + b0, nb, d_ooff, d_ph, P.ord, d_rp, d_nrp, d_err);
 								}
 								const uint16_t *d_sc_use = ctx->d_scc; const uint64_t *d_scoff_use = ctx->d_scc_off; uint64_t sc_rid0 = 0;
+								std::vector<uint16_t> h_scc_b; std::vector<uint64_t> h_scoff_b; unsigned long long h_nec_b = 0;
 								if (so->cns) { // row a14: the edit scripts of the batch's reads by window consensus, on the device
 									uint32_t *d_entcap = ba.zero<uint32_t>(nb + 1), *d_scn = ba.zero<uint32_t>(nb + 1); uint64_t *d_entoff = ba.get<uint64_t>(nb + 2), *d_slot = ba.get<uint64_t>(nb + 2), *d_scoff_b = ba.get<uint64_t>(nb + 2);
 									uint8_t *d_status = ba.zero<uint8_t>(nb + 8); unsigned long long *d_nec = ba.zero<unsigned long long>(1); CnsOv *d_cov = ba.get<CnsOv>(n_ov + 1);
@@ -931,11 +1028,10 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 									uint16_t *d_scd = ba.get<uint16_t>(h_scoff[nb] + 1); HB_ALLOC_CHECK(ba);
 									k_sc_compact<<<nblk(nb, 128), 128, 0, ctx->stream>>>(nb, d_slot, d_scoff_b, d_scslot, d_scd);
 									HB_CUDA(cudaGetLastError());
-									const size_t base = so->h_scc->size(); so->h_scc->resize(base + h_scoff[nb]);
-									if (h_scoff[nb]) HB_CUDA(cudaMemcpyAsync(so->h_scc->data() + base, d_scd, h_scoff[nb] * 2, cudaMemcpyDeviceToHost, ctx->stream));
+									h_scc_b.resize(h_scoff[nb] + 1); // the batch's scripts; added to the pass's in batch order below
+									if (h_scoff[nb]) HB_CUDA(cudaMemcpyAsync(h_scc_b.data(), d_scd, h_scoff[nb] * 2, cudaMemcpyDeviceToHost, ctx->stream));
 									HB_CUDA(cudaStreamSynchronize(ctx->stream));
-									for (uint64_t i = 0; i <= nb; i++) (*so->h_scc_off)[b0 + i] = base + h_scoff[i];
-									so->n_corrected += h_nec;
+									h_scoff_b.swap(h_scoff); h_nec_b = h_nec;
 									d_sc_use = d_scd; d_scoff_use = d_scoff_b; sc_rid0 = r0 + b0;
 								}
 								{
@@ -949,14 +1045,22 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 								if (so->flags) HB_CUDA(cudaMemcpyAsync(so->flags + 2 * b0, d_fl, 2 * nb, cudaMemcpyDeviceToHost, ctx->stream));
 								HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 								if (h_err2 & 128) { hb_set_err(ctx, HB_E_OVERFLOW, "dedup_chains: radix-sort stack"); return HB_E_OVERFLOW; }
-								for (uint64_t i = 0; i < nb; i++) {
-									st3_off[b0 + i] = st3_n; st3_hit_off[b0 + i] = st3_nh;
-									if ((so->rec && st3_n + h_nsp[i] > so->rec_cap) || (so->rec2 && st3_nh + h_nrp[i] > so->rec2_cap)) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
-									if (so->rec) memcpy((hb_ma_hit_t *)so->rec + st3_n, h_sp.data() + h_ooff[i], h_nsp[i] * sizeof(hb_ma_hit_t));
-									if (so->rec2) memcpy(so->rec2 + st3_nh, h_rp.data() + h_ooff[i], h_nrp[i] * sizeof(hb_ma_hit_t));
-									st3_n += h_nsp[i]; st3_nh += h_nrp[i];
-								}
-								st3_off[b0 + nb] = st3_n; st3_hit_off[b0 + nb] = st3_nh;
+								if ((rc = order.commit(bk, [&]() -> int { // the pass's lists and scripts grow in batch order
+									if (so->cns) {
+										const size_t base = so->h_scc->size(); so->h_scc->resize(base + h_scoff_b[nb]);
+										if (h_scoff_b[nb]) memcpy(so->h_scc->data() + base, h_scc_b.data(), h_scoff_b[nb] * 2);
+										for (uint64_t i = 0; i <= nb; i++) (*so->h_scc_off)[b0 + i] = base + h_scoff_b[i];
+										so->n_corrected += h_nec_b;
+									}
+									for (uint64_t i = 0; i < nb; i++) {
+										st3_off[b0 + i] = st3_n; st3_hit_off[b0 + i] = st3_nh;
+										if ((so->rec && st3_n + h_nsp[i] > so->rec_cap) || (so->rec2 && st3_nh + h_nrp[i] > so->rec2_cap)) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
+										if (so->rec) memcpy((hb_ma_hit_t *)so->rec + st3_n, h_sp.data() + h_ooff[i], h_nsp[i] * sizeof(hb_ma_hit_t));
+										if (so->rec2) memcpy(so->rec2 + st3_nh, h_rp.data() + h_ooff[i], h_nrp[i] * sizeof(hb_ma_hit_t));
+										st3_n += h_nsp[i]; st3_nh += h_nrp[i];
+									}
+									st3_off[b0 + nb] = st3_n; st3_hit_off[b0 + nb] = st3_nh;
+									return HB_OK; }))) return rc;
 								break;
 							}
 							if (mode == 8) { // the round's reverse_paf lists of the batch
@@ -1011,7 +1115,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						if (attempt >= 2) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: cigar pool"); return HB_E_OVERFLOW; }
 						poolb_cap = poolb_used + 65536; n_def = 0; // the need is known now: only the merge is repeated
 					}
-					b0 = b1; continue;
+					return HB_OK;
 				}
 				if (so->rec && st3_n + n_ov > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "overlap output capacity"); return HB_E_OVERFLOW; }
 				if (so->wl && so->n_wl + n_win > so->wl_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "window-list output capacity"); return HB_E_OVERFLOW; }
@@ -1024,14 +1128,14 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 				if (so->wl && so->n_cig) for (uint64_t i = 0; i < n_win; i++) if (so->wl[so->n_wl + i].clen) so->wl[so->n_wl + i].cidx += (uint32_t)so->n_cig;
 				for (uint64_t i = 0; i <= nb; i++) st3_off[b0 + i] = st3_n + h_ooff[i];
 				st3_n += n_ov; so->n_wl += n_win; so->n_cig += pool_used;
-				b0 = b1; continue;
+				return HB_OK;
 			}
 			if (so->rec && st3_n + n_win > so->rec_cap) { hb_set_err(ctx, HB_E_OVERFLOW, "window output capacity"); return HB_E_OVERFLOW; }
 			if (so->rec) HB_CUDA(cudaMemcpyAsync((hb_win_t *)so->rec + st3_n, d_wout, n_win * sizeof(hb_win_t), cudaMemcpyDeviceToHost, ctx->stream));
 			HB_CUDA(cudaStreamSynchronize(ctx->stream));
 			for (uint64_t i = 0; i <= nb; i++) st3_off[b0 + i] = st3_n + h_woff[i];
 			st3_n += n_win;
-			b0 = b1; continue;
+			return HB_OK;
 		}
 		if (mode == 3) { // assemble the stage-3 view of this batch and copy it out
 			uint32_t *d_nh = ba.get<uint32_t>(nb + 1), *d_nf = ba.get<uint32_t>(nb + 1); uint64_t *d_och = ba.get<uint64_t>(nb + 2), *d_oh = ba.get<uint64_t>(nb + 2), *d_of = ba.get<uint64_t>(nb + 2), *d_fcb = ba.get<uint64_t>(n_slots + 1);
@@ -1055,7 +1159,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 			HB_CUDA(cudaStreamSynchronize(ctx->stream));
 			for (uint64_t i = 0; i <= nb; i++) { st3_off[b0 + i] = st3_n + h_och[i]; st3_hit_off[b0 + i] = st3_nh + h_oh[i]; st3_fc_off[b0 + i] = st3_nf + h_of[i]; }
 			st3_n += h_och[nb]; st3_nh += h_oh[nb]; st3_nf += h_of[nb];
-			b0 = b1; continue;
+			return HB_OK;
 		}
 
 		// exact + merge (final pass)
@@ -1090,9 +1194,11 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	TRACE("merge");
 		HB_CUDA(cudaMemcpyAsync(d_ooff_keep, d_ooff, (nb + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 		BatchRes br; br.o0 = d_o0; br.o1 = d_o1; br.ooff = d_ooff_keep; br.b0 = b0; br.b1 = b1;
-		bres.push_back(br);
-		b0 = b1;
-	}
+		HB_CUDA(cudaStreamSynchronize(ctx->stream)); // (the gather below runs on the pass's stream)
+		order.commit(bk, [&]() { bres.push_back(br); return HB_OK; });
+		return HB_OK;
+	};
+	if ((rc = run_batches(pass_ctx, mode, batches.size(), order, batch_body))) return rc;
 
 	TRACE("batches done");
 	{ unsigned long long h_dbg[2] = { 0, 0 }; HB_CUDA(cudaMemcpyAsync(h_dbg, d_stat + 8, 16, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream)); ctx->counters[6] = h_dbg[0]; ctx->counters[7] = h_dbg[1]; }

@@ -46,7 +46,9 @@ struct hb_ctx {
 	// cached pinned staging buffer and capacities of the read-store arrays
 	uint8_t *h_stage; uint64_t h_stage_cap, packed_cap, reads_cap, npos_cap;
 	void *stage_buf; // hb_stage_run's host-side lists (stage.cu)
+	int n_lanes; hb_ctx *lane2; // batches of a pass on two streams (HB_LANES, read once in hb_create; engine.cu run_batches); lane2 = the second lane's context, owned
 };
+void hb_lane_free(hb_ctx *ctx);
 void hb_stage_buf_free(hb_ctx *ctx);
 struct GroupDir;
 int hb_group_sort(hb_ctx *ctx, uint64_t nb, uint64_t r0_batch, const uint64_t *d_aoff, uint64_t a_base, uint64_t B, const hb_hit_t *d_raw, hb_hit_t *d_hits,

@@ -28,20 +28,35 @@ def _cmp_files(td, a, b):
     return diff
 
 
-def test_whole_stage_files_equal_reference_binary_at_scale(tmp_path):
+@pytest.fixture(scope="module")
+def ref_run(tmp_path_factory):
+    """the seeded read set and the reference binary's files for it (one run for the module)"""
     import simgen
-    from hifiasm_b200 import stage
     ref = os.path.join(ROOT, "oracle", "_ref", "hifiasm")
     if not os.path.exists(ref):
         pytest.skip("oracle/_ref/hifiasm is not built (make -C oracle ref where /root/reference exists)")
-    mb = float(os.environ.get("HB_SCALE_MB", "4")); td = str(tmp_path)
+    mb = float(os.environ.get("HB_SCALE_MB", "4")); td = str(tmp_path_factory.mktemp("scale"))
     fa = os.path.join(td, "reads.fa")
     rs = simgen.make(mb, 30, seed=int(os.environ.get("HB_SCALE_SEED", "77")), n_rate=0.0002, fasta=fa)
     thr = len(os.sched_getaffinity(0))
     p = subprocess.run([ref, "-o", os.path.join(td, "ref"), "-t%d" % thr, "-f0", "--write-paf", "--write-ec", fa], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-2000:]
-    info = stage.run_stage(fa, os.path.join(td, "gpu"))
+    return mb, td, fa, rs
+
+
+# default: the batches the anchor budget gives at this size (two), on two lanes.  Then many small batches on two lanes (each lane's host thread takes
+# batches in turn on its own stream; what they add to the lists is added in batch order) and on one lane: the files must not depend on either.
+@pytest.mark.parametrize("budget,lanes", [(None, None), ("6000000", "2"), ("6000000", "1")])
+def test_whole_stage_files_equal_reference_binary_at_scale(ref_run, monkeypatch, budget, lanes):
+    from hifiasm_b200 import stage
+    mb, td, fa, rs = ref_run
+    if budget:
+        monkeypatch.setenv("HB_ANCHOR_BUDGET", budget)
+    if lanes:
+        monkeypatch.setenv("HB_LANES", lanes)
+    out = "gpu_%s_%s" % (budget, lanes)
+    info = stage.run_stage(fa, os.path.join(td, out))
     assert info["reads"] == rs.n and info["bases"] == rs.bases
-    diff = _cmp_files(td, "ref", "gpu")
-    print("scale parity: %g Mb genome, %d reads, %d bases, corrected per round %s, overlaps %d + %d: %s" % (mb, rs.n, rs.bases, info["corrected_bases"], info["overlaps_src"], info["overlaps_rev"], "identical" if not diff else diff))
+    diff = _cmp_files(td, "ref", out)
+    print("scale parity (budget %s, lanes %s): %g Mb genome, %d reads, %d bases, corrected per round %s, overlaps %d + %d: %s" % (budget, lanes, mb, rs.n, rs.bases, info["corrected_bases"], info["overlaps_src"], info["overlaps_rev"], "identical" if not diff else diff))
     assert not diff, diff
