@@ -181,7 +181,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 4096; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
 	ctx->trace = getenv("HB_TRACE") != 0; ctx->trace_ec = getenv("HB_TRACE_EC") != 0;
-	ctx->n_lanes = getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 2; if (ctx->n_lanes < 1 || ctx->n_lanes > 2) ctx->n_lanes = 2; ctx->lane2 = 0;
+	ctx->n_lanes = getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 2; if (ctx->n_lanes < 1 || ctx->n_lanes > HB_MAX_LANES) ctx->n_lanes = 2; for (int i = 0; i < HB_MAX_LANES - 1; i++) ctx->lane[i] = 0;
 	ctx->cns_g_nodes = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096; ctx->cns_g_arcs = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_post_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, POST_WARPS * POST_SMEM_PER_WARP);
@@ -495,7 +495,15 @@ static int run_pass(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, 
 		rc = run_pass_impl(ctx, r0, r1, mode, bw, so, stat_out);
 		hb_ws_reset(ctx);
 		if (rc != HB_E_WS) break;
-		if (ctx->lane2 && ctx->lane2->ws_need) { hb_ws_reset(ctx->lane2); if ((rc = hb_ws_grow(ctx->lane2))) { hb_set_err(ctx, rc, "%s", ctx->lane2->err.c_str()); break; } if (!ctx->ws_need) { rc = HB_E_WS; continue; } } // (only the second lane ran short)
+		{ bool grew = false, fail = false;
+			for (int i = 0; i < HB_MAX_LANES - 1 && !fail; i++) {
+				hb_ctx *L = ctx->lane[i]; if (!L || !L->ws_need) continue;
+				hb_ws_reset(L); grew = true;
+				if ((rc = hb_ws_grow(L)) == HB_E_NOMEM) { ctx->n_lanes = i + 1; L->ws_need = 0; } // no room for this lane's workspace: the pass is rerun on fewer lanes
+				else if (rc) { hb_set_err(ctx, rc, "%s", L->err.c_str()); fail = true; }
+			}
+			if (fail) break;
+			if (grew && !ctx->ws_need) { rc = HB_E_WS; continue; } } // (only other lanes ran short)
 		if ((rc = hb_ws_grow(ctx))) break;
 		cudaEventRecord(a, ctx->stream); // time the attempt that succeeds
 		rc = HB_E_WS;
@@ -533,24 +541,32 @@ struct PassOrder {
 };
 // the second lane's context: a copy of the pass's context (read store, index, staged lists, options: shared, read-only inside a pass) with a stream, workspace,
 // profile and counters of its own.  Owns only its stream and workspace (hb_lane_free).
-static int lane_refresh(hb_ctx *ctx)
+static int lane_refresh(hb_ctx *ctx, int li)
 {
-	hb_ctx *L = ctx->lane2; cudaStream_t st = 0; uint8_t *ws = 0; size_t ws_cap = 0, ws_need = 0;
+	hb_ctx *L = ctx->lane[li]; cudaStream_t st = 0; uint8_t *ws = 0; size_t ws_cap = 0, ws_need = 0;
 	if (L) { st = L->stream; ws = L->ws; ws_cap = L->ws_cap; ws_need = L->ws_need; }
-	else { L = new hb_ctx(); if (cudaStreamCreate(&st) != cudaSuccess) { delete L; hb_set_err(ctx, HB_E_CUDA, "second stream"); return HB_E_CUDA; } }
+	else { L = new hb_ctx(); if (cudaStreamCreate(&st) != cudaSuccess) { delete L; hb_set_err(ctx, HB_E_CUDA, "stream of lane %d", li + 1); return HB_E_CUDA; } }
 	*L = *ctx;
-	L->stream = st; L->ws = ws; L->ws_cap = ws_cap; L->ws_need = ws_need; L->lane2 = 0; L->n_lanes = 1; L->stage_buf = 0; L->h_stage = 0; L->h_stage_cap = 0;
+	L->stream = st; L->ws = ws; L->ws_cap = ws_cap; L->ws_need = ws_need; for (int i = 0; i < HB_MAX_LANES - 1; i++) L->lane[i] = 0; L->n_lanes = 1; L->stage_buf = 0; L->h_stage = 0; L->h_stage_cap = 0;
 	L->prof.clear(); L->prof_stage.clear(); L->in_stage = 0; memset(L->counters, 0, sizeof(L->counters)); memset(L->stage_counters, 0, sizeof(L->stage_counters)); L->err.clear();
-	ctx->lane2 = L;
+	ctx->lane[li] = L;
 	if (!L->ws) { L->ws_need = std::max<size_t>(L->ws_need, std::max<size_t>(ctx->ws_cap / 2, (size_t)256 << 20)); /* a first guess: half of what the pass's own lane has grown to */ int rc = hb_ws_grow(L); if (rc) { hb_set_err(ctx, rc, "%s", L->err.c_str()); return rc; } }
 	hb_ws_reset(L);
 	return HB_OK;
 }
 void hb_lane_free(hb_ctx *ctx)
 {
-	hb_ctx *L = ctx->lane2; if (!L) return;
-	cudaStreamSynchronize(L->stream); cudaFree(L->ws); cudaStreamDestroy(L->stream);
-	delete L; ctx->lane2 = 0;
+	for (int i = 0; i < HB_MAX_LANES - 1; i++) {
+		hb_ctx *L = ctx->lane[i]; if (!L) continue;
+		cudaStreamSynchronize(L->stream); cudaFree(L->ws); cudaStreamDestroy(L->stream);
+		delete L; ctx->lane[i] = 0;
+	}
+}
+void hb_ws_release(hb_ctx *ctx)
+{ // between passes: give the workspaces back (an index build needs the room); the lanes keep their streams
+	cudaStreamSynchronize(ctx->stream);
+	size_t keep = ctx->ws_cap; if (ctx->ws) cudaFree(ctx->ws); ctx->ws = 0; ctx->ws_cap = 0; ctx->ws_need = keep - (keep >> 3); hb_ws_reset(ctx); // (regrown to about the old size in one step)
+	for (int i = 0; i < HB_MAX_LANES - 1; i++) { hb_ctx *L = ctx->lane[i]; if (!L || !L->ws) continue; cudaStreamSynchronize(L->stream); keep = L->ws_cap; cudaFree(L->ws); L->ws = 0; L->ws_cap = 0; L->ws_need = keep - (keep >> 3); }
 }
 static void lane_merge(hb_ctx *ctx, hb_ctx *L)
 { // the lane's kernel times and counters into the pass's
@@ -572,22 +588,24 @@ static int run_batches(hb_ctx *ctx, int mode, size_t n, PassOrder &order, const 
 		return rc;
 	};
 	if (lanes < 2) { for (size_t k = 0; k < n; k++) { const int rc = one(ctx, k); if (rc) return rc; } return HB_OK; }
-	int rc = lane_refresh(ctx); if (rc) return rc;
-	hb_ctx *L = ctx->lane2; std::atomic<size_t> nextk(0); int rcs[2] = { HB_OK, HB_OK };
+	int extra = (int)std::min<size_t>((size_t)lanes, n) - 1; int rc;
+	for (int i = 0; i < extra; i++) if ((rc = lane_refresh(ctx, i))) { if (rc != HB_E_NOMEM) return rc; extra = i; break; } // no room for another workspace: fewer lanes
+	std::atomic<size_t> nextk(0); int rcs[HB_MAX_LANES]; for (int i = 0; i < HB_MAX_LANES; i++) rcs[i] = HB_OK;
 	auto worker = [&](hb_ctx *c, int *out) {
 		cudaSetDevice(c->device);
 		for (;;) { const size_t k = nextk.fetch_add(1); if (k >= n) break; { std::lock_guard<std::mutex> lk(order.mu); if (order.aborted) break; } const int r = one(c, k); if (r) { *out = r; break; } }
 		cudaStreamSynchronize(c->stream);
 	};
-	std::thread t2(worker, L, &rcs[1]);
+	std::vector<std::thread> th;
+	for (int i = 0; i < extra; i++) th.emplace_back(worker, ctx->lane[i], &rcs[i + 1]);
 	worker(ctx, &rcs[0]);
-	t2.join();
-	lane_merge(ctx, L);
-	// which error to report: a workspace that was too small on either lane first (the pass is rerun after growing it), then the lane that failed by itself
-	if (rcs[0] == HB_E_WS || rcs[1] == HB_E_WS) return HB_E_WS;
+	for (auto &t : th) t.join();
+	for (int i = 0; i < extra; i++) lane_merge(ctx, ctx->lane[i]);
+	// which error to report: a workspace that was too small on any lane first (the pass is rerun after growing it), then the lane that failed by itself
+	for (int i = 0; i <= extra; i++) if (rcs[i] == HB_E_WS) return HB_E_WS;
 	if (rcs[0] && rcs[0] != HB_E_ABORTED) return rcs[0];
-	if (rcs[1] && rcs[1] != HB_E_ABORTED) { hb_set_err(ctx, rcs[1], "%s", L->err.c_str()); return rcs[1]; }
-	if (rcs[0] || rcs[1]) { hb_set_err(ctx, HB_E_STATE, "a batch was abandoned without an error"); return HB_E_STATE; }
+	for (int i = 1; i <= extra; i++) if (rcs[i] && rcs[i] != HB_E_ABORTED) { hb_set_err(ctx, rcs[i], "%s", ctx->lane[i - 1]->err.c_str()); return rcs[i]; }
+	for (int i = 0; i <= extra; i++) if (rcs[i]) { hb_set_err(ctx, HB_E_STATE, "a batch was abandoned without an error"); return HB_E_STATE; }
 	return HB_OK;
 }
 
@@ -643,7 +661,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	if (mode == 0) { d_m0 = ar.zero<uint32_t>(nR + 1); d_m1 = ar.zero<uint32_t>(nR + 1); }
 	HB_ALLOC_CHECK(ar);
 
-	// ---- batches bounded by the anchor budget.  The batches are independent: with two lanes (HB_LANES, default 2) two host threads take them in turn, each with
+	// ---- batches bounded by the anchor budget.  The batches are independent: with more than one lane (HB_LANES, default 2, at most 4) as many host threads take them in turn, each with
 	// its own stream and workspace (a clone of the context, lane_refresh), so that the launches of one batch whose time is set by their heaviest read (phasing, chain
 	// post-processing, the merge of step B: one wave of warps, most SMs idle behind the last one) share the device with the throughput-bound launches of the other.
 	// What a batch adds to the pass's host-side results is added in batch order (PassOrder), so the results do not depend on which lane ran what.

@@ -13,6 +13,7 @@
 
 struct ProfEntry { const char *name; uint64_t launches; double ms; };
 
+#define HB_MAX_LANES 4
 struct hb_ctx {
 	int device; cudaStream_t stream; hb_opt_t opt; std::string err;
 	int sm_count;
@@ -46,9 +47,10 @@ struct hb_ctx {
 	// cached pinned staging buffer and capacities of the read-store arrays
 	uint8_t *h_stage; uint64_t h_stage_cap, packed_cap, reads_cap, npos_cap;
 	void *stage_buf; // hb_stage_run's host-side lists (stage.cu)
-	int n_lanes; hb_ctx *lane2; // batches of a pass on two streams (HB_LANES, read once in hb_create; engine.cu run_batches); lane2 = the second lane's context, owned
+	int n_lanes; hb_ctx *lane[3]; // batches of a pass on n_lanes streams (HB_LANES, read once in hb_create; engine.cu run_batches); lane[] = the other lanes' contexts, owned
 };
 void hb_lane_free(hb_ctx *ctx);
+void hb_ws_release(hb_ctx *ctx); // frees the workspaces of all lanes (between passes only)
 void hb_stage_buf_free(hb_ctx *ctx);
 struct GroupDir;
 int hb_group_sort(hb_ctx *ctx, uint64_t nb, uint64_t r0_batch, const uint64_t *d_aoff, uint64_t a_base, uint64_t B, const hb_hit_t *d_raw, hb_hit_t *d_hits,

@@ -21,7 +21,12 @@
 struct TmpBufs {
 	hb_ctx *ctx; std::vector<void *> p;
 	TmpBufs(hb_ctx *c) : ctx(c) {}
-	template <typename T> T *get(uint64_t n) { void *q = 0; if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return 0; } p.push_back(q); return (T *)q; }
+	template <typename T> T *get(uint64_t n)
+	{ // an index build that does not fit beside the pass workspaces takes their memory (they are scratch: the next pass grows them again)
+		void *q = 0;
+		if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); hb_ws_release(ctx); if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return 0; } }
+		p.push_back(q); return (T *)q;
+	}
 	void drop(void *q) { for (auto &x : p) if (x == q) { cudaFree(x); x = 0; } }
 	void *steal(void *q) { for (auto &x : p) if (x == q) x = 0; return q; }
 	~TmpBufs() { for (void *q : p) if (q) cudaFree(q); }
