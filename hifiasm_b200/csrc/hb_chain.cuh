@@ -188,46 +188,6 @@ HB_HD void hb_chain_quick(const hb_hit_t *a, int32_t a_n, int32_t *f, int32_t *p
 	S.plus = plus; S.msc = msc; S.msc_i = msc_i; S.movl = movl; S.si = si; S.ei = ei;
 }
 
-// the chaining DP over [si,ei), Hash_Table.cpp:2124-2176 (one thread)
-HB_HD void hb_chain_dp(const hb_hit_t *a, int32_t a_n, int32_t *f, int32_t *p, int64_t *t, int32_t *ii, const ChainPar &P, int64_t xl, int64_t yl, ChainState &S)
-{
-	int64_t max_f, n_skip, st, max_j, end_j, sc, msc = S.msc, msc_i = S.msc_i, max_ii, ovl, movl = S.movl, plus = S.plus, si = S.si, ei = S.ei, i, j;
-	int32_t max, tmp;
-	(void)a_n;
-	for (i = st = si, max_ii = -1; i < ei; ++i) {
-		max_f = a[i].cnt & 0xffu;
-		n_skip = 0; max_j = end_j = -1;
-		if (i - st > P.max_iter) st = i - P.max_iter;
-		while (HB_HIT_ST(a[i]) != HB_HIT_ST(a[st])) ++st;
-		for (j = i - 1; j >= st; --j) {
-			int32_t s = hb_link_sc(a[i], a[j], P, xl, yl, 0);
-			if (s == HB_LINK_FAIL) continue;
-			sc = (int64_t)s + f[j];
-			if (sc > max_f) { max_f = sc; max_j = j; if (n_skip > 0) --n_skip; }
-			else if (t[j] == (int32_t)i) { if (++n_skip > P.max_skip) break; }
-			if (p[j] >= 0) t[p[j]] = i;
-		}
-		end_j = j;
-		if (max_ii < 0 || (int64_t)a[i].self_offset > (int64_t)a[max_ii].self_offset + P.max_dis || HB_HIT_ST(a[i]) != HB_HIT_ST(a[max_ii])) {
-			max = INT32_MIN; max_ii = -1;
-			for (j = i - 1; j >= st && (int64_t)a[i].self_offset <= (int64_t)P.max_dis + (int64_t)a[j].self_offset && HB_HIT_ST(a[i]) == HB_HIT_ST(a[j]); --j)
-				if (max < f[j]) { max = f[j]; max_ii = j; }
-		}
-		if (max_ii >= 0 && max_ii < end_j && HB_HIT_ST(a[i]) == HB_HIT_ST(a[max_ii])) {
-			tmp = hb_link_sc(a[i], a[max_ii], P, xl, yl, 0);
-			if (tmp != HB_LINK_FAIL && max_f < (int64_t)tmp + f[max_ii]) { max_f = (int64_t)tmp + f[max_ii]; max_j = max_ii; }
-		}
-		f[i] = (int32_t)max_f; p[i] = (int32_t)max_j;
-		if (max_ii < 0 || ((int64_t)a[i].self_offset <= (int64_t)P.max_dis + (int64_t)a[max_ii].self_offset && HB_HIT_ST(a[i]) == HB_HIT_ST(a[max_ii]) && f[max_ii] < f[i])) max_ii = i;
-		if (f[i] >= msc) {
-			ovl = hb_chain_len(a[i].self_offset, a[i].self_offset, xl, a[i].offset, a[i].offset, yl);
-			if (f[i] > msc || ovl < movl) { msc = f[i]; msc_i = i; movl = ovl; }
-		}
-		if (f[i] < plus) plus = f[i];
-		ii[i] = 0;
-	}
-	S.plus = plus; S.msc = msc; S.msc_i = msc_i; S.movl = movl;
-}
 
 // backtrack, secondary chains (mcopy), emission: Hash_Table.cpp:2178-2283
 HB_HD int32_t hb_chain_finish(const hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t des_abs, int32_t *f, int32_t *p, int64_t *t, int32_t *ii,
@@ -282,24 +242,6 @@ HB_HD int32_t hb_chain_finish(const hb_hit_t *a, int32_t a_n, hb_hit_t *des, uin
 	return (int32_t)cL;
 }
 
-// Chain one target group (one thread): order + quick check + DP + finish.
-// a[0..a_n): the group's anchors (same target id, both strands), ordered here by
-// (strand, self_offset, offset) — the order minimizers_qgen0's sort produces
-// (anchor.cpp:1046-1049).  des: a_n-sized output slice for the chain anchors.
-// f,p,ii (int32) and t (int64): a_n-sized scratch.  out: the group's chain slots
-// (n_slots = a_n>=mcopy_khit_cutoff ? mcopy_num : 1).  Returns the number of
-// chain anchors written to des.
-HB_HD int32_t hb_chain_group(hb_hit_t *a, int32_t a_n, hb_hit_t *des, uint64_t des_abs, int32_t *f, int32_t *p, int64_t *t, int32_t *ii,
-                             const ChainPar &P, int64_t xl, int64_t yl, hb_chain_t *out, int32_t n_slots, FcOut &fc)
-{
-	ChainState S;
-	for (int32_t i = 0; i < n_slots; i++) out[i].n_hits = 0;
-	if (a_n <= 0) return 0;
-	hb_order_group(a, a_n);
-	hb_chain_quick(a, a_n, f, p, t, ii, P, xl, yl, S);
-	hb_chain_dp(a, a_n, f, p, t, ii, P, xl, yl, S);
-	return hb_chain_finish(a, a_n, des, des_abs, f, p, t, ii, P, xl, yl, out, n_slots, fc, S);
-}
 
 // ---------------------------------------------------------------------------
 // klib sorts restated on index arrays: the comparisons read keys through the

@@ -10,6 +10,7 @@
 // straight from the 2-bit packed reads.  Everything is integer work except three double comparisons.
 #pragma once
 #include "hb_common.cuh"
+#include "hb_warp.cuh"
 
 #define HB_THRE_MAX 31        // THRESHOLD_MAX_SIZE, Hash_Table.h:24
 #define HB_OVLP_CUT 0.9       // OVERLAP_THRESHOLD_HIFI_FILTER, Hash_Table.h:19
@@ -1066,37 +1067,51 @@ HB_HD int64_t hb_cal_exz_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, in
 
 // hc_aln_exz_adv_hc, Correct.cpp:16178-16260 (maxl = MAX_SIN_L, maxe = MAX_SIN_E, force_l = FORCE_SIN_L, estimate_err = -1) without its
 // push_alnw: returns 1 = aligned (C.ez holds the result), 2 = empty segment (nothing to push), 0 = not aligned (or C.ez.ovf)
-HB_HD int hb_seg_align(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode)
+// CONV (device, thread-per-segment kernels): every lane of the warp calls this together (`live` = the lane has a segment) and nobody leaves before the
+// end; the lanes meet (hb_wsync) in front of every aligner call, so that the aligner — a function call the compiler does not reconverge the warp for: ncu
+// showed it entered 2.8 times per warp with 11 lanes each — runs once per warp and step with every lane that needs it.
+template <bool CONV>
+HB_HD int hb_seg_align_t(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode, bool live)
 {
-	MwEz &ez = C.ez; int64_t thre, thre0, pthre = -1, full = 0; const int64_t ql = qe - qs;
+	MwEz &ez = C.ez; int64_t thre = 0, thre0 = -1, pthre = -1, full = 0, est = 0; const int64_t ql = qe - qs;
+	int ret = -1; // undecided
 	ez.err = INT32_MAX; ez.thre = 0;
-	if (ts == -1 && te == -1) mode = 3;
-	if (ql == 0 && te - ts == 0) return 2;
-	if (ql <= 0 || te - ts <= 0) return 0;
-	const int64_t est = hb_cal_estimate_err_hc(z, C.w_l, qs, qe, ts, te, C.e_rate, &full);
-	if (est == 0) {
-		if (full) { hb_set_exact(ez, qs, qe, ts, te); return 1; }
-		else if (hb_cal_exact(C, z, qs, qe, ts, te, mode)) return 1;
+	if (!live) ret = 0;
+	if (ret < 0) {
+		if (ts == -1 && te == -1) mode = 3;
+		if (ql == 0 && te - ts == 0) ret = 2;
+		else if (ql <= 0 || te - ts <= 0) ret = 0;
 	}
-	if (ql <= HB_MAX_SIN_L && (est >> 1) <= HB_MAX_SIN_E) {
-		if (C.no_myers) return 5;
-		// thresholds in the reference's order: the estimate, len*e_rate, twice that, 0.51*len, and the maximum for short segments; each one
-		// (but the first and the last) only if it exceeds the one before — one call site, so the aligner exists once in the kernel
-		thre = 0; thre0 = -1;
-		for (int step = 0; step < 5; step++) {
-			bool go = true;
+	if (ret < 0) {
+		est = hb_cal_estimate_err_hc(z, C.w_l, qs, qe, ts, te, C.e_rate, &full);
+		if (est == 0) {
+			if (full) { hb_set_exact(ez, qs, qe, ts, te); ret = 1; }
+			else if (hb_cal_exact(C, z, qs, qe, ts, te, mode)) ret = 1;
+		}
+	}
+	bool want = ret < 0 && ql <= HB_MAX_SIN_L && (est >> 1) <= HB_MAX_SIN_E;
+	if (want && C.no_myers) { ret = 5; want = false; }
+	// thresholds in the reference's order: the estimate, len*e_rate, twice that, 0.51*len, and the maximum for short segments; each one
+	// (but the first and the last) only if it exceeds the one before — one call site, so the aligner exists once in the kernel
+	for (int step = 0; step < 5; step++) {
+		bool go = false;
+		if (want) {
+			go = true;
 			if (step == 0) thre = hb_scale_ed_thre((uint32_t)est, HB_MAX_SIN_E);
 			else if (step == 1) { thre0 = thre; thre = (int64_t)((double)ql * C.e_rate); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E); go = thre > thre0; }
 			else if (step == 2) { thre0 = thre; thre <<= 1; thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E); go = thre > thre0; }
 			else if (step == 3) { thre0 = thre; thre = (int64_t)((double)ql * 0.51); thre = hb_scale_ed_thre((uint32_t)thre, HB_MAX_SIN_E); go = thre > thre0; }
 			else { go = ql <= HB_FORCE_SIN_L; thre = HB_MAX_SIN_E; }
-			if (!go) continue;
-			if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) return 1;
-			if (ez.ovf) return 0;
+		}
+		if (CONV) hb_wsync();
+		if (go) {
+			if (hb_cal_exz_adv(C, z, qs, qe, ts, te, thre, &pthre, mode)) { ret = 1; want = false; }
+			else if (ez.ovf) { ret = 0; want = false; }
 		}
 	}
-	return 0;
+	return ret < 0 ? 0 : ret;
 }
+HB_HD int hb_seg_align(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode) { return hb_seg_align_t<false>(C, z, qs, qe, ts, te, mode, true); }
 
 // ---- the three pieces of step B ---------------------------------------------------------------------------------
 // prep   : return_t_chain (refine the chain in place) + hc_ovlp_base_direct's whole-overlap exact shortcut (Correct.cpp:17430-17459)
@@ -1128,20 +1143,24 @@ HB_HD void hb_ecb_prep(const EcZ &zA, int64_t re_A, int64_t ql, int64_t tl, hb_h
 	}
 }
 // segment i of an overlap with refined chain ch_a[0..ch_n): returns hb_seg_align's status; unmapped coordinates in uq / ut
-HB_HD int hb_ecb_segment(EcBCtx &C, const EcZ &zA, const hb_hit_t *ch_a, int64_t ch_n, int64_t i, int64_t *uq, int64_t *ut, int64_t *umode)
+template <bool CONV>
+HB_HD int hb_ecb_segment_t(EcBCtx &C, const EcZ &zA, const hb_hit_t *ch_a, int64_t ch_n, int64_t i, int64_t *uq, int64_t *ut, int64_t *umode, bool live)
 {
-	int64_t q[2], t[2], mode; const int64_t l = i - 1;
+	int64_t q[2], t[2], mode = 3; const int64_t l = i - 1;
 	q[0] = q[1] = t[0] = t[1] = -1;
-	if (l >= 0) { q[0] = ch_a[l].self_offset; t[0] = ch_a[l].offset; } else q[0] = 0;
-	if (i < ch_n) { q[1] = ch_a[i].self_offset; t[1] = ch_a[i].offset; } else q[1] = C.ql;
-	if (t[0] != -1 && t[1] != -1) mode = 0;
-	else if (t[0] != -1 && t[1] == -1) mode = 1;
-	else if (t[0] == -1 && t[1] != -1) mode = 2;
-	else mode = 3;
-	if (mode == 1 || mode == 2) hb_adjust_ext_offset(&q[0], &q[1], &t[0], &t[1], C.ql, C.tl, 0, mode);
+	if (live) {
+		if (l >= 0) { q[0] = ch_a[l].self_offset; t[0] = ch_a[l].offset; } else q[0] = 0;
+		if (i < ch_n) { q[1] = ch_a[i].self_offset; t[1] = ch_a[i].offset; } else q[1] = C.ql;
+		if (t[0] != -1 && t[1] != -1) mode = 0;
+		else if (t[0] != -1 && t[1] == -1) mode = 1;
+		else if (t[0] == -1 && t[1] != -1) mode = 2;
+		else mode = 3;
+		if (mode == 1 || mode == 2) hb_adjust_ext_offset(&q[0], &q[1], &t[0], &t[1], C.ql, C.tl, 0, mode);
+	}
 	uq[0] = q[0]; uq[1] = q[1]; ut[0] = t[0]; ut[1] = t[1]; *umode = mode;
-	return hb_seg_align(C, zA, q[0], q[1], t[0], t[1], mode);
+	return hb_seg_align_t<CONV>(C, zA, q[0], q[1], t[0], t[1], mode, live);
 }
+HB_HD int hb_ecb_segment(EcBCtx &C, const EcZ &zA, const hb_hit_t *ch_a, int64_t ch_n, int64_t i, int64_t *uq, int64_t *ut, int64_t *umode) { return hb_ecb_segment_t<false>(C, zA, ch_a, ch_n, i, uq, ut, umode, true); }
 // what hc_ovlp_base_direct does with a segment's result
 HB_HD void hb_ecb_apply(EcBCtx &C, int status, const AlnRes &r, const int64_t *uq, const int64_t *ut, int64_t umode)
 {

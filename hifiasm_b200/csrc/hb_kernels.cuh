@@ -286,9 +286,9 @@ struct ChainArgs {
 // already co-linear, which is what quick_ck_lchain (Hash_Table.cpp:2007-2094)
 // detects with a linear scan — is evaluated by the whole warp: 32 link scores
 // per step, chain scores by warp prefix sums, best end / minimum by warp
-// reductions, chain anchors copied with 128-bit loads.  Anything else (DP needed,
-// secondary chains possible, unordered group) is handed to lane 0, which runs the
-// sequential hb_chain_group on the same buffers: identical results by construction.
+// reductions, chain anchors copied with 128-bit loads.  A group that needs the DP runs
+// warp_chain_dp (the predecessor scan of an anchor spread over the lanes, the reference's
+// early-exit order kept); only the ordering of an unordered group (rare) is left to lane 0.
 // ----------------------------------------------------------------------------
 static __device__ __forceinline__ hb_hit_t hit_shfl_up1(const hb_hit_t &h)
 {
@@ -1072,21 +1072,26 @@ __global__ void __launch_bounds__(128) k_ecb_seg(EcCigArgs A)
 	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
 	C.ez.path = l_path; C.ez.pcap = ECB_T0_PATH; C.ez.vec = l_vec; C.ez.vstride = ECB_T0_VS; C.ez.warp = 0; C.ez.cig = l_cig; C.ez.ccap = ECB_T0_CIG;
 	const uint64_t n_work = (uint64_t)*A.q_in_n;
-	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
-		const uint64_t sidx = A.q_in[wk];
-		uint64_t lo = 0, hi = A.n_ov; // overlap of the segment: last o with seg_off[o] <= sidx
-		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
-		const uint64_t o = lo; const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
-		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
-		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
-		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+	for (uint64_t wk0 = tid - (threadIdx.x & 31); wk0 < n_work; wk0 += nthr) { // warp-uniform trip count: the lanes of a warp stay together (hb_seg_align_t<true> syncs them)
+		const uint64_t wk = wk0 + (threadIdx.x & 31); const bool live = wk < n_work;
+		uint64_t sidx = 0, o = 0; EcPrep pr; pr.ch_n = 0; OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a = 0; uint64_t dpo;
+		if (live) {
+			sidx = A.q_in[wk];
+			uint64_t lo = 0, hi = A.n_ov; // overlap of the segment: last o with seg_off[o] <= sidx
+			while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
+			o = lo; const hb_aln_t a = A.aln[o]; pr = A.prep[o];
+			ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+			C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+		}
 		C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
 		int64_t uq[2], ut[2], um;
-		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
-		if (C.bad) atomicOr(A.err, 32);
-		EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
-		if (sg.status == 4 && A.q_out) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; }
-		A.segs[sidx] = sg;
+		const int st = hb_ecb_segment_t<true>(C, z, ch_a, pr.ch_n, (int64_t)(sidx - (live ? A.seg_off[o] : 0)), uq, ut, &um, live);
+		if (live) {
+			if (C.bad) atomicOr(A.err, 32);
+			EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
+			if (sg.status == 4 && A.q_out) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; }
+			A.segs[sidx] = sg;
+		}
 	}
 }
 // segment alignment, tier 1: one thread per queued segment, grid-stride, with a launch-sized slice of global scratch (4096 trace words, 8-word band): the
@@ -1097,21 +1102,26 @@ __global__ void __launch_bounds__(128) k_ecb_seg_g(EcCigArgs A)
 	EcBCtx C; C.gout = 0; C.gcap = 0; C.e_rate = A.e_rate; C.w_l = A.w_l; C.do_gaps = 0; C.no_myers = 0; C.pool = 0; C.pool_used = 0; C.pool_cap = 0; C.aw = 0; C.awcap = 0; C.wc = 0; C.wccap = 0;
 	C.ez.path = A.path + tid * A.path_words; C.ez.pcap = A.path_words; C.ez.vec = A.vec + tid * 11 * (uint64_t)A.vstride; C.ez.vstride = A.vstride; C.ez.warp = 0; C.ez.cig = A.cig_tmp + tid * (uint64_t)A.cig_words; C.ez.ccap = A.cig_words;
 	const uint64_t n_work = (uint64_t)*A.q_in_n;
-	for (uint64_t wk = tid; wk < n_work; wk += nthr) {
-		const uint64_t sidx = A.q_in[wk];
-		uint64_t lo = 0, hi = A.n_ov;
-		while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
-		const uint64_t o = lo; const hb_aln_t a = A.aln[o]; const EcPrep pr = A.prep[o];
-		OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a; uint64_t dpo;
-		ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
-		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+	for (uint64_t wk0 = tid - (threadIdx.x & 31); wk0 < n_work; wk0 += nthr) { // warp-uniform trip count (see k_ecb_seg)
+		const uint64_t wk = wk0 + (threadIdx.x & 31); const bool live = wk < n_work;
+		uint64_t sidx = 0, o = 0; EcPrep pr; pr.ch_n = 0; OvDesc d; hb_chain_t c; EcZ z; hb_hit_t *ch_a = 0; uint64_t dpo;
+		if (live) {
+			sidx = A.q_in[wk];
+			uint64_t lo = 0, hi = A.n_ov;
+			while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (A.seg_off[mid] <= sidx) lo = mid; else hi = mid; }
+			o = lo; const hb_aln_t a = A.aln[o]; pr = A.prep[o];
+			ecb_overlap_view(A, o, a, d, c, z, ch_a, dpo);
+			C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
+		}
 		C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
 		int64_t uq[2], ut[2], um;
-		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
-		if (C.bad) atomicOr(A.err, 32);
-		EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
-		if (sg.status == 4 && A.q_out) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; }
-		A.segs[sidx] = sg;
+		const int st = hb_ecb_segment_t<true>(C, z, ch_a, pr.ch_n, (int64_t)(sidx - (live ? A.seg_off[o] : 0)), uq, ut, &um, live);
+		if (live) {
+			if (C.bad) atomicOr(A.err, 32);
+			EcSeg sg; hb_seg_store(C, st, uq, ut, um, &sg, A.spool, A.spool_used, A.spool_cap);
+			if (sg.status == 4 && A.q_out) { const uint32_t qi = atomicAdd(A.q_out_n, 1u); A.q_out[qi] = (uint32_t)sidx; }
+			A.segs[sidx] = sg;
+		}
 	}
 }
 // segment alignment, warp tiers: one WARP per queued segment, handed out dynamically (A.work).  Every lane runs the reference's scalar logic of the

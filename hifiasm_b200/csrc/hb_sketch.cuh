@@ -152,80 +152,6 @@ HB_HD void sk_select_mz_h(SketchOut &o, int32_t len, int32_t sample_dist, int32_
 	o.n = (uint32_t)n;
 }
 
-// Sketch read `rid`; rx/rm/rl = this thread's candidate ring (w slots).
-// rid_out is written into ha_mz1_t.rid of the results (sketch.cpp:577).
-HB_HD void hb_sketch_read(const DevReads &R, const DevFt &ft, const SketchPar &P, uint64_t rid, uint32_t rid_out,
-                          RingRef<uint64_t> rx, RingRef<uint64_t> rm, RingRef<uint32_t> rl, SketchOut &o)
-{
-	const int32_t w = P.w, k = P.k, len = (int32_t)R.len[rid];
-	const uint64_t shift1 = k - 1, mask = (1ULL << k) - 1;
-	const uint8_t *seq = R.packed + R.off[rid];
-	const uint64_t *seq64 = (const uint64_t *)seq;
-	uint64_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, minx = ~0ULL, minm = SK_DUMMY_META, word = 0;
-	int32_t i, j, l = 0, tl = 0, bp = 0, min_bp = 0, span = 0, qf = 0, qc = 0;
-	uint32_t min_l = 0xffffffffu;
-	uint64_t ni = R.noff ? R.noff[rid] : 0, ne = R.noff ? R.noff[rid + 1] : 0;
-	int32_t next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX;
-	uint8_t q[64]; // run lengths of the last k HPC symbols (tiny_queue_t, htab.h:39-57); capped at 255: spans >= 256 are never candidates
-	o.n = 0; o.ovf = 0;
-	for (j = 0; j < w; j++) { rx[j] = ~0ULL; rm[j] = ~0ULL; rl[j] = 0; } // memset 0xff, sketch.cpp:470
-	int32_t wbase = -1; // index of the 64-bit word (32 bases) held in `word`
-#define SK_BASE(ii) ((int)(((((ii) >> 5) != wbase ? (wbase = (ii) >> 5, word = seq64[wbase]) : word) >> ((((ii) & 31) >> 2 << 3) + ((3 - ((ii) & 3)) << 1))) & 3))
-	for (i = 0; i < len; ++i) {
-		int c = SK_BASE(i);
-		uint64_t ix = ~0ULL, im = SK_DUMMY_META;
-		if (i == next_n) { c = 4; ++ni; next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX; }
-		if (c < 4) {
-			int z;
-			if (P.is_hpc) { // sketch.cpp:480-492
-				int32_t run = 1;
-				while (i + run < len && i + run != next_n && SK_BASE(i + run) == c) ++run;
-				i += run - 1;
-				q[(qc++ + qf) & 0x3f] = (uint8_t)(run > 255 ? 255 : run);
-				span += run > 255 ? 255 : run;
-				if (qc > k) { span -= q[qf++]; qf &= 0x3f; --qc; }
-			} else span = l + 1 < k ? l + 1 : k;
-			pl0 = (pl0 << 1 | (uint64_t)(c & 1)) & mask;
-			pl1 = (pl1 << 1 | (uint64_t)(c >> 1)) & mask;
-			pl2 = pl2 >> 1 | (uint64_t)(1 - (c & 1)) << shift1;
-			pl3 = pl3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift1;
-			if (pl1 == pl3) continue; // sketch.cpp:502
-			z = pl1 < pl3 ? 0 : 1;
-			++l; ++tl;
-			if (l >= k && span < 256) {
-				uint64_t y = z ? hb_hash64(pl2) + hb_hash64(pl3) : hb_hash64(pl0) + hb_hash64(pl1);
-				int32_t cnt = hb_ft_lookup(ft, y);
-				if (!(cnt >= 1 << 28)) { ix = y; im = (uint64_t)(uint32_t)cnt | (uint64_t)i << 28 | (uint64_t)z << 55 | (uint64_t)span << 56; }
-			}
-		} else { l = 0; qc = qf = 0; span = 0; }
-		rx[bp] = ix; rm[bp] = im; rl[bp] = (uint32_t)l;
-#define SK_POS(m) ((uint32_t)(((m) >> 28) & 0x7ffffffULL))
-		if (l == w + k - 1 && minx != ~0ULL) { // sketch.cpp:523-534
-			for (j = bp + 1; j < w; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(bm) != SK_POS(minm)) o.push(bx, bm, rl[j]); }
-			for (j = 0; j < bp; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(bm) != SK_POS(minm)) o.push(bx, bm, rl[j]); }
-		}
-		if (sk_cmp(minx, minm, ix, im) >= 0) { // sketch.cpp:543-547
-			if (l >= w + k && minx != ~0ULL) o.push(minx, minm, min_l);
-			minx = ix; minm = im; min_bp = bp; min_l = (uint32_t)l;
-		} else if (bp == min_bp) { // sketch.cpp:548-568
-			if (l >= w + k - 1 && minx != ~0ULL) o.push(minx, minm, min_l);
-			minx = ~0ULL; minm = SK_DUMMY_META;
-			for (j = bp + 1; j < w; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) >= 0) { minx = bx; minm = bm; min_bp = j; min_l = rl[j]; } }
-			for (j = 0; j <= bp; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) >= 0) { minx = bx; minm = bm; min_bp = j; min_l = rl[j]; } }
-			if (l >= w + k - 1 && minx != ~0ULL) {
-				for (j = bp + 1; j < w; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(minm) != SK_POS(bm)) o.push(bx, bm, rl[j]); }
-				for (j = 0; j <= bp; ++j) { uint64_t bx = rx[j], bm = rm[j]; if (sk_cmp(minx, minm, bx, bm) == 0 && SK_POS(minm) != SK_POS(bm)) o.push(bx, bm, rl[j]); }
-			}
-		}
-		if (++bp == w) bp = 0;
-	}
-	if (minx != ~0ULL) o.push(minx, minm, min_l);
-	if (o.ovf) return;
-	if (P.sample_dist > w && ft.mask != 0) sk_select_mz_h(o, len, P.sample_dist, P.rewin, k, tl); // sketch.cpp:575 (a no-op without filter-table hits)
-	for (i = 0; i < (int32_t)o.n; ++i) o.mz[i].info = (o.mz[i].info & ~0xfffffffULL) | (rid_out & 0xfffffff);
-#undef SK_BASE
-#undef SK_POS
-}
 
 // ===========================================================================
 // Two-stage sketch (the production path): the sequential scan of a read only

@@ -34,48 +34,37 @@ struct TmpBufs {
 #define NEED(ptr) do { if (!(ptr)) { hb_set_err(ctx, HB_E_NOMEM, "device allocation failed at %s:%d", __FILE__, __LINE__); return HB_E_NOMEM; } } while (0)
 static inline unsigned nblk(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
-// ---- ha_analyze_count (hist.cpp:74-157), host side on the 4096-bin histogram
-static int adj_peak_hom(int m_peak_hom, int max_i, int max2_i, int max3_i, int *peak_het)
-{ // adj_m_peak_hom, hist.cpp:46-72
-	int64_t mm[3], d, min_i = -1, min_d = -1, i;
-	mm[0] = max2_i; mm[1] = max_i; mm[2] = max3_i;
-	for (i = 0; i < 3; i++) {
-		if (mm[i] <= 0) continue;
-		d = mm[i] >= m_peak_hom ? mm[i] - m_peak_hom : m_peak_hom - mm[i];
-		if (min_d == -1 || min_d > d || (min_d == d && i == 1)) min_d = d, min_i = i;
-	}
-	if (min_i < 0) return m_peak_hom;
-	if (mm[min_i] < m_peak_hom) { d = m_peak_hom - mm[min_i]; if (d >= mm[min_i] * 0.51) { *peak_het = (int)mm[min_i]; return m_peak_hom; } }
-	for (i = min_i - 1; i >= 0; i--) { if (mm[i] <= 0) continue; *peak_het = (int)mm[i]; break; }
-	return (int)mm[min_i];
-}
-static int analyze_count(int n_cnt, int start_cnt, int m_peak_hom, const int64_t *cnt, int *peak_het)
+// ---- coverage peaks of the k-mer count histogram (host side, 4096 bins) ----
+// What ha_analyze_count (hist.cpp:74-157) decides when no homozygous peak is imposed (both call sites pass -1, htab.cpp:1155, 1252):
+//   * the histogram falls from the error k-mers to a trough; the highest bin right of the trough is the main peak;
+//   * a lower local maximum on one side is a second peak if it reaches 5 % of the main peak and the valley between the two drops below 95 % of it
+//     (on the right also: not beyond 2.5 x the main peak's count);
+//   * a right-hand second peak makes the main peak the heterozygous one; otherwise a left-hand one is the heterozygous peak.
+// Ties follow the reference's scan directions: the main peak is the first bin holding the maximum, the left candidate the one nearest to the main peak,
+// the right candidate the one nearest to it as well.
+struct HistPeaks { int hom, het; };
+static HistPeaks hist_peaks(const int64_t *h, int n_bins, int first_bin)
 {
-	int i, start, low_i, max_i, max2_i, max3_i; int64_t max, max2, max3, min;
-	*peak_het = -1;
-	start = cnt[1] > 0 ? 1 : 2;
-	low_i = start > start_cnt ? start : start_cnt;
-	for (i = low_i + 1; i < n_cnt; ++i) if (cnt[i] > cnt[i - 1]) break;
-	low_i = i - 1;
-	if (low_i == n_cnt - 1) return -1;
-	max_i = low_i + 1, max = cnt[max_i];
-	for (i = low_i + 1; i < n_cnt; ++i) if (cnt[i] > max) max = cnt[i], max_i = i;
-	max2 = -1; max2_i = -1;
-	for (i = max_i - 1; i > low_i; --i) if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1]) if (cnt[i] > max2) max2 = cnt[i], max2_i = i;
-	if (max2_i > low_i && max2_i < max_i) {
-		for (i = max2_i + 1, min = max; i < max_i; ++i) if (cnt[i] < min) min = cnt[i];
-		if (max2 < max * 0.05 || min > max2 * 0.95) max2 = -1, max2_i = -1;
-	}
-	max3 = -1; max3_i = -1;
-	for (i = max_i + 1; i < n_cnt - 1; ++i) if (cnt[i] >= cnt[i - 1] && cnt[i] >= cnt[i + 1]) if (cnt[i] > max3) max3 = cnt[i], max3_i = i;
-	if (max3_i > max_i) {
-		for (i = max_i + 1, min = max; i < max3_i; ++i) if (cnt[i] < min) min = cnt[i];
-		if (max3 < max * 0.05 || min > max3 * 0.95 || max3_i > max_i * 2.5) max3 = -1, max3_i = -1;
-	}
-	if (m_peak_hom > 0) return adj_peak_hom(m_peak_hom, max_i, max2_i, max3_i, peak_het);
-	if (max3_i > 0) { *peak_het = max_i; return max3_i; }
-	if (max2_i > 0) *peak_het = max2_i;
-	return max_i;
+	HistPeaks r = { -1, -1 };
+	int trough = std::max(h[1] > 0 ? 1 : 2, first_bin);
+	while (trough + 1 < n_bins && h[trough + 1] <= h[trough]) trough++;
+	if (trough == n_bins - 1) return r; // never rises again: no peak
+	int top = trough + 1;
+	for (int i = top + 1; i < n_bins; i++) if (h[i] > h[top]) top = i;
+	const int64_t top_v = h[top];
+	auto is_local_max = [&](int i) { return h[i] >= h[i - 1] && h[i] >= h[i + 1]; };
+	auto separated = [&](int peak, int from, int to) { // valley strictly between the two bins, against the candidate's height
+		int64_t valley = top_v; for (int i = from + 1; i < to; i++) valley = std::min(valley, h[i]);
+		return !((double)h[peak] < (double)top_v * 0.05 || (double)valley > (double)h[peak] * 0.95);
+	};
+	int left = -1, right = -1;
+	for (int i = top - 1; i > trough; i--) if (is_local_max(i) && (left < 0 || h[i] > h[left])) left = i;
+	if (left >= 0 && !separated(left, left, top)) left = -1;
+	for (int i = top + 1; i < n_bins - 1; i++) if (is_local_max(i) && (right < 0 || h[i] > h[right])) right = i;
+	if (right >= 0 && (!separated(right, top, right) || (double)right > (double)top * 2.5)) right = -1;
+	if (right > 0) { r.hom = right; r.het = top; }
+	else { r.hom = top; if (left > 0) r.het = left; }
+	return r;
 }
 
 // ---- kernels ---------------------------------------------------------------
@@ -285,7 +274,7 @@ extern "C" int hb_ft_gen(hb_ctx_t *ctx, int *hom_cov)
 		tb.drop(d_sk); tb.drop(d_sk2); tb.drop(d_ri); tb.drop(d_ri2); tb.drop((void *)d_ord);
 		rc = hist_of(ctx, tb, d_head, n_runs, n_real, d_fp, hist); if (rc) return rc;
 	}
-	int peak_het, peak_hom = analyze_count(4096, ctx->opt.min_hist_kmer_cnt, -1, hist, &peak_het); // htab.cpp:1155-1161
+	const HistPeaks pk = hist_peaks(hist, 4096, ctx->opt.min_hist_kmer_cnt); const int peak_het = pk.het, peak_hom = pk.hom; // htab.cpp:1155-1161
 	if (hom_cov) *hom_cov = peak_hom;
 	int cutoff = (int)(peak_hom * ctx->opt.high_factor); if (cutoff > YAK_MAX_COUNT - 1) cutoff = YAK_MAX_COUNT - 1;
 	int max_cnt = ctx->opt.max_kmer_cnt; if (max_cnt > YAK_MAX_COUNT - 1) max_cnt = YAK_MAX_COUNT - 1;
@@ -346,11 +335,11 @@ extern "C" int hb_pt_gen(hb_ctx_t *ctx, int *hom_cov, int *het_cov)
 	tb.drop(tmp); tb.drop(dk.Alternate()); tb.drop(dv.Alternate());
 	uint64_t *d_keys = dk.Current(), *d_infos = dv.Current(), *d_head = 0, n_runs = 0; int64_t hist[4096];
 	rc = runs_of(ctx, tb, d_keys, n, &d_head, &n_runs, hist); if (rc) return rc;
-	int peak_het, peak_hom = analyze_count(4096, ctx->opt.min_hist_kmer_cnt, -1, hist, &peak_het); // htab.cpp:1252-1257
+	const HistPeaks pk = hist_peaks(hist, 4096, ctx->opt.min_hist_kmer_cnt); const int peak_het = pk.het, peak_hom = pk.hom; // htab.cpp:1252-1257
 	if (hom_cov) *hom_cov = peak_hom;
 	if (het_cov) *het_cov = peak_het;
 	int lo = 2, hi = YAK_MAX_COUNT - 1; // htab.cpp:1259-1270
-	if (ctx->ft_n == 0 && ctx->d_ft_key == 0 && getenv("HB_NO_KMER_FLT")) { hi = (int)(peak_hom * ctx->opt.high_factor); if (hi > YAK_MAX_COUNT - 1) hi = YAK_MAX_COUNT - 1; }
+	if (ctx->ft_n == 0 && ctx->d_ft_key == 0 && ctx->no_kmer_flt) { /* HA_F_NO_KMER_FLT without a filter table (htab.cpp:1261) */ hi = (int)(peak_hom * ctx->opt.high_factor); if (hi > YAK_MAX_COUNT - 1) hi = YAK_MAX_COUNT - 1; }
 	uint64_t n_keys = 0, n_pos = 0;
 	for (int i = lo; i <= hi; i++) { n_keys += (uint64_t)hist[i]; n_pos += (uint64_t)hist[i] * i; }
 	uint64_t cap = 64; while (cap < 2 * n_keys) cap <<= 1;

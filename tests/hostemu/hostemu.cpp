@@ -20,6 +20,7 @@
 #include "../../hifiasm_b200/csrc/hb_ecround.cuh"
 #include "../../hifiasm_b200/csrc/hb_eccns.cuh"
 #include "../../hifiasm_b200/csrc/hb_eccns_full.cuh"
+#include "seq_ref.h"
 
 struct EmuReads { DevReads d; std::vector<uint8_t> packed; std::vector<uint64_t> off, noff; std::vector<uint32_t> len, npos; };
 struct EmuFt { DevFt d; std::vector<uint64_t> key; std::vector<int32_t> val; };
