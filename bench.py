@@ -276,6 +276,15 @@ def _main():
                 "algorithmic_bytes_per_launch": (alg / launches) if launches else None, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes of all its launches in a step (DESIGN.md §4) / their summed CUDA-event time; the kernel is latency / integer-issue bound, not byte bound (SURVEY.md §8d)",
                 "kernels_ms_per_step": {k: round(v, 2) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+    lanes = int(os.environ.get("HB_LANES", "2"))
+    roofline["lanes"] = lanes
+    if lanes > 1:
+        roofline["note"] += "; the batches of a pass run on %d lanes (streams), so a kernel's event time includes what ran beside it and the per-kernel times add up to more than the step: HB_LANES=1 gives exclusive times" % lanes
+    # the one kernel of the stage that IS byte bound (the seed-hash probe): its own line, from the same run
+    if "k_expand" in per_step and per_step["k_expand"] > 0:
+        xb = algorithmic_bytes("k_expand", counters, bases)
+        roofline["byte_bound_kernel"] = {"kernel": "k_expand", "kernel_ms_per_step": round(per_step["k_expand"], 2), "achieved": xb / (per_step["k_expand"] / 1e3) / 1e9, "unit": "GB/s",
+                                         "frac": xb / (per_step["k_expand"] / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": xb / max(1, kms["k_expand"][0] // args.steps)}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         runs, why = run_reference_stage(REF_SAMPLE_MB, threads, reps=1)
@@ -288,7 +297,7 @@ def _main():
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
            "config": {"workload": workload_name(GENOME_MB), "reads": n, "bases": bases, "parallelism": "query reads of every pass sharded x%d; reads + index replicated; one all-gather of edit scripts + lists per EC round" % world,
                       "l2": "inputs larger than L2 (packed reads %.2f GB + index + %.0f M anchors per pass)" % (h_flat.nbytes / 1e9, counters["anchors"] / 4e6),
-                      "hom_cov": hom, "corrected_bases_per_round": corrected, "overlaps_src": n_src, "overlaps_rev": n_rev, "result_digest": digest,
+                      "lanes": int(os.environ.get("HB_LANES", "2")), "hom_cov": hom, "corrected_bases_per_round": corrected, "overlaps_src": n_src, "overlaps_rev": n_rev, "result_digest": digest,
                       "step_device_ms": step_ms, "last_step_host_ms": {k: (round(v, 1) if not isinstance(v, list) else [round(x, 1) for x in v]) for k, v in last_ms.items()},
                       "upload_s_per_step": round(up_s / args.steps, 3), "exchange_ms_per_step": round(ex_ms / args.steps, 1), "setup_s": {"generate": round(t_gen, 1)}, "counters": counters},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in kms.values())), "roofline": roofline, "cpu_baseline": cpu}

@@ -26,6 +26,18 @@ struct RdView {
 		const int b = hb_base(p, fp); return rev ? 3 - b : b;
 	}
 };
+// the same through a cursor that keeps the 64-bit word (32 bases) it last touched: the aligner walks both reads base by base, in one direction
+// (a read's packed slot is 32-byte aligned and padded, so the word holding its last base can be loaded whole)
+struct RdCur { uint64_t w; uint32_t idx; };
+HB_HD int hb_rd_at(const RdView &v, RdCur &c, int64_t j)
+{
+	const uint32_t fp = v.rev ? (uint32_t)(v.len - 1 - j) : (uint32_t)j;
+	if (v.nn) { uint32_t lo = 0, hi = v.nn; while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (v.npos[mid] < fp) lo = mid + 1; else hi = mid; } if (lo < v.nn && v.npos[lo] == fp) return 4; }
+	const uint32_t wi = fp >> 5;
+	if (wi != c.idx) { c.w = ((const uint64_t *)v.p)[wi]; c.idx = wi; }
+	const int b = (int)((c.w >> ((((fp & 31) >> 2) << 3) + ((3 - (fp & 3)) << 1))) & 3);
+	return v.rev ? 3 - b : b;
+}
 HB_HD RdView hb_rd_view(const DevReads &R, uint64_t id, uint32_t rev)
 {
 	RdView v; v.p = R.packed + R.off[id]; v.npos = R.npos + R.noff[id]; v.nn = (uint32_t)(R.noff[id + 1] - R.noff[id]); v.len = R.len[id]; v.rev = rev;
@@ -580,8 +592,9 @@ HB_HD_NI void hb_mw_align(int mode, const RdView &T, int64_t ps0, int32_t pn, co
 	ez.compact = nword == 1 ? (pk21 ? 3 : 1) : 0;
 	if (nword == 1) { // the band fits one word (thre <= 31: the bulk of the segments): same algorithm with the vectors in registers
 		uint64_t P0 = 0, P1 = 0, P2 = 0, P3 = 0, VP, VN, X, D0 = 0, HN = 0, HP = 0;
-		auto pch1 = [&](int32_t j) -> int { return T.at(ps0 + (mode == 2 ? pidx - j : j)); };
-		auto tch1 = [&](int32_t j) -> int { return Q.at(qs0 + (mode == 2 ? tidx - j : j)); };
+		RdCur curT, curQ; curT.idx = curQ.idx = 0xffffffffu; curT.w = curQ.w = 0;
+		auto pch1 = [&](int32_t j) -> int { return hb_rd_at(T, curT, ps0 + (mode == 2 ? pidx - j : j)); };
+		auto tch1 = [&](int32_t j) -> int { return hb_rd_at(Q, curQ, qs0 + (mode == 2 ? tidx - j : j)); };
 		auto peq_or = [&](int cc, uint64_t m) { if (cc == 0) P0 |= m; else if (cc == 1) P1 |= m; else if (cc == 2) P2 |= m; else if (cc == 3) P3 |= m; };
 		if (mode == 3) { VP = 0; VN = (1ULL << abs_diag) - 1; bd = ((thre << 1) + 1) - abs_diag; bd = bd <= pn ? bd : pn; i_bd = abs_diag; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = (thre << 1) - abs_diag; err = abs_diag; }
 		else { bd = thre + 1; bd = bd <= pn ? bd : pn; i_bd = thre; for (i = 0; i < bd; i++, i_bd++) peq_or(pch1(i), 1ULL << i_bd); i_bd = thre; err = thre; VN = (1ULL << thre) - 1; VP = ((1ULL << ((thre << 1) + 1)) - 1) ^ VN; }
