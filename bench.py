@@ -93,9 +93,10 @@ def run_reference_stage(genome_mb, threads, reps=1):
     with tempfile.TemporaryDirectory() as td:
         fa = os.path.join(td, "reads.fa")
         rs = simgen.make(genome_mb, COV, seed=SEED, fasta=fa)
-        for _ in range(reps):
+        for rep in range(reps):
             t = time.time()
-            p = subprocess.run([ref, "-o", os.path.join(td, "ref"), "-t%d" % threads, "-f0", "--bin-only", fa], capture_output=True, text=True)
+            # (a prefix of its own per repetition: hifiasm reloads <prefix>.ec.bin / .ovlp.*.bin of an earlier run instead of computing the stage again)
+            p = subprocess.run([ref, "-o", os.path.join(td, "ref%d" % rep), "-t%d" % threads, "-f0", "--bin-only", fa], capture_output=True, text=True)
             wall = time.time() - t
             m = re.search(r"\[M::ha_assemble::([0-9.]+)\*[0-9.]+@[0-9.]+GB\] ==> found overlaps for the final round", p.stderr)
             if p.returncode != 0 or not m:
@@ -276,7 +277,7 @@ def _main():
                 "algorithmic_bytes_per_launch": (alg / launches) if launches else None, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes of all its launches in a step (DESIGN.md §4) / their summed CUDA-event time; the kernel is latency / integer-issue bound, not byte bound (SURVEY.md §8d)",
                 "kernels_ms_per_step": {k: round(v, 2) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
-    lanes = int(os.environ.get("HB_LANES", "2"))
+    lanes = int(os.environ.get("HB_LANES", "3"))
     roofline["lanes"] = lanes
     if lanes > 1:
         roofline["note"] += "; the batches of a pass run on %d lanes (streams), so a kernel's event time includes what ran beside it and the per-kernel times add up to more than the step: HB_LANES=1 gives exclusive times" % lanes
@@ -297,7 +298,7 @@ def _main():
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
            "config": {"workload": workload_name(GENOME_MB), "reads": n, "bases": bases, "parallelism": "query reads of every pass sharded x%d; reads + index replicated; one all-gather of edit scripts + lists per EC round" % world,
                       "l2": "inputs larger than L2 (packed reads %.2f GB + index + %.0f M anchors per pass)" % (h_flat.nbytes / 1e9, counters["anchors"] / 4e6),
-                      "lanes": int(os.environ.get("HB_LANES", "2")), "hom_cov": hom, "corrected_bases_per_round": corrected, "overlaps_src": n_src, "overlaps_rev": n_rev, "result_digest": digest,
+                      "lanes": int(os.environ.get("HB_LANES", "3")), "hom_cov": hom, "corrected_bases_per_round": corrected, "overlaps_src": n_src, "overlaps_rev": n_rev, "result_digest": digest,
                       "step_device_ms": step_ms, "last_step_host_ms": {k: (round(v, 1) if not isinstance(v, list) else [round(x, 1) for x in v]) for k, v in last_ms.items()},
                       "upload_s_per_step": round(up_s / args.steps, 3), "exchange_ms_per_step": round(ex_ms / args.steps, 1), "setup_s": {"generate": round(t_gen, 1)}, "counters": counters},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(v[0] for v in kms.values())), "roofline": roofline, "cpu_baseline": cpu}

@@ -181,7 +181,8 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 4096; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
 	ctx->trace = getenv("HB_TRACE") != 0; ctx->trace_ec = getenv("HB_TRACE_EC") != 0; ctx->no_kmer_flt = getenv("HB_NO_KMER_FLT") != 0;
-	ctx->n_lanes = getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 2; if (ctx->n_lanes < 1 || ctx->n_lanes > HB_MAX_LANES) ctx->n_lanes = 2; for (int i = 0; i < HB_MAX_LANES - 1; i++) ctx->lane[i] = 0;
+	ctx->d_sk_mz = 0; ctx->d_sk_off = 0; ctx->sk_reads = ctx->sk_total = ctx->sk_mz_cap = ctx->sk_off_cap = 0; ctx->sk_reuse = getenv("HB_NO_SKETCH_REUSE") == 0;
+	ctx->n_lanes = getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 3; if (ctx->n_lanes < 1 || ctx->n_lanes > HB_MAX_LANES) ctx->n_lanes = 3; for (int i = 0; i < HB_MAX_LANES - 1; i++) ctx->lane[i] = 0;
 	ctx->cns_g_nodes = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096; ctx->cns_g_arcs = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;
 	hb_prof_reset(ctx);
 	cudaFuncSetAttribute(k_post_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, POST_WARPS * POST_SMEM_PER_WARP);
@@ -210,7 +211,7 @@ extern "C" void hb_destroy(hb_ctx_t *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
 	free_reads(ctx); hb_ft_destroy(ctx); hb_pt_destroy(ctx); free_prev(ctx); free_out(ctx); cudaFree(ctx->d_scc); cudaFree(ctx->d_scc_off); cudaFree(ctx->ws); if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-	hb_stage_buf_free(ctx); hb_lane_free(ctx);
+	hb_stage_buf_free(ctx); hb_lane_free(ctx); cudaFree(ctx->d_sk_mz); cudaFree(ctx->d_sk_off);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -628,7 +629,12 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	if (nR == 0) { if (so && so->off) so->off[0] = 0; return HB_OK; }
 
 	// ---- sketch + probe for the whole range
-	DevSketch sk; rc = hb_run_sketch(ctx, r0, r1, 0, &sk); if (rc) return rc;
+	DevSketch sk;
+	if (ctx->sk_reads && ctx->sk_reads == ctx->n_reads) { // hb_pt_gen sketched these very reads with this filter table when it built the index: the pass reads that sketch
+		const uint64_t base = ctx->h_sk_off[r0]; uint64_t *d_o = ar.get<uint64_t>(nR + 2); HB_ALLOC_CHECK(ar);
+		k_rebase<<<nblk(nR + 1, 256), 256, 0, ctx->stream>>>(nR + 1, ctx->d_sk_off + r0, base, d_o);
+		sk.mz = ctx->d_sk_mz + base; sk.off = d_o; sk.total = ctx->h_sk_off[r1] - base;
+	} else { rc = hb_run_sketch(ctx, r0, r1, 0, &sk); if (rc) return rc; }
 	TRACE("sketch");
 	uint64_t *d_seeds = ar.get<uint64_t>(sk.total + 1); uint32_t *d_spre = ar.get<uint32_t>(sk.total + 1), *d_acnt = ar.zero<uint32_t>(nR + 1), *d_wtab = ar.get<uint32_t>(4096);
 	uint64_t *d_aoff = ar.get<uint64_t>(nR + 2);
@@ -661,7 +667,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 	if (mode == 0) { d_m0 = ar.zero<uint32_t>(nR + 1); d_m1 = ar.zero<uint32_t>(nR + 1); }
 	HB_ALLOC_CHECK(ar);
 
-	// ---- batches bounded by the anchor budget.  The batches are independent: with more than one lane (HB_LANES, default 2, at most 4) as many host threads take them in turn, each with
+	// ---- batches bounded by the anchor budget.  The batches are independent: with more than one lane (HB_LANES, default 3, at most 4) as many host threads take them in turn, each with
 	// its own stream and workspace (a clone of the context, lane_refresh), so that the launches of one batch whose time is set by their heaviest read (phasing, chain
 	// post-processing, the merge of step B: one wave of warps, most SMs idle behind the last one) share the device with the throughput-bound launches of the other.
 	// What a batch adds to the pass's host-side results is added in batch order (PassOrder), so the results do not depend on which lane ran what.

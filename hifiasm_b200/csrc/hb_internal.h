@@ -48,6 +48,9 @@ struct hb_ctx {
 	// cached pinned staging buffer and capacities of the read-store arrays
 	uint8_t *h_stage; uint64_t h_stage_cap, packed_cap, reads_cap, npos_cap;
 	void *stage_buf; // hb_stage_run's host-side lists (stage.cu)
+	// the sketch of the resident reads that built the position index (hb_pt_gen), kept for the pass that follows: same reads, same filter table, same
+	// parameters, so the pass reads its minimizers instead of sketching every read a second time.  Invalid (sk_reads = 0) whenever the index is.
+	hb_mz_t *d_sk_mz; uint64_t *d_sk_off; uint64_t sk_reads, sk_total, sk_mz_cap, sk_off_cap; std::vector<uint64_t> h_sk_off; int sk_reuse;
 	int n_lanes; hb_ctx *lane[3]; // batches of a pass on n_lanes streams (HB_LANES, read once in hb_create; engine.cu run_batches); lane[] = the other lanes' contexts, owned
 };
 void hb_lane_free(hb_ctx *ctx);

@@ -216,6 +216,7 @@ extern "C" void hb_ft_destroy(hb_ctx_t *ctx)
 {
 	if (!ctx) return;
 	cudaFree(ctx->d_ft_key); cudaFree(ctx->d_ft_val); ctx->d_ft_key = 0; ctx->d_ft_val = 0; ctx->ft_n = ctx->ft_cap = 0;
+	ctx->sk_reads = 0; // a kept sketch was made with this filter table
 }
 extern "C" int hb_ft_size(const hb_ctx_t *ctx, uint64_t *n) { *n = ctx->ft_n; return HB_OK; }
 
@@ -310,6 +311,7 @@ extern "C" void hb_pt_destroy(hb_ctx_t *ctx)
 {
 	if (!ctx) return;
 	cudaFree(ctx->d_pt_slot); cudaFree(ctx->d_pt_pos); ctx->d_pt_slot = 0; ctx->d_pt_pos = 0; ctx->pt_keys = ctx->pt_npos = ctx->pt_cap = 0;
+	ctx->sk_reads = 0; // the kept sketch belongs to the index
 }
 extern "C" int hb_pt_stat(const hb_ctx_t *ctx, uint64_t *n_keys, uint64_t *n_pos) { *n_keys = ctx->pt_keys; *n_pos = ctx->pt_npos; return HB_OK; }
 
@@ -321,6 +323,19 @@ extern "C" int hb_pt_gen(hb_ctx_t *ctx, int *hom_cov, int *het_cov)
 	TmpBufs tb(ctx); DevSketch sk; int rc = hb_run_sketch_retry(ctx, 0, ctx->n_reads, &sk); if (rc) return rc;
 	HB_CUDA(cudaStreamSynchronize(ctx->stream));
 	const uint64_t n = sk.total;
+	if (ctx->sk_reuse) { // keep the minimizers for the pass over this index (engine.cu run_pass_impl); without room for the copy the pass simply sketches again
+		const uint64_t nr = ctx->n_reads; bool ok = true;
+		if (ctx->sk_mz_cap < n + 2) { cudaFree(ctx->d_sk_mz); ctx->d_sk_mz = 0; ctx->sk_mz_cap = 0; if (cudaMalloc((void **)&ctx->d_sk_mz, (n + 2 + (n >> 4)) * sizeof(hb_mz_t)) == cudaSuccess) ctx->sk_mz_cap = n + 2 + (n >> 4); else { cudaGetLastError(); ok = false; } }
+		if (ok && ctx->sk_off_cap < nr + 2) { cudaFree(ctx->d_sk_off); ctx->d_sk_off = 0; ctx->sk_off_cap = 0; if (cudaMalloc((void **)&ctx->d_sk_off, (nr + 2) * 8) == cudaSuccess) ctx->sk_off_cap = nr + 2; else { cudaGetLastError(); ok = false; } }
+		if (ok) {
+			ctx->h_sk_off.resize(nr + 1);
+			HB_CUDA(cudaMemcpyAsync(ctx->d_sk_mz, sk.mz, (n + 2) * sizeof(hb_mz_t), cudaMemcpyDeviceToDevice, ctx->stream)); // (+ the two pad entries behind the array)
+			HB_CUDA(cudaMemcpyAsync(ctx->d_sk_off, sk.off, (nr + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+			HB_CUDA(cudaMemcpyAsync(ctx->h_sk_off.data(), sk.off, (nr + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			ctx->sk_total = n; ctx->sk_reads = nr;
+		}
+	}
 	// split {x,info} into key / value arrays and sort by key (stable LSD radix)
 	uint64_t *d_k0 = tb.get<uint64_t>(n + 1), *d_k1 = tb.get<uint64_t>(n + 1), *d_v0 = tb.get<uint64_t>(n + 1), *d_v1 = tb.get<uint64_t>(n + 1);
 	NEED(d_k0); NEED(d_k1); NEED(d_v0); NEED(d_v1);

@@ -54,6 +54,8 @@ def test_whole_stage_files_equal_reference_binary_at_scale(ref_run, monkeypatch,
         monkeypatch.setenv("HB_ANCHOR_BUDGET", budget)
     if lanes:
         monkeypatch.setenv("HB_LANES", lanes)
+    if lanes == "1":
+        monkeypatch.setenv("HB_NO_SKETCH_REUSE", "1")        # (this variant also sketches the query reads again instead of reading the index build's sketch)
     out = "gpu_%s_%s" % (budget, lanes)
     info = stage.run_stage(fa, os.path.join(td, out))
     assert info["reads"] == rs.n and info["bases"] == rs.bases
