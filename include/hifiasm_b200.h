@@ -89,8 +89,10 @@ int hb_reads_upload_ptrs(hb_ctx_t *ctx, uint64_t n_reads, const uint64_t *read_l
                          uint8_t *const *read_sperate, uint64_t *const *N_site);
 
 /* ---- index: ha_ft_gen / ha_pt_gen (htab.h:77,83; htab.cpp:1136,1232) -------
- * hb_ft_gen counts all (HPC) k-mers of the resident reads exactly (-f0
- * semantics) and keeps those occurring >= high_factor*peak_hom times.
+ * hb_ft_gen counts all (HPC) k-mers of the resident reads — exactly when
+ * opt.bf_shift = 0 (hifiasm -f0, the default of hb_opt_init), behind a Bloom
+ * filter of 2^bf_shift bits like hifiasm -f<bf_shift> otherwise (its own default
+ * is 37) — and keeps those occurring >= high_factor*peak_hom times.
  * hb_pt_gen sketches every read, counts minimizers, derives hom/het peaks
  * (ha_analyze_count, hist.cpp:74) and builds the position index in HBM.      */
 int hb_ft_gen(hb_ctx_t *ctx, int *hom_cov);
