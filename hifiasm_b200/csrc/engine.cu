@@ -841,7 +841,7 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 					HB_ALLOC_CHECK(ba);
 					G.n_seg = n_seg; G.segs = d_segs;
 					// ---- segments: tier 0 (private scratch) -> queue -> tier 1 (16 K trace words) -> queue -> tier 2 (the largest alignment the reference allows)
-					uint64_t spool_cap = n_seg / 2 + 65536, spool_used = 0; uint16_t *d_spool = 0; uint32_t h_q[6] = { 0, 0, 0, 0, 0, 0 };
+					uint64_t spool_cap = n_seg / 2 + 65536, spool_used = 0; uint16_t *d_spool = 0; uint32_t h_q[5] = { 0, 0, 0, 0, 0 };
 					for (int attempt = 0;; attempt++) {
 						d_spool = ba.get<uint16_t>(spool_cap); HB_ALLOC_CHECK(ba);
 						HB_CUDA(cudaMemsetAsync(d_spused, 0, 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_qn, 0, 32, ctx->stream));
@@ -853,43 +853,40 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 							if (n_seg) hb_k_ecb(HB_K_ECB_SEG_FAST, nblk(n_seg, 128), 128, ctx->stream, G);
 						}
 						HB_CUDA(cudaGetLastError());
-						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 24, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+						HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 						G.q_key = 0;
 						if (h_q[0]) { // the queue ordered by segment length (12-bit key): the 32 segments of a warp of tier 0 need about the same number of columns
 							Arena sa(ctx);
 							if ((rc = hb_sort_pairs_u32(ctx, d_qkey, d_q2, d_q1, h_q[0], 12))) return rc;
 						}
-						// alignment tiers 0..4; a segment that overflows one tier queues for the next (queues ping-pong between two arrays):
-						//   0  thread / segment, private scratch (local memory)
-						//   1  thread / segment, 4096 trace words of global scratch, 8-word band: the few-word bands that only outgrew the private trace
-						//   2  thread / segment, 16 x that, fewer threads: kilobase segments with a 2..8-word band (a repeat copy without anchors, ~1 % diverged) —
-						//      the warp form would keep 2..8 of its 32 lanes busy on them
-						//   3  WARP / segment (k_ecb_seg_w, the band's words over the lanes), 64 x tier 1's trace words
-						//   4  WARP / segment with the longest alignment the reference attempts (HB_MAX_SIN_L columns x 64 band words x 3 trace words)
-						const struct { int kind; uint64_t pw; int32_t cw; unsigned units; const char *name; } TIER[5] = {
-							{ 0, 0, 0, 0, "k_ecb_seg" }, { 1, path_words1, 256, (unsigned)ctx->sm_count * 8 * 128, "k_ecb_seg_tier1" }, { 1, path_words1 * 16, 2048, (unsigned)ctx->sm_count * 64, "k_ecb_seg_tier1b" },
-							{ 2, path_words1 * 64, 8192, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier2" }, { 2, (uint64_t)HB_MW_MAXW * (2 + 3 * (uint64_t)HB_MAX_SIN_L), 65535, (unsigned)ctx->sm_count * 2, "k_ecb_seg_tier3" } };
-						for (int tier = 0; tier <= 4 && h_q[tier]; tier++) {
+						// alignment tiers 0..3: {trace words, band words, cigar runs, blocks of 128 threads}; tier 0 keeps its scratch private (local memory);
+						// a segment that overflows one tier queues for the next (queues ping-pong between two arrays)
+						// tier 1: thread / segment with global scratch (trace words per thread, 8-word band); tiers 2..3 give a WARP to a segment (k_ecb_seg_w): {trace words per
+						// unit, cigar runs, units}; the largest holds the longest alignment the reference attempts (HB_MAX_SIN_L columns x 64 band words x 3 trace words)
+						const struct { uint64_t pw; int32_t cw; unsigned units; const char *name; } TIER[4] = {
+							{ 0, 0, 0, "k_ecb_seg" }, { path_words1, 256, (unsigned)ctx->sm_count * 8 * 128, "k_ecb_seg_tier1" }, { path_words1 * 64, 8192, (unsigned)ctx->sm_count * 8, "k_ecb_seg_tier2" },
+							{ (uint64_t)HB_MW_MAXW * (2 + 3 * (uint64_t)HB_MAX_SIN_L), 65535, (unsigned)ctx->sm_count * 2, "k_ecb_seg_tier3" } };
+						for (int tier = 0; tier <= 3 && h_q[tier]; tier++) {
 							Arena sa(ctx);
 							unsigned bl = (unsigned)(((uint64_t)h_q[tier] + 127) / 128);
-							if (TIER[tier].kind == 1) {
-								bl = std::max(1u, std::min(bl, std::max(1u, TIER[tier].units / 128))); const uint64_t nt = (uint64_t)bl * 128;
-								G.path = sa.get<uint64_t>(nt * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nt * 11 * 8); G.vstride = 8;
-								G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw;
+							if (tier == 1) {
+								bl = std::max(1u, std::min(bl, TIER[1].units / 128)); const uint64_t nt = (uint64_t)bl * 128;
+								G.path = sa.get<uint64_t>(nt * TIER[1].pw); G.path_words = TIER[1].pw; G.vec = sa.get<uint64_t>(nt * 11 * 8); G.vstride = 8;
+								G.cig_tmp = sa.get<uint16_t>(nt * (uint64_t)TIER[1].cw); G.cig_words = TIER[1].cw;
 								if (sa.failed) return HB_E_WS;
-							} else if (TIER[tier].kind == 2) {
+							} else if (tier > 1) {
 								const uint64_t nw = std::max<uint64_t>(4, std::min<uint64_t>(((uint64_t)h_q[tier] + 3) & ~3ull, TIER[tier].units)); bl = (unsigned)(nw / 4);
 								G.path = sa.get<uint64_t>(nw * TIER[tier].pw); G.path_words = TIER[tier].pw; G.vec = sa.get<uint64_t>(nw * 2 * (uint64_t)HB_MW_MAXW); G.vstride = HB_MW_MAXW;
 								G.cig_tmp = sa.get<uint16_t>(nw * (uint64_t)TIER[tier].cw); G.cig_words = TIER[tier].cw; G.work = sa.zero<uint32_t>(1);
 								if (sa.failed) return HB_E_WS;
 							}
-							G.q_in = (tier & 1) ? d_q2 : d_q1; G.q_in_n = d_qn + tier; G.q_out = tier < 4 ? ((tier & 1) ? d_q1 : d_q2) : 0; G.q_out_n = d_qn + tier + 1;
+							G.q_in = (tier & 1) ? d_q2 : d_q1; G.q_in_n = d_qn + tier; G.q_out = tier < 3 ? ((tier & 1) ? d_q1 : d_q2) : 0; G.q_out_n = d_qn + tier + 1;
 							{
 								ProfScope ps(ctx, TIER[tier].name);
-								hb_k_ecb(TIER[tier].kind == 0 ? HB_K_ECB_SEG : TIER[tier].kind == 1 ? HB_K_ECB_SEG_G : HB_K_ECB_SEG_W, bl, 128, ctx->stream, G);
+								hb_k_ecb(tier == 0 ? HB_K_ECB_SEG : tier == 1 ? HB_K_ECB_SEG_G : HB_K_ECB_SEG_W, bl, 128, ctx->stream, G);
 							}
 							HB_CUDA(cudaGetLastError());
-							HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 24, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+							HB_CUDA(cudaMemcpyAsync(h_q, d_qn, 20, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 						}
 						HB_CUDA(cudaMemcpyAsync(&spool_used, d_spused, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaMemcpyAsync(&h_err2, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 						HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -898,9 +895,9 @@ static int run_pass_impl(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double
 						if (attempt >= 2 || spool_used >= (1ull << 32)) { hb_set_err(ctx, HB_E_OVERFLOW, "EC base alignment: segment cigar pool"); return HB_E_OVERFLOW; }
 						spool_cap = spool_used + 65536; // the need is known now; the segments are recomputed (the chains stay refined)
 					}
-					ctx->counters[10] += h_q[4]; // segments that needed the largest scratch tier
-					if (ctx->trace_ec) fprintf(stderr, "[hb] EC base alignment: %llu overlaps, %llu segments; queued for alignment %u, past tier 0 %u, past tier 1 %u, past tier 1b %u, past tier 2 %u; segment cigar pool %llu\n",
-					                                    (unsigned long long)n_ov, (unsigned long long)n_seg, h_q[0], h_q[1], h_q[2], h_q[3], h_q[4], (unsigned long long)spool_used);
+					ctx->counters[10] += h_q[3]; // segments that needed the largest scratch tier
+					if (ctx->trace_ec) fprintf(stderr, "[hb] EC base alignment: %llu overlaps, %llu segments; queued for alignment %u, past tier 0 %u, past tier 1 %u, past tier 2 %u; segment cigar pool %llu\n",
+					                                    (unsigned long long)n_ov, (unsigned long long)n_seg, h_q[0], h_q[1], h_q[2], h_q[3], (unsigned long long)spool_used);
 					// ---- merge
 					uint64_t poolb_cap = n_seg / 4 + 16 * n_ov + 65536, poolb_used = 0; uint16_t *d_poolb = 0; unsigned int n_def = 0;
 					for (int attempt = 0;; attempt++) {
