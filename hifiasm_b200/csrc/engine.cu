@@ -180,7 +180,7 @@ extern "C" int hb_create(hb_ctx_t **out, int device, const hb_opt_t *opt)
 	ctx->ws = 0; ctx->ws_cap = ctx->ws_lo = ctx->ws_hi = ctx->ws_need = ctx->ws_virt = 0; ctx->h_stage = 0; ctx->h_stage_cap = 0; ctx->packed_cap = ctx->reads_cap = ctx->npos_cap = 0; ctx->out0_cap = ctx->out1_cap = ctx->outoff_cap = 0;
 	const char *e = getenv("HB_ANCHOR_BUDGET"); if (e) ctx->anchor_budget = strtoull(e, 0, 10);
 	ctx->ecb_path_words = getenv("HB_ECB_PATH_WORDS") ? strtoull(getenv("HB_ECB_PATH_WORDS"), 0, 10) : 4096; ctx->ecb_cig_words = getenv("HB_ECB_CIG_WORDS") ? atoi(getenv("HB_ECB_CIG_WORDS")) : 4096;
-	ctx->trace = getenv("HB_TRACE") != 0; ctx->trace_ec = getenv("HB_TRACE_EC") != 0; ctx->no_kmer_flt = getenv("HB_NO_KMER_FLT") != 0;
+	ctx->trace = getenv("HB_TRACE") != 0; ctx->trace_ec = getenv("HB_TRACE_EC") != 0; ctx->no_kmer_flt = getenv("HB_NO_KMER_FLT") != 0; ctx->ft_chunk_bits = getenv("HB_FT_CHUNK_BITS") ? atoi(getenv("HB_FT_CHUNK_BITS")) : -1; if (ctx->ft_chunk_bits > 12) ctx->ft_chunk_bits = 12;
 	ctx->d_sk_mz = 0; ctx->d_sk_off = 0; ctx->sk_reads = ctx->sk_total = ctx->sk_mz_cap = ctx->sk_off_cap = 0; ctx->sk_reuse = getenv("HB_NO_SKETCH_REUSE") == 0;
 	ctx->n_lanes = getenv("HB_LANES") ? atoi(getenv("HB_LANES")) : 3; if (ctx->n_lanes < 1 || ctx->n_lanes > HB_MAX_LANES) ctx->n_lanes = 3; for (int i = 0; i < HB_MAX_LANES - 1; i++) ctx->lane[i] = 0;
 	ctx->cns_g_nodes = getenv("HB_CNS_G_NODES") ? (uint32_t)atoi(getenv("HB_CNS_G_NODES")) : 4096; ctx->cns_g_arcs = getenv("HB_CNS_G_ARCS") ? (uint32_t)atoi(getenv("HB_CNS_G_ARCS")) : 32768;

@@ -1083,7 +1083,8 @@ HB_HD int64_t hb_cal_exz_adv(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, in
 // CONV (device, thread-per-segment kernels): every lane of the warp calls this together (`live` = the lane has a segment) and nobody leaves before the
 // end; the lanes meet (hb_wsync) in front of every aligner call, so that the aligner — a function call the compiler does not reconverge the warp for: ncu
 // showed it entered 2.8 times per warp with 11 lanes each — runs once per warp and step with every lane that needs it.
-template <bool CONV>
+// NOALN (the pre-pass kernel): stops where an alignment would start (returns 5), with no aligner code in the instantiation at all.
+template <bool CONV, bool NOALN = false>
 HB_HD int hb_seg_align_t(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_t ts, int64_t te, int64_t mode, bool live)
 {
 	MwEz &ez = C.ez; int64_t thre = 0, thre0 = -1, pthre = -1, full = 0, est = 0; const int64_t ql = qe - qs;
@@ -1103,7 +1104,9 @@ HB_HD int hb_seg_align_t(EcBCtx &C, const EcZ &z, int64_t qs, int64_t qe, int64_
 		}
 	}
 	bool want = ret < 0 && ql <= HB_MAX_SIN_L && (est >> 1) <= HB_MAX_SIN_E;
+	if (NOALN) return want ? 5 : (ret < 0 ? 0 : ret);
 	if (want && C.no_myers) { ret = 5; want = false; }
+	if (!CONV && !want) return ret < 0 ? 0 : ret;
 	// thresholds in the reference's order: the estimate, len*e_rate, twice that, 0.51*len, and the maximum for short segments; each one
 	// (but the first and the last) only if it exceeds the one before — one call site, so the aligner exists once in the kernel
 	for (int step = 0; step < 5; step++) {
@@ -1156,7 +1159,7 @@ HB_HD void hb_ecb_prep(const EcZ &zA, int64_t re_A, int64_t ql, int64_t tl, hb_h
 	}
 }
 // segment i of an overlap with refined chain ch_a[0..ch_n): returns hb_seg_align's status; unmapped coordinates in uq / ut
-template <bool CONV>
+template <bool CONV, bool NOALN = false>
 HB_HD int hb_ecb_segment_t(EcBCtx &C, const EcZ &zA, const hb_hit_t *ch_a, int64_t ch_n, int64_t i, int64_t *uq, int64_t *ut, int64_t *umode, bool live)
 {
 	int64_t q[2], t[2], mode = 3; const int64_t l = i - 1;
@@ -1171,7 +1174,7 @@ HB_HD int hb_ecb_segment_t(EcBCtx &C, const EcZ &zA, const hb_hit_t *ch_a, int64
 		if (mode == 1 || mode == 2) hb_adjust_ext_offset(&q[0], &q[1], &t[0], &t[1], C.ql, C.tl, 0, mode);
 	}
 	uq[0] = q[0]; uq[1] = q[1]; ut[0] = t[0]; ut[1] = t[1]; *umode = mode;
-	return hb_seg_align_t<CONV>(C, zA, q[0], q[1], t[0], t[1], mode, live);
+	return hb_seg_align_t<CONV, NOALN>(C, zA, q[0], q[1], t[0], t[1], mode, live);
 }
 HB_HD int hb_ecb_segment(EcBCtx &C, const EcZ &zA, const hb_hit_t *ch_a, int64_t ch_n, int64_t i, int64_t *uq, int64_t *ut, int64_t *umode) { return hb_ecb_segment_t<false>(C, zA, ch_a, ch_n, i, uq, ut, umode, true); }
 // what hc_ovlp_base_direct does with a segment's result

@@ -36,6 +36,7 @@ struct hb_ctx {
 	std::vector<ProfEntry> prof, prof_stage; uint64_t counters[12], stage_counters[12]; int in_stage; // prof_stage / stage_counters: sums over all passes of the running hb_stage_run
 	uint64_t anchor_budget; // anchors per batch
 	uint64_t ecb_path_words; int32_t ecb_cig_words; // step B: trace words per warp of alignment tier 1, cigar words of the first merge launch (HB_ECB_PATH_WORDS / HB_ECB_CIG_WORDS, read once in hb_create: the tests shrink them so that the deferral paths run)
+	int ft_chunk_bits; // HB_FT_CHUNK_BITS: exact k-mer counting in 2^bits hash ranges (-1 = as many as the free memory asks for), read once in hb_create
 	int no_kmer_flt; // HB_NO_KMER_FLT (hifiasm --no-kmer-flt), read once in hb_create
 	int trace, trace_ec; // HB_TRACE / HB_TRACE_EC (diagnostics), read once in hb_create
 	uint32_t cns_g_nodes, cns_g_arcs; // arena of the graph consensus per warp (HB_CNS_G_NODES / HB_CNS_G_ARCS, read once in hb_create: the overflow report is tested with tiny ones)

@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(128) k_ecb_seg_fast(EcCigArgs A)
 		C.ez.path = 0; C.ez.pcap = 0; C.ez.vec = 0; C.ez.vstride = 0; C.ez.warp = 0; C.ez.cig = one; C.ez.ccap = 2; C.ez.ovf = 0; C.ez.cn = 0; C.bad = 0;
 		C.q = hb_rd_view(A.R, A.r0 + d.read, 0); C.t = hb_rd_view(A.R, c.y_id, c.y_pos_strand); C.ql = C.q.len; C.tl = C.t.len;
 		int64_t uq[2], ut[2], um;
-		const int st = hb_ecb_segment(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um);
+		const int st = hb_ecb_segment_t<false, true>(C, z, ch_a, pr.ch_n, (int64_t)(sidx - A.seg_off[o]), uq, ut, &um, true);
 		if (C.bad) atomicOr(A.err, 32);
 		need = st == 5 || C.ez.ovf; // an alignment (or a > 32 k-base exact run) is needed
 		{ const int64_t l = uq[1] - uq[0]; qlen = (uint32_t)(l < 0 ? 0 : l > 4095 ? 4095 : l); } // sort key of the queue: lanes of a warp of the alignment kernel then step about the same number of columns

@@ -71,12 +71,15 @@ static HistPeaks hist_peaks(const int64_t *h, int n_bins, int first_bin)
 // every (HPC) k-mer of a read, hashed like yak_hash_long (htab.h:162-167):
 // mz1_count_seq_buf_HPC / mz1_count_seq_buf (htab.cpp:608-645).  One thread per
 // read; slot i of the read's slice is written or left as the ~0 filler.
-__global__ void k_all_kmers(DevReads R, int k, int is_hpc, const uint64_t *__restrict__ koff, uint64_t *__restrict__ out, unsigned long long *__restrict__ n_real)
+// pbits != 0: only the hashes whose top pbits bits equal pid (chunked counting: one hash range per pass); cnt_only != NULL: count them per read
+// instead of writing them (the write pass then gets koff = the scan of the counts)
+__global__ void k_all_kmers(DevReads R, int k, int is_hpc, const uint64_t *__restrict__ koff, uint64_t *__restrict__ out, unsigned long long *__restrict__ n_real,
+                            int pbits, uint64_t pid, uint32_t *__restrict__ cnt_only)
 {
 	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= R.n) return;
 	const uint8_t *seq = R.packed + R.off[r]; int32_t len = (int32_t)R.len[r], i, l = 0, last = -1;
-	uint64_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, mask = (1ULL << k) - 1, shift = k - 1, *dst = out + koff[r]; uint32_t w = 0;
+	uint64_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, mask = (1ULL << k) - 1, shift = k - 1, *dst = cnt_only ? 0 : out + koff[r]; uint32_t w = 0;
 	uint64_t ni = R.noff[r], ne = R.noff[r + 1]; int32_t next_n = ni < ne ? (int32_t)R.npos[ni] : INT32_MAX;
 	for (i = 0; i < len; ++i) {
 		int c = hb_base(seq, (uint64_t)i);
@@ -85,12 +88,16 @@ __global__ void k_all_kmers(DevReads R, int k, int is_hpc, const uint64_t *__res
 			if (!is_hpc || c != last) {
 				x0 = (x0 << 1 | (uint64_t)(c & 1)) & mask; x1 = (x1 << 1 | (uint64_t)(c >> 1)) & mask;
 				x2 = x2 >> 1 | (uint64_t)(1 - (c & 1)) << shift; x3 = x3 >> 1 | (uint64_t)(1 - (c >> 1)) << shift;
-				if (++l >= k) dst[w++] = x1 < x3 ? hb_hash64(x0) + hb_hash64(x1) : hb_hash64(x2) + hb_hash64(x3);
+				if (++l >= k) {
+					const uint64_t h = x1 < x3 ? hb_hash64(x0) + hb_hash64(x1) : hb_hash64(x2) + hb_hash64(x3);
+					if (!pbits || (h >> (64 - pbits)) == pid) { if (!cnt_only) dst[w] = h; w++; }
+				}
 				last = c;
 			}
 		} else { l = 0; last = -1; x0 = x1 = x2 = x3 = 0; }
 	}
-	if (w) atomicAdd(n_real, (unsigned long long)w);
+	if (cnt_only) cnt_only[r] = w;
+	else if (w && n_real) atomicAdd(n_real, (unsigned long long)w);
 }
 
 __global__ void k_iota(uint64_t n, uint64_t *__restrict__ out) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = i; }
@@ -211,6 +218,63 @@ static int runs_of(hb_ctx *ctx, TmpBufs &tb, const uint64_t *d_keys, uint64_t n_
 	return h_hist ? hist_of(ctx, tb, d_out, *n_runs, n_real, 0, h_hist) : HB_OK;
 }
 
+// ---- exact counting in P passes, one hash range each (row a3 at sizes whose k-mers do not fit HBM at once) --------------------------------------
+// ha_ft_gen counts in 2^12 sub-tables by the low hash bits and, above a size, in several rounds over the input (htab.cpp:1136-1169); here a pass takes the
+// k-mers whose hash starts with pid (top pbits bits): counts per read, scan, write, sort, run lengths.  The cut-off needs the histogram of ALL ranges, so the
+// passes run twice: histogram first, then the kept (key, count) pairs into the table.  Same table contents as the one-pass build (slots may differ).
+struct U32ToU64i { __host__ __device__ uint64_t operator()(uint32_t v) const { return v; } };
+static int ft_gen_chunked(hb_ctx *ctx, int pbits, int *hom_cov)
+{
+	const int k = ctx->opt.k_mer_length; const uint64_t n = ctx->n_reads, P = 1ull << pbits; int rc;
+	TmpBufs keep(ctx); uint32_t *d_cnt = keep.get<uint32_t>(n + 1); uint64_t *d_off = keep.get<uint64_t>(n + 2); NEED(d_cnt); NEED(d_off);
+	int64_t hist[4096]; memset(hist, 0, sizeof(hist));
+	int cutoff = 0, max_cnt = 0; uint64_t cap = 0;
+	for (int phase = 0; phase < 2; phase++) {
+		for (uint64_t pid = 0; pid < P; pid++) {
+			TmpBufs tb(ctx);
+			HB_CUDA(cudaMemsetAsync(d_cnt, 0, (n + 1) * 4, ctx->stream));
+			{ ProfScope ps(ctx, "k_all_kmers"); k_all_kmers<<<nblk(n, 64), 64, 0, ctx->stream>>>(hb_dev_reads(ctx), k, ctx->opt.is_hpc, 0, 0, 0, pbits, pid, d_cnt); }
+			HB_CUDA(cudaGetLastError());
+			{ size_t tbs = 0; cub::TransformInputIterator<uint64_t, U32ToU64i, const uint32_t *> in(d_cnt, U32ToU64i());
+				HB_CUDA(cub::DeviceScan::ExclusiveSum(0, tbs, in, d_off, (int64_t)(n + 1), ctx->stream));
+				void *tmp = tb.get<uint8_t>(tbs + 256); NEED(tmp);
+				HB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tbs, in, d_off, (int64_t)(n + 1), ctx->stream)); tb.drop(tmp); }
+			uint64_t np = 0; HB_CUDA(cudaMemcpyAsync(&np, d_off + n, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (!np) continue;
+			uint64_t *d_a = tb.get<uint64_t>(np + 1), *d_b = tb.get<uint64_t>(np + 1); NEED(d_a); NEED(d_b);
+			{ ProfScope ps(ctx, "k_all_kmers"); k_all_kmers<<<nblk(n, 64), 64, 0, ctx->stream>>>(hb_dev_reads(ctx), k, ctx->opt.is_hpc, d_off, d_a, 0, pbits, pid, 0); }
+			HB_CUDA(cudaGetLastError());
+			size_t tmpb = 0; cub::DoubleBuffer<uint64_t> db(d_a, d_b);
+			HB_CUDA(cub::DeviceRadixSort::SortKeys(0, tmpb, db, (int64_t)np, 0, 64 - pbits, ctx->stream)); // (the top bits are the same in the whole range)
+			void *tmp = tb.get<uint8_t>(tmpb + 256); NEED(tmp);
+			{ ProfScope ps(ctx, "sort_kmers"); HB_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmpb, db, (int64_t)np, 0, 64 - pbits, ctx->stream)); }
+			tb.drop(tmp); tb.drop(db.Alternate());
+			const uint64_t *d_keys = db.Current(); uint64_t *d_head = 0, n_runs = 0; int64_t hp[4096];
+			if ((rc = runs_of(ctx, tb, d_keys, np, &d_head, &n_runs, phase == 0 ? hp : 0))) return rc;
+			if (phase == 0) { for (int i = 0; i < 4096; i++) hist[i] += hp[i]; continue; }
+			uint32_t *d_keep = tb.get<uint32_t>(n_runs + 1); NEED(d_keep);
+			k_run_keep<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, np, cutoff < 1 ? 1 : (uint32_t)cutoff, YAK_MAX_COUNT, 0, d_keep);
+			k_ft_insert<<<nblk(n_runs, 256), 256, 0, ctx->stream>>>(n_runs, d_head, d_keys, d_keep, (uint32_t)max_cnt, cap - 1, ctx->d_ft_key, ctx->d_ft_val);
+			HB_CUDA(cudaGetLastError()); HB_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
+		if (phase == 0) {
+			const HistPeaks pk = hist_peaks(hist, 4096, ctx->opt.min_hist_kmer_cnt); // htab.cpp:1155-1161
+			if (hom_cov) *hom_cov = pk.hom;
+			cutoff = (int)(pk.hom * ctx->opt.high_factor); if (cutoff > YAK_MAX_COUNT - 1) cutoff = YAK_MAX_COUNT - 1;
+			max_cnt = ctx->opt.max_kmer_cnt; if (max_cnt > YAK_MAX_COUNT - 1) max_cnt = YAK_MAX_COUNT - 1;
+			uint64_t n_keep = 0; for (int i = cutoff < 0 ? 0 : cutoff; i <= YAK_MAX_COUNT; i++) n_keep += (uint64_t)hist[i];
+			ctx->ft_n = n_keep;
+			if (!n_keep) break;
+			cap = 64; while (cap < 2 * n_keep) cap <<= 1;
+			HB_CUDA(cudaMalloc((void **)&ctx->d_ft_key, cap * 8)); HB_CUDA(cudaMalloc((void **)&ctx->d_ft_val, cap * 4));
+			HB_CUDA(cudaMemsetAsync(ctx->d_ft_key, 0, cap * 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(ctx->d_ft_val, 0, cap * 4, ctx->stream));
+			ctx->ft_cap = cap;
+		}
+	}
+	HB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return HB_OK;
+}
+
 // ---- ha_ft_gen ---------------------------------------------------------------
 extern "C" void hb_ft_destroy(hb_ctx_t *ctx)
 {
@@ -229,11 +293,20 @@ extern "C" int hb_ft_gen(hb_ctx_t *ctx, int *hom_cov)
 	std::vector<uint64_t> koff(n + 1); uint64_t tot = 0;
 	for (uint64_t i = 0; i < n; i++) { koff[i] = tot; tot += ctx->h_rlen[i] >= (uint32_t)k ? ctx->h_rlen[i] - k + 1 : 0; }
 	koff[n] = tot;
+	if (!hb_bf_active(ctx->opt.bf_shift)) { // exact counting: one pass when the hashes fit (two arrays of them + the run heads), else 2^pbits hash ranges
+		int pbits = ctx->ft_chunk_bits;
+		if (pbits < 0) {
+			size_t fr = 0, tt = 0; cudaMemGetInfo(&fr, &tt); size_t avail = fr + ctx->ws_cap;
+			for (int i = 0; i < HB_MAX_LANES - 1; i++) if (ctx->lane[i]) avail += ctx->lane[i]->ws_cap; // (the workspaces are given back when an allocation fails)
+			for (pbits = 0; pbits < 12 && (double)(tot >> pbits) * 17.0 > (double)avail * 0.9; pbits++) {}
+		}
+		if (pbits > 0) return ft_gen_chunked(ctx, pbits, hom_cov);
+	}
 	uint64_t *d_koff = tb.get<uint64_t>(n + 1), *d_a = tb.get<uint64_t>(tot + 1), *d_b = tb.get<uint64_t>(tot + 1); unsigned long long *d_nreal = tb.get<unsigned long long>(1);
 	NEED(d_koff); NEED(d_a); NEED(d_b); NEED(d_nreal);
 	HB_CUDA(cudaMemcpyAsync(d_koff, koff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 	HB_CUDA(cudaMemsetAsync(d_a, 0xff, (tot + 1) * 8, ctx->stream)); HB_CUDA(cudaMemsetAsync(d_nreal, 0, 8, ctx->stream));
-	{ ProfScope ps(ctx, "k_all_kmers"); k_all_kmers<<<nblk(n, 64), 64, 0, ctx->stream>>>(hb_dev_reads(ctx), k, ctx->opt.is_hpc, d_koff, d_a, d_nreal); }
+	{ ProfScope ps(ctx, "k_all_kmers"); k_all_kmers<<<nblk(n, 64), 64, 0, ctx->stream>>>(hb_dev_reads(ctx), k, ctx->opt.is_hpc, d_koff, d_a, d_nreal, 0, 0, 0); }
 	HB_CUDA(cudaGetLastError());
 	unsigned long long n_real = 0; HB_CUDA(cudaMemcpyAsync(&n_real, d_nreal, 8, cudaMemcpyDeviceToHost, ctx->stream)); HB_CUDA(cudaStreamSynchronize(ctx->stream));
 	size_t tmpb = 0; cub::DoubleBuffer<uint64_t> db(d_a, d_b);
