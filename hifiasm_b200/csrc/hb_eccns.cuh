@@ -80,38 +80,6 @@ HB_HD uint32_t hb_cns_iter(CnsCtx &C, CnsIt &z, int64_t s, int64_t e, int64_t is
 	return (uint32_t)z.act_n;
 }
 
-// extract_sub_cigar_mm, ecovlp.cpp:283-360: votes of one window alignment over [s, e); ct[2 k] = column k, ct[2 k + 1] = the gap in front of it,
-// each word = matches << 32 | voters.  (k counts from the clamped s: the caller offsets ct — see hb_cns_vote.)
-HB_HD void hb_cns_sub_mm(CnsCtx &C, CnsEnt &p, int64_t s, int64_t e, uint64_t *ct)
-{
-	const hb_wl_t &w = C.ov[p.ov].w[p.wid];
-	int64_t xk = p.xoff, yk = p.yoff, ck = p.coff, os, oe, t;
-	const int64_t s0 = w.x_start, e0 = (int64_t)w.x_end + 1;
-	if (s < s0) s = s0; if (e > e0) e = e0;
-	if (s >= e) return;
-	const uint16_t *cg = C.pool + w.cidx; const int64_t cn = w.clen;
-	if (!cn) return;
-	int64_t op, ws, we, ovlp;
-	if (ck < 0 || ck > cn) { ck = 0; xk = w.x_start; yk = w.y_start; }
-	while (ck > 0 && xk >= s) { --ck; op = cg[ck] >> 14; if (op != 2) xk -= cg[ck] & 0x3fff; if (op != 3) yk -= cg[ck] & 0x3fff; }
-	while (ck < cn && xk < e) {
-		ws = xk; op = cg[ck] >> 14;
-		if (op != 2) xk += cg[ck] & 0x3fff; if (op != 3) yk += cg[ck] & 0x3fff;
-		ck++; we = xk;
-		os = s > ws ? s : ws; oe = e < we ? e : we; ovlp = oe > os ? oe - os : 0;
-		if (op != 2) { if (!ovlp) continue; } else { if (ws < s || ws >= e) continue; }
-		if (op == 0) {
-			for (t = os + 1; t < oe; t++) { ct[(t - s) << 1] += 0x100000001ULL; ct[((t - s) << 1) + 1] += 0x100000001ULL; }
-			t = os;
-			if (t < oe) { ct[(t - s) << 1] += 0x100000001ULL; if (os > ws) ct[((t - s) << 1) + 1] += 0x100000001ULL; }
-		} else if (op != 2) {
-			for (t = os + 1; t < oe; t++) { ct[(t - s) << 1]++; ct[((t - s) << 1) + 1]++; }
-			t = os;
-			if (t < oe) { ct[(t - s) << 1]++; if (os > ws) ct[((t - s) << 1) + 1]++; }
-		} else ct[((ws - s) << 1) + 1]++;
-	}
-	p.xoff = (uint32_t)xk; p.yoff = (uint32_t)yk; p.coff = (int32_t)ck;
-}
 
 // extract_sub_cigar_ii, ecovlp.cpp:365-517: the variant one window alignment proposes for the stretch [iws, iwe) (s..e = its part inside the
 // window): [cigar length:4][cigar:12][base count:4][bases:12], or -1 when the alignment does not span the stretch or the variant is longer than 6
@@ -250,94 +218,11 @@ template <bool GRAPH> HB_HD uint64_t hb_cns_anchor(CnsCtx &C, uint64_t s, uint64
 	return nec;
 }
 
-// wcns_vote, ecovlp.cpp:2185-2272: one block [s, e) of the sweep; id_a = the entries covering it (iterator A), the stretches are voted through iterator B
-template <bool GRAPH> HB_HD int64_t hb_cns_vote(CnsCtx &C, uint32_t id_n, uint64_t s, uint64_t e, uint64_t *nec)
-{
-	uint64_t k, rr = 0, os, oe, wl, oc0, oc1, fI; CnsIt &occ = C.B;
-	for (k = 0; k < id_n; k++) {
-		CnsEnt &p = C.ent[C.A.act[k]]; const hb_wl_t &w = C.ov[p.ov].w[p.wid];
-		const uint64_t q0 = (uint64_t)(int64_t)w.x_start, q1 = (uint64_t)((int64_t)w.x_end + 1);
-		if (q1 <= e) rr = 1;
-		os = q0 > s ? q0 : s; oe = q1 < e ? q1 : e;
-		if (oe > os) hb_cns_sub_mm(C, p, (int64_t)os, (int64_t)oe, C.ct + (os - s)); // the reference offsets the count array by os - s WORDS (not 2 (os - s)): kept
-	}
-	wl = e - s; os = occ.mms; oe = occ.mme;
-	for (k = 0; k < wl; k++) {
-		oc0 = (C.ct[k << 1] >> 32) + 1; oc1 = (uint32_t)C.ct[k << 1] + 1;
-		if (hb_cns_pass(oc0, oc1, 3, 0.500001) || oc1 < 3) {
-			fI = 1;
-			oc0 = (C.ct[(k << 1) + 1] >> 32) + 1; oc1 = (uint32_t)C.ct[(k << 1) + 1] + 1;
-			if (hb_cns_pass(oc0, oc1, 3, 0.500001) || oc1 < 3) fI = 0;
-			if (fI) {
-				if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor<GRAPH>(C, os, oe, 0); if (C.need_full) return 0; }
-				os = oe = (uint64_t)-1;
-			}
-			if (s + k == oe) oe++;
-			else {
-				if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor<GRAPH>(C, os, oe, 0); if (C.need_full) return 0; }
-				os = s + k; oe = s + k + 1;
-			}
-		} else {
-			if (oe > os && os != (uint64_t)-1) { *nec += hb_cns_anchor<GRAPH>(C, os, oe, 0); if (C.need_full) return 0; }
-			os = oe = (uint64_t)-1;
-		}
-		C.ct[k << 1] = C.ct[(k << 1) + 1] = 0;
-	}
-	occ.mms = occ.mme = (uint64_t)-1;
-	if (oe > os && os != (uint64_t)-1) { occ.mms = os; occ.mme = oe; }
-	return (int64_t)rr;
-}
 
-// wcns_gen, ecovlp.cpp:2293-2424.  ov[0..n_ov) = the read's same-haplotype overlaps in the order of the de-duplicated list; ent / srt / act_a / act_b:
-// room for one entry per aligned window of those overlaps (b32 too); key: one word per entry; ct: 2 * HB_CNS_WL words (zeroed here).
-// Returns the number of corrected bases; C.out / C.out_n = the edit script; C.need_full / C.ovf tell when there is none.
-template <bool GRAPH> HB_HD uint64_t hb_cns_read(CnsCtx &C, uint32_t n_ov, uint32_t *srt, uint32_t *act_a, uint32_t *act_b, uint64_t *key)
-{
-	uint32_t n_ent = 0; uint64_t nec = 0;
-	for (uint32_t k = 0; k < n_ov; k++) {
-		const CnsOv &z = C.ov[k];
-		for (uint32_t i = 0; i < z.wn; i++) {
-			if (hb_ualn_w(z.w[i])) continue;
-			if (z.w[i].x_end >= z.w[i].x_start) {
-				key[n_ent] = ((uint64_t)(uint32_t)z.w[i].x_start << 32) + n_ent;
-				CnsEnt &p = C.ent[n_ent]; p.ov = k; p.wid = i; p.xoff = (uint32_t)z.w[i].x_start; p.yoff = (uint32_t)z.w[i].y_start; p.coff = 0;
-				n_ent++;
-			}
-		}
-	}
-	hb_heapsort64(key, n_ent); // radix_sort_ec64 on distinct keys
-	{ // entries that start together are ordered by their end — except the LAST such group, which the reference's loop never reaches (2362-2378): kept
-		int64_t k, i, t;
-		for (k = 1, i = 0; k < (int64_t)n_ent; k++) {
-			if ((key[k] >> 32) != (key[i] >> 32)) {
-				if (k - i > 1) {
-					for (t = i; t < k; t++) { const CnsEnt &cp = C.ent[(uint32_t)key[t]]; uint64_t m = (uint64_t)((int64_t)C.ov[cp.ov].w[cp.wid].x_end + 1); m <<= 32; m += (uint32_t)key[t]; key[t] = m; }
-					hb_heapsort64(key + i, (uint32_t)(k - i));
-				}
-				i = k;
-			}
-		}
-	}
-	for (uint32_t t = 0; t < n_ent; t++) srt[t] = (uint32_t)key[t];
-	for (uint32_t t = 0; t < 2 * HB_CNS_WL; t++) C.ct[t] = 0;
-	C.A.srt = srt; C.A.act = act_a; C.A.i = 0; C.A.srt_n = n_ent; C.A.act_n = 0; C.A.rr = C.A.ru = 0; C.A.mms = C.A.mme = (uint64_t)-1;
-	C.B.srt = srt; C.B.act = act_b; C.B.i = 0; C.B.srt_n = n_ent; C.B.act_n = 0; C.B.rr = C.B.ru = 0; C.B.mms = C.B.mme = (uint64_t)-1;
-	C.out_n = 0; C.has_win = 0; C.ax_start = C.ax_end = -1; C.ovf = 0; C.need_full = 0; C.b32_n = 0;
-	int64_t s = 0, e = HB_CNS_WL, rr = 0; if (e > C.ql) e = C.ql;
-	for (; s < C.ql;) {
-		const uint32_t rn = hb_cns_iter(C, C.A, s, e, rr, 0);
-		rr = hb_cns_vote<GRAPH>(C, rn, (uint64_t)s, (uint64_t)e, &nec);
-		if (C.need_full) return nec;
-		s += HB_CNS_WL; e += HB_CNS_WL; if (e > C.ql) e = C.ql;
-	}
-	if (C.B.mme > C.B.mms && C.B.mms != (uint64_t)-1) { nec += hb_cns_anchor<GRAPH>(C, C.B.mms, C.B.mme, 0); if (C.need_full) return nec; }
-	nec += hb_cns_anchor<GRAPH>(C, (uint64_t)C.ql, (uint64_t)C.ql, 1);
-	return nec;
-}
 
 // =====================================================================================================================================
 // The same consensus with one WARP per read (hb_warp.cuh).  What changes is the shape of the work, not its result:
-//   * the pile-up of a 512-column block — wcns_vote's first loop, which in the reference (and in hb_cns_vote above) touches two counters per
+//   * the pile-up of a 512-column block — wcns_vote's first loop, which in the reference (and in the one-thread form kept in tests/hostemu/seq_ref.h) touches two counters per
 //     column per covering alignment — becomes RANGE UPDATES on a difference array in shared memory: a lane owns a covering alignment, walks its
 //     cigar RUNS and adds +v / -v at the two ends of the word range a run votes on (the reference's misplaced count-array offset, os - s WORDS,
 //     only shifts where the range lands: a range of words base + 2 (t - s) + c is contiguous inside its parity class, so there is one
@@ -454,7 +339,7 @@ template <bool GRAPH> HB_HD int64_t hb_cns_vote_w(CnsCtx &C, uint64_t *S, uint32
 	return rr;
 }
 
-// wcns_gen for a warp: same arguments as hb_cns_read, called by every lane; S = the warp's shared-memory words.  The edit script, nec, C.need_full, C.ovf are lane 0's.
+// wcns_gen for a warp, called by every lane; S = the warp's shared-memory words.  The edit script, nec, C.need_full, C.ovf are lane 0's.
 template <bool GRAPH> HB_HD uint64_t hb_cns_read_w(CnsCtx &C, uint64_t *S, uint32_t n_ov, uint32_t *srt, uint32_t *act_a, uint32_t *act_b, uint64_t *key)
 {
 	const int lane = hb_lane(); uint32_t n_ent = 0; uint64_t nec = 0;

@@ -224,7 +224,7 @@ HB_HD void hb_ph_decide_w(const DevReads &R, uint64_t qid, PhOv *ov, uint32_t n_
 		if (o > 0) ord[n_ord++] = ((uint64_t)(0xffffffffu - o) << 32) | ov_off[j]; // more alleles first, then list position
 	}
 	if (n_ord) {
-		for (uint32_t a = 1; a < n_ord; a++) { const uint64_t v = ord[a]; int32_t b = (int32_t)a - 1; while (b >= 0 && ord[b] > v) { ord[b + 1] = ord[b]; b--; } ord[b + 1] = v; } // keys are unique
+		hb_heapsort64(ord, n_ord); // keys are unique (list positions): any sort gives the reference's order; an insertion sort is quadratic on repeat-rich reads
 		for (uint32_t k = 0; k < n_ord; k++) {
 			const uint32_t l = (uint32_t)ord[k], j = L[l].ov; uint64_t o = 0;
 			for (uint32_t i = l; i < ov_off[j + 1]; i++) { if (L[i].type != 1) continue; sp = L[i].osite; const PhSnp &q = snp[sp]; if (PH_REAL(q) && PH_ALLELE(q)) o++; }
