@@ -76,7 +76,12 @@ def test_anchors_chains(ctx, mode):
         assert dg(chits.tobytes()) == int(g.digest(mode, "chain_hits")[i]), "chain hits read %d" % i
 
 
-def test_ec_align_step_A(ctx):
+# "warp": the forms the product runs (warp kernels as a warp of one lane, the band over virtual lanes); "thread": the one-thread forms kept in
+# tests/hostemu/seq_ref.h and the thread aligner for every tier — both must reproduce the reference's fixtures
+@pytest.mark.parametrize("forms", ["warp", "thread"])
+def test_ec_align_step_A(ctx, forms, monkeypatch):
+    if forms == "thread":
+        monkeypatch.setenv("HB_EMU_CNS_THREAD", "1"); monkeypatch.setenv("HB_EMU_ALN_THREAD", "1")
     """body of k_ec_overlap (hb_ecaln.cuh) on the raw reads: gap filling, traced windows, extension estimate"""
     import alnlib
     g, opt, ft, eft = ctx
