@@ -524,22 +524,7 @@ static int run_pass(hb_ctx *ctx, uint64_t r0, uint64_t r1, int mode, double bw, 
 
 // ---- lanes: the batches of a pass on two streams (see run_pass_impl) ----
 // What a batch adds to the host-side results of the pass is added in batch order: commit(k, fn) runs fn when the batches before k have committed.
-#define HB_E_ABORTED (-101) /* internal: the batch gave up because another one failed */
-struct PassOrder {
-	std::mutex mu; std::condition_variable cv; size_t next; bool aborted; std::vector<char> done;
-	explicit PassOrder(size_t n) : next(0), aborted(false), done(n, 0) {}
-	template <typename F> int commit(size_t k, F fn)
-	{
-		std::unique_lock<std::mutex> lk(mu);
-		cv.wait(lk, [&]() { return next == k || aborted; });
-		if (aborted) return HB_E_ABORTED; // (another batch failed: its error is the one reported)
-		const int rc = fn();
-		if (rc) aborted = true; else { done[k] = 1; next = k + 1; }
-		lk.unlock(); cv.notify_all();
-		return rc;
-	}
-	void abort() { { std::lock_guard<std::mutex> lk(mu); aborted = true; } cv.notify_all(); }
-};
+#include "hb_order.h"
 // the second lane's context: a copy of the pass's context (read store, index, staged lists, options: shared, read-only inside a pass) with a stream, workspace,
 // profile and counters of its own.  Owns only its stream and workspace (hb_lane_free).
 static int lane_refresh(hb_ctx *ctx, int li)

@@ -132,3 +132,56 @@ def test_allgather_callback_world2():
     want = b"".join(bytes([(r * 37 + i) & 0xff for i in range(nbytes)]) for r in range(world))
     for rank, rc, got in res:
         assert rc == 0 and got == want   # every rank holds every rank's bytes, in rank order
+
+
+# ---- a failing rank must not leave the others waiting in the exchange: cal_ec_r_sharded agrees on the worst status first (round-1 advice) ----
+class _FakeEngine:
+    """Engine stand-in for the CPU: rank 1's first ec_round call overflows its buffers (HB_E_OVERFLOW = -5), every later call succeeds"""
+    def __init__(self, rank, n):
+        self.rank, self.n_reads, self.calls, self.caps = rank, n, 0, []
+
+    def ec_stage_prev(self, *a): pass
+    def read_lengths(self): return np.full(self.n_reads, 1000, np.uint32)
+    def ec_stage_scc(self, *a): pass
+    def ec_apply(self): pass
+    def ec_update_paf(self, src, soff): return src, 0, 0
+    def ec_post_rev(self, upd, soff, rev, roff): return upd, soff, rev, roff
+
+    def ec_round(self, r0, r1, bw, e_rate, w_l, use_prev=1, caps=None):
+        from hifiasm_b200.engine import HBError
+        self.calls += 1; self.caps.append(caps[0])
+        if self.rank == 1 and self.calls == 1:
+            e = HBError("overlap output capacity"); e.code = -5; raise e
+        m = r1 - r0; z = np.zeros(0, hdist_ma()); o = np.zeros(m + 1, np.uint64)
+        return dict(src=z, src_off=o, rev=z.copy(), rev_off=o.copy(), scc=np.zeros(0, np.uint16), scc_off=o.copy(), is_fully_corrected=np.zeros(m, np.uint8),
+                    is_abnormal=np.zeros(m, np.uint8), status=np.zeros(m, np.uint8), n_corrected=0)
+
+
+def hdist_ma():
+    from hifiasm_b200 import binio
+    return binio.MA_MEM
+
+
+def _worker_retry(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeEngine(rank, 10)
+    r = hdist.cal_ec_r_sharded(eng, 0, 0, np.zeros(0, hdist_ma()), np.zeros(11, np.uint64))
+    q.put((rank, eng.calls, eng.caps, int(r["src_off"].size)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_round_retries_on_every_rank_when_one_overflows():
+    world = 2
+    ctx = mp.get_context("spawn"); q = ctx.Queue(); port = _free_port()
+    ps = [ctx.Process(target=_worker_retry, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, calls, caps, n_off in res:
+        assert calls == 2 and caps[1] == 4 * caps[0], (rank, calls, caps)     # both ranks repeated the round, with four times the room
+        assert n_off == 11                                                      # and left with all reads' (empty) lists
